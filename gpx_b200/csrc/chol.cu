@@ -1,0 +1,268 @@
+// Blocked FP64 Cholesky, triangular solves, log-det and SPD inverse for sm_100a.
+//
+// Replaces jsp.linalg.cholesky / solve_triangular / log(diag) in the reference
+// (gpx/models/_gpr.py:457-458, 759-763, 860-861; _sgpr.py:459-462, 684-691) and supplies
+// A^-1 for the analytic LML gradient (what value_and_grad yields,
+// gpx/optimizers/scipy_optimize.py:72-78).
+//
+// Structure: fully recursive lower Cholesky on row-major storage; every O(n^3)
+// flop is a DMMA GEMM (gemm.cu) -- SYRK trailing updates and TRSMs that multiply
+// by explicitly inverted 128x128 diagonal blocks.  The 128x128 leaves are
+// factorised AND inverted by one CTA in shared memory.
+#include "chol.cuh"
+#include "gemm.cuh"
+#include "mma.cuh"
+
+namespace gpxb {
+
+namespace {
+
+constexpr int LB = CHOL_LEAF;  // 128
+constexpr int LS = LB + 1;     // padded smem stride (odd -> conflict-free columns)
+constexpr int LEAF_NT = 512;
+constexpr int LEAF_SMEM = (LB * LS + LB) * (int)sizeof(double);
+
+// One CTA: factor the n x n (n <= 128) lower block in place, then write its inverse
+// (full 128x128 block, zero upper / zero padding) to inv.
+__global__ void __launch_bounds__(LEAF_NT, 1)
+potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;             // [LB][LS]
+  double* Ld = sm + LB * LS;  // [LB] diagonal of L
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;  // 32 x 16
+
+  for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    double v = 0.0;
+    if (i < n && k <= i) v = A[(long long)i * lda + k];
+    S[i * LS + k] = v;
+  }
+  __syncthreads();
+
+  // ---- right-looking unblocked Cholesky, 2 barriers per column ----
+  for (int j = 0; j < n; ++j) {
+    const double d = sqrt(S[j * LS + j]);  // NaN for a non-PD pivot: propagates like JAX
+    for (int i = j + 1 + tid; i < n; i += LEAF_NT) S[i * LS + j] /= d;
+    if (tid == 0) Ld[j] = d;
+    __syncthreads();
+    for (int i = j + 1 + ty; i < n; i += 16) {
+      const double lij = S[i * LS + j];
+      for (int k = j + 1 + tx; k <= i; k += 32) S[i * LS + k] -= lij * S[k * LS + j];
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < n; j += LEAF_NT) S[j * LS + j] = Ld[j];
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += LEAF_NT) {
+    const int i = idx / n, k = idx - i * n;
+    if (k <= i) A[(long long)i * lda + k] = S[i * LS + k];
+  }
+  if (inv == nullptr) return;
+
+  // ---- in-place inverse of the lower factor (dtrti2, columns right to left) ----
+  // X[j][j] = 1/L[j][j];  X[i][j] = -(sum_{k=j+1..i} X[i][k] L[k][j]) * X[j][j], i > j.
+  // 4 lanes cooperate on one row i.
+  const int sub = tid & 3, rowslot = tid >> 2;  // 128 row slots
+  for (int j = n - 1; j >= 0; --j) {
+    const double xjj = 1.0 / S[j * LS + j];
+    double r = 0.0;
+    const int i = j + 1 + rowslot;
+    if (i < n) {
+      for (int k = j + 1 + sub; k <= i; k += 4) r += S[i * LS + k] * S[k * LS + j];
+    }
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    __syncthreads();  // all reads of column j (original L) done
+    if (i < n && sub == 0) S[i * LS + j] = -r * xjj;
+    if (tid == 0) S[j * LS + j] = xjj;
+    __syncthreads();
+  }
+  for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    inv[idx] = (i < n && k <= i) ? S[i * LS + k] : 0.0;
+  }
+}
+
+__global__ void logdet_kernel(const double* __restrict__ L, long long ld, int n,
+                              double* __restrict__ out, double scale) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) s += log(L[(long long)i * ld + i]);
+  s = block_sum<1024>(s, sh);
+  if (threadIdx.x == 0) *out = scale * s;
+}
+
+__global__ void copy_block_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                  long long ldd, int n) {
+  // src: packed 128x128 leaf inverse; dst: n x n lower block
+  for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < n * n; idx += blockDim.x * gridDim.x) {
+    const int i = idx / n, k = idx - i * n;
+    if (k <= i) dst[(long long)i * ldd + k] = src[i * LB + k];
+  }
+}
+
+int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s) {
+  GPXB_CUDA_CHECK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       LEAF_SMEM));
+  potrf_leaf_kernel<<<1, LEAF_NT, LEAF_SMEM, s>>>(A, lda, n, inv);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+inline int split_point(int n) {
+  const int nb = (n + LB - 1) / LB;
+  return (nb / 2) * LB;
+}
+
+}  // namespace
+
+// X * L^T = B  (X = B L^-T), B is m x n row-major, overwritten.  inv: leaf inverses of L's
+// diagonal blocks (128x128 packed each), L n x n lower.
+int trsm_right_lt(Ctx* ctx, const double* L, long long ldl, const double* inv, double* B,
+                  long long ldb, int m, int n, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return 0;
+  if (n <= LB) {
+    GemmArgs g;
+    g.M = m; g.N = n; g.K = n;
+    g.A = B; g.lda = ldb; g.a_kmajor = true;
+    g.B = inv; g.ldb = LB; g.b_kmajor = true;  // (B inv^T)[i][j] = sum_k B[i][k] inv[j][k]
+    g.C = B; g.ldc = ldb;                       // in place: single column tile, rows private per CTA
+    return gemm_f64(ctx, g, s);
+  }
+  const int n1 = split_point(n), n2 = n - n1;
+  GPXB_TRY(trsm_right_lt(ctx, L, ldl, inv, B, ldb, m, n1, s));
+  {
+    GemmArgs g;  // B2 -= X1 * L21^T
+    g.M = m; g.N = n2; g.K = n1;
+    g.A = B; g.lda = ldb; g.a_kmajor = true;
+    g.B = L + (long long)n1 * ldl; g.ldb = ldl; g.b_kmajor = true;
+    g.C = B + n1; g.ldc = ldb;
+    g.alpha = -1.0; g.beta = 1.0;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  return trsm_right_lt(ctx, L + (long long)n1 * ldl + n1, ldl, inv + (long long)(n1 / LB) * LB * LB,
+                       B + n1, ldb, m, n2, s);
+}
+
+// X * L = B  (X = B L^-1), B is m x n row-major, overwritten.
+int trsm_right_l(Ctx* ctx, const double* L, long long ldl, const double* inv, double* B,
+                 long long ldb, int m, int n, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return 0;
+  if (n <= LB) {
+    GemmArgs g;
+    g.M = m; g.N = n; g.K = n;
+    g.A = B; g.lda = ldb; g.a_kmajor = true;
+    g.B = inv; g.ldb = LB; g.b_kmajor = false;  // (B inv)[i][j] = sum_k B[i][k] inv[k][j]
+    g.C = B; g.ldc = ldb;
+    return gemm_f64(ctx, g, s);
+  }
+  const int n1 = split_point(n), n2 = n - n1;
+  GPXB_TRY(trsm_right_l(ctx, L + (long long)n1 * ldl + n1, ldl, inv + (long long)(n1 / LB) * LB * LB,
+                        B + n1, ldb, m, n2, s));
+  {
+    GemmArgs g;  // B1 -= X2 * L21
+    g.M = m; g.N = n1; g.K = n2;
+    g.A = B + n1; g.lda = ldb; g.a_kmajor = true;
+    g.B = L + (long long)n1 * ldl; g.ldb = ldl; g.b_kmajor = false;
+    g.C = B; g.ldc = ldb;
+    g.alpha = -1.0; g.beta = 1.0;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  return trsm_right_l(ctx, L, ldl, inv, B, ldb, m, n1, s);
+}
+
+// In-place lower Cholesky of the n x n row-major matrix A (only the lower triangle is
+// read or written).  inv receives ceil(n/128) packed 128x128 inverses of L's diagonal blocks.
+int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (n <= LB) return leaf(ctx, A, lda, n, inv, s);
+  const int n1 = split_point(n), n2 = n - n1;
+  GPXB_TRY(potrf_lower(ctx, A, lda, n1, inv, s));
+  double* A21 = A + (long long)n1 * lda;
+  double* A22 = A21 + n1;
+  GPXB_TRY(trsm_right_lt(ctx, A, lda, inv, A21, lda, n2, n1, s));
+  {
+    GemmArgs g;  // A22 -= A21 A21^T (lower)
+    g.M = n2; g.N = n2; g.K = n1;
+    g.A = A21; g.lda = lda; g.a_kmajor = true;
+    g.B = A21; g.ldb = lda; g.b_kmajor = true;
+    g.C = A22; g.ldc = lda;
+    g.alpha = -1.0; g.beta = 1.0;
+    g.lower_only = 1;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  return potrf_lower(ctx, A22, lda, n2, inv + (long long)(n1 / LB) * LB * LB, s);
+}
+
+namespace {
+// W (n x n, zero-initialised, lower) <- L^-1.  T: scratch with leading dimension ldt >= n/2.
+int trtri_rec(Ctx* ctx, const double* L, long long ldl, const double* inv, double* W, long long ldw,
+              int n, double* T, long long ldt, cudaStream_t s) {
+  if (n <= LB) {
+    copy_block_kernel<<<32, 256, 0, s>>>(inv, W, ldw, n);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+    return 0;
+  }
+  const int n1 = split_point(n), n2 = n - n1;
+  const double* inv2 = inv + (long long)(n1 / LB) * LB * LB;
+  GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, ldw, n1, T, ldt, s));
+  GPXB_TRY(trtri_rec(ctx, L + (long long)n1 * ldl + n1, ldl, inv2, W + (long long)n1 * ldw + n1, ldw,
+                     n2, T, ldt, s));
+  {
+    GemmArgs g;  // T = L21 * W11   (W11 lower: k starts at the tile's first column)
+    g.M = n2; g.N = n1; g.K = n1;
+    g.A = L + (long long)n1 * ldl; g.lda = ldl; g.a_kmajor = true;
+    g.B = W; g.ldb = ldw; g.b_kmajor = false;
+    g.C = T; g.ldc = ldt;
+    g.klo_mode = 1;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  {
+    GemmArgs g;  // W21 = -W22 * T   (W22 lower: k ends at the tile's last row)
+    g.M = n2; g.N = n1; g.K = n2;
+    g.A = W + (long long)n1 * ldw + n1; g.lda = ldw; g.a_kmajor = true;
+    g.B = T; g.ldb = ldt; g.b_kmajor = false;
+    g.C = W + (long long)n1 * ldw; g.ldc = ldw;
+    g.alpha = -1.0;
+    g.khi_mode = 1;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  return 0;
+}
+}  // namespace
+
+// Ainv (lower triangle, n x n, ld ldo) <- (L L^T)^-1 given the factor L and its leaf inverses.
+// W: n x n workspace (ld n), T: (n/2+128)^2 workspace.  out may alias L's storage.
+int potri_lower(Ctx* ctx, const double* L, long long ldl, const double* inv, int n, double* W,
+                double* T, double* out, long long ldo, cudaStream_t s) {
+  if (n <= 0) return 0;
+  GPXB_CUDA_CHECK(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)n * (size_t)n, s));
+  const long long ldt = (n <= LB) ? LB : (long long)(n - split_point(n));
+  GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, n, n, T, ldt, s));
+  GemmArgs g;  // out = W^T W (lower); W[k][i] = 0 for k < i -> k starts at the tile's first row
+  g.M = n; g.N = n; g.K = n;
+  g.A = W; g.lda = n; g.a_kmajor = false;
+  g.B = W; g.ldb = n; g.b_kmajor = false;
+  g.C = out; g.ldc = ldo;
+  g.lower_only = 1;
+  g.klo_mode = 2;
+  return gemm_f64(ctx, g, s);
+}
+
+int logdet_lower(Ctx* ctx, const double* L, long long ld, int n, double* out, double scale,
+                 cudaStream_t s) {
+  logdet_kernel<<<1, 1024, 0, s>>>(L, ld, n, out, scale);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+size_t potri_scratch_doubles(int n) {
+  const long long h = (n <= LB) ? LB : (long long)(n - split_point(n));
+  return (size_t)(h * h);
+}
+
+}  // namespace gpxb

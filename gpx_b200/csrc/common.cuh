@@ -1,0 +1,85 @@
+// Common device/host helpers for libgpxb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+namespace gpxb {
+
+// ---------------------------------------------------------------------------
+// Error convention: 0 = OK, <0 = argument error, >0 = CUDA/NCCL.
+// The message is kept per thread and read back through gpxb_last_error().
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define GPXB_CUDA_CHECK(expr)                                                        \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ::gpxb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                 \
+                        cudaGetErrorString(_e));                                      \
+      return (int)_e > 0 ? (int)_e : 1;                                               \
+    }                                                                                 \
+  } while (0)
+
+#define GPXB_ARG_CHECK(cond, code)                                                   \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      ::gpxb::set_error("%s:%d: argument check failed: %s", __FILE__, __LINE__, #cond); \
+      return (code);                                                                  \
+    }                                                                                 \
+  } while (0)
+
+#define GPXB_TRY(expr)                 \
+  do {                                 \
+    int _rc = (expr);                  \
+    if (_rc != 0) return _rc;          \
+  } while (0)
+
+#define GPXB_LAUNCH_CHECK() GPXB_CUDA_CHECK(cudaGetLastError())
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------
+// Device context: device properties, a side stream + events for fork/join of
+// independent sub-problems inside one call, a launch counter, and (optionally)
+// a NCCL communicator for the row-sharded matrix-free paths (comm.cu).
+// All scratch memory is stream-ordered (cudaMallocAsync on the caller's stream),
+// so every entry point is enqueue-only and re-entrant per context.
+// ---------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  unsigned long long launches = 0;  // kernels launched by this library via this ctx
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+// Stream-ordered scratch buffer (RAII). alloc() returns 0 or a CUDA error code.
+struct DevBuf {
+  void* p = nullptr;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  int alloc(size_t bytes, cudaStream_t stream) {
+    s = stream;
+    if (bytes == 0) bytes = 8;
+    GPXB_CUDA_CHECK(cudaMallocAsync(&p, bytes, stream));
+    return 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+  }
+  ~DevBuf() { release(); }
+};
+
+}  // namespace gpxb

@@ -1,0 +1,38 @@
+// Internal FP64 DMMA GEMM interface (row-major everywhere).
+#pragma once
+#include "common.cuh"
+
+namespace gpxb {
+
+// C[M x N] = alpha * opA * opB + beta * C, all row-major with leading dimensions.
+//   a_kmajor: A is stored [M][K] (element (i,k) at A[i*lda + k]); else stored [K][M].
+//   b_kmajor: B is stored [N][K] (element (k,j) at B[j*ldb + k]); else stored [K][N].
+// lower_only: only 128x128 tiles with tile_row >= tile_col are computed and only
+//   entries with global row >= col are written (M == N expected).
+// klo_mode: 0 -> k starts at 0; 1 -> at the tile's first column (B is lower
+//   triangular, B[k][j] = 0 for k < j); 2 -> at the tile's first row.
+// khi_mode: 0 -> k ends at K; 1 -> at the tile's last row + 1 (A is lower
+//   triangular, A[i][k] = 0 for k > i).
+// The skipped parts of triangular operands must hold real zeros (partial tiles are read).
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const double* A = nullptr;
+  long long lda = 0;
+  bool a_kmajor = true;
+  const double* B = nullptr;
+  long long ldb = 0;
+  bool b_kmajor = true;
+  double* C = nullptr;
+  long long ldc = 0;
+  double alpha = 1.0, beta = 0.0;
+  int lower_only = 0;
+  int klo_mode = 0;
+  int khi_mode = 0;
+};
+
+int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream);
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 128;
+
+}  // namespace gpxb

@@ -1,0 +1,255 @@
+// Family 1: fused stationary kernel-matrix construction for sm_100a.
+//
+// Replaces gpx/utils.py:55-72 (squared_distances) + gpx/kernels/kernels.py:751-757 (SE),
+// 922-927 (Matern-1/2), 966-971 (Matern-3/2), 1050-1055 (Matern-5/2), the noise diagonal of
+// gpx/models/_gpr.py:39-63, and -- in contraction mode -- the d/d lengthscale part of
+// jit(value_and_grad(loss)) (gpx/optimizers/scipy_optimize.py:72-78).
+//
+// One CTA = one 128x128 tile.  Both pre-scaled operand tiles (128 rows x S doubles,
+// contiguous) arrive by one 1-D bulk TMA copy each (cp.async.bulk + mbarrier); the pair
+// dot products run on the FP64 tensor pipe (DMMA.8x8x4, K = D); the epilogue forms
+//   d2 = |z_i|^2 - 2 z_i.z_j + |z_j|^2 + 1e-12
+// applies the kernel nonlinearity and either stores K (+ diagonal shift) or contracts
+// dK/d ell with W = alpha alpha^T - A^-1 without materialising dK.
+#include "gram.cuh"
+#include "mma.cuh"
+
+namespace gpxb {
+
+namespace {
+
+constexpr int TB = 128;
+constexpr int NT = 256;
+
+struct GramParams {
+  int kind;
+  const double* Z1;
+  int n1;
+  const double* Z2;
+  int n2;
+  int S, Dp;
+  double ell, diag_add;
+  int sym, lower_only;
+  double* out;
+  long long ldo;
+  int vec_out;
+  const double* Ainv;
+  long long ldainv;
+  const double* alpha;
+  int t;
+  double* partials;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ double kfun(int kind, double d2) {
+  if (kind == KIND_SE) return exp(-d2);
+  const double r = sqrt(fmax(d2, 1e-36));
+  if (kind == KIND_M12) return exp(-r);
+  if (kind == KIND_M32) {
+    const double d = 1.7320508075688772 * r;
+    return (1.0 + d) * exp(-d);
+  }
+  const double d = 2.23606797749979 * r;
+  return (1.0 + d + d * d / 3.0) * exp(-d);
+}
+
+// dK/d ell given d2 = s + 1e-12 (the jitter is a constant; the clamp passes no gradient)
+__device__ __forceinline__ double kfun_dl(int kind, double d2, double s, double ell) {
+  if (kind == KIND_SE) return exp(-d2) * 2.0 * s / ell;
+  if (!(d2 > 1e-36)) return 0.0;
+  const double r = sqrt(d2);
+  if (kind == KIND_M12) return exp(-r) * s / (r * ell);
+  if (kind == KIND_M32) {
+    const double d = 1.7320508075688772 * r;
+    return 3.0 * s * exp(-d) / ell;
+  }
+  const double d = 2.23606797749979 * r;
+  return (5.0 * s / (3.0 * ell)) * (1.0 + d) * exp(-d);
+}
+
+__global__ void prep_z_kernel(const double* __restrict__ x, long long ldx, int n, int D, int Dp,
+                              int S, double ell, double* __restrict__ Z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* xi = x + (long long)i * ldx;
+  double* zi = Z + (long long)i * S;
+  double nrm = 0.0;
+  for (int d = 0; d < D; ++d) {
+    const double z = xi[d] / ell;
+    zi[d] = z;
+    nrm += z * z;
+  }
+  for (int d = D; d < S; ++d) zi[d] = 0.0;
+  zi[Dp] = nrm;
+}
+
+template <bool CONTRACT>
+__global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* sZ1 = reinterpret_cast<double*>(smem_raw + 128);
+  double* sZ2 = sZ1 + TB * p.S;
+  __shared__ double red[NT / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lq = lane & 3;
+
+  int ti, tj;
+  if (p.lower_only) {
+    const long long t = blockIdx.x;
+    long long i = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (i * (i + 1) / 2 > t) --i;
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    ti = (int)i;
+    tj = (int)(t - i * (i + 1) / 2);
+  } else {
+    ti = blockIdx.x / p.tiles_n;
+    tj = blockIdx.x % p.tiles_n;
+  }
+  const int row0 = ti * TB, col0 = tj * TB;
+  const int rows1 = min(TB, p.n1 - row0), rows2 = min(TB, p.n2 - col0);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t b1 = (uint32_t)rows1 * p.S * 8u, b2 = (uint32_t)rows2 * p.S * 8u;
+    mbar_arrive_expect_tx(bar, b1 + b2);
+    tma_bulk_g2s(sZ1, p.Z1 + (long long)row0 * p.S, b1, bar);
+    tma_bulk_g2s(sZ2, p.Z2 + (long long)col0 * p.S, b2, bar);
+  }
+  mbar_wait(bar, 0);
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const double* a_base = sZ1 + (wm * 64 + lr) * p.S + lq;
+  const double* b_base = sZ2 + (wn * 32 + lr) * p.S + lq;
+  const int S8 = 8 * p.S;
+  for (int k = 0; k < p.Dp; k += 4) {
+    double a[8], b[4];
+#pragma unroll
+    for (int mf = 0; mf < 8; ++mf) a[mf] = a_base[mf * S8 + k];
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) b[nf] = b_base[nf * S8 + k];
+#pragma unroll
+    for (int mf = 0; mf < 8; ++mf)
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
+  }
+
+  // ---- fused epilogue ----
+  double nj[4][2];
+#pragma unroll
+  for (int nf = 0; nf < 4; ++nf) {
+    const int c = wn * 32 + nf * 8 + lq * 2;
+    nj[nf][0] = sZ2[c * p.S + p.Dp];
+    nj[nf][1] = sZ2[(c + 1) * p.S + p.Dp];
+  }
+  double local = 0.0;
+#pragma unroll
+  for (int mf = 0; mf < 8; ++mf) {
+    const int rl = wm * 64 + mf * 8 + lr;
+    const int gi = row0 + rl;
+    const double ni = sZ1[rl * p.S + p.Dp];
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) {
+      const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
+      double v[2];
+      bool ok[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = gj + e;
+        ok[e] = (gi < p.n1) && (j < p.n2) && (!p.lower_only || j <= gi);
+        double d2 = ((ni - 2.0 * acc[mf][nf][e]) + nj[nf][e]) + 1e-12;
+        const bool on_diag = p.sym && (gi == j);
+        if (on_diag) d2 = 1e-12;
+        if (!CONTRACT) {
+          v[e] = kfun(p.kind, d2) + ((gi == j) ? p.diag_add : 0.0);
+        } else {
+          v[e] = 0.0;
+          if (ok[e]) {
+            const double s = on_diag ? 0.0 : d2 - 1e-12;
+            const double dk = kfun_dl(p.kind, d2, s, p.ell);
+            double w = -p.Ainv[(long long)gi * p.ldainv + j];
+            for (int t = 0; t < p.t; ++t)
+              w += p.alpha[(long long)t * p.n1 + gi] * p.alpha[(long long)t * p.n1 + j];
+            v[e] = ((gi == j) ? 1.0 : 2.0) * w * dk;
+          }
+        }
+      }
+      if (!CONTRACT) {
+        double* o = p.out + (long long)gi * p.ldo + gj;
+        if (p.vec_out && ok[0] && ok[1]) {
+          *reinterpret_cast<double2*>(o) = make_double2(v[0], v[1]);
+        } else {
+          if (ok[0]) o[0] = v[0];
+          if (ok[1]) o[1] = v[1];
+        }
+      } else {
+        local += v[0] + v[1];
+      }
+    }
+  }
+  if (CONTRACT) {
+    const double tot = block_sum<NT>(local, red);
+    if (tid == 0) p.partials[blockIdx.x] = tot;
+  }
+}
+
+}  // namespace
+
+int prep_z(Ctx* ctx, const double* x, long long ldx, int n, ZLayout zl, double ell, double* Z,
+           cudaStream_t s) {
+  if (n <= 0) return 0;
+  prep_z_kernel<<<ceil_div(n, 128), 128, 0, s>>>(x, ldx, n, zl.D, zl.Dp, zl.S, ell, Z);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+long long gram_num_ctas(const GramArgs& a) {
+  const long long tm = ceil_div(a.n1, TB), tn = ceil_div(a.n2, TB);
+  return a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+}
+
+int gram_launch(Ctx* ctx, const GramArgs& a, cudaStream_t s) {
+  if (a.n1 <= 0 || a.n2 <= 0) return 0;
+  GPXB_ARG_CHECK(a.zl.S <= GRAM_MAX_S, -10);
+  GPXB_ARG_CHECK(!a.lower_only || a.n1 == a.n2, -11);
+  GramParams p;
+  p.kind = a.kind;
+  p.Z1 = a.Z1; p.n1 = a.n1; p.Z2 = a.Z2; p.n2 = a.n2;
+  p.S = a.zl.S; p.Dp = a.zl.Dp;
+  p.ell = a.ell; p.diag_add = a.diag_add;
+  p.sym = a.sym; p.lower_only = a.lower_only;
+  p.out = a.out; p.ldo = a.ldo;
+  p.vec_out = a.out && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) && (a.ldo % 2 == 0);
+  p.Ainv = a.Ainv; p.ldainv = a.ldainv; p.alpha = a.alpha; p.t = a.t; p.partials = a.partials;
+  p.tiles_m = ceil_div(a.n1, TB);
+  p.tiles_n = ceil_div(a.n2, TB);
+  const long long grid = gram_num_ctas(a);
+  GPXB_ARG_CHECK(grid < (1LL << 31), -12);
+  const int smem = 128 + 2 * TB * p.S * (int)sizeof(double);
+  if (a.out) {
+    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gram_kernel<false><<<(int)grid, NT, smem, s>>>(p);
+  } else {
+    GPXB_ARG_CHECK(a.sym && a.lower_only && a.Ainv && a.alpha && a.partials, -13);
+    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gram_kernel<true><<<(int)grid, NT, smem, s>>>(p);
+  }
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+}  // namespace gpxb

@@ -1,0 +1,100 @@
+/* libgpxb200 -- B200-native (sm_100a) Gaussian-process hot path behind a plain C ABI.
+ *
+ * The reference (Molecolab-Pisa/GPX) is pure Python on JAX and has no FFI of its own; the seam
+ * this library sits behind is the set of jit'd numerical-core functions the gpx.models facade
+ * calls.  Each entry point cites the reference function it replaces (paths relative to the
+ * GPX repository root).  Under JAX these symbols are what an XLA-FFI (jax.ffi) custom call
+ * would bind; here they are bound by ctypes (gpx_b200/_lib.py).
+ *
+ * Conventions
+ *   - every pointer argument is a DEVICE pointer to row-major FP64 (or int64 / uint32 where
+ *     stated), owned by the caller; outputs are pre-allocated by the caller;
+ *   - every call is enqueue-only on the given CUDA stream (no host synchronisation) and
+ *     re-entrant per context; scratch memory is stream-ordered (cudaMallocAsync);
+ *   - return value: 0 = OK, < 0 = argument error, > 0 = CUDA / NCCL error code;
+ *     gpxb_last_error() returns the message of the calling thread's last failure;
+ *   - numerical failure (a non positive-definite matrix) is NOT an error: NaN propagates to
+ *     the outputs exactly as jax.scipy.linalg.cholesky does in the reference.
+ *   - kind: 0 = SquaredExponential, 1 = Matern12, 2 = Matern32, 3 = Matern52
+ *     (gpx/kernels/kernels.py:1623-1754); lengthscale is a scalar.
+ */
+#ifndef GPXB200_H
+#define GPXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpxb_ctx gpxb_ctx;
+typedef void* gpxb_stream; /* cudaStream_t */
+
+enum { GPXB_SE = 0, GPXB_M12 = 1, GPXB_M32 = 2, GPXB_M52 = 3 };
+enum { GPXB_MEAN_ZERO = 0, GPXB_MEAN_DATA = 1 }; /* gpx/mean_functions.py:25-30 */
+
+/* ---- library / context ------------------------------------------------------------- */
+int gpxb_version(void);
+int gpxb_last_error(char* buf, size_t buflen);
+int gpxb_ctx_create(int device, gpxb_ctx** out);
+int gpxb_ctx_destroy(gpxb_ctx* ctx);
+/* number of CUDA kernels this library has launched through ctx (bench.py "gpu_launches") */
+unsigned long long gpxb_ctx_launches(gpxb_ctx* ctx);
+
+/* ---- Family 1: fused kernel-matrix construction ------------------------------------- */
+/* out[n1 x n2] (ld ldo) = k(x1, x2) + diag_add * I.  Replaces Kernel.k -> squared_distances +
+ * nonlinearity (gpx/utils.py:55-72, gpx/kernels/kernels.py:751-757, 922-927, 966-971, 1050-1055)
+ * and the noise diagonal of _A_lhs (gpx/models/_gpr.py:39-63).  x2 == x1 (same pointer, n2 == n1)
+ * selects the symmetric path; lower_only then writes only entries with row >= col. */
+int gpxb_gram(gpxb_ctx* ctx, int kind, const double* x1, int n1, const double* x2, int n2, int D,
+              double ell, double diag_add, double* out, long long ldo, int lower_only,
+              gpxb_stream stream);
+
+/* ---- Family 2: blocked FP64 Cholesky / TRSM / log-det / inverse ---------------------- */
+/* C[M x N] = alpha * op(A) * op(B) + beta * C on the FP64 tensor pipe.  transa = 0: A is M x K
+ * row-major; 1: A is stored K x M.  transb = 0: B is K x N row-major; 1: B is stored N x K. */
+int gpxb_gemm(gpxb_ctx* ctx, int transa, int transb, int M, int N, int K, double alpha,
+              const double* A, long long lda, const double* B, long long ldb, double beta, double* C,
+              long long ldc, int lower_only, gpxb_stream stream);
+/* number of doubles of the diagonal-block-inverse buffer potrf fills for an n x n matrix */
+size_t gpxb_potrf_inv_size(int n);
+/* In-place lower Cholesky of row-major A (only the lower triangle is read / written); replaces
+ * jsp.linalg.cholesky(lower=True) (gpx/models/_gpr.py:759, 457, 860).  inv (device,
+ * gpxb_potrf_inv_size(n) doubles) receives the inverses of L's 128x128 diagonal blocks, which
+ * gpxb_trsm / gpxb_potri consume. */
+int gpxb_potrf(gpxb_ctx* ctx, double* A, long long lda, int n, double* inv, gpxb_stream stream);
+/* B[m x n] <- B * L^-T (trans = 1) or B * L^-1 (trans = 0); replaces solve_triangular
+ * (gpx/models/_gpr.py:760, 458): L^-1 y is the row form y^T L^-T. */
+int gpxb_trsm(gpxb_ctx* ctx, const double* L, long long ldl, const double* inv, int n, double* B,
+              long long ldb, int m, int trans, gpxb_stream stream);
+/* *out (device) = sum_i log L[i][i]   (gpx/models/_gpr.py:763) */
+int gpxb_logdet(gpxb_ctx* ctx, const double* L, long long ldl, int n, double* out,
+                gpxb_stream stream);
+/* out (lower triangle, n x n) = (L L^T)^-1; out may alias L. */
+int gpxb_potri(gpxb_ctx* ctx, const double* L, long long ldl, const double* inv, int n, double* out,
+               long long ldo, gpxb_stream stream);
+
+/* Exact-GPR log marginal likelihood and its gradient, fused on device.
+ * out[0] = lml / N (gpx/models/_gpr.py:737-769), and if want_grad:
+ * out[1] = d(lml/N)/d lengthscale, out[2] = d(lml/N)/d sigma -- the constrained-space gradient
+ * jit(value_and_grad) produces before the bijector chain rule
+ * (gpx/optimizers/scipy_optimize.py:72-78).  y is N x T row-major. */
+int gpxb_gpr_lml_grad(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,
+                      double ell, double sigma, int mean_mode, int want_grad, double* out3,
+                      gpxb_stream stream);
+/* c[N x T] = (K + (sigma^2+1e-10) I)^-1 (y - mu), *mu_out = mean_function(y)
+ * (gpx/models/_gpr.py:262-282; the reference's LU solve is replaced by the Cholesky solve). */
+int gpxb_gpr_fit(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,
+                 double ell, double sigma, int mean_mode, double* c_out, double* mu_out,
+                 gpxb_stream stream);
+/* mean_out[ns x T] = mu + K(x, x_train) c; if cov_out != NULL also the full predictive
+ * covariance [ns x ns] (gpx/models/_gpr.py:434-463).  mu is a device scalar. */
+int gpxb_gpr_predict(gpxb_ctx* ctx, int kind, const double* x_train, int N, int D, const double* x,
+                     int ns, const double* c, int T, const double* mu, double ell, double sigma,
+                     double* mean_out, double* cov_out, gpxb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPXB200_H */

@@ -1,0 +1,667 @@
+"""CPU oracle: NumPy/SciPy FP64 restatement of the GPX Gaussian-process hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``gpx_b200/`` imports this module; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may use it, and only as the checker / CPU baseline.
+
+Every function cites the reference file:line (relative to the GPX repository
+root) whose arithmetic it restates.  JAX is not installable in this image, so
+the reference itself cannot be run here.
+
+Parity pinning status
+---------------------
+* kernel-matrix entries (SE, Matern-1/2, 3/2, 5/2):  PINNED by the reference's own
+  closed-form tests (tests/gpx/kernels/test_kernels.py:58-81, 104-164) restated in
+  tests/test_oracle_kernels.py.
+* derivative (Hessian/Jacobian) kernels: PINNED the way the reference pins them
+  (tests/gpx/kernels/test_kernels.py:172-324: hand-written vs automatic
+  differentiation of the ``*_base`` pair kernel) with complex-step / finite
+  differences standing in for autodiff.
+* Threefry-2x32-20: PINNED by the Random123 known-answer vectors.
+* LML, LML gradient, fit coefficients, predictions, SGPR, RPCholesky pivots,
+  Lanczos/SLQ: **parity unpinned** -- the reference has no test or golden vector
+  for them and cannot be executed here.  They are anchored
+  by self-consistency (analytic gradient vs finite differences, Woodbury vs
+  the reference's N x N form, SLQ vs exact log-det).
+* ``jax.random`` bit layouts (split / random_bits) are restated from the
+  published JAX algorithm for both values of ``jax_threefry_partitionable``
+  (default True since JAX 0.5.0); the reference does not pin a JAX version.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.linalg as sla
+
+# =============================================================================
+# jax.random restatement (third-party dependency of the reference: jax, unpinned;
+# call sites gpx/kernels/approximations.py:100-101, gpx/lanczos.py:94,103,168-169)
+# =============================================================================
+
+_ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def threefry2x32(k0, k1, x0, x1):
+    """Threefry-2x32, 20 rounds (Salmon et al., Random123).  Inputs broadcast;
+    arithmetic is done in uint64 and masked to 32 bits."""
+    k0 = np.asarray(k0, dtype=np.uint64)
+    k1 = np.asarray(k1, dtype=np.uint64)
+    x0 = np.asarray(x0, dtype=np.uint64).copy()
+    x1 = np.asarray(x1, dtype=np.uint64).copy()
+    ks = (k0, k1, (k0 ^ k1 ^ np.uint64(0x1BD11BDA)) & _M32)
+
+    def rotl(v, r):
+        return ((v << np.uint64(r)) | (v >> np.uint64(32 - r))) & _M32
+
+    x0 = (x0 + ks[0]) & _M32
+    x1 = (x1 + ks[1]) & _M32
+    for i in range(5):
+        for r in _ROT[i % 2]:
+            x0 = (x0 + x1) & _M32
+            x1 = rotl(x1, r)
+            x1 = x1 ^ x0
+        x0 = (x0 + ks[(i + 1) % 3]) & _M32
+        x1 = (x1 + ks[(i + 2) % 3] + np.uint64(i + 1)) & _M32
+    return x0.astype(np.uint32), x1.astype(np.uint32)
+
+
+def PRNGKey(seed: int) -> np.ndarray:
+    """jax.random.PRNGKey: [hi32, lo32] of the 64-bit seed."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return np.array([seed >> 32, seed & 0xFFFFFFFF], dtype=np.uint32)
+
+
+def _threefry_2x32_flat(key, counts):
+    """jax._src.prng.threefry_2x32 on a flat uint32 counter array (odd sizes are
+    zero padded, counters split into first/second half, outputs concatenated)."""
+    counts = np.asarray(counts, dtype=np.uint32).ravel()
+    odd = counts.size % 2
+    if odd:
+        counts = np.concatenate([counts, np.zeros(1, np.uint32)])
+    h = counts.size // 2
+    y0, y1 = threefry2x32(key[0], key[1], counts[:h], counts[h:])
+    out = np.concatenate([y0, y1])
+    return out[:-1] if odd else out
+
+
+def split(key, num: int = 2, partitionable: bool = True) -> np.ndarray:
+    """jax.random.split -> (num, 2) uint32."""
+    key = np.asarray(key, dtype=np.uint32)
+    if partitionable:  # _threefry_split_foldlike
+        lo = np.arange(num, dtype=np.uint64)
+        b1, b2 = threefry2x32(key[0], key[1], lo >> np.uint64(32), lo & _M32)
+        return np.stack([b1, b2], axis=1)
+    out = _threefry_2x32_flat(key, np.arange(2 * num, dtype=np.uint32))
+    return out.reshape(num, 2)
+
+
+def random_bits64(key, shape, partitionable: bool = True) -> np.ndarray:
+    """jax._src.prng.threefry_random_bits, bit_width=64."""
+    key = np.asarray(key, dtype=np.uint32)
+    size = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+    if partitionable:
+        idx = np.arange(size, dtype=np.uint64)
+        hi, lo = threefry2x32(key[0], key[1], idx >> np.uint64(32), idx & _M32)
+    else:
+        bits = _threefry_2x32_flat(key, np.arange(2 * size, dtype=np.uint32))
+        hi, lo = bits[:size], bits[size:]
+    out = (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
+    return out.reshape(shape)
+
+
+def uniform(key, shape=(), partitionable: bool = True) -> np.ndarray:
+    """jax.random.uniform(key, shape, float64) in [0, 1)."""
+    bits = random_bits64(key, shape, partitionable)
+    fb = (bits >> np.uint64(12)) | np.uint64(0x3FF0000000000000)
+    return fb.view(np.float64) - 1.0
+
+
+def rademacher(key, shape, partitionable: bool = True) -> np.ndarray:
+    """jax.random.rademacher: 2*bernoulli(0.5)-1 with bernoulli = uniform < p."""
+    return 2 * (uniform(key, shape, partitionable) < 0.5).astype(np.int64) - 1
+
+
+def normal(key, shape, partitionable: bool = True) -> np.ndarray:
+    """jax.random.normal float64: sqrt(2)*erfinv(uniform(-1+eps, 1)).  Only used on
+    the Lanczos breakdown branch (gpx/lanczos.py:94-96); erfinv is SciPy's, so the
+    last bits may differ from XLA's polynomial."""
+    from scipy.special import erfinv
+
+    lo = np.nextafter(-1.0, 0.0)
+    u = uniform(key, shape, partitionable)
+    u = np.maximum(lo, u * (1.0 - lo) + lo)
+    return math.sqrt(2.0) * erfinv(u)
+
+
+def choice_p(key, p: np.ndarray, partitionable: bool = True) -> int:
+    """jax.random.choice(key, arange(n), p=p, shape=(), replace=True)."""
+    cum = np.cumsum(p)
+    r = cum[-1] * (1.0 - uniform(key, (), partitionable))
+    return int(np.searchsorted(cum, r, side="left"))
+
+
+# =============================================================================
+# bijectors / mean functions (gpx/bijectors.py:27-71, gpx/mean_functions.py:25-30)
+# =============================================================================
+
+
+def softplus(t):
+    return np.logaddexp(t, 0.0) + 1e-300
+
+
+def inverse_softplus(x):
+    return x + np.log(-np.expm1(-x))
+
+
+def sigmoid(t):
+    return 1.0 / (1.0 + np.exp(-t))
+
+
+def data_mean(y):
+    return float(np.mean(y))
+
+
+def zero_mean(y):
+    return 0.0
+
+
+# =============================================================================
+# kernels (gpx/utils.py:55-72; gpx/kernels/kernels.py:751-757, 922-927, 966-971,
+# 1050-1055)
+# =============================================================================
+
+KINDS = ("se", "m12", "m32", "m52")
+
+
+def squared_distances(x1, x2):
+    """gpx/utils.py:55-72 -- GEMM trick with +1e-12 jitter, no clamp."""
+    x1s = np.sum(np.square(x1), axis=-1)
+    x2s = np.sum(np.square(x2), axis=-1)
+    return x1s[:, None] - 2.0 * np.dot(x1, x2.T) + x2s + 1e-12
+
+
+def kernel(kind: str, x1, x2, ell: float):
+    """Batched stationary kernels on z = x / ell."""
+    z1 = x1 / ell
+    z2 = x2 / ell
+    d2 = squared_distances(z1, z2)
+    if kind == "se":  # kernels.py:751-757
+        return np.exp(-d2)
+    r = np.sqrt(np.maximum(d2, 1e-36))
+    if kind == "m12":  # kernels.py:922-927
+        return np.exp(-r)
+    if kind == "m32":  # kernels.py:966-971
+        d = np.sqrt(3.0) * r
+        return (1.0 + d) * np.exp(-d)
+    if kind == "m52":  # kernels.py:1050-1055
+        d = np.sqrt(5.0) * r
+        return (1.0 + d + d**2 / 3.0) * np.exp(-d)
+    raise ValueError(kind)
+
+
+def kernel_dl(kind: str, x1, x2, ell: float):
+    """(K, dK/d ell): what reverse-mode autodiff of ``kernel`` yields.
+    s = d2 - jitter is formed exactly as autodiff forms it: -ell/2 * d(d2)/d ell."""
+    z1 = x1 / ell
+    z2 = x2 / ell
+    d2 = squared_distances(z1, z2)
+    s = d2 - 1e-12
+    if kind == "se":
+        K = np.exp(-d2)
+        return K, K * 2.0 * s / ell
+    live = d2 > 1e-36  # the maximum() passes no gradient when clamped
+    r = np.sqrt(np.maximum(d2, 1e-36))
+    if kind == "m12":
+        K = np.exp(-r)
+        return K, np.where(live, K * s / (r * ell), 0.0)
+    if kind == "m32":
+        d = np.sqrt(3.0) * r
+        e = np.exp(-d)
+        return (1.0 + d) * e, np.where(live, 3.0 * s * e / ell, 0.0)
+    if kind == "m52":
+        d = np.sqrt(5.0) * r
+        e = np.exp(-d)
+        return (1.0 + d + d**2 / 3.0) * e, np.where(live, (5.0 * s / (3.0 * ell)) * (1.0 + d) * e, 0.0)
+    raise ValueError(kind)
+
+
+def kernel_base(kind: str, x1, x2, ell: float):
+    """Single-pair kernels without jitter (kernels.py:731-736, 902-910, 945-953,
+    1029-1037); the autodiff kernelizers differentiate these."""
+    z = (np.asarray(x1) - np.asarray(x2)) / ell
+    d2 = np.sum(z * z)
+    if kind == "se":
+        return np.exp(-d2)
+    c = {"m12": 1.0, "m32": 3.0, "m52": 5.0}[kind]
+    d = np.sqrt(np.maximum(c * d2, 1e-36))
+    if kind == "m12":
+        return np.exp(-d)
+    if kind == "m32":
+        return (1.0 + d) * np.exp(-d)
+    return (1.0 + d + c * d2 / 3.0) * np.exp(-d)
+
+
+def d01kj(kind: str, x1, x2, ell: float, J1, J2):
+    """Hessian-Jacobian kernel, literal einsum form.
+    SE: kernels.py:804-831; Matern-5/2: kernels.py:1253-1283."""
+    ns1, nf = x1.shape
+    ns2 = x2.shape[0]
+    nv1, nv2 = J1.shape[2], J2.shape[2]
+    z1, z2 = x1 / ell, x2 / ell
+    d2 = squared_distances(z1, z2)
+    if kind == "se":
+        ed2 = np.exp(-d2)
+        diff = (2.0 / ell) * (z1[:, None] - z2)
+        c_ab = -ed2
+        c_g = ed2 * (2.0 / ell**2)
+    elif kind == "m52":
+        diff = np.sqrt(5.0) * (z1[:, None] - z2)
+        d = np.sqrt(5.0) * np.sqrt(np.maximum(d2, 1e-36))
+        c = (5.0 / (3.0 * ell**2)) * np.exp(-d)
+        c_ab = -c
+        c_g = c * (1.0 + d)
+    else:
+        raise ValueError(kind)
+    a = np.einsum("stf,sfv->stv", diff, J1)
+    b = np.einsum("stf,tfu->stu", diff, J2)
+    out = np.einsum("st,stv,stu->svtu", c_ab, a, b)
+    G = np.einsum("sfv,tfu->svtu", J1, J2)
+    out = out + c_g[:, None, :, None] * G
+    return out.reshape(ns1 * nv1, ns2 * nv2)
+
+
+def d01kjc(kind: str, x1, x2, ell: float, jaccoef, J2):
+    """Hessian kernel contracted with jaccoef on the first side
+    (kernels.py:851-877 SE, 1304-1332 Matern-5/2) -> (ns1, ns2*nv2)."""
+    out = d01kj(kind, x1, x2, ell, jaccoef[:, :, None], J2)
+    return out.reshape(x1.shape[0], -1)
+
+
+# =============================================================================
+# exact GPR (gpx/models/_gpr.py)
+# =============================================================================
+
+
+def A_lhs(kind, x1, x2, ell, sigma, noise=True):
+    """_gpr.py:39-63."""
+    C = kernel(kind, x1, x2, ell)
+    if noise:
+        C = C + (sigma**2 + 1e-10) * np.eye(x1.shape[0])
+    return C
+
+
+def lml_dense(kind, x, y, ell, sigma, mean_function=data_mean):
+    """_gpr.py:737-769."""
+    m = y.shape[0]
+    mu = mean_function(y)
+    r = y - mu
+    A = A_lhs(kind, x, x, ell, sigma)
+    L = sla.cholesky(A, lower=True, check_finite=False)
+    cy = sla.solve_triangular(L, r, lower=True, check_finite=False)
+    mll = -0.5 * np.sum(np.square(cy))
+    mll -= np.sum(np.log(np.diag(L)))
+    mll -= m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
+
+
+def lml_grad_dense(kind, x, y, ell, sigma, mean_function=data_mean):
+    """(lml, d lml/d ell, d lml/d sigma): value_and_grad of _lml_dense
+    (optimizers/scipy_optimize.py:72-78) in analytic form."""
+    m = y.shape[0]
+    mu = mean_function(y)
+    r = y - mu
+    K, dK = kernel_dl(kind, x, x, ell)
+    A = K + (sigma**2 + 1e-10) * np.eye(m)
+    L = sla.cholesky(A, lower=True, check_finite=False)
+    cy = sla.solve_triangular(L, r, lower=True, check_finite=False)
+    lml = (-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - m * 0.5 * np.log(2.0 * np.pi)) / m
+    alpha = sla.solve_triangular(L, cy, lower=True, trans="T", check_finite=False)
+    Ainv = sla.cho_solve((L, True), np.eye(m), check_finite=False)
+    # multi-output y (m, t): quadratic summed over outputs, log-det counted once
+    W = alpha.reshape(m, -1) @ alpha.reshape(m, -1).T - Ainv
+    g_ell = 0.5 * np.sum(W * dK) / m
+    g_sigma = sigma * np.trace(W) / m
+    return lml, g_ell, g_sigma
+
+
+def neg_lml_and_grad_unconstrained(kind, x, y, t_ell, t_sigma, mean_function=data_mean):
+    """loss(t) and d loss/d t with Softplus bijectors on both parameters
+    (optimizers/utils.py:97-131, bijectors.py:27-47)."""
+    ell, sigma = softplus(t_ell), softplus(t_sigma)
+    lml, gl, gs = lml_grad_dense(kind, x, y, ell, sigma, mean_function)
+    return -lml, np.array([-gl * sigmoid(t_ell), -gs * sigmoid(t_sigma)])
+
+
+def fit_dense(kind, x, y, ell, sigma, mean_function=data_mean):
+    """_gpr.py:262-282 (LU solve)."""
+    mu = mean_function(y)
+    A = A_lhs(kind, x, x, ell, sigma)
+    c = np.linalg.solve(A, y - mu)
+    return c, mu
+
+
+def predict_dense(kind, x_train, x, c, mu, ell, sigma, full_covariance=False):
+    """_gpr.py:434-463."""
+    K_mn = kernel(kind, x_train, x, ell)
+    mean = mu + K_mn.T @ c
+    if not full_covariance:
+        return mean
+    A = A_lhs(kind, x_train, x_train, ell, sigma)
+    L = sla.cholesky(A, lower=True, check_finite=False)
+    G = sla.solve_triangular(L, K_mn, lower=True, check_finite=False)
+    C = kernel(kind, x, x, ell) - G.T @ G
+    return mean, C
+
+
+def lml_derivs_dense(kind, x, y, J, ell, sigma):
+    """_gpr.py:824-870 (zero mean forced by gpr.py:160,173)."""
+    yf = y.reshape(-1, 1)
+    m = yf.shape[0]
+    A = d01kj(kind, x, x, ell, J, J) + (sigma**2 + 1e-10) * np.eye(m)
+    L = sla.cholesky(A, lower=True, check_finite=False)
+    cy = sla.solve_triangular(L, yf, lower=True, check_finite=False)
+    mll = -0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
+
+
+def fit_derivs_dense(kind, x, y, J, ell, sigma):
+    """_gpr.py:313-344 + gpr.py:475-476 (jaccoef)."""
+    yf = y.reshape(-1, 1)
+    m = yf.shape[0]
+    A = d01kj(kind, x, x, ell, J, J) + (sigma**2 + 1e-10) * np.eye(m)
+    c = np.linalg.solve(A, yf)
+    ns, _, nv = J.shape
+    jaccoef = np.einsum("sv,sfv->sf", c.reshape(ns, nv), J)
+    return c, 0.0, jaccoef
+
+
+# =============================================================================
+# matrix-free mat-vec, Lanczos, SLQ, PCG
+# (gpx/operations.py:32-123, gpx/lanczos.py:29-183, _gpr.py:94-119, 180-216, 285-310,
+#  772-821; jax.scipy.sparse.linalg.cg restated)
+# =============================================================================
+
+
+def make_matvec(kind, x, ell, sigma, noise=True, block=2048):
+    """(K + (sigma^2+1e-10) I) z without storing K; row blocks stand in for the
+    reference's one-row-per-scan-step loop (operations.py:93-107)."""
+    n = x.shape[0]
+    shift = sigma**2 + 1e-10 if noise else 0.0
+
+    def matvec(z):
+        out = np.empty_like(z, dtype=np.float64)
+        for i0 in range(0, n, block):
+            i1 = min(n, i0 + block)
+            rows = kernel(kind, x[i0:i1], x, ell)
+            if noise:
+                rows[np.arange(i1 - i0), np.arange(i0, i1)] += shift
+            out[i0:i1] = rows @ z
+        return out
+
+    return matvec
+
+
+def _orthogonalize(v, vecs):
+    """lanczos.py:29-37 -- modified Gram-Schmidt in column order."""
+    for j in range(vecs.shape[1]):
+        v = v - np.dot(v, vecs[:, j]) * vecs[:, j]
+    return v
+
+
+def lanczos_tridiagonal(matvec, m, v1, key=None, partitionable=True):
+    """lanczos.py:46-133."""
+    n = v1.shape[0]
+    vecs = np.zeros((n, m))
+    vecs[:, 0] = v1
+    T = np.zeros((m, m))
+    w = matvec(v1)
+    alpha = np.dot(w, v1)
+    w = w - alpha * v1
+    beta = np.linalg.norm(w)
+    T[0, 0] = alpha
+    for j in range(m - 1):
+        if key is not None:
+            sk = split(key, 2, partitionable)
+            subkey, key = sk[0], sk[1]
+        if beta > 1e-12:
+            v = w / beta
+        else:
+            rv = normal(subkey, (n,), partitionable)
+            rv = _orthogonalize(rv, vecs)
+            v = rv / np.linalg.norm(rv)
+        vecs[:, j + 1] = v
+        w = matvec(v)
+        alpha = np.dot(w, v)
+        w = w - alpha * v - beta * vecs[:, j]
+        w = _orthogonalize(w, vecs)
+        T[j + 1, j + 1] = alpha
+        T[j, j + 1] = beta
+        T[j + 1, j] = beta
+        beta = np.linalg.norm(w)
+    return T, vecs
+
+
+def slq_from_tridiag(T):
+    """lanczos.py:175-180."""
+    evals, evecs = np.linalg.eigh(T)
+    evals = np.maximum(evals, 1e-36)
+    return float(np.sum(np.square(evecs[0, :]) * np.log(evals)))
+
+
+def rademacher_probes(key, n, num_evals, partitionable=True):
+    """lanczos.py:168-170: returns (normalised probes (n, P), carried key)."""
+    sk = split(key, 2, partitionable)
+    subkey, key = sk[0], sk[1]
+    us = rademacher(subkey, (n, num_evals), partitionable).astype(np.float64)
+    us = us / np.linalg.norm(us, axis=0)
+    return us, key
+
+
+def lanczos_logdet(matvec, num_evals, dim_mat, num_lanczos, key, partitionable=True):
+    """lanczos.py:136-183."""
+    us, key = rademacher_probes(key, dim_mat, num_evals, partitionable)
+    acc = 0.0
+    for p in range(num_evals):
+        T, _ = lanczos_tridiagonal(matvec, num_lanczos, us[:, p], key, partitionable)
+        acc += slq_from_tridiag(T)
+    return (dim_mat / num_evals) * acc
+
+
+def rpcholesky(kind, x, n_pivots, ell, key, partitionable=True):
+    """gpx/kernels/approximations.py:30-129."""
+    n = x.shape[0]
+    F = np.zeros((n, n_pivots))
+    pivots = np.zeros(n_pivots, dtype=np.int64)
+    # diagonal via the batched kernel on single points (approximations.py:88-93)
+    z = x / ell
+    zs = np.sum(z * z, axis=1)
+    d2 = zs - 2.0 * zs + zs + 1e-12
+    diag = _phi(kind, d2)
+    key = np.asarray(key, dtype=np.uint32)
+    for i in range(n_pivots):
+        prob = diag / np.sum(diag)
+        key = split(key, 2, partitionable)[0]  # key, subkey = split(key); sample with key
+        s = choice_p(key, prob, partitionable)
+        pivots[i] = s
+        g = kernel(kind, x[s : s + 1], x, ell)[0] - F @ F[s]
+        F[:, i] = g / (g[s] ** 0.5 + 1e-6)
+        diag = diag - F[:, i] ** 2
+    return F, pivots
+
+
+def _phi(kind, d2):
+    if kind == "se":
+        return np.exp(-d2)
+    r = np.sqrt(np.maximum(d2, 1e-36))
+    if kind == "m12":
+        return np.exp(-r)
+    if kind == "m32":
+        d = np.sqrt(3.0) * r
+        return (1.0 + d) * np.exp(-d)
+    d = np.sqrt(5.0) * r
+    return (1.0 + d + d**2 / 3.0) * np.exp(-d)
+
+
+def precond_rpcholesky(kind, x, ell, sigma, n_pivots, key, partitionable=True):
+    """_gpr.py:180-216 (explicit inverse, sigma^2 without the 1e-10)."""
+    F, _ = rpcholesky(kind, x, n_pivots, ell, key, partitionable)
+    P = np.linalg.inv(sigma**2 * np.eye(n_pivots) + F.T @ F)
+
+    def precond(z):
+        res = F.T @ z
+        res = P @ res
+        res = -(sigma ** (-2)) * (F @ res)
+        return res + sigma ** (-2) * z
+
+    return precond
+
+
+def cg(A, b, M=None, tol=1e-5, atol=0.0, maxiter=None):
+    """jax.scipy.sparse.linalg.cg (third-party; restated).
+    Returns (x, iterations)."""
+    if M is None:
+        M = lambda v: v  # noqa: E731
+        ident = True
+    else:
+        ident = False
+    if maxiter is None:
+        maxiter = 10 * b.size
+    bs = float(np.vdot(b, b))
+    atol2 = max(tol**2 * bs, atol**2)
+    x = np.zeros_like(b)
+    r = b - A(x)
+    z = M(r)
+    p = z
+    gamma = float(np.vdot(r, z))
+    k = 0
+    while k < maxiter:
+        rs = gamma if ident else float(np.vdot(r, r))
+        if not rs > atol2:
+            break
+        Ap = A(p)
+        alpha = gamma / float(np.vdot(p, Ap))
+        x = x + alpha * p
+        r = r - alpha * Ap
+        z = M(r)
+        gamma_new = float(np.vdot(r, z))
+        p = z + (gamma_new / gamma) * p
+        gamma = gamma_new
+        k += 1
+    return x, k
+
+
+def fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function=data_mean, partitionable=True):
+    """_gpr.py:285-310."""
+    mu = mean_function(y)
+    r = y - mu
+    mv = make_matvec(kind, x, ell, sigma)
+    pre = precond_rpcholesky(kind, x, ell, sigma, n_pivots, key_precond, partitionable)
+    c, iters = cg(mv, r, M=pre, atol=1e-7)
+    return c, mu, iters
+
+
+def lml_iter(kind, x, y, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
+             mean_function=data_mean, partitionable=True):
+    """_gpr.py:772-821."""
+    m = y.shape[0]
+    c, mu, _ = fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function, partitionable)
+    r = y - mu
+    mv = make_matvec(kind, x, ell, sigma)
+    mll = -0.5 * np.sum(r.T @ c)
+    mll -= 0.5 * lanczos_logdet(lambda v: mv(v), num_evals, m, num_lanczos, key_lanczos, partitionable)
+    mll -= m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
+
+
+# =============================================================================
+# SGPR, Projected Processes (gpx/models/_sgpr.py, _sgpr_rpchol.py)
+# =============================================================================
+
+
+def sgpr_A_lhs(kind, x_locs, x, ell, sigma):
+    """_sgpr.py:39-61."""
+    m = x_locs.shape[0]
+    K_mn = kernel(kind, x_locs, x, ell)
+    C = sigma**2 * kernel(kind, x_locs, x_locs, ell) + K_mn @ K_mn.T + 1e-10 * np.eye(m)
+    return C, K_mn
+
+
+def sgpr_fit_dense(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
+    """_sgpr.py:319-339."""
+    mu = mean_function(y)
+    C, K_mn = sgpr_A_lhs(kind, x_locs, x, ell, sigma)
+    c = np.linalg.solve(C, K_mn @ (y - mu))
+    return c, mu
+
+
+def sgpr_predict_dense(kind, x_locs, x, c, mu, ell, sigma, full_covariance=False):
+    """_sgpr.py:434-467."""
+    m = x_locs.shape[0]
+    K_nm = kernel(kind, x, x_locs, ell)
+    mean = mu + K_nm @ c
+    if not full_covariance:
+        return mean
+    C, K_mn = sgpr_A_lhs(kind, x_locs, x, ell, sigma)
+    K_mm = kernel(kind, x_locs, x_locs, ell) + 1e-10 * np.eye(m)
+    L = sla.cholesky(K_mm, lower=True, check_finite=False)
+    G = sla.solve_triangular(L, K_mn, lower=True, check_finite=False)
+    L2 = sla.cholesky(C, lower=True, check_finite=False)
+    H = sla.solve_triangular(L2, K_mn, lower=True, check_finite=False)
+    C_nn = kernel(kind, x, x, ell) - G.T @ G + sigma**2 * (H.T @ H)
+    return mean, C_nn
+
+
+def sgpr_lml_dense_nxn(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
+    """_sgpr.py:659-697, literal N x N form (feasible for small N only)."""
+    m = x_locs.shape[0]
+    mu = mean_function(y)
+    r = y - mu
+    n = y.shape[0]
+    K_mm = kernel(kind, x_locs, x_locs, ell)
+    K_mn = kernel(kind, x_locs, x, ell)
+    L = sla.cholesky(K_mm + 1e-10 * np.eye(m), lower=True, check_finite=False)
+    G = sla.solve_triangular(L, K_mn, lower=True, check_finite=False)
+    C = G.T @ G + sigma**2 * np.eye(n) + 1e-10 * np.eye(n)
+    Ln = sla.cholesky(C, lower=True, check_finite=False)
+    cy = sla.solve_triangular(Ln, r, lower=True, check_finite=False)
+    mll = -0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(Ln))) - n * 0.5 * np.log(2.0 * np.pi)
+    return mll / n
+
+
+def sgpr_lml_dense(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
+    """Woodbury / matrix-determinant-lemma form of _sgpr.py:659-697;
+    algebraically identical, O(N M^2)."""
+    m = x_locs.shape[0]
+    mu = mean_function(y)
+    r = y - mu
+    n = y.shape[0]
+    s2 = sigma**2 + 1e-10
+    K_mm = kernel(kind, x_locs, x_locs, ell)
+    K_mn = kernel(kind, x_locs, x, ell)
+    L = sla.cholesky(K_mm + 1e-10 * np.eye(m), lower=True, check_finite=False)
+    G = sla.solve_triangular(L, K_mn, lower=True, check_finite=False)
+    B = s2 * np.eye(m) + G @ G.T
+    LB = sla.cholesky(B, lower=True, check_finite=False)
+    t = sla.solve_triangular(LB, G @ r, lower=True, check_finite=False)
+    quad = (np.sum(r * r) - np.sum(t * t)) / s2
+    logdet = (n - m) * np.log(s2) + 2.0 * np.sum(np.log(np.diag(LB)))
+    return (-0.5 * quad - 0.5 * logdet - n * 0.5 * np.log(2.0 * np.pi)) / n
+
+
+def sgpr_rpchol_lml_dense(kind, x, y, ell, sigma, key, n_locs, mean_function=data_mean,
+                          partitionable=True, nxn=False):
+    """_sgpr_rpchol.py:178-208."""
+    _, pivots = rpcholesky(kind, x, n_locs, ell, key, partitionable)
+    x_locs = x[pivots].copy()
+    f = sgpr_lml_dense_nxn if nxn else sgpr_lml_dense
+    return f(kind, x_locs, x, y, ell, sigma, mean_function), pivots
+
+
+def sgpr_rpchol_fit_dense(kind, x, y, ell, sigma, key, n_locs, mean_function=data_mean, partitionable=True):
+    """_sgpr_rpchol.py:36-67."""
+    _, pivots = rpcholesky(kind, x, n_locs, ell, key, partitionable)
+    x_locs = x[pivots].copy()
+    c, mu = sgpr_fit_dense(kind, x_locs, x, y, ell, sigma, mean_function)
+    return c, mu, x_locs
