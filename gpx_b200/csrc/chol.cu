@@ -5,15 +5,21 @@
 // A^-1 for the analytic LML gradient (what value_and_grad yields,
 // gpx/optimizers/scipy_optimize.py:72-78).
 //
-// Structure: fully recursive lower Cholesky on row-major storage; every O(n^3)
+// Structure: two-level right-looking lower Cholesky on row-major storage; every O(n^3)
 // flop is a DMMA GEMM (gemm.cu) -- SYRK trailing updates and TRSMs that multiply
 // by explicitly inverted 128x128 diagonal blocks.  The 128x128 leaves are
-// factorised AND inverted by one CTA in shared memory.
+// factorised AND inverted by one CTA in shared memory.  Solves and the triangular
+// inverse recurse on halves so that their flops are large GEMMs too.
 #include "chol.cuh"
 #include "gemm.cuh"
 #include "mma.cuh"
 
+#include <algorithm>
+
 namespace gpxb {
+
+using std::max;
+using std::min;
 
 namespace {
 
@@ -175,25 +181,59 @@ int trsm_right_l(Ctx* ctx, const double* L, long long ldl, const double* inv, do
 
 // In-place lower Cholesky of the n x n row-major matrix A (only the lower triangle is
 // read or written).  inv receives ceil(n/128) packed 128x128 inverses of L's diagonal blocks.
+//
+// Two-level right-looking: 1024-wide panels; inside a panel each 128-column step is
+// leaf (one CTA) -> tall TRSM (multiply by the inverted leaf) -> rank-128 update of the rest
+// of the panel; then one rank-1024 SYRK on the trailing matrix.  Every GEMM is tall, so only
+// the leaves run on a single SM.
 int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s) {
   if (n <= 0) return 0;
-  if (n <= LB) return leaf(ctx, A, lda, n, inv, s);
-  const int n1 = split_point(n), n2 = n - n1;
-  GPXB_TRY(potrf_lower(ctx, A, lda, n1, inv, s));
-  double* A21 = A + (long long)n1 * lda;
-  double* A22 = A21 + n1;
-  GPXB_TRY(trsm_right_lt(ctx, A, lda, inv, A21, lda, n2, n1, s));
-  {
-    GemmArgs g;  // A22 -= A21 A21^T (lower)
-    g.M = n2; g.N = n2; g.K = n1;
-    g.A = A21; g.lda = lda; g.a_kmajor = true;
-    g.B = A21; g.ldb = lda; g.b_kmajor = true;
-    g.C = A22; g.ldc = lda;
-    g.alpha = -1.0; g.beta = 1.0;
-    g.lower_only = 1;
-    GPXB_TRY(gemm_f64(ctx, g, s));
+  constexpr int NB = 1024;
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int w = min(NB, n - k0);
+    for (int j = 0; j < w; j += LB) {
+      const int jb = min(LB, w - j);
+      const int c0 = k0 + j;  // global first column of this step
+      double* Ajj = A + (long long)c0 * lda + c0;
+      double* invj = inv + (long long)(c0 / LB) * LB * LB;
+      GPXB_TRY(leaf(ctx, Ajj, lda, jb, invj, s));
+      const int below = n - c0 - jb;
+      if (below <= 0) continue;
+      double* B = A + (long long)(c0 + jb) * lda + c0;  // below x jb
+      {
+        GemmArgs g;  // B <- B inv^T (in place: one column tile, rows private per CTA)
+        g.M = below; g.N = jb; g.K = jb;
+        g.A = B; g.lda = lda; g.a_kmajor = true;
+        g.B = invj; g.ldb = LB; g.b_kmajor = true;
+        g.C = B; g.ldc = lda;
+        GPXB_TRY(gemm_f64(ctx, g, s));
+      }
+      const int wr = w - j - jb;  // panel columns still to update
+      if (wr > 0) {
+        GemmArgs g;  // C -= B B[0:wr]^T on the lower trapezoid
+        g.M = below; g.N = wr; g.K = jb;
+        g.A = B; g.lda = lda; g.a_kmajor = true;
+        g.B = B; g.ldb = lda; g.b_kmajor = true;
+        g.C = B + jb; g.ldc = lda;
+        g.alpha = -1.0; g.beta = 1.0;
+        g.lower_only = 1;
+        GPXB_TRY(gemm_f64(ctx, g, s));
+      }
+    }
+    const int mt = n - k0 - w;
+    if (mt > 0) {
+      double* P = A + (long long)(k0 + w) * lda + k0;  // mt x w
+      GemmArgs g;  // trailing A22 -= P P^T (lower)
+      g.M = mt; g.N = mt; g.K = w;
+      g.A = P; g.lda = lda; g.a_kmajor = true;
+      g.B = P; g.ldb = lda; g.b_kmajor = true;
+      g.C = P + w; g.ldc = lda;
+      g.alpha = -1.0; g.beta = 1.0;
+      g.lower_only = 1;
+      GPXB_TRY(gemm_f64(ctx, g, s));
+    }
   }
-  return potrf_lower(ctx, A22, lda, n2, inv + (long long)(n1 / LB) * LB * LB, s);
+  return 0;
 }
 
 namespace {
@@ -240,7 +280,7 @@ int potri_lower(Ctx* ctx, const double* L, long long ldl, const double* inv, int
                 double* T, double* out, long long ldo, cudaStream_t s) {
   if (n <= 0) return 0;
   GPXB_CUDA_CHECK(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)n * (size_t)n, s));
-  const long long ldt = (n <= LB) ? LB : (long long)(n - split_point(n));
+  const long long ldt = (n <= LB) ? LB : (long long)max(split_point(n), n - split_point(n));
   GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, n, n, T, ldt, s));
   GemmArgs g;  // out = W^T W (lower); W[k][i] = 0 for k < i -> k starts at the tile's first row
   g.M = n; g.N = n; g.K = n;
@@ -261,7 +301,7 @@ int logdet_lower(Ctx* ctx, const double* L, long long ld, int n, double* out, do
 }
 
 size_t potri_scratch_doubles(int n) {
-  const long long h = (n <= LB) ? LB : (long long)(n - split_point(n));
+  const long long h = (n <= LB) ? LB : (long long)max(split_point(n), n - split_point(n));
   return (size_t)(h * h);
 }
 

@@ -87,12 +87,20 @@ __global__ void __launch_bounds__(NT, 1) gemm_f64_kernel(const GemmParams p) {
   // ---- tile coordinates ----
   int ti, tj;
   if (p.lower_only) {
+    // trapezoid (M >= N): tiles_n*(tiles_n+1)/2 triangular tiles, then full tile rows
     const long long t = blockIdx.x;
-    long long i = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while (i * (i + 1) / 2 > t) --i;
-    while ((i + 1) * (i + 2) / 2 <= t) ++i;
-    ti = (int)i;
-    tj = (int)(t - i * (i + 1) / 2);
+    const long long ntri = (long long)p.tiles_n * (p.tiles_n + 1) / 2;
+    if (t < ntri) {
+      long long i = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while (i * (i + 1) / 2 > t) --i;
+      while ((i + 1) * (i + 2) / 2 <= t) ++i;
+      ti = (int)i;
+      tj = (int)(t - i * (i + 1) / 2);
+    } else {
+      const long long r = t - ntri;
+      ti = p.tiles_n + (int)(r / p.tiles_n);
+      tj = (int)(r % p.tiles_n);
+    }
   } else {
     // grouped raster: 8 tile-rows share their B column panels in L2
     const int GM = 8;
@@ -223,8 +231,8 @@ int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream) {
   p.vecC = aligned16(g.C) && (g.ldc % 2 == 0);
   long long grid;
   if (g.lower_only) {
-    GPXB_ARG_CHECK(g.M == g.N, -2);
-    grid = (long long)p.tiles_m * (p.tiles_m + 1) / 2;
+    GPXB_ARG_CHECK(g.M >= g.N, -2);
+    grid = (long long)p.tiles_n * (p.tiles_n + 1) / 2 + (long long)(p.tiles_m - p.tiles_n) * p.tiles_n;
   } else {
     grid = (long long)p.tiles_m * p.tiles_n;
   }

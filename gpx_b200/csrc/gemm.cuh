@@ -8,7 +8,7 @@ namespace gpxb {
 //   a_kmajor: A is stored [M][K] (element (i,k) at A[i*lda + k]); else stored [K][M].
 //   b_kmajor: B is stored [N][K] (element (k,j) at B[j*ldb + k]); else stored [K][N].
 // lower_only: only 128x128 tiles with tile_row >= tile_col are computed and only
-//   entries with global row >= col are written (M == N expected).
+//   entries with global row >= col are written (a lower trapezoid; M >= N).
 // klo_mode: 0 -> k starts at 0; 1 -> at the tile's first column (B is lower
 //   triangular, B[k][j] = 0 for k < j); 2 -> at the tile's first row.
 // khi_mode: 0 -> k ends at K; 1 -> at the tile's last row + 1 (A is lower

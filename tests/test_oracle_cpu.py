@@ -1,0 +1,195 @@
+"""CPU tests pinning the oracle (oracle/ref_numpy.py).
+
+* kernel entries against the closed forms the reference's own tests use
+  (tests/gpx/kernels/test_kernels.py:58-81, 104-164; dims {1,10}, lengthscale {0.5,1,2});
+* Hessian/Jacobian kernels against differentiation of the pair kernel, on the reference's
+  5-point (sin, cos) descriptor (tests/gpx/kernels/test_kernels.py:172-189, 204-324);
+* Threefry-2x32-20 against the Random123 known-answer vectors;
+* Softplus round trip (tests/gpx/test_utils.py:56-100);
+* self-consistency anchors for the parts the reference does not test.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.special import gamma, kv
+
+from oracle import ref_numpy as R
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def reference_squared_exponential_kernel(x1, x2, ell):
+    K = np.zeros((x1.shape[0], x2.shape[0]))
+    for i in range(x1.shape[0]):
+        for j in range(x2.shape[0]):
+            dist = x1[i] - x2[j]
+            K[i, j] = np.exp(-np.dot(dist, dist) / ell**2)
+    return K
+
+
+def reference_matern_kernel(x1, x2, nu, ell):
+    K = np.zeros((x1.shape[0], x2.shape[0]))
+    for i in range(x1.shape[0]):
+        for j in range(x2.shape[0]):
+            dist = x1[i] - x2[j]
+            dist = np.dot(dist, dist) ** 0.5 / ell
+            fact = np.sqrt(2 * nu) * dist
+            K[i, j] = ((2.0 ** (1.0 - nu)) / gamma(nu)) * (fact**nu) * kv(nu, fact)
+    return K
+
+
+def _x12(dim):
+    rng = np.random.default_rng(2022)
+    return rng.standard_normal((10, dim)), rng.standard_normal((20, dim))
+
+
+@pytest.mark.parametrize("dim", [1, 10])
+@pytest.mark.parametrize("ell", [0.5, 1.0, 2.0])
+def test_squared_exponential_kernel(dim, ell):
+    x1, x2 = _x12(dim)
+    np.testing.assert_allclose(R.kernel("se", x1, x2, ell), reference_squared_exponential_kernel(x1, x2, ell))
+
+
+@pytest.mark.parametrize("dim", [1, 10])
+@pytest.mark.parametrize("ell", [0.5, 1.0, 2.0])
+@pytest.mark.parametrize("kind,nu", [("m12", 0.5), ("m32", 1.5), ("m52", 2.5)])
+def test_matern_kernels(dim, ell, kind, nu):
+    x1, x2 = _x12(dim)
+    np.testing.assert_allclose(R.kernel(kind, x1, x2, ell), reference_matern_kernel(x1, x2, nu, ell))
+
+
+def x_desc_jac():
+    x = np.linspace(-3, 3, 5).reshape(-1, 1)
+    desc = np.concatenate([np.sin(x), np.cos(x)], axis=1)  # (5, 2)
+    jac = np.stack([np.cos(x), -np.sin(x)], axis=1)  # (5, 2, 1)
+    return x, desc, jac
+
+
+def _hessian_fd(kind, a, b, ell, h=1e-4):
+    nf = a.shape[0]
+    H = np.zeros((nf, nf))
+    for f in range(nf):
+        for e in range(nf):
+            ef, ee = np.eye(nf)[f] * h, np.eye(nf)[e] * h
+            H[f, e] = (
+                R.kernel_base(kind, a + ef, b + ee, ell) - R.kernel_base(kind, a + ef, b - ee, ell)
+                - R.kernel_base(kind, a - ef, b + ee, ell) + R.kernel_base(kind, a - ef, b - ee, ell)
+            ) / (4 * h * h)
+    return H
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+@pytest.mark.parametrize("ell", [0.7, 1.3])
+def test_d01kj_vs_differentiated_pair_kernel(kind, ell):
+    _, desc, jac = x_desc_jac()
+    rng = np.random.default_rng(1)
+    desc2 = desc[:4] + 0.3 * rng.standard_normal((4, 2))
+    jac2 = jac[:4] + 0.1 * rng.standard_normal((4, 2, 1))
+    out = R.d01kj(kind, desc, desc2, ell, jac, jac2)
+    ns1, ns2, nv = 5, 4, 1
+    ref = np.zeros((ns1 * nv, ns2 * nv))
+    for s in range(ns1):
+        for t in range(ns2):
+            H = _hessian_fd(kind, desc[s], desc2[t], ell)
+            ref[s * nv:(s + 1) * nv, t * nv:(t + 1) * nv] = jac[s].T @ H @ jac2[t]
+    np.testing.assert_allclose(out, ref, atol=2e-6)
+    coef = rng.standard_normal((5, 2))
+    outc = R.d01kjc(kind, desc, desc2, ell, coef, jac2)
+    refc = np.zeros((ns1, ns2 * nv))
+    for s in range(ns1):
+        for t in range(ns2):
+            H = _hessian_fd(kind, desc[s], desc2[t], ell)
+            refc[s, t * nv:(t + 1) * nv] = coef[s] @ H @ jac2[t]
+    np.testing.assert_allclose(outc, refc, atol=2e-6)
+
+
+def test_threefry_random123_kat():
+    vec = json.load(open(os.path.join(GOLDEN, "threefry2x32_kat.json")))
+    for v in vec["vectors"]:
+        k, c, e = (int(a, 16) for a in v["key"]), (int(a, 16) for a in v["ctr"]), [int(a, 16) for a in v["out"]]
+        k, c = list(k), list(c)
+        y0, y1 = R.threefry2x32(k[0], k[1], c[0], c[1])
+        assert [int(y0), int(y1)] == e
+
+
+@pytest.mark.parametrize("partitionable", [True, False])
+def test_prng_restatement_is_self_consistent(partitionable):
+    key = R.PRNGKey(2023)
+    assert key.tolist() == [0, 2023]
+    ks = R.split(key, 2, partitionable)
+    assert ks.shape == (2, 2) and ks.dtype == np.uint32
+    u = R.uniform(ks[0], (1000,), partitionable)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.05
+    r = R.rademacher(ks[1], (64, 3), partitionable)
+    assert set(np.unique(r)) == {-1, 1}
+    # scalar draw == first element of the vector draw in partitionable mode only
+    u0 = R.uniform(ks[0], (), partitionable)
+    if partitionable:
+        assert u0 == u[0]
+
+
+def test_softplus_roundtrip():
+    x = np.array([-5.0, -1.0, 0.0, 0.3, 4.0, 30.0])
+    np.testing.assert_allclose(R.inverse_softplus(R.softplus(x)), x, rtol=1e-10, atol=1e-12)
+
+
+def _data(N=300, D=6, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((N, D))
+    y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    return x, y
+
+
+@pytest.mark.parametrize("kind", ["se", "m32", "m52"])
+def test_analytic_gradient_matches_finite_differences(kind):
+    x, y = _data()
+    _, gl, gs = R.lml_grad_dense(kind, x, y, 1.8, 0.2)
+    h = 1e-6
+    fl = (R.lml_dense(kind, x, y, 1.8 + h, 0.2) - R.lml_dense(kind, x, y, 1.8 - h, 0.2)) / (2 * h)
+    fs = (R.lml_dense(kind, x, y, 1.8, 0.2 + h) - R.lml_dense(kind, x, y, 1.8, 0.2 - h)) / (2 * h)
+    assert abs(gl - fl) < 1e-7 * max(1, abs(fl)) and abs(gs - fs) < 1e-7 * max(1, abs(fs))
+
+
+def test_woodbury_equals_reference_nxn_form():
+    x, y = _data(400)
+    key = R.PRNGKey(2023)
+    for (ell, sigma) in [(2.0, 0.1), (3.0, 0.01), (1.0, 1.0)]:
+        a, piv = R.sgpr_rpchol_lml_dense("se", x, y, ell, sigma, key, 24)
+        b, piv2 = R.sgpr_rpchol_lml_dense("se", x, y, ell, sigma, key, 24, nxn=True)
+        assert np.array_equal(piv, piv2)
+        assert abs(a - b) < 1e-9 * abs(b)
+
+
+def test_rpcholesky_converges_and_slq_tracks_logdet():
+    x, y = _data(200)
+    F, piv = R.rpcholesky("se", x, 200, 1.0, R.PRNGKey(7))
+    K = R.kernel("se", x, x, 1.0)
+    assert np.max(np.abs(F @ F.T - K)) < 1e-4
+    mv = R.make_matvec("se", x, 1.0, 0.5)
+    est = R.lanczos_logdet(mv, 30, 200, 50, R.PRNGKey(2023))
+    exact = np.linalg.slogdet(R.A_lhs("se", x, x, 1.0, 0.5))[1]
+    assert abs(est - exact) < 0.05 * abs(exact)
+
+
+def test_iterative_lml_close_to_dense():
+    x, y = _data(250)
+    key = R.PRNGKey(2023)
+    it = R.lml_iter("se", x, y, 1.5, 0.5, 30, 50, key, 20, key)
+    de = R.lml_dense("se", x, y, 1.5, 0.5)
+    assert abs(it - de) < 0.02 * abs(de)
+
+
+def test_golden_fixture_matches_oracle():
+    """tests/golden/oracle_small.npz is produced by tools/make_golden.py from the oracle; it
+    freezes the oracle's outputs so later edits cannot silently change them."""
+    g = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
+    x, y = g["x"], g["y"]
+    for kind in R.KINDS:
+        out = np.array(R.lml_grad_dense(kind, x, y, float(g["ell"]), float(g["sigma"])))
+        np.testing.assert_allclose(out, g[f"lml_grad_{kind}"], rtol=1e-11)
+    _, piv = R.rpcholesky("se", x, 16, float(g["ell"]), R.PRNGKey(2023), True)
+    assert np.array_equal(piv, g["pivots_part"])
+    _, piv = R.rpcholesky("se", x, 16, float(g["ell"]), R.PRNGKey(2023), False)
+    assert np.array_equal(piv, g["pivots_legacy"])
