@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GP hot path on B200.
+
+Workload (BASELINE.json configs[1]): exact GPR, Matern-5/2, N=32768, D=16, FP64;
+one "step" = one LML + gradient evaluation (Gram build, blocked Cholesky, triangular
+solves, SPD inverse, fused dK/d-lengthscale contraction).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun): the dense Cholesky path does not shard ("replicas only") --
+every rank evaluates an independent replica (its own hyper-parameter point, as the
+reference's random restarts do) and `value` is the whole-job evaluations per second.
+
+`--impl reference` times the CPU restatement of the reference (oracle/ref_numpy.py; the
+reference itself needs JAX, which this image does not have) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(kind="m52", N=32768, D=16, ell=4.0, sigma=0.1, seed=1)
+CPU_SAMPLE_N = 4096
+
+
+def synth(N, D, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((N, D))
+    y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    return x, y
+
+
+def alg_flops(N, D):
+    return float(N) ** 3 + 2.0 * float(N) ** 2 * D
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample_seconds(steps, warmup, n0):
+    from oracle import ref_numpy as R  # the checker, timed as the CPU baseline
+
+    x, y = synth(n0, CFG["D"], CFG["seed"])
+    for _ in range(warmup):
+        R.lml_grad_dense(CFG["kind"], x, y, CFG["ell"], CFG["sigma"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.lml_grad_dense(CFG["kind"], x, y, CFG["ell"], CFG["sigma"])
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    N = args.n or CFG["N"]
+    n0 = min(CPU_SAMPLE_N, N)
+    t = cpu_sample_seconds(max(args.steps, 1), min(args.warmup, 1), n0)
+    scale = (N / n0) ** 3
+    value = 1.0 / (t * scale)
+    sample = (f"NumPy/OpenBLAS restatement of GPX _lml_dense + analytic gradient (oracle/ref_numpy.py) at "
+              f"N={n0}, D={CFG['D']}: {t:.3f} s per evaluation; scaled x(N/{n0})^3 to N={N}")
+    line = {
+        "impl": "reference", "metric": "LML+grad evals/s (exact GPR, Matern-5/2, N=32768, D=16, FP64)",
+        "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * scale * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"exact GPR Matern-5/2 N={N} D={CFG['D']} LML+grad", "cpu_sample_N": n0},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cpu_cores(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().strip().splitlines():
+            c = [a.strip() for a in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])), mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from gpx_b200 import ops
+    from gpx_b200.kernels import Matern52
+    from gpx_b200.models import GPR
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    N, D = args.n or CFG["N"], CFG["D"]
+    kind, sigma = CFG["kind"], CFG["sigma"]
+    ell = CFG["ell"] * (1.0 + 0.05 * rank)  # replicas evaluate different hyper-parameter points
+    x_np, y_np = synth(N, D, CFG["seed"])
+    x = torch.as_tensor(x_np).cuda()
+    y = torch.as_tensor(y_np).cuda()
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = None
+    for _ in range(W):
+        out = ops.gpr_lml_grad(kind, x, y, ell, sigma)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = ops.gpr_lml_grad(kind, x, y, ell, sigma)
+    e1.record()
+    barrier()
+    launches = ops.launches() - l0
+    ms = max_over_ranks(e0.elapsed_time(e1)) / K
+    clocks = sampler.stop() if sampler else None
+    res = out.cpu().numpy()
+
+    # ---- end to end through the public facade with (pinned) HOST buffers ----
+    model = GPR(Matern52(),
+                kernel_params=dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior())),
+                sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+    xh, yh = torch.as_tensor(x_np).pin_memory(), torch.as_tensor(y_np).pin_memory()
+    model.loss_and_grad(xh, yh)
+    barrier()
+    Ke = max(1, min(K, 5))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        loss, grads = model.loss_and_grad(xh, yh)  # H2D of x, y; D2H of (lml, grad)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / Ke)
+    assert abs(-loss - res[0]) <= 1e-12 * abs(res[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (DMMA GEMM, trailing-update shape), timed live ----
+    m_t, k_t = min(N - 2048, 16384) if N > 4096 else N, 1024 if N > 4096 else min(N, 1024)
+    A = torch.randn((m_t, k_t), dtype=torch.float64, device="cuda")
+    C = torch.zeros((m_t, m_t), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        ops.gemm(A, A, transb=True, alpha=-1.0, beta=1.0, C=C, lower_only=True)
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    a0.record()
+    for _ in range(reps):
+        ops.gemm(A, A, transb=True, alpha=-1.0, beta=1.0, C=C, lower_only=True)
+    a1.record()
+    torch.cuda.synchronize()
+    t_k = a0.elapsed_time(a1) * 1e-3 / reps
+    tiles = (m_t + 127) // 128
+    flops_k = tiles * (tiles + 1) / 2 * 128 * 128 * k_t * 2.0
+    achieved = flops_k / t_k / 1e12
+    del A, C
+    # FP64 tensor denominator: MEASURED_PEAKS.json has no FP64 entry -> cuBLAS Dgemm measured here
+    nb = 8192 if N >= 8192 else 4096
+    P, Q = torch.randn((nb, nb), dtype=torch.float64, device="cuda"), torch.randn((nb, nb), dtype=torch.float64, device="cuda")
+    R_ = torch.empty_like(P)
+    best = 1e9
+    for i in range(6):
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        torch.matmul(P, Q.T, out=R_)
+        b1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = min(best, b0.elapsed_time(b1) * 1e-3)
+    peak = 2.0 * nb**3 / best / 1e12
+    del P, Q, R_
+
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        n0 = min(CPU_SAMPLE_N, N)
+        t = cpu_sample_seconds(3, 1, n0)
+        cpu = {"value": 1.0 / (t * (N / n0) ** 3), "unit": "evals/s", "cores": cpu_cores(), "kind": "port",
+               "sample": (f"oracle/ref_numpy.py (NumPy/OpenBLAS restatement of GPX; JAX absent) at N={n0}: "
+                          f"{t:.3f} s per LML+grad; scaled x(N/{n0})^3 to N={N}")}
+
+    step_tflops = alg_flops(N, D) / (ms * 1e-3) / 1e12
+    line = {
+        "metric": "LML+grad evals/s (exact GPR, Matern-5/2, N=32768, D=16, FP64)",
+        "value": world * 1e3 / ms, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"exact GPR Matern-5/2 N={N} D={D} LML+grad (BASELINE configs[1])",
+                   "parallelism": "replicas only" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (A is %.1f GB)" % (8.0 * N * N / 1e9),
+                   "lml": float(res[0]), "grad": [float(res[1]), float(res[2])]},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "gemm_f64_kernel<1,1> (DMMA SYRK, lower trapezoid)",
+                     "shape": f"M=N={m_t} K={k_t}", "peak_source": f"cuBLAS Dgemm {nb}^3 measured in this run",
+                     "step_tflops": step_tflops, "step_frac": step_tflops / peak},
+        "cpu_baseline": cpu,
+        "e2e": {"value": world / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(x_np.nbytes + y_np.nbytes),
+                "d2h_bytes_per_step": 24},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpxb", choices=["gpxb", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="override N (debugging only; the bench line names it)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -50,7 +50,9 @@ int gpxb_ctx_create(int device, gpxb_ctx** out) {
   Ctx* c = new Ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  GPXB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  GPXB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  GPXB_CUDA_CHECK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
   GPXB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   GPXB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   // keep stream-ordered scratch cached between calls (multi-GB workspaces are reused)
@@ -68,6 +70,7 @@ int gpxb_ctx_destroy(gpxb_ctx* ctx) {
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   delete c;
   return 0;
 }

@@ -186,53 +186,96 @@ int trsm_right_l(Ctx* ctx, const double* L, long long ldl, const double* inv, do
 // leaf (one CTA) -> tall TRSM (multiply by the inverted leaf) -> rank-128 update of the rest
 // of the panel; then one rank-1024 SYRK on the trailing matrix.  Every GEMM is tall, so only
 // the leaves run on a single SM.
-int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s) {
-  if (n <= 0) return 0;
-  constexpr int NB = 1024;
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int w = min(NB, n - k0);
-    for (int j = 0; j < w; j += LB) {
-      const int jb = min(LB, w - j);
-      const int c0 = k0 + j;  // global first column of this step
-      double* Ajj = A + (long long)c0 * lda + c0;
-      double* invj = inv + (long long)(c0 / LB) * LB * LB;
-      GPXB_TRY(leaf(ctx, Ajj, lda, jb, invj, s));
-      const int below = n - c0 - jb;
-      if (below <= 0) continue;
-      double* B = A + (long long)(c0 + jb) * lda + c0;  // below x jb
-      {
-        GemmArgs g;  // B <- B inv^T (in place: one column tile, rows private per CTA)
-        g.M = below; g.N = jb; g.K = jb;
-        g.A = B; g.lda = lda; g.a_kmajor = true;
-        g.B = invj; g.ldb = LB; g.b_kmajor = true;
-        g.C = B; g.ldc = lda;
-        GPXB_TRY(gemm_f64(ctx, g, s));
-      }
-      const int wr = w - j - jb;  // panel columns still to update
-      if (wr > 0) {
-        GemmArgs g;  // C -= B B[0:wr]^T on the lower trapezoid
-        g.M = below; g.N = wr; g.K = jb;
-        g.A = B; g.lda = lda; g.a_kmajor = true;
-        g.B = B; g.ldb = lda; g.b_kmajor = true;
-        g.C = B + jb; g.ldc = lda;
-        g.alpha = -1.0; g.beta = 1.0;
-        g.lower_only = 1;
-        GPXB_TRY(gemm_f64(ctx, g, s));
-      }
+namespace {
+// Factor the tall panel A[k0:n, k0:k0+w] (its w x w head is the diagonal block).
+int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, double* inv,
+                 cudaStream_t s) {
+  for (int j = 0; j < w; j += LB) {
+    const int jb = min(LB, w - j);
+    const int c0 = k0 + j;  // global first column of this step
+    double* Ajj = A + (long long)c0 * lda + c0;
+    double* invj = inv + (long long)(c0 / LB) * LB * LB;
+    GPXB_TRY(leaf(ctx, Ajj, lda, jb, invj, s));
+    const int below = n - c0 - jb;
+    if (below <= 0) continue;
+    double* B = A + (long long)(c0 + jb) * lda + c0;  // below x jb
+    {
+      GemmArgs g;  // B <- B inv^T (in place: one column tile, rows private per CTA)
+      g.M = below; g.N = jb; g.K = jb;
+      g.A = B; g.lda = lda; g.a_kmajor = true;
+      g.B = invj; g.ldb = LB; g.b_kmajor = true;
+      g.C = B; g.ldc = lda;
+      GPXB_TRY(gemm_f64(ctx, g, s));
     }
-    const int mt = n - k0 - w;
-    if (mt > 0) {
-      double* P = A + (long long)(k0 + w) * lda + k0;  // mt x w
-      GemmArgs g;  // trailing A22 -= P P^T (lower)
-      g.M = mt; g.N = mt; g.K = w;
-      g.A = P; g.lda = lda; g.a_kmajor = true;
-      g.B = P; g.ldb = lda; g.b_kmajor = true;
-      g.C = P + w; g.ldc = lda;
+    const int wr = w - j - jb;  // panel columns still to update
+    if (wr > 0) {
+      GemmArgs g;  // C -= B B[0:wr]^T on the lower trapezoid
+      g.M = below; g.N = wr; g.K = jb;
+      g.A = B; g.lda = lda; g.a_kmajor = true;
+      g.B = B; g.ldb = lda; g.b_kmajor = true;
+      g.C = B + jb; g.ldc = lda;
       g.alpha = -1.0; g.beta = 1.0;
       g.lower_only = 1;
       GPXB_TRY(gemm_f64(ctx, g, s));
     }
   }
+  return 0;
+}
+
+// C[r0:n, c0:c0+nc] -= P[r0.., :] P[c0.., :]^T on the lower trapezoid, P = A[:, k0:k0+w].
+int panel_update(Ctx* ctx, double* A, long long lda, int n, int k0, int w, int c0, int nc,
+                 cudaStream_t s) {
+  const int m = n - c0;
+  if (m <= 0 || nc <= 0) return 0;
+  double* P = A + (long long)c0 * lda + k0;
+  GemmArgs g;
+  g.M = m; g.N = nc; g.K = w;
+  g.A = P; g.lda = lda; g.a_kmajor = true;
+  g.B = P; g.ldb = lda; g.b_kmajor = true;
+  g.C = A + (long long)c0 * lda + c0; g.ldc = lda;
+  g.alpha = -1.0; g.beta = 1.0;
+  g.lower_only = 1;
+  return gemm_f64(ctx, g, s);
+}
+}  // namespace
+
+int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s) {
+  if (n <= 0) return 0;
+  constexpr int NB = 1024;
+  if (n <= NB) return factor_panel(ctx, A, lda, n, 0, n, inv, s);
+  // Depth-1 look-ahead: panel p+1 is factorised on the high-priority stream hp while the
+  // caller's stream s applies panel p's rank-NB update to the columns right of panel p+1.
+  cudaStream_t hp = ctx->side;
+  cudaEvent_t ev, ev_rest_prev = nullptr;
+  GPXB_TRY(ctx->next_event(&ev));
+  GPXB_CUDA_CHECK(cudaEventRecord(ev, s));
+  GPXB_CUDA_CHECK(cudaStreamWaitEvent(hp, ev, 0));
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int w = min(NB, n - k0);
+    GPXB_TRY(factor_panel(ctx, A, lda, n, k0, w, inv, hp));
+    const int c1 = k0 + w;  // first column of the next panel
+    if (c1 >= n) break;
+    const int w1 = min(NB, n - c1);
+    cudaEvent_t ev_factor;
+    GPXB_TRY(ctx->next_event(&ev_factor));
+    GPXB_CUDA_CHECK(cudaEventRecord(ev_factor, hp));
+    // look-ahead part (next panel's columns) on hp, after the previous rest-update wrote them
+    if (ev_rest_prev) GPXB_CUDA_CHECK(cudaStreamWaitEvent(hp, ev_rest_prev, 0));
+    GPXB_TRY(panel_update(ctx, A, lda, n, k0, w, c1, w1, hp));
+    // the rest of the trailing matrix on s
+    const int c2 = c1 + w1;
+    if (c2 < n) {
+      GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_factor, 0));
+      GPXB_TRY(panel_update(ctx, A, lda, n, k0, w, c2, n - c2, s));
+      GPXB_TRY(ctx->next_event(&ev_rest_prev));
+      GPXB_CUDA_CHECK(cudaEventRecord(ev_rest_prev, s));
+    } else {
+      ev_rest_prev = nullptr;
+    }
+  }
+  GPXB_TRY(ctx->next_event(&ev));
+  GPXB_CUDA_CHECK(cudaEventRecord(ev, hp));
+  GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
   return 0;
 }
 

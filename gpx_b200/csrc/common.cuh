@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace gpxb {
 
@@ -53,8 +54,23 @@ static inline long long round_up(long long a, long long b) { return (a + b - 1) 
 struct Ctx {
   int device = 0;
   int num_sms = 148;
-  cudaStream_t side = nullptr;
+  cudaStream_t side = nullptr;  // high-priority stream (panel factorisation look-ahead)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_pool;  // reusable timing-free events, grown on demand
+  size_t ev_next = 0;
+  // round-robin event from the pool (safe to reuse: an event is re-recorded only after
+  // far more than pool-size later records on in-order streams)
+  int next_event(cudaEvent_t* out) {
+    if (ev_pool.size() < 256) {
+      cudaEvent_t e;
+      GPXB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev_pool.push_back(e);
+      *out = e;
+      return 0;
+    }
+    *out = ev_pool[ev_next++ % ev_pool.size()];
+    return 0;
+  }
   unsigned long long launches = 0;  // kernels launched by this library via this ctx
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;

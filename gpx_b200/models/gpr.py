@@ -1,0 +1,157 @@
+"""Exact Gaussian-process regression facade (mirror of gpx/models/gpr.py:70-118, 251-273,
+397-434, 542-593, 863-976).  Numerics run on the device through the C ABI:
+gpxb_gpr_lml_grad / gpxb_gpr_fit / gpxb_gpr_predict (include/gpxb200.h)."""
+from __future__ import annotations
+
+from typing import Callable, Dict
+
+import numpy as np
+
+from .. import ops
+from ..bijectors import Softplus
+from ..defaults import gpxargs
+from ..kernels import Kernel, _to_device
+from ..mean_functions import data_mean, mean_mode
+from ..parameters import ModelState, Parameter
+from ..priors import GammaPrior
+from .base import BaseGP
+
+
+def _hyper(state):
+    kernel: Kernel = state.kernel
+    ell = kernel.lengthscale(state.params["kernel_params"])
+    sigma = float(np.asarray(state.params["sigma"].value))
+    return kernel, ell, sigma
+
+
+def _xy(state, x, y):
+    xd = _to_device(state.kernel._slice(x))
+    yd = _to_device(y)
+    if yd.dim() == 1:
+        yd = yd.reshape(-1, 1)
+    return xd, yd
+
+
+def log_marginal_likelihood(state, x, y, iterative=False, num_evals=gpxargs.num_evals,
+                            num_lanczos=gpxargs.num_lanczos, key_lanczos=gpxargs.key_lanczos,
+                            n_pivots=None, key_precond=None):
+    """gpx/models/gpr.py:70-118 -> _lml_dense / _lml_iter (gpx/models/_gpr.py:737-821)."""
+    kernel, ell, sigma = _hyper(state)
+    xd, yd = _xy(state, x, y)
+    if iterative:
+        from . import _iterative
+
+        return _iterative.lml_iter(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots,
+                                   key_precond)
+    out = ops.gpr_lml_grad(kernel.kind, xd, yd, ell, sigma, mean_mode(state.mean_function), want_grad=False)
+    return float(out.cpu().numpy()[0])
+
+
+def neg_log_marginal_likelihood(state, x, y, **kwargs):
+    """gpx/models/gpr.py:251-273."""
+    return -log_marginal_likelihood(state, x, y, **kwargs)
+
+
+def loss_and_grad(state, x, y, iterative=False, **kwargs):
+    """Negative LML and its gradient w.r.t. the constrained hyper-parameters, from one fused
+    device call (stands in for jit(value_and_grad(loss)), gpx/optimizers/scipy_optimize.py:72-78).
+    Non-trainable parameters get no gradient entry (stop_gradient, model_state.py:93-103)."""
+    if iterative:
+        raise NotImplementedError("gradient of the iterative LML is a 'next' row (SURVEY.md 8f N1)")
+    if state.loss_fn is not neg_log_marginal_likelihood:
+        raise NotImplementedError("only neg_log_marginal_likelihood has a fused device gradient")
+    kernel, ell, sigma = _hyper(state)
+    xd, yd = _xy(state, x, y)
+    out = ops.gpr_lml_grad(kernel.kind, xd, yd, ell, sigma, mean_mode(state.mean_function), want_grad=True)
+    lml, g_ell, g_sigma = (float(v) for v in out.cpu().numpy())
+    grads = {}
+    if state.params["kernel_params"]["lengthscale"].trainable:
+        grads[("kernel_params", "lengthscale")] = -g_ell
+    if state.params["sigma"].trainable:
+        grads[("sigma",)] = -g_sigma
+    return -lml, grads
+
+
+def fit(state, x, y, iterative=False, n_pivots=None, key_precond=None):
+    """gpx/models/gpr.py:397-434 -> _fit_dense / _fit_iter (gpx/models/_gpr.py:262-310)."""
+    kernel, ell, sigma = _hyper(state)
+    xd, yd = _xy(state, x, y)
+    if iterative:
+        from . import _iterative
+
+        c, mu = _iterative.fit_iter(state, xd, yd, ell, sigma, n_pivots, key_precond)
+    else:
+        c, mu = ops.gpr_fit(kernel.kind, xd, yd, ell, sigma, mean_mode(state.mean_function))
+        c, mu = c.cpu().numpy(), np.float64(mu.cpu().numpy()[0])
+    return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), c=c, mu=mu, is_fitted=True,
+                             is_fitted_derivs=False))
+
+
+def predict(state, x, full_covariance=False, iterative=False):
+    """gpx/models/gpr.py:542-593 -> _predict_dense (gpx/models/_gpr.py:434-463)."""
+    if not state.is_fitted:
+        raise RuntimeError("Model is not fitted. Run `fit` to fit the model before prediction.")
+    if state.is_fitted_derivs:
+        raise RuntimeError("Model is trained on derivatives. For the prediction,"
+                           " run `predict_derivs` and `predict_y_derivs`")
+    if full_covariance and iterative:
+        raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
+    kernel, ell, sigma = _hyper(state)
+    import torch
+
+    xt = _to_device(kernel._slice(state.x_train))
+    xs = _to_device(kernel._slice(x))
+    c = _to_device(state.c)
+    if c.dim() == 1:
+        c = c.reshape(-1, 1)
+    mu = torch.full((1,), float(state.mu), dtype=torch.float64, device="cuda")
+    if iterative:
+        # matrix-free mean: same value, no (n* x N) kernel block stored
+        out = ops.kmatvec(kernel.kind, xs, xt, c, ell, diag_add=0.0) + mu
+        return out.cpu().numpy()
+    out = ops.gpr_predict(kernel.kind, xt, xs, c, mu, ell, sigma, full_covariance=full_covariance)
+    if full_covariance:
+        return out[0].cpu().numpy(), out[1].cpu().numpy()
+    return out.cpu().numpy()
+
+
+def default_params() -> Dict[str, Parameter]:
+    """gpx/models/gpr.py:863-870."""
+    return dict(sigma=Parameter(value=1.0, trainable=True, bijector=Softplus(), prior=GammaPrior()))
+
+
+def init(kernel: Callable, mean_function: Callable = data_mean, kernel_params=None, sigma=None,
+         loss_fn: Callable = neg_log_marginal_likelihood) -> ModelState:
+    """gpx/models/gpr.py:873-917."""
+    if not callable(kernel):
+        raise TypeError(f"kernel must be callable, you provided {type(kernel)}")
+    if kernel_params is None:
+        kernel_params = kernel.default_params()
+    elif not isinstance(kernel_params, dict) or not all(isinstance(v, Parameter) for v in kernel_params.values()):
+        raise TypeError("kernel_params must be a dict of Parameter")
+    if sigma is None:
+        sigma = default_params()["sigma"]
+    elif not isinstance(sigma, Parameter):
+        raise TypeError(f"sigma must be a Parameter, you provided {type(sigma)}")
+    params = {"kernel_params": kernel_params, "sigma": sigma}
+    opt = dict(x_train=None, y_train=None, loss_fn=loss_fn, is_fitted=False, is_fitted_derivs=False, c=None,
+               mu=None)
+    return ModelState(kernel, mean_function, params, **opt)
+
+
+class GPR(BaseGP):
+    """gpx/models/gpr.py:925-976."""
+
+    _init_default = dict(is_fitted=False, is_fitted_derivs=False, c=None, mu=None)
+
+    def __init__(self, kernel, mean_function=data_mean, kernel_params=None, sigma=None,
+                 loss_fn=neg_log_marginal_likelihood) -> None:
+        self.state = init(kernel=kernel, mean_function=mean_function, kernel_params=kernel_params, sigma=sigma,
+                          loss_fn=loss_fn)
+
+    _default_params_fun = staticmethod(default_params)
+    _init_fun = staticmethod(init)
+    _lml_fun = staticmethod(log_marginal_likelihood)
+    _loss_and_grad_fun = staticmethod(loss_and_grad)
+    _fit_fun = staticmethod(fit)
+    _predict_fun = staticmethod(predict)

@@ -1,0 +1,54 @@
+"""CPU checks of the boundary: the shared library loads and exports every symbol that
+include/gpxb200.h declares; the ctypes table mirrors the header; no compute is called."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "gpxb200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpxb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gpx_b200 import _build, _lib
+
+    _build.build()
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    syms = header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/gpxb200.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    from gpx_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+    lib = _lib.load()
+    assert lib.gpxb_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gpx_b200 import _lib
+
+    with pytest.raises(_lib.GpxbError):
+        _lib.context()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "gpx_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f"{fn} references the oracle"

@@ -1,0 +1,63 @@
+"""Host-side facade logic that needs no GPU: construction, parameter table, bijectors,
+checkpoint round trip, error behaviour (mirrors tests/gpx/models/test_models.py:139-155,
+tests/gpx/parameters/*, tests/gpx/test_utils.py:56-100 of the reference)."""
+import numpy as np
+import pytest
+
+from gpx_b200.bijectors import Identity, Softplus
+from gpx_b200.kernels import Matern12, Matern32, Matern52, SquaredExponential
+from gpx_b200.models import GPR
+from gpx_b200.parameters import Parameter
+from gpx_b200.priors import GammaPrior, NormalPrior
+
+
+@pytest.mark.parametrize("K", [SquaredExponential, Matern12, Matern32, Matern52])
+def test_gpr_construction(K):
+    m = GPR(kernel=K())
+    assert isinstance(m, GPR)
+    assert m.state.params["kernel_params"]["lengthscale"].value == 1.0
+    assert m.state.params["sigma"].value == 1.0 and m.state.params["sigma"].trainable
+    assert m.state.is_fitted is False and m.c_ is None and m.mu_ is None
+
+
+def test_predict_unfitted_raises():
+    m = GPR(kernel=SquaredExponential())
+    with pytest.raises(RuntimeError):
+        m.predict(np.zeros((3, 2)))
+
+
+def test_softplus_roundtrip_and_grad():
+    b = Softplus()
+    x = np.array([-5.0, -1.0, 0.0, 0.3, 4.0, 30.0])
+    np.testing.assert_allclose(b.backward(b.forward(x)), x, rtol=1e-10, atol=1e-12)
+    h = 1e-6
+    np.testing.assert_allclose(b.grad_forward(x), (b.forward(x + h) - b.forward(x - h)) / (2 * h), rtol=1e-6)
+    assert np.array_equal(Identity().forward(x), x)
+
+
+def test_parameter_shape_check_and_update():
+    with pytest.raises(ValueError):
+        Parameter(np.ones(3), True, Softplus(), NormalPrior())
+    p = Parameter(2.0, True, Softplus(), GammaPrior())
+    q = p.update(dict(value=3.0, trainable=False))
+    assert p.value == 2.0 and q.value == 3.0 and not q.trainable
+
+
+def test_state_save_load_roundtrip(tmp_path):
+    m = GPR(kernel=Matern52(), sigma=Parameter(0.3, False, Softplus(), GammaPrior()))
+    f = str(tmp_path / "state.npz")
+    d = m.save(f)
+    assert "params:kernel_params:lengthscale" in d and "params:sigma" in d
+    m2 = GPR(kernel=Matern52()).load(f)
+    assert float(m2.state.params["sigma"].value) == 0.3
+
+
+def test_trainable_flattening_and_chain_rule():
+    from gpx_b200.optimizers import ravel_backward_trainables, unravel_forward
+
+    m = GPR(kernel=SquaredExponential(), sigma=Parameter(0.5, False, Softplus(), GammaPrior()))
+    x0, paths = ravel_backward_trainables(m.state)
+    assert paths == [("kernel_params", "lengthscale")]
+    st = unravel_forward(m.state, paths, x0 + 0.1)
+    assert st.params["kernel_params"]["lengthscale"].value > 1.0
+    assert st.params["sigma"].value == 0.5

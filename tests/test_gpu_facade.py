@@ -1,0 +1,66 @@
+"""GPU: the GPX-style facade (GPR.fit / predict / log_marginal_likelihood) against the oracle."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_numpy as R  # noqa: E402
+
+
+def _data(N=400, D=3, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-2, 2, (N, D))
+    y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    return x, y
+
+
+def test_lml_and_loss_grad_match_oracle():
+    from gpx_b200.kernels import Matern52
+    from gpx_b200.models import GPR
+
+    x, y = _data()
+    m = GPR(Matern52())
+    lml = m.log_marginal_likelihood(x, y)
+    ref = R.lml_dense("m52", x, y, 1.0, 1.0)
+    assert abs(lml - ref) < 1e-8 * abs(ref)
+    assert m.log_marginal_likelihood(x, y, return_negative=True) == -lml
+    loss, grads = m.loss_and_grad(x, y)
+    _, gl, gs = R.lml_grad_dense("m52", x, y, 1.0, 1.0)
+    assert abs(grads[("kernel_params", "lengthscale")] + gl) < 1e-8 * max(abs(gl), abs(ref))
+    assert abs(grads[("sigma",)] + gs) < 1e-8 * max(abs(gs), abs(ref))
+
+
+def test_fit_minimize_follows_oracle_optimiser():
+    """L-BFGS-B on the device (value, grad) must land where the same optimiser lands with the
+    oracle's (value, grad)."""
+    from scipy.optimize import minimize
+
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import GPR
+
+    x, y = _data(300, 1, 3)
+    m = GPR(SquaredExponential()).fit(x, y)
+    assert m.optimize_results_.success
+    t0 = R.inverse_softplus(np.array([1.0, 1.0]))
+    res = minimize(lambda t: R.neg_lml_and_grad_unconstrained("se", x, y, t[0], t[1]), t0, jac=True,
+                   method="L-BFGS-B")
+    ell, sig = float(m.state.params["kernel_params"]["lengthscale"].value), float(m.state.params["sigma"].value)
+    assert abs(m.optimize_results_.fun - res.fun) < 1e-6 * max(1.0, abs(res.fun))
+    assert abs(ell - R.softplus(res.x[0])) < 1e-3 and abs(sig - R.softplus(res.x[1])) < 1e-3
+    xs = np.linspace(-2, 2, 50).reshape(-1, 1)
+    mean, cov = m.predict(xs, full_covariance=True)
+    c, mu = R.fit_dense("se", x, y, ell, sig)
+    mr, cr = R.predict_dense("se", x, xs, c, mu, ell, sig, full_covariance=True)
+    assert np.max(np.abs(mean - mr)) < 1e-7 and np.max(np.abs(cov - cr)) < 1e-7
+    assert m.c_.shape == (300, 1) and abs(m.mu_ - np.mean(y)) < 1e-14
+
+
+def test_kernel_call_and_active_dims():
+    from gpx_b200.kernels import Matern32
+
+    x, _ = _data(50, 4)
+    k = Matern32(active_dims=[0, 2])
+    p = k.default_params()
+    K = k(x, x, p)
+    assert np.max(np.abs(K - R.kernel("m32", x[:, [0, 2]], x[:, [0, 2]], 1.0))) < 1e-13
