@@ -74,6 +74,7 @@ struct Ctx {
   unsigned long long launches = 0;  // kernels launched by this library via this ctx
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  long long shard_N = 0;  // global row count of the sharded problem in flight
 };
 
 // Stream-ordered scratch buffer (RAII). alloc() returns 0 or a CUDA error code.

@@ -8,11 +8,13 @@
 #include "gemm.cuh"
 #include "mma.cuh"
 
+#include <cstdlib>
+
 namespace gpxb {
 
 namespace {
 
-constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = 16, STAGES = 4, NT = 256;
+constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = 16, STAGES = 4;
 constexpr int LDK = BK + 4;   // row stride of a K-major tile  [128][16]  (doubles)
 constexpr int LDM = BM + 4;   // row stride of an MN-major tile [16][128] (doubles)
 constexpr int TILE_DBL = BM * LDK;  // 2560 doubles >= BK*LDM = 2112
@@ -33,55 +35,98 @@ struct GemmParams {
   int vecA, vecB, vecC;
 };
 
-// Loads one operand tile (128 rows of the M/N index x 16 of K) into shared memory.
-template <bool KMAJ>
-__device__ __forceinline__ void load_tile(double* __restrict__ s, const double* g,
-                                          long long ld, int r0, int rmax, int k0, int kmax, int vec,
-                                          int tid) {
+// Per-thread loader state for one operand: the thread's 16-byte chunks of a tile
+// (128 rows of the M/N index x 16 of K).  Row/column validity is fixed for the whole K
+// loop, so interior K tiles cost one LDGSTS per chunk and a pointer bump.
+template <bool KMAJ, int NTHR>
+struct TileLoader {
+  static constexpr int CH = 1024 / NTHR;
+  const double* ptr[CH];  // global address of the chunk at k = k_lo (clamped when invalid)
+  int soff[CH];           // smem offset in doubles
+  int nb[CH];             // bytes valid along the fixed index (0, 8 or 16)
+  int kk[CH];             // chunk's k offset inside the tile
+  const double* base;
+  long long ld;
+  long long kstep;        // pointer increment per K tile
+  int vec;
+  // slow-path bookkeeping
+  int r0, rmax, tid;
+
+  __device__ __forceinline__ void init(const double* g, long long ld_, int r0_, int rmax_, int k_lo,
+                                       int vec_, int tid_) {
+    base = g; ld = ld_; vec = vec_; r0 = r0_; rmax = rmax_; tid = tid_;
+    kstep = KMAJ ? (long long)BK : (long long)BK * ld_;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = tid + i * NT;
-    if (KMAJ) {
-      const int r = c >> 3, kc = (c & 7) * 2;
-      const int gr = r0 + r, gk = k0 + kc;
-      double* dst = s + r * LDK + kc;
-      if (vec) {
-        int nb = (gr < rmax) ? (kmax - gk) * 8 : 0;
-        nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-        const double* src = nb > 0 ? g + (long long)gr * ld + gk : g;
-        cp_async16(dst, src, nb);
+    for (int i = 0; i < CH; ++i) {
+      const int c = tid_ + i * NTHR;
+      if (KMAJ) {
+        const int r = c >> 3, kc = (c & 7) * 2;
+        const int gr = r0_ + r;
+        soff[i] = r * LDK + kc;
+        kk[i] = kc;
+        nb[i] = gr < rmax_ ? 16 : 0;
+        ptr[i] = nb[i] ? g + (long long)gr * ld_ + k_lo + kc : g;
       } else {
+        const int k = c >> 6, mc = (c & 63) * 2;
+        const int gm = r0_ + mc;
+        soff[i] = k * LDM + mc;
+        kk[i] = k;
+        int b = (rmax_ - gm) * 8;
+        nb[i] = b < 0 ? 0 : (b > 16 ? 16 : b);
+        ptr[i] = nb[i] ? g + (long long)(k_lo + k) * ld_ + gm : g;
+      }
+    }
+  }
+
+  // k0: first k of this tile; kmax: true K bound; interior tiles skip every check.
+  __device__ __forceinline__ void load(double* __restrict__ s, int k0, int kmax, int tile_idx) {
+    if (vec) {
+      const bool interior = (k0 + BK <= kmax);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const bool ok = (gr < rmax) && (gk + e < kmax);
-          dst[e] = ok ? g[(long long)gr * ld + gk + e] : 0.0;  // unaligned slow path
+      for (int i = 0; i < CH; ++i) {
+        int b = nb[i];
+        if (!interior) {
+          if (KMAJ) {
+            int kb = (kmax - (k0 + kk[i])) * 8;
+            kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
+            b = b < kb ? b : kb;
+          } else {
+            if (k0 + kk[i] >= kmax) b = 0;
+          }
         }
+        const double* src = ptr[i] + (long long)tile_idx * kstep;
+        cp_async16(s + soff[i], b > 0 ? src : base, b);
       }
     } else {
-      const int kk = c >> 6, mc = (c & 63) * 2;
-      const int gk = k0 + kk, gm = r0 + mc;
-      double* dst = s + kk * LDM + mc;
-      if (vec) {
-        int nb = (gk < kmax) ? (rmax - gm) * 8 : 0;
-        nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-        const double* src = nb > 0 ? g + (long long)gk * ld + gm : g;
-        cp_async16(dst, src, nb);
-      } else {
+      // unaligned slow path: plain loads, element by element
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int c = tid + i * NTHR;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const bool ok = (gk < kmax) && (gm + e < rmax);
-          dst[e] = ok ? g[(long long)gk * ld + gm + e] : 0.0;  // unaligned slow path
+          if (KMAJ) {
+            const int gr = r0 + (c >> 3), gk = k0 + (c & 7) * 2 + e;
+            const bool ok = (gr < rmax) && (gk < kmax);
+            s[soff[i] + e] = ok ? base[(long long)gr * ld + gk] : 0.0;
+          } else {
+            const int gk = k0 + (c >> 6), gm = r0 + (c & 63) * 2 + e;
+            const bool ok = (gk < kmax) && (gm < rmax);
+            s[soff[i] + e] = ok ? base[(long long)gk * ld + gm] : 0.0;
+          }
         }
       }
     }
   }
-}
+};
 
-template <bool AK, bool BKM>
-__global__ void __launch_bounds__(NT, 1) gemm_f64_kernel(const GemmParams p) {
+// WM x WN warps, each a (8*MF) x (8*NF) tile:  2x4 warps of 64x32, or 4x4 warps of 32x32.
+template <bool AK, bool BKM, int WM, int WN>
+__global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmParams p) {
+  constexpr int NTHR = WM * WN * 32;
+  constexpr int MF = BM / (8 * WM), NF = BN / (8 * WN);
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp / WN, wn = warp % WN;
   const int lr = lane >> 2, lq = lane & 3;
 
   // ---- tile coordinates ----
@@ -120,22 +165,30 @@ __global__ void __launch_bounds__(NT, 1) gemm_f64_kernel(const GemmParams p) {
   int k_hi = (p.khi_mode == 1) ? min(p.K, row0 + BM) : p.K;
   const int nk = k_hi > k_lo ? (k_hi - k_lo + BK - 1) / BK : 0;
 
-  double acc[8][4][2];
+  double acc[MF][NF][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MF; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  TileLoader<AK, NTHR> la;
+  TileLoader<BKM, NTHR> lb;
+  la.init(p.A, p.lda, row0, p.M, k_lo, p.vecA, tid);
+  lb.init(p.B, p.ldb, col0, p.N, k_lo, p.vecB, tid);
 
   // ---- pipeline prologue ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
       double* sa = smem + s * STAGE_DBL;
-      load_tile<AK>(sa, p.A, p.lda, row0, p.M, k_lo + s * BK, p.K, p.vecA, tid);
-      load_tile<BKM>(sa + TILE_DBL, p.B, p.ldb, col0, p.N, k_lo + s * BK, p.K, p.vecB, tid);
+      la.load(sa, k_lo + s * BK, p.K, s);
+      lb.load(sa + TILE_DBL, k_lo + s * BK, p.K, s);
     }
     cp_async_commit();
   }
+
+  const int a_off = AK ? (wm * (8 * MF) + lr) * LDK + lq : lq * LDM + wm * (8 * MF) + lr;
+  const int b_off = BKM ? (wn * (8 * NF) + lr) * LDK + lq : lq * LDM + wn * (8 * NF) + lr;
 
   for (int kt = 0; kt < nk; ++kt) {
     cp_async_wait<STAGES - 2>();
@@ -144,30 +197,24 @@ __global__ void __launch_bounds__(NT, 1) gemm_f64_kernel(const GemmParams p) {
       const int nxt = kt + STAGES - 1;
       if (nxt < nk) {
         double* sa = smem + (nxt % STAGES) * STAGE_DBL;
-        load_tile<AK>(sa, p.A, p.lda, row0, p.M, k_lo + nxt * BK, p.K, p.vecA, tid);
-        load_tile<BKM>(sa + TILE_DBL, p.B, p.ldb, col0, p.N, k_lo + nxt * BK, p.K, p.vecB, tid);
+        la.load(sa, k_lo + nxt * BK, p.K, nxt);
+        lb.load(sa + TILE_DBL, k_lo + nxt * BK, p.K, nxt);
       }
       cp_async_commit();
     }
-    const double* sA = smem + (kt % STAGES) * STAGE_DBL;
-    const double* sB = sA + TILE_DBL;
+    const double* sA = smem + (kt % STAGES) * STAGE_DBL + a_off;
+    const double* sB = smem + (kt % STAGES) * STAGE_DBL + TILE_DBL + b_off;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
-      double a[8], b[4];
+      double a[MF], b[NF];
 #pragma unroll
-      for (int mf = 0; mf < 8; ++mf) {
-        a[mf] = AK ? sA[(wm * 64 + mf * 8 + lr) * LDK + ks * 4 + lq]
-                   : sA[(ks * 4 + lq) * LDM + wm * 64 + mf * 8 + lr];
-      }
+      for (int mf = 0; mf < MF; ++mf) a[mf] = AK ? sA[mf * 8 * LDK + ks * 4] : sA[ks * 4 * LDM + mf * 8];
 #pragma unroll
-      for (int nf = 0; nf < 4; ++nf) {
-        b[nf] = BKM ? sB[(wn * 32 + nf * 8 + lr) * LDK + ks * 4 + lq]
-                    : sB[(ks * 4 + lq) * LDM + wn * 32 + nf * 8 + lr];
-      }
+      for (int nf = 0; nf < NF; ++nf) b[nf] = BKM ? sB[nf * 8 * LDK + ks * 4] : sB[ks * 4 * LDM + nf * 8];
 #pragma unroll
-      for (int mf = 0; mf < 8; ++mf)
+      for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
-        for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
+        for (int nf = 0; nf < NF; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
     }
   }
   cp_async_wait<0>();
@@ -175,12 +222,12 @@ __global__ void __launch_bounds__(NT, 1) gemm_f64_kernel(const GemmParams p) {
   // ---- epilogue ----
   const bool use_beta = (p.beta != 0.0);
 #pragma unroll
-  for (int mf = 0; mf < 8; ++mf) {
-    const int row = row0 + wm * 64 + mf * 8 + lr;
+  for (int mf = 0; mf < MF; ++mf) {
+    const int row = row0 + wm * (8 * MF) + mf * 8 + lr;
     if (row >= p.M) continue;
 #pragma unroll
-    for (int nf = 0; nf < 4; ++nf) {
-      const int col = col0 + wn * 32 + nf * 8 + lq * 2;
+    for (int nf = 0; nf < NF; ++nf) {
+      const int col = col0 + wn * (8 * NF) + nf * 8 + lq * 2;
       if (col >= p.N) continue;
       double* cp = p.C + (long long)row * p.ldc + col;
       const bool ok0 = !p.lower_only || col <= row;
@@ -201,11 +248,26 @@ __global__ void __launch_bounds__(NT, 1) gemm_f64_kernel(const GemmParams p) {
   }
 }
 
+int gemm_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GPXB_GEMM_WARPS");
+    v = (e && atoi(e) == 8) ? 8 : 16;
+  }
+  return v;
+}
+
 template <bool AK, bool BKM>
 int launch(Ctx* ctx, const GemmParams& p, int grid, cudaStream_t stream) {
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<AK, BKM>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  gemm_f64_kernel<AK, BKM><<<grid, NT, SMEM_BYTES, stream>>>(p);
+  if (gemm_variant() == 8) {
+    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<AK, BKM, 2, 4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    gemm_f64_kernel<AK, BKM, 2, 4><<<grid, 256, SMEM_BYTES, stream>>>(p);
+  } else {
+    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<AK, BKM, 4, 4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    gemm_f64_kernel<AK, BKM, 4, 4><<<grid, 512, SMEM_BYTES, stream>>>(p);
+  }
   GPXB_LAUNCH_CHECK();
   if (ctx) ctx->launches++;
   return 0;

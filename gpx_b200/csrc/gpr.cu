@@ -10,64 +10,13 @@
 #include "gemm.cuh"
 #include "gram.cuh"
 #include "mma.cuh"
+#include "small_kernels.cuh"
 
 namespace gpxb {
 
 namespace {
 
-// mean over all n elements (data_mean, gpx/mean_functions.py:29-30); fixed-order reduction.
-__global__ void mean_kernel(const double* __restrict__ y, long long n, int mode,
-                            double* __restrict__ mu) {
-  __shared__ double sh[32];
-  double s = 0.0;
-  if (mode == GPXB_MEAN_DATA)
-    for (long long i = threadIdx.x; i < n; i += 1024) s += y[i];
-  s = block_sum<1024>(s, sh);
-  if (threadIdx.x == 0) *mu = (mode == GPXB_MEAN_DATA) ? s / (double)n : 0.0;
-}
-
-// rT[t][i] = y[i][t] - mu
-__global__ void center_transpose_kernel(const double* __restrict__ y, int N, int T,
-                                        const double* __restrict__ mu, double* __restrict__ rT) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * T) return;
-  const int i = (int)(idx / T), t = (int)(idx % T);
-  rT[(long long)t * N + i] = y[idx] - *mu;
-}
-
-// out[i][t] = in[t][i]
-__global__ void transpose_out_kernel(const double* __restrict__ in, int N, int T,
-                                     double* __restrict__ out) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * T) return;
-  const int i = (int)(idx / T), t = (int)(idx % T);
-  out[idx] = in[(long long)t * N + i];
-}
-
-__global__ void sumsq_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
-  __shared__ double sh[32];
-  double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += 1024) s += v[i] * v[i];
-  s = block_sum<1024>(s, sh);
-  if (threadIdx.x == 0) *out = s;
-}
-
-__global__ void sum_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
-  __shared__ double sh[32];
-  double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += 1024) s += v[i];
-  s = block_sum<1024>(s, sh);
-  if (threadIdx.x == 0) *out = s;
-}
-
-__global__ void diag_sum_kernel(const double* __restrict__ A, long long ld, int n,
-                                double* __restrict__ out) {
-  __shared__ double sh[32];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024) s += A[(long long)i * ld + i];
-  s = block_sum<1024>(s, sh);
-  if (threadIdx.x == 0) *out = s;
-}
+using namespace sk;
 
 // scal: [0] quad, [1] sum log L_ii, [2] sum W dK, [3] sum alpha^2, [4] tr(Ainv)
 __global__ void finalize_lml_kernel(const double* __restrict__ scal, int N, double sigma,
@@ -82,17 +31,6 @@ __global__ void finalize_lml_kernel(const double* __restrict__ scal, int N, doub
     out3[2] = 0.0;
   }
 }
-
-__global__ void add_scalar_kernel(double* __restrict__ v, long long n, const double* __restrict__ mu) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < n) v[idx] += *mu;
-}
-
-#define LAUNCHED(ctx)      \
-  do {                     \
-    GPXB_LAUNCH_CHECK();   \
-    (ctx)->launches++;     \
-  } while (0)
 
 }  // namespace
 
@@ -131,26 +69,26 @@ int gpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int N, in
   double *scal = bScal.as<double>(), *mu = bMu.as<double>();
   GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 8, s));
 
-  mean_kernel<<<1, 1024, 0, s>>>(y, (long long)N * T, mean_mode, mu);
-  LAUNCHED(ctx);
+  mean_kernel<<<1, 1024, 0, s>>>(y, (long long)N * T, mean_mode == GPXB_MEAN_DATA, mu);
+  GPXB_LAUNCHED(ctx);
   center_transpose_kernel<<<ceil_div((long long)N * T, 256), 256, 0, s>>>(y, N, T, mu, rT);
-  LAUNCHED(ctx);
+  GPXB_LAUNCHED(ctx);
 
   GPXB_TRY(build_and_factor(ctx, kind, x, N, D, ell, s2, Z, A, inv, s));
   GPXB_TRY(logdet_lower(ctx, A, N, N, scal + 1, 1.0, s));
   GPXB_TRY(trsm_right_lt(ctx, A, N, inv, rT, N, T, N, s));  // rT <- (L^-1 r)^T
-  sumsq_kernel<<<1, 1024, 0, s>>>(rT, (long long)N * T, scal + 0);
-  LAUNCHED(ctx);
+  sumsq_kernel<<<1, 1024, 0, s>>>(rT, (long long)N * T, scal + 0, 0);
+  GPXB_LAUNCHED(ctx);
 
   if (want_grad) {
     GPXB_TRY(trsm_right_l(ctx, A, N, inv, rT, N, T, N, s));  // rT <- alpha^T
-    sumsq_kernel<<<1, 1024, 0, s>>>(rT, (long long)N * T, scal + 3);
-    LAUNCHED(ctx);
+    sumsq_kernel<<<1, 1024, 0, s>>>(rT, (long long)N * T, scal + 3, 0);
+    GPXB_LAUNCHED(ctx);
     GPXB_TRY(bW.alloc(sizeof(double) * nn, s));
     GPXB_TRY(bT.alloc(sizeof(double) * potri_scratch_doubles(N), s));
     GPXB_TRY(potri_lower(ctx, A, N, inv, N, bW.as<double>(), bT.as<double>(), A, N, s));
     diag_sum_kernel<<<1, 1024, 0, s>>>(A, N, N, scal + 4);
-    LAUNCHED(ctx);
+    GPXB_LAUNCHED(ctx);
     GramArgs g;
     g.kind = kind;
     g.Z1 = Z; g.n1 = N; g.Z2 = Z; g.n2 = N; g.zl = zl;
@@ -161,10 +99,10 @@ int gpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int N, in
     g.partials = bPart.as<double>();
     GPXB_TRY(gram_launch(ctx, g, s));
     sum_kernel<<<1, 1024, 0, s>>>(g.partials, nparts, scal + 2);
-    LAUNCHED(ctx);
+    GPXB_LAUNCHED(ctx);
   }
   finalize_lml_kernel<<<1, 1, 0, s>>>(scal, N, sigma, want_grad, out3);
-  LAUNCHED(ctx);
+  GPXB_LAUNCHED(ctx);
   return 0;
 }
 
@@ -181,16 +119,16 @@ int gpr_fit(Ctx* ctx, int kind, const double* x, const double* y, int N, int D, 
   GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles(N), s));
   GPXB_TRY(bR.alloc(sizeof(double) * (size_t)N * T, s));
   double* rT = bR.as<double>();
-  mean_kernel<<<1, 1024, 0, s>>>(y, (long long)N * T, mean_mode, mu_out);
-  LAUNCHED(ctx);
+  mean_kernel<<<1, 1024, 0, s>>>(y, (long long)N * T, mean_mode == GPXB_MEAN_DATA, mu_out);
+  GPXB_LAUNCHED(ctx);
   center_transpose_kernel<<<ceil_div((long long)N * T, 256), 256, 0, s>>>(y, N, T, mu_out, rT);
-  LAUNCHED(ctx);
+  GPXB_LAUNCHED(ctx);
   GPXB_TRY(build_and_factor(ctx, kind, x, N, D, ell, s2, bZ.as<double>(), bA.as<double>(),
                             bInv.as<double>(), s));
   GPXB_TRY(trsm_right_lt(ctx, bA.as<double>(), N, bInv.as<double>(), rT, N, T, N, s));
   GPXB_TRY(trsm_right_l(ctx, bA.as<double>(), N, bInv.as<double>(), rT, N, T, N, s));
   transpose_out_kernel<<<ceil_div((long long)N * T, 256), 256, 0, s>>>(rT, N, T, c_out);
-  LAUNCHED(ctx);
+  GPXB_LAUNCHED(ctx);
   return 0;
 }
 
@@ -224,7 +162,7 @@ int gpr_predict(Ctx* ctx, int kind, const double* x_train, int N, int D, const d
     GPXB_TRY(gemm_f64(ctx, g, s));
   }
   add_scalar_kernel<<<ceil_div((long long)ns * T, 256), 256, 0, s>>>(mean_out, (long long)ns * T, mu);
-  LAUNCHED(ctx);
+  GPXB_LAUNCHED(ctx);
   if (cov_out) {
     const double s2 = sigma * sigma + 1e-10;
     DevBuf bA, bInv;

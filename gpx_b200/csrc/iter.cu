@@ -1,0 +1,445 @@
+// Family 3b: block Lanczos tridiagonalisation (for stochastic Lanczos quadrature) and
+// preconditioned conjugate gradients over the matrix-free mat-vec (matvec.cu).
+//
+// Replaces gpx/lanczos.py:29-183 (lanczos_tridiagonal with full modified-Gram-Schmidt
+// re-orthogonalisation, lanczos_logdet's Rademacher probes), jax.scipy.sparse.linalg.cg as
+// called by gpx/models/_gpr.py:285-310 and the RPCholesky preconditioner of
+// gpx/models/_gpr.py:180-216.  The reference runs the probes one after the other; here all
+// P probes advance together as the columns of an N x P block, so one pass over the
+// recomputed kernel tiles serves every probe.
+#include <cmath>
+
+#include "../../include/gpxb200.h"
+#include "chol.cuh"
+#include "comm.cuh"
+#include "gemm.cuh"
+#include "matvec.cuh"
+#include "mma.cuh"
+#include "threefry.cuh"
+
+namespace gpxb {
+
+namespace {
+
+constexpr int RB = 256;   // rows per CTA in the column-wise reductions
+constexpr int MAXP = 32;  // columns per block
+
+// part[blockIdx.x][p] = sum over this CTA's rows of X[i][p] * Y[i][p]   (fixed order)
+__global__ void __launch_bounds__(256) coldot_partial_kernel(const double* __restrict__ X,
+                                                             const double* __restrict__ Y, int n, int PS,
+                                                             int P, double* __restrict__ part) {
+  __shared__ double sh[8][MAXP];
+  const int p = threadIdx.x & 31, g = threadIdx.x >> 5;  // 8 row groups x 32 columns
+  const long long r0 = (long long)blockIdx.x * RB;
+  double s = 0.0;
+  if (p < P) {
+    for (int i = g; i < RB; i += 8) {
+      const long long r = r0 + i;
+      if (r < n) s += X[r * PS + p] * Y[r * PS + p];
+    }
+  }
+  sh[g][p] = s;
+  __syncthreads();
+  if (g == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][p];
+    part[(long long)blockIdx.x * MAXP + p] = t;
+  }
+}
+
+// out[p] = sum_b part[b][p] in block order (one CTA, 32 columns x 32 lanes of blocks)
+__global__ void __launch_bounds__(1024) coldot_final_kernel(const double* __restrict__ part, int nblk,
+                                                            double* __restrict__ out) {
+  __shared__ double sh[32][MAXP + 1];
+  const int p = threadIdx.x & 31, g = threadIdx.x >> 5;
+  double s = 0.0;
+  for (int b = g; b < nblk; b += 32) s += part[(long long)b * MAXP + p];
+  sh[g][p] = s;
+  __syncthreads();
+  if (g == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 32; ++k) t += sh[k][p];
+    out[p] = t;
+  }
+}
+
+// W[:,p] -= a[p] * X[:,p] (+ b[p] * Y[:,p] if Y)
+__global__ void colaxpy_kernel(double* __restrict__ W, const double* __restrict__ a,
+                               const double* __restrict__ X, const double* __restrict__ b,
+                               const double* __restrict__ Y, int n, int PS, int P) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * PS) return;
+  const int p = (int)(idx % PS);
+  if (p >= P) return;
+  double w = W[idx] - a[p] * X[idx];
+  if (Y) w -= b[p] * Y[idx];
+  W[idx] = w;
+}
+
+// beta[p] = sqrt(nrm2[p]); Vn[:,p] = W[:,p] / beta[p]; flags breakdown (beta <= 1e-12)
+__global__ void colnormalize_kernel(const double* __restrict__ W, const double* __restrict__ nrm2,
+                                    double* __restrict__ Vn, int n, int PS, int P, int* __restrict__ flag) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * PS) return;
+  const int p = (int)(idx % PS);
+  if (p >= P) {
+    Vn[idx] = 0.0;
+    return;
+  }
+  const double beta = sqrt(nrm2[p]);
+  if (!(beta > 1e-12) && idx < PS) atomicOr(flag, 1);
+  Vn[idx] = W[idx] / beta;
+}
+
+// T bookkeeping: alpha_out[p][j] = alpha[p];  beta_out[p][j] = sqrt(nrm2[p])
+__global__ void store_ab_kernel(const double* __restrict__ alpha, const double* __restrict__ nrm2, int P,
+                                int m, int j, double* __restrict__ alpha_out, double* __restrict__ beta_out,
+                                double* __restrict__ beta_cur) {
+  const int p = threadIdx.x;
+  if (p >= P) return;
+  alpha_out[p * m + j] = alpha[p];
+  const double b = sqrt(nrm2[p]);
+  beta_out[p * m + j] = b;
+  beta_cur[p] = b;
+}
+
+// Rademacher probes normalised to unit length: jax.random.rademacher(subkey, (N, P)) / sqrt(N)
+// (gpx/lanczos.py:168-170).  row0: global index of the first local row.
+__global__ void rademacher_kernel(uint32_t k0, uint32_t k1, long long Ntot, int P, long long row0, int n_rows,
+                                  int PS, int partitionable, double* __restrict__ U) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_rows * PS) return;
+  const long long i = idx / PS;
+  const int p = (int)(idx % PS);
+  if (p >= P) {
+    U[idx] = 0.0;
+    return;
+  }
+  const unsigned long long e = (unsigned long long)(row0 + i) * P + p;
+  const double u = jax_uniform_f64(k0, k1, e, (unsigned long long)Ntot * P, partitionable);
+  const double sgn = (u < 0.5) ? 1.0 : -1.0;
+  U[idx] = sgn / sqrt((double)Ntot);
+}
+
+int coldot(Ctx* ctx, const double* X, const double* Y, int n, int PS, int P, double* part, double* out,
+           cudaStream_t s) {
+  const int nblk = ceil_div(n, RB);
+  coldot_partial_kernel<<<nblk, 256, 0, s>>>(X, Y, n, PS, P, part);
+  GPXB_LAUNCH_CHECK();
+  coldot_final_kernel<<<1, 1024, 0, s>>>(part, nblk, out);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches += 2;
+  return comm_allreduce_sum(ctx, out, MAXP, s);  // no-op on one GPU
+}
+
+}  // namespace
+
+// Block Lanczos on A = K(x,x) + diag_add*I restricted to this rank's rows.
+//   Zr: this rank's pre-scaled rows (n_loc x S), Za: all rows (N x S), row0: first local row.
+//   U: normalised start block, local rows, padded stride PS.
+//   alpha_out / beta_out: [P][m] device.  T_p = tridiag(alpha_out[p], beta_out[p][0..m-2]).
+//   flag: device int set to 1 on breakdown (beta <= 1e-12).
+int lanczos_block(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
+                  ZLayout zl, double diag_add, const double* U, int P, int PS, int m, double* alpha_out,
+                  double* beta_out, int* flag, cudaStream_t s) {
+  GPXB_ARG_CHECK(P >= 1 && P <= MAXP && m >= 1, -30);
+  ctx->shard_N = N;
+  const size_t blk = (size_t)n_loc * PS;
+  const size_t blk_all = (size_t)N * PS;
+  DevBuf bVecs, bW, bVall, bPart, bSc;
+  GPXB_TRY(bVecs.alloc(sizeof(double) * blk * m, s));
+  GPXB_TRY(bW.alloc(sizeof(double) * blk, s));
+  GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)ceil_div(n_loc, RB) * MAXP, s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * MAXP * 4, s));
+  double *vecs = bVecs.as<double>(), *W = bW.as<double>(), *part = bPart.as<double>();
+  double *alpha = bSc.as<double>(), *nrm2 = alpha + MAXP, *coef = alpha + 2 * MAXP, *beta = alpha + 3 * MAXP;
+  // the mat-vec needs the full block V on every rank: all-gather when sharded
+  double* Vall = nullptr;
+  if (ctx->world > 1) {
+    GPXB_TRY(bVall.alloc(sizeof(double) * (blk_all + 16), s));
+    Vall = bVall.as<double>();
+  }
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(vecs, U, sizeof(double) * blk, cudaMemcpyDeviceToDevice, s));
+  const int nthr = 256;
+  const int nblk_e = ceil_div((long long)blk, nthr);
+
+  for (int j = 0; j < m; ++j) {
+    double* vj = vecs + blk * j;
+    const double* vfull = vj;
+    if (ctx->world > 1) {
+      GPXB_TRY(comm_allgather_rows(ctx, vj, Vall, n_loc, PS, s));
+      vfull = Vall;
+    }
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
+    a.V = vfull; a.PS = PS; a.P = P; a.W = W; a.ldw = PS; a.diag_add = diag_add;
+    GPXB_TRY(kmatvec_launch(ctx, a, s));                        // w = A v_j
+    GPXB_TRY(coldot(ctx, W, vj, n_loc, PS, P, part, alpha, s));  // alpha = w . v_j
+    colaxpy_kernel<<<nblk_e, nthr, 0, s>>>(W, alpha, vj, beta, j > 0 ? vecs + blk * (j - 1) : nullptr, n_loc, PS,
+                                           P);                  // w -= alpha v_j + beta v_{j-1}
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+    if (j > 0) {
+      // full re-orthogonalisation, modified Gram-Schmidt in column order (lanczos.py:29-37);
+      // columns beyond j are still zero in the reference and are skipped
+      for (int c = 0; c <= j; ++c) {
+        const double* vc = vecs + blk * c;
+        GPXB_TRY(coldot(ctx, W, vc, n_loc, PS, P, part, coef, s));
+        colaxpy_kernel<<<nblk_e, nthr, 0, s>>>(W, coef, vc, nullptr, nullptr, n_loc, PS, P);
+        GPXB_LAUNCH_CHECK();
+        ctx->launches++;
+      }
+    }
+    GPXB_TRY(coldot(ctx, W, W, n_loc, PS, P, part, nrm2, s));
+    store_ab_kernel<<<1, MAXP, 0, s>>>(alpha, nrm2, P, m, j, alpha_out, beta_out, beta);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+    if (j + 1 < m) {
+      colnormalize_kernel<<<nblk_e, nthr, 0, s>>>(W, nrm2, vecs + blk * (j + 1), n_loc, PS, P, flag);
+      GPXB_LAUNCH_CHECK();
+      ctx->launches++;
+    }
+  }
+  return 0;
+}
+
+int rademacher_probes(Ctx* ctx, const uint32_t key[2], long long Ntot, int P, long long row0, int n_rows,
+                      int PS, int partitionable, double* U, cudaStream_t s) {
+  const long long tot = (long long)n_rows * PS;
+  rademacher_kernel<<<ceil_div(tot, 256), 256, 0, s>>>(key[0], key[1], Ntot, P, row0, n_rows, PS,
+                                                        partitionable, U);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Preconditioned CG (jax.scipy.sparse.linalg.cg semantics: x0 = 0, tol = 1e-5, atol given,
+// stop when r.r <= max(tol^2 b.b, atol^2) or k == maxiter).
+// ------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void vdot_partial_kernel(const double* __restrict__ x, int sx, const double* __restrict__ y, int sy,
+                                    int n, double* __restrict__ part) {
+  __shared__ double sh[8];
+  double s = 0.0;
+  const long long r0 = (long long)blockIdx.x * 1024;
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    const long long r = r0 + i;
+    if (r < n) s += x[r * sx] * y[r * sy];
+  }
+  s = block_sum<256>(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void vsum_final_kernel(const double* __restrict__ part, int nblk, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 1024) s += part[b];
+  s = block_sum<1024>(s, sh);
+  if (threadIdx.x == 0) *out = s;
+}
+// y[i*sy] = a*x[i*sx] + b*y[i*sy] with device scalars a = num/den * sign (den may be null)
+__global__ void vaxpby_kernel(double* __restrict__ y, int sy, const double* __restrict__ x, int sx, int n,
+                              const double* __restrict__ num, const double* __restrict__ den, double sign,
+                              double b) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = sign * (den ? (*num / *den) : *num);
+  y[i * sy] = a * x[i * sx] + b * y[i * sy];
+}
+// p = z + (gn/g) p
+__global__ void vxpby_kernel(double* __restrict__ p, int sp, const double* __restrict__ z, int n,
+                             const double* __restrict__ gn, const double* __restrict__ g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  p[i * sp] = z[i] + (*gn / *g) * p[i * sp];
+}
+// t1[c] = sum_r F[c][r] z[r]   (one CTA per pivot column; F stored [k][ldf])
+__global__ void ftz_kernel(const double* __restrict__ F, long long ldf, int n, const double* __restrict__ z,
+                           double* __restrict__ t1) {
+  __shared__ double sh[32];
+  const double* f = F + (long long)blockIdx.x * ldf;
+  double s = 0.0;
+  for (int r = threadIdx.x; r < n; r += 1024) s += f[r] * z[r];
+  s = block_sum<1024>(s, sh);
+  if (threadIdx.x == 0) t1[blockIdx.x] = s;
+}
+// t2 = Pkk t1 (k x k full symmetric, tiny)
+__global__ void small_matvec_kernel(const double* __restrict__ Pkk, int k, const double* __restrict__ t1,
+                                    double* __restrict__ t2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  double s = 0.0;
+  for (int c = 0; c < k; ++c) s += Pkk[(long long)i * k + c] * t1[c];
+  t2[i] = s;
+}
+// out[r] = -(sigma^-2) * sum_c F[c][r] t2[c] + sigma^-2 z[r]     (gpx/models/_gpr.py:208-214)
+__global__ void precond_apply_kernel(const double* __restrict__ F, long long ldf, int k, int n,
+                                     const double* __restrict__ t2, const double* __restrict__ z,
+                                     double isig2, double* __restrict__ out) {
+  extern __shared__ double st2[];
+  for (int c = threadIdx.x; c < k; c += blockDim.x) st2[c] = t2[c];
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < k; ++c) s += F[(long long)c * ldf + r] * st2[c];
+  out[r] = -isig2 * s + isig2 * z[r];
+}
+// symmetrise a lower-stored k x k matrix in place and add nothing else
+__global__ void symmetrize_kernel(double* __restrict__ A, int k) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= k * k) return;
+  const int i = idx / k, j = idx % k;
+  if (j > i) A[idx] = A[(long long)j * k + i];
+}
+__global__ void add_diag_kernel(double* __restrict__ A, int k, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) A[(long long)i * k + i] += v;
+}
+__global__ void pad_copy_kernel(const double* __restrict__ x, int n, double* __restrict__ xp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  xp[2 * i] = x[i];
+  xp[2 * i + 1] = 0.0;
+}
+
+struct VecOps {
+  Ctx* ctx;
+  cudaStream_t s;
+  double* part;
+  int n;
+  int dot(const double* x, int sx, const double* y, int sy, double* out) {
+    const int nblk = ceil_div(n, 1024);
+    vdot_partial_kernel<<<nblk, 256, 0, s>>>(x, sx, y, sy, n, part);
+    GPXB_LAUNCH_CHECK();
+    vsum_final_kernel<<<1, 1024, 0, s>>>(part, nblk, out);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches += 2;
+    return comm_allreduce_sum(ctx, out, 1, s);
+  }
+};
+
+}  // namespace
+
+// Builds the RPCholesky preconditioner pieces from F (stored [k][ldf], local rows):
+// Pkk = inv(sigma^2 I + F^T F) (full symmetric k x k, device).
+int precond_build(Ctx* ctx, const double* F, long long ldf, int k, int n_loc, double sigma, double* Pkk,
+                  cudaStream_t s) {
+  GemmArgs g;  // C = F F^T over the local rows  (A stored [k][n]: K-major both)
+  g.M = k; g.N = k; g.K = n_loc;
+  g.A = F; g.lda = ldf; g.a_kmajor = true;
+  g.B = F; g.ldb = ldf; g.b_kmajor = true;
+  g.C = Pkk; g.ldc = k;
+  g.lower_only = 1;
+  GPXB_CUDA_CHECK(cudaMemsetAsync(Pkk, 0, sizeof(double) * (size_t)k * k, s));
+  GPXB_TRY(gemm_f64(ctx, g, s));
+  symmetrize_kernel<<<ceil_div((long long)k * k, 256), 256, 0, s>>>(Pkk, k);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  GPXB_TRY(comm_allreduce_sum(ctx, Pkk, (size_t)k * k, s));
+  add_diag_kernel<<<ceil_div(k, 256), 256, 0, s>>>(Pkk, k, sigma * sigma);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  DevBuf inv, W, T;
+  GPXB_TRY(inv.alloc(sizeof(double) * leaf_inv_doubles(k), s));
+  GPXB_TRY(W.alloc(sizeof(double) * (size_t)k * k, s));
+  GPXB_TRY(T.alloc(sizeof(double) * potri_scratch_doubles(k), s));
+  GPXB_TRY(potrf_lower(ctx, Pkk, k, k, inv.as<double>(), s));
+  GPXB_TRY(potri_lower(ctx, Pkk, k, inv.as<double>(), k, W.as<double>(), T.as<double>(), Pkk, k, s));
+  symmetrize_kernel<<<ceil_div((long long)k * k, 256), 256, 0, s>>>(Pkk, k);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+// Solves (K + diag_add I) x = b (b: local rows, length n_loc).  F/Pkk: preconditioner (k may be 0:
+// identity).  Host-synchronous: one scalar read per iteration for the stopping test.
+int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
+              ZLayout zl, double diag_add, const double* b, const double* F, long long ldf, int k,
+              const double* Pkk, double sigma, double tol, double atol, int maxiter, double* x, int* iters_out,
+              cudaStream_t s) {
+  DevBuf bR, bZ, bP, bAp, bPart, bSc, bT, bPall;
+  ctx->shard_N = N;
+  GPXB_TRY(bR.alloc(sizeof(double) * n_loc, s));
+  GPXB_TRY(bZ.alloc(sizeof(double) * n_loc, s));
+  GPXB_TRY(bP.alloc(sizeof(double) * ((size_t)n_loc * 2 + 16), s));
+  GPXB_TRY(bAp.alloc(sizeof(double) * n_loc, s));
+  GPXB_TRY(bPart.alloc(sizeof(double) * (ceil_div(n_loc, 1024) + 1), s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * 8, s));
+  GPXB_TRY(bT.alloc(sizeof(double) * (2 * (size_t)std::max(k, 1)), s));
+  double *r = bR.as<double>(), *z = bZ.as<double>(), *p = bP.as<double>(), *Ap = bAp.as<double>();
+  double* sc = bSc.as<double>();  // [0] bs, [1] gamma, [2] pAp, [3] gamma_new, [4] rs
+  double *t1 = bT.as<double>(), *t2 = t1 + std::max(k, 1);
+  double* Pall = nullptr;
+  if (ctx->world > 1) {
+    GPXB_TRY(bPall.alloc(sizeof(double) * ((size_t)N * 2 + 16), s));
+    Pall = bPall.as<double>();
+  }
+  VecOps vo{ctx, s, bPart.as<double>(), n_loc};
+  const int nb = ceil_div(n_loc, 256);
+  const double isig2 = 1.0 / (sigma * sigma);
+
+  auto precond = [&](const double* in, double* out) -> int {
+    if (k <= 0) {
+      GPXB_CUDA_CHECK(cudaMemcpyAsync(out, in, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, s));
+      return 0;
+    }
+    ftz_kernel<<<k, 1024, 0, s>>>(F, ldf, n_loc, in, t1);
+    GPXB_LAUNCH_CHECK();
+    GPXB_TRY(comm_allreduce_sum(ctx, t1, k, s));
+    small_matvec_kernel<<<ceil_div(k, 128), 128, 0, s>>>(Pkk, k, t1, t2);
+    GPXB_LAUNCH_CHECK();
+    precond_apply_kernel<<<nb, 256, sizeof(double) * k, s>>>(F, ldf, k, n_loc, t2, in, isig2, out);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches += 3;
+    return 0;
+  };
+
+  GPXB_CUDA_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * n_loc, s));
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(r, b, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, s));
+  GPXB_TRY(vo.dot(b, 1, b, 1, sc + 0));
+  GPXB_TRY(precond(r, z));
+  pad_copy_kernel<<<nb, 256, 0, s>>>(z, n_loc, p);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  GPXB_TRY(vo.dot(r, 1, z, 1, sc + 1));
+  double h[2];
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(h, sc, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+  GPXB_CUDA_CHECK(cudaStreamSynchronize(s));
+  const double atol2 = std::max(tol * tol * h[0], atol * atol);
+  double rs = (k <= 0) ? h[1] : h[0];  // r0 = b
+  int it = 0;
+  while (rs > atol2 && it < maxiter) {
+    const double* pfull = p;
+    if (ctx->world > 1) {
+      GPXB_TRY(comm_allgather_rows(ctx, p, Pall, n_loc, 2, s));
+      pfull = Pall;
+    }
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
+    a.V = pfull; a.PS = 2; a.P = 1; a.W = Ap; a.ldw = 1; a.diag_add = diag_add;
+    GPXB_TRY(kmatvec_launch(ctx, a, s));
+    GPXB_TRY(vo.dot(p, 2, Ap, 1, sc + 2));
+    vaxpby_kernel<<<nb, 256, 0, s>>>(x, 1, p, 2, n_loc, sc + 1, sc + 2, 1.0, 1.0);    // x += alpha p
+    vaxpby_kernel<<<nb, 256, 0, s>>>(r, 1, Ap, 1, n_loc, sc + 1, sc + 2, -1.0, 1.0);  // r -= alpha Ap
+    GPXB_LAUNCH_CHECK();
+    ctx->launches += 2;
+    GPXB_TRY(precond(r, z));
+    GPXB_TRY(vo.dot(r, 1, z, 1, sc + 3));
+    vxpby_kernel<<<nb, 256, 0, s>>>(p, 2, z, n_loc, sc + 3, sc + 1);  // p = z + (gn/g) p
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+    GPXB_TRY(vo.dot(r, 1, r, 1, sc + 4));
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(sc + 1, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(h, sc + 3, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+    GPXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    rs = (k <= 0) ? h[0] : h[1];
+    ++it;
+  }
+  if (iters_out) *iters_out = it;
+  return 0;
+}
+
+}  // namespace gpxb

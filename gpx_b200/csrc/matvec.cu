@@ -1,0 +1,342 @@
+// Family 3a: matrix-free block mat-vec  W = (K(x_rows, x_all) + diag_add*I) V  for sm_100a.
+//
+// Replaces gpx/operations.py:54-123 (rowfun_to_matvec: one kernel row per lax.scan step)
+// driven by _Ax_lhs_fun (gpx/models/_gpr.py:94-119) and update_row_diagonal
+// (gpx/operations.py:32-51).  K is never materialised: every 256 x 128 tile of it is
+// recomputed on the fly and consumed from registers.
+//
+// One CTA owns 256 rows (8 warps x 32 rows) and streams over the columns j in tiles of 128:
+//   - the pre-scaled column tile of Z and the matching rows of V arrive by 1-D bulk TMA
+//     copies (cp.async.bulk + mbarrier), double buffered;
+//   - GEMM 1 (DMMA, K = D):   dot = Z_rows . Z_cols^T   (8x8 fragments)
+//   - epilogue in registers:  k = phi(|z_i|^2 - 2 dot + |z_j|^2 + 1e-12)
+//   - GEMM 2 (DMMA, K = 128): W_rows += k . V_cols.  The 8x8 accumulator fragment of GEMM 1
+//     is fed straight back as two A operands of GEMM 2 (columns {0,2,4,6} and {1,3,5,7}: the
+//     contraction index may be permuted as long as A and B agree), so no shuffle is needed.
+// V is stored with a padded row stride PS (PS % 8 == 2) so that a tile is contiguous (one
+// bulk copy) and the GEMM-2 B-fragment reads are bank-conflict free.
+#include "matvec.cuh"
+#include "mma.cuh"
+
+namespace gpxb {
+
+namespace {
+
+constexpr int BJ = 128;
+constexpr int NT = 256;
+
+struct KmvParams {
+  int kind;
+  const double* Zr;
+  int n_rows;
+  long long row_offset;  // global index (in x_all) of row 0, or -1: no diagonal treatment
+  const double* Za;
+  int N;
+  int S, Dp;
+  const double* V;
+  int PS, P;
+  double* W;  // jsplit == 1: [n_rows][ldw]; else partial [jsplit][n_rows][8*NPF]
+  long long ldw;
+  double diag_add;
+  int jsplit, jps;  // columns per split (multiple of BJ)
+};
+
+__device__ __forceinline__ double kfun(int kind, double d2) {
+  if (kind == KIND_SE) return exp(-d2);
+  const double r = sqrt(fmax(d2, 1e-36));
+  if (kind == KIND_M12) return exp(-r);
+  if (kind == KIND_M32) {
+    const double d = 1.7320508075688772 * r;
+    return (1.0 + d) * exp(-d);
+  }
+  const double d = 2.23606797749979 * r;
+  return (1.0 + d + d * d / 3.0) * exp(-d);
+}
+
+// MF: 8-row fragments per warp (rows per CTA = 64*MF); KS: Dp/4 when the row operand lives in
+// registers, 0 = read it from shared memory; NPF: 8-column fragments of V/W (P <= 8*NPF).
+template <int MF, int KS, int NPF>
+__global__ void __launch_bounds__(NT, 1) kmatvec_kernel(const KmvParams p) {
+  constexpr int BR = 64 * MF;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // bar[0], bar[1]
+  double* sZr = reinterpret_cast<double*>(smem_raw + 128);
+  const int za_dbl = BJ * p.S, v_dbl = BJ * p.PS + 8;
+  double* stage0 = sZr + BR * p.S;
+  const int stage_dbl = za_dbl + v_dbl;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lq = lane & 3;
+  const int row0 = blockIdx.x * BR;
+  const int rows1 = min(BR, p.n_rows - row0);
+  const int jbeg = blockIdx.y * p.jps, jend = min(p.N, jbeg + p.jps);
+  const int ntiles = (jend - jbeg + BJ - 1) / BJ;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int t) {
+    const int j0 = jbeg + t * BJ;
+    const int rows2 = min(BJ, jend - j0);
+    double* sa = stage0 + (t & 1) * stage_dbl;
+    const uint32_t b1 = (uint32_t)rows2 * p.S * 8u, b2 = (uint32_t)rows2 * p.PS * 8u;
+    uint32_t tot = b1 + b2;
+    if (t == 0) tot += (uint32_t)rows1 * p.S * 8u;
+    mbar_arrive_expect_tx(&bar[t & 1], tot);
+    if (t == 0) tma_bulk_g2s(sZr, p.Zr + (long long)row0 * p.S, (uint32_t)rows1 * p.S * 8u, &bar[0]);
+    tma_bulk_g2s(sa, p.Za + (long long)j0 * p.S, b1, &bar[t & 1]);
+    tma_bulk_g2s(sa + za_dbl, p.V + (long long)j0 * p.PS, b2, &bar[t & 1]);
+  };
+  if (tid == 0 && ntiles > 0) issue(0);
+
+  double w[MF][NPF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i)
+#pragma unroll
+    for (int j = 0; j < NPF; ++j) w[i][j][0] = w[i][j][1] = 0.0;
+
+  double a1[MF][KS > 0 ? KS : 1];
+  double ni[MF];
+  const double* zr_base = sZr + (warp * 8 * MF + lr) * p.S;
+
+  for (int t = 0; t < ntiles; ++t) {
+    if (tid == 0 && t + 1 < ntiles) issue(t + 1);
+    mbar_wait(&bar[t & 1], (t >> 1) & 1);
+    const int j0 = jbeg + t * BJ;
+    const int rows2 = min(BJ, jend - j0);
+    double* sZa = stage0 + (t & 1) * stage_dbl;
+    double* sV = sZa + za_dbl;
+    if (t == 0) {
+#pragma unroll
+      for (int mf = 0; mf < MF; ++mf) {
+        ni[mf] = zr_base[mf * 8 * p.S + p.Dp];
+        if (KS > 0) {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) a1[mf][ks] = zr_base[mf * 8 * p.S + ks * 4 + lq];
+        }
+      }
+    }
+    if (rows2 < BJ) {  // last tile: rows beyond the data must contribute exactly zero
+      for (int idx = rows2 * p.PS + tid; idx < v_dbl; idx += NT) sV[idx] = 0.0;
+      __syncthreads();
+    }
+#pragma unroll 2
+    for (int jf = 0; jf < BJ / 8; ++jf) {
+      double c[MF][2];
+#pragma unroll
+      for (int mf = 0; mf < MF; ++mf) c[mf][0] = c[mf][1] = 0.0;
+      const double* zb = sZa + (jf * 8 + lr) * p.S + lq;
+      if (KS > 0) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const double b = zb[ks * 4];
+#pragma unroll
+          for (int mf = 0; mf < MF; ++mf) dmma884(c[mf][0], c[mf][1], a1[mf][ks], b);
+        }
+      } else {
+        for (int k = 0; k < p.Dp; k += 4) {
+          const double b = zb[k];
+#pragma unroll
+          for (int mf = 0; mf < MF; ++mf) dmma884(c[mf][0], c[mf][1], zr_base[mf * 8 * p.S + k + lq], b);
+        }
+      }
+      const int jl = jf * 8 + lq * 2;
+      const double nj0 = sZa[jl * p.S + p.Dp], nj1 = sZa[(jl + 1) * p.S + p.Dp];
+      const int gj = j0 + jl;
+#pragma unroll
+      for (int mf = 0; mf < MF; ++mf) {
+        const long long gi = p.row_offset + row0 + warp * 8 * MF + mf * 8 + lr;
+        double d20 = ((ni[mf] - 2.0 * c[mf][0]) + nj0) + 1e-12;
+        double d21 = ((ni[mf] - 2.0 * c[mf][1]) + nj1) + 1e-12;
+        const bool dg0 = (p.row_offset >= 0) && (gi == gj), dg1 = (p.row_offset >= 0) && (gi == gj + 1);
+        if (dg0) d20 = 1e-12;
+        if (dg1) d21 = 1e-12;
+        double k0 = kfun(p.kind, d20), k1 = kfun(p.kind, d21);
+        if (dg0) k0 += p.diag_add;
+        if (dg1) k1 += p.diag_add;
+        c[mf][0] = (gj < jend) ? k0 : 0.0;
+        c[mf][1] = (gj + 1 < jend) ? k1 : 0.0;
+      }
+      const double* vb = sV + (jf * 8 + 2 * lq) * p.PS + lr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int pf = 0; pf < NPF; ++pf) {
+          const double v = vb[h * p.PS + pf * 8];
+#pragma unroll
+          for (int mf = 0; mf < MF; ++mf) dmma884(w[mf][pf][0], w[mf][pf][1], c[mf][h], v);
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled
+  }
+
+  // ---- write the row block ----
+  const int pw = 8 * NPF;
+#pragma unroll
+  for (int mf = 0; mf < MF; ++mf) {
+    const int i = row0 + warp * 8 * MF + mf * 8 + lr;
+    if (i >= p.n_rows) continue;
+#pragma unroll
+    for (int pf = 0; pf < NPF; ++pf) {
+      const int pc = pf * 8 + 2 * lq;
+      if (p.jsplit == 1) {
+        double* o = p.W + (long long)i * p.ldw + pc;
+        if (pc < p.P) o[0] = w[mf][pf][0];
+        if (pc + 1 < p.P) o[1] = w[mf][pf][1];
+      } else {
+        double* o = p.W + ((long long)blockIdx.y * p.n_rows + i) * pw + pc;
+        o[0] = w[mf][pf][0];
+        o[1] = w[mf][pf][1];
+      }
+    }
+  }
+}
+
+// fixed-order sum of the column-split partials
+__global__ void kmv_reduce_kernel(const double* __restrict__ part, int jsplit, int n_rows, int pw,
+                                  int P, double* __restrict__ W, long long ldw) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_rows * pw) return;
+  const int i = (int)(idx / pw), pc = (int)(idx % pw);
+  if (pc >= P) return;
+  double s = 0.0;
+  for (int js = 0; js < jsplit; ++js) s += part[((long long)js * n_rows + i) * pw + pc];
+  W[(long long)i * ldw + pc] = s;
+}
+
+// Vp[i][0..PS) = V[i][c0..c0+P) zero padded
+__global__ void pack_v_kernel(const double* __restrict__ V, long long ldv, int n, int c0, int P, int PS,
+                              double* __restrict__ Vp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * PS) return;
+  const int i = (int)(idx / PS), c = (int)(idx % PS);
+  Vp[idx] = c < P ? V[(long long)i * ldv + c0 + c] : 0.0;
+}
+
+template <int MF, int KS, int NPF>
+int launch_t(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) {
+  GPXB_CUDA_CHECK(cudaFuncSetAttribute(kmatvec_kernel<MF, KS, NPF>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kmatvec_kernel<MF, KS, NPF><<<grid, NT, smem, s>>>(p);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+inline int smem_bytes(int BR, int S, int PS) {
+  return 128 + (BR * S + 2 * (BJ * S + BJ * PS + 8)) * (int)sizeof(double);
+}
+
+}  // namespace
+
+int v_padded_stride(int P) {
+  int ps = P < 2 ? 2 : P;
+  while (ps % 8 != 2) ++ps;
+  return ps;
+}
+
+int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
+  if (a.n_rows <= 0) return 0;
+  GPXB_ARG_CHECK(a.P >= 1 && a.P <= 32, -20);
+  GPXB_ARG_CHECK(a.PS % 8 == 2 && a.PS >= 2 && a.PS <= 34, -21);
+  GPXB_ARG_CHECK(a.PS >= a.P || a.P > 0, -22);
+  KmvParams p;
+  p.kind = a.kind;
+  p.Zr = a.Zr; p.n_rows = a.n_rows; p.row_offset = a.row_offset;
+  p.Za = a.Za; p.N = a.N; p.S = a.zl.S; p.Dp = a.zl.Dp;
+  p.V = a.V; p.PS = a.PS; p.P = a.P;
+  p.diag_add = a.diag_add;
+  const int NPF = a.P <= 8 ? 1 : 4;
+  const int limit = 232448;
+  int MF = 4;
+  if (smem_bytes(256, p.S, p.PS) > limit) MF = 2;
+  GPXB_ARG_CHECK(smem_bytes(64 * MF, p.S, p.PS) <= limit, -23);
+  const int BR = 64 * MF;
+  const int row_ctas = ceil_div(a.n_rows, BR);
+  // column split so that small row counts still fill the GPU (deterministic two-pass reduce)
+  int jsplit = 1;
+  const int jt = ceil_div(a.N, BJ);
+  const int target = 2 * ctx->num_sms;
+  if (row_ctas < target) jsplit = std::min(jt, std::max(1, target / row_ctas));
+  int jps = ceil_div(jt, jsplit) * BJ;
+  jsplit = ceil_div(a.N, jps);
+  p.jsplit = jsplit; p.jps = jps;
+  DevBuf part;
+  const int pw = 8 * NPF;
+  if (jsplit > 1) {
+    GPXB_TRY(part.alloc(sizeof(double) * (size_t)jsplit * a.n_rows * pw, s));
+    p.W = part.as<double>();
+    p.ldw = pw;
+  } else {
+    p.W = a.W;
+    p.ldw = a.ldw;
+  }
+  dim3 grid(row_ctas, jsplit);
+  const int smem = smem_bytes(BR, p.S, p.PS);
+  const int KS = (MF == 4 && (p.Dp == 8 || p.Dp == 16 || p.Dp == 32)) ? p.Dp / 4 : 0;
+  int rc;
+#define GO(mf, ks, npf) rc = launch_t<mf, ks, npf>(ctx, p, grid, smem, s)
+  if (MF == 2) { if (NPF == 1) GO(2, 0, 1); else GO(2, 0, 4); }
+  else if (KS == 2) { if (NPF == 1) GO(4, 2, 1); else GO(4, 2, 4); }
+  else if (KS == 4) { if (NPF == 1) GO(4, 4, 1); else GO(4, 4, 4); }
+  else if (KS == 8) { if (NPF == 1) GO(4, 8, 1); else GO(4, 8, 4); }
+  else { if (NPF == 1) GO(4, 0, 1); else GO(4, 0, 4); }
+#undef GO
+  GPXB_TRY(rc);
+  if (jsplit > 1) {
+    const long long tot = (long long)a.n_rows * pw;
+    kmv_reduce_kernel<<<ceil_div(tot, 256), 256, 0, s>>>(part.as<double>(), jsplit, a.n_rows, pw, a.P,
+                                                          a.W, a.ldw);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+  }
+  return 0;
+}
+
+int pack_v(Ctx* ctx, const double* V, long long ldv, int n, int c0, int P, int PS, double* Vp,
+           cudaStream_t s) {
+  const long long tot = (long long)n * PS;
+  pack_v_kernel<<<ceil_div(tot, 256), 256, 0, s>>>(V, ldv, n, c0, P, PS, Vp);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+// General entry: any ldv / P; columns are processed in blocks of 32.
+int kmatvec(Ctx* ctx, int kind, const double* x_rows, int n_rows, long long row_offset,
+            const double* x_all, int N, int D, double ell, double diag_add, const double* V,
+            long long ldv, int P, double* W, long long ldw, cudaStream_t s) {
+  GPXB_ARG_CHECK(n_rows >= 0 && N > 0 && D > 0 && P > 0, -1);
+  if (n_rows == 0) return 0;
+  const ZLayout zl = z_layout(D);
+  DevBuf za, zr, vp;
+  GPXB_TRY(za.alloc(sizeof(double) * ((size_t)N * zl.S + 16), s));
+  GPXB_TRY(prep_z(ctx, x_all, D, N, zl, ell, za.as<double>(), s));
+  const double* Zr = za.as<double>();
+  if (!(x_rows == x_all && n_rows == N)) {
+    GPXB_TRY(zr.alloc(sizeof(double) * ((size_t)n_rows * zl.S + 16), s));
+    GPXB_TRY(prep_z(ctx, x_rows, D, n_rows, zl, ell, zr.as<double>(), s));
+    Zr = zr.as<double>();
+  }
+  for (int c0 = 0; c0 < P; c0 += 32) {
+    const int pb = std::min(32, P - c0);
+    const int PS = v_padded_stride(pb);
+    GPXB_TRY(vp.alloc(sizeof(double) * ((size_t)N * PS + 16), s));
+    GPXB_TRY(pack_v(ctx, V, ldv, N, c0, pb, PS, vp.as<double>(), s));
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_rows; a.row_offset = row_offset;
+    a.Za = za.as<double>(); a.N = N; a.zl = zl;
+    a.V = vp.as<double>(); a.PS = PS; a.P = pb;
+    a.W = W + c0; a.ldw = ldw; a.diag_add = diag_add;
+    GPXB_TRY(kmatvec_launch(ctx, a, s));
+    vp.release();
+  }
+  return 0;
+}
+
+}  // namespace gpxb

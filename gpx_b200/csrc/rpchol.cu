@@ -1,0 +1,303 @@
+// Family 3c: randomly pivoted Cholesky landmark loop on device (no host round trip per pivot).
+//
+// Replaces gpx/kernels/approximations.py:30-129 (rpcholesky).  Per pivot i:
+//   prob = diag / sum(diag);  key, _ = split(key);  s = choice(key, N, p = prob)
+//   g = k(x_s, X) - F[:, :i] F[s, :i]^T;  F[:, i] = g / (sqrt(g_s) + 1e-6);  diag -= F[:, i]^2
+// The factor is kept transposed (F_T[c][r], one contiguous row per pivot) so that the
+// per-pivot GEMV -- the HBM-bound part, 8*N*i bytes at step i -- is a fully coalesced stream
+// with one thread per data row; the kernel column, the scaling, the diagonal update and the
+// fixed-order block sums for the next draw are fused into the same pass.
+// Sampling reproduces jax.random.choice (inverse CDF: cumsum, r = cum[-1]*(1-u),
+// searchsorted-left) with a two-level scan over fixed 1024-row blocks, so the result does not
+// depend on the launch geometry.
+#include "../../include/gpxb200.h"
+#include "gram.cuh"
+#include "mma.cuh"
+#include "rpchol.cuh"
+#include "threefry.cuh"
+
+namespace gpxb {
+
+namespace {
+
+constexpr int BLK = 1024;
+
+__device__ __forceinline__ double kfun(int kind, double d2) {
+  if (kind == KIND_SE) return exp(-d2);
+  const double r = sqrt(fmax(d2, 1e-36));
+  if (kind == KIND_M12) return exp(-r);
+  if (kind == KIND_M32) {
+    const double d = 1.7320508075688772 * r;
+    return (1.0 + d) * exp(-d);
+  }
+  const double d = 2.23606797749979 * r;
+  return (1.0 + d + d * d / 3.0) * exp(-d);
+}
+
+// inclusive scan of one value per thread across a 1024-thread CTA (fixed tree order)
+__device__ __forceinline__ double block_scan_1024(double v, double* sh /*32*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  __syncthreads();
+  if (lane == 31) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double s = sh[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    sh[lane] = s;
+  }
+  __syncthreads();
+  if (w > 0) v += sh[w - 1];
+  return v;
+}
+
+struct RpState {
+  double* diag;       // [n]
+  double* blocksum;   // [nblk]
+  double* FT;         // [M][ldf]
+  long long ldf;
+  const double* Z;    // [n][S]
+  int n, S, Dp, nblk, kind;
+  long long* pivots;  // [M]
+  uint32_t* key;      // [2] carried key
+  double* zs;         // [S] pivot row of Z
+  double* frow;       // [M] pivot row of F
+  double* scal;       // [0] g_s
+  int partitionable;
+};
+
+__global__ void rp_init_kernel(RpState st, double d0) {
+  __shared__ double sh[32];
+  const long long r = (long long)blockIdx.x * BLK + threadIdx.x;
+  double v = 0.0;
+  if (r < st.n) {
+    st.diag[r] = d0;
+    v = d0;
+  }
+  v = block_sum<BLK>(v, sh);
+  if (threadIdx.x == 0) st.blocksum[blockIdx.x] = v;
+}
+
+// One CTA: draw the pivot for step i, gather its rows, compute g_s.
+__global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
+  __shared__ double sh[32];
+  __shared__ double s_total, s_r, s_prefix;
+  __shared__ int s_cnt, s_bstar;
+  const int tid = threadIdx.x;
+
+  // total = sum(diag) from the block sums (fixed order)
+  double t = 0.0;
+  for (int b = tid; b < st.nblk; b += BLK) t += st.blocksum[b];
+  t = block_sum<BLK>(t, sh);
+  if (tid == 0) {
+    s_total = t;
+    // key, subkey = split(key); the draw uses the carried key (approximations.py:100-101)
+    uint32_t k0, k1;
+    jax_split2(st.key[0], st.key[1], 0, st.partitionable, k0, k1);
+    st.key[0] = k0;
+    st.key[1] = k1;
+    const double u = jax_uniform_f64(k0, k1, 0ULL, 1ULL, st.partitionable);
+    s_r = 1.0 - u;  // scaled by cum[-1] below
+    s_cnt = 0;
+  }
+  __syncthreads();
+  const double total = s_total;
+
+  // level 1: scan of the per-block probabilities, BLK blocks per sweep
+  double carry = 0.0;
+  // first sweep to get cum[-1]
+  for (int base = 0; base < st.nblk; base += BLK) {
+    const int b = base + tid;
+    double v = (b < st.nblk) ? st.blocksum[b] / total : 0.0;
+    v = block_scan_1024(v, sh);
+    __syncthreads();
+    if (tid == BLK - 1) sh[0] = v;
+    __syncthreads();
+    carry += sh[0];
+    __syncthreads();
+  }
+  const double cum_last = carry;
+  const double rr = cum_last * s_r;
+  // second sweep: count blocks whose cumulative probability is < r
+  carry = 0.0;
+  for (int base = 0; base < st.nblk; base += BLK) {
+    const int b = base + tid;
+    double v = (b < st.nblk) ? st.blocksum[b] / total : 0.0;
+    v = block_scan_1024(v, sh) + carry;
+    const int below = (b < st.nblk && v < rr) ? 1 : 0;
+    const int wcnt = __popc(__ballot_sync(0xffffffffu, below));
+    if ((tid & 31) == 0 && wcnt) atomicAdd(&s_cnt, wcnt);
+    __syncthreads();
+    if (tid == BLK - 1) sh[0] = v;
+    __syncthreads();
+    carry = sh[0];
+    __syncthreads();
+  }
+  if (tid == 0) s_bstar = min(s_cnt, st.nblk - 1);
+  __syncthreads();
+  const int bstar = s_bstar;
+  // prefix = cumulative probability of the blocks before bstar (recomputed in the same order)
+  carry = 0.0;
+  double prefix = 0.0;
+  for (int base = 0; base <= bstar; base += BLK) {
+    const int b = base + tid;
+    double v = (b < st.nblk) ? st.blocksum[b] / total : 0.0;
+    v = block_scan_1024(v, sh) + carry;
+    if (b == bstar - 1) s_prefix = v;
+    __syncthreads();
+    if (tid == BLK - 1) sh[0] = v;
+    __syncthreads();
+    carry = sh[0];
+    __syncthreads();
+  }
+  if (bstar > 0) prefix = s_prefix;
+  __syncthreads();
+
+  // level 2: scan inside block bstar
+  const long long r = (long long)bstar * BLK + tid;
+  double pv = (r < st.n) ? st.diag[r] / total : 0.0;
+  pv = block_scan_1024(pv, sh) + prefix;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  {
+    const int below = (r < st.n && pv < rr) ? 1 : 0;
+    const int wcnt = __popc(__ballot_sync(0xffffffffu, below));
+    if ((tid & 31) == 0 && wcnt) atomicAdd(&s_cnt, wcnt);
+  }
+  __syncthreads();
+  const long long nin = min((long long)BLK, (long long)st.n - (long long)bstar * BLK);
+  const long long s = (long long)bstar * BLK + min((long long)s_cnt, nin - 1);
+  if (tid == 0) st.pivots[i] = s;
+
+  // gather the pivot's rows and g_s = k(x_s, x_s) - F[s].F[s]
+  for (int d = tid; d < st.S; d += BLK) st.zs[d] = st.Z[s * st.S + d];
+  double acc = 0.0;
+  for (int c = tid; c < i; c += BLK) {
+    const double f = st.FT[(long long)c * st.ldf + s];
+    st.frow[c] = f;
+    acc += f * f;
+  }
+  acc = block_sum<BLK>(acc, sh);
+  if (tid == 0) st.scal[0] = kfun(st.kind, 1e-12) - acc;
+}
+
+// One thread per data row: kernel column, GEMV against the pivot row, scale, diagonal
+// update, block sum of the new diagonal.
+__global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
+  extern __shared__ double sm[];  // frow[i], zs[S]
+  __shared__ double sh[32];
+  double* sf = sm;
+  double* sz = sm + i;
+  for (int c = threadIdx.x; c < i; c += BLK) sf[c] = st.frow[c];
+  for (int d = threadIdx.x; d < st.S; d += BLK) sz[d] = st.zs[d];
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * BLK + threadIdx.x;
+  double dnew = 0.0;
+  if (r < st.n) {
+    const long long s = st.pivots[i];
+    const double* zr = st.Z + r * st.S;
+    double dot = 0.0;
+    for (int d = 0; d < st.Dp; ++d) dot += sz[d] * zr[d];
+    double d2 = ((sz[st.Dp] - 2.0 * dot) + zr[st.Dp]) + 1e-12;
+    if (r == s) d2 = 1e-12;
+    double g = kfun(st.kind, d2);
+    const double* f = st.FT + r;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = 0;
+    for (; c + 4 <= i; c += 4) {
+      a0 += f[(long long)(c + 0) * st.ldf] * sf[c + 0];
+      a1 += f[(long long)(c + 1) * st.ldf] * sf[c + 1];
+      a2 += f[(long long)(c + 2) * st.ldf] * sf[c + 2];
+      a3 += f[(long long)(c + 3) * st.ldf] * sf[c + 3];
+    }
+    for (; c < i; ++c) a0 += f[(long long)c * st.ldf] * sf[c];
+    g -= (a0 + a1) + (a2 + a3);
+    const double fnew = g / (sqrt(st.scal[0]) + 1e-6);
+    st.FT[(long long)i * st.ldf + r] = fnew;
+    dnew = st.diag[r] - fnew * fnew;
+    st.diag[r] = dnew;
+  }
+  dnew = block_sum<BLK>(dnew, sh);
+  if (threadIdx.x == 0) st.blocksum[blockIdx.x] = dnew;
+}
+
+__global__ void transpose_f_kernel(const double* __restrict__ FT, long long ldf, int n, int M,
+                                   double* __restrict__ F) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + threadIdx.x;
+    tile[k][threadIdx.x] = (c < M && r < n) ? FT[(long long)c * ldf + r] : 0.0;
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + threadIdx.x;
+    if (r < n && c < M) F[(long long)r * M + c] = tile[threadIdx.x][k];
+  }
+}
+
+}  // namespace
+
+// Z: pre-scaled rows (z_layout).  FT: [M][ldf] device (ldf >= n).  pivots: [M] int64 device.
+int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, ZLayout zl, const uint32_t key[2], int M,
+                 int partitionable, double* FT, long long ldf, long long* pivots, cudaStream_t s) {
+  GPXB_ARG_CHECK(n > 0 && M > 0 && M <= 6000, -40);  // frow + zs must fit in 48 KB of smem
+  GPXB_ARG_CHECK(ldf >= n, -41);
+  const int nblk = ceil_div(n, BLK);
+  DevBuf bDiag, bBs, bKey, bZs, bFrow, bSc;
+  GPXB_TRY(bDiag.alloc(sizeof(double) * n, s));
+  GPXB_TRY(bBs.alloc(sizeof(double) * nblk, s));
+  GPXB_TRY(bKey.alloc(sizeof(uint32_t) * 2, s));
+  GPXB_TRY(bZs.alloc(sizeof(double) * zl.S, s));
+  GPXB_TRY(bFrow.alloc(sizeof(double) * M, s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * 4, s));
+  RpState st;
+  st.diag = bDiag.as<double>(); st.blocksum = bBs.as<double>();
+  st.FT = FT; st.ldf = ldf; st.Z = Z; st.n = n; st.S = zl.S; st.Dp = zl.Dp; st.nblk = nblk; st.kind = kind;
+  st.pivots = pivots; st.key = bKey.as<uint32_t>(); st.zs = bZs.as<double>(); st.frow = bFrow.as<double>();
+  st.scal = bSc.as<double>(); st.partitionable = partitionable;
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(st.key, key, sizeof(uint32_t) * 2, cudaMemcpyHostToDevice, s));
+  // diag_i = k(x_i, x_i) via the batched kernel: d2 = 1e-12 (approximations.py:88-93)
+  double d0;
+  {
+    const double d2 = 1e-12;
+    if (kind == KIND_SE) d0 = std::exp(-d2);
+    else {
+      const double r = std::sqrt(d2);
+      if (kind == KIND_M12) d0 = std::exp(-r);
+      else if (kind == KIND_M32) { const double d = 1.7320508075688772 * r; d0 = (1.0 + d) * std::exp(-d); }
+      else { const double d = 2.23606797749979 * r; d0 = (1.0 + d + d * d / 3.0) * std::exp(-d); }
+    }
+  }
+  rp_init_kernel<<<nblk, BLK, 0, s>>>(st, d0);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  GPXB_CUDA_CHECK(cudaFuncSetAttribute(rp_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(double) * (M + zl.S)));
+  for (int i = 0; i < M; ++i) {
+    rp_pivot_kernel<<<1, BLK, 0, s>>>(st, i);
+    GPXB_LAUNCH_CHECK();
+    rp_column_kernel<<<nblk, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches += 2;
+  }
+  return 0;
+}
+
+int transpose_f(Ctx* ctx, const double* FT, long long ldf, int n, int M, double* F, cudaStream_t s) {
+  dim3 grid(ceil_div(n, 32), ceil_div(M, 32)), blk(32, 8);
+  transpose_f_kernel<<<grid, blk, 0, s>>>(FT, ldf, n, M, F);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+}  // namespace gpxb

@@ -1,0 +1,287 @@
+// Sparse GPR (Projected Processes) on device: Woodbury LML, fit, predict.
+//
+// Replaces gpx/models/_sgpr.py:_lml_dense (659-697), _A_lhs (39-61), _fit_dense (319-339),
+// _predict_dense (434-467).  The reference's LML factors a dense N x N matrix
+// C = G^T G + (sigma^2 + 1e-10) I; the identical value is obtained here in O(N M^2) with
+//   B = s2 I_M + G G^T,  L_B = chol(B),  t = L_B^-1 G r,
+//   quad = (r.r - t.t)/s2,  logdet = (N - M) log s2 + 2 sum log L_B,ii        
+// K_mn is never stored: rows of x are streamed in chunks; each chunk's kernel block is built
+// by the fused Gram kernel, solved against L_m and accumulated into B on the FP64 tensor pipe.
+// Row-sharded: every rank streams its own rows; B, G r and r.r are all-reduced once.
+#include "../../include/gpxb200.h"
+#include "chol.cuh"
+#include "comm.cuh"
+#include "gemm.cuh"
+#include "gram.cuh"
+#include "small_kernels.cuh"
+
+namespace gpxb {
+
+namespace {
+using namespace sk;
+
+constexpr int CHUNK = 32768;
+
+// scal: [0] r.r, [1] t.t, [2] sum log L_B,ii
+__global__ void finalize_sgpr_kernel(const double* __restrict__ scal, long long N, int M, double s2,
+                                     double* __restrict__ out) {
+  const double n = (double)N;
+  const double quad = (scal[0] - scal[1]) / s2;
+  const double logdet = (n - (double)M) * log(s2) + 2.0 * scal[2];
+  out[0] = (-0.5 * quad - 0.5 * logdet - n * 0.5 * log(2.0 * 3.141592653589793)) / n;
+}
+}  // namespace
+
+// x: this rank's rows (n_loc x D), y: (n_loc x T); N: global row count; mu: device scalar with
+// the GLOBAL mean (computed by the caller).  out: device scalar lml / N.
+int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, long long N, int D, int T,
+             const double* x_locs, int M, double ell, double sigma, const double* mu, double* out,
+             cudaStream_t s) {
+  GPXB_ARG_CHECK(n_loc >= 0 && D > 0 && T > 0 && M > 0, -1);
+  const ZLayout zl = z_layout(D);
+  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
+  const double s2 = sigma * sigma + 1e-10;
+  const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
+  DevBuf bZl, bKmm, bInv, bB, bV, bZc, bKc, bRc, bSc, bInvB;
+  GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
+  GPXB_TRY(bKmm.alloc(sizeof(double) * (size_t)M * M, s));
+  GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles(M), s));
+  GPXB_TRY(bB.alloc(sizeof(double) * (size_t)M * M, s));
+  GPXB_TRY(bV.alloc(sizeof(double) * (size_t)M * T, s));
+  GPXB_TRY(bZc.alloc(sizeof(double) * (size_t)nc_max * zl.S, s));
+  GPXB_TRY(bKc.alloc(sizeof(double) * (size_t)nc_max * M, s));
+  GPXB_TRY(bRc.alloc(sizeof(double) * (size_t)nc_max * T, s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * 8, s));
+  GPXB_TRY(bInvB.alloc(sizeof(double) * leaf_inv_doubles(M), s));
+  double *Zl = bZl.as<double>(), *Kmm = bKmm.as<double>(), *inv = bInv.as<double>(), *B = bB.as<double>();
+  double *v = bV.as<double>(), *Zc = bZc.as<double>(), *Kc = bKc.as<double>(), *rc = bRc.as<double>();
+  double* scal = bSc.as<double>();
+  GPXB_CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(double) * (size_t)M * M, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * (size_t)M * T, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 8, s));
+
+  // L_m = chol(K_mm + 1e-10 I)
+  GPXB_TRY(prep_z(ctx, x_locs, D, M, zl, ell, Zl, s));
+  {
+    GramArgs g;
+    g.kind = kind; g.Z1 = Zl; g.n1 = M; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
+    g.diag_add = 1e-10; g.sym = 1; g.lower_only = 1; g.out = Kmm; g.ldo = M;
+    GPXB_TRY(gram_launch(ctx, g, s));
+  }
+  GPXB_TRY(potrf_lower(ctx, Kmm, M, M, inv, s));
+
+  for (int r0 = 0; r0 < n_loc; r0 += CHUNK) {
+    const int nc = std::min(CHUNK, n_loc - r0);
+    GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, Zc, s));
+    {
+      GramArgs g;  // Kc = K(x_chunk, x_locs)  [nc x M]
+      g.kind = kind; g.Z1 = Zc; g.n1 = nc; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
+      g.out = Kc; g.ldo = M;
+      GPXB_TRY(gram_launch(ctx, g, s));
+    }
+    GPXB_TRY(trsm_right_lt(ctx, Kmm, M, inv, Kc, M, nc, M, s));  // Kc <- G_c^T = Kc L_m^-T
+    center_kernel<<<ceil_div((long long)nc * T, 256), 256, 0, s>>>(y + (long long)r0 * T, (long long)nc * T, mu, rc);
+    GPXB_LAUNCHED(ctx);
+    sumsq_kernel<<<1, 1024, 0, s>>>(rc, (long long)nc * T, scal + 0, 1);
+    GPXB_LAUNCHED(ctx);
+    {
+      GemmArgs g;  // B += G_c G_c^T  (A, B stored [K = nc][M])
+      g.M = M; g.N = M; g.K = nc;
+      g.A = Kc; g.lda = M; g.a_kmajor = false;
+      g.B = Kc; g.ldb = M; g.b_kmajor = false;
+      g.C = B; g.ldc = M; g.beta = 1.0; g.lower_only = 1;
+      GPXB_TRY(gemm_f64(ctx, g, s));
+    }
+    {
+      GemmArgs g;  // v += G_c r_c   [M x T]
+      g.M = M; g.N = T; g.K = nc;
+      g.A = Kc; g.lda = M; g.a_kmajor = false;
+      g.B = rc; g.ldb = T; g.b_kmajor = false;
+      g.C = v; g.ldc = T; g.beta = 1.0;
+      GPXB_TRY(gemm_f64(ctx, g, s));
+    }
+  }
+  if (ctx->world > 1) {
+    // upper triangle of B is untouched zero, so the full buffer can be summed
+    GPXB_TRY(comm_allreduce_sum(ctx, B, (size_t)M * M, s));
+    GPXB_TRY(comm_allreduce_sum(ctx, v, (size_t)M * T, s));
+    GPXB_TRY(comm_allreduce_sum(ctx, scal, 1, s));
+  }
+  add_diag_kernel<<<ceil_div(M, 256), 256, 0, s>>>(B, M, M, s2);
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(potrf_lower(ctx, B, M, M, bInvB.as<double>(), s));
+  GPXB_TRY(logdet_lower(ctx, B, M, M, scal + 2, 1.0, s));
+  // t^T = v^T L_B^-T  (v is M x T; its transpose T x M is needed)
+  DevBuf bVt;
+  GPXB_TRY(bVt.alloc(sizeof(double) * (size_t)M * T, s));
+  transpose_out_kernel<<<ceil_div((long long)M * T, 256), 256, 0, s>>>(v, T, M, bVt.as<double>());
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(trsm_right_lt(ctx, B, M, bInvB.as<double>(), bVt.as<double>(), M, T, M, s));
+  sumsq_kernel<<<1, 1024, 0, s>>>(bVt.as<double>(), (long long)M * T, scal + 1, 0);
+  GPXB_LAUNCHED(ctx);
+  finalize_sgpr_kernel<<<1, 1, 0, s>>>(scal, N, M, s2, out);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
+// c[M x T] = (sigma^2 K_mm + K_mn K_nm + 1e-10 I)^-1 K_mn (y - mu)      (_sgpr.py:39-61, 319-339)
+int sgpr_fit(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, int D, int T,
+             const double* x_locs, int M, double ell, double sigma, const double* mu, double* c_out,
+             cudaStream_t s) {
+  GPXB_ARG_CHECK(n_loc >= 0 && D > 0 && T > 0 && M > 0, -1);
+  const ZLayout zl = z_layout(D);
+  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
+  const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
+  DevBuf bZl, bC, bInv, bV, bZc, bKc, bRc, bVt;
+  GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
+  GPXB_TRY(bC.alloc(sizeof(double) * (size_t)M * M, s));
+  GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles(M), s));
+  GPXB_TRY(bV.alloc(sizeof(double) * (size_t)M * T, s));
+  GPXB_TRY(bVt.alloc(sizeof(double) * (size_t)M * T, s));
+  GPXB_TRY(bZc.alloc(sizeof(double) * (size_t)nc_max * zl.S, s));
+  GPXB_TRY(bKc.alloc(sizeof(double) * (size_t)nc_max * M, s));
+  GPXB_TRY(bRc.alloc(sizeof(double) * (size_t)nc_max * T, s));
+  double *Zl = bZl.as<double>(), *C = bC.as<double>(), *v = bV.as<double>();
+  double *Zc = bZc.as<double>(), *Kc = bKc.as<double>(), *rc = bRc.as<double>();
+  GPXB_CUDA_CHECK(cudaMemsetAsync(C, 0, sizeof(double) * (size_t)M * M, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * (size_t)M * T, s));
+  GPXB_TRY(prep_z(ctx, x_locs, D, M, zl, ell, Zl, s));
+  for (int r0 = 0; r0 < n_loc; r0 += CHUNK) {
+    const int nc = std::min(CHUNK, n_loc - r0);
+    GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, Zc, s));
+    GramArgs g;
+    g.kind = kind; g.Z1 = Zc; g.n1 = nc; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
+    g.out = Kc; g.ldo = M;
+    GPXB_TRY(gram_launch(ctx, g, s));
+    center_kernel<<<ceil_div((long long)nc * T, 256), 256, 0, s>>>(y + (long long)r0 * T, (long long)nc * T, mu, rc);
+    GPXB_LAUNCHED(ctx);
+    GemmArgs a;  // C += K_c^T K_c
+    a.M = M; a.N = M; a.K = nc;
+    a.A = Kc; a.lda = M; a.a_kmajor = false;
+    a.B = Kc; a.ldb = M; a.b_kmajor = false;
+    a.C = C; a.ldc = M; a.beta = 1.0; a.lower_only = 1;
+    GPXB_TRY(gemm_f64(ctx, a, s));
+    GemmArgs b;  // v += K_c^T r_c
+    b.M = M; b.N = T; b.K = nc;
+    b.A = Kc; b.lda = M; b.a_kmajor = false;
+    b.B = rc; b.ldb = T; b.b_kmajor = false;
+    b.C = v; b.ldc = T; b.beta = 1.0;
+    GPXB_TRY(gemm_f64(ctx, b, s));
+  }
+  if (ctx->world > 1) {
+    GPXB_TRY(comm_allreduce_sum(ctx, C, (size_t)M * M, s));
+    GPXB_TRY(comm_allreduce_sum(ctx, v, (size_t)M * T, s));
+  }
+  {
+    // C += sigma^2 K_mm + 1e-10 I : build K_mm into scratch (reuse Kc: nc_max*M >= ? not
+    // guaranteed) -> dedicated buffer
+    DevBuf bK;
+    GPXB_TRY(bK.alloc(sizeof(double) * (size_t)M * M, s));
+    GPXB_CUDA_CHECK(cudaMemsetAsync(bK.as<double>(), 0, sizeof(double) * (size_t)M * M, s));
+    GramArgs g;
+    g.kind = kind; g.Z1 = Zl; g.n1 = M; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
+    g.sym = 1; g.lower_only = 1; g.out = bK.as<double>(); g.ldo = M;
+    GPXB_TRY(gram_launch(ctx, g, s));
+    // C = C + sigma^2 * K_mm  via GEMM-free axpy: scale then add with a tiny kernel pair
+    scale_kernel<<<ceil_div((long long)M * M, 256), 256, 0, s>>>(bK.as<double>(), (long long)M * M, sigma * sigma);
+    GPXB_LAUNCHED(ctx);
+    add_vec_kernel<<<ceil_div((long long)M * M, 256), 256, 0, s>>>(C, bK.as<double>(), (long long)M * M);
+    GPXB_LAUNCHED(ctx);
+    add_diag_kernel<<<ceil_div(M, 256), 256, 0, s>>>(C, M, M, 1e-10);
+    GPXB_LAUNCHED(ctx);
+  }
+  GPXB_TRY(potrf_lower(ctx, C, M, M, bInv.as<double>(), s));
+  transpose_out_kernel<<<ceil_div((long long)M * T, 256), 256, 0, s>>>(v, T, M, bVt.as<double>());
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(trsm_right_lt(ctx, C, M, bInv.as<double>(), bVt.as<double>(), M, T, M, s));
+  GPXB_TRY(trsm_right_l(ctx, C, M, bInv.as<double>(), bVt.as<double>(), M, T, M, s));
+  transpose_out_kernel<<<ceil_div((long long)M * T, 256), 256, 0, s>>>(bVt.as<double>(), M, T, c_out);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
+// mean[ns x T] = mu + K(x, x_locs) c; optional covariance exactly as the reference builds it
+// (from the TEST points: C_mm = sigma^2 K_mm + K_m* K_*m + 1e-10 I, _sgpr.py:452-465).
+int sgpr_predict(Ctx* ctx, int kind, const double* x_locs, int M, int D, const double* x, int ns,
+                 const double* c, int T, const double* mu, double ell, double sigma, double* mean_out,
+                 double* cov_out, cudaStream_t s) {
+  GPXB_ARG_CHECK(ns > 0 && D > 0 && T > 0 && M > 0, -1);
+  const ZLayout zl = z_layout(D);
+  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
+  DevBuf bZl, bZs, bKs;
+  GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
+  GPXB_TRY(bZs.alloc(sizeof(double) * (size_t)ns * zl.S, s));
+  GPXB_TRY(bKs.alloc(sizeof(double) * (size_t)ns * M, s));
+  double *Zl = bZl.as<double>(), *Zs = bZs.as<double>(), *Ks = bKs.as<double>();
+  GPXB_TRY(prep_z(ctx, x_locs, D, M, zl, ell, Zl, s));
+  GPXB_TRY(prep_z(ctx, x, D, ns, zl, ell, Zs, s));
+  {
+    GramArgs g;  // Ks = K(x, x_locs) [ns x M]
+    g.kind = kind; g.Z1 = Zs; g.n1 = ns; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
+    g.out = Ks; g.ldo = M;
+    GPXB_TRY(gram_launch(ctx, g, s));
+  }
+  {
+    GemmArgs g;
+    g.M = ns; g.N = T; g.K = M;
+    g.A = Ks; g.lda = M; g.a_kmajor = true;
+    g.B = c; g.ldb = T; g.b_kmajor = false;
+    g.C = mean_out; g.ldc = T;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  add_scalar_kernel<<<ceil_div((long long)ns * T, 256), 256, 0, s>>>(mean_out, (long long)ns * T, mu);
+  GPXB_LAUNCHED(ctx);
+  if (!cov_out) return 0;
+
+  DevBuf bKmm, bC, bInv1, bInv2, bGt, bHt;
+  GPXB_TRY(bKmm.alloc(sizeof(double) * (size_t)M * M, s));
+  GPXB_TRY(bC.alloc(sizeof(double) * (size_t)M * M, s));
+  GPXB_TRY(bInv1.alloc(sizeof(double) * leaf_inv_doubles(M), s));
+  GPXB_TRY(bInv2.alloc(sizeof(double) * leaf_inv_doubles(M), s));
+  GPXB_TRY(bGt.alloc(sizeof(double) * (size_t)ns * M, s));
+  GPXB_TRY(bHt.alloc(sizeof(double) * (size_t)ns * M, s));
+  double *Kmm = bKmm.as<double>(), *C = bC.as<double>(), *Gt = bGt.as<double>(), *Ht = bHt.as<double>();
+  GramArgs g;
+  g.kind = kind; g.Z1 = Zl; g.n1 = M; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
+  g.sym = 1; g.lower_only = 1; g.out = Kmm; g.ldo = M;
+  GPXB_CUDA_CHECK(cudaMemsetAsync(Kmm, 0, sizeof(double) * (size_t)M * M, s));
+  GPXB_TRY(gram_launch(ctx, g, s));
+  // C = sigma^2 K_mm + Ks^T Ks + 1e-10 I
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(C, Kmm, sizeof(double) * (size_t)M * M, cudaMemcpyDeviceToDevice, s));
+  scale_kernel<<<ceil_div((long long)M * M, 256), 256, 0, s>>>(C, (long long)M * M, sigma * sigma);
+  GPXB_LAUNCHED(ctx);
+  {
+    GemmArgs a;
+    a.M = M; a.N = M; a.K = ns;
+    a.A = Ks; a.lda = M; a.a_kmajor = false;
+    a.B = Ks; a.ldb = M; a.b_kmajor = false;
+    a.C = C; a.ldc = M; a.beta = 1.0; a.lower_only = 1;
+    GPXB_TRY(gemm_f64(ctx, a, s));
+  }
+  add_diag_kernel<<<ceil_div(M, 256), 256, 0, s>>>(C, M, M, 1e-10);
+  GPXB_LAUNCHED(ctx);
+  add_diag_kernel<<<ceil_div(M, 256), 256, 0, s>>>(Kmm, M, M, 1e-10);
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(potrf_lower(ctx, Kmm, M, M, bInv1.as<double>(), s));
+  GPXB_TRY(potrf_lower(ctx, C, M, M, bInv2.as<double>(), s));
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(Gt, Ks, sizeof(double) * (size_t)ns * M, cudaMemcpyDeviceToDevice, s));
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(Ht, Ks, sizeof(double) * (size_t)ns * M, cudaMemcpyDeviceToDevice, s));
+  GPXB_TRY(trsm_right_lt(ctx, Kmm, M, bInv1.as<double>(), Gt, M, ns, M, s));
+  GPXB_TRY(trsm_right_lt(ctx, C, M, bInv2.as<double>(), Ht, M, ns, M, s));
+  GramArgs h;
+  h.kind = kind; h.Z1 = Zs; h.n1 = ns; h.Z2 = Zs; h.n2 = ns; h.zl = zl; h.ell = ell; h.sym = 1;
+  h.out = cov_out; h.ldo = ns;
+  GPXB_TRY(gram_launch(ctx, h, s));
+  GemmArgs m1;  // cov -= Gt Gt^T
+  m1.M = ns; m1.N = ns; m1.K = M;
+  m1.A = Gt; m1.lda = M; m1.a_kmajor = true;
+  m1.B = Gt; m1.ldb = M; m1.b_kmajor = true;
+  m1.C = cov_out; m1.ldc = ns; m1.alpha = -1.0; m1.beta = 1.0;
+  GPXB_TRY(gemm_f64(ctx, m1, s));
+  GemmArgs m2 = m1;  // cov += sigma^2 Ht Ht^T
+  m2.A = Ht; m2.B = Ht; m2.alpha = sigma * sigma;
+  GPXB_TRY(gemm_f64(ctx, m2, s));
+  return 0;
+}
+
+}  // namespace gpxb

@@ -149,5 +149,169 @@ def gpr_predict(kind, x_train, x, c, mu, ell, sigma, full_covariance=False):
     return (mean, cov) if full_covariance else mean
 
 
+def kmatvec(kind, x_rows, x_all, V, ell, diag_add=0.0, row_offset=None):
+    """(K(x_rows, x_all) + diag_add*I) V without storing K.  Passing the same tensor for
+    x_rows and x_all puts the shifted diagonal in place (row_offset = 0)."""
+    ctx = context()
+    x_all = _f64(x_all)
+    same = x_rows is x_all
+    x_rows = x_all if same else _f64(x_rows)
+    V = _f64(V)
+    if V.dim() == 1:
+        V = V.reshape(-1, 1)
+    n_rows, D = x_rows.shape
+    N, P = V.shape
+    assert x_all.shape[0] == N
+    if row_offset is None:
+        row_offset = 0 if same else -1
+    W = torch.empty((n_rows, P), dtype=torch.float64, device=V.device)
+    check(
+        ctx.lib.gpxb_kmatvec(ctx.handle, _kind(kind), ptr(x_rows), n_rows, int(row_offset), ptr(x_all), N, D,
+                             float(ell), float(diag_add), ptr(V), V.stride(0), P, ptr(W), W.stride(0), stream_ptr()),
+        "gpxb_kmatvec",
+    )
+    return W
+
+
+def rpcholesky(kind, x, n_pivots, ell, key, partitionable=True, want_factor=True):
+    """(F (N, M) or None, pivots int64 (M,)) -- gpx/kernels/approximations.py:30-129."""
+    ctx = context()
+    x = _f64(x)
+    N, D = x.shape
+    piv = torch.empty(n_pivots, dtype=torch.int64, device=x.device)
+    F = torch.empty((N, n_pivots), dtype=torch.float64, device=x.device) if want_factor else None
+    check(
+        ctx.lib.gpxb_rpcholesky(ctx.handle, _kind(kind), ptr(x), N, D, float(ell), int(key[0]), int(key[1]),
+                                int(n_pivots), int(bool(partitionable)), ptr(F), ptr(piv), stream_ptr()),
+        "gpxb_rpcholesky",
+    )
+    return F, piv
+
+
+def rademacher_probes(key, N, P, partitionable=True):
+    ctx = context()
+    U = torch.empty((N, P), dtype=torch.float64, device="cuda")
+    check(
+        ctx.lib.gpxb_rademacher_probes(ctx.handle, int(key[0]), int(key[1]), N, P, int(bool(partitionable)), ptr(U),
+                                       stream_ptr()),
+        "gpxb_rademacher_probes",
+    )
+    return U
+
+
+def lanczos(kind, x, ell, diag_add, U, m):
+    """(alpha (P, m), beta (P, m), breakdown) for the unit start vectors in U's columns."""
+    ctx = context()
+    x, U = _f64(x), _f64(U)
+    N, D = x.shape
+    P = U.shape[1]
+    alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    check(
+        ctx.lib.gpxb_lanczos(ctx.handle, _kind(kind), ptr(x), N, D, float(ell), float(diag_add), ptr(U), U.stride(0),
+                             P, int(m), ptr(alpha), ptr(beta), ptr(flag), stream_ptr()),
+        "gpxb_lanczos",
+    )
+    return alpha, beta, flag
+
+
+def gpr_fit_iter(kind, x, y, ell, sigma, n_pivots, key, mean_mode=MEAN_DATA, partitionable=True, tol=1e-5,
+                 atol=1e-7, maxiter=0):
+    """(c (N, 1), mu (1,), iterations) -- PCG with the RPCholesky preconditioner."""
+    import ctypes
+
+    ctx = context()
+    x, y = _f64(x), _f64(y)
+    N, D = x.shape
+    assert y.numel() == N, "the iterative path supports a single output column"
+    c = torch.empty((N, 1), dtype=torch.float64, device=x.device)
+    mu = torch.empty(1, dtype=torch.float64, device=x.device)
+    iters = ctypes.c_int(0)
+    check(
+        ctx.lib.gpxb_gpr_fit_iter(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, float(ell), float(sigma),
+                                  int(mean_mode), int(n_pivots), int(key[0]), int(key[1]), int(bool(partitionable)),
+                                  float(tol), float(atol), int(maxiter), ptr(c), ptr(mu), ctypes.byref(iters),
+                                  stream_ptr()),
+        "gpxb_gpr_fit_iter",
+    )
+    return c, mu, iters.value
+
+
+def sgpr_lml(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
+    ctx = context()
+    x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    N, D = x.shape
+    T = y.shape[1] if y.dim() > 1 else 1
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_sgpr_lml(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, T, ptr(x_locs), x_locs.shape[0],
+                              float(ell), float(sigma), int(mean_mode), ptr(out), stream_ptr()),
+        "gpxb_sgpr_lml",
+    )
+    return out
+
+
+def sgpr_fit(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
+    ctx = context()
+    x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    N, D = x.shape
+    T = y.shape[1] if y.dim() > 1 else 1
+    M = x_locs.shape[0]
+    c = torch.empty((M, T), dtype=torch.float64, device=x.device)
+    mu = torch.empty(1, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_sgpr_fit(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, T, ptr(x_locs), M, float(ell),
+                              float(sigma), int(mean_mode), ptr(c), ptr(mu), stream_ptr()),
+        "gpxb_sgpr_fit",
+    )
+    return c, mu
+
+
+def sgpr_predict(kind, x_locs, x, c, mu, ell, sigma, full_covariance=False):
+    ctx = context()
+    x_locs, x, c = _f64(x_locs), _f64(x), _f64(c)
+    M, D = x_locs.shape
+    ns = x.shape[0]
+    T = c.shape[1] if c.dim() > 1 else 1
+    mean = torch.empty((ns, T), dtype=torch.float64, device=x.device)
+    cov = torch.empty((ns, ns), dtype=torch.float64, device=x.device) if full_covariance else None
+    check(
+        ctx.lib.gpxb_sgpr_predict(ctx.handle, _kind(kind), ptr(x_locs), M, D, ptr(x), ns, ptr(c), T, ptr(mu),
+                                  float(ell), float(sigma), ptr(mean), ptr(cov), stream_ptr()),
+        "gpxb_sgpr_predict",
+    )
+    return (mean, cov) if full_covariance else mean
+
+
+def gather_rows(x, idx):
+    ctx = context()
+    x = _f64(x)
+    M, D = idx.shape[0], x.shape[1]
+    out = torch.empty((M, D), dtype=torch.float64, device=x.device)
+    check(ctx.lib.gpxb_gather_rows(ctx.handle, ptr(x), D, ptr(idx), M, ptr(out), stream_ptr()), "gpxb_gather_rows")
+    return out
+
+
+def comm_init_from_torch_distributed():
+    """Bootstrap the library's NCCL communicator from an initialised torch.distributed group
+    (the unique id travels through a broadcast of 128 bytes)."""
+    import ctypes
+
+    import torch.distributed as dist
+
+    ctx = context()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    buf = (ctypes.c_char * 128)()
+    if rank == 0:
+        check(ctx.lib.gpxb_comm_unique_id(buf), "gpxb_comm_unique_id")
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    cbuf = ctypes.create_string_buffer(raw, 128)
+    check(ctx.lib.gpxb_comm_init(ctx.handle, cbuf, rank, world), "gpxb_comm_init")
+    return rank, world
+
+
 def launches() -> int:
     return _lib.context().launches()

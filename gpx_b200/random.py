@@ -1,11 +1,32 @@
-"""Minimal jax.random-style key handling for the host side (PRNGKey only); the Threefry
-generator that consumes keys runs on the device (csrc/rpchol.cu, csrc/lanczos.cu)."""
+"""jax.random-style key handling for the host side: PRNGKey and split.  Bulk sampling
+(Rademacher probes, RPCholesky pivot draws) runs on the device (csrc/threefry.cuh); the host
+only derives sub-keys, a handful of Threefry-2x32-20 blocks (Random123 algorithm)."""
 import numpy as np
+
+_M = 0xFFFFFFFF
+
+
+def _rotl(v, r):
+    return ((v << r) | (v >> (32 - r))) & _M
+
+
+def _threefry2x32(k0, k1, x0, x1):
+    ks = (k0, k1, (k0 ^ k1 ^ 0x1BD11BDA) & _M)
+    rot = ((13, 15, 26, 6), (17, 29, 16, 24))
+    x0 = (x0 + ks[0]) & _M
+    x1 = (x1 + ks[1]) & _M
+    for i in range(5):
+        for r in rot[i % 2]:
+            x0 = (x0 + x1) & _M
+            x1 = _rotl(x1, r) ^ x0
+        x0 = (x0 + ks[(i + 1) % 3]) & _M
+        x1 = (x1 + ks[(i + 2) % 3] + i + 1) & _M
+    return x0, x1
 
 
 def PRNGKey(seed: int) -> np.ndarray:
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    return np.array([seed >> 32, seed & 0xFFFFFFFF], dtype=np.uint32)
+    return np.array([seed >> 32, seed & _M], dtype=np.uint32)
 
 
 def as_key(key) -> np.ndarray:
@@ -13,3 +34,18 @@ def as_key(key) -> np.ndarray:
     if k.shape != (2,):
         raise ValueError("a PRNG key is two uint32 words, e.g. gpx_b200.random.PRNGKey(2023)")
     return k.astype(np.uint32)
+
+
+def split(key, num: int = 2, partitionable: bool = True) -> np.ndarray:
+    """jax.random.split(key, num) -> (num, 2) uint32, for either jax_threefry_partitionable mode."""
+    k0, k1 = (int(v) for v in as_key(key))
+    out = np.zeros((num, 2), dtype=np.uint32)
+    if partitionable:
+        for i in range(num):
+            out[i] = _threefry2x32(k0, k1, 0, i)
+        return out
+    flat = []
+    n = 2 * num
+    ys = [_threefry2x32(k0, k1, i, n // 2 + i) for i in range(n // 2)]
+    flat = [y[0] for y in ys] + [y[1] for y in ys]
+    return np.array(flat, dtype=np.uint32).reshape(num, 2)

@@ -94,6 +94,63 @@ int gpxb_gpr_predict(gpxb_ctx* ctx, int kind, const double* x_train, int N, int 
                      int ns, const double* c, int T, const double* mu, double ell, double sigma,
                      double* mean_out, double* cov_out, gpxb_stream stream);
 
+/* ---- Family 3: matrix-free mat-vec, Lanczos / SLQ, PCG, randomly pivoted Cholesky ------ */
+/* W[n_rows x P] = (K(x_rows, x_all) + diag_add * I) V, K never stored.  row_offset is the index of
+ * x_rows[0] inside x_all (the shifted diagonal sits at column row_offset + i), or -1 for a plain
+ * cross-kernel product.  Replaces rowfun_to_matvec + _Ax_lhs_fun + update_row_diagonal
+ * (gpx/operations.py:32-123, gpx/models/_gpr.py:94-119). */
+int gpxb_kmatvec(gpxb_ctx* ctx, int kind, const double* x_rows, int n_rows, long long row_offset,
+                 const double* x_all, int N, int D, double ell, double diag_add, const double* V,
+                 long long ldv, int P, double* W, long long ldw, gpxb_stream stream);
+/* Randomly pivoted Cholesky (gpx/kernels/approximations.py:30-129).  key = (key0, key1) as
+ * jax.random.PRNGKey words; partitionable = jax_threefry_partitionable of the JAX being matched.
+ * pivots_out: int64[M] device.  F_out: N x M row-major device, or NULL when only pivots are wanted. */
+int gpxb_rpcholesky(gpxb_ctx* ctx, int kind, const double* x, int N, int D, double ell, uint32_t key0,
+                    uint32_t key1, int M, int partitionable, double* F_out, long long* pivots_out,
+                    gpxb_stream stream);
+/* U_out[N x P] = jax.random.rademacher(key, (N, P)) / sqrt(N)   (gpx/lanczos.py:168-170) */
+int gpxb_rademacher_probes(gpxb_ctx* ctx, uint32_t key0, uint32_t key1, int N, int P, int partitionable,
+                           double* U_out, gpxb_stream stream);
+/* m-step Lanczos with full MGS re-orthogonalisation on A = K(x,x) + diag_add I for the P unit
+ * start vectors in the columns of U (gpx/lanczos.py:46-133, all probes advanced together).
+ * alpha_out[P x m]: diagonals; beta_out[P x m]: beta_out[p][j] = T_p[j][j+1] for j < m-1.
+ * *breakdown_flag (device int) is set when some beta <= 1e-12 (the reference would restart with a
+ * random vector; this build reports it instead). */
+int gpxb_lanczos(gpxb_ctx* ctx, int kind, const double* x, int N, int D, double ell, double diag_add,
+                 const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out,
+                 int* breakdown_flag, gpxb_stream stream);
+/* c[N] = PCG solve of (K + (sigma^2+1e-10) I) c = y - mu with the RPCholesky preconditioner
+ * (gpx/models/_gpr.py:285-310, 180-216; jax.scipy.sparse.linalg.cg semantics: x0 = 0, stop when
+ * r.r <= max(tol^2 b.b, atol^2) or after maxiter (<= 0: 10 N) iterations).  n_pivots = 0: no
+ * preconditioner.  Host-synchronous (one scalar read per iteration); *iters_out is a HOST int. */
+int gpxb_gpr_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, double ell,
+                      double sigma, int mean_mode, int n_pivots, uint32_t key0, uint32_t key1,
+                      int partitionable, double tol, double atol, int maxiter, double* c_out, double* mu_out,
+                      int* iters_out, gpxb_stream stream);
+
+/* ---- SGPR, Projected Processes --------------------------------------------------------- */
+/* *out (device) = lml / N of gpx/models/_sgpr.py:659-697, evaluated in the Woodbury form. */
+int gpxb_sgpr_lml(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,
+                  const double* x_locs, int M, double ell, double sigma, int mean_mode, double* out,
+                  gpxb_stream stream);
+/* c[M x T] = (sigma^2 K_mm + K_mn K_nm + 1e-10 I)^-1 K_mn (y - mu)  (gpx/models/_sgpr.py:39-61, 319-339) */
+int gpxb_sgpr_fit(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,
+                  const double* x_locs, int M, double ell, double sigma, int mean_mode, double* c_out,
+                  double* mu_out, gpxb_stream stream);
+/* gpx/models/_sgpr.py:434-467 (covariance built from the test points, as the reference does) */
+int gpxb_sgpr_predict(gpxb_ctx* ctx, int kind, const double* x_locs, int M, int D, const double* x, int ns,
+                      const double* c, int T, const double* mu, double ell, double sigma, double* mean_out,
+                      double* cov_out, gpxb_stream stream);
+/* out[k][:] = x[idx[k]][:]  (x_locs = x[pivots], gpx/models/_sgpr_rpchol.py:50, 200) */
+int gpxb_gather_rows(gpxb_ctx* ctx, const double* x, int D, const long long* idx, int M, double* out,
+                     gpxb_stream stream);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) --------------------------------- */
+/* Arrays are passed whole on every rank; each rank works on its own row range of x.  Rows are
+ * sharded for gpxb_lanczos, gpxb_gpr_fit_iter, gpxb_sgpr_lml and gpxb_sgpr_fit. */
+int gpxb_comm_unique_id(void* out128);
+int gpxb_comm_init(gpxb_ctx* ctx, const void* id128, int rank, int world);
+
 #ifdef __cplusplus
 }
 #endif
