@@ -1,1 +1,3 @@
 from .gpr import GPR  # noqa: F401
+from .sgpr import SGPR  # noqa: F401
+from .sgpr_rpchol import SGPR_RPChol  # noqa: F401

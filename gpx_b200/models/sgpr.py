@@ -1,0 +1,122 @@
+"""Sparse GPR, Projected Processes (mirror of gpx/models/sgpr.py:70-118, 309-338, 540-600,
+676-804).  Numerics: gpxb_sgpr_lml / gpxb_sgpr_fit / gpxb_sgpr_predict (include/gpxb200.h)."""
+from __future__ import annotations
+
+from typing import Callable, Dict
+
+import numpy as np
+
+from .. import ops
+from ..bijectors import Identity, Softplus
+from ..defaults import gpxargs
+from ..kernels import _to_device
+from ..mean_functions import data_mean, mean_mode
+from ..parameters import ModelState, Parameter
+from ..priors import NormalPrior
+from .base import BaseGP
+from .gpr import _hyper, _xy
+
+
+def _locs(state):
+    return _to_device(state.kernel._slice(np.asarray(state.params["x_locs"].value)))
+
+
+def log_marginal_likelihood(state, x, y, iterative=False, num_evals=gpxargs.num_evals,
+                            num_lanczos=gpxargs.num_lanczos, key_lanczos=gpxargs.key_lanczos, **_ignored):
+    """gpx/models/sgpr.py:70-118 -> _sgpr._lml_dense (gpx/models/_sgpr.py:659-697)."""
+    if iterative:
+        raise NotImplementedError("SGPR iterative LML (_sgpr.py:700-737) is a 'next' row (SURVEY.md 8a a-16)")
+    kernel, ell, sigma = _hyper(state)
+    xd, yd = _xy(state, x, y)
+    out = ops.sgpr_lml(kernel.kind, xd, yd, _locs(state), ell, sigma, mean_mode(state.mean_function))
+    return float(out.cpu().numpy()[0])
+
+
+def neg_log_marginal_likelihood(state, x, y, **kwargs):
+    return -log_marginal_likelihood(state, x, y, **kwargs)
+
+
+def loss_and_grad(state, x, y, **kwargs):
+    raise NotImplementedError("gradient of the SGPR LML is a 'next' row (SURVEY.md 8f N1); "
+                              "fit with minimize=False or optimise hyper-parameters with GPR")
+
+
+def fit(state, x, y, iterative=False, **_ignored):
+    """gpx/models/sgpr.py:309-338 -> _sgpr._fit_dense (gpx/models/_sgpr.py:319-339).  The extra
+    keywords BaseGP.fit passes (n_pivots, key_precond) are accepted and ignored."""
+    if iterative:
+        raise NotImplementedError("SGPR CG fit (_sgpr.py:342-362) is a 'next' row")
+    kernel, ell, sigma = _hyper(state)
+    xd, yd = _xy(state, x, y)
+    c, mu = ops.sgpr_fit(kernel.kind, xd, yd, _locs(state), ell, sigma, mean_mode(state.mean_function))
+    return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), c=c.cpu().numpy(),
+                             mu=np.float64(mu.cpu().numpy()[0]), is_fitted=True, is_fitted_derivs=False))
+
+
+def _predict_with_locs(state, x_locs_dev, x, full_covariance):
+    import torch
+
+    kernel, ell, sigma = _hyper(state)
+    xs = _to_device(kernel._slice(x))
+    c = _to_device(state.c)
+    if c.dim() == 1:
+        c = c.reshape(-1, 1)
+    mu = torch.full((1,), float(state.mu), dtype=torch.float64, device="cuda")
+    out = ops.sgpr_predict(kernel.kind, x_locs_dev, xs, c, mu, ell, sigma, full_covariance=full_covariance)
+    if full_covariance:
+        return out[0].cpu().numpy(), out[1].cpu().numpy()
+    return out.cpu().numpy()
+
+
+def predict(state, x, full_covariance=False, iterative=False):
+    """gpx/models/sgpr.py:540-600 -> _sgpr._predict_dense (gpx/models/_sgpr.py:434-467)."""
+    if not state.is_fitted:
+        raise RuntimeError("Model is not fitted. Run `fit` to fit the model before prediction.")
+    if full_covariance and iterative:
+        raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
+    return _predict_with_locs(state, _locs(state), x, full_covariance)
+
+
+def default_params() -> Dict[str, Parameter]:
+    """gpx/models/sgpr.py:676-684."""
+    return dict(sigma=Parameter(value=1.0, trainable=True, bijector=Softplus(), prior=NormalPrior(loc=0.0, scale=1.0)))
+
+
+def init(kernel: Callable, mean_function: Callable = data_mean, x_locs: Parameter = None, jacobian_locs=None,
+         kernel_params=None, sigma=None, loss_fn: Callable = neg_log_marginal_likelihood) -> ModelState:
+    """gpx/models/sgpr.py:687-747."""
+    if not callable(kernel):
+        raise TypeError(f"kernel must be callable, you provided {type(kernel)}")
+    if not isinstance(x_locs, Parameter):
+        raise TypeError(f"x_locs must be a Parameter, you provided {type(x_locs)}")
+    if kernel_params is None:
+        kernel_params = kernel.default_params()
+    if sigma is None:
+        sigma = default_params()["sigma"]
+    params = {"kernel_params": kernel_params, "sigma": sigma, "x_locs": x_locs}
+    opt = dict(x_train=None, y_train=None, loss_fn=loss_fn, is_fitted=False, is_fitted_derivs=False, c=None, mu=None)
+    return ModelState(kernel, mean_function, params, **opt)
+
+
+def locs_parameter(x_locs, trainable=False) -> Parameter:
+    """Convenience: wrap landmark coordinates as the Parameter the constructor expects."""
+    x_locs = np.asarray(x_locs, dtype=np.float64)
+    return Parameter(x_locs, trainable, Identity(), NormalPrior(shape=x_locs.shape))
+
+
+class SGPR(BaseGP):
+    """gpx/models/sgpr.py:750-804."""
+
+    _init_default = dict(is_fitted=False, is_fitted_derivs=False, c=None, mu=None)
+
+    def __init__(self, kernel, mean_function=data_mean, x_locs=None, jacobian_locs=None, kernel_params=None,
+                 sigma=None, loss_fn=neg_log_marginal_likelihood) -> None:
+        self.state = init(kernel=kernel, mean_function=mean_function, x_locs=x_locs, jacobian_locs=jacobian_locs,
+                          kernel_params=kernel_params, sigma=sigma, loss_fn=loss_fn)
+
+    _default_params_fun = staticmethod(default_params)
+    _init_fun = staticmethod(init)
+    _lml_fun = staticmethod(log_marginal_likelihood)
+    _loss_and_grad_fun = staticmethod(loss_and_grad)
+    _fit_fun = staticmethod(fit)
+    _predict_fun = staticmethod(predict)

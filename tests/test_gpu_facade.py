@@ -64,3 +64,46 @@ def test_kernel_call_and_active_dims():
     p = k.default_params()
     K = k(x, x, p)
     assert np.max(np.abs(K - R.kernel("m32", x[:, [0, 2]], x[:, [0, 2]], 1.0))) < 1e-13
+
+
+def test_sgpr_and_sgpr_rpchol_facades():
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import SGPR, SGPR_RPChol
+    from gpx_b200.models.sgpr import locs_parameter
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior, NormalPrior
+
+    x, y = _data(1500, 4, 11)
+    ell, sigma, M = 1.7, 0.2, 48
+    key = R.PRNGKey(2023)
+    kp = dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior()))
+    sg = Parameter(sigma, True, Softplus(), NormalPrior())
+    m = SGPR_RPChol(SquaredExponential(), n_locs=M, key=key, kernel_params=kp, sigma=sg)
+    ref, piv = R.sgpr_rpchol_lml_dense("se", x, y, ell, sigma, key, M)
+    lml = m.log_marginal_likelihood(x, y)
+    assert abs(lml - ref) < 1e-8 * abs(ref)
+    m.fit(x, y, minimize=False)  # the reference's BaseGP.fit kwargs bug (F9) is tolerated here
+    assert np.array_equal(m.state.pivots, piv)
+    assert np.array_equal(m.state.x_locs, x[piv])
+    xs = np.random.default_rng(1).standard_normal((40, 4))
+    c_ref, mu_ref, xl = R.sgpr_rpchol_fit_dense("se", x, y, ell, sigma, key, M)
+    mean_ref = R.sgpr_predict_dense("se", xl, xs, c_ref, mu_ref, ell, sigma)
+    assert np.max(np.abs(m.predict(xs) - mean_ref)) < 1e-6
+    # plain SGPR with the same landmarks gives the same numbers
+    s = SGPR(SquaredExponential(), x_locs=locs_parameter(x[piv]), kernel_params=kp, sigma=sg)
+    assert abs(s.log_marginal_likelihood(x, y) - ref) < 1e-8 * abs(ref)
+    s.fit(x, y, minimize=False)
+    mean, cov = s.predict(xs, full_covariance=True)
+    mr, cr = R.sgpr_predict_dense("se", xl, xs, c_ref, mu_ref, ell, sigma, full_covariance=True)
+    assert np.max(np.abs(mean - mr)) < 1e-6 and np.max(np.abs(cov - cr)) < 1e-6
+
+
+def test_iterative_predict_matches_dense():
+    from gpx_b200.kernels import Matern52
+    from gpx_b200.models import GPR
+
+    x, y = _data(700, 3, 5)
+    m = GPR(Matern52()).fit(x, y, minimize=False)
+    xs = np.random.default_rng(2).standard_normal((90, 3))
+    assert np.max(np.abs(m.predict(xs, iterative=True) - m.predict(xs))) < 1e-10

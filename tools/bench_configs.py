@@ -1,0 +1,84 @@
+"""Throughput of the matrix-free / sparse paths at the BASELINE.json shapes (configs[3], [4]),
+one JSON line per measurement, each with its roofline figure.
+
+    python tools/bench_configs.py rpchol [N] [M]     # configs[3] part 1 (HBM bound)
+    python tools/bench_configs.py sgpr   [N] [M]     # configs[3] part 2 (FP64 tensor bound)
+    python tools/bench_configs.py matvec [N] [P]     # configs[4]: one block mat-vec (FP64 pipe bound)
+    python tools/bench_configs.py slq    [N] [P] [m] # configs[4]: Lanczos/SLQ log-det end to end
+"""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from gpx_b200 import ops  # noqa: E402
+
+HBM = 6554.2  # GB/s, MEASURED_PEAKS.json
+
+
+def ev_time(fn, reps=1, warm=0):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        out = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps, out
+
+
+def data(N, D, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((N, D), dtype=torch.float64, device="cuda", generator=g)
+    y = torch.sin(x.sum(1, keepdim=True)) + 0.1 * torch.randn((N, 1), dtype=torch.float64, device="cuda", generator=g)
+    return x, y
+
+
+def main():
+    what = sys.argv[1]
+    a = [int(v) for v in sys.argv[2:]]
+    key = np.array([0, 2023], dtype=np.uint32)
+    if what == "rpchol":
+        N, M = (a + [1_000_000, 4096])[:2] if len(a) < 2 else a[:2]
+        x, _ = data(N, 32, 3)
+        t, (F, piv) = ev_time(lambda: ops.rpcholesky("se", x, M, 32**0.5, key, True, want_factor=False))
+        alg = 8.0 * N * M * (M - 1) / 2 + 5 * 8.0 * N * M
+        print(json.dumps(dict(what="rpcholesky", N=N, M=M, D=32, s=t, alg_bytes=alg, gbs=alg / t / 1e9,
+                              hbm_frac=alg / t / 1e9 / HBM, pivots_head=piv[:6].cpu().tolist())), flush=True)
+    elif what == "sgpr":
+        N, M = a[:2] if len(a) >= 2 else (1_000_000, 4096)
+        x, y = data(N, 32, 3)
+        _, piv = ops.rpcholesky("se", x[:65536].contiguous(), M, 32**0.5, key, True, want_factor=False)
+        xl = ops.gather_rows(x, piv)
+        t, out = ev_time(lambda: ops.sgpr_lml("se", x, y, xl, 32**0.5, 0.1), reps=1, warm=1)
+        fl = 2.0 * N * M * 32 + 2.0 * M * M * N + 2.0 * M**3 / 3
+        print(json.dumps(dict(what="sgpr_lml_woodbury", N=N, M=M, D=32, s=t, alg_flops=fl, tflops=fl / t / 1e12,
+                              lml=float(out.cpu()[0]))), flush=True)
+    elif what == "matvec":
+        N, P = a[:2] if len(a) >= 2 else (2_000_000, 30)
+        x, _ = data(N, 16, 4)
+        V = torch.randn((N, P), dtype=torch.float64, device="cuda")
+        t, W = ev_time(lambda: ops.kmatvec("se", x, x, V, 4.0, diag_add=0.25 + 1e-10), reps=1, warm=0)
+        fl = float(N) ** 2 * (2 * 16 + 4 + 2 * P)
+        print(json.dumps(dict(what="kmatvec_block", N=N, D=16, P=P, s=t, alg_flops=fl, tflops=fl / t / 1e12,
+                              pair_evals_per_s=float(N) ** 2 / t, checksum=float(W.sum().cpu()))), flush=True)
+    elif what == "slq":
+        N, P, m = a[:3] if len(a) >= 3 else (262144, 30, 50)
+        x, _ = data(N, 16, 4)
+        U = ops.rademacher_probes(key, N, P, True)
+        t, (al, be, fl_) = ev_time(lambda: ops.lanczos("se", x, 4.0, 0.25 + 1e-10, U, m))
+        from gpx_b200.models._iterative import slq_logdet
+
+        ld = slq_logdet(al.cpu().numpy(), be.cpu().numpy(), N)
+        fl = m * float(N) ** 2 * (2 * 16 + 4 + 2 * P)
+        print(json.dumps(dict(what="lanczos_slq", N=N, D=16, P=P, m=m, s=t, matvec_flops=fl, tflops=fl / t / 1e12,
+                              logdet=ld, breakdown=int(fl_.cpu()[0]))), flush=True)
+
+
+if __name__ == "__main__":
+    main()
