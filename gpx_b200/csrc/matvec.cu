@@ -18,12 +18,13 @@
 #include "matvec.cuh"
 #include "mma.cuh"
 
+#include <cstdlib>
+
 namespace gpxb {
 
 namespace {
 
 constexpr int BJ = 128;
-constexpr int NT = 256;
 
 struct KmvParams {
   int kind;
@@ -55,9 +56,10 @@ __device__ __forceinline__ double kfun(int kind, double d2) {
 
 // MF: 8-row fragments per warp (rows per CTA = 64*MF); KS: Dp/4 when the row operand lives in
 // registers, 0 = read it from shared memory; NPF: 8-column fragments of V/W (P <= 8*NPF).
-template <int MF, int KS, int NPF>
-__global__ void __launch_bounds__(NT, 1) kmatvec_kernel(const KmvParams p) {
-  constexpr int BR = 64 * MF;
+template <int MF, int KS, int NPF, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams p) {
+  constexpr int BR = NWARP * 8 * MF;
+  constexpr int NT = NWARP * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // bar[0], bar[1]
   double* sZr = reinterpret_cast<double*>(smem_raw + 128);
@@ -218,11 +220,11 @@ __global__ void pack_v_kernel(const double* __restrict__ V, long long ldv, int n
   Vp[idx] = c < P ? V[(long long)i * ldv + c0 + c] : 0.0;
 }
 
-template <int MF, int KS, int NPF>
+template <int MF, int KS, int NPF, int NWARP>
 int launch_t(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) {
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(kmatvec_kernel<MF, KS, NPF>,
+  GPXB_CUDA_CHECK(cudaFuncSetAttribute(kmatvec_kernel<MF, KS, NPF, NWARP>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kmatvec_kernel<MF, KS, NPF><<<grid, NT, smem, s>>>(p);
+  kmatvec_kernel<MF, KS, NPF, NWARP><<<grid, NWARP * 32, smem, s>>>(p);
   GPXB_LAUNCH_CHECK();
   ctx->launches++;
   return 0;
@@ -253,10 +255,16 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   p.diag_add = a.diag_add;
   const int NPF = a.P <= 8 ? 1 : 4;
   const int limit = 232448;
-  int MF = 4;
-  if (smem_bytes(256, p.S, p.PS) > limit) MF = 2;
-  GPXB_ARG_CHECK(smem_bytes(64 * MF, p.S, p.PS) <= limit, -23);
-  const int BR = 64 * MF;
+  // variants: (MF=2, 16 warps, 256 rows) default; (MF=4, 8 warps, 256 rows) via GPXB_KMV_WARPS=8;
+  // (MF=2, 8 warps, 128 rows) when the 256-row tile does not fit in shared memory
+  static int warps_pref = -1;
+  if (warps_pref < 0) {
+    const char* e = getenv("GPXB_KMV_WARPS");
+    warps_pref = (e && atoi(e) == 8) ? 8 : 16;
+  }
+  int BR = 256, MF = warps_pref == 16 ? 2 : 4, NW = warps_pref;
+  if (smem_bytes(256, p.S, p.PS) > limit) { BR = 128; MF = 2; NW = 8; }
+  GPXB_ARG_CHECK(smem_bytes(BR, p.S, p.PS) <= limit, -23);
   const int row_ctas = ceil_div(a.n_rows, BR);
   // column split so that small row counts still fill the GPU (deterministic two-pass reduce)
   int jsplit = 1;
@@ -278,14 +286,17 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   }
   dim3 grid(row_ctas, jsplit);
   const int smem = smem_bytes(BR, p.S, p.PS);
-  const int KS = (MF == 4 && (p.Dp == 8 || p.Dp == 16 || p.Dp == 32)) ? p.Dp / 4 : 0;
+  const int KS = (BR == 256 && (p.Dp == 8 || p.Dp == 16 || p.Dp == 32)) ? p.Dp / 4 : 0;
   int rc;
-#define GO(mf, ks, npf) rc = launch_t<mf, ks, npf>(ctx, p, grid, smem, s)
-  if (MF == 2) { if (NPF == 1) GO(2, 0, 1); else GO(2, 0, 4); }
-  else if (KS == 2) { if (NPF == 1) GO(4, 2, 1); else GO(4, 2, 4); }
-  else if (KS == 4) { if (NPF == 1) GO(4, 4, 1); else GO(4, 4, 4); }
-  else if (KS == 8) { if (NPF == 1) GO(4, 8, 1); else GO(4, 8, 4); }
-  else { if (NPF == 1) GO(4, 0, 1); else GO(4, 0, 4); }
+#define GO(mf, ks, npf, nw) rc = launch_t<mf, ks, npf, nw>(ctx, p, grid, smem, s)
+#define GO2(mf, ks, nw) do { if (NPF == 1) GO(mf, ks, 1, nw); else GO(mf, ks, 4, nw); } while (0)
+  if (BR == 128) GO2(2, 0, 8);
+  else if (NW == 16) {
+    if (KS == 2) GO2(2, 2, 16); else if (KS == 4) GO2(2, 4, 16); else if (KS == 8) GO2(2, 8, 16); else GO2(2, 0, 16);
+  } else {
+    if (KS == 2) GO2(4, 2, 8); else if (KS == 4) GO2(4, 4, 8); else if (KS == 8) GO2(4, 8, 8); else GO2(4, 0, 8);
+  }
+#undef GO2
 #undef GO
   GPXB_TRY(rc);
   if (jsplit > 1) {

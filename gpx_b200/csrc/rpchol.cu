@@ -210,16 +210,19 @@ __global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
     if (r == s) d2 = 1e-12;
     double g = kfun(st.kind, d2);
     const double* f = st.FT + r;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = 0.0;
     int c = 0;
-    for (; c + 4 <= i; c += 4) {
-      a0 += f[(long long)(c + 0) * st.ldf] * sf[c + 0];
-      a1 += f[(long long)(c + 1) * st.ldf] * sf[c + 1];
-      a2 += f[(long long)(c + 2) * st.ldf] * sf[c + 2];
-      a3 += f[(long long)(c + 3) * st.ldf] * sf[c + 3];
+    for (; c + 8 <= i; c += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(f + (long long)(c + u) * st.ldf);  // streaming: read once
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += v[u] * sf[c + u];
     }
-    for (; c < i; ++c) a0 += f[(long long)c * st.ldf] * sf[c];
-    g -= (a0 + a1) + (a2 + a3);
+    for (; c < i; ++c) a[0] += f[(long long)c * st.ldf] * sf[c];
+    g -= ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     const double fnew = g / (sqrt(st.scal[0]) + 1e-6);
     st.FT[(long long)i * st.ldf + r] = fnew;
     dnew = st.diag[r] - fnew * fnew;
