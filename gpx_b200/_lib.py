@@ -44,6 +44,7 @@ SIGNATURES = {
     "gpxb_sgpr_predict": (_int, [C.c_void_p, _int, _c_dp, _int, _int, _c_dp, _int, _c_dp, _int, _c_dp, _dbl, _dbl, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_gather_rows": (_int, [C.c_void_p, _c_dp, _int, _c_dp, _int, _c_dp, C.c_void_p]),
     "gpxb_comm_unique_id": (_int, [C.c_void_p]),
+    "gpxb_shard_range": (_int, [_ll, _int, _int, C.POINTER(_ll), C.POINTER(_ll)]),
     "gpxb_comm_init": (_int, [C.c_void_p, C.c_void_p, _int, _int]),
 }
 

@@ -54,6 +54,13 @@ int gpxb_comm_init(gpxb_ctx* ctx, const void* id128, int rank, int world) {
   return comm_init(reinterpret_cast<Ctx*>(ctx), id128, rank, world);
 }
 
+int gpxb_shard_range(long long N, int world, int rank, long long* begin, long long* end) {
+  GPXB_ARG_CHECK(begin && end && N >= 0 && world >= 1 && rank >= 0 && rank < world, -1);
+  *begin = shard_begin(N, world, rank);
+  *end = shard_begin(N, world, rank + 1);
+  return 0;
+}
+
 int gpxb_gather_rows(gpxb_ctx* ctx_, const double* x, int D, const long long* idx, int M, double* out,
                      gpxb_stream stream) {
   GPXB_ARG_CHECK(ctx_ && x && idx && out && D > 0 && M >= 0, -1);
@@ -85,12 +92,10 @@ int gpxb_rpcholesky(gpxb_ctx* ctx_, int kind, const double* x, int N, int D, dou
   DevBuf z, ft;
   GPXB_TRY(z.alloc(sizeof(double) * (size_t)N * zl.S, s));
   GPXB_TRY(prep_z(ctx, x, D, N, zl, ell, z.as<double>(), s));
-  const long long ldf = round_up(N, 2);
-  GPXB_TRY(ft.alloc(sizeof(double) * (size_t)M * ldf, s));
+  GPXB_TRY(ft.alloc(sizeof(double) * rp_factor_doubles(N, M), s));
   const uint32_t key[2] = {key0, key1};
-  GPXB_TRY(rpcholesky_z(ctx, kind, z.as<double>(), N, zl, key, M, partitionable, ft.as<double>(), ldf,
-                        pivots_out, s));
-  if (F_out) GPXB_TRY(transpose_f(ctx, ft.as<double>(), ldf, N, M, F_out, s));
+  GPXB_TRY(rpcholesky_z(ctx, kind, z.as<double>(), N, zl, key, M, partitionable, ft.as<double>(), pivots_out, s));
+  if (F_out) GPXB_TRY(rp_unblock_rowmajor(ctx, ft.as<double>(), N, M, F_out, s));
   return 0;
 }
 
@@ -150,12 +155,15 @@ int gpxb_gpr_fit_iter(gpxb_ctx* ctx_, int kind, const double* x, const double* y
   const long long ldf = round_up(N, 2);
   if (n_pivots > 0) {
     // preconditioner: RPCholesky over all rows (replicated on every rank), P_kk = inv(sigma^2 I + F^T F)
+    DevBuf fb;
+    GPXB_TRY(fb.alloc(sizeof(double) * rp_factor_doubles(N, n_pivots), s));
     GPXB_TRY(ft.alloc(sizeof(double) * (size_t)n_pivots * ldf, s));
     GPXB_TRY(piv.alloc(sizeof(long long) * n_pivots, s));
     GPXB_TRY(pkk.alloc(sizeof(double) * (size_t)n_pivots * n_pivots, s));
     const uint32_t key[2] = {key0, key1};
-    GPXB_TRY(rpcholesky_z(ctx, kind, za.as<double>(), N, zl, key, n_pivots, partitionable, ft.as<double>(),
-                          ldf, piv.as<long long>(), s));
+    GPXB_TRY(rpcholesky_z(ctx, kind, za.as<double>(), N, zl, key, n_pivots, partitionable, fb.as<double>(),
+                          piv.as<long long>(), s));
+    GPXB_TRY(rp_unblock_transposed(ctx, fb.as<double>(), N, n_pivots, ft.as<double>(), ldf, s));
     GPXB_TRY(precond_build(ctx, ft.as<double>() + sh.b, ldf, n_pivots, sh.n(), sigma, pkk.as<double>(), s));
   }
   GPXB_TRY(xl.alloc(sizeof(double) * std::max(sh.n(), 1), s));

@@ -3,10 +3,12 @@
 // Replaces gpx/kernels/approximations.py:30-129 (rpcholesky).  Per pivot i:
 //   prob = diag / sum(diag);  key, _ = split(key);  s = choice(key, N, p = prob)
 //   g = k(x_s, X) - F[:, :i] F[s, :i]^T;  F[:, i] = g / (sqrt(g_s) + 1e-6);  diag -= F[:, i]^2
-// The factor is kept transposed (F_T[c][r], one contiguous row per pivot) so that the
-// per-pivot GEMV -- the HBM-bound part, 8*N*i bytes at step i -- is a fully coalesced stream
-// with one thread per data row; the kernel column, the scaling, the diagonal update and the
-// fixed-order block sums for the next draw are fused into the same pass.
+// The factor is kept in a row-blocked transposed layout: for every block of 1024 data rows the
+// pivot columns are consecutive 8 KB chunks (element (c, r) at ((r/1024)*M + c)*1024 + r%1024),
+// so the per-pivot GEMV -- the HBM-bound part, 8*N*i bytes at step i -- is, for each CTA, one
+// sequential stream (no page hopping), fully coalesced with one thread per data row; the
+// kernel column, the scaling, the diagonal update and the fixed-order block sums for the next
+// draw are fused into the same pass.
 // Sampling reproduces jax.random.choice (inverse CDF: cumsum, r = cum[-1]*(1-u),
 // searchsorted-left) with a two-level scan over fixed 1024-row blocks, so the result does not
 // depend on the launch geometry.
@@ -62,8 +64,8 @@ __device__ __forceinline__ double block_scan_1024(double v, double* sh /*32*/) {
 struct RpState {
   double* diag;       // [n]
   double* blocksum;   // [nblk]
-  double* FT;         // [M][ldf]
-  long long ldf;
+  double* FB;         // row-blocked factor, see fb_index
+  int M;
   const double* Z;    // [n][S]
   int n, S, Dp, nblk, kind;
   long long* pivots;  // [M]
@@ -73,6 +75,10 @@ struct RpState {
   double* scal;       // [0] g_s
   int partitionable;
 };
+
+__host__ __device__ __forceinline__ long long fb_index(long long r, int c, int M) {
+  return ((r >> 10) * M + c) * BLK + (r & (BLK - 1));
+}
 
 __global__ void rp_init_kernel(RpState st, double d0) {
   __shared__ double sh[32];
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
   for (int d = tid; d < st.S; d += BLK) st.zs[d] = st.Z[s * st.S + d];
   double acc = 0.0;
   for (int c = tid; c < i; c += BLK) {
-    const double f = st.FT[(long long)c * st.ldf + s];
+    const double f = st.FB[fb_index(s, c, st.M)];
     st.frow[c] = f;
     acc += f * f;
   }
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
     double d2 = ((sz[st.Dp] - 2.0 * dot) + zr[st.Dp]) + 1e-12;
     if (r == s) d2 = 1e-12;
     double g = kfun(st.kind, d2);
-    const double* f = st.FT + r;
+    const double* f = st.FB + fb_index(r, 0, st.M);
     double a[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) a[u] = 0.0;
@@ -217,14 +223,14 @@ __global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
     for (; c + 8 <= i; c += 8) {
       double v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcs(f + (long long)(c + u) * st.ldf);  // streaming: read once
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(f + (long long)(c + u) * BLK);  // streaming: read once
 #pragma unroll
       for (int u = 0; u < 8; ++u) a[u] += v[u] * sf[c + u];
     }
-    for (; c < i; ++c) a[0] += f[(long long)c * st.ldf] * sf[c];
+    for (; c < i; ++c) a[0] += f[(long long)c * BLK] * sf[c];
     g -= ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     const double fnew = g / (sqrt(st.scal[0]) + 1e-6);
-    st.FT[(long long)i * st.ldf + r] = fnew;
+    st.FB[fb_index(r, i, st.M)] = fnew;
     dnew = st.diag[r] - fnew * fnew;
     st.diag[r] = dnew;
   }
@@ -232,13 +238,13 @@ __global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
   if (threadIdx.x == 0) st.blocksum[blockIdx.x] = dnew;
 }
 
-__global__ void transpose_f_kernel(const double* __restrict__ FT, long long ldf, int n, int M,
-                                   double* __restrict__ F) {
+// F[r][c] (row-major N x M) <- blocked factor
+__global__ void unblock_rowmajor_kernel(const double* __restrict__ FB, int n, int M, double* __restrict__ F) {
   __shared__ double tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int k = threadIdx.y; k < 32; k += 8) {
     const int c = c0 + k, r = r0 + threadIdx.x;
-    tile[k][threadIdx.x] = (c < M && r < n) ? FT[(long long)c * ldf + r] : 0.0;
+    tile[k][threadIdx.x] = (c < M && r < n) ? FB[fb_index(r, c, M)] : 0.0;
   }
   __syncthreads();
   for (int k = threadIdx.y; k < 32; k += 8) {
@@ -247,13 +253,24 @@ __global__ void transpose_f_kernel(const double* __restrict__ FT, long long ldf,
   }
 }
 
+// FT[c][r] (M x ldf, one contiguous row per pivot) <- blocked factor
+__global__ void unblock_transposed_kernel(const double* __restrict__ FB, int n, int M, double* __restrict__ FT,
+                                          long long ldf) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * M) return;
+  const int c = (int)(idx / n);
+  const long long r = idx % n;
+  FT[(long long)c * ldf + r] = FB[fb_index(r, c, M)];
+}
+
 }  // namespace
 
-// Z: pre-scaled rows (z_layout).  FT: [M][ldf] device (ldf >= n).  pivots: [M] int64 device.
+size_t rp_factor_doubles(int n, int M) { return (size_t)ceil_div(n, BLK) * (size_t)M * BLK; }
+
+// Z: pre-scaled rows (z_layout).  FB: rp_factor_doubles(n, M) doubles.  pivots: [M] int64 device.
 int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, ZLayout zl, const uint32_t key[2], int M,
-                 int partitionable, double* FT, long long ldf, long long* pivots, cudaStream_t s) {
+                 int partitionable, double* FB, long long* pivots, cudaStream_t s) {
   GPXB_ARG_CHECK(n > 0 && M > 0 && M <= 6000, -40);  // frow + zs must fit in 48 KB of smem
-  GPXB_ARG_CHECK(ldf >= n, -41);
   const int nblk = ceil_div(n, BLK);
   DevBuf bDiag, bBs, bKey, bZs, bFrow, bSc;
   GPXB_TRY(bDiag.alloc(sizeof(double) * n, s));
@@ -264,7 +281,7 @@ int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, ZLayout zl, const u
   GPXB_TRY(bSc.alloc(sizeof(double) * 4, s));
   RpState st;
   st.diag = bDiag.as<double>(); st.blocksum = bBs.as<double>();
-  st.FT = FT; st.ldf = ldf; st.Z = Z; st.n = n; st.S = zl.S; st.Dp = zl.Dp; st.nblk = nblk; st.kind = kind;
+  st.FB = FB; st.M = M; st.Z = Z; st.n = n; st.S = zl.S; st.Dp = zl.Dp; st.nblk = nblk; st.kind = kind;
   st.pivots = pivots; st.key = bKey.as<uint32_t>(); st.zs = bZs.as<double>(); st.frow = bFrow.as<double>();
   st.scal = bSc.as<double>(); st.partitionable = partitionable;
   GPXB_CUDA_CHECK(cudaMemcpyAsync(st.key, key, sizeof(uint32_t) * 2, cudaMemcpyHostToDevice, s));
@@ -295,9 +312,16 @@ int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, ZLayout zl, const u
   return 0;
 }
 
-int transpose_f(Ctx* ctx, const double* FT, long long ldf, int n, int M, double* F, cudaStream_t s) {
+int rp_unblock_rowmajor(Ctx* ctx, const double* FB, int n, int M, double* F, cudaStream_t s) {
   dim3 grid(ceil_div(n, 32), ceil_div(M, 32)), blk(32, 8);
-  transpose_f_kernel<<<grid, blk, 0, s>>>(FT, ldf, n, M, F);
+  unblock_rowmajor_kernel<<<grid, blk, 0, s>>>(FB, n, M, F);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+int rp_unblock_transposed(Ctx* ctx, const double* FB, int n, int M, double* FT, long long ldf, cudaStream_t s) {
+  unblock_transposed_kernel<<<ceil_div((long long)n * M, 256), 256, 0, s>>>(FB, n, M, FT, ldf);
   GPXB_LAUNCH_CHECK();
   ctx->launches++;
   return 0;

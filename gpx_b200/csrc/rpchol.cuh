@@ -4,7 +4,12 @@
 #include "gram.cuh"
 
 namespace gpxb {
+// number of doubles of the row-blocked factor buffer for n rows and M pivots
+size_t rp_factor_doubles(int n, int M);
 int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, ZLayout zl, const uint32_t key[2], int M,
-                 int partitionable, double* FT, long long ldf, long long* pivots, cudaStream_t s);
-int transpose_f(Ctx* ctx, const double* FT, long long ldf, int n, int M, double* F, cudaStream_t s);
+                 int partitionable, double* FB, long long* pivots, cudaStream_t s);
+// F (N x M row-major) <- blocked factor
+int rp_unblock_rowmajor(Ctx* ctx, const double* FB, int n, int M, double* F, cudaStream_t s);
+// FT (M x ldf, one contiguous row per pivot) <- blocked factor
+int rp_unblock_transposed(Ctx* ctx, const double* FB, int n, int M, double* FT, long long ldf, cudaStream_t s);
 }  // namespace gpxb

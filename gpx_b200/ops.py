@@ -293,6 +293,26 @@ def gather_rows(x, idx):
     return out
 
 
+def shard_range(N, world, rank):
+    """Row range [begin, end) that `rank` of `world` owns (host-only; no GPU needed)."""
+    import ctypes
+
+    lib = _lib.load()
+    b, e = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    check(lib.gpxb_shard_range(int(N), int(world), int(rank), ctypes.byref(b), ctypes.byref(e)), "gpxb_shard_range")
+    return b.value, e.value
+
+
+def broadcast_bytes(raw: bytes, n: int, src: int = 0) -> bytes:
+    """Broadcast n bytes over torch.distributed (CPU tensor for gloo, CUDA tensor for nccl)."""
+    import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(raw[:n].ljust(n, b"\0")), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src)
+    return bytes(t.cpu().tolist())
+
+
 def comm_init_from_torch_distributed():
     """Bootstrap the library's NCCL communicator from an initialised torch.distributed group
     (the unique id travels through a broadcast of 128 bytes)."""
@@ -305,9 +325,7 @@ def comm_init_from_torch_distributed():
     buf = (ctypes.c_char * 128)()
     if rank == 0:
         check(ctx.lib.gpxb_comm_unique_id(buf), "gpxb_comm_unique_id")
-    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
-    dist.broadcast(t, 0)
-    raw = bytes(t.cpu().tolist())
+    raw = broadcast_bytes(bytes(buf), 128, 0)
     cbuf = ctypes.create_string_buffer(raw, 128)
     check(ctx.lib.gpxb_comm_init(ctx.handle, cbuf, rank, world), "gpxb_comm_init")
     return rank, world

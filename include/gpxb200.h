@@ -149,6 +149,8 @@ int gpxb_gather_rows(gpxb_ctx* ctx, const double* x, int D, const long long* idx
 /* Arrays are passed whole on every rank; each rank works on its own row range of x.  Rows are
  * sharded for gpxb_lanczos, gpxb_gpr_fit_iter, gpxb_sgpr_lml and gpxb_sgpr_fit. */
 int gpxb_comm_unique_id(void* out128);
+/* host-only: the row range [begin, end) rank owns out of N rows (256-row aligned partition) */
+int gpxb_shard_range(long long N, int world, int rank, long long* begin, long long* end);
 int gpxb_comm_init(gpxb_ctx* ctx, const void* id128, int rank, int world);
 
 #ifdef __cplusplus

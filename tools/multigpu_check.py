@@ -1,0 +1,65 @@
+"""Real multi-GPU check of the row-sharded paths (run under torchrun, one rank per GPU):
+results with world > 1 (NCCL all-reduce / all-gather inside libgpxb200) must equal the
+single-GPU results computed by the same rank before the communicator is created.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/multigpu_check.py
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+from gpx_b200 import ops  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    N, D, P, m, M = int(os.environ.get("CHK_N", "20000")), 16, 30, 12, 256
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((N, D), dtype=torch.float64, device="cuda", generator=g)
+    y = torch.sin(x.sum(1, keepdim=True)) + 0.1 * torch.randn((N, 1), dtype=torch.float64, device="cuda", generator=g)
+    key = np.array([0, 2023], dtype=np.uint32)
+    ell, sigma = 4.0, 0.5
+
+    def run():
+        U = ops.rademacher_probes(key, N, P, True)
+        al, be, fl = ops.lanczos("se", x, ell, sigma**2 + 1e-10, U, m)
+        c, mu, it = ops.gpr_fit_iter("se", x, y, ell, sigma, 50, key)
+        _, piv = ops.rpcholesky("se", x, M, ell, key, True, want_factor=False)
+        xl = ops.gather_rows(x, piv)
+        lml = ops.sgpr_lml("se", x, y, xl, ell, sigma)
+        cs, mus = ops.sgpr_fit("se", x, y, xl, ell, sigma)
+        torch.cuda.synchronize()
+        return dict(alpha=al.cpu().numpy(), beta=be.cpu().numpy(), c=c.cpu().numpy(), it=it,
+                    lml=lml.cpu().numpy(), cs=cs.cpu().numpy())
+
+    ref = run()  # world == 1 context
+    ops.comm_init_from_torch_distributed()
+    dist.barrier()
+    t0 = time.perf_counter()
+    out = run()
+    dt = time.perf_counter() - t0
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))  # noqa: E731
+    rep = dict(rank=rank, world=world, N=N, alpha=rel(out["alpha"], ref["alpha"]), beta=rel(out["beta"], ref["beta"]),
+               c=rel(out["c"], ref["c"]), iters=(out["it"], ref["it"]), sgpr_lml=rel(out["lml"], ref["lml"]),
+               sgpr_c=rel(out["cs"], ref["cs"]), seconds=dt)
+    ok = rep["alpha"] < 1e-9 and rep["beta"] < 1e-9 and rep["c"] < 1e-8 and out["it"] == ref["it"] and \
+        rep["sgpr_lml"] < 1e-10 and rep["sgpr_c"] < 1e-6
+    rep["ok"] = bool(ok)
+    print(json.dumps(rep), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
