@@ -1,0 +1,333 @@
+// Family 1b: Hessian-Jacobian kernel matrix (training on derivative values) for sm_100a.
+//
+// Replaces _squared_exponential_kernel_d01kj (gpx/kernels/kernels.py:804-831) and
+// _matern52_kernel_d01kj (gpx/kernels/kernels.py:1253-1283), _A_derivs_lhs
+// (gpx/models/_gpr.py:66-91), _lml_derivs_dense (824-870) and _fit_derivs_dense (313-344).
+//
+// With row index i = s*nv + v and A[i][f] = J[s][f][v] the reference's einsums collapse to
+//   out[i][j] = c1[s][t] * (A1 A2^T)[i][j] - c2[s][t] * a_i,t * b_j,s
+//   a_i,t = kappa (q1_i - (A1 x2^T)[i][t]),  b_j,s = kappa ((A2 x1^T)[j][s] - q2_j),  q_i = A[i] . x_s
+//   SE:   kappa = 2/l^2,   c2 = exp(-d2),             c1 = (2/l^2) c2
+//   M52:  kappa = sqrt5/l, c2 = 5/(3 l^2) exp(-d),    c1 = c2 (1 + d)          
+// so the (N nv) x (N nv) matrix is ONE FP64 tensor-core GEMM (K = nf, operand tiles by bulk TMA)
+// with a fused per-(s,t) scalar / rank-1 epilogue; the reference's (N, N, nf) temporaries are
+// never formed.
+#include "../../include/gpxb200.h"
+#include "chol.cuh"
+#include "gemm.cuh"
+#include "gram.cuh"
+#include "mma.cuh"
+#include "small_kernels.cuh"
+
+namespace gpxb {
+
+namespace {
+
+constexpr int TB = 128;
+constexpr int NT = 256;
+
+struct HessParams {
+  const double* A1;
+  int n1;
+  const double* A2;
+  int n2;
+  int S, Dp, nv1, nv2, Ns1, Ns2;
+  const double* C1;
+  const double* C2;
+  const double* P12;  // [n1][Ns2]
+  const double* P21;  // [n2][Ns1]
+  double kappa, diag_add;
+  int sym, lower_only;
+  double* out;
+  long long ldo;
+  int vec_out, tiles_m, tiles_n;
+};
+
+// AJ[i = s*nv + v][f] = J[s][f][v];  AJ[i][Dp] = q_i = sum_f J[s][f][v] x[s][f]
+__global__ void prep_hess_kernel(const double* __restrict__ x, const double* __restrict__ J, int N, int nf,
+                                 int nv, int S, int Dp, double* __restrict__ AJ) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * nv) return;
+  const int s = (int)(i / nv), v = (int)(i % nv);
+  const double* Js = J + (long long)s * nf * nv + v;
+  const double* xs = x + (long long)s * nf;
+  double* a = AJ + i * S;
+  double q = 0.0;
+  for (int f = 0; f < nf; ++f) {
+    const double jv = Js[(long long)f * nv];
+    a[f] = jv;
+    q += jv * xs[f];
+  }
+  for (int f = nf; f < S; ++f) a[f] = 0.0;
+  a[Dp] = q;
+}
+
+// per sample pair: c1, c2 from d2 = |z_s|^2 - 2 z_s.z_t + |z_t|^2 + 1e-12 (exact 1e-12 on the diagonal)
+__global__ void pair_coef_kernel(const double* __restrict__ Z1, int Ns1, const double* __restrict__ Z2,
+                                 int Ns2, int S, int Dp, int kind, double ell, int sym,
+                                 double* __restrict__ C1, double* __restrict__ C2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Ns1 * Ns2) return;
+  const int s = (int)(idx / Ns2), t = (int)(idx % Ns2);
+  const double* a = Z1 + (long long)s * S;
+  const double* b = Z2 + (long long)t * S;
+  double dot = 0.0;
+  for (int f = 0; f < Dp; ++f) dot += a[f] * b[f];
+  double d2 = ((a[Dp] - 2.0 * dot) + b[Dp]) + 1e-12;
+  if (sym && s == t) d2 = 1e-12;
+  if (kind == KIND_SE) {
+    const double e = exp(-d2);
+    C2[idx] = e;
+    C1[idx] = (2.0 / (ell * ell)) * e;
+  } else {
+    const double d = 2.23606797749979 * sqrt(fmax(d2, 1e-36));
+    const double c = (5.0 / (3.0 * ell * ell)) * exp(-d);
+    C2[idx] = c;
+    C1[idx] = c * (1.0 + d);
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) hess_kernel(const HessParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* sA1 = reinterpret_cast<double*>(smem_raw + 128);
+  double* sA2 = sA1 + TB * p.S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lq = lane & 3;
+
+  int ti, tj;
+  if (p.lower_only) {
+    const long long t = blockIdx.x;
+    long long i = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (i * (i + 1) / 2 > t) --i;
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    ti = (int)i;
+    tj = (int)(t - i * (i + 1) / 2);
+  } else {
+    ti = blockIdx.x / p.tiles_n;
+    tj = blockIdx.x % p.tiles_n;
+  }
+  const int row0 = ti * TB, col0 = tj * TB;
+  const int rows1 = min(TB, p.n1 - row0), rows2 = min(TB, p.n2 - col0);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t b1 = (uint32_t)rows1 * p.S * 8u, b2 = (uint32_t)rows2 * p.S * 8u;
+    mbar_arrive_expect_tx(bar, b1 + b2);
+    tma_bulk_g2s(sA1, p.A1 + (long long)row0 * p.S, b1, bar);
+    tma_bulk_g2s(sA2, p.A2 + (long long)col0 * p.S, b2, bar);
+  }
+  mbar_wait(bar, 0);
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const double* a_base = sA1 + (wm * 64 + lr) * p.S + lq;
+  const double* b_base = sA2 + (wn * 32 + lr) * p.S + lq;
+  const int S8 = 8 * p.S;
+  for (int k = 0; k < p.Dp; k += 4) {
+    double a[8], b[4];
+#pragma unroll
+    for (int mf = 0; mf < 8; ++mf) a[mf] = a_base[mf * S8 + k];
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) b[nf] = b_base[nf * S8 + k];
+#pragma unroll
+    for (int mf = 0; mf < 8; ++mf)
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
+  }
+
+  // ---- fused epilogue: per-(s,t) scalars and the rank-1 term ----
+#pragma unroll
+  for (int nf = 0; nf < 4; ++nf) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int cl = wn * 32 + nf * 8 + lq * 2 + e;
+      const int gj = col0 + cl;
+      if (gj >= p.n2) continue;
+      const int t = gj / p.nv2;
+      const double q2 = sA2[cl * p.S + p.Dp];
+#pragma unroll
+      for (int mf = 0; mf < 8; ++mf) {
+        const int rl = wm * 64 + mf * 8 + lr;
+        const int gi = row0 + rl;
+        if (gi >= p.n1 || (p.lower_only && gj > gi)) continue;
+        const int s = gi / p.nv1;
+        const double q1 = sA1[rl * p.S + p.Dp];
+        const double a = p.kappa * (q1 - p.P12[(long long)gi * p.Ns2 + t]);
+        const double b = p.kappa * (p.P21[(long long)gj * p.Ns1 + s] - q2);
+        const long long st = (long long)s * p.Ns2 + t;
+        double v = p.C1[st] * acc[mf][nf][e] - p.C2[st] * a * b;
+        if (p.sym && gi == gj) v += p.diag_add;
+        p.out[(long long)gi * p.ldo + gj] = v;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// out[(n1*nv1) x (n2*nv2)] = d01kj(x1, x2; J1, J2) (+ diag_add I when the operands are the same).
+int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, int nv1, const double* x2,
+              const double* J2, int Ns2, int nv2, int nf, double ell, double diag_add, double* out, long long ldo,
+              int lower_only, cudaStream_t s) {
+  GPXB_ARG_CHECK(kind == KIND_SE || kind == KIND_M52, -50);  // the reference hand-writes d01kj for these two
+  GPXB_ARG_CHECK(Ns1 > 0 && Ns2 > 0 && nv1 > 0 && nv2 > 0 && nf > 0, -51);
+  const ZLayout zl = z_layout(nf);
+  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -52);
+  const bool sym = (x1 == x2) && (J1 == J2) && (Ns1 == Ns2) && (nv1 == nv2);
+  GPXB_ARG_CHECK(!lower_only || sym, -53);
+  const long long n1 = (long long)Ns1 * nv1, n2 = (long long)Ns2 * nv2;
+  GPXB_ARG_CHECK(n1 < (1LL << 31) && n2 < (1LL << 31), -54);
+  DevBuf bA1, bA2, bZ1, bZ2, bX1, bX2, bC1, bC2, bP12, bP21;
+  GPXB_TRY(bA1.alloc(sizeof(double) * (size_t)n1 * zl.S, s));
+  GPXB_TRY(bZ1.alloc(sizeof(double) * (size_t)Ns1 * zl.S, s));
+  GPXB_TRY(bX1.alloc(sizeof(double) * (size_t)Ns1 * zl.S, s));
+  GPXB_TRY(bC1.alloc(sizeof(double) * (size_t)Ns1 * Ns2, s));
+  GPXB_TRY(bC2.alloc(sizeof(double) * (size_t)Ns1 * Ns2, s));
+  GPXB_TRY(bP12.alloc(sizeof(double) * (size_t)n1 * Ns2, s));
+  double *A1 = bA1.as<double>(), *Z1 = bZ1.as<double>(), *X1 = bX1.as<double>();
+  double *A2 = A1, *Z2 = Z1, *X2 = X1;
+  prep_hess_kernel<<<ceil_div(n1, 128), 128, 0, s>>>(x1, J1, Ns1, nf, nv1, zl.S, zl.Dp, A1);
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(prep_z(ctx, x1, nf, Ns1, zl, ell, Z1, s));
+  GPXB_TRY(prep_z(ctx, x1, nf, Ns1, zl, 1.0, X1, s));
+  if (!sym) {
+    GPXB_TRY(bA2.alloc(sizeof(double) * (size_t)n2 * zl.S, s));
+    GPXB_TRY(bZ2.alloc(sizeof(double) * (size_t)Ns2 * zl.S, s));
+    GPXB_TRY(bX2.alloc(sizeof(double) * (size_t)Ns2 * zl.S, s));
+    A2 = bA2.as<double>(); Z2 = bZ2.as<double>(); X2 = bX2.as<double>();
+    prep_hess_kernel<<<ceil_div(n2, 128), 128, 0, s>>>(x2, J2, Ns2, nf, nv2, zl.S, zl.Dp, A2);
+    GPXB_LAUNCHED(ctx);
+    GPXB_TRY(prep_z(ctx, x2, nf, Ns2, zl, ell, Z2, s));
+    GPXB_TRY(prep_z(ctx, x2, nf, Ns2, zl, 1.0, X2, s));
+  }
+  pair_coef_kernel<<<ceil_div((long long)Ns1 * Ns2, 256), 256, 0, s>>>(Z1, Ns1, Z2, Ns2, zl.S, zl.Dp, kind, ell,
+                                                                         sym ? 1 : 0, bC1.as<double>(),
+                                                                         bC2.as<double>());
+  GPXB_LAUNCHED(ctx);
+  {
+    GemmArgs g;  // P12 = A1 X2^T   [n1 x Ns2]
+    g.M = (int)n1; g.N = Ns2; g.K = zl.Dp;
+    g.A = A1; g.lda = zl.S; g.a_kmajor = true;
+    g.B = X2; g.ldb = zl.S; g.b_kmajor = true;
+    g.C = bP12.as<double>(); g.ldc = Ns2;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  const double* P21 = bP12.as<double>();
+  if (!sym) {
+    GPXB_TRY(bP21.alloc(sizeof(double) * (size_t)n2 * Ns1, s));
+    GemmArgs g;  // P21 = A2 X1^T   [n2 x Ns1]
+    g.M = (int)n2; g.N = Ns1; g.K = zl.Dp;
+    g.A = A2; g.lda = zl.S; g.a_kmajor = true;
+    g.B = X1; g.ldb = zl.S; g.b_kmajor = true;
+    g.C = bP21.as<double>(); g.ldc = Ns1;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+    P21 = bP21.as<double>();
+  }
+  HessParams p;
+  p.A1 = A1; p.n1 = (int)n1; p.A2 = A2; p.n2 = (int)n2;
+  p.S = zl.S; p.Dp = zl.Dp; p.nv1 = nv1; p.nv2 = nv2; p.Ns1 = Ns1; p.Ns2 = Ns2;
+  p.C1 = bC1.as<double>(); p.C2 = bC2.as<double>(); p.P12 = bP12.as<double>(); p.P21 = P21;
+  p.kappa = (kind == KIND_SE) ? 2.0 / (ell * ell) : 2.23606797749979 / ell;
+  p.diag_add = diag_add; p.sym = sym ? 1 : 0; p.lower_only = lower_only;
+  p.out = out; p.ldo = ldo; p.vec_out = 0;
+  p.tiles_m = ceil_div(n1, TB); p.tiles_n = ceil_div(n2, TB);
+  const long long grid = lower_only ? (long long)p.tiles_m * (p.tiles_m + 1) / 2 : (long long)p.tiles_m * p.tiles_n;
+  GPXB_ARG_CHECK(grid < (1LL << 31), -55);
+  const int smem = 128 + 2 * TB * p.S * (int)sizeof(double);
+  GPXB_CUDA_CHECK(cudaFuncSetAttribute(hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  hess_kernel<<<(int)grid, NT, smem, s>>>(p);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
+namespace {
+// scal: [0] quad, [1] sum log L_ii
+__global__ void finalize_derivs_kernel(const double* __restrict__ scal, long long n, double* __restrict__ out) {
+  const double m = (double)n;
+  out[0] = (-0.5 * scal[0] - scal[1] - m * 0.5 * log(2.0 * 3.141592653589793)) / m;
+}
+// jaccoef[s][f] = sum_v c[s*nv + v] J[s][f][v]     (gpx/models/gpr.py:475-476)
+__global__ void jaccoef_kernel(const double* __restrict__ c, const double* __restrict__ J, int N, int nf, int nv,
+                               double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * nf) return;
+  const int s = (int)(idx / nf);
+  const double* Jr = J + idx * nv;
+  const double* cs = c + (long long)s * nv;
+  double a = 0.0;
+  for (int v = 0; v < nv; ++v) a += cs[v] * Jr[v];
+  out[idx] = a;
+}
+}  // namespace
+
+// lml/n of _lml_derivs_dense (zero mean); if c_out: also c = A^-1 y (n) and jaccoef (N x nf).
+int gpr_derivs(Ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf, int nv,
+               double ell, double sigma, double* lml_out, double* c_out, double* jaccoef_out, cudaStream_t s) {
+  const long long n = (long long)N * nv;
+  GPXB_ARG_CHECK(n > 0 && n < (1LL << 31), -1);
+  const double s2 = sigma * sigma + 1e-10;
+  DevBuf bA, bInv, bR, bSc;
+  GPXB_TRY(bA.alloc(sizeof(double) * (size_t)n * n, s));
+  GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles((int)n), s));
+  GPXB_TRY(bR.alloc(sizeof(double) * (size_t)n, s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * 4, s));
+  double *A = bA.as<double>(), *inv = bInv.as<double>(), *r = bR.as<double>(), *scal = bSc.as<double>();
+  GPXB_TRY(hess_gram(ctx, kind, x, J, N, nv, x, J, N, nv, nf, ell, s2, A, n, 1, s));
+  GPXB_TRY(potrf_lower(ctx, A, n, (int)n, inv, s));
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(r, y, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  GPXB_TRY(trsm_right_lt(ctx, A, n, inv, r, n, 1, (int)n, s));
+  if (lml_out) {
+    GPXB_TRY(logdet_lower(ctx, A, n, (int)n, scal + 1, 1.0, s));
+    sk::sumsq_kernel<<<1, 1024, 0, s>>>(r, n, scal + 0, 0);
+    GPXB_LAUNCHED(ctx);
+    finalize_derivs_kernel<<<1, 1, 0, s>>>(scal, n, lml_out);
+    GPXB_LAUNCHED(ctx);
+  }
+  if (c_out) {
+    GPXB_TRY(trsm_right_l(ctx, A, n, inv, r, n, 1, (int)n, s));
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(c_out, r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    if (jaccoef_out) {
+      jaccoef_kernel<<<ceil_div((long long)N * nf, 256), 256, 0, s>>>(r, J, N, nf, nv, jaccoef_out);
+      GPXB_LAUNCHED(ctx);
+    }
+  }
+  return 0;
+}
+
+}  // namespace gpxb
+
+using gpxb::Ctx;
+
+extern "C" {
+
+int gpxb_hess_gram(gpxb_ctx* ctx, int kind, const double* x1, const double* J1, int n1, int nv1,
+                   const double* x2, const double* J2, int n2, int nv2, int nf, double ell, double diag_add,
+                   double* out, long long ldo, int lower_only, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x1 && J1 && x2 && J2 && out, -1);
+  return gpxb::hess_gram(reinterpret_cast<Ctx*>(ctx), kind, x1, J1, n1, nv1, x2, J2, n2, nv2, nf, ell, diag_add,
+                         out, ldo, lower_only, (cudaStream_t)stream);
+}
+
+int gpxb_gpr_lml_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,
+                        int nv, double ell, double sigma, double* out, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && y && out, -1);
+  return gpxb::gpr_derivs(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, N, nf, nv, ell, sigma, out, nullptr, nullptr,
+                          (cudaStream_t)stream);
+}
+
+int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,
+                        int nv, double ell, double sigma, double* c_out, double* jaccoef_out, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && y && c_out, -1);
+  return gpxb::gpr_derivs(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, N, nf, nv, ell, sigma, nullptr, c_out,
+                          jaccoef_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

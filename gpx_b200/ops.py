@@ -149,6 +149,53 @@ def gpr_predict(kind, x_train, x, c, mu, ell, sigma, full_covariance=False):
     return (mean, cov) if full_covariance else mean
 
 
+def hess_gram(kind, x1, J1, x2, J2, ell, diag_add=0.0, lower_only=False):
+    """Kernel.d01kj(x1, x2, params, J1, J2): ((n1*nv1), (n2*nv2)).  Same tensors twice -> symmetric path."""
+    ctx = context()
+    x1, J1 = _f64(x1), _f64(J1)
+    sym = (x2 is x1 or x2 is None) and (J2 is J1 or J2 is None)
+    x2, J2 = (x1, J1) if sym else (_f64(x2), _f64(J2))
+    n1, nf, nv1 = J1.shape
+    n2, _, nv2 = J2.shape
+    out = torch.empty((n1 * nv1, n2 * nv2), dtype=torch.float64, device=x1.device)
+    if lower_only:
+        out.zero_()
+    check(
+        ctx.lib.gpxb_hess_gram(ctx.handle, _kind(kind), ptr(x1), ptr(J1), n1, nv1, ptr(x2), ptr(J2), n2, nv2, nf,
+                               float(ell), float(diag_add), ptr(out), out.stride(0), int(bool(lower_only)),
+                               stream_ptr()),
+        "gpxb_hess_gram",
+    )
+    return out
+
+
+def gpr_lml_derivs(kind, x, J, y, ell, sigma):
+    ctx = context()
+    x, J, y = _f64(x), _f64(J), _f64(y)
+    N, nf, nv = J.shape
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_gpr_lml_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), N, nf, nv, float(ell),
+                                    float(sigma), ptr(out), stream_ptr()),
+        "gpxb_gpr_lml_derivs",
+    )
+    return out
+
+
+def gpr_fit_derivs(kind, x, J, y, ell, sigma):
+    ctx = context()
+    x, J, y = _f64(x), _f64(J), _f64(y)
+    N, nf, nv = J.shape
+    c = torch.empty((N * nv, 1), dtype=torch.float64, device=x.device)
+    jc = torch.empty((N, nf), dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_gpr_fit_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), N, nf, nv, float(ell),
+                                    float(sigma), ptr(c), ptr(jc), stream_ptr()),
+        "gpxb_gpr_fit_derivs",
+    )
+    return c, jc
+
+
 def kmatvec(kind, x_rows, x_all, V, ell, diag_add=0.0, row_offset=None):
     """(K(x_rows, x_all) + diag_add*I) V without storing K.  Passing the same tensor for
     x_rows and x_all puts the shifted diagonal in place (row_offset = 0)."""

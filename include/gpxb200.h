@@ -51,6 +51,23 @@ int gpxb_gram(gpxb_ctx* ctx, int kind, const double* x1, int n1, const double* x
               double ell, double diag_add, double* out, long long ldo, int lower_only,
               gpxb_stream stream);
 
+/* ---- Family 1b: Hessian-Jacobian kernel (training on derivative values) --------------- */
+/* out[(n1*nv1) x (n2*nv2)] = Kernel.d01kj(x1, x2, params, J1, J2) (+ diag_add * I when both operands
+ * are the same arrays); row index = sample * nv + variable.  x: n x nf, J: n x nf x nv row-major.
+ * kind: GPXB_SE (gpx/kernels/kernels.py:804-831) or GPXB_M52 (:1253-1283); _A_derivs_lhs
+ * (gpx/models/_gpr.py:66-91).  lower_only requires identical operands. */
+int gpxb_hess_gram(gpxb_ctx* ctx, int kind, const double* x1, const double* J1, int n1, int nv1,
+                   const double* x2, const double* J2, int n2, int nv2, int nf, double ell, double diag_add,
+                   double* out, long long ldo, int lower_only, gpxb_stream stream);
+/* *out (device) = lml / (N nv) of _lml_derivs_dense (gpx/models/_gpr.py:824-870; zero mean as forced by
+ * gpx/models/gpr.py:160, 173).  y: N x nv. */
+int gpxb_gpr_lml_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,
+                        int nv, double ell, double sigma, double* out, gpxb_stream stream);
+/* c[N nv] = (d01kj + (sigma^2+1e-10) I)^-1 y and jaccoef[N x nf] = einsum("sv,sfv->sf", c, J)
+ * (gpx/models/_gpr.py:313-344, gpx/models/gpr.py:475-476); jaccoef_out may be NULL. */
+int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,
+                        int nv, double ell, double sigma, double* c_out, double* jaccoef_out, gpxb_stream stream);
+
 /* ---- Family 2: blocked FP64 Cholesky / TRSM / log-det / inverse ---------------------- */
 /* C[M x N] = alpha * op(A) * op(B) + beta * C on the FP64 tensor pipe.  transa = 0: A is M x K
  * row-major; 1: A is stored K x M.  transb = 0: B is K x N row-major; 1: B is stored N x K. */

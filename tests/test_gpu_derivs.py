@@ -1,0 +1,68 @@
+"""GPU parity: Hessian-Jacobian kernel (Family 1b) and GPR on derivative values (config 3 shape:
+x = coordinates, J = identity + dense perturbation) against the oracle's literal einsum form."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_numpy as R  # noqa: E402
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def _xj(N, nf, nv, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((N, nf))
+    J = 0.1 * rng.standard_normal((N, nf, nv))
+    for k in range(min(nf, nv)):
+        J[:, k, k] += 1.0
+    y = rng.standard_normal((N, nv))
+    return x, J, y
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+@pytest.mark.parametrize("N1,N2,nf,nv1,nv2", [(7, 5, 6, 6, 4), (20, 31, 9, 9, 9), (5, 5, 2, 1, 1), (12, 3, 90, 90, 90)])
+def test_d01kj_entries(kind, N1, N2, nf, nv1, nv2):
+    from gpx_b200 import ops
+
+    x1, J1, _ = _xj(N1, nf, nv1, 1)
+    x2, J2, _ = _xj(N2, nf, nv2, 2)
+    ell = 0.9 * np.sqrt(nf)
+    ref = R.d01kj(kind, x1, x2, ell, J1, J2)
+    out = host(ops.hess_gram(kind, dev(x1), dev(J1), dev(x2), dev(J2), ell))
+    assert np.max(np.abs(out - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_d01kj_symmetric_lower_with_noise(kind):
+    from gpx_b200 import ops
+
+    x, J, _ = _xj(40, 12, 12, 3)
+    ell = 3.0
+    ref = R.d01kj(kind, x, x, ell, J, J) + 0.04 * np.eye(480)
+    xd, Jd = dev(x), dev(J)
+    out = host(ops.hess_gram(kind, xd, Jd, xd, Jd, ell, diag_add=0.04, lower_only=True))
+    assert np.max(np.abs(np.tril(out) - np.tril(ref))) < 1e-12
+    assert np.all(np.triu(out, 1) == 0.0)
+
+
+@pytest.mark.parametrize("kind,N,nf,nv", [("se", 64, 90, 90), ("m52", 50, 30, 30), ("se", 128, 12, 9)])
+def test_lml_and_fit_derivs(kind, N, nf, nv):
+    from gpx_b200 import ops
+
+    x, J, y = _xj(N, nf, nv, 2)
+    ell, sigma = np.sqrt(nf), 0.05
+    ref = R.lml_derivs_dense(kind, x, y, J, ell, sigma)
+    out = float(host(ops.gpr_lml_derivs(kind, dev(x), dev(J), dev(y), ell, sigma))[0])
+    assert abs(out - ref) < 1e-8 * abs(ref)
+    c_ref, _, jc_ref = R.fit_derivs_dense(kind, x, y, J, ell, sigma)
+    c, jc = ops.gpr_fit_derivs(kind, dev(x), dev(J), dev(y), ell, sigma)
+    assert np.max(np.abs(host(c) - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
+    assert np.max(np.abs(host(jc) - jc_ref)) < 1e-8 * np.max(np.abs(jc_ref))
