@@ -78,6 +78,13 @@ struct TileLoader {
     }
   }
 
+  // interior K tile of an aligned operand: one LDGSTS per chunk, nothing else
+  __device__ __forceinline__ void load_fast(double* __restrict__ s, int tile_idx) {
+    const long long off = (long long)tile_idx * kstep;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) cp_async16(s + soff[i], ptr[i] + off, nb[i]);
+  }
+
   // k0: first k of this tile; kmax: true K bound; interior tiles skip every check.
   __device__ __forceinline__ void load(double* __restrict__ s, int k0, int kmax, int tile_idx) {
     if (vec) {
@@ -190,22 +197,33 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
   const int a_off = AK ? (wm * (8 * MF) + lr) * LDK + lq : lq * LDM + wm * (8 * MF) + lr;
   const int b_off = BKM ? (wn * (8 * NF) + lr) * LDK + lq : lq * LDM + wn * (8 * NF) + lr;
 
+  // Warps of one scheduler (warp % 4) issue their global->shared copies at different k-steps
+  // of the tile, so the tensor pipe always has DMMAs from the other warps to run.
+  const int lpos = (warp >> 2) & 3;
+  const bool fast = p.vecA && p.vecB;
   for (int kt = 0; kt < nk; ++kt) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int nxt = kt + STAGES - 1;
-      if (nxt < nk) {
-        double* sa = smem + (nxt % STAGES) * STAGE_DBL;
-        la.load(sa, k_lo + nxt * BK, p.K, nxt);
-        lb.load(sa + TILE_DBL, k_lo + nxt * BK, p.K, nxt);
-      }
-      cp_async_commit();
-    }
+    const int nxt = kt + STAGES - 1;
+    const bool do_load = nxt < nk;
+    const bool interior = fast && (k_lo + (nxt + 1) * BK <= p.K);
+    double* sn = smem + (nxt % STAGES) * STAGE_DBL;
     const double* sA = smem + (kt % STAGES) * STAGE_DBL + a_off;
     const double* sB = smem + (kt % STAGES) * STAGE_DBL + TILE_DBL + b_off;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
+      if (ks == lpos) {
+        if (do_load) {
+          if (interior) {
+            la.load_fast(sn, nxt);
+            lb.load_fast(sn + TILE_DBL, nxt);
+          } else {
+            la.load(sn, k_lo + nxt * BK, p.K, nxt);
+            lb.load(sn + TILE_DBL, k_lo + nxt * BK, p.K, nxt);
+          }
+        }
+        cp_async_commit();
+      }
       double a[MF], b[NF];
 #pragma unroll
       for (int mf = 0; mf < MF; ++mf) a[mf] = AK ? sA[mf * 8 * LDK + ks * 4] : sA[ks * 4 * LDM + mf * 8];
