@@ -52,9 +52,21 @@ potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restri
     for (int i = j + 1 + tid; i < n; i += LEAF_NT) S[i * LS + j] /= d;
     if (tid == 0) Ld[j] = d;
     __syncthreads();
-    for (int i = j + 1 + ty; i < n; i += 16) {
-      const double lij = S[i * LS + j];
-      for (int k = j + 1 + tx; k <= i; k += 32) S[i * LS + k] -= lij * S[k * LS + j];
+    // trailing update; every thread keeps 4 independent rows in flight to hide LDS latency
+    for (int i0 = j + 1 + ty; i0 < n; i0 += 64) {
+      const int i1 = i0 + 16, i2 = i0 + 32, i3 = i0 + 48;
+      const double l0 = S[i0 * LS + j];
+      const double l1 = i1 < n ? S[i1 * LS + j] : 0.0;
+      const double l2 = i2 < n ? S[i2 * LS + j] : 0.0;
+      const double l3 = i3 < n ? S[i3 * LS + j] : 0.0;
+      const int kmax = min(n - 1, i3);
+      for (int k = j + 1 + tx; k <= kmax; k += 32) {
+        const double lk = S[k * LS + j];
+        if (k <= i0) S[i0 * LS + k] -= l0 * lk;
+        if (i1 < n && k <= i1) S[i1 * LS + k] -= l1 * lk;
+        if (i2 < n && k <= i2) S[i2 * LS + k] -= l2 * lk;
+        if (i3 < n && k <= i3) S[i3 * LS + k] -= l3 * lk;
+      }
     }
     __syncthreads();
   }
@@ -75,7 +87,16 @@ potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restri
     double r = 0.0;
     const int i = j + 1 + rowslot;
     if (i < n) {
-      for (int k = j + 1 + sub; k <= i; k += 4) r += S[i * LS + k] * S[k * LS + j];
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+      int k = j + 1 + sub;
+      for (; k + 12 <= i; k += 16) {
+        r0 += S[i * LS + k] * S[k * LS + j];
+        r1 += S[i * LS + k + 4] * S[(k + 4) * LS + j];
+        r2 += S[i * LS + k + 8] * S[(k + 8) * LS + j];
+        r3 += S[i * LS + k + 12] * S[(k + 12) * LS + j];
+      }
+      for (; k <= i; k += 4) r0 += S[i * LS + k] * S[k * LS + j];
+      r = (r0 + r1) + (r2 + r3);
     }
     r += __shfl_xor_sync(0xffffffffu, r, 1);
     r += __shfl_xor_sync(0xffffffffu, r, 2);
@@ -124,11 +145,135 @@ inline int split_point(int n) {
 
 }  // namespace
 
+namespace {
+constexpr int TRSV_MAXM = 4;
+
+// x_k = inv_kk b_k (forward, trans_inv = 0: x = inv b) or inv_kk^T b_k (backward) for m right-hand
+// sides stored as rows of B (ld ldb); one CTA, 128 threads, in place.
+__global__ void __launch_bounds__(LB) trsv_diag_kernel(const double* __restrict__ inv, double* __restrict__ B,
+                                                       long long ldb, int m, int nb, int backward) {
+  __shared__ double sb[TRSV_MAXM][LB];
+  const int t = threadIdx.x;
+  for (int r = 0; r < m; ++r) sb[r][t] = (t < nb) ? B[(long long)r * ldb + t] : 0.0;
+  __syncthreads();
+  if (t >= nb) return;
+  double acc[TRSV_MAXM];
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
+  if (!backward) {
+    // x[t] = sum_{c <= t} inv[t][c] b[c]
+    for (int c = 0; c <= t; ++c) {
+      const double v = inv[t * LB + c];
+#pragma unroll
+      for (int r = 0; r < TRSV_MAXM; ++r)
+        if (r < m) acc[r] += v * sb[r][c];
+    }
+  } else {
+    // x[t] = sum_{c >= t} inv[c][t] b[c]
+    for (int c = t; c < nb; ++c) {
+      const double v = inv[c * LB + t];
+#pragma unroll
+      for (int r = 0; r < TRSV_MAXM; ++r)
+        if (r < m) acc[r] += v * sb[r][c];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r)
+    if (r < m) B[(long long)r * ldb + t] = acc[r];
+}
+
+// forward: B[:, j] -= sum_c L[j][c] x[c] for the rows j below the block (one warp per row j)
+__global__ void __launch_bounds__(256) trsv_fwd_update_kernel(const double* __restrict__ Lblk, long long ldl,
+                                                              const double* __restrict__ X, double* __restrict__ B,
+                                                              long long ldb, int m, int nb, int nrows) {
+  __shared__ double sx[TRSV_MAXM][LB];
+  for (int i = threadIdx.x; i < TRSV_MAXM * LB; i += 256) {
+    const int r = i / LB, c = i % LB;
+    sx[r][c] = (r < m && c < nb) ? X[(long long)r * ldb + c] : 0.0;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= nrows) return;
+  const double* lrow = Lblk + (long long)j * ldl;
+  double acc[TRSV_MAXM];
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
+  for (int c = lane; c < nb; c += 32) {
+    const double v = lrow[c];
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) acc[r] += v * sx[r][c];
+  }
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r) {
+    const double sum = warp_sum(acc[r]);
+    if (lane == 0 && r < m) B[(long long)r * ldb + j] -= sum;
+  }
+}
+
+// backward: B[:, j] -= sum_c L[c][j] x[c] for the columns j left of the block (one thread per j)
+__global__ void __launch_bounds__(256) trsv_bwd_update_kernel(const double* __restrict__ Lrows, long long ldl,
+                                                              const double* __restrict__ X, double* __restrict__ B,
+                                                              long long ldb, int m, int nb, int ncols) {
+  __shared__ double sx[TRSV_MAXM][LB];
+  for (int i = threadIdx.x; i < TRSV_MAXM * LB; i += 256) {
+    const int r = i / LB, c = i % LB;
+    sx[r][c] = (r < m && c < nb) ? X[(long long)r * ldb + c] : 0.0;
+  }
+  __syncthreads();
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= ncols) return;
+  double acc[TRSV_MAXM];
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
+#pragma unroll 4
+  for (int c = 0; c < nb; ++c) {
+    const double v = Lrows[(long long)c * ldl + j];
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) acc[r] += v * sx[r][c];
+  }
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r)
+    if (r < m) B[(long long)r * ldb + j] -= acc[r];
+}
+
+// few right-hand sides (m <= 4): blocked substitution with GEMV updates -- HBM bound (reads L once)
+int trsv_few(Ctx* ctx, const double* L, long long ldl, const double* inv, double* B, long long ldb, int m, int n,
+             bool transposed_solve, cudaStream_t s) {
+  const int nblk = (n + LB - 1) / LB;
+  if (transposed_solve) {
+    // X L^T = B  <=>  L x = b: forward over blocks
+    for (int k = 0; k < nblk; ++k) {
+      const int c0 = k * LB, nb = min(LB, n - c0);
+      trsv_diag_kernel<<<1, LB, 0, s>>>(inv + (long long)k * LB * LB, B + c0, ldb, m, nb, 0);
+      const int below = n - c0 - nb;
+      if (below > 0)
+        trsv_fwd_update_kernel<<<(below + 7) / 8, 256, 0, s>>>(L + (long long)(c0 + nb) * ldl + c0, ldl, B + c0,
+                                                                B + c0 + nb, ldb, m, nb, below);
+      ctx->launches += below > 0 ? 2 : 1;
+    }
+  } else {
+    // X L = B  <=>  L^T x = b: backward over blocks
+    for (int k = nblk - 1; k >= 0; --k) {
+      const int c0 = k * LB, nb = min(LB, n - c0);
+      trsv_diag_kernel<<<1, LB, 0, s>>>(inv + (long long)k * LB * LB, B + c0, ldb, m, nb, 1);
+      if (c0 > 0)
+        trsv_bwd_update_kernel<<<(c0 + 255) / 256, 256, 0, s>>>(L + (long long)c0 * ldl, ldl, B + c0, B, ldb, m, nb,
+                                                                 c0);
+      ctx->launches += c0 > 0 ? 2 : 1;
+    }
+  }
+  GPXB_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
 // X * L^T = B  (X = B L^-T), B is m x n row-major, overwritten.  inv: leaf inverses of L's
 // diagonal blocks (128x128 packed each), L n x n lower.
 int trsm_right_lt(Ctx* ctx, const double* L, long long ldl, const double* inv, double* B,
                   long long ldb, int m, int n, cudaStream_t s) {
   if (m <= 0 || n <= 0) return 0;
+  if (m <= TRSV_MAXM && n > LB) return trsv_few(ctx, L, ldl, inv, B, ldb, m, n, true, s);
   if (n <= LB) {
     GemmArgs g;
     g.M = m; g.N = n; g.K = n;
@@ -156,6 +301,7 @@ int trsm_right_lt(Ctx* ctx, const double* L, long long ldl, const double* inv, d
 int trsm_right_l(Ctx* ctx, const double* L, long long ldl, const double* inv, double* B,
                  long long ldb, int m, int n, cudaStream_t s) {
   if (m <= 0 || n <= 0) return 0;
+  if (m <= TRSV_MAXM && n > LB) return trsv_few(ctx, L, ldl, inv, B, ldb, m, n, false, s);
   if (n <= LB) {
     GemmArgs g;
     g.M = m; g.N = n; g.K = n;

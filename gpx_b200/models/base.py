@@ -81,6 +81,28 @@ class BaseGP:
                             key_precond=key_precond if key_precond is not None else gpxargs.key_precond)
         return -lml if return_negative else lml
 
+    def log_marginal_likelihood_derivs(self, x, y, jacobian, return_negative=False, iterative=False, **kwargs):
+        """gpx/models/base.py:304-345."""
+        lml = self._lml_derivs_fun(self.state, x=x, y=y, jacobian=jacobian, iterative=iterative, **kwargs)
+        return -lml if return_negative else lml
+
+    def fit_derivs(self, x, y, jacobian, minimize=False, iterative=False, **kwargs):
+        """gpx/models/base.py:487-589.  Hyper-parameter optimisation on derivative targets needs the
+        gradient of the derivative LML, a 'next' row: pass minimize=False."""
+        if minimize:
+            raise NotImplementedError("fit_derivs(minimize=True) needs d lml_derivs / d theta (next row)")
+        self.state = self._fit_derivs_fun(self.state, x=x, y=y, jacobian=jacobian, iterative=iterative)
+        return self
+
+    def predict_derivs(self, x, jacobian, full_covariance=False, iterative=False):
+        """gpx/models/base.py:189-225."""
+        return self._predict_derivs_fun(self.state, x=x, jacobian=jacobian, full_covariance=full_covariance,
+                                        iterative=iterative)
+
+    @property
+    def jacobian_train(self):
+        return self.state.jacobian_train
+
     def loss_and_grad(self, x, y, **loss_kwargs):
         """(loss, {param path: d loss/d value}) -- what jit(value_and_grad(loss)) returns in the
         reference's optimiser loop (gpx/optimizers/scipy_optimize.py:72-78)."""

@@ -115,6 +115,57 @@ def predict(state, x, full_covariance=False, iterative=False):
     return out.cpu().numpy()
 
 
+def _xyj(state, x, y, jacobian):
+    if state.kernel.active_dims is not None:
+        raise NotImplementedError("active_dims with derivative training is not supported")
+    xd = _to_device(x)
+    Jd = _to_device(jacobian)
+    yd = None if y is None else _to_device(y)
+    return xd, yd, Jd
+
+
+def log_marginal_likelihood_derivs(state, x, y, jacobian, iterative=False, **_ignored):
+    """gpx/models/gpr.py:121-174 -> _lml_derivs_dense (gpx/models/_gpr.py:824-870); zero mean."""
+    if iterative:
+        raise NotImplementedError("matrix-free Hessian mat-vec is a 'next' row (SURVEY.md 8f N2)")
+    kernel, ell, sigma = _hyper(state)
+    xd, yd, Jd = _xyj(state, x, y, jacobian)
+    out = ops.gpr_lml_derivs(kernel.kind, xd, Jd, yd, ell, sigma)
+    return float(out.cpu().numpy()[0])
+
+
+def fit_derivs(state, x, y, jacobian, iterative=False, **_ignored):
+    """gpx/models/gpr.py:437-489 -> _fit_derivs_dense (gpx/models/_gpr.py:313-344) + jaccoef."""
+    if iterative:
+        raise NotImplementedError("matrix-free Hessian mat-vec is a 'next' row (SURVEY.md 8f N2)")
+    kernel, ell, sigma = _hyper(state)
+    xd, yd, Jd = _xyj(state, x, y, jacobian)
+    c, jc = ops.gpr_fit_derivs(kernel.kind, xd, Jd, yd, ell, sigma)
+    return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), jacobian_train=np.asarray(jacobian),
+                             jaccoef=jc.cpu().numpy(), c=c.cpu().numpy(), mu=np.float64(0.0), is_fitted=False,
+                             is_fitted_derivs=True))
+
+
+def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):
+    """gpx/models/gpr.py:596-660 -> _predict_derivs_dense fast path (gpx/models/_gpr.py:509-528):
+    mu + sum_s d01kjc(x_train, x, jaccoef, jacobian)[s], reshaped (ns, nv)."""
+    if not getattr(state, "is_fitted_derivs", False):
+        raise RuntimeError("Model is not fitted on derivatives. Run `fit_derivs` first.")
+    if full_covariance:
+        raise NotImplementedError("predictive covariance of derivative values is a 'next' row (SURVEY.md 8f N2)")
+    import torch
+
+    kernel, ell, _ = _hyper(state)
+    xt = _to_device(state.x_train)
+    jc = _to_device(state.jaccoef).unsqueeze(2).contiguous()  # (N, nf, 1): the contracted Jacobian
+    xs, _, Js = _xyj(state, x, None, jacobian)
+    K = ops.hess_gram(kernel.kind, xt, jc, xs, Js, ell)  # (N, ns*nv)
+    ones = torch.ones((1, K.shape[0]), dtype=torch.float64, device="cuda")
+    mean = ops.gemm(ones, K) + float(state.mu)
+    ns, _, nv = Js.shape
+    return mean.reshape(ns, nv).cpu().numpy()
+
+
 def default_params() -> Dict[str, Parameter]:
     """gpx/models/gpr.py:863-870."""
     return dict(sigma=Parameter(value=1.0, trainable=True, bijector=Softplus(), prior=GammaPrior()))
@@ -135,7 +186,7 @@ def init(kernel: Callable, mean_function: Callable = data_mean, kernel_params=No
         raise TypeError(f"sigma must be a Parameter, you provided {type(sigma)}")
     params = {"kernel_params": kernel_params, "sigma": sigma}
     opt = dict(x_train=None, y_train=None, loss_fn=loss_fn, is_fitted=False, is_fitted_derivs=False, c=None,
-               mu=None)
+               mu=None, jacobian_train=None, jaccoef=None)
     return ModelState(kernel, mean_function, params, **opt)
 
 
@@ -155,3 +206,6 @@ class GPR(BaseGP):
     _loss_and_grad_fun = staticmethod(loss_and_grad)
     _fit_fun = staticmethod(fit)
     _predict_fun = staticmethod(predict)
+    _lml_derivs_fun = staticmethod(log_marginal_likelihood_derivs)
+    _fit_derivs_fun = staticmethod(fit_derivs)
+    _predict_derivs_fun = staticmethod(predict_derivs)

@@ -66,3 +66,31 @@ def test_lml_and_fit_derivs(kind, N, nf, nv):
     c, jc = ops.gpr_fit_derivs(kind, dev(x), dev(J), dev(y), ell, sigma)
     assert np.max(np.abs(host(c) - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
     assert np.max(np.abs(host(jc) - jc_ref)) < 1e-8 * np.max(np.abs(jc_ref))
+
+
+def test_facade_fit_and_predict_derivs():
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import GPR
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    N, nf, nv = 40, 6, 6
+    x, J, y = _xj(N, nf, nv, 5)
+    xs, Js, _ = _xj(11, nf, nv, 6)
+    ell, sigma = 2.0, 0.1
+    m = GPR(SquaredExponential(), kernel_params=dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior())),
+            sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+    ref = R.lml_derivs_dense("se", x, y, J, ell, sigma)
+    assert abs(m.log_marginal_likelihood_derivs(x, y, J) - ref) < 1e-8 * abs(ref)
+    m.fit_derivs(x, y, J)
+    c_ref, _, jc_ref = R.fit_derivs_dense("se", x, y, J, ell, sigma)
+    assert np.max(np.abs(m.state.jaccoef - jc_ref)) < 1e-8 * np.max(np.abs(jc_ref))
+    pred = m.predict_derivs(xs, Js)
+    ref_pred = (R.d01kj("se", x, xs, ell, J, Js).T @ c_ref).reshape(11, nv)
+    assert np.max(np.abs(pred - ref_pred)) < 1e-8 * np.max(np.abs(ref_pred))
+    # the contracted route of the reference (d01kjc) gives the same numbers
+    ref_c = R.d01kjc("se", x, xs, ell, jc_ref, Js).sum(0).reshape(11, nv)
+    assert np.max(np.abs(pred - ref_c)) < 1e-8 * np.max(np.abs(ref_c))
+    with pytest.raises(RuntimeError):
+        m.predict(xs)
