@@ -89,13 +89,21 @@ int gpxb_rpcholesky(gpxb_ctx* ctx_, int kind, const double* x, int N, int D, dou
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   cudaStream_t s = (cudaStream_t)stream;
   const ZLayout zl = z_layout(D);
+  const Shard sh = shard_of(ctx, N);  // rows are sharded over the ranks (1024-row aligned)
   DevBuf z, ft;
-  GPXB_TRY(z.alloc(sizeof(double) * (size_t)N * zl.S, s));
-  GPXB_TRY(prep_z(ctx, x, D, N, zl, ell, z.as<double>(), s));
-  GPXB_TRY(ft.alloc(sizeof(double) * rp_factor_doubles(N, M), s));
+  GPXB_TRY(z.alloc(sizeof(double) * (size_t)std::max(sh.n(), 1) * zl.S, s));
+  GPXB_TRY(prep_z(ctx, x + sh.b * D, D, sh.n(), zl, ell, z.as<double>(), s));
+  GPXB_TRY(ft.alloc(sizeof(double) * std::max<size_t>(rp_factor_doubles(sh.n(), M), 8), s));
   const uint32_t key[2] = {key0, key1};
-  GPXB_TRY(rpcholesky_z(ctx, kind, z.as<double>(), N, zl, key, M, partitionable, ft.as<double>(), pivots_out, s));
-  if (F_out) GPXB_TRY(rp_unblock_rowmajor(ctx, ft.as<double>(), N, M, F_out, s));
+  GPXB_TRY(rpcholesky_z(ctx, kind, z.as<double>(), sh.n(), sh.b, N, zl, key, M, partitionable, ft.as<double>(),
+                        pivots_out, s));
+  if (F_out) {
+    GPXB_TRY(rp_unblock_rowmajor(ctx, ft.as<double>(), sh.n(), M, F_out + sh.b * M, s));
+    if (ctx->world > 1) {
+      ctx->shard_N = N;
+      GPXB_TRY(comm_allgather_rows(ctx, F_out + sh.b * M, F_out, sh.n(), M, s));
+    }
+  }
   return 0;
 }
 
@@ -154,22 +162,23 @@ int gpxb_gpr_fit_iter(gpxb_ctx* ctx_, int kind, const double* x, const double* y
   GPXB_LAUNCHED(ctx);
   const long long ldf = round_up(N, 2);
   if (n_pivots > 0) {
-    // preconditioner: RPCholesky over all rows (replicated on every rank), P_kk = inv(sigma^2 I + F^T F)
+    // preconditioner: row-sharded RPCholesky, P_kk = inv(sigma^2 I + F^T F) (all-reduced)
     DevBuf fb;
-    GPXB_TRY(fb.alloc(sizeof(double) * rp_factor_doubles(N, n_pivots), s));
+    GPXB_TRY(fb.alloc(sizeof(double) * std::max<size_t>(rp_factor_doubles(sh.n(), n_pivots), 8), s));
     GPXB_TRY(ft.alloc(sizeof(double) * (size_t)n_pivots * ldf, s));
     GPXB_TRY(piv.alloc(sizeof(long long) * n_pivots, s));
     GPXB_TRY(pkk.alloc(sizeof(double) * (size_t)n_pivots * n_pivots, s));
     const uint32_t key[2] = {key0, key1};
-    GPXB_TRY(rpcholesky_z(ctx, kind, za.as<double>(), N, zl, key, n_pivots, partitionable, fb.as<double>(),
-                          piv.as<long long>(), s));
-    GPXB_TRY(rp_unblock_transposed(ctx, fb.as<double>(), N, n_pivots, ft.as<double>(), ldf, s));
-    GPXB_TRY(precond_build(ctx, ft.as<double>() + sh.b, ldf, n_pivots, sh.n(), sigma, pkk.as<double>(), s));
+    GPXB_TRY(rpcholesky_z(ctx, kind, za.as<double>() + sh.b * zl.S, sh.n(), sh.b, N, zl, key, n_pivots,
+                          partitionable, fb.as<double>(), piv.as<long long>(), s));
+    // local rows of F, transposed: ft[c][0 .. n_loc)
+    GPXB_TRY(rp_unblock_transposed(ctx, fb.as<double>(), sh.n(), n_pivots, ft.as<double>(), ldf, s));
+    GPXB_TRY(precond_build(ctx, ft.as<double>(), ldf, n_pivots, sh.n(), sigma, pkk.as<double>(), s));
   }
   GPXB_TRY(xl.alloc(sizeof(double) * std::max(sh.n(), 1), s));
   if (maxiter <= 0) maxiter = 10 * N;
   GPXB_TRY(pcg_solve(ctx, kind, za.as<double>() + sh.b * zl.S, sh.n(), sh.b, za.as<double>(), N, zl, s2,
-                     r.as<double>() + sh.b, n_pivots > 0 ? ft.as<double>() + sh.b : nullptr, ldf, n_pivots,
+                     r.as<double>() + sh.b, n_pivots > 0 ? ft.as<double>() : nullptr, ldf, n_pivots,
                      pkk.as<double>(), sigma, tol, atol, maxiter, xl.as<double>(), iters_out, s));
   if (ctx->world > 1) {
     ctx->shard_N = N;

@@ -99,6 +99,16 @@ int comm_allreduce_sum(Ctx* ctx, double* buf, size_t count, cudaStream_t s) {
   return 0;
 }
 
+int comm_allreduce_sum2(Ctx* ctx, const double* send, double* recv, size_t count, cudaStream_t s) {
+  if (ctx->world <= 1) {
+    if (send != recv)
+      GPXB_CUDA_CHECK(cudaMemcpyAsync(recv, send, sizeof(double) * count, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  NCCL_CHECK(g.AllReduce(send, recv, count, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
+  return 0;
+}
+
 int comm_allgather_rows(Ctx* ctx, const double* local, double* all, int n_loc, int PS, cudaStream_t s) {
   if (ctx->world <= 1) return 0;
   // unequal row counts: one broadcast per owner, grouped into a single launch

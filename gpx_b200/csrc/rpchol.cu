@@ -16,6 +16,9 @@
 #include "gram.cuh"
 #include "mma.cuh"
 #include "rpchol.cuh"
+#include "comm.cuh"
+
+#include <algorithm>
 #include "threefry.cuh"
 
 namespace gpxb {
@@ -63,16 +66,19 @@ __device__ __forceinline__ double block_scan_1024(double v, double* sh /*32*/) {
 
 struct RpState {
   double* diag;       // [n]
-  double* blocksum;   // [nblk]
+  double* blocksum;   // [nblk] block sums of diag over ALL rows (after the all-reduce)
   double* FB;         // row-blocked factor, see fb_index
   int M;
   const double* Z;    // [n][S]
   int n, S, Dp, nblk, kind;
   long long* pivots;  // [M]
   uint32_t* key;      // [2] carried key
-  double* zs;         // [S] pivot row of Z
-  double* frow;       // [M] pivot row of F
-  double* scal;       // [0] g_s
+  double* pbuf;       // pivot buffer: [0] s, [1] g_s, [2, 2+S) z_s, [2+S, 2+S+M) F[s, :]  (all-reduced)
+  double* l1;         // [0] block b*, [1] prefix, [2] r, [3] total   (identical on every rank)
+  double* bs_local;   // [nblk] this rank's block sums, zero elsewhere (send buffer)
+  long long row0;     // global index of local row 0
+  int blk0;           // global index of local block 0
+  int nblk_loc;
   int partitionable;
 };
 
@@ -89,11 +95,12 @@ __global__ void rp_init_kernel(RpState st, double d0) {
     v = d0;
   }
   v = block_sum<BLK>(v, sh);
-  if (threadIdx.x == 0) st.blocksum[blockIdx.x] = v;
+  if (threadIdx.x == 0) st.bs_local[st.blk0 + blockIdx.x] = v;
 }
 
-// One CTA: draw the pivot for step i, gather its rows, compute g_s.
-__global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
+// One CTA, identical on every rank: draw u, scan the block sums, locate the block b* that holds the
+// pivot.  Writes l1 = {b*, prefix, r, total}.
+__global__ void __launch_bounds__(BLK, 1) rp_pivot_l1_kernel(RpState st) {
   __shared__ double sh[32];
   __shared__ double s_total, s_r, s_prefix;
   __shared__ int s_cnt, s_bstar;
@@ -117,9 +124,8 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
   __syncthreads();
   const double total = s_total;
 
-  // level 1: scan of the per-block probabilities, BLK blocks per sweep
+  // first sweep over the per-block probabilities to get cum[-1]
   double carry = 0.0;
-  // first sweep to get cum[-1]
   for (int base = 0; base < st.nblk; base += BLK) {
     const int b = base + tid;
     double v = (b < st.nblk) ? st.blocksum[b] / total : 0.0;
@@ -130,8 +136,7 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
     carry += sh[0];
     __syncthreads();
   }
-  const double cum_last = carry;
-  const double rr = cum_last * s_r;
+  const double rr = carry * s_r;
   // second sweep: count blocks whose cumulative probability is < r
   carry = 0.0;
   for (int base = 0; base < st.nblk; base += BLK) {
@@ -152,7 +157,6 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
   const int bstar = s_bstar;
   // prefix = cumulative probability of the blocks before bstar (recomputed in the same order)
   carry = 0.0;
-  double prefix = 0.0;
   for (int base = 0; base <= bstar; base += BLK) {
     const int b = base + tid;
     double v = (b < st.nblk) ? st.blocksum[b] / total : 0.0;
@@ -164,11 +168,29 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
     carry = sh[0];
     __syncthreads();
   }
-  if (bstar > 0) prefix = s_prefix;
-  __syncthreads();
+  if (tid == 0) {
+    st.l1[0] = (double)bstar;
+    st.l1[1] = bstar > 0 ? s_prefix : 0.0;
+    st.l1[2] = rr;
+    st.l1[3] = total;
+  }
+}
 
-  // level 2: scan inside block bstar
-  const long long r = (long long)bstar * BLK + tid;
+// One CTA: the rank that owns block b* finds the pivot row inside it and fills the pivot buffer
+// (s, g_s, z_s, F[s, :i]); every other rank zeroes its buffer so that a sum all-reduce
+// distributes the owner's values.
+__global__ void __launch_bounds__(BLK, 1) rp_pivot_l2_kernel(RpState st, int i) {
+  __shared__ double sh[32];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x;
+  const int bstar = (int)st.l1[0];
+  const int nbuf = 2 + st.S + i;
+  if (bstar < st.blk0 || bstar >= st.blk0 + st.nblk_loc) {
+    for (int k = tid; k < nbuf; k += BLK) st.pbuf[k] = 0.0;
+    return;
+  }
+  const double prefix = st.l1[1], rr = st.l1[2], total = st.l1[3];
+  const long long r = (long long)(bstar - st.blk0) * BLK + tid;  // local row
   double pv = (r < st.n) ? st.diag[r] / total : 0.0;
   pv = block_scan_1024(pv, sh) + prefix;
   if (tid == 0) s_cnt = 0;
@@ -179,20 +201,23 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
     if ((tid & 31) == 0 && wcnt) atomicAdd(&s_cnt, wcnt);
   }
   __syncthreads();
-  const long long nin = min((long long)BLK, (long long)st.n - (long long)bstar * BLK);
-  const long long s = (long long)bstar * BLK + min((long long)s_cnt, nin - 1);
-  if (tid == 0) st.pivots[i] = s;
+  const long long nin = min((long long)BLK, (long long)st.n - (long long)(bstar - st.blk0) * BLK);
+  const long long sl = (long long)(bstar - st.blk0) * BLK + min((long long)s_cnt, nin - 1);  // local pivot row
 
-  // gather the pivot's rows and g_s = k(x_s, x_s) - F[s].F[s]
-  for (int d = tid; d < st.S; d += BLK) st.zs[d] = st.Z[s * st.S + d];
+  double* zs = st.pbuf + 2;
+  double* frow = st.pbuf + 2 + st.S;
+  for (int d = tid; d < st.S; d += BLK) zs[d] = st.Z[sl * st.S + d];
   double acc = 0.0;
   for (int c = tid; c < i; c += BLK) {
-    const double f = st.FB[fb_index(s, c, st.M)];
-    st.frow[c] = f;
+    const double f = st.FB[fb_index(sl, c, st.M)];
+    frow[c] = f;
     acc += f * f;
   }
   acc = block_sum<BLK>(acc, sh);
-  if (tid == 0) st.scal[0] = kfun(st.kind, 1e-12) - acc;
+  if (tid == 0) {
+    st.pbuf[0] = (double)(st.row0 + sl);
+    st.pbuf[1] = kfun(st.kind, 1e-12) - acc;
+  }
 }
 
 // One thread per data row: kernel column, GEMV against the pivot row, scale, diagonal
@@ -202,18 +227,19 @@ __global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
   __shared__ double sh[32];
   double* sf = sm;
   double* sz = sm + i;
-  for (int c = threadIdx.x; c < i; c += BLK) sf[c] = st.frow[c];
-  for (int d = threadIdx.x; d < st.S; d += BLK) sz[d] = st.zs[d];
+  for (int c = threadIdx.x; c < i; c += BLK) sf[c] = st.pbuf[2 + st.S + c];
+  for (int d = threadIdx.x; d < st.S; d += BLK) sz[d] = st.pbuf[2 + d];
   __syncthreads();
   const long long r = (long long)blockIdx.x * BLK + threadIdx.x;
+  const long long s = (long long)st.pbuf[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) st.pivots[i] = s;
   double dnew = 0.0;
   if (r < st.n) {
-    const long long s = st.pivots[i];
     const double* zr = st.Z + r * st.S;
     double dot = 0.0;
     for (int d = 0; d < st.Dp; ++d) dot += sz[d] * zr[d];
     double d2 = ((sz[st.Dp] - 2.0 * dot) + zr[st.Dp]) + 1e-12;
-    if (r == s) d2 = 1e-12;
+    if (r + st.row0 == s) d2 = 1e-12;
     double g = kfun(st.kind, d2);
     const double* f = st.FB + fb_index(r, 0, st.M);
     double a[8];
@@ -229,13 +255,13 @@ __global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
     }
     for (; c < i; ++c) a[0] += f[(long long)c * BLK] * sf[c];
     g -= ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-    const double fnew = g / (sqrt(st.scal[0]) + 1e-6);
+    const double fnew = g / (sqrt(st.pbuf[1]) + 1e-6);
     st.FB[fb_index(r, i, st.M)] = fnew;
     dnew = st.diag[r] - fnew * fnew;
     st.diag[r] = dnew;
   }
   dnew = block_sum<BLK>(dnew, sh);
-  if (threadIdx.x == 0) st.blocksum[blockIdx.x] = dnew;
+  if (threadIdx.x == 0) st.bs_local[st.blk0 + blockIdx.x] = dnew;
 }
 
 // F[r][c] (row-major N x M) <- blocked factor
@@ -267,24 +293,32 @@ __global__ void unblock_transposed_kernel(const double* __restrict__ FB, int n, 
 
 size_t rp_factor_doubles(int n, int M) { return (size_t)ceil_div(n, BLK) * (size_t)M * BLK; }
 
-// Z: pre-scaled rows (z_layout).  FB: rp_factor_doubles(n, M) doubles.  pivots: [M] int64 device.
-int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, ZLayout zl, const uint32_t key[2], int M,
-                 int partitionable, double* FB, long long* pivots, cudaStream_t s) {
-  GPXB_ARG_CHECK(n > 0 && M > 0 && M <= 6000, -40);  // frow + zs must fit in 48 KB of smem
-  const int nblk = ceil_div(n, BLK);
-  DevBuf bDiag, bBs, bKey, bZs, bFrow, bSc;
-  GPXB_TRY(bDiag.alloc(sizeof(double) * n, s));
+// Z: this rank's pre-scaled rows (n x S), global rows [row0, row0 + n) of Ntot (row0 a multiple of
+// 1024).  FB: rp_factor_doubles(n, M) doubles (local rows).  pivots: [M] int64 device (global indices,
+// identical on every rank).  With world > 1 two small all-reduces per pivot distribute the block
+// sums and the pivot's rows.
+int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, long long row0, long long Ntot, ZLayout zl,
+                 const uint32_t key[2], int M, int partitionable, double* FB, long long* pivots, cudaStream_t s) {
+  GPXB_ARG_CHECK(n >= 0 && M > 0 && M <= 6000, -40);  // frow + zs must fit in 48 KB of smem
+  GPXB_ARG_CHECK(row0 % BLK == 0, -41);
+  const int nblk = ceil_div(Ntot, BLK);
+  const int nblk_loc = ceil_div(n, BLK);
+  DevBuf bDiag, bBs, bBsl, bKey, bP, bL1;
+  GPXB_TRY(bDiag.alloc(sizeof(double) * std::max(n, 1), s));
   GPXB_TRY(bBs.alloc(sizeof(double) * nblk, s));
+  GPXB_TRY(bBsl.alloc(sizeof(double) * nblk, s));
   GPXB_TRY(bKey.alloc(sizeof(uint32_t) * 2, s));
-  GPXB_TRY(bZs.alloc(sizeof(double) * zl.S, s));
-  GPXB_TRY(bFrow.alloc(sizeof(double) * M, s));
-  GPXB_TRY(bSc.alloc(sizeof(double) * 4, s));
+  GPXB_TRY(bP.alloc(sizeof(double) * (2 + zl.S + M), s));
+  GPXB_TRY(bL1.alloc(sizeof(double) * 4, s));
   RpState st;
-  st.diag = bDiag.as<double>(); st.blocksum = bBs.as<double>();
+  st.diag = bDiag.as<double>(); st.blocksum = bBs.as<double>(); st.bs_local = bBsl.as<double>();
   st.FB = FB; st.M = M; st.Z = Z; st.n = n; st.S = zl.S; st.Dp = zl.Dp; st.nblk = nblk; st.kind = kind;
-  st.pivots = pivots; st.key = bKey.as<uint32_t>(); st.zs = bZs.as<double>(); st.frow = bFrow.as<double>();
-  st.scal = bSc.as<double>(); st.partitionable = partitionable;
+  st.pivots = pivots; st.key = bKey.as<uint32_t>(); st.pbuf = bP.as<double>(); st.l1 = bL1.as<double>();
+  st.row0 = row0; st.blk0 = (int)(row0 / BLK); st.nblk_loc = nblk_loc; st.partitionable = partitionable;
+  const bool multi = ctx->world > 1;
+  if (!multi) st.blocksum = st.bs_local;  // one buffer, no reduction
   GPXB_CUDA_CHECK(cudaMemcpyAsync(st.key, key, sizeof(uint32_t) * 2, cudaMemcpyHostToDevice, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(st.bs_local, 0, sizeof(double) * nblk, s));
   // diag_i = k(x_i, x_i) via the batched kernel: d2 = 1e-12 (approximations.py:88-93)
   double d0;
   {
@@ -297,17 +331,26 @@ int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, ZLayout zl, const u
       else { const double d = 2.23606797749979 * r; d0 = (1.0 + d + d * d / 3.0) * std::exp(-d); }
     }
   }
-  rp_init_kernel<<<nblk, BLK, 0, s>>>(st, d0);
-  GPXB_LAUNCH_CHECK();
-  ctx->launches++;
+  if (nblk_loc > 0) {
+    rp_init_kernel<<<nblk_loc, BLK, 0, s>>>(st, d0);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+  }
   GPXB_CUDA_CHECK(cudaFuncSetAttribute(rp_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(double) * (M + zl.S)));
   for (int i = 0; i < M; ++i) {
-    rp_pivot_kernel<<<1, BLK, 0, s>>>(st, i);
+    if (multi) GPXB_TRY(comm_allreduce_sum2(ctx, st.bs_local, bBs.as<double>(), nblk, s));
+    rp_pivot_l1_kernel<<<1, BLK, 0, s>>>(st);
     GPXB_LAUNCH_CHECK();
-    rp_column_kernel<<<nblk, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
+    rp_pivot_l2_kernel<<<1, BLK, 0, s>>>(st, i);
     GPXB_LAUNCH_CHECK();
+    if (multi) GPXB_TRY(comm_allreduce_sum(ctx, st.pbuf, 2 + zl.S + i, s));
     ctx->launches += 2;
+    if (nblk_loc > 0) {
+      rp_column_kernel<<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
+      GPXB_LAUNCH_CHECK();
+      ctx->launches++;
+    }
   }
   return 0;
 }

@@ -34,12 +34,12 @@ def main():
         U = ops.rademacher_probes(key, N, P, True)
         al, be, fl = ops.lanczos("se", x, ell, sigma**2 + 1e-10, U, m)
         c, mu, it = ops.gpr_fit_iter("se", x, y, ell, sigma, 50, key)
-        _, piv = ops.rpcholesky("se", x, M, ell, key, True, want_factor=False)
+        F, piv = ops.rpcholesky("se", x, M, ell, key, True, want_factor=True)
         xl = ops.gather_rows(x, piv)
         lml = ops.sgpr_lml("se", x, y, xl, ell, sigma)
         cs, mus = ops.sgpr_fit("se", x, y, xl, ell, sigma)
         torch.cuda.synchronize()
-        return dict(alpha=al.cpu().numpy(), beta=be.cpu().numpy(), c=c.cpu().numpy(), it=it,
+        return dict(piv=piv.cpu().numpy(), F=F.cpu().numpy(), alpha=al.cpu().numpy(), beta=be.cpu().numpy(), c=c.cpu().numpy(), it=it,
                     lml=lml.cpu().numpy(), cs=cs.cpu().numpy())
 
     ref = run()  # world == 1 context
@@ -49,10 +49,11 @@ def main():
     out = run()
     dt = time.perf_counter() - t0
     rel = lambda a, b: float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))  # noqa: E731
-    rep = dict(rank=rank, world=world, N=N, alpha=rel(out["alpha"], ref["alpha"]), beta=rel(out["beta"], ref["beta"]),
+    rep = dict(rank=rank, world=world, N=N, pivots_equal=bool(np.array_equal(out["piv"], ref["piv"])),
+               F=float(np.max(np.abs(out["F"] - ref["F"]))), alpha=rel(out["alpha"], ref["alpha"]), beta=rel(out["beta"], ref["beta"]),
                c=rel(out["c"], ref["c"]), iters=(out["it"], ref["it"]), sgpr_lml=rel(out["lml"], ref["lml"]),
                sgpr_c=rel(out["cs"], ref["cs"]), seconds=dt)
-    ok = rep["alpha"] < 1e-9 and rep["beta"] < 1e-9 and rep["c"] < 1e-8 and out["it"] == ref["it"] and \
+    ok = rep["pivots_equal"] and rep["F"] < 1e-12 and rep["alpha"] < 1e-9 and rep["beta"] < 1e-9 and rep["c"] < 1e-8 and out["it"] == ref["it"] and \
         rep["sgpr_lml"] < 1e-10 and rep["sgpr_c"] < 1e-6
     rep["ok"] = bool(ok)
     print(json.dumps(rep), flush=True)
