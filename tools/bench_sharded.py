@@ -70,6 +70,13 @@ def main():
             print(json.dumps(dict(what="sgpr_lml_woodbury", n_gpus=world, N=N2, M=M, D=32, s=t,
                                   tflops_total=fl / t / 1e12, tflops_per_gpu=fl / t / 1e12 / world,
                                   lml=float(out.cpu()[0]), scaling="strong")), flush=True)
+    if N2 > 0 and os.environ.get("BENCH_RPCHOL", "1") == "1":
+        t, (_, piv) = timed(lambda: ops.rpcholesky("se", x, M, 32**0.5, key, True, want_factor=False))
+        alg = 8.0 * N2 * M * (M - 1) / 2 + 5 * 8.0 * N2 * M
+        if rank == 0:
+            print(json.dumps(dict(what="rpcholesky", n_gpus=world, N=N2, M=M, D=32, s=t, gbs_total=alg / t / 1e9,
+                                  hbm_frac_per_gpu=alg / t / 1e9 / world / 6554.2,
+                                  pivots_head=piv[:6].cpu().tolist(), scaling="strong")), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
