@@ -18,6 +18,7 @@
 #include "matvec.cuh"
 #include "mma.cuh"
 
+#include <cmath>
 #include <cstdlib>
 
 namespace gpxb {
@@ -270,7 +271,17 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   int jsplit = 1;
   const int jt = ceil_div(a.N, BJ);
   const int target = 2 * ctx->num_sms;
-  if (row_ctas < target) jsplit = std::min(jt, std::max(1, target / row_ctas));
+  if (row_ctas < target) {
+    jsplit = std::min(jt, std::max(1, target / row_ctas));
+  } else {
+    // few, fractional waves (e.g. 6.6 on a row shard): pick the column split with the smallest tail
+    double best = 0.0;
+    for (int k = 1; k <= 8 && k <= jt; ++k) {
+      const double w = (double)row_ctas * k / ctx->num_sms;
+      const double eff = w / std::ceil(w);
+      if (eff > best + 0.015) { best = eff; jsplit = k; }
+    }
+  }
   int jps = ceil_div(jt, jsplit) * BJ;
   jsplit = ceil_div(a.N, jps);
   p.jsplit = jsplit; p.jps = jps;
