@@ -35,7 +35,8 @@ struct GramParams {
   int vec_out;
   const double* Ainv;
   long long ldainv;
-  const double* alpha;
+  const double* alpha;   // row weights  [t][n1]
+  const double* alpha2;  // column weights [t][n2]
   int t;
   double* partials;
   int tiles_m, tiles_n;
@@ -179,8 +180,9 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
             const double dk = kfun_dl(p.kind, d2, s, p.ell);
             double w = -p.Ainv[(long long)gi * p.ldainv + j];
             for (int t = 0; t < p.t; ++t)
-              w += p.alpha[(long long)t * p.n1 + gi] * p.alpha[(long long)t * p.n1 + j];
-            v[e] = ((gi == j) ? 1.0 : 2.0) * w * dk;
+              w += p.alpha[(long long)t * p.n1 + gi] * p.alpha2[(long long)t * p.n2 + j];
+            // lower-triangle evaluation of a symmetric sum counts off-diagonal entries twice
+            v[e] = ((p.lower_only && gi != j) ? 2.0 : 1.0) * w * dk;
           }
         }
       }
@@ -231,7 +233,8 @@ int gram_launch(Ctx* ctx, const GramArgs& a, cudaStream_t s) {
   p.sym = a.sym; p.lower_only = a.lower_only;
   p.out = a.out; p.ldo = a.ldo;
   p.vec_out = a.out && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) && (a.ldo % 2 == 0);
-  p.Ainv = a.Ainv; p.ldainv = a.ldainv; p.alpha = a.alpha; p.t = a.t; p.partials = a.partials;
+  p.Ainv = a.Ainv; p.ldainv = a.ldainv; p.alpha = a.alpha; p.alpha2 = a.alpha2 ? a.alpha2 : a.alpha;
+  p.t = a.t; p.partials = a.partials;
   p.tiles_m = ceil_div(a.n1, TB);
   p.tiles_n = ceil_div(a.n2, TB);
   const long long grid = gram_num_ctas(a);
@@ -242,7 +245,8 @@ int gram_launch(Ctx* ctx, const GramArgs& a, cudaStream_t s) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     gram_kernel<false><<<(int)grid, NT, smem, s>>>(p);
   } else {
-    GPXB_ARG_CHECK(a.sym && a.lower_only && a.Ainv && a.alpha && a.partials, -13);
+    GPXB_ARG_CHECK(a.Ainv && a.alpha && a.partials, -13);
+    GPXB_ARG_CHECK(a.alpha2 || (a.sym && a.n1 == a.n2), -14);
     GPXB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     gram_kernel<true><<<(int)grid, NT, smem, s>>>(p);

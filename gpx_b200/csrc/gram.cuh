@@ -41,11 +41,13 @@ struct GramArgs {
   // store mode
   double* out = nullptr;
   long long ldo = 0;
-  // contraction mode (out == nullptr): sum_ij (sum_t a_t[i] a_t[j] - Ainv[i][j]) dK_ij/d ell over
-  // the full symmetric matrix, evaluated on the lower triangle (requires sym && lower_only).
-  const double* Ainv = nullptr;
+  // contraction mode (out == nullptr): sum_ij (sum_t a_t[i] b_t[j] - Y[i][j]) dK_ij/d ell.  With
+  // sym && lower_only the sum over the full symmetric matrix is evaluated on the lower triangle
+  // (Y = lower-stored A^-1, b = a); otherwise every (i, j) of the n1 x n2 block counts once.
+  const double* Ainv = nullptr;  // Y
   long long ldainv = 0;
-  const double* alpha = nullptr;  // [t][n1]
+  const double* alpha = nullptr;   // a: [t][n1]
+  const double* alpha2 = nullptr;  // b: [t][n2] (nullptr: same as a)
   int t = 0;
   double* partials = nullptr;  // one double per CTA
 };

@@ -94,6 +94,45 @@ static __global__ void gather_rows_kernel(const double* __restrict__ x, int D, c
   out[t] = x[idx[k] * D + d];
 }
 
+// mirror the lower triangle of a k x k matrix (ld k) into the upper one
+static __global__ void symmetrize_lower_kernel(double* __restrict__ A, int k) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)k * k) return;
+  const int i = (int)(idx / k), j = (int)(idx % k);
+  if (j > i) A[idx] = A[(long long)j * k + i];
+}
+
+// out = a*X + b*Y (element-wise, n elements)
+static __global__ void axpby_kernel(double* __restrict__ out, double a, const double* __restrict__ X, double b,
+                                    const double* __restrict__ Y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a * X[i] + b * Y[i];
+}
+
+// *out = sum_ij X_ij Y_ij over the full symmetric k x k matrices given by their lower triangles
+static __global__ void sym_frobenius_kernel(const double* __restrict__ X, const double* __restrict__ Y, int k,
+                                            double* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (long long idx = threadIdx.x; idx < (long long)k * k; idx += 1024) {
+    const int i = (int)(idx / k), j = (int)(idx % k);
+    if (j < i) s += 2.0 * X[idx] * Y[idx];
+    else if (j == i) s += X[idx] * Y[idx];
+  }
+  s = block_sum<1024>(s, sh);
+  if (threadIdx.x == 0) *out = s;
+}
+
+// *out = sum_i x_i y_i (single CTA, fixed order)
+static __global__ void dot_kernel(const double* __restrict__ x, const double* __restrict__ y, long long n,
+                                  double* __restrict__ out, int accumulate) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) s += x[i] * y[i];
+  s = block_sum<1024>(s, sh);
+  if (threadIdx.x == 0) *out = accumulate ? *out + s : s;
+}
+
 // A *= a
 static __global__ void scale_kernel(double* __restrict__ A, long long n, double a) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

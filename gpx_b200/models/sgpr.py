@@ -36,9 +36,27 @@ def neg_log_marginal_likelihood(state, x, y, **kwargs):
     return -log_marginal_likelihood(state, x, y, **kwargs)
 
 
-def loss_and_grad(state, x, y, **kwargs):
-    raise NotImplementedError("gradient of the SGPR LML is a 'next' row (SURVEY.md 8f N1); "
-                              "fit with minimize=False or optimise hyper-parameters with GPR")
+def _loss_and_grad_with_locs(state, xd, yd, x_locs_dev):
+    kernel, ell, sigma = _hyper(state)
+    out = ops.sgpr_lml_grad(kernel.kind, xd, yd, x_locs_dev, ell, sigma, mean_mode(state.mean_function))
+    lml, g_ell, g_sigma = (float(v) for v in out.cpu().numpy())
+    grads = {}
+    if state.params["kernel_params"]["lengthscale"].trainable:
+        grads[("kernel_params", "lengthscale")] = -g_ell
+    if state.params["sigma"].trainable:
+        grads[("sigma",)] = -g_sigma
+    return -lml, grads
+
+
+def loss_and_grad(state, x, y, iterative=False, **kwargs):
+    """Negative SGPR LML and its gradient w.r.t. (lengthscale, sigma) from one fused device call
+    (stands in for jit(value_and_grad(loss))).  Landmarks must be fixed."""
+    if iterative:
+        raise NotImplementedError("gradient of the iterative SGPR LML is not implemented")
+    if state.params["x_locs"].trainable:
+        raise NotImplementedError("trainable landmark coordinates need d lml / d x_locs (not implemented)")
+    xd, yd = _xy(state, x, y)
+    return _loss_and_grad_with_locs(state, xd, yd, _locs(state))
 
 
 def fit(state, x, y, iterative=False, **_ignored):

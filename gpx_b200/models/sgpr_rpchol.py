@@ -42,8 +42,14 @@ def neg_log_marginal_likelihood(state, x, y, **kwargs):
     return -log_marginal_likelihood(state, x, y, **kwargs)
 
 
-def loss_and_grad(state, x, y, **kwargs):
-    raise NotImplementedError("gradient of the SGPR_RPChol LML is a 'next' row (SURVEY.md 8f N1)")
+def loss_and_grad(state, x, y, iterative=False, **kwargs):
+    """Pivots are re-drawn with the current hyper-parameters and treated as constants (integer
+    indices carry no gradient in the reference either), then the SGPR gradient applies."""
+    if iterative:
+        raise NotImplementedError("gradient of the iterative SGPR_RPChol LML is not implemented")
+    xd, yd = _xy(state, x, y)
+    x_locs, _ = _select_locs(state, xd)
+    return _sgpr._loss_and_grad_with_locs(state, xd, yd, x_locs)
 
 
 def fit(state, x, y, iterative=False, **_ignored):

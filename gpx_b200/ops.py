@@ -299,6 +299,22 @@ def sgpr_lml(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     return out
 
 
+def sgpr_lml_grad(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, want_grad=True):
+    """Device tensor [lml/N, d/d ell, d/d sigma] of the SGPR LML with fixed landmarks."""
+    ctx = context()
+    x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    N, D = x.shape
+    assert y.numel() == N, "the SGPR gradient supports a single output column"
+    out = torch.empty(3, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_sgpr_lml_grad(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, ptr(x_locs), x_locs.shape[0],
+                                   float(ell), float(sigma), int(mean_mode), int(bool(want_grad)), ptr(out),
+                                   stream_ptr()),
+        "gpxb_sgpr_lml_grad",
+    )
+    return out
+
+
 def sgpr_fit(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)

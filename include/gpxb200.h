@@ -150,6 +150,12 @@ int gpxb_gpr_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* y,
 int gpxb_sgpr_lml(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,
                   const double* x_locs, int M, double ell, double sigma, int mean_mode, double* out,
                   gpxb_stream stream);
+/* out3 (device) = [lml/N, d(lml/N)/d lengthscale, d(lml/N)/d sigma] of the SGPR LML with fixed
+ * landmarks: the (value, grad) jit(value_and_grad) of gpx/models/_sgpr.py:659-697 yields, in analytic
+ * O(N M^2) form (SGPR_RPChol: the pivots carry no gradient).  Single output column. */
+int gpxb_sgpr_lml_grad(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D,
+                       const double* x_locs, int M, double ell, double sigma, int mean_mode, int want_grad,
+                       double* out3, gpxb_stream stream);
 /* c[M x T] = (sigma^2 K_mm + K_mn K_nm + 1e-10 I)^-1 K_mn (y - mu)  (gpx/models/_sgpr.py:39-61, 319-339) */
 int gpxb_sgpr_fit(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,
                   const double* x_locs, int M, double ell, double sigma, int mean_mode, double* c_out,
