@@ -125,18 +125,18 @@ int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, lo
 }
 
 namespace {
-// scal: [0] r.r  [1] v.w  [2] sum log diag L_A  [3] sum log diag L_Bt  [4] tr(Bt^-1 A)  [5] alpha.alpha
-//       [6] g1 = sum dK_nm (alpha_n w_m - Y_nm)   [7] g2 = sum dA_mm' (w_m w_m' - F_mm')
+// scal: [0] r.r  [1] u.what  [2] sum log diag L_B  [3] tr(B^-1)  [4] alpha.alpha
+//       [5] g1 = sum dK_nm (alpha_n w_m - Y_nm)   [6] g2 = sum dA_mm' (w_m w_m' - F_mm')
 __global__ void finalize_sgpr_grad_kernel(const double* __restrict__ scal, long long N, int M, double s2,
                                           double sigma, int want_grad, double* __restrict__ out3) {
   const double n = (double)N;
   const double quad = (scal[0] - scal[1]) / s2;
-  const double logdet = (n - (double)M) * log(s2) + 2.0 * scal[3] - 2.0 * scal[2];
+  const double logdet = (n - (double)M) * log(s2) + 2.0 * scal[2];
   out3[0] = (-0.5 * quad - 0.5 * logdet - n * 0.5 * log(2.0 * 3.141592653589793)) / n;
   if (want_grad) {
-    const double trCinv = (n - (double)M + s2 * scal[4]) / s2;
-    out3[1] = (scal[6] - 0.5 * scal[7]) / n;
-    out3[2] = sigma * (scal[5] - trCinv) / n;
+    const double trCinv = (n - (double)M + s2 * scal[3]) / s2;
+    out3[1] = (scal[5] - 0.5 * scal[6]) / n;
+    out3[2] = sigma * (scal[4] - trCinv) / n;
   } else {
     out3[1] = out3[2] = 0.0;
   }
@@ -146,15 +146,37 @@ __global__ void alpha_chunk_kernel(const double* __restrict__ r, double* __restr
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] = (r[i] - t[i]) / s2;
 }
+// H = I - s2 * Binv (full M x M)
+__global__ void i_minus_scaled_kernel(const double* __restrict__ Binv, int M, double s2, double* __restrict__ H) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * M) return;
+  const int i = (int)(idx / M), j = (int)(idx % M);
+  H[idx] = (i == j ? 1.0 : 0.0) - s2 * Binv[idx];
+}
+__global__ void transpose_sq_kernel(const double* __restrict__ in, int M, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + threadIdx.x;
+    tile[k][threadIdx.x] = (r < M && c < M) ? in[(long long)r * M + c] : 0.0;
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int r = c0 + k, c = r0 + threadIdx.x;
+    if (r < M && c < M) out[(long long)r * M + c] = tile[threadIdx.x][k];
+  }
+}
 }  // namespace
 
 // SGPR LML and its gradient w.r.t. (lengthscale, sigma) with fixed landmarks -- what
-// jit(value_and_grad) of _sgpr._lml_dense yields, in O(N M^2):
-//   A = K_mm + 1e-10 I,  Bt = s2 A + K_mn K_nm,  w = Bt^-1 K_mn r,  alpha = (r - K_nm w)/s2,
-//   lml N = -1/2 (r.r - v.w)/s2 - 1/2 [(N-M) log s2 + log|Bt| - log|A|] - N/2 log 2pi
-//   d/d ell  = sum_nm dK_nm (alpha_n w_m - (K_nm Bt^-1)_nm) - 1/2 sum_mm' dA_mm' (w_m w_m' - F_mm'),
-//              F = A^-1 - s2 Bt^-1
-//   d/d sigma = sigma (alpha.alpha - tr C^-1),  tr C^-1 = (N - M + s2 tr(Bt^-1 A))/s2
+// jit(value_and_grad) of _sgpr._lml_dense yields, in O(N M^2).  Everything is
+// expressed through the well-conditioned B = s2 I + G G^T (eigenvalues >= s2), G = L_A^-1 K_mn,
+// A = K_mm + 1e-10 I = L_A L_A^T:
+//   what = B^-1 G r,  w = L_A^-T what,  alpha = (r - G^T what)/s2
+//   lml N = -1/2 (r.r - (G r).what)/s2 - 1/2 [(N-M) log s2 + log|B|] - N/2 log 2pi
+//   d/d ell  = sum_nm dK_nm (alpha_n w_m - Y_nm) - 1/2 sum_mm' dA_mm' (w_m w_m' - F_mm'),
+//              Y = G^T B^-1 L_A^-1 (per chunk),  F = L_A^-T (I - s2 B^-1) L_A^-1
+//   d/d sigma = sigma (alpha.alpha - tr C^-1),  tr C^-1 = (N - M + s2 tr(B^-1))/s2
 // Single output column (T = 1).  out3: device [lml/N, d/d ell, d/d sigma].
 int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, long long N, int D,
                   const double* x_locs, int M, double ell, double sigma, const double* mu, int want_grad,
@@ -165,117 +187,120 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
   const double s2 = sigma * sigma + 1e-10;
   const size_t mm = (size_t)M * M;
   const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
-  DevBuf bZl, bA0, bA, bInvA, bBt, bInvB, bV, bW, bZc, bKc, bRc, bTc, bY, bSc, bWk, bTs, bPart;
+  DevBuf bZl, bA, bInvA, bB, bInvB, bU, bWh, bW, bZc, bKc, bRc, bTc, bY, bSc, bWk, bTs, bPart, bH, bHt;
   GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
-  GPXB_TRY(bA0.alloc(sizeof(double) * mm, s));
   GPXB_TRY(bA.alloc(sizeof(double) * mm, s));
   GPXB_TRY(bInvA.alloc(sizeof(double) * leaf_inv_doubles(M), s));
-  GPXB_TRY(bBt.alloc(sizeof(double) * mm, s));
+  GPXB_TRY(bB.alloc(sizeof(double) * mm, s));
   GPXB_TRY(bInvB.alloc(sizeof(double) * leaf_inv_doubles(M), s));
-  GPXB_TRY(bV.alloc(sizeof(double) * M, s));
+  GPXB_TRY(bU.alloc(sizeof(double) * M, s));
+  GPXB_TRY(bWh.alloc(sizeof(double) * M, s));
   GPXB_TRY(bW.alloc(sizeof(double) * M, s));
   GPXB_TRY(bZc.alloc(sizeof(double) * (size_t)nc_max * zl.S, s));
   GPXB_TRY(bKc.alloc(sizeof(double) * (size_t)nc_max * M, s));
   GPXB_TRY(bRc.alloc(sizeof(double) * nc_max, s));
   GPXB_TRY(bTc.alloc(sizeof(double) * nc_max, s));
   GPXB_TRY(bSc.alloc(sizeof(double) * 8, s));
-  double *Zl = bZl.as<double>(), *A0 = bA0.as<double>(), *A = bA.as<double>(), *Bt = bBt.as<double>();
-  double *v = bV.as<double>(), *w = bW.as<double>(), *Zc = bZc.as<double>(), *Kc = bKc.as<double>();
-  double *rc = bRc.as<double>(), *tc = bTc.as<double>(), *scal = bSc.as<double>();
-  GPXB_CUDA_CHECK(cudaMemsetAsync(A0, 0, sizeof(double) * mm, s));
-  GPXB_CUDA_CHECK(cudaMemsetAsync(Bt, 0, sizeof(double) * mm, s));
-  GPXB_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * M, s));
+  double *Zl = bZl.as<double>(), *A = bA.as<double>(), *B = bB.as<double>(), *invA = bInvA.as<double>();
+  double *u = bU.as<double>(), *wh = bWh.as<double>(), *w = bW.as<double>(), *Zc = bZc.as<double>();
+  double *Kc = bKc.as<double>(), *rc = bRc.as<double>(), *tc = bTc.as<double>(), *scal = bSc.as<double>();
+  GPXB_CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(double) * mm, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(u, 0, sizeof(double) * M, s));
   GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 8, s));
   const int eb = ceil_div((long long)mm, 256);
 
-  // A0 = K_mm + 1e-10 I (lower), A = chol(A0)
+  // L_A = chol(K_mm + 1e-10 I)
   GPXB_TRY(prep_z(ctx, x_locs, D, M, zl, ell, Zl, s));
   {
     GramArgs g;
     g.kind = kind; g.Z1 = Zl; g.n1 = M; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
-    g.diag_add = 1e-10; g.sym = 1; g.lower_only = 1; g.out = A0; g.ldo = M;
+    g.diag_add = 1e-10; g.sym = 1; g.lower_only = 1; g.out = A; g.ldo = M;
     GPXB_TRY(gram_launch(ctx, g, s));
   }
-  GPXB_CUDA_CHECK(cudaMemcpyAsync(A, A0, sizeof(double) * mm, cudaMemcpyDeviceToDevice, s));
-  GPXB_TRY(potrf_lower(ctx, A, M, M, bInvA.as<double>(), s));
-  GPXB_TRY(logdet_lower(ctx, A, M, M, scal + 2, 1.0, s));
+  GPXB_TRY(potrf_lower(ctx, A, M, M, invA, s));
 
-  // pass 1: Bt += K_c^T K_c, v += K_c^T r_c, r.r
-  for (int r0 = 0; r0 < n_loc; r0 += CHUNK) {
-    const int nc = std::min(CHUNK, n_loc - r0);
+  auto chunk_G = [&](int r0, int nc) -> int {  // Kc <- G_c^T = K(x_chunk, locs) L_A^-T ; rc <- r_c
     GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, Zc, s));
     GramArgs g;
     g.kind = kind; g.Z1 = Zc; g.n1 = nc; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell; g.out = Kc; g.ldo = M;
     GPXB_TRY(gram_launch(ctx, g, s));
+    GPXB_TRY(trsm_right_lt(ctx, A, M, invA, Kc, M, nc, M, s));
     center_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(y + r0, nc, mu, rc);
     GPXB_LAUNCHED(ctx);
+    return 0;
+  };
+
+  // pass 1: B += G_c G_c^T, u += G_c r_c, r.r
+  for (int r0 = 0; r0 < n_loc; r0 += CHUNK) {
+    const int nc = std::min(CHUNK, n_loc - r0);
+    GPXB_TRY(chunk_G(r0, nc));
     sumsq_kernel<<<1, 1024, 0, s>>>(rc, nc, scal + 0, 1);
     GPXB_LAUNCHED(ctx);
     GemmArgs a;
     a.M = M; a.N = M; a.K = nc;
     a.A = Kc; a.lda = M; a.a_kmajor = false;
     a.B = Kc; a.ldb = M; a.b_kmajor = false;
-    a.C = Bt; a.ldc = M; a.beta = 1.0; a.lower_only = 1;
+    a.C = B; a.ldc = M; a.beta = 1.0; a.lower_only = 1;
     GPXB_TRY(gemm_f64(ctx, a, s));
     GemmArgs b;
     b.M = M; b.N = 1; b.K = nc;
     b.A = Kc; b.lda = M; b.a_kmajor = false;
     b.B = rc; b.ldb = 1; b.b_kmajor = false;
-    b.C = v; b.ldc = 1; b.beta = 1.0;
+    b.C = u; b.ldc = 1; b.beta = 1.0;
     GPXB_TRY(gemm_f64(ctx, b, s));
   }
   if (ctx->world > 1) {
-    GPXB_TRY(comm_allreduce_sum(ctx, Bt, mm, s));
-    GPXB_TRY(comm_allreduce_sum(ctx, v, M, s));
+    GPXB_TRY(comm_allreduce_sum(ctx, B, mm, s));
+    GPXB_TRY(comm_allreduce_sum(ctx, u, M, s));
     GPXB_TRY(comm_allreduce_sum(ctx, scal, 1, s));
   }
-  axpby_kernel<<<eb, 256, 0, s>>>(Bt, s2, A0, 1.0, Bt, (long long)mm);  // Bt = s2 A0 + K_mn K_nm (lower)
+  add_diag_kernel<<<ceil_div(M, 256), 256, 0, s>>>(B, M, M, s2);
   GPXB_LAUNCHED(ctx);
-  GPXB_TRY(potrf_lower(ctx, Bt, M, M, bInvB.as<double>(), s));
-  GPXB_TRY(logdet_lower(ctx, Bt, M, M, scal + 3, 1.0, s));
-  GPXB_CUDA_CHECK(cudaMemcpyAsync(w, v, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
-  GPXB_TRY(trsm_right_lt(ctx, Bt, M, bInvB.as<double>(), w, M, 1, M, s));
-  GPXB_TRY(trsm_right_l(ctx, Bt, M, bInvB.as<double>(), w, M, 1, M, s));  // w = Bt^-1 v
-  dot_kernel<<<1, 1024, 0, s>>>(v, w, M, scal + 1, 0);
+  GPXB_TRY(potrf_lower(ctx, B, M, M, bInvB.as<double>(), s));
+  GPXB_TRY(logdet_lower(ctx, B, M, M, scal + 2, 1.0, s));
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(wh, u, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
+  GPXB_TRY(trsm_right_lt(ctx, B, M, bInvB.as<double>(), wh, M, 1, M, s));
+  GPXB_TRY(trsm_right_l(ctx, B, M, bInvB.as<double>(), wh, M, 1, M, s));  // what = B^-1 u
+  dot_kernel<<<1, 1024, 0, s>>>(u, wh, M, scal + 1, 0);
   GPXB_LAUNCHED(ctx);
 
   if (want_grad) {
     GPXB_TRY(bWk.alloc(sizeof(double) * mm, s));
     GPXB_TRY(bTs.alloc(sizeof(double) * potri_scratch_doubles(M), s));
     GPXB_TRY(bY.alloc(sizeof(double) * (size_t)nc_max * M, s));
-    // A <- A^-1 (lower), Bt <- Bt^-1 (lower, then mirrored to full)
-    GPXB_TRY(potri_lower(ctx, A, M, bInvA.as<double>(), M, bWk.as<double>(), bTs.as<double>(), A, M, s));
-    GPXB_TRY(potri_lower(ctx, Bt, M, bInvB.as<double>(), M, bWk.as<double>(), bTs.as<double>(), Bt, M, s));
-    sym_frobenius_kernel<<<1, 1024, 0, s>>>(Bt, A0, M, scal + 4);  // tr(Bt^-1 A)
+    GPXB_TRY(bH.alloc(sizeof(double) * mm, s));
+    GPXB_TRY(bHt.alloc(sizeof(double) * mm, s));
+    double *Y = bY.as<double>(), *H = bH.as<double>(), *Ht = bHt.as<double>();
+    // w = L_A^-T what (landmark weights)
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(w, wh, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
+    GPXB_TRY(trsm_right_l(ctx, A, M, invA, w, M, 1, M, s));
+    // B <- B^-1 (full symmetric)
+    GPXB_TRY(potri_lower(ctx, B, M, bInvB.as<double>(), M, bWk.as<double>(), bTs.as<double>(), B, M, s));
+    diag_sum_kernel<<<1, 1024, 0, s>>>(B, M, M, scal + 3);  // tr(B^-1)
     GPXB_LAUNCHED(ctx);
-    symmetrize_lower_kernel<<<eb, 256, 0, s>>>(Bt, M);
+    symmetrize_lower_kernel<<<eb, 256, 0, s>>>(B, M);
     GPXB_LAUNCHED(ctx);
-    double* Y = bY.as<double>();
-    // pass 2: per chunk Y = K_c Bt^-1, alpha_c = (r_c - K_c w)/s2, g1 += sum dK (alpha w^T - Y)
+    // pass 2: per chunk Y = G_c^T B^-1 L_A^-1, alpha_c = (r_c - G_c^T what)/s2, g1 += sum dK (alpha w^T - Y)
     for (int r0 = 0; r0 < n_loc; r0 += CHUNK) {
       const int nc = std::min(CHUNK, n_loc - r0);
-      GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, Zc, s));
-      GramArgs g;
-      g.kind = kind; g.Z1 = Zc; g.n1 = nc; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell; g.out = Kc; g.ldo = M;
-      GPXB_TRY(gram_launch(ctx, g, s));
-      center_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(y + r0, nc, mu, rc);
-      GPXB_LAUNCHED(ctx);
-      GemmArgs a;  // Y = K_c Bt^-1
-      a.M = nc; a.N = M; a.K = M;
-      a.A = Kc; a.lda = M; a.a_kmajor = true;
-      a.B = Bt; a.ldb = M; a.b_kmajor = false;
-      a.C = Y; a.ldc = M;
-      GPXB_TRY(gemm_f64(ctx, a, s));
-      GemmArgs b;  // t_c = K_c w
+      GPXB_TRY(chunk_G(r0, nc));
+      GemmArgs b;  // t_c = G_c^T what
       b.M = nc; b.N = 1; b.K = M;
       b.A = Kc; b.lda = M; b.a_kmajor = true;
-      b.B = w; b.ldb = 1; b.b_kmajor = false;
+      b.B = wh; b.ldb = 1; b.b_kmajor = false;
       b.C = tc; b.ldc = 1;
       GPXB_TRY(gemm_f64(ctx, b, s));
       alpha_chunk_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(rc, tc, nc, s2);
       GPXB_LAUNCHED(ctx);
-      sumsq_kernel<<<1, 1024, 0, s>>>(tc, nc, scal + 5, 1);
+      sumsq_kernel<<<1, 1024, 0, s>>>(tc, nc, scal + 4, 1);
       GPXB_LAUNCHED(ctx);
+      GemmArgs a;  // Y = G_c^T B^-1
+      a.M = nc; a.N = M; a.K = M;
+      a.A = Kc; a.lda = M; a.a_kmajor = true;
+      a.B = B; a.ldb = M; a.b_kmajor = false;
+      a.C = Y; a.ldc = M;
+      GPXB_TRY(gemm_f64(ctx, a, s));
+      GPXB_TRY(trsm_right_l(ctx, A, M, invA, Y, M, nc, M, s));  // Y <- Y L_A^-1
       GramArgs c;
       c.kind = kind; c.Z1 = Zc; c.n1 = nc; c.Z2 = Zl; c.n2 = M; c.zl = zl; c.ell = ell;
       c.Ainv = Y; c.ldainv = M; c.alpha = tc; c.alpha2 = w; c.t = 1;
@@ -285,22 +310,29 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
       GPXB_TRY(gram_launch(ctx, c, s));
       sum_kernel<<<1, 1024, 0, s>>>(c.partials, nparts, c.partials + nparts);
       GPXB_LAUNCHED(ctx);
-      add_vec_kernel<<<1, 1, 0, s>>>(scal + 6, c.partials + nparts, 1);
+      add_vec_kernel<<<1, 1, 0, s>>>(scal + 5, c.partials + nparts, 1);
       GPXB_LAUNCHED(ctx);
       bPart.release();
     }
-    if (ctx->world > 1) GPXB_TRY(comm_allreduce_sum(ctx, scal + 5, 2, s));
-    // F = A^-1 - s2 Bt^-1 (lower) into A;  g2 = sum dA (w w^T - F)
-    axpby_kernel<<<eb, 256, 0, s>>>(A, 1.0, A, -s2, Bt, (long long)mm);
+    if (ctx->world > 1) GPXB_TRY(comm_allreduce_sum(ctx, scal + 4, 2, s));
+    // F = L_A^-T (I - s2 B^-1) L_A^-1:  H = I - s2 B^-1;  H <- H L_A^-1;  F = (H^T L_A^-1)^T = H^T L_A^-1
+    i_minus_scaled_kernel<<<eb, 256, 0, s>>>(B, M, s2, H);
     GPXB_LAUNCHED(ctx);
+    GPXB_TRY(trsm_right_l(ctx, A, M, invA, H, M, M, M, s));
+    {
+      dim3 grid(ceil_div(M, 32), ceil_div(M, 32)), blk(32, 8);
+      transpose_sq_kernel<<<grid, blk, 0, s>>>(H, M, Ht);
+      GPXB_LAUNCHED(ctx);
+    }
+    GPXB_TRY(trsm_right_l(ctx, A, M, invA, Ht, M, M, M, s));  // Ht = F (symmetric, full)
     GramArgs c;
     c.kind = kind; c.Z1 = Zl; c.n1 = M; c.Z2 = Zl; c.n2 = M; c.zl = zl; c.ell = ell; c.sym = 1; c.lower_only = 1;
-    c.Ainv = A; c.ldainv = M; c.alpha = w; c.t = 1;
+    c.Ainv = Ht; c.ldainv = M; c.alpha = w; c.t = 1;
     const long long nparts = gram_num_ctas(c);
     GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)nparts, s));
     c.partials = bPart.as<double>();
     GPXB_TRY(gram_launch(ctx, c, s));
-    sum_kernel<<<1, 1024, 0, s>>>(c.partials, nparts, scal + 7);
+    sum_kernel<<<1, 1024, 0, s>>>(c.partials, nparts, scal + 6);
     GPXB_LAUNCHED(ctx);
   }
   finalize_sgpr_grad_kernel<<<1, 1, 0, s>>>(scal, N, M, s2, sigma, want_grad, out3);
