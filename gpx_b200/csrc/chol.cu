@@ -426,9 +426,19 @@ int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStre
 }
 
 namespace {
-// W (n x n, zero-initialised, lower) <- L^-1.  T: scratch with leading dimension ldt >= n/2.
+size_t trtri_scratch(int n) {
+  if (n <= LB) return 0;
+  const int n1 = split_point(n), n2 = n - n1;
+  return (size_t)n1 * n2 + trtri_scratch(n1) + trtri_scratch(n2);
+}
+
+// W (n x n, zero-initialised, lower) <- L^-1.  T: trtri_scratch(n) doubles.  The two half-size
+// inversions are independent; down to depth 2 they run on separate streams (4-way concurrency)
+// so that the small GEMMs deep in the recursion still fill the GPU.  st[0] is the caller's stream.
 int trtri_rec(Ctx* ctx, const double* L, long long ldl, const double* inv, double* W, long long ldw,
-              int n, double* T, long long ldt, cudaStream_t s) {
+              int n, double* T, cudaStream_t* st, int depth, int branch) {
+  cudaStream_t s = st[depth <= 2 ? branch * (4 >> depth) : 0];
+  if (depth > 2) s = st[branch];  // below the fork levels 'branch' carries the stream index
   if (n <= LB) {
     copy_block_kernel<<<32, 256, 0, s>>>(inv, W, ldw, n);
     GPXB_LAUNCH_CHECK();
@@ -437,23 +447,42 @@ int trtri_rec(Ctx* ctx, const double* L, long long ldl, const double* inv, doubl
   }
   const int n1 = split_point(n), n2 = n - n1;
   const double* inv2 = inv + (long long)(n1 / LB) * LB * LB;
-  GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, ldw, n1, T, ldt, s));
-  GPXB_TRY(trtri_rec(ctx, L + (long long)n1 * ldl + n1, ldl, inv2, W + (long long)n1 * ldw + n1, ldw,
-                     n2, T, ldt, s));
+  double* Tc1 = T + (size_t)n1 * n2;
+  double* Tc2 = Tc1 + trtri_scratch(n1);
+  const double* L22 = L + (long long)n1 * ldl + n1;
+  double* W22 = W + (long long)n1 * ldw + n1;
+  if (depth < 2 && n >= 2048) {
+    const int b1 = 2 * branch, b2 = 2 * branch + 1;
+    cudaStream_t s2 = st[b2 * (4 >> (depth + 1))];
+    cudaEvent_t e0, e1;
+    GPXB_TRY(ctx->next_event(&e0));
+    GPXB_CUDA_CHECK(cudaEventRecord(e0, s));
+    GPXB_CUDA_CHECK(cudaStreamWaitEvent(s2, e0, 0));
+    GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, ldw, n1, Tc1, st, depth + 1, b1));
+    GPXB_TRY(trtri_rec(ctx, L22, ldl, inv2, W22, ldw, n2, Tc2, st, depth + 1, b2));
+    GPXB_TRY(ctx->next_event(&e1));
+    GPXB_CUDA_CHECK(cudaEventRecord(e1, s2));
+    GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, e1, 0));
+  } else {
+    // sequential on this node's stream
+    const int sidx = (depth <= 2) ? branch * (4 >> depth) : branch;
+    GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, ldw, n1, Tc1, st, 3, sidx));
+    GPXB_TRY(trtri_rec(ctx, L22, ldl, inv2, W22, ldw, n2, Tc2, st, 3, sidx));
+  }
   {
     GemmArgs g;  // T = L21 * W11   (W11 lower: k starts at the tile's first column)
     g.M = n2; g.N = n1; g.K = n1;
     g.A = L + (long long)n1 * ldl; g.lda = ldl; g.a_kmajor = true;
     g.B = W; g.ldb = ldw; g.b_kmajor = false;
-    g.C = T; g.ldc = ldt;
+    g.C = T; g.ldc = n1;
     g.klo_mode = 1;
     GPXB_TRY(gemm_f64(ctx, g, s));
   }
   {
     GemmArgs g;  // W21 = -W22 * T   (W22 lower: k ends at the tile's last row)
     g.M = n2; g.N = n1; g.K = n2;
-    g.A = W + (long long)n1 * ldw + n1; g.lda = ldw; g.a_kmajor = true;
-    g.B = T; g.ldb = ldt; g.b_kmajor = false;
+    g.A = W22; g.lda = ldw; g.a_kmajor = true;
+    g.B = T; g.ldb = n1; g.b_kmajor = false;
     g.C = W + (long long)n1 * ldw; g.ldc = ldw;
     g.alpha = -1.0;
     g.khi_mode = 1;
@@ -464,13 +493,13 @@ int trtri_rec(Ctx* ctx, const double* L, long long ldl, const double* inv, doubl
 }  // namespace
 
 // Ainv (lower triangle, n x n, ld ldo) <- (L L^T)^-1 given the factor L and its leaf inverses.
-// W: n x n workspace (ld n), T: (n/2+128)^2 workspace.  out may alias L's storage.
+// W: n x n workspace (ld n), T: potri_scratch_doubles(n) workspace.  out may alias L's storage.
 int potri_lower(Ctx* ctx, const double* L, long long ldl, const double* inv, int n, double* W,
                 double* T, double* out, long long ldo, cudaStream_t s) {
   if (n <= 0) return 0;
   GPXB_CUDA_CHECK(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)n * (size_t)n, s));
-  const long long ldt = (n <= LB) ? LB : (long long)max(split_point(n), n - split_point(n));
-  GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, n, n, T, ldt, s));
+  cudaStream_t st[4] = {s, ctx->aux[0], ctx->aux[1], ctx->aux[2]};
+  GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, n, n, T, st, 0, 0));
   GemmArgs g;  // out = W^T W (lower); W[k][i] = 0 for k < i -> k starts at the tile's first row
   g.M = n; g.N = n; g.K = n;
   g.A = W; g.lda = n; g.a_kmajor = false;
@@ -489,9 +518,6 @@ int logdet_lower(Ctx* ctx, const double* L, long long ld, int n, double* out, do
   return 0;
 }
 
-size_t potri_scratch_doubles(int n) {
-  const long long h = (n <= LB) ? LB : (long long)max(split_point(n), n - split_point(n));
-  return (size_t)(h * h);
-}
+size_t potri_scratch_doubles(int n) { return trtri_scratch(n) + 64; }
 
 }  // namespace gpxb
