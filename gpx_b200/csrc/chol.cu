@@ -25,18 +25,26 @@ namespace {
 
 constexpr int LB = CHOL_LEAF;  // 128
 constexpr int LS = LB + 1;     // padded smem stride (odd -> conflict-free columns)
-constexpr int LEAF_NT = 512;
-constexpr int LEAF_SMEM = (LB * LS + LB) * (int)sizeof(double);
+constexpr int LEAF_NT = 256;
+constexpr int PB = 8;          // panel width inside the leaf
+constexpr int PTS = LB + 8;    // row stride of the transposed panel buffer
+constexpr int LEAF_SMEM = (LB * LS + PB * PTS + 128) * (int)sizeof(double);
 
 // One CTA: factor the n x n (n <= 128) lower block in place, then write its inverse
 // (full 128x128 block, zero upper / zero padding) to inv.
+//
+// Blocked inside shared memory with 8-column panels: the panel is factorised with one thread per
+// row holding its 8 entries in registers (two barriers per column, almost no work between them);
+// the rank-8 trailing update and the inverse's block column use 4x4 / 1x8 register tiles.
 __global__ void __launch_bounds__(LEAF_NT, 1)
 potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv) {
   extern __shared__ __align__(16) double sm[];
-  double* S = sm;             // [LB][LS]
-  double* Ld = sm + LB * LS;  // [LB] diagonal of L
+  double* S = sm;                 // [LB][LS]
+  double* PT = sm + LB * LS;      // [PB][PTS]  transposed panel: PT[c][row]
+  double* lsh = PT + PB * PTS;    // [8] multipliers of the diagonal-block rows, [8] pivot
+  double* xbb = lsh + 16;         // [8][8] inverse of a diagonal 8x8 block
+  double* rdg = S + LB;           // rdg[j * LS] = 1 / L[j][j], kept in the padding column of S
   const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;  // 32 x 16
 
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
     const int i = idx >> 7, k = idx & (LB - 1);
@@ -46,63 +54,144 @@ potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restri
   }
   __syncthreads();
 
-  // ---- right-looking unblocked Cholesky, 2 barriers per column ----
-  for (int j = 0; j < n; ++j) {
-    const double d = sqrt(S[j * LS + j]);  // NaN for a non-PD pivot: propagates like JAX
-    for (int i = j + 1 + tid; i < n; i += LEAF_NT) S[i * LS + j] /= d;
-    if (tid == 0) Ld[j] = d;
+  // ---------------- factorisation ----------------
+  for (int jb = 0; jb < n; jb += PB) {
+    const int bw = (n - jb < PB) ? (n - jb) : PB;
+    const int i = jb + tid;  // this thread's row in the panel
+    const bool act = (tid < LB) && (i < n);
+    double a[PB];
+#pragma unroll
+    for (int c = 0; c < PB; ++c) a[c] = (act && c < bw) ? S[i * LS + jb + c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < PB; ++c) {
+      if (c < bw) {  // uniform
+        if (act && i == jb + c) lsh[8] = a[c];
+        __syncthreads();
+        const double piv = lsh[8];
+        const double rd = rsqrt(piv);  // NaN for a non-PD pivot: propagates like JAX
+        if (act) {
+          if (i == jb + c) {
+            a[c] = piv * rd;
+            rdg[i * LS] = rd;
+          } else if (i > jb + c) {
+            a[c] = a[c] * rd;
+          }
+          if (i - jb < PB) lsh[i - jb] = a[c];
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+          for (int c2 = c + 1; c2 < PB; ++c2)
+            if (c2 < bw && i >= jb + c2) a[c2] -= a[c] * lsh[c2];
+        }
+      }
+    }
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        if (c < bw && jb + c <= i) S[i * LS + jb + c] = a[c];
+        if (i >= jb + PB) PT[c * PTS + i] = (c < bw) ? a[c] : 0.0;
+      }
+    }
     __syncthreads();
-    // trailing update; every thread keeps 4 independent rows in flight to hide LDS latency
-    for (int i0 = j + 1 + ty; i0 < n; i0 += 64) {
-      const int i1 = i0 + 16, i2 = i0 + 32, i3 = i0 + 48;
-      const double l0 = S[i0 * LS + j];
-      const double l1 = i1 < n ? S[i1 * LS + j] : 0.0;
-      const double l2 = i2 < n ? S[i2 * LS + j] : 0.0;
-      const double l3 = i3 < n ? S[i3 * LS + j] : 0.0;
-      const int kmax = min(n - 1, i3);
-      for (int k = j + 1 + tx; k <= kmax; k += 32) {
-        const double lk = S[k * LS + j];
-        if (k <= i0) S[i0 * LS + k] -= l0 * lk;
-        if (i1 < n && k <= i1) S[i1 * LS + k] -= l1 * lk;
-        if (i2 < n && k <= i2) S[i2 * LS + k] -= l2 * lk;
-        if (i3 < n && k <= i3) S[i3 * LS + k] -= l3 * lk;
+    // rank-8 trailing update on 4x4 register tiles of the lower triangle
+    const int t0 = jb + PB;
+    const int t = n - t0;
+    if (t > 0) {
+      const int nt = (t + 3) >> 2;
+      const int ntiles = nt * (nt + 1) / 2;
+      for (int idx = tid; idx < ntiles; idx += LEAF_NT) {
+        int ti = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+        while (ti * (ti + 1) / 2 > idx) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= idx) ++ti;
+        const int tk = idx - ti * (ti + 1) / 2;
+        const int i0 = t0 + 4 * ti, k0 = t0 + 4 * tk;
+        double acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+#pragma unroll
+        for (int c = 0; c < PB; ++c) {
+          double pi[4], pk[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            pi[x] = (i0 + x < n) ? PT[c * PTS + i0 + x] : 0.0;
+            pk[x] = (k0 + x < n) ? PT[c * PTS + k0 + x] : 0.0;
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] += pi[x] * pk[y];
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) {
+            const int r = i0 + x, k = k0 + y;
+            if (r < n && k <= r) S[r * LS + k] -= acc[x][y];
+          }
       }
     }
     __syncthreads();
   }
-  for (int j = tid; j < n; j += LEAF_NT) S[j * LS + j] = Ld[j];
-  __syncthreads();
   for (int idx = tid; idx < n * n; idx += LEAF_NT) {
     const int i = idx / n, k = idx - i * n;
     if (k <= i) A[(long long)i * lda + k] = S[i * LS + k];
   }
   if (inv == nullptr) return;
+  __syncthreads();
 
-  // ---- in-place inverse of the lower factor (dtrti2, columns right to left) ----
-  // X[j][j] = 1/L[j][j];  X[i][j] = -(sum_{k=j+1..i} X[i][k] L[k][j]) * X[j][j], i > j.
-  // 4 lanes cooperate on one row i.
-  const int sub = tid & 3, rowslot = tid >> 2;  // 128 row slots
-  for (int j = n - 1; j >= 0; --j) {
-    const double xjj = 1.0 / S[j * LS + j];
-    double r = 0.0;
-    const int i = j + 1 + rowslot;
-    if (i < n) {
-      double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-      int k = j + 1 + sub;
-      for (; k + 12 <= i; k += 16) {
-        r0 += S[i * LS + k] * S[k * LS + j];
-        r1 += S[i * LS + k + 4] * S[(k + 4) * LS + j];
-        r2 += S[i * LS + k + 8] * S[(k + 8) * LS + j];
-        r3 += S[i * LS + k + 12] * S[(k + 12) * LS + j];
+  // ---------------- in-place inverse, block columns right to left ----------------
+  // X11 = inv(L11);  X21 = -X22 L21 X11  with X22 (rows/cols > block) already inverted in place.
+  const int jlast = ((n - 1) / PB) * PB;
+  for (int jb = jlast; jb >= 0; jb -= PB) {
+    const int bw = (n - jb < PB) ? (n - jb) : PB;
+    // inverse of the 8x8 diagonal block: lane c of the LAST warp (idle otherwise) solves column c
+    // by forward substitution, multiplying by the reciprocals saved during the factorisation
+    if (tid >= LEAF_NT - 32 && tid < LEAF_NT - 32 + PB) {
+      const int c = tid - (LEAF_NT - 32);
+      double x[PB];
+#pragma unroll
+      for (int r = 0; r < PB; ++r) {
+        double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < PB; ++k)
+          if (k < r && k >= c && r < bw) v -= S[(jb + r) * LS + jb + k] * x[k];
+        x[r] = (r < bw && r >= c && c < bw) ? v * rdg[(jb + r) * LS] : 0.0;
       }
-      for (; k <= i; k += 4) r0 += S[i * LS + k] * S[k * LS + j];
-      r = (r0 + r1) + (r2 + r3);
+#pragma unroll
+      for (int r = 0; r < PB; ++r) xbb[r * PB + c] = x[r];
     }
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    __syncthreads();  // all reads of column j (original L) done
-    if (i < n && sub == 0) S[i * LS + j] = -r * xjj;
-    if (tid == 0) S[j * LS + j] = xjj;
+    const int i = jb + PB + tid;  // one thread per row below the block
+    const bool act = (tid < LB) && (i < n);
+    double r8[PB];
+#pragma unroll
+    for (int c = 0; c < PB; ++c) r8[c] = 0.0;
+    if (act) {
+#pragma unroll 4
+      for (int k = jb + PB; k <= i; ++k) {
+        const double xik = S[i * LS + k];
+        const double* lk = S + k * LS + jb;
+#pragma unroll
+        for (int c = 0; c < PB; ++c) r8[c] += xik * lk[c];
+      }
+    }
+    __syncthreads();  // xbb ready; every read of the L panel (columns jb..jb+7) is done
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        double v = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < PB; ++c2)
+          if (c2 >= c) v += r8[c2] * xbb[c2 * PB + c];
+        if (c < bw) S[i * LS + jb + c] = -v;
+      }
+    }
+    if (tid < PB * PB) {
+      const int r = tid / PB, c = tid % PB;
+      if (r < bw && c <= r) S[(jb + r) * LS + jb + c] = xbb[r * PB + c];
+    }
     __syncthreads();
   }
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
