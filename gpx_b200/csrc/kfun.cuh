@@ -1,0 +1,53 @@
+// Stationary kernel nonlinearities k = phi(d2) on the device, with one exponential call site and a
+// branch-free FP64 exp for non-positive arguments (the hot loop of the matrix-free mat-vec).
+//   SE   exp(-d2)                                   gpx/kernels/kernels.py:751-757
+//   M12  exp(-r),            r = sqrt(max(d2,1e-36))                     :922-927
+//   M32  (1 + d) exp(-d),    d = sqrt(3) r                               :966-971
+//   M52  (1 + d + d^2/3) exp(-d), d = sqrt(5) r                          :1050-1055
+#pragma once
+#include "gram.cuh"
+
+namespace gpxb {
+
+// exp(x) for x <= ~0 (|relative error| < 2 ulp for x >= -708; exactly 0 below, where the true
+// value is < 3e-308).  n = rint(x log2 e), r = x - n ln2 (two-term Cody-Waite), degree-13 Taylor
+// polynomial on |r| <= 0.347 (truncation 4e-18), scaling by 2^n through the exponent field.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52
+  const double kf = fma(x, 1.4426950408889634, SHIFT);
+  const int ki = __double2loint(kf);
+  const double kd = kf - SHIFT;
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;            // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double s = __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
+  return x < -708.0 ? 0.0 : s;
+}
+
+__device__ __forceinline__ double kfun_fast(int kind, double d2) {
+  double t = d2;
+  if (kind != KIND_SE) {
+    const double c = kind == KIND_M12 ? 1.0 : (kind == KIND_M32 ? 1.7320508075688772 : 2.23606797749979);
+    t = c * sqrt(fmax(d2, 1e-36));
+  }
+  const double e = exp_nonpos(-t);
+  double poly = 1.0;
+  if (kind == KIND_M32) poly = 1.0 + t;
+  if (kind == KIND_M52) poly = 1.0 + t + t * t / 3.0;
+  return poly * e;
+}
+
+}  // namespace gpxb

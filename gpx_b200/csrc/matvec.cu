@@ -15,6 +15,7 @@
 //     contraction index may be permuted as long as A and B agree), so no shuffle is needed.
 // V is stored with a padded row stride PS (PS % 8 == 2) so that a tile is contiguous (one
 // bulk copy) and the GEMM-2 B-fragment reads are bank-conflict free.
+#include "kfun.cuh"
 #include "matvec.cuh"
 #include "mma.cuh"
 
@@ -42,18 +43,6 @@ struct KmvParams {
   double diag_add;
   int jsplit, jps;  // columns per split (multiple of BJ)
 };
-
-__device__ __forceinline__ double kfun(int kind, double d2) {
-  if (kind == KIND_SE) return exp(-d2);
-  const double r = sqrt(fmax(d2, 1e-36));
-  if (kind == KIND_M12) return exp(-r);
-  if (kind == KIND_M32) {
-    const double d = 1.7320508075688772 * r;
-    return (1.0 + d) * exp(-d);
-  }
-  const double d = 2.23606797749979 * r;
-  return (1.0 + d + d * d / 3.0) * exp(-d);
-}
 
 // MF: 8-row fragments per warp (rows per CTA = 64*MF); KS: Dp/4 when the row operand lives in
 // registers, 0 = read it from shared memory; NPF: 8-column fragments of V/W (P <= 8*NPF).
@@ -158,7 +147,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
         const bool dg0 = (p.row_offset >= 0) && (gi == gj), dg1 = (p.row_offset >= 0) && (gi == gj + 1);
         if (dg0) d20 = 1e-12;
         if (dg1) d21 = 1e-12;
-        double k0 = kfun(p.kind, d20), k1 = kfun(p.kind, d21);
+        double k0 = kfun_fast(p.kind, d20), k1 = kfun_fast(p.kind, d21);
         if (dg0) k0 += p.diag_add;
         if (dg1) k1 += p.diag_add;
         c[mf][0] = (gj < jend) ? k0 : 0.0;
