@@ -46,7 +46,24 @@ struct KmvParams {
 
 // MF: 8-row fragments per warp (rows per CTA = 64*MF); KS: Dp/4 when the row operand lives in
 // registers, 0 = read it from shared memory; NPF: 8-column fragments of V/W (P <= 8*NPF).
-template <int MF, int KS, int NPF, int NWARP>
+// KMODE: 0 = kind chosen at run time (libm exp), 1 = SquaredExponential with libm exp,
+//        2 = SquaredExponential with the branch-free exp_nonpos
+template <int KMODE>
+__device__ __forceinline__ double kfun_mode(int kind, double d2) {
+  if (KMODE == 1) return exp(-d2);
+  if (KMODE == 2) return exp_nonpos(-d2);
+  if (kind == KIND_SE) return exp(-d2);
+  const double r = sqrt(fmax(d2, 1e-36));
+  if (kind == KIND_M12) return exp(-r);
+  if (kind == KIND_M32) {
+    const double d = 1.7320508075688772 * r;
+    return (1.0 + d) * exp(-d);
+  }
+  const double d = 2.23606797749979 * r;
+  return (1.0 + d + d * d / 3.0) * exp(-d);
+}
+
+template <int MF, int KS, int NPF, int NWARP, int KMODE>
 __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams p) {
   constexpr int BR = NWARP * 8 * MF;
   constexpr int NT = NWARP * 32;
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
         const bool dg0 = (p.row_offset >= 0) && (gi == gj), dg1 = (p.row_offset >= 0) && (gi == gj + 1);
         if (dg0) d20 = 1e-12;
         if (dg1) d21 = 1e-12;
-        double k0 = kfun_fast(p.kind, d20), k1 = kfun_fast(p.kind, d21);
+        double k0 = kfun_mode<KMODE>(p.kind, d20), k1 = kfun_mode<KMODE>(p.kind, d21);
         if (dg0) k0 += p.diag_add;
         if (dg1) k1 += p.diag_add;
         c[mf][0] = (gj < jend) ? k0 : 0.0;
@@ -210,11 +227,33 @@ __global__ void pack_v_kernel(const double* __restrict__ V, long long ldv, int n
   Vp[idx] = c < P ? V[(long long)i * ldv + c0 + c] : 0.0;
 }
 
+template <int MF, int KS, int NPF, int NWARP, int KMODE>
+int launch_k(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) {
+  GPXB_CUDA_CHECK(cudaFuncSetAttribute(kmatvec_kernel<MF, KS, NPF, NWARP, KMODE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kmatvec_kernel<MF, KS, NPF, NWARP, KMODE><<<grid, NWARP * 32, smem, s>>>(p);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
 template <int MF, int KS, int NPF, int NWARP>
 int launch_t(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) {
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(kmatvec_kernel<MF, KS, NPF, NWARP>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kmatvec_kernel<MF, KS, NPF, NWARP><<<grid, NWARP * 32, smem, s>>>(p);
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("GPXB_KMV_EXP");  // "libm" (default, measured fastest) or "fast" (exp_nonpos)
+    mode = (e && e[0] == 'f') ? 2 : 1;
+  }
+  if (p.kind == KIND_SE) {
+    if (mode == 1) return launch_k<MF, KS, NPF, NWARP, 1>(ctx, p, grid, smem, s);
+    return launch_k<MF, KS, NPF, NWARP, 2>(ctx, p, grid, smem, s);
+  }
+  return launch_k<MF, KS, NPF, NWARP, 0>(ctx, p, grid, smem, s);
+}
+
+template <int MF, int KS, int NPF, int NWARP>
+int launch_unused(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) {
+  kmatvec_kernel<MF, KS, NPF, NWARP, 0><<<grid, NWARP * 32, smem, s>>>(p);
   GPXB_LAUNCH_CHECK();
   ctx->launches++;
   return 0;
