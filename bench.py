@@ -46,15 +46,21 @@ def alg_flops(N, D):
 
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_sample_seconds(steps, warmup, n0):
+    """Seconds per LML+grad of the CPU restatement with every host core the process may use
+    (torchrun exports OMP_NUM_THREADS=1; the BLAS pool is widened explicitly)."""
+    from threadpoolctl import threadpool_limits
+
     from oracle import ref_numpy as R  # the checker, timed as the CPU baseline
 
     x, y = synth(n0, CFG["D"], CFG["seed"])
-    for _ in range(warmup):
-        R.lml_grad_dense(CFG["kind"], x, y, CFG["ell"], CFG["sigma"])
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        R.lml_grad_dense(CFG["kind"], x, y, CFG["ell"], CFG["sigma"])
-    return (time.perf_counter() - t0) / steps
+    nthr = cpu_cores()
+    with threadpool_limits(limits=nthr):
+        for _ in range(warmup):
+            R.lml_grad_dense(CFG["kind"], x, y, CFG["ell"], CFG["sigma"], threads=nthr)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            R.lml_grad_dense(CFG["kind"], x, y, CFG["ell"], CFG["sigma"], threads=nthr)
+        return (time.perf_counter() - t0) / steps
 
 
 def cpu_cores():
