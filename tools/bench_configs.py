@@ -68,6 +68,21 @@ def main():
         fl = float(N) ** 2 * (2 * 16 + 4 + 2 * P)
         print(json.dumps(dict(what="kmatvec_block", N=N, D=16, P=P, s=t, alg_flops=fl, tflops=fl / t / 1e12,
                               pair_evals_per_s=float(N) ** 2 / t, checksum=float(W.sum().cpu()))), flush=True)
+    elif what == "derivs":
+        # configs[2]: GPR on derivative values, nf = nv = 90 (30 atoms); the named N = 2000 needs 259 GB as a
+        # square matrix, so the largest N that fits one B200 is measured and stated
+        N = a[0] if a else 1200
+        nf = nv = 90
+        g = torch.Generator(device="cuda").manual_seed(2)
+        x = torch.randn((N, nf), dtype=torch.float64, device="cuda", generator=g)
+        J = 0.1 * torch.randn((N, nf, nv), dtype=torch.float64, device="cuda", generator=g)
+        J += torch.eye(nf, dtype=torch.float64, device="cuda").unsqueeze(0)
+        y = torch.randn((N, nv), dtype=torch.float64, device="cuda", generator=g)
+        n = N * nv
+        t, out = ev_time(lambda: ops.gpr_lml_derivs("se", x, J, y, 90**0.5, 0.05))
+        fl = n**3 / 3.0 + float(n) ** 2 * nf
+        print(json.dumps(dict(what="gpr_lml_derivs", N=N, nf=nf, nv=nv, rows=n, s=t, alg_flops=fl,
+                              tflops=fl / t / 1e12, matrix_gb=8.0 * n * n / 1e9, lml=float(out.cpu()[0]))), flush=True)
     elif what == "slq":
         N, P, m = a[:3] if len(a) >= 3 else (262144, 30, 50)
         x, _ = data(N, 16, 4)
