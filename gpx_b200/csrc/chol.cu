@@ -237,38 +237,55 @@ inline int split_point(int n) {
 namespace {
 constexpr int TRSV_MAXM = 4;
 
-// x_k = inv_kk b_k (forward, trans_inv = 0: x = inv b) or inv_kk^T b_k (backward) for m right-hand
-// sides stored as rows of B (ld ldb); one CTA, 128 threads, in place.
-__global__ void __launch_bounds__(LB) trsv_diag_kernel(const double* __restrict__ inv, double* __restrict__ B,
-                                                       long long ldb, int m, int nb, int backward) {
+// x_k = inv_kk b_k (forward) or inv_kk^T b_k (backward) for m right-hand sides stored as rows of B
+// (ld ldb); one CTA of 256 threads, in place.  Both directions read the 128x128 inverse coalesced:
+// forward: one warp per output row (lanes over the columns, warp reduction);
+// backward: one thread per output index (lanes over consecutive columns of inv).
+__global__ void __launch_bounds__(256) trsv_diag_kernel(const double* __restrict__ inv, double* __restrict__ B,
+                                                        long long ldb, int m, int nb, int backward) {
   __shared__ double sb[TRSV_MAXM][LB];
-  const int t = threadIdx.x;
-  for (int r = 0; r < m; ++r) sb[r][t] = (t < nb) ? B[(long long)r * ldb + t] : 0.0;
+  __shared__ double so[TRSV_MAXM][LB];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
+    const int r = i / LB, c = i % LB;
+    sb[r][c] = (r < m && c < nb) ? B[(long long)r * ldb + c] : 0.0;
+  }
   __syncthreads();
-  if (t >= nb) return;
-  double acc[TRSV_MAXM];
-#pragma unroll
-  for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
   if (!backward) {
-    // x[t] = sum_{c <= t} inv[t][c] b[c]
-    for (int c = 0; c <= t; ++c) {
-      const double v = inv[t * LB + c];
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int t = warp; t < nb; t += 8) {  // x[t] = sum_{c <= t} inv[t][c] b[c]
+      double acc[TRSV_MAXM];
 #pragma unroll
-      for (int r = 0; r < TRSV_MAXM; ++r)
-        if (r < m) acc[r] += v * sb[r][c];
+      for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
+      for (int c = lane; c <= t; c += 32) {
+        const double v = inv[t * LB + c];
+#pragma unroll
+        for (int r = 0; r < TRSV_MAXM; ++r) acc[r] += v * sb[r][c];
+      }
+#pragma unroll
+      for (int r = 0; r < TRSV_MAXM; ++r) {
+        const double sum = warp_sum(acc[r]);
+        if (lane == 0) so[r][t] = sum;
+      }
     }
-  } else {
-    // x[t] = sum_{c >= t} inv[c][t] b[c]
+  } else if (tid < nb) {
+    const int t = tid;  // x[t] = sum_{c >= t} inv[c][t] b[c]
+    double acc[TRSV_MAXM];
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
     for (int c = t; c < nb; ++c) {
       const double v = inv[c * LB + t];
 #pragma unroll
-      for (int r = 0; r < TRSV_MAXM; ++r)
-        if (r < m) acc[r] += v * sb[r][c];
+      for (int r = 0; r < TRSV_MAXM; ++r) acc[r] += v * sb[r][c];
     }
-  }
 #pragma unroll
-  for (int r = 0; r < TRSV_MAXM; ++r)
-    if (r < m) B[(long long)r * ldb + t] = acc[r];
+    for (int r = 0; r < TRSV_MAXM; ++r) so[r][t] = acc[r];
+  }
+  __syncthreads();
+  for (int i = tid; i < m * nb; i += 256) {
+    const int r = i / nb, c = i % nb;
+    B[(long long)r * ldb + c] = so[r][c];
+  }
 }
 
 // forward: B[:, j] -= sum_c L[j][c] x[c] for the rows j below the block (one warp per row j)
@@ -334,7 +351,7 @@ int trsv_few(Ctx* ctx, const double* L, long long ldl, const double* inv, double
     // X L^T = B  <=>  L x = b: forward over blocks
     for (int k = 0; k < nblk; ++k) {
       const int c0 = k * LB, nb = min(LB, n - c0);
-      trsv_diag_kernel<<<1, LB, 0, s>>>(inv + (long long)k * LB * LB, B + c0, ldb, m, nb, 0);
+      trsv_diag_kernel<<<1, 256, 0, s>>>(inv + (long long)k * LB * LB, B + c0, ldb, m, nb, 0);
       const int below = n - c0 - nb;
       if (below > 0)
         trsv_fwd_update_kernel<<<(below + 7) / 8, 256, 0, s>>>(L + (long long)(c0 + nb) * ldl + c0, ldl, B + c0,
@@ -345,7 +362,7 @@ int trsv_few(Ctx* ctx, const double* L, long long ldl, const double* inv, double
     // X L = B  <=>  L^T x = b: backward over blocks
     for (int k = nblk - 1; k >= 0; --k) {
       const int c0 = k * LB, nb = min(LB, n - c0);
-      trsv_diag_kernel<<<1, LB, 0, s>>>(inv + (long long)k * LB * LB, B + c0, ldb, m, nb, 1);
+      trsv_diag_kernel<<<1, 256, 0, s>>>(inv + (long long)k * LB * LB, B + c0, ldb, m, nb, 1);
       if (c0 > 0)
         trsv_bwd_update_kernel<<<(c0 + 255) / 256, 256, 0, s>>>(L + (long long)c0 * ldl, ldl, B + c0, B, ldb, m, nb,
                                                                  c0);
