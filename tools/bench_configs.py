@@ -83,6 +83,30 @@ def main():
         fl = n**3 / 3.0 + float(n) ** 2 * nf
         print(json.dumps(dict(what="gpr_lml_derivs", N=N, nf=nf, nv=nv, rows=n, s=t, alg_flops=fl,
                               tflops=fl / t / 1e12, matrix_gb=8.0 * n * n / 1e9, lml=float(out.cpu()[0]))), flush=True)
+    elif what == "lml_iter":
+        # configs[4] end to end at a reduced N (the named N = 2e6 costs (2e6/N)^2 more per mat-vec):
+        # PCG fit (RPCholesky preconditioner, n_pivots = 100) + 30-probe, 50-step SLQ log-det
+        N = a[0] if a else 262144
+        x, y = data(N, 16, 4)
+        import time as _t
+
+        from gpx_b200.models._iterative import slq_logdet
+
+        torch.cuda.synchronize()
+        t0 = _t.perf_counter()
+        c, mu, iters = ops.gpr_fit_iter("se", x, y, 4.0, 0.5, 100, key)
+        torch.cuda.synchronize()
+        t1 = _t.perf_counter()
+        U = ops.rademacher_probes(key, N, 30, True)
+        al, be, fl_ = ops.lanczos("se", x, 4.0, 0.25 + 1e-10, U, 50)
+        ld = slq_logdet(al.cpu().numpy(), be.cpu().numpy(), N)
+        r = (y - mu).cpu().numpy()
+        lml = (-0.5 * float(r.T @ c.cpu().numpy()) - 0.5 * ld - N * 0.5 * np.log(2 * np.pi)) / N
+        t2 = _t.perf_counter()
+        print(json.dumps(dict(what="gpr_lml_iter", N=N, D=16, P=30, m=50, n_pivots=100, pcg_iters=iters,
+                              s_pcg=t1 - t0, s_slq=t2 - t1, s_total=t2 - t0, lml=lml,
+                              matvec_flops=(50 * (2 * 16 + 4 + 60) + iters * (2 * 16 + 4 + 2)) * float(N) ** 2,
+                              breakdown=int(fl_.cpu()[0]))), flush=True)
     elif what == "slq":
         N, P, m = a[:3] if len(a) >= 3 else (262144, 30, 50)
         x, _ = data(N, 16, 4)
