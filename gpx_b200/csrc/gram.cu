@@ -54,18 +54,19 @@ __device__ __forceinline__ double kfun(int kind, double d2) {
   return (1.0 + d + d * d / 3.0) * exp(-d);
 }
 
-// dK/d ell given d2 = s + 1e-12 (the jitter is a constant; the clamp passes no gradient)
-__device__ __forceinline__ double kfun_dl(int kind, double d2, double s, double ell) {
-  if (kind == KIND_SE) return exp(-d2) * 2.0 * s / ell;
+// dK/d ell given d2 = s + 1e-12 (the jitter is a constant; the clamp passes no gradient).
+// rl = 1/ell is hoisted by the caller: no FP64 division in the inner loop except Matern-1/2's 1/r.
+__device__ __forceinline__ double kfun_dl(int kind, double d2, double s, double rl) {
+  if (kind == KIND_SE) return exp(-d2) * (2.0 * rl) * s;
   if (!(d2 > 1e-36)) return 0.0;
   const double r = sqrt(d2);
-  if (kind == KIND_M12) return exp(-r) * s / (r * ell);
+  if (kind == KIND_M12) return exp(-r) * s * rl / r;
   if (kind == KIND_M32) {
     const double d = 1.7320508075688772 * r;
-    return 3.0 * s * exp(-d) / ell;
+    return (3.0 * rl) * s * exp(-d);
   }
   const double d = 2.23606797749979 * r;
-  return (5.0 * s / (3.0 * ell)) * (1.0 + d) * exp(-d);
+  return ((5.0 / 3.0) * rl) * s * (1.0 + d) * exp(-d);
 }
 
 __global__ void prep_z_kernel(const double* __restrict__ x, long long ldx, int n, int D, int Dp,
@@ -154,11 +155,12 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
     nj[nf][1] = sZ2[(c + 1) * p.S + p.Dp];
   }
   double local = 0.0;
+  const double rl = 1.0 / p.ell;
 #pragma unroll
   for (int mf = 0; mf < 8; ++mf) {
-    const int rl = wm * 64 + mf * 8 + lr;
-    const int gi = row0 + rl;
-    const double ni = sZ1[rl * p.S + p.Dp];
+    const int rloc = wm * 64 + mf * 8 + lr;
+    const int gi = row0 + rloc;
+    const double ni = sZ1[rloc * p.S + p.Dp];
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
       const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
           v[e] = 0.0;
           if (ok[e]) {
             const double s = on_diag ? 0.0 : d2 - 1e-12;
-            const double dk = kfun_dl(p.kind, d2, s, p.ell);
+            const double dk = kfun_dl(p.kind, d2, s, rl);
             double w = -p.Ainv[(long long)gi * p.ldainv + j];
             for (int t = 0; t < p.t; ++t)
               w += p.alpha[(long long)t * p.n1 + gi] * p.alpha2[(long long)t * p.n2 + j];
