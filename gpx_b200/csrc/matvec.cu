@@ -47,11 +47,11 @@ struct KmvParams {
 // MF: 8-row fragments per warp (rows per CTA = 64*MF); KS: Dp/4 when the row operand lives in
 // registers, 0 = read it from shared memory; NPF: 8-column fragments of V/W (P <= 8*NPF).
 // KMODE: 0 = kind chosen at run time (libm exp), 1 = SquaredExponential with libm exp,
-//        2 = SquaredExponential with the branch-free exp_nonpos
+//        2 = SquaredExponential with the table-driven exp_tab (10 FP64 ops)
 template <int KMODE>
-__device__ __forceinline__ double kfun_mode(int kind, double d2) {
+__device__ __forceinline__ double kfun_mode(int kind, double d2, const double* __restrict__ tab) {
   if (KMODE == 1) return exp(-d2);
-  if (KMODE == 2) return exp_nonpos(-d2);
+  if (KMODE == 2) return exp_tab(-d2, tab);
   if (kind == KIND_SE) return exp(-d2);
   const double r = sqrt(fmax(d2, 1e-36));
   if (kind == KIND_M12) return exp(-r);
@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
   const int jbeg = blockIdx.y * p.jps, jend = min(p.N, jbeg + p.jps);
   const int ntiles = (jend - jbeg + BJ - 1) / BJ;
 
+  __shared__ double etab[64];  // 2^(j/64) for exp_tab
+  if (KMODE == 2 && tid < 64) etab[tid] = exp2((double)tid * (1.0 / 64.0));
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
         const bool dg0 = (p.row_offset >= 0) && (gi == gj), dg1 = (p.row_offset >= 0) && (gi == gj + 1);
         if (dg0) d20 = 1e-12;
         if (dg1) d21 = 1e-12;
-        double k0 = kfun_mode<KMODE>(p.kind, d20), k1 = kfun_mode<KMODE>(p.kind, d21);
+        double k0 = kfun_mode<KMODE>(p.kind, d20, etab), k1 = kfun_mode<KMODE>(p.kind, d21, etab);
         if (dg0) k0 += p.diag_add;
         if (dg1) k1 += p.diag_add;
         c[mf][0] = (gj < jend) ? k0 : 0.0;
@@ -241,8 +243,8 @@ template <int MF, int KS, int NPF, int NWARP>
 int launch_t(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) {
   static int mode = -1;
   if (mode < 0) {
-    const char* e = getenv("GPXB_KMV_EXP");  // "libm" (default, measured fastest) or "fast" (exp_nonpos)
-    mode = (e && e[0] == 'f') ? 2 : 1;
+    const char* e = getenv("GPXB_KMV_EXP");  // "fast" (default: table-driven exp_tab, +10%) or "libm"
+    mode = (e && e[0] == 'l') ? 1 : 2;
   }
   if (p.kind == KIND_SE) {
     if (mode == 1) return launch_k<MF, KS, NPF, NWARP, 1>(ctx, p, grid, smem, s);
@@ -284,12 +286,12 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   p.diag_add = a.diag_add;
   const int NPF = a.P <= 8 ? 1 : 4;
   const int limit = 232448;
-  // variants: (MF=2, 16 warps, 256 rows) default; (MF=4, 8 warps, 256 rows) via GPXB_KMV_WARPS=8;
+  // variants: (MF=4, 8 warps, 256 rows) default; (MF=2, 16 warps, 256 rows) via GPXB_KMV_WARPS=16;
   // (MF=2, 8 warps, 128 rows) when the 256-row tile does not fit in shared memory
   static int warps_pref = -1;
   if (warps_pref < 0) {
     const char* e = getenv("GPXB_KMV_WARPS");
-    warps_pref = (e && atoi(e) == 8) ? 8 : 16;
+    warps_pref = (e && atoi(e) == 16) ? 16 : 8;  // 8 warps x 32 rows measured fastest with exp_tab
   }
   int BR = 256, MF = warps_pref == 16 ? 2 : 4, NW = warps_pref;
   if (smem_bytes(256, p.S, p.PS) > limit) { BR = 128; MF = 2; NW = 8; }
