@@ -57,7 +57,7 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ T
   p = fma(p, r, 1.0);
   p *= T[ki & 63];
   const double s = __hiloint2double(__double2hiint(p) + ((ki >> 6) << 20), __double2loint(p));
-  return x < -708.0 ? 0.0 : s;
+  return ki < -65372 ? 0.0 : s;  // x < -708 (integer compare: no FP64 op); the true value is < 3e-308
 }
 
 __device__ __forceinline__ double kfun_fast(int kind, double d2) {
