@@ -18,9 +18,14 @@ Parity pinning status
   differentiation of the ``*_base`` pair kernel) with complex-step / finite
   differences standing in for autodiff.
 * Threefry-2x32-20: PINNED by the Random123 known-answer vectors.
-* LML, LML gradient, fit coefficients, predictions, SGPR, RPCholesky pivots,
-  Lanczos/SLQ: **parity unpinned** -- the reference has no test or golden vector
-  for them and cannot be executed here.  They are anchored
+* exact-GPR LML, its optimum under L-BFGS-B (hence the gradient's zero), the SGPR LML, and the
+  legacy jax.random layout (PRNGKey -> random_bits -> uniform -> normal): PINNED to 8 digits by the
+  numbers the reference's own notebooks print (examples/gpr.ipynb cells 11, 14, 19;
+  examples/sgpr.ipynb cells 5, 7; tests/golden/notebook_anchors.json): with the data regenerated
+  through the restated PRNG this oracle reproduces the fitted lengthscale/sigma and the LML.
+* predictions, fit coefficients, RPCholesky pivots (jax.random.choice path), Lanczos/SLQ, PCG and the
+  partitionable PRNG mode: **parity unpinned** -- the reference has no test, golden vector or
+  printed output for them and cannot be executed here.  They are anchored
   by self-consistency (analytic gradient vs finite differences, Woodbury vs
   the reference's N x N form, SLQ vs exact log-det).
 * ``jax.random`` bit layouts (split / random_bits) are restated from the

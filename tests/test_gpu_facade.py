@@ -107,3 +107,39 @@ def test_iterative_predict_matches_dense():
     m = GPR(Matern52()).fit(x, y, minimize=False)
     xs = np.random.default_rng(2).standard_normal((90, 3))
     assert np.max(np.abs(m.predict(xs, iterative=True) - m.predict(xs))) < 1e-10
+
+
+def test_reference_notebook_anchors_through_the_facade():
+    """The drop-in reproduces what the GPX authors' own notebooks print (examples/gpr.ipynb cells 11, 14,
+    19; examples/sgpr.ipynb cells 5, 7): fitted hyper-parameters and (negative) LML."""
+    import json
+    import os
+
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.mean_functions import zero_mean
+    from gpx_b200.models import GPR, SGPR
+    from gpx_b200.models.sgpr import locs_parameter
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import NormalPrior
+
+    from test_oracle_cpu import notebook_gpr_data, notebook_sgpr_data
+
+    a = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_anchors.json")))
+    x, y = notebook_gpr_data()
+    m = GPR(kernel=SquaredExponential()).fit(x, y)
+    fd = a["gpr"]["fit_default"]
+    assert abs(float(m.state.params["kernel_params"]["lengthscale"].value) - fd["lengthscale"]) < 2e-6
+    assert abs(float(m.state.params["sigma"].value) - fd["sigma"]) < 2e-6
+    assert abs(m.log_marginal_likelihood(x, y, return_negative=True) - fd["neg_lml"]) < 5e-9
+    m2 = GPR(kernel=SquaredExponential(), mean_function=zero_mean,
+             kernel_params=dict(lengthscale=Parameter(1.0, True, Softplus(), NormalPrior(loc=1.0, scale=2.0))),
+             sigma=Parameter(0.2, False, Softplus(), NormalPrior())).fit(x, y)
+    assert abs(m2.log_marginal_likelihood(x, y, return_negative=True)
+               - a["gpr"]["fit_zero_mean_sigma_fixed_0.2"]["neg_lml"]) < 5e-9
+    X, ys, xl = notebook_sgpr_data()
+    fs = a["sgpr"]["fit_fixed_landmarks"]
+    s = SGPR(kernel=SquaredExponential(), x_locs=locs_parameter(xl)).fit(X, ys)
+    assert abs(float(s.state.params["kernel_params"]["lengthscale"].value) - fs["lengthscale"]) < 5e-6
+    assert abs(float(s.state.params["sigma"].value) - fs["sigma"]) < 5e-6
+    assert abs(s.log_marginal_likelihood(X, ys) - fs["lml"]) < 5e-8

@@ -193,3 +193,48 @@ def test_golden_fixture_matches_oracle():
     assert np.array_equal(piv, g["pivots_part"])
     _, piv = R.rpcholesky("se", x, 16, float(g["ell"]), R.PRNGKey(2023), False)
     assert np.array_equal(piv, g["pivots_legacy"])
+
+
+# ---------------------------------------------------------------------------------------------
+# Anchors printed by the reference itself (examples/*.ipynb): these pin the oracle -- kernel
+# convention, jitter, /n normalisation, data_mean, Softplus chain, the analytic gradient (through the
+# optimum L-BFGS-B reaches) and the legacy jax.random bit layout -- against real GPX-on-JAX output.
+# ---------------------------------------------------------------------------------------------
+def notebook_gpr_data():
+    x = np.linspace(0, 1, 100).reshape(-1, 1)
+    eps = R.normal(R.PRNGKey(0), (100,), partitionable=False)
+    y = (np.sin(x[:, 0] * (2 * np.pi)) + eps * np.sqrt(0.04)).reshape(-1, 1)
+    return x, y
+
+
+def notebook_sgpr_data():
+    n = 1000
+    X = np.linspace(-1.0, 1.0, n).reshape(-1, 1)
+    f = 1.0 * np.sin(X * 3 * np.pi) + 0.3 * np.cos(X * 9 * np.pi) + 0.5 * np.sin(X * 7 * np.pi)
+    y = f + 0.2 * R.normal(R.PRNGKey(0), (n, 1), partitionable=False)
+    return X, y, X[::100].copy()
+
+
+def test_notebook_anchor_gpr_lml_and_fit():
+    from scipy.optimize import minimize
+
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["gpr"]
+    x, y = notebook_gpr_data()
+    fd = a["fit_default"]
+    assert abs(-R.lml_dense("se", x, y, fd["lengthscale"], fd["sigma"]) - fd["neg_lml"]) < 5e-9
+    res = minimize(lambda t: R.neg_lml_and_grad_unconstrained("se", x, y, t[0], t[1]),
+                   R.inverse_softplus(np.array([1.0, 1.0])), jac=True, method="L-BFGS-B")
+    ell, sig = R.softplus(res.x)
+    assert abs(ell - fd["lengthscale"]) < 2e-6 and abs(sig - fd["sigma"]) < 2e-6
+    assert abs(res.fun - fd["neg_lml"]) < 5e-9
+    # model2: zero mean, sigma fixed at 0.2, lengthscale optimised
+    f2 = lambda t: -R.lml_dense("se", x, y, float(R.softplus(t[0])), 0.2, mean_function=R.zero_mean)  # noqa: E731
+    res2 = minimize(f2, R.inverse_softplus(np.array([1.0])), method="L-BFGS-B")
+    assert abs(res2.fun - a["fit_zero_mean_sigma_fixed_0.2"]["neg_lml"]) < 5e-9
+
+
+def test_notebook_anchor_sgpr_lml():
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["sgpr"]["fit_fixed_landmarks"]
+    X, y, xl = notebook_sgpr_data()
+    for f in (R.sgpr_lml_dense, R.sgpr_lml_dense_nxn):
+        assert abs(f("se", xl, X, y, a["lengthscale"], a["sigma"]) - a["lml"]) < 5e-8
