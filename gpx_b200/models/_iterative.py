@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import ops
-from ..defaults import THREEFRY_PARTITIONABLE, gpxargs
+from ..defaults import gpxargs, threefry_partitionable
 from ..mean_functions import mean_mode
 from ..random import as_key, split
 
@@ -19,7 +19,7 @@ def fit_iter(state, xd, yd, ell, sigma, n_pivots, key_precond, return_iters=Fals
         raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
     key = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
     c, mu, iters = ops.gpr_fit_iter(state.kernel.kind, xd, yd, ell, sigma, int(n_pivots), key,
-                                    mean_mode(state.mean_function), THREEFRY_PARTITIONABLE)
+                                    mean_mode(state.mean_function), threefry_partitionable())
     c, mu = c.cpu().numpy(), np.float64(mu.cpu().numpy()[0])
     return (c, mu, iters) if return_iters else (c, mu)
 
@@ -39,9 +39,9 @@ def slq_logdet(alpha: np.ndarray, beta: np.ndarray, dim_mat: int) -> float:
 
 
 def lanczos_logdet(kind, xd, ell, diag_add, num_evals, num_lanczos, key):
-    subkey, _ = split(key, 2, THREEFRY_PARTITIONABLE)
+    subkey, _ = split(key, 2, threefry_partitionable())
     N = xd.shape[0]
-    U = ops.rademacher_probes(subkey, N, int(num_evals), THREEFRY_PARTITIONABLE)
+    U = ops.rademacher_probes(subkey, N, int(num_evals), threefry_partitionable())
     alpha, beta, flag = ops.lanczos(kind, xd, ell, diag_add, U, int(num_lanczos))
     if int(flag.cpu().numpy()[0]) != 0:
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "

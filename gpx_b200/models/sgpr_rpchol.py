@@ -10,7 +10,7 @@ from typing import Callable
 import numpy as np
 
 from .. import ops
-from ..defaults import THREEFRY_PARTITIONABLE, gpxargs
+from ..defaults import gpxargs, threefry_partitionable
 from ..mean_functions import data_mean, mean_mode
 from ..parameters import ModelState
 from ..random import PRNGKey, as_key
@@ -21,7 +21,7 @@ from .gpr import _hyper, _xy
 
 def _select_locs(state, xd):
     kernel, ell, _ = _hyper(state)
-    _, piv = ops.rpcholesky(kernel.kind, xd, int(state.n_locs), ell, as_key(state.key), THREEFRY_PARTITIONABLE,
+    _, piv = ops.rpcholesky(kernel.kind, xd, int(state.n_locs), ell, as_key(state.key), threefry_partitionable(),
                             want_factor=False)
     return ops.gather_rows(xd, piv), piv
 

@@ -143,3 +143,30 @@ def test_reference_notebook_anchors_through_the_facade():
     assert abs(float(s.state.params["kernel_params"]["lengthscale"].value) - fs["lengthscale"]) < 5e-6
     assert abs(float(s.state.params["sigma"].value) - fs["sigma"]) < 5e-6
     assert abs(s.log_marginal_likelihood(X, ys) - fs["lml"]) < 5e-8
+
+
+def test_reference_notebook_anchor_sgpr_rpchol_through_the_facade():
+    """examples/sgpr_with_rpcholesky.ipynb cell 7 on the device: device-side Threefry + inverse-CDF draws
+    (legacy jax.random layout), device SGPR gradient, host L-BFGS-B -> the printed end point."""
+    import json
+    import os
+    import warnings
+
+    from gpx_b200 import defaults
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import SGPR_RPChol
+
+    from test_oracle_cpu import notebook_sgpr_data
+
+    a = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_anchors.json")))["sgpr_rpchol"]["fit"]
+    X, y, _ = notebook_sgpr_data()
+    old = defaults.threefry_partitionable()
+    defaults.set_threefry_partitionable(False)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = SGPR_RPChol(kernel=SquaredExponential(), n_locs=15, key=R.PRNGKey(2023)).fit(X, y)
+    finally:
+        defaults.set_threefry_partitionable(old)
+    assert abs(float(m.state.params["kernel_params"]["lengthscale"].value) - a["lengthscale"]) < 5e-6
+    assert abs(float(m.state.params["sigma"].value) - a["sigma"]) < 5e-6

@@ -238,3 +238,29 @@ def test_notebook_anchor_sgpr_lml():
     X, y, xl = notebook_sgpr_data()
     for f in (R.sgpr_lml_dense, R.sgpr_lml_dense_nxn):
         assert abs(f("se", xl, X, y, a["lengthscale"], a["sigma"]) - a["lml"]) < 5e-8
+
+
+def test_notebook_anchor_sgpr_rpchol_fit_pins_the_pivot_path():
+    """examples/sgpr_with_rpcholesky.ipynb cell 7: L-BFGS-B over a loss that re-draws the RPCholesky
+    pivots at every evaluation stops (abnormally, as printed) at lengthscale 0.113579, sigma 0.308062.
+    The oracle lands there only if split / uniform / choice / the pivot loop reproduce JAX's stream."""
+    from scipy.optimize import minimize
+
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["sgpr_rpchol"]["fit"]
+    X, y, _ = notebook_sgpr_data()
+    key = R.PRNGKey(2023)
+
+    def loss_grad(t):
+        ell, sig = R.softplus(t[0]), R.softplus(t[1])
+        _, piv = R.rpcholesky("se", X, 15, ell, key, False)
+        xl = X[piv].copy()
+        v = R.sgpr_lml_dense("se", xl, X, y, ell, sig)
+        h = 1e-6  # gradient with the landmarks held fixed (integer pivots carry no gradient)
+        gl = (R.sgpr_lml_dense("se", xl, X, y, ell + h, sig) - R.sgpr_lml_dense("se", xl, X, y, ell - h, sig)) / (2 * h)
+        gs = (R.sgpr_lml_dense("se", xl, X, y, ell, sig + h) - R.sgpr_lml_dense("se", xl, X, y, ell, sig - h)) / (2 * h)
+        return -v, np.array([-gl * R.sigmoid(t[0]), -gs * R.sigmoid(t[1])])
+
+    res = minimize(loss_grad, R.inverse_softplus(np.array([1.0, 1.0])), jac=True, method="L-BFGS-B")
+    ell, sig = R.softplus(res.x)
+    assert abs(ell - a["lengthscale"]) < 2e-6 and abs(sig - a["sigma"]) < 2e-6
+    assert res.status == 2  # ABNORMAL_TERMINATION_IN_LNSRCH, as the notebook printed
