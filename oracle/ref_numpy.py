@@ -23,8 +23,10 @@ Parity pinning status
   numbers the reference's own notebooks print (examples/gpr.ipynb cells 11, 14, 19;
   examples/sgpr.ipynb cells 5, 7; tests/golden/notebook_anchors.json): with the data regenerated
   through the restated PRNG this oracle reproduces the fitted lengthscale/sigma and the LML.
-* predictions, fit coefficients, RPCholesky pivots (jax.random.choice path), Lanczos/SLQ, PCG and the
-  partitionable PRNG mode: **parity unpinned** -- the reference has no test, golden vector or
+* the RPCholesky pivot stream (split -> uniform -> choice -> pivot loop, legacy mode): PINNED by
+  examples/sgpr_with_rpcholesky.ipynb cell 7 (the printed end point of a fit whose loss re-draws the
+  pivots at every evaluation is reproduced, including the abnormal L-BFGS-B termination).
+* predictions, fit coefficients, Lanczos/SLQ, PCG and the partitionable PRNG mode: **parity unpinned** -- the reference has no test, golden vector or
   printed output for them and cannot be executed here.  They are anchored
   by self-consistency (analytic gradient vs finite differences, Woodbury vs
   the reference's N x N form, SLQ vs exact log-det).
