@@ -170,3 +170,33 @@ def test_reference_notebook_anchor_sgpr_rpchol_through_the_facade():
         defaults.set_threefry_partitionable(old)
     assert abs(float(m.state.params["kernel_params"]["lengthscale"].value) - a["lengthscale"]) < 5e-6
     assert abs(float(m.state.params["sigma"].value) - a["sigma"]) < 5e-6
+
+
+def test_reference_notebook_anchors_multioutput_and_hessian_kernel():
+    """examples/multioutput.ipynb cell 8 (GPR.fit on two outputs) and
+    examples/gpr_with_derivatives_only.ipynb cell 25 (optimum of the Hessian-kernel GPR) on the device."""
+    import json
+    import os
+
+    from gpx_b200 import ops
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import GPR
+
+    from test_oracle_cpu import derivs_nll, notebook_derivs_data, notebook_multioutput_data
+
+    a = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_anchors.json")))
+    x, y = notebook_multioutput_data()
+    m = GPR(kernel=SquaredExponential()).fit(x, y)
+    assert abs(float(m.state.params["kernel_params"]["lengthscale"].value) - a["multioutput"]["fit"]["lengthscale"]) < 2e-6
+    assert abs(float(m.state.params["sigma"].value) - a["multioutput"]["fit"]["sigma"]) < 2e-6
+
+    d, J, yd = notebook_derivs_data()
+    dd, Jd = torch.as_tensor(d).cuda(), torch.as_tensor(J).cuda()
+    A_dev = lambda ell: ops.hess_gram("se", dd, Jd, dd, Jd, ell).cpu().numpy()  # noqa: E731
+    fd = a["derivatives_only"]["fit"]
+    t = R.inverse_softplus(np.array([fd["lengthscale"], fd["sigma"]]))
+    f = lambda tt: derivs_nll(A_dev, yd, tt)  # noqa: E731
+    h = 1e-6
+    g = np.array([(f(t + np.eye(2)[i] * h) - f(t - np.eye(2)[i] * h)) / (2 * h) for i in range(2)])
+    assert np.max(np.abs(g)) < 5e-6
+    assert abs(f(t) - derivs_nll(lambda ell: R.d01kj("se", d, d, ell, J, J), yd, t)) < 1e-9

@@ -264,3 +264,56 @@ def test_notebook_anchor_sgpr_rpchol_fit_pins_the_pivot_path():
     ell, sig = R.softplus(res.x)
     assert abs(ell - a["lengthscale"]) < 2e-6 and abs(sig - a["sigma"]) < 2e-6
     assert res.status == 2  # ABNORMAL_TERMINATION_IN_LNSRCH, as the notebook printed
+
+
+def notebook_multioutput_data():
+    x = np.linspace(0, 1, 100).reshape(-1, 1)
+    e = R.normal(R.PRNGKey(0), (100,), partitionable=False) * np.sqrt(0.04)
+    return x, np.c_[np.sin(x[:, 0] * 2 * np.pi) + e, np.sin(x[:, 0] * 3 * np.pi) + e]
+
+
+def notebook_derivs_data():
+    xx = np.linspace(-3, 3, 20).reshape(-1, 1)
+    d = np.concatenate([np.sin(xx), np.cos(xx)], axis=1)
+    J = np.stack([np.cos(xx), -np.sin(xx)], axis=1)  # (20, 2, 1)
+    y = (np.cos(xx) + 2 * np.sin(xx)).reshape(-1, 1)
+    return d, J, y
+
+
+def derivs_nll(A_of, y, t):
+    """-lml/n of a plain GPR (data_mean) whose kernel matrix is the Hessian kernel A_of(ell)."""
+    import scipy.linalg as sla
+
+    ell, sig = R.softplus(t[0]), R.softplus(t[1])
+    n = y.shape[0]
+    A = A_of(ell) + (sig**2 + 1e-10) * np.eye(n)
+    r = y - np.mean(y)
+    L = sla.cholesky(A, lower=True)
+    cy = sla.solve_triangular(L, r, lower=True)
+    return -(-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - n * 0.5 * np.log(2 * np.pi)) / n
+
+
+def test_notebook_anchor_multioutput_fit():
+    from scipy.optimize import minimize
+
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["multioutput"]["fit"]
+    x, y = notebook_multioutput_data()
+    res = minimize(lambda t: R.neg_lml_and_grad_unconstrained("se", x, y, t[0], t[1]),
+                   R.inverse_softplus(np.array([1.0, 1.0])), jac=True, method="L-BFGS-B")
+    ell, sig = R.softplus(res.x)
+    assert abs(ell - a["lengthscale"]) < 2e-6 and abs(sig - a["sigma"]) < 2e-6
+
+
+def test_notebook_anchor_hessian_kernel_optimum():
+    """examples/gpr_with_derivatives_only.ipynb cell 25: the optimum of a GPR whose kernel is the
+    autodiff Hessian kernel.  The oracle's hand-written d01kj has its stationary point at the printed
+    hyper-parameters, which pins its formula and (sample, variable) layout against the reference."""
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["derivatives_only"]["fit"]
+    d, J, y = notebook_derivs_data()
+    t = R.inverse_softplus(np.array([a["lengthscale"], a["sigma"]]))
+    f = lambda tt: derivs_nll(lambda ell: R.d01kj("se", d, d, ell, J, J), y, tt)  # noqa: E731
+    h = 1e-6
+    g = np.array([(f(t + np.eye(2)[i] * h) - f(t - np.eye(2)[i] * h)) / (2 * h) for i in range(2)])
+    assert np.max(np.abs(g)) < 5e-6  # stationary (the printed values carry 6 digits)
+    assert f(t) < f(t + np.array([0.05, 0.0])) and f(t) < f(t - np.array([0.05, 0.0]))
+    assert f(t) < f(t + np.array([0.0, 0.05])) and f(t) < f(t - np.array([0.0, 0.05]))
