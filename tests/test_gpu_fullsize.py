@@ -1,0 +1,100 @@
+"""GPU checks at BASELINE.json's full sizes through size-independent properties (the oracle cannot run
+there): gradient vs finite differences of the device LML, A A^-1 = I on probes, symmetry of the
+matrix-free operator, RPCholesky residual invariants, Woodbury vs matrix-free quadratic form."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _synth(N, D, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((N, D), dtype=torch.float64, device="cuda", generator=g)
+    y = torch.sin(x.sum(1, keepdim=True)) + 0.1 * torch.randn((N, 1), dtype=torch.float64, device="cuda", generator=g)
+    return x, y
+
+
+def test_config1_lml_gradient_vs_finite_differences_N32768():
+    from gpx_b200 import ops
+
+    N, D, ell, sigma = 32768, 16, 4.0, 0.1
+    x, y = _synth(N, D, 1)
+    out = ops.gpr_lml_grad("m52", x, y, ell, sigma).cpu().numpy()
+    h = 1e-4
+    lp = ops.gpr_lml_grad("m52", x, y, ell + h, sigma, want_grad=False).cpu().numpy()[0]
+    lm = ops.gpr_lml_grad("m52", x, y, ell - h, sigma, want_grad=False).cpu().numpy()[0]
+    sp = ops.gpr_lml_grad("m52", x, y, ell, sigma + h, want_grad=False).cpu().numpy()[0]
+    sm = ops.gpr_lml_grad("m52", x, y, ell, sigma - h, want_grad=False).cpu().numpy()[0]
+    assert np.isfinite(out).all()
+    assert abs(out[1] - (lp - lm) / (2 * h)) < 1e-6 * max(1.0, abs(out[1]))
+    assert abs(out[2] - (sp - sm) / (2 * h)) < 1e-6 * max(1.0, abs(out[2]))
+
+
+def test_cholesky_inverse_identity_on_probes_N16384():
+    from gpx_b200 import ops
+
+    N = 16384
+    x, _ = _synth(N, 16, 2)
+    A = ops.gram("m52", x, x, 4.0, diag_add=0.01)  # full symmetric matrix
+    L, inv = ops.potrf(A.clone())
+    Ainv = ops.potri(L, inv)
+    Ainv = torch.tril(Ainv) + torch.tril(Ainv, -1).T
+    V = torch.randn((N, 4), dtype=torch.float64, device="cuda")
+    R1 = ops.gemm(A, ops.gemm(Ainv, V)) - V
+    assert float(R1.abs().max()) < 1e-8 * float(V.abs().max())
+    # log-det through the factor equals the sum of the logs of L's diagonal
+    assert abs(float(ops.logdet(L)[0]) - float(torch.log(torch.diagonal(L)).sum())) < 1e-8 * N
+
+
+def test_matrix_free_operator_is_symmetric_and_matches_dense_rows_N262144():
+    from gpx_b200 import ops
+
+    N = 262144
+    x, _ = _synth(N, 16, 4)
+    u = torch.randn((N, 1), dtype=torch.float64, device="cuda")
+    v = torch.randn((N, 1), dtype=torch.float64, device="cuda")
+    UV = torch.cat([u, v], dim=1).contiguous()
+    W = ops.kmatvec("se", x, x, UV, 4.0, diag_add=0.25)
+    a, b = float((u * W[:, 1:2]).sum()), float((v * W[:, 0:1]).sum())  # u^T A v == v^T A u
+    assert abs(a - b) < 1e-10 * max(abs(a), abs(b), 1.0)
+    rows = torch.tensor([0, 1, 12345, N // 2, N - 1], device="cuda")
+    Kr = ops.gram("se", x[rows].contiguous(), x, 4.0)  # dense rows of K
+    ref = Kr @ UV + 0.25 * UV[rows]
+    assert float((W[rows] - ref).abs().max()) < 1e-9 * float(ref.abs().max())
+
+
+def test_rpcholesky_invariants_N1M():
+    from gpx_b200 import ops
+
+    N, M = 1_000_000, 48
+    x, _ = _synth(N, 32, 3)
+    key = np.array([0, 2023], dtype=np.uint32)
+    F, piv = ops.rpcholesky("se", x, M, 32**0.5, key, True)
+    piv_h = piv.cpu().numpy()
+    assert piv_h.min() >= 0 and piv_h.max() < N and len(set(piv_h.tolist())) == M
+    # F F^T interpolates K on the pivot rows: K[piv, :] ~= F[piv] F^T (up to the 1e-6 regulariser)
+    Kp = ops.gram("se", x[piv].contiguous(), x[:200000].contiguous(), 32**0.5)
+    approx = F[piv] @ F[:200000].T
+    assert float((Kp - approx).abs().max()) < 1e-4
+    # residual diagonal k(x,x) - |F_i|^2 stays in [-eps, 1]
+    res = float(np.exp(-1e-12)) - (F * F).sum(1)
+    assert float(res.min()) > -1e-9 and float(res.max()) <= 1.0
+    # the same call again gives the same pivots (deterministic, no atomics)
+    _, piv2 = ops.rpcholesky("se", x, M, 32**0.5, key, True, want_factor=False)
+    assert torch.equal(piv, piv2)
+
+
+def test_sgpr_gradient_vs_finite_differences_N1M():
+    from gpx_b200 import ops
+
+    N, M = 1_000_000, 512
+    x, y = _synth(N, 32, 3)
+    xl = x[torch.randperm(N, device="cuda")[:M]].contiguous()
+    ell, sigma = 32**0.5, 0.3
+    out = ops.sgpr_lml_grad("se", x, y, xl, ell, sigma).cpu().numpy()
+    assert abs(out[0] - float(ops.sgpr_lml("se", x, y, xl, ell, sigma)[0])) < 1e-9 * abs(out[0])
+    h = 1e-4
+    fl = (float(ops.sgpr_lml("se", x, y, xl, ell + h, sigma)[0]) - float(ops.sgpr_lml("se", x, y, xl, ell - h, sigma)[0])) / (2 * h)
+    fs = (float(ops.sgpr_lml("se", x, y, xl, ell, sigma + h)[0]) - float(ops.sgpr_lml("se", x, y, xl, ell, sigma - h)[0])) / (2 * h)
+    assert abs(out[1] - fl) < 1e-5 * max(1.0, abs(fl)) and abs(out[2] - fs) < 1e-5 * max(1.0, abs(fs))
