@@ -22,18 +22,22 @@ using namespace sk;
 
 constexpr int CHUNK = 32768;
 
-// scal: [0] r.r, [1] t.t, [2] sum log L_B,ii
+// scal: [0] r.r, [4] t.t, [5] sum log L_B,ii
 __global__ void finalize_sgpr_kernel(const double* __restrict__ scal, long long N, int M, double s2,
                                      double* __restrict__ out) {
   const double n = (double)N;
-  const double quad = (scal[0] - scal[1]) / s2;
-  const double logdet = (n - (double)M) * log(s2) + 2.0 * scal[2];
+  const double quad = (scal[0] - scal[4]) / s2;
+  const double logdet = (n - (double)M) * log(s2) + 2.0 * scal[5];
   out[0] = (-0.5 * quad - 0.5 * logdet - n * 0.5 * log(2.0 * 3.141592653589793)) / n;
 }
 }  // namespace
 
 // x: this rank's rows (n_loc x D), y: (n_loc x T); N: global row count; mu: device scalar with
 // the GLOBAL mean (computed by the caller).  out: device scalar lml / N.
+// The row chunks are independent until the final reduction, so they are pipelined round-robin over
+// three streams with private buffers and private B / v / r.r accumulators (summed in a fixed order at
+// the end): the tails of one chunk's kernels (528 lower tiles = 3.6 waves of the SYRK) overlap the next
+// chunk's work.
 int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, long long N, int D, int T,
              const double* x_locs, int M, double ell, double sigma, const double* mu, double* out,
              cudaStream_t s) {
@@ -42,23 +46,25 @@ int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, lo
   GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
   const double s2 = sigma * sigma + 1e-10;
   const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
+  const int nchunks = ceil_div(std::max(n_loc, 1), CHUNK);
+  const int NS = nchunks >= 3 ? 3 : 1;  // concurrent chunk pipelines
+  const size_t mm = (size_t)M * M;
   DevBuf bZl, bKmm, bInv, bB, bV, bZc, bKc, bRc, bSc, bInvB;
   GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
-  GPXB_TRY(bKmm.alloc(sizeof(double) * (size_t)M * M, s));
+  GPXB_TRY(bKmm.alloc(sizeof(double) * mm, s));
   GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles(M), s));
-  GPXB_TRY(bB.alloc(sizeof(double) * (size_t)M * M, s));
-  GPXB_TRY(bV.alloc(sizeof(double) * (size_t)M * T, s));
-  GPXB_TRY(bZc.alloc(sizeof(double) * (size_t)nc_max * zl.S, s));
-  GPXB_TRY(bKc.alloc(sizeof(double) * (size_t)nc_max * M, s));
-  GPXB_TRY(bRc.alloc(sizeof(double) * (size_t)nc_max * T, s));
-  GPXB_TRY(bSc.alloc(sizeof(double) * 8, s));
+  GPXB_TRY(bB.alloc(sizeof(double) * mm * NS, s));
+  GPXB_TRY(bV.alloc(sizeof(double) * (size_t)M * T * NS, s));
+  GPXB_TRY(bZc.alloc(sizeof(double) * (size_t)nc_max * zl.S * NS, s));
+  GPXB_TRY(bKc.alloc(sizeof(double) * (size_t)nc_max * M * NS, s));
+  GPXB_TRY(bRc.alloc(sizeof(double) * (size_t)nc_max * T * NS, s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * 16, s));
   GPXB_TRY(bInvB.alloc(sizeof(double) * leaf_inv_doubles(M), s));
   double *Zl = bZl.as<double>(), *Kmm = bKmm.as<double>(), *inv = bInv.as<double>(), *B = bB.as<double>();
-  double *v = bV.as<double>(), *Zc = bZc.as<double>(), *Kc = bKc.as<double>(), *rc = bRc.as<double>();
-  double* scal = bSc.as<double>();
-  GPXB_CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(double) * (size_t)M * M, s));
-  GPXB_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * (size_t)M * T, s));
-  GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 8, s));
+  double *v = bV.as<double>(), *scal = bSc.as<double>();  // scal[0..2]: r.r per pipeline, [4] t.t, [5] sum log
+  GPXB_CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(double) * mm * NS, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * (size_t)M * T * NS, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 16, s));
 
   // L_m = chol(K_mm + 1e-10 I)
   GPXB_TRY(prep_z(ctx, x_locs, D, M, zl, ell, Zl, s));
@@ -70,54 +76,81 @@ int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, lo
   }
   GPXB_TRY(potrf_lower(ctx, Kmm, M, M, inv, s));
 
-  for (int r0 = 0; r0 < n_loc; r0 += CHUNK) {
+  cudaStream_t st[3] = {s, ctx->aux[0], ctx->aux[1]};
+  if (NS > 1) {
+    cudaEvent_t e;
+    GPXB_TRY(ctx->next_event(&e));
+    GPXB_CUDA_CHECK(cudaEventRecord(e, s));
+    for (int k = 1; k < NS; ++k) GPXB_CUDA_CHECK(cudaStreamWaitEvent(st[k], e, 0));
+  }
+  int ci = 0;
+  for (int r0 = 0; r0 < n_loc; r0 += CHUNK, ++ci) {
     const int nc = std::min(CHUNK, n_loc - r0);
-    GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, Zc, s));
+    const int k = ci % NS;
+    cudaStream_t sk = st[k];
+    double* Zc = bZc.as<double>() + (size_t)k * nc_max * zl.S;
+    double* Kc = bKc.as<double>() + (size_t)k * nc_max * M;
+    double* rc = bRc.as<double>() + (size_t)k * nc_max * T;
+    GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, Zc, sk));
     {
       GramArgs g;  // Kc = K(x_chunk, x_locs)  [nc x M]
       g.kind = kind; g.Z1 = Zc; g.n1 = nc; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
       g.out = Kc; g.ldo = M;
-      GPXB_TRY(gram_launch(ctx, g, s));
+      GPXB_TRY(gram_launch(ctx, g, sk));
     }
-    GPXB_TRY(trsm_right_lt(ctx, Kmm, M, inv, Kc, M, nc, M, s));  // Kc <- G_c^T = Kc L_m^-T
-    center_kernel<<<ceil_div((long long)nc * T, 256), 256, 0, s>>>(y + (long long)r0 * T, (long long)nc * T, mu, rc);
+    GPXB_TRY(trsm_right_lt(ctx, Kmm, M, inv, Kc, M, nc, M, sk));  // Kc <- G_c^T = Kc L_m^-T
+    center_kernel<<<ceil_div((long long)nc * T, 256), 256, 0, sk>>>(y + (long long)r0 * T, (long long)nc * T, mu, rc);
     GPXB_LAUNCHED(ctx);
-    sumsq_kernel<<<1, 1024, 0, s>>>(rc, (long long)nc * T, scal + 0, 1);
+    sumsq_kernel<<<1, 1024, 0, sk>>>(rc, (long long)nc * T, scal + k, 1);
     GPXB_LAUNCHED(ctx);
     {
-      GemmArgs g;  // B += G_c G_c^T  (A, B stored [K = nc][M])
+      GemmArgs g;  // B_k += G_c G_c^T  (A, B stored [K = nc][M])
       g.M = M; g.N = M; g.K = nc;
       g.A = Kc; g.lda = M; g.a_kmajor = false;
       g.B = Kc; g.ldb = M; g.b_kmajor = false;
-      g.C = B; g.ldc = M; g.beta = 1.0; g.lower_only = 1;
-      GPXB_TRY(gemm_f64(ctx, g, s));
+      g.C = B + (size_t)k * mm; g.ldc = M; g.beta = 1.0; g.lower_only = 1;
+      GPXB_TRY(gemm_f64(ctx, g, sk));
     }
     {
-      GemmArgs g;  // v += G_c r_c   [M x T]
+      GemmArgs g;  // v_k += G_c r_c   [M x T]
       g.M = M; g.N = T; g.K = nc;
       g.A = Kc; g.lda = M; g.a_kmajor = false;
       g.B = rc; g.ldb = T; g.b_kmajor = false;
-      g.C = v; g.ldc = T; g.beta = 1.0;
-      GPXB_TRY(gemm_f64(ctx, g, s));
+      g.C = v + (size_t)k * M * T; g.ldc = T; g.beta = 1.0;
+      GPXB_TRY(gemm_f64(ctx, g, sk));
     }
+  }
+  for (int k = 1; k < NS; ++k) {  // join, then reduce the private accumulators in a fixed order
+    cudaEvent_t e;
+    GPXB_TRY(ctx->next_event(&e));
+    GPXB_CUDA_CHECK(cudaEventRecord(e, st[k]));
+    GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, e, 0));
+  }
+  for (int k = 1; k < NS; ++k) {
+    add_vec_kernel<<<ceil_div((long long)mm, 256), 256, 0, s>>>(B, B + (size_t)k * mm, (long long)mm);
+    GPXB_LAUNCHED(ctx);
+    add_vec_kernel<<<ceil_div((long long)M * T, 256), 256, 0, s>>>(v, v + (size_t)k * M * T, (long long)M * T);
+    GPXB_LAUNCHED(ctx);
+    add_vec_kernel<<<1, 1, 0, s>>>(scal, scal + k, 1);
+    GPXB_LAUNCHED(ctx);
   }
   if (ctx->world > 1) {
     // upper triangle of B is untouched zero, so the full buffer can be summed
-    GPXB_TRY(comm_allreduce_sum(ctx, B, (size_t)M * M, s));
+    GPXB_TRY(comm_allreduce_sum(ctx, B, mm, s));
     GPXB_TRY(comm_allreduce_sum(ctx, v, (size_t)M * T, s));
     GPXB_TRY(comm_allreduce_sum(ctx, scal, 1, s));
   }
   add_diag_kernel<<<ceil_div(M, 256), 256, 0, s>>>(B, M, M, s2);
   GPXB_LAUNCHED(ctx);
   GPXB_TRY(potrf_lower(ctx, B, M, M, bInvB.as<double>(), s));
-  GPXB_TRY(logdet_lower(ctx, B, M, M, scal + 2, 1.0, s));
+  GPXB_TRY(logdet_lower(ctx, B, M, M, scal + 5, 1.0, s));
   // t^T = v^T L_B^-T  (v is M x T; its transpose T x M is needed)
   DevBuf bVt;
   GPXB_TRY(bVt.alloc(sizeof(double) * (size_t)M * T, s));
   transpose_out_kernel<<<ceil_div((long long)M * T, 256), 256, 0, s>>>(v, T, M, bVt.as<double>());
   GPXB_LAUNCHED(ctx);
   GPXB_TRY(trsm_right_lt(ctx, B, M, bInvB.as<double>(), bVt.as<double>(), M, T, M, s));
-  sumsq_kernel<<<1, 1024, 0, s>>>(bVt.as<double>(), (long long)M * T, scal + 1, 0);
+  sumsq_kernel<<<1, 1024, 0, s>>>(bVt.as<double>(), (long long)M * T, scal + 4, 0);
   GPXB_LAUNCHED(ctx);
   finalize_sgpr_kernel<<<1, 1, 0, s>>>(scal, N, M, s2, out);
   GPXB_LAUNCHED(ctx);
