@@ -78,6 +78,32 @@ int gpxb_ctx_destroy(gpxb_ctx* ctx) {
   return 0;
 }
 
+int gpxb_prof_enable(gpxb_ctx* ctx, int on) {
+  GPXB_ARG_CHECK(ctx != nullptr, -1);
+  reinterpret_cast<Ctx*>(ctx)->prof = (on != 0);
+  return 0;
+}
+
+int gpxb_prof_collect(gpxb_ctx* ctx_, double* total_ms, double* total_flops, int* n_launches) {
+  GPXB_ARG_CHECK(ctx_ && total_ms && total_flops && n_launches, -1);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  GPXB_CUDA_CHECK(cudaDeviceSynchronize());
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : ctx->prof_recs) {
+    float t = 0.f;
+    GPXB_CUDA_CHECK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t;
+    fl += r.flops;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  *total_ms = ms;
+  *total_flops = fl;
+  *n_launches = (int)ctx->prof_recs.size();
+  ctx->prof_recs.clear();
+  return 0;
+}
+
 unsigned long long gpxb_ctx_launches(gpxb_ctx* ctx) {
   return ctx ? reinterpret_cast<Ctx*>(ctx)->launches : 0ULL;
 }

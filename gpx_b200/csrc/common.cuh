@@ -73,6 +73,10 @@ struct Ctx {
     return 0;
   }
   unsigned long long launches = 0;  // kernels launched by this library via this ctx
+  // optional per-launch timing of the DMMA GEMM (bench.py roofline): event pairs + algorithmic flops
+  bool prof = false;
+  struct ProfRec { cudaEvent_t e0, e1; double flops; };
+  std::vector<ProfRec> prof_recs;
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   long long shard_N = 0;  // global row count of the sharded problem in flight

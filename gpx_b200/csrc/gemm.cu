@@ -281,8 +281,32 @@ int gemm_variant() {
   return v;
 }
 
+// algorithmic flops of one launch: 2 * (output tiles' area, clipped) * K_effective is approximated
+// by the tile count x 128 x 128 x 2K for full-K launches; triangular k-ranges halve it.
+double launch_flops(const GemmParams& p, long long grid) {
+  double k = (double)p.K;
+  if (p.klo_mode != 0 || p.khi_mode != 0) k *= 0.5;  // triangular operand: half of the k range on average
+  double area;
+  if (p.lower_only) {
+    const double n = (double)p.N, m = (double)p.M;
+    area = n * (n + 1.0) * 0.5 + (m - n) * n;
+  } else {
+    area = (double)p.M * (double)p.N;
+  }
+  (void)grid;
+  return 2.0 * area * k;
+}
+
 template <bool AK, bool BKM>
 int launch(Ctx* ctx, const GemmParams& p, int grid, cudaStream_t stream) {
+  Ctx::ProfRec rec{nullptr, nullptr, 0.0};
+  const bool prof = ctx && ctx->prof;
+  if (prof) {
+    GPXB_CUDA_CHECK(cudaEventCreate(&rec.e0));
+    GPXB_CUDA_CHECK(cudaEventCreate(&rec.e1));
+    rec.flops = launch_flops(p, grid);
+    GPXB_CUDA_CHECK(cudaEventRecord(rec.e0, stream));
+  }
   if (gemm_variant() == 8) {
     GPXB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<AK, BKM, 2, 4>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -293,6 +317,10 @@ int launch(Ctx* ctx, const GemmParams& p, int grid, cudaStream_t stream) {
     gemm_f64_kernel<AK, BKM, 4, 4><<<grid, 512, SMEM_BYTES, stream>>>(p);
   }
   GPXB_LAUNCH_CHECK();
+  if (prof) {
+    GPXB_CUDA_CHECK(cudaEventRecord(rec.e1, stream));
+    ctx->prof_recs.push_back(rec);
+  }
   if (ctx) ctx->launches++;
   return 0;
 }

@@ -394,5 +394,21 @@ def comm_init_from_torch_distributed():
     return rank, world
 
 
+def prof_enable(on: bool) -> None:
+    ctx = context()
+    check(ctx.lib.gpxb_prof_enable(ctx.handle, int(bool(on))), "gpxb_prof_enable")
+
+
+def prof_collect():
+    """(total ms, total algorithmic flops, launches) of the DMMA GEMM launches since prof_enable(True)."""
+    import ctypes
+
+    ctx = context()
+    ms, fl, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
+    check(ctx.lib.gpxb_prof_collect(ctx.handle, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)),
+          "gpxb_prof_collect")
+    return ms.value, fl.value, n.value
+
+
 def launches() -> int:
     return _lib.context().launches()

@@ -41,6 +41,11 @@ int gpxb_ctx_create(int device, gpxb_ctx** out);
 int gpxb_ctx_destroy(gpxb_ctx* ctx);
 /* number of CUDA kernels this library has launched through ctx (bench.py "gpu_launches") */
 unsigned long long gpxb_ctx_launches(gpxb_ctx* ctx);
+/* Measurement aid (bench.py "roofline"): while enabled, every DMMA GEMM launch is bracketed by CUDA
+ * events on the stream it is launched on; collect synchronises the device and returns the summed
+ * launch durations, their algorithmic flops and the launch count, then clears the records. */
+int gpxb_prof_enable(gpxb_ctx* ctx, int on);
+int gpxb_prof_collect(gpxb_ctx* ctx, double* total_ms, double* total_flops, int* n_launches);
 
 /* ---- Family 1: fused kernel-matrix construction ------------------------------------- */
 /* out[n1 x n2] (ld ldo) = k(x1, x2) + diag_add * I.  Replaces Kernel.k -> squared_distances +
