@@ -286,7 +286,8 @@ def run_gpu(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": traffic,
                      "kernel": "gemm_f64_kernel (DMMA GEMM / SYRK, all layouts): %d launches in the timed region, "
-                               "%.1f ms of %.1f ms" % (gemm_n, gemm_ms, ms * K),
+                               "summed launch durations %.1f ms in a %.1f ms region (look-ahead launches run concurrently)"
+                               % (gemm_n, gemm_ms, ms * K),
                      "avg_launch_ms": gemm_ms / max(gemm_n, 1), "alg_flops_per_launch": gemm_flops / max(gemm_n, 1),
                      "probe": {"shape": f"lower SYRK M=N={m_t} K={k_t}", "tflops": probe},
                      "peak_source": f"cuBLAS Dgemm {nb}^3 measured in this run",
