@@ -156,19 +156,19 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
         }
       }
       const int jl = jf * 8 + lq * 2;
-      const double nj0 = sZa[jl * p.S + p.Dp], nj1 = sZa[(jl + 1) * p.S + p.Dp];
+      // |z_j|^2 + 1e-12 once per column (amortised over the MF row fragments); the shifted diagonal
+      // (diag_add * V) is added after the column loop, so the inner loop carries no extra FP64 add
+      const double nj0 = sZa[jl * p.S + p.Dp] + 1e-12, nj1 = sZa[(jl + 1) * p.S + p.Dp] + 1e-12;
       const int gj = j0 + jl;
 #pragma unroll
       for (int mf = 0; mf < MF; ++mf) {
         const long long gi = p.row_offset + row0 + warp * 8 * MF + mf * 8 + lr;
-        double d20 = ((ni[mf] - 2.0 * c[mf][0]) + nj0) + 1e-12;
-        double d21 = ((ni[mf] - 2.0 * c[mf][1]) + nj1) + 1e-12;
+        double d20 = fma(-2.0, c[mf][0], ni[mf]) + nj0;
+        double d21 = fma(-2.0, c[mf][1], ni[mf]) + nj1;
         const bool dg0 = (p.row_offset >= 0) && (gi == gj), dg1 = (p.row_offset >= 0) && (gi == gj + 1);
         if (dg0) d20 = 1e-12;
         if (dg1) d21 = 1e-12;
-        double k0 = kfun_mode<KMODE>(p.kind, d20, etab), k1 = kfun_mode<KMODE>(p.kind, d21, etab);
-        if (dg0) k0 += p.diag_add;
-        if (dg1) k1 += p.diag_add;
+        const double k0 = kfun_mode<KMODE>(p.kind, d20, etab), k1 = kfun_mode<KMODE>(p.kind, d21, etab);
         c[mf][0] = (gj < jend) ? k0 : 0.0;
         c[mf][1] = (gj + 1 < jend) ? k1 : 0.0;
       }
@@ -186,23 +186,30 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
     __syncthreads();  // everyone is done with this stage before it is refilled
   }
 
-  // ---- write the row block ----
+  // ---- write the row block (+ diag_add * V[i] from the CTA whose column range holds the diagonal) ----
   const int pw = 8 * NPF;
 #pragma unroll
   for (int mf = 0; mf < MF; ++mf) {
     const int i = row0 + warp * 8 * MF + mf * 8 + lr;
     if (i >= p.n_rows) continue;
+    const long long gi = p.row_offset + i;
+    const bool own_diag = (p.row_offset >= 0) && (gi >= jbeg) && (gi < jend) && (p.diag_add != 0.0);
 #pragma unroll
     for (int pf = 0; pf < NPF; ++pf) {
       const int pc = pf * 8 + 2 * lq;
+      double w0 = w[mf][pf][0], w1 = w[mf][pf][1];
+      if (own_diag) {
+        if (pc < p.P) w0 += p.diag_add * p.V[gi * p.PS + pc];
+        if (pc + 1 < p.P) w1 += p.diag_add * p.V[gi * p.PS + pc + 1];
+      }
       if (p.jsplit == 1) {
         double* o = p.W + (long long)i * p.ldw + pc;
-        if (pc < p.P) o[0] = w[mf][pf][0];
-        if (pc + 1 < p.P) o[1] = w[mf][pf][1];
+        if (pc < p.P) o[0] = w0;
+        if (pc + 1 < p.P) o[1] = w1;
       } else {
         double* o = p.W + ((long long)blockIdx.y * p.n_rows + i) * pw + pc;
-        o[0] = w[mf][pf][0];
-        o[1] = w[mf][pf][1];
+        o[0] = w0;
+        o[1] = w1;
       }
     }
   }
