@@ -343,6 +343,42 @@ __global__ void __launch_bounds__(256) trsv_bwd_update_kernel(const double* __re
     if (r < m) B[(long long)r * ldb + j] -= acc[r];
 }
 
+// backward update on the block-column packed layout: the row strip L[c0:c0+nb, 0:ncols] crosses panels
+__global__ void __launch_bounds__(256) trsv_bwd_update_bcp_kernel(const double* __restrict__ Lp, BcpLayout lay, int c0,
+                                                                  const double* __restrict__ X, double* __restrict__ B,
+                                                                  long long ldb, int m, int nb, int ncols) {
+  __shared__ double sx[TRSV_MAXM][LB];
+  for (int i = threadIdx.x; i < TRSV_MAXM * LB; i += 256) {
+    const int r = i / LB, c = i % LB;
+    sx[r][c] = (r < m && c < nb) ? X[(long long)r * ldb + c] : 0.0;
+  }
+  __syncthreads();
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= ncols) return;
+  const double* Lrows = Lp + lay.index(c0, j);
+  double acc[TRSV_MAXM];
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
+#pragma unroll 4
+  for (int c = 0; c < nb; ++c) {
+    const double v = Lrows[(long long)c * BcpLayout::NB];
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) acc[r] += v * sx[r][c];
+  }
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r)
+    if (r < m) B[(long long)r * ldb + j] -= acc[r];
+}
+
+__global__ void logdet_bcp_kernel(const double* __restrict__ Lp, BcpLayout lay, double* __restrict__ out,
+                                  double scale) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < lay.n; i += 1024) s += log(Lp[lay.index(i, i)]);
+  s = block_sum<1024>(s, sh);
+  if (threadIdx.x == 0) *out = scale * s;
+}
+
 // few right-hand sides (m <= 4): blocked substitution with GEMV updates -- HBM bound (reads L once)
 int trsv_few(Ctx* ctx, const double* L, long long ldl, const double* inv, double* B, long long ldb, int m, int n,
              bool transposed_solve, cudaStream_t s) {
@@ -528,6 +564,95 @@ int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStre
   GPXB_TRY(ctx->next_event(&ev));
   GPXB_CUDA_CHECK(cudaEventRecord(ev, hp));
   GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
+  return 0;
+}
+
+// Same algorithm on the block-column packed layout (chol.cuh: BcpLayout): the trailing update is one
+// trapezoid GEMM per block column instead of one for the whole trailing matrix.
+int potrf_lower_bcp(Ctx* ctx, double* Ap, int n, double* inv, cudaStream_t s) {
+  if (n <= 0) return 0;
+  constexpr int NB = BcpLayout::NB;
+  const BcpLayout lay{n};
+  if (n <= NB) return factor_panel(ctx, Ap, NB, n, 0, n, inv, s);
+  const int np = lay.panels();
+  auto update = [&](int p, int q, cudaStream_t st) -> int {  // block column q -= L[q.., p] L[q, p]^T
+    const long long k0 = (long long)p * NB, c0 = (long long)q * NB;
+    const double* P = lay.vbase(Ap, p) + c0 * NB + k0;
+    GemmArgs g;
+    g.M = (int)(n - c0); g.N = (int)std::min<long long>(NB, n - c0); g.K = NB;
+    g.A = P; g.lda = NB; g.a_kmajor = true;
+    g.B = P; g.ldb = NB; g.b_kmajor = true;
+    g.C = lay.vbase(Ap, q) + c0 * NB + c0; g.ldc = NB;
+    g.alpha = -1.0; g.beta = 1.0;
+    g.lower_only = 1;
+    return gemm_f64(ctx, g, st);
+  };
+  cudaStream_t hp = ctx->side;
+  cudaEvent_t ev, ev_next_prev = nullptr;
+  GPXB_TRY(ctx->next_event(&ev));
+  GPXB_CUDA_CHECK(cudaEventRecord(ev, s));
+  GPXB_CUDA_CHECK(cudaStreamWaitEvent(hp, ev, 0));
+  for (int p = 0; p < np; ++p) {
+    const int k0 = p * NB, w = min(NB, n - k0);
+    GPXB_TRY(factor_panel(ctx, lay.vbase(Ap, p), NB, n, k0, w, inv, hp));
+    if (p + 1 >= np) break;
+    cudaEvent_t ev_factor;
+    GPXB_TRY(ctx->next_event(&ev_factor));
+    GPXB_CUDA_CHECK(cudaEventRecord(ev_factor, hp));
+    // look-ahead: block column p+1 on hp, once the earlier panels' updates of it (on s) are done
+    if (ev_next_prev) GPXB_CUDA_CHECK(cudaStreamWaitEvent(hp, ev_next_prev, 0));
+    GPXB_TRY(update(p, p + 1, hp));
+    ev_next_prev = nullptr;
+    if (p + 2 < np) {
+      GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_factor, 0));
+      for (int q = p + 2; q < np; ++q) {
+        GPXB_TRY(update(p, q, s));
+        if (q == p + 2) {  // all the next look-ahead needs
+          GPXB_TRY(ctx->next_event(&ev_next_prev));
+          GPXB_CUDA_CHECK(cudaEventRecord(ev_next_prev, s));
+        }
+      }
+    }
+  }
+  GPXB_TRY(ctx->next_event(&ev));
+  GPXB_CUDA_CHECK(cudaEventRecord(ev, hp));
+  GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
+  return 0;
+}
+
+int trsv_bcp(Ctx* ctx, const double* Lp, int n, const double* inv, double* B, long long ldb, int m, bool forward,
+             cudaStream_t s) {
+  GPXB_ARG_CHECK(m >= 1 && m <= TRSV_MAXM, -30);
+  constexpr int NB = BcpLayout::NB;
+  const BcpLayout lay{n};
+  const int nblk = (n + LB - 1) / LB;
+  if (forward) {
+    for (int k = 0; k < nblk; ++k) {
+      const int c0 = k * LB, nb = min(LB, n - c0);
+      trsv_diag_kernel<<<1, 256, 0, s>>>(inv + (long long)k * LB * LB, B + c0, ldb, m, nb, 0);
+      const int below = n - c0 - nb;
+      if (below > 0)
+        trsv_fwd_update_kernel<<<(below + 7) / 8, 256, 0, s>>>(
+            lay.vbase(Lp, c0 / NB) + (long long)(c0 + nb) * NB + c0, NB, B + c0, B + c0 + nb, ldb, m, nb, below);
+      ctx->launches += below > 0 ? 2 : 1;
+    }
+  } else {
+    for (int k = nblk - 1; k >= 0; --k) {
+      const int c0 = k * LB, nb = min(LB, n - c0);
+      trsv_diag_kernel<<<1, 256, 0, s>>>(inv + (long long)k * LB * LB, B + c0, ldb, m, nb, 1);
+      if (c0 > 0)
+        trsv_bwd_update_bcp_kernel<<<(c0 + 255) / 256, 256, 0, s>>>(Lp, lay, c0, B + c0, B, ldb, m, nb, c0);
+      ctx->launches += c0 > 0 ? 2 : 1;
+    }
+  }
+  GPXB_LAUNCH_CHECK();
+  return 0;
+}
+
+int logdet_bcp(Ctx* ctx, const double* Lp, int n, double* out, double scale, cudaStream_t s) {
+  logdet_bcp_kernel<<<1, 1024, 0, s>>>(Lp, BcpLayout{n}, out, scale);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
   return 0;
 }
 

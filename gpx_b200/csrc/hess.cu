@@ -39,7 +39,7 @@ struct HessParams {
   double kappa, diag_add;
   int sym, lower_only;
   double* out;
-  long long ldo;
+  long long ldo;  // ldo < 0: block-column packed lower storage (chol.cuh: BcpLayout) of an n1 x n1 matrix
   int vec_out, tiles_m, tiles_n;
 };
 
@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(NT, 1) hess_kernel(const HessParams p) {
         const long long st = (long long)s * p.Ns2 + t;
         double v = p.C1[st] * acc[mf][nf][e] - p.C2[st] * a * b;
         if (p.sym && gi == gj) v += p.diag_add;
-        p.out[(long long)gi * p.ldo + gj] = v;
+        const long long o = p.ldo >= 0 ? (long long)gi * p.ldo + gj : BcpLayout{p.n1}.index(gi, gj);
+        p.out[o] = v;
       }
     }
   }
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(NT, 1) hess_kernel(const HessParams p) {
 }  // namespace
 
 // out[(n1*nv1) x (n2*nv2)] = d01kj(x1, x2; J1, J2) (+ diag_add I when the operands are the same).
+// ldo < 0 (with lower_only): out is block-column packed (BcpLayout).
 int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, int nv1, const double* x2,
               const double* J2, int Ns2, int nv2, int nf, double ell, double diag_add, double* out, long long ldo,
               int lower_only, cudaStream_t s) {
@@ -183,6 +185,7 @@ int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, i
   GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -52);
   const bool sym = (x1 == x2) && (J1 == J2) && (Ns1 == Ns2) && (nv1 == nv2);
   GPXB_ARG_CHECK(!lower_only || sym, -53);
+  GPXB_ARG_CHECK(ldo >= 0 || lower_only, -56);
   const long long n1 = (long long)Ns1 * nv1, n2 = (long long)Ns2 * nv2;
   GPXB_ARG_CHECK(n1 < (1LL << 31) && n2 < (1LL << 31), -54);
   DevBuf bA1, bA2, bZ1, bZ2, bX1, bX2, bC1, bC2, bP12, bP21;
@@ -274,25 +277,39 @@ int gpr_derivs(Ctx* ctx, int kind, const double* x, const double* J, const doubl
   const long long n = (long long)N * nv;
   GPXB_ARG_CHECK(n > 0 && n < (1LL << 31), -1);
   const double s2 = sigma * sigma + 1e-10;
+  // square storage while it fits comfortably, block-column packed lower storage beyond that
+  // (GPXB_DERIVS_LAYOUT=packed|square overrides; read per call so that tests can flip it)
+  size_t free_b = 0, total_b = 0;
+  GPXB_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  bool packed = sizeof(double) * (double)n * (double)n > 0.45 * (double)total_b;
+  if (const char* e = getenv("GPXB_DERIVS_LAYOUT")) packed = (e[0] == 'p') ? true : (e[0] == 's' ? false : packed);
+  const BcpLayout lay{n};
   DevBuf bA, bInv, bR, bSc;
-  GPXB_TRY(bA.alloc(sizeof(double) * (size_t)n * n, s));
+  GPXB_TRY(bA.alloc(sizeof(double) * (packed ? lay.doubles() : (size_t)n * n), s));
   GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles((int)n), s));
   GPXB_TRY(bR.alloc(sizeof(double) * (size_t)n, s));
   GPXB_TRY(bSc.alloc(sizeof(double) * 4, s));
   double *A = bA.as<double>(), *inv = bInv.as<double>(), *r = bR.as<double>(), *scal = bSc.as<double>();
-  GPXB_TRY(hess_gram(ctx, kind, x, J, N, nv, x, J, N, nv, nf, ell, s2, A, n, 1, s));
-  GPXB_TRY(potrf_lower(ctx, A, n, (int)n, inv, s));
+  GPXB_TRY(hess_gram(ctx, kind, x, J, N, nv, x, J, N, nv, nf, ell, s2, A, packed ? -1 : n, 1, s));
   GPXB_CUDA_CHECK(cudaMemcpyAsync(r, y, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-  GPXB_TRY(trsm_right_lt(ctx, A, n, inv, r, n, 1, (int)n, s));
+  if (packed) {
+    GPXB_TRY(potrf_lower_bcp(ctx, A, (int)n, inv, s));
+    GPXB_TRY(trsv_bcp(ctx, A, (int)n, inv, r, n, 1, true, s));
+  } else {
+    GPXB_TRY(potrf_lower(ctx, A, n, (int)n, inv, s));
+    GPXB_TRY(trsm_right_lt(ctx, A, n, inv, r, n, 1, (int)n, s));
+  }
   if (lml_out) {
-    GPXB_TRY(logdet_lower(ctx, A, n, (int)n, scal + 1, 1.0, s));
+    if (packed) GPXB_TRY(logdet_bcp(ctx, A, (int)n, scal + 1, 1.0, s));
+    else GPXB_TRY(logdet_lower(ctx, A, n, (int)n, scal + 1, 1.0, s));
     sk::sumsq_kernel<<<1, 1024, 0, s>>>(r, n, scal + 0, 0);
     GPXB_LAUNCHED(ctx);
     finalize_derivs_kernel<<<1, 1, 0, s>>>(scal, n, lml_out);
     GPXB_LAUNCHED(ctx);
   }
   if (c_out) {
-    GPXB_TRY(trsm_right_l(ctx, A, n, inv, r, n, 1, (int)n, s));
+    if (packed) GPXB_TRY(trsv_bcp(ctx, A, (int)n, inv, r, n, 1, false, s));
+    else GPXB_TRY(trsm_right_l(ctx, A, n, inv, r, n, 1, (int)n, s));
     GPXB_CUDA_CHECK(cudaMemcpyAsync(c_out, r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
     if (jaccoef_out) {
       jaccoef_kernel<<<ceil_div((long long)N * nf, 256), 256, 0, s>>>(r, J, N, nf, nv, jaccoef_out);

@@ -68,6 +68,32 @@ def test_lml_and_fit_derivs(kind, N, nf, nv):
     assert np.max(np.abs(host(jc) - jc_ref)) < 1e-8 * np.max(np.abs(jc_ref))
 
 
+@pytest.mark.parametrize("kind,N,nf,nv", [("se", 20, 30, 30), ("se", 64, 32, 32), ("m52", 100, 30, 30), ("se", 37, 90, 90)])
+def test_packed_lower_storage_matches_square(kind, N, nf, nv, monkeypatch):
+    """Block-column packed lower storage (used when the square Hessian system does not fit in HBM:
+    config 3 at N = 2000 is 259 GB square) against the square-storage path and the oracle; the sizes
+    cover one panel, an exact multiple of the 1024 panel width, and ragged last panels."""
+    from gpx_b200 import ops
+
+    x, J, y = _xj(N, nf, nv, 11)
+    ell, sigma = np.sqrt(nf), 0.05
+    xd, Jd, yd = dev(x), dev(J), dev(y)
+    monkeypatch.setenv("GPXB_DERIVS_LAYOUT", "square")
+    lml_sq = float(host(ops.gpr_lml_derivs(kind, xd, Jd, yd, ell, sigma))[0])
+    c_sq, jc_sq = [host(t) for t in ops.gpr_fit_derivs(kind, xd, Jd, yd, ell, sigma)]
+    monkeypatch.setenv("GPXB_DERIVS_LAYOUT", "packed")
+    lml_pk = float(host(ops.gpr_lml_derivs(kind, xd, Jd, yd, ell, sigma))[0])
+    c_pk, jc_pk = [host(t) for t in ops.gpr_fit_derivs(kind, xd, Jd, yd, ell, sigma)]
+    assert abs(lml_pk - lml_sq) <= 1e-12 * abs(lml_sq)
+    assert np.max(np.abs(c_pk - c_sq)) <= 1e-10 * np.max(np.abs(c_sq))
+    assert np.max(np.abs(jc_pk - jc_sq)) <= 1e-10 * np.max(np.abs(jc_sq))
+    if N * nv <= 2100:
+        ref = R.lml_derivs_dense(kind, x, y, J, ell, sigma)
+        assert abs(lml_pk - ref) < 1e-8 * abs(ref)
+        c_ref, _, _ = R.fit_derivs_dense(kind, x, y, J, ell, sigma)
+        assert np.max(np.abs(c_pk - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
+
+
 def test_facade_fit_and_predict_derivs():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import GPR

@@ -41,7 +41,7 @@ def data(N, D, seed):
 
 def main():
     what = sys.argv[1]
-    a = [int(v) for v in sys.argv[2:]]
+    a = [int(v) for v in sys.argv[2:] if v.lstrip('-').isdigit()]
     key = np.array([0, 2023], dtype=np.uint32)
     if what == "rpchol":
         N, M = (a + [1_000_000, 4096])[:2] if len(a) < 2 else a[:2]
@@ -69,20 +69,43 @@ def main():
         print(json.dumps(dict(what="kmatvec_block", N=N, D=16, P=P, s=t, alg_flops=fl, tflops=fl / t / 1e12,
                               pair_evals_per_s=float(N) ** 2 / t, checksum=float(W.sum().cpu()))), flush=True)
     elif what == "derivs":
-        # configs[2]: GPR on derivative values, nf = nv = 90 (30 atoms); the named N = 2000 needs 259 GB as a
-        # square matrix, so the largest N that fits one B200 is measured and stated
-        N = a[0] if a else 1200
+        # configs[2]: GPR on derivative values, nf = nv = 90 (30 atoms), N = 2000 -> 180 000 rows: 259 GB as a
+        # square matrix, 131 GB in the block-column packed lower storage the library switches to by itself.
+        # `derivs N check` also runs the fit and verifies it through the residual |A c - y| with A rebuilt in
+        # row blocks (an independent pass over the Hessian kernel; nothing of the factorisation is reused).
+        N = a[0] if a else 2000
+        check = "check" in sys.argv[2:]
         nf = nv = 90
+        ell, sigma = 90**0.5, 0.05
         g = torch.Generator(device="cuda").manual_seed(2)
         x = torch.randn((N, nf), dtype=torch.float64, device="cuda", generator=g)
         J = 0.1 * torch.randn((N, nf, nv), dtype=torch.float64, device="cuda", generator=g)
         J += torch.eye(nf, dtype=torch.float64, device="cuda").unsqueeze(0)
         y = torch.randn((N, nv), dtype=torch.float64, device="cuda", generator=g)
         n = N * nv
-        t, out = ev_time(lambda: ops.gpr_lml_derivs("se", x, J, y, 90**0.5, 0.05))
+        t, out = ev_time(lambda: ops.gpr_lml_derivs("se", x, J, y, ell, sigma))
         fl = n**3 / 3.0 + float(n) ** 2 * nf
+        import os
         print(json.dumps(dict(what="gpr_lml_derivs", N=N, nf=nf, nv=nv, rows=n, s=t, alg_flops=fl,
-                              tflops=fl / t / 1e12, matrix_gb=8.0 * n * n / 1e9, lml=float(out.cpu()[0]))), flush=True)
+                              tflops=fl / t / 1e12, square_gb=8.0 * n * n / 1e9,
+                              layout=os.environ.get("GPXB_DERIVS_LAYOUT", "auto"),
+                              peak_alloc_gb=(torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9,
+                              lml=float(out.cpu()[0]))), flush=True)
+        if check:
+            t, (c, jc) = ev_time(lambda: ops.gpr_fit_derivs("se", x, J, y, ell, sigma))
+            cf, yf = c.reshape(-1), y.reshape(-1)
+            s2 = sigma * sigma + 1e-10
+            blk = 50
+            num = 0.0
+            for s0 in range(0, N, blk):
+                s1 = min(N, s0 + blk)
+                K = ops.hess_gram("se", x[s0:s1], J[s0:s1], x, J, ell)
+                r = K @ cf + s2 * cf[s0 * nv:s1 * nv] - yf[s0 * nv:s1 * nv]
+                num += float((r * r).sum().cpu())
+                del K
+            print(json.dumps(dict(what="gpr_fit_derivs", N=N, rows=n, s=t,
+                                  rel_residual=(num ** 0.5) / float(yf.norm().cpu()),
+                                  c_norm=float(cf.norm().cpu()))), flush=True)
     elif what == "lml_iter":
         # configs[4] end to end at a reduced N (the named N = 2e6 costs (2e6/N)^2 more per mat-vec):
         # PCG fit (RPCholesky preconditioner, n_pivots = 100) + 30-probe, 50-step SLQ log-det
