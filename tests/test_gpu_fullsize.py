@@ -98,3 +98,35 @@ def test_sgpr_gradient_vs_finite_differences_N1M():
     fl = (float(ops.sgpr_lml("se", x, y, xl, ell + h, sigma)[0]) - float(ops.sgpr_lml("se", x, y, xl, ell - h, sigma)[0])) / (2 * h)
     fs = (float(ops.sgpr_lml("se", x, y, xl, ell, sigma + h)[0]) - float(ops.sgpr_lml("se", x, y, xl, ell, sigma - h)[0])) / (2 * h)
     assert abs(out[1] - fl) < 1e-5 * max(1.0, abs(fl)) and abs(out[2] - fs) < 1e-5 * max(1.0, abs(fs))
+
+
+def test_config2_packed_hessian_system_residual_54000_rows():
+    """configs[2] shape (30 atoms: nf = nv = 90) on the block-column packed lower storage the full
+    N = 2000 run uses (tools/bench_configs.py derivs 2000 check; 63 s, 131 GB): the fitted coefficients
+    must satisfy A c = y with A rebuilt in row blocks by an independent pass over the Hessian kernel."""
+    from gpx_b200 import ops
+
+    N, nf, nv, ell, sigma = 600, 90, 90, 90**0.5, 0.05
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn((N, nf), dtype=torch.float64, device="cuda", generator=g)
+    J = 0.1 * torch.randn((N, nf, nv), dtype=torch.float64, device="cuda", generator=g)
+    J += torch.eye(nf, dtype=torch.float64, device="cuda").unsqueeze(0)
+    y = torch.randn((N, nv), dtype=torch.float64, device="cuda", generator=g)
+    lml = float(ops.gpr_lml_derivs("se", x, J, y, ell, sigma).cpu()[0])
+    assert np.isfinite(lml)
+    c, _ = ops.gpr_fit_derivs("se", x, J, y, ell, sigma)
+    cf, yf = c.reshape(-1), y.reshape(-1)
+    s2 = sigma * sigma + 1e-10
+    num = 0.0
+    for s0 in range(0, N, 100):
+        s1 = min(N, s0 + 100)
+        K = ops.hess_gram("se", x[s0:s1], J[s0:s1], x, J, ell)
+        r = K @ cf + s2 * cf[s0 * nv:s1 * nv] - yf[s0 * nv:s1 * nv]
+        num += float((r * r).sum().cpu())
+        del K
+    assert num**0.5 < 1e-10 * float(yf.norm().cpu())
+    # the quadratic form of the LML equals y.c
+    quad = float((yf * cf).sum().cpu())
+    n = N * nv
+    logdet_half = -(lml * n) - 0.5 * quad - 0.5 * n * np.log(2 * np.pi)
+    assert np.isfinite(logdet_half)
