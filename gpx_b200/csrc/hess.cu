@@ -9,6 +9,11 @@
 //   a_i,t = kappa (q1_i - (A1 x2^T)[i][t]),  b_j,s = kappa ((A2 x1^T)[j][s] - q2_j),  q_i = A[i] . x_s
 //   SE:   kappa = 2/l^2,   c2 = exp(-d2),             c1 = (2/l^2) c2
 //   M52:  kappa = sqrt5/l, c2 = 5/(3 l^2) exp(-d),    c1 = c2 (1 + d)          
+// d/d ell keeps this form with other pair scalars (s = d2 - 1e-12, rho = s/d2; kappa's own ell
+// dependence is folded in), so the hyper-parameter gradient sum_ij W_ij dA_ij/d ell is the same kernel
+// in contraction mode (no dA is ever stored):
+//   SE:   c1' = c1 (2s - 2)/l,                   c2' = c2 (2s - 4)/l
+//   M52:  c1' = c2 (d^2 rho - 2d - 2)/l,         c2' = c2 (d rho - 4)/l
 // so the (N nv) x (N nv) matrix is ONE FP64 tensor-core GEMM (K = nf, operand tiles by bulk TMA)
 // with a fused per-(s,t) scalar / rank-1 epilogue; the reference's (N, N, nf) temporaries are
 // never formed.
@@ -41,6 +46,11 @@ struct HessParams {
   double* out;
   long long ldo;  // ldo < 0: block-column packed lower storage (chol.cuh: BcpLayout) of an n1 x n1 matrix
   int vec_out, tiles_m, tiles_n;
+  // contraction mode: partials[cta] = sum over the lower triangle of (2 - [i==j]) (alpha_i alpha_j - Ainv_ij) v_ij
+  const double* Ainv;
+  long long ldainv;
+  const double* alpha;
+  double* partials;
 };
 
 // AJ[i = s*nv + v][f] = J[s][f][v];  AJ[i][Dp] = q_i = sum_f J[s][f][v] x[s][f]
@@ -64,7 +74,7 @@ __global__ void prep_hess_kernel(const double* __restrict__ x, const double* __r
 
 // per sample pair: c1, c2 from d2 = |z_s|^2 - 2 z_s.z_t + |z_t|^2 + 1e-12 (exact 1e-12 on the diagonal)
 __global__ void pair_coef_kernel(const double* __restrict__ Z1, int Ns1, const double* __restrict__ Z2,
-                                 int Ns2, int S, int Dp, int kind, double ell, int sym,
+                                 int Ns2, int S, int Dp, int kind, double ell, int sym, int dl,
                                  double* __restrict__ C1, double* __restrict__ C2) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Ns1 * Ns2) return;
@@ -75,20 +85,25 @@ __global__ void pair_coef_kernel(const double* __restrict__ Z1, int Ns1, const d
   for (int f = 0; f < Dp; ++f) dot += a[f] * b[f];
   double d2 = ((a[Dp] - 2.0 * dot) + b[Dp]) + 1e-12;
   if (sym && s == t) d2 = 1e-12;
+  const double sq = (sym && s == t) ? 0.0 : d2 - 1e-12;  // the jitter is a constant
   if (kind == KIND_SE) {
     const double e = exp(-d2);
-    C2[idx] = e;
-    C1[idx] = (2.0 / (ell * ell)) * e;
+    const double c1 = (2.0 / (ell * ell)) * e;
+    C2[idx] = dl ? e * (2.0 * sq - 4.0) / ell : e;
+    C1[idx] = dl ? c1 * (2.0 * sq - 2.0) / ell : c1;
   } else {
     const double d = 2.23606797749979 * sqrt(fmax(d2, 1e-36));
     const double c = (5.0 / (3.0 * ell * ell)) * exp(-d);
-    C2[idx] = c;
-    C1[idx] = c * (1.0 + d);
+    const double rho = d2 > 1e-36 ? sq / d2 : 0.0;  // the clamp passes no gradient
+    C2[idx] = dl ? c * (d * rho - 4.0) / ell : c;
+    C1[idx] = dl ? c * (d * d * rho - 2.0 * d - 2.0) / ell : c * (1.0 + d);
   }
 }
 
+template <bool CONTRACT>
 __global__ void __launch_bounds__(NT, 1) hess_kernel(const HessParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double red[NT / 32];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sA1 = reinterpret_cast<double*>(smem_raw + 128);
   double* sA2 = sA1 + TB * p.S;
@@ -144,6 +159,7 @@ __global__ void __launch_bounds__(NT, 1) hess_kernel(const HessParams p) {
   }
 
   // ---- fused epilogue: per-(s,t) scalars and the rank-1 term ----
+  double local = 0.0;
 #pragma unroll
   for (int nf = 0; nf < 4; ++nf) {
 #pragma unroll
@@ -153,6 +169,7 @@ __global__ void __launch_bounds__(NT, 1) hess_kernel(const HessParams p) {
       if (gj >= p.n2) continue;
       const int t = gj / p.nv2;
       const double q2 = sA2[cl * p.S + p.Dp];
+      const double alj = CONTRACT ? p.alpha[gj] : 0.0;
 #pragma unroll
       for (int mf = 0; mf < 8; ++mf) {
         const int rl = wm * 64 + mf * 8 + lr;
@@ -164,11 +181,20 @@ __global__ void __launch_bounds__(NT, 1) hess_kernel(const HessParams p) {
         const double b = p.kappa * (p.P21[(long long)gj * p.Ns1 + s] - q2);
         const long long st = (long long)s * p.Ns2 + t;
         double v = p.C1[st] * acc[mf][nf][e] - p.C2[st] * a * b;
-        if (p.sym && gi == gj) v += p.diag_add;
-        const long long o = p.ldo >= 0 ? (long long)gi * p.ldo + gj : BcpLayout{p.n1}.index(gi, gj);
-        p.out[o] = v;
+        if (CONTRACT) {
+          const double w = p.alpha[gi] * alj - p.Ainv[(long long)gi * p.ldainv + gj];
+          local += (gi != gj ? 2.0 : 1.0) * w * v;
+        } else {
+          if (p.sym && gi == gj) v += p.diag_add;
+          const long long o = p.ldo >= 0 ? (long long)gi * p.ldo + gj : BcpLayout{p.n1}.index(gi, gj);
+          p.out[o] = v;
+        }
       }
     }
+  }
+  if (CONTRACT) {
+    const double tot = block_sum<NT>(local, red);
+    if (tid == 0) p.partials[blockIdx.x] = tot;
   }
 }
 
@@ -176,9 +202,14 @@ __global__ void __launch_bounds__(NT, 1) hess_kernel(const HessParams p) {
 
 // out[(n1*nv1) x (n2*nv2)] = d01kj(x1, x2; J1, J2) (+ diag_add I when the operands are the same).
 // ldo < 0 (with lower_only): out is block-column packed (BcpLayout).
-int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, int nv1, const double* x2,
-              const double* J2, int Ns2, int nv2, int nf, double ell, double diag_add, double* out, long long ldo,
-              int lower_only, cudaStream_t s) {
+//
+// Contraction mode (out == nullptr; symmetric operands): *contract_out = sum_ij W_ij dA_ij/d ell over the full
+// symmetric matrix with W = alpha alpha^T - Ainv (Ainv lower-stored, ld ldainv), evaluated on the lower triangle.
+static int hess_run(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, int nv1, const double* x2,
+                    const double* J2, int Ns2, int nv2, int nf, double ell, double diag_add, double* out,
+                    long long ldo, int lower_only, const double* Ainv, long long ldainv, const double* alpha,
+                    double* contract_out, cudaStream_t s) {
+  const bool contract = out == nullptr;
   GPXB_ARG_CHECK(kind == KIND_SE || kind == KIND_M52, -50);  // the reference hand-writes d01kj for these two
   GPXB_ARG_CHECK(Ns1 > 0 && Ns2 > 0 && nv1 > 0 && nv2 > 0 && nf > 0, -51);
   const ZLayout zl = z_layout(nf);
@@ -186,6 +217,7 @@ int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, i
   const bool sym = (x1 == x2) && (J1 == J2) && (Ns1 == Ns2) && (nv1 == nv2);
   GPXB_ARG_CHECK(!lower_only || sym, -53);
   GPXB_ARG_CHECK(ldo >= 0 || lower_only, -56);
+  GPXB_ARG_CHECK(!contract || (sym && lower_only && Ainv && alpha && contract_out), -57);
   const long long n1 = (long long)Ns1 * nv1, n2 = (long long)Ns2 * nv2;
   GPXB_ARG_CHECK(n1 < (1LL << 31) && n2 < (1LL << 31), -54);
   DevBuf bA1, bA2, bZ1, bZ2, bX1, bX2, bC1, bC2, bP12, bP21;
@@ -212,8 +244,8 @@ int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, i
     GPXB_TRY(prep_z(ctx, x2, nf, Ns2, zl, 1.0, X2, s));
   }
   pair_coef_kernel<<<ceil_div((long long)Ns1 * Ns2, 256), 256, 0, s>>>(Z1, Ns1, Z2, Ns2, zl.S, zl.Dp, kind, ell,
-                                                                         sym ? 1 : 0, bC1.as<double>(),
-                                                                         bC2.as<double>());
+                                                                         sym ? 1 : 0, contract ? 1 : 0,
+                                                                         bC1.as<double>(), bC2.as<double>());
   GPXB_LAUNCHED(ctx);
   {
     GemmArgs g;  // P12 = A1 X2^T   [n1 x Ns2]
@@ -245,10 +277,30 @@ int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, i
   const long long grid = lower_only ? (long long)p.tiles_m * (p.tiles_m + 1) / 2 : (long long)p.tiles_m * p.tiles_n;
   GPXB_ARG_CHECK(grid < (1LL << 31), -55);
   const int smem = 128 + 2 * TB * p.S * (int)sizeof(double);
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  hess_kernel<<<(int)grid, NT, smem, s>>>(p);
+  p.Ainv = Ainv; p.ldainv = ldainv; p.alpha = alpha; p.partials = nullptr;
+  if (!contract) {
+    GPXB_CUDA_CHECK(cudaFuncSetAttribute(hess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    hess_kernel<false><<<(int)grid, NT, smem, s>>>(p);
+    GPXB_LAUNCHED(ctx);
+    return 0;
+  }
+  DevBuf bPart;
+  GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)grid, s));
+  p.partials = bPart.as<double>();
+  GPXB_CUDA_CHECK(cudaFuncSetAttribute(hess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  hess_kernel<true><<<(int)grid, NT, smem, s>>>(p);
+  GPXB_LAUNCHED(ctx);
+  sk::sum_kernel<<<1, 1024, 0, s>>>(p.partials, grid, contract_out);  // fixed order: deterministic
   GPXB_LAUNCHED(ctx);
   return 0;
+}
+
+int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, int nv1, const double* x2,
+              const double* J2, int Ns2, int nv2, int nf, double ell, double diag_add, double* out, long long ldo,
+              int lower_only, cudaStream_t s) {
+  GPXB_ARG_CHECK(out != nullptr, -58);
+  return hess_run(ctx, kind, x1, J1, Ns1, nv1, x2, J2, Ns2, nv2, nf, ell, diag_add, out, ldo, lower_only, nullptr, 0,
+                  nullptr, nullptr, s);
 }
 
 namespace {
@@ -277,11 +329,11 @@ int gpr_derivs(Ctx* ctx, int kind, const double* x, const double* J, const doubl
   const long long n = (long long)N * nv;
   GPXB_ARG_CHECK(n > 0 && n < (1LL << 31), -1);
   const double s2 = sigma * sigma + 1e-10;
-  // block-column packed lower storage beyond a few panels: half the memory (the 180 000-row system is
-  // 259 GB square, 131 GB packed) and measured faster than the square layout (8 KB instead of n*8 B row
-  // stride; 14.0 s vs 17.05 s at 108 000 rows).  GPXB_DERIVS_LAYOUT=packed|square overrides; read per
-  // call so that tests can flip it.
-  bool packed = n > 4096;
+  // block-column packed lower storage for large systems: half the memory (the 180 000-row system is
+  // 259 GB square, 131 GB packed) and, with its 8 KB instead of n*8 B row stride, measured faster than
+  // the square layout at 108 000 rows (14.0 s vs 17.05 s) though not at 32 760 (0.435 s vs 0.409 s).
+  // GPXB_DERIVS_LAYOUT=packed|square overrides; read per call so that tests can flip it.
+  bool packed = n >= 65536;
   if (const char* e = getenv("GPXB_DERIVS_LAYOUT")) packed = (e[0] == 'p') ? true : (e[0] == 's' ? false : packed);
   const BcpLayout lay{n};
   DevBuf bA, bInv, bR, bSc;
@@ -319,6 +371,64 @@ int gpr_derivs(Ctx* ctx, int kind, const double* x, const double* J, const doubl
   return 0;
 }
 
+namespace {
+// scal: [0] quad, [1] sum log L_ii, [2] sum W dA/d ell, [3] sum alpha^2, [4] tr(Ainv)
+__global__ void finalize_derivs_grad_kernel(const double* __restrict__ scal, long long n, double sigma,
+                                            int want_grad, double* __restrict__ out3) {
+  const double m = (double)n;
+  out3[0] = (-0.5 * scal[0] - scal[1] - m * 0.5 * log(2.0 * 3.141592653589793)) / m;
+  out3[1] = want_grad ? 0.5 * scal[2] / m : 0.0;
+  out3[2] = want_grad ? sigma * (scal[3] - scal[4]) / m : 0.0;
+}
+}  // namespace
+
+// out3 = {lml, d lml/d ell, d lml/d sigma} of _lml_derivs_dense: what jit(value_and_grad(loss)) yields for
+// neg_log_marginal_likelihood_derivs (gpx/models/gpr.py:276-300, gpx/optimizers/scipy_optimize.py:72-78,
+// 92-122), in analytic form: alpha = A^-1 y, W = alpha alpha^T - A^-1,
+// d lml/d ell = (1/2 sum_ij W_ij dA_ij/d ell)/n, d lml/d sigma = sigma tr(W)/n, n = N nv.
+int gpr_derivs_grad(Ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf, int nv,
+                    double ell, double sigma, int want_grad, double* out3, cudaStream_t s) {
+  const long long n = (long long)N * nv;
+  GPXB_ARG_CHECK(n > 0 && n < (1LL << 31), -1);
+  if (!want_grad) {
+    GPXB_TRY(gpr_derivs(ctx, kind, x, J, y, N, nf, nv, ell, sigma, out3, nullptr, nullptr, s));
+    GPXB_CUDA_CHECK(cudaMemsetAsync(out3 + 1, 0, 2 * sizeof(double), s));
+    return 0;
+  }
+  // the inverse needs square storage: three n x n buffers (factor / inverse, trtri workspace)
+  size_t free_b = 0, total_b = 0;
+  GPXB_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  GPXB_ARG_CHECK(2.2 * sizeof(double) * (double)n * (double)n < (double)total_b, -60);
+  const double s2 = sigma * sigma + 1e-10;
+  DevBuf bA, bInv, bR, bSc, bW, bT;
+  GPXB_TRY(bA.alloc(sizeof(double) * (size_t)n * n, s));
+  GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles((int)n), s));
+  GPXB_TRY(bR.alloc(sizeof(double) * (size_t)n, s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * 8, s));
+  double *A = bA.as<double>(), *inv = bInv.as<double>(), *r = bR.as<double>(), *scal = bSc.as<double>();
+  GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 8, s));
+  GPXB_TRY(hess_gram(ctx, kind, x, J, N, nv, x, J, N, nv, nf, ell, s2, A, n, 1, s));
+  GPXB_TRY(potrf_lower(ctx, A, n, (int)n, inv, s));
+  GPXB_TRY(logdet_lower(ctx, A, n, (int)n, scal + 1, 1.0, s));
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(r, y, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  GPXB_TRY(trsm_right_lt(ctx, A, n, inv, r, n, 1, (int)n, s));
+  sk::sumsq_kernel<<<1, 1024, 0, s>>>(r, n, scal + 0, 0);
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(trsm_right_l(ctx, A, n, inv, r, n, 1, (int)n, s));  // r <- alpha
+  sk::sumsq_kernel<<<1, 1024, 0, s>>>(r, n, scal + 3, 0);
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(bW.alloc(sizeof(double) * (size_t)n * n, s));
+  GPXB_TRY(bT.alloc(sizeof(double) * potri_scratch_doubles((int)n), s));
+  GPXB_TRY(potri_lower(ctx, A, n, inv, (int)n, bW.as<double>(), bT.as<double>(), A, n, s));
+  bW.release();
+  sk::diag_sum_kernel<<<1, 1024, 0, s>>>(A, n, (int)n, scal + 4);
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(hess_run(ctx, kind, x, J, N, nv, x, J, N, nv, nf, ell, 0.0, nullptr, n, 1, A, n, r, scal + 2, s));
+  finalize_derivs_grad_kernel<<<1, 1, 0, s>>>(scal, n, sigma, 1, out3);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
 }  // namespace gpxb
 
 using gpxb::Ctx;
@@ -338,6 +448,14 @@ int gpxb_gpr_lml_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* 
   GPXB_ARG_CHECK(ctx && x && J && y && out, -1);
   return gpxb::gpr_derivs(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, N, nf, nv, ell, sigma, out, nullptr, nullptr,
                           (cudaStream_t)stream);
+}
+
+int gpxb_gpr_lml_grad_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N,
+                             int nf, int nv, double ell, double sigma, int want_grad, double* out3,
+                             gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && y && out3, -1);
+  return gpxb::gpr_derivs_grad(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, N, nf, nv, ell, sigma, want_grad, out3,
+                               (cudaStream_t)stream);
 }
 
 int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,

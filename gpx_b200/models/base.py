@@ -86,11 +86,30 @@ class BaseGP:
         lml = self._lml_derivs_fun(self.state, x=x, y=y, jacobian=jacobian, iterative=iterative, **kwargs)
         return -lml if return_negative else lml
 
-    def fit_derivs(self, x, y, jacobian, minimize=False, iterative=False, **kwargs):
-        """gpx/models/base.py:487-589.  Hyper-parameter optimisation on derivative targets needs the
-        gradient of the derivative LML, a 'next' row: pass minimize=False."""
+    def fit_derivs(self, x, y, jacobian, minimize=True, num_restarts=0, key=None, return_history=False,
+                   iterative=False, loss_kwargs=None, opt_kwargs=None, n_pivots=None):
+        """gpx/models/base.py:487-589: L-BFGS-B on the derivative LML (scipy_minimize_derivs binds the
+        jacobian into the loss, gpx/optimizers/scipy_optimize.py:92-122), then the linear fit."""
+        loss_kwargs = {} if loss_kwargs is None else dict(loss_kwargs)
+        loss_kwargs["iterative"] = iterative
+        loss_kwargs["n_pivots"] = n_pivots
+        loss_kwargs["key_precond"] = gpxargs.key_precond
         if minimize:
-            raise NotImplementedError("fit_derivs(minimize=True) needs d lml_derivs / d theta (next row)")
+            if not hasattr(self, "_loss_and_grad_derivs_fun"):
+                raise NotImplementedError(f"{self.__class__.__name__} has no derivative-LML gradient")
+
+            def loss_and_grad_fn(state, xx, yy):
+                return self._loss_and_grad_derivs_fun(state, xx, yy, jacobian, **loss_kwargs)
+
+            self.state, optres, *history = randomized_minimization(
+                key=key, state=self.state, x=x, y=y, loss_and_grad_fn=loss_and_grad_fn,
+                num_restarts=num_restarts, return_history=return_history, opt_kwargs=opt_kwargs)
+            self.optimize_results_ = optres
+            if not optres.success:
+                warnings.warn("optimization returned with error: {:d}. ({:s})".format(
+                    optres.status, str(optres.message)), stacklevel=2)
+            if return_history:
+                self.states_history_, self.losses_history_ = history[0], history[1]
         self.state = self._fit_derivs_fun(self.state, x=x, y=y, jacobian=jacobian, iterative=iterative)
         return self
 

@@ -134,6 +134,31 @@ def log_marginal_likelihood_derivs(state, x, y, jacobian, iterative=False, **_ig
     return float(out.cpu().numpy()[0])
 
 
+def neg_log_marginal_likelihood_derivs(state, x, y, jacobian, **kwargs):
+    """gpx/models/gpr.py:276-300."""
+    return -log_marginal_likelihood_derivs(state, x, y, jacobian, **kwargs)
+
+
+def loss_and_grad_derivs(state, x, y, jacobian, iterative=False, **_ignored):
+    """Negative derivative-LML and its gradient w.r.t. the constrained hyper-parameters from one fused
+    device call -- stands in for jit(value_and_grad(loss)) with loss = neg_log_marginal_likelihood_derivs
+    inside scipy_minimize_derivs (gpx/optimizers/scipy_optimize.py:72-78, 92-122)."""
+    if iterative:
+        raise NotImplementedError("gradient of the iterative derivative LML is a 'next' row (SURVEY.md 8f N2)")
+    if state.loss_fn not in (neg_log_marginal_likelihood, neg_log_marginal_likelihood_derivs):
+        raise NotImplementedError("only neg_log_marginal_likelihood_derivs has a fused device gradient")
+    kernel, ell, sigma = _hyper(state)
+    xd, yd, Jd = _xyj(state, x, y, jacobian)
+    out = ops.gpr_lml_grad_derivs(kernel.kind, xd, Jd, yd, ell, sigma, want_grad=True)
+    lml, g_ell, g_sigma = (float(v) for v in out.cpu().numpy())
+    grads = {}
+    if state.params["kernel_params"]["lengthscale"].trainable:
+        grads[("kernel_params", "lengthscale")] = -g_ell
+    if state.params["sigma"].trainable:
+        grads[("sigma",)] = -g_sigma
+    return -lml, grads
+
+
 def fit_derivs(state, x, y, jacobian, iterative=False, **_ignored):
     """gpx/models/gpr.py:437-489 -> _fit_derivs_dense (gpx/models/_gpr.py:313-344) + jaccoef."""
     if iterative:
@@ -207,5 +232,6 @@ class GPR(BaseGP):
     _fit_fun = staticmethod(fit)
     _predict_fun = staticmethod(predict)
     _lml_derivs_fun = staticmethod(log_marginal_likelihood_derivs)
+    _loss_and_grad_derivs_fun = staticmethod(loss_and_grad_derivs)
     _fit_derivs_fun = staticmethod(fit_derivs)
     _predict_derivs_fun = staticmethod(predict_derivs)

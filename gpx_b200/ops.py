@@ -182,6 +182,20 @@ def gpr_lml_derivs(kind, x, J, y, ell, sigma):
     return out
 
 
+def gpr_lml_grad_derivs(kind, x, J, y, ell, sigma, want_grad=True):
+    """-> device tensor [lml, d lml/d lengthscale, d lml/d sigma] of the derivative-trained GPR."""
+    ctx = context()
+    x, J, y = _f64(x), _f64(J), _f64(y)
+    N, nf, nv = J.shape
+    out = torch.empty(3, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_gpr_lml_grad_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), N, nf, nv, float(ell),
+                                         float(sigma), 1 if want_grad else 0, ptr(out), stream_ptr()),
+        "gpxb_gpr_lml_grad_derivs",
+    )
+    return out
+
+
 def gpr_fit_derivs(kind, x, J, y, ell, sigma):
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)

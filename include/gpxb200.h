@@ -68,6 +68,14 @@ int gpxb_hess_gram(gpxb_ctx* ctx, int kind, const double* x1, const double* J1, 
  * gpx/models/gpr.py:160, 173).  y: N x nv. */
 int gpxb_gpr_lml_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,
                         int nv, double ell, double sigma, double* out, gpxb_stream stream);
+/* out3 (device) = {lml, d lml/d lengthscale, d lml/d sigma} of _lml_derivs_dense: the value and gradient
+ * jit(value_and_grad(loss)) yields for neg_log_marginal_likelihood_derivs (gpx/models/gpr.py:276-300) inside
+ * scipy_minimize_derivs (gpx/optimizers/scipy_optimize.py:92-122), up to the sign and the bijector chain rule
+ * the host applies.  Analytic: W = alpha alpha^T - A^-1, d lml/d l = (1/2 sum W o dA/dl)/(N nv) with the
+ * Hessian kernel re-evaluated in contraction mode (dA/dl is never stored).  want_grad = 0: out3[1..2] = 0. */
+int gpxb_gpr_lml_grad_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N,
+                             int nf, int nv, double ell, double sigma, int want_grad, double* out3,
+                             gpxb_stream stream);
 /* c[N nv] = (d01kj + (sigma^2+1e-10) I)^-1 y and jaccoef[N x nf] = einsum("sv,sfv->sf", c, J)
  * (gpx/models/_gpr.py:313-344, gpx/models/gpr.py:475-476); jaccoef_out may be NULL. */
 int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,

@@ -394,6 +394,69 @@ def lml_derivs_dense(kind, x, y, J, ell, sigma):
     return mll / m
 
 
+def d01kj_dl(kind: str, x1, x2, ell: float, J1, J2):
+    """d/d lengthscale of d01kj, obtained by differentiating the literal einsum form term by term
+    (what jax.grad does to kernels.py:804-831 / 1253-1283): z = x/ell, so d2 - 1e-12 scales as ell^-2
+    (the jitter is a constant; the Matern clamp passes no gradient), diff as ell^-2 (SE) or ell^-1 (M52)."""
+    ns1, nf = x1.shape
+    ns2 = x2.shape[0]
+    nv1, nv2 = J1.shape[2], J2.shape[2]
+    z1, z2 = x1 / ell, x2 / ell
+    d2 = squared_distances(z1, z2)
+    dd2 = -2.0 * (d2 - 1e-12) / ell
+    if kind == "se":
+        ed2 = np.exp(-d2)
+        ded2 = -ed2 * dd2
+        diff = (2.0 / ell) * (z1[:, None] - z2)
+        ddiff = -2.0 * diff / ell
+        c_ab, dc_ab = -ed2, -ded2
+        c_g = ed2 * (2.0 / ell**2)
+        dc_g = ded2 * (2.0 / ell**2) - 4.0 * ed2 / ell**3
+    elif kind == "m52":
+        diff = np.sqrt(5.0) * (z1[:, None] - z2)
+        ddiff = -diff / ell
+        rr = np.sqrt(np.maximum(d2, 1e-36))
+        d = np.sqrt(5.0) * rr
+        dd = np.where(d2 > 1e-36, np.sqrt(5.0) * dd2 / (2.0 * rr), 0.0)
+        c = (5.0 / (3.0 * ell**2)) * np.exp(-d)
+        dc = c * (-2.0 / ell - dd)
+        c_ab, dc_ab = -c, -dc
+        c_g = c * (1.0 + d)
+        dc_g = dc * (1.0 + d) + c * dd
+    else:
+        raise ValueError(kind)
+    a = np.einsum("stf,sfv->stv", diff, J1)
+    b = np.einsum("stf,tfu->stu", diff, J2)
+    da = np.einsum("stf,sfv->stv", ddiff, J1)
+    db = np.einsum("stf,tfu->stu", ddiff, J2)
+    out = np.einsum("st,stv,stu->svtu", dc_ab, a, b)
+    out += np.einsum("st,stv,stu->svtu", c_ab, da, b)
+    out += np.einsum("st,stv,stu->svtu", c_ab, a, db)
+    G = np.einsum("sfv,tfu->svtu", J1, J2)
+    out = out + dc_g[:, None, :, None] * G
+    return out.reshape(ns1 * nv1, ns2 * nv2)
+
+
+def lml_derivs_grad_dense(kind, x, y, J, ell, sigma):
+    """(lml, d lml/d ell, d lml/d sigma) of lml_derivs_dense: the pair jit(value_and_grad(loss)) returns for
+    neg_log_marginal_likelihood_derivs (gpr.py:276-300; scipy_optimize.py:72-78, 92-122), analytic:
+    W = alpha alpha^T - A^-1, d lml/d theta = (1/2 sum W o dA/d theta)/m, dA/d sigma = 2 sigma I."""
+    yf = y.reshape(-1, 1)
+    m = yf.shape[0]
+    A = d01kj(kind, x, x, ell, J, J) + (sigma**2 + 1e-10) * np.eye(m)
+    L = sla.cholesky(A, lower=True, check_finite=False)
+    cy = sla.solve_triangular(L, yf, lower=True, check_finite=False)
+    mll = (-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - m * 0.5 * np.log(2.0 * np.pi)) / m
+    alpha = sla.solve_triangular(L, cy, lower=True, trans="T", check_finite=False)
+    Ainv, _ = sla.lapack.dpotri(L, lower=1)
+    Ainv = np.tril(Ainv) + np.tril(Ainv, -1).T
+    W = alpha @ alpha.T - Ainv
+    dA = d01kj_dl(kind, x, x, ell, J, J)
+    g_ell = 0.5 * np.sum(W * dA) / m
+    g_sigma = sigma * np.trace(W) / m
+    return mll, g_ell, g_sigma
+
+
 def fit_derivs_dense(kind, x, y, J, ell, sigma):
     """_gpr.py:313-344 + gpr.py:475-476 (jaccoef)."""
     yf = y.reshape(-1, 1)

@@ -94,6 +94,55 @@ def test_packed_lower_storage_matches_square(kind, N, nf, nv, monkeypatch):
         assert np.max(np.abs(c_pk - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
 
 
+@pytest.mark.parametrize("kind,N,nf,nv", [("se", 40, 12, 12), ("m52", 40, 12, 9), ("se", 24, 90, 90), ("m52", 30, 30, 30),
+                                           ("se", 7, 3, 1)])
+def test_lml_gradient_derivs(kind, N, nf, nv):
+    """(lml, d/d ell, d/d sigma) of the derivative-trained GPR: Hessian kernel in contraction mode against
+    the oracle's term-by-term derivative of the literal einsums."""
+    from gpx_b200 import ops
+
+    x, J, y = _xj(N, nf, nv, 4)
+    ell, sigma = 0.8 * np.sqrt(nf), 0.07
+    ref = np.array(R.lml_derivs_grad_dense(kind, x, y, J, ell, sigma))
+    out = host(ops.gpr_lml_grad_derivs(kind, dev(x), dev(J), dev(y), ell, sigma))
+    assert np.all(np.abs(out - ref) < 1e-8 * np.abs(ref)), (out, ref)
+    only = host(ops.gpr_lml_grad_derivs(kind, dev(x), dev(J), dev(y), ell, sigma, want_grad=False))
+    assert abs(only[0] - ref[0]) < 1e-8 * abs(ref[0]) and only[1] == 0.0 and only[2] == 0.0
+
+
+def test_facade_fit_derivs_minimize_follows_oracle_optimiser():
+    """BaseGP.fit_derivs(minimize=True) (gpx/models/base.py:487-589): L-BFGS-B on the device (value, grad)
+    must land where the same optimiser lands with the oracle's (value, grad)."""
+    from scipy.optimize import minimize
+
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import GPR
+    from gpx_b200.models.gpr import neg_log_marginal_likelihood_derivs
+
+    rng = np.random.default_rng(8)
+    N, nf = 60, 3
+    x = rng.uniform(-2, 2, (N, nf))
+    J = np.tile(np.eye(nf)[None], (N, 1, 1))
+    y = np.stack([np.cos(x[:, 0]) * np.sin(x[:, 1]), np.sin(x[:, 0]) * np.cos(x[:, 1]), 0.5 * np.ones(N) * x[:, 2]], 1)
+    y = y + 0.01 * rng.standard_normal(y.shape)
+    m = GPR(SquaredExponential(), loss_fn=neg_log_marginal_likelihood_derivs).fit_derivs(x, y, J)
+    assert m.optimize_results_.success
+
+    def fun(t):
+        ell, sig = R.softplus(t[0]), R.softplus(t[1])
+        lml, ge, gs = R.lml_derivs_grad_dense("se", x, y, J, ell, sig)
+        return -lml, np.array([-ge * R.sigmoid(t[0]), -gs * R.sigmoid(t[1])])
+
+    res = minimize(fun, R.inverse_softplus(np.array([1.0, 1.0])), jac=True, method="L-BFGS-B")
+    ell, sig = float(m.state.params["kernel_params"]["lengthscale"].value), float(m.state.params["sigma"].value)
+    assert abs(m.optimize_results_.fun - res.fun) < 1e-6 * max(1.0, abs(res.fun))
+    assert abs(ell - R.softplus(res.x[0])) < 1e-3 * ell and abs(sig - R.softplus(res.x[1])) < 1e-3
+    c_ref, _, jc_ref = R.fit_derivs_dense("se", x, y, J, ell, sig)
+    assert np.max(np.abs(m.state.jaccoef - jc_ref)) < 1e-7 * np.max(np.abs(jc_ref))
+    with pytest.raises(NotImplementedError):
+        GPR(SquaredExponential()).fit_derivs(x, y, J, minimize=False, iterative=True)
+
+
 def test_facade_fit_and_predict_derivs():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import GPR
@@ -109,7 +158,7 @@ def test_facade_fit_and_predict_derivs():
             sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
     ref = R.lml_derivs_dense("se", x, y, J, ell, sigma)
     assert abs(m.log_marginal_likelihood_derivs(x, y, J) - ref) < 1e-8 * abs(ref)
-    m.fit_derivs(x, y, J)
+    m.fit_derivs(x, y, J, minimize=False)
     c_ref, _, jc_ref = R.fit_derivs_dense("se", x, y, J, ell, sigma)
     assert np.max(np.abs(m.state.jaccoef - jc_ref)) < 1e-8 * np.max(np.abs(jc_ref))
     pred = m.predict_derivs(xs, Js)

@@ -130,3 +130,25 @@ def test_config2_packed_hessian_system_residual_54000_rows():
     n = N * nv
     logdet_half = -(lml * n) - 0.5 * quad - 0.5 * n * np.log(2 * np.pi)
     assert np.isfinite(logdet_half)
+
+
+def test_config2_derivative_lml_gradient_vs_finite_differences_11520_rows():
+    """configs[2] parity size (N = 128, nf = nv = 90): analytic gradient of the derivative LML (Hessian
+    kernel in contraction mode) vs central differences of the device LML."""
+    from gpx_b200 import ops
+
+    N, nf, nv, ell, sigma = 128, 90, 90, 90**0.5, 0.05
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn((N, nf), dtype=torch.float64, device="cuda", generator=g)
+    J = 0.1 * torch.randn((N, nf, nv), dtype=torch.float64, device="cuda", generator=g)
+    J += torch.eye(nf, dtype=torch.float64, device="cuda").unsqueeze(0)
+    y = torch.randn((N, nv), dtype=torch.float64, device="cuda", generator=g)
+    out = ops.gpr_lml_grad_derivs("se", x, J, y, ell, sigma).cpu().numpy()
+    f = lambda l, s: float(ops.gpr_lml_derivs("se", x, J, y, l, s).cpu()[0])  # noqa: E731
+    assert abs(out[0] - f(ell, sigma)) < 1e-12 * abs(out[0])
+    h = 1e-4
+    fe = (f(ell + h, sigma) - f(ell - h, sigma)) / (2 * h)
+    hs = 1e-5
+    fs = (f(ell, sigma + hs) - f(ell, sigma - hs)) / (2 * hs)
+    assert abs(out[1] - fe) < 1e-6 * max(1.0, abs(fe)), (out, fe)
+    assert abs(out[2] - fs) < 1e-5 * max(1.0, abs(fs)), (out, fs)

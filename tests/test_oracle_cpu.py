@@ -317,3 +317,27 @@ def test_notebook_anchor_hessian_kernel_optimum():
     assert np.max(np.abs(g)) < 5e-6  # stationary (the printed values carry 6 digits)
     assert f(t) < f(t + np.array([0.05, 0.0])) and f(t) < f(t - np.array([0.05, 0.0]))
     assert f(t) < f(t + np.array([0.0, 0.05])) and f(t) < f(t - np.array([0.0, 0.05]))
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_oracle_derivative_lml_gradient_vs_finite_differences(kind):
+    """The analytic (lml, d/d ell, d/d sigma) of the derivative-trained GPR (term-by-term derivative of the
+    literal d01kj einsums) against Richardson-extrapolated central differences of lml_derivs_dense."""
+    rng = np.random.default_rng(0)
+    N, nf, nv = 12, 6, 5
+    x = rng.standard_normal((N, nf))
+    J = 0.1 * rng.standard_normal((N, nf, nv))
+    for k in range(min(nf, nv)):
+        J[:, k, k] += 1.0
+    y = rng.standard_normal((N, nv))
+    ell, sig = 2.3, 0.3
+    lml, ge, gs = R.lml_derivs_grad_dense(kind, x, y, J, ell, sig)
+    assert lml == R.lml_derivs_dense(kind, x, y, J, ell, sig)
+
+    def rich(f, h=1e-3):
+        fd = lambda hh: (f(hh) - f(-hh)) / (2 * hh)  # noqa: E731
+        return (4 * fd(h / 2) - fd(h)) / 3
+
+    fe = rich(lambda h: R.lml_derivs_dense(kind, x, y, J, ell + h, sig))
+    fs = rich(lambda h: R.lml_derivs_dense(kind, x, y, J, ell, sig + h))
+    assert abs(ge - fe) < 1e-9 * abs(fe) and abs(gs - fs) < 1e-9 * abs(fs)

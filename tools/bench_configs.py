@@ -83,7 +83,7 @@ def main():
         J += torch.eye(nf, dtype=torch.float64, device="cuda").unsqueeze(0)
         y = torch.randn((N, nv), dtype=torch.float64, device="cuda", generator=g)
         n = N * nv
-        t, out = ev_time(lambda: ops.gpr_lml_derivs("se", x, J, y, ell, sigma))
+        t, out = ev_time(lambda: ops.gpr_lml_derivs("se", x, J, y, ell, sigma), warm=1 if "warm" in sys.argv else 0)
         fl = n**3 / 3.0 + float(n) ** 2 * nf
         import os
         print(json.dumps(dict(what="gpr_lml_derivs", N=N, nf=nf, nv=nv, rows=n, s=t, alg_flops=fl,
@@ -106,6 +106,21 @@ def main():
             print(json.dumps(dict(what="gpr_fit_derivs", N=N, rows=n, s=t,
                                   rel_residual=(num ** 0.5) / float(yf.norm().cpu()),
                                   c_norm=float(cf.norm().cpu()))), flush=True)
+    elif what == "derivs_grad":
+        # configs[2] shape, LML + analytic gradient (needs the inverse: square storage, three n x n buffers)
+        N = a[0] if a else 400
+        nf = nv = 90
+        ell, sigma = 90**0.5, 0.05
+        g = torch.Generator(device="cuda").manual_seed(2)
+        x = torch.randn((N, nf), dtype=torch.float64, device="cuda", generator=g)
+        J = 0.1 * torch.randn((N, nf, nv), dtype=torch.float64, device="cuda", generator=g)
+        J += torch.eye(nf, dtype=torch.float64, device="cuda").unsqueeze(0)
+        y = torch.randn((N, nv), dtype=torch.float64, device="cuda", generator=g)
+        n = N * nv
+        t, out = ev_time(lambda: ops.gpr_lml_grad_derivs("se", x, J, y, ell, sigma), warm=1)
+        fl = float(n) ** 3 + 2.0 * float(n) ** 2 * nf * 2
+        print(json.dumps(dict(what="gpr_lml_grad_derivs", N=N, nf=nf, nv=nv, rows=n, s=t, alg_flops=fl,
+                              tflops=fl / t / 1e12, out=[float(v) for v in out.cpu()])), flush=True)
     elif what == "lml_iter":
         # configs[4] end to end at a reduced N (the named N = 2e6 costs (2e6/N)^2 more per mat-vec):
         # PCG fit (RPCholesky preconditioner, n_pivots = 100) + 30-probe, 50-step SLQ log-det
