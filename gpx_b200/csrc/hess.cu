@@ -21,6 +21,7 @@
 #include "chol.cuh"
 #include "gemm.cuh"
 #include "gram.cuh"
+#include "matvec.cuh"
 #include "mma.cuh"
 #include "small_kernels.cuh"
 
@@ -429,6 +430,85 @@ int gpr_derivs_grad(Ctx* ctx, int kind, const double* x, const double* J, const 
   return 0;
 }
 
+namespace {
+// V[s] = (q_s, jaccoef[s][0..nf)),  q_s = jaccoef[s] . x[s]
+__global__ void d0_pack_kernel(const double* __restrict__ x, const double* __restrict__ jc, int N, int nf,
+                               double* __restrict__ V) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  double q = 0.0;
+  for (int f = 0; f < nf; ++f) {
+    const double c = jc[(long long)s * nf + f];
+    V[(long long)s * (nf + 1) + 1 + f] = c;
+    q += c * x[(long long)s * nf + f];
+  }
+  V[(long long)s * (nf + 1)] = q;
+}
+// mean[t] = mu - factor (W[t][0] - sum_f x[t][f] W[t][1+f])
+__global__ void d0_finish_kernel(const double* __restrict__ W, const double* __restrict__ x, int ns, int nf,
+                                 double factor, double mu, double* __restrict__ mean) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ns) return;
+  const double* w = W + (long long)t * (nf + 1);
+  double acc = w[0];
+  for (int f = 0; f < nf; ++f) acc -= x[(long long)t * nf + f] * w[1 + f];
+  mean[t] = mu - factor * acc;
+}
+}  // namespace
+
+// mean[ns] = mu + sum_s d0kjc(x_train, x, jaccoef)[s, :]  (_predict_y_derivs_dense fast path,
+// gpx/models/_gpr.py:630-638).  d k(x_s, x_t)/d x_s = -g(x_s, x_t) (x_s - x_t) with the radial profile
+//   SE:  g = (2/l^2) exp(-d2)                              = (2/l^2) k_SE(l)
+//   M52: g = (5/(3 l^2)) (1 + d) exp(-d), d = sqrt5 r/l    = (5/(3 l^2)) k_M32(l sqrt(3/5))
+// so sum_s jc_s . dk/dx_s = -factor [ (G q)_t - x_t . (G JC)_t ]: ONE matrix-free block mat-vec
+// G(x, x_train) [q | JC] with nf + 1 columns; no (N, n*, nf) temporary is formed.
+int gpr_predict_y_derivs(Ctx* ctx, int kind, const double* x_train, const double* jaccoef, int N, int nf,
+                         const double* x, int ns, double ell, double mu, double* mean_out, cudaStream_t s) {
+  GPXB_ARG_CHECK(kind == KIND_SE || kind == KIND_M52, -50);
+  GPXB_ARG_CHECK(N > 0 && nf > 0 && ns > 0, -51);
+  const int P = nf + 1;
+  DevBuf bV, bW;
+  GPXB_TRY(bV.alloc(sizeof(double) * (size_t)N * P, s));
+  GPXB_TRY(bW.alloc(sizeof(double) * (size_t)ns * P, s));
+  d0_pack_kernel<<<ceil_div(N, 128), 128, 0, s>>>(x_train, jaccoef, N, nf, bV.as<double>());
+  GPXB_LAUNCHED(ctx);
+  const int pkind = kind == KIND_SE ? KIND_SE : KIND_M32;
+  const double pell = kind == KIND_SE ? ell : ell * 0.7745966692414834;  // sqrt(3/5)
+  const double factor = kind == KIND_SE ? 2.0 / (ell * ell) : 5.0 / (3.0 * ell * ell);
+  if (kmatvec_supports(nf)) {
+    GPXB_TRY(kmatvec(ctx, pkind, x, ns, -1, x_train, N, nf, pell, 0.0, bV.as<double>(), P, P, bW.as<double>(), P, s));
+  } else {
+    // wide features (the 90 coordinates of config 2): the profile block G(x, x_train) is stored in row
+    // chunks (<= 1 GiB) by the fused Gram kernel and multiplied on the tensor pipe
+    const ZLayout zl = z_layout(nf);
+    GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -52);
+    const int chunk = (int)std::max<long long>(128, std::min<long long>(ns, (1LL << 27) / N / 128 * 128));
+    DevBuf bZt, bZs, bG;
+    GPXB_TRY(bZt.alloc(sizeof(double) * (size_t)N * zl.S, s));
+    GPXB_TRY(bZs.alloc(sizeof(double) * (size_t)ns * zl.S, s));
+    GPXB_TRY(bG.alloc(sizeof(double) * (size_t)chunk * N, s));
+    GPXB_TRY(prep_z(ctx, x_train, nf, N, zl, pell, bZt.as<double>(), s));
+    GPXB_TRY(prep_z(ctx, x, nf, ns, zl, pell, bZs.as<double>(), s));
+    for (int r0 = 0; r0 < ns; r0 += chunk) {
+      const int nr = std::min(chunk, ns - r0);
+      GramArgs g;
+      g.kind = pkind;
+      g.Z1 = bZs.as<double>() + (size_t)r0 * zl.S; g.n1 = nr; g.Z2 = bZt.as<double>(); g.n2 = N; g.zl = zl;
+      g.ell = pell; g.out = bG.as<double>(); g.ldo = N;
+      GPXB_TRY(gram_launch(ctx, g, s));
+      GemmArgs m;  // W[r0:r0+nr] = G [q | JC]
+      m.M = nr; m.N = P; m.K = N;
+      m.A = bG.as<double>(); m.lda = N; m.a_kmajor = true;
+      m.B = bV.as<double>(); m.ldb = P; m.b_kmajor = false;
+      m.C = bW.as<double>() + (size_t)r0 * P; m.ldc = P;
+      GPXB_TRY(gemm_f64(ctx, m, s));
+    }
+  }
+  d0_finish_kernel<<<ceil_div(ns, 128), 128, 0, s>>>(bW.as<double>(), x, ns, nf, factor, mu, mean_out);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
 }  // namespace gpxb
 
 using gpxb::Ctx;
@@ -456,6 +536,14 @@ int gpxb_gpr_lml_grad_derivs(gpxb_ctx* ctx, int kind, const double* x, const dou
   GPXB_ARG_CHECK(ctx && x && J && y && out3, -1);
   return gpxb::gpr_derivs_grad(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, N, nf, nv, ell, sigma, want_grad, out3,
                                (cudaStream_t)stream);
+}
+
+int gpxb_gpr_predict_y_derivs(gpxb_ctx* ctx, int kind, const double* x_train, const double* jaccoef, int N, int nf,
+                              const double* x, int ns, double ell, double mu, double* mean_out,
+                              gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x_train && jaccoef && x && mean_out, -1);
+  return gpxb::gpr_predict_y_derivs(reinterpret_cast<Ctx*>(ctx), kind, x_train, jaccoef, N, nf, x, ns, ell, mu,
+                                    mean_out, (cudaStream_t)stream);
 }
 
 int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,

@@ -274,6 +274,9 @@ inline int smem_bytes(int BR, int S, int PS) {
 
 }  // namespace
 
+// largest feature count the matrix-free kernel's shared-memory tiles hold (S <= 68: D <= 64)
+bool kmatvec_supports(int D) { return smem_bytes(128, z_layout(D).S, v_padded_stride(8)) <= 232448; }
+
 int v_padded_stride(int P) {
   int ps = P < 2 ? 2 : P;
   while (ps % 8 != 2) ++ps;

@@ -9,6 +9,7 @@ namespace gpxb {
 
 // Padded row stride of a V block with P (<= 32) columns: smallest PS >= max(P, 2), PS % 8 == 2.
 int v_padded_stride(int P);
+bool kmatvec_supports(int D);
 
 struct KmvArgs {
   int kind = KIND_SE;

@@ -118,6 +118,12 @@ class BaseGP:
         return self._predict_derivs_fun(self.state, x=x, jacobian=jacobian, full_covariance=full_covariance,
                                         iterative=iterative)
 
+    def predict_y_derivs(self, x, full_covariance=False, iterative=False):
+        """gpx/models/base.py:217-240."""
+        if not hasattr(self, "_predict_y_derivs_fun"):
+            raise NotImplementedError(f"{self.__class__.__name__} has no predict_y_derivs")
+        return self._predict_y_derivs_fun(self.state, x=x, full_covariance=full_covariance, iterative=iterative)
+
     @property
     def jacobian_train(self):
         return self.state.jacobian_train

@@ -191,6 +191,23 @@ def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):
     return mean.reshape(ns, nv).cpu().numpy()
 
 
+def predict_y_derivs(state, x, full_covariance=False, iterative=False):
+    """gpx/models/gpr.py:660-717 -> _predict_y_derivs_dense fast path (gpx/models/_gpr.py:630-638):
+    mu + sum_s d0kjc(x_train, x, jaccoef)[s], shape (n, 1)."""
+    if not getattr(state, "is_fitted_derivs", False):
+        raise RuntimeError("Model is not fitted. Run `fit_derivs` to fit the model before prediction.")
+    if full_covariance and iterative:
+        raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
+    if full_covariance:
+        raise NotImplementedError("predictive covariance of a derivative-trained model is a 'next' row (SURVEY.md 8f N2)")
+    kernel, ell, _ = _hyper(state)
+    if kernel.active_dims is not None:
+        raise NotImplementedError("active_dims with derivative training is not supported")
+    out = ops.gpr_predict_y_derivs(kernel.kind, _to_device(state.x_train), _to_device(state.jaccoef), _to_device(x),
+                                   ell, float(state.mu))
+    return out.cpu().numpy().reshape(-1, 1)
+
+
 def default_params() -> Dict[str, Parameter]:
     """gpx/models/gpr.py:863-870."""
     return dict(sigma=Parameter(value=1.0, trainable=True, bijector=Softplus(), prior=GammaPrior()))
@@ -234,4 +251,5 @@ class GPR(BaseGP):
     _lml_derivs_fun = staticmethod(log_marginal_likelihood_derivs)
     _loss_and_grad_derivs_fun = staticmethod(loss_and_grad_derivs)
     _fit_derivs_fun = staticmethod(fit_derivs)
+    _predict_y_derivs_fun = staticmethod(predict_y_derivs)
     _predict_derivs_fun = staticmethod(predict_derivs)

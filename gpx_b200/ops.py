@@ -196,6 +196,21 @@ def gpr_lml_grad_derivs(kind, x, J, y, ell, sigma, want_grad=True):
     return out
 
 
+def gpr_predict_y_derivs(kind, x_train, jaccoef, x, ell, mu=0.0):
+    """-> (ns,) predicted target values of a derivative-trained model."""
+    ctx = context()
+    x_train, jaccoef, x = _f64(x_train), _f64(jaccoef), _f64(x)
+    N, nf = x_train.shape
+    ns = x.shape[0]
+    out = torch.empty(ns, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_gpr_predict_y_derivs(ctx.handle, _kind(kind), ptr(x_train), ptr(jaccoef), N, nf, ptr(x), ns,
+                                          float(ell), float(mu), ptr(out), stream_ptr()),
+        "gpxb_gpr_predict_y_derivs",
+    )
+    return out
+
+
 def gpr_fit_derivs(kind, x, J, y, ell, sigma):
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)

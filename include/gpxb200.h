@@ -81,6 +81,14 @@ int gpxb_gpr_lml_grad_derivs(gpxb_ctx* ctx, int kind, const double* x, const dou
 int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,
                         int nv, double ell, double sigma, double* c_out, double* jaccoef_out, gpxb_stream stream);
 
+/* mean_out[ns] = mu + sum_s Kernel.d0kjc(x_train, x, params, jaccoef)[s, :]: target values predicted by a
+ * model trained on derivatives (_predict_y_derivs_dense fast path, gpx/models/_gpr.py:630-638; d0kjc =
+ * grad_kernelize(argnums=0, with_jaccoef) gpx/kernels/kernels.py:1474-1480).  Evaluated matrix-free as one
+ * block mat-vec with nf + 1 columns.  jaccoef: N x nf (from gpxb_gpr_fit_derivs); mu: host scalar. */
+int gpxb_gpr_predict_y_derivs(gpxb_ctx* ctx, int kind, const double* x_train, const double* jaccoef, int N, int nf,
+                              const double* x, int ns, double ell, double mu, double* mean_out,
+                              gpxb_stream stream);
+
 /* ---- Family 2: blocked FP64 Cholesky / TRSM / log-det / inverse ---------------------- */
 /* C[M x N] = alpha * op(A) * op(B) + beta * C on the FP64 tensor pipe.  transa = 0: A is M x K
  * row-major; 1: A is stored K x M.  transb = 0: B is K x N row-major; 1: B is stored N x K. */

@@ -286,6 +286,28 @@ def d01kjc(kind: str, x1, x2, ell: float, jaccoef, J2):
     return out.reshape(x1.shape[0], -1)
 
 
+def d0kjc(kind: str, x1, x2, ell: float, jaccoef):
+    """Kernel.d0kjc (kernels.py:1474-1480: grad_kernelize(argnums=0, with_jaccoef, trace_samples=False)) of
+    the pair kernels kernels.py:731-737 (SE, plain autodiff: no 1e-12 jitter in the pair form) and 1030-1037
+    with its custom JVP 1068-1075 (Matern-5/2) -> (ns1, ns2): sum_f jaccoef[s,f] d k(x1_s, x2_t)/d x1_sf."""
+    dz = x1[:, None, :] / ell - x2[None, :, :] / ell
+    if kind == "se":
+        k = np.exp(-np.sum(dz**2, axis=2))
+        g = -(2.0 / ell) * dz * k[:, :, None]
+    elif kind == "m52":
+        diff = np.sqrt(5.0) * dz
+        d = np.sqrt(np.maximum(np.sum(diff**2, axis=2), 1e-36))
+        g = -(np.sqrt(5.0) / (3.0 * ell)) * ((1.0 + d) * np.exp(-d))[:, :, None] * diff
+    else:
+        raise ValueError(kind)
+    return np.einsum("sf,stf->st", jaccoef, g)
+
+
+def predict_y_derivs_dense(kind, x_train, x, jaccoef, mu, ell):
+    """_gpr.py:630-638 (contracted-jacobian fast path of _predict_y_derivs_dense)."""
+    return (mu + np.sum(d0kjc(kind, x_train, x, ell, jaccoef), axis=0)).reshape(-1, 1)
+
+
 # =============================================================================
 # exact GPR (gpx/models/_gpr.py)
 # =============================================================================

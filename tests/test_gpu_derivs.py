@@ -143,6 +143,21 @@ def test_facade_fit_derivs_minimize_follows_oracle_optimiser():
         GPR(SquaredExponential()).fit_derivs(x, y, J, minimize=False, iterative=True)
 
 
+@pytest.mark.parametrize("kind", ["se", "m52"])
+@pytest.mark.parametrize("N,nf,ns", [(50, 6, 11), (300, 90, 257), (1000, 31, 64), (3, 1, 1)])
+def test_predict_y_derivs(kind, N, nf, ns):
+    """Target values from a derivative-trained model: one matrix-free block mat-vec with nf + 1 columns
+    against the oracle's literal d0kjc."""
+    from gpx_b200 import ops
+
+    rng = np.random.default_rng(12)
+    xt, xs, jc = rng.standard_normal((N, nf)), rng.standard_normal((ns, nf)), rng.standard_normal((N, nf))
+    ell, mu = 0.9 * np.sqrt(nf), 0.3
+    ref = R.predict_y_derivs_dense(kind, xt, xs, jc, mu, ell)[:, 0]
+    out = host(ops.gpr_predict_y_derivs(kind, dev(xt), dev(jc), dev(xs), ell, mu))
+    assert np.max(np.abs(out - ref)) < 1e-8 * max(1.0, np.max(np.abs(ref)))
+
+
 def test_facade_fit_and_predict_derivs():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import GPR
@@ -167,5 +182,8 @@ def test_facade_fit_and_predict_derivs():
     # the contracted route of the reference (d01kjc) gives the same numbers
     ref_c = R.d01kjc("se", x, xs, ell, jc_ref, Js).sum(0).reshape(11, nv)
     assert np.max(np.abs(pred - ref_c)) < 1e-8 * np.max(np.abs(ref_c))
+    yp = m.predict_y_derivs(xs)
+    ref_y = R.predict_y_derivs_dense("se", x, xs, jc_ref, 0.0, ell)
+    assert yp.shape == (11, 1) and np.max(np.abs(yp - ref_y)) < 1e-8 * np.max(np.abs(ref_y))
     with pytest.raises(RuntimeError):
         m.predict(xs)

@@ -341,3 +341,18 @@ def test_oracle_derivative_lml_gradient_vs_finite_differences(kind):
     fe = rich(lambda h: R.lml_derivs_dense(kind, x, y, J, ell + h, sig))
     fs = rich(lambda h: R.lml_derivs_dense(kind, x, y, J, ell, sig + h))
     assert abs(ge - fe) < 1e-9 * abs(fe) and abs(gs - fs) < 1e-9 * abs(fs)
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_oracle_d0kjc_vs_finite_differences_of_the_kernel(kind):
+    rng = np.random.default_rng(3)
+    x1, x2, jc = rng.standard_normal((6, 4)), rng.standard_normal((5, 4)), rng.standard_normal((6, 4))
+    ell, h = 1.7, 1e-5
+    ref = np.zeros((6, 5))
+    for f in range(4):
+        e = np.zeros(4)
+        e[f] = h
+        dk = (R.kernel(kind, x1 + e, x2, ell) - R.kernel(kind, x1 - e, x2, ell)) / (2 * h)
+        ref += jc[:, f:f + 1] * dk
+    out = R.d0kjc(kind, x1, x2, ell, jc)
+    assert np.max(np.abs(out - ref)) < 1e-8
