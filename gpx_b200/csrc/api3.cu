@@ -30,7 +30,7 @@ int sgpr_fit(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, in
              cudaStream_t s);
 int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, long long N, int D,
                   const double* x_locs, int M, double ell, double sigma, const double* mu, int want_grad,
-                  double* out3, cudaStream_t s);
+                  double* out3, double* grad_locs, cudaStream_t s);
 int sgpr_predict(Ctx* ctx, int kind, const double* x_locs, int M, int D, const double* x, int ns,
                  const double* c, int T, const double* mu, double ell, double sigma, double* mean_out,
                  double* cov_out, cudaStream_t s);
@@ -221,7 +221,23 @@ int gpxb_sgpr_lml_grad(gpxb_ctx* ctx_, int kind, const double* x, const double* 
   sk::mean_kernel<<<1, 1024, 0, s>>>(y, (long long)N, mean_mode == GPXB_MEAN_DATA, mu.as<double>());
   GPXB_LAUNCHED(ctx);
   return sgpr_lml_grad(ctx, kind, x + sh.b * D, y + sh.b, sh.n(), N, D, x_locs, M, ell, sigma, mu.as<double>(),
-                       want_grad, out3, s);
+                       want_grad, out3, nullptr, s);
+}
+
+int gpxb_sgpr_lml_grad_locs(gpxb_ctx* ctx_, int kind, const double* x, const double* y, int N, int D,
+                            const double* x_locs, int M, double ell, double sigma, int mean_mode, double* out3,
+                            double* grad_locs, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && x && y && x_locs && out3 && grad_locs, -1);
+  GPXB_ARG_CHECK(kind >= 0 && kind <= 3 && N > 0, -2);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  cudaStream_t s = (cudaStream_t)stream;
+  const Shard sh = shard_of(ctx, N);
+  DevBuf mu;
+  GPXB_TRY(mu.alloc(sizeof(double), s));
+  sk::mean_kernel<<<1, 1024, 0, s>>>(y, (long long)N, mean_mode == GPXB_MEAN_DATA, mu.as<double>());
+  GPXB_LAUNCHED(ctx);
+  return sgpr_lml_grad(ctx, kind, x + sh.b * D, y + sh.b, sh.n(), N, D, x_locs, M, ell, sigma, mu.as<double>(), 1,
+                       out3, grad_locs, s);
 }
 
 int gpxb_sgpr_fit(gpxb_ctx* ctx_, int kind, const double* x, const double* y, int N, int D, int T,

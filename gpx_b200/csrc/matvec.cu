@@ -42,16 +42,33 @@ struct KmvParams {
   long long ldw;
   double diag_add;
   int jsplit, jps;  // columns per split (multiple of BJ)
+  // KMODE 3 (weighted derivative profile): k_ij <- g(d2_ij) * (wrow[i] * wcol[j] - wt(i, j)),
+  // wt(i, j) = wt[i * ldwt + j] or, transposed storage, wt[j * ldwt + i]
+  const double* wrow;
+  const double* wcol;
+  const double* wt;
+  long long ldwt;
+  int wt_trans;
 };
 
 // MF: 8-row fragments per warp (rows per CTA = 64*MF); KS: Dp/4 when the row operand lives in
 // registers, 0 = read it from shared memory; NPF: 8-column fragments of V/W (P <= 8*NPF).
 // KMODE: 0 = kind chosen at run time (libm exp), 1 = SquaredExponential with libm exp,
-//        2 = SquaredExponential with the table-driven exp_tab (10 FP64 ops)
+//        2 = SquaredExponential with the table-driven exp_tab (10 FP64 ops),
+//        3 = radial derivative profile g of the kind chosen at run time, d k/d x1 = -c(l) g (x1 - x2):
+//            SE exp(-d2) [c = 2/l^2], M12 exp(-r)/r [1/l^2], M32 exp(-d) [3/l^2], M52 (1+d) exp(-d) [5/(3 l^2)]
 template <int KMODE>
 __device__ __forceinline__ double kfun_mode(int kind, double d2, const double* __restrict__ tab) {
   if (KMODE == 1) return exp(-d2);
   if (KMODE == 2) return exp_tab(-d2, tab);
+  if (KMODE == 3) {
+    if (kind == KIND_SE) return exp(-d2);
+    const double r = sqrt(fmax(d2, 1e-36));
+    if (kind == KIND_M12) return exp(-r) / r;
+    if (kind == KIND_M32) return exp(-1.7320508075688772 * r);
+    const double d = 2.23606797749979 * r;
+    return (1.0 + d) * exp(-d);
+  }
   if (kind == KIND_SE) return exp(-d2);
   const double r = sqrt(fmax(d2, 1e-36));
   if (kind == KIND_M12) return exp(-r);
@@ -168,7 +185,18 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
         const bool dg0 = (p.row_offset >= 0) && (gi == gj), dg1 = (p.row_offset >= 0) && (gi == gj + 1);
         if (dg0) d20 = 1e-12;
         if (dg1) d21 = 1e-12;
-        const double k0 = kfun_mode<KMODE>(p.kind, d20, etab), k1 = kfun_mode<KMODE>(p.kind, d21, etab);
+        double k0 = kfun_mode<KMODE>(p.kind, d20, etab), k1 = kfun_mode<KMODE>(p.kind, d21, etab);
+        if (KMODE == 3) {
+          const int il = row0 + warp * 8 * MF + mf * 8 + lr;  // local row (wrow / wt are indexed locally)
+          const bool rok = il < p.n_rows;
+          const double wr = rok ? p.wrow[il] : 0.0;
+          double t0 = 0.0, t1 = 0.0;
+          if (rok && gj < jend) t0 = p.wt_trans ? p.wt[(long long)gj * p.ldwt + il] : p.wt[(long long)il * p.ldwt + gj];
+          if (rok && gj + 1 < jend)
+            t1 = p.wt_trans ? p.wt[(long long)(gj + 1) * p.ldwt + il] : p.wt[(long long)il * p.ldwt + gj + 1];
+          k0 *= (gj < jend) ? wr * p.wcol[gj] - t0 : 0.0;
+          k1 *= (gj + 1 < jend) ? wr * p.wcol[gj + 1] - t1 : 0.0;
+        }
         c[mf][0] = (gj < jend) ? k0 : 0.0;
         c[mf][1] = (gj + 1 < jend) ? k1 : 0.0;
       }
@@ -253,6 +281,7 @@ int launch_t(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) 
     const char* e = getenv("GPXB_KMV_EXP");  // "fast" (default: table-driven exp_tab, +10%) or "libm"
     mode = (e && e[0] == 'l') ? 1 : 2;
   }
+  if (p.wt) return launch_k<MF, KS, NPF, NWARP, 3>(ctx, p, grid, smem, s);
   if (p.kind == KIND_SE) {
     if (mode == 1) return launch_k<MF, KS, NPF, NWARP, 1>(ctx, p, grid, smem, s);
     return launch_k<MF, KS, NPF, NWARP, 2>(ctx, p, grid, smem, s);
@@ -294,6 +323,8 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   p.Za = a.Za; p.N = a.N; p.S = a.zl.S; p.Dp = a.zl.Dp;
   p.V = a.V; p.PS = a.PS; p.P = a.P;
   p.diag_add = a.diag_add;
+  p.wrow = a.wrow; p.wcol = a.wcol; p.wt = a.wt; p.ldwt = a.ldwt; p.wt_trans = a.wt_trans;
+  GPXB_ARG_CHECK(!a.wt || (a.wrow && a.wcol), -24);
   const int NPF = a.P <= 8 ? 1 : 4;
   const int limit = 232448;
   // variants: (MF=4, 8 warps, 256 rows) default; (MF=2, 16 warps, 256 rows) via GPXB_KMV_WARPS=16;
@@ -395,6 +426,31 @@ int kmatvec(Ctx* ctx, int kind, const double* x_rows, int n_rows, long long row_
     a.Za = za.as<double>(); a.N = N; a.zl = zl;
     a.V = vp.as<double>(); a.PS = PS; a.P = pb;
     a.W = W + c0; a.ldw = ldw; a.diag_add = diag_add;
+    GPXB_TRY(kmatvec_launch(ctx, a, s));
+    vp.release();
+  }
+  return 0;
+}
+
+// W[n_rows x P] (+)= (g(Zr, Za) o (wrow wcol^T - wt)) V: the weighted derivative-profile product behind the
+// gradient w.r.t. landmark coordinates.  Zr / Za are pre-scaled operands (z_layout), V is N x ldv.
+int kprofile_weighted(Ctx* ctx, int kind, const double* Zr, int n_rows, long long row_offset, const double* Za,
+                      int N, ZLayout zl, const double* V, long long ldv, int P, const double* wrow,
+                      const double* wcol, const double* wt, long long ldwt, int wt_trans, double* W,
+                      long long ldw, cudaStream_t s) {
+  GPXB_ARG_CHECK(n_rows > 0 && N > 0 && P > 0 && wrow && wcol && wt, -1);
+  DevBuf vp;
+  for (int c0 = 0; c0 < P; c0 += 32) {
+    const int pb = std::min(32, P - c0);
+    const int PS = v_padded_stride(pb);
+    GPXB_TRY(vp.alloc(sizeof(double) * ((size_t)N * PS + 16), s));
+    GPXB_TRY(pack_v(ctx, V, ldv, N, c0, pb, PS, vp.as<double>(), s));
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_rows; a.row_offset = row_offset;
+    a.Za = Za; a.N = N; a.zl = zl;
+    a.V = vp.as<double>(); a.PS = PS; a.P = pb;
+    a.W = W + c0; a.ldw = ldw;
+    a.wrow = wrow; a.wcol = wcol; a.wt = wt; a.ldwt = ldwt; a.wt_trans = wt_trans;
     GPXB_TRY(kmatvec_launch(ctx, a, s));
     vp.release();
   }

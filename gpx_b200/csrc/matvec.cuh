@@ -24,6 +24,12 @@ struct KmvArgs {
   double* W = nullptr;  // n_rows x ldw, P columns written
   long long ldw = 0;
   double diag_add = 0.0;
+  // weighted derivative-profile mode (wt != nullptr): see matvec.cu KMODE 3
+  const double* wrow = nullptr;
+  const double* wcol = nullptr;
+  const double* wt = nullptr;
+  long long ldwt = 0;
+  int wt_trans = 0;
 };
 int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s);
 int pack_v(Ctx* ctx, const double* V, long long ldv, int n, int c0, int P, int PS, double* Vp,
@@ -31,5 +37,10 @@ int pack_v(Ctx* ctx, const double* V, long long ldv, int n, int c0, int P, int P
 int kmatvec(Ctx* ctx, int kind, const double* x_rows, int n_rows, long long row_offset,
             const double* x_all, int N, int D, double ell, double diag_add, const double* V,
             long long ldv, int P, double* W, long long ldw, cudaStream_t s);
+
+int kprofile_weighted(Ctx* ctx, int kind, const double* Zr, int n_rows, long long row_offset, const double* Za,
+                      int N, ZLayout zl, const double* V, long long ldv, int P, const double* wrow,
+                      const double* wcol, const double* wt, long long ldwt, int wt_trans, double* W,
+                      long long ldw, cudaStream_t s);
 
 }  // namespace gpxb

@@ -13,6 +13,7 @@
 #include "comm.cuh"
 #include "gemm.cuh"
 #include "gram.cuh"
+#include "matvec.cuh"
 #include "small_kernels.cuh"
 
 namespace gpxb {
@@ -199,6 +200,25 @@ __global__ void transpose_sq_kernel(const double* __restrict__ in, int M, double
     if (r < M && c < M) out[(long long)r * M + c] = tile[threadIdx.x][k];
   }
 }
+// V[i] = (1, x[i][0..D))
+__global__ void ones_x_kernel(const double* __restrict__ x, int n, int D, double* __restrict__ V) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * (D + 1)) return;
+  const int i = (int)(idx / (D + 1)), c = (int)(idx % (D + 1));
+  V[idx] = c == 0 ? 1.0 : x[(long long)i * D + c - 1];
+}
+// grad[m][f] = scale (-(z_mf acc1[m][0] - acc1[m][1+f]) + (z_mf acc2[m][0] - acc2[m][1+f]))
+__global__ void grad_locs_kernel(const double* __restrict__ acc1, const double* __restrict__ acc2,
+                                 const double* __restrict__ z, int M, int D, double scale,
+                                 double* __restrict__ grad) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * D) return;
+  const int m = (int)(idx / D), f = (int)(idx % D);
+  const double zf = z[idx];
+  const double* a1 = acc1 + (long long)m * (D + 1);
+  const double* a2 = acc2 + (long long)m * (D + 1);
+  grad[idx] = scale * (-(zf * a1[0] - a1[1 + f]) + (zf * a2[0] - a2[1 + f]));
+}
 }  // namespace
 
 // SGPR LML and its gradient w.r.t. (lengthscale, sigma) with fixed landmarks -- what
@@ -211,9 +231,15 @@ __global__ void transpose_sq_kernel(const double* __restrict__ in, int M, double
 //              Y = G^T B^-1 L_A^-1 (per chunk),  F = L_A^-T (I - s2 B^-1) L_A^-1
 //   d/d sigma = sigma (alpha.alpha - tr C^-1),  tr C^-1 = (N - M + s2 tr(B^-1))/s2
 // Single output column (T = 1).  out3: device [lml/N, d/d ell, d/d sigma].
+//
+// grad_locs (optional, M x D): d(lml/N)/d x_locs for trainable landmark coordinates.  With
+// d k(x, z)/d z_f = -c g(x, z) (z_f - x_f) (g: radial derivative profile, matvec.cu KMODE 3) the same weights give
+//   grad[m][f] = -c sum_n g_nm (alpha_n w_m - Y_nm) (z_mf - x_nf) + c sum_m' g_mm' (w_m w_m' - F_mm') (z_mf - z_m'f)
+// = two weighted profile products H [1 | X] of the matrix-free kernel (no M x N x D temporary).
 int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, long long N, int D,
                   const double* x_locs, int M, double ell, double sigma, const double* mu, int want_grad,
-                  double* out3, cudaStream_t s) {
+                  double* out3, double* grad_locs, cudaStream_t s) {
+  GPXB_ARG_CHECK(!grad_locs || (want_grad && kmatvec_supports(D)), -4);
   GPXB_ARG_CHECK(n_loc >= 0 && D > 0 && M > 0, -1);
   const ZLayout zl = z_layout(D);
   GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
@@ -221,6 +247,8 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
   const size_t mm = (size_t)M * M;
   const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
   DevBuf bZl, bA, bInvA, bB, bInvB, bU, bWh, bW, bZc, bKc, bRc, bTc, bY, bSc, bWk, bTs, bPart, bH, bHt;
+  DevBuf bVx, bAcc1, bAcc2, bTmp;
+  const int P1 = D + 1;
   GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
   GPXB_TRY(bA.alloc(sizeof(double) * mm, s));
   GPXB_TRY(bInvA.alloc(sizeof(double) * leaf_inv_doubles(M), s));
@@ -304,6 +332,13 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
     GPXB_TRY(bH.alloc(sizeof(double) * mm, s));
     GPXB_TRY(bHt.alloc(sizeof(double) * mm, s));
     double *Y = bY.as<double>(), *H = bH.as<double>(), *Ht = bHt.as<double>();
+    if (grad_locs) {
+      GPXB_TRY(bVx.alloc(sizeof(double) * (size_t)std::max(nc_max, M) * P1, s));
+      GPXB_TRY(bAcc1.alloc(sizeof(double) * (size_t)M * P1, s));
+      GPXB_TRY(bAcc2.alloc(sizeof(double) * (size_t)M * P1, s));
+      GPXB_TRY(bTmp.alloc(sizeof(double) * (size_t)M * P1, s));
+      GPXB_CUDA_CHECK(cudaMemsetAsync(bAcc1.as<double>(), 0, sizeof(double) * (size_t)M * P1, s));
+    }
     // w = L_A^-T what (landmark weights)
     GPXB_CUDA_CHECK(cudaMemcpyAsync(w, wh, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
     GPXB_TRY(trsm_right_l(ctx, A, M, invA, w, M, 1, M, s));
@@ -346,7 +381,17 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
       add_vec_kernel<<<1, 1, 0, s>>>(scal + 5, c.partials + nparts, 1);
       GPXB_LAUNCHED(ctx);
       bPart.release();
+      if (grad_locs) {  // acc1 += (g o (w alpha_c^T - Y^T)) [1 | x_c]   (rows: landmarks, columns: chunk points)
+        ones_x_kernel<<<ceil_div((long long)nc * P1, 256), 256, 0, s>>>(x + (long long)r0 * D, nc, D, bVx.as<double>());
+        GPXB_LAUNCHED(ctx);
+        GPXB_TRY(kprofile_weighted(ctx, kind, Zl, M, -1, Zc, nc, zl, bVx.as<double>(), P1, P1, w, tc, Y, M, 1,
+                                   bTmp.as<double>(), P1, s));
+        add_vec_kernel<<<ceil_div((long long)M * P1, 256), 256, 0, s>>>(bAcc1.as<double>(), bTmp.as<double>(),
+                                                                         (long long)M * P1);
+        GPXB_LAUNCHED(ctx);
+      }
     }
+    if (grad_locs && ctx->world > 1) GPXB_TRY(comm_allreduce_sum(ctx, bAcc1.as<double>(), (size_t)M * P1, s));
     if (ctx->world > 1) GPXB_TRY(comm_allreduce_sum(ctx, scal + 4, 2, s));
     // F = L_A^-T (I - s2 B^-1) L_A^-1:  H = I - s2 B^-1;  H <- H L_A^-1;  F = (H^T L_A^-1)^T = H^T L_A^-1
     i_minus_scaled_kernel<<<eb, 256, 0, s>>>(B, M, s2, H);
@@ -367,6 +412,17 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
     GPXB_TRY(gram_launch(ctx, c, s));
     sum_kernel<<<1, 1024, 0, s>>>(c.partials, nparts, scal + 6);
     GPXB_LAUNCHED(ctx);
+    if (grad_locs) {  // acc2 = (g o (w w^T - F)) [1 | z]   (rows = columns = landmarks)
+      ones_x_kernel<<<ceil_div((long long)M * P1, 256), 256, 0, s>>>(x_locs, M, D, bVx.as<double>());
+      GPXB_LAUNCHED(ctx);
+      GPXB_TRY(kprofile_weighted(ctx, kind, Zl, M, 0, Zl, M, zl, bVx.as<double>(), P1, P1, w, w, Ht, M, 0,
+                                 bAcc2.as<double>(), P1, s));
+      const double cprof = kind == KIND_SE ? 2.0 : (kind == KIND_M12 ? 1.0 : (kind == KIND_M32 ? 3.0 : 5.0 / 3.0));
+      grad_locs_kernel<<<ceil_div((long long)M * D, 256), 256, 0, s>>>(bAcc1.as<double>(), bAcc2.as<double>(), x_locs,
+                                                                      M, D, cprof / (ell * ell) / (double)N,
+                                                                      grad_locs);
+      GPXB_LAUNCHED(ctx);
+    }
   }
   finalize_sgpr_grad_kernel<<<1, 1, 0, s>>>(scal, N, M, s2, sigma, want_grad, out3);
   GPXB_LAUNCHED(ctx);

@@ -36,27 +36,35 @@ def neg_log_marginal_likelihood(state, x, y, **kwargs):
     return -log_marginal_likelihood(state, x, y, **kwargs)
 
 
-def _loss_and_grad_with_locs(state, xd, yd, x_locs_dev):
+def _loss_and_grad_with_locs(state, xd, yd, x_locs_dev, locs_trainable=False):
     kernel, ell, sigma = _hyper(state)
-    out = ops.sgpr_lml_grad(kernel.kind, xd, yd, x_locs_dev, ell, sigma, mean_mode(state.mean_function))
+    g_locs = None
+    if locs_trainable:
+        if kernel.active_dims is not None:
+            raise NotImplementedError("trainable x_locs with active_dims is not supported")
+        out, g_locs = ops.sgpr_lml_grad_locs(kernel.kind, xd, yd, x_locs_dev, ell, sigma,
+                                             mean_mode(state.mean_function))
+    else:
+        out = ops.sgpr_lml_grad(kernel.kind, xd, yd, x_locs_dev, ell, sigma, mean_mode(state.mean_function))
     lml, g_ell, g_sigma = (float(v) for v in out.cpu().numpy())
     grads = {}
     if state.params["kernel_params"]["lengthscale"].trainable:
         grads[("kernel_params", "lengthscale")] = -g_ell
     if state.params["sigma"].trainable:
         grads[("sigma",)] = -g_sigma
+    if g_locs is not None:
+        grads[("x_locs",)] = -g_locs.cpu().numpy()
     return -lml, grads
 
 
 def loss_and_grad(state, x, y, iterative=False, **kwargs):
-    """Negative SGPR LML and its gradient w.r.t. (lengthscale, sigma) from one fused device call
-    (stands in for jit(value_and_grad(loss))).  Landmarks must be fixed."""
+    """Negative SGPR LML and its gradient w.r.t. (lengthscale, sigma) and, when the `x_locs` Parameter is
+    trainable, the landmark coordinates, from one fused device call (stands in for
+    jit(value_and_grad(loss)))."""
     if iterative:
         raise NotImplementedError("gradient of the iterative SGPR LML is not implemented")
-    if state.params["x_locs"].trainable:
-        raise NotImplementedError("trainable landmark coordinates need d lml / d x_locs (not implemented)")
     xd, yd = _xy(state, x, y)
-    return _loss_and_grad_with_locs(state, xd, yd, _locs(state))
+    return _loss_and_grad_with_locs(state, xd, yd, _locs(state), bool(state.params["x_locs"].trainable))
 
 
 def fit(state, x, y, iterative=False, **_ignored):

@@ -344,6 +344,22 @@ def sgpr_lml_grad(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, want_grad
     return out
 
 
+def sgpr_lml_grad_locs(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
+    """-> ([lml/N, d/d ell, d/d sigma], d(lml/N)/d x_locs (M, D)) for trainable landmark coordinates."""
+    ctx = context()
+    x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    N, D = x.shape
+    assert y.numel() == N, "the SGPR gradient supports a single output column"
+    out = torch.empty(3, dtype=torch.float64, device=x.device)
+    g = torch.empty_like(x_locs)
+    check(
+        ctx.lib.gpxb_sgpr_lml_grad_locs(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, ptr(x_locs), x_locs.shape[0],
+                                        float(ell), float(sigma), int(mean_mode), ptr(out), ptr(g), stream_ptr()),
+        "gpxb_sgpr_lml_grad_locs",
+    )
+    return out, g
+
+
 def sgpr_fit(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)

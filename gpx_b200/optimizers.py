@@ -11,20 +11,29 @@ from scipy.optimize import minimize
 
 
 def ravel_backward_trainables(state):
+    """Flat vector of the unconstrained trainables (gpx/optimizers/utils.py:73-94, ravel_pytree order) and
+    the (path, shape) list needed to undo it."""
     paths, x0 = [], []
     for path, p in state.flat_params():
         if p.trainable:
-            if p.value.shape != ():
-                raise NotImplementedError("only scalar trainable hyper-parameters are supported")
-            paths.append(path)
-            x0.append(float(p.bijector.backward(p.value)))
-    return np.asarray(x0, dtype=np.float64), paths
+            v = np.asarray(p.bijector.backward(p.value), dtype=np.float64)
+            paths.append((path, v.shape))
+            x0.append(v.reshape(-1))
+    return (np.concatenate(x0) if x0 else np.zeros(0)), paths
+
+
+def _split(paths, xt):
+    o = 0
+    for path, shape in paths:
+        n = int(np.prod(shape)) if shape else 1
+        yield path, np.asarray(xt[o:o + n]).reshape(shape)
+        o += n
 
 
 def unravel_forward(state, paths, xt):
-    for path, t in zip(paths, xt):
-        p = dict(state.flat_params())[path]
-        state = state.with_param_value(path, p.bijector.forward(t))
+    flat = dict(state.flat_params())
+    for path, t in _split(paths, xt):
+        state = state.with_param_value(path, flat[path].bijector.forward(t))
     return state
 
 
@@ -36,8 +45,9 @@ def scipy_minimize(state, x, y, loss_and_grad_fn: Callable, callback=None, **opt
         st = unravel_forward(state, paths, xt)
         loss, grads = loss_and_grad_fn(st, x, y)
         flat = dict(st.flat_params())
-        g = np.array([grads[path] * float(flat[path].bijector.grad_forward(t)) for path, t in zip(paths, xt)])
-        return float(loss), g
+        g = [np.asarray(grads[path] * flat[path].bijector.grad_forward(t), dtype=np.float64).reshape(-1)
+             for path, t in _split(paths, xt)]
+        return float(loss), np.concatenate(g)
 
     optres = minimize(fun, x0=x0, method="L-BFGS-B", jac=True, callback=callback, **opt_kwargs)
     return unravel_forward(state, paths, optres.x), optres

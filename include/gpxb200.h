@@ -177,6 +177,12 @@ int gpxb_sgpr_lml(gpxb_ctx* ctx, int kind, const double* x, const double* y, int
 int gpxb_sgpr_lml_grad(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D,
                        const double* x_locs, int M, double ell, double sigma, int mean_mode, int want_grad,
                        double* out3, gpxb_stream stream);
+/* As gpxb_sgpr_lml_grad (with the gradient), plus grad_locs[M x D] = d(lml/N)/d x_locs: the entry of
+ * jit(value_and_grad) for a trainable `x_locs` Parameter of SGPR (gpx/models/sgpr.py:690-732).  Evaluated
+ * as two weighted products of the kernel's radial derivative profile with [1 | X], matrix-free. */
+int gpxb_sgpr_lml_grad_locs(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D,
+                            const double* x_locs, int M, double ell, double sigma, int mean_mode, double* out3,
+                            double* grad_locs, gpxb_stream stream);
 /* c[M x T] = (sigma^2 K_mm + K_mn K_nm + 1e-10 I)^-1 K_mn (y - mu)  (gpx/models/_sgpr.py:39-61, 319-339) */
 int gpxb_sgpr_fit(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,
                   const double* x_locs, int M, double ell, double sigma, int mean_mode, double* c_out,

@@ -763,6 +763,46 @@ def sgpr_lml_dense(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
     return (-0.5 * quad - 0.5 * logdet - n * 0.5 * np.log(2.0 * np.pi)) / n
 
 
+def kernel_dx_profile(kind: str, x1, x2, ell: float):
+    """h with d kernel(x1_i, x2_j)/d x1_if = -h_ij (x1_if - x2_jf): h = -(2/ell^2) dk/d(d2) of the matrix
+    kernels above (d2 carries the 1e-12 jitter of squared_distances; the Matern clamp is inactive)."""
+    d2 = squared_distances(x1 / ell, x2 / ell)
+    if kind == "se":
+        return (2.0 / ell**2) * np.exp(-d2)
+    r = np.sqrt(np.maximum(d2, 1e-36))
+    if kind == "m12":
+        return np.exp(-r) / (ell**2 * r)
+    if kind == "m32":
+        return (3.0 / ell**2) * np.exp(-np.sqrt(3.0) * r)
+    if kind == "m52":
+        d = np.sqrt(5.0) * r
+        return (5.0 / (3.0 * ell**2)) * (1.0 + d) * np.exp(-d)
+    raise ValueError(kind)
+
+
+def sgpr_lml_grad_locs_nxn(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
+    """d(lml/n)/d x_locs of _sgpr.py:659-697 (what value_and_grad yields for a trainable `x_locs` Parameter,
+    sgpr.py:690-732) from the literal N x N form: C = K_nm A^-1 K_mn + s2 I, S = beta beta^T - C^-1,
+    d(lml n) = tr(S K_nm A^-1 dK_mn) - 1/2 tr(A^-1 K_mn S K_nm A^-1 dA)."""
+    m, n = x_locs.shape[0], y.shape[0]
+    r = y - mean_function(y)
+    A = kernel(kind, x_locs, x_locs, ell) + 1e-10 * np.eye(m)
+    K_mn = kernel(kind, x_locs, x, ell)
+    P = np.linalg.solve(A, K_mn)
+    C = K_mn.T @ P + (sigma**2 + 1e-10) * np.eye(n)
+    Cinv = np.linalg.inv(C)
+    beta = Cinv @ r
+    S = beta @ beta.T - Cinv
+    T = P @ S                      # (m, n)
+    U = T @ P.T                    # (m, m)
+    h_mn = kernel_dx_profile(kind, x_locs, x, ell)
+    h_mm = kernel_dx_profile(kind, x_locs, x_locs, ell)
+    dz_mn = x_locs[:, None, :] - x[None, :, :]
+    dz_mm = x_locs[:, None, :] - x_locs[None, :, :]
+    g = -np.einsum("mn,mn,mnf->mf", T, h_mn, dz_mn) + np.einsum("ab,ab,abf->af", U, h_mm, dz_mm)
+    return g / n
+
+
 def sgpr_rpchol_lml_dense(kind, x, y, ell, sigma, key, n_locs, mean_function=data_mean,
                           partitionable=True, nxn=False):
     """_sgpr_rpchol.py:178-208."""

@@ -57,7 +57,7 @@ def test_trainable_flattening_and_chain_rule():
 
     m = GPR(kernel=SquaredExponential(), sigma=Parameter(0.5, False, Softplus(), GammaPrior()))
     x0, paths = ravel_backward_trainables(m.state)
-    assert paths == [("kernel_params", "lengthscale")]
+    assert paths == [(("kernel_params", "lengthscale"), ())]
     st = unravel_forward(m.state, paths, x0 + 0.1)
     assert st.params["kernel_params"]["lengthscale"].value > 1.0
     assert st.params["sigma"].value == 0.5

@@ -196,6 +196,55 @@ def test_sgpr_lml_gradient_vs_finite_differences(kind, N, D, M, ell, sigma):
     assert only[0] == out[0]
 
 
+@pytest.mark.parametrize("kind,N,D,M,ell,sigma", [("se", 300, 4, 20, 1.0, 0.2), ("m52", 260, 8, 33, 2.5, 0.3),
+                                                   ("m32", 200, 3, 130, 1.2, 0.5), ("se", 400, 32, 17, 5.0, 0.1),
+                                                   ("m12", 150, 2, 10, 1.0, 0.4)])
+def test_sgpr_gradient_wrt_landmark_coordinates(kind, N, D, M, ell, sigma):
+    """d(lml/N)/d x_locs (trainable `x_locs` Parameter): two weighted derivative-profile products of the
+    matrix-free kernel against the oracle's literal N x N form."""
+    from gpx_b200 import ops
+
+    x, y = _data(N, D, 9)
+    rng = np.random.default_rng(2)
+    xl = x[rng.choice(N, M, replace=False)] + 0.3 * rng.standard_normal((M, D))
+    out, g = ops.sgpr_lml_grad_locs(kind, dev(x), dev(y), dev(xl), ell, sigma)
+    out, g = host(out), host(g)
+    ref = R.sgpr_lml_grad_locs_nxn(kind, xl, x, y, ell, sigma)
+    assert np.max(np.abs(g - ref)) < 1e-8 * np.max(np.abs(ref)), (np.max(np.abs(g - ref)), np.max(np.abs(ref)))
+    plain = host(ops.sgpr_lml_grad(kind, dev(x), dev(y), dev(xl), ell, sigma))
+    assert np.array_equal(out, plain)
+
+
+def test_sgpr_fit_with_trainable_landmarks_follows_oracle_optimiser():
+    """SGPR.fit with a trainable `x_locs` Parameter: L-BFGS-B over (lengthscale, sigma, M x D coordinates) on
+    the device (value, grad) lands where the same optimiser lands with the oracle's (value, grad)."""
+    from scipy.optimize import minimize
+
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import SGPR
+    from gpx_b200.models.sgpr import locs_parameter
+
+    x, y = _data(200, 1, 5)
+    xl0 = np.linspace(-1.5, 1.5, 6).reshape(-1, 1)
+    m = SGPR(SquaredExponential(), x_locs=locs_parameter(xl0, trainable=True)).fit(x, y, opt_kwargs=dict(options=dict(maxiter=60)))
+    assert np.asarray(m.state.params["x_locs"].value).shape == (6, 1)
+    assert np.max(np.abs(np.asarray(m.state.params["x_locs"].value) - xl0)) > 1e-3  # the landmarks moved
+
+    def fun(t):
+        ell, sig, z = R.softplus(t[0]), R.softplus(t[1]), t[2:].reshape(6, 1)
+        val = R.sgpr_lml_dense(kind := "se", z, x, y, ell, sig)
+        h = 1e-6
+        ge = (R.sgpr_lml_dense(kind, z, x, y, ell + h, sig) - R.sgpr_lml_dense(kind, z, x, y, ell - h, sig)) / (2 * h)
+        gs = (R.sgpr_lml_dense(kind, z, x, y, ell, sig + h) - R.sgpr_lml_dense(kind, z, x, y, ell, sig - h)) / (2 * h)
+        gz = R.sgpr_lml_grad_locs_nxn(kind, z, x, y, ell, sig)
+        return -val, -np.concatenate([[ge * R.sigmoid(t[0]), gs * R.sigmoid(t[1])], gz.reshape(-1)])
+
+    t0 = np.concatenate([R.inverse_softplus(np.array([1.0, 1.0])), xl0.reshape(-1)])
+    res = minimize(fun, t0, jac=True, method="L-BFGS-B", options=dict(maxiter=60))
+    assert abs(m.optimize_results_.fun - res.fun) < 1e-5 * max(1.0, abs(res.fun))
+    assert m.optimize_results_.fun < fun(t0)[0] - 1e-3
+
+
 def test_sgpr_rpchol_fit_minimize_runs_end_to_end():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import SGPR_RPChol

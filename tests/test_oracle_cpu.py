@@ -356,3 +356,20 @@ def test_oracle_d0kjc_vs_finite_differences_of_the_kernel(kind):
         ref += jc[:, f:f + 1] * dk
     out = R.d0kjc(kind, x1, x2, ell, jc)
     assert np.max(np.abs(out - ref)) < 1e-8
+
+
+@pytest.mark.parametrize("kind", ["se", "m32", "m52"])
+def test_oracle_sgpr_landmark_gradient_vs_finite_differences(kind):
+    rng = np.random.default_rng(1)
+    N, D, M = 40, 3, 6
+    x = rng.standard_normal((N, D))
+    y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    z = x[rng.choice(N, M, replace=False)] + 0.05 * rng.standard_normal((M, D))
+    g = R.sgpr_lml_grad_locs_nxn(kind, z, x, y, 1.4, 0.2)
+    fd, h = np.zeros_like(g), 1e-5
+    for a in range(M):
+        for f in range(D):
+            e = np.zeros_like(z)
+            e[a, f] = h
+            fd[a, f] = (R.sgpr_lml_dense_nxn(kind, z + e, x, y, 1.4, 0.2) - R.sgpr_lml_dense_nxn(kind, z - e, x, y, 1.4, 0.2)) / (2 * h)
+    assert np.max(np.abs(g - fd)) < 1e-8 * max(1.0, np.max(np.abs(g)))
