@@ -22,6 +22,10 @@ int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, c
               ZLayout zl, double diag_add, const double* b, const double* F, long long ldf, int k,
               const double* Pkk, double sigma, double tol, double atol, int maxiter, double* x, int* iters_out,
               cudaStream_t s);
+int lanczos_block_grad(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
+                       ZLayout zl, double ell, double sigma, const double* U, int P, int PS, int m,
+                       double* alpha_out, double* beta_out, double* dalpha_out, double* dbeta_out, int Ptot,
+                       int* flag, cudaStream_t s);
 int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, long long N, int D, int T,
              const double* x_locs, int M, double ell, double sigma, const double* mu, double* out,
              cudaStream_t s);
@@ -140,6 +144,57 @@ int gpxb_lanczos(gpxb_ctx* ctx_, int kind, const double* x, int N, int D, double
                            diag_add, up.as<double>(), pb, PS, m, alpha_out + (size_t)c0 * m,
                            beta_out + (size_t)c0 * m, breakdown_flag, s));
     up.release();
+  }
+  return 0;
+}
+
+int gpxb_lanczos_grad(gpxb_ctx* ctx_, int kind, const double* x, int N, int D, double ell, double sigma,
+                      const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out,
+                      double* dalpha_out, double* dbeta_out, int* breakdown_flag, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && x && U && alpha_out && beta_out && dalpha_out && dbeta_out && breakdown_flag, -1);
+  GPXB_ARG_CHECK(kind >= 0 && kind <= 3 && N > 0 && D > 0 && P > 0 && m > 0, -2);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  cudaStream_t s = (cudaStream_t)stream;
+  const ZLayout zl = z_layout(D);
+  const Shard sh = shard_of(ctx, N);
+  DevBuf za, up;
+  GPXB_TRY(za.alloc(sizeof(double) * ((size_t)N * zl.S + 16), s));
+  GPXB_TRY(prep_z(ctx, x, D, N, zl, ell, za.as<double>(), s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(breakdown_flag, 0, sizeof(int), s));
+  for (int c0 = 0; c0 < P; c0 += 32) {
+    const int pb = std::min(32, P - c0);
+    const int PS = v_padded_stride(pb);
+    GPXB_TRY(up.alloc(sizeof(double) * ((size_t)std::max(sh.n(), 1) * PS + 16), s));
+    GPXB_TRY(pack_v(ctx, U + sh.b * ldu, ldu, sh.n(), c0, pb, PS, up.as<double>(), s));
+    GPXB_TRY(lanczos_block_grad(ctx, kind, za.as<double>() + sh.b * zl.S, sh.n(), sh.b, za.as<double>(), N, zl, ell,
+                                sigma, up.as<double>(), pb, PS, m, alpha_out + (size_t)c0 * m,
+                                beta_out + (size_t)c0 * m, dalpha_out + (size_t)c0 * m, dbeta_out + (size_t)c0 * m, P,
+                                breakdown_flag, s));
+    up.release();
+  }
+  return 0;
+}
+
+int gpxb_kmatvec_dl(gpxb_ctx* ctx_, int kind, const double* x, int N, int D, double ell, const double* V,
+                    long long ldv, int P, double* W, long long ldw, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && x && V && W, -1);
+  GPXB_ARG_CHECK(kind >= 0 && kind <= 3 && N > 0 && D > 0 && P > 0, -2);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  cudaStream_t s = (cudaStream_t)stream;
+  const ZLayout zl = z_layout(D);
+  DevBuf za, vp;
+  GPXB_TRY(za.alloc(sizeof(double) * ((size_t)N * zl.S + 16), s));
+  GPXB_TRY(prep_z(ctx, x, D, N, zl, ell, za.as<double>(), s));
+  for (int c0 = 0; c0 < P; c0 += 32) {
+    const int pb = std::min(32, P - c0);
+    const int PS = v_padded_stride(pb);
+    GPXB_TRY(vp.alloc(sizeof(double) * ((size_t)N * PS + 16), s));
+    GPXB_TRY(pack_v(ctx, V, ldv, N, c0, pb, PS, vp.as<double>(), s));
+    KmvArgs a;
+    a.kind = kind; a.Zr = za.as<double>(); a.n_rows = N; a.row_offset = 0; a.Za = za.as<double>(); a.N = N; a.zl = zl;
+    a.V = vp.as<double>(); a.PS = PS; a.P = pb; a.W = W + c0; a.ldw = ldw; a.dl_ell = ell;
+    GPXB_TRY(kmatvec_launch(ctx, a, s));
+    vp.release();
   }
   return 0;
 }

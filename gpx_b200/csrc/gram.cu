@@ -12,6 +12,7 @@
 // applies the kernel nonlinearity and either stores K (+ diagonal shift) or contracts
 // dK/d ell with W = alpha alpha^T - A^-1 without materialising dK.
 #include "gram.cuh"
+#include "kfun.cuh"
 #include "mma.cuh"
 
 namespace gpxb {
@@ -52,21 +53,6 @@ __device__ __forceinline__ double kfun(int kind, double d2) {
   }
   const double d = 2.23606797749979 * r;
   return (1.0 + d + d * d / 3.0) * exp(-d);
-}
-
-// dK/d ell given d2 = s + 1e-12 (the jitter is a constant; the clamp passes no gradient).
-// rl = 1/ell is hoisted by the caller: no FP64 division in the inner loop except Matern-1/2's 1/r.
-__device__ __forceinline__ double kfun_dl(int kind, double d2, double s, double rl) {
-  if (kind == KIND_SE) return exp(-d2) * (2.0 * rl) * s;
-  if (!(d2 > 1e-36)) return 0.0;
-  const double r = sqrt(d2);
-  if (kind == KIND_M12) return exp(-r) * s * rl / r;
-  if (kind == KIND_M32) {
-    const double d = 1.7320508075688772 * r;
-    return (3.0 * rl) * s * exp(-d);
-  }
-  const double d = 2.23606797749979 * r;
-  return ((5.0 / 3.0) * rl) * s * (1.0 + d) * exp(-d);
 }
 
 __global__ void prep_z_kernel(const double* __restrict__ x, long long ldx, int n, int D, int Dp,

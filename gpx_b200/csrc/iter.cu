@@ -15,6 +15,7 @@
 #include "gemm.cuh"
 #include "matvec.cuh"
 #include "mma.cuh"
+#include "small_kernels.cuh"
 #include "threefry.cuh"
 
 namespace gpxb {
@@ -199,6 +200,173 @@ int lanczos_block(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row
       colnormalize_kernel<<<nblk_e, nthr, 0, s>>>(W, nrm2, vecs + blk * (j + 1), n_loc, PS, P, flag);
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
+    }
+  }
+  return 0;
+}
+
+namespace {
+// out[p] = a[p] + b[p]
+__global__ void padd_kernel(const double* __restrict__ a, const double* __restrict__ b, int P, double* __restrict__ out) {
+  const int p = threadIdx.x;
+  if (p < P) out[p] = a[p] + b[p];
+}
+// Y = c * X (all PS columns)
+__global__ void colscale_copy_kernel(const double* __restrict__ X, double c, long long n, double* __restrict__ Y) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) Y[idx] = c * X[idx];
+}
+__global__ void vadd_kernel(double* __restrict__ Y, const double* __restrict__ X, long long n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) Y[idx] += X[idx];
+}
+// d beta[p] = (w . dw)[p] / beta[p];  d alpha_out[p][j] = d alpha[p];  d beta_out[p][j] = d beta[p]
+__global__ void store_dab_kernel(const double* __restrict__ dalpha, const double* __restrict__ wdw,
+                                 const double* __restrict__ beta, int P, int m, int j, double* __restrict__ dalpha_out,
+                                 double* __restrict__ dbeta_out, double* __restrict__ dbeta_cur) {
+  const int p = threadIdx.x;
+  if (p >= P) return;
+  dalpha_out[p * m + j] = dalpha[p];
+  const double db = wdw[p] / beta[p];
+  dbeta_out[p * m + j] = db;
+  dbeta_cur[p] = db;
+}
+// dVn[:,p] = (dW[:,p] - Vn[:,p] dbeta[p]) / beta[p]
+__global__ void coltangent_kernel(const double* __restrict__ dW, const double* __restrict__ Vn,
+                                  const double* __restrict__ dbeta, const double* __restrict__ beta,
+                                  double* __restrict__ dVn, int n, int PS, int P) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * PS) return;
+  const int p = (int)(idx % PS);
+  dVn[idx] = p < P ? (dW[idx] - Vn[idx] * dbeta[p]) / beta[p] : 0.0;
+}
+}  // namespace
+
+// Block Lanczos together with its forward-mode derivative w.r.t. (lengthscale, sigma) of
+// A = K(x, x; ell) + (sigma^2 + 1e-10) I: every statement of gpx/lanczos.py:46-133 is differentiated
+// (tangent of the recursion jit(value_and_grad) differentiates in reverse through the fori_loop;
+// SURVEY.md 8f N1).  Per step: A [v | dv_l | dv_s] (three block mat-vecs) and (dK/d ell) v (one block
+// mat-vec with the d/d ell kernel profile); dA/d sigma = 2 sigma I.
+//   dalpha_out / dbeta_out: [2][P][m] (q = 0: lengthscale, q = 1: sigma).
+int lanczos_block_grad(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
+                       ZLayout zl, double ell, double sigma, const double* U, int P, int PS, int m,
+                       double* alpha_out, double* beta_out, double* dalpha_out, double* dbeta_out, int Ptot,
+                       int* flag, cudaStream_t s) {
+  GPXB_ARG_CHECK(P >= 1 && P <= MAXP && m >= 1, -30);
+  ctx->shard_N = N;
+  const double diag_add = sigma * sigma + 1e-10;
+  const size_t blk = (size_t)n_loc * PS;
+  const size_t blk_all = (size_t)N * PS;
+  DevBuf bVecs, bDv[2], bW, bT[2], bX, bVall, bPart, bSc;
+  GPXB_TRY(bVecs.alloc(sizeof(double) * blk * m, s));
+  for (int q = 0; q < 2; ++q) {
+    GPXB_TRY(bDv[q].alloc(sizeof(double) * blk * m, s));
+    GPXB_TRY(bT[q].alloc(sizeof(double) * blk, s));
+    GPXB_CUDA_CHECK(cudaMemsetAsync(bDv[q].as<double>(), 0, sizeof(double) * blk, s));  // d v_0 = 0
+  }
+  GPXB_TRY(bW.alloc(sizeof(double) * blk, s));
+  GPXB_TRY(bX.alloc(sizeof(double) * blk, s));
+  GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)ceil_div(n_loc, RB) * MAXP, s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * MAXP * 16, s));
+  double *vecs = bVecs.as<double>(), *W = bW.as<double>(), *X = bX.as<double>(), *part = bPart.as<double>();
+  double* dvecs[2] = {bDv[0].as<double>(), bDv[1].as<double>()};
+  double* T[2] = {bT[0].as<double>(), bT[1].as<double>()};
+  double* sc = bSc.as<double>();
+  double *alpha = sc, *nrm2 = sc + MAXP, *coef = sc + 2 * MAXP, *beta = sc + 3 * MAXP, *t1 = sc + 4 * MAXP,
+         *t2 = sc + 5 * MAXP;
+  double* dalpha[2] = {sc + 6 * MAXP, sc + 7 * MAXP};
+  double* dcoef[2] = {sc + 8 * MAXP, sc + 9 * MAXP};
+  double* dbeta[2] = {sc + 10 * MAXP, sc + 11 * MAXP};
+  double* wdw[2] = {sc + 12 * MAXP, sc + 13 * MAXP};
+  GPXB_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(double) * MAXP * 16, s));
+  double* Vall = nullptr;
+  if (ctx->world > 1) {
+    GPXB_TRY(bVall.alloc(sizeof(double) * (blk_all + 16), s));
+    Vall = bVall.as<double>();
+  }
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(vecs, U, sizeof(double) * blk, cudaMemcpyDeviceToDevice, s));
+  const int nthr = 256;
+  const int nblk_e = ceil_div((long long)blk, nthr);
+
+  // out = Op * v for this rank's rows; dl: the d K / d ell operator instead of A
+  auto matvec = [&](const double* v, double* out, bool dl) -> int {
+    const double* vfull = v;
+    if (ctx->world > 1) {
+      GPXB_TRY(comm_allgather_rows(ctx, v, Vall, n_loc, PS, s));
+      vfull = Vall;
+    }
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
+    a.V = vfull; a.PS = PS; a.P = P; a.W = out; a.ldw = PS;
+    a.diag_add = dl ? 0.0 : diag_add;
+    a.dl_ell = dl ? ell : 0.0;
+    return kmatvec_launch(ctx, a, s);
+  };
+  auto axpy2 = [&](double* Wd, const double* a, const double* Xv, const double* b, const double* Yv) -> int {
+    colaxpy_kernel<<<nblk_e, nthr, 0, s>>>(Wd, a, Xv, b, Yv, n_loc, PS, P);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+    return 0;
+  };
+
+  for (int j = 0; j < m; ++j) {
+    double* vj = vecs + blk * j;
+    double* dvj[2] = {dvecs[0] + blk * j, dvecs[1] + blk * j};
+    const double* vjm = j > 0 ? vecs + blk * (j - 1) : nullptr;
+    GPXB_TRY(matvec(vj, W, false));      // w = A v
+    GPXB_TRY(matvec(vj, T[0], true));    // dw_l = (dK/d ell) v
+    colscale_copy_kernel<<<nblk_e, nthr, 0, s>>>(vj, 2.0 * sigma, (long long)blk, T[1]);  // dw_s = 2 sigma v
+    GPXB_LAUNCHED(ctx);
+    if (j > 0) {
+      for (int q = 0; q < 2; ++q) {      // + A dv
+        GPXB_TRY(matvec(dvj[q], X, false));
+        vadd_kernel<<<nblk_e, nthr, 0, s>>>(T[q], X, (long long)blk);
+        GPXB_LAUNCHED(ctx);
+      }
+    }
+    GPXB_TRY(coldot(ctx, W, vj, n_loc, PS, P, part, alpha, s));
+    for (int q = 0; q < 2; ++q) {        // d alpha = dw . v + w . dv
+      GPXB_TRY(coldot(ctx, T[q], vj, n_loc, PS, P, part, t1, s));
+      GPXB_TRY(coldot(ctx, W, dvj[q], n_loc, PS, P, part, t2, s));
+      padd_kernel<<<1, MAXP, 0, s>>>(t1, t2, P, dalpha[q]);
+      GPXB_LAUNCHED(ctx);
+      // dw -= d alpha v + alpha dv + d beta v_{j-1} + beta dv_{j-1}
+      GPXB_TRY(axpy2(T[q], dalpha[q], vj, alpha, dvj[q]));
+      if (j > 0) GPXB_TRY(axpy2(T[q], dbeta[q], vjm, beta, dvecs[q] + blk * (j - 1)));
+    }
+    GPXB_TRY(axpy2(W, alpha, vj, beta, vjm));  // w -= alpha v + beta v_{j-1}
+    if (j > 0) {
+      for (int c = 0; c <= j; ++c) {  // modified Gram-Schmidt and its tangent, column order
+        const double* vc = vecs + blk * c;
+        GPXB_TRY(coldot(ctx, W, vc, n_loc, PS, P, part, coef, s));
+        for (int q = 0; q < 2; ++q) {
+          const double* dvc = dvecs[q] + blk * c;
+          GPXB_TRY(coldot(ctx, T[q], vc, n_loc, PS, P, part, t1, s));
+          GPXB_TRY(coldot(ctx, W, dvc, n_loc, PS, P, part, t2, s));
+          padd_kernel<<<1, MAXP, 0, s>>>(t1, t2, P, dcoef[q]);
+          GPXB_LAUNCHED(ctx);
+          GPXB_TRY(axpy2(T[q], dcoef[q], vc, coef, dvc));
+        }
+        GPXB_TRY(axpy2(W, coef, vc, nullptr, nullptr));
+      }
+    }
+    GPXB_TRY(coldot(ctx, W, W, n_loc, PS, P, part, nrm2, s));
+    for (int q = 0; q < 2; ++q) GPXB_TRY(coldot(ctx, W, T[q], n_loc, PS, P, part, wdw[q], s));
+    store_ab_kernel<<<1, MAXP, 0, s>>>(alpha, nrm2, P, m, j, alpha_out, beta_out, beta);
+    GPXB_LAUNCHED(ctx);
+    for (int q = 0; q < 2; ++q) {
+      store_dab_kernel<<<1, MAXP, 0, s>>>(dalpha[q], wdw[q], beta, P, m, j, dalpha_out + (size_t)q * Ptot * m,
+                                          dbeta_out + (size_t)q * Ptot * m, dbeta[q]);
+      GPXB_LAUNCHED(ctx);
+    }
+    if (j + 1 < m) {
+      double* vn = vecs + blk * (j + 1);
+      colnormalize_kernel<<<nblk_e, nthr, 0, s>>>(W, nrm2, vn, n_loc, PS, P, flag);
+      GPXB_LAUNCHED(ctx);
+      for (int q = 0; q < 2; ++q) {
+        coltangent_kernel<<<nblk_e, nthr, 0, s>>>(T[q], vn, dbeta[q], beta, dvecs[q] + blk * (j + 1), n_loc, PS, P);
+        GPXB_LAUNCHED(ctx);
+      }
     }
   }
   return 0;

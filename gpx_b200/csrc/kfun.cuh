@@ -60,6 +60,21 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ T
   return ki < -65372 ? 0.0 : s;  // x < -708 (integer compare: no FP64 op); the true value is < 3e-308
 }
 
+// dK/d ell given d2 = s + 1e-12 (the jitter is a constant; the clamp passes no gradient).
+// rl = 1/ell is hoisted by the caller: no FP64 division in the inner loop except Matern-1/2's 1/r.
+__device__ __forceinline__ double kfun_dl(int kind, double d2, double s, double rl) {
+  if (kind == KIND_SE) return exp(-d2) * (2.0 * rl) * s;
+  if (!(d2 > 1e-36)) return 0.0;
+  const double r = sqrt(d2);
+  if (kind == KIND_M12) return exp(-r) * s * rl / r;
+  if (kind == KIND_M32) {
+    const double d = 1.7320508075688772 * r;
+    return (3.0 * rl) * s * exp(-d);
+  }
+  const double d = 2.23606797749979 * r;
+  return ((5.0 / 3.0) * rl) * s * (1.0 + d) * exp(-d);
+}
+
 __device__ __forceinline__ double kfun_fast(int kind, double d2) {
   double t = d2;
   if (kind != KIND_SE) {

@@ -49,6 +49,7 @@ struct KmvParams {
   const double* wt;
   long long ldwt;
   int wt_trans;
+  double rl;  // KMODE 4 (d K / d lengthscale): 1 / lengthscale
 };
 
 // MF: 8-row fragments per warp (rows per CTA = 64*MF); KS: Dp/4 when the row operand lives in
@@ -57,6 +58,7 @@ struct KmvParams {
 //        2 = SquaredExponential with the table-driven exp_tab (10 FP64 ops),
 //        3 = radial derivative profile g of the kind chosen at run time, d k/d x1 = -c(l) g (x1 - x2):
 //            SE exp(-d2) [c = 2/l^2], M12 exp(-r)/r [1/l^2], M32 exp(-d) [3/l^2], M52 (1+d) exp(-d) [5/(3 l^2)]
+//        4 = d k/d lengthscale (kfun_dl) of the kind chosen at run time, evaluated in the loop body
 template <int KMODE>
 __device__ __forceinline__ double kfun_mode(int kind, double d2, const double* __restrict__ tab) {
   if (KMODE == 1) return exp(-d2);
@@ -185,7 +187,14 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
         const bool dg0 = (p.row_offset >= 0) && (gi == gj), dg1 = (p.row_offset >= 0) && (gi == gj + 1);
         if (dg0) d20 = 1e-12;
         if (dg1) d21 = 1e-12;
-        double k0 = kfun_mode<KMODE>(p.kind, d20, etab), k1 = kfun_mode<KMODE>(p.kind, d21, etab);
+        double k0, k1;
+        if (KMODE == 4) {
+          k0 = kfun_dl(p.kind, d20, dg0 ? 0.0 : d20 - 1e-12, p.rl);
+          k1 = kfun_dl(p.kind, d21, dg1 ? 0.0 : d21 - 1e-12, p.rl);
+        } else {
+          k0 = kfun_mode<KMODE>(p.kind, d20, etab);
+          k1 = kfun_mode<KMODE>(p.kind, d21, etab);
+        }
         if (KMODE == 3) {
           const int il = row0 + warp * 8 * MF + mf * 8 + lr;  // local row (wrow / wt are indexed locally)
           const bool rok = il < p.n_rows;
@@ -282,6 +291,7 @@ int launch_t(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) 
     mode = (e && e[0] == 'l') ? 1 : 2;
   }
   if (p.wt) return launch_k<MF, KS, NPF, NWARP, 3>(ctx, p, grid, smem, s);
+  if (p.rl != 0.0) return launch_k<MF, KS, NPF, NWARP, 4>(ctx, p, grid, smem, s);
   if (p.kind == KIND_SE) {
     if (mode == 1) return launch_k<MF, KS, NPF, NWARP, 1>(ctx, p, grid, smem, s);
     return launch_k<MF, KS, NPF, NWARP, 2>(ctx, p, grid, smem, s);
@@ -325,6 +335,8 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   p.diag_add = a.diag_add;
   p.wrow = a.wrow; p.wcol = a.wcol; p.wt = a.wt; p.ldwt = a.ldwt; p.wt_trans = a.wt_trans;
   GPXB_ARG_CHECK(!a.wt || (a.wrow && a.wcol), -24);
+  p.rl = a.dl_ell != 0.0 ? 1.0 / a.dl_ell : 0.0;
+  GPXB_ARG_CHECK(!(a.wt && a.dl_ell != 0.0), -25);
   const int NPF = a.P <= 8 ? 1 : 4;
   const int limit = 232448;
   // variants: (MF=4, 8 warps, 256 rows) default; (MF=2, 16 warps, 256 rows) via GPXB_KMV_WARPS=16;

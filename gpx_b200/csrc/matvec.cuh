@@ -30,6 +30,7 @@ struct KmvArgs {
   const double* wt = nullptr;
   long long ldwt = 0;
   int wt_trans = 0;
+  double dl_ell = 0.0;  // != 0: the operator is d K / d lengthscale at this lengthscale (diag_add must be 0)
 };
 int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s);
 int pack_v(Ctx* ctx, const double* V, long long ldv, int n, int c0, int P, int PS, double* Vp,

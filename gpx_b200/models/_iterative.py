@@ -58,3 +58,58 @@ def lml_iter(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_p
                                 as_key(key_lanczos))
     mll -= m * 0.5 * np.log(2.0 * np.pi)
     return mll / m
+
+
+def _tridiag(alpha_p, beta_p):
+    m = alpha_p.shape[0]
+    T = np.diag(alpha_p)
+    if m > 1:
+        T = T + np.diag(beta_p[: m - 1], 1) + np.diag(beta_p[: m - 1], -1)
+    return T
+
+
+def slq_logdet_grad(alpha, beta, dalpha, dbeta, dim_mat):
+    """SLQ log-determinant and its derivatives: d/d theta of sum_k Q0k^2 log lam_k is
+    e1^T Dlog(T)[dT] e1 = sum_kl Q0k Q0l (Q^T dT Q)_kl (log lam_k - log lam_l)/(lam_k - lam_l)
+    (1/lam_k on the diagonal) -- the closed form of the eigh JVP jax applies (gpx/lanczos.py:171-183)."""
+    P, m = alpha.shape
+    acc, dacc = 0.0, np.zeros(dalpha.shape[0])
+    for p in range(P):
+        lam, Q = np.linalg.eigh(_tridiag(alpha[p], beta[p]))
+        lam = np.maximum(lam, 1e-36)
+        q0 = Q[0, :]
+        acc += float(np.sum(np.square(q0) * np.log(lam)))
+        dl = lam[:, None] - lam[None, :]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dd = np.where(np.abs(dl) > 1e-14 * np.abs(lam[:, None]),
+                          (np.log(lam)[:, None] - np.log(lam)[None, :]) / dl, 1.0 / lam[:, None])
+        for q in range(dalpha.shape[0]):
+            M = Q.T @ _tridiag(dalpha[q, p], dbeta[q, p]) @ Q
+            dacc[q] += float(q0 @ (M * dd) @ q0)
+    return (dim_mat / P) * acc, (dim_mat / P) * dacc
+
+
+def lml_iter_grad(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond):
+    """(lml, d lml/d lengthscale, d lml/d sigma) of _lml_iter as jit(value_and_grad) propagates it
+    (gpx/models/_gpr.py:772-821 under gpx/optimizers/scipy_optimize.py:72-78): the CG solve is a
+    lax.custom_linear_solve, so d(r.c) = -c^T dA c with c the computed PCG solution; the SLQ term is
+    differentiated through the Lanczos recursion (gpxb_lanczos_grad) and the eigendecomposition."""
+    import torch
+
+    kind = state.kernel.kind
+    N = yd.shape[0]
+    c, mu = fit_iter(state, xd, yd, ell, sigma, n_pivots, key_precond)
+    r = yd.cpu().numpy() - mu
+    cd = torch.as_tensor(c, dtype=torch.float64, device=xd.device).reshape(-1, 1)
+    c_dK_c = float((cd * ops.kmatvec_dl(kind, xd, cd, ell)).sum().cpu())
+    subkey, _ = split(as_key(key_lanczos), 2, threefry_partitionable())
+    U = ops.rademacher_probes(subkey, N, int(num_evals), threefry_partitionable())
+    alpha, beta, dalpha, dbeta, flag = ops.lanczos_grad(kind, xd, ell, sigma, U, int(num_lanczos))
+    if int(flag.cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
+                           "use fewer Lanczos steps than data points")
+    ld, dld = slq_logdet_grad(alpha.cpu().numpy(), beta.cpu().numpy(), dalpha.cpu().numpy(), dbeta.cpu().numpy(), N)
+    mll = (-0.5 * float(np.sum(r.T @ c)) - 0.5 * ld - N * 0.5 * np.log(2.0 * np.pi)) / N
+    g_ell = (0.5 * c_dK_c - 0.5 * dld[0]) / N
+    g_sigma = (sigma * float(np.sum(c * c)) - 0.5 * dld[1]) / N
+    return mll, g_ell, g_sigma

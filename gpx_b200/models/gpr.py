@@ -56,20 +56,30 @@ def loss_and_grad(state, x, y, iterative=False, **kwargs):
     """Negative LML and its gradient w.r.t. the constrained hyper-parameters, from one fused
     device call (stands in for jit(value_and_grad(loss)), gpx/optimizers/scipy_optimize.py:72-78).
     Non-trainable parameters get no gradient entry (stop_gradient, model_state.py:93-103)."""
-    if iterative:
-        raise NotImplementedError("gradient of the iterative LML is a 'next' row (SURVEY.md 8f N1)")
     if state.loss_fn is not neg_log_marginal_likelihood:
         raise NotImplementedError("only neg_log_marginal_likelihood has a fused device gradient")
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
+    if iterative:
+        from . import _iterative
+
+        lml, g_ell, g_sigma = _iterative.lml_iter_grad(
+            state, xd, yd, ell, sigma, kwargs.get("num_evals", gpxargs.num_evals),
+            kwargs.get("num_lanczos", gpxargs.num_lanczos), kwargs.get("key_lanczos", gpxargs.key_lanczos),
+            kwargs.get("n_pivots"), kwargs.get("key_precond"))
+        return -lml, _grads_dict(state, g_ell, g_sigma)
     out = ops.gpr_lml_grad(kernel.kind, xd, yd, ell, sigma, mean_mode(state.mean_function), want_grad=True)
     lml, g_ell, g_sigma = (float(v) for v in out.cpu().numpy())
+    return -lml, _grads_dict(state, g_ell, g_sigma)
+
+
+def _grads_dict(state, g_ell, g_sigma):
     grads = {}
     if state.params["kernel_params"]["lengthscale"].trainable:
         grads[("kernel_params", "lengthscale")] = -g_ell
     if state.params["sigma"].trainable:
         grads[("sigma",)] = -g_sigma
-    return -lml, grads
+    return grads
 
 
 def fit(state, x, y, iterative=False, n_pivots=None, key_precond=None):

@@ -292,6 +292,43 @@ def lanczos(kind, x, ell, diag_add, U, m):
     return alpha, beta, flag
 
 
+def lanczos_grad(kind, x, ell, sigma, U, m):
+    """(alpha (P, m), beta (P, m), dalpha (2, P, m), dbeta (2, P, m), breakdown): block Lanczos on
+    K + (sigma^2+1e-10) I with its forward-mode derivative w.r.t. (lengthscale, sigma)."""
+    ctx = context()
+    x, U = _f64(x), _f64(U)
+    N, D = x.shape
+    P = U.shape[1]
+    alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    dalpha = torch.empty((2, P, m), dtype=torch.float64, device=x.device)
+    dbeta = torch.empty((2, P, m), dtype=torch.float64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    check(
+        ctx.lib.gpxb_lanczos_grad(ctx.handle, _kind(kind), ptr(x), N, D, float(ell), float(sigma), ptr(U), U.stride(0),
+                                  P, int(m), ptr(alpha), ptr(beta), ptr(dalpha), ptr(dbeta), ptr(flag), stream_ptr()),
+        "gpxb_lanczos_grad",
+    )
+    return alpha, beta, dalpha, dbeta, flag
+
+
+def kmatvec_dl(kind, x, V, ell):
+    """(d K(x, x)/d lengthscale) V, matrix-free."""
+    ctx = context()
+    x, V = _f64(x), _f64(V)
+    if V.dim() == 1:
+        V = V.reshape(-1, 1)
+    N, D = x.shape
+    P = V.shape[1]
+    W = torch.empty((N, P), dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_kmatvec_dl(ctx.handle, _kind(kind), ptr(x), N, D, float(ell), ptr(V), V.stride(0), P, ptr(W),
+                                W.stride(0), stream_ptr()),
+        "gpxb_kmatvec_dl",
+    )
+    return W
+
+
 def gpr_fit_iter(kind, x, y, ell, sigma, n_pivots, key, mean_mode=MEAN_DATA, partitionable=True, tol=1e-5,
                  atol=1e-7, maxiter=0):
     """(c (N, 1), mu (1,), iterations) -- PCG with the RPCholesky preconditioner."""

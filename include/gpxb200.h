@@ -157,6 +157,17 @@ int gpxb_rademacher_probes(gpxb_ctx* ctx, uint32_t key0, uint32_t key1, int N, i
 int gpxb_lanczos(gpxb_ctx* ctx, int kind, const double* x, int N, int D, double ell, double diag_add,
                  const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out,
                  int* breakdown_flag, gpxb_stream stream);
+/* gpxb_lanczos on A = K(x,x; ell) + (sigma^2+1e-10) I together with its forward-mode derivative w.r.t.
+ * (lengthscale, sigma): dalpha_out / dbeta_out [2 x P x m] (index 0: lengthscale, 1: sigma) are the tangents
+ * of the tridiagonals -- the derivative jit(value_and_grad(loss)) propagates through lanczos_tridiagonal's
+ * fori_loop (gpx/lanczos.py:46-133) when the iterative LML is trained. */
+int gpxb_lanczos_grad(gpxb_ctx* ctx, int kind, const double* x, int N, int D, double ell, double sigma,
+                      const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out,
+                      double* dalpha_out, double* dbeta_out, int* breakdown_flag, gpxb_stream stream);
+/* W[N x P] = (d K(x, x)/d lengthscale) V, matrix-free (the cotangent contraction c^T dA c of the CG solve,
+ * jax.lax.custom_linear_solve under value_and_grad of gpx/models/_gpr.py:772-821). */
+int gpxb_kmatvec_dl(gpxb_ctx* ctx, int kind, const double* x, int N, int D, double ell, const double* V,
+                    long long ldv, int P, double* W, long long ldw, gpxb_stream stream);
 /* c[N] = PCG solve of (K + (sigma^2+1e-10) I) c = y - mu with the RPCholesky preconditioner
  * (gpx/models/_gpr.py:285-310, 180-216; jax.scipy.sparse.linalg.cg semantics: x0 = 0, stop when
  * r.r <= max(tol^2 b.b, atol^2) or after maxiter (<= 0: 10 N) iterations).  n_pivots = 0: no

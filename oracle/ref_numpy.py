@@ -665,6 +665,105 @@ def cg(A, b, M=None, tol=1e-5, atol=0.0, maxiter=None):
     return x, k
 
 
+def lanczos_tridiagonal_jvp(matvec, dmatvecs, m, v1):
+    """Forward-mode derivative of lanczos_tridiagonal (lanczos.py:46-133) w.r.t. parameters theta_q of the
+    operator: every statement of the recursion is differentiated (v1 is constant; the breakdown branch of
+    the jnp.where is not selected and carries no derivative).  dmatvecs[q](v) = (dA/d theta_q) v.
+    Returns (T, [dT_q]).  This is the derivative jit(value_and_grad) propagates through the fori_loop,
+    evaluated in tangent instead of cotangent form."""
+    n, nq = v1.shape[0], len(dmatvecs)
+    vecs = np.zeros((n, m))
+    dvecs = [np.zeros((n, m)) for _ in range(nq)]
+    vecs[:, 0] = v1
+    T = np.zeros((m, m))
+    dT = [np.zeros((m, m)) for _ in range(nq)]
+    w = matvec(v1)
+    dw = [dmv(v1) for dmv in dmatvecs]
+    alpha = np.dot(w, v1)
+    dalpha = [np.dot(dwq, v1) for dwq in dw]
+    w = w - alpha * v1
+    dw = [dwq - da * v1 for dwq, da in zip(dw, dalpha)]
+    beta = np.linalg.norm(w)
+    dbeta = [np.dot(w, dwq) / beta for dwq in dw]
+    T[0, 0] = alpha
+    for q in range(nq):
+        dT[q][0, 0] = dalpha[q]
+    for j in range(m - 1):
+        if not beta > 1e-12:
+            raise FloatingPointError("Lanczos breakdown: the tangent recursion is undefined")
+        v = w / beta
+        dv = [(dwq - v * db) / beta for dwq, db in zip(dw, dbeta)]
+        vecs[:, j + 1] = v
+        for q in range(nq):
+            dvecs[q][:, j + 1] = dv[q]
+        w = matvec(v)
+        dw = [dmatvecs[q](v) + matvec(dv[q]) for q in range(nq)]
+        alpha = np.dot(w, v)
+        dalpha = [np.dot(dw[q], v) + np.dot(w, dv[q]) for q in range(nq)]
+        dw = [dw[q] - dalpha[q] * v - alpha * dv[q] - dbeta[q] * vecs[:, j] - beta * dvecs[q][:, j] for q in range(nq)]
+        w = w - alpha * v - beta * vecs[:, j]
+        for k in range(m):  # _orthogonalize, column order; zero columns are no-ops
+            coef = np.dot(w, vecs[:, k])
+            dcoef = [np.dot(dw[q], vecs[:, k]) + np.dot(w, dvecs[q][:, k]) for q in range(nq)]
+            dw = [dw[q] - dcoef[q] * vecs[:, k] - coef * dvecs[q][:, k] for q in range(nq)]
+            w = w - coef * vecs[:, k]
+        T[j + 1, j + 1] = alpha
+        T[j, j + 1] = T[j + 1, j] = beta
+        for q in range(nq):
+            dT[q][j + 1, j + 1] = dalpha[q]
+            dT[q][j, j + 1] = dT[q][j + 1, j] = dbeta[q]
+        beta = np.linalg.norm(w)
+        dbeta = [np.dot(w, dw[q]) / beta for q in range(nq)]
+    return T, dT
+
+
+def slq_from_tridiag_jvp(T, dT):
+    """d/d theta of slq_from_tridiag (lanczos.py:175-180) = e1^T Dlog(T)[dT] e1: with T = Q diag(lam) Q^T and
+    M = Q^T dT Q, sum_kl Q0k Q0l M_kl (log lam_k - log lam_l)/(lam_k - lam_l) (1/lam_k on the diagonal) -- the
+    closed form of the eigh JVP applied to sum_k Q0k^2 log lam_k."""
+    lam, Q = np.linalg.eigh(T)
+    lam = np.maximum(lam, 1e-36)
+    M = Q.T @ dT @ Q
+    dl = lam[:, None] - lam[None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dd = np.where(np.abs(dl) > 1e-14 * np.abs(lam[:, None]), (np.log(lam)[:, None] - np.log(lam)[None, :]) / dl,
+                      1.0 / lam[:, None])
+    q0 = Q[0, :]
+    return float(q0 @ (M * dd) @ q0)
+
+
+def lanczos_logdet_grad(kind, x, ell, sigma, num_evals, num_lanczos, key, partitionable=True):
+    """(logdet_SLQ, d/d ell, d/d sigma) of lanczos_logdet applied to A = K + (sigma^2+1e-10) I."""
+    n = x.shape[0]
+    K, dK = kernel_dl(kind, x, x, ell)
+    A = K + (sigma**2 + 1e-10) * np.eye(n)
+    us, _ = rademacher_probes(key, n, num_evals, partitionable)
+    acc, dacc = 0.0, np.zeros(2)
+    for p in range(num_evals):
+        T, dT = lanczos_tridiagonal_jvp(lambda v: A @ v, [lambda v: dK @ v, lambda v: 2.0 * sigma * v], num_lanczos,
+                                        us[:, p])
+        acc += slq_from_tridiag(T)
+        dacc += np.array([slq_from_tridiag_jvp(T, dT[0]), slq_from_tridiag_jvp(T, dT[1])])
+    return (n / num_evals) * acc, (n / num_evals) * dacc[0], (n / num_evals) * dacc[1]
+
+
+def lml_iter_grad(kind, x, y, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
+                  mean_function=data_mean, partitionable=True):
+    """(lml, d/d ell, d/d sigma) of _lml_iter (_gpr.py:772-821) as jit(value_and_grad) propagates it:
+    the CG solve is a lax.custom_linear_solve, so d(r.c) = -c^T dA c with c the computed PCG solution
+    (nothing flows through the preconditioner or the iteration count); the SLQ term is differentiated
+    through the Lanczos recursion and the eigendecomposition."""
+    m = y.shape[0]
+    c, mu, _ = fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function, partitionable)
+    r = y - mu
+    ld, ld_l, ld_s = lanczos_logdet_grad(kind, x, ell, sigma, num_evals, num_lanczos, key_lanczos, partitionable)
+    _, dK = kernel_dl(kind, x, x, ell)
+    mll = (-0.5 * np.sum(r.T @ c) - 0.5 * ld - m * 0.5 * np.log(2.0 * np.pi)) / m
+    g_l = (0.5 * np.sum(c * (dK @ c)) - 0.5 * ld_l) / m
+    g_s = (0.5 * 2.0 * sigma * np.sum(c * c) - 0.5 * ld_s) / m
+    return mll, g_l, g_s
+
+
 def fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function=data_mean, partitionable=True):
     """_gpr.py:285-310."""
     mu = mean_function(y)

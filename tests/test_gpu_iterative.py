@@ -141,6 +141,73 @@ def test_lml_iter_facade_matches_oracle():
     assert abs(out - ref) < 1e-8 * abs(ref)
 
 
+@pytest.mark.parametrize("kind,N,D,P", [("se", 700, 16, 5), ("m52", 513, 8, 33), ("m32", 300, 3, 1), ("m12", 260, 2, 2)])
+def test_kmatvec_dl_matches_oracle(kind, N, D, P):
+    from gpx_b200 import ops
+
+    x, _ = _data(N, D, 6)
+    V = np.random.default_rng(1).standard_normal((N, P))
+    ell = 0.8 * np.sqrt(D)
+    _, dK = R.kernel_dl(kind, x, x, ell)
+    np.fill_diagonal(dK, 0.0)  # s = d2 - jitter is exactly 0 on the diagonal of a symmetric block
+    out = host(ops.kmatvec_dl(kind, dev(x), dev(V), ell))
+    ref = dK @ V
+    assert rel(out, ref) < 1e-10
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_lanczos_tangents_match_oracle(kind):
+    """Forward-mode derivative of the Lanczos recursion w.r.t. (lengthscale, sigma) against the oracle's
+    statement-by-statement tangent (itself checked against finite differences on the CPU)."""
+    from gpx_b200 import ops
+
+    N, D, P, m = 600, 8, 5, 14
+    x, _ = _data(N, D, 4)
+    ell, sigma = 2.5, 0.4
+    us, _ = R.rademacher_probes(R.PRNGKey(11), N, P)
+    alpha, beta, dalpha, dbeta, flag = [host(t) for t in ops.lanczos_grad(kind, dev(x), ell, sigma, dev(us), m)]
+    assert int(flag[0]) == 0
+    K, dK = R.kernel_dl(kind, x, x, ell)
+    A = K + (sigma**2 + 1e-10) * np.eye(N)
+    for p in range(P):
+        T, dT = R.lanczos_tridiagonal_jvp(lambda v: A @ v, [lambda v: dK @ v, lambda v: 2.0 * sigma * v], m, us[:, p])
+        assert rel(alpha[p], np.diag(T)) < 1e-8 and rel(beta[p, : m - 1], np.diag(T, 1)) < 1e-8
+        for q in range(2):
+            # one scale per tangent matrix: d beta/d sigma is exactly 0 in exact arithmetic (a diagonal shift
+            # leaves the Lanczos vectors unchanged), so it only holds rounding noise
+            scale = np.max(np.abs(dT[q]))
+            assert np.max(np.abs(dalpha[q, p] - np.diag(dT[q]))) < 1e-7 * scale, (q, p)
+            assert np.max(np.abs(dbeta[q, p, : m - 1] - np.diag(dT[q], 1))) < 1e-7 * scale, (q, p)
+
+
+def test_lml_iter_gradient_facade_matches_oracle_and_trains():
+    """value_and_grad of the iterative LML (PCG solve + SLQ log-det) through GPR.loss_and_grad(iterative=True)
+    against the oracle; then GPR.fit(iterative=True) runs L-BFGS-B on it and lowers the loss."""
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import GPR
+
+    N, D = 1024, 4
+    x, y = _data(N, D, 4)
+    ell, sigma = 1.5, 0.5
+    key = R.PRNGKey(2023)
+    ref = R.lml_iter_grad("se", x, y, ell, sigma, 6, 15, key, 25, key)
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    mk = lambda: GPR(SquaredExponential(),  # noqa: E731
+                     kernel_params=dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior())),
+                     sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+    kw = dict(iterative=True, num_evals=6, num_lanczos=15, key_lanczos=key, n_pivots=25, key_precond=key)
+    loss, grads = mk().loss_and_grad(x, y, **kw)
+    assert abs(-loss - ref[0]) < 1e-8 * abs(ref[0])
+    assert abs(-grads[("kernel_params", "lengthscale")] - ref[1]) < 1e-6 * max(abs(ref[1]), abs(ref[0]))
+    assert abs(-grads[("sigma",)] - ref[2]) < 1e-6 * max(abs(ref[2]), abs(ref[0]))
+    m = mk().fit(x, y, iterative=True, n_pivots=25, loss_kwargs=dict(num_evals=6, num_lanczos=15, key_lanczos=key),
+                 opt_kwargs=dict(options=dict(maxiter=5)))
+    assert m.optimize_results_.fun < loss
+
+
 @pytest.mark.parametrize("kind,N,D,M,ell,sigma,T", [("se", 3000, 8, 64, 2.0, 0.1, 1), ("m52", 2500, 16, 200, 4.0, 0.3, 1),
                                                      ("se", 1000, 4, 32, 1.5, 0.01, 2)])
 def test_sgpr_lml_fit_predict(kind, N, D, M, ell, sigma, T):

@@ -373,3 +373,20 @@ def test_oracle_sgpr_landmark_gradient_vs_finite_differences(kind):
             e[a, f] = h
             fd[a, f] = (R.sgpr_lml_dense_nxn(kind, z + e, x, y, 1.4, 0.2) - R.sgpr_lml_dense_nxn(kind, z - e, x, y, 1.4, 0.2)) / (2 * h)
     assert np.max(np.abs(g - fd)) < 1e-8 * max(1.0, np.max(np.abs(g)))
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_oracle_slq_logdet_gradient_vs_finite_differences(kind):
+    """Tangent of the Lanczos recursion + closed-form eigh JVP (what value_and_grad propagates through
+    lanczos_logdet) against central differences of lanczos_logdet itself (fixed probes: a smooth function)."""
+    rng = np.random.default_rng(0)
+    N, P, m = 300, 6, 12
+    x = rng.standard_normal((N, 4))
+    key = R.PRNGKey(7)
+    ell, sig, h = 1.8, 0.4, 1e-5
+    f = lambda l, s: R.lanczos_logdet(R.make_matvec(kind, x, l, s), P, N, m, key)  # noqa: E731
+    ld, gl, gs = R.lanczos_logdet_grad(kind, x, ell, sig, P, m, key)
+    assert abs(ld - f(ell, sig)) < 1e-10 * abs(ld)
+    fl = (f(ell + h, sig) - f(ell - h, sig)) / (2 * h)
+    fs = (f(ell, sig + h) - f(ell, sig - h)) / (2 * h)
+    assert abs(gl - fl) < 1e-7 * abs(fl) and abs(gs - fs) < 1e-7 * abs(fs)
