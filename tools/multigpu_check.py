@@ -33,6 +33,7 @@ def main():
     def run():
         U = ops.rademacher_probes(key, N, P, True)
         al, be, fl = ops.lanczos("se", x, ell, sigma**2 + 1e-10, U, m)
+        lg = ops.lanczos_grad("se", x, ell, sigma, U[:, :8].contiguous(), 6)
         c, mu, it = ops.gpr_fit_iter("se", x, y, ell, sigma, 50, key)
         F, piv = ops.rpcholesky("se", x, M, ell, key, True, want_factor=True)
         xl = ops.gather_rows(x, piv)
@@ -41,7 +42,7 @@ def main():
         g3, gz = ops.sgpr_lml_grad_locs("se", x, y, xl + 0.01, ell, sigma)
         torch.cuda.synchronize()
         return dict(piv=piv.cpu().numpy(), F=F.cpu().numpy(), alpha=al.cpu().numpy(), beta=be.cpu().numpy(), c=c.cpu().numpy(), it=it,
-                    lml=lml.cpu().numpy(), cs=cs.cpu().numpy(), g3=g3.cpu().numpy(), gz=gz.cpu().numpy())
+                    lml=lml.cpu().numpy(), cs=cs.cpu().numpy(), dal=lg[2].cpu().numpy(), dbe=lg[3].cpu().numpy(), g3=g3.cpu().numpy(), gz=gz.cpu().numpy())
 
     ref = run()  # world == 1 context
     ops.comm_init_from_torch_distributed()
@@ -53,10 +54,10 @@ def main():
     rep = dict(rank=rank, world=world, N=N, pivots_equal=bool(np.array_equal(out["piv"], ref["piv"])),
                F=float(np.max(np.abs(out["F"] - ref["F"]))), alpha=rel(out["alpha"], ref["alpha"]), beta=rel(out["beta"], ref["beta"]),
                c=rel(out["c"], ref["c"]), iters=(out["it"], ref["it"]), sgpr_lml=rel(out["lml"], ref["lml"]),
-               sgpr_c=rel(out["cs"], ref["cs"]), sgpr_grad=rel(out["g3"], ref["g3"]), sgpr_grad_locs=rel(out["gz"], ref["gz"]),
+               sgpr_c=rel(out["cs"], ref["cs"]), lanczos_dalpha=rel(out["dal"], ref["dal"]), lanczos_dbeta=rel(out["dbe"], ref["dbe"]), sgpr_grad=rel(out["g3"], ref["g3"]), sgpr_grad_locs=rel(out["gz"], ref["gz"]),
                seconds=dt)
     ok = rep["pivots_equal"] and rep["F"] < 1e-12 and rep["alpha"] < 1e-9 and rep["beta"] < 1e-9 and rep["c"] < 1e-8 and out["it"] == ref["it"] and \
-        rep["sgpr_lml"] < 1e-10 and rep["sgpr_c"] < 1e-6 and rep["sgpr_grad"] < 1e-8 and rep["sgpr_grad_locs"] < 1e-8
+        rep["sgpr_lml"] < 1e-10 and rep["sgpr_c"] < 1e-6 and rep["sgpr_grad"] < 1e-8 and rep["lanczos_dalpha"] < 1e-8 and rep["lanczos_dbeta"] < 1e-8 and rep["sgpr_grad_locs"] < 1e-8
     rep["ok"] = bool(ok)
     print(json.dumps(rep), flush=True)
     dist.barrier()
