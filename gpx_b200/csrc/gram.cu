@@ -43,16 +43,36 @@ struct GramParams {
   int tiles_m, tiles_n;
 };
 
-__device__ __forceinline__ double kfun(int kind, double d2) {
-  if (kind == KIND_SE) return exp(-d2);
+// Kernel nonlinearity with the kind fixed at compile time: the 64-element epilogue is fully unrolled, and
+// with a run-time switch per element it grew to ~29 000 SASS instructions (470 KB: every tile streamed
+// through more code than the instruction caches hold).  exp is the table-driven exp_tab (kfun.cuh).
+template <int KIND>
+__device__ __forceinline__ double kfun_t(double d2, const double* __restrict__ tab) {
+  if (KIND == KIND_SE) return exp_tab(-d2, tab);
   const double r = sqrt(fmax(d2, 1e-36));
-  if (kind == KIND_M12) return exp(-r);
-  if (kind == KIND_M32) {
+  if (KIND == KIND_M12) return exp_tab(-r, tab);
+  if (KIND == KIND_M32) {
     const double d = 1.7320508075688772 * r;
-    return (1.0 + d) * exp(-d);
+    return (1.0 + d) * exp_tab(-d, tab);
   }
   const double d = 2.23606797749979 * r;
-  return (1.0 + d + d * d / 3.0) * exp(-d);
+  return (1.0 + d + d * d * 0.3333333333333333) * exp_tab(-d, tab);
+}
+
+// dK/d ell given d2 = s + 1e-12 (the jitter is a constant; the clamp passes no gradient).
+// rl = 1/ell is hoisted by the caller: no FP64 division in the inner loop except Matern-1/2's 1/r.
+template <int KIND>
+__device__ __forceinline__ double kfun_dl_t(double d2, double s, double rl, const double* __restrict__ tab) {
+  if (KIND == KIND_SE) return exp_tab(-d2, tab) * (2.0 * rl) * s;
+  if (!(d2 > 1e-36)) return 0.0;
+  const double r = sqrt(d2);
+  if (KIND == KIND_M12) return exp_tab(-r, tab) * s * rl / r;
+  if (KIND == KIND_M32) {
+    const double d = 1.7320508075688772 * r;
+    return (3.0 * rl) * s * exp_tab(-d, tab);
+  }
+  const double d = 2.23606797749979 * r;
+  return ((5.0 / 3.0) * rl) * s * (1.0 + d) * exp_tab(-d, tab);
 }
 
 __global__ void prep_z_kernel(const double* __restrict__ x, long long ldx, int n, int D, int Dp,
@@ -71,16 +91,18 @@ __global__ void prep_z_kernel(const double* __restrict__ x, long long ldx, int n
   zi[Dp] = nrm;
 }
 
-template <bool CONTRACT>
+template <bool CONTRACT, int KIND>
 __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sZ1 = reinterpret_cast<double*>(smem_raw + 128);
   double* sZ2 = sZ1 + TB * p.S;
   __shared__ double red[NT / 32];
+  __shared__ double etab[64];  // 2^(j/64) for exp_tab
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
+  if (tid < 64) etab[tid] = exp2((double)tid * (1.0 / 64.0));
   const int lr = lane >> 2, lq = lane & 3;
 
   int ti, tj;
@@ -160,12 +182,12 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
         const bool on_diag = p.sym && (gi == j);
         if (on_diag) d2 = 1e-12;
         if (!CONTRACT) {
-          v[e] = kfun(p.kind, d2) + ((gi == j) ? p.diag_add : 0.0);
+          v[e] = kfun_t<KIND>(d2, etab) + ((gi == j) ? p.diag_add : 0.0);
         } else {
           v[e] = 0.0;
           if (ok[e]) {
             const double s = on_diag ? 0.0 : d2 - 1e-12;
-            const double dk = kfun_dl(p.kind, d2, s, rl);
+            const double dk = kfun_dl_t<KIND>(d2, s, rl, etab);
             double w = -p.Ainv[(long long)gi * p.ldainv + j];
             for (int t = 0; t < p.t; ++t)
               w += p.alpha[(long long)t * p.n1 + gi] * p.alpha2[(long long)t * p.n2 + j];
@@ -228,17 +250,28 @@ int gram_launch(Ctx* ctx, const GramArgs& a, cudaStream_t s) {
   const long long grid = gram_num_ctas(a);
   GPXB_ARG_CHECK(grid < (1LL << 31), -12);
   const int smem = 128 + 2 * TB * p.S * (int)sizeof(double);
-  if (a.out) {
-    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gram_kernel<false><<<(int)grid, NT, smem, s>>>(p);
-  } else {
+  if (!a.out) {
     GPXB_ARG_CHECK(a.Ainv && a.alpha && a.partials, -13);
     GPXB_ARG_CHECK(a.alpha2 || (a.sym && a.n1 == a.n2), -14);
-    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gram_kernel<true><<<(int)grid, NT, smem, s>>>(p);
   }
+#define GPXB_GRAM_GO(C, K)                                                                                   \
+  do {                                                                                                       \
+    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    gram_kernel<C, K><<<(int)grid, NT, smem, s>>>(p);                                                        \
+  } while (0)
+#define GPXB_GRAM_KIND(C)                                  \
+  do {                                                     \
+    switch (a.kind) {                                      \
+      case KIND_SE: GPXB_GRAM_GO(C, KIND_SE); break;       \
+      case KIND_M12: GPXB_GRAM_GO(C, KIND_M12); break;     \
+      case KIND_M32: GPXB_GRAM_GO(C, KIND_M32); break;     \
+      default: GPXB_GRAM_GO(C, KIND_M52); break;           \
+    }                                                      \
+  } while (0)
+  if (a.out) GPXB_GRAM_KIND(false);
+  else GPXB_GRAM_KIND(true);
+#undef GPXB_GRAM_KIND
+#undef GPXB_GRAM_GO
   GPXB_LAUNCH_CHECK();
   ctx->launches++;
   return 0;

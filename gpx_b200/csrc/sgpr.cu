@@ -239,35 +239,39 @@ __global__ void grad_locs_kernel(const double* __restrict__ acc1, const double* 
 int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, long long N, int D,
                   const double* x_locs, int M, double ell, double sigma, const double* mu, int want_grad,
                   double* out3, double* grad_locs, cudaStream_t s) {
-  GPXB_ARG_CHECK(!grad_locs || (want_grad && kmatvec_supports(D)), -4);
   GPXB_ARG_CHECK(n_loc >= 0 && D > 0 && M > 0, -1);
+  GPXB_ARG_CHECK(!grad_locs || (want_grad && kmatvec_supports(D)), -4);
   const ZLayout zl = z_layout(D);
   GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
   const double s2 = sigma * sigma + 1e-10;
   const size_t mm = (size_t)M * M;
   const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
-  DevBuf bZl, bA, bInvA, bB, bInvB, bU, bWh, bW, bZc, bKc, bRc, bTc, bY, bSc, bWk, bTs, bPart, bH, bHt;
-  DevBuf bVx, bAcc1, bAcc2, bTmp;
+  const int nchunks = ceil_div(std::max(n_loc, 1), CHUNK);
+  const int NS = nchunks >= 3 ? 3 : 1;  // concurrent chunk pipelines, as in sgpr_lml
   const int P1 = D + 1;
+  DevBuf bZl, bA, bInvA, bB, bInvB, bU, bWh, bW, bZc, bKc, bRc, bTc, bY, bSc, bWk, bTs, bH, bHt;
+  DevBuf bVx, bAcc1, bAcc2, bTmp;
   GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
   GPXB_TRY(bA.alloc(sizeof(double) * mm, s));
   GPXB_TRY(bInvA.alloc(sizeof(double) * leaf_inv_doubles(M), s));
-  GPXB_TRY(bB.alloc(sizeof(double) * mm, s));
+  GPXB_TRY(bB.alloc(sizeof(double) * mm * NS, s));
   GPXB_TRY(bInvB.alloc(sizeof(double) * leaf_inv_doubles(M), s));
-  GPXB_TRY(bU.alloc(sizeof(double) * M, s));
+  GPXB_TRY(bU.alloc(sizeof(double) * M * NS, s));
   GPXB_TRY(bWh.alloc(sizeof(double) * M, s));
   GPXB_TRY(bW.alloc(sizeof(double) * M, s));
-  GPXB_TRY(bZc.alloc(sizeof(double) * (size_t)nc_max * zl.S, s));
-  GPXB_TRY(bKc.alloc(sizeof(double) * (size_t)nc_max * M, s));
-  GPXB_TRY(bRc.alloc(sizeof(double) * nc_max, s));
-  GPXB_TRY(bTc.alloc(sizeof(double) * nc_max, s));
-  GPXB_TRY(bSc.alloc(sizeof(double) * 8, s));
+  GPXB_TRY(bZc.alloc(sizeof(double) * (size_t)nc_max * zl.S * NS, s));
+  GPXB_TRY(bKc.alloc(sizeof(double) * (size_t)nc_max * M * NS, s));
+  GPXB_TRY(bRc.alloc(sizeof(double) * (size_t)nc_max * NS, s));
+  GPXB_TRY(bTc.alloc(sizeof(double) * (size_t)nc_max * NS, s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * 8 * (NS + 1), s));
   double *Zl = bZl.as<double>(), *A = bA.as<double>(), *B = bB.as<double>(), *invA = bInvA.as<double>();
-  double *u = bU.as<double>(), *wh = bWh.as<double>(), *w = bW.as<double>(), *Zc = bZc.as<double>();
-  double *Kc = bKc.as<double>(), *rc = bRc.as<double>(), *tc = bTc.as<double>(), *scal = bSc.as<double>();
-  GPXB_CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(double) * mm, s));
-  GPXB_CUDA_CHECK(cudaMemsetAsync(u, 0, sizeof(double) * M, s));
-  GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 8, s));
+  double *u = bU.as<double>(), *wh = bWh.as<double>(), *w = bW.as<double>();
+  // scal: the combined scalars (layout of finalize_sgpr_grad_kernel); pscal[k]: pipeline k's partial sums
+  double* scal = bSc.as<double>();
+  auto pscal = [&](int k) { return scal + 8 * (k + 1); };
+  GPXB_CUDA_CHECK(cudaMemsetAsync(B, 0, sizeof(double) * mm * NS, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(u, 0, sizeof(double) * M * NS, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 8 * (NS + 1), s));
   const int eb = ceil_div((long long)mm, 256);
 
   // L_A = chol(K_mm + 1e-10 I)
@@ -280,35 +284,81 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
   }
   GPXB_TRY(potrf_lower(ctx, A, M, M, invA, s));
 
-  auto chunk_G = [&](int r0, int nc) -> int {  // Kc <- G_c^T = K(x_chunk, locs) L_A^-T ; rc <- r_c
-    GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, Zc, s));
+  cudaStream_t st[3] = {s, ctx->aux[0], ctx->aux[1]};
+  auto fork = [&]() -> int {
+    if (NS == 1) return 0;
+    cudaEvent_t e;
+    GPXB_TRY(ctx->next_event(&e));
+    GPXB_CUDA_CHECK(cudaEventRecord(e, s));
+    for (int k = 1; k < NS; ++k) GPXB_CUDA_CHECK(cudaStreamWaitEvent(st[k], e, 0));
+    return 0;
+  };
+  auto join = [&]() -> int {
+    for (int k = 1; k < NS; ++k) {
+      cudaEvent_t e;
+      GPXB_TRY(ctx->next_event(&e));
+      GPXB_CUDA_CHECK(cudaEventRecord(e, st[k]));
+      GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, e, 0));
+    }
+    return 0;
+  };
+  struct Pipe {
+    double *Zc, *Kc, *rc, *tc;
+    cudaStream_t sk;
+  };
+  auto pipe = [&](int k) {
+    Pipe p;
+    p.Zc = bZc.as<double>() + (size_t)k * nc_max * zl.S;
+    p.Kc = bKc.as<double>() + (size_t)k * nc_max * M;
+    p.rc = bRc.as<double>() + (size_t)k * nc_max;
+    p.tc = bTc.as<double>() + (size_t)k * nc_max;
+    p.sk = st[k];
+    return p;
+  };
+  auto chunk_G = [&](const Pipe& p, int r0, int nc) -> int {  // Kc <- G_c^T = K(x_chunk, locs) L_A^-T ; rc <- r_c
+    GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, p.Zc, p.sk));
     GramArgs g;
-    g.kind = kind; g.Z1 = Zc; g.n1 = nc; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell; g.out = Kc; g.ldo = M;
-    GPXB_TRY(gram_launch(ctx, g, s));
-    GPXB_TRY(trsm_right_lt(ctx, A, M, invA, Kc, M, nc, M, s));
-    center_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(y + r0, nc, mu, rc);
+    g.kind = kind; g.Z1 = p.Zc; g.n1 = nc; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell; g.out = p.Kc; g.ldo = M;
+    GPXB_TRY(gram_launch(ctx, g, p.sk));
+    GPXB_TRY(trsm_right_lt(ctx, A, M, invA, p.Kc, M, nc, M, p.sk));
+    center_kernel<<<ceil_div(nc, 256), 256, 0, p.sk>>>(y + r0, nc, mu, p.rc);
     GPXB_LAUNCHED(ctx);
     return 0;
   };
 
-  // pass 1: B += G_c G_c^T, u += G_c r_c, r.r
-  for (int r0 = 0; r0 < n_loc; r0 += CHUNK) {
+  // pass 1: B_k += G_c G_c^T, u_k += G_c r_c, r.r (private accumulators per pipeline, summed in a fixed order)
+  GPXB_TRY(fork());
+  int ci = 0;
+  for (int r0 = 0; r0 < n_loc; r0 += CHUNK, ++ci) {
     const int nc = std::min(CHUNK, n_loc - r0);
-    GPXB_TRY(chunk_G(r0, nc));
-    sumsq_kernel<<<1, 1024, 0, s>>>(rc, nc, scal + 0, 1);
+    const int k = ci % NS;
+    const Pipe p = pipe(k);
+    GPXB_TRY(chunk_G(p, r0, nc));
+    sumsq_kernel<<<1, 1024, 0, p.sk>>>(p.rc, nc, pscal(k) + 0, 1);
     GPXB_LAUNCHED(ctx);
     GemmArgs a;
     a.M = M; a.N = M; a.K = nc;
-    a.A = Kc; a.lda = M; a.a_kmajor = false;
-    a.B = Kc; a.ldb = M; a.b_kmajor = false;
-    a.C = B; a.ldc = M; a.beta = 1.0; a.lower_only = 1;
-    GPXB_TRY(gemm_f64(ctx, a, s));
+    a.A = p.Kc; a.lda = M; a.a_kmajor = false;
+    a.B = p.Kc; a.ldb = M; a.b_kmajor = false;
+    a.C = B + (size_t)k * mm; a.ldc = M; a.beta = 1.0; a.lower_only = 1;
+    GPXB_TRY(gemm_f64(ctx, a, p.sk));
     GemmArgs b;
     b.M = M; b.N = 1; b.K = nc;
-    b.A = Kc; b.lda = M; b.a_kmajor = false;
-    b.B = rc; b.ldb = 1; b.b_kmajor = false;
-    b.C = u; b.ldc = 1; b.beta = 1.0;
-    GPXB_TRY(gemm_f64(ctx, b, s));
+    b.A = p.Kc; b.lda = M; b.a_kmajor = false;
+    b.B = p.rc; b.ldb = 1; b.b_kmajor = false;
+    b.C = u + (size_t)k * M; b.ldc = 1; b.beta = 1.0;
+    GPXB_TRY(gemm_f64(ctx, b, p.sk));
+  }
+  GPXB_TRY(join());
+  for (int k = 1; k < NS; ++k) {
+    add_vec_kernel<<<eb, 256, 0, s>>>(B, B + (size_t)k * mm, (long long)mm);
+    GPXB_LAUNCHED(ctx);
+    add_vec_kernel<<<ceil_div(M, 256), 256, 0, s>>>(u, u + (size_t)k * M, M);
+    GPXB_LAUNCHED(ctx);
+  }
+  for (int k = 0; k < NS; ++k) {
+    add_vec_kernel<<<1, 1, 0, s>>>(scal + 0, pscal(k) + 0, 1);
+    GPXB_LAUNCHED(ctx);
   }
   if (ctx->world > 1) {
     GPXB_TRY(comm_allreduce_sum(ctx, B, mm, s));
@@ -328,16 +378,16 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
   if (want_grad) {
     GPXB_TRY(bWk.alloc(sizeof(double) * mm, s));
     GPXB_TRY(bTs.alloc(sizeof(double) * potri_scratch_doubles(M), s));
-    GPXB_TRY(bY.alloc(sizeof(double) * (size_t)nc_max * M, s));
+    GPXB_TRY(bY.alloc(sizeof(double) * (size_t)nc_max * M * NS, s));
     GPXB_TRY(bH.alloc(sizeof(double) * mm, s));
     GPXB_TRY(bHt.alloc(sizeof(double) * mm, s));
-    double *Y = bY.as<double>(), *H = bH.as<double>(), *Ht = bHt.as<double>();
+    double *H = bH.as<double>(), *Ht = bHt.as<double>();
     if (grad_locs) {
-      GPXB_TRY(bVx.alloc(sizeof(double) * (size_t)std::max(nc_max, M) * P1, s));
-      GPXB_TRY(bAcc1.alloc(sizeof(double) * (size_t)M * P1, s));
+      GPXB_TRY(bVx.alloc(sizeof(double) * (size_t)std::max(nc_max, M) * P1 * NS, s));
+      GPXB_TRY(bAcc1.alloc(sizeof(double) * (size_t)M * P1 * NS, s));
       GPXB_TRY(bAcc2.alloc(sizeof(double) * (size_t)M * P1, s));
-      GPXB_TRY(bTmp.alloc(sizeof(double) * (size_t)M * P1, s));
-      GPXB_CUDA_CHECK(cudaMemsetAsync(bAcc1.as<double>(), 0, sizeof(double) * (size_t)M * P1, s));
+      GPXB_TRY(bTmp.alloc(sizeof(double) * (size_t)M * P1 * NS, s));
+      GPXB_CUDA_CHECK(cudaMemsetAsync(bAcc1.as<double>(), 0, sizeof(double) * (size_t)M * P1 * NS, s));
     }
     // w = L_A^-T what (landmark weights)
     GPXB_CUDA_CHECK(cudaMemcpyAsync(w, wh, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
@@ -349,50 +399,67 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
     symmetrize_lower_kernel<<<eb, 256, 0, s>>>(B, M);
     GPXB_LAUNCHED(ctx);
     // pass 2: per chunk Y = G_c^T B^-1 L_A^-1, alpha_c = (r_c - G_c^T what)/s2, g1 += sum dK (alpha w^T - Y)
-    for (int r0 = 0; r0 < n_loc; r0 += CHUNK) {
+    GPXB_TRY(fork());
+    ci = 0;
+    for (int r0 = 0; r0 < n_loc; r0 += CHUNK, ++ci) {
       const int nc = std::min(CHUNK, n_loc - r0);
-      GPXB_TRY(chunk_G(r0, nc));
+      const int k = ci % NS;
+      const Pipe p = pipe(k);
+      double* Y = bY.as<double>() + (size_t)k * nc_max * M;
+      GPXB_TRY(chunk_G(p, r0, nc));
       GemmArgs b;  // t_c = G_c^T what
       b.M = nc; b.N = 1; b.K = M;
-      b.A = Kc; b.lda = M; b.a_kmajor = true;
+      b.A = p.Kc; b.lda = M; b.a_kmajor = true;
       b.B = wh; b.ldb = 1; b.b_kmajor = false;
-      b.C = tc; b.ldc = 1;
-      GPXB_TRY(gemm_f64(ctx, b, s));
-      alpha_chunk_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(rc, tc, nc, s2);
+      b.C = p.tc; b.ldc = 1;
+      GPXB_TRY(gemm_f64(ctx, b, p.sk));
+      alpha_chunk_kernel<<<ceil_div(nc, 256), 256, 0, p.sk>>>(p.rc, p.tc, nc, s2);
       GPXB_LAUNCHED(ctx);
-      sumsq_kernel<<<1, 1024, 0, s>>>(tc, nc, scal + 4, 1);
+      sumsq_kernel<<<1, 1024, 0, p.sk>>>(p.tc, nc, pscal(k) + 4, 1);
       GPXB_LAUNCHED(ctx);
       GemmArgs a;  // Y = G_c^T B^-1
       a.M = nc; a.N = M; a.K = M;
-      a.A = Kc; a.lda = M; a.a_kmajor = true;
+      a.A = p.Kc; a.lda = M; a.a_kmajor = true;
       a.B = B; a.ldb = M; a.b_kmajor = false;
       a.C = Y; a.ldc = M;
-      GPXB_TRY(gemm_f64(ctx, a, s));
-      GPXB_TRY(trsm_right_l(ctx, A, M, invA, Y, M, nc, M, s));  // Y <- Y L_A^-1
+      GPXB_TRY(gemm_f64(ctx, a, p.sk));
+      GPXB_TRY(trsm_right_l(ctx, A, M, invA, Y, M, nc, M, p.sk));  // Y <- Y L_A^-1
       GramArgs c;
-      c.kind = kind; c.Z1 = Zc; c.n1 = nc; c.Z2 = Zl; c.n2 = M; c.zl = zl; c.ell = ell;
-      c.Ainv = Y; c.ldainv = M; c.alpha = tc; c.alpha2 = w; c.t = 1;
+      c.kind = kind; c.Z1 = p.Zc; c.n1 = nc; c.Z2 = Zl; c.n2 = M; c.zl = zl; c.ell = ell;
+      c.Ainv = Y; c.ldainv = M; c.alpha = p.tc; c.alpha2 = w; c.t = 1;
       const long long nparts = gram_num_ctas(c);
-      GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)(nparts + 1), s));
+      DevBuf bPart;
+      GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)(nparts + 1), p.sk));
       c.partials = bPart.as<double>();
-      GPXB_TRY(gram_launch(ctx, c, s));
-      sum_kernel<<<1, 1024, 0, s>>>(c.partials, nparts, c.partials + nparts);
+      GPXB_TRY(gram_launch(ctx, c, p.sk));
+      sum_kernel<<<1, 1024, 0, p.sk>>>(c.partials, nparts, c.partials + nparts);
       GPXB_LAUNCHED(ctx);
-      add_vec_kernel<<<1, 1, 0, s>>>(scal + 5, c.partials + nparts, 1);
+      add_vec_kernel<<<1, 1, 0, p.sk>>>(pscal(k) + 5, c.partials + nparts, 1);
       GPXB_LAUNCHED(ctx);
-      bPart.release();
-      if (grad_locs) {  // acc1 += (g o (w alpha_c^T - Y^T)) [1 | x_c]   (rows: landmarks, columns: chunk points)
-        ones_x_kernel<<<ceil_div((long long)nc * P1, 256), 256, 0, s>>>(x + (long long)r0 * D, nc, D, bVx.as<double>());
+      if (grad_locs) {  // acc1_k += (g o (w alpha_c^T - Y^T)) [1 | x_c]   (rows: landmarks, columns: chunk points)
+        double* Vx = bVx.as<double>() + (size_t)k * std::max(nc_max, M) * P1;
+        double* tmp = bTmp.as<double>() + (size_t)k * M * P1;
+        ones_x_kernel<<<ceil_div((long long)nc * P1, 256), 256, 0, p.sk>>>(x + (long long)r0 * D, nc, D, Vx);
         GPXB_LAUNCHED(ctx);
-        GPXB_TRY(kprofile_weighted(ctx, kind, Zl, M, -1, Zc, nc, zl, bVx.as<double>(), P1, P1, w, tc, Y, M, 1,
-                                   bTmp.as<double>(), P1, s));
-        add_vec_kernel<<<ceil_div((long long)M * P1, 256), 256, 0, s>>>(bAcc1.as<double>(), bTmp.as<double>(),
+        GPXB_TRY(kprofile_weighted(ctx, kind, Zl, M, -1, p.Zc, nc, zl, Vx, P1, P1, w, p.tc, Y, M, 1, tmp, P1, p.sk));
+        add_vec_kernel<<<ceil_div((long long)M * P1, 256), 256, 0, p.sk>>>(bAcc1.as<double>() + (size_t)k * M * P1, tmp,
+                                                                          (long long)M * P1);
+        GPXB_LAUNCHED(ctx);
+      }
+    }
+    GPXB_TRY(join());
+    for (int k = 0; k < NS; ++k) {
+      add_vec_kernel<<<1, 2, 0, s>>>(scal + 4, pscal(k) + 4, 2);  // alpha.alpha and g1
+      GPXB_LAUNCHED(ctx);
+      if (grad_locs && k > 0) {
+        add_vec_kernel<<<ceil_div((long long)M * P1, 256), 256, 0, s>>>(bAcc1.as<double>(),
+                                                                         bAcc1.as<double>() + (size_t)k * M * P1,
                                                                          (long long)M * P1);
         GPXB_LAUNCHED(ctx);
       }
     }
-    if (grad_locs && ctx->world > 1) GPXB_TRY(comm_allreduce_sum(ctx, bAcc1.as<double>(), (size_t)M * P1, s));
     if (ctx->world > 1) GPXB_TRY(comm_allreduce_sum(ctx, scal + 4, 2, s));
+    if (grad_locs && ctx->world > 1) GPXB_TRY(comm_allreduce_sum(ctx, bAcc1.as<double>(), (size_t)M * P1, s));
     // F = L_A^-T (I - s2 B^-1) L_A^-1:  H = I - s2 B^-1;  H <- H L_A^-1;  F = (H^T L_A^-1)^T = H^T L_A^-1
     i_minus_scaled_kernel<<<eb, 256, 0, s>>>(B, M, s2, H);
     GPXB_LAUNCHED(ctx);
@@ -407,6 +474,7 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
     c.kind = kind; c.Z1 = Zl; c.n1 = M; c.Z2 = Zl; c.n2 = M; c.zl = zl; c.ell = ell; c.sym = 1; c.lower_only = 1;
     c.Ainv = Ht; c.ldainv = M; c.alpha = w; c.t = 1;
     const long long nparts = gram_num_ctas(c);
+    DevBuf bPart;
     GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)nparts, s));
     c.partials = bPart.as<double>();
     GPXB_TRY(gram_launch(ctx, c, s));
