@@ -509,6 +509,125 @@ int gpr_predict_y_derivs(Ctx* ctx, int kind, const double* x_train, const double
   return 0;
 }
 
+namespace {
+__global__ void add_const_kernel(double* __restrict__ v, long long n, double c) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] += c;
+}
+// Knm[t][i] = d0kj(x_train, x, J_train)[i][t] = -g_st (q_i - (A1 x_t^T)[i]),  i = s nv + v
+__global__ void d0kj_t_kernel(const double* __restrict__ A1, int S, int Dp, const double* __restrict__ P12,
+                              const double* __restrict__ G, int nv, long long n, int ns, double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ns) return;
+  const long long i = idx % n;
+  const int t = (int)(idx / n);
+  const long long sidx = i / nv;
+  out[idx] = -G[sidx * ns + t] * (A1[i * S + Dp] - P12[i * ns + t]);
+}
+
+// Shared tail of the two full-covariance predictions: Knm (m x n) holds the cross block (rows: test).
+//   mean = mu + Knm c;  cov (already holding the prior block K_**) -= (Knm L^-T)(Knm L^-T)^T,
+//   L = chol(d01kj(x_train) + shift I).
+int predict_cov_tail(Ctx* ctx, int kind, const double* xt, const double* Jt, int N, int nf, int nv, double ell,
+                     double shift, double* Knm, long long n, int m, const double* c, double mu, double* mean_out,
+                     double* cov_out, cudaStream_t s) {
+  {
+    GemmArgs g;  // mean = Knm c
+    g.M = m; g.N = 1; g.K = (int)n;
+    g.A = Knm; g.lda = n; g.a_kmajor = true;
+    g.B = c; g.ldb = 1; g.b_kmajor = false;
+    g.C = mean_out; g.ldc = 1;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  if (mu != 0.0) {
+    add_const_kernel<<<ceil_div(m, 256), 256, 0, s>>>(mean_out, m, mu);
+    GPXB_LAUNCHED(ctx);
+  }
+  if (!cov_out) return 0;
+  DevBuf bA, bInv;
+  GPXB_TRY(bA.alloc(sizeof(double) * (size_t)n * n, s));
+  GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles((int)n), s));
+  double *A = bA.as<double>(), *inv = bInv.as<double>();
+  GPXB_TRY(hess_gram(ctx, kind, xt, Jt, N, nv, xt, Jt, N, nv, nf, ell, shift, A, n, 1, s));
+  GPXB_TRY(potrf_lower(ctx, A, n, (int)n, inv, s));
+  GPXB_TRY(trsm_right_lt(ctx, A, n, inv, Knm, n, m, (int)n, s));  // Knm <- G^T = Knm L^-T
+  GemmArgs g;  // cov -= G^T G
+  g.M = m; g.N = m; g.K = (int)n;
+  g.A = Knm; g.lda = n; g.a_kmajor = true;
+  g.B = Knm; g.ldb = n; g.b_kmajor = true;
+  g.C = cov_out; g.ldc = m;
+  g.alpha = -1.0; g.beta = 1.0;
+  return gemm_f64(ctx, g, s);
+}
+}  // namespace
+
+// _predict_derivs_dense without the contracted jacobian (gpx/models/_gpr.py:488-560): mean[ns nvs] = mu +
+// K_nm c with K = d01kj; cov_out (optional, (ns nvs)^2) = d01kj(x, x) - G^T G, G = chol(d01kj(x_train) +
+// (sigma^2 + 1e-10) I)^-1 K_mn.
+int gpr_predict_derivs_full(Ctx* ctx, int kind, const double* xt, const double* Jt, int N, int nf, int nv,
+                            const double* x, const double* J, int ns, int nvs, const double* c, double mu,
+                            double ell, double sigma, double* mean_out, double* cov_out, cudaStream_t s) {
+  const long long n = (long long)N * nv, m = (long long)ns * nvs;
+  GPXB_ARG_CHECK(n > 0 && m > 0 && n < (1LL << 31) && m < (1LL << 31), -1);
+  DevBuf bK;
+  GPXB_TRY(bK.alloc(sizeof(double) * (size_t)m * n, s));
+  GPXB_TRY(hess_gram(ctx, kind, x, J, ns, nvs, xt, Jt, N, nv, nf, ell, 0.0, bK.as<double>(), n, 0, s));
+  if (cov_out) GPXB_TRY(hess_gram(ctx, kind, x, J, ns, nvs, x, J, ns, nvs, nf, ell, 0.0, cov_out, m, 0, s));
+  return predict_cov_tail(ctx, kind, xt, Jt, N, nf, nv, ell, sigma * sigma + 1e-10, bK.as<double>(), n, (int)m, c, mu,
+                          mean_out, cov_out, s);
+}
+
+// _predict_y_derivs_dense without the contracted jacobian (gpx/models/_gpr.py:608-660): mean[ns] = mu +
+// K_nm c with K_mn = d0kj(x_train, x, J_train); cov_out (optional, ns^2) = k(x, x) - G^T G,
+// G = chol(d01kj(x_train) + sigma^2 I)^-1 K_mn (no 1e-10 here, as in the reference).
+int gpr_predict_y_derivs_full(Ctx* ctx, int kind, const double* xt, const double* Jt, int N, int nf, int nv,
+                              const double* x, int ns, const double* c, double mu, double ell, double sigma,
+                              double* mean_out, double* cov_out, cudaStream_t s) {
+  GPXB_ARG_CHECK(kind == KIND_SE || kind == KIND_M52, -50);
+  const long long n = (long long)N * nv;
+  GPXB_ARG_CHECK(n > 0 && ns > 0 && n < (1LL << 31), -1);
+  const ZLayout zl = z_layout(nf);
+  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -52);
+  DevBuf bK, bA1, bZ1, bZ2, bX2, bG, bG2, bP;
+  GPXB_TRY(bK.alloc(sizeof(double) * (size_t)ns * n, s));
+  GPXB_TRY(bA1.alloc(sizeof(double) * (size_t)n * zl.S, s));
+  GPXB_TRY(bZ1.alloc(sizeof(double) * (size_t)N * zl.S, s));
+  GPXB_TRY(bZ2.alloc(sizeof(double) * (size_t)ns * zl.S, s));
+  GPXB_TRY(bX2.alloc(sizeof(double) * (size_t)ns * zl.S, s));
+  GPXB_TRY(bG.alloc(sizeof(double) * (size_t)N * ns, s));
+  GPXB_TRY(bG2.alloc(sizeof(double) * (size_t)N * ns, s));
+  GPXB_TRY(bP.alloc(sizeof(double) * (size_t)n * ns, s));
+  prep_hess_kernel<<<ceil_div(n, 128), 128, 0, s>>>(xt, Jt, N, nf, nv, zl.S, zl.Dp, bA1.as<double>());
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(prep_z(ctx, xt, nf, N, zl, ell, bZ1.as<double>(), s));
+  GPXB_TRY(prep_z(ctx, x, nf, ns, zl, ell, bZ2.as<double>(), s));
+  GPXB_TRY(prep_z(ctx, x, nf, ns, zl, 1.0, bX2.as<double>(), s));
+  // c1 of the Hessian kernel is exactly the radial derivative profile: SE (2/l^2) exp(-d2), M52 (5/(3 l^2)) (1+d) exp(-d)
+  pair_coef_kernel<<<ceil_div((long long)N * ns, 256), 256, 0, s>>>(bZ1.as<double>(), N, bZ2.as<double>(), ns, zl.S,
+                                                                     zl.Dp, kind, ell, 0, 0, bG.as<double>(),
+                                                                     bG2.as<double>());
+  GPXB_LAUNCHED(ctx);
+  {
+    GemmArgs g;  // P12 = A1 X2^T   [n x ns]
+    g.M = (int)n; g.N = ns; g.K = zl.Dp;
+    g.A = bA1.as<double>(); g.lda = zl.S; g.a_kmajor = true;
+    g.B = bX2.as<double>(); g.ldb = zl.S; g.b_kmajor = true;
+    g.C = bP.as<double>(); g.ldc = ns;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  d0kj_t_kernel<<<ceil_div(n * ns, 256), 256, 0, s>>>(bA1.as<double>(), zl.S, zl.Dp, bP.as<double>(), bG.as<double>(),
+                                                       nv, n, ns, bK.as<double>());
+  GPXB_LAUNCHED(ctx);
+  if (cov_out) {
+    GramArgs h;  // prior block k(x, x)
+    h.kind = kind; h.Z1 = bZ2.as<double>(); h.n1 = ns; h.Z2 = bZ2.as<double>(); h.n2 = ns; h.zl = zl; h.ell = ell;
+    h.sym = 1; h.out = cov_out; h.ldo = ns;
+    GPXB_TRY(gram_launch(ctx, h, s));
+  }
+  return predict_cov_tail(ctx, kind, xt, Jt, N, nf, nv, ell, sigma * sigma, bK.as<double>(), n, ns, c, mu, mean_out,
+                          cov_out, s);
+}
+
 }  // namespace gpxb
 
 using gpxb::Ctx;
@@ -544,6 +663,23 @@ int gpxb_gpr_predict_y_derivs(gpxb_ctx* ctx, int kind, const double* x_train, co
   GPXB_ARG_CHECK(ctx && x_train && jaccoef && x && mean_out, -1);
   return gpxb::gpr_predict_y_derivs(reinterpret_cast<Ctx*>(ctx), kind, x_train, jaccoef, N, nf, x, ns, ell, mu,
                                     mean_out, (cudaStream_t)stream);
+}
+
+int gpxb_gpr_predict_derivs_full(gpxb_ctx* ctx, int kind, const double* x_train, const double* J_train, int N, int nf,
+                                 int nv, const double* x, const double* J, int ns, int nvs, const double* c,
+                                 double mu, double ell, double sigma, double* mean_out, double* cov_out,
+                                 gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x_train && J_train && x && J && c && mean_out, -1);
+  return gpxb::gpr_predict_derivs_full(reinterpret_cast<Ctx*>(ctx), kind, x_train, J_train, N, nf, nv, x, J, ns, nvs,
+                                       c, mu, ell, sigma, mean_out, cov_out, (cudaStream_t)stream);
+}
+
+int gpxb_gpr_predict_y_derivs_full(gpxb_ctx* ctx, int kind, const double* x_train, const double* J_train, int N,
+                                   int nf, int nv, const double* x, int ns, const double* c, double mu, double ell,
+                                   double sigma, double* mean_out, double* cov_out, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x_train && J_train && x && c && mean_out, -1);
+  return gpxb::gpr_predict_y_derivs_full(reinterpret_cast<Ctx*>(ctx), kind, x_train, J_train, N, nf, nv, x, ns, c, mu,
+                                         ell, sigma, mean_out, cov_out, (cudaStream_t)stream);
 }
 
 int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,

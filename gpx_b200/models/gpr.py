@@ -186,9 +186,16 @@ def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):
     mu + sum_s d01kjc(x_train, x, jaccoef, jacobian)[s], reshaped (ns, nv)."""
     if not getattr(state, "is_fitted_derivs", False):
         raise RuntimeError("Model is not fitted on derivatives. Run `fit_derivs` first.")
-    if full_covariance:
-        raise NotImplementedError("predictive covariance of derivative values is a 'next' row (SURVEY.md 8f N2)")
     import torch
+
+    if full_covariance:
+        # the reference returns the unreshaped (ns*nv, 1) mean beside the covariance (_gpr.py:552-556)
+        kernel, ell, sigma = _hyper(state)
+        xs, _, Js = _xyj(state, x, None, jacobian)
+        mean, cov = ops.gpr_predict_derivs_full(kernel.kind, _to_device(state.x_train), _to_device(state.jacobian_train),
+                                                xs, Js, _to_device(state.c).reshape(-1), ell, sigma, float(state.mu),
+                                                full_covariance=True)
+        return mean.cpu().numpy().reshape(-1, 1), cov.cpu().numpy()
 
     kernel, ell, _ = _hyper(state)
     xt = _to_device(state.x_train)
@@ -208,11 +215,15 @@ def predict_y_derivs(state, x, full_covariance=False, iterative=False):
         raise RuntimeError("Model is not fitted. Run `fit_derivs` to fit the model before prediction.")
     if full_covariance and iterative:
         raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
-    if full_covariance:
-        raise NotImplementedError("predictive covariance of a derivative-trained model is a 'next' row (SURVEY.md 8f N2)")
-    kernel, ell, _ = _hyper(state)
+    kernel, ell, sigma = _hyper(state)
     if kernel.active_dims is not None:
         raise NotImplementedError("active_dims with derivative training is not supported")
+    if full_covariance:
+        mean, cov = ops.gpr_predict_y_derivs_full(kernel.kind, _to_device(state.x_train),
+                                                  _to_device(state.jacobian_train), _to_device(x),
+                                                  _to_device(state.c).reshape(-1), ell, sigma, float(state.mu),
+                                                  full_covariance=True)
+        return mean.cpu().numpy().reshape(-1, 1), cov.cpu().numpy()
     out = ops.gpr_predict_y_derivs(kernel.kind, _to_device(state.x_train), _to_device(state.jaccoef), _to_device(x),
                                    ell, float(state.mu))
     return out.cpu().numpy().reshape(-1, 1)

@@ -211,6 +211,40 @@ def gpr_predict_y_derivs(kind, x_train, jaccoef, x, ell, mu=0.0):
     return out
 
 
+def gpr_predict_derivs_full(kind, x_train, J_train, x, J, c, ell, sigma, mu=0.0, full_covariance=False):
+    """Derivative values from the uncontracted coefficients: mean (ns*nvs,) [, covariance (ns*nvs, ns*nvs)]."""
+    ctx = context()
+    x_train, J_train, x, J, c = _f64(x_train), _f64(J_train), _f64(x), _f64(J), _f64(c)
+    N, nf, nv = J_train.shape
+    ns, _, nvs = J.shape
+    mean = torch.empty(ns * nvs, dtype=torch.float64, device=x.device)
+    cov = torch.empty((ns * nvs, ns * nvs), dtype=torch.float64, device=x.device) if full_covariance else None
+    check(
+        ctx.lib.gpxb_gpr_predict_derivs_full(ctx.handle, _kind(kind), ptr(x_train), ptr(J_train), N, nf, nv, ptr(x),
+                                             ptr(J), ns, nvs, ptr(c), float(mu), float(ell), float(sigma), ptr(mean),
+                                             ptr(cov) if cov is not None else None, stream_ptr()),
+        "gpxb_gpr_predict_derivs_full",
+    )
+    return (mean, cov) if full_covariance else mean
+
+
+def gpr_predict_y_derivs_full(kind, x_train, J_train, x, c, ell, sigma, mu=0.0, full_covariance=False):
+    """Target values from the uncontracted coefficients: mean (ns,) [, covariance (ns, ns)]."""
+    ctx = context()
+    x_train, J_train, x, c = _f64(x_train), _f64(J_train), _f64(x), _f64(c)
+    N, nf, nv = J_train.shape
+    ns = x.shape[0]
+    mean = torch.empty(ns, dtype=torch.float64, device=x.device)
+    cov = torch.empty((ns, ns), dtype=torch.float64, device=x.device) if full_covariance else None
+    check(
+        ctx.lib.gpxb_gpr_predict_y_derivs_full(ctx.handle, _kind(kind), ptr(x_train), ptr(J_train), N, nf, nv, ptr(x),
+                                               ns, ptr(c), float(mu), float(ell), float(sigma), ptr(mean),
+                                               ptr(cov) if cov is not None else None, stream_ptr()),
+        "gpxb_gpr_predict_y_derivs_full",
+    )
+    return (mean, cov) if full_covariance else mean
+
+
 def gpr_fit_derivs(kind, x, J, y, ell, sigma):
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)

@@ -89,6 +89,20 @@ int gpxb_gpr_predict_y_derivs(gpxb_ctx* ctx, int kind, const double* x_train, co
                               const double* x, int ns, double ell, double mu, double* mean_out,
                               gpxb_stream stream);
 
+/* Predictions of a derivative-trained model from the uncontracted coefficients c[N nv], with the optional
+ * full predictive covariance (cov_out may be NULL):
+ *  - derivative values (_predict_derivs_dense, gpx/models/_gpr.py:488-560): mean[ns nvs] = mu + d01kj(x, x_train) c,
+ *    cov[(ns nvs)^2] = d01kj(x, x) - G^T G, G = chol(d01kj(x_train) + (sigma^2+1e-10) I)^-1 d01kj(x_train, x);
+ *  - target values (_predict_y_derivs_dense, :608-660): mean[ns] = mu + d0kj(x_train, x, J_train)^T c,
+ *    cov[ns^2] = k(x, x) - G^T G with G = chol(d01kj(x_train) + sigma^2 I)^-1 d0kj(x_train, x, J_train). */
+int gpxb_gpr_predict_derivs_full(gpxb_ctx* ctx, int kind, const double* x_train, const double* J_train, int N, int nf,
+                                 int nv, const double* x, const double* J, int ns, int nvs, const double* c,
+                                 double mu, double ell, double sigma, double* mean_out, double* cov_out,
+                                 gpxb_stream stream);
+int gpxb_gpr_predict_y_derivs_full(gpxb_ctx* ctx, int kind, const double* x_train, const double* J_train, int N,
+                                   int nf, int nv, const double* x, int ns, const double* c, double mu, double ell,
+                                   double sigma, double* mean_out, double* cov_out, gpxb_stream stream);
+
 /* ---- Family 2: blocked FP64 Cholesky / TRSM / log-det / inverse ---------------------- */
 /* C[M x N] = alpha * op(A) * op(B) + beta * C on the FP64 tensor pipe.  transa = 0: A is M x K
  * row-major; 1: A is stored K x M.  transb = 0: B is K x N row-major; 1: B is stored N x K. */

@@ -303,6 +303,45 @@ def d0kjc(kind: str, x1, x2, ell: float, jaccoef):
     return np.einsum("sf,stf->st", jaccoef, g)
 
 
+def d0kj(kind: str, x1, x2, ell: float, J1):
+    """Kernel.d0kj -> (ns1*nv, ns2).  SE: grad_kernelize(argnums=0, with_jacob) of the pair kernel
+    kernels.py:731-737, 1459-1462; Matern-5/2: the hand-written kernels.py:1108-1149 (d2 from squared_distances,
+    i.e. with the 1e-12 jitter)."""
+    ns1, nf = x1.shape
+    nv = J1.shape[2]
+    z1, z2 = x1 / ell, x2 / ell
+    dz = z1[:, None, :] - z2[None, :, :]
+    if kind == "se":
+        d0k = -(2.0 / ell) * dz * np.exp(-np.sum(dz**2, axis=2))[:, :, None]
+    elif kind == "m52":
+        d2 = squared_distances(z1, z2)
+        d = np.sqrt(5.0) * np.sqrt(np.maximum(d2, 1e-36))
+        d0k = -(np.sqrt(5.0) / (3.0 * ell)) * ((1.0 + d) * np.exp(-d))[:, :, None] * (np.sqrt(5.0) * dz)
+    else:
+        raise ValueError(kind)
+    return np.einsum("sfv,stf->svt", J1, d0k).reshape(ns1 * nv, x2.shape[0])
+
+
+def predict_derivs_dense_full(kind, x_train, J_train, x, J, c, mu, ell, sigma):
+    """_gpr.py:488-560 without jaccoef, full_covariance=True: returns (mu (ns*nv, 1), C_nn)."""
+    K_mn = d01kj(kind, x_train, x, ell, J_train, J)
+    mean = mu + K_mn.T @ c.reshape(-1, 1)
+    C_mm = d01kj(kind, x_train, x_train, ell, J_train, J_train) + (sigma**2 + 1e-10) * np.eye(K_mn.shape[0])
+    L = sla.cholesky(C_mm, lower=True, check_finite=False)
+    G = sla.solve_triangular(L, K_mn, lower=True, check_finite=False)
+    return mean, d01kj(kind, x, x, ell, J, J) - G.T @ G
+
+
+def predict_y_derivs_dense_full(kind, x_train, J_train, x, c, mu, ell, sigma):
+    """_gpr.py:608-660 without jaccoef, full_covariance=True (sigma^2 I without the 1e-10, as written there)."""
+    K_mn = d0kj(kind, x_train, x, ell, J_train)
+    mean = mu + K_mn.T @ c.reshape(-1, 1)
+    C_mm = d01kj(kind, x_train, x_train, ell, J_train, J_train) + sigma**2 * np.eye(K_mn.shape[0])
+    L = sla.cholesky(C_mm, lower=True, check_finite=False)
+    G = sla.solve_triangular(L, K_mn, lower=True, check_finite=False)
+    return mean, kernel(kind, x, x, ell) - G.T @ G
+
+
 def predict_y_derivs_dense(kind, x_train, x, jaccoef, mu, ell):
     """_gpr.py:630-638 (contracted-jacobian fast path of _predict_y_derivs_dense)."""
     return (mu + np.sum(d0kjc(kind, x_train, x, ell, jaccoef), axis=0)).reshape(-1, 1)

@@ -158,6 +158,32 @@ def test_predict_y_derivs(kind, N, nf, ns):
     assert np.max(np.abs(out - ref)) < 1e-8 * max(1.0, np.max(np.abs(ref)))
 
 
+@pytest.mark.parametrize("kind,N,nf,nv,ns", [("se", 30, 6, 6, 7), ("m52", 25, 9, 4, 5), ("se", 12, 90, 90, 3)])
+def test_predict_derivs_and_targets_with_full_covariance(kind, N, nf, nv, ns):
+    """_predict_derivs_dense / _predict_y_derivs_dense with full_covariance=True (uncontracted coefficients)."""
+    from gpx_b200 import ops
+
+    x, J, y = _xj(N, nf, nv, 21)
+    xs, Js, _ = _xj(ns, nf, nv, 22)
+    ell, sigma = 0.9 * np.sqrt(nf), 0.1
+    c_ref, _, jc_ref = R.fit_derivs_dense(kind, x, y, J, ell, sigma)
+    m_ref, C_ref = R.predict_derivs_dense_full(kind, x, J, xs, Js, c_ref, 0.0, ell, sigma)
+    mean, cov = ops.gpr_predict_derivs_full(kind, dev(x), dev(J), dev(xs), dev(Js), dev(c_ref[:, 0]), ell, sigma,
+                                            full_covariance=True)
+    assert np.max(np.abs(host(mean) - m_ref[:, 0])) < 1e-8 * np.max(np.abs(m_ref))
+    assert np.max(np.abs(host(cov) - C_ref)) < 1e-8 * np.max(np.abs(C_ref))
+    only = ops.gpr_predict_derivs_full(kind, dev(x), dev(J), dev(xs), dev(Js), dev(c_ref[:, 0]), ell, sigma)
+    assert np.array_equal(host(only), host(mean))
+    my_ref, Cy_ref = R.predict_y_derivs_dense_full(kind, x, J, xs, c_ref, 0.25, ell, sigma)
+    ymean, ycov = ops.gpr_predict_y_derivs_full(kind, dev(x), dev(J), dev(xs), dev(c_ref[:, 0]), ell, sigma, mu=0.25,
+                                                full_covariance=True)
+    assert np.max(np.abs(host(ymean) - my_ref[:, 0])) < 1e-8 * np.max(np.abs(my_ref))
+    assert np.max(np.abs(host(ycov) - Cy_ref)) < 1e-8 * max(1.0, np.max(np.abs(Cy_ref)))
+    # the contracted fast path gives the same mean
+    fast = host(ops.gpr_predict_y_derivs(kind, dev(x), dev(jc_ref), dev(xs), ell, 0.25))
+    assert np.max(np.abs(fast - my_ref[:, 0])) < 1e-8 * np.max(np.abs(my_ref))
+
+
 def test_facade_fit_and_predict_derivs():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import GPR
@@ -182,6 +208,13 @@ def test_facade_fit_and_predict_derivs():
     # the contracted route of the reference (d01kjc) gives the same numbers
     ref_c = R.d01kjc("se", x, xs, ell, jc_ref, Js).sum(0).reshape(11, nv)
     assert np.max(np.abs(pred - ref_c)) < 1e-8 * np.max(np.abs(ref_c))
+    mu_c, cov_c = m.predict_derivs(xs, Js, full_covariance=True)
+    m_ref, C_ref = R.predict_derivs_dense_full("se", x, J, xs, Js, c_ref, 0.0, ell, sigma)
+    assert mu_c.shape == (11 * nv, 1) and np.max(np.abs(cov_c - C_ref)) < 1e-8 * np.max(np.abs(C_ref))
+    assert np.max(np.abs(mu_c - m_ref)) < 1e-8 * np.max(np.abs(m_ref))
+    y_c, ycov_c = m.predict_y_derivs(xs, full_covariance=True)
+    my_ref, Cy_ref = R.predict_y_derivs_dense_full("se", x, J, xs, c_ref, 0.0, ell, sigma)
+    assert np.max(np.abs(ycov_c - Cy_ref)) < 1e-8 and np.max(np.abs(y_c - my_ref)) < 1e-8 * np.max(np.abs(my_ref))
     yp = m.predict_y_derivs(xs)
     ref_y = R.predict_y_derivs_dense("se", x, xs, jc_ref, 0.0, ell)
     assert yp.shape == (11, 1) and np.max(np.abs(yp - ref_y)) < 1e-8 * np.max(np.abs(ref_y))
