@@ -509,6 +509,161 @@ int gpr_predict_y_derivs(Ctx* ctx, int kind, const double* x_train, const double
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Matrix-free Hessian-kernel operator  W = (d01kj(x1, x2; J1, J2) [+ diag_add I]) V   (replaces
+// _Ax_derivs_lhs_fun, gpx/models/_gpr.py:122-152: one kernel ROW of (N nv) entries per lax.scan step).
+// With m_t = sum_u A2_(t,u) V_(t,u) (the contracted jacobian of V) the sum over the (t, u) columns collapses to
+//   (H V)_(s,v) = A1_(s,v) . h_s,   h_s = sum_t [ c1_st m_t - kappa^2 c2_st (m_t . D_st) D_st ],  D_st = x1_s - x2_t,
+// i.e. h = C1 M - (rowsum(E) o X1 - E X2) with E = kappa^2 C2 o (X1 M^T - 1 r^T), r_t = m_t . x2_t:
+// three (N1 x N2 x nf) GEMMs on the configuration level instead of an (N1 nv)(N2 nv) nf product.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void rowdot_kernel(const double* __restrict__ A, const double* __restrict__ B, int n, int d,
+                              double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int f = 0; f < d; ++f) a += A[(long long)i * d + f] * B[(long long)i * d + f];
+  out[i] = a;
+}
+// R[s][t] <- kappa2 * C2[s][t] * (R[s][t] - r[t])
+__global__ void hessop_e_kernel(double* __restrict__ R, const double* __restrict__ C2, const double* __restrict__ r,
+                                long long n1, int n2, double kappa2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n1 * n2) return;
+  R[idx] = kappa2 * C2[idx] * (R[idx] - r[idx % n2]);
+}
+// X2e[t] = (x2[t][0..nf), 1)
+__global__ void append_one_kernel(const double* __restrict__ x, int n, int d, double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * (d + 1)) return;
+  const int i = (int)(idx / (d + 1)), c = (int)(idx % (d + 1));
+  out[idx] = c < d ? x[(long long)i * d + c] : 1.0;
+}
+// W[(s,v)] = sum_f J1[s][f][v] (H1[s][f] - (H2[s][nf] x1[s][f] - H2[s][f])) + diag_add * V[(s,v)]
+__global__ void hessop_out_kernel(const double* __restrict__ J1, const double* __restrict__ x1,
+                                  const double* __restrict__ H1, const double* __restrict__ H2, int N1, int nf, int nv,
+                                  double diag_add, const double* __restrict__ V, long long ldv,
+                                  double* __restrict__ W, long long ldw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N1 * nv) return;
+  const int sidx = (int)(i / nv), v = (int)(i % nv);
+  const double* Js = J1 + (long long)sidx * nf * nv + v;
+  const double* h1 = H1 + (long long)sidx * nf;
+  const double* h2 = H2 + (long long)sidx * (nf + 1);
+  const double* xs = x1 + (long long)sidx * nf;
+  const double rs = h2[nf];
+  double a = 0.0;
+  for (int f = 0; f < nf; ++f) a += Js[(long long)f * nv] * (h1[f] - (rs * xs[f] - h2[f]));
+  if (diag_add != 0.0) a += diag_add * V[i * ldv];
+  W[i * ldw] = a;
+}
+// strided jaccoef: M[t][f] = sum_u J[t][f][u] V[(t nv + u) ldv]
+__global__ void jaccoef_strided_kernel(const double* __restrict__ V, long long ldv, const double* __restrict__ J, int N,
+                                       int nf, int nv, double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * nf) return;
+  const int t = (int)(idx / nf);
+  const double* Jr = J + idx * nv;
+  double a = 0.0;
+  for (int u = 0; u < nv; ++u) a += V[((long long)t * nv + u) * ldv] * Jr[u];
+  out[idx] = a;
+}
+}  // namespace
+
+struct HessOp {
+  int kind = 0, N1 = 0, nv1 = 0, N2 = 0, nv2 = 0, nf = 0;
+  const double *x1 = nullptr, *J1 = nullptr, *x2 = nullptr, *J2 = nullptr;
+  double ell = 1.0, kappa2 = 0.0, diag_add = 0.0;
+  DevBuf C1, C2, X2e, M, r, R, H1, H2;
+  long long rows() const { return (long long)N1 * nv1; }
+  long long cols() const { return (long long)N2 * nv2; }
+};
+
+int hess_op_prepare(Ctx* ctx, HessOp& op, cudaStream_t s) {
+  GPXB_ARG_CHECK(op.kind == KIND_SE || op.kind == KIND_M52, -50);
+  GPXB_ARG_CHECK(op.N1 > 0 && op.N2 > 0 && op.nv1 > 0 && op.nv2 > 0 && op.nf > 0, -51);
+  const ZLayout zl = z_layout(op.nf);
+  const bool sym = (op.x1 == op.x2) && (op.J1 == op.J2) && (op.N1 == op.N2) && (op.nv1 == op.nv2);
+  const double kappa = (op.kind == KIND_SE) ? 2.0 / (op.ell * op.ell) : 2.23606797749979 / op.ell;
+  op.kappa2 = kappa * kappa;
+  const size_t nn = (size_t)op.N1 * op.N2;
+  DevBuf bZ1, bZ2;
+  GPXB_TRY(bZ1.alloc(sizeof(double) * (size_t)op.N1 * zl.S, s));
+  GPXB_TRY(bZ2.alloc(sizeof(double) * (size_t)op.N2 * zl.S, s));
+  GPXB_TRY(op.C1.alloc(sizeof(double) * nn, s));
+  GPXB_TRY(op.C2.alloc(sizeof(double) * nn, s));
+  GPXB_TRY(op.R.alloc(sizeof(double) * nn, s));
+  GPXB_TRY(op.X2e.alloc(sizeof(double) * (size_t)op.N2 * (op.nf + 1), s));
+  GPXB_TRY(op.M.alloc(sizeof(double) * (size_t)op.N2 * op.nf, s));
+  GPXB_TRY(op.r.alloc(sizeof(double) * (size_t)op.N2, s));
+  GPXB_TRY(op.H1.alloc(sizeof(double) * (size_t)op.N1 * op.nf, s));
+  GPXB_TRY(op.H2.alloc(sizeof(double) * (size_t)op.N1 * (op.nf + 1), s));
+  GPXB_TRY(prep_z(ctx, op.x1, op.nf, op.N1, zl, op.ell, bZ1.as<double>(), s));
+  GPXB_TRY(prep_z(ctx, op.x2, op.nf, op.N2, zl, op.ell, bZ2.as<double>(), s));
+  pair_coef_kernel<<<ceil_div((long long)nn, 256), 256, 0, s>>>(bZ1.as<double>(), op.N1, bZ2.as<double>(), op.N2, zl.S,
+                                                                 zl.Dp, op.kind, op.ell, sym ? 1 : 0, 0,
+                                                                 op.C1.as<double>(), op.C2.as<double>());
+  GPXB_LAUNCHED(ctx);
+  append_one_kernel<<<ceil_div((long long)op.N2 * (op.nf + 1), 256), 256, 0, s>>>(op.x2, op.N2, op.nf,
+                                                                                    op.X2e.as<double>());
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
+// one column: W[i * ldw] = (H V)[i] + diag_add V[i] (diag_add only makes sense for the symmetric operator)
+int hess_op_apply(Ctx* ctx, HessOp& op, const double* V, long long ldv, double* W, long long ldw, cudaStream_t s) {
+  const int N1 = op.N1, N2 = op.N2, nf = op.nf;
+  double *M = op.M.as<double>(), *R = op.R.as<double>();
+  jaccoef_strided_kernel<<<ceil_div((long long)N2 * nf, 256), 256, 0, s>>>(V, ldv, op.J2, N2, nf, op.nv2, M);
+  GPXB_LAUNCHED(ctx);
+  rowdot_kernel<<<ceil_div(N2, 128), 128, 0, s>>>(M, op.x2, N2, nf, op.r.as<double>());
+  GPXB_LAUNCHED(ctx);
+  {
+    GemmArgs g;  // R = X1 M^T
+    g.M = N1; g.N = N2; g.K = nf;
+    g.A = op.x1; g.lda = nf; g.a_kmajor = true;
+    g.B = M; g.ldb = nf; g.b_kmajor = true;
+    g.C = R; g.ldc = N2;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  hessop_e_kernel<<<ceil_div((long long)N1 * N2, 256), 256, 0, s>>>(R, op.C2.as<double>(), op.r.as<double>(), N1, N2,
+                                                                     op.kappa2);
+  GPXB_LAUNCHED(ctx);
+  {
+    GemmArgs g;  // H1 = C1 M
+    g.M = N1; g.N = nf; g.K = N2;
+    g.A = op.C1.as<double>(); g.lda = N2; g.a_kmajor = true;
+    g.B = M; g.ldb = nf; g.b_kmajor = false;
+    g.C = op.H1.as<double>(); g.ldc = nf;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  {
+    GemmArgs g;  // H2 = E [X2 | 1]
+    g.M = N1; g.N = nf + 1; g.K = N2;
+    g.A = R; g.lda = N2; g.a_kmajor = true;
+    g.B = op.X2e.as<double>(); g.ldb = nf + 1; g.b_kmajor = false;
+    g.C = op.H2.as<double>(); g.ldc = nf + 1;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  hessop_out_kernel<<<ceil_div(op.rows(), 128), 128, 0, s>>>(op.J1, op.x1, op.H1.as<double>(), op.H2.as<double>(), N1, nf,
+                                                            op.nv1, op.diag_add, V, ldv, W, ldw);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
+int hess_matvec(Ctx* ctx, int kind, const double* x1, const double* J1, int N1, int nv1, const double* x2,
+                const double* J2, int N2, int nv2, int nf, double ell, double diag_add, const double* V,
+                long long ldv, int P, double* W, long long ldw, cudaStream_t s) {
+  HessOp op;
+  op.kind = kind; op.N1 = N1; op.nv1 = nv1; op.N2 = N2; op.nv2 = nv2; op.nf = nf;
+  op.x1 = x1; op.J1 = J1; op.x2 = x2; op.J2 = J2; op.ell = ell; op.diag_add = diag_add;
+  GPXB_ARG_CHECK(diag_add == 0.0 || op.rows() == op.cols(), -59);
+  GPXB_TRY(hess_op_prepare(ctx, op, s));
+  for (int p = 0; p < P; ++p) GPXB_TRY(hess_op_apply(ctx, op, V + p, ldv, W + p, ldw, s));
+  return 0;
+}
+
 namespace {
 __global__ void add_const_kernel(double* __restrict__ v, long long n, double c) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -680,6 +835,14 @@ int gpxb_gpr_predict_y_derivs_full(gpxb_ctx* ctx, int kind, const double* x_trai
   GPXB_ARG_CHECK(ctx && x_train && J_train && x && c && mean_out, -1);
   return gpxb::gpr_predict_y_derivs_full(reinterpret_cast<Ctx*>(ctx), kind, x_train, J_train, N, nf, nv, x, ns, c, mu,
                                          ell, sigma, mean_out, cov_out, (cudaStream_t)stream);
+}
+
+int gpxb_hess_matvec(gpxb_ctx* ctx, int kind, const double* x1, const double* J1, int n1, int nv1, const double* x2,
+                     const double* J2, int n2, int nv2, int nf, double ell, double diag_add, const double* V,
+                     long long ldv, int P, double* W, long long ldw, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x1 && J1 && x2 && J2 && V && W && P > 0, -1);
+  return gpxb::hess_matvec(reinterpret_cast<Ctx*>(ctx), kind, x1, J1, n1, nv1, x2, J2, n2, nv2, nf, ell, diag_add, V,
+                           ldv, P, W, ldw, (cudaStream_t)stream);
 }
 
 int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,

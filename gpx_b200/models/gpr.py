@@ -188,6 +188,8 @@ def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):
         raise RuntimeError("Model is not fitted on derivatives. Run `fit_derivs` first.")
     import torch
 
+    if full_covariance and iterative:
+        raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
     if full_covariance:
         # the reference returns the unreshaped (ns*nv, 1) mean beside the covariance (_gpr.py:552-556)
         kernel, ell, sigma = _hyper(state)
@@ -199,8 +201,14 @@ def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):
 
     kernel, ell, _ = _hyper(state)
     xt = _to_device(state.x_train)
-    jc = _to_device(state.jaccoef).unsqueeze(2).contiguous()  # (N, nf, 1): the contracted Jacobian
     xs, _, Js = _xyj(state, x, None, jacobian)
+    if iterative:
+        # _predict_derivs_iter (gpx/models/_gpr.py:563-605): the cross operator applied to c, never formed
+        ns, _, nv = Js.shape
+        mean = ops.hess_matvec(kernel.kind, xs, Js, xt, _to_device(state.jacobian_train),
+                               _to_device(state.c).reshape(-1), ell) + float(state.mu)
+        return mean.reshape(ns, nv).cpu().numpy()
+    jc = _to_device(state.jaccoef).unsqueeze(2).contiguous()  # (N, nf, 1): the contracted Jacobian
     K = ops.hess_gram(kernel.kind, xt, jc, xs, Js, ell)  # (N, ns*nv)
     ones = torch.ones((1, K.shape[0]), dtype=torch.float64, device="cuda")
     mean = ops.gemm(ones, K) + float(state.mu)

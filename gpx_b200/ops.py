@@ -245,6 +245,25 @@ def gpr_predict_y_derivs_full(kind, x_train, J_train, x, c, ell, sigma, mu=0.0, 
     return (mean, cov) if full_covariance else mean
 
 
+def hess_matvec(kind, x1, J1, x2, J2, V, ell, diag_add=0.0):
+    """(d01kj(x1, x2; J1, J2) [+ diag_add I]) V without forming the matrix; V: (n2*nv2, P) or (n2*nv2,)."""
+    ctx = context()
+    x1, J1, x2, J2, V = _f64(x1), _f64(J1), _f64(x2), _f64(J2), _f64(V)
+    one_d = V.dim() == 1
+    if one_d:
+        V = V.reshape(-1, 1)
+    n1, nf, nv1 = J1.shape
+    n2, _, nv2 = J2.shape
+    P = V.shape[1]
+    W = torch.empty((n1 * nv1, P), dtype=torch.float64, device=V.device)
+    check(
+        ctx.lib.gpxb_hess_matvec(ctx.handle, _kind(kind), ptr(x1), ptr(J1), n1, nv1, ptr(x2), ptr(J2), n2, nv2, nf,
+                                 float(ell), float(diag_add), ptr(V), V.stride(0), P, ptr(W), W.stride(0), stream_ptr()),
+        "gpxb_hess_matvec",
+    )
+    return W.reshape(-1) if one_d else W
+
+
 def gpr_fit_derivs(kind, x, J, y, ell, sigma):
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)

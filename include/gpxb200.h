@@ -89,6 +89,13 @@ int gpxb_gpr_predict_y_derivs(gpxb_ctx* ctx, int kind, const double* x_train, co
                               const double* x, int ns, double ell, double mu, double* mean_out,
                               gpxb_stream stream);
 
+/* W[(n1 nv1) x P] = (d01kj(x1, x2; J1, J2) [+ diag_add I]) V without forming the matrix: _Ax_derivs_lhs_fun
+ * (gpx/models/_gpr.py:122-152; rowfun_to_matvec, gpx/operations.py:54-123).  The sum over the (sample,
+ * variable) columns collapses onto the contracted jacobian of V, so the cost is three (n1 x n2 x nf) GEMMs
+ * per column instead of an (n1 nv1)(n2 nv2) nf product.  diag_add needs identical operands. */
+int gpxb_hess_matvec(gpxb_ctx* ctx, int kind, const double* x1, const double* J1, int n1, int nv1, const double* x2,
+                     const double* J2, int n2, int nv2, int nf, double ell, double diag_add, const double* V,
+                     long long ldv, int P, double* W, long long ldw, gpxb_stream stream);
 /* Predictions of a derivative-trained model from the uncontracted coefficients c[N nv], with the optional
  * full predictive covariance (cov_out may be NULL):
  *  - derivative values (_predict_derivs_dense, gpx/models/_gpr.py:488-560): mean[ns nvs] = mu + d01kj(x, x_train) c,

@@ -184,6 +184,26 @@ def test_predict_derivs_and_targets_with_full_covariance(kind, N, nf, nv, ns):
     assert np.max(np.abs(fast - my_ref[:, 0])) < 1e-8 * np.max(np.abs(my_ref))
 
 
+@pytest.mark.parametrize("kind", ["se", "m52"])
+@pytest.mark.parametrize("N1,N2,nf,nv1,nv2,P", [(30, 30, 6, 6, 6, 3), (17, 40, 9, 4, 9, 1), (8, 5, 90, 90, 90, 2), (5, 5, 1, 1, 1, 1)])
+def test_matrix_free_hessian_operator(kind, N1, N2, nf, nv1, nv2, P):
+    """_Ax_derivs_lhs_fun collapsed onto the configuration level against the dense Hessian kernel."""
+    from gpx_b200 import ops
+
+    x1, J1, _ = _xj(N1, nf, nv1, 31)
+    x2, J2, _ = _xj(N2, nf, nv2, 32)
+    V = np.random.default_rng(5).standard_normal((N2 * nv2, P))
+    ell = 0.9 * np.sqrt(nf)
+    ref = R.d01kj(kind, x1, x2, ell, J1, J2) @ V
+    out = host(ops.hess_matvec(kind, dev(x1), dev(J1), dev(x2), dev(J2), dev(V), ell))
+    assert np.max(np.abs(out - ref)) < 1e-10 * max(1.0, np.max(np.abs(ref)))
+    if N1 == N2 and nv1 == nv2:  # the symmetric operator with the noise shift
+        xd, Jd = dev(x1), dev(J1)
+        refs = (R.d01kj(kind, x1, x1, ell, J1, J1) + 0.3 * np.eye(N1 * nv1)) @ V
+        outs = host(ops.hess_matvec(kind, xd, Jd, xd, Jd, dev(V), ell, diag_add=0.3))
+        assert np.max(np.abs(outs - refs)) < 1e-10 * max(1.0, np.max(np.abs(refs)))
+
+
 def test_facade_fit_and_predict_derivs():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import GPR
@@ -208,6 +228,8 @@ def test_facade_fit_and_predict_derivs():
     # the contracted route of the reference (d01kjc) gives the same numbers
     ref_c = R.d01kjc("se", x, xs, ell, jc_ref, Js).sum(0).reshape(11, nv)
     assert np.max(np.abs(pred - ref_c)) < 1e-8 * np.max(np.abs(ref_c))
+    pred_it = m.predict_derivs(xs, Js, iterative=True)
+    assert np.max(np.abs(pred_it - ref_pred)) < 1e-8 * np.max(np.abs(ref_pred))
     mu_c, cov_c = m.predict_derivs(xs, Js, full_covariance=True)
     m_ref, C_ref = R.predict_derivs_dense_full("se", x, J, xs, Js, c_ref, 0.0, ell, sigma)
     assert mu_c.shape == (11 * nv, 1) and np.max(np.abs(cov_c - C_ref)) < 1e-8 * np.max(np.abs(C_ref))
