@@ -23,6 +23,7 @@
 #include "gram.cuh"
 #include "matvec.cuh"
 #include "mma.cuh"
+#include "rpchol.cuh"
 #include "small_kernels.cuh"
 
 namespace gpxb {
@@ -664,6 +665,147 @@ int hess_matvec(Ctx* ctx, int kind, const double* x1, const double* J1, int N1, 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Iterative derivative-GPR: PCG fit with the rpcholesky_derivs preconditioner and the SLQ log-determinant
+// on the matrix-free Hessian operator (_fit_derivs_iter gpx/models/_gpr.py:347-390, _precond_rpcholesky_derivs
+// :219-256, rpcholesky_derivs gpx/kernels/approximations.py:132-242, _lml_derivs_iter _gpr.py:873-935).
+// Replicas only: the operator costs O(N^2 nf) per product, there is nothing worth sharding.
+// ------------------------------------------------------------------------------------------------
+int precond_build(Ctx* ctx, const double* F, long long ldf, int k, int n_loc, double sigma, double* Pkk,
+                  cudaStream_t s);
+int pcg_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+             const double* b, const double* F, long long ldf, int k, const double* Pkk, double sigma, double tol,
+             double atol, int maxiter, double* x, int* iters_out, cudaStream_t s);
+int lanczos_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+                 const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
+                 cudaStream_t s);
+
+namespace {
+// diag0[(s,v)] = d01kj(x_s, x_s, J_s, J_s)[v][v] = c1(d2 = 1e-12) |A_(s,v)|^2
+__global__ void hess_diag_kernel(const double* __restrict__ AJ, int S, int nf, long long n, double c1_0,
+                                 double* __restrict__ diag0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* a = AJ + i * S;
+  double q = 0.0;
+  for (int f = 0; f < nf; ++f) q += a[f] * a[f];
+  diag0[i] = c1_0 * q;
+}
+// col[(t,u)] = d01kj(x_s1, x, J_s1, J)[v1][(t,u)] for the pivot row (s1, v1) = pbuf[0]; its A row is pbuf[2..]
+__global__ void hess_column_kernel(const double* __restrict__ AJ, int S, const double* __restrict__ X, int nf, int nv,
+                                   long long n, int kind, double ell, const double* __restrict__ pbuf,
+                                   double* __restrict__ col) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const long long piv = (long long)pbuf[0];
+  const long long s1 = piv / nv, t = r / nv;
+  const double* a = pbuf + 2;
+  const double* ar = AJ + r * S;
+  const double* xt = X + t * nf;
+  const double* xs = X + s1 * nf;
+  double dd = 0.0, ara = 0.0, ard = 0.0, ad = 0.0;
+  for (int f = 0; f < nf; ++f) {
+    const double d = xt[f] - xs[f];
+    dd += d * d;
+    ara += ar[f] * a[f];
+    ard += ar[f] * d;
+    ad += a[f] * d;
+  }
+  double d2 = dd / (ell * ell) + 1e-12;
+  if (t == s1) d2 = 1e-12;
+  double c1, c2, kappa;
+  if (kind == KIND_SE) {
+    c2 = exp(-d2);
+    kappa = 2.0 / (ell * ell);
+    c1 = kappa * c2;
+  } else {
+    const double d = 2.23606797749979 * sqrt(fmax(d2, 1e-36));
+    c2 = (5.0 / (3.0 * ell * ell)) * exp(-d);
+    c1 = c2 * (1.0 + d);
+    kappa = 2.23606797749979 / ell;
+  }
+  col[r] = c1 * ara - kappa * kappa * c2 * ard * ad;
+}
+}  // namespace
+
+// c[n] = (d01kj + (sigma^2+1e-10) I)^-1 y by PCG (tol, atol as jax.scipy.sparse.linalg.cg); n_pivots = 0: no
+// preconditioner.  lanczos_* (optional): also run the m-step block Lanczos on the same operator for the P
+// start vectors U (n x ldu), as _lml_derivs_iter does after the fit.
+int gpr_derivs_iter(Ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf, int nv,
+                    double ell, double sigma, int n_pivots, const uint32_t key[2], int partitionable, double tol,
+                    double atol, int maxiter, double* c_out, double* jaccoef_out, int* iters_out, const double* U,
+                    long long ldu, int P, int m, double* alpha_out, double* beta_out, int* flag, cudaStream_t s) {
+  GPXB_ARG_CHECK(ctx->world == 1, -61);  // replicas only
+  const long long n = (long long)N * nv;
+  GPXB_ARG_CHECK(n > 0 && n < (1LL << 31) && n_pivots >= 0, -1);
+  const double s2 = sigma * sigma + 1e-10;
+  HessOp op;
+  op.kind = kind; op.N1 = N; op.nv1 = nv; op.N2 = N; op.nv2 = nv; op.nf = nf;
+  op.x1 = x; op.J1 = J; op.x2 = x; op.J2 = J; op.ell = ell; op.diag_add = s2;
+  GPXB_TRY(hess_op_prepare(ctx, op, s));
+  if (c_out) {
+    DevBuf bAJ, bD0, bCol, bFB, bFT, bPiv, bPkk;
+    const long long ldf = (n + 1) / 2 * 2;
+    const int k = n_pivots;
+    if (k > 0) {
+      const ZLayout zl = z_layout(nf);
+      GPXB_TRY(bAJ.alloc(sizeof(double) * (size_t)n * zl.S, s));
+      GPXB_TRY(bD0.alloc(sizeof(double) * (size_t)n, s));
+      GPXB_TRY(bCol.alloc(sizeof(double) * (size_t)n, s));
+      GPXB_TRY(bFB.alloc(sizeof(double) * std::max<size_t>(rp_factor_doubles((int)n, k), 8), s));
+      GPXB_TRY(bFT.alloc(sizeof(double) * (size_t)k * ldf, s));
+      GPXB_TRY(bPiv.alloc(sizeof(long long) * k, s));
+      GPXB_TRY(bPkk.alloc(sizeof(double) * (size_t)k * k, s));
+      double *AJ = bAJ.as<double>(), *col = bCol.as<double>();
+      prep_hess_kernel<<<ceil_div(n, 128), 128, 0, s>>>(x, J, N, nf, nv, zl.S, zl.Dp, AJ);
+      GPXB_LAUNCHED(ctx);
+      double c1_0;
+      if (kind == KIND_SE) c1_0 = (2.0 / (ell * ell)) * std::exp(-1e-12);
+      else {
+        const double d = 2.23606797749979 * 1e-6;
+        c1_0 = (5.0 / (3.0 * ell * ell)) * std::exp(-d) * (1.0 + d);
+      }
+      hess_diag_kernel<<<ceil_div(n, 256), 256, 0, s>>>(AJ, zl.S, nf, n, c1_0, bD0.as<double>());
+      GPXB_LAUNCHED(ctx);
+      RpColumnGen gen = [&](const double* pbuf, cudaStream_t st) -> int {
+        hess_column_kernel<<<ceil_div(n, 256), 256, 0, st>>>(AJ, zl.S, x, nf, nv, n, kind, ell, pbuf, col);
+        GPXB_LAUNCHED(ctx);
+        return 0;
+      };
+      GPXB_TRY(rpcholesky_ext(ctx, AJ, (int)n, zl, bD0.as<double>(), col, gen, key, k, partitionable,
+                              bFB.as<double>(), bPiv.as<long long>(), s));
+      GPXB_TRY(rp_unblock_transposed(ctx, bFB.as<double>(), (int)n, k, bFT.as<double>(), ldf, s));
+      bFB.release();
+      GPXB_TRY(precond_build(ctx, bFT.as<double>(), ldf, k, (int)n, sigma, bPkk.as<double>(), s));
+    }
+    auto apply = [&](const double* p, double* Ap) -> int { return hess_op_apply(ctx, op, p, 2, Ap, 1, s); };
+    GPXB_TRY(pcg_core(ctx, (int)n, n, apply, y, bFT.as<double>(), ldf, k, bPkk.as<double>(), sigma, tol, atol,
+                      maxiter > 0 ? maxiter : (int)std::min<long long>(10 * n, 2000000000LL), c_out, iters_out, s));
+    if (jaccoef_out) {
+      jaccoef_kernel<<<ceil_div((long long)N * nf, 256), 256, 0, s>>>(c_out, J, N, nf, nv, jaccoef_out);
+      GPXB_LAUNCHED(ctx);
+    }
+  }
+  if (U && alpha_out) {
+    GPXB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    DevBuf up;
+    for (int c0 = 0; c0 < P; c0 += 32) {
+      const int pb = std::min(32, P - c0);
+      const int PS = v_padded_stride(pb);
+      GPXB_TRY(up.alloc(sizeof(double) * ((size_t)n * PS + 16), s));
+      GPXB_TRY(pack_v(ctx, U, ldu, (int)n, c0, pb, PS, up.as<double>(), s));
+      auto apply = [&](const double* v, double* w) -> int {
+        for (int p = 0; p < pb; ++p) GPXB_TRY(hess_op_apply(ctx, op, v + p, PS, w + p, PS, s));
+        return 0;
+      };
+      GPXB_TRY(lanczos_core(ctx, (int)n, n, apply, up.as<double>(), pb, PS, m, alpha_out + (size_t)c0 * m,
+                            beta_out + (size_t)c0 * m, flag, s));
+      up.release();
+    }
+  }
+  return 0;
+}
+
 namespace {
 __global__ void add_const_kernel(double* __restrict__ v, long long n, double c) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -843,6 +985,27 @@ int gpxb_hess_matvec(gpxb_ctx* ctx, int kind, const double* x1, const double* J1
   GPXB_ARG_CHECK(ctx && x1 && J1 && x2 && J2 && V && W && P > 0, -1);
   return gpxb::hess_matvec(reinterpret_cast<Ctx*>(ctx), kind, x1, J1, n1, nv1, x2, J2, n2, nv2, nf, ell, diag_add, V,
                            ldv, P, W, ldw, (cudaStream_t)stream);
+}
+
+int gpxb_gpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N,
+                             int nf, int nv, double ell, double sigma, int n_pivots, uint32_t key0, uint32_t key1,
+                             int partitionable, double tol, double atol, int maxiter, double* c_out,
+                             double* jaccoef_out, int* iters_out, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && y && c_out, -1);
+  const uint32_t key[2] = {key0, key1};
+  return gpxb::gpr_derivs_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, N, nf, nv, ell, sigma, n_pivots, key,
+                               partitionable, tol, atol, maxiter, c_out, jaccoef_out, iters_out, nullptr, 0, 0, 0,
+                               nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int gpxb_lanczos_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                        double sigma, const double* U, long long ldu, int P, int m, double* alpha_out,
+                        double* beta_out, int* breakdown_flag, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && U && alpha_out && beta_out && breakdown_flag && P > 0 && m > 0, -1);
+  const uint32_t key[2] = {0, 0};
+  return gpxb::gpr_derivs_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, nullptr, N, nf, nv, ell, sigma, 0, key, 1, 0.0,
+                               0.0, 0, nullptr, nullptr, nullptr, U, ldu, P, m, alpha_out, beta_out, breakdown_flag,
+                               (cudaStream_t)stream);
 }
 
 int gpxb_gpr_fit_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf,

@@ -8,6 +8,7 @@
 // P probes advance together as the columns of an N x P block, so one pass over the
 // recomputed kernel tiles serves every probe.
 #include <cmath>
+#include <functional>
 
 #include "../../include/gpxb200.h"
 #include "chol.cuh"
@@ -141,41 +142,27 @@ int coldot(Ctx* ctx, const double* X, const double* Y, int n, int PS, int P, dou
 //   U: normalised start block, local rows, padded stride PS.
 //   alpha_out / beta_out: [P][m] device.  T_p = tridiag(alpha_out[p], beta_out[p][0..m-2]).
 //   flag: device int set to 1 on breakdown (beta <= 1e-12).
-int lanczos_block(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
-                  ZLayout zl, double diag_add, const double* U, int P, int PS, int m, double* alpha_out,
-                  double* beta_out, int* flag, cudaStream_t s) {
+// apply(v, w): w = A v for this rank's rows; v, w are n_loc x PS blocks with P live columns.
+int lanczos_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+                 const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
+                 cudaStream_t s) {
   GPXB_ARG_CHECK(P >= 1 && P <= MAXP && m >= 1, -30);
   ctx->shard_N = N;
   const size_t blk = (size_t)n_loc * PS;
-  const size_t blk_all = (size_t)N * PS;
-  DevBuf bVecs, bW, bVall, bPart, bSc;
+  DevBuf bVecs, bW, bPart, bSc;
   GPXB_TRY(bVecs.alloc(sizeof(double) * blk * m, s));
   GPXB_TRY(bW.alloc(sizeof(double) * blk, s));
   GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)ceil_div(n_loc, RB) * MAXP, s));
   GPXB_TRY(bSc.alloc(sizeof(double) * MAXP * 4, s));
   double *vecs = bVecs.as<double>(), *W = bW.as<double>(), *part = bPart.as<double>();
   double *alpha = bSc.as<double>(), *nrm2 = alpha + MAXP, *coef = alpha + 2 * MAXP, *beta = alpha + 3 * MAXP;
-  // the mat-vec needs the full block V on every rank: all-gather when sharded
-  double* Vall = nullptr;
-  if (ctx->world > 1) {
-    GPXB_TRY(bVall.alloc(sizeof(double) * (blk_all + 16), s));
-    Vall = bVall.as<double>();
-  }
   GPXB_CUDA_CHECK(cudaMemcpyAsync(vecs, U, sizeof(double) * blk, cudaMemcpyDeviceToDevice, s));
   const int nthr = 256;
   const int nblk_e = ceil_div((long long)blk, nthr);
 
   for (int j = 0; j < m; ++j) {
     double* vj = vecs + blk * j;
-    const double* vfull = vj;
-    if (ctx->world > 1) {
-      GPXB_TRY(comm_allgather_rows(ctx, vj, Vall, n_loc, PS, s));
-      vfull = Vall;
-    }
-    KmvArgs a;
-    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
-    a.V = vfull; a.PS = PS; a.P = P; a.W = W; a.ldw = PS; a.diag_add = diag_add;
-    GPXB_TRY(kmatvec_launch(ctx, a, s));                        // w = A v_j
+    GPXB_TRY(apply(vj, W));                                      // w = A v_j
     GPXB_TRY(coldot(ctx, W, vj, n_loc, PS, P, part, alpha, s));  // alpha = w . v_j
     colaxpy_kernel<<<nblk_e, nthr, 0, s>>>(W, alpha, vj, beta, j > 0 ? vecs + blk * (j - 1) : nullptr, n_loc, PS,
                                            P);                  // w -= alpha v_j + beta v_{j-1}
@@ -203,6 +190,30 @@ int lanczos_block(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row
     }
   }
   return 0;
+}
+
+int lanczos_block(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
+                  ZLayout zl, double diag_add, const double* U, int P, int PS, int m, double* alpha_out,
+                  double* beta_out, int* flag, cudaStream_t s) {
+  // the mat-vec needs the full block V on every rank: all-gather when sharded
+  DevBuf bVall;
+  double* Vall = nullptr;
+  if (ctx->world > 1) {
+    GPXB_TRY(bVall.alloc(sizeof(double) * ((size_t)N * PS + 16), s));
+    Vall = bVall.as<double>();
+  }
+  auto apply = [&](const double* v, double* w) -> int {
+    const double* vfull = v;
+    if (ctx->world > 1) {
+      GPXB_TRY(comm_allgather_rows(ctx, v, Vall, n_loc, PS, s));
+      vfull = Vall;
+    }
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
+    a.V = vfull; a.PS = PS; a.P = P; a.W = w; a.ldw = PS; a.diag_add = diag_add;
+    return kmatvec_launch(ctx, a, s);
+  };
+  return lanczos_core(ctx, n_loc, N, apply, U, P, PS, m, alpha_out, beta_out, flag, s);
 }
 
 namespace {
@@ -524,11 +535,11 @@ int precond_build(Ctx* ctx, const double* F, long long ldf, int k, int n_loc, do
 
 // Solves (K + diag_add I) x = b (b: local rows, length n_loc).  F/Pkk: preconditioner (k may be 0:
 // identity).  Host-synchronous: one scalar read per iteration for the stopping test.
-int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
-              ZLayout zl, double diag_add, const double* b, const double* F, long long ldf, int k,
-              const double* Pkk, double sigma, double tol, double atol, int maxiter, double* x, int* iters_out,
-              cudaStream_t s) {
-  DevBuf bR, bZ, bP, bAp, bPart, bSc, bT, bPall;
+// apply(p, Ap): Ap[n_loc] = A p for this rank's rows; p is the local search direction stored with stride 2.
+int pcg_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+             const double* b, const double* F, long long ldf, int k, const double* Pkk, double sigma, double tol,
+             double atol, int maxiter, double* x, int* iters_out, cudaStream_t s) {
+  DevBuf bR, bZ, bP, bAp, bPart, bSc, bT;
   ctx->shard_N = N;
   GPXB_TRY(bR.alloc(sizeof(double) * n_loc, s));
   GPXB_TRY(bZ.alloc(sizeof(double) * n_loc, s));
@@ -540,11 +551,6 @@ int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, c
   double *r = bR.as<double>(), *z = bZ.as<double>(), *p = bP.as<double>(), *Ap = bAp.as<double>();
   double* sc = bSc.as<double>();  // [0] bs, [1] gamma, [2] pAp, [3] gamma_new, [4] rs
   double *t1 = bT.as<double>(), *t2 = t1 + std::max(k, 1);
-  double* Pall = nullptr;
-  if (ctx->world > 1) {
-    GPXB_TRY(bPall.alloc(sizeof(double) * ((size_t)N * 2 + 16), s));
-    Pall = bPall.as<double>();
-  }
   VecOps vo{ctx, s, bPart.as<double>(), n_loc};
   const int nb = ceil_div(n_loc, 256);
   const double isig2 = 1.0 / (sigma * sigma);
@@ -580,15 +586,7 @@ int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, c
   double rs = (k <= 0) ? h[1] : h[0];  // r0 = b
   int it = 0;
   while (rs > atol2 && it < maxiter) {
-    const double* pfull = p;
-    if (ctx->world > 1) {
-      GPXB_TRY(comm_allgather_rows(ctx, p, Pall, n_loc, 2, s));
-      pfull = Pall;
-    }
-    KmvArgs a;
-    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
-    a.V = pfull; a.PS = 2; a.P = 1; a.W = Ap; a.ldw = 1; a.diag_add = diag_add;
-    GPXB_TRY(kmatvec_launch(ctx, a, s));
+    GPXB_TRY(apply(p, Ap));
     GPXB_TRY(vo.dot(p, 2, Ap, 1, sc + 2));
     vaxpby_kernel<<<nb, 256, 0, s>>>(x, 1, p, 2, n_loc, sc + 1, sc + 2, 1.0, 1.0);    // x += alpha p
     vaxpby_kernel<<<nb, 256, 0, s>>>(r, 1, Ap, 1, n_loc, sc + 1, sc + 2, -1.0, 1.0);  // r -= alpha Ap
@@ -608,6 +606,31 @@ int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, c
   }
   if (iters_out) *iters_out = it;
   return 0;
+}
+
+// PCG on the matrix-free stationary-kernel operator (row-sharded: the search direction is all-gathered)
+int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
+              ZLayout zl, double diag_add, const double* b, const double* F, long long ldf, int k,
+              const double* Pkk, double sigma, double tol, double atol, int maxiter, double* x, int* iters_out,
+              cudaStream_t s) {
+  DevBuf bPall;
+  double* Pall = nullptr;
+  if (ctx->world > 1) {
+    GPXB_TRY(bPall.alloc(sizeof(double) * ((size_t)N * 2 + 16), s));
+    Pall = bPall.as<double>();
+  }
+  auto apply = [&](const double* p, double* Ap) -> int {
+    const double* pfull = p;
+    if (ctx->world > 1) {
+      GPXB_TRY(comm_allgather_rows(ctx, p, Pall, n_loc, 2, s));
+      pfull = Pall;
+    }
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
+    a.V = pfull; a.PS = 2; a.P = 1; a.W = Ap; a.ldw = 1; a.diag_add = diag_add;
+    return kmatvec_launch(ctx, a, s);
+  };
+  return pcg_core(ctx, n_loc, N, apply, b, F, ldf, k, Pkk, sigma, tol, atol, maxiter, x, iters_out, s);
 }
 
 }  // namespace gpxb

@@ -80,6 +80,10 @@ struct RpState {
   int blk0;           // global index of local block 0
   int nblk_loc;
   int partitionable;
+  // external-column mode (rpcholesky_derivs): the kernel column of the pivot and the initial diagonal come
+  // from buffers instead of the stationary kernel of Z
+  const double* ext_col;  // [n] column of the pivot, refreshed by the caller's generator each step
+  const double* diag0;    // [n] initial diagonal
 };
 
 __host__ __device__ __forceinline__ long long fb_index(long long r, int c, int M) {
@@ -91,8 +95,8 @@ __global__ void rp_init_kernel(RpState st, double d0) {
   const long long r = (long long)blockIdx.x * BLK + threadIdx.x;
   double v = 0.0;
   if (r < st.n) {
-    st.diag[r] = d0;
-    v = d0;
+    v = st.diag0 ? st.diag0[r] : d0;
+    st.diag[r] = v;
   }
   v = block_sum<BLK>(v, sh);
   if (threadIdx.x == 0) st.bs_local[st.blk0 + blockIdx.x] = v;
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_l2_kernel(RpState st, int i) 
   acc = block_sum<BLK>(acc, sh);
   if (tid == 0) {
     st.pbuf[0] = (double)(st.row0 + sl);
-    st.pbuf[1] = kfun(st.kind, 1e-12) - acc;
+    st.pbuf[1] = (st.diag0 ? st.diag0[sl] : kfun(st.kind, 1e-12)) - acc;
   }
 }
 
@@ -235,12 +239,17 @@ __global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
   if (blockIdx.x == 0 && threadIdx.x == 0) st.pivots[i] = s;
   double dnew = 0.0;
   if (r < st.n) {
-    const double* zr = st.Z + r * st.S;
-    double dot = 0.0;
-    for (int d = 0; d < st.Dp; ++d) dot += sz[d] * zr[d];
-    double d2 = ((sz[st.Dp] - 2.0 * dot) + zr[st.Dp]) + 1e-12;
-    if (r + st.row0 == s) d2 = 1e-12;
-    double g = kfun(st.kind, d2);
+    double g;
+    if (st.ext_col) {
+      g = st.ext_col[r];
+    } else {
+      const double* zr = st.Z + r * st.S;
+      double dot = 0.0;
+      for (int d = 0; d < st.Dp; ++d) dot += sz[d] * zr[d];
+      double d2 = ((sz[st.Dp] - 2.0 * dot) + zr[st.Dp]) + 1e-12;
+      if (r + st.row0 == s) d2 = 1e-12;
+      g = kfun(st.kind, d2);
+    }
     const double* f = st.FB + fb_index(r, 0, st.M);
     double a[8];
 #pragma unroll
@@ -297,8 +306,27 @@ size_t rp_factor_doubles(int n, int M) { return (size_t)ceil_div(n, BLK) * (size
 // 1024).  FB: rp_factor_doubles(n, M) doubles (local rows).  pivots: [M] int64 device (global indices,
 // identical on every rank).  With world > 1 two small all-reduces per pivot distribute the block
 // sums and the pivot's rows.
+static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, long long Ntot, ZLayout zl,
+                   const uint32_t key[2], int M, int partitionable, double* FB, long long* pivots,
+                   const double* diag0, const double* ext_col, const RpColumnGen* gen, cudaStream_t s);
+
 int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, long long row0, long long Ntot, ZLayout zl,
                  const uint32_t key[2], int M, int partitionable, double* FB, long long* pivots, cudaStream_t s) {
+  return rp_core(ctx, kind, Z, n, row0, Ntot, zl, key, M, partitionable, FB, pivots, nullptr, nullptr, nullptr, s);
+}
+
+// External-column variant (single rank): rows [n x S] are only copied into the pivot buffer (pbuf[2 + d]) for
+// the generator, which must fill ext_col[n] with the pivot's column of the matrix before every column step.
+int rpcholesky_ext(Ctx* ctx, const double* rows, int n, ZLayout zl, const double* diag0, double* ext_col,
+                   const RpColumnGen& gen, const uint32_t key[2], int M, int partitionable, double* FB,
+                   long long* pivots, cudaStream_t s) {
+  GPXB_ARG_CHECK(diag0 && ext_col && gen, -42);
+  return rp_core(ctx, KIND_SE, rows, n, 0, n, zl, key, M, partitionable, FB, pivots, diag0, ext_col, &gen, s);
+}
+
+static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, long long Ntot, ZLayout zl,
+                   const uint32_t key[2], int M, int partitionable, double* FB, long long* pivots,
+                   const double* diag0, const double* ext_col, const RpColumnGen* gen, cudaStream_t s) {
   GPXB_ARG_CHECK(n >= 0 && M > 0 && M <= 6000, -40);  // frow + zs must fit in 48 KB of smem
   GPXB_ARG_CHECK(row0 % BLK == 0, -41);
   const int nblk = ceil_div(Ntot, BLK);
@@ -315,7 +343,8 @@ int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, long long row0, lon
   st.FB = FB; st.M = M; st.Z = Z; st.n = n; st.S = zl.S; st.Dp = zl.Dp; st.nblk = nblk; st.kind = kind;
   st.pivots = pivots; st.key = bKey.as<uint32_t>(); st.pbuf = bP.as<double>(); st.l1 = bL1.as<double>();
   st.row0 = row0; st.blk0 = (int)(row0 / BLK); st.nblk_loc = nblk_loc; st.partitionable = partitionable;
-  const bool multi = ctx->world > 1;
+  st.ext_col = ext_col; st.diag0 = diag0;
+  const bool multi = ctx->world > 1 && !gen;  // the external-column variant runs replicated
   if (!multi) st.blocksum = st.bs_local;  // one buffer, no reduction
   GPXB_CUDA_CHECK(cudaMemcpyAsync(st.key, key, sizeof(uint32_t) * 2, cudaMemcpyHostToDevice, s));
   GPXB_CUDA_CHECK(cudaMemsetAsync(st.bs_local, 0, sizeof(double) * nblk, s));
@@ -346,6 +375,7 @@ int rpcholesky_z(Ctx* ctx, int kind, const double* Z, int n, long long row0, lon
     GPXB_LAUNCH_CHECK();
     if (multi) GPXB_TRY(comm_allreduce_sum(ctx, st.pbuf, 2 + zl.S + i, s));
     ctx->launches += 2;
+    if (gen) GPXB_TRY((*gen)(st.pbuf, s));
     if (nblk_loc > 0) {
       rp_column_kernel<<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
       GPXB_LAUNCH_CHECK();

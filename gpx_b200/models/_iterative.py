@@ -113,3 +113,27 @@ def lml_iter_grad(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos
     g_ell = (0.5 * c_dK_c - 0.5 * dld[0]) / N
     g_sigma = (sigma * float(np.sum(c * c)) - 0.5 * dld[1]) / N
     return mll, g_ell, g_sigma
+
+
+def fit_derivs_iter(kind, xd, Jd, yd, ell, sigma, n_pivots, key_precond, return_iters=False):
+    """_fit_derivs_iter (gpx/models/_gpr.py:347-390): PCG on the matrix-free Hessian operator."""
+    if n_pivots is None:
+        raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
+    key = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
+    c, jc, iters = ops.gpr_fit_derivs_iter(kind, xd, Jd, yd, ell, sigma, int(n_pivots), key,
+                                           threefry_partitionable())
+    return (c, jc, iters) if return_iters else (c, jc)
+
+
+def lml_derivs_iter(kind, xd, Jd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond):
+    """_lml_derivs_iter (gpx/models/_gpr.py:873-935), zero mean."""
+    n = yd.numel()
+    c, _ = fit_derivs_iter(kind, xd, Jd, yd, ell, sigma, n_pivots, key_precond)
+    quad = float((yd.reshape(-1) * c).sum().cpu())
+    subkey, _ = split(as_key(key_lanczos), 2, threefry_partitionable())
+    U = ops.rademacher_probes(subkey, n, int(num_evals), threefry_partitionable())
+    alpha, beta, flag = ops.lanczos_derivs(kind, xd, Jd, ell, sigma, U, int(num_lanczos))
+    if int(flag.cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps than rows")
+    logdet = slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), n)
+    return (-0.5 * quad - 0.5 * logdet - n * 0.5 * np.log(2.0 * np.pi)) / n

@@ -110,7 +110,8 @@ class BaseGP:
                     optres.status, str(optres.message)), stacklevel=2)
             if return_history:
                 self.states_history_, self.losses_history_ = history[0], history[1]
-        self.state = self._fit_derivs_fun(self.state, x=x, y=y, jacobian=jacobian, iterative=iterative)
+        self.state = self._fit_derivs_fun(self.state, x=x, y=y, jacobian=jacobian, iterative=iterative,
+                                          n_pivots=n_pivots, key_precond=gpxargs.key_precond)
         return self
 
     def predict_derivs(self, x, jacobian, full_covariance=False, iterative=False):

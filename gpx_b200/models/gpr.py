@@ -134,12 +134,17 @@ def _xyj(state, x, y, jacobian):
     return xd, yd, Jd
 
 
-def log_marginal_likelihood_derivs(state, x, y, jacobian, iterative=False, **_ignored):
-    """gpx/models/gpr.py:121-174 -> _lml_derivs_dense (gpx/models/_gpr.py:824-870); zero mean."""
-    if iterative:
-        raise NotImplementedError("matrix-free Hessian mat-vec is a 'next' row (SURVEY.md 8f N2)")
+def log_marginal_likelihood_derivs(state, x, y, jacobian, iterative=False, num_evals=gpxargs.num_evals,
+                                   num_lanczos=gpxargs.num_lanczos, key_lanczos=gpxargs.key_lanczos, n_pivots=None,
+                                   key_precond=None, **_ignored):
+    """gpx/models/gpr.py:121-174 -> _lml_derivs_dense / _lml_derivs_iter (gpx/models/_gpr.py:824-935); zero mean."""
     kernel, ell, sigma = _hyper(state)
     xd, yd, Jd = _xyj(state, x, y, jacobian)
+    if iterative:
+        from . import _iterative
+
+        return _iterative.lml_derivs_iter(kernel.kind, xd, Jd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos,
+                                          n_pivots, key_precond)
     out = ops.gpr_lml_derivs(kernel.kind, xd, Jd, yd, ell, sigma)
     return float(out.cpu().numpy()[0])
 
@@ -169,16 +174,19 @@ def loss_and_grad_derivs(state, x, y, jacobian, iterative=False, **_ignored):
     return -lml, grads
 
 
-def fit_derivs(state, x, y, jacobian, iterative=False, **_ignored):
-    """gpx/models/gpr.py:437-489 -> _fit_derivs_dense (gpx/models/_gpr.py:313-344) + jaccoef."""
-    if iterative:
-        raise NotImplementedError("matrix-free Hessian mat-vec is a 'next' row (SURVEY.md 8f N2)")
+def fit_derivs(state, x, y, jacobian, iterative=False, n_pivots=None, key_precond=None, **_ignored):
+    """gpx/models/gpr.py:437-489 -> _fit_derivs_dense / _fit_derivs_iter (gpx/models/_gpr.py:313-390) + jaccoef."""
     kernel, ell, sigma = _hyper(state)
     xd, yd, Jd = _xyj(state, x, y, jacobian)
-    c, jc = ops.gpr_fit_derivs(kernel.kind, xd, Jd, yd, ell, sigma)
+    if iterative:
+        from . import _iterative
+
+        c, jc = _iterative.fit_derivs_iter(kernel.kind, xd, Jd, yd, ell, sigma, n_pivots, key_precond)
+    else:
+        c, jc = ops.gpr_fit_derivs(kernel.kind, xd, Jd, yd, ell, sigma)
     return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), jacobian_train=np.asarray(jacobian),
-                             jaccoef=jc.cpu().numpy(), c=c.cpu().numpy(), mu=np.float64(0.0), is_fitted=False,
-                             is_fitted_derivs=True))
+                             jaccoef=jc.cpu().numpy(), c=c.cpu().numpy().reshape(-1, 1), mu=np.float64(0.0),
+                             is_fitted=False, is_fitted_derivs=True))
 
 
 def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):

@@ -245,6 +245,45 @@ def gpr_predict_y_derivs_full(kind, x_train, J_train, x, c, ell, sigma, mu=0.0, 
     return (mean, cov) if full_covariance else mean
 
 
+def gpr_fit_derivs_iter(kind, x, J, y, ell, sigma, n_pivots, key, partitionable=True, tol=1e-5, atol=1e-7,
+                        maxiter=0):
+    """(c (N*nv,), jaccoef (N, nf), iterations): PCG on the matrix-free Hessian operator with the
+    rpcholesky_derivs preconditioner (n_pivots = 0: none)."""
+    import ctypes
+
+    ctx = context()
+    x, J, y = _f64(x), _f64(J), _f64(y)
+    N, nf, nv = J.shape
+    c = torch.empty(N * nv, dtype=torch.float64, device=x.device)
+    jc = torch.empty((N, nf), dtype=torch.float64, device=x.device)
+    iters = ctypes.c_int(0)
+    check(
+        ctx.lib.gpxb_gpr_fit_derivs_iter(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), N, nf, nv, float(ell),
+                                         float(sigma), int(n_pivots), int(key[0]), int(key[1]),
+                                         int(bool(partitionable)), float(tol), float(atol), int(maxiter), ptr(c),
+                                         ptr(jc), ctypes.byref(iters), stream_ptr()),
+        "gpxb_gpr_fit_derivs_iter",
+    )
+    return c, jc, iters.value
+
+
+def lanczos_derivs(kind, x, J, ell, sigma, U, m):
+    """(alpha (P, m), beta (P, m), breakdown) of the block Lanczos on d01kj + (sigma^2+1e-10) I, matrix-free."""
+    ctx = context()
+    x, J, U = _f64(x), _f64(J), _f64(U)
+    N, nf, nv = J.shape
+    P = U.shape[1]
+    alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    check(
+        ctx.lib.gpxb_lanczos_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), float(sigma), ptr(U),
+                                    U.stride(0), P, int(m), ptr(alpha), ptr(beta), ptr(flag), stream_ptr()),
+        "gpxb_lanczos_derivs",
+    )
+    return alpha, beta, flag
+
+
 def hess_matvec(kind, x1, J1, x2, J2, V, ell, diag_add=0.0):
     """(d01kj(x1, x2; J1, J2) [+ diag_add I]) V without forming the matrix; V: (n2*nv2, P) or (n2*nv2,)."""
     ctx = context()

@@ -96,6 +96,19 @@ int gpxb_gpr_predict_y_derivs(gpxb_ctx* ctx, int kind, const double* x_train, co
 int gpxb_hess_matvec(gpxb_ctx* ctx, int kind, const double* x1, const double* J1, int n1, int nv1, const double* x2,
                      const double* J2, int n2, int nv2, int nf, double ell, double diag_add, const double* V,
                      long long ldv, int P, double* W, long long ldw, gpxb_stream stream);
+/* Iterative fit on derivative values: c[N nv] = PCG((d01kj + (sigma^2+1e-10) I), y) with the
+ * rpcholesky_derivs preconditioner (_fit_derivs_iter gpx/models/_gpr.py:347-390, _precond_rpcholesky_derivs
+ * :219-256, rpcholesky_derivs gpx/kernels/approximations.py:132-242), tol / atol / maxiter as
+ * jax.scipy.sparse.linalg.cg (maxiter <= 0: 10 N nv).  jaccoef_out, iters_out (host) may be NULL. */
+int gpxb_gpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N,
+                             int nf, int nv, double ell, double sigma, int n_pivots, uint32_t key0, uint32_t key1,
+                             int partitionable, double tol, double atol, int maxiter, double* c_out,
+                             double* jaccoef_out, int* iters_out, gpxb_stream stream);
+/* gpxb_lanczos on the matrix-free operator d01kj + (sigma^2+1e-10) I (the SLQ part of _lml_derivs_iter,
+ * gpx/models/_gpr.py:873-935); U: (N nv) x P unit start vectors. */
+int gpxb_lanczos_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                        double sigma, const double* U, long long ldu, int P, int m, double* alpha_out,
+                        double* beta_out, int* breakdown_flag, gpxb_stream stream);
 /* Predictions of a derivative-trained model from the uncontracted coefficients c[N nv], with the optional
  * full predictive covariance (cov_out may be NULL):
  *  - derivative values (_predict_derivs_dense, gpx/models/_gpr.py:488-560): mean[ns nvs] = mu + d01kj(x, x_train) c,

@@ -803,6 +803,56 @@ def lml_iter_grad(kind, x, y, ell, sigma, num_evals, num_lanczos, key_lanczos, n
     return mll, g_l, g_s
 
 
+def rpcholesky_derivs(kind, x, J, n_pivots, ell, key, partitionable=True):
+    """gpx/kernels/approximations.py:132-242: RPCholesky of the Hessian kernel over the (sample, variable) rows."""
+    n, _ = x.shape
+    jv = J.shape[2]
+    F = np.zeros((n * jv, n_pivots))
+    pivots = np.zeros(n_pivots, dtype=np.int64)
+    diag = np.concatenate([np.diagonal(d01kj(kind, x[i:i + 1], x[i:i + 1], ell, J[i:i + 1], J[i:i + 1]))
+                           for i in range(n)])
+    key = np.asarray(key, dtype=np.uint32)
+    for i in range(n_pivots):
+        prob = diag / np.sum(diag)
+        key = split(key, 2, partitionable)[0]
+        s = choice_p(key, prob, partitionable)
+        pivots[i] = s
+        i1, i2 = int(s) // jv, int(s) % jv
+        g = d01kj(kind, x[i1:i1 + 1], x, ell, J[i1:i1 + 1], J)[i2] - F @ F[s]
+        F[:, i] = g / (g[s] ** 0.5 + 1e-6)
+        diag = diag - F[:, i] ** 2
+    return F, pivots
+
+
+def fit_derivs_iter(kind, x, y, J, ell, sigma, n_pivots, key_precond, partitionable=True):
+    """_fit_derivs_iter _gpr.py:347-390 with _precond_rpcholesky_derivs :219-256 (zero mean)."""
+    yf = y.reshape(-1, 1)
+    m = yf.shape[0]
+    A = d01kj(kind, x, x, ell, J, J) + (sigma**2 + 1e-10) * np.eye(m)
+    F, _ = rpcholesky_derivs(kind, x, J, n_pivots, ell, key_precond, partitionable)
+    P = np.linalg.inv(sigma**2 * np.eye(n_pivots) + F.T @ F)
+
+    def precond(z):
+        res = P @ (F.T @ z)
+        return -(sigma ** (-2)) * (F @ res) + sigma ** (-2) * z
+
+    c, iters = cg(lambda v: A @ v, yf, M=precond, atol=1e-7)
+    return c, iters
+
+
+def lml_derivs_iter(kind, x, y, J, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
+                    partitionable=True):
+    """_lml_derivs_iter _gpr.py:873-935."""
+    yf = y.reshape(-1, 1)
+    m = yf.shape[0]
+    c, _ = fit_derivs_iter(kind, x, y, J, ell, sigma, n_pivots, key_precond, partitionable)
+    A = d01kj(kind, x, x, ell, J, J) + (sigma**2 + 1e-10) * np.eye(m)
+    mll = -0.5 * np.sum(yf.T @ c)
+    mll -= 0.5 * lanczos_logdet(lambda v: A @ v, num_evals, m, num_lanczos, key_lanczos, partitionable)
+    mll -= m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
+
+
 def fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function=data_mean, partitionable=True):
     """_gpr.py:285-310."""
     mu = mean_function(y)
