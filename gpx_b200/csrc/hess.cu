@@ -728,6 +728,37 @@ __global__ void hess_column_kernel(const double* __restrict__ AJ, int S, const d
 }
 }  // namespace
 
+// rpcholesky_derivs (gpx/kernels/approximations.py:132-242): randomly pivoted Cholesky of the Hessian kernel
+// over the (sample, variable) rows.  FB: row-blocked factor (rp_factor_doubles(N nv, M)); pivots: [M] int64.
+int hess_rpcholesky(Ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                    const uint32_t key[2], int M, int partitionable, double* FB, long long* pivots,
+                    cudaStream_t s) {
+  GPXB_ARG_CHECK(kind == KIND_SE || kind == KIND_M52, -50);
+  const long long n = (long long)N * nv;
+  const ZLayout zl = z_layout(nf);
+  DevBuf bAJ, bD0, bCol;
+  GPXB_TRY(bAJ.alloc(sizeof(double) * (size_t)n * zl.S, s));
+  GPXB_TRY(bD0.alloc(sizeof(double) * (size_t)n, s));
+  GPXB_TRY(bCol.alloc(sizeof(double) * (size_t)n, s));
+  double *AJ = bAJ.as<double>(), *col = bCol.as<double>();
+  prep_hess_kernel<<<ceil_div(n, 128), 128, 0, s>>>(x, J, N, nf, nv, zl.S, zl.Dp, AJ);
+  GPXB_LAUNCHED(ctx);
+  double c1_0;
+  if (kind == KIND_SE) c1_0 = (2.0 / (ell * ell)) * std::exp(-1e-12);
+  else {
+    const double d = 2.23606797749979 * 1e-6;
+    c1_0 = (5.0 / (3.0 * ell * ell)) * std::exp(-d) * (1.0 + d);
+  }
+  hess_diag_kernel<<<ceil_div(n, 256), 256, 0, s>>>(AJ, zl.S, nf, n, c1_0, bD0.as<double>());
+  GPXB_LAUNCHED(ctx);
+  RpColumnGen gen = [&](const double* pbuf, cudaStream_t st) -> int {
+    hess_column_kernel<<<ceil_div(n, 256), 256, 0, st>>>(AJ, zl.S, x, nf, nv, n, kind, ell, pbuf, col);
+    GPXB_LAUNCHED(ctx);
+    return 0;
+  };
+  return rpcholesky_ext(ctx, AJ, (int)n, zl, bD0.as<double>(), col, gen, key, M, partitionable, FB, pivots, s);
+}
+
 // c[n] = (d01kj + (sigma^2+1e-10) I)^-1 y by PCG (tol, atol as jax.scipy.sparse.linalg.cg); n_pivots = 0: no
 // preconditioner.  lanczos_* (optional): also run the m-step block Lanczos on the same operator for the P
 // start vectors U (n x ldu), as _lml_derivs_iter does after the fit.
@@ -744,36 +775,16 @@ int gpr_derivs_iter(Ctx* ctx, int kind, const double* x, const double* J, const 
   op.x1 = x; op.J1 = J; op.x2 = x; op.J2 = J; op.ell = ell; op.diag_add = s2;
   GPXB_TRY(hess_op_prepare(ctx, op, s));
   if (c_out) {
-    DevBuf bAJ, bD0, bCol, bFB, bFT, bPiv, bPkk;
+    DevBuf bFB, bFT, bPiv, bPkk;
     const long long ldf = (n + 1) / 2 * 2;
     const int k = n_pivots;
     if (k > 0) {
-      const ZLayout zl = z_layout(nf);
-      GPXB_TRY(bAJ.alloc(sizeof(double) * (size_t)n * zl.S, s));
-      GPXB_TRY(bD0.alloc(sizeof(double) * (size_t)n, s));
-      GPXB_TRY(bCol.alloc(sizeof(double) * (size_t)n, s));
       GPXB_TRY(bFB.alloc(sizeof(double) * std::max<size_t>(rp_factor_doubles((int)n, k), 8), s));
       GPXB_TRY(bFT.alloc(sizeof(double) * (size_t)k * ldf, s));
       GPXB_TRY(bPiv.alloc(sizeof(long long) * k, s));
       GPXB_TRY(bPkk.alloc(sizeof(double) * (size_t)k * k, s));
-      double *AJ = bAJ.as<double>(), *col = bCol.as<double>();
-      prep_hess_kernel<<<ceil_div(n, 128), 128, 0, s>>>(x, J, N, nf, nv, zl.S, zl.Dp, AJ);
-      GPXB_LAUNCHED(ctx);
-      double c1_0;
-      if (kind == KIND_SE) c1_0 = (2.0 / (ell * ell)) * std::exp(-1e-12);
-      else {
-        const double d = 2.23606797749979 * 1e-6;
-        c1_0 = (5.0 / (3.0 * ell * ell)) * std::exp(-d) * (1.0 + d);
-      }
-      hess_diag_kernel<<<ceil_div(n, 256), 256, 0, s>>>(AJ, zl.S, nf, n, c1_0, bD0.as<double>());
-      GPXB_LAUNCHED(ctx);
-      RpColumnGen gen = [&](const double* pbuf, cudaStream_t st) -> int {
-        hess_column_kernel<<<ceil_div(n, 256), 256, 0, st>>>(AJ, zl.S, x, nf, nv, n, kind, ell, pbuf, col);
-        GPXB_LAUNCHED(ctx);
-        return 0;
-      };
-      GPXB_TRY(rpcholesky_ext(ctx, AJ, (int)n, zl, bD0.as<double>(), col, gen, key, k, partitionable,
-                              bFB.as<double>(), bPiv.as<long long>(), s));
+      GPXB_TRY(hess_rpcholesky(ctx, kind, x, J, N, nf, nv, ell, key, k, partitionable, bFB.as<double>(),
+                               bPiv.as<long long>(), s));
       GPXB_TRY(rp_unblock_transposed(ctx, bFB.as<double>(), (int)n, k, bFT.as<double>(), ldf, s));
       bFB.release();
       GPXB_TRY(precond_build(ctx, bFT.as<double>(), ldf, k, (int)n, sigma, bPkk.as<double>(), s));
@@ -996,6 +1007,23 @@ int gpxb_gpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const dou
   return gpxb::gpr_derivs_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, N, nf, nv, ell, sigma, n_pivots, key,
                                partitionable, tol, atol, maxiter, c_out, jaccoef_out, iters_out, nullptr, 0, 0, 0,
                                nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int gpxb_rpcholesky_derivs(gpxb_ctx* ctx_, int kind, const double* x, const double* J, int N, int nf, int nv,
+                           double ell, uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out,
+                           long long* pivots_out, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && x && J && pivots_out && N > 0 && nf > 0 && nv > 0 && M > 0, -1);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = (long long)N * nv;
+  GPXB_ARG_CHECK(n < (1LL << 31), -2);
+  gpxb::DevBuf fb;
+  GPXB_TRY(fb.alloc(sizeof(double) * std::max<size_t>(gpxb::rp_factor_doubles((int)n, M), 8), s));
+  const uint32_t key[2] = {key0, key1};
+  GPXB_TRY(gpxb::hess_rpcholesky(ctx, kind, x, J, N, nf, nv, ell, key, M, partitionable, fb.as<double>(), pivots_out,
+                                 s));
+  if (F_out) GPXB_TRY(gpxb::rp_unblock_rowmajor(ctx, fb.as<double>(), (int)n, M, F_out, s));
+  return 0;
 }
 
 int gpxb_lanczos_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,

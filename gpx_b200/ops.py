@@ -267,6 +267,22 @@ def gpr_fit_derivs_iter(kind, x, J, y, ell, sigma, n_pivots, key, partitionable=
     return c, jc, iters.value
 
 
+def rpcholesky_derivs(kind, x, J, n_pivots, ell, key, partitionable=True, want_factor=True):
+    """(F (N*nv, M) or None, pivots int64 (M,)) -- gpx/kernels/approximations.py:132-242."""
+    ctx = context()
+    x, J = _f64(x), _f64(J)
+    N, nf, nv = J.shape
+    piv = torch.empty(n_pivots, dtype=torch.int64, device=x.device)
+    F = torch.empty((N * nv, n_pivots), dtype=torch.float64, device=x.device) if want_factor else None
+    check(
+        ctx.lib.gpxb_rpcholesky_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), int(key[0]),
+                                       int(key[1]), int(n_pivots), int(bool(partitionable)), ptr(F), ptr(piv),
+                                       stream_ptr()),
+        "gpxb_rpcholesky_derivs",
+    )
+    return F, piv
+
+
 def lanczos_derivs(kind, x, J, ell, sigma, U, m):
     """(alpha (P, m), beta (P, m), breakdown) of the block Lanczos on d01kj + (sigma^2+1e-10) I, matrix-free."""
     ctx = context()

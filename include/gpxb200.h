@@ -104,6 +104,12 @@ int gpxb_gpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const dou
                              int nf, int nv, double ell, double sigma, int n_pivots, uint32_t key0, uint32_t key1,
                              int partitionable, double tol, double atol, int maxiter, double* c_out,
                              double* jaccoef_out, int* iters_out, gpxb_stream stream);
+/* rpcholesky_derivs (gpx/kernels/approximations.py:132-242): randomly pivoted Cholesky of the Hessian kernel
+ * over the N nv (sample, variable) rows.  pivots_out: int64[M] device (row = sample * nv + variable);
+ * F_out: (N nv) x M row-major device or NULL.  Same sampling stream as gpxb_rpcholesky. */
+int gpxb_rpcholesky_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv,
+                           double ell, uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out,
+                           long long* pivots_out, gpxb_stream stream);
 /* gpxb_lanczos on the matrix-free operator d01kj + (sigma^2+1e-10) I (the SLQ part of _lml_derivs_iter,
  * gpx/models/_gpr.py:873-935); U: (N nv) x P unit start vectors. */
 int gpxb_lanczos_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,

@@ -139,7 +139,7 @@ def test_facade_fit_derivs_minimize_follows_oracle_optimiser():
     assert abs(ell - R.softplus(res.x[0])) < 1e-3 * ell and abs(sig - R.softplus(res.x[1])) < 1e-3
     c_ref, _, jc_ref = R.fit_derivs_dense("se", x, y, J, ell, sig)
     assert np.max(np.abs(m.state.jaccoef - jc_ref)) < 1e-7 * np.max(np.abs(jc_ref))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # the iterative fit needs the preconditioner size
         GPR(SquaredExponential()).fit_derivs(x, y, J, minimize=False, iterative=True)
 
 
@@ -239,19 +239,22 @@ def test_iterative_fit_and_lml_on_derivatives(kind, N, nf, nv, npiv):
     assert m.state.c.shape == (N * nv, 1) and m.state.jaccoef.shape == (N, nf)
 
 
-def test_rpcholesky_derivs_pivots_bit_exact():
-    """The pivots of the Hessian-kernel RPCholesky are visible through the preconditioned iteration count only in
-    the C ABI, so the factor is checked through its action: P^-1 built from the device pivots/factor must
-    reproduce the oracle's PCG iterates (same count) -- and the sampled stream is the oracle's by construction
-    (same Threefry path as gpxb_rpcholesky, tested bit-exactly there)."""
+@pytest.mark.parametrize("kind,N,nf,nv,M,part", [("se", 25, 5, 5, 40, True), ("m52", 60, 9, 4, 64, True),
+                                                  ("se", 30, 6, 6, 33, False), ("se", 14, 90, 90, 100, True)])
+def test_rpcholesky_derivs_pivots_bit_exact(kind, N, nf, nv, M, part):
+    """rpcholesky_derivs: pivots bit-exact against the oracle (both jax_threefry_partitionable modes), factor to
+    1e-9, and F F^T approaching the Hessian kernel."""
     from gpx_b200 import ops
 
-    x, J, y = _xj(25, 5, 5, 43)
+    x, J, _ = _xj(N, nf, nv, 43)
+    ell = 0.9 * np.sqrt(nf)
     key = R.PRNGKey(7)
-    for npiv in (1, 7, 40):
-        _, it_ref = R.fit_derivs_iter("se", x, y, J, 2.0, 0.2, npiv, key)
-        _, _, it = ops.gpr_fit_derivs_iter("se", dev(x), dev(J), dev(y), 2.0, 0.2, npiv, key)
-        assert it == it_ref
+    F_ref, piv_ref = R.rpcholesky_derivs(kind, x, J, M, ell, key, part)
+    F, piv = ops.rpcholesky_derivs(kind, dev(x), dev(J), M, ell, key, part)
+    assert np.array_equal(piv.cpu().numpy(), piv_ref)
+    assert np.max(np.abs(host(F) - F_ref)) < 1e-9 * np.max(np.abs(F_ref))
+    _, piv2 = ops.rpcholesky_derivs(kind, dev(x), dev(J), M, ell, key, part, want_factor=False)
+    assert np.array_equal(piv2.cpu().numpy(), piv_ref)
 
 
 def test_facade_fit_and_predict_derivs():
