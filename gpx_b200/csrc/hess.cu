@@ -576,6 +576,7 @@ struct HessOp {
   int kind = 0, N1 = 0, nv1 = 0, N2 = 0, nv2 = 0, nf = 0;
   const double *x1 = nullptr, *J1 = nullptr, *x2 = nullptr, *J2 = nullptr;
   double ell = 1.0, kappa2 = 0.0, diag_add = 0.0;
+  int dl = 0;  // 1: the operator is d(d01kj)/d lengthscale (same form, d/d ell pair scalars; no shift)
   DevBuf C1, C2, X2e, M, r, R, H1, H2;
   long long rows() const { return (long long)N1 * nv1; }
   long long cols() const { return (long long)N2 * nv2; }
@@ -603,7 +604,7 @@ int hess_op_prepare(Ctx* ctx, HessOp& op, cudaStream_t s) {
   GPXB_TRY(prep_z(ctx, op.x1, op.nf, op.N1, zl, op.ell, bZ1.as<double>(), s));
   GPXB_TRY(prep_z(ctx, op.x2, op.nf, op.N2, zl, op.ell, bZ2.as<double>(), s));
   pair_coef_kernel<<<ceil_div((long long)nn, 256), 256, 0, s>>>(bZ1.as<double>(), op.N1, bZ2.as<double>(), op.N2, zl.S,
-                                                                 zl.Dp, op.kind, op.ell, sym ? 1 : 0, 0,
+                                                                 zl.Dp, op.kind, op.ell, sym ? 1 : 0, op.dl,
                                                                  op.C1.as<double>(), op.C2.as<double>());
   GPXB_LAUNCHED(ctx);
   append_one_kernel<<<ceil_div((long long)op.N2 * (op.nf + 1), 256), 256, 0, s>>>(op.x2, op.N2, op.nf,
@@ -654,9 +655,10 @@ int hess_op_apply(Ctx* ctx, HessOp& op, const double* V, long long ldv, double* 
 }
 
 int hess_matvec(Ctx* ctx, int kind, const double* x1, const double* J1, int N1, int nv1, const double* x2,
-                const double* J2, int N2, int nv2, int nf, double ell, double diag_add, const double* V,
+                const double* J2, int N2, int nv2, int nf, double ell, double diag_add, int dl, const double* V,
                 long long ldv, int P, double* W, long long ldw, cudaStream_t s) {
   HessOp op;
+  op.dl = dl;
   op.kind = kind; op.N1 = N1; op.nv1 = nv1; op.N2 = N2; op.nv2 = nv2; op.nf = nf;
   op.x1 = x1; op.J1 = J1; op.x2 = x2; op.J2 = J2; op.ell = ell; op.diag_add = diag_add;
   GPXB_ARG_CHECK(diag_add == 0.0 || op.rows() == op.cols(), -59);
@@ -813,6 +815,44 @@ int gpr_derivs_iter(Ctx* ctx, int kind, const double* x, const double* J, const 
                             beta_out + (size_t)c0 * m, flag, s));
       up.release();
     }
+  }
+  return 0;
+}
+
+int lanczos_grad_core(Ctx* ctx, int n_loc, long long N,
+                      const std::function<int(const double*, double*, bool)>& matvec, double sigma, const double* U,
+                      int P, int PS, int m, double* alpha_out, double* beta_out, double* dalpha_out,
+                      double* dbeta_out, int Ptot, int* flag, cudaStream_t s);
+
+// Block Lanczos on d01kj + (sigma^2+1e-10) I with its forward-mode derivative w.r.t. (lengthscale, sigma):
+// the SLQ part of value_and_grad of _lml_derivs_iter (gpx/models/_gpr.py:873-935).
+int lanczos_grad_derivs(Ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                        double sigma, const double* U, long long ldu, int P, int m, double* alpha_out,
+                        double* beta_out, double* dalpha_out, double* dbeta_out, int* flag, cudaStream_t s) {
+  GPXB_ARG_CHECK(ctx->world == 1, -61);
+  const long long n = (long long)N * nv;
+  GPXB_ARG_CHECK(n > 0 && n < (1LL << 31), -1);
+  HessOp op, dop;
+  op.kind = dop.kind = kind; op.N1 = op.N2 = dop.N1 = dop.N2 = N; op.nv1 = op.nv2 = dop.nv1 = dop.nv2 = nv;
+  op.nf = dop.nf = nf; op.x1 = op.x2 = dop.x1 = dop.x2 = x; op.J1 = op.J2 = dop.J1 = dop.J2 = J;
+  op.ell = dop.ell = ell; op.diag_add = sigma * sigma + 1e-10; dop.dl = 1;
+  GPXB_TRY(hess_op_prepare(ctx, op, s));
+  GPXB_TRY(hess_op_prepare(ctx, dop, s));
+  GPXB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  DevBuf up;
+  for (int c0 = 0; c0 < P; c0 += 32) {
+    const int pb = std::min(32, P - c0);
+    const int PS = v_padded_stride(pb);
+    GPXB_TRY(up.alloc(sizeof(double) * ((size_t)n * PS + 16), s));
+    GPXB_TRY(pack_v(ctx, U, ldu, (int)n, c0, pb, PS, up.as<double>(), s));
+    auto matvec = [&](const double* v, double* w, bool dl) -> int {
+      for (int p = 0; p < pb; ++p) GPXB_TRY(hess_op_apply(ctx, dl ? dop : op, v + p, PS, w + p, PS, s));
+      return 0;
+    };
+    GPXB_TRY(lanczos_grad_core(ctx, (int)n, n, matvec, sigma, up.as<double>(), pb, PS, m, alpha_out + (size_t)c0 * m,
+                               beta_out + (size_t)c0 * m, dalpha_out + (size_t)c0 * m, dbeta_out + (size_t)c0 * m, P,
+                               flag, s));
+    up.release();
   }
   return 0;
 }
@@ -994,8 +1034,25 @@ int gpxb_hess_matvec(gpxb_ctx* ctx, int kind, const double* x1, const double* J1
                      const double* J2, int n2, int nv2, int nf, double ell, double diag_add, const double* V,
                      long long ldv, int P, double* W, long long ldw, gpxb_stream stream) {
   GPXB_ARG_CHECK(ctx && x1 && J1 && x2 && J2 && V && W && P > 0, -1);
-  return gpxb::hess_matvec(reinterpret_cast<Ctx*>(ctx), kind, x1, J1, n1, nv1, x2, J2, n2, nv2, nf, ell, diag_add, V,
+  return gpxb::hess_matvec(reinterpret_cast<Ctx*>(ctx), kind, x1, J1, n1, nv1, x2, J2, n2, nv2, nf, ell, diag_add, 0, V,
                            ldv, P, W, ldw, (cudaStream_t)stream);
+}
+
+int gpxb_hess_matvec_dl(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nv, int nf, double ell,
+                        const double* V, long long ldv, int P, double* W, long long ldw, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && V && W && P > 0, -1);
+  return gpxb::hess_matvec(reinterpret_cast<Ctx*>(ctx), kind, x, J, N, nv, x, J, N, nv, nf, ell, 0.0, 1, V, ldv, P, W,
+                           ldw, (cudaStream_t)stream);
+}
+
+int gpxb_lanczos_grad_derivs(gpxb_ctx* ctx_, int kind, const double* x, const double* J, int N, int nf, int nv,
+                             double ell, double sigma, const double* U, long long ldu, int P, int m,
+                             double* alpha_out, double* beta_out, double* dalpha_out, double* dbeta_out,
+                             int* breakdown_flag, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && x && J && U && alpha_out && beta_out && dalpha_out && dbeta_out && breakdown_flag, -1);
+  GPXB_ARG_CHECK(P > 0 && m > 0, -2);
+  return gpxb::lanczos_grad_derivs(reinterpret_cast<Ctx*>(ctx_), kind, x, J, N, nf, nv, ell, sigma, U, ldu, P, m,
+                                   alpha_out, beta_out, dalpha_out, dbeta_out, breakdown_flag, (cudaStream_t)stream);
 }
 
 int gpxb_gpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N,

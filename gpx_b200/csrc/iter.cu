@@ -253,22 +253,21 @@ __global__ void coltangent_kernel(const double* __restrict__ dW, const double* _
 }
 }  // namespace
 
-// Block Lanczos together with its forward-mode derivative w.r.t. (lengthscale, sigma) of
-// A = K(x, x; ell) + (sigma^2 + 1e-10) I: every statement of gpx/lanczos.py:46-133 is differentiated
+// Block Lanczos together with its forward-mode derivative w.r.t. (lengthscale, sigma) of an operator
+// A(ell) + (sigma^2 + 1e-10) I given by matvec(v, out, dl) (dl: apply dA/d ell instead of A + shift):
+// every statement of gpx/lanczos.py:46-133 is differentiated
 // (tangent of the recursion jit(value_and_grad) differentiates in reverse through the fori_loop;
 // SURVEY.md 8f N1).  Per step: A [v | dv_l | dv_s] (three block mat-vecs) and (dK/d ell) v (one block
 // mat-vec with the d/d ell kernel profile); dA/d sigma = 2 sigma I.
 //   dalpha_out / dbeta_out: [2][P][m] (q = 0: lengthscale, q = 1: sigma).
-int lanczos_block_grad(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
-                       ZLayout zl, double ell, double sigma, const double* U, int P, int PS, int m,
-                       double* alpha_out, double* beta_out, double* dalpha_out, double* dbeta_out, int Ptot,
-                       int* flag, cudaStream_t s) {
+int lanczos_grad_core(Ctx* ctx, int n_loc, long long N,
+                      const std::function<int(const double*, double*, bool)>& matvec, double sigma, const double* U,
+                      int P, int PS, int m, double* alpha_out, double* beta_out, double* dalpha_out,
+                      double* dbeta_out, int Ptot, int* flag, cudaStream_t s) {
   GPXB_ARG_CHECK(P >= 1 && P <= MAXP && m >= 1, -30);
   ctx->shard_N = N;
-  const double diag_add = sigma * sigma + 1e-10;
   const size_t blk = (size_t)n_loc * PS;
-  const size_t blk_all = (size_t)N * PS;
-  DevBuf bVecs, bDv[2], bW, bT[2], bX, bVall, bPart, bSc;
+  DevBuf bVecs, bDv[2], bW, bT[2], bX, bPart, bSc;
   GPXB_TRY(bVecs.alloc(sizeof(double) * blk * m, s));
   for (int q = 0; q < 2; ++q) {
     GPXB_TRY(bDv[q].alloc(sizeof(double) * blk * m, s));
@@ -290,29 +289,10 @@ int lanczos_block_grad(Ctx* ctx, int kind, const double* Zr, int n_loc, long lon
   double* dbeta[2] = {sc + 10 * MAXP, sc + 11 * MAXP};
   double* wdw[2] = {sc + 12 * MAXP, sc + 13 * MAXP};
   GPXB_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(double) * MAXP * 16, s));
-  double* Vall = nullptr;
-  if (ctx->world > 1) {
-    GPXB_TRY(bVall.alloc(sizeof(double) * (blk_all + 16), s));
-    Vall = bVall.as<double>();
-  }
   GPXB_CUDA_CHECK(cudaMemcpyAsync(vecs, U, sizeof(double) * blk, cudaMemcpyDeviceToDevice, s));
   const int nthr = 256;
   const int nblk_e = ceil_div((long long)blk, nthr);
 
-  // out = Op * v for this rank's rows; dl: the d K / d ell operator instead of A
-  auto matvec = [&](const double* v, double* out, bool dl) -> int {
-    const double* vfull = v;
-    if (ctx->world > 1) {
-      GPXB_TRY(comm_allgather_rows(ctx, v, Vall, n_loc, PS, s));
-      vfull = Vall;
-    }
-    KmvArgs a;
-    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
-    a.V = vfull; a.PS = PS; a.P = P; a.W = out; a.ldw = PS;
-    a.diag_add = dl ? 0.0 : diag_add;
-    a.dl_ell = dl ? ell : 0.0;
-    return kmatvec_launch(ctx, a, s);
-  };
   auto axpy2 = [&](double* Wd, const double* a, const double* Xv, const double* b, const double* Yv) -> int {
     colaxpy_kernel<<<nblk_e, nthr, 0, s>>>(Wd, a, Xv, b, Yv, n_loc, PS, P);
     GPXB_LAUNCH_CHECK();
@@ -381,6 +361,37 @@ int lanczos_block_grad(Ctx* ctx, int kind, const double* Zr, int n_loc, long lon
     }
   }
   return 0;
+}
+
+// Block Lanczos together with its forward-mode derivative w.r.t. (lengthscale, sigma) of
+// A = K(x, x; ell) + (sigma^2 + 1e-10) I on the matrix-free stationary-kernel operator (row-sharded).
+int lanczos_block_grad(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
+                       ZLayout zl, double ell, double sigma, const double* U, int P, int PS, int m,
+                       double* alpha_out, double* beta_out, double* dalpha_out, double* dbeta_out, int Ptot,
+                       int* flag, cudaStream_t s) {
+  const double diag_add = sigma * sigma + 1e-10;
+  DevBuf bVall;
+  double* Vall = nullptr;
+  if (ctx->world > 1) {
+    GPXB_TRY(bVall.alloc(sizeof(double) * ((size_t)N * PS + 16), s));
+    Vall = bVall.as<double>();
+  }
+  // out = Op * v for this rank's rows; dl: the d K / d ell operator instead of A
+  auto matvec = [&](const double* v, double* out, bool dl) -> int {
+    const double* vfull = v;
+    if (ctx->world > 1) {
+      GPXB_TRY(comm_allgather_rows(ctx, v, Vall, n_loc, PS, s));
+      vfull = Vall;
+    }
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
+    a.V = vfull; a.PS = PS; a.P = P; a.W = out; a.ldw = PS;
+    a.diag_add = dl ? 0.0 : diag_add;
+    a.dl_ell = dl ? ell : 0.0;
+    return kmatvec_launch(ctx, a, s);
+  };
+  return lanczos_grad_core(ctx, n_loc, N, matvec, sigma, U, P, PS, m, alpha_out, beta_out, dalpha_out, dbeta_out, Ptot,
+                           flag, s);
 }
 
 int rademacher_probes(Ctx* ctx, const uint32_t key[2], long long Ntot, int P, long long row0, int n_rows,

@@ -137,3 +137,22 @@ def lml_derivs_iter(kind, xd, Jd, yd, ell, sigma, num_evals, num_lanczos, key_la
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps than rows")
     logdet = slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), n)
     return (-0.5 * quad - 0.5 * logdet - n * 0.5 * np.log(2.0 * np.pi)) / n
+
+
+def lml_derivs_iter_grad(kind, xd, Jd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond):
+    """(lml, d/d lengthscale, d/d sigma) of _lml_derivs_iter as jit(value_and_grad) propagates it: same structure
+    as lml_iter_grad on the matrix-free Hessian operator (gpxb_hess_matvec_dl, gpxb_lanczos_grad_derivs)."""
+    n = yd.numel()
+    c, _ = fit_derivs_iter(kind, xd, Jd, yd, ell, sigma, n_pivots, key_precond)
+    quad = float((yd.reshape(-1) * c).sum().cpu())
+    c_dA_c = float((c * ops.hess_matvec_dl(kind, xd, Jd, c, ell)).sum().cpu())
+    subkey, _ = split(as_key(key_lanczos), 2, threefry_partitionable())
+    U = ops.rademacher_probes(subkey, n, int(num_evals), threefry_partitionable())
+    alpha, beta, dalpha, dbeta, flag = ops.lanczos_grad_derivs(kind, xd, Jd, ell, sigma, U, int(num_lanczos))
+    if int(flag.cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps than rows")
+    ld, dld = slq_logdet_grad(alpha.cpu().numpy(), beta.cpu().numpy(), dalpha.cpu().numpy(), dbeta.cpu().numpy(), n)
+    mll = (-0.5 * quad - 0.5 * ld - n * 0.5 * np.log(2.0 * np.pi)) / n
+    g_ell = (0.5 * c_dA_c - 0.5 * dld[0]) / n
+    g_sigma = (sigma * float((c * c).sum().cpu()) - 0.5 * dld[1]) / n
+    return mll, g_ell, g_sigma

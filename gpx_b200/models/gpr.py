@@ -154,24 +154,25 @@ def neg_log_marginal_likelihood_derivs(state, x, y, jacobian, **kwargs):
     return -log_marginal_likelihood_derivs(state, x, y, jacobian, **kwargs)
 
 
-def loss_and_grad_derivs(state, x, y, jacobian, iterative=False, **_ignored):
+def loss_and_grad_derivs(state, x, y, jacobian, iterative=False, **kwargs):
     """Negative derivative-LML and its gradient w.r.t. the constrained hyper-parameters from one fused
     device call -- stands in for jit(value_and_grad(loss)) with loss = neg_log_marginal_likelihood_derivs
     inside scipy_minimize_derivs (gpx/optimizers/scipy_optimize.py:72-78, 92-122)."""
-    if iterative:
-        raise NotImplementedError("gradient of the iterative derivative LML is a 'next' row (SURVEY.md 8f N2)")
     if state.loss_fn not in (neg_log_marginal_likelihood, neg_log_marginal_likelihood_derivs):
         raise NotImplementedError("only neg_log_marginal_likelihood_derivs has a fused device gradient")
     kernel, ell, sigma = _hyper(state)
     xd, yd, Jd = _xyj(state, x, y, jacobian)
+    if iterative:
+        from . import _iterative
+
+        lml, g_ell, g_sigma = _iterative.lml_derivs_iter_grad(
+            kernel.kind, xd, Jd, yd, ell, sigma, kwargs.get("num_evals", gpxargs.num_evals),
+            kwargs.get("num_lanczos", gpxargs.num_lanczos), kwargs.get("key_lanczos", gpxargs.key_lanczos),
+            kwargs.get("n_pivots"), kwargs.get("key_precond"))
+        return -lml, _grads_dict(state, g_ell, g_sigma)
     out = ops.gpr_lml_grad_derivs(kernel.kind, xd, Jd, yd, ell, sigma, want_grad=True)
     lml, g_ell, g_sigma = (float(v) for v in out.cpu().numpy())
-    grads = {}
-    if state.params["kernel_params"]["lengthscale"].trainable:
-        grads[("kernel_params", "lengthscale")] = -g_ell
-    if state.params["sigma"].trainable:
-        grads[("sigma",)] = -g_sigma
-    return -lml, grads
+    return -lml, _grads_dict(state, g_ell, g_sigma)
 
 
 def fit_derivs(state, x, y, jacobian, iterative=False, n_pivots=None, key_precond=None, **_ignored):

@@ -267,6 +267,44 @@ def gpr_fit_derivs_iter(kind, x, J, y, ell, sigma, n_pivots, key, partitionable=
     return c, jc, iters.value
 
 
+def hess_matvec_dl(kind, x, J, V, ell):
+    """(d d01kj(x, x; J, J)/d lengthscale) V, matrix-free."""
+    ctx = context()
+    x, J, V = _f64(x), _f64(J), _f64(V)
+    one_d = V.dim() == 1
+    if one_d:
+        V = V.reshape(-1, 1)
+    N, nf, nv = J.shape
+    P = V.shape[1]
+    W = torch.empty((N * nv, P), dtype=torch.float64, device=V.device)
+    check(
+        ctx.lib.gpxb_hess_matvec_dl(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nv, nf, float(ell), ptr(V), V.stride(0),
+                                    P, ptr(W), W.stride(0), stream_ptr()),
+        "gpxb_hess_matvec_dl",
+    )
+    return W.reshape(-1) if one_d else W
+
+
+def lanczos_grad_derivs(kind, x, J, ell, sigma, U, m):
+    """lanczos_derivs plus the tangents (2, P, m) of the tridiagonals w.r.t. (lengthscale, sigma)."""
+    ctx = context()
+    x, J, U = _f64(x), _f64(J), _f64(U)
+    N, nf, nv = J.shape
+    P = U.shape[1]
+    alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    dalpha = torch.empty((2, P, m), dtype=torch.float64, device=x.device)
+    dbeta = torch.empty((2, P, m), dtype=torch.float64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    check(
+        ctx.lib.gpxb_lanczos_grad_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), float(sigma),
+                                         ptr(U), U.stride(0), P, int(m), ptr(alpha), ptr(beta), ptr(dalpha),
+                                         ptr(dbeta), ptr(flag), stream_ptr()),
+        "gpxb_lanczos_grad_derivs",
+    )
+    return alpha, beta, dalpha, dbeta, flag
+
+
 def rpcholesky_derivs(kind, x, J, n_pivots, ell, key, partitionable=True, want_factor=True):
     """(F (N*nv, M) or None, pivots int64 (M,)) -- gpx/kernels/approximations.py:132-242."""
     ctx = context()

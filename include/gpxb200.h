@@ -104,6 +104,16 @@ int gpxb_gpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const dou
                              int nf, int nv, double ell, double sigma, int n_pivots, uint32_t key0, uint32_t key1,
                              int partitionable, double tol, double atol, int maxiter, double* c_out,
                              double* jaccoef_out, int* iters_out, gpxb_stream stream);
+/* W = (d d01kj(x, x; J, J)/d lengthscale) V, matrix-free (the c^T dA c term of the CG solve's cotangent), and
+ * gpxb_lanczos_derivs with the forward-mode derivative of the tridiagonals w.r.t. (lengthscale, sigma)
+ * [2 x P x m]: together the gradient jit(value_and_grad) yields for the iterative derivative LML
+ * (_lml_derivs_iter, gpx/models/_gpr.py:873-935), as for gpxb_lanczos_grad / gpxb_kmatvec_dl. */
+int gpxb_hess_matvec_dl(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nv, int nf, double ell,
+                        const double* V, long long ldv, int P, double* W, long long ldw, gpxb_stream stream);
+int gpxb_lanczos_grad_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv,
+                             double ell, double sigma, const double* U, long long ldu, int P, int m,
+                             double* alpha_out, double* beta_out, double* dalpha_out, double* dbeta_out,
+                             int* breakdown_flag, gpxb_stream stream);
 /* rpcholesky_derivs (gpx/kernels/approximations.py:132-242): randomly pivoted Cholesky of the Hessian kernel
  * over the N nv (sample, variable) rows.  pivots_out: int64[M] device (row = sample * nv + variable);
  * F_out: (N nv) x M row-major device or NULL.  Same sampling stream as gpxb_rpcholesky. */

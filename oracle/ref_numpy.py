@@ -853,6 +853,28 @@ def lml_derivs_iter(kind, x, y, J, ell, sigma, num_evals, num_lanczos, key_lancz
     return mll / m
 
 
+def lml_derivs_iter_grad(kind, x, y, J, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
+                         partitionable=True):
+    """(lml, d/d ell, d/d sigma) of _lml_derivs_iter as value_and_grad propagates it (see lml_iter_grad)."""
+    yf = y.reshape(-1, 1)
+    m = yf.shape[0]
+    c, _ = fit_derivs_iter(kind, x, y, J, ell, sigma, n_pivots, key_precond, partitionable)
+    A = d01kj(kind, x, x, ell, J, J) + (sigma**2 + 1e-10) * np.eye(m)
+    dA = d01kj_dl(kind, x, x, ell, J, J)
+    us, _ = rademacher_probes(key_lanczos, m, num_evals, partitionable)
+    acc, dacc = 0.0, np.zeros(2)
+    for p in range(num_evals):
+        T, dT = lanczos_tridiagonal_jvp(lambda v: A @ v, [lambda v: dA @ v, lambda v: 2.0 * sigma * v], num_lanczos,
+                                        us[:, p])
+        acc += slq_from_tridiag(T)
+        dacc += np.array([slq_from_tridiag_jvp(T, dT[0]), slq_from_tridiag_jvp(T, dT[1])])
+    ld, dld = (m / num_evals) * acc, (m / num_evals) * dacc
+    mll = (-0.5 * np.sum(yf.T @ c) - 0.5 * ld - m * 0.5 * np.log(2.0 * np.pi)) / m
+    g_l = (0.5 * np.sum(c * (dA @ c)) - 0.5 * dld[0]) / m
+    g_s = (sigma * np.sum(c * c) - 0.5 * dld[1]) / m
+    return mll, g_l, g_s
+
+
 def fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function=data_mean, partitionable=True):
     """_gpr.py:285-310."""
     mu = mean_function(y)

@@ -239,6 +239,39 @@ def test_iterative_fit_and_lml_on_derivatives(kind, N, nf, nv, npiv):
     assert m.state.c.shape == (N * nv, 1) and m.state.jaccoef.shape == (N, nf)
 
 
+@pytest.mark.parametrize("kind,N,nf,nv", [("se", 40, 6, 6), ("m52", 30, 9, 4)])
+def test_iterative_derivative_lml_gradient(kind, N, nf, nv):
+    """value_and_grad of _lml_derivs_iter: d/d ell operator of the matrix-free Hessian product and the tangent
+    Lanczos on it against the oracle; fit_derivs(minimize=True, iterative=True) then trains on it."""
+    from gpx_b200 import ops
+    from gpx_b200.kernels import Matern52, SquaredExponential
+    from gpx_b200.models import GPR
+    from gpx_b200.models.gpr import neg_log_marginal_likelihood_derivs
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    x, J, y = _xj(N, nf, nv, 47)
+    ell, sigma = 0.9 * np.sqrt(nf), 0.3
+    key = R.PRNGKey(2023)
+    V = np.random.default_rng(3).standard_normal((N * nv, 2))
+    ref_dl = R.d01kj_dl(kind, x, x, ell, J, J) @ V
+    out_dl = host(ops.hess_matvec_dl(kind, dev(x), dev(J), dev(V), ell))
+    assert np.max(np.abs(out_dl - ref_dl)) < 1e-10 * max(1.0, np.max(np.abs(ref_dl)))
+    ref = R.lml_derivs_iter_grad(kind, x, y, J, ell, sigma, 5, 10, key, 20, key)
+    kern = SquaredExponential() if kind == "se" else Matern52()
+    mk = lambda: GPR(kern, kernel_params=dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior())),  # noqa: E731
+                     sigma=Parameter(sigma, True, Softplus(), GammaPrior()), loss_fn=neg_log_marginal_likelihood_derivs)
+    loss, grads = mk()._loss_and_grad_derivs_fun(mk().state, x, y, J, iterative=True, num_evals=5, num_lanczos=10,
+                                                 key_lanczos=key, n_pivots=20, key_precond=key)
+    assert abs(-loss - ref[0]) < 1e-8 * abs(ref[0])
+    assert abs(-grads[("kernel_params", "lengthscale")] - ref[1]) < 1e-6 * max(abs(ref[1]), abs(ref[0]))
+    assert abs(-grads[("sigma",)] - ref[2]) < 1e-6 * max(abs(ref[2]), abs(ref[0]))
+    m = mk().fit_derivs(x, y, J, iterative=True, n_pivots=20, loss_kwargs=dict(num_evals=5, num_lanczos=10, key_lanczos=key),
+                        opt_kwargs=dict(options=dict(maxiter=4)))
+    assert m.optimize_results_.fun < loss
+
+
 @pytest.mark.parametrize("kind,N,nf,nv,M,part", [("se", 25, 5, 5, 40, True), ("m52", 60, 9, 4, 64, True),
                                                   ("se", 30, 6, 6, 33, False), ("se", 14, 90, 90, 100, True)])
 def test_rpcholesky_derivs_pivots_bit_exact(kind, N, nf, nv, M, part):

@@ -121,6 +121,34 @@ def main():
         fl = float(n) ** 3 + 2.0 * float(n) ** 2 * nf * 2
         print(json.dumps(dict(what="gpr_lml_grad_derivs", N=N, nf=nf, nv=nv, rows=n, s=t, alg_flops=fl,
                               tflops=fl / t / 1e12, out=[float(v) for v in out.cpu()])), flush=True)
+    elif what == "derivs_iter":
+        # configs[2] at its named size through the matrix-free Hessian operator: iterative LML + gradient
+        # (PCG with the rpcholesky_derivs preconditioner, 30-probe / 50-step SLQ with tangents)
+        from gpx_b200.models import _iterative as it
+        N = a[0] if a else 2000
+        npiv = a[1] if len(a) > 1 else 200
+        nf = nv = 90
+        ell, sigma = 90**0.5, 0.05
+        g = torch.Generator(device="cuda").manual_seed(2)
+        x = torch.randn((N, nf), dtype=torch.float64, device="cuda", generator=g)
+        J = 0.1 * torch.randn((N, nf, nv), dtype=torch.float64, device="cuda", generator=g)
+        J += torch.eye(nf, dtype=torch.float64, device="cuda").unsqueeze(0)
+        y = torch.randn((N, nv), dtype=torch.float64, device="cuda", generator=g)
+        key = np.array([0, 2023], dtype=np.uint32)
+        t0 = time.perf_counter()
+        c, jc, iters = ops.gpr_fit_derivs_iter("se", x, J, y, ell, sigma, npiv, key)
+        torch.cuda.synchronize()
+        t_fit = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        lml = it.lml_derivs_iter("se", x, J, y, ell, sigma, 30, 50, key, npiv, key)
+        torch.cuda.synchronize()
+        t_lml = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        out = it.lml_derivs_iter_grad("se", x, J, y, ell, sigma, 30, 50, key, npiv, key)
+        torch.cuda.synchronize()
+        t_grad = time.perf_counter() - t0
+        print(json.dumps(dict(what="derivs_iterative", N=N, rows=N * nv, n_pivots=npiv, pcg_iters=iters, s_fit=t_fit,
+                              s_lml=t_lml, s_lml_grad=t_grad, lml=lml, lml_grad=list(out))), flush=True)
     elif what == "lml_iter":
         # configs[4] end to end at a reduced N (the named N = 2e6 costs (2e6/N)^2 more per mat-vec):
         # PCG fit (RPCholesky preconditioner, n_pivots = 100) + 30-probe, 50-step SLQ log-det
