@@ -24,12 +24,30 @@ def _locs(state):
 def log_marginal_likelihood(state, x, y, iterative=False, num_evals=gpxargs.num_evals,
                             num_lanczos=gpxargs.num_lanczos, key_lanczos=gpxargs.key_lanczos, **_ignored):
     """gpx/models/sgpr.py:70-118 -> _sgpr._lml_dense (gpx/models/_sgpr.py:659-697)."""
-    if iterative:
-        raise NotImplementedError("SGPR iterative LML (_sgpr.py:700-737) is a 'next' row (SURVEY.md 8a a-16)")
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
+    if iterative:
+        return _lml_iter_with_locs(state, xd, yd, _locs(state), num_evals, num_lanczos, key_lanczos)
     out = ops.sgpr_lml(kernel.kind, xd, yd, _locs(state), ell, sigma, mean_mode(state.mean_function))
     return float(out.cpu().numpy()[0])
+
+
+def _lml_iter_with_locs(state, xd, yd, x_locs_dev, num_evals, num_lanczos, key_lanczos):
+    """_sgpr._lml_iter (gpx/models/_sgpr.py:701-737): CG + SLQ on the Nystrom operator H + (sigma^2+1e-10) I."""
+    from ..defaults import threefry_partitionable
+    from ..random import as_key, split
+    from ._iterative import slq_logdet
+
+    kernel, ell, sigma = _hyper(state)
+    N = yd.shape[0]
+    subkey, _ = split(as_key(key_lanczos), 2, threefry_partitionable())
+    U = ops.rademacher_probes(subkey, N, int(num_evals), threefry_partitionable())
+    quad, _, alpha, beta, flag = ops.sgpr_lml_iter_parts(kernel.kind, xd, yd, x_locs_dev, ell, sigma, U,
+                                                         int(num_lanczos), mean_mode(state.mean_function))
+    if int(flag.cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps")
+    logdet = slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), N)
+    return (-0.5 * float(quad.cpu().numpy()[0]) - 0.5 * logdet - N * 0.5 * np.log(2.0 * np.pi)) / N
 
 
 def neg_log_marginal_likelihood(state, x, y, **kwargs):
@@ -70,16 +88,17 @@ def loss_and_grad(state, x, y, iterative=False, **kwargs):
 def fit(state, x, y, iterative=False, **_ignored):
     """gpx/models/sgpr.py:309-338 -> _sgpr._fit_dense (gpx/models/_sgpr.py:319-339).  The extra
     keywords BaseGP.fit passes (n_pivots, key_precond) are accepted and ignored."""
-    if iterative:
-        raise NotImplementedError("SGPR CG fit (_sgpr.py:342-362) is a 'next' row")
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
-    c, mu = ops.sgpr_fit(kernel.kind, xd, yd, _locs(state), ell, sigma, mean_mode(state.mean_function))
+    if iterative:  # _sgpr._fit_iter (gpx/models/_sgpr.py:343-363)
+        c, mu, _ = ops.sgpr_fit_iter(kernel.kind, xd, yd, _locs(state), ell, sigma, mean_mode(state.mean_function))
+    else:
+        c, mu = ops.sgpr_fit(kernel.kind, xd, yd, _locs(state), ell, sigma, mean_mode(state.mean_function))
     return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), c=c.cpu().numpy(),
                              mu=np.float64(mu.cpu().numpy()[0]), is_fitted=True, is_fitted_derivs=False))
 
 
-def _predict_with_locs(state, x_locs_dev, x, full_covariance):
+def _predict_with_locs(state, x_locs_dev, x, full_covariance, iterative=False):
     import torch
 
     kernel, ell, sigma = _hyper(state)
@@ -87,6 +106,8 @@ def _predict_with_locs(state, x_locs_dev, x, full_covariance):
     c = _to_device(state.c)
     if c.dim() == 1:
         c = c.reshape(-1, 1)
+    if iterative:  # _sgpr._predict_iter (gpx/models/_sgpr.py:530-546): mu + K_nm c, matrix-free
+        return (ops.kmatvec(kernel.kind, xs, x_locs_dev, c, ell) + float(state.mu)).cpu().numpy()
     mu = torch.full((1,), float(state.mu), dtype=torch.float64, device="cuda")
     out = ops.sgpr_predict(kernel.kind, x_locs_dev, xs, c, mu, ell, sigma, full_covariance=full_covariance)
     if full_covariance:
@@ -100,7 +121,7 @@ def predict(state, x, full_covariance=False, iterative=False):
         raise RuntimeError("Model is not fitted. Run `fit` to fit the model before prediction.")
     if full_covariance and iterative:
         raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
-    return _predict_with_locs(state, _locs(state), x, full_covariance)
+    return _predict_with_locs(state, _locs(state), x, full_covariance, iterative)
 
 
 def default_params() -> Dict[str, Parameter]:

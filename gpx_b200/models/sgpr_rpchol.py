@@ -29,11 +29,11 @@ def _select_locs(state, xd):
 def log_marginal_likelihood(state, x, y, iterative=False, num_evals=gpxargs.num_evals,
                             num_lanczos=gpxargs.num_lanczos, key_lanczos=gpxargs.key_lanczos, **_ignored):
     """gpx/models/sgpr_rpchol.py:63-106 -> _sgpr_rpchol._lml_dense (178-208)."""
-    if iterative:
-        raise NotImplementedError("SGPR_RPChol iterative LML is a 'next' row")
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     x_locs, _ = _select_locs(state, xd)
+    if iterative:
+        return _sgpr._lml_iter_with_locs(state, xd, yd, x_locs, num_evals, num_lanczos, key_lanczos)
     out = ops.sgpr_lml(kernel.kind, xd, yd, x_locs, ell, sigma, mean_mode(state.mean_function))
     return float(out.cpu().numpy()[0])
 
@@ -54,12 +54,13 @@ def loss_and_grad(state, x, y, iterative=False, **kwargs):
 
 def fit(state, x, y, iterative=False, **_ignored):
     """gpx/models/sgpr_rpchol.py:309-348 -> _sgpr_rpchol._fit_dense (36-67)."""
-    if iterative:
-        raise NotImplementedError("SGPR_RPChol CG fit is a 'next' row")
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     x_locs, piv = _select_locs(state, xd)
-    c, mu = ops.sgpr_fit(kernel.kind, xd, yd, x_locs, ell, sigma, mean_mode(state.mean_function))
+    if iterative:
+        c, mu, _ = ops.sgpr_fit_iter(kernel.kind, xd, yd, x_locs, ell, sigma, mean_mode(state.mean_function))
+    else:
+        c, mu = ops.sgpr_fit(kernel.kind, xd, yd, x_locs, ell, sigma, mean_mode(state.mean_function))
     return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), c=c.cpu().numpy(),
                              mu=np.float64(mu.cpu().numpy()[0]), is_fitted=True, is_fitted_derivs=False,
                              x_locs=x_locs.cpu().numpy(), pivots=piv.cpu().numpy()))
@@ -72,7 +73,7 @@ def predict(state, x, full_covariance=False, iterative=False):
         raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
     from ..kernels import _to_device
 
-    return _sgpr._predict_with_locs(state, _to_device(state.x_locs), x, full_covariance)
+    return _sgpr._predict_with_locs(state, _to_device(state.x_locs), x, full_covariance, iterative)
 
 
 def init(kernel: Callable, n_locs, key=None, mean_function: Callable = data_mean, kernel_params=None, sigma=None,

@@ -527,6 +527,51 @@ def sgpr_lml_grad(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, want_grad
     return out
 
 
+def sgpr_fit_iter(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, tol=1e-5, atol=0.0, maxiter=0):
+    """(c (M, 1), mu (1,), iterations): CG on the M x M SGPR normal equations, matrix-free."""
+    import ctypes
+
+    ctx = context()
+    x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    N, D = x.shape
+    assert y.numel() == N, "the iterative SGPR path supports a single output column"
+    M = x_locs.shape[0]
+    c = torch.empty((M, 1), dtype=torch.float64, device=x.device)
+    mu = torch.empty(1, dtype=torch.float64, device=x.device)
+    iters = ctypes.c_int(0)
+    check(
+        ctx.lib.gpxb_sgpr_fit_iter(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, ptr(x_locs), M, float(ell),
+                                   float(sigma), int(mean_mode), float(tol), float(atol), int(maxiter), ptr(c), ptr(mu),
+                                   ctypes.byref(iters), stream_ptr()),
+        "gpxb_sgpr_fit_iter",
+    )
+    return c, mu, iters.value
+
+
+def sgpr_lml_iter_parts(kind, x, y, x_locs, ell, sigma, U, m, mean_mode=MEAN_DATA, tol=1e-5, atol=0.0, maxiter=0):
+    """(quad (1,), iterations, alpha (P, m), beta (P, m), breakdown) on the Nystrom operator H + (sigma^2+1e-10) I."""
+    import ctypes
+
+    ctx = context()
+    x, y, x_locs, U = _f64(x), _f64(y), _f64(x_locs), _f64(U)
+    N, D = x.shape
+    assert y.numel() == N, "the iterative SGPR path supports a single output column"
+    P = U.shape[1]
+    quad = torch.empty(1, dtype=torch.float64, device=x.device)
+    alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    iters = ctypes.c_int(0)
+    check(
+        ctx.lib.gpxb_sgpr_lml_iter_parts(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, ptr(x_locs), x_locs.shape[0],
+                                         float(ell), float(sigma), int(mean_mode), float(tol), float(atol), int(maxiter),
+                                         ptr(quad), ctypes.byref(iters), ptr(U), U.stride(0), P, int(m), ptr(alpha),
+                                         ptr(beta), ptr(flag), stream_ptr()),
+        "gpxb_sgpr_lml_iter_parts",
+    )
+    return quad, iters.value, alpha, beta, flag
+
+
 def sgpr_lml_grad_locs(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     """-> ([lml/N, d/d ell, d/d sigma], d(lml/N)/d x_locs (M, D)) for trainable landmark coordinates."""
     ctx = context()

@@ -248,6 +248,19 @@ int gpxb_sgpr_lml_grad_locs(gpxb_ctx* ctx, int kind, const double* x, const doub
 int gpxb_sgpr_fit(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,
                   const double* x_locs, int M, double ell, double sigma, int mean_mode, double* c_out,
                   double* mu_out, gpxb_stream stream);
+/* Iterative SGPR (single GPU).  gpxb_sgpr_fit_iter: c[M] = cg(sigma^2 K_mm + K_mn K_nm + 1e-10 I, K_mn (y - mu)),
+ * _Ax_lhs_fun / _fit_iter (gpx/models/_sgpr.py:96-143, 343-363), every product a matrix-free block mat-vec.
+ * gpxb_sgpr_lml_iter_parts: the two device parts of _lml_iter (:701-737) on the Nystrom operator
+ * H + (sigma^2+1e-10) I, H = K_nm (K_mm + 1e-10 I)^-1 K_mn (_Hx_fun :204-239): *quad_out = r^T cg(.., r) and the
+ * m-step Lanczos tridiagonals for the P start vectors U.  tol / atol / maxiter as jax.scipy.sparse.linalg.cg. */
+int gpxb_sgpr_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, const double* x_locs,
+                       int M, double ell, double sigma, int mean_mode, double tol, double atol, int maxiter,
+                       double* c_out, double* mu_out, int* iters_out, gpxb_stream stream);
+int gpxb_sgpr_lml_iter_parts(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D,
+                             const double* x_locs, int M, double ell, double sigma, int mean_mode, double tol,
+                             double atol, int maxiter, double* quad_out, int* iters_out, const double* U,
+                             long long ldu, int P, int m, double* alpha_out, double* beta_out, int* breakdown_flag,
+                             gpxb_stream stream);
 /* gpx/models/_sgpr.py:434-467 (covariance built from the test points, as the reference does) */
 int gpxb_sgpr_predict(gpxb_ctx* ctx, int kind, const double* x_locs, int M, int D, const double* x, int ns,
                       const double* c, int T, const double* mu, double ell, double sigma, double* mean_out,

@@ -973,6 +973,38 @@ def sgpr_lml_dense(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
     return (-0.5 * quad - 0.5 * logdet - n * 0.5 * np.log(2.0 * np.pi)) / n
 
 
+def sgpr_fit_iter(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
+    """_sgpr.py:343-363 with _Ax_lhs_fun :96-143: cg(sigma^2 K_mm + K_mn K_nm + 1e-10 I, K_mn (y - mu)), default
+    tolerances (tol 1e-5, atol 0), no preconditioner."""
+    mu = mean_function(y)
+    K_mm = kernel(kind, x_locs, x_locs, ell)
+    K_mn = kernel(kind, x_locs, x, ell)
+    m = x_locs.shape[0]
+    A = sigma**2 * K_mm + K_mn @ K_mn.T + 1e-10 * np.eye(m)
+    c, iters = cg(lambda v: A @ v, K_mn @ (y - mu))
+    return c, mu, iters
+
+
+def sgpr_lml_iter(kind, x_locs, x, y, ell, sigma, num_evals, num_lanczos, key_lanczos, mean_function=data_mean,
+                  partitionable=True):
+    """_sgpr.py:701-737 with _Hx_fun :204-239 (explicit inverse of K_mm + 1e-10 I)."""
+    mu = mean_function(y)
+    r = y - mu
+    n, m = y.shape[0], x_locs.shape[0]
+    Kmm_inv = np.linalg.inv(kernel(kind, x_locs, x_locs, ell) + 1e-10 * np.eye(m))
+    K_nm = kernel(kind, x, x_locs, ell)
+    shift = sigma**2 + 1e-10
+
+    def mv(v):
+        return K_nm @ (Kmm_inv @ (K_nm.T @ v)) + shift * v
+
+    c, _ = cg(mv, r)
+    mll = -0.5 * np.sum(r.T @ c)
+    mll -= 0.5 * lanczos_logdet(mv, num_evals, n, num_lanczos, key_lanczos, partitionable)
+    mll -= n * 0.5 * np.log(2.0 * np.pi)
+    return mll / n
+
+
 def kernel_dx_profile(kind: str, x1, x2, ell: float):
     """h with d kernel(x1_i, x2_j)/d x1_if = -h_ij (x1_if - x2_jf): h = -(2/ell^2) dk/d(d2) of the matrix
     kernels above (d2 carries the 1e-12 jitter of squared_distances; the Matern clamp is inactive)."""
