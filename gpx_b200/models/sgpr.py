@@ -124,6 +124,77 @@ def predict(state, x, full_covariance=False, iterative=False):
     return _predict_with_locs(state, _locs(state), x, full_covariance, iterative)
 
 
+def _locs_jac(state):
+    if "jacobian_locs" not in state.params:
+        raise RuntimeError("training on derivatives needs the `jacobian_locs` Parameter (gpx/models/sgpr.py:721-730)")
+    if state.kernel.active_dims is not None:
+        raise NotImplementedError("active_dims with derivative training is not supported")
+    xl = _to_device(np.asarray(state.params["x_locs"].value))
+    Jl = _to_device(np.asarray(state.params["jacobian_locs"].value))
+    return xl, Jl
+
+
+def fit_derivs(state, x, y, jacobian, iterative=False, **_ignored):
+    """gpx/models/sgpr.py:340-390 -> _sgpr._fit_derivs_dense (gpx/models/_sgpr.py:366-396) with _A_derivs_lhs
+    (:65-93): c = (sigma^2 K_mm + K_mn K_nm + 1e-10 I)^-1 K_mn y with K = d01kj, zero mean; the Hessian-kernel
+    blocks, the SYRK, the Cholesky factorisation and the solves are device calls (the reference's LU solve is a
+    Cholesky solve here)."""
+    import torch
+
+    if iterative:
+        raise NotImplementedError("SGPR CG fit on derivatives (_sgpr.py:399-432) is not implemented")
+    kernel, ell, sigma = _hyper(state)
+    xl, Jl = _locs_jac(state)
+    xd, Jd = _to_device(x), _to_device(jacobian)
+    yd = _to_device(y).reshape(1, -1)
+    K_mn = ops.hess_gram(kernel.kind, xl, Jl, xd, Jd, ell)                      # (M nv_l, N nv)
+    C = ops.hess_gram(kernel.kind, xl, Jl, xl, Jl, ell)                         # K_mm (full)
+    C = ops.gemm(K_mn, K_mn, transb=True, alpha=1.0, beta=sigma**2, C=C)        # sigma^2 K_mm + K_mn K_nm
+    C.diagonal().add_(1e-10)
+    rhs = ops.gemm(yd, K_mn, transb=True)                                       # (K_mn y)^T, 1 x M'
+    L, inv = ops.potrf(C)
+    ops.trsm(L, inv, rhs, trans=True)
+    ops.trsm(L, inv, rhs, trans=False)
+    c = rhs.reshape(-1, 1)
+    ml, _, nvl = Jl.shape
+    jaccoef = torch.einsum("sv,sfv->sf", c.reshape(ml, nvl), Jl)
+    return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), jacobian_train=np.asarray(jacobian),
+                             jaccoef=jaccoef.cpu().numpy(), c=c.cpu().numpy(), mu=np.float64(0.0), is_fitted=False,
+                             is_fitted_derivs=True))
+
+
+def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):
+    """gpx/models/sgpr.py -> _sgpr._predict_derivs_dense fast path (gpx/models/_sgpr.py:489-496):
+    mu + sum_s d01kjc(x_locs, x, jaccoef, jacobian)[s], reshaped (ns, nv)."""
+    if not getattr(state, "is_fitted_derivs", False):
+        raise RuntimeError("Model is not fitted on derivatives. Run `fit_derivs` first.")
+    if full_covariance or iterative:
+        raise NotImplementedError("only the contracted-jacobian mean of the SGPR derivative model is implemented")
+    import torch
+
+    kernel, ell, _ = _hyper(state)
+    xl, _ = _locs_jac(state)
+    jc = _to_device(state.jaccoef).unsqueeze(2).contiguous()
+    xs, Js = _to_device(x), _to_device(jacobian)
+    K = ops.hess_gram(kernel.kind, xl, jc, xs, Js, ell)
+    ones = torch.ones((1, K.shape[0]), dtype=torch.float64, device="cuda")
+    mean = ops.gemm(ones, K) + float(state.mu)
+    ns, _, nv = Js.shape
+    return mean.reshape(ns, nv).cpu().numpy()
+
+
+def predict_y_derivs(state, x, full_covariance=False, iterative=False):
+    """_sgpr._predict_y_derivs_dense fast path (gpx/models/_sgpr.py:581-625): mu + sum_s d0kjc(x_locs, x, jaccoef)."""
+    if not getattr(state, "is_fitted_derivs", False):
+        raise RuntimeError("Model is not fitted. Run `fit_derivs` to fit the model before prediction.")
+    if full_covariance:
+        raise NotImplementedError("only the contracted-jacobian mean of the SGPR derivative model is implemented")
+    kernel, ell, _ = _hyper(state)
+    xl, _ = _locs_jac(state)
+    out = ops.gpr_predict_y_derivs(kernel.kind, xl, _to_device(state.jaccoef), _to_device(x), ell, float(state.mu))
+    return out.cpu().numpy().reshape(-1, 1)
+
+
 def default_params() -> Dict[str, Parameter]:
     """gpx/models/sgpr.py:676-684."""
     return dict(sigma=Parameter(value=1.0, trainable=True, bijector=Softplus(), prior=NormalPrior(loc=0.0, scale=1.0)))
@@ -141,6 +212,10 @@ def init(kernel: Callable, mean_function: Callable = data_mean, x_locs: Paramete
     if sigma is None:
         sigma = default_params()["sigma"]
     params = {"kernel_params": kernel_params, "sigma": sigma, "x_locs": x_locs}
+    if jacobian_locs is not None:  # gpx/models/sgpr.py:721-730
+        if not isinstance(jacobian_locs, Parameter):
+            raise TypeError(f"jacobian_locs must be a Parameter, you provided {type(jacobian_locs)}")
+        params["jacobian_locs"] = jacobian_locs
     opt = dict(x_train=None, y_train=None, loss_fn=loss_fn, is_fitted=False, is_fitted_derivs=False, c=None, mu=None)
     return ModelState(kernel, mean_function, params, **opt)
 
@@ -167,3 +242,6 @@ class SGPR(BaseGP):
     _loss_and_grad_fun = staticmethod(loss_and_grad)
     _fit_fun = staticmethod(fit)
     _predict_fun = staticmethod(predict)
+    _fit_derivs_fun = staticmethod(fit_derivs)
+    _predict_derivs_fun = staticmethod(predict_derivs)
+    _predict_y_derivs_fun = staticmethod(predict_y_derivs)

@@ -973,6 +973,16 @@ def sgpr_lml_dense(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
     return (-0.5 * quad - 0.5 * logdet - n * 0.5 * np.log(2.0 * np.pi)) / n
 
 
+def sgpr_fit_derivs_dense(kind, x_locs, J_locs, x, y, J, ell, sigma):
+    """_sgpr.py:366-396 with _A_derivs_lhs :65-93 (zero mean) + the contracted jacobian of sgpr.py:372-375."""
+    yf = y.reshape(-1, 1)
+    K_mn = d01kj(kind, x_locs, x, ell, J_locs, J)
+    C = sigma**2 * d01kj(kind, x_locs, x_locs, ell, J_locs, J_locs) + K_mn @ K_mn.T + 1e-10 * np.eye(K_mn.shape[0])
+    c = np.linalg.solve(C, K_mn @ yf)
+    ns, _, nv = J_locs.shape
+    return c, np.einsum("sv,sfv->sf", c.reshape(ns, nv), J_locs)
+
+
 def sgpr_fit_iter(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
     """_sgpr.py:343-363 with _Ax_lhs_fun :96-143: cg(sigma^2 K_mm + K_mn K_nm + 1e-10 I, K_mn (y - mu)), default
     tolerances (tol 1e-5, atol 0), no preconditioner."""

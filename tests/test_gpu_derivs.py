@@ -290,6 +290,37 @@ def test_rpcholesky_derivs_pivots_bit_exact(kind, N, nf, nv, M, part):
     assert np.array_equal(piv2.cpu().numpy(), piv_ref)
 
 
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_sgpr_fit_and_predict_on_derivatives(kind):
+    """SGPR.fit_derivs / predict_derivs / predict_y_derivs (projected processes on the Hessian kernel)."""
+    from gpx_b200.kernels import Matern52, SquaredExponential
+    from gpx_b200.models import SGPR
+    from gpx_b200.models.sgpr import locs_parameter
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Identity, Softplus
+    from gpx_b200.priors import GammaPrior, NormalPrior
+
+    N, nf, nv, Ml = 60, 5, 4, 12
+    x, J, y = _xj(N, nf, nv, 51)
+    xl, Jl, _ = _xj(Ml, nf, nv, 52)
+    xs, Js, _ = _xj(9, nf, nv, 53)
+    ell, sigma = 2.0, 0.2
+    kern = SquaredExponential() if kind == "se" else Matern52()
+    m = SGPR(kern, x_locs=locs_parameter(xl), jacobian_locs=Parameter(Jl, False, Identity(), NormalPrior(shape=Jl.shape)),
+             kernel_params=dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior())),
+             sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+    m.fit_derivs(x, y, J, minimize=False)
+    c_ref, jc_ref = R.sgpr_fit_derivs_dense(kind, xl, Jl, x, y, J, ell, sigma)
+    assert np.max(np.abs(m.state.c - c_ref)) < 1e-7 * np.max(np.abs(c_ref))
+    assert np.max(np.abs(m.state.jaccoef - jc_ref)) < 1e-7 * np.max(np.abs(jc_ref))
+    pred = m.predict_derivs(xs, Js)
+    ref = (R.d01kj(kind, xs, xl, ell, Js, Jl) @ c_ref).reshape(9, nv)
+    assert np.max(np.abs(pred - ref)) < 1e-7 * np.max(np.abs(ref))
+    yp = m.predict_y_derivs(xs)
+    ref_y = R.predict_y_derivs_dense(kind, xl, xs, jc_ref, 0.0, ell)
+    assert np.max(np.abs(yp - ref_y)) < 1e-7 * np.max(np.abs(ref_y))
+
+
 def test_facade_fit_and_predict_derivs():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import GPR
