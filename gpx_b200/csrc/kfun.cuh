@@ -60,6 +60,26 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ T
   return ki < -65372 ? 0.0 : s;  // x < -708 (integer compare: no FP64 op); the true value is < 3e-308
 }
 
+// 2^(u/256) for u <= ~0 with u already on the table's grid (u = -d2 * 256 log2 e, produced by the caller's FMA):
+// k = rint(u) by the shift trick (DADD), r = u - k exactly (|r| <= 1/2), 2^(r/256) = exp(r ln2/256) by a
+// degree-4 polynomial (truncation 3.8e-17), times T[k mod 256] = 2^((k mod 256)/256) and 2^(k div 256) through
+// the exponent field: 3 DADD + 4 DFMA + 1 DMUL -- no range-reduction multiplies at all.
+constexpr double EXP2_256_SCALE = 369.3299304675746;  // 256 log2(e)
+__device__ __forceinline__ double exp2_tab256(double u, const double* __restrict__ T) {
+  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52
+  const double kf = u + SHIFT;
+  const int ki = __double2loint(kf);
+  const double r = u - (kf - SHIFT);
+  double p = 2.239395190875157e-12;            // a^4/24, a = ln2/256
+  p = fma(p, r, 3.308302680541371e-09);        // a^3/6
+  p = fma(p, r, 3.665565596910106e-06);        // a^2/2
+  p = fma(p, r, 2.7076061740622863e-03);       // a
+  p = fma(p, r, 1.0);
+  p *= T[ki & 255];
+  const double s = __hiloint2double(__double2hiint(p) + ((ki >> 8) << 20), __double2loint(p));
+  return ki < -261632 ? 0.0 : s;  // u < -1022 * 256: below the normal range (true value < 2.3e-308)
+}
+
 // dK/d ell given d2 = s + 1e-12 (the jitter is a constant; the clamp passes no gradient).
 // rl = 1/ell is hoisted by the caller: no FP64 division in the inner loop except Matern-1/2's 1/r.
 __device__ __forceinline__ double kfun_dl(int kind, double d2, double s, double rl) {

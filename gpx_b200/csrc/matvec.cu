@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
   const int jbeg = blockIdx.y * p.jps, jend = min(p.N, jbeg + p.jps);
   const int ntiles = (jend - jbeg + BJ - 1) / BJ;
 
-  __shared__ double etab[64];  // 2^(j/64) for exp_tab
-  if (KMODE == 2 && tid < 64) etab[tid] = exp2((double)tid * (1.0 / 64.0));
+  __shared__ double etab[256];  // 2^(j/256) for exp2_tab256
+  if (KMODE == 2 && tid < 256) etab[tid] = exp2((double)tid * (1.0 / 256.0));
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
 #pragma unroll
       for (int mf = 0; mf < MF; ++mf) {
         ni[mf] = zr_base[mf * 8 * p.S + p.Dp];
+        if (KMODE == 2) ni[mf] *= -EXP2_256_SCALE;  // the fast path works on u = -d2 * 256 log2(e)
         if (KS > 0) {
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) a1[mf][ks] = zr_base[mf * 8 * p.S + ks * 4 + lq];
@@ -179,6 +180,22 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
       // (diag_add * V) is added after the column loop, so the inner loop carries no extra FP64 add
       const double nj0 = sZa[jl * p.S + p.Dp] + 1e-12, nj1 = sZa[(jl + 1) * p.S + p.Dp] + 1e-12;
       const int gj = j0 + jl;
+      if (KMODE == 2) {
+        // SquaredExponential fast path: u = -d2 * 256 log2(e) comes straight out of one FMA and one add per
+        // element (the scale is folded into the row / column norms), then exp(-d2) = 2^(u/256)
+        const double njc0 = EXP2_256_SCALE * nj0, njc1 = EXP2_256_SCALE * nj1;
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf) {
+          const long long gi = p.row_offset + row0 + warp * 8 * MF + mf * 8 + lr;
+          double u0 = fma(c[mf][0], 2.0 * EXP2_256_SCALE, ni[mf]) - njc0;
+          double u1 = fma(c[mf][1], 2.0 * EXP2_256_SCALE, ni[mf]) - njc1;
+          if ((p.row_offset >= 0) && (gi == gj)) u0 = -EXP2_256_SCALE * 1e-12;
+          if ((p.row_offset >= 0) && (gi == gj + 1)) u1 = -EXP2_256_SCALE * 1e-12;
+          const double k0 = exp2_tab256(u0, etab), k1 = exp2_tab256(u1, etab);
+          c[mf][0] = (gj < jend) ? k0 : 0.0;
+          c[mf][1] = (gj + 1 < jend) ? k1 : 0.0;
+        }
+      } else
 #pragma unroll
       for (int mf = 0; mf < MF; ++mf) {
         const long long gi = p.row_offset + row0 + warp * 8 * MF + mf * 8 + lr;

@@ -62,7 +62,7 @@ def main():
     elif what == "matvec":
         N, P = a[:2] if len(a) >= 2 else (2_000_000, 30)
         x, _ = data(N, 16, 4)
-        V = torch.randn((N, P), dtype=torch.float64, device="cuda")
+        V = torch.randn((N, P), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
         t, W = ev_time(lambda: ops.kmatvec("se", x, x, V, 4.0, diag_add=0.25 + 1e-10), reps=1,
                        warm=1 if N <= 600_000 else 0)
         fl = float(N) ** 2 * (2 * 16 + 4 + 2 * P)
