@@ -54,32 +54,34 @@ struct KmvParams {
 
 // MF: 8-row fragments per warp (rows per CTA = 64*MF); KS: Dp/4 when the row operand lives in
 // registers, 0 = read it from shared memory; NPF: 8-column fragments of V/W (P <= 8*NPF).
-// KMODE: 0 = kind chosen at run time (libm exp), 1 = SquaredExponential with libm exp,
-//        2 = SquaredExponential with the table-driven exp_tab (10 FP64 ops),
+// KMODE: 0 = kind chosen at run time (table exp), 1 = SquaredExponential with libm exp (GPXB_KMV_EXP=libm),
+//        2 = SquaredExponential fast path: the distance FMA produces u = -d2 * 256 log2(e) directly and
+//            exp(-d2) = 2^(u/256) by exp2_tab256 (10.25 FP64 ops per entry in all),
 //        3 = radial derivative profile g of the kind chosen at run time, d k/d x1 = -c(l) g (x1 - x2):
 //            SE exp(-d2) [c = 2/l^2], M12 exp(-r)/r [1/l^2], M32 exp(-d) [3/l^2], M52 (1+d) exp(-d) [5/(3 l^2)]
 //        4 = d k/d lengthscale (kfun_dl) of the kind chosen at run time, evaluated in the loop body
 template <int KMODE>
 __device__ __forceinline__ double kfun_mode(int kind, double d2, const double* __restrict__ tab) {
   if (KMODE == 1) return exp(-d2);
-  if (KMODE == 2) return exp_tab(-d2, tab);
+  // exp(-t) = 2^(-t * 256 log2(e) / 256) through the shared 256-entry table (kfun.cuh: exp2_tab256)
+  auto expn = [&](double t) { return exp2_tab256(-EXP2_256_SCALE * t, tab); };
   if (KMODE == 3) {
-    if (kind == KIND_SE) return exp(-d2);
+    if (kind == KIND_SE) return expn(d2);
     const double r = sqrt(fmax(d2, 1e-36));
-    if (kind == KIND_M12) return exp(-r) / r;
-    if (kind == KIND_M32) return exp(-1.7320508075688772 * r);
+    if (kind == KIND_M12) return expn(r) / r;
+    if (kind == KIND_M32) return expn(1.7320508075688772 * r);
     const double d = 2.23606797749979 * r;
-    return (1.0 + d) * exp(-d);
+    return (1.0 + d) * expn(d);
   }
-  if (kind == KIND_SE) return exp(-d2);
+  if (kind == KIND_SE) return expn(d2);
   const double r = sqrt(fmax(d2, 1e-36));
-  if (kind == KIND_M12) return exp(-r);
+  if (kind == KIND_M12) return expn(r);
   if (kind == KIND_M32) {
     const double d = 1.7320508075688772 * r;
-    return (1.0 + d) * exp(-d);
+    return (1.0 + d) * expn(d);
   }
   const double d = 2.23606797749979 * r;
-  return (1.0 + d + d * d / 3.0) * exp(-d);
+  return (1.0 + d + d * d * 0.3333333333333333) * expn(d);
 }
 
 template <int MF, int KS, int NPF, int NWARP, int KMODE>
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
   const int ntiles = (jend - jbeg + BJ - 1) / BJ;
 
   __shared__ double etab[256];  // 2^(j/256) for exp2_tab256
-  if (KMODE == 2 && tid < 256) etab[tid] = exp2((double)tid * (1.0 / 256.0));
+  if (KMODE != 1 && tid < 256) etab[tid] = exp2((double)tid * (1.0 / 256.0));
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
