@@ -162,41 +162,25 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
     nj[nf][0] = sZ2[c * p.S + p.Dp];
     nj[nf][1] = sZ2[(c + 1) * p.S + p.Dp];
   }
-  double local = 0.0;
-  const double rl = 1.0 / p.ell;
+  if (!CONTRACT) {
 #pragma unroll
-  for (int mf = 0; mf < 8; ++mf) {
-    const int rloc = wm * 64 + mf * 8 + lr;
-    const int gi = row0 + rloc;
-    const double ni = sZ1[rloc * p.S + p.Dp];
+    for (int mf = 0; mf < 8; ++mf) {
+      const int rloc = wm * 64 + mf * 8 + lr;
+      const int gi = row0 + rloc;
+      const double ni = sZ1[rloc * p.S + p.Dp];
 #pragma unroll
-    for (int nf = 0; nf < 4; ++nf) {
-      const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
-      double v[2];
-      bool ok[2];
+      for (int nf = 0; nf < 4; ++nf) {
+        const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
+        double v[2];
+        bool ok[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = gj + e;
-        ok[e] = (gi < p.n1) && (j < p.n2) && (!p.lower_only || j <= gi);
-        double d2 = ((ni - 2.0 * acc[mf][nf][e]) + nj[nf][e]) + 1e-12;
-        const bool on_diag = p.sym && (gi == j);
-        if (on_diag) d2 = 1e-12;
-        if (!CONTRACT) {
+        for (int e = 0; e < 2; ++e) {
+          const int j = gj + e;
+          ok[e] = (gi < p.n1) && (j < p.n2) && (!p.lower_only || j <= gi);
+          double d2 = ((ni - 2.0 * acc[mf][nf][e]) + nj[nf][e]) + 1e-12;
+          if (p.sym && (gi == j)) d2 = 1e-12;
           v[e] = kfun_t<KIND>(d2, etab) + ((gi == j) ? p.diag_add : 0.0);
-        } else {
-          v[e] = 0.0;
-          if (ok[e]) {
-            const double s = on_diag ? 0.0 : d2 - 1e-12;
-            const double dk = kfun_dl_t<KIND>(d2, s, rl, etab);
-            double w = -p.Ainv[(long long)gi * p.ldainv + j];
-            for (int t = 0; t < p.t; ++t)
-              w += p.alpha[(long long)t * p.n1 + gi] * p.alpha2[(long long)t * p.n2 + j];
-            // lower-triangle evaluation of a symmetric sum counts off-diagonal entries twice
-            v[e] = ((p.lower_only && gi != j) ? 2.0 : 1.0) * w * dk;
-          }
         }
-      }
-      if (!CONTRACT) {
         double* o = p.out + (long long)gi * p.ldo + gj;
         if (p.vec_out && ok[0] && ok[1]) {
           *reinterpret_cast<double2*>(o) = make_double2(v[0], v[1]);
@@ -204,15 +188,79 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
           if (ok[0]) o[0] = v[0];
           if (ok[1]) o[1] = v[1];
         }
-      } else {
-        local += v[0] + v[1];
+      }
+    }
+    return;
+  }
+  // contraction: sum_ij (sum_t a_t[i] b_t[j] - Y[i][j]) dK_ij/d ell.  Tiles that lie fully inside the matrix
+  // and strictly below the diagonal take the unmasked path, where every load of Y is unconditional and can
+  // be scheduled ahead of the FP64 work; the (few) edge / diagonal tiles keep the per-element masks.
+  const double rl = 1.0 / p.ell;
+  const bool full = (row0 + TB <= p.n1) && (col0 + TB <= p.n2) && (!p.lower_only || col0 + TB <= row0) && (p.t == 1) &&
+                    !(p.sym && row0 == col0);
+  double local = 0.0;
+  if (full) {
+    const double wscale = p.lower_only ? 2.0 : 1.0;  // off-diagonal entries of a symmetric sum count twice
+    double bj[4][2];
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) {
+      const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
+      bj[nf][0] = p.alpha2[gj];
+      bj[nf][1] = p.alpha2[gj + 1];
+    }
+#pragma unroll
+    for (int mf = 0; mf < 8; ++mf) {
+      const int rloc = wm * 64 + mf * 8 + lr;
+      const int gi = row0 + rloc;
+      const double ni = sZ1[rloc * p.S + p.Dp];
+      const double ai = p.alpha[gi];
+      double2 y[4];
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) {
+        const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
+        const double* yp = p.Ainv + (long long)gi * p.ldainv + gj;
+        y[nf] = make_double2(yp[0], yp[1]);
+      }
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) {
+        const double d20 = ((ni - 2.0 * acc[mf][nf][0]) + nj[nf][0]) + 1e-12;
+        const double d21 = ((ni - 2.0 * acc[mf][nf][1]) + nj[nf][1]) + 1e-12;
+        const double dk0 = kfun_dl_t<KIND>(d20, d20 - 1e-12, rl, etab);
+        const double dk1 = kfun_dl_t<KIND>(d21, d21 - 1e-12, rl, etab);
+        local += (ai * bj[nf][0] - y[nf].x) * dk0 + (ai * bj[nf][1] - y[nf].y) * dk1;
+      }
+    }
+    local *= wscale;
+  } else {
+#pragma unroll
+    for (int mf = 0; mf < 8; ++mf) {
+      const int rloc = wm * 64 + mf * 8 + lr;
+      const int gi = row0 + rloc;
+      const double ni = sZ1[rloc * p.S + p.Dp];
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) {
+        const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = gj + e;
+          const bool ok = (gi < p.n1) && (j < p.n2) && (!p.lower_only || j <= gi);
+          if (!ok) continue;
+          double d2 = ((ni - 2.0 * acc[mf][nf][e]) + nj[nf][e]) + 1e-12;
+          const bool on_diag = p.sym && (gi == j);
+          if (on_diag) d2 = 1e-12;
+          const double s = on_diag ? 0.0 : d2 - 1e-12;
+          const double dk = kfun_dl_t<KIND>(d2, s, rl, etab);
+          double w = -p.Ainv[(long long)gi * p.ldainv + j];
+          for (int t = 0; t < p.t; ++t)
+            w += p.alpha[(long long)t * p.n1 + gi] * p.alpha2[(long long)t * p.n2 + j];
+          // lower-triangle evaluation of a symmetric sum counts off-diagonal entries twice
+          local += ((p.lower_only && gi != j) ? 2.0 : 1.0) * w * dk;
+        }
       }
     }
   }
-  if (CONTRACT) {
-    const double tot = block_sum<NT>(local, red);
-    if (tid == 0) p.partials[blockIdx.x] = tot;
-  }
+  const double tot = block_sum<NT>(local, red);
+  if (tid == 0) p.partials[blockIdx.x] = tot;
 }
 
 }  // namespace
