@@ -167,3 +167,45 @@ def test_nonpd_gives_nan_not_error():
     L, _ = ops.potrf(dev(A))
     torch.cuda.synchronize()
     assert np.isnan(host(L)).any()
+
+
+def test_random_shape_sweep_against_torch_fp64():
+    """Seeded sweep over irregular sizes (panel / leaf / tile boundaries +-1, primes, tiny and multi-panel):
+    Cholesky, both triangular solves (few and many right-hand sides), the SPD inverse and the GEMM with
+    alpha / beta / lower_only against torch's FP64 linear algebra on the same device."""
+    from gpx_b200 import ops
+
+    rng = np.random.default_rng(2024)
+    sizes = [1, 2, 127, 128, 129, 255, 257, 1023, 1024, 1025, 1151, 2047, 2049, 3071, 3201] + \
+        [int(v) for v in rng.integers(3, 3400, 8)]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for n in sizes:
+        G = torch.randn((n, n + 3), dtype=torch.float64, device="cuda", generator=g)
+        A = G @ G.T / (n + 3) + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")
+        Lref = torch.linalg.cholesky(A)
+        L, inv = ops.potrf(torch.tril(A).clone())
+        assert float((torch.tril(L) - Lref).abs().max() / Lref.abs().max()) < 1e-11, n
+        for m in (1, 3, 40):
+            B = torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g)
+            X = ops.trsm(L, inv, B.clone(), trans=True)    # X L^T = B
+            assert float((X @ Lref.T - B).abs().max()) < 1e-9 * max(1.0, float(B.abs().max())), (n, m)
+            X = ops.trsm(L, inv, B.clone(), trans=False)   # X L = B
+            assert float((X @ Lref - B).abs().max()) < 1e-9 * max(1.0, float(B.abs().max())), (n, m)
+        Ainv = torch.tril(ops.potri(L, inv))
+        ref = torch.tril(torch.cholesky_inverse(Lref))
+        assert float((Ainv - ref).abs().max() / ref.abs().max()) < 1e-9, n
+    for _ in range(12):
+        M, N, K = (int(v) for v in rng.integers(1, 700, 3))
+        ta, tb = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        A = torch.randn((K, M) if ta else (M, K), dtype=torch.float64, device="cuda", generator=g)
+        B = torch.randn((N, K) if tb else (K, N), dtype=torch.float64, device="cuda", generator=g)
+        C0 = torch.randn((M, N), dtype=torch.float64, device="cuda", generator=g)
+        alpha, beta = float(rng.standard_normal()), float(rng.standard_normal())
+        ref = alpha * ((A.T if ta else A) @ (B.T if tb else B)) + beta * C0
+        out = ops.gemm(A, B, transa=ta, transb=tb, alpha=alpha, beta=beta, C=C0.clone())
+        assert float((out - ref).abs().max()) < 1e-11 * max(1.0, float(ref.abs().max())), (M, N, K, ta, tb)
+        S = min(M, N)  # lower trapezoid of the leading S x S block
+        out = ops.gemm(A[:, :S] if ta else A[:S], B[:S] if tb else B[:, :S], transa=ta, transb=tb, alpha=alpha,
+                       beta=beta, C=C0[:S, :S].clone(), lower_only=True)
+        assert float((torch.tril(out) - torch.tril(ref[:S, :S])).abs().max()) < 1e-11 * max(1.0, float(ref.abs().max()))
+        assert torch.equal(torch.triu(out, 1), torch.triu(C0[:S, :S], 1))  # the strict upper triangle is untouched
