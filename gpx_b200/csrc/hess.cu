@@ -21,6 +21,7 @@
 #include "chol.cuh"
 #include "gemm.cuh"
 #include "gram.cuh"
+#include "hess.cuh"
 #include "matvec.cuh"
 #include "mma.cuh"
 #include "rpchol.cuh"
@@ -295,6 +296,14 @@ static int hess_run(Ctx* ctx, int kind, const double* x1, const double* J1, int 
   sk::sum_kernel<<<1, 1024, 0, s>>>(p.partials, grid, contract_out);  // fixed order: deterministic
   GPXB_LAUNCHED(ctx);
   return 0;
+}
+
+// *contract_out = sum_ij (alpha_i alpha_j - Ainv_ij) d(d01kj(x, x; J, J))_ij / d lengthscale over the full symmetric
+// matrix (Ainv lower-stored with ld ldainv); dA is never formed.
+int hess_contract_dl(Ctx* ctx, int kind, const double* x, const double* J, int N, int nv, int nf, double ell,
+                     const double* Ainv, long long ldainv, const double* alpha, double* contract_out, cudaStream_t s) {
+  return hess_run(ctx, kind, x, J, N, nv, x, J, N, nv, nf, ell, 0.0, nullptr, ldainv, 1, Ainv, ldainv, alpha,
+                  contract_out, s);
 }
 
 int hess_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int Ns1, int nv1, const double* x2,
@@ -862,15 +871,35 @@ __global__ void add_const_kernel(double* __restrict__ v, long long n, double c) 
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] += c;
 }
-// Knm[t][i] = d0kj(x_train, x, J_train)[i][t] = -g_st (q_i - (A1 x_t^T)[i]),  i = s nv + v
-__global__ void d0kj_t_kernel(const double* __restrict__ A1, int S, int Dp, const double* __restrict__ P12,
-                              const double* __restrict__ G, int nv, long long n, int ns, double* __restrict__ out) {
+// d0kj(x1, x2, J1)[i][t] = -g_st (q_i - (A1 x2_t^T)[i]),  i = s nv + v, stored at out[i * ld_i + t * ld_t]
+__global__ void d0kj_kernel(const double* __restrict__ A1, int S, int Dp, const double* __restrict__ P12,
+                            const double* __restrict__ G, int nv, long long n, int ns, double* __restrict__ out,
+                            long long ld_i, long long ld_t) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * ns) return;
-  const long long i = idx % n;
-  const int t = (int)(idx / n);
+  const long long i = idx / ns;
+  const int t = (int)(idx % ns);
   const long long sidx = i / nv;
-  out[idx] = -G[sidx * ns + t] * (A1[i * S + Dp] - P12[i * ns + t]);
+  out[i * ld_i + t * ld_t] = -G[sidx * ns + t] * (A1[i * S + Dp] - P12[idx]);
+}
+// partials[cta] = sum over this CTA's (i, t) of (a_i b_t - Y[i * ldy + t]) * d0kj-like entry (G: d/d ell scalars)
+__global__ void __launch_bounds__(256) d0kj_contract_kernel(const double* __restrict__ A1, int S, int Dp,
+                                                            const double* __restrict__ P12,
+                                                            const double* __restrict__ G, int nv, long long n, int ns,
+                                                            const double* __restrict__ a, const double* __restrict__ b,
+                                                            const double* __restrict__ Y, long long ldy,
+                                                            double* __restrict__ partials) {
+  __shared__ double red[8];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (idx < n * ns) {
+    const long long i = idx / ns;
+    const int t = (int)(idx % ns);
+    const double e = -G[(i / nv) * ns + t] * (A1[i * S + Dp] - P12[idx]);
+    v = (a[i] * b[t] - Y[i * ldy + t]) * e;
+  }
+  v = block_sum<256>(v, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v;
 }
 
 // Shared tail of the two full-covariance predictions: Knm (m x n) holds the cross block (rows: test).
@@ -925,6 +954,63 @@ int gpr_predict_derivs_full(Ctx* ctx, int kind, const double* xt, const double* 
                           mean_out, cov_out, s);
 }
 
+// Block d0kj(x1, x2, J1) ((N1 nv) x N2; kernels.py:1108-1149 / grad_kernelize(argnums=0, with_jacob)) written at
+// out[i * ld_i + t * ld_t] -- or, when out == nullptr, its d/d lengthscale (dl = 1) / value contracted with
+// the weights (a_i b_t - Y[i][t]) into *contract_out (deterministic).  d1kj(x2, x1, J1) is its transpose.
+int d0kj_block(Ctx* ctx, int kind, const double* x1, const double* J1, int N1, int nv, const double* x2, int N2,
+               int nf, double ell, int dl, double* out, long long ld_i, long long ld_t, const double* a,
+               const double* b, const double* Y, long long ldy, double* contract_out, cudaStream_t s) {
+  GPXB_ARG_CHECK(kind == KIND_SE || kind == KIND_M52, -50);
+  const long long n = (long long)N1 * nv;
+  GPXB_ARG_CHECK(n > 0 && N2 > 0 && n < (1LL << 31), -1);
+  const ZLayout zl = z_layout(nf);
+  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -52);
+  DevBuf bA1, bZ1, bZ2, bX2, bG, bG2, bP, bPart;
+  GPXB_TRY(bA1.alloc(sizeof(double) * (size_t)n * zl.S, s));
+  GPXB_TRY(bZ1.alloc(sizeof(double) * (size_t)N1 * zl.S, s));
+  GPXB_TRY(bZ2.alloc(sizeof(double) * (size_t)N2 * zl.S, s));
+  GPXB_TRY(bX2.alloc(sizeof(double) * (size_t)N2 * zl.S, s));
+  GPXB_TRY(bG.alloc(sizeof(double) * (size_t)N1 * N2, s));
+  GPXB_TRY(bG2.alloc(sizeof(double) * (size_t)N1 * N2, s));
+  GPXB_TRY(bP.alloc(sizeof(double) * (size_t)n * N2, s));
+  prep_hess_kernel<<<ceil_div(n, 128), 128, 0, s>>>(x1, J1, N1, nf, nv, zl.S, zl.Dp, bA1.as<double>());
+  GPXB_LAUNCHED(ctx);
+  GPXB_TRY(prep_z(ctx, x1, nf, N1, zl, ell, bZ1.as<double>(), s));
+  GPXB_TRY(prep_z(ctx, x2, nf, N2, zl, ell, bZ2.as<double>(), s));
+  GPXB_TRY(prep_z(ctx, x2, nf, N2, zl, 1.0, bX2.as<double>(), s));
+  // c1 of the Hessian kernel is exactly the radial derivative profile g: SE (2/l^2) exp(-d2), M52 (5/(3 l^2)) (1+d)
+  // exp(-d); with dl = 1 the kernel yields dg/d ell.  sym: exact d2 = 1e-12 on coincident samples of one set.
+  const int sym = (x1 == x2 && N1 == N2) ? 1 : 0;
+  pair_coef_kernel<<<ceil_div((long long)N1 * N2, 256), 256, 0, s>>>(bZ1.as<double>(), N1, bZ2.as<double>(), N2, zl.S,
+                                                                      zl.Dp, kind, ell, sym, dl, bG.as<double>(),
+                                                                      bG2.as<double>());
+  GPXB_LAUNCHED(ctx);
+  {
+    GemmArgs g;  // P12 = A1 X2^T   [n x N2]
+    g.M = (int)n; g.N = N2; g.K = zl.Dp;
+    g.A = bA1.as<double>(); g.lda = zl.S; g.a_kmajor = true;
+    g.B = bX2.as<double>(); g.ldb = zl.S; g.b_kmajor = true;
+    g.C = bP.as<double>(); g.ldc = N2;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  const long long tot = n * N2;
+  if (out) {
+    d0kj_kernel<<<ceil_div(tot, 256), 256, 0, s>>>(bA1.as<double>(), zl.S, zl.Dp, bP.as<double>(), bG.as<double>(), nv, n,
+                                                   N2, out, ld_i, ld_t);
+    GPXB_LAUNCHED(ctx);
+    return 0;
+  }
+  GPXB_ARG_CHECK(a && b && Y && contract_out, -57);
+  const long long nb = ceil_div(tot, 256);
+  GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)nb, s));
+  d0kj_contract_kernel<<<(unsigned)nb, 256, 0, s>>>(bA1.as<double>(), zl.S, zl.Dp, bP.as<double>(), bG.as<double>(), nv,
+                                                    n, N2, a, b, Y, ldy, bPart.as<double>());
+  GPXB_LAUNCHED(ctx);
+  sk::sum_kernel<<<1, 1024, 0, s>>>(bPart.as<double>(), nb, contract_out);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
 // _predict_y_derivs_dense without the contracted jacobian (gpx/models/_gpr.py:608-660): mean[ns] = mu +
 // K_nm c with K_mn = d0kj(x_train, x, J_train); cov_out (optional, ns^2) = k(x, x) - G^T G,
 // G = chol(d01kj(x_train) + sigma^2 I)^-1 K_mn (no 1e-10 here, as in the reference).
@@ -936,36 +1022,13 @@ int gpr_predict_y_derivs_full(Ctx* ctx, int kind, const double* xt, const double
   GPXB_ARG_CHECK(n > 0 && ns > 0 && n < (1LL << 31), -1);
   const ZLayout zl = z_layout(nf);
   GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -52);
-  DevBuf bK, bA1, bZ1, bZ2, bX2, bG, bG2, bP;
+  DevBuf bK, bZ2;
   GPXB_TRY(bK.alloc(sizeof(double) * (size_t)ns * n, s));
-  GPXB_TRY(bA1.alloc(sizeof(double) * (size_t)n * zl.S, s));
-  GPXB_TRY(bZ1.alloc(sizeof(double) * (size_t)N * zl.S, s));
   GPXB_TRY(bZ2.alloc(sizeof(double) * (size_t)ns * zl.S, s));
-  GPXB_TRY(bX2.alloc(sizeof(double) * (size_t)ns * zl.S, s));
-  GPXB_TRY(bG.alloc(sizeof(double) * (size_t)N * ns, s));
-  GPXB_TRY(bG2.alloc(sizeof(double) * (size_t)N * ns, s));
-  GPXB_TRY(bP.alloc(sizeof(double) * (size_t)n * ns, s));
-  prep_hess_kernel<<<ceil_div(n, 128), 128, 0, s>>>(xt, Jt, N, nf, nv, zl.S, zl.Dp, bA1.as<double>());
-  GPXB_LAUNCHED(ctx);
-  GPXB_TRY(prep_z(ctx, xt, nf, N, zl, ell, bZ1.as<double>(), s));
   GPXB_TRY(prep_z(ctx, x, nf, ns, zl, ell, bZ2.as<double>(), s));
-  GPXB_TRY(prep_z(ctx, x, nf, ns, zl, 1.0, bX2.as<double>(), s));
-  // c1 of the Hessian kernel is exactly the radial derivative profile: SE (2/l^2) exp(-d2), M52 (5/(3 l^2)) (1+d) exp(-d)
-  pair_coef_kernel<<<ceil_div((long long)N * ns, 256), 256, 0, s>>>(bZ1.as<double>(), N, bZ2.as<double>(), ns, zl.S,
-                                                                     zl.Dp, kind, ell, 0, 0, bG.as<double>(),
-                                                                     bG2.as<double>());
-  GPXB_LAUNCHED(ctx);
-  {
-    GemmArgs g;  // P12 = A1 X2^T   [n x ns]
-    g.M = (int)n; g.N = ns; g.K = zl.Dp;
-    g.A = bA1.as<double>(); g.lda = zl.S; g.a_kmajor = true;
-    g.B = bX2.as<double>(); g.ldb = zl.S; g.b_kmajor = true;
-    g.C = bP.as<double>(); g.ldc = ns;
-    GPXB_TRY(gemm_f64(ctx, g, s));
-  }
-  d0kj_t_kernel<<<ceil_div(n * ns, 256), 256, 0, s>>>(bA1.as<double>(), zl.S, zl.Dp, bP.as<double>(), bG.as<double>(),
-                                                       nv, n, ns, bK.as<double>());
-  GPXB_LAUNCHED(ctx);
+  // cross block stored transposed: Knm[t][i]
+  GPXB_TRY(d0kj_block(ctx, kind, xt, Jt, N, nv, x, ns, nf, ell, 0, bK.as<double>(), 1, n, nullptr, nullptr, nullptr, 0,
+                      nullptr, s));
   if (cov_out) {
     GramArgs h;  // prior block k(x, x)
     h.kind = kind; h.Z1 = bZ2.as<double>(); h.n1 = ns; h.Z2 = bZ2.as<double>(); h.n2 = ns; h.zl = zl; h.ell = ell;

@@ -357,6 +357,55 @@ def hess_matvec(kind, x1, J1, x2, J2, V, ell, diag_add=0.0):
     return W.reshape(-1) if one_d else W
 
 
+def td_gram(kind, x1, J1, x2, J2, ell, add_targets=0.0, add_derivs=0.0, lower_only=False):
+    """Block kernel matrix of GPR_TD: [[k, d1kj], [d0kj, d01kj]] -> (n1 + n1*nv1, n2 + n2*nv2)."""
+    ctx = context()
+    x1, J1, x2, J2 = _f64(x1), _f64(J1), _f64(x2), _f64(J2)
+    n1, nf, nv1 = J1.shape
+    n2, _, nv2 = J2.shape
+    out = torch.zeros((n1 + n1 * nv1, n2 + n2 * nv2), dtype=torch.float64, device=x1.device)
+    check(
+        ctx.lib.gpxb_td_gram(ctx.handle, _kind(kind), ptr(x1), ptr(J1), n1, nv1, ptr(x2), ptr(J2), n2, nv2, nf,
+                             float(ell), float(add_targets), float(add_derivs), ptr(out), out.stride(0),
+                             int(bool(lower_only)), stream_ptr()),
+        "gpxb_td_gram",
+    )
+    return out
+
+
+def gpr_td_lml_grad(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_mode=MEAN_DATA, want_grad=True):
+    """-> device tensor [lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs]."""
+    ctx = context()
+    x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    N, nf, nv = J.shape
+    assert y.numel() == N and yd.numel() == N * nv
+    out = torch.empty(4, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_gpr_td_lml_grad(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv, float(ell),
+                                     float(sigma_targets), float(sigma_derivs), int(mean_mode),
+                                     1 if want_grad else 0, ptr(out), stream_ptr()),
+        "gpxb_gpr_td_lml_grad",
+    )
+    return out
+
+
+def gpr_td_fit(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_mode=MEAN_DATA):
+    """-> (c (N + N*nv, 1), mu (1,))."""
+    ctx = context()
+    x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    N, nf, nv = J.shape
+    assert y.numel() == N and yd.numel() == N * nv
+    c = torch.empty((N + N * nv, 1), dtype=torch.float64, device=x.device)
+    mu = torch.empty(1, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_gpr_td_fit(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv, float(ell),
+                                float(sigma_targets), float(sigma_derivs), int(mean_mode), ptr(c), ptr(mu),
+                                stream_ptr()),
+        "gpxb_gpr_td_fit",
+    )
+    return c, mu
+
+
 def gpr_fit_derivs(kind, x, J, y, ell, sigma):
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)

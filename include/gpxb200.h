@@ -139,6 +139,24 @@ int gpxb_gpr_predict_y_derivs_full(gpxb_ctx* ctx, int kind, const double* x_trai
                                    int nf, int nv, const double* x, int ns, const double* c, double mu, double ell,
                                    double sigma, double* mean_out, double* cov_out, gpxb_stream stream);
 
+/* ---- GPR on targets and derivatives (GPR_TD, gpx/models/gpr_td.py) ------------------------------------ */
+/* out[(n1 + n1 nv1) x (n2 + n2 nv2)] = [[k + add_targets I, d1kj], [d0kj, d01kj + add_derivs I]] between (x1, J1)
+ * and (x2, J2): _A_lhs (gpx/models/gpr_td.py:43-159) with one derivative block.  Rows / columns: the n targets,
+ * then the n nv derivative values (sample-major).  The shifts and lower_only need identical operands. */
+int gpxb_td_gram(gpxb_ctx* ctx, int kind, const double* x1, const double* J1, int n1, int nv1, const double* x2,
+                 const double* J2, int n2, int nv2, int nf, double ell, double add_targets, double add_derivs,
+                 double* out, long long ldo, int lower_only, gpxb_stream stream);
+/* out4 (device) = {lml, d lml/d lengthscale, d lml/d sigma_targets, d lml/d sigma_derivs} of _lml_dense
+ * (gpx/models/gpr_td.py:507-560), lml normalised by m = N + N nv: the (value, grad) of the loss inside
+ * scipy_minimize_ol.  y: N targets, y_derivs: N x nv.  mean_mode acts on the targets only. */
+int gpxb_gpr_td_lml_grad(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y,
+                         const double* y_derivs, int N, int nf, int nv, double ell, double sigma_targets,
+                         double sigma_derivs, int mean_mode, int want_grad, double* out4, gpxb_stream stream);
+/* c[N + N nv] = A^-1 [y - mu; y_derivs], *mu_out = mean_function(y)  (_fit_dense, gpx/models/gpr_td.py:639-683) */
+int gpxb_gpr_td_fit(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, const double* y_derivs,
+                    int N, int nf, int nv, double ell, double sigma_targets, double sigma_derivs, int mean_mode,
+                    double* c_out, double* mu_out, gpxb_stream stream);
+
 /* ---- Family 2: blocked FP64 Cholesky / TRSM / log-det / inverse ---------------------- */
 /* C[M x N] = alpha * op(A) * op(B) + beta * C on the FP64 tensor pipe.  transa = 0: A is M x K
  * row-major; 1: A is stored K x M.  transb = 0: B is K x N row-major; 1: B is stored N x K. */

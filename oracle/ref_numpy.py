@@ -342,6 +342,46 @@ def predict_y_derivs_dense_full(kind, x_train, J_train, x, c, mu, ell, sigma):
     return mean, kernel(kind, x, x, ell) - G.T @ G
 
 
+def td_A_lhs(kind, x1, J1, x2, J2, ell, sigma_t, sigma_d, noise=True):
+    """gpr_td.py:43-159 (one derivative block): [[K + s_t I, d1kj], [d0kj, d01kj + s_d I]];
+    d1kj(x1, x2, J2) = d0kj(x2, x1, J2)^T."""
+    K = kernel(kind, x1, x2, ell)
+    D01 = d01kj(kind, x1, x2, ell, J1, J2)
+    if noise:
+        K = K + (sigma_t**2 + 1e-10) * np.eye(K.shape[0])
+        D01 = D01 + (sigma_d**2 + 1e-10) * np.eye(D01.shape[0])
+    D0 = d0kj(kind, x1, x2, ell, J1)
+    D1 = d0kj(kind, x2, x1, ell, J2).T
+    return np.block([[K, D1], [D0, D01]])
+
+
+def td_lml_dense(kind, x, y, J, y_derivs, ell, sigma_t, sigma_d, mean_function=data_mean):
+    """gpr_td.py:507-560."""
+    mu = mean_function(y)
+    ym = np.concatenate([(y - mu).reshape(-1, 1), y_derivs.reshape(-1, 1)])
+    m = ym.shape[0]
+    A = td_A_lhs(kind, x, J, x, J, ell, sigma_t, sigma_d)
+    L = sla.cholesky(A, lower=True, check_finite=False)
+    cy = sla.solve_triangular(L, ym, lower=True, check_finite=False)
+    return (-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - m * 0.5 * np.log(2.0 * np.pi)) / m
+
+
+def td_fit_dense(kind, x, y, J, y_derivs, ell, sigma_t, sigma_d, mean_function=data_mean):
+    """gpr_td.py:639-683."""
+    mu = mean_function(y)
+    ym = np.concatenate([(y - mu).reshape(-1, 1), y_derivs.reshape(-1, 1)])
+    return np.linalg.solve(td_A_lhs(kind, x, J, x, J, ell, sigma_t, sigma_d), ym), mu
+
+
+def td_predict_dense(kind, x_train, J_train, x, J, c, mu, ell):
+    """gpr_td.py:749-797."""
+    K_mn = td_A_lhs(kind, x_train, J_train, x, J, ell, 0.0, 0.0, noise=False)
+    pred = K_mn.T @ c
+    ns, _, nv = J.shape
+    pred[:ns] += mu
+    return pred[:ns], pred[ns:ns + ns * nv].reshape(ns, -1)
+
+
 def predict_y_derivs_dense(kind, x_train, x, jaccoef, mu, ell):
     """_gpr.py:630-638 (contracted-jacobian fast path of _predict_y_derivs_dense)."""
     return (mu + np.sum(d0kjc(kind, x_train, x, ell, jaccoef), axis=0)).reshape(-1, 1)

@@ -1,0 +1,118 @@
+"""GPU parity: GPR on targets and derivatives (GPR_TD) against the oracle's literal block
+assembly (oracle/ref_numpy.py: td_A_lhs / td_lml_dense / td_fit_dense / td_predict_dense)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_numpy as R  # noqa: E402
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def _data(N, nf, nv, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((N, nf))
+    J = 0.1 * rng.standard_normal((N, nf, nv))
+    for k in range(min(nf, nv)):
+        J[:, k, k] += 1.0
+    y = np.sin(x.sum(1, keepdims=True)) + 0.05 * rng.standard_normal((N, 1))
+    yd = rng.standard_normal((N, nv))
+    return x, J, y, yd
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+@pytest.mark.parametrize("N1,N2,nf,nv1,nv2", [(20, 20, 5, 5, 5), (13, 31, 6, 3, 6), (7, 5, 90, 90, 90)])
+def test_td_block_matrix(kind, N1, N2, nf, nv1, nv2):
+    from gpx_b200 import ops
+
+    x1, J1, _, _ = _data(N1, nf, nv1, 1)
+    x2, J2, _, _ = _data(N2, nf, nv2, 2)
+    ell = 0.9 * np.sqrt(nf)
+    ref = R.td_A_lhs(kind, x1, J1, x2, J2, ell, 0.0, 0.0, noise=False)
+    out = host(ops.td_gram(kind, dev(x1), dev(J1), dev(x2), dev(J2), ell))
+    assert np.max(np.abs(out - ref)) < 1e-11 * max(1.0, np.max(np.abs(ref)))
+    if N1 == N2 and nv1 == nv2:
+        xd, Jd = dev(x1), dev(J1)
+        refs = R.td_A_lhs(kind, x1, J1, x1, J1, ell, 0.3, 0.2)
+        outs = host(ops.td_gram(kind, xd, Jd, xd, Jd, ell, add_targets=0.3**2 + 1e-10, add_derivs=0.2**2 + 1e-10))
+        assert np.max(np.abs(outs - refs)) < 1e-11 * max(1.0, np.max(np.abs(refs)))
+        low = host(ops.td_gram(kind, xd, Jd, xd, Jd, ell, add_targets=0.3**2 + 1e-10, add_derivs=0.2**2 + 1e-10,
+                               lower_only=True))
+        assert np.max(np.abs(np.tril(low) - np.tril(refs))) < 1e-11 * max(1.0, np.max(np.abs(refs)))
+        assert np.all(np.triu(low, 1) == 0.0)
+
+
+@pytest.mark.parametrize("kind,N,nf,nv,mean", [("se", 40, 6, 6, "zero"), ("m52", 30, 9, 4, "data"), ("se", 10, 90, 90, "zero")])
+def test_td_lml_gradient_fit_predict(kind, N, nf, nv, mean):
+    from gpx_b200 import ops
+    from gpx_b200.mean_functions import data_mean, zero_mean
+
+    x, J, y, yd = _data(N, nf, nv, 3)
+    xs, Js, _, _ = _data(9, nf, nv, 4)
+    ell, st, sd = 0.9 * np.sqrt(nf), 0.3, 0.2
+    mf_o = R.data_mean if mean == "data" else R.zero_mean
+    mode = 1 if mean == "data" else 0
+    f = lambda l, a, b: R.td_lml_dense(kind, x, y, J, yd, l, a, b, mf_o)  # noqa: E731
+    out = host(ops.gpr_td_lml_grad(kind, dev(x), dev(J), dev(y), dev(yd), ell, st, sd, mode))
+    ref = f(ell, st, sd)
+    assert abs(out[0] - ref) < 1e-8 * abs(ref)
+
+    def rich(g, h=1e-3):
+        fd = lambda hh: (g(hh) - g(-hh)) / (2 * hh)  # noqa: E731
+        return (4 * fd(h / 2) - fd(h)) / 3
+
+    g_ref = [rich(lambda h: f(ell + h, st, sd)), rich(lambda h: f(ell, st + h, sd)), rich(lambda h: f(ell, st, sd + h))]
+    for k in range(3):
+        assert abs(out[1 + k] - g_ref[k]) < 1e-7 * max(abs(g_ref[k]), abs(ref)), (k, out, g_ref)
+    only = host(ops.gpr_td_lml_grad(kind, dev(x), dev(J), dev(y), dev(yd), ell, st, sd, mode, want_grad=False))
+    assert only[0] == out[0] and np.all(only[1:] == 0.0)
+    c_ref, mu_ref = R.td_fit_dense(kind, x, y, J, yd, ell, st, sd, mf_o)
+    c, mu = ops.gpr_td_fit(kind, dev(x), dev(J), dev(y), dev(yd), ell, st, sd, mode)
+    assert abs(float(host(mu)[0]) - mu_ref) < 1e-14
+    assert np.max(np.abs(host(c) - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
+
+    from gpx_b200.kernels import Matern52, SquaredExponential
+    from gpx_b200.models import GPR_TD
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    par = lambda v: Parameter(v, True, Softplus(), GammaPrior())  # noqa: E731
+    kern = SquaredExponential() if kind == "se" else Matern52()
+    m = GPR_TD(kern, mean_function=data_mean if mean == "data" else zero_mean,
+               kernel_params=dict(lengthscale=par(ell)), sigma_targets=par(st), sigma_derivs=par(sd))
+    assert abs(m.log_marginal_likelihood(x, y, J, yd) - ref) < 1e-8 * abs(ref)
+    m.fit(x, y, J, yd, minimize=False)
+    yp, ydp = m.predict(xs, Js)
+    yr, ydr = R.td_predict_dense(kind, x, J, xs, Js, c_ref, mu_ref, ell)
+    assert np.max(np.abs(yp - yr)) < 1e-8 * max(1.0, np.max(np.abs(yr)))
+    assert np.max(np.abs(ydp - ydr)) < 1e-8 * max(1.0, np.max(np.abs(ydr)))
+
+
+def test_td_fit_minimize_lowers_the_loss():
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import GPR_TD
+
+    rng = np.random.default_rng(6)
+    N = 50
+    x = rng.uniform(-2, 2, (N, 2))
+    J = np.tile(np.eye(2)[None], (N, 1, 1))
+    y = (np.sin(x[:, 0]) * np.cos(x[:, 1])).reshape(-1, 1) + 0.01 * rng.standard_normal((N, 1))
+    yd = np.stack([np.cos(x[:, 0]) * np.cos(x[:, 1]), -np.sin(x[:, 0]) * np.sin(x[:, 1])], 1)
+    yd = yd + 0.01 * rng.standard_normal(yd.shape)
+    m = GPR_TD(SquaredExponential())
+    l0, _ = m.loss_and_grad(x, y, J, yd)
+    m.fit(x, y, J, yd)
+    assert m.optimize_results_.fun < l0 - 0.1
+    xs = rng.uniform(-1.5, 1.5, (20, 2))
+    yp, ydp = m.predict(xs, np.tile(np.eye(2)[None], (20, 1, 1)))
+    truth = (np.sin(xs[:, 0]) * np.cos(xs[:, 1])).reshape(-1, 1)
+    assert np.max(np.abs(yp - truth)) < 0.05  # targets + gradients pin the surface
