@@ -390,3 +390,18 @@ def test_oracle_slq_logdet_gradient_vs_finite_differences(kind):
     fl = (f(ell + h, sig) - f(ell - h, sig)) / (2 * h)
     fs = (f(ell, sig + h) - f(ell, sig - h)) / (2 * h)
     assert abs(gl - fl) < 1e-7 * abs(fl) and abs(gs - fs) < 1e-7 * abs(fs)
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_oracle_d0kj_and_td_block_matrix(kind):
+    """d0kj against central differences of the kernel along the jacobian directions, and the GPR_TD block
+    matrix (gpr_td.py:43-159) symmetric positive definite for identical operands."""
+    rng = np.random.default_rng(0)
+    x1, x2, J = rng.standard_normal((5, 3)), rng.standard_normal((4, 3)), rng.standard_normal((5, 3, 2))
+    out = R.d0kj(kind, x1, x2, 1.3, J)
+    h, ref = 1e-6, np.zeros((5, 2, 4))
+    for v in range(2):
+        ref[:, v, :] = (R.kernel(kind, x1 + h * J[:, :, v], x2, 1.3) - R.kernel(kind, x1 - h * J[:, :, v], x2, 1.3)) / (2 * h)
+    assert np.max(np.abs(out - ref.reshape(10, 4))) < 1e-8
+    A = R.td_A_lhs(kind, x1, J, x1, J, 1.3, 0.3, 0.2)
+    assert np.max(np.abs(A - A.T)) < 1e-14 and np.linalg.eigvalsh(A).min() > 0
