@@ -6,6 +6,7 @@
 #include "chol.cuh"
 #include "gemm.cuh"
 #include "gram.cuh"
+#include "small_kernels.cuh"
 
 namespace gpxb {
 
@@ -135,6 +136,54 @@ int gpxb_gram(gpxb_ctx* ctx_, int kind, const double* x1, int n1, const double* 
   g.ell = ell; g.diag_add = diag_add; g.sym = sym ? 1 : 0; g.lower_only = lower_only;
   g.out = out; g.ldo = ldo;
   return gpxb::gram_launch(ctx, g, s);
+}
+
+int gpxb_gram_dl_contract(gpxb_ctx* ctx_, int kind, const double* x1, int n1, const double* x2, int n2, int D,
+                          double ell, const double* Y, long long ldy, int sym_lower, double* out,
+                          gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && x1 && x2 && Y && out, -1);
+  GPXB_ARG_CHECK(kind >= 0 && kind <= 3 && D > 0 && n1 > 0 && n2 > 0, -2);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  cudaStream_t s = (cudaStream_t)stream;
+  const gpxb::ZLayout zl = gpxb::z_layout(D);
+  GPXB_ARG_CHECK(zl.S <= gpxb::GRAM_MAX_S, -3);
+  const bool sym = (x1 == x2) && (n1 == n2);
+  GPXB_ARG_CHECK(!sym_lower || sym, -4);
+  DevBuf z1, z2, part;
+  GPXB_TRY(z1.alloc(sizeof(double) * (size_t)n1 * zl.S, s));
+  GPXB_TRY(gpxb::prep_z(ctx, x1, D, n1, zl, ell, z1.as<double>(), s));
+  const double* Z2 = z1.as<double>();
+  if (!sym) {
+    GPXB_TRY(z2.alloc(sizeof(double) * (size_t)n2 * zl.S, s));
+    GPXB_TRY(gpxb::prep_z(ctx, x2, D, n2, zl, ell, z2.as<double>(), s));
+    Z2 = z2.as<double>();
+  }
+  gpxb::GramArgs g;
+  g.kind = kind;
+  g.Z1 = z1.as<double>(); g.n1 = n1; g.Z2 = Z2; g.n2 = n2; g.zl = zl;
+  g.ell = ell; g.sym = sym ? 1 : 0; g.lower_only = sym_lower;
+  g.Ainv = Y; g.ldainv = ldy; g.t = 0;  // weights -Y: the sign is undone below
+  const long long nparts = gpxb::gram_num_ctas(g);
+  GPXB_TRY(part.alloc(sizeof(double) * (size_t)nparts, s));
+  g.partials = part.as<double>();
+  GPXB_TRY(gpxb::gram_launch(ctx, g, s));
+  gpxb::sk::sum_kernel<<<1, 1024, 0, s>>>(g.partials, nparts, out);
+  GPXB_LAUNCHED(ctx);
+  gpxb::sk::scale_kernel<<<1, 1, 0, s>>>(out, 1, -1.0);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
+int gpxb_elementwise(gpxb_ctx* ctx_, int op, long long n, double a, const double* X, double b, const double* Y,
+                     double* out, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && X && Y && out && n >= 0 && (op == 0 || op == 1), -1);
+  if (n == 0) return 0;
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (op == 0) gpxb::sk::axpby_kernel<<<gpxb::ceil_div(n, 256), 256, 0, s>>>(out, a, X, b, Y, n);
+  else gpxb::sk::hadamard_kernel<<<gpxb::ceil_div(n, 256), 256, 0, s>>>(out, a, X, Y, n);
+  GPXB_LAUNCHED(ctx);
+  return 0;
 }
 
 int gpxb_gemm(gpxb_ctx* ctx, int transa, int transb, int M, int N, int K, double alpha,

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
   // and strictly below the diagonal take the unmasked path, where every load of Y is unconditional and can
   // be scheduled ahead of the FP64 work; the (few) edge / diagonal tiles keep the per-element masks.
   const double rl = 1.0 / p.ell;
-  const bool full = (row0 + TB <= p.n1) && (col0 + TB <= p.n2) && (!p.lower_only || col0 + TB <= row0) && (p.t == 1) &&
+  const bool full = (row0 + TB <= p.n1) && (col0 + TB <= p.n2) && (!p.lower_only || col0 + TB <= row0) && (p.t <= 1) &&
                     !(p.sym && row0 == col0);
   double local = 0.0;
   if (full) {
@@ -205,15 +205,15 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
       const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
-      bj[nf][0] = p.alpha2[gj];
-      bj[nf][1] = p.alpha2[gj + 1];
+      bj[nf][0] = p.t ? p.alpha2[gj] : 0.0;
+      bj[nf][1] = p.t ? p.alpha2[gj + 1] : 0.0;
     }
 #pragma unroll
     for (int mf = 0; mf < 8; ++mf) {
       const int rloc = wm * 64 + mf * 8 + lr;
       const int gi = row0 + rloc;
       const double ni = sZ1[rloc * p.S + p.Dp];
-      const double ai = p.alpha[gi];
+      const double ai = p.t ? p.alpha[gi] : 0.0;
       double2 y[4];
 #pragma unroll
       for (int nf = 0; nf < 4; ++nf) {
@@ -299,8 +299,8 @@ int gram_launch(Ctx* ctx, const GramArgs& a, cudaStream_t s) {
   GPXB_ARG_CHECK(grid < (1LL << 31), -12);
   const int smem = 128 + 2 * TB * p.S * (int)sizeof(double);
   if (!a.out) {
-    GPXB_ARG_CHECK(a.Ainv && a.alpha && a.partials, -13);
-    GPXB_ARG_CHECK(a.alpha2 || (a.sym && a.n1 == a.n2), -14);
+    GPXB_ARG_CHECK(a.Ainv && a.partials && (a.alpha || a.t == 0), -13);
+    GPXB_ARG_CHECK(a.t == 0 || a.alpha2 || (a.sym && a.n1 == a.n2), -14);
   }
 #define GPXB_GRAM_GO(C, K)                                                                                   \
   do {                                                                                                       \

@@ -103,10 +103,15 @@ static __global__ void symmetrize_lower_kernel(double* __restrict__ A, int k) {
 }
 
 // out = a*X + b*Y (element-wise, n elements)
-static __global__ void axpby_kernel(double* __restrict__ out, double a, const double* __restrict__ X, double b,
-                                    const double* __restrict__ Y, long long n) {
+static __global__ void axpby_kernel(double* out, double a, const double* X, double b, const double* Y, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a * X[i] + b * Y[i];
+}
+
+// out = a * X o Y (element-wise product, n elements; out may alias X or Y)
+static __global__ void hadamard_kernel(double* out, double a, const double* X, const double* Y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a * X[i] * Y[i];
 }
 
 // *out = sum_ij X_ij Y_ij over the full symmetric k x k matrices given by their lower triangles

@@ -71,3 +71,81 @@ class Matern32(Kernel):
 
 class Matern52(Kernel):
     kind = "m52"
+
+
+class _Composite(Kernel):
+    """Sum / Schur product of two stationary kernels (gpx/kernels/kernels.py:1794-1942, kernels/operations.py:103-426).
+    Parameters: {"kernel1": params1, "kernel2": params2}.  Each component matrix comes from the fused Gram
+    kernel; they are combined on the device (gpxb_elementwise).  Supported by the dense exact-GPR paths
+    (LML, gradient, fit, predict); nesting is allowed."""
+
+    op = ""
+
+    def __init__(self, kernel1: Kernel, kernel2: Kernel) -> None:
+        super().__init__(None)
+        self.kernel1, self.kernel2 = kernel1, kernel2
+
+    @property
+    def kind(self):
+        raise NotImplementedError(f"{self.__class__.__name__} kernels are supported by the dense exact-GPR paths only")
+
+    def lengthscale(self, params):
+        raise NotImplementedError(f"{self.__class__.__name__} has one lengthscale per component")
+
+    def default_params(self):
+        return {"kernel1": self.kernel1.default_params(), "kernel2": self.kernel2.default_params()}
+
+    def leaves(self, params, prefix=()):
+        """[(path prefix, leaf kernel, leaf params)] in evaluation order."""
+        out = []
+        for name, k in (("kernel1", self.kernel1), ("kernel2", self.kernel2)):
+            if isinstance(k, _Composite):
+                out += k.leaves(params[name], prefix + (name,))
+            else:
+                out.append((prefix + (name,), k, params[name]))
+        return out
+
+    def k_device(self, x1d, x2d, params):
+        """Device kernel matrix from (already sliced per leaf) raw device inputs."""
+        from . import ops
+
+        mats = []
+        for name, k in (("kernel1", self.kernel1), ("kernel2", self.kernel2)):
+            if isinstance(k, _Composite):
+                mats.append(k.k_device(x1d, x2d, params[name]))
+            else:
+                a = x1d if k.active_dims is None else x1d[:, k.active_dims].contiguous()
+                b = a if x2d is x1d else (x2d if k.active_dims is None else x2d[:, k.active_dims].contiguous())
+                mats.append(ops.gram(k.kind, a, b, k.lengthscale(params[name])))
+        return ops.elementwise("axpby" if self.op == "sum" else "mul", mats[0], mats[1], out=mats[0])
+
+    def k(self, x1, x2, params, as_numpy: bool = True):
+        d1 = _to_device(x1)
+        d2 = d1 if x2 is x1 else _to_device(x2)
+        out = self.k_device(d1, d2, params)
+        return out.cpu().numpy() if as_numpy else out
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.kernel1!r}, {self.kernel2!r})"
+
+
+class Sum(_Composite):
+    """k1 + k2  (gpx/kernels/kernels.py:1794-1848)."""
+    op = "sum"
+
+
+class Prod(_Composite):
+    """k1 * k2, element-wise  (gpx/kernels/kernels.py:1851-1942)."""
+    op = "prod"
+
+
+def _kernel_add(self, other):
+    return Sum(self, other)
+
+
+def _kernel_mul(self, other):
+    return Prod(self, other)
+
+
+Kernel.__add__ = _kernel_add   # gpx/kernels/kernels.py:1490-1500
+Kernel.__mul__ = _kernel_mul

@@ -14,6 +14,7 @@ from ..kernels import Kernel, _to_device
 from ..mean_functions import data_mean, mean_mode
 from ..parameters import ModelState, Parameter
 from ..priors import GammaPrior
+from . import _composite
 from .base import BaseGP
 
 
@@ -36,6 +37,10 @@ def log_marginal_likelihood(state, x, y, iterative=False, num_evals=gpxargs.num_
                             num_lanczos=gpxargs.num_lanczos, key_lanczos=gpxargs.key_lanczos,
                             n_pivots=None, key_precond=None):
     """gpx/models/gpr.py:70-118 -> _lml_dense / _lml_iter (gpx/models/_gpr.py:737-821)."""
+    if _composite.is_composite(state.kernel):
+        if iterative:
+            raise NotImplementedError("composite kernels are supported by the dense paths only")
+        return _composite.lml_and_grad(state, x, y, want_grad=False)[0]
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     if iterative:
@@ -58,6 +63,12 @@ def loss_and_grad(state, x, y, iterative=False, **kwargs):
     Non-trainable parameters get no gradient entry (stop_gradient, model_state.py:93-103)."""
     if state.loss_fn is not neg_log_marginal_likelihood:
         raise NotImplementedError("only neg_log_marginal_likelihood has a fused device gradient")
+    if _composite.is_composite(state.kernel):
+        if iterative:
+            raise NotImplementedError("composite kernels are supported by the dense paths only")
+        lml, g = _composite.lml_and_grad(state, x, y, want_grad=True)
+        flat = dict(state.flat_params())
+        return -lml, {path: -v for path, v in g.items() if flat[path].trainable}
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     if iterative:
@@ -84,6 +95,10 @@ def _grads_dict(state, g_ell, g_sigma):
 
 def fit(state, x, y, iterative=False, n_pivots=None, key_precond=None):
     """gpx/models/gpr.py:397-434 -> _fit_dense / _fit_iter (gpx/models/_gpr.py:262-310)."""
+    if _composite.is_composite(state.kernel):
+        if iterative:
+            raise NotImplementedError("composite kernels are supported by the dense paths only")
+        return _composite.fit(state, x, y)
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     if iterative:
@@ -106,6 +121,10 @@ def predict(state, x, full_covariance=False, iterative=False):
                            " run `predict_derivs` and `predict_y_derivs`")
     if full_covariance and iterative:
         raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
+    if _composite.is_composite(state.kernel):
+        if iterative:
+            raise NotImplementedError("composite kernels are supported by the dense paths only")
+        return _composite.predict(state, x, full_covariance)
     kernel, ell, sigma = _hyper(state)
     import torch
 

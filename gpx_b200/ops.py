@@ -44,6 +44,34 @@ def gram(kind, x1, x2, ell, diag_add=0.0, lower_only=False, out=None):
     return out
 
 
+def gram_dl_contract(kind, x1, x2, ell, Y, sym_lower=False):
+    """sum_ij Y_ij d k(x1_i, x2_j)/d lengthscale (device scalar tensor), dK never formed."""
+    ctx = context()
+    x1, x2, Y = _f64(x1), _f64(x2), _f64(Y)
+    n1, D = x1.shape
+    out = torch.empty(1, dtype=torch.float64, device=x1.device)
+    check(
+        ctx.lib.gpxb_gram_dl_contract(ctx.handle, _kind(kind), ptr(x1), n1, ptr(x2), x2.shape[0], D, float(ell), ptr(Y),
+                                      Y.stride(0), int(bool(sym_lower)), ptr(out), stream_ptr()),
+        "gpxb_gram_dl_contract",
+    )
+    return out
+
+
+def elementwise(op, X, Y, a=1.0, b=1.0, out=None):
+    """out = a X + b Y (op "axpby") or a X o Y (op "mul") on contiguous device tensors; out may alias X or Y."""
+    ctx = context()
+    assert X.is_contiguous() and Y.is_contiguous() and X.shape == Y.shape
+    if out is None:
+        out = torch.empty_like(X)
+    check(
+        ctx.lib.gpxb_elementwise(ctx.handle, 0 if op == "axpby" else 1, X.numel(), float(a), ptr(X), float(b), ptr(Y),
+                                 ptr(out), stream_ptr()),
+        "gpxb_elementwise",
+    )
+    return out
+
+
 def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower_only=False):
     ctx = context()
     A, B = _f64(A), _f64(B)

@@ -56,6 +56,18 @@ int gpxb_gram(gpxb_ctx* ctx, int kind, const double* x1, int n1, const double* x
               double ell, double diag_add, double* out, long long ldo, int lower_only,
               gpxb_stream stream);
 
+/* *out (device) = sum_ij Y_ij d k(x1_i, x2_j)/d lengthscale without forming dK (the contraction epilogue of
+ * the Gram kernel): the building block of hyper-parameter gradients of composite kernels
+ * (gpx/kernels/kernels.py:1794-1942 Sum / Prod under value_and_grad).  sym_lower (identical operands): Y is the
+ * lower triangle of a symmetric matrix and the sum runs over the full matrix. */
+int gpxb_gram_dl_contract(gpxb_ctx* ctx, int kind, const double* x1, int n1, const double* x2, int n2, int D,
+                          double ell, const double* Y, long long ldy, int sym_lower, double* out,
+                          gpxb_stream stream);
+/* out[i] = a X[i] + b Y[i] (op = 0) or a X[i] Y[i] (op = 1) on n contiguous doubles; out may alias X or Y
+ * (sum_kernels / prod_kernels, gpx/kernels/operations.py:103-426, applied to device matrices). */
+int gpxb_elementwise(gpxb_ctx* ctx, int op, long long n, double a, const double* X, double b, const double* Y,
+                     double* out, gpxb_stream stream);
+
 /* ---- Family 1b: Hessian-Jacobian kernel (training on derivative values) --------------- */
 /* out[(n1*nv1) x (n2*nv2)] = Kernel.d01kj(x1, x2, params, J1, J2) (+ diag_add * I when both operands
  * are the same arrays); row index = sample * nv + variable.  x: n x nf, J: n x nf x nv row-major.

@@ -208,6 +208,27 @@ def kernel(kind: str, x1, x2, ell: float):
     raise ValueError(kind)
 
 
+def composite_kernel(spec, x1, x2):
+    """Sum / Prod kernels (kernels.py:1794-1942; operations.py:103-426).  spec: ("leaf", kind, ell, active_dims)
+    or ("sum" | "prod", spec1, spec2)."""
+    if spec[0] == "leaf":
+        _, kind, ell, dims = spec
+        a, b = (x1, x2) if dims is None else (x1[:, dims], x2[:, dims])
+        return kernel(kind, a, b, ell)
+    K1, K2 = composite_kernel(spec[1], x1, x2), composite_kernel(spec[2], x1, x2)
+    return K1 + K2 if spec[0] == "sum" else K1 * K2
+
+
+def composite_lml_dense(spec, x, y, sigma, mean_function=data_mean):
+    """_gpr.py:737-769 with a composite kernel."""
+    m = y.shape[0]
+    r = y - mean_function(y)
+    A = composite_kernel(spec, x, x) + (sigma**2 + 1e-10) * np.eye(m)
+    L = sla.cholesky(A, lower=True, check_finite=False)
+    cy = sla.solve_triangular(L, r, lower=True, check_finite=False)
+    return (-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - m * 0.5 * np.log(2.0 * np.pi)) / m
+
+
 def kernel_dl(kind: str, x1, x2, ell: float):
     """(K, dK/d ell): what reverse-mode autodiff of ``kernel`` yields.
     s = d2 - jitter is formed exactly as autodiff forms it: -ell/2 * d(d2)/d ell."""
