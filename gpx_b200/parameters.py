@@ -115,16 +115,25 @@ class ModelState:
         np.savez(state_file, **d)
         return d
 
-    def load(self, state_file: str) -> "ModelState":
-        z = np.load(state_file, allow_pickle=False)
+    def load(self, state_file: str, allow_pickle: bool = False) -> "ModelState":
+        """Loads a checkpoint written by `save` here or by the reference (gpx/parameters/model_state.py:246-347).
+        The reference stores unset auxiliary entries (None) as pickled 0-d object arrays; those carry no data
+        and are skipped unless allow_pickle=True is passed (never unpickle files you do not trust)."""
+        z = np.load(state_file, allow_pickle=allow_pickle)
         st = self
         upd = {}
         for k in z.files:
-            if k.startswith("params:"):
-                st = st.with_param_value(k.split(":")[1:], z[k])
-            elif k in self._register:
+            try:
                 v = z[k]
-                upd[k] = bool(v) if v.dtype == bool and v.shape == () else v
+            except ValueError:  # object array and allow_pickle=False: a None placeholder of the reference
+                continue
+            if k.startswith("params:"):
+                st = st.with_param_value(k.split(":")[1:], np.asarray(v, dtype=np.float64))
+            elif k in self._register:
+                if v.dtype == object:
+                    upd[k] = None if v.ndim == 0 and v.item() is None else v
+                else:
+                    upd[k] = bool(v) if v.dtype == bool and v.shape == () else v
         return st.update(upd)
 
     def __repr__(self):

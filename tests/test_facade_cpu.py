@@ -61,3 +61,21 @@ def test_trainable_flattening_and_chain_rule():
     st = unravel_forward(m.state, paths, x0 + 0.1)
     assert st.params["kernel_params"]["lengthscale"].value > 1.0
     assert st.params["sigma"].value == 0.5
+
+
+def test_load_reference_style_checkpoint(tmp_path):
+    """A checkpoint laid out as the reference's ModelState.save writes it (gpx/parameters/model_state.py:246-300):
+    "params:kernel_params:lengthscale"-style keys plus every registered auxiliary entry, unset ones as pickled
+    None placeholders."""
+    f = str(tmp_path / "ref_state.npz")
+    np.savez(f, **{"params:kernel_params:lengthscale": np.float64(0.7), "params:sigma": np.float64(0.2),
+                   "x_train": np.arange(6.0).reshape(3, 2), "y_train": np.ones((3, 1)), "c": np.full((3, 1), 2.0),
+                   "mu": np.float64(1.5), "is_fitted": np.bool_(True), "is_fitted_derivs": np.bool_(False),
+                   "jacobian_train": np.array(None, dtype=object), "jaccoef": np.array(None, dtype=object)})
+    m = GPR(kernel=Matern52()).load(f)
+    assert float(m.state.params["kernel_params"]["lengthscale"].value) == 0.7
+    assert float(m.state.params["sigma"].value) == 0.2
+    assert m.state.is_fitted is True and m.state.c.shape == (3, 1) and float(m.state.mu) == 1.5
+    m2 = GPR(kernel=Matern52())
+    m2.state = m2.state.load(f, allow_pickle=True)
+    assert m2.state.is_fitted is True
