@@ -21,8 +21,6 @@ def _slice_leaf(k, xd):
 
 
 def _center(state, y):
-    import torch
-
     yd = _to_device(y)
     if yd.dim() == 1:
         yd = yd.reshape(-1, 1)
@@ -41,8 +39,6 @@ def _factor(state, xd):
 
 def lml_and_grad(state, x, y, want_grad):
     """(lml, {param path: d lml / d value})."""
-    import torch
-
     xd = _to_device(x)
     rT, _ = _center(state, y)
     N = xd.shape[0]

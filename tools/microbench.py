@@ -2,7 +2,6 @@
 libgpxb200's GEMM / Cholesky / LML.  Prints one JSON line per measurement."""
 import json
 import sys
-import time
 
 import numpy as np
 import torch
