@@ -10,6 +10,9 @@
 // by explicitly inverted 128x128 diagonal blocks.  The 128x128 leaves are
 // factorised AND inverted by one CTA in shared memory.  Solves and the triangular
 // inverse recurse on halves so that their flops are large GEMMs too.
+#include <cstdlib>
+#include <vector>
+
 #include "chol.cuh"
 #include "gemm.cuh"
 #include "mma.cuh"
@@ -200,6 +203,173 @@ potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Leaf, second generation (default): the same contract as potrf_leaf_kernel, organised so that only the
+// four 32x32 diagonal blocks are eliminated column by column -- by ONE warp each, rows in registers, pivots
+// and multipliers exchanged by warp shuffles (no block barrier inside the 32 column steps) -- while every
+// off-diagonal operation (panel solve against the inverted diagonal block, rank-32 trailing update, the two
+// merge levels of the inverse) runs on the FP64 tensor pipe from shared memory.  12 block barriers in the
+// factorisation instead of 256.
+constexpr int L2S = 132;   // row stride of the 128x128 matrix in smem (== 4 mod 16: conflict-free fragment reads)
+constexpr int DIS = 36;    // row stride of a 32x32 diagonal-block inverse
+constexpr int T2S = 68;    // row stride of the 64x64 scratch
+constexpr int LEAF2_SMEM = (LB * L2S + 4 * 32 * DIS + 64 * T2S + 32) * (int)sizeof(double);
+
+// C[M x N] (ldc) = alpha * A[M x K] (row-major, lda) * B[K x N] (row-major, ldb); 8x8 tiles over the CTA's 8 warps
+__device__ __forceinline__ void cta_mm(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
+                                       int N, int K, double alpha, int warp, int lane) {
+  const int lr = lane >> 2, lq = lane & 3;
+  const int tn = N >> 3, nt = (M >> 3) * tn;
+  for (int t = warp; t < nt; t += 8) {
+    const int ti = t / tn, tj = t - ti * tn;
+    double c0 = 0.0, c1 = 0.0;
+    const double* ap = A + (ti * 8 + lr) * lda + lq;
+    const double* bp = B + lq * ldb + tj * 8 + lr;
+    for (int k = 0; k < K; k += 4) dmma884(c0, c1, ap[k], bp[k * ldb]);
+    double* cp = C + (ti * 8 + lr) * ldc + tj * 8 + 2 * lq;
+    cp[0] = alpha * c0;
+    cp[1] = alpha * c1;
+  }
+}
+
+__global__ void __launch_bounds__(LEAF_NT, 1)
+potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;                       // [128][L2S]  A -> L -> inverse, in place
+  double* DI = S + LB * L2S;            // [4][32][DIS] inverses of the diagonal blocks
+  double* T = DI + 4 * 32 * DIS;        // [64][T2S]
+  double* rds = T + 64 * T2S;           // [32] reciprocals of the current diagonal block's pivots
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lq = lane & 3;
+
+  // lower triangle in, identity padding beyond n (keeps every block operation well defined)
+  for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    double v = 0.0;
+    if (i < n) { if (k <= i) v = A[(long long)i * lda + k]; }
+    else if (k == i) v = 1.0;
+    S[i * L2S + k] = v;
+  }
+  __syncthreads();
+
+  for (int jb = 0; jb < LB; jb += 32) {
+    double* Dinv = DI + (jb >> 5) * 32 * DIS;
+    if (warp == 0) {
+      // ---- 32x32 diagonal block: lane = row; right-looking elimination through shuffles ----
+      double a[32];
+      const double* row = S + (jb + lane) * L2S + jb;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? row[c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, a[c], c);
+        const double rd = rsqrt(piv);  // NaN for a non-PD pivot: propagates like JAX
+        if (lane == c) {
+          a[c] = piv * rd;
+          rds[c] = rd;
+        } else if (lane > c) {
+          a[c] *= rd;
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < 32; ++c2) {  // rectangular bounds: the triangular condition folds after unrolling
+          if (c2 > c) {
+            const double l2 = __shfl_sync(0xffffffffu, a[c], c2);  // L[c2][c]
+            if (lane >= c2) a[c2] -= a[c] * l2;
+          }
+        }
+      }
+      double* rowo = S + (jb + lane) * L2S + jb;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c <= lane) rowo[c] = a[c];
+      __syncwarp();
+      // ---- its inverse: lane = column j of X, forward substitution; L[r][k] is a broadcast read of smem ----
+      double x[32];
+      const double* Lb = S + jb * L2S + jb;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        double v = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (k < r) v -= Lb[r * L2S + k] * x[k];
+        x[r] = (r >= lane) ? v * rds[r] : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < 32; ++r) Dinv[r * DIS + lane] = x[r];
+    }
+    __syncthreads();
+    const int r0 = jb + 32, R = LB - r0;  // rows below the block
+    if (R > 0) {
+      // ---- panel: L21 = A21 Dinv^T, one warp per 8-row block (in place: fragments first, stores last) ----
+      for (int rb = warp; rb < (R >> 3); rb += 8) {
+        double* ab = S + (r0 + rb * 8 + lr) * L2S + jb;
+        double av[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) av[ks] = ab[ks * 4 + lq];
+        double c[4][2];
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) {
+          c[nf][0] = c[nf][1] = 0.0;
+          const double* bp = Dinv + (nf * 8 + lr) * DIS + lq;  // B[k][n] = Dinv[n][k]
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) dmma884(c[nf][0], c[nf][1], av[ks], bp[ks * 4]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) {
+          ab[nf * 8 + 2 * lq] = c[nf][0];
+          ab[nf * 8 + 2 * lq + 1] = c[nf][1];
+        }
+      }
+      __syncthreads();
+      // ---- trailing update: A22 -= L21 L21^T on the lower 8x8 tiles ----
+      const int nt = R >> 3, ntiles = nt * (nt + 1) / 2;
+      for (int t = warp; t < ntiles; t += 8) {
+        int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while (ti * (ti + 1) / 2 > t) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        const double* ap = S + (r0 + ti * 8 + lr) * L2S + jb + lq;
+        const double* bp = S + (r0 + tj * 8 + lr) * L2S + jb + lq;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) dmma884(c0, c1, ap[ks * 4], bp[ks * 4]);
+        double* cp = S + (r0 + ti * 8 + lr) * L2S + r0 + tj * 8 + 2 * lq;
+        cp[0] -= c0;
+        cp[1] -= c1;
+      }
+      __syncthreads();
+    }
+  }
+  for (int idx = tid; idx < n * n; idx += LEAF_NT) {
+    const int i = idx / n, k = idx - i * n;
+    if (k <= i) A[(long long)i * lda + k] = S[i * L2S + k];
+  }
+  if (inv == nullptr) return;
+  __syncthreads();
+  // ---- inverse in place: diagonal blocks, then X21 = -X22 (L21 X11) for the 32 -> 64 and 64 -> 128 merges ----
+  for (int idx = tid; idx < 4 * 32 * 32; idx += LEAF_NT) {
+    const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
+    S[(b * 32 + r) * L2S + b * 32 + c] = DI[(b * 32 + r) * DIS + c];
+  }
+  __syncthreads();
+  for (int p = 0; p < LB; p += 64)  // T_p = L21 X11   (32 x 32 x 32)
+    cta_mm(T + (p >> 1) * T2S, T2S, S + (p + 32) * L2S + p, L2S, S + p * L2S + p, L2S, 32, 32, 32, 1.0, warp, lane);
+  __syncthreads();
+  for (int p = 0; p < LB; p += 64)  // X21 = -X22 T_p
+    cta_mm(S + (p + 32) * L2S + p, L2S, S + (p + 32) * L2S + p + 32, L2S, T + (p >> 1) * T2S, T2S, 32, 32, 32, -1.0,
+           warp, lane);
+  __syncthreads();
+  cta_mm(T, T2S, S + 64 * L2S, L2S, S, L2S, 64, 64, 64, 1.0, warp, lane);
+  __syncthreads();
+  cta_mm(S + 64 * L2S, L2S, S + 64 * L2S + 64, L2S, T, T2S, 64, 64, 64, -1.0, warp, lane);
+  __syncthreads();
+  for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    inv[idx] = (i < n && k <= i) ? S[i * L2S + k] : 0.0;
+  }
+}
+
 __global__ void logdet_kernel(const double* __restrict__ L, long long ld, int n,
                               double* __restrict__ out, double scale) {
   __shared__ double sh[32];
@@ -209,16 +379,20 @@ __global__ void logdet_kernel(const double* __restrict__ L, long long ld, int n,
   if (threadIdx.x == 0) *out = scale * s;
 }
 
-__global__ void copy_block_kernel(const double* __restrict__ src, double* __restrict__ dst,
-                                  long long ldd, int n) {
-  // src: packed 128x128 leaf inverse; dst: n x n lower block
-  for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < n * n; idx += blockDim.x * gridDim.x) {
-    const int i = idx / n, k = idx - i * n;
-    if (k <= i) dst[(long long)i * ldd + k] = src[i * LB + k];
-  }
-}
-
 int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s) {
+  static int gen = -1;
+  if (gen < 0) {
+    const char* e = getenv("GPXB_LEAF");  // "v1": the register-panel leaf kept for comparison
+    gen = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+  }
+  if (gen == 2) {
+    GPXB_CUDA_CHECK(cudaFuncSetAttribute(potrf_leaf_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         LEAF2_SMEM));
+    potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+    return 0;
+  }
   GPXB_CUDA_CHECK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        LEAF_SMEM));
   potrf_leaf_kernel<<<1, LEAF_NT, LEAF_SMEM, s>>>(A, lda, n, inv);
@@ -657,67 +831,75 @@ int logdet_bcp(Ctx* ctx, const double* Lp, int n, double* out, double scale, cud
 }
 
 namespace {
+// scratch of the level-wise triangular inverse: one level's T blocks (at most n^2/4 at the top level, plus the
+// ragged pairs), rounded up generously
 size_t trtri_scratch(int n) {
   if (n <= LB) return 0;
-  const int n1 = split_point(n), n2 = n - n1;
-  return (size_t)n1 * n2 + trtri_scratch(n1) + trtri_scratch(n2);
+  return (size_t)n * (size_t)n / 2 + (size_t)LB * n;
 }
 
-// W (n x n, zero-initialised, lower) <- L^-1.  T: trtri_scratch(n) doubles.  The two half-size
-// inversions are independent; down to depth 2 they run on separate streams (4-way concurrency)
-// so that the small GEMMs deep in the recursion still fill the GPU.  st[0] is the caller's stream.
-int trtri_rec(Ctx* ctx, const double* L, long long ldl, const double* inv, double* W, long long ldw,
-              int n, double* T, cudaStream_t* st, int depth, int branch) {
-  cudaStream_t s = st[depth <= 2 ? branch * (4 >> depth) : 0];
-  if (depth > 2) s = st[branch];  // below the fork levels 'branch' carries the stream index
-  if (n <= LB) {
-    copy_block_kernel<<<32, 256, 0, s>>>(inv, W, ldw, n);
-    GPXB_LAUNCH_CHECK();
-    ctx->launches++;
-    return 0;
+// all leaf inverses into the diagonal blocks of W in one launch
+__global__ void copy_leaves_kernel(const double* __restrict__ inv, double* __restrict__ W, long long ldw, int n) {
+  const int k = blockIdx.x, c0 = k * LB, nb = (n - c0 < LB) ? n - c0 : LB;
+  const double* src = inv + (long long)k * LB * LB;
+  for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+    const int i = idx / nb, j = idx - i * nb;
+    if (j <= i) W[(long long)(c0 + i) * ldw + c0 + j] = src[i * LB + j];
   }
-  const int n1 = split_point(n), n2 = n - n1;
-  const double* inv2 = inv + (long long)(n1 / LB) * LB * LB;
-  double* Tc1 = T + (size_t)n1 * n2;
-  double* Tc2 = Tc1 + trtri_scratch(n1);
-  const double* L22 = L + (long long)n1 * ldl + n1;
-  double* W22 = W + (long long)n1 * ldw + n1;
-  if (depth < 2 && n >= 2048) {
-    const int b1 = 2 * branch, b2 = 2 * branch + 1;
-    cudaStream_t s2 = st[b2 * (4 >> (depth + 1))];
-    cudaEvent_t e0, e1;
-    GPXB_TRY(ctx->next_event(&e0));
-    GPXB_CUDA_CHECK(cudaEventRecord(e0, s));
-    GPXB_CUDA_CHECK(cudaStreamWaitEvent(s2, e0, 0));
-    GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, ldw, n1, Tc1, st, depth + 1, b1));
-    GPXB_TRY(trtri_rec(ctx, L22, ldl, inv2, W22, ldw, n2, Tc2, st, depth + 1, b2));
-    GPXB_TRY(ctx->next_event(&e1));
-    GPXB_CUDA_CHECK(cudaEventRecord(e1, s2));
-    GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, e1, 0));
-  } else {
-    // sequential on this node's stream
-    const int sidx = (depth <= 2) ? branch * (4 >> depth) : branch;
-    GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, ldw, n1, Tc1, st, 3, sidx));
-    GPXB_TRY(trtri_rec(ctx, L22, ldl, inv2, W22, ldw, n2, Tc2, st, 3, sidx));
-  }
-  {
+}
+
+// W (n x n, zero-initialised, lower) <- L^-1, bottom-up: the leaf inverses are in place; at every level
+// neighbouring diagonal blocks [W11, W22] are merged by  W21 = -W22 (L21 W11)  (two GEMMs that skip the zero
+// halves of the triangular operands).  All merges of a level have the same shape except possibly the last, so
+// each level is TWO batched GEMM launches: the many small products deep in the tree fill the GPU together
+// instead of running as single-tile launches.  T: trtri_scratch(n) doubles.
+int trtri_levels(Ctx* ctx, const double* L, long long ldl, const double* inv, double* W, long long ldw, int n,
+                 double* T, cudaStream_t s) {
+  const int nleaf = (n + LB - 1) / LB;
+  copy_leaves_kernel<<<nleaf, 256, 0, s>>>(inv, W, ldw, n);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  struct Blk { int start, size; };
+  std::vector<Blk> cur;
+  for (int k = 0; k < nleaf; ++k) cur.push_back({k * LB, min(LB, n - k * LB)});
+  auto merge = [&](int start, int n1, int n2, int batch, double* Tb) -> int {
+    const long long step = (long long)(n1 + n2);  // distance between consecutive pairs along the diagonal
     GemmArgs g;  // T = L21 * W11   (W11 lower: k starts at the tile's first column)
     g.M = n2; g.N = n1; g.K = n1;
-    g.A = L + (long long)n1 * ldl; g.lda = ldl; g.a_kmajor = true;
-    g.B = W; g.ldb = ldw; g.b_kmajor = false;
-    g.C = T; g.ldc = n1;
+    g.A = L + (long long)(start + n1) * ldl + start; g.lda = ldl; g.a_kmajor = true;
+    g.B = W + (long long)start * ldw + start; g.ldb = ldw; g.b_kmajor = false;
+    g.C = Tb; g.ldc = n1;
     g.klo_mode = 1;
+    g.batch = batch; g.strideA = step * ldl + step; g.strideB = step * ldw + step; g.strideC = (long long)n1 * n2;
     GPXB_TRY(gemm_f64(ctx, g, s));
-  }
-  {
-    GemmArgs g;  // W21 = -W22 * T   (W22 lower: k ends at the tile's last row)
-    g.M = n2; g.N = n1; g.K = n2;
-    g.A = W22; g.lda = ldw; g.a_kmajor = true;
-    g.B = T; g.ldb = n1; g.b_kmajor = false;
-    g.C = W + (long long)n1 * ldw; g.ldc = ldw;
-    g.alpha = -1.0;
-    g.khi_mode = 1;
-    GPXB_TRY(gemm_f64(ctx, g, s));
+    GemmArgs h;  // W21 = -W22 * T   (W22 lower: k ends at the tile's last row)
+    h.M = n2; h.N = n1; h.K = n2;
+    h.A = W + (long long)(start + n1) * ldw + start + n1; h.lda = ldw; h.a_kmajor = true;
+    h.B = Tb; h.ldb = n1; h.b_kmajor = false;
+    h.C = W + (long long)(start + n1) * ldw + start; h.ldc = ldw;
+    h.alpha = -1.0;
+    h.khi_mode = 1;
+    h.batch = batch; h.strideA = step * ldw + step; h.strideB = (long long)n1 * n2; h.strideC = step * ldw + step;
+    return gemm_f64(ctx, h, s);
+  };
+  while (cur.size() > 1) {
+    const int npairs = (int)cur.size() / 2;
+    const int b = cur[0].size;
+    int nu = 0;  // leading run of uniform pairs
+    while (nu < npairs && cur[2 * nu].size == b && cur[2 * nu + 1].size == b && cur[2 * nu].start == 2 * nu * b) ++nu;
+    double* Tb = T;
+    if (nu > 0) {
+      GPXB_TRY(merge(0, b, b, nu, Tb));
+      Tb += (size_t)nu * b * b;
+    }
+    for (int i = nu; i < npairs; ++i) {
+      GPXB_TRY(merge(cur[2 * i].start, cur[2 * i].size, cur[2 * i + 1].size, 1, Tb));
+      Tb += (size_t)cur[2 * i].size * cur[2 * i + 1].size;
+    }
+    std::vector<Blk> nxt;
+    for (int i = 0; i < npairs; ++i) nxt.push_back({cur[2 * i].start, cur[2 * i].size + cur[2 * i + 1].size});
+    if (cur.size() % 2) nxt.push_back(cur.back());
+    cur.swap(nxt);
   }
   return 0;
 }
@@ -729,8 +911,7 @@ int potri_lower(Ctx* ctx, const double* L, long long ldl, const double* inv, int
                 double* T, double* out, long long ldo, cudaStream_t s) {
   if (n <= 0) return 0;
   GPXB_CUDA_CHECK(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)n * (size_t)n, s));
-  cudaStream_t st[4] = {s, ctx->aux[0], ctx->aux[1], ctx->aux[2]};
-  GPXB_TRY(trtri_rec(ctx, L, ldl, inv, W, n, n, T, st, 0, 0));
+  GPXB_TRY(trtri_levels(ctx, L, ldl, inv, W, n, n, T, s));
   GemmArgs g;  // out = W^T W (lower); W[k][i] = 0 for k < i -> k starts at the tile's first row
   g.M = n; g.N = n; g.K = n;
   g.A = W; g.lda = n; g.a_kmajor = false;

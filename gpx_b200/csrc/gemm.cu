@@ -39,6 +39,7 @@ struct GemmParams {
   int lower_only, klo_mode, khi_mode;
   int tiles_m, tiles_n;
   int vecA, vecB, vecC;
+  long long strideA, strideB, strideC;  // batched launch: blockIdx.y selects the product
 };
 
 // Per-thread loader state for one operand: the thread's 16-byte chunks of a tile
@@ -186,8 +187,11 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
 
   TileLoader<AK, NTHR> la;
   TileLoader<BKM, NTHR> lb;
-  la.init(p.A, p.lda, row0, p.M, k_lo, p.vecA, tid);
-  lb.init(p.B, p.ldb, col0, p.N, k_lo, p.vecB, tid);
+  const double* Ab = p.A + (long long)blockIdx.y * p.strideA;
+  const double* Bb = p.B + (long long)blockIdx.y * p.strideB;
+  double* Cb = p.C + (long long)blockIdx.y * p.strideC;
+  la.init(Ab, p.lda, row0, p.M, k_lo, p.vecA, tid);
+  lb.init(Bb, p.ldb, col0, p.N, k_lo, p.vecB, tid);
 
   // ---- pipeline prologue ----
 #pragma unroll
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
     for (int nf = 0; nf < NF; ++nf) {
       const int col = col0 + wn * (8 * NF) + nf * 8 + lq * 2;
       if (col >= p.N) continue;
-      double* cp = p.C + (long long)row * p.ldc + col;
+      double* cp = Cb + (long long)row * p.ldc + col;
       const bool ok0 = !p.lower_only || col <= row;
       const bool ok1 = (col + 1 < p.N) && (!p.lower_only || col + 1 <= row);
       double v0 = p.alpha * acc[mf][nf][0], v1 = p.alpha * acc[mf][nf][1];
@@ -298,13 +302,14 @@ double launch_flops(const GemmParams& p, long long grid) {
 }
 
 template <bool AK, bool BKM>
-int launch(Ctx* ctx, const GemmParams& p, int grid, cudaStream_t stream) {
+int launch(Ctx* ctx, const GemmParams& p, int grid1, int batch, cudaStream_t stream) {
+  const dim3 grid(grid1, batch);
   Ctx::ProfRec rec{nullptr, nullptr, 0.0};
   const bool prof = ctx && ctx->prof;
   if (prof) {
     GPXB_CUDA_CHECK(cudaEventCreate(&rec.e0));
     GPXB_CUDA_CHECK(cudaEventCreate(&rec.e1));
-    rec.flops = launch_flops(p, grid);
+    rec.flops = launch_flops(p, grid1) * batch;
     GPXB_CUDA_CHECK(cudaEventRecord(rec.e0, stream));
   }
   if (gemm_variant() == 8) {
@@ -340,9 +345,12 @@ int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream) {
   p.lower_only = g.lower_only; p.klo_mode = g.klo_mode; p.khi_mode = g.khi_mode;
   p.tiles_m = ceil_div(g.M, BM);
   p.tiles_n = ceil_div(g.N, BN);
-  p.vecA = aligned16(g.A) && (g.lda % 2 == 0);
-  p.vecB = aligned16(g.B) && (g.ldb % 2 == 0);
-  p.vecC = aligned16(g.C) && (g.ldc % 2 == 0);
+  GPXB_ARG_CHECK(g.batch >= 1 && g.batch <= 65535, -4);
+  p.strideA = g.strideA; p.strideB = g.strideB; p.strideC = g.strideC;
+  const bool even_strides = g.batch == 1 || (g.strideA % 2 == 0 && g.strideB % 2 == 0 && g.strideC % 2 == 0);
+  p.vecA = aligned16(g.A) && (g.lda % 2 == 0) && even_strides;
+  p.vecB = aligned16(g.B) && (g.ldb % 2 == 0) && even_strides;
+  p.vecC = aligned16(g.C) && (g.ldc % 2 == 0) && even_strides;
   long long grid;
   if (g.lower_only) {
     GPXB_ARG_CHECK(g.M >= g.N, -2);
@@ -351,10 +359,10 @@ int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream) {
     grid = (long long)p.tiles_m * p.tiles_n;
   }
   GPXB_ARG_CHECK(grid < (1LL << 31), -3);
-  if (g.a_kmajor && g.b_kmajor) return launch<true, true>(ctx, p, (int)grid, stream);
-  if (g.a_kmajor && !g.b_kmajor) return launch<true, false>(ctx, p, (int)grid, stream);
-  if (!g.a_kmajor && g.b_kmajor) return launch<false, true>(ctx, p, (int)grid, stream);
-  return launch<false, false>(ctx, p, (int)grid, stream);
+  if (g.a_kmajor && g.b_kmajor) return launch<true, true>(ctx, p, (int)grid, g.batch, stream);
+  if (g.a_kmajor && !g.b_kmajor) return launch<true, false>(ctx, p, (int)grid, g.batch, stream);
+  if (!g.a_kmajor && g.b_kmajor) return launch<false, true>(ctx, p, (int)grid, g.batch, stream);
+  return launch<false, false>(ctx, p, (int)grid, g.batch, stream);
 }
 
 }  // namespace gpxb

@@ -28,6 +28,10 @@ struct GemmArgs {
   int lower_only = 0;
   int klo_mode = 0;
   int khi_mode = 0;
+  // batch > 1: `batch` independent products of identical shape in one launch; operand z starts strideX * z
+  // doubles after operand 0 (same leading dimensions)
+  int batch = 1;
+  long long strideA = 0, strideB = 0, strideC = 0;
 };
 
 int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream);
