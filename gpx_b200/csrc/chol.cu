@@ -288,11 +288,11 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
       const double* Lb = S + jb * L2S + jb;
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        double v = (r == lane) ? 1.0 : 0.0;
+        double v[4] = {(r == lane) ? 1.0 : 0.0, 0.0, 0.0, 0.0};  // four independent chains: FP64 FMA latency
 #pragma unroll
         for (int k = 0; k < 32; ++k)
-          if (k < r) v -= Lb[r * L2S + k] * x[k];
-        x[r] = (r >= lane) ? v * rds[r] : 0.0;
+          if (k < r) v[k & 3] -= Lb[r * L2S + k] * x[k];
+        x[r] = (r >= lane) ? ((v[0] + v[1]) + (v[2] + v[3])) * rds[r] : 0.0;
       }
 #pragma unroll
       for (int r = 0; r < 32; ++r) Dinv[r * DIS + lane] = x[r];
