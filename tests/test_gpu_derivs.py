@@ -234,7 +234,7 @@ def test_iterative_fit_and_lml_on_derivatives(kind, N, nf, nv, npiv):
     ref = R.lml_derivs_iter(kind, x, y, J, ell, sigma, 5, 10, key, npiv, key)
     out = m.log_marginal_likelihood_derivs(x, y, J, iterative=True, num_evals=5, num_lanczos=10, key_lanczos=key,
                                            n_pivots=npiv, key_precond=key)
-    assert abs(out - ref) < 1e-8 * abs(ref)
+    assert abs(out - ref) < 1e-7 * abs(ref)  # PCG at tol 1e-5 inside (see test_iterative_derivative_lml_gradient)
     m.fit_derivs(x, y, J, minimize=False, iterative=True, n_pivots=npiv)
     assert m.state.c.shape == (N * nv, 1) and m.state.jaccoef.shape == (N, nf)
 
@@ -264,7 +264,9 @@ def test_iterative_derivative_lml_gradient(kind, N, nf, nv):
                      sigma=Parameter(sigma, True, Softplus(), GammaPrior()), loss_fn=neg_log_marginal_likelihood_derivs)
     loss, grads = mk()._loss_and_grad_derivs_fun(mk().state, x, y, J, iterative=True, num_evals=5, num_lanczos=10,
                                                  key_lanczos=key, n_pivots=20, key_precond=key)
-    assert abs(-loss - ref[0]) < 1e-8 * abs(ref[0])
+    # the value goes through PCG stopped at a 1e-5 relative residual: rounding-level differences in the
+    # preconditioner move the iterates, and with them y.c, at the 1e-8 level
+    assert abs(-loss - ref[0]) < 1e-7 * abs(ref[0])
     assert abs(-grads[("kernel_params", "lengthscale")] - ref[1]) < 1e-6 * max(abs(ref[1]), abs(ref[0]))
     assert abs(-grads[("sigma",)] - ref[2]) < 1e-6 * max(abs(ref[2]), abs(ref[0]))
     m = mk().fit_derivs(x, y, J, iterative=True, n_pivots=20, loss_kwargs=dict(num_evals=5, num_lanczos=10, key_lanczos=key),

@@ -139,7 +139,9 @@ def test_lml_iter_facade_matches_oracle():
                      sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
     out = gpr.log_marginal_likelihood(state, x, y, iterative=True, num_evals=8, num_lanczos=20,
                                       key_lanczos=key, n_pivots=30, key_precond=key)
-    assert abs(out - ref) < 1e-8 * abs(ref)
+    # PCG stops at a 1e-5 relative residual: rounding-level differences in the preconditioner's inverse move the
+    # iterates and with them y.c at the 1e-8 level, so the iterative LML is compared at 1e-7
+    assert abs(out - ref) < 1e-7 * abs(ref)
 
 
 @pytest.mark.parametrize("kind,N,D,P", [("se", 700, 16, 5), ("m52", 513, 8, 33), ("m32", 300, 3, 1), ("m12", 260, 2, 2)])
@@ -201,7 +203,7 @@ def test_lml_iter_gradient_facade_matches_oracle_and_trains():
                      sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
     kw = dict(iterative=True, num_evals=6, num_lanczos=15, key_lanczos=key, n_pivots=25, key_precond=key)
     loss, grads = mk().loss_and_grad(x, y, **kw)
-    assert abs(-loss - ref[0]) < 1e-8 * abs(ref[0])
+    assert abs(-loss - ref[0]) < 1e-7 * abs(ref[0])  # PCG inside (see test_lml_iter_facade_matches_oracle)
     assert abs(-grads[("kernel_params", "lengthscale")] - ref[1]) < 1e-6 * max(abs(ref[1]), abs(ref[0]))
     assert abs(-grads[("sigma",)] - ref[2]) < 1e-6 * max(abs(ref[2]), abs(ref[0]))
     m = mk().fit(x, y, iterative=True, n_pivots=25, loss_kwargs=dict(num_evals=6, num_lanczos=15, key_lanczos=key),
