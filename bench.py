@@ -194,8 +194,16 @@ def run_gpu(args):
     e1.record()
     barrier()
     ops.prof_enable(False)
-    gemm_ms, gemm_flops, gemm_n = ops.prof_collect()
+    reg_ms, reg_flops, reg_n = ops.prof_collect()
     launches = ops.launches() - l0
+    # one more, untimed, step with the look-ahead serialised: no two launches overlap, so the summed event
+    # durations are pure kernel time (in the timed region the panel factorisation runs concurrently with the
+    # trailing update and overlapped time is counted twice)
+    ops.prof_enable(2)
+    ops.gpr_lml_grad(kind, x, y, ell, sigma)
+    torch.cuda.synchronize()
+    ops.prof_enable(False)
+    gemm_ms, gemm_flops, gemm_n = ops.prof_collect()
     ms = max_over_ranks(e0.elapsed_time(e1)) / K
     clocks = sampler.stop() if sampler else None
     res = out.cpu().numpy()
@@ -285,9 +293,12 @@ def run_gpu(args):
                    "lml": float(res[0]), "grad": [float(res[1]), float(res[2])]},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "gemm_f64_kernel (DMMA GEMM / SYRK, all layouts): %d launches in the timed region, "
-                               "summed launch durations %.1f ms in a %.1f ms region (look-ahead launches run concurrently)"
-                               % (gemm_n, gemm_ms, ms * K),
+                     "kernel": "gemm_f64_kernel (DMMA GEMM / SYRK, all layouts): %d launches of one step with the "
+                               "look-ahead serialised (no overlapping launches), summed launch durations %.1f ms; "
+                               "algorithmic flops counted exactly per tile" % (gemm_n, gemm_ms),
+                     "in_timed_region": {"launches": reg_n, "summed_launch_ms": reg_ms, "region_ms": ms * K,
+                                         "tflops_over_summed_ms": reg_flops / (reg_ms * 1e-3) / 1e12,
+                                         "note": "look-ahead launches overlap here: overlapped time is counted twice"},
                      "avg_launch_ms": gemm_ms / max(gemm_n, 1), "alg_flops_per_launch": gemm_flops / max(gemm_n, 1),
                      "probe": {"shape": f"lower SYRK M=N={m_t} K={k_t}", "tflops": probe},
                      "peak_source": f"cuBLAS Dgemm {nb}^3 measured in this run",

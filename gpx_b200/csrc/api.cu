@@ -82,6 +82,7 @@ int gpxb_ctx_destroy(gpxb_ctx* ctx) {
 int gpxb_prof_enable(gpxb_ctx* ctx, int on) {
   GPXB_ARG_CHECK(ctx != nullptr, -1);
   reinterpret_cast<Ctx*>(ctx)->prof = (on != 0);
+  reinterpret_cast<Ctx*>(ctx)->serialize = (on == 2);
   return 0;
 }
 

@@ -707,7 +707,7 @@ int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStre
   if (n <= NB) return factor_panel(ctx, A, lda, n, 0, n, inv, s);
   // Depth-1 look-ahead: panel p+1 is factorised on the high-priority stream hp while the
   // caller's stream s applies panel p's rank-NB update to the columns right of panel p+1.
-  cudaStream_t hp = ctx->side;
+  cudaStream_t hp = ctx->serialize ? s : ctx->side;
   cudaEvent_t ev, ev_rest_prev = nullptr;
   GPXB_TRY(ctx->next_event(&ev));
   GPXB_CUDA_CHECK(cudaEventRecord(ev, s));
@@ -761,7 +761,7 @@ int potrf_lower_bcp(Ctx* ctx, double* Ap, int n, double* inv, cudaStream_t s) {
     g.lower_only = 1;
     return gemm_f64(ctx, g, st);
   };
-  cudaStream_t hp = ctx->side;
+  cudaStream_t hp = ctx->serialize ? s : ctx->side;
   cudaEvent_t ev, ev_next_prev = nullptr;
   GPXB_TRY(ctx->next_event(&ev));
   GPXB_CUDA_CHECK(cudaEventRecord(ev, s));

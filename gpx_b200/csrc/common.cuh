@@ -75,6 +75,7 @@ struct Ctx {
   unsigned long long launches = 0;  // kernels launched by this library via this ctx
   // optional per-launch timing of the DMMA GEMM (bench.py roofline): event pairs + algorithmic flops
   bool prof = false;
+  bool serialize = false;  // profiling aid: look-ahead work stays on the caller's stream (clean per-launch times)
   struct ProfRec { cudaEvent_t e0, e1; double flops; };
   std::vector<ProfRec> prof_recs;
   void* nccl_comm = nullptr;

@@ -5,6 +5,8 @@
 //
 // Replaces the XLA dot_general / cholesky / triangular_solve lowering the reference
 // relies on (gpx/models/_gpr.py:759-763, _sgpr.py:684-691).
+#include <algorithm>
+
 #include "gemm.cuh"
 #include "mma.cuh"
 
@@ -285,20 +287,38 @@ int gemm_variant() {
   return v;
 }
 
-// algorithmic flops of one launch: 2 * (output tiles' area, clipped) * K_effective is approximated
-// by the tile count x 128 x 128 x 2K for full-K launches; triangular k-ranges halve it.
+// Algorithmic flops of one launch (one batch member), used only by the profiling hooks: 2 x (output entries
+// that are part of the result) x (length of the k range the tile's mode prescribes).  Lower-only launches count
+// the lower triangle of the diagonal tiles only; triangular-operand modes count each tile's own k range, as the
+// kernel executes it (within 128/N of the exact triangular count).
 double launch_flops(const GemmParams& p, long long grid) {
-  double k = (double)p.K;
-  if (p.klo_mode != 0 || p.khi_mode != 0) k *= 0.5;  // triangular operand: half of the k range on average
-  double area;
-  if (p.lower_only) {
-    const double n = (double)p.N, m = (double)p.M;
-    area = n * (n + 1.0) * 0.5 + (m - n) * n;
-  } else {
-    area = (double)p.M * (double)p.N;
-  }
   (void)grid;
-  return 2.0 * area * k;
+  if (p.klo_mode == 0 && p.khi_mode == 0) {
+    double area;
+    if (p.lower_only) {
+      const double n = (double)p.N, m = (double)p.M;
+      area = n * (n + 1.0) * 0.5 + (m - n) * n;
+    } else {
+      area = (double)p.M * (double)p.N;
+    }
+    return 2.0 * area * (double)p.K;
+  }
+  double fl = 0.0;
+  for (int ti = 0; ti < p.tiles_m; ++ti) {
+    const int row0 = ti * BM, rows = std::min(BM, p.M - row0);
+    const int tj_end = p.lower_only ? std::min(p.tiles_n, ti + 1) : p.tiles_n;
+    for (int tj = 0; tj < tj_end; ++tj) {
+      const int col0 = tj * BN, cols = std::min(BN, p.N - col0);
+      int k_lo = (p.klo_mode == 1) ? col0 : (p.klo_mode == 2 ? row0 : 0);
+      k_lo = std::min(k_lo, p.K);
+      const int k_hi = (p.khi_mode == 1) ? std::min(p.K, row0 + BM) : p.K;
+      if (k_hi <= k_lo) continue;
+      double area = (double)rows * cols;
+      if (p.lower_only && ti == tj) area = (double)rows * (rows + 1) * 0.5;
+      fl += 2.0 * area * (double)(k_hi - k_lo);
+    }
+  }
+  return fl;
 }
 
 template <bool AK, bool BKM>

@@ -744,9 +744,11 @@ def comm_init_from_torch_distributed():
     return rank, world
 
 
-def prof_enable(on: bool) -> None:
+def prof_enable(on) -> None:
+    """False / True: bracket every DMMA GEMM launch with CUDA events; 2: additionally serialise the look-ahead
+    work so that the recorded durations do not overlap."""
     ctx = context()
-    check(ctx.lib.gpxb_prof_enable(ctx.handle, int(bool(on))), "gpxb_prof_enable")
+    check(ctx.lib.gpxb_prof_enable(ctx.handle, int(on)), "gpxb_prof_enable")
 
 
 def prof_collect():

@@ -43,7 +43,9 @@ int gpxb_ctx_destroy(gpxb_ctx* ctx);
 unsigned long long gpxb_ctx_launches(gpxb_ctx* ctx);
 /* Measurement aid (bench.py "roofline"): while enabled, every DMMA GEMM launch is bracketed by CUDA
  * events on the stream it is launched on; collect synchronises the device and returns the summed
- * launch durations, their algorithmic flops and the launch count, then clears the records. */
+ * launch durations, their algorithmic flops and the launch count, then clears the records.  on = 2 also keeps
+ * the look-ahead work of the Cholesky factorisation on the caller's stream, so that no two launches overlap and
+ * the summed durations are pure kernel time. */
 int gpxb_prof_enable(gpxb_ctx* ctx, int on);
 int gpxb_prof_collect(gpxb_ctx* ctx, double* total_ms, double* total_flops, int* n_launches);
 
