@@ -321,7 +321,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpxb", choices=["gpxb", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="override N (debugging only; the bench line names it)")
+    ap.add_argument("--rows", "--n", dest="n", type=int, default=0,
+                    help="override N (debugging only; the bench line names it).  Under torchrun use --rows: "
+                         "torchrun's own parser rejects the abbreviation-ambiguous --n")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
