@@ -48,6 +48,14 @@ class Kernel:
         out = ops.gram(self.kind, d1, d2, self.lengthscale(params))
         return out.cpu().numpy() if as_numpy else out
 
+    def k_device(self, x1d, x2d, params):
+        """Device kernel matrix from raw (unsliced) device inputs; `x2d is x1d` marks the symmetric case."""
+        from . import ops
+
+        a = x1d if self.active_dims is None else x1d[:, self.active_dims].contiguous()
+        b = a if x2d is x1d else (x2d if self.active_dims is None else x2d[:, self.active_dims].contiguous())
+        return ops.gram(self.kind, a, b, self.lengthscale(params))
+
     def default_params(self) -> Dict[str, Parameter]:
         # gpx/kernels/kernels.py:1650-1658
         return dict(lengthscale=Parameter(value=1.0, trainable=True, bijector=Softplus(), prior=GammaPrior()))
@@ -71,6 +79,31 @@ class Matern32(Kernel):
 
 class Matern52(Kernel):
     kind = "m52"
+
+
+class Linear(Kernel):
+    """x1 . x2 on the active dimensions, no parameters (gpx/kernels/kernels.py:226-236, class at :1535-1576).
+    One DMMA GEMM (gpxb_gemm); available as a component of Sum / Prod kernels and in the dense exact-GPR paths."""
+    kind = "linear"
+
+    def lengthscale(self, params):
+        raise NotImplementedError("the Linear kernel has no lengthscale")
+
+    def default_params(self) -> Dict[str, Parameter]:
+        return {}
+
+    def k_device(self, x1d, x2d, params):
+        from . import ops
+
+        a = x1d if self.active_dims is None else x1d[:, self.active_dims].contiguous()
+        b = a if x2d is x1d else (x2d if self.active_dims is None else x2d[:, self.active_dims].contiguous())
+        return ops.gemm(a, b, transb=True)
+
+    def k(self, x1, x2, params, as_numpy: bool = True):
+        d1 = _to_device(x1)
+        d2 = d1 if x2 is x1 else _to_device(x2)
+        out = self.k_device(d1, d2, params)
+        return out.cpu().numpy() if as_numpy else out
 
 
 class _Composite(Kernel):
@@ -109,14 +142,8 @@ class _Composite(Kernel):
         """Device kernel matrix from (already sliced per leaf) raw device inputs."""
         from . import ops
 
-        mats = []
-        for name, k in (("kernel1", self.kernel1), ("kernel2", self.kernel2)):
-            if isinstance(k, _Composite):
-                mats.append(k.k_device(x1d, x2d, params[name]))
-            else:
-                a = x1d if k.active_dims is None else x1d[:, k.active_dims].contiguous()
-                b = a if x2d is x1d else (x2d if k.active_dims is None else x2d[:, k.active_dims].contiguous())
-                mats.append(ops.gram(k.kind, a, b, k.lengthscale(params[name])))
+        mats = [k.k_device(x1d, x2d, params[name])
+                for name, k in (("kernel1", self.kernel1), ("kernel2", self.kernel2))]
         return ops.elementwise("axpby" if self.op == "sum" else "mul", mats[0], mats[1], out=mats[0])
 
     def k(self, x1, x2, params, as_numpy: bool = True):

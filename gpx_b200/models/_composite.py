@@ -8,12 +8,13 @@ from __future__ import annotations
 import numpy as np
 
 from .. import ops
-from ..kernels import _Composite, _to_device
+from ..kernels import Linear, _Composite, _to_device
 from ..mean_functions import mean_mode
 
 
 def is_composite(kernel) -> bool:
-    return isinstance(kernel, _Composite)
+    """Kernels served by this generic dense path: Sum / Prod trees and the parameter-free Linear kernel."""
+    return isinstance(kernel, (_Composite, Linear))
 
 
 def _slice_leaf(k, xd):
@@ -54,7 +55,10 @@ def lml_and_grad(state, x, y, want_grad):
     ops.gemm(alphaT, alphaT, transa=True, alpha=-1.0, beta=1.0, C=Wn, lower_only=True)   # Wn = A^-1 - sum_t a a^T
     grads = {("sigma",): sigma * (float((alphaT * alphaT).sum().cpu()) - tr_inv) / N}
     kp = state.params["kernel_params"]
-    for path, k, lp in state.kernel.leaves(kp):
+    leaves = state.kernel.leaves(kp) if isinstance(state.kernel, _Composite) else []
+    for path, k, lp in leaves:
+        if "lengthscale" not in lp:  # Linear: no parameters, no gradient entry
+            continue
         xl = _slice_leaf(k, xd)
         Y = Wn
         w = _other_factors(state.kernel, kp, path, xd)
@@ -72,9 +76,7 @@ def _other_factors(kernel, params, path, xd):
     for name in path:
         other = "kernel2" if name == "kernel1" else "kernel1"
         if node.op == "prod":
-            ok = getattr(node, other)
-            M = ok.k_device(xd, xd, p[other]) if isinstance(ok, _Composite) else \
-                ops.gram(ok.kind, _slice_leaf(ok, xd), _slice_leaf(ok, xd), ok.lengthscale(p[other]))
+            M = getattr(node, other).k_device(xd, xd, p[other])
             F = M if F is None else ops.elementwise("mul", F, M, out=F)
         node, p = getattr(node, name), p[name]
     return F

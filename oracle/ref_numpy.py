@@ -210,10 +210,13 @@ def kernel(kind: str, x1, x2, ell: float):
 
 def composite_kernel(spec, x1, x2):
     """Sum / Prod kernels (kernels.py:1794-1942; operations.py:103-426).  spec: ("leaf", kind, ell, active_dims)
-    or ("sum" | "prod", spec1, spec2)."""
+    or ("sum" | "prod", spec1, spec2); kind "linear" is x1 . x2 on the active dimensions (kernels.py:226-236),
+    its ell entry is ignored."""
     if spec[0] == "leaf":
         _, kind, ell, dims = spec
         a, b = (x1, x2) if dims is None else (x1[:, dims], x2[:, dims])
+        if kind == "linear":
+            return a @ b.T
         return kernel(kind, a, b, ell)
     K1, K2 = composite_kernel(spec[1], x1, x2), composite_kernel(spec[2], x1, x2)
     return K1 + K2 if spec[0] == "sum" else K1 * K2

@@ -1,0 +1,154 @@
+"""CPU stand-ins for the device calls of gpx_b200.ops, for HOST-LOGIC tests only (tests/test_host_glue_cpu.py).
+
+The facade modules that are compositions of device calls (gpx_b200/models/_composite.py, ...) contain index
+bookkeeping, adjoint algebra and parameter plumbing that can be wrong independently of any kernel.  `patched()`
+swaps the handful of ops those modules use for NumPy restatements with the SAME contracts (in-place updates,
+lower-triangle-only reads and writes, argument meaning) so that glue can be exercised by `-m "not gpu"` tests.
+This is test infrastructure: nothing under gpx_b200/ imports it, and the GPU tests run the same glue on the
+real kernels."""
+from __future__ import annotations
+
+import contextlib
+
+import numpy as np
+import torch
+
+from oracle import ref_numpy as R
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _t(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
+
+
+def to_device(a):
+    if isinstance(a, torch.Tensor):
+        return a.to(dtype=torch.float64).contiguous()
+    return _t(a)
+
+
+def gram(kind, x1, x2, ell, diag_add=0.0, lower_only=False, out=None):
+    sym = x2 is x1 or x2 is None
+    a = _np(x1)
+    b = a if sym else _np(x2)
+    K = R.kernel(kind, a, b, float(ell))
+    if sym:
+        K = K.copy()
+        K[np.diag_indices_from(K)] = R.kernel(kind, a[:1], a[:1], float(ell))[0, 0]  # exact diagonal
+    if diag_add:
+        K = K + diag_add * np.eye(K.shape[0], K.shape[1])
+    if out is None:
+        out = torch.zeros(K.shape, dtype=torch.float64)
+    if lower_only:
+        assert sym
+        o = _np(out)
+        il = np.tril_indices(K.shape[0])
+        o[il] = K[il]
+        out.copy_(_t(o))
+    else:
+        out.copy_(_t(K))
+    return out
+
+
+def gram_dl_contract(kind, x1, x2, ell, Y, sym_lower=False):
+    dK = R.kernel_dl(kind, _np(x1), _np(x2), float(ell))[1]
+    Yn = _np(Y)
+    if sym_lower:
+        Yl = np.tril(Yn)
+        Yn = Yl + np.tril(Yn, -1).T
+    return _t(np.array([np.sum(Yn * dK)]))
+
+
+def elementwise(op, X, Y, a=1.0, b=1.0, out=None):
+    assert X.is_contiguous() and Y.is_contiguous() and X.shape == Y.shape
+    res = a * X + b * Y if op == "axpby" else a * X * Y
+    if out is None:
+        return res.clone()
+    out.copy_(res)
+    return out
+
+
+def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower_only=False):
+    a = _np(A).T if transa else _np(A)
+    b = _np(B).T if transb else _np(B)
+    prod = a @ b
+    if C is None:
+        C = torch.zeros(prod.shape, dtype=torch.float64)
+    c = _np(C)
+    new = alpha * prod + beta * c
+    if lower_only:
+        il = np.tril_indices(new.shape[0], 0, new.shape[1])
+        c = c.copy()
+        c[il] = new[il]
+        new = c
+    C.copy_(_t(new))
+    return C
+
+
+def potrf(A):
+    a = _np(A)
+    low = np.tril(a)
+    sym = low + np.tril(a, -1).T
+    L = np.linalg.cholesky(sym)
+    out = np.triu(a, 1) + L  # the strict upper triangle is never touched
+    A.copy_(_t(out))
+    return A, torch.zeros(1, dtype=torch.float64)
+
+
+def trsm(L, inv, B, trans=True):
+    import scipy.linalg as sla
+
+    Ln = np.tril(_np(L))
+    b = _np(B)
+    # B <- B L^-T  <=>  B^T <- L^-1 B^T ;   B <- B L^-1  <=>  B^T <- L^-T B^T
+    x = sla.solve_triangular(Ln, b.T, lower=True, trans="N" if trans else "T")
+    B.copy_(_t(x.T))
+    return B
+
+
+def logdet(L):
+    return _t(np.array([np.sum(np.log(np.diag(_np(L))))]))
+
+
+def potri(L, inv, out=None):
+    Ln = np.tril(_np(L))
+    Li = np.linalg.inv(Ln)
+    Ainv = np.tril(Li.T @ Li)
+    if out is None:
+        out = torch.zeros(Ainv.shape, dtype=torch.float64)
+    o = _np(out).copy()
+    il = np.tril_indices(Ainv.shape[0])
+    o[il] = Ainv[il]
+    out.copy_(_t(o))
+    return out
+
+
+FAKES = dict(gram=gram, gram_dl_contract=gram_dl_contract, elementwise=elementwise, gemm=gemm, potrf=potrf, trsm=trsm,
+             logdet=logdet, potri=potri)
+
+
+@contextlib.contextmanager
+def patched():
+    """Swap the listed gpx_b200.ops entry points and every module-level `_to_device` for the CPU stand-ins."""
+    import sys
+
+    from gpx_b200 import ops
+
+    saved_ops = {k: getattr(ops, k) for k in FAKES}
+    saved_td = []
+    for name, mod in list(sys.modules.items()):
+        if name.startswith("gpx_b200") and mod is not None and hasattr(mod, "_to_device"):
+            saved_td.append((mod, mod._to_device))
+    try:
+        for k, f in FAKES.items():
+            setattr(ops, k, f)
+        for mod, _ in saved_td:
+            mod._to_device = to_device
+        yield
+    finally:
+        for k, f in saved_ops.items():
+            setattr(ops, k, f)
+        for mod, f in saved_td:
+            mod._to_device = f

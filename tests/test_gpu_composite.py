@@ -16,6 +16,11 @@ def _data(N, D, seed, T=1):
     return x, y
 
 
+def _ell_leaves(kernel, params):
+    """Leaves that carry a lengthscale (Linear has no parameters)."""
+    return [lf for lf in kernel.leaves(params) if "lengthscale" in lf[2]]
+
+
 def _model(kernel, ells, sigma):
     from gpx_b200.models import GPR
     from gpx_b200.parameters import Parameter
@@ -24,7 +29,7 @@ def _model(kernel, ells, sigma):
 
     m = GPR(kernel, sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
     st = m.state
-    for (path, _, _), ell in zip(kernel.leaves(st.params["kernel_params"]), ells):
+    for (path, _, _), ell in zip(_ell_leaves(kernel, st.params["kernel_params"]), ells):
         st = st.with_param_value(("kernel_params",) + path + ("lengthscale",), np.float64(ell))
     m.state = st
     return m
@@ -38,6 +43,10 @@ CASES = {
     "nested": (lambda K: K.SquaredExponential(active_dims=[0, 1]) + K.Matern52() * K.Matern12(active_dims=[2]),
                lambda e: ("sum", ("leaf", "se", e[0], [0, 1]),
                           ("prod", ("leaf", "m52", e[1], None), ("leaf", "m12", e[2], [2]))), [1.2, 2.5, 1.9]),
+    "linear": (lambda K: K.Linear(active_dims=[0, 1]) + K.Linear() * K.Matern52(active_dims=[1, 2]) + K.SquaredExponential(),
+               lambda e: ("sum", ("sum", ("leaf", "linear", None, [0, 1]),
+                                  ("prod", ("leaf", "linear", None, None), ("leaf", "m52", e[0], [1, 2]))),
+                          ("leaf", "se", e[1], None)), [1.6, 2.2]),
 }
 
 
@@ -64,7 +73,7 @@ def test_composite_kernel_lml_gradient_fit_predict(name, T):
         fd = lambda hh: (g(hh) - g(-hh)) / (2 * hh)  # noqa: E731
         return (4 * fd(h / 2) - fd(h)) / 3
 
-    leaves = kernel.leaves(m.state.params["kernel_params"])
+    leaves = _ell_leaves(kernel, m.state.params["kernel_params"])
     for i, (path, _, _) in enumerate(leaves):
         def g(h, i=i):
             e = list(ells)
@@ -97,3 +106,51 @@ def test_composite_kernel_fit_minimize():
     assert m.optimize_results_.fun < l0 - 0.05
     with pytest.raises(NotImplementedError):
         m.log_marginal_likelihood(x, y, iterative=True)
+
+
+def test_reference_notebook_composite_kernel_matrices_on_the_device():
+    """examples/kernel_operations.ipynb cells 6, 10, 13, 16: the printed corners of Linear / Matern52 Sum / Prod kernel
+    matrices (tests/golden/notebook_anchors.json) from the device path (DMMA GEMM + fused Gram + gpxb_elementwise)."""
+    import json
+    import os
+
+    import gpx_b200.kernels as K
+    from test_oracle_cpu import (KERNEL_OPERATIONS_SPECS, check_kernel_operations_corners,
+                                 notebook_kernel_operations_data)
+
+    anchors = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_anchors.json")))["kernel_operations"]
+    X = notebook_kernel_operations_data()
+    a4, b6 = [0, 1, 2, 3], [4, 5, 6, 7, 8, 9]
+    kernels = {
+        "linear_plus_linear_times_matern52": K.Linear(active_dims=a4) + K.Linear(active_dims=a4) * K.Matern52(active_dims=b6),
+        "linear_plus_linear_times_matern52_same_dims": K.Linear(active_dims=b6) + K.Linear(active_dims=a4) * K.Matern52(active_dims=a4),
+    }
+    for name, kernel in kernels.items():
+        Kd = kernel.k(X, X, kernel.default_params())  # every lengthscale 1.0, as in the notebook
+        check_kernel_operations_corners(Kd, anchors[name])
+        assert np.max(np.abs(Kd - R.composite_kernel(KERNEL_OPERATIONS_SPECS[name], X, X))) < 1e-13 * np.max(np.abs(Kd))
+
+
+def test_linear_kernel_alone_in_the_dense_gpr_path():
+    import gpx_b200.kernels as K
+    from gpx_b200.models import GPR
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    x, y = _data(150, 4, 11)
+    sigma = 0.4
+    m = GPR(K.Linear(), sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+    spec = ("leaf", "linear", None, None)
+    ref = R.composite_lml_dense(spec, x, y, sigma)
+    assert abs(m.log_marginal_likelihood(x, y) - ref) < 1e-8 * abs(ref)
+    loss, grads = m.loss_and_grad(x, y)
+    h = 1e-4
+    gs = (R.composite_lml_dense(spec, x, y, sigma + h) - R.composite_lml_dense(spec, x, y, sigma - h)) / (2 * h)
+    assert set(grads) == {("sigma",)} and abs(-grads[("sigma",)] - gs) < 1e-6 * abs(gs)
+    m.fit(x, y, minimize=False)
+    A = x @ x.T + (sigma**2 + 1e-10) * np.eye(150)
+    c_ref = np.linalg.solve(A, y - np.mean(y))
+    assert np.max(np.abs(m.c_ - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
+    xs, _ = _data(10, 4, 12)
+    assert np.max(np.abs(m.predict(xs) - (np.mean(y) + xs @ x.T @ c_ref))) < 1e-8

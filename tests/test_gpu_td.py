@@ -116,3 +116,32 @@ def test_td_fit_minimize_lowers_the_loss():
     yp, ydp = m.predict(xs, np.tile(np.eye(2)[None], (20, 1, 1)))
     truth = (np.sin(xs[:, 0]) * np.cos(xs[:, 1])).reshape(-1, 1)
     assert np.max(np.abs(yp - truth)) < 0.05  # targets + gradients pin the surface
+
+
+def test_reference_notebook_derivative_block_kernel_on_the_device():
+    """examples/derivatives_solak.ipynb cell 4 prints [[k, d1k], [d0k, d0d1k]](x0 = 0, x = linspace(-3, 3, 1000)) for the
+    SE kernel at lengthscale 1 (tests/golden/notebook_anchors.json).  The 1-feature problem is embedded in 5 features /
+    3 derivative variables (zero padding), the regime the other tests of gpxb_td_gram cover."""
+    import json
+    import os
+
+    from gpx_b200 import ops
+
+    a = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_anchors.json")))["derivatives_solak"]
+    N1, N2, nf, nv = 7, 1000, 5, 3
+    x1, x2 = np.zeros((N1, nf)), np.zeros((N2, nf))
+    x1[:, 0] = np.linspace(0.0, 1.5, N1)  # row 0 is the notebook's x0 = 0
+    x2[:, 0] = np.linspace(-3.0, 3.0, N2)
+    J1, J2 = np.zeros((N1, nf, nv)), np.zeros((N2, nf, nv))
+    J1[:, 0, 0] = 1.0
+    J2[:, 0, 0] = 1.0
+    out = host(ops.td_gram("se", dev(x1), dev(J1), dev(x2), dev(J2), 1.0))
+    assert out.shape == (N1 + N1 * nv, N2 + N2 * nv)
+    ref = R.td_A_lhs("se", x1, J1, x2, J2, 1.0, 0.0, 0.0, noise=False)
+    assert np.max(np.abs(out - ref)) < 1e-12
+    k, d1k = out[0, :N2], out[0, N2::nv]            # targets row of x0: [k | d1k]
+    d0k, d01k = out[N1, :N2], out[N1, N2::nv]       # first derivative row of x0: [d0k | d0d1k]
+    np.testing.assert_allclose(k[:3], a["row0_first3"], rtol=0, atol=6e-9)
+    np.testing.assert_allclose(d1k[-3:], a["row0_last3"], rtol=0, atol=6e-9)
+    np.testing.assert_allclose(d0k[:3], a["row1_first3"], rtol=0, atol=6e-9)
+    np.testing.assert_allclose(d01k[-3:], a["row1_last3"], rtol=0, atol=6e-9)

@@ -319,6 +319,67 @@ def test_notebook_anchor_hessian_kernel_optimum():
     assert f(t) < f(t + np.array([0.0, 0.05])) and f(t) < f(t - np.array([0.0, 0.05]))
 
 
+def test_notebook_anchor_hessian_kernel_printed_loss_value():
+    """examples/gpr_with_derivatives_only.ipynb cell 27 prints scipy's OptimizeResult: fun = -1.5536783384709247.
+    L-BFGS-B on the oracle's loss (hand-written d01kj) reaches the same minimum value to 1e-10."""
+    from scipy.optimize import minimize
+
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["derivatives_only"]["optimize_results"]
+    d, J, y = notebook_derivs_data()
+    f = lambda tt: derivs_nll(lambda ell: R.d01kj("se", d, d, ell, J, J), y, tt)  # noqa: E731
+
+    def fg(t, h=1e-6):
+        return f(t), np.array([(f(t + np.eye(2)[i] * h) - f(t - np.eye(2)[i] * h)) / (2 * h) for i in range(2)])
+
+    res = minimize(fg, R.inverse_softplus(np.array([1.0, 1.0])), jac=True, method="L-BFGS-B")
+    assert abs(res.fun - a["fun"]) < 1e-9 * abs(a["fun"])
+    assert np.max(np.abs(res.x - np.array(a["x"]))) < 1e-3  # printed with 4 digits
+
+
+def notebook_kernel_operations_data():
+    return R.normal(R.PRNGKey(2023), (100, 10), partitionable=False)
+
+
+KERNEL_OPERATIONS_SPECS = {
+    "linear_plus_linear_times_matern52": (
+        "sum", ("leaf", "linear", None, [0, 1, 2, 3]),
+        ("prod", ("leaf", "linear", None, [0, 1, 2, 3]), ("leaf", "m52", 1.0, [4, 5, 6, 7, 8, 9]))),
+    "linear_plus_linear_times_matern52_same_dims": (
+        "sum", ("leaf", "linear", None, [4, 5, 6, 7, 8, 9]),
+        ("prod", ("leaf", "linear", None, [0, 1, 2, 3]), ("leaf", "m52", 1.0, [0, 1, 2, 3]))),
+}
+
+
+def check_kernel_operations_corners(K, a):
+    for name, blk in (("top_left", K[:3, :3]), ("top_right", K[:3, -3:]), ("bottom_right", K[-3:, -3:])):
+        np.testing.assert_allclose(blk, np.array(a[name]), rtol=0, atol=6e-9, err_msg=name)
+    np.testing.assert_allclose(K[-3:, :3], np.array(a["top_right"]).T, rtol=0, atol=6e-9)
+
+
+@pytest.mark.parametrize("name", list(KERNEL_OPERATIONS_SPECS))
+def test_notebook_anchor_composite_kernel_matrices(name):
+    """examples/kernel_operations.ipynb cells 6, 10, 13, 16 print the corners of Sum / Prod kernel matrices built
+    from Linear and Matern52 leaves with active_dims on X = normal(PRNGKey(2023), (100, 10)): pins the composite
+    kernels, active_dims, the Matern-5/2 entries and the 2-D legacy normal() layout to the printed 8 digits."""
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["kernel_operations"][name]
+    X = notebook_kernel_operations_data()
+    check_kernel_operations_corners(R.composite_kernel(KERNEL_OPERATIONS_SPECS[name], X, X), a)
+
+
+def test_notebook_anchor_derivative_block_kernel():
+    """examples/derivatives_solak.ipynb cell 4 prints [[k, d1k], [d0k, d0d1k]](x0, x) for the SE pair kernel
+    (autodiff kernelizers): pins the sign / scaling conventions of d0kj, d1kj and d01kj (1 feature, jacobian 1),
+    i.e. the GPR_TD block matrix td_A_lhs, to the printed digits."""
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["derivatives_solak"]
+    x = np.linspace(-3.0, 3.0, 1000).reshape(-1, 1)
+    x0 = np.zeros((1, 1))
+    B = R.td_A_lhs("se", x0, np.ones((1, 1, 1)), x, np.ones((1000, 1, 1)), 1.0, 0.0, 0.0, noise=False)
+    assert B.shape == (2, 2000)
+    for row, lo, hi in ((0, "row0_first3", "row0_last3"), (1, "row1_first3", "row1_last3")):
+        np.testing.assert_allclose(B[row, :3], a[lo], rtol=0, atol=6e-9)
+        np.testing.assert_allclose(B[row, -3:], a[hi], rtol=0, atol=6e-9)
+
+
 @pytest.mark.parametrize("kind", ["se", "m52"])
 def test_oracle_derivative_lml_gradient_vs_finite_differences(kind):
     """The analytic (lml, d/d ell, d/d sigma) of the derivative-trained GPR (term-by-term derivative of the

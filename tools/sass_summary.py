@@ -44,7 +44,7 @@ def main():
         if m:
             cur = m.group(1)
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)(?:\.[A-Z0-9_.]+)?\s", ln)
+        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)(?:\.[A-Za-z0-9_.]+)?\s", ln)
         if m and cur:
             op = m.group(1)
             total[cur] += 1
