@@ -13,8 +13,18 @@ from ..kernels import _to_device
 from ..mean_functions import data_mean, mean_mode
 from ..parameters import ModelState, Parameter
 from ..priors import NormalPrior
+from . import _composite, _composite_sparse
 from .base import BaseGP
 from .gpr import _hyper, _xy
+
+
+def _composite_guard(state, iterative=False, what="composite kernels in SGPR"):
+    """True when the kernel is a Sum / Prod / Linear one (served by _composite_sparse: dense paths, fixed landmarks)."""
+    if not _composite.is_composite(state.kernel):
+        return False
+    if iterative:
+        raise NotImplementedError(f"{what}: the dense paths only")
+    return True
 
 
 def _locs(state):
@@ -24,6 +34,8 @@ def _locs(state):
 def log_marginal_likelihood(state, x, y, iterative=False, num_evals=gpxargs.num_evals,
                             num_lanczos=gpxargs.num_lanczos, key_lanczos=gpxargs.key_lanczos, **_ignored):
     """gpx/models/sgpr.py:70-118 -> _sgpr._lml_dense (gpx/models/_sgpr.py:659-697)."""
+    if _composite_guard(state, iterative):
+        return _composite_sparse.lml_and_grad(state, x, y, want_grad=False)[0]
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     if iterative:
@@ -81,6 +93,12 @@ def loss_and_grad(state, x, y, iterative=False, **kwargs):
     jit(value_and_grad(loss)))."""
     if iterative:
         raise NotImplementedError("gradient of the iterative SGPR LML is not implemented")
+    if _composite_guard(state):
+        if state.params["x_locs"].trainable:
+            raise NotImplementedError("trainable x_locs with a composite kernel is not supported")
+        lml, g = _composite_sparse.lml_and_grad(state, x, y, want_grad=True)
+        flat = dict(state.flat_params())
+        return -lml, {path: -v for path, v in g.items() if flat[path].trainable}
     xd, yd = _xy(state, x, y)
     return _loss_and_grad_with_locs(state, xd, yd, _locs(state), bool(state.params["x_locs"].trainable))
 
@@ -88,6 +106,8 @@ def loss_and_grad(state, x, y, iterative=False, **kwargs):
 def fit(state, x, y, iterative=False, **_ignored):
     """gpx/models/sgpr.py:309-338 -> _sgpr._fit_dense (gpx/models/_sgpr.py:319-339).  The extra
     keywords BaseGP.fit passes (n_pivots, key_precond) are accepted and ignored."""
+    if _composite_guard(state, iterative):
+        return _composite_sparse.fit(state, x, y)
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     if iterative:  # _sgpr._fit_iter (gpx/models/_sgpr.py:343-363)
@@ -121,6 +141,8 @@ def predict(state, x, full_covariance=False, iterative=False):
         raise RuntimeError("Model is not fitted. Run `fit` to fit the model before prediction.")
     if full_covariance and iterative:
         raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
+    if _composite_guard(state, iterative):
+        return _composite_sparse.predict(state, x, full_covariance)
     return _predict_with_locs(state, _locs(state), x, full_covariance, iterative)
 
 

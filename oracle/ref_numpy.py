@@ -1037,6 +1037,41 @@ def sgpr_lml_dense(kind, x_locs, x, y, ell, sigma, mean_function=data_mean):
     return (-0.5 * quad - 0.5 * logdet - n * 0.5 * np.log(2.0 * np.pi)) / n
 
 
+def sgpr_composite_lml_dense_nxn(spec, x_locs, x, y, sigma, mean_function=data_mean):
+    """_sgpr.py:659-697, literal N x N form, with a composite kernel (composite_kernel spec)."""
+    m, n = x_locs.shape[0], y.shape[0]
+    r = y - mean_function(y)
+    K_mm = composite_kernel(spec, x_locs, x_locs)
+    K_mn = composite_kernel(spec, x_locs, x)
+    L = sla.cholesky(K_mm + 1e-10 * np.eye(m), lower=True, check_finite=False)
+    G = sla.solve_triangular(L, K_mn, lower=True, check_finite=False)
+    C = G.T @ G + sigma**2 * np.eye(n) + 1e-10 * np.eye(n)
+    Ln = sla.cholesky(C, lower=True, check_finite=False)
+    cy = sla.solve_triangular(Ln, r, lower=True, check_finite=False)
+    return (-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(Ln))) - n * 0.5 * np.log(2.0 * np.pi)) / n
+
+
+def sgpr_composite_fit_dense(spec, x_locs, x, y, sigma, mean_function=data_mean):
+    """_sgpr.py:39-61, 319-339 with a composite kernel."""
+    mu = mean_function(y)
+    K_mn = composite_kernel(spec, x_locs, x)
+    C = sigma**2 * composite_kernel(spec, x_locs, x_locs) + K_mn @ K_mn.T + 1e-10 * np.eye(x_locs.shape[0])
+    return np.linalg.solve(C, K_mn @ (y - mu)), mu
+
+
+def sgpr_composite_predict_dense(spec, x_locs, x, c, mu, sigma):
+    """_sgpr.py:434-467 with a composite kernel, full covariance (C_mm from the prediction inputs, as written
+    there: `_A_lhs(x1=x_locs, x2=x)`)."""
+    m = x_locs.shape[0]
+    mean = mu + composite_kernel(spec, x, x_locs) @ c
+    K_ms = composite_kernel(spec, x_locs, x)
+    K_mm = composite_kernel(spec, x_locs, x_locs)
+    C = sigma**2 * K_mm + K_ms @ K_ms.T + 1e-10 * np.eye(m)
+    G = sla.solve_triangular(sla.cholesky(K_mm + 1e-10 * np.eye(m), lower=True), K_ms, lower=True)
+    H = sla.solve_triangular(sla.cholesky(C, lower=True), K_ms, lower=True)
+    return mean, composite_kernel(spec, x, x) - G.T @ G + sigma**2 * (H.T @ H)
+
+
 def sgpr_fit_derivs_dense(kind, x_locs, J_locs, x, y, J, ell, sigma):
     """_sgpr.py:366-396 with _A_derivs_lhs :65-93 (zero mean) + the contracted jacobian of sgpr.py:372-375."""
     yf = y.reshape(-1, 1)

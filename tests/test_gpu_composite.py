@@ -154,3 +154,80 @@ def test_linear_kernel_alone_in_the_dense_gpr_path():
     assert np.max(np.abs(m.c_ - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
     xs, _ = _data(10, 4, 12)
     assert np.max(np.abs(m.predict(xs) - (np.mean(y) + xs @ x.T @ c_ref))) < 1e-8
+
+
+def _sgpr_model(kernel, ells, sigma, x_locs):
+    from gpx_b200.models import SGPR
+    from gpx_b200.models.sgpr import locs_parameter
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    m = SGPR(kernel, x_locs=locs_parameter(x_locs), sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+    st = m.state
+    for (path, _, _), ell in zip(_ell_leaves(kernel, st.params["kernel_params"]), ells):
+        st = st.with_param_value(("kernel_params",) + path + ("lengthscale",), np.float64(ell))
+    m.state = st
+    return m
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("T", [1, 2])
+def test_composite_kernel_sgpr_lml_gradient_fit_predict(name, T):
+    """SGPR (Projected Processes) with a Sum / Prod / Linear kernel against the oracle's literal N x N form
+    (oracle/ref_numpy.py: sgpr_composite_*); gradients against Richardson-extrapolated central differences."""
+    import gpx_b200.kernels as K
+
+    mk, spec_of, ells = CASES[name]
+    kernel = mk(K)
+    N, M, D, sigma = 400, 24, 3, 0.3
+    x, y = _data(N, D, 17, T)
+    xs, _ = _data(30, D, 18)
+    xl = x[:: N // M][:M].copy()
+    m = _sgpr_model(kernel, ells, sigma, xl)
+    f = lambda e, s: R.sgpr_composite_lml_dense_nxn(spec_of(e), xl, x, y, s)  # noqa: E731
+    ref = f(ells, sigma)
+    assert abs(m.log_marginal_likelihood(x, y) - ref) < 1e-8 * abs(ref)
+    loss, grads = m.loss_and_grad(x, y)
+    assert abs(-loss - ref) < 1e-8 * abs(ref)
+    assert ("x_locs",) not in grads
+
+    def rich(g, h=1e-3):
+        fd = lambda hh: (g(hh) - g(-hh)) / (2 * hh)  # noqa: E731
+        return (4 * fd(h / 2) - fd(h)) / 3
+
+    for i, (path, _, _) in enumerate(_ell_leaves(kernel, m.state.params["kernel_params"])):
+        def g(h, i=i):
+            e = list(ells)
+            e[i] += h
+            return f(e, sigma)
+        gi = rich(g)
+        assert abs(-grads[("kernel_params",) + path + ("lengthscale",)] - gi) < 1e-6 * max(abs(gi), abs(ref)), (name, i)
+    gs = rich(lambda h: f(ells, sigma + h))
+    assert abs(-grads[("sigma",)] - gs) < 1e-6 * max(abs(gs), abs(ref))
+    m.fit(x, y, minimize=False)
+    c_ref, mu_ref = R.sgpr_composite_fit_dense(spec_of(ells), xl, x, y, sigma)
+    assert np.max(np.abs(m.c_ - c_ref)) < 1e-6 * np.max(np.abs(c_ref))  # normal equations: cond^2
+    mean, cov = m.predict(xs, full_covariance=True)
+    mean_ref, cov_ref = R.sgpr_composite_predict_dense(spec_of(ells), xl, xs, c_ref, mu_ref, sigma)
+    assert np.max(np.abs(mean - mean_ref)) < 1e-7 * max(1.0, np.max(np.abs(mean_ref)))
+    assert np.max(np.abs(cov - cov_ref)) < 1e-7 * max(1.0, np.max(np.abs(cov_ref)))
+    assert np.max(np.abs(m.predict(xs) - mean_ref)) < 1e-7 * max(1.0, np.max(np.abs(mean_ref)))
+
+
+def test_composite_kernel_sgpr_fit_minimize_and_limits():
+    import gpx_b200.kernels as K
+    from gpx_b200.models import SGPR
+    from gpx_b200.models.sgpr import locs_parameter
+
+    x, y = _data(300, 2, 19)
+    xl = x[::20].copy()
+    m = SGPR(K.SquaredExponential() + K.Matern32(), x_locs=locs_parameter(xl))
+    l0, _ = m.loss_and_grad(x, y)
+    m.fit(x, y)
+    assert m.optimize_results_.fun < l0 - 0.05
+    with pytest.raises(NotImplementedError):
+        m.log_marginal_likelihood(x, y, iterative=True)
+    mt = SGPR(K.SquaredExponential() + K.Matern32(), x_locs=locs_parameter(xl, trainable=True))
+    with pytest.raises(NotImplementedError):
+        mt.loss_and_grad(x, y)

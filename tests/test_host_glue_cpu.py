@@ -24,3 +24,15 @@ def test_composite_notebook_anchor_glue():
 def test_linear_kernel_glue():
     with patched():
         G.test_linear_kernel_alone_in_the_dense_gpr_path()
+
+
+@pytest.mark.parametrize("name", list(G.CASES))
+@pytest.mark.parametrize("T", [1, 2])
+def test_composite_sgpr_glue(name, T):
+    with patched():
+        G.test_composite_kernel_sgpr_lml_gradient_fit_predict(name, T)
+
+
+def test_composite_sgpr_minimize_glue():
+    with patched():
+        G.test_composite_kernel_sgpr_fit_minimize_and_limits()
