@@ -133,7 +133,7 @@ def predict(state, x, full_covariance=False, iterative=False):
     c = _to_device(state.c)
     if c.dim() == 1:
         c = c.reshape(-1, 1)
-    mu = torch.full((1,), float(state.mu), dtype=torch.float64, device="cuda")
+    mu = torch.full((1,), float(state.mu), dtype=torch.float64, device=xs.device)
     if iterative:
         # matrix-free mean: same value, no (n* x N) kernel block stored
         out = ops.kmatvec(kernel.kind, xs, xt, c, ell, diag_add=0.0) + mu
@@ -238,7 +238,7 @@ def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):
         return mean.reshape(ns, nv).cpu().numpy()
     jc = _to_device(state.jaccoef).unsqueeze(2).contiguous()  # (N, nf, 1): the contracted Jacobian
     K = ops.hess_gram(kernel.kind, xt, jc, xs, Js, ell)  # (N, ns*nv)
-    ones = torch.ones((1, K.shape[0]), dtype=torch.float64, device="cuda")
+    ones = torch.ones((1, K.shape[0]), dtype=torch.float64, device=K.device)
     mean = ops.gemm(ones, K) + float(state.mu)
     ns, _, nv = Js.shape
     return mean.reshape(ns, nv).cpu().numpy()

@@ -128,7 +128,7 @@ def _predict_with_locs(state, x_locs_dev, x, full_covariance, iterative=False):
         c = c.reshape(-1, 1)
     if iterative:  # _sgpr._predict_iter (gpx/models/_sgpr.py:530-546): mu + K_nm c, matrix-free
         return (ops.kmatvec(kernel.kind, xs, x_locs_dev, c, ell) + float(state.mu)).cpu().numpy()
-    mu = torch.full((1,), float(state.mu), dtype=torch.float64, device="cuda")
+    mu = torch.full((1,), float(state.mu), dtype=torch.float64, device=xs.device)
     out = ops.sgpr_predict(kernel.kind, x_locs_dev, xs, c, mu, ell, sigma, full_covariance=full_covariance)
     if full_covariance:
         return out[0].cpu().numpy(), out[1].cpu().numpy()
@@ -199,7 +199,7 @@ def predict_derivs(state, x, jacobian, full_covariance=False, iterative=False):
     jc = _to_device(state.jaccoef).unsqueeze(2).contiguous()
     xs, Js = _to_device(x), _to_device(jacobian)
     K = ops.hess_gram(kernel.kind, xl, jc, xs, Js, ell)
-    ones = torch.ones((1, K.shape[0]), dtype=torch.float64, device="cuda")
+    ones = torch.ones((1, K.shape[0]), dtype=torch.float64, device=K.device)
     mean = ops.gemm(ones, K) + float(state.mu)
     ns, _, nv = Js.shape
     return mean.reshape(ns, nv).cpu().numpy()

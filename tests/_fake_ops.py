@@ -125,8 +125,87 @@ def potri(L, inv, out=None):
     return out
 
 
+# ---- fused entry points (csrc/gpr.cu, sgpr.cu, rpchol.cu, matvec.cu): the oracle's restatement of each ----
+def _mean_fn(mean_mode):
+    return R.data_mean if int(mean_mode) == 1 else R.zero_mean
+
+
+def _col(y):
+    y = _np(y)
+    return y.reshape(-1, 1) if y.ndim == 1 else y
+
+
+def gpr_lml_grad(kind, x, y, ell, sigma, mean_mode=1, want_grad=True):
+    x, y = _np(x), _col(y)
+    if not want_grad:
+        return _t(np.array([R.lml_dense(kind, x, y, float(ell), float(sigma), _mean_fn(mean_mode)), 0.0, 0.0]))
+    return _t(np.array(R.lml_grad_dense(kind, x, y, float(ell), float(sigma), _mean_fn(mean_mode))))
+
+
+def gpr_fit(kind, x, y, ell, sigma, mean_mode=1):
+    c, mu = R.fit_dense(kind, _np(x), _col(y), float(ell), float(sigma), _mean_fn(mean_mode))
+    return _t(c), _t(np.array([float(mu)]))
+
+
+def gpr_predict(kind, x_train, x, c, mu, ell, sigma, full_covariance=False):
+    out = R.predict_dense(kind, _np(x_train), _np(x), _col(c), float(_np(mu)[0]), float(ell), float(sigma),
+                          full_covariance=full_covariance)
+    return (_t(out[0]), _t(out[1])) if full_covariance else _t(out)
+
+
+def kmatvec(kind, x_rows, x_all, V, ell, diag_add=0.0, row_offset=None):
+    K = R.kernel(kind, _np(x_rows), _np(x_all), float(ell))
+    if diag_add:
+        off = int(row_offset or 0)
+        for i in range(K.shape[0]):
+            K[i, off + i] += diag_add
+    v = _np(V)
+    return _t(K @ (v.reshape(-1, 1) if v.ndim == 1 else v))
+
+
+def rpcholesky(kind, x, n_pivots, ell, key, partitionable=True, want_factor=True):
+    F, piv = R.rpcholesky(kind, _np(x), int(n_pivots), float(ell), np.asarray(key, dtype=np.uint32), bool(partitionable))
+    return (_t(F) if want_factor else None), torch.as_tensor(np.asarray(piv, dtype=np.int64))
+
+
+def gather_rows(x, idx):
+    return x[idx.to(torch.long)].contiguous()
+
+
+def sgpr_lml(kind, x, y, x_locs, ell, sigma, mean_mode=1):
+    return _t(np.array([R.sgpr_lml_dense(kind, _np(x_locs), _np(x), _col(y), float(ell), float(sigma), _mean_fn(mean_mode))]))
+
+
+def sgpr_lml_grad(kind, x, y, x_locs, ell, sigma, mean_mode=1, want_grad=True):
+    xl, xn, yn, mf = _np(x_locs), _np(x), _col(y), _mean_fn(mean_mode)
+    f = lambda e, s: R.sgpr_lml_dense(kind, xl, xn, yn, e, s, mf)  # noqa: E731
+    ell, sigma = float(ell), float(sigma)
+    if not want_grad:
+        return _t(np.array([f(ell, sigma), 0.0, 0.0]))
+
+    def rich(g, h):  # Richardson-extrapolated central difference, O(h^4)
+        fd = lambda hh: (g(hh) - g(-hh)) / (2 * hh)  # noqa: E731
+        return (4 * fd(h / 2) - fd(h)) / 3
+
+    return _t(np.array([f(ell, sigma), rich(lambda h: f(ell + h, sigma), 1e-3 * ell),
+                        rich(lambda h: f(ell, sigma + h), 1e-3 * sigma)]))
+
+
+def sgpr_fit(kind, x, y, x_locs, ell, sigma, mean_mode=1):
+    c, mu = R.sgpr_fit_dense(kind, _np(x_locs), _np(x), _col(y), float(ell), float(sigma), _mean_fn(mean_mode))
+    return _t(c), _t(np.array([float(mu)]))
+
+
+def sgpr_predict(kind, x_locs, x, c, mu, ell, sigma, full_covariance=False):
+    out = R.sgpr_predict_dense(kind, _np(x_locs), _np(x), _col(c), float(_np(mu)[0]), float(ell), float(sigma),
+                               full_covariance=full_covariance)
+    return (_t(out[0]), _t(out[1])) if full_covariance else _t(out)
+
+
 FAKES = dict(gram=gram, gram_dl_contract=gram_dl_contract, elementwise=elementwise, gemm=gemm, potrf=potrf, trsm=trsm,
-             logdet=logdet, potri=potri)
+             logdet=logdet, potri=potri, gpr_lml_grad=gpr_lml_grad, gpr_fit=gpr_fit, gpr_predict=gpr_predict,
+             kmatvec=kmatvec, rpcholesky=rpcholesky, gather_rows=gather_rows, sgpr_lml=sgpr_lml,
+             sgpr_lml_grad=sgpr_lml_grad, sgpr_fit=sgpr_fit, sgpr_predict=sgpr_predict)
 
 
 @contextlib.contextmanager

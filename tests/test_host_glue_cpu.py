@@ -6,6 +6,7 @@ import pytest
 torch = pytest.importorskip("torch")
 
 import test_gpu_composite as G  # noqa: E402  (its tests are plain functions; the gpu mark stays on that module)
+import test_gpu_facade as F  # noqa: E402
 from _fake_ops import patched  # noqa: E402
 
 
@@ -36,3 +37,19 @@ def test_composite_sgpr_glue(name, T):
 def test_composite_sgpr_minimize_glue():
     with patched():
         G.test_composite_kernel_sgpr_fit_minimize_and_limits()
+
+
+# The GPX-style facade (GPR / SGPR / SGPR_RPChol: parameters, bijector chain rule, L-BFGS-B driver, state updates,
+# landmark bookkeeping) with the fused entry points replaced by the oracle's restatement of each.
+@pytest.mark.parametrize("test", [
+    F.test_lml_and_loss_grad_match_oracle,
+    F.test_fit_minimize_follows_oracle_optimiser,
+    F.test_kernel_call_and_active_dims,
+    F.test_sgpr_and_sgpr_rpchol_facades,
+    F.test_iterative_predict_matches_dense,
+    F.test_reference_notebook_anchors_through_the_facade,
+    F.test_reference_notebook_anchor_sgpr_rpchol_through_the_facade,
+], ids=lambda f: f.__name__)
+def test_facade_glue(test):
+    with patched():
+        test()
