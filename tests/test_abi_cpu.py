@@ -52,3 +52,28 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{fn} references the oracle"
+
+
+def test_header_is_plain_c_and_a_c_program_links_the_library(tmp_path):
+    """include/gpxb200.h compiles as C99 and a C consumer (tests/c/abi_consumer.c) links and runs against the shared
+    library: the boundary is a C ABI.  Without a GPU it checks the error contract (positive CUDA code + message from
+    gpxb_last_error, negative code for argument errors); with one, context creation / destruction."""
+    import shutil
+    import subprocess
+
+    from gpx_b200 import _build, _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    _build.build()
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, "gpxb200.h")],
+                   check=True)
+    exe = str(tmp_path / "abi_consumer")
+    libdir = os.path.dirname(str(_lib.LIB_PATH))
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", inc, os.path.join(ROOT, "tests", "c", "abi_consumer.c"),
+                    "-o", exe, "-L", libdir, "-lgpxb200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "version" in r.stdout
