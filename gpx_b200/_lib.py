@@ -53,6 +53,8 @@ SIGNATURES = {
     "gpxb_td_gram": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _dbl, _c_dp, _ll, _int, C.c_void_p]),
     "gpxb_gpr_td_lml_grad": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _dbl, _int, _int, _c_dp, C.c_void_p]),
     "gpxb_gpr_td_fit": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _dbl, _int, _c_dp, _c_dp, C.c_void_p]),
+    "gpxb_gpr_td2_lml_grad": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _int, _dbl, _dbl, _dbl, _dbl, _int, _int, _c_dp, C.c_void_p]),
+    "gpxb_gpr_td2_fit": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _int, _dbl, _dbl, _dbl, _dbl, _int, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_gpr_fit_derivs": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_kmatvec": (_int, [C.c_void_p, _int, _c_dp, _int, _ll, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _ll, _int, _c_dp, _ll, C.c_void_p]),
     "gpxb_rpcholesky": (_int, [C.c_void_p, _int, _c_dp, _int, _int, _dbl, C.c_uint32, C.c_uint32, _int, _int, _c_dp, _c_dp, C.c_void_p]),

@@ -8,7 +8,11 @@
 // the d0kj block kernel and the Hessian kernel (hess.cu); the factorisation, the inverse and the
 // gradient contractions are the exact-GPR machinery (chol.cu, gemm.cu) applied block by block:
 //   d lml/d ell = 1/2 [ sum W_TT o dK + 2 sum W_DT o d(d0kj) + sum W_DD o d(d01kj) ] / m,  W = alpha alpha^T - A^-1.
-// One derivative block (jacobian_2 of the reference is not mirrored).
+// The reference's optional SECOND derivative block (jacobian_2 / y_derivs_2 / sigma_derivs2, gpr_td.py:114-158) is the
+// same matrix for the jacobian concatenated along the variable axis, J = [J_1 | J_2] (nv = nv_1 + nv_2), up to a
+// symmetric permutation of the derivative rows -- (sample, variable) interleaved here, block after block there --
+// which leaves the LML unchanged; the only new ingredient is the per-block noise: variables v >= nv_a carry
+// sigma_derivs2.  The facade permutes the coefficient vector to the reference's order.
 #include "../../include/gpxb200.h"
 #include "chol.cuh"
 #include "gemm.cuh"
@@ -28,15 +32,40 @@ __global__ void td_rhs_kernel(const double* __restrict__ y, int N, const double*
   if (i < N) r[i] = y[i] - *mu;
   else if (i < N + n) r[i] = yd[i - N];
 }
+// DD[i][i] += delta for the derivative rows i = s nv + v of the second block (v >= nv_a)
+__global__ void td_diag2_kernel(double* __restrict__ DD, long long ld, long long n, int nv, int nv_a, double delta) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (int)(i % nv) >= nv_a) DD[i * ld + i] += delta;
+}
+// out2[0] = sum alpha_D[i]^2, out2[1] = sum Ainv_DD[i][i], both over the rows of the second block (v >= nv_a)
+__global__ void td_block2_sums_kernel(const double* __restrict__ aD, const double* __restrict__ DD, long long ld,
+                                      long long n, int nv, int nv_a, double* __restrict__ out2) {
+  __shared__ double sh[32];
+  double s0 = 0.0, s1 = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024)
+    if ((int)(i % nv) >= nv_a) {
+      s0 += aD[i] * aD[i];
+      s1 += DD[i * ld + i];
+    }
+  s0 = block_sum<1024>(s0, sh);
+  __syncthreads();
+  s1 = block_sum<1024>(s1, sh);
+  if (threadIdx.x == 0) {
+    out2[0] = s0;
+    out2[1] = s1;
+  }
+}
 // scal: [0] quad, [1] sum log L_ii, [2] TT, [3] DT, [4] DD contractions, [5] |alpha_T|^2, [6] |alpha_D|^2,
-//       [7] tr(Ainv_TT), [8] tr(Ainv_DD)
+//       [7] tr(Ainv_TT), [8] tr(Ainv_DD), [9] / [10]: the second block's share of [6] / [8]
+// out5 = {lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs, d/d sigma_derivs2}
 __global__ void td_finalize_kernel(const double* __restrict__ scal, long long m, double sig_t, double sig_d,
-                                   int want_grad, double* __restrict__ out4) {
+                                   double sig_d2, int want_grad, double* __restrict__ out5) {
   const double mm = (double)m;
-  out4[0] = (-0.5 * scal[0] - scal[1] - mm * 0.5 * log(2.0 * 3.141592653589793)) / mm;
-  out4[1] = want_grad ? 0.5 * (scal[2] + 2.0 * scal[3] + scal[4]) / mm : 0.0;
-  out4[2] = want_grad ? sig_t * (scal[5] - scal[7]) / mm : 0.0;
-  out4[3] = want_grad ? sig_d * (scal[6] - scal[8]) / mm : 0.0;
+  out5[0] = (-0.5 * scal[0] - scal[1] - mm * 0.5 * log(2.0 * 3.141592653589793)) / mm;
+  out5[1] = want_grad ? 0.5 * (scal[2] + 2.0 * scal[3] + scal[4]) / mm : 0.0;
+  out5[2] = want_grad ? sig_t * (scal[5] - scal[7]) / mm : 0.0;
+  out5[3] = want_grad ? sig_d * ((scal[6] - scal[9]) - (scal[8] - scal[10])) / mm : 0.0;
+  out5[4] = want_grad ? sig_d2 * (scal[9] - scal[10]) / mm : 0.0;
 }
 }  // namespace
 
@@ -79,12 +108,16 @@ int td_gram(Ctx* ctx, int kind, const double* x1, const double* J1, int N1, int 
                    lower_only, s);
 }
 
-// out4 = {lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs}; c_out (optional, m) = A^-1 r; mu_out (optional).
+// out5 = {lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs, d/d sigma_derivs2}; c_out (optional, m) = A^-1 r;
+// mu_out (optional).  nv_a: number of variables of the first derivative block (nv_a == nv: one block, sig_d2 unused).
 int gpr_td(Ctx* ctx, int kind, const double* x, const double* J, const double* y, const double* yd, int N, int nf,
-           int nv, double ell, double sig_t, double sig_d, int mean_mode, int want_grad, double* out4, double* c_out,
-           double* mu_out, cudaStream_t s) {
+           int nv, int nv_a, double ell, double sig_t, double sig_d, double sig_d2, int mean_mode, int want_grad,
+           double* out5, double* c_out, double* mu_out, cudaStream_t s) {
   const long long n = (long long)N * nv, m = N + n;
   GPXB_ARG_CHECK(N > 0 && nv > 0 && nf > 0 && m < (1LL << 31), -1);
+  GPXB_ARG_CHECK(nv_a > 0 && nv_a <= nv, -2);
+  const bool two = nv_a < nv;
+  double* out4 = out5;
   DevBuf bA, bInv, bR, bSc, bMu, bW, bT;
   GPXB_TRY(bA.alloc(sizeof(double) * (size_t)m * m, s));
   GPXB_TRY(bInv.alloc(sizeof(double) * leaf_inv_doubles((int)m), s));
@@ -99,6 +132,11 @@ int gpr_td(Ctx* ctx, int kind, const double* x, const double* J, const double* y
   td_rhs_kernel<<<ceil_div(m, 256), 256, 0, s>>>(y, N, yd, n, mu, r);
   GPXB_LAUNCHED(ctx);
   GPXB_TRY(td_gram(ctx, kind, x, J, N, nv, x, J, N, nv, nf, ell, sig_t * sig_t + 1e-10, sig_d * sig_d + 1e-10, A, m, 1, s));
+  if (two) {
+    td_diag2_kernel<<<ceil_div(n, 256), 256, 0, s>>>(A + (long long)N * m + N, m, n, nv, nv_a,
+                                                      sig_d2 * sig_d2 - sig_d * sig_d);
+    GPXB_LAUNCHED(ctx);
+  }
   GPXB_TRY(potrf_lower(ctx, A, m, (int)m, inv, s));
   if (out4) GPXB_TRY(logdet_lower(ctx, A, m, (int)m, scal + 1, 1.0, s));
   GPXB_TRY(trsm_right_lt(ctx, A, m, inv, r, m, 1, (int)m, s));
@@ -119,6 +157,10 @@ int gpr_td(Ctx* ctx, int kind, const double* x, const double* J, const double* y
     GPXB_LAUNCHED(ctx);
     diag_sum_kernel<<<1, 1024, 0, s>>>(A + (long long)N * m + N, m, (int)n, scal + 8);
     GPXB_LAUNCHED(ctx);
+    if (two) {
+      td_block2_sums_kernel<<<1, 1024, 0, s>>>(r + N, A + (long long)N * m + N, m, n, nv, nv_a, scal + 9);
+      GPXB_LAUNCHED(ctx);
+    }
     // TT block: the exact-GPR contraction epilogue of the Gram kernel on the leading N x N block
     const ZLayout zl = z_layout(nf);
     DevBuf bZ, bPart;
@@ -140,7 +182,7 @@ int gpr_td(Ctx* ctx, int kind, const double* x, const double* J, const double* y
     GPXB_TRY(hess_contract_dl(ctx, kind, x, J, N, nv, nf, ell, A + (long long)N * m + N, m, r + N, scal + 4, s));
   }
   if (out4) {
-    td_finalize_kernel<<<1, 1, 0, s>>>(scal, m, sig_t, sig_d, want_grad, out4);
+    td_finalize_kernel<<<1, 1, 0, s>>>(scal, m, sig_t, sig_d, two ? sig_d2 : 0.0, want_grad, out4);
     GPXB_LAUNCHED(ctx);
   }
   return 0;
@@ -164,16 +206,38 @@ int gpxb_gpr_td_lml_grad(gpxb_ctx* ctx, int kind, const double* x, const double*
                          const double* y_derivs, int N, int nf, int nv, double ell, double sigma_targets,
                          double sigma_derivs, int mean_mode, int want_grad, double* out4, gpxb_stream stream) {
   GPXB_ARG_CHECK(ctx && x && J && y && y_derivs && out4, -1);
-  return gpxb::gpr_td(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, ell, sigma_targets, sigma_derivs,
-                      mean_mode, want_grad, out4, nullptr, nullptr, (cudaStream_t)stream);
+  gpxb::DevBuf b5;  // the kernel writes five values; the one-block entry point exposes the first four
+  cudaStream_t s = (cudaStream_t)stream;
+  GPXB_TRY(b5.alloc(sizeof(double) * 5, s));
+  GPXB_TRY(gpxb::gpr_td(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, nv, ell, sigma_targets,
+                        sigma_derivs, 0.0, mean_mode, want_grad, b5.as<double>(), nullptr, nullptr, s));
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(out4, b5.as<double>(), sizeof(double) * 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int gpxb_gpr_td2_lml_grad(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y,
+                          const double* y_derivs, int N, int nf, int nv, int nv_first, double ell, double sigma_targets,
+                          double sigma_derivs, double sigma_derivs2, int mean_mode, int want_grad, double* out5,
+                          gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && y && y_derivs && out5, -1);
+  return gpxb::gpr_td(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, nv_first, ell, sigma_targets,
+                      sigma_derivs, sigma_derivs2, mean_mode, want_grad, out5, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int gpxb_gpr_td2_fit(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, const double* y_derivs,
+                     int N, int nf, int nv, int nv_first, double ell, double sigma_targets, double sigma_derivs,
+                     double sigma_derivs2, int mean_mode, double* c_out, double* mu_out, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && y && y_derivs && c_out && mu_out, -1);
+  return gpxb::gpr_td(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, nv_first, ell, sigma_targets,
+                      sigma_derivs, sigma_derivs2, mean_mode, 0, nullptr, c_out, mu_out, (cudaStream_t)stream);
 }
 
 int gpxb_gpr_td_fit(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, const double* y_derivs,
                     int N, int nf, int nv, double ell, double sigma_targets, double sigma_derivs, int mean_mode,
                     double* c_out, double* mu_out, gpxb_stream stream) {
   GPXB_ARG_CHECK(ctx && x && J && y && y_derivs && c_out && mu_out, -1);
-  return gpxb::gpr_td(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, ell, sigma_targets, sigma_derivs,
-                      mean_mode, 0, nullptr, c_out, mu_out, (cudaStream_t)stream);
+  return gpxb::gpr_td(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, nv, ell, sigma_targets,
+                      sigma_derivs, 0.0, mean_mode, 0, nullptr, c_out, mu_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,7 +1,12 @@
-"""GPR trained on targets AND derivatives (mirror of gpx/models/gpr_td.py:848-1170, the dense paths with one
-derivative block).  Numerics run on the device through gpxb_td_gram / gpxb_gpr_td_lml_grad / gpxb_gpr_td_fit
-(include/gpxb200.h): the block kernel matrix [[K + s_t I, d1kj], [d0kj, d01kj + s_d I]] is assembled by the
-fused Gram, d0kj and Hessian kernels and factorised by the blocked FP64 Cholesky."""
+"""GPR trained on targets AND derivatives (mirror of gpx/models/gpr_td.py:848-1170, the dense paths, with the
+optional second derivative block).  Numerics run on the device through gpxb_td_gram / gpxb_gpr_td[2]_lml_grad /
+gpxb_gpr_td[2]_fit (include/gpxb200.h): the block kernel matrix [[K + s_t I, d1kj], [d0kj, d01kj + s_d I]] is
+assembled by the fused Gram, d0kj and Hessian kernels and factorised by the blocked FP64 Cholesky.
+
+Second block (jacobian_2, y_derivs_2, sigma_derivs2; gpr_td.py:114-158): the device works on the two jacobians
+concatenated along the variable axis, which is the reference's 3 x 3 block system with the derivative rows ordered
+(sample, variable) instead of block after block -- a symmetric permutation, so the LML and its gradient are
+unchanged; `c` is permuted to the reference's order [targets; block 1; block 2] before it is stored."""
 from __future__ import annotations
 
 import warnings
@@ -27,21 +32,66 @@ def _hyper(state):
             float(np.asarray(state.params["sigma_derivs"].value)))
 
 
-def _single_block(jacobian_2, y_derivs_2, iterative):
-    if jacobian_2 is not None or y_derivs_2 is not None:
-        raise NotImplementedError("the second derivative block (jacobian_2) of GPR_TD is not implemented")
+def _dense_only(iterative):
     if iterative:
         raise NotImplementedError("the iterative GPR_TD paths (gpr_td.py:162-505, 562-747) are not implemented")
+
+
+def _cat_blocks(state, jacobian, y_derivs, jacobian_2, y_derivs_2):
+    """(J, y_derivs) of both derivative blocks concatenated along the variable axis, the number of variables of the
+    first block and sigma_derivs2 (None / nv / 0.0 without a second block)."""
+    J = np.asarray(jacobian, dtype=np.float64)
+    yd = None if y_derivs is None else np.asarray(y_derivs, dtype=np.float64).reshape(J.shape[0], J.shape[2])
+    if jacobian_2 is None:
+        if y_derivs_2 is not None:
+            raise ValueError("y_derivs_2 needs jacobian_2")
+        return J, yd, J.shape[2], 0.0
+    if "sigma_derivs2" not in state.params:
+        raise ValueError("a second derivative block needs the sigma_derivs2 Parameter (gpx/models/gpr_td.py:955, 68-69)")
+    J2 = np.asarray(jacobian_2, dtype=np.float64)
+    if J2.shape[:2] != J.shape[:2]:
+        raise ValueError(f"jacobian_2 {J2.shape} does not match jacobian {J.shape} in (samples, features)")
+    if yd is not None:
+        if y_derivs_2 is None:
+            raise ValueError("jacobian_2 needs y_derivs_2")
+        yd = np.concatenate([yd, np.asarray(y_derivs_2, dtype=np.float64).reshape(J2.shape[0], J2.shape[2])], axis=1)
+    return (np.concatenate([J, J2], axis=2), yd, J.shape[2], float(np.asarray(state.params["sigma_derivs2"].value)))
+
+
+def _to_ref_order(c, ns, nv1, nv2):
+    """[targets; (sample, variable of block 1 | block 2)] -> the reference's [targets; block 1; block 2]."""
+    if nv2 == 0:
+        return c
+    d = c[ns:].reshape(ns, nv1 + nv2, -1)
+    return np.concatenate([c[:ns], d[:, :nv1].reshape(ns * nv1, -1), d[:, nv1:].reshape(ns * nv2, -1)])
+
+
+def _to_lib_order(c, ns, nv1, nv2):
+    if nv2 == 0:
+        return c
+    a = c[ns:ns + ns * nv1].reshape(ns, nv1, -1)
+    b = c[ns + ns * nv1:ns + ns * (nv1 + nv2)].reshape(ns, nv2, -1)
+    return np.concatenate([c[:ns], np.concatenate([a, b], axis=1).reshape(ns * (nv1 + nv2), -1)])
+
+
+def _lml_grad(state, x, y, jacobian, y_derivs, jacobian_2, y_derivs_2, want_grad):
+    """[lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs, d/d sigma_derivs2] (host floats)."""
+    kernel, ell, st, sd = _hyper(state)
+    J, yd, nv1, sd2 = _cat_blocks(state, jacobian, y_derivs, jacobian_2, y_derivs_2)
+    if J.shape[2] == nv1:
+        out = ops.gpr_td_lml_grad(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), ell, st, sd,
+                                  mean_mode(state.mean_function), want_grad=want_grad)
+        return [float(v) for v in out.cpu().numpy()] + [0.0]
+    out = ops.gpr_td2_lml_grad(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), nv1, ell, st, sd,
+                               sd2, mean_mode(state.mean_function), want_grad=want_grad)
+    return [float(v) for v in out.cpu().numpy()]
 
 
 def log_marginal_likelihood(state, x, y, jacobian, y_derivs, jacobian_2=None, y_derivs_2=None, iterative=False,
                             **_ignored):
     """gpx/models/gpr_td.py:848-911 -> _lml_dense (507-560)."""
-    _single_block(jacobian_2, y_derivs_2, iterative)
-    kernel, ell, st, sd = _hyper(state)
-    out = ops.gpr_td_lml_grad(kernel.kind, _to_device(x), _to_device(jacobian), _to_device(y), _to_device(y_derivs), ell,
-                              st, sd, mean_mode(state.mean_function), want_grad=False)
-    return float(out.cpu().numpy()[0])
+    _dense_only(iterative)
+    return _lml_grad(state, x, y, jacobian, y_derivs, jacobian_2, y_derivs_2, want_grad=False)[0]
 
 
 def neg_log_marginal_likelihood(state, x, y, jacobian, y_derivs, **kwargs):
@@ -50,16 +100,15 @@ def neg_log_marginal_likelihood(state, x, y, jacobian, y_derivs, **kwargs):
 
 
 def loss_and_grad(state, x, y, jacobian, y_derivs, jacobian_2=None, y_derivs_2=None, iterative=False, **_ignored):
-    """Negative LML and its gradient w.r.t. the constrained (lengthscale, sigma_targets, sigma_derivs) from one
-    fused device call: what jit(value_and_grad(loss)) returns inside scipy_minimize_ol."""
-    _single_block(jacobian_2, y_derivs_2, iterative)
+    """Negative LML and its gradient w.r.t. the constrained (lengthscale, sigma_targets, sigma_derivs[, sigma_derivs2])
+    from one fused device call: what jit(value_and_grad(loss)) returns inside scipy_minimize_ol."""
+    _dense_only(iterative)
     if state.loss_fn is not neg_log_marginal_likelihood:
         raise NotImplementedError("only neg_log_marginal_likelihood has a fused device gradient")
-    kernel, ell, st, sd = _hyper(state)
-    out = ops.gpr_td_lml_grad(kernel.kind, _to_device(x), _to_device(jacobian), _to_device(y), _to_device(y_derivs), ell,
-                              st, sd, mean_mode(state.mean_function), want_grad=True)
-    lml, g_ell, g_st, g_sd = (float(v) for v in out.cpu().numpy())
+    lml, g_ell, g_st, g_sd, g_sd2 = _lml_grad(state, x, y, jacobian, y_derivs, jacobian_2, y_derivs_2, want_grad=True)
     grads = {}
+    if jacobian_2 is not None and state.params["sigma_derivs2"].trainable:
+        grads[("sigma_derivs2",)] = -g_sd2
     if state.params["kernel_params"]["lengthscale"].trainable:
         grads[("kernel_params", "lengthscale")] = -g_ell
     if state.params["sigma_targets"].trainable:
@@ -75,25 +124,27 @@ def default_params() -> Dict[str, Parameter]:
 
 
 class GPR_TD:
-    """gpx/models/gpr_td.py:947-1170 (dense paths, one derivative block)."""
+    """gpx/models/gpr_td.py:947-1170 (dense paths; one or two derivative blocks)."""
 
     def __init__(self, kernel: Callable, mean_function: Callable = zero_mean, kernel_params=None, sigma_targets=None,
                  sigma_derivs=None, sigma_derivs2=None, loss_fn: Callable = neg_log_marginal_likelihood) -> None:
         if not callable(kernel):
             raise TypeError(f"kernel must be callable, you provided {type(kernel)}")
-        if sigma_derivs2 is not None:
-            raise NotImplementedError("the second derivative block (sigma_derivs2) of GPR_TD is not implemented")
         if kernel_params is None:
             kernel_params = kernel.default_params()
         d = default_params()
         params = {"kernel_params": kernel_params,
                   "sigma_targets": sigma_targets if sigma_targets is not None else d["sigma_targets"],
                   "sigma_derivs": sigma_derivs if sigma_derivs is not None else d["sigma_derivs"]}
-        opt = dict(x_train=None, jacobian_train=None, jaccoef=None, y_train=None, y_derivs_train=None, is_fitted=False,
-                   c=None, c_targets=None, mu=None, loss_fn=loss_fn)
+        if sigma_derivs2 is not None:  # the reference keeps a None entry otherwise (gpr_td.py:959-964)
+            params["sigma_derivs2"] = sigma_derivs2
+        opt = dict(x_train=None, jacobian_train=None, jacobian_train_2=None, jaccoef=None, jaccoef_2=None, y_train=None,
+                   y_derivs_train=None, y_derivs_train_2=None, is_fitted=False, c=None, c_targets=None, mu=None,
+                   loss_fn=loss_fn)
         self.state = ModelState(kernel, mean_function, params, **opt)
 
     def log_marginal_likelihood(self, x, y, jacobian, y_derivs, return_negative=False, **kwargs):
+        """kwargs: jacobian_2, y_derivs_2 (second derivative block), iterative."""
         lml = log_marginal_likelihood(self.state, x, y, jacobian, y_derivs, **kwargs)
         return -lml if return_negative else lml
 
@@ -104,10 +155,10 @@ class GPR_TD:
             minimize=True, return_history=False, loss_kwargs=None, n_pivots=None, key_precond=None, c_guess=None,
             opt_kwargs=None):
         """gpx/models/gpr_td.py:982-1108."""
-        _single_block(jacobian_2, y_derivs_2, iterative)
+        _dense_only(iterative)
         if minimize:
             def loss_and_grad_fn(state, xx, yy):
-                return loss_and_grad(state, xx, yy, jacobian, y_derivs)
+                return loss_and_grad(state, xx, yy, jacobian, y_derivs, jacobian_2=jacobian_2, y_derivs_2=y_derivs_2)
 
             self.state, optres, *history = randomized_minimization(
                 key=key, state=self.state, x=x, y=y, loss_and_grad_fn=loss_and_grad_fn, num_restarts=num_restarts,
@@ -119,31 +170,51 @@ class GPR_TD:
             if return_history:
                 self.states_history_, self.losses_history_ = history[0], history[1]
         kernel, ell, st, sd = _hyper(self.state)
-        Jd = _to_device(jacobian)
-        c, mu = ops.gpr_td_fit(kernel.kind, _to_device(x), Jd, _to_device(y), _to_device(y_derivs), ell, st, sd,
-                               mean_mode(self.state.mean_function))
-        ns, _, nv = Jd.shape
-        c_np = c.cpu().numpy()
-        jaccoef = np.einsum("sv,sfv->sf", c_np[ns:ns + ns * nv].reshape(ns, nv), np.asarray(jacobian, dtype=np.float64))
+        J, yd, nv1, sd2 = _cat_blocks(self.state, jacobian, y_derivs, jacobian_2, y_derivs_2)
+        ns, _, nv = J.shape
+        nv2 = nv - nv1
+        if nv2 == 0:
+            c, mu = ops.gpr_td_fit(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), ell, st, sd,
+                                   mean_mode(self.state.mean_function))
+        else:
+            c, mu = ops.gpr_td2_fit(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), nv1, ell,
+                                    st, sd, sd2, mean_mode(self.state.mean_function))
+        c_np = _to_ref_order(c.cpu().numpy(), ns, nv1, nv2)
+        jaccoef = np.einsum("sv,sfv->sf", c_np[ns:ns + ns * nv1].reshape(ns, nv1), J[:, :, :nv1])
+        jaccoef_2 = None
+        if nv2:  # gpx/models/gpr_td.py:1076-1083
+            jaccoef_2 = np.einsum("sv,sfv->sf", c_np[ns + ns * nv1:ns + ns * nv].reshape(ns, nv2), J[:, :, nv1:])
         self.state = self.state.update(dict(
-            x_train=np.asarray(x), y_train=np.asarray(y), jacobian_train=np.asarray(jacobian), jaccoef=jaccoef,
-            y_derivs_train=np.asarray(y_derivs), c=c_np, c_targets=c_np[:ns].reshape(-1),
-            mu=np.float64(mu.cpu().numpy()[0]), is_fitted=True))
+            x_train=np.asarray(x), y_train=np.asarray(y), jacobian_train=np.asarray(jacobian),
+            jacobian_train_2=None if jacobian_2 is None else np.asarray(jacobian_2), jaccoef=jaccoef,
+            jaccoef_2=jaccoef_2, y_derivs_train=np.asarray(y_derivs),
+            y_derivs_train_2=None if y_derivs_2 is None else np.asarray(y_derivs_2), c=c_np,
+            c_targets=c_np[:ns].reshape(-1), mu=np.float64(mu.cpu().numpy()[0]), is_fitted=True))
         return self
 
     def predict(self, x, jacobian, jacobian_2=None, iterative=False):
-        """gpx/models/gpr_td.py:1110-1160 -> _predict_dense (749-797): (targets (ns, 1), derivatives (ns, nv))."""
+        """gpx/models/gpr_td.py:1110-1160 -> _predict_dense (749-797): (targets (ns, 1), derivatives (ns, nv_1)
+        [, derivatives of the second block (ns, nv_2)])."""
         if not self.state.is_fitted:
             raise RuntimeError("Model is not fitted. Run `fit` to fit the model before prediction.")
-        _single_block(jacobian_2, None, iterative)
+        _dense_only(iterative)
         kernel, ell, _, _ = _hyper(self.state)
-        Js = _to_device(jacobian)
-        K_nm = ops.td_gram(kernel.kind, _to_device(x), Js, _to_device(self.state.x_train),
-                           _to_device(self.state.jacobian_train), ell)   # (test rows) x (train rows) = K_mn^T
-        pred = ops.gemm(K_nm, _to_device(self.state.c).reshape(-1, 1)).cpu().numpy()
+        Jt2 = getattr(self.state, "jacobian_train_2", None)
+        if (jacobian_2 is None) != (Jt2 is None):
+            raise ValueError("jacobian_2 must be given exactly when the model was fitted with a second derivative block")
+        Js, _, nv1, _ = _cat_blocks(self.state, jacobian, None, jacobian_2, None)
+        Jt, _, nt1, _ = _cat_blocks(self.state, self.state.jacobian_train, None, Jt2, None)
+        nt = Jt.shape[0]
+        c_lib = _to_lib_order(np.asarray(self.state.c, dtype=np.float64).reshape(-1, 1), nt, nt1, Jt.shape[2] - nt1)
+        K_nm = ops.td_gram(kernel.kind, _to_device(x), _to_device(Js), _to_device(self.state.x_train), _to_device(Jt),
+                           ell)                                            # (test rows) x (train rows) = K_mn^T
+        pred = ops.gemm(K_nm, _to_device(c_lib)).cpu().numpy()
         ns, _, nv = Js.shape
         pred[:ns] += float(self.state.mu)
-        return pred[:ns], pred[ns:ns + ns * nv].reshape(ns, -1)
+        d = pred[ns:ns + ns * nv].reshape(ns, nv)
+        if jacobian_2 is None:
+            return pred[:ns], d
+        return pred[:ns], d[:, :nv1].copy(), d[:, nv1:].copy()
 
     def print(self) -> None:
         print(self.state)

@@ -434,6 +434,42 @@ def gpr_td_fit(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_m
     return c, mu
 
 
+def gpr_td2_lml_grad(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_derivs, sigma_derivs2,
+                     mean_mode=MEAN_DATA, want_grad=True):
+    """GPR_TD with two derivative blocks concatenated along the variable axis (block 1 = the first nv_first variables)
+    -> device tensor [lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs, d/d sigma_derivs2]."""
+    ctx = context()
+    x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    N, nf, nv = J.shape
+    assert y.numel() == N and yd.numel() == N * nv and 0 < nv_first <= nv
+    out = torch.empty(5, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_gpr_td2_lml_grad(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv, int(nv_first),
+                                      float(ell), float(sigma_targets), float(sigma_derivs), float(sigma_derivs2),
+                                      int(mean_mode), 1 if want_grad else 0, ptr(out), stream_ptr()),
+        "gpxb_gpr_td2_lml_grad",
+    )
+    return out
+
+
+def gpr_td2_fit(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_derivs, sigma_derivs2,
+                mean_mode=MEAN_DATA):
+    """-> (c (N + N*nv, 1) in the library's row order [targets; (sample, variable)], mu (1,))."""
+    ctx = context()
+    x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    N, nf, nv = J.shape
+    assert y.numel() == N and yd.numel() == N * nv and 0 < nv_first <= nv
+    c = torch.empty((N + N * nv, 1), dtype=torch.float64, device=x.device)
+    mu = torch.empty(1, dtype=torch.float64, device=x.device)
+    check(
+        ctx.lib.gpxb_gpr_td2_fit(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv, int(nv_first),
+                                 float(ell), float(sigma_targets), float(sigma_derivs), float(sigma_derivs2),
+                                 int(mean_mode), ptr(c), ptr(mu), stream_ptr()),
+        "gpxb_gpr_td2_fit",
+    )
+    return c, mu
+
+
 def gpr_fit_derivs(kind, x, J, y, ell, sigma):
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)

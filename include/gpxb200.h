@@ -170,6 +170,20 @@ int gpxb_gpr_td_lml_grad(gpxb_ctx* ctx, int kind, const double* x, const double*
 int gpxb_gpr_td_fit(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, const double* y_derivs,
                     int N, int nf, int nv, double ell, double sigma_targets, double sigma_derivs, int mean_mode,
                     double* c_out, double* mu_out, gpxb_stream stream);
+/* The same with the reference's optional SECOND derivative block (jacobian_2, y_derivs_2, sigma_derivs2:
+ * gpx/models/gpr_td.py:114-158, 507-560, 639-683).  J (N, nf, nv) and y_derivs (N, nv) hold the two blocks
+ * concatenated along the variable axis, the first nv_first variables being block 1; variables >= nv_first carry the
+ * noise sigma_derivs2.  The system is the reference's 3 x 3 block matrix up to a symmetric permutation of the
+ * derivative rows ((sample, variable) interleaved here), which leaves the LML unchanged; c_out is in this library's
+ * row order [N targets; (sample, variable)].  out5 = {lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs,
+ * d/d sigma_derivs2}, lml normalised by m = N + N nv. */
+int gpxb_gpr_td2_lml_grad(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y,
+                          const double* y_derivs, int N, int nf, int nv, int nv_first, double ell, double sigma_targets,
+                          double sigma_derivs, double sigma_derivs2, int mean_mode, int want_grad, double* out5,
+                          gpxb_stream stream);
+int gpxb_gpr_td2_fit(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, const double* y_derivs,
+                     int N, int nf, int nv, int nv_first, double ell, double sigma_targets, double sigma_derivs,
+                     double sigma_derivs2, int mean_mode, double* c_out, double* mu_out, gpxb_stream stream);
 
 /* ---- Family 2: blocked FP64 Cholesky / TRSM / log-det / inverse ---------------------- */
 /* C[M x N] = alpha * op(A) * op(B) + beta * C on the FP64 tensor pipe.  transa = 0: A is M x K

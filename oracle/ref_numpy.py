@@ -406,6 +406,50 @@ def td_predict_dense(kind, x_train, J_train, x, J, c, mu, ell):
     return pred[:ns], pred[ns:ns + ns * nv].reshape(ns, -1)
 
 
+def td2_A_lhs(kind, x1, J1a, J1b, x2, J2a, J2b, ell, sigma_t, sigma_d, sigma_d2, noise=True):
+    """gpr_td.py:43-159 with the second derivative block, literal 3 x 3 assembly:
+    [[K, d1kj_1, d1kj_2], [d0kj_1, d01kj_11, d01kj_12], [d0kj_2, d01kj_21, d01kj_22]]."""
+    K = kernel(kind, x1, x2, ell)
+    D11 = d01kj(kind, x1, x2, ell, J1a, J2a)
+    D22 = d01kj(kind, x1, x2, ell, J1b, J2b)
+    if noise:
+        K = K + (sigma_t**2 + 1e-10) * np.eye(K.shape[0])
+        D11 = D11 + (sigma_d**2 + 1e-10) * np.eye(D11.shape[0])
+        D22 = D22 + (sigma_d2**2 + 1e-10) * np.eye(D22.shape[0])
+    D12 = d01kj(kind, x1, x2, ell, J1a, J2b)
+    D21 = d01kj(kind, x1, x2, ell, J1b, J2a)
+    D0a, D0b = d0kj(kind, x1, x2, ell, J1a), d0kj(kind, x1, x2, ell, J1b)
+    D1a, D1b = d0kj(kind, x2, x1, ell, J2a).T, d0kj(kind, x2, x1, ell, J2b).T
+    return np.block([[K, D1a, D1b], [D0a, D11, D12], [D0b, D21, D22]])
+
+
+def td2_lml_dense(kind, x, y, Ja, Jb, yd_a, yd_b, ell, sigma_t, sigma_d, sigma_d2, mean_function=data_mean):
+    """gpr_td.py:507-560 with jacobian_2 / y_derivs_2."""
+    mu = mean_function(y)
+    ym = np.concatenate([(y - mu).reshape(-1, 1), yd_a.reshape(-1, 1), yd_b.reshape(-1, 1)])
+    m = ym.shape[0]
+    A = td2_A_lhs(kind, x, Ja, Jb, x, Ja, Jb, ell, sigma_t, sigma_d, sigma_d2)
+    L = sla.cholesky(A, lower=True, check_finite=False)
+    cy = sla.solve_triangular(L, ym, lower=True, check_finite=False)
+    return (-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - m * 0.5 * np.log(2.0 * np.pi)) / m
+
+
+def td2_fit_dense(kind, x, y, Ja, Jb, yd_a, yd_b, ell, sigma_t, sigma_d, sigma_d2, mean_function=data_mean):
+    """gpr_td.py:639-683 with jacobian_2 / y_derivs_2: c in the reference's order [targets; block 1; block 2]."""
+    mu = mean_function(y)
+    ym = np.concatenate([(y - mu).reshape(-1, 1), yd_a.reshape(-1, 1), yd_b.reshape(-1, 1)])
+    return np.linalg.solve(td2_A_lhs(kind, x, Ja, Jb, x, Ja, Jb, ell, sigma_t, sigma_d, sigma_d2), ym), mu
+
+
+def td2_predict_dense(kind, x_train, Ja_train, Jb_train, x, Ja, Jb, c, mu, ell):
+    """gpr_td.py:749-797 with jacobian_2: (targets (ns, 1), derivatives block 1 (ns, nv_1), block 2 (ns, nv_2))."""
+    K_mn = td2_A_lhs(kind, x_train, Ja_train, Jb_train, x, Ja, Jb, ell, 0.0, 0.0, 0.0, noise=False)
+    pred = K_mn.T @ c
+    ns, n1, n2 = x.shape[0], Ja.shape[2], Jb.shape[2]
+    pred[:ns] += mu
+    return pred[:ns], pred[ns:ns + ns * n1].reshape(ns, -1), pred[ns + ns * n1:ns + ns * (n1 + n2)].reshape(ns, -1)
+
+
 def predict_y_derivs_dense(kind, x_train, x, jaccoef, mu, ell):
     """_gpr.py:630-638 (contracted-jacobian fast path of _predict_y_derivs_dense)."""
     return (mu + np.sum(d0kjc(kind, x_train, x, ell, jaccoef), axis=0)).reshape(-1, 1)

@@ -202,10 +202,73 @@ def sgpr_predict(kind, x_locs, x, c, mu, ell, sigma, full_covariance=False):
     return (_t(out[0]), _t(out[1])) if full_covariance else _t(out)
 
 
+# ---- GPR on targets and derivatives (csrc/td.cu).  Library row order: [targets; (sample, variable)] ----
+def td_gram(kind, x1, J1, x2, J2, ell, add_targets=0.0, add_derivs=0.0, lower_only=False):
+    assert not lower_only
+    A = R.td_A_lhs(kind, _np(x1), _np(J1), _np(x2), _np(J2), float(ell), 0.0, 0.0, noise=False)
+    n1 = x1.shape[0]
+    if add_targets or add_derivs:
+        A[np.arange(n1), np.arange(n1)] += add_targets
+        i = np.arange(n1, A.shape[0])
+        A[i, i] += add_derivs
+    return _t(A)
+
+
+def _rich(g, h):
+    fd = lambda hh: (g(hh) - g(-hh)) / (2 * hh)  # noqa: E731
+    return (4 * fd(h / 2) - fd(h)) / 3
+
+
+def gpr_td_lml_grad(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_mode=1, want_grad=True):
+    xn, Jn, yn, ydn, mf = _np(x), _np(J), _col(y), _np(y_derivs), _mean_fn(mean_mode)
+    f = lambda e, a, b: R.td_lml_dense(kind, xn, yn, Jn, ydn, e, a, b, mf)  # noqa: E731
+    e, a, b = float(ell), float(sigma_targets), float(sigma_derivs)
+    if not want_grad:
+        return _t(np.array([f(e, a, b), 0.0, 0.0, 0.0]))
+    return _t(np.array([f(e, a, b), _rich(lambda h: f(e + h, a, b), 1e-3 * e), _rich(lambda h: f(e, a + h, b), 1e-3 * a),
+                        _rich(lambda h: f(e, a, b + h), 1e-3 * b)]))
+
+
+def gpr_td_fit(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_mode=1):
+    c, mu = R.td_fit_dense(kind, _np(x), _col(y), _np(J), _np(y_derivs), float(ell), float(sigma_targets),
+                           float(sigma_derivs), _mean_fn(mean_mode))
+    return _t(c), _t(np.array([float(mu)]))
+
+
+def _td2_split(J, y_derivs, nv_first):
+    Jn, ydn = _np(J), _np(y_derivs).reshape(J.shape[0], J.shape[2])
+    return Jn[:, :, :nv_first], Jn[:, :, nv_first:], ydn[:, :nv_first], ydn[:, nv_first:]
+
+
+def gpr_td2_lml_grad(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_derivs, sigma_derivs2, mean_mode=1,
+                     want_grad=True):
+    Ja, Jb, ya, yb = _td2_split(J, y_derivs, nv_first)
+    xn, yn, mf = _np(x), _col(y), _mean_fn(mean_mode)
+    f = lambda e, a, b, c: R.td2_lml_dense(kind, xn, yn, Ja, Jb, ya, yb, e, a, b, c, mf)  # noqa: E731
+    e, a, b, c = float(ell), float(sigma_targets), float(sigma_derivs), float(sigma_derivs2)
+    if not want_grad:
+        return _t(np.array([f(e, a, b, c), 0.0, 0.0, 0.0, 0.0]))
+    return _t(np.array([f(e, a, b, c), _rich(lambda h: f(e + h, a, b, c), 1e-3 * e),
+                        _rich(lambda h: f(e, a + h, b, c), 1e-3 * a), _rich(lambda h: f(e, a, b + h, c), 1e-3 * b),
+                        _rich(lambda h: f(e, a, b, c + h), 1e-3 * c)]))
+
+
+def gpr_td2_fit(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_derivs, sigma_derivs2, mean_mode=1):
+    Ja, Jb, ya, yb = _td2_split(J, y_derivs, nv_first)
+    c, mu = R.td2_fit_dense(kind, _np(x), _col(y), Ja, Jb, ya, yb, float(ell), float(sigma_targets), float(sigma_derivs),
+                            float(sigma_derivs2), _mean_fn(mean_mode))
+    n, n1, n2 = x.shape[0], Ja.shape[2], Jb.shape[2]   # reference order [targets; block 1; block 2] -> library order
+    a, b = c[n:n + n * n1].reshape(n, n1), c[n + n * n1:].reshape(n, n2)
+    lib = np.concatenate([c[:n, 0], np.concatenate([a, b], axis=1).reshape(-1)]).reshape(-1, 1)
+    return _t(lib), _t(np.array([float(mu)]))
+
+
 FAKES = dict(gram=gram, gram_dl_contract=gram_dl_contract, elementwise=elementwise, gemm=gemm, potrf=potrf, trsm=trsm,
              logdet=logdet, potri=potri, gpr_lml_grad=gpr_lml_grad, gpr_fit=gpr_fit, gpr_predict=gpr_predict,
              kmatvec=kmatvec, rpcholesky=rpcholesky, gather_rows=gather_rows, sgpr_lml=sgpr_lml,
-             sgpr_lml_grad=sgpr_lml_grad, sgpr_fit=sgpr_fit, sgpr_predict=sgpr_predict)
+             sgpr_lml_grad=sgpr_lml_grad, sgpr_fit=sgpr_fit, sgpr_predict=sgpr_predict, td_gram=td_gram,
+             gpr_td_lml_grad=gpr_td_lml_grad, gpr_td_fit=gpr_td_fit, gpr_td2_lml_grad=gpr_td2_lml_grad,
+             gpr_td2_fit=gpr_td2_fit)
 
 
 @contextlib.contextmanager

@@ -145,3 +145,61 @@ def test_reference_notebook_derivative_block_kernel_on_the_device():
     np.testing.assert_allclose(d1k[-3:], a["row0_last3"], rtol=0, atol=6e-9)
     np.testing.assert_allclose(d0k[:3], a["row1_first3"], rtol=0, atol=6e-9)
     np.testing.assert_allclose(d01k[-3:], a["row1_last3"], rtol=0, atol=6e-9)
+
+
+@pytest.mark.parametrize("kind,N,nf,nv1,nv2,mean", [("se", 30, 6, 4, 3, "data"), ("m52", 24, 8, 2, 5, "zero"), ("se", 12, 7, 7, 1, "zero")])
+def test_td_second_derivative_block(kind, N, nf, nv1, nv2, mean):
+    """GPR_TD with jacobian_2 / y_derivs_2 / sigma_derivs2 (gpr_td.py:114-158) through the facade against the oracle's
+    literal 3 x 3 block assembly: LML, gradient (Richardson central differences of the oracle), fit coefficients in
+    the reference's order, contracted jacobians, predictions of all three outputs, and L-BFGS-B training."""
+    from gpx_b200.kernels import Matern52, SquaredExponential
+    from gpx_b200.mean_functions import data_mean, zero_mean
+    from gpx_b200.models import GPR_TD
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    x, Jc, y, ydc = _data(N, nf, nv1 + nv2, 21)
+    xs, Jsc, _, _ = _data(8, nf, nv1 + nv2, 22)
+    Ja, Jb, ya, yb = Jc[:, :, :nv1].copy(), Jc[:, :, nv1:].copy(), ydc[:, :nv1].copy(), ydc[:, nv1:].copy()
+    ell, st, sd, sd2 = 0.9 * np.sqrt(nf), 0.3, 0.2, 0.45
+    mf_o = R.data_mean if mean == "data" else R.zero_mean
+    par = lambda v: Parameter(v, True, Softplus(), GammaPrior())  # noqa: E731
+    kern = SquaredExponential() if kind == "se" else Matern52()
+    mk = lambda: GPR_TD(kern, mean_function=data_mean if mean == "data" else zero_mean,  # noqa: E731
+                        kernel_params=dict(lengthscale=par(ell)), sigma_targets=par(st), sigma_derivs=par(sd),
+                        sigma_derivs2=par(sd2))
+    m = mk()
+    f = lambda l, a, b, c2: R.td2_lml_dense(kind, x, y, Ja, Jb, ya, yb, l, a, b, c2, mf_o)  # noqa: E731
+    ref = f(ell, st, sd, sd2)
+    assert abs(m.log_marginal_likelihood(x, y, Ja, ya, jacobian_2=Jb, y_derivs_2=yb) - ref) < 1e-8 * abs(ref)
+    loss, grads = m.loss_and_grad(x, y, Ja, ya, jacobian_2=Jb, y_derivs_2=yb)
+    assert abs(-loss - ref) < 1e-8 * abs(ref)
+
+    def rich(g, h=1e-3):
+        fd = lambda hh: (g(hh) - g(-hh)) / (2 * hh)  # noqa: E731
+        return (4 * fd(h / 2) - fd(h)) / 3
+
+    g_ref = {("kernel_params", "lengthscale"): rich(lambda h: f(ell + h, st, sd, sd2)),
+             ("sigma_targets",): rich(lambda h: f(ell, st + h, sd, sd2)),
+             ("sigma_derivs",): rich(lambda h: f(ell, st, sd + h, sd2)),
+             ("sigma_derivs2",): rich(lambda h: f(ell, st, sd, sd2 + h))}
+    assert set(grads) == set(g_ref)
+    for k, g in g_ref.items():
+        assert abs(-grads[k] - g) < 1e-7 * max(abs(g), abs(ref)), (k, grads[k], g)
+    m.fit(x, y, Ja, ya, jacobian_2=Jb, y_derivs_2=yb, minimize=False)
+    c_ref, mu_ref = R.td2_fit_dense(kind, x, y, Ja, Jb, ya, yb, ell, st, sd, sd2, mf_o)
+    assert abs(float(m.state.mu) - mu_ref) < 1e-14
+    assert np.max(np.abs(m.state.c - c_ref)) < 1e-8 * np.max(np.abs(c_ref))  # the reference's row order
+    assert np.max(np.abs(m.state.jaccoef_2 - np.einsum("sv,sfv->sf", c_ref[N + N * nv1:].reshape(N, nv2), Jb))) < 1e-8 * np.max(np.abs(c_ref))
+    yp, d1, d2 = m.predict(xs, Jsc[:, :, :nv1].copy(), jacobian_2=Jsc[:, :, nv1:].copy())
+    yr, d1r, d2r = R.td2_predict_dense(kind, x, Ja, Jb, xs, Jsc[:, :, :nv1], Jsc[:, :, nv1:], c_ref, mu_ref, ell)
+    for got, want in ((yp, yr), (d1, d1r), (d2, d2r)):
+        assert got.shape == want.shape and np.max(np.abs(got - want)) < 1e-8 * max(1.0, np.max(np.abs(want)))
+    with pytest.raises(ValueError):
+        m.predict(xs, Jsc[:, :, :nv1].copy())  # fitted with two blocks: jacobian_2 is required
+    if kind == "se" and mean == "data":
+        m2 = mk()
+        l0, _ = m2.loss_and_grad(x, y, Ja, ya, jacobian_2=Jb, y_derivs_2=yb)
+        m2.fit(x, y, Ja, ya, jacobian_2=Jb, y_derivs_2=yb, opt_kwargs=dict(options=dict(maxiter=15)))
+        assert m2.optimize_results_.fun < l0

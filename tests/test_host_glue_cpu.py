@@ -7,6 +7,7 @@ torch = pytest.importorskip("torch")
 
 import test_gpu_composite as G  # noqa: E402  (its tests are plain functions; the gpu mark stays on that module)
 import test_gpu_facade as F  # noqa: E402
+import test_gpu_td as TD  # noqa: E402
 from _fake_ops import patched  # noqa: E402
 
 
@@ -53,3 +54,16 @@ def test_composite_sgpr_minimize_glue():
 def test_facade_glue(test):
     with patched():
         test()
+
+
+@pytest.mark.parametrize("kind,N,nf,nv1,nv2,mean", [("se", 30, 6, 4, 3, "data"), ("m52", 24, 8, 2, 5, "zero")])
+def test_gpr_td_second_block_glue(kind, N, nf, nv1, nv2, mean):
+    """Concatenation of the two jacobians, the permutation of `c` to the reference's row order and back, the
+    contracted jacobians and the three-way split of the predictions."""
+    with patched():
+        TD.test_td_second_derivative_block(kind, N, nf, nv1, nv2, mean)
+
+
+def test_gpr_td_single_block_glue():
+    with patched():
+        TD.test_td_fit_minimize_lowers_the_loss()
