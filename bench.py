@@ -86,7 +86,8 @@ def run_reference(args):
         "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * scale * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"exact GPR Matern-5/2 N={N} D={CFG['D']} LML+grad", "cpu_sample_N": n0},
+        "config": {"workload": f"exact GPR Matern-5/2 N={N} D={CFG['D']} LML+grad (BASELINE configs[1])",
+                   "parallelism": "host cores (CPU restatement of the reference)", "cpu_sample_N": n0},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cpu_cores(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
