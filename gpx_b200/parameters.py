@@ -13,14 +13,17 @@ from .priors import Prior
 
 class Parameter:
     def __init__(self, value, trainable: bool, bijector: Bijector, prior: Prior) -> None:
-        self.value = np.asarray(value, dtype=np.float64)
+        raw = np.asarray(value)
         self.trainable = bool(trainable)
         self.bijector = bijector
         self.prior = prior
-        if tuple(self.value.shape) != tuple(getattr(prior, "shape", ())):
-            raise ValueError(
-                f"Shape of value ({self.value.shape}) and prior ({prior.shape}) do not match."
-            )
+        # value and prior must agree in shape and dtype (gpx/parameters/parameter.py:45-47, utils.py:26-37): a Python
+        # int is int64 under jax_enable_x64 and is rejected against the default float64 prior, as in the reference
+        if tuple(raw.shape) != tuple(getattr(prior, "shape", ())):
+            raise ValueError(f"value.shape={raw.shape} and prior.shape={getattr(prior, 'shape', ())} do not match.")
+        if raw.dtype != np.dtype(getattr(prior, "dtype", np.float64)):
+            raise ValueError(f"value.dtype={raw.dtype} and prior.dtype={np.dtype(prior.dtype)} do not match.")
+        self.value = np.array(raw, dtype=np.float64)  # own copy; the numerical path is FP64 throughout
 
     def __repr__(self) -> str:
         return (f"Parameter(value={self.value}, trainable={self.trainable}, "
@@ -73,7 +76,12 @@ class ModelState:
         return ModelState(base["kernel"], base["mean_function"], base["params"], **d)
 
     def copy(self) -> "ModelState":
-        return self.update({})
+        """Shallow copy: kernel and Parameter objects are shared, the (nested) parameter dictionaries are new, so
+        re-assigning an entry of one state leaves the other untouched (tests/gpx/parameters/test_model_state.py:91-110)."""
+        def dicts(d):
+            return {k: dicts(v) if isinstance(v, dict) else v for k, v in d.items()}
+
+        return self.update(dict(params=dicts(self.params)))
 
     def flat_params(self):
         return list(_flatten_params(self.params))
@@ -83,6 +91,11 @@ class ModelState:
         return self.update(dict(params=_set_path(self.params, tuple(path), p.update(dict(value=value)))))
 
     def randomize(self, rng, opt=None) -> "ModelState":
+        """New state with every trainable parameter re-drawn from its prior (gpx/parameters/model_state.py:349-404).
+        `rng`: a numpy Generator, or a PRNG key of two uint32 words as the reference takes."""
+        if not isinstance(rng, np.random.Generator):
+            k = np.asarray(rng, dtype=np.uint64)
+            rng = np.random.default_rng(int((k[0] << np.uint64(32)) | k[1]))
         params = self.params
         for path, p in _flatten_params(self.params):
             if p.trainable:
