@@ -169,5 +169,6 @@ def ptr(t):
     """Device pointer of a contiguous float64/int64/uint32 CUDA tensor (or None)."""
     if t is None:
         return C.c_void_p(0)
-    assert t.is_cuda and t.is_contiguous(), "device buffers must be contiguous CUDA tensors"
+    if not (t.is_cuda and t.is_contiguous()):  # a host pointer would fault inside a kernel: refuse it here
+        raise GpxbError("device buffers must be contiguous CUDA tensors (there is no CPU path)")
     return C.c_void_p(t.data_ptr())

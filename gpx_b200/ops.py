@@ -19,7 +19,8 @@ def _kind(kind) -> int:
 
 
 def _f64(t: torch.Tensor) -> torch.Tensor:
-    assert t.is_cuda and t.dtype == torch.float64, "expected a CUDA float64 tensor"
+    if not (t.is_cuda and t.dtype == torch.float64):
+        raise _lib.GpxbError(f"expected a CUDA float64 tensor, got {t.device} {t.dtype} (there is no CPU path)")
     return t.contiguous()
 
 

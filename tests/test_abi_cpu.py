@@ -77,3 +77,15 @@ def test_header_is_plain_c_and_a_c_program_links_the_library(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "version" in r.stdout
+
+
+def test_host_tensors_are_refused_not_computed_on():
+    """A CPU tensor handed to a device entry point is an error raised before any kernel launch (no CPU path)."""
+    import torch
+
+    from gpx_b200 import _lib, ops
+
+    with pytest.raises(_lib.GpxbError):
+        ops._f64(torch.zeros((2, 2), dtype=torch.float64))
+    with pytest.raises(_lib.GpxbError):
+        _lib.ptr(torch.zeros(3, dtype=torch.float64))
