@@ -18,6 +18,12 @@ def _kind(kind) -> int:
     return KINDS[kind] if isinstance(kind, str) else int(kind)
 
 
+def _require(cond, msg) -> None:
+    """Argument validation that survives `python -O` (the C ABI cannot see tensor shapes)."""
+    if not cond:
+        raise ValueError(msg)
+
+
 def _f64(t: torch.Tensor) -> torch.Tensor:
     if not (t.is_cuda and t.dtype == torch.float64):
         raise _lib.GpxbError(f"expected a CUDA float64 tensor, got {t.device} {t.dtype} (there is no CPU path)")
@@ -32,7 +38,7 @@ def gram(kind, x1, x2, ell, diag_add=0.0, lower_only=False, out=None):
     x2 = x1 if sym else _f64(x2)
     n1, D = x1.shape
     n2 = x2.shape[0]
-    assert x2.shape[1] == D
+    _require(x2.shape[1] == D, "shape mismatch between the operands")
     if out is None:
         out = torch.empty((n1, n2), dtype=torch.float64, device=x1.device)
         if lower_only:
@@ -62,7 +68,7 @@ def gram_dl_contract(kind, x1, x2, ell, Y, sym_lower=False):
 def elementwise(op, X, Y, a=1.0, b=1.0, out=None):
     """out = a X + b Y (op "axpby") or a X o Y (op "mul") on contiguous device tensors; out may alias X or Y."""
     ctx = context()
-    assert X.is_contiguous() and Y.is_contiguous() and X.shape == Y.shape
+    _require(X.is_contiguous() and Y.is_contiguous() and X.shape == Y.shape, "shape mismatch between the operands")
     if out is None:
         out = torch.empty_like(X)
     check(
@@ -78,7 +84,7 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower_on
     A, B = _f64(A), _f64(B)
     M, K = (A.shape[1], A.shape[0]) if transa else A.shape
     N = B.shape[0] if transb else B.shape[1]
-    assert (B.shape[1] if transb else B.shape[0]) == K
+    _require((B.shape[1] if transb else B.shape[0]) == K, "shape mismatch between the operands")
     if C is None:
         C = torch.zeros((M, N), dtype=torch.float64, device=A.device)
     check(
@@ -407,7 +413,7 @@ def gpr_td_lml_grad(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, m
     ctx = context()
     x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
     N, nf, nv = J.shape
-    assert y.numel() == N and yd.numel() == N * nv
+    _require(y.numel() == N and yd.numel() == N * nv, "shape mismatch between the operands")
     out = torch.empty(4, dtype=torch.float64, device=x.device)
     check(
         ctx.lib.gpxb_gpr_td_lml_grad(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv, float(ell),
@@ -423,7 +429,7 @@ def gpr_td_fit(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_m
     ctx = context()
     x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
     N, nf, nv = J.shape
-    assert y.numel() == N and yd.numel() == N * nv
+    _require(y.numel() == N and yd.numel() == N * nv, "shape mismatch between the operands")
     c = torch.empty((N + N * nv, 1), dtype=torch.float64, device=x.device)
     mu = torch.empty(1, dtype=torch.float64, device=x.device)
     check(
@@ -442,7 +448,7 @@ def gpr_td2_lml_grad(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigm
     ctx = context()
     x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
     N, nf, nv = J.shape
-    assert y.numel() == N and yd.numel() == N * nv and 0 < nv_first <= nv
+    _require(y.numel() == N and yd.numel() == N * nv and 0 < nv_first <= nv, "shape mismatch between the operands")
     out = torch.empty(5, dtype=torch.float64, device=x.device)
     check(
         ctx.lib.gpxb_gpr_td2_lml_grad(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv, int(nv_first),
@@ -459,7 +465,7 @@ def gpr_td2_fit(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_der
     ctx = context()
     x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
     N, nf, nv = J.shape
-    assert y.numel() == N and yd.numel() == N * nv and 0 < nv_first <= nv
+    _require(y.numel() == N and yd.numel() == N * nv and 0 < nv_first <= nv, "shape mismatch between the operands")
     c = torch.empty((N + N * nv, 1), dtype=torch.float64, device=x.device)
     mu = torch.empty(1, dtype=torch.float64, device=x.device)
     check(
@@ -497,7 +503,7 @@ def kmatvec(kind, x_rows, x_all, V, ell, diag_add=0.0, row_offset=None):
         V = V.reshape(-1, 1)
     n_rows, D = x_rows.shape
     N, P = V.shape
-    assert x_all.shape[0] == N
+    _require(x_all.shape[0] == N, "shape mismatch between the operands")
     if row_offset is None:
         row_offset = 0 if same else -1
     W = torch.empty((n_rows, P), dtype=torch.float64, device=V.device)
@@ -597,7 +603,7 @@ def gpr_fit_iter(kind, x, y, ell, sigma, n_pivots, key, mean_mode=MEAN_DATA, par
     ctx = context()
     x, y = _f64(x), _f64(y)
     N, D = x.shape
-    assert y.numel() == N, "the iterative path supports a single output column"
+    _require(y.numel() == N, "the iterative path supports a single output column")
     c = torch.empty((N, 1), dtype=torch.float64, device=x.device)
     mu = torch.empty(1, dtype=torch.float64, device=x.device)
     iters = ctypes.c_int(0)
@@ -630,7 +636,7 @@ def sgpr_lml_grad(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, want_grad
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
     N, D = x.shape
-    assert y.numel() == N, "the SGPR gradient supports a single output column"
+    _require(y.numel() == N, "the SGPR gradient supports a single output column")
     out = torch.empty(3, dtype=torch.float64, device=x.device)
     check(
         ctx.lib.gpxb_sgpr_lml_grad(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, ptr(x_locs), x_locs.shape[0],
@@ -648,7 +654,7 @@ def sgpr_fit_iter(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, tol=1e-5,
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
     N, D = x.shape
-    assert y.numel() == N, "the iterative SGPR path supports a single output column"
+    _require(y.numel() == N, "the iterative SGPR path supports a single output column")
     M = x_locs.shape[0]
     c = torch.empty((M, 1), dtype=torch.float64, device=x.device)
     mu = torch.empty(1, dtype=torch.float64, device=x.device)
@@ -669,7 +675,7 @@ def sgpr_lml_iter_parts(kind, x, y, x_locs, ell, sigma, U, m, mean_mode=MEAN_DAT
     ctx = context()
     x, y, x_locs, U = _f64(x), _f64(y), _f64(x_locs), _f64(U)
     N, D = x.shape
-    assert y.numel() == N, "the iterative SGPR path supports a single output column"
+    _require(y.numel() == N, "the iterative SGPR path supports a single output column")
     P = U.shape[1]
     quad = torch.empty(1, dtype=torch.float64, device=x.device)
     alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
@@ -691,7 +697,7 @@ def sgpr_lml_grad_locs(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
     N, D = x.shape
-    assert y.numel() == N, "the SGPR gradient supports a single output column"
+    _require(y.numel() == N, "the SGPR gradient supports a single output column")
     out = torch.empty(3, dtype=torch.float64, device=x.device)
     g = torch.empty_like(x_locs)
     check(
