@@ -89,3 +89,10 @@ def test_host_tensors_are_refused_not_computed_on():
         ops._f64(torch.zeros((2, 2), dtype=torch.float64))
     with pytest.raises(_lib.GpxbError):
         _lib.ptr(torch.zeros(3, dtype=torch.float64))
+
+
+def test_integration_doc_names_every_symbol():
+    """INTEGRATION.md maps every exported entry point to the reference call site it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in header_symbols() if s not in doc]
+    assert not missing, f"not mapped in INTEGRATION.md: {missing}"
