@@ -187,7 +187,10 @@ int gpxb_gpr_td2_fit(gpxb_ctx* ctx, int kind, const double* x, const double* J, 
 
 /* ---- Family 2: blocked FP64 Cholesky / TRSM / log-det / inverse ---------------------- */
 /* C[M x N] = alpha * op(A) * op(B) + beta * C on the FP64 tensor pipe.  transa = 0: A is M x K
- * row-major; 1: A is stored K x M.  transb = 0: B is K x N row-major; 1: B is stored N x K. */
+ * row-major; 1: A is stored K x M.  transb = 0: B is K x N row-major; 1: B is stored N x K.
+ * Replaces the jnp.dot / @ products of the dense paths (gpx/models/_gpr.py:441, 459-461: K_mn^T c and
+ * G^T G; gpx/models/_sgpr.py:58, 463-465, 689: K_mn K_nm, G^T G, H^T H; gpx/kernels/kernels.py:226-227: the
+ * Linear kernel).  lower_only: only entries with row >= col are updated (symmetric results). */
 int gpxb_gemm(gpxb_ctx* ctx, int transa, int transb, int M, int N, int K, double alpha,
               const double* A, long long lda, const double* B, long long ldb, double beta, double* C,
               long long ldc, int lower_only, gpxb_stream stream);
@@ -205,7 +208,10 @@ int gpxb_trsm(gpxb_ctx* ctx, const double* L, long long ldl, const double* inv, 
 /* *out (device) = sum_i log L[i][i]   (gpx/models/_gpr.py:763) */
 int gpxb_logdet(gpxb_ctx* ctx, const double* L, long long ldl, int n, double* out,
                 gpxb_stream stream);
-/* out (lower triangle, n x n) = (L L^T)^-1; out may alias L. */
+/* out (lower triangle, n x n) = (L L^T)^-1; out may alias L.  The A^-1 of the analytic LML gradient
+ * W = alpha alpha^T - A^-1, i.e. what reverse-mode autodiff through jsp.linalg.cholesky amounts to under
+ * jit(value_and_grad(loss)) (gpx/optimizers/scipy_optimize.py:72-78); also the explicit jnp.linalg.inv of the
+ * preconditioner (gpx/models/_gpr.py:205, 245). */
 int gpxb_potri(gpxb_ctx* ctx, const double* L, long long ldl, const double* inv, int n, double* out,
                long long ldo, gpxb_stream stream);
 
@@ -316,8 +322,11 @@ int gpxb_gather_rows(gpxb_ctx* ctx, const double* x, int D, const long long* idx
                      gpxb_stream stream);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) --------------------------------- */
-/* Arrays are passed whole on every rank; each rank works on its own row range of x.  Rows are
- * sharded for gpxb_lanczos, gpxb_gpr_fit_iter, gpxb_sgpr_lml and gpxb_sgpr_fit. */
+/* No counterpart in the reference (GPX is single-process; SURVEY.md 8e defines the sharding).  Arrays are
+ * passed whole on every rank; each rank works on its own row range of x.  Rows are sharded for gpxb_lanczos,
+ * gpxb_gpr_fit_iter, gpxb_sgpr_lml and gpxb_sgpr_fit; the collectives are the all-reduces of the column dot
+ * products (gpx/lanczos.py:29-37, 84-118), of the CDF block sums (gpx/kernels/approximations.py:95-105) and of
+ * B = G G^T (gpx/models/_sgpr.py:684-689). */
 int gpxb_comm_unique_id(void* out128);
 /* host-only: the row range [begin, end) rank owns out of N rows (256-row aligned partition) */
 int gpxb_shard_range(long long N, int world, int rank, long long* begin, long long* end);
