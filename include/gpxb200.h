@@ -188,9 +188,9 @@ int gpxb_gpr_td2_fit(gpxb_ctx* ctx, int kind, const double* x, const double* J, 
 /* ---- Family 2: blocked FP64 Cholesky / TRSM / log-det / inverse ---------------------- */
 /* C[M x N] = alpha * op(A) * op(B) + beta * C on the FP64 tensor pipe.  transa = 0: A is M x K
  * row-major; 1: A is stored K x M.  transb = 0: B is K x N row-major; 1: B is stored N x K.
- * Replaces the jnp.dot / @ products of the dense paths (gpx/models/_gpr.py:441, 459-461: K_mn^T c and
- * G^T G; gpx/models/_sgpr.py:58, 463-465, 689: K_mn K_nm, G^T G, H^T H; gpx/kernels/kernels.py:226-227: the
- * Linear kernel).  lower_only: only entries with row >= col are updated (symmetric results). */
+ * Replaces the jnp.dot / @ products of the dense paths (gpx/models/_gpr.py:453, 460: K_mn^T c and
+ * G^T G; gpx/models/_sgpr.py:59, 338, 454, 464, 686: K_mn K_nm, K_mn y, K_nm c, G^T G, H^T H;
+ * gpx/kernels/kernels.py:226-227: the Linear kernel).  lower_only: only entries with row >= col are updated (symmetric results). */
 int gpxb_gemm(gpxb_ctx* ctx, int transa, int transb, int M, int N, int K, double alpha,
               const double* A, long long lda, const double* B, long long ldb, double beta, double* C,
               long long ldc, int lower_only, gpxb_stream stream);
@@ -326,7 +326,7 @@ int gpxb_gather_rows(gpxb_ctx* ctx, const double* x, int D, const long long* idx
  * passed whole on every rank; each rank works on its own row range of x.  Rows are sharded for gpxb_lanczos,
  * gpxb_gpr_fit_iter, gpxb_sgpr_lml and gpxb_sgpr_fit; the collectives are the all-reduces of the column dot
  * products (gpx/lanczos.py:29-37, 84-118), of the CDF block sums (gpx/kernels/approximations.py:95-105) and of
- * B = G G^T (gpx/models/_sgpr.py:684-689). */
+ * B = G G^T (the Woodbury form of gpx/models/_sgpr.py:684-688). */
 int gpxb_comm_unique_id(void* out128);
 /* host-only: the row range [begin, end) rank owns out of N rows (256-row aligned partition) */
 int gpxb_shard_range(long long N, int world, int rank, long long* begin, long long* end);
