@@ -104,3 +104,32 @@ def test_host_prng_matches_the_oracle_bit_for_bit():
                 assert np.array_equal(PR.split(key, num, part), R.split(key, num, part)), (key, part, num)
     with pytest.raises(ValueError):
         PR.as_key(np.zeros(3, dtype=np.uint32))
+
+
+def test_slq_host_numerics_value_and_closed_form_derivative():
+    """Host part of the SLQ log-determinant (gpx_b200/models/_iterative.py; gpx/lanczos.py:171-183): the value against
+    the oracle on tridiagonals produced by the oracle's Lanczos, and the closed-form eigh JVP against central
+    differences of the value along a tridiagonal perturbation."""
+    from gpx_b200.models._iterative import slq_logdet, slq_logdet_grad
+    from oracle import ref_numpy as R
+
+    rng = np.random.default_rng(5)
+    n, P, m = 60, 3, 7
+    x = rng.standard_normal((n, 2))
+    A = R.kernel("se", x, x, 1.3) + 0.3 * np.eye(n)
+    us, key = R.rademacher_probes(R.PRNGKey(2023), n, P)
+    alpha, beta = np.zeros((P, m)), np.zeros((P, m))
+    ref = 0.0
+    for p in range(P):
+        T, _ = R.lanczos_tridiagonal(lambda v: A @ v, m, us[:, p], key)
+        alpha[p], beta[p, : m - 1] = np.diag(T), np.diag(T, 1)
+        ref += R.slq_from_tridiag(T)
+    assert abs(slq_logdet(alpha, beta, n) - (n / P) * ref) < 1e-12 * abs(ref)
+    dalpha, dbeta = rng.standard_normal((2, P, m)), rng.standard_normal((2, P, m))
+    val, grad = slq_logdet_grad(alpha, beta, dalpha, dbeta, n)
+    assert abs(val - (n / P) * ref) < 1e-12 * abs(ref)
+    h = 1e-6
+    for q in range(2):
+        fd = (slq_logdet(alpha + h * dalpha[q], beta + h * dbeta[q], n)
+              - slq_logdet(alpha - h * dalpha[q], beta - h * dbeta[q], n)) / (2 * h)
+        assert abs(grad[q] - fd) < 1e-7 * max(1.0, abs(fd)), (q, grad[q], fd)
