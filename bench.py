@@ -5,7 +5,10 @@ Workload (BASELINE.json configs[1]): exact GPR, Matern-5/2, N=32768, D=16, FP64;
 one "step" = one LML + gradient evaluation (Gram build, blocked Cholesky, triangular
 solves, SPD inverse, fused dK/d-lengthscale contraction).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-cpu] [--no-extra]
+
+At N = 1 the JSON line also carries `other_configs`: RPCholesky, the SGPR Woodbury LML and one block mat-vec of the
+Lanczos / SLQ log-det at N = 1e6 (BASELINE configs[3], [4]) with their rooflines, measured after the headline.
 
 N > 1 (torchrun): the dense Cholesky path does not shard ("replicas only") --
 every rank evaluates an independent replica (its own hyper-parameter point, as the
@@ -142,6 +145,96 @@ class ClockSampler:
         except OSError:
             pass
         return out
+
+
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling
+    recipe's fallback."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6554.2, "fallback (B200_PROFILING.md)"
+
+
+def other_configs(dgemm_tflops, scale=1.0):
+    """The SGPR / Lanczos half of BASELINE.json's metric line (configs[3], configs[4]) at N = 1e6 on this GPU, one
+    measurement each, device-timed with CUDA events on torch's current stream (the stream the library launches on);
+    inputs are created on the device and are far larger than L2.  Reported next to the headline, never instead of
+    it; every entry is isolated (a failure is reported as {"error": ...} and cannot affect the main line, whose
+    numbers are already on the host).  `scale` shrinks the sizes for smoke tests (GPXB_BENCH_EXTRA_SCALE)."""
+    import torch
+
+    from gpx_b200 import ops
+
+    key = np.array([0, 2023], dtype=np.uint32)
+    N = max(4096, int(1_000_000 * scale))
+    M = 4096 if scale >= 1.0 else max(64, int(4096 * scale * 4) // 64 * 64)
+    hbm, hbm_src = hbm_peak_gbs()
+    out = []
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3, res
+
+    def data(n, d, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        x = torch.randn((n, d), dtype=torch.float64, device="cuda", generator=g)
+        y = torch.sin(x.sum(1, keepdim=True)) + 0.1 * torch.randn((n, 1), dtype=torch.float64, device="cuda", generator=g)
+        return x, y
+
+    def entry(name, fn):
+        try:
+            out.append(dict(config=name, **fn()))
+        except Exception as e:  # noqa: BLE001 -- reported, never fatal for the headline
+            out.append(dict(config=name, error=f"{type(e).__name__}: {e}"[:300]))
+
+    x32, y32 = data(N, 32, 3)
+    ell32 = 32**0.5
+    state = {}
+
+    def rpchol():
+        t, (_, piv) = timed(lambda: ops.rpcholesky("se", x32, M, ell32, key, True, want_factor=False))
+        state["piv"], state["t_rp"] = piv, t
+        alg = 8.0 * N * M * (M - 1) / 2 + 5 * 8.0 * N * M
+        return dict(what="RPCholesky landmark loop (pivots only)", N=N, D=32, M=M, s=t, bound="hbm",
+                    alg_bytes=alg, achieved_gbs=alg / t / 1e9, peak_gbs=hbm, peak_source=hbm_src,
+                    frac=alg / t / 1e9 / hbm, pivots_head=[int(v) for v in piv[:4].cpu().tolist()])
+
+    def sgpr():
+        piv = state.get("piv")
+        if piv is None:
+            _, piv = ops.rpcholesky("se", x32[:65536].contiguous(), M, ell32, key, True, want_factor=False)
+        xl = ops.gather_rows(x32, piv)
+        ops.sgpr_lml("se", x32, y32, xl, ell32, 0.1)  # warm-up (allocator pools)
+        t, res = timed(lambda: ops.sgpr_lml("se", x32, y32, xl, ell32, 0.1))
+        fl = 2.0 * N * M * 32 + 2.0 * M * M * N + 2.0 * M**3 / 3
+        d = dict(what="SGPR Woodbury LML (fixed landmarks)", N=N, D=32, M=M, s=t, evals_per_s=1.0 / t,
+                 bound="tensor", alg_flops=fl, achieved_tflops=fl / t / 1e12, peak_tflops=dgemm_tflops,
+                 frac=fl / t / 1e12 / dgemm_tflops, lml=float(res.cpu()[0]))
+        if "t_rp" in state:  # SGPR_RPChol re-draws the landmarks at every LML evaluation (_sgpr_rpchol.py:193-200)
+            d["evals_per_s_with_landmark_selection"] = 1.0 / (t + state["t_rp"])
+        return d
+
+    def lanczos_step():
+        P = 30
+        x16, _ = data(N, 16, 4)
+        V = torch.randn((N, P), dtype=torch.float64, device="cuda",
+                        generator=torch.Generator(device="cuda").manual_seed(9))
+        t, W = timed(lambda: ops.kmatvec("se", x16, x16, V, 4.0, diag_add=0.25 + 1e-10))
+        fl = float(N) ** 2 * (2 * 16 + 4 + 2 * P)
+        return dict(what="matrix-free block mat-vec (K + s2 I) V: one of the 50 steps of each 30-probe SLQ log-det",
+                    N=N, D=16, P=P, s=t, bound="tensor", alg_flops=fl, achieved_tflops=fl / t / 1e12,
+                    peak_tflops=dgemm_tflops, frac=fl / t / 1e12 / dgemm_tflops, checksum=float(W.sum().cpu()))
+
+    entry(f"configs[3] SGPR + RPCholesky, N={N} D=32 M={M}: landmark selection", rpchol)
+    entry(f"configs[3] SGPR + RPCholesky, N={N} D=32 M={M}: LML", sgpr)
+    entry(f"configs[4] Lanczos/SLQ, SE kernel, D=16, 30 probes, at N={N}", lanczos_step)
+    return out
 
 
 def run_gpu(args):
@@ -283,6 +376,14 @@ def run_gpu(args):
                           f"{t:.3f} s per LML+grad; scaled x(N/{n0})^3 to N={N}")}
 
     step_tflops = alg_flops(N, D) / (ms * 1e-3) / 1e12
+    extra = None
+    if world == 1 and not args.no_extra:
+        del x, y, model
+        torch.cuda.empty_cache()
+        try:
+            extra = other_configs(peak, float(os.environ.get("GPXB_BENCH_EXTRA_SCALE", "1.0")))
+        except Exception as e:  # noqa: BLE001
+            extra = [{"error": f"{type(e).__name__}: {e}"[:300]}]
     line = {
         "metric": "LML+grad evals/s (exact GPR, Matern-5/2, N=32768, D=16, FP64)",
         "value": world * 1e3 / ms, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -309,6 +410,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": 24},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "other_configs": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -326,6 +428,8 @@ def main():
                     help="override N (debugging only; the bench line names it).  Under torchrun use --rows: "
                          "torchrun's own parser rejects the abbreviation-ambiguous --n")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the other_configs section (SGPR / RPCholesky / Lanczos at N=1e6, about 20 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
