@@ -265,6 +265,12 @@ def predict_y_derivs(state, x, full_covariance=False, iterative=False):
     return out.cpu().numpy().reshape(-1, 1)
 
 
+def _is_parameter_dict(d) -> bool:
+    """Recursive type check of gpx/models/utils.py:42-51: composite kernels nest {"kernel1": ..., "kernel2": ...}."""
+    return isinstance(d, dict) and all(_is_parameter_dict(v) if isinstance(v, dict) else isinstance(v, Parameter)
+                                       for v in d.values())
+
+
 def default_params() -> Dict[str, Parameter]:
     """gpx/models/gpr.py:863-870."""
     return dict(sigma=Parameter(value=1.0, trainable=True, bijector=Softplus(), prior=GammaPrior()))
@@ -277,8 +283,8 @@ def init(kernel: Callable, mean_function: Callable = data_mean, kernel_params=No
         raise TypeError(f"kernel must be callable, you provided {type(kernel)}")
     if kernel_params is None:
         kernel_params = kernel.default_params()
-    elif not isinstance(kernel_params, dict) or not all(isinstance(v, Parameter) for v in kernel_params.values()):
-        raise TypeError("kernel_params must be a dict of Parameter")
+    elif not _is_parameter_dict(kernel_params):
+        raise TypeError("kernel_params must be a (nested, for Sum / Prod kernels) dict of Parameter")
     if sigma is None:
         sigma = default_params()["sigma"]
     elif not isinstance(sigma, Parameter):

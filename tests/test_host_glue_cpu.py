@@ -7,6 +7,7 @@ torch = pytest.importorskip("torch")
 
 import test_gpu_composite as G  # noqa: E402  (its tests are plain functions; the gpu mark stays on that module)
 import test_gpu_facade as F  # noqa: E402
+import test_gpu_golden as GF  # noqa: E402
 import test_gpu_td as TD  # noqa: E402
 from _fake_ops import patched  # noqa: E402
 
@@ -67,3 +68,12 @@ def test_gpr_td_second_block_glue(kind, N, nf, nv1, nv2, mean):
 def test_gpr_td_single_block_glue():
     with patched():
         TD.test_td_fit_minimize_lowers_the_loss()
+
+
+# The fixture-based device tests, dry-run: the facade calls and the bookkeeping of tests/test_gpu_golden.py itself.
+def test_golden_fixture_tests_glue():
+    with patched():
+        GF.test_exact_gpr_against_the_fixture()
+        GF.test_rpcholesky_pivots_against_the_fixture_bit_exact(True, "pivots_part")
+        GF.test_rpcholesky_pivots_against_the_fixture_bit_exact(False, "pivots_legacy")
+        GF.test_sgpr_composite_and_td_against_the_fixture()

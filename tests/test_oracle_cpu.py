@@ -193,6 +193,17 @@ def test_golden_fixture_matches_oracle():
     assert np.array_equal(piv, g["pivots_part"])
     _, piv = R.rpcholesky("se", x, 16, float(g["ell"]), R.PRNGKey(2023), False)
     assert np.array_equal(piv, g["pivots_legacy"])
+    ell, sigma, xl, xs = float(g["ell"]), float(g["sigma"]), g["x_locs"], g["xs"]
+    np.testing.assert_allclose(R.sgpr_lml_dense("se", xl, x, y, ell, sigma), g["sgpr_lml_se"], rtol=1e-11)
+    np.testing.assert_allclose(R.sgpr_lml_dense_nxn("se", xl, x, y, ell, sigma), g["sgpr_lml_nxn_se"], rtol=1e-11)
+    np.testing.assert_allclose(R.sgpr_fit_dense("se", xl, x, y, ell, sigma)[0], g["sgpr_c_se"], rtol=1e-7)
+    np.testing.assert_allclose(R.composite_lml_dense(GOLDEN_COMPOSITE_SPEC, x, y, sigma), g["composite_lml"], rtol=1e-11)
+    np.testing.assert_allclose(R.sgpr_composite_lml_dense_nxn(GOLDEN_COMPOSITE_SPEC, xl, x, y, sigma),
+                               g["composite_sgpr_lml"], rtol=1e-11)
+    J, yd, Nt = g["td_J"], g["td_yd"], g["td_J"].shape[0]
+    np.testing.assert_allclose(R.td_lml_dense("se", x[:Nt], y[:Nt], J, yd, ell, 0.3, 0.2), g["td_lml_se"], rtol=1e-11)
+    np.testing.assert_allclose(R.td2_lml_dense("m52", x[:Nt], y[:Nt], J[:, :, :3], J[:, :, 3:], yd[:, :3], yd[:, 3:], ell,
+                                               0.3, 0.2, 0.4), g["td2_lml_m52"], rtol=1e-11)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -200,6 +211,11 @@ def test_golden_fixture_matches_oracle():
 # convention, jitter, /n normalisation, data_mean, Softplus chain, the analytic gradient (through the
 # optimum L-BFGS-B reaches) and the legacy jax.random bit layout -- against real GPX-on-JAX output.
 # ---------------------------------------------------------------------------------------------
+# the nested composite kernel frozen in tests/golden/oracle_small.npz (tools/make_golden.py)
+GOLDEN_COMPOSITE_SPEC = ("sum", ("leaf", "se", 1.4, [0, 1]),
+                         ("prod", ("leaf", "m52", 2.2, None), ("leaf", "linear", None, [2, 3])))
+
+
 def notebook_gpr_data():
     x = np.linspace(0, 1, 100).reshape(-1, 1)
     eps = R.normal(R.PRNGKey(0), (100,), partitionable=False)
