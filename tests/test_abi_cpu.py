@@ -96,3 +96,13 @@ def test_integration_doc_names_every_symbol():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = [s for s in header_symbols() if s not in doc]
     assert not missing, f"not mapped in INTEGRATION.md: {missing}"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """Without the built extension the product raises at load time; nothing falls back to a CPU path."""
+    from gpx_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libgpxb200.so")
+    with pytest.raises(_lib.GpxbError, match="no CPU fallback"):
+        _lib.load()
