@@ -263,12 +263,66 @@ def gpr_td2_fit(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_der
     return _t(lib), _t(np.array([float(mu)]))
 
 
+# ---- derivative-trained GPR (csrc/hess.cu) ----
+def hess_gram(kind, x1, J1, x2, J2, ell, diag_add=0.0, lower_only=False):
+    sym = (x2 is x1 or x2 is None) and (J2 is J1 or J2 is None)
+    a, Ja = _np(x1), _np(J1)
+    b, Jb = (a, Ja) if sym else (_np(x2), _np(J2))
+    K = R.d01kj(kind, a, b, float(ell), Ja, Jb)
+    if diag_add:
+        K = K + diag_add * np.eye(K.shape[0], K.shape[1])
+    return _t(np.tril(K) if lower_only else K)
+
+
+def gpr_lml_derivs(kind, x, J, y, ell, sigma):
+    return _t(np.array([R.lml_derivs_dense(kind, _np(x), _np(y), _np(J), float(ell), float(sigma))]))
+
+
+def gpr_lml_grad_derivs(kind, x, J, y, ell, sigma, want_grad=True):
+    out = np.array(R.lml_derivs_grad_dense(kind, _np(x), _np(y), _np(J), float(ell), float(sigma)))
+    if not want_grad:
+        out[1:] = 0.0
+    return _t(out)
+
+
+def gpr_fit_derivs(kind, x, J, y, ell, sigma):
+    c, _, jc = R.fit_derivs_dense(kind, _np(x), _np(y), _np(J), float(ell), float(sigma))
+    return _t(c), _t(jc)
+
+
+def gpr_predict_y_derivs(kind, x_train, jaccoef, x, ell, mu=0.0):
+    return _t(np.asarray(R.predict_y_derivs_dense(kind, _np(x_train), _np(x), _np(jaccoef), float(mu), float(ell))).reshape(-1))
+
+
+def gpr_predict_derivs_full(kind, x_train, J_train, x, J, c, ell, sigma, mu=0.0, full_covariance=False):
+    mean, cov = R.predict_derivs_dense_full(kind, _np(x_train), _np(J_train), _np(x), _np(J), _np(c).reshape(-1, 1),
+                                            float(mu), float(ell), float(sigma))
+    return (_t(mean.reshape(-1)), _t(cov)) if full_covariance else _t(mean.reshape(-1))
+
+
+def gpr_predict_y_derivs_full(kind, x_train, J_train, x, c, ell, sigma, mu=0.0, full_covariance=False):
+    mean, cov = R.predict_y_derivs_dense_full(kind, _np(x_train), _np(J_train), _np(x), _np(c).reshape(-1, 1), float(mu),
+                                              float(ell), float(sigma))
+    return (_t(mean.reshape(-1)), _t(cov)) if full_covariance else _t(mean.reshape(-1))
+
+
+def hess_matvec(kind, x1, J1, x2, J2, V, ell, diag_add=0.0):
+    K = R.d01kj(kind, _np(x1), _np(x2), float(ell), _np(J1), _np(J2))
+    if diag_add:
+        K = K + diag_add * np.eye(K.shape[0], K.shape[1])
+    v = _np(V)
+    return _t(K @ v)
+
+
 FAKES = dict(gram=gram, gram_dl_contract=gram_dl_contract, elementwise=elementwise, gemm=gemm, potrf=potrf, trsm=trsm,
              logdet=logdet, potri=potri, gpr_lml_grad=gpr_lml_grad, gpr_fit=gpr_fit, gpr_predict=gpr_predict,
              kmatvec=kmatvec, rpcholesky=rpcholesky, gather_rows=gather_rows, sgpr_lml=sgpr_lml,
              sgpr_lml_grad=sgpr_lml_grad, sgpr_fit=sgpr_fit, sgpr_predict=sgpr_predict, td_gram=td_gram,
              gpr_td_lml_grad=gpr_td_lml_grad, gpr_td_fit=gpr_td_fit, gpr_td2_lml_grad=gpr_td2_lml_grad,
-             gpr_td2_fit=gpr_td2_fit)
+             gpr_td2_fit=gpr_td2_fit, hess_gram=hess_gram, gpr_lml_derivs=gpr_lml_derivs,
+             gpr_lml_grad_derivs=gpr_lml_grad_derivs, gpr_fit_derivs=gpr_fit_derivs,
+             gpr_predict_y_derivs=gpr_predict_y_derivs, gpr_predict_derivs_full=gpr_predict_derivs_full,
+             gpr_predict_y_derivs_full=gpr_predict_y_derivs_full, hess_matvec=hess_matvec)
 
 
 @contextlib.contextmanager

@@ -6,6 +6,7 @@ import pytest
 torch = pytest.importorskip("torch")
 
 import test_gpu_composite as G  # noqa: E402  (its tests are plain functions; the gpu mark stays on that module)
+import test_gpu_derivs as DV  # noqa: E402
 import test_gpu_facade as F  # noqa: E402
 import test_gpu_golden as GF  # noqa: E402
 import test_gpu_td as TD  # noqa: E402
@@ -77,3 +78,20 @@ def test_golden_fixture_tests_glue():
         GF.test_rpcholesky_pivots_against_the_fixture_bit_exact(True, "pivots_part")
         GF.test_rpcholesky_pivots_against_the_fixture_bit_exact(False, "pivots_legacy")
         GF.test_sgpr_composite_and_td_against_the_fixture()
+
+
+# Derivative-trained models through the facade: (sample, variable) flattening, contracted jacobians, the fast
+# d01kjc / d0kjc prediction routes, full covariances, the L-BFGS-B driver on the derivative loss.
+@pytest.mark.parametrize("test", [
+    DV.test_facade_fit_and_predict_derivs,
+    DV.test_facade_fit_derivs_minimize_follows_oracle_optimiser,
+], ids=lambda f: f.__name__)
+def test_derivs_facade_glue(test):
+    with patched():
+        test()
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_sgpr_derivs_facade_glue(kind):
+    with patched():
+        DV.test_sgpr_fit_and_predict_on_derivatives(kind)
