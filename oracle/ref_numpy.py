@@ -26,6 +26,11 @@ Parity pinning status
 * the RPCholesky pivot stream (split -> uniform -> choice -> pivot loop, legacy mode): PINNED by
   examples/sgpr_with_rpcholesky.ipynb cell 7 (the printed end point of a fit whose loss re-draws the
   pivots at every evaluation is reproduced, including the abnormal L-BFGS-B termination).
+* Sum / Prod composite kernels with per-leaf active_dims, the Linear and Matern-5/2 entries and the 2-D legacy
+  normal() layout: PINNED to 8 digits by the kernel-matrix corners examples/kernel_operations.ipynb prints
+  (cells 6, 10, 13, 16); the sign / scaling conventions of d0kj, d1kj, d01kj (the GPR_TD block matrix): PINNED by the
+  entries examples/derivatives_solak.ipynb cell 4 prints; the Hessian-kernel LML value: PINNED to 10 digits by the
+  scipy OptimizeResult examples/gpr_with_derivatives_only.ipynb cell 27 prints (fun = -1.5536783384709247).
 * predictions, fit coefficients, Lanczos/SLQ, PCG and the partitionable PRNG mode: **parity unpinned** -- the reference has no test, golden vector or
   printed output for them and cannot be executed here.  They are anchored
   by self-consistency (analytic gradient vs finite differences, Woodbury vs
