@@ -328,7 +328,7 @@ int gpxb_gather_rows(gpxb_ctx* ctx, const double* x, int D, const long long* idx
  * products (gpx/lanczos.py:29-37, 84-118), of the CDF block sums (gpx/kernels/approximations.py:95-105) and of
  * B = G G^T (the Woodbury form of gpx/models/_sgpr.py:684-688). */
 int gpxb_comm_unique_id(void* out128);
-/* host-only: the row range [begin, end) rank owns out of N rows (256-row aligned partition) */
+/* host-only: the row range [begin, end) rank owns out of N rows (1024-row aligned partition: the block size of the RPCholesky CDF sums, so pivots do not depend on the GPU count) */
 int gpxb_shard_range(long long N, int world, int rank, long long* begin, long long* end);
 int gpxb_comm_init(gpxb_ctx* ctx, const void* id128, int rank, int world);
 

@@ -1,5 +1,5 @@
 """world_size-2 gloo tests (CPU) of the host-side logic of the sharded paths: every rank derives
-the same 256-aligned row partition, the ranges tile [0, N), and the 128-byte communicator id
+the same 1024-aligned row partition, the ranges tile [0, N), and the 128-byte communicator id
 travels intact through the broadcast used by ops.comm_init_from_torch_distributed."""
 import os
 import socket
@@ -60,5 +60,26 @@ def test_row_partition_and_id_broadcast_world2():
         for a, b in zip(rr[:-1], rr[1:]):
             assert a[1] == b[0]  # contiguous, no gap, no overlap
         for b, e in rr[:-1]:
-            assert b % 256 == 0 and e % 256 == 0 or e == N
+            assert (b % 1024 == 0 and e % 1024 == 0) or e == N
     assert res[0][1] == res[1][1]
+
+
+def test_row_partition_properties_for_every_world_size():
+    """gpxb_shard_range (host-only): for 1..8 ranks the ranges tile [0, N) in order, every interior boundary is a
+    multiple of 1024 (the RPCholesky block-sum granularity) and the loads differ by at most one block."""
+    import numpy as np
+
+    from gpx_b200 import ops
+
+    rng = np.random.default_rng(0)
+    sizes = [1, 2, 1023, 1024, 1025, 4096, 10_000, 1_000_000, 2_000_000] + [int(v) for v in rng.integers(1, 3_000_000, 40)]
+    for N in sizes:
+        for world in range(1, 9):
+            rr = [ops.shard_range(N, world, r) for r in range(world)]
+            assert rr[0][0] == 0 and rr[-1][1] == N
+            for (b0, e0), (b1, e1) in zip(rr[:-1], rr[1:]):
+                assert e0 == b1 and b0 <= e0
+            for b, e in rr:
+                assert b % 1024 == 0 or b == N
+            blocks = [-(-(e - b) // 1024) for b, e in rr]
+            assert max(blocks) - min(blocks) <= 1
