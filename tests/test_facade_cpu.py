@@ -133,3 +133,25 @@ def test_slq_host_numerics_value_and_closed_form_derivative():
         fd = (slq_logdet(alpha + h * dalpha[q], beta + h * dbeta[q], n)
               - slq_logdet(alpha - h * dalpha[q], beta - h * dbeta[q], n)) / (2 * h)
         assert abs(grad[q] - fd) < 1e-7 * max(1.0, abs(fd)), (q, grad[q], fd)
+
+
+def test_array_valued_trainables_ravel_like_ravel_pytree():
+    """Flat vector of unconstrained trainables (gpx/optimizers/utils.py:73-131): scalars and a trainable (M, D) landmark
+    array are concatenated in parameter-tree order and restored shape by shape; the chain rule uses each bijector."""
+    from gpx_b200.models import SGPR
+    from gpx_b200.models.sgpr import locs_parameter
+    from gpx_b200.optimizers import _split, ravel_backward_trainables, unravel_forward
+
+    xl = np.arange(12.0).reshape(6, 2) / 7.0
+    m = SGPR(kernel=SquaredExponential(), x_locs=locs_parameter(xl, trainable=True))
+    x0, paths = ravel_backward_trainables(m.state)
+    assert [p for p, _ in paths] == [("kernel_params", "lengthscale"), ("sigma",), ("x_locs",)]
+    assert x0.shape == (2 + 12,) and np.array_equal(x0[2:], xl.reshape(-1))  # Identity bijector on the landmarks
+    np.testing.assert_allclose(x0[:2], Softplus().backward(np.array([1.0, 1.0])))
+    xt = x0 + np.linspace(0.01, 0.14, 14)
+    st = unravel_forward(m.state, paths, xt)
+    assert st.params["x_locs"].value.shape == (6, 2)
+    np.testing.assert_allclose(st.params["x_locs"].value, xt[2:].reshape(6, 2))
+    np.testing.assert_allclose(st.params["sigma"].value, Softplus().forward(xt[1]))
+    assert [v.shape for _, v in _split(paths, xt)] == [(), (), (6, 2)]
+    assert m.state.params["x_locs"].value[0, 0] == 0.0  # the original state is untouched
