@@ -106,3 +106,33 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libgpxb200.so")
     with pytest.raises(_lib.GpxbError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_ffi_shim_calls_match_the_header():
+    """gpx_b200/csrc/ffi/ffi_shim.cc (the jax.ffi layer, compile-guarded because the image has no jaxlib headers) must
+    not drift from the C ABI: every gpxb_* call in it passes as many arguments as the header declares."""
+    hdr = open(os.path.join(ROOT, "include", "gpxb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    nargs = {}
+    for m in re.finditer(r"\b(gpxb_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        nargs[m.group(1)] = len([a for a in m.group(2).split(",") if a.strip() and a.strip() != "void"])
+    src = open(os.path.join(ROOT, "gpx_b200", "csrc", "ffi", "ffi_shim.cc")).read()
+    src = re.sub(r"//[^\n]*", "", src)
+    calls = 0
+    for m in re.finditer(r"\b(gpxb_[a-z0-9_]+)\s*\(", src):
+        i = j = m.end()
+        depth, n, cur = 1, 0, ""
+        while depth:
+            ch = src[j]
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if ch == "," and depth == 1:
+                n += 1
+            elif depth:
+                cur += ch
+            j += 1
+        n = n + 1 if src[i:j - 1].strip() else 0
+        assert m.group(1) in nargs, f"{m.group(1)} is not declared in include/gpxb200.h"
+        assert nargs[m.group(1)] == n, f"{m.group(1)}: shim passes {n} arguments, header declares {nargs[m.group(1)]}"
+        calls += 1
+    assert calls >= 4
