@@ -2,8 +2,11 @@
 // north star names.  NOT built in this repository: JAX / jaxlib (and xla/ffi/api/ffi.h) are absent
 // from the image.  Where jaxlib exists:
 //
-//   g++ -std=c++17 -shared -fPIC ffi_shim.cc -I$(python -c "import jax.ffi; print(jax.ffi.include_dir())") \
-//       -I../../../include -L../.. -lgpxb200 -lcudart -o libgpxb200_ffi.so
+//   g++ -std=c++17 -shared -fPIC ffi_shim.cc -I$(python -c "import jax.ffi; print(jax.ffi.include_dir())")
+//       -I../../../include -L../.. -lgpxb200 -lcudart -o libgpxb200_ffi.so        (one command line)
+//
+// tests/test_abi_cpu.py type-checks this file against include/gpxb200.h with a MOCK of the few XLA-FFI names it
+// uses (tests/c/mock_xla), so the handler bodies cannot drift from the C ABI unnoticed.
 //
 // and on the Python side:
 //   jax.ffi.register_ffi_target("gpxb_gpr_lml_grad", jax.ffi.pycapsule(lib.GpxbGprLmlGrad), platform="CUDA")
@@ -123,6 +126,144 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(GpxbRpcholesky, RpcholeskyImpl,
                                   .Attr<int32_t>("kind")
                                   .Attr<int32_t>("partitionable")
                                   .Ret<ffi::Buffer<ffi::S64>>());
+
+// (c (N, T), mu (1,)) = _fit_dense  (gpx/models/_gpr.py:262-282)
+static ffi::Error GprFitImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> x, ffi::Buffer<ffi::F64> y, double ell,
+                             double sigma, int32_t kind, int32_t mean_mode, ffi::ResultBuffer<ffi::F64> c,
+                             ffi::ResultBuffer<ffi::F64> mu) {
+  const auto dx = x.dimensions();
+  const auto dy = y.dimensions();
+  const int T = dy.size() > 1 ? (int)dy[1] : 1;
+  return status(gpxb_gpr_fit(ctx_for_current_device(), kind, x.typed_data(), y.typed_data(), (int)dx[0], (int)dx[1], T,
+                             ell, sigma, mean_mode, c->typed_data(), mu->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(GpxbGprFit, GprFitImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Attr<double>("ell")
+                                  .Attr<double>("sigma")
+                                  .Attr<int32_t>("kind")
+                                  .Attr<int32_t>("mean_mode")
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
+
+// mean (ns, T) and the full covariance (ns, ns) of _predict_dense  (gpx/models/_gpr.py:434-463); mu is a device scalar
+static ffi::Error GprPredictImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> x_train, ffi::Buffer<ffi::F64> x,
+                                 ffi::Buffer<ffi::F64> c, ffi::Buffer<ffi::F64> mu, double ell, double sigma,
+                                 int32_t kind, ffi::ResultBuffer<ffi::F64> mean, ffi::ResultBuffer<ffi::F64> cov) {
+  const auto dt = x_train.dimensions();
+  const auto dc = c.dimensions();
+  const int T = dc.size() > 1 ? (int)dc[1] : 1;
+  return status(gpxb_gpr_predict(ctx_for_current_device(), kind, x_train.typed_data(), (int)dt[0], (int)dt[1],
+                                 x.typed_data(), (int)x.dimensions()[0], c.typed_data(), T, mu.typed_data(), ell, sigma,
+                                 mean->typed_data(), cov->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(GpxbGprPredict, GprPredictImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Attr<double>("ell")
+                                  .Attr<double>("sigma")
+                                  .Attr<int32_t>("kind")
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
+
+// out3 = [lml/N, d/d ell, d/d sigma] of the SGPR LML with fixed landmarks  (gpx/models/_sgpr.py:659-697 + value_and_grad)
+static ffi::Error SgprLmlGradImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> x, ffi::Buffer<ffi::F64> y,
+                                  ffi::Buffer<ffi::F64> x_locs, double ell, double sigma, int32_t kind,
+                                  int32_t mean_mode, int32_t want_grad, ffi::ResultBuffer<ffi::F64> out3) {
+  const auto dx = x.dimensions();
+  return status(gpxb_sgpr_lml_grad(ctx_for_current_device(), kind, x.typed_data(), y.typed_data(), (int)dx[0],
+                                   (int)dx[1], x_locs.typed_data(), (int)x_locs.dimensions()[0], ell, sigma, mean_mode,
+                                   want_grad, out3->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(GpxbSgprLmlGrad, SgprLmlGradImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Attr<double>("ell")
+                                  .Attr<double>("sigma")
+                                  .Attr<int32_t>("kind")
+                                  .Attr<int32_t>("mean_mode")
+                                  .Attr<int32_t>("want_grad")
+                                  .Ret<ffi::Buffer<ffi::F64>>());
+
+// (c (M, T), mu (1,)) = _sgpr._fit_dense  (gpx/models/_sgpr.py:319-339)
+static ffi::Error SgprFitImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> x, ffi::Buffer<ffi::F64> y,
+                              ffi::Buffer<ffi::F64> x_locs, double ell, double sigma, int32_t kind, int32_t mean_mode,
+                              ffi::ResultBuffer<ffi::F64> c, ffi::ResultBuffer<ffi::F64> mu) {
+  const auto dx = x.dimensions();
+  const auto dy = y.dimensions();
+  const int T = dy.size() > 1 ? (int)dy[1] : 1;
+  return status(gpxb_sgpr_fit(ctx_for_current_device(), kind, x.typed_data(), y.typed_data(), (int)dx[0], (int)dx[1], T,
+                              x_locs.typed_data(), (int)x_locs.dimensions()[0], ell, sigma, mean_mode, c->typed_data(),
+                              mu->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(GpxbSgprFit, SgprFitImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Attr<double>("ell")
+                                  .Attr<double>("sigma")
+                                  .Attr<int32_t>("kind")
+                                  .Attr<int32_t>("mean_mode")
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
+
+// mean (ns, T) and full covariance (ns, ns) of _sgpr._predict_dense  (gpx/models/_sgpr.py:434-467)
+static ffi::Error SgprPredictImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> x_locs, ffi::Buffer<ffi::F64> x,
+                                  ffi::Buffer<ffi::F64> c, ffi::Buffer<ffi::F64> mu, double ell, double sigma,
+                                  int32_t kind, ffi::ResultBuffer<ffi::F64> mean, ffi::ResultBuffer<ffi::F64> cov) {
+  const auto dl = x_locs.dimensions();
+  const auto dc = c.dimensions();
+  const int T = dc.size() > 1 ? (int)dc[1] : 1;
+  return status(gpxb_sgpr_predict(ctx_for_current_device(), kind, x_locs.typed_data(), (int)dl[0], (int)dl[1],
+                                  x.typed_data(), (int)x.dimensions()[0], c.typed_data(), T, mu.typed_data(), ell, sigma,
+                                  mean->typed_data(), cov->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(GpxbSgprPredict, SgprPredictImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Attr<double>("ell")
+                                  .Attr<double>("sigma")
+                                  .Attr<int32_t>("kind")
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
+
+// out3 = [lml, d/d ell, d/d sigma] of the derivative-trained GPR  (gpx/models/_gpr.py:824-870 + value_and_grad);
+// x (N, nf), jacobian (N, nf, nv), y (N, nv)
+static ffi::Error GprLmlGradDerivsImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> x, ffi::Buffer<ffi::F64> jac,
+                                       ffi::Buffer<ffi::F64> y, double ell, double sigma, int32_t kind,
+                                       int32_t want_grad, ffi::ResultBuffer<ffi::F64> out3) {
+  const auto dj = jac.dimensions();
+  return status(gpxb_gpr_lml_grad_derivs(ctx_for_current_device(), kind, x.typed_data(), jac.typed_data(),
+                                         y.typed_data(), (int)dj[0], (int)dj[1], (int)dj[2], ell, sigma, want_grad,
+                                         out3->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(GpxbGprLmlGradDerivs, GprLmlGradDerivsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Attr<double>("ell")
+                                  .Attr<double>("sigma")
+                                  .Attr<int32_t>("kind")
+                                  .Attr<int32_t>("want_grad")
+                                  .Ret<ffi::Buffer<ffi::F64>>());
 #else
 // jaxlib headers not present: nothing to build (see the header comment).
 #endif

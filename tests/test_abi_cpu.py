@@ -136,3 +136,22 @@ def test_ffi_shim_calls_match_the_header():
         assert nargs[m.group(1)] == n, f"{m.group(1)}: shim passes {n} arguments, header declares {nargs[m.group(1)]}"
         calls += 1
     assert calls >= 4
+
+
+def test_ffi_shim_type_checks_against_the_header_with_mock_xla_headers():
+    """g++ -fsyntax-only of the jax.ffi shim with tests/c/mock_xla standing in for jaxlib's xla/ffi/api/ffi.h (absent
+    from the image): every handler body must be valid C++ against include/gpxb200.h -- pointer types, argument order
+    and counts of the gpxb_* calls.  (The real binding still has to be built where jaxlib exists: SURVEY.md 8f N4.)"""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if gxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA runtime headers")
+    r = subprocess.run([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "c", "mock_xla"),
+                        "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+                        os.path.join(ROOT, "gpx_b200", "csrc", "ffi", "ffi_shim.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "gpx_b200", "csrc", "ffi", "ffi_shim.cc")).read()
+    assert src.count("XLA_FFI_DEFINE_HANDLER_SYMBOL(") >= 10
