@@ -60,6 +60,86 @@ class Kernel:
         # gpx/kernels/kernels.py:1650-1658
         return dict(lengthscale=Parameter(value=1.0, trainable=True, bijector=Softplus(), prior=GammaPrior()))
 
+    # ---- derivative kernels (gpx/kernels/kernels.py:1433-1488; shapes as the kernelizers return them,
+    # gpx/kernels/kernelizers.py:106-392).  All of them are blocks of the two device kernels gpxb_hess_gram
+    # (d01kj) and gpxb_td_gram ([[k, d1kj], [d0kj, d01kj]]); the jacobian-free forms use identity jacobians.
+    # SquaredExponential and Matern52 only (the kinds csrc/hess.cu implements).  With `active_dims` the jacobian
+    # is restricted to the active feature rows (the kernel does not depend on the others).
+    def _deriv_operands(self, x, jacobian=None):
+        if self.kind not in ("se", "m52"):
+            raise NotImplementedError(f"derivative kernels of {self.__class__.__name__} are not implemented "
+                                      "(SquaredExponential and Matern52 only)")
+        xd = _to_device(self._slice(np.asarray(x, dtype=np.float64)))
+        if jacobian is None:
+            if self.active_dims is not None:
+                raise NotImplementedError("jacobian-free derivative kernels with active_dims are not supported")
+            import torch
+
+            n, nf = xd.shape
+            J = torch.eye(nf, dtype=torch.float64, device=xd.device).unsqueeze(0).expand(n, nf, nf).contiguous()
+            return xd, J
+        J = np.asarray(jacobian, dtype=np.float64)
+        if self.active_dims is not None:
+            J = J[:, self.active_dims, :]
+        return xd, _to_device(J)
+
+    @staticmethod
+    def _zero_jacobian(xd, nv=3):
+        import torch
+
+        return torch.zeros((xd.shape[0], xd.shape[1], nv), dtype=torch.float64, device=xd.device)
+
+    def d01kj(self, x1, x2, params, jacobian1, jacobian2, as_numpy: bool = True):
+        """Hessian kernel contracted with both jacobians: (n1 nv1, n2 nv2), row index sample * nv + variable."""
+        from . import ops
+
+        a, Ja = self._deriv_operands(x1, jacobian1)
+        b, Jb = self._deriv_operands(x2, jacobian2)
+        out = ops.hess_gram(self.kind, a, Ja, b, Jb, self.lengthscale(params))
+        return out.cpu().numpy() if as_numpy else out
+
+    def d01kjc(self, x1, x2, params, jaccoef, jacobian, as_numpy: bool = True):
+        """d01kj with the first jacobian already contracted with the coefficients: (n1, n2 nv)."""
+        jc = np.asarray(jaccoef, dtype=np.float64)[:, :, None]
+        return self.d01kj(x1, x2, params, jc, jacobian, as_numpy)
+
+    def d0kj(self, x1, x2, params, jacobian, as_numpy: bool = True):
+        """Derivative w.r.t. the first argument contracted with its jacobian: (n1 nv, n2)."""
+        from . import ops
+
+        a, Ja = self._deriv_operands(x1, jacobian)
+        b = _to_device(self._slice(np.asarray(x2, dtype=np.float64)))
+        full = ops.td_gram(self.kind, a, Ja, b, self._zero_jacobian(b), self.lengthscale(params))
+        out = full[a.shape[0]:, : b.shape[0]].contiguous()
+        return out.cpu().numpy() if as_numpy else out
+
+    def d1kj(self, x1, x2, params, jacobian, as_numpy: bool = True):
+        """Derivative w.r.t. the second argument contracted with its jacobian: (n1, n2 nv)."""
+        from . import ops
+
+        a = _to_device(self._slice(np.asarray(x1, dtype=np.float64)))
+        b, Jb = self._deriv_operands(x2, jacobian)
+        full = ops.td_gram(self.kind, a, self._zero_jacobian(a), b, Jb, self.lengthscale(params))
+        out = full[: a.shape[0], b.shape[0]:].contiguous()
+        return out.cpu().numpy() if as_numpy else out
+
+    def d0kjc(self, x1, x2, params, jaccoef, as_numpy: bool = True):
+        """d0kj with the jacobian already contracted with the coefficients: (n1, n2)."""
+        return self.d0kj(x1, x2, params, np.asarray(jaccoef, dtype=np.float64)[:, :, None], as_numpy)
+
+    def d0k(self, x1, x2, params, as_numpy: bool = True):
+        """(n1 nf, n2): d k / d x1."""
+        return self.d0kj(x1, x2, params, self._deriv_operands(x1)[1].cpu().numpy(), as_numpy)
+
+    def d1k(self, x1, x2, params, as_numpy: bool = True):
+        """(n1, n2 nf): d k / d x2."""
+        return self.d1kj(x1, x2, params, self._deriv_operands(x2)[1].cpu().numpy(), as_numpy)
+
+    def d01k(self, x1, x2, params, as_numpy: bool = True):
+        """(n1 nf, n2 nf): d^2 k / d x1 d x2."""
+        return self.d01kj(x1, x2, params, self._deriv_operands(x1)[1].cpu().numpy(),
+                          self._deriv_operands(x2)[1].cpu().numpy(), as_numpy)
+
     def __repr__(self):
         return f"{self.__class__.__name__}()"
 

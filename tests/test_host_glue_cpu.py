@@ -95,3 +95,49 @@ def test_derivs_facade_glue(test):
 def test_sgpr_derivs_facade_glue(kind):
     with patched():
         DV.test_sgpr_fit_and_predict_on_derivatives(kind)
+
+
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_kernel_derivative_methods_glue(kind):
+    """Kernel.d0k / d1k / d01k / d0kj / d1kj / d01kj / d0kjc / d01kjc (gpx/kernels/kernels.py:1433-1488): argument order,
+    block extraction from the [[k, d1kj], [d0kj, d01kj]] device matrix, identity jacobians of the jacobian-free forms,
+    active_dims restriction of the jacobian rows, and the shapes the reference's kernelizers return."""
+    import numpy as np
+
+    import gpx_b200.kernels as K
+    from oracle import ref_numpy as R
+
+    rng = np.random.default_rng(0)
+    n1, n2, nf, nv1, nv2 = 7, 5, 4, 3, 2
+    x1, x2 = rng.standard_normal((n1, nf)), rng.standard_normal((n2, nf))
+    J1, J2 = rng.standard_normal((n1, nf, nv1)), rng.standard_normal((n2, nf, nv2))
+    jc = rng.standard_normal((n1, nf))
+    I1, I2 = np.tile(np.eye(nf)[None], (n1, 1, 1)), np.tile(np.eye(nf)[None], (n2, 1, 1))
+    ell = 1.7
+    cls = K.SquaredExponential if kind == "se" else K.Matern52
+    k = cls()
+    p = {"lengthscale": k.default_params()["lengthscale"].update(dict(value=ell))}
+    with patched():
+        checks = [
+            (k.d01kj(x1, x2, p, J1, J2), R.d01kj(kind, x1, x2, ell, J1, J2), (n1 * nv1, n2 * nv2)),
+            (k.d01kjc(x1, x2, p, jc, J2), R.d01kjc(kind, x1, x2, ell, jc, J2), (n1, n2 * nv2)),
+            (k.d0kj(x1, x2, p, J1), R.d0kj(kind, x1, x2, ell, J1), (n1 * nv1, n2)),
+            (k.d1kj(x1, x2, p, J2), R.d0kj(kind, x2, x1, ell, J2).T, (n1, n2 * nv2)),
+            (k.d0kjc(x1, x2, p, jc), R.d0kjc(kind, x1, x2, ell, jc), (n1, n2)),
+            (k.d0k(x1, x2, p), R.d0kj(kind, x1, x2, ell, I1), (n1 * nf, n2)),
+            (k.d1k(x1, x2, p), R.d0kj(kind, x2, x1, ell, I2).T, (n1, n2 * nf)),
+            (k.d01k(x1, x2, p), R.d01kj(kind, x1, x2, ell, I1, I2), (n1 * nf, n2 * nf)),
+        ]
+        for got, want, shape in checks:
+            assert got.shape == shape and np.max(np.abs(got - want)) < 1e-12
+        dims = [0, 2]
+        ka = cls(active_dims=dims)
+        got = ka.d01kj(x1, x2, p, J1, J2)
+        want = R.d01kj(kind, x1[:, dims], x2[:, dims], ell, J1[:, dims, :], J2[:, dims, :])
+        assert np.max(np.abs(got - want)) < 1e-12
+        with pytest.raises(NotImplementedError):
+            ka.d0k(x1, x2, p)
+        with pytest.raises(NotImplementedError):
+            K.Matern32().d01kj(x1, x2, p, J1, J2)
+        with pytest.raises(NotImplementedError):
+            (K.SquaredExponential() + K.Matern52()).d01kj(x1, x2, {"kernel1": p, "kernel2": p}, J1, J2)
