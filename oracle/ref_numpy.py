@@ -31,7 +31,11 @@ Parity pinning status
   (cells 6, 10, 13, 16); the sign / scaling conventions of d0kj, d1kj, d01kj (the GPR_TD block matrix): PINNED by the
   entries examples/derivatives_solak.ipynb cell 4 prints; the Hessian-kernel LML value: PINNED to 10 digits by the
   scipy OptimizeResult examples/gpr_with_derivatives_only.ipynb cell 27 prints (fun = -1.5536783384709247).
-* predictions, fit coefficients, Lanczos/SLQ, PCG and the partitionable PRNG mode: **parity unpinned** -- the reference has no test, golden vector or
+* jax.scipy.sparse.linalg.cg (third-party, restated in `cg`): cross-checked against scipy.sparse.linalg.cg, an
+  independent implementation of the same textbook PCG and stopping rule -- identical iteration counts and
+  solutions with and without the RPCholesky preconditioner (tests/test_oracle_cpu.py).  Not a pin against JAX
+  itself, which cannot run here.
+* predictions, fit coefficients, Lanczos/SLQ and the partitionable PRNG mode: **parity unpinned** -- the reference has no test, golden vector or
   printed output for them and cannot be executed here.  They are anchored
   by self-consistency (analytic gradient vs finite differences, Woodbury vs
   the reference's N x N form, SLQ vs exact log-det).

@@ -482,3 +482,32 @@ def test_oracle_d0kj_and_td_block_matrix(kind):
     assert np.max(np.abs(out - ref.reshape(10, 4))) < 1e-8
     A = R.td_A_lhs(kind, x1, J, x1, J, 1.3, 0.3, 0.2)
     assert np.max(np.abs(A - A.T)) < 1e-14 and np.linalg.eigvalsh(A).min() > 0
+
+
+def test_oracle_cg_is_scipy_cg_iteration_for_iteration():
+    """The restated jax.scipy.sparse.linalg.cg (third-party, absent here) against scipy.sparse.linalg.cg, which
+    implements the same textbook preconditioned CG with the same stopping rule |r| <= max(tol |b|, atol): identical
+    iteration counts and solutions, with and without the RPCholesky preconditioner of _gpr.py:180-216."""
+    from scipy.sparse.linalg import LinearOperator
+    from scipy.sparse.linalg import cg as scipy_cg
+
+    rng = np.random.default_rng(0)
+    for n, sig in ((300, 0.3), (500, 0.1), (400, 1.0)):
+        x = rng.standard_normal((n, 3))
+        A = R.kernel("se", x, x, 1.5) + (sig**2 + 1e-10) * np.eye(n)
+        b = rng.standard_normal(n)
+        F, _ = R.rpcholesky("se", x, 20, 1.5, R.PRNGKey(1))
+        P = np.linalg.inv(sig**2 * np.eye(20) + F.T @ F)
+        precond = lambda z: z / sig**2 - (F @ (P @ (F.T @ z))) / sig**2  # noqa: E731
+        for M in (None, precond):
+            xo, k = R.cg(lambda v: A @ v, b, M=M, tol=1e-5, atol=1e-7)
+            its = [0]
+
+            def cb(_xk):
+                its[0] += 1
+
+            xs, info = scipy_cg(A, b, rtol=1e-5, atol=1e-7, maxiter=10 * n, callback=cb,
+                                M=None if M is None else LinearOperator((n, n), matvec=M))
+            assert info == 0 and k == its[0], (n, sig, k, its[0])
+            assert np.max(np.abs(xo - xs)) <= 1e-12 * np.max(np.abs(xs))
+    assert k < 25  # the preconditioner helps (13 against 25 iterations in the last case)
