@@ -35,7 +35,12 @@ Parity pinning status
   independent implementation of the same textbook PCG and stopping rule -- identical iteration counts and
   solutions with and without the RPCholesky preconditioner (tests/test_oracle_cpu.py).  Not a pin against JAX
   itself, which cannot run here.
-* predictions, fit coefficients, Lanczos/SLQ and the partitionable PRNG mode: **parity unpinned** -- the reference has no test, golden vector or
+* exact-GPR LML, its gradient, fit coefficients, predictive mean and covariance (all four kernels): cross-checked
+  to ~1e-12 against scikit-learn's GaussianProcessRegressor with the equivalent kernels (an independent third-party
+  implementation; Matern-1/2 agrees to 1e-6 only, because GPX's 1e-12 jitter under the square root is GPX's own
+  semantics) -- tests/test_oracle_cpu.py::test_oracle_exact_gpr_against_scikit_learn.
+* predictions and fit coefficients of the sparse / derivative models, Lanczos/SLQ and the partitionable PRNG mode:
+  **parity unpinned** -- the reference has no test, golden vector or
   printed output for them and cannot be executed here.  They are anchored
   by self-consistency (analytic gradient vs finite differences, Woodbury vs
   the reference's N x N form, SLQ vs exact log-det).

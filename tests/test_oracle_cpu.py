@@ -511,3 +511,40 @@ def test_oracle_cg_is_scipy_cg_iteration_for_iteration():
             assert info == 0 and k == its[0], (n, sig, k, its[0])
             assert np.max(np.abs(xo - xs)) <= 1e-12 * np.max(np.abs(xs))
     assert k < 25  # the preconditioner helps (13 against 25 iterations in the last case)
+
+
+@pytest.mark.parametrize("kind", ["se", "m12", "m32", "m52"])
+def test_oracle_exact_gpr_against_scikit_learn(kind):
+    """Independent third-party cross-check of the rows the reference does not test (LML, its gradient, fit
+    coefficients, predictive mean and covariance): scikit-learn's GaussianProcessRegressor with the equivalent
+    kernel (RBF at lengthscale l/sqrt(2) = GPX's exp(-d^2/l^2); Matern nu = 1/2, 3/2, 5/2 at the same lengthscale)
+    plus WhiteKernel(sigma^2) and alpha = 1e-10 (GPX's diagonal jitter), zero mean.  Agreement ~1e-12 for SE,
+    Matern-3/2, -5/2.  Matern-1/2 differs at the 1e-6 level BY CONSTRUCTION: GPX evaluates r = sqrt(d^2 + 1e-12),
+    so k(x, x) = exp(-1e-6) instead of 1 (gpx/utils.py:55-72, kernels.py:922-927) -- the oracle follows
+    GPX, not scikit-learn, there."""
+    sk = pytest.importorskip("sklearn.gaussian_process")
+    from sklearn.gaussian_process.kernels import RBF, Matern, WhiteKernel
+
+    rng = np.random.default_rng(0)
+    n, D, ns = 150, 3, 20
+    x = rng.standard_normal((n, D))
+    y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((n, 1))
+    xs = rng.standard_normal((ns, D))
+    ell, sigma = 1.7, 0.3
+    kern = {"se": RBF(ell / np.sqrt(2.0)), "m12": Matern(ell, nu=0.5), "m32": Matern(ell, nu=1.5),
+            "m52": Matern(ell, nu=2.5)}[kind] + WhiteKernel(sigma**2)
+    g = sk.GaussianProcessRegressor(kernel=kern, alpha=1e-10, optimizer=None, normalize_y=False).fit(x, y)
+    lml_sk, grad_sk = g.log_marginal_likelihood(g.kernel_.theta, eval_gradient=True)
+    lml, ge, gs = R.lml_grad_dense(kind, x, y, ell, sigma, mean_function=R.zero_mean)
+    tol = 1e-5 if kind == "m12" else 1e-10
+    assert abs(lml * n - lml_sk) < tol * abs(lml_sk)
+    # scikit-learn differentiates w.r.t. log(length_scale) and log(noise_level = sigma^2)
+    assert abs(ge * n * ell - grad_sk[0]) < tol * abs(grad_sk[0])
+    assert abs(gs * n * sigma / 2.0 - grad_sk[1]) < tol * abs(grad_sk[1])
+    c, mu = R.fit_dense(kind, x, y, ell, sigma, mean_function=R.zero_mean)
+    assert mu == 0.0 and np.max(np.abs(c.ravel() - g.alpha_.ravel())) < 10 * tol * np.max(np.abs(c))
+    mean, cov = R.predict_dense(kind, x, xs, c, mu, ell, sigma, full_covariance=True)
+    mean_sk, cov_sk = g.predict(xs, return_cov=True)
+    assert np.max(np.abs(mean.ravel() - mean_sk.ravel())) < 10 * tol
+    # scikit-learn adds the WhiteKernel to the predictive covariance; GPX adds no noise there (_gpr.py:459-461)
+    assert np.max(np.abs(cov - (cov_sk - sigma**2 * np.eye(ns)))) < 10 * tol
