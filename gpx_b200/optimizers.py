@@ -51,3 +51,24 @@ def scipy_minimize(state, x, y, loss_and_grad_fn: Callable, callback=None, **opt
 
     optres = minimize(fun, x0=x0, method="L-BFGS-B", jac=True, callback=callback, **opt_kwargs)
     return unravel_forward(state, paths, optres.x), optres
+
+
+class StateCheckpointer:
+    """Callback for `scipy_minimize` that writes the model state after every L-BFGS-B iteration (mirror of
+    gpx/optimizers/scipy_optimize.py:175-229): `StateCheckpointer(state, "run.npz")` saves `run.000.npz`,
+    `run.001.npz`, ... in the `.npz` layout of `ModelState.save`, so that `model.load(...)` can inspect or restart a
+    long optimisation.  Pass it as `model.fit(x, y, opt_kwargs=dict(callback=StateCheckpointer(model.state)))`."""
+
+    def __init__(self, state, chk_file: str = "optim_chk.npz") -> None:
+        import os
+
+        self.state = state
+        self.counter = 0
+        name, ext = os.path.splitext(chk_file)
+        self.fmt_chk_file = name + ".{:03d}" + ext
+        _, self._paths = ravel_backward_trainables(state)
+
+    def __call__(self, x) -> None:
+        st = unravel_forward(self.state, self._paths, np.asarray(x, dtype=np.float64))
+        st.save(self.fmt_chk_file.format(self.counter))
+        self.counter += 1

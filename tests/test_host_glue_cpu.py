@@ -141,3 +141,31 @@ def test_kernel_derivative_methods_glue(kind):
             K.Matern32().d01kj(x1, x2, p, J1, J2)
         with pytest.raises(NotImplementedError):
             (K.SquaredExponential() + K.Matern52()).d01kj(x1, x2, {"kernel1": p, "kernel2": p}, J1, J2)
+
+
+def test_state_checkpointer_callback(tmp_path):
+    """StateCheckpointer (gpx/optimizers/scipy_optimize.py:175-229) through GPR.fit: one loadable .npz per L-BFGS-B
+    iteration, the last one holding the fitted hyper-parameters."""
+    import numpy as np
+
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import GPR
+    from gpx_b200.optimizers import StateCheckpointer
+
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-2, 2, (80, 1))
+    y = np.sin(2 * x) + 0.1 * rng.standard_normal((80, 1))
+    with patched():
+        m = GPR(SquaredExponential())
+        chk = StateCheckpointer(m.state, str(tmp_path / "run.npz"))
+        m.fit(x, y, opt_kwargs=dict(callback=chk))
+    assert chk.counter == m.optimize_results_.nit and chk.counter >= 2
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert files[0] == "run.000.npz" and len(files) == chk.counter
+    last = GPR(SquaredExponential()).load(str(tmp_path / files[-1]))
+    for path in (("kernel_params", "lengthscale"), ("sigma",)):
+        a = dict(last.state.flat_params())[path].value
+        b = dict(m.state.flat_params())[path].value
+        assert abs(a - b) < 1e-12
+    first = GPR(SquaredExponential()).load(str(tmp_path / files[0]))
+    assert first.state.params["sigma"].value != m.state.params["sigma"].value
