@@ -65,6 +65,15 @@ class BaseGP:
                 f"{self.__class__.__name__} is not fitted yet. Call 'fit' before using this model for prediction."
             )
 
+    def sample(self, key, x, n_samples=1, kind="prior"):
+        """Draws samples from the GP prior or posterior (gpx/models/base.py:99-128)."""
+        if kind not in ("prior", "posterior"):
+            raise ValueError(f"kind can be either 'prior' or 'posterior', you provided {kind}")
+        fun = getattr(self, "_sample_prior_fun" if kind == "prior" else "_sample_posterior_fun", None)
+        if fun is None:
+            raise NotImplementedError(f"{self.__class__.__name__}.sample(kind={kind!r}) is not implemented")
+        return fun(key, state=self.state, x=x, n_samples=n_samples)
+
     # ---- hot path -------------------------------------------------------------------
     def predict(self, x, full_covariance=False, iterative=False):
         """gpx/models/base.py:167-187."""

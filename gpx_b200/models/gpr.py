@@ -265,6 +265,34 @@ def predict_y_derivs(state, x, full_covariance=False, iterative=False):
     return out.cpu().numpy().reshape(-1, 1)
 
 
+def sample_prior(key, state, x, n_samples=1):
+    """gpx/models/gpr.py:761-780: zero mean of the shape of x (so the key is split once per FEATURE column, as the
+    reference does), covariance K(x, x) + (sigma^2 + 1e-10) I."""
+    from .utils import sample
+
+    if _composite.is_composite(state.kernel):
+        xd = _to_device(x)
+        cov = state.kernel.k_device(xd, xd, state.params["kernel_params"])
+        cov.diagonal().add_(float(np.asarray(state.params["sigma"].value)) ** 2 + 1e-10)
+    else:
+        kernel, ell, sigma = _hyper(state)
+        xd = _to_device(kernel._slice(x))
+        cov = ops.gram(kernel.kind, xd, xd, ell, diag_add=sigma * sigma + 1e-10)
+    return sample(key, np.zeros(np.asarray(x).shape), cov, n_samples)
+
+
+def sample_posterior(key, state, x, n_samples=1):
+    """gpx/models/gpr.py:809-832: predictive mean and covariance (+ 1e-10 I) of the fitted model."""
+    from .utils import sample
+
+    if not state.is_fitted:
+        raise RuntimeError("Cannot sample from the posterior if the model is not fitted")
+    mean, cov = predict(state, x, full_covariance=True)
+    cov_dev = _to_device(cov)
+    cov_dev.diagonal().add_(1e-10)
+    return sample(key, mean, cov_dev, n_samples)
+
+
 def _is_parameter_dict(d) -> bool:
     """Recursive type check of gpx/models/utils.py:42-51: composite kernels nest {"kernel1": ..., "kernel2": ...}."""
     return isinstance(d, dict) and all(_is_parameter_dict(v) if isinstance(v, dict) else isinstance(v, Parameter)
@@ -316,3 +344,5 @@ class GPR(BaseGP):
     _fit_derivs_fun = staticmethod(fit_derivs)
     _predict_y_derivs_fun = staticmethod(predict_y_derivs)
     _predict_derivs_fun = staticmethod(predict_derivs)
+    _sample_prior_fun = staticmethod(sample_prior)
+    _sample_posterior_fun = staticmethod(sample_posterior)

@@ -651,6 +651,37 @@ def fit_derivs_dense(kind, x, y, J, ell, sigma):
     return c, 0.0, jaccoef
 
 
+def multivariate_normal(key, mean, cov, shape=(), partitionable=True):
+    """jax.random.multivariate_normal, default method "cholesky" (third-party; restated from the published
+    algorithm): mean + normal(key, shape + (n,)) @ cholesky(cov)^T."""
+    L = np.linalg.cholesky(cov)
+    z = normal(key, tuple(shape) + (mean.shape[-1],), partitionable)
+    return mean + np.einsum("...ij,...j->...i", L, z)
+
+
+def sample(key, mean, cov, n_samples=1, partitionable=True):
+    """gpx/models/utils.py:52-75, quirks included: a 2-D mean is drawn column by column with the carried half of
+    each split and only the LAST column's draw is returned; a 1-D mean ignores n_samples."""
+    if mean.ndim > 1:
+        out = None
+        for dim in range(mean.shape[1]):
+            key = split(key, 2, partitionable)[1]
+            out = multivariate_normal(key, mean[:, dim], cov, (n_samples,), partitionable)
+        return out
+    return multivariate_normal(key, mean, cov, (), partitionable)
+
+
+def sample_prior(kind, key, x, ell, sigma, n_samples=1, partitionable=True):
+    """gpx/models/gpr.py:761-780."""
+    return sample(key, np.zeros(x.shape), A_lhs(kind, x, x, ell, sigma), n_samples, partitionable)
+
+
+def sample_posterior(kind, key, x_train, x, c, mu, ell, sigma, n_samples=1, partitionable=True):
+    """gpx/models/gpr.py:809-832."""
+    mean, cov = predict_dense(kind, x_train, x, c, mu, ell, sigma, full_covariance=True)
+    return sample(key, mean, cov + 1e-10 * np.eye(cov.shape[0]), n_samples, partitionable)
+
+
 # =============================================================================
 # matrix-free mat-vec, Lanczos, SLQ, PCG
 # (gpx/operations.py:32-123, gpx/lanczos.py:29-183, _gpr.py:94-119, 180-216, 285-310,

@@ -104,6 +104,14 @@ def test_host_prng_matches_the_oracle_bit_for_bit():
                 assert np.array_equal(PR.split(key, num, part), R.split(key, num, part)), (key, part, num)
     with pytest.raises(ValueError):
         PR.as_key(np.zeros(3, dtype=np.uint32))
+    for key in keys[:8]:
+        for part in (True, False):
+            for shape in ((), (1,), (7,), (4, 5), (100,)):
+                a, b = np.asarray(PR.uniform(key, shape, part)), np.asarray(R.uniform(key, shape, part))
+                assert a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+                if shape:
+                    assert np.array_equal(PR.normal(key, shape, part).view(np.uint64),
+                                          R.normal(key, shape, part).view(np.uint64))
 
 
 def test_slq_host_numerics_value_and_closed_form_derivative():

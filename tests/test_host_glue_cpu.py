@@ -169,3 +169,46 @@ def test_state_checkpointer_callback(tmp_path):
         assert abs(a - b) < 1e-12
     first = GPR(SquaredExponential()).load(str(tmp_path / files[0]))
     assert first.state.params["sigma"].value != m.state.params["sigma"].value
+
+
+@pytest.mark.parametrize("partitionable", [True, False])
+def test_sampling_glue(partitionable):
+    """GPR.sample(kind="prior" / "posterior") (gpx/models/base.py:99-128 -> gpr.py:761-832 -> models/utils.py:52-75)
+    against the oracle's literal restatement, including the reference's quirks (one key split per column of the mean,
+    only the last column's draw returned).  The normal deviates come from the product's own host PRNG."""
+    import numpy as np
+
+    from gpx_b200 import defaults
+    from gpx_b200.kernels import Matern52
+    from gpx_b200.models import GPR
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+    from gpx_b200.random import PRNGKey
+    from oracle import ref_numpy as R
+
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-2, 2, (40, 2))
+    y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((40, 1))
+    xs = rng.uniform(-2, 2, (15, 2))
+    ell, sigma = 1.3, 0.2
+    old = defaults.threefry_partitionable()
+    defaults.set_threefry_partitionable(partitionable)
+    try:
+        with patched():
+            m = GPR(Matern52(), kernel_params=dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior())),
+                    sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+            prior = m.sample(PRNGKey(0), xs, n_samples=4, kind="prior")
+            with pytest.raises(RuntimeError):
+                m.sample(PRNGKey(0), xs, kind="posterior")
+            m.fit(x, y, minimize=False)
+            post = m.sample(PRNGKey(7), xs, n_samples=3, kind="posterior")
+            with pytest.raises(ValueError):
+                m.sample(PRNGKey(0), xs, kind="both")
+    finally:
+        defaults.set_threefry_partitionable(old)
+    ref_prior = R.sample_prior("m52", R.PRNGKey(0), xs, ell, sigma, 4, partitionable)
+    assert prior.shape == (4, 15) and np.max(np.abs(prior - ref_prior)) < 1e-9
+    c, mu = R.fit_dense("m52", x, y, ell, sigma)
+    ref_post = R.sample_posterior("m52", R.PRNGKey(7), x, xs, c, mu, ell, sigma, 3, partitionable)
+    assert post.shape == (3, 15) and np.max(np.abs(post - ref_post)) < 1e-7
