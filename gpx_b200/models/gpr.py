@@ -57,12 +57,39 @@ def neg_log_marginal_likelihood(state, x, y, **kwargs):
     return -log_marginal_likelihood(state, x, y, **kwargs)
 
 
+def log_prior(state):
+    """log p(theta) assuming independent hyper-parameters: the sum of prior.logpdf(value) over EVERY parameter,
+    trainable or not (gpx/models/gpr.py:177-184)."""
+    return float(sum(np.sum(p.prior.logpdf(p.value)) for _, p in state.flat_params()))
+
+
+def log_posterior(state, x, y, **kwargs):
+    """gpx/models/gpr.py:187-215: log p(theta | y) = lml (normalised by n, as the reference's is) + log p(theta)."""
+    return log_marginal_likelihood(state, x, y, **kwargs) + log_prior(state)
+
+
+def neg_log_posterior(state, x, y, **kwargs):
+    """gpx/models/gpr.py:303-325: the MAP loss (`loss_fn=neg_log_posterior`)."""
+    return -log_posterior(state, x, y, **kwargs)
+
+
+def _add_prior_gradient(state, loss, grads):
+    """MAP loss from the LML loss: subtract log p(theta) and its derivative w.r.t. every trainable value."""
+    flat = dict(state.flat_params())
+    for path in list(grads):
+        grads[path] = grads[path] - np.asarray(flat[path].prior.dlogpdf(flat[path].value), dtype=np.float64)
+    return loss - log_prior(state), grads
+
+
 def loss_and_grad(state, x, y, iterative=False, **kwargs):
     """Negative LML and its gradient w.r.t. the constrained hyper-parameters, from one fused
     device call (stands in for jit(value_and_grad(loss)), gpx/optimizers/scipy_optimize.py:72-78).
     Non-trainable parameters get no gradient entry (stop_gradient, model_state.py:93-103)."""
+    if state.loss_fn is neg_log_posterior:  # MAP estimate: the LML part below, the prior part on the host
+        loss, grads = loss_and_grad(state.update(dict(loss_fn=neg_log_marginal_likelihood)), x, y, iterative, **kwargs)
+        return _add_prior_gradient(state, loss, grads)
     if state.loss_fn is not neg_log_marginal_likelihood:
-        raise NotImplementedError("only neg_log_marginal_likelihood has a fused device gradient")
+        raise NotImplementedError("only neg_log_marginal_likelihood and neg_log_posterior have a device gradient")
     if _composite.is_composite(state.kernel):
         if iterative:
             raise NotImplementedError("composite kernels are supported by the dense paths only")

@@ -17,6 +17,10 @@ class Prior:
     def logpdf(self, x):
         raise NotImplementedError
 
+    def dlogpdf(self, x):
+        """d logpdf / d x (what autodiff of the MAP loss yields in the reference)."""
+        raise NotImplementedError
+
     def __repr__(self):
         return f"{self.__class__.__name__}()"
 
@@ -31,6 +35,9 @@ class NormalPrior(Prior):
     def logpdf(self, x):
         return stats.norm.logpdf(x, self.loc, self.scale)
 
+    def dlogpdf(self, x):
+        return -(np.asarray(x, dtype=np.float64) - self.loc) / self.scale**2
+
 
 class GammaPrior(Prior):
     def __init__(self, concentration=1.0, rate=1.0, shape=(), dtype=np.float64):
@@ -41,3 +48,6 @@ class GammaPrior(Prior):
 
     def logpdf(self, x):
         return stats.gamma.logpdf(x, self.concentration, scale=1.0 / self.rate)
+
+    def dlogpdf(self, x):
+        return (self.concentration - 1.0) / np.asarray(x, dtype=np.float64) - self.rate

@@ -212,3 +212,37 @@ def test_sampling_glue(partitionable):
     c, mu = R.fit_dense("m52", x, y, ell, sigma)
     ref_post = R.sample_posterior("m52", R.PRNGKey(7), x, xs, c, mu, ell, sigma, 3, partitionable)
     assert post.shape == (3, 15) and np.max(np.abs(post - ref_post)) < 1e-7
+
+
+def test_map_estimate_notebook_anchor_through_the_facade():
+    """examples/map_estimate.ipynb: GPR(loss_fn=neg_log_posterior).fit lands on the printed MAP hyper-parameters
+    (lengthscale 1.99896, sigma 0.4502): the prior term and its gradient are added on the host to the device LML."""
+    import json
+    import os
+
+    import numpy as np
+
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import GPR
+    from gpx_b200.models.gpr import log_prior, neg_log_posterior
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.priors import NormalPrior
+    from test_oracle_cpu import notebook_gpr_data
+
+    a = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_anchors.json")))["map_estimate"]["fit"]
+    x, y = notebook_gpr_data()
+    with patched():
+        m = GPR(SquaredExponential(),
+                kernel_params=dict(lengthscale=Parameter(2.0, True, Softplus(), NormalPrior(2.0, 0.15))),
+                sigma=Parameter(1.0, True, Softplus(), NormalPrior()), loss_fn=neg_log_posterior)
+        l0, g0 = m.loss_and_grad(x, y)
+        assert abs(l0 - (-m.log_marginal_likelihood(x, y) - log_prior(m.state))) < 1e-12
+        h = 1e-6  # the gradient of the MAP loss w.r.t. the constrained lengthscale, by central differences
+        st = m.state
+        fp = neg_log_posterior(st.with_param_value(("kernel_params", "lengthscale"), np.float64(2.0 + h)), x, y)
+        fm = neg_log_posterior(st.with_param_value(("kernel_params", "lengthscale"), np.float64(2.0 - h)), x, y)
+        assert abs(g0[("kernel_params", "lengthscale")] - (fp - fm) / (2 * h)) < 1e-6
+        m.fit(x, y)
+    assert abs(float(m.state.params["kernel_params"]["lengthscale"].value) - a["lengthscale"]) < 2e-5
+    assert abs(float(m.state.params["sigma"].value) - a["sigma"]) < 1e-4

@@ -548,3 +548,25 @@ def test_oracle_exact_gpr_against_scikit_learn(kind):
     assert np.max(np.abs(mean.ravel() - mean_sk.ravel())) < 10 * tol
     # scikit-learn adds the WhiteKernel to the predictive covariance; GPX adds no noise there (_gpr.py:459-461)
     assert np.max(np.abs(cov - (cov_sk - sigma**2 * np.eye(ns)))) < 10 * tol
+
+
+def test_notebook_anchor_map_estimate():
+    """examples/map_estimate.ipynb cells 8-13: MAP fit (loss = -(lml/n + log prior)) with a Normal(2, 0.15) prior on
+    the lengthscale and a Normal(0, 1) prior on sigma prints lengthscale 1.99896, sigma 0.4502.  Pins the prior term,
+    its (missing) normalisation relative to lml/n, and the MAP optimum."""
+    from scipy.optimize import minimize
+    from scipy.stats import norm
+
+    a = json.load(open(os.path.join(GOLDEN, "notebook_anchors.json")))["map_estimate"]["fit"]
+    x, y = notebook_gpr_data()
+
+    def loss_grad(t):
+        ell, sig = R.softplus(t[0]), R.softplus(t[1])
+        lml, ge, gs = R.lml_grad_dense("se", x, y, ell, sig)
+        lp = norm.logpdf(ell, 2.0, 0.15) + norm.logpdf(sig, 0.0, 1.0)
+        dle, dls = -(ell - 2.0) / 0.15**2, -sig
+        return -(lml + lp), np.array([-(ge + dle) * R.sigmoid(t[0]), -(gs + dls) * R.sigmoid(t[1])])
+
+    res = minimize(loss_grad, R.inverse_softplus(np.array([2.0, 1.0])), jac=True, method="L-BFGS-B")
+    ell, sig = R.softplus(res.x)
+    assert abs(ell - a["lengthscale"]) < 2e-5 and abs(sig - a["sigma"]) < 1e-4
