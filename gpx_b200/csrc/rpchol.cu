@@ -226,7 +226,11 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_l2_kernel(RpState st, int i) 
 
 // One thread per data row: kernel column, GEMV against the pivot row, scale, diagonal
 // update, block sum of the new diagonal.
-__global__ void __launch_bounds__(BLK, 2) rp_column_kernel(RpState st, int i) {
+// MINB: CTAs per SM ptxas must allow for.  2 (default) caps the kernel at 32 registers per thread and spills part of
+// the 8 + 8 FP64 values of the inner loop (profiles/r1_sass_summary.txt); 1 (GPXB_RP_MINBLOCKS=1) gives 64 registers
+// and no spill at half the resident threads -- kept switchable for the round-2 measurement.
+template <int MINB>
+__global__ void __launch_bounds__(BLK, MINB) rp_column_kernel(RpState st, int i) {
   extern __shared__ double sm[];  // frow[i], zs[S]
   __shared__ double sh[32];
   double* sf = sm;
@@ -365,8 +369,12 @@ static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, l
     GPXB_LAUNCH_CHECK();
     ctx->launches++;
   }
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(rp_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(double) * (M + zl.S)));
+  static const bool one_cta = [] {
+    const char* e = getenv("GPXB_RP_MINBLOCKS");
+    return e && atoi(e) == 1;
+  }();
+  GPXB_CUDA_CHECK(cudaFuncSetAttribute(one_cta ? rp_column_kernel<1> : rp_column_kernel<2>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(double) * (M + zl.S)));
   for (int i = 0; i < M; ++i) {
     if (multi) GPXB_TRY(comm_allreduce_sum2(ctx, st.bs_local, bBs.as<double>(), nblk, s));
     rp_pivot_l1_kernel<<<1, BLK, 0, s>>>(st);
@@ -377,7 +385,8 @@ static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, l
     ctx->launches += 2;
     if (gen) GPXB_TRY((*gen)(st.pbuf, s));
     if (nblk_loc > 0) {
-      rp_column_kernel<<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
+      if (one_cta) rp_column_kernel<1><<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
+      else rp_column_kernel<2><<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
     }
