@@ -131,3 +131,34 @@ def test_models_from_state():
                                     "x_locs": Parameter(_x_locs(), False, Identity(), NormalPrior(shape=_x_locs().shape))})
     assert isinstance(GPR.from_state(state_gpr), GPR)
     assert isinstance(SGPR.from_state(state_sgpr), SGPR)
+
+
+# ---- bijectors (tests/gpx/test_utils.py:44-100) ------------------------------------------------------------
+@pytest.mark.parametrize("value", [-1e4, -1e2, -50.0, 0.0, 1e3])
+def test_softplus(value):
+    assert Softplus().forward(np.array([value])) >= 0
+
+
+@pytest.mark.parametrize("value", [-600.0, -1e2, 0.0, 1e2, 1e5, 1e10])
+def test_inverse_softplus(value):
+    x = np.array([value])
+    bij = Softplus()
+    assert_equal(x, bij.backward(bij.forward(x)))  # exact recovery, as the reference asserts
+
+
+@pytest.mark.parametrize("value", [-1e10, -1e3, -1e-5, -1e-300])
+def test_inverse_softplus_negative(value):
+    with np.errstate(invalid="ignore", over="ignore"):
+        assert np.isnan(Softplus().backward(np.array([value])))
+
+
+@pytest.mark.parametrize("value", [-1e10, -1e1, 0.0, 1e1, 1e10])
+def test_softplus_plus_inversion_stability(value):
+    bij = Softplus()
+    with np.errstate(over="ignore"):
+        assert np.isfinite(bij.backward(bij.forward(np.array([value]))))
+
+
+def test_identity():
+    x = np.array([1.0])
+    assert_equal(x, Identity().forward(x))
