@@ -65,19 +65,19 @@ class Kernel:
     # (d01kj) and gpxb_td_gram ([[k, d1kj], [d0kj, d01kj]]); the jacobian-free forms use identity jacobians.
     # SquaredExponential and Matern52 only (the kinds csrc/hess.cu implements).  With `active_dims` the jacobian
     # is restricted to the active feature rows (the kernel does not depend on the others).
-    def _deriv_operands(self, x, jacobian=None):
+    @staticmethod
+    def _identity_jacobian(x):
+        """(n, nf, nf) identity jacobians over ALL features: the jacobian-free forms d0k / d1k / d01k are the *kj forms
+        with these; under active_dims the inactive feature ROWS are dropped by _deriv_operands, which leaves exact
+        zeros for the inactive VARIABLES in the output (tests/gpx/kernels/test_kernels.py:551-580)."""
+        x = np.asarray(x)
+        return np.tile(np.eye(x.shape[1])[None], (x.shape[0], 1, 1))
+
+    def _deriv_operands(self, x, jacobian):
         if self.kind not in ("se", "m52"):
             raise NotImplementedError(f"derivative kernels of {self.__class__.__name__} are not implemented "
                                       "(SquaredExponential and Matern52 only)")
         xd = _to_device(self._slice(np.asarray(x, dtype=np.float64)))
-        if jacobian is None:
-            if self.active_dims is not None:
-                raise NotImplementedError("jacobian-free derivative kernels with active_dims are not supported")
-            import torch
-
-            n, nf = xd.shape
-            J = torch.eye(nf, dtype=torch.float64, device=xd.device).unsqueeze(0).expand(n, nf, nf).contiguous()
-            return xd, J
         J = np.asarray(jacobian, dtype=np.float64)
         if self.active_dims is not None:
             J = J[:, self.active_dims, :]
@@ -129,16 +129,15 @@ class Kernel:
 
     def d0k(self, x1, x2, params, as_numpy: bool = True):
         """(n1 nf, n2): d k / d x1."""
-        return self.d0kj(x1, x2, params, self._deriv_operands(x1)[1].cpu().numpy(), as_numpy)
+        return self.d0kj(x1, x2, params, self._identity_jacobian(x1), as_numpy)
 
     def d1k(self, x1, x2, params, as_numpy: bool = True):
         """(n1, n2 nf): d k / d x2."""
-        return self.d1kj(x1, x2, params, self._deriv_operands(x2)[1].cpu().numpy(), as_numpy)
+        return self.d1kj(x1, x2, params, self._identity_jacobian(x2), as_numpy)
 
     def d01k(self, x1, x2, params, as_numpy: bool = True):
         """(n1 nf, n2 nf): d^2 k / d x1 d x2."""
-        return self.d01kj(x1, x2, params, self._deriv_operands(x1)[1].cpu().numpy(),
-                          self._deriv_operands(x2)[1].cpu().numpy(), as_numpy)
+        return self.d01kj(x1, x2, params, self._identity_jacobian(x1), self._identity_jacobian(x2), as_numpy)
 
     def __repr__(self):
         return f"{self.__class__.__name__}()"

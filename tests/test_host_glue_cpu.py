@@ -135,8 +135,16 @@ def test_kernel_derivative_methods_glue(kind):
         got = ka.d01kj(x1, x2, p, J1, J2)
         want = R.d01kj(kind, x1[:, dims], x2[:, dims], ell, J1[:, dims, :], J2[:, dims, :])
         assert np.max(np.abs(got - want)) < 1e-12
-        with pytest.raises(NotImplementedError):
-            ka.d0k(x1, x2, p)
+        # jacobian-free forms with active_dims: exact zeros for the inactive features (test_kernels.py:551-580)
+        a0 = ka.d0k(x1, x2, p).reshape(n1, nf, n2)
+        assert np.all(a0[:, [1, 3], :] == 0.0) and np.max(np.abs(a0[:, dims, :].reshape(n1 * 2, n2)
+                                                                  - cls().d0k(x1[:, dims], x2[:, dims], p))) < 1e-12
+        a1 = ka.d1k(x1, x2, p).reshape(n1, n2, nf)
+        assert np.all(a1[:, :, [1, 3]] == 0.0)
+        a01 = ka.d01k(x1, x2, p).reshape(n1, nf, n2, nf)
+        assert np.all(a01[:, [1, 3]] == 0.0) and np.all(a01[:, :, :, [1, 3]] == 0.0)
+        assert np.max(np.abs(a01[:, dims][:, :, :, dims].reshape(n1 * 2, n2 * 2)
+                             - cls().d01k(x1[:, dims], x2[:, dims], p))) < 1e-12
         with pytest.raises(NotImplementedError):
             K.Matern32().d01kj(x1, x2, p, J1, J2)
         with pytest.raises(NotImplementedError):
