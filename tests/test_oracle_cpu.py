@@ -570,3 +570,45 @@ def test_notebook_anchor_map_estimate():
     res = minimize(loss_grad, R.inverse_softplus(np.array([2.0, 1.0])), jac=True, method="L-BFGS-B")
     ell, sig = R.softplus(res.x)
     assert abs(ell - a["lengthscale"]) < 2e-5 and abs(sig - a["sigma"]) < 1e-4
+
+
+def test_two_level_inverse_cdf_search_equals_the_sequential_one():
+    """Documented deviation (iii) of the device RPCholesky: the pivot draw is located by a
+    two-level search -- 1024-row block sums, then a scan inside the chosen block (csrc/rpchol.cu: rp_pivot_l1 / l2) --
+    instead of searchsorted on one sequential cumsum (approximations.py:100-105).  Both count the entries of the same
+    CDF below r = cum[-1] (1 - u); they can differ only when r falls within rounding distance (~1e-16) of a CDF step.
+    Restated here in NumPy and compared over many diagonals and draws: identical picks."""
+    rng = np.random.default_rng(0)
+    BLK = 1024
+    trials = mismatches = 0
+    for n in (1, 5, 1023, 1024, 1025, 5000, 40_000):
+        for _ in range(12):
+            diag = rng.uniform(0.0, 1.0, n) ** rng.integers(1, 6)  # heavy and light tails
+            if n > 10:
+                diag[rng.integers(0, n, n // 10)] = 0.0  # exhausted rows, as late in the pivot loop
+            if diag.sum() == 0.0:
+                continue
+            us = rng.uniform(0.0, 1.0, 300)
+            # sequential reference (the oracle's choice_p)
+            prob = diag / diag.sum()
+            cum = np.cumsum(prob)
+            ref = np.minimum(np.searchsorted(cum, cum[-1] * (1.0 - us), side="left"), n - 1)
+            # two-level scheme
+            nblk = -(-n // BLK)
+            pad = np.zeros(nblk * BLK)
+            pad[:n] = diag
+            bs = pad.reshape(nblk, BLK).sum(axis=1)
+            total = bs.sum()
+            bcum = np.cumsum(bs / total)
+            rr = bcum[-1] * (1.0 - us)
+            bstar = np.minimum(np.sum(bcum[None, :] < rr[:, None], axis=1), nblk - 1)
+            prefix = np.where(bstar > 0, bcum[np.maximum(bstar - 1, 0)], 0.0)
+            got = np.empty_like(ref)
+            for k in range(us.size):
+                b = bstar[k]
+                pv = np.cumsum(pad[b * BLK:(b + 1) * BLK] / total) + prefix[k]
+                nin = min(BLK, n - b * BLK)
+                got[k] = b * BLK + min(int(np.sum(pv[:nin] < rr[k])), nin - 1)
+            trials += us.size
+            mismatches += int(np.sum(got != ref))
+    assert trials > 20_000 and mismatches == 0, (trials, mismatches)
