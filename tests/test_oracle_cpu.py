@@ -612,3 +612,31 @@ def test_two_level_inverse_cdf_search_equals_the_sequential_one():
             trials += us.size
             mismatches += int(np.sum(got != ref))
     assert trials > 20_000 and mismatches == 0, (trials, mismatches)
+
+
+@pytest.mark.parametrize("kind", ["se", "m12", "m32", "m52"])
+def test_exact_diagonal_deviation_is_far_below_the_parity_tolerance(kind):
+    """Documented deviation (i) of the device Gram kernel: on the diagonal of a symmetric kernel
+    matrix it uses d2 = 1e-12 exactly, while the reference's GEMM trick leaves cancellation noise ~1e-16 |z|^2 there
+    (amplified ~5e5 x through sqrt for Matern-1/2).  Effect on the LML, measured with the oracle on
+    inputs with large |z| (worst case): orders of magnitude below the 1e-8 tolerance."""
+    rng = np.random.default_rng(0)
+    n = 300
+    x = 30.0 + rng.standard_normal((n, 6))  # |x/ell|^2 ~ 2000: large cancellation in x.x - 2 x.x' + x'.x'
+    y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((n, 1))
+    ell, sigma = 1.6, 0.2
+    K = R.kernel(kind, x, x, ell)
+    noise = np.max(np.abs(np.diag(K) - R.kernel(kind, np.zeros((1, 6)), np.zeros((1, 6)), ell)[0, 0]))
+    Kx = K.copy()
+    Kx[np.diag_indices(n)] = R.kernel(kind, np.zeros((1, 6)), np.zeros((1, 6)), ell)[0, 0]
+
+    def lml(Kmat):
+        import scipy.linalg as sla
+
+        r = y - np.mean(y)
+        L = sla.cholesky(Kmat + (sigma**2 + 1e-10) * np.eye(n), lower=True)
+        cy = sla.solve_triangular(L, r, lower=True)
+        return (-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - n * 0.5 * np.log(2 * np.pi)) / n
+
+    a, b = lml(K), lml(Kx)
+    assert abs(a - b) < (1e-9 if kind == "m12" else 1e-12) * abs(a), (noise, a, b)
