@@ -39,13 +39,23 @@ class Kernel:
         return float(ell)
 
     def k(self, x1, x2, params, as_numpy: bool = True):
-        """Kernel matrix k(x1, x2) (gpx/kernels/kernels.py:760-769 et al.)."""
+        """Kernel matrix k(x1, x2) (gpx/kernels/kernels.py:760-769 et al.).  A length-D lengthscale (one per active
+        feature) is accepted HERE ONLY, as in the reference, where it broadcasts in x / lengthscale for `.k` while the
+        derivative kernels and the models assume a scalar: the inputs are pre-scaled."""
         from . import ops
 
         same = x2 is x1
         d1 = _to_device(self._slice(x1))
         d2 = d1 if same else _to_device(self._slice(x2))
-        out = ops.gram(self.kind, d1, d2, self.lengthscale(params))
+        ell = np.asarray(params["lengthscale"].value, dtype=np.float64)
+        if ell.shape == ():
+            out = ops.gram(self.kind, d1, d2, float(ell))
+        else:
+            if ell.shape != (d1.shape[1],):
+                raise ValueError(f"lengthscale of shape {ell.shape} does not match {d1.shape[1]} active features")
+            inv = _to_device(1.0 / ell)
+            s1 = (d1 * inv).contiguous()
+            out = ops.gram(self.kind, s1, s1 if same else (d2 * inv).contiguous(), 1.0)
         return out.cpu().numpy() if as_numpy else out
 
     def k_device(self, x1d, x2d, params):

@@ -254,3 +254,31 @@ def test_map_estimate_notebook_anchor_through_the_facade():
         m.fit(x, y)
     assert abs(float(m.state.params["kernel_params"]["lengthscale"].value) - a["lengthscale"]) < 2e-5
     assert abs(float(m.state.params["sigma"].value) - a["sigma"]) < 1e-4
+
+
+def test_vector_lengthscale_in_kernel_k_only():
+    """A per-feature lengthscale broadcasts in Kernel.k (as x / lengthscale does in the reference) and is refused by
+    the models, which assume the reference's default scalar."""
+    import numpy as np
+
+    import gpx_b200.kernels as K
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.models import GPR
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.priors import GammaPrior
+    from oracle import ref_numpy as R
+
+    rng = np.random.default_rng(0)
+    x1, x2 = rng.standard_normal((9, 3)), rng.standard_normal((4, 3))
+    ell = np.array([0.7, 1.9, 3.1])
+    p = {"lengthscale": Parameter(ell, True, Softplus(), GammaPrior(shape=(3,)))}
+    with patched():
+        for kind, cls in (("se", K.SquaredExponential), ("m52", K.Matern52)):
+            got = cls().k(x1, x2, p)
+            assert np.max(np.abs(got - R.kernel(kind, x1 / ell, x2 / ell, 1.0))) < 1e-14
+            sym = cls().k(x1, x1, p)
+            assert np.max(np.abs(sym - R.kernel(kind, x1 / ell, x1 / ell, 1.0))) < 1e-12
+        with pytest.raises(ValueError):
+            K.SquaredExponential(active_dims=[0, 1]).k(x1, x2, p)
+        with pytest.raises(NotImplementedError):
+            GPR(K.SquaredExponential(), kernel_params=p).log_marginal_likelihood(x1, rng.standard_normal((9, 1)))
