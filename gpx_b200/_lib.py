@@ -26,6 +26,8 @@ SIGNATURES = {
     "gpxb_ctx_launches": (C.c_ulonglong, [C.c_void_p]),
     "gpxb_prof_enable": (_int, [C.c_void_p, _int]),
     "gpxb_prof_collect": (_int, [C.c_void_p, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_int)]),
+    "gpxb_phase_enable": (_int, [C.c_void_p, _int]),
+    "gpxb_phase_collect": (_int, [C.c_void_p, C.POINTER(_dbl), C.POINTER(_int), _int]),
     "gpxb_gram": (_int, [C.c_void_p, _int, _c_dp, _int, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _ll, _int, C.c_void_p]),
     "gpxb_gemm": (_int, [C.c_void_p, _int, _int, _int, _int, _int, _dbl, _c_dp, _ll, _c_dp, _ll, _dbl, _c_dp, _ll, _int, C.c_void_p]),
     "gpxb_potrf_inv_size": (C.c_size_t, [_int]),

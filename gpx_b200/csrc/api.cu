@@ -106,6 +106,31 @@ int gpxb_prof_collect(gpxb_ctx* ctx_, double* total_ms, double* total_flops, int
   return 0;
 }
 
+int gpxb_phase_enable(gpxb_ctx* ctx, int on) {
+  GPXB_ARG_CHECK(ctx != nullptr, -1);
+  reinterpret_cast<Ctx*>(ctx)->phase_prof = (on != 0);
+  return 0;
+}
+
+int gpxb_phase_collect(gpxb_ctx* ctx_, double* ms_out, int* count_out, int n) {
+  GPXB_ARG_CHECK(ctx_ && ms_out && count_out && n >= 1, -1);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  GPXB_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < n; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  for (auto& r : ctx->phase_recs) {
+    float t = 0.f;
+    if (r.id >= 0 && r.id < n && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      ms_out[r.id] += t * r.weight;
+      count_out[r.id]++;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->phase_recs.clear();
+  (void)cudaGetLastError();
+  return 0;
+}
+
 unsigned long long gpxb_ctx_launches(gpxb_ctx* ctx) {
   return ctx ? reinterpret_cast<Ctx*>(ctx)->launches : 0ULL;
 }

@@ -17,7 +17,9 @@ struct Nccl {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -44,7 +46,9 @@ int load_nccl() {
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce")
-  SYM(Broadcast, "ncclBroadcast")
+  SYM(AllGather, "ncclAllGather")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
   SYM(GroupStart, "ncclGroupStart")
   SYM(GroupEnd, "ncclGroupEnd")
   SYM(GetErrorString, "ncclGetErrorString")
@@ -95,6 +99,7 @@ int comm_destroy(Ctx* ctx) {
 
 int comm_allreduce_sum(Ctx* ctx, double* buf, size_t count, cudaStream_t s) {
   if (ctx->world <= 1) return 0;
+  PhaseScope ph(ctx, PH_ALLREDUCE, s);
   NCCL_CHECK(g.AllReduce(buf, buf, count, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
   return 0;
 }
@@ -105,28 +110,42 @@ int comm_allreduce_sum2(Ctx* ctx, const double* send, double* recv, size_t count
       GPXB_CUDA_CHECK(cudaMemcpyAsync(recv, send, sizeof(double) * count, cudaMemcpyDeviceToDevice, s));
     return 0;
   }
+  PhaseScope ph(ctx, PH_ALLREDUCE, s);
   NCCL_CHECK(g.AllReduce(send, recv, count, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
   return 0;
 }
 
+// The row partition is 1024-row aligned, so shards may differ by one 1024-row chunk.  Equal shards: one in-place
+// ncclAllGather.  Unequal shards: the "all-gather-v" pattern, every rank sends its rows to every peer and receives
+// theirs, all transfers of one call fused into a single NCCL group (one kernel; over NVSwitch every pair has its own
+// full-bandwidth path, so the transfers run concurrently).
 int comm_allgather_rows(Ctx* ctx, const double* local, double* all, int n_loc, int PS, cudaStream_t s) {
   if (ctx->world <= 1) return 0;
-  // unequal row counts: one broadcast per owner, grouped into a single launch
-  long long N = 0;
-  // every rank derives the same partition from the global row count, which is the sum of
-  // n_loc over ranks; callers pass consistent shards, so recompute from shard_begin
-  // (N is recovered by the caller-side convention: ctx->shard_N)
-  N = ctx->shard_N;
-  NCCL_CHECK(g.GroupStart());
-  for (int r = 0; r < ctx->world; ++r) {
-    const long long b = shard_begin(N, ctx->world, r), e = shard_begin(N, ctx->world, r + 1);
-    const size_t cnt = (size_t)(e - b) * PS;
-    if (cnt == 0) continue;
-    const void* src = (r == ctx->rank) ? (const void*)local : (const void*)(all + b * PS);
-    NCCL_CHECK(g.Broadcast(src, all + b * PS, cnt, ncclFloat64, r, (ncclComm_t)ctx->nccl_comm, s));
+  PhaseScope ph(ctx, PH_ALLGATHER, s);
+  const long long N = ctx->shard_N;  // every rank derives the same partition from the global row count
+  const int W = ctx->world, me = ctx->rank;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  const long long b_me = shard_begin(N, W, me), e_me = shard_begin(N, W, me + 1);
+  GPXB_ARG_CHECK(e_me - b_me == (long long)n_loc, -50);
+  bool equal = true;
+  for (int r = 0; r < W; ++r) equal = equal && (shard_begin(N, W, r + 1) - shard_begin(N, W, r) == e_me - b_me);
+  double* mine = all + b_me * PS;
+  if (local != mine)
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(mine, local, sizeof(double) * (size_t)n_loc * PS, cudaMemcpyDeviceToDevice, s));
+  if (equal) {
+    NCCL_CHECK(g.AllGather(mine, all, (size_t)n_loc * PS, ncclFloat64, comm, s));
+    return 0;
   }
-  NCCL_CHECK(g.GroupEnd());
-  (void)n_loc;
+  ncclResult_t rc = g.GroupStart();
+  for (int k = 1; k < W && rc == 0; ++k) {
+    const int to = (me + k) % W, from = (me - k + W) % W;
+    const long long bf = shard_begin(N, W, from), ef = shard_begin(N, W, from + 1);
+    if (n_loc > 0) rc = g.Send(mine, (size_t)n_loc * PS, ncclFloat64, to, comm, s);
+    if (rc == 0 && ef > bf) rc = g.Recv(all + bf * PS, (size_t)(ef - bf) * PS, ncclFloat64, from, comm, s);
+  }
+  const ncclResult_t rc_end = g.GroupEnd();  // always closed, also on the error path
+  NCCL_CHECK(rc);
+  NCCL_CHECK(rc_end);
   return 0;
 }
 

@@ -81,6 +81,46 @@ struct Ctx {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   long long shard_N = 0;  // global row count of the sharded problem in flight
+  // optional per-phase timing of the row-sharded paths (bench.py "phases"): event pairs per phase id
+  bool phase_prof = false;
+  double phase_weight = 1.0;  // a loop that brackets only every k-th iteration records with weight k
+  struct PhaseRec { cudaEvent_t e0, e1; int id; double weight; };
+  std::vector<PhaseRec> phase_recs;
+};
+
+// Phase ids of gpxb_phase_collect (include/gpxb200.h lists the same names).
+enum Phase {
+  PH_MATVEC = 0,      // matrix-free block mat-vec (+ its column-split reduction)
+  PH_ALLGATHER = 1,   // all-gather of the N x P vector block (NCCL; includes waiting for the slowest rank)
+  PH_DOTS = 2,        // column dot products / norms (local partial sums)
+  PH_ALLREDUCE = 3,   // every all-reduce (NCCL; includes waiting for the slowest rank)
+  PH_VECOPS = 4,      // axpy / normalise / copy passes over the local vector blocks
+  PH_RP_PIVOT = 5,    // RPCholesky: draw + inverse-CDF search + pivot row gather
+  PH_RP_COLUMN = 6,   // RPCholesky: fused kernel column / GEMV / diagonal update
+  PH_SGPR_CHUNK = 7,  // SGPR: per-chunk K_nm block, TRSM against L_m, SYRK into B (streams overlap)
+  PH_POTRF_REPL = 8,  // SGPR: replicated M x M Cholesky factorisations (K_mm and B) and the final solves
+  PH_PRECOND = 9,     // PCG: preconditioner application
+  PH_COUNT = 16
+};
+
+// Brackets the work enqueued on stream s during its lifetime with a CUDA event pair when phase profiling is on.
+struct PhaseScope {
+  Ctx* ctx;
+  cudaStream_t s;
+  int idx = -1;
+  PhaseScope(Ctx* c, int id, cudaStream_t stream) : ctx(c), s(stream) {
+    if (!c || !c->phase_prof) return;
+    Ctx::PhaseRec r{nullptr, nullptr, id, c->phase_weight};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, s);
+    idx = (int)c->phase_recs.size();
+    c->phase_recs.push_back(r);
+  }
+  ~PhaseScope() {
+    if (idx >= 0) cudaEventRecord(ctx->phase_recs[idx].e1, s);
+  }
+  PhaseScope(const PhaseScope&) = delete;
+  PhaseScope& operator=(const PhaseScope&) = delete;
 };
 
 // Stream-ordered scratch buffer (RAII). alloc() returns 0 or a CUDA error code.

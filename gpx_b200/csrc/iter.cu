@@ -127,11 +127,14 @@ __global__ void rademacher_kernel(uint32_t k0, uint32_t k1, long long Ntot, int 
 int coldot(Ctx* ctx, const double* X, const double* Y, int n, int PS, int P, double* part, double* out,
            cudaStream_t s) {
   const int nblk = ceil_div(n, RB);
-  coldot_partial_kernel<<<nblk, 256, 0, s>>>(X, Y, n, PS, P, part);
-  GPXB_LAUNCH_CHECK();
-  coldot_final_kernel<<<1, 1024, 0, s>>>(part, nblk, out);
-  GPXB_LAUNCH_CHECK();
-  ctx->launches += 2;
+  {
+    PhaseScope ph(ctx, PH_DOTS, s);
+    coldot_partial_kernel<<<nblk, 256, 0, s>>>(X, Y, n, PS, P, part);
+    GPXB_LAUNCH_CHECK();
+    coldot_final_kernel<<<1, 1024, 0, s>>>(part, nblk, out);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches += 2;
+  }
   return comm_allreduce_sum(ctx, out, MAXP, s);  // no-op on one GPU
 }
 
@@ -164,22 +167,27 @@ int lanczos_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const
     double* vj = vecs + blk * j;
     GPXB_TRY(apply(vj, W));                                      // w = A v_j
     GPXB_TRY(coldot(ctx, W, vj, n_loc, PS, P, part, alpha, s));  // alpha = w . v_j
-    colaxpy_kernel<<<nblk_e, nthr, 0, s>>>(W, alpha, vj, beta, j > 0 ? vecs + blk * (j - 1) : nullptr, n_loc, PS,
-                                           P);                  // w -= alpha v_j + beta v_{j-1}
-    GPXB_LAUNCH_CHECK();
-    ctx->launches++;
+    {
+      PhaseScope ph(ctx, PH_VECOPS, s);
+      colaxpy_kernel<<<nblk_e, nthr, 0, s>>>(W, alpha, vj, beta, j > 0 ? vecs + blk * (j - 1) : nullptr, n_loc, PS,
+                                             P);                  // w -= alpha v_j + beta v_{j-1}
+      GPXB_LAUNCH_CHECK();
+      ctx->launches++;
+    }
     if (j > 0) {
       // full re-orthogonalisation, modified Gram-Schmidt in column order (lanczos.py:29-37);
       // columns beyond j are still zero in the reference and are skipped
       for (int c = 0; c <= j; ++c) {
         const double* vc = vecs + blk * c;
         GPXB_TRY(coldot(ctx, W, vc, n_loc, PS, P, part, coef, s));
+        PhaseScope ph(ctx, PH_VECOPS, s);
         colaxpy_kernel<<<nblk_e, nthr, 0, s>>>(W, coef, vc, nullptr, nullptr, n_loc, PS, P);
         GPXB_LAUNCH_CHECK();
         ctx->launches++;
       }
     }
     GPXB_TRY(coldot(ctx, W, W, n_loc, PS, P, part, nrm2, s));
+    PhaseScope ph(ctx, PH_VECOPS, s);
     store_ab_kernel<<<1, MAXP, 0, s>>>(alpha, nrm2, P, m, j, alpha_out, beta_out, beta);
     GPXB_LAUNCH_CHECK();
     ctx->launches++;
@@ -502,11 +510,14 @@ struct VecOps {
   int n;
   int dot(const double* x, int sx, const double* y, int sy, double* out) {
     const int nblk = ceil_div(n, 1024);
-    vdot_partial_kernel<<<nblk, 256, 0, s>>>(x, sx, y, sy, n, part);
-    GPXB_LAUNCH_CHECK();
-    vsum_final_kernel<<<1, 1024, 0, s>>>(part, nblk, out);
-    GPXB_LAUNCH_CHECK();
-    ctx->launches += 2;
+    {
+      PhaseScope ph(ctx, PH_DOTS, s);
+      vdot_partial_kernel<<<nblk, 256, 0, s>>>(x, sx, y, sy, n, part);
+      GPXB_LAUNCH_CHECK();
+      vsum_final_kernel<<<1, 1024, 0, s>>>(part, nblk, out);
+      GPXB_LAUNCH_CHECK();
+      ctx->launches += 2;
+    }
     return comm_allreduce_sum(ctx, out, 1, s);
   }
 };
@@ -571,6 +582,7 @@ int pcg_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const dou
       GPXB_CUDA_CHECK(cudaMemcpyAsync(out, in, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, s));
       return 0;
     }
+    PhaseScope ph(ctx, PH_PRECOND, s);
     ftz_kernel<<<k, 1024, 0, s>>>(F, ldf, n_loc, in, t1);
     GPXB_LAUNCH_CHECK();
     GPXB_TRY(comm_allreduce_sum(ctx, t1, k, s));

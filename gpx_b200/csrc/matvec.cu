@@ -343,6 +343,7 @@ int v_padded_stride(int P) {
 
 int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   if (a.n_rows <= 0) return 0;
+  PhaseScope ph(ctx, PH_MATVEC, s);
   GPXB_ARG_CHECK(a.P >= 1 && a.P <= 32, -20);
   GPXB_ARG_CHECK(a.PS % 8 == 2 && a.PS >= 2 && a.PS <= 34, -21);
   GPXB_ARG_CHECK(a.PS >= a.P || a.P > 0, -22);

@@ -375,16 +375,29 @@ static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, l
   }();
   GPXB_CUDA_CHECK(cudaFuncSetAttribute(one_cta ? rp_column_kernel<1> : rp_column_kernel<2>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(double) * (M + zl.S)));
+  // phase profiling brackets every 16th pivot only (weight 16): thousands of event pairs would perturb the loop
+  struct PhaseSampling {
+    Ctx* c; bool on; double w;
+    explicit PhaseSampling(Ctx* ctx) : c(ctx), on(ctx->phase_prof), w(ctx->phase_weight) {}
+    ~PhaseSampling() { c->phase_prof = on; c->phase_weight = w; }
+  } sampling(ctx);
+  const int every = M >= 64 ? 16 : 1;
+  ctx->phase_weight = every;
   for (int i = 0; i < M; ++i) {
+    ctx->phase_prof = sampling.on && (i % every == 0);
     if (multi) GPXB_TRY(comm_allreduce_sum2(ctx, st.bs_local, bBs.as<double>(), nblk, s));
-    rp_pivot_l1_kernel<<<1, BLK, 0, s>>>(st);
-    GPXB_LAUNCH_CHECK();
-    rp_pivot_l2_kernel<<<1, BLK, 0, s>>>(st, i);
-    GPXB_LAUNCH_CHECK();
+    {
+      PhaseScope ph(ctx, PH_RP_PIVOT, s);
+      rp_pivot_l1_kernel<<<1, BLK, 0, s>>>(st);
+      GPXB_LAUNCH_CHECK();
+      rp_pivot_l2_kernel<<<1, BLK, 0, s>>>(st, i);
+      GPXB_LAUNCH_CHECK();
+    }
     if (multi) GPXB_TRY(comm_allreduce_sum(ctx, st.pbuf, 2 + zl.S + i, s));
     ctx->launches += 2;
     if (gen) GPXB_TRY((*gen)(st.pbuf, s));
     if (nblk_loc > 0) {
+      PhaseScope ph(ctx, PH_RP_COLUMN, s);
       if (one_cta) rp_column_kernel<1><<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
       else rp_column_kernel<2><<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
       GPXB_LAUNCH_CHECK();

@@ -68,14 +68,15 @@ int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, lo
   GPXB_CUDA_CHECK(cudaMemsetAsync(scal, 0, sizeof(double) * 16, s));
 
   // L_m = chol(K_mm + 1e-10 I)
-  GPXB_TRY(prep_z(ctx, x_locs, D, M, zl, ell, Zl, s));
   {
+    PhaseScope ph(ctx, PH_POTRF_REPL, s);
+    GPXB_TRY(prep_z(ctx, x_locs, D, M, zl, ell, Zl, s));
     GramArgs g;
     g.kind = kind; g.Z1 = Zl; g.n1 = M; g.Z2 = Zl; g.n2 = M; g.zl = zl; g.ell = ell;
     g.diag_add = 1e-10; g.sym = 1; g.lower_only = 1; g.out = Kmm; g.ldo = M;
     GPXB_TRY(gram_launch(ctx, g, s));
+    GPXB_TRY(potrf_lower(ctx, Kmm, M, M, inv, s));
   }
-  GPXB_TRY(potrf_lower(ctx, Kmm, M, M, inv, s));
 
   cudaStream_t st[3] = {s, ctx->aux[0], ctx->aux[1]};
   if (NS > 1) {
@@ -92,6 +93,7 @@ int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, lo
     double* Zc = bZc.as<double>() + (size_t)k * nc_max * zl.S;
     double* Kc = bKc.as<double>() + (size_t)k * nc_max * M;
     double* rc = bRc.as<double>() + (size_t)k * nc_max * T;
+    PhaseScope ph(ctx, PH_SGPR_CHUNK, sk);
     GPXB_TRY(prep_z(ctx, x + (long long)r0 * D, D, nc, zl, ell, Zc, sk));
     {
       GramArgs g;  // Kc = K(x_chunk, x_locs)  [nc x M]
@@ -141,6 +143,7 @@ int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, lo
     GPXB_TRY(comm_allreduce_sum(ctx, v, (size_t)M * T, s));
     GPXB_TRY(comm_allreduce_sum(ctx, scal, 1, s));
   }
+  PhaseScope ph(ctx, PH_POTRF_REPL, s);
   add_diag_kernel<<<ceil_div(M, 256), 256, 0, s>>>(B, M, M, s2);
   GPXB_LAUNCHED(ctx);
   GPXB_TRY(potrf_lower(ctx, B, M, M, bInvB.as<double>(), s));

@@ -805,5 +805,26 @@ def prof_collect():
     return ms.value, fl.value, n.value
 
 
+PHASES = ("matvec", "allgather", "dots", "allreduce", "vecops", "rp_pivot", "rp_column", "sgpr_chunk", "potrf_repl",
+          "precond")
+
+
+def phase_enable(on) -> None:
+    """Bracket the phases of the row-sharded paths with CUDA events (measurement aid, see include/gpxb200.h)."""
+    ctx = context()
+    check(ctx.lib.gpxb_phase_enable(ctx.handle, int(bool(on))), "gpxb_phase_enable")
+
+
+def phase_collect() -> dict:
+    """{phase name: (summed ms, brackets)} since phase_enable(True); synchronises the device."""
+    import ctypes
+
+    ctx = context()
+    n = 16
+    ms, cnt = (ctypes.c_double * n)(), (ctypes.c_int * n)()
+    check(ctx.lib.gpxb_phase_collect(ctx.handle, ms, cnt, n), "gpxb_phase_collect")
+    return {name: (ms[i], cnt[i]) for i, name in enumerate(PHASES) if cnt[i]}
+
+
 def launches() -> int:
     return _lib.context().launches()

@@ -49,6 +49,26 @@ unsigned long long gpxb_ctx_launches(gpxb_ctx* ctx);
 int gpxb_prof_enable(gpxb_ctx* ctx, int on);
 int gpxb_prof_collect(gpxb_ctx* ctx, double* total_ms, double* total_flops, int* n_launches);
 
+/* Measurement aid for the row-sharded paths (bench.py "phases"): while enabled, the phases of gpxb_lanczos,
+ * gpxb_gpr_fit_iter, gpxb_rpcholesky and gpxb_sgpr_lml are bracketed by CUDA events on the stream they run on;
+ * collect synchronises the device and returns, per phase id, the summed durations (ms) and the number of brackets,
+ * then clears the records.  Collective phases include the time spent waiting for the slowest rank. */
+enum {
+  GPXB_PH_MATVEC = 0,     /* matrix-free block mat-vec */
+  GPXB_PH_ALLGATHER = 1,  /* all-gather of the N x P vector block */
+  GPXB_PH_DOTS = 2,       /* local column dot products / norms */
+  GPXB_PH_ALLREDUCE = 3,  /* every all-reduce */
+  GPXB_PH_VECOPS = 4,     /* axpy / normalise passes over the local vector blocks */
+  GPXB_PH_RP_PIVOT = 5,   /* RPCholesky: draw, inverse-CDF search, pivot row gather */
+  GPXB_PH_RP_COLUMN = 6,  /* RPCholesky: fused kernel column / GEMV / diagonal update */
+  GPXB_PH_SGPR_CHUNK = 7, /* SGPR: K_nm block, TRSM against L_m, SYRK into B (the chunk streams overlap) */
+  GPXB_PH_POTRF_REPL = 8, /* SGPR: replicated M x M factorisations and final solves */
+  GPXB_PH_PRECOND = 9,    /* PCG: preconditioner application */
+  GPXB_PH_COUNT = 16
+};
+int gpxb_phase_enable(gpxb_ctx* ctx, int on);
+int gpxb_phase_collect(gpxb_ctx* ctx, double* ms_out, int* count_out, int n);
+
 /* ---- Family 1: fused kernel-matrix construction ------------------------------------- */
 /* out[n1 x n2] (ld ldo) = k(x1, x2) + diag_add * I.  Replaces Kernel.k -> squared_distances +
  * nonlinearity (gpx/utils.py:55-72, gpx/kernels/kernels.py:751-757, 922-927, 966-971, 1050-1055)

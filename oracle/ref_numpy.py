@@ -537,6 +537,48 @@ def lml_grad_dense(kind, x, y, ell, sigma, mean_function=data_mean, threads=1):
     return lml, g_ell, g_sigma
 
 
+def lml_grad_dense_lowmem(kind, x, y, ell, sigma, mean_function=data_mean, threads=1, timings=None):
+    """lml_grad_dense for sizes where its temporaries do not fit in host memory (N = 32768: K, dK, A, L,
+    A^-1, its mirrored copy and W would need ~60 GB).  Same algorithm and the same arithmetic per entry
+    (_gpr.py:737-769); the differences are storage only: the noise is added on K's diagonal in
+    place, LAPACK's dpotrf / dpotri overwrite that buffer (through its transposed view, which is
+    Fortran-contiguous), and sum(W o dK) is accumulated in row blocks over the lower triangle
+    (W and dK are symmetric).  Peak memory: two N x N matrices.  Equal to lml_grad_dense to ~1e-14
+    relative (tests/test_oracle_cpu.py).  `timings` (dict) receives the seconds spent per phase."""
+    import time
+
+    m = y.shape[0]
+    mu = mean_function(y)
+    r = y - mu
+    t0 = time.perf_counter()
+    K, dK = kernel_dl(kind, x, x, ell) if threads <= 1 else kernel_dl_threaded(kind, x, x, ell, threads)
+    K[np.diag_indices(m)] += sigma**2 + 1e-10
+    t1 = time.perf_counter()
+    # K is symmetric: its transposed view is Fortran-contiguous, so LAPACK factorises in place
+    L = sla.cholesky(K.T, lower=True, overwrite_a=True, check_finite=False)
+    t2 = time.perf_counter()
+    cy = sla.solve_triangular(L, r, lower=True, check_finite=False)
+    lml = (-0.5 * np.sum(cy**2) - np.sum(np.log(np.diag(L))) - m * 0.5 * np.log(2.0 * np.pi)) / m
+    alpha = sla.solve_triangular(L, cy, lower=True, trans="T", check_finite=False).reshape(m, -1)
+    t3 = time.perf_counter()
+    Ainv, info = sla.lapack.dpotri(L, lower=1, overwrite_c=1)  # lower triangle of A^-1, in place
+    t4 = time.perf_counter()
+    acc, tr = 0.0, 0.0
+    step = 1024
+    for i0 in range(0, m, step):
+        i1 = min(m, i0 + step)
+        Wb = alpha[i0:i1] @ alpha[:i1].T - Ainv[i0:i1, :i1]  # rows i0..i1 of W, columns 0..i1
+        Wb *= dK[i0:i1, :i1]
+        d = np.diagonal(Wb[:, i0:i1]).copy()
+        blk = np.tril(Wb[:, i0:i1], -1)
+        acc += 2.0 * (np.sum(Wb[:, :i0]) + np.sum(blk)) + np.sum(d)
+        tr += np.sum(np.sum(alpha[i0:i1] ** 2, axis=1) - np.diagonal(Ainv)[i0:i1])
+    t5 = time.perf_counter()
+    if timings is not None:
+        timings.update(kernel=t1 - t0, potrf=t2 - t1, solves=t3 - t2, potri=t4 - t3, contraction=t5 - t4)
+    return lml, 0.5 * acc / m, sigma * tr / m
+
+
 def neg_lml_and_grad_unconstrained(kind, x, y, t_ell, t_sigma, mean_function=data_mean):
     """loss(t) and d loss/d t with Softplus bijectors on both parameters
     (optimizers/utils.py:97-131, bijectors.py:27-47)."""
