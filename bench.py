@@ -297,6 +297,22 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
         except Exception as e:  # noqa: BLE001 -- reported, never fatal for the headline
             out.append(dict(config=name, n_gpus=world, error=f"{type(e).__name__}: {e}"[:300]))
 
+    COLLECTIVE = ("allgather", "allreduce")
+
+    def non_compute(t, ph):
+        """Wall time not covered by this rank's compute brackets: collectives, waiting for the slowest rank and
+        launch gaps (robust against what an event pair around a collective can and cannot see)."""
+        return t - sum(v["ms_max_over_ranks"] for k, v in ph.items() if k not in COLLECTIVE) * 1e-3
+
+    # NCCL connects lazily: the first all-reduce / all-gather / send-recv on a communicator sets up its channels
+    # (hundreds of ms).  Run every collective pattern once at toy size, untimed, before anything is measured.
+    xw, yw = data(16384, 16, 1)
+    ops.rpcholesky("se", xw, 16, 4.0, key, True, want_factor=False)
+    ops.lanczos("se", xw, 4.0, 0.25, ops.rademacher_probes(key, 16384, 4, True), 2)
+    ops.gpr_fit_iter("se", xw, yw, 4.0, 0.5, 8, key, maxiter=2)
+    torch.cuda.synchronize()
+    del xw, yw
+
     x32, y32 = data(N, 32, 3)
     ell32 = 32**0.5
     state = {}
@@ -309,7 +325,7 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
                     bound="hbm", alg_bytes=alg, achieved_gbs_total=alg / t / 1e9, achieved_gbs_per_gpu=alg / t / 1e9 / world,
                     peak_gbs=hbm, peak_source=hbm_src, frac=alg / t / 1e9 / world / hbm,
                     pivots_head=[int(v) for v in piv[:6].cpu().tolist()],
-                    pivots_checksum=int(piv.sum().cpu()), phases=ph,
+                    pivots_checksum=int(piv.sum().cpu()), phases=ph, non_compute_s=non_compute(t, ph),
                     phases_note="phase events are sampled on every 16th pivot and scaled by 16")
 
     def sgpr():
@@ -343,7 +359,7 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
                     achieved_tflops_total=fl / t / 1e12, achieved_tflops_per_gpu=fl / t / 1e12 / world,
                     peak_tflops=dgemm_tflops, frac=fl / t / 1e12 / world / dgemm_tflops,
                     matvec_only_tflops_per_gpu=(fl / mv / 1e12 / world) if mv > 0 else None,
-                    alpha00=float(al[0, 0].cpu()), phases=ph)
+                    alpha00=float(al[0, 0].cpu()), phases=ph, non_compute_s=non_compute(t, ph))
 
     def pcg_iters():
         it = 3
@@ -355,7 +371,8 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
                     "pivots; the time includes building the preconditioner), rows sharded", N=N2, D=D16, iters=int(iters),
                     s=t, s_matvec_per_iter=mv / max(iters, 1), bound="tensor", alg_flops_per_iter=fl / max(iters, 1),
                     matvec_tflops_per_gpu=(fl / mv / 1e12 / world) if mv > 0 else None, peak_tflops=dgemm_tflops,
-                    frac=(fl / mv / 1e12 / world / dgemm_tflops) if mv > 0 else None, phases=ph)
+                    frac=(fl / mv / 1e12 / world / dgemm_tflops) if mv > 0 else None, phases=ph,
+                    non_compute_s=non_compute(t, ph))
 
     def lml_iter_full():
         Nf = max(4096, int(131072 * scale))
@@ -378,7 +395,8 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
                     "RPCholesky preconditioner + SLQ log-det, 30 probes x 50 Lanczos steps), rows sharded; host eigh of the "
                     "30 tridiagonals excluded", N=Nf, D=D16, P=P, m=m, pcg_iters=int(iters), s=t, evals_per_s=1.0 / t,
                     bound="tensor", alg_flops=fl, achieved_tflops_per_gpu=fl / t / 1e12 / world, peak_tflops=dgemm_tflops,
-                    frac=fl / t / 1e12 / world / dgemm_tflops, lml=lml, breakdown=int(flag.cpu()[0]), phases=ph)
+                    frac=fl / t / 1e12 / world / dgemm_tflops, lml=lml, breakdown=int(flag.cpu()[0]), phases=ph,
+                    non_compute_s=non_compute(t, ph))
 
     entry(f"configs[3] SGPR + RPCholesky, N={N} D=32 M={M}: landmark selection", rpchol)
     entry(f"configs[3] SGPR + RPCholesky, N={N} D=32 M={M}: LML", sgpr)
@@ -397,6 +415,10 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # ONE JSON line on stdout: NCCL writes its version banner to fd 1, so everything but the final line goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -599,7 +621,8 @@ def run_gpu(args):
         "clocks": clocks,
         "other_configs": extra,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -4,13 +4,17 @@
 
 #include <dlfcn.h>
 
+#include <cstdlib>
+
+#include "peer.cuh"
+
 namespace gpxb {
 
 namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8, ncclSum = 0 };
+enum { ncclUint8 = 1, ncclFloat64 = 8, ncclSum = 0 };
 struct Nccl {
   void* h = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -66,6 +70,112 @@ int load_nccl() {
   } while (0)
 }  // namespace
 
+struct PeerState {
+  PeerView view{};
+  double* local = nullptr;
+  unsigned long long seq = 0;
+};
+
+namespace {
+// all-reduce (sum, fixed rank order) of count <= PEER_SLOT doubles through the mailboxes; one CTA
+__global__ void __launch_bounds__(1024, 1) peer_allreduce_kernel(PeerView pv, double* __restrict__ buf, int count,
+                                                                 unsigned long long seq) {
+  const int par = (int)(seq & 1ULL), tid = threadIdx.x, W = pv.world, me = pv.me;
+  // publish my contribution in slot `me` of every rank's mailbox (my own included)
+  for (int r = 0; r < W; ++r) {
+    double* dst = pv.base[r] + peer_off_ar(par, me);
+    for (int i = tid; i < count; i += 1024) dst[i] = buf[i];
+  }
+  __syncthreads();
+  if (tid < W) {
+    __threadfence_system();
+    peer_st_release(peer_flags(pv.base[tid]) + peer_flag_ar(par, me), seq);
+  }
+  // wait for every rank's contribution in MY mailbox
+  if (tid < W) peer_wait(peer_flags(pv.base[me]) + peer_flag_ar(par, tid), seq);
+  __syncthreads();
+  const double* mine = pv.base[me] + peer_off_ar(par, 0);
+  for (int i = tid; i < count; i += 1024) {
+    double s = 0.0;
+    for (int r = 0; r < W; ++r) s += __ldcg(mine + (size_t)r * PEER_SLOT + i);
+    buf[i] = s;
+  }
+}
+
+// Maps every rank's mailbox.  Any failure leaves ctx->peer null (the callers then use NCCL).
+int peer_setup(Ctx* ctx) {
+  const char* e = getenv("GPXB_PEER");
+  if (e && e[0] == '0') return 0;
+  if (ctx->world > PEER_MAX_WORLD) return 0;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  const int W = ctx->world, me = ctx->rank;
+  PeerState* ps = new PeerState();
+  unsigned char* stage = nullptr;
+  cudaStream_t st = nullptr;
+  bool ok = cudaMalloc(&ps->local, peer_mailbox_bytes()) == cudaSuccess &&
+            cudaMemset(ps->local, 0, peer_mailbox_bytes()) == cudaSuccess &&
+            cudaMalloc(&stage, (size_t)W * 64) == cudaSuccess && cudaStreamCreate(&st) == cudaSuccess &&
+            cudaDeviceSynchronize() == cudaSuccess;
+  cudaIpcMemHandle_t mine, all[PEER_MAX_WORLD];
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  int have = ok && cudaIpcGetMemHandle(&mine, ps->local) == cudaSuccess ? 1 : 0;
+  if (!have) memset(&mine, 0, sizeof(mine));
+  // the exchange is collective: every rank takes part even when its own export failed (zero handle = "no")
+  if (stage && st) {
+    cudaMemcpyAsync(stage + (size_t)me * 64, &mine, 64, cudaMemcpyHostToDevice, st);
+    if (g.AllGather(stage + (size_t)me * 64, stage, 64, ncclUint8, comm, st) != 0) have = 0;
+    if (cudaMemcpyAsync(all, stage, (size_t)W * 64, cudaMemcpyDeviceToHost, st) != cudaSuccess) have = 0;
+    if (cudaStreamSynchronize(st) != cudaSuccess) have = 0;
+  } else {
+    have = 0;
+  }
+  ps->view.world = W;
+  ps->view.me = me;
+  for (int r = 0; r < PEER_MAX_WORLD; ++r) ps->view.base[r] = nullptr;
+  cudaIpcMemHandle_t zero;
+  memset(&zero, 0, sizeof(zero));
+  for (int r = 0; r < W && have; ++r) {
+    if (r == me) { ps->view.base[r] = ps->local; continue; }
+    if (memcmp(&all[r], &zero, 64) == 0) { have = 0; break; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { have = 0; break; }
+    ps->view.base[r] = (double*)p;
+  }
+  // agree: the mailbox is used only if EVERY rank mapped every peer (sum of `have` == world)
+  double agree = have ? 1.0 : 0.0, *dagree = nullptr;
+  if (stage && st && cudaMalloc(&dagree, sizeof(double)) == cudaSuccess) {
+    cudaMemcpyAsync(dagree, &agree, sizeof(double), cudaMemcpyHostToDevice, st);
+    g.AllReduce(dagree, dagree, 1, ncclFloat64, ncclSum, comm, st);
+    cudaMemcpyAsync(&agree, dagree, sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(dagree);
+  } else {
+    agree = 0.0;
+  }
+  if (stage) cudaFree(stage);
+  if (st) cudaStreamDestroy(st);
+  (void)cudaGetLastError();
+  if ((int)(agree + 0.5) == W) {
+    ctx->peer = ps;
+  } else {
+    for (int r = 0; r < W; ++r)
+      if (r != me && ps->view.base[r]) cudaIpcCloseMemHandle(ps->view.base[r]);
+    if (ps->local) cudaFree(ps->local);
+    delete ps;
+    (void)cudaGetLastError();
+  }
+  return 0;
+}
+}  // namespace
+
+bool comm_peer_ready(const Ctx* ctx) { return ctx && ctx->peer != nullptr; }
+bool comm_peer_view(const Ctx* ctx, PeerView* v) {
+  if (!comm_peer_ready(ctx)) return false;
+  *v = reinterpret_cast<const PeerState*>(ctx->peer)->view;
+  return true;
+}
+unsigned long long comm_peer_next_seq(Ctx* ctx) { return ++reinterpret_cast<PeerState*>(ctx->peer)->seq; }
+
 int comm_unique_id(void* out) {
   GPXB_TRY(load_nccl());
   ncclUniqueId id;
@@ -86,10 +196,18 @@ int comm_init(Ctx* ctx, const void* uid, int rank, int world) {
   GPXB_CUDA_CHECK(cudaSetDevice(ctx->device));
   NCCL_CHECK(g.CommInitRank(&c, world, id, rank));
   ctx->nccl_comm = c;
-  return 0;
+  return peer_setup(ctx);
 }
 
 int comm_destroy(Ctx* ctx) {
+  if (ctx && ctx->peer) {
+    PeerState* ps = reinterpret_cast<PeerState*>(ctx->peer);
+    for (int r = 0; r < ps->view.world; ++r)
+      if (r != ps->view.me && ps->view.base[r]) cudaIpcCloseMemHandle(ps->view.base[r]);
+    cudaFree(ps->local);
+    delete ps;
+    ctx->peer = nullptr;
+  }
   if (ctx && ctx->nccl_comm) {
     g.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
@@ -100,6 +218,13 @@ int comm_destroy(Ctx* ctx) {
 int comm_allreduce_sum(Ctx* ctx, double* buf, size_t count, cudaStream_t s) {
   if (ctx->world <= 1) return 0;
   PhaseScope ph(ctx, PH_ALLREDUCE, s);
+  if (ctx->peer && count <= (size_t)PEER_SLOT) {  // latency-bound: one kernel over the peer mailboxes
+    PeerState* ps = reinterpret_cast<PeerState*>(ctx->peer);
+    peer_allreduce_kernel<<<1, 1024, 0, s>>>(ps->view, buf, (int)count, ++ps->seq);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+    return 0;
+  }
   NCCL_CHECK(g.AllReduce(buf, buf, count, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
   return 0;
 }

@@ -79,6 +79,7 @@ struct Ctx {
   struct ProfRec { cudaEvent_t e0, e1; double flops; };
   std::vector<ProfRec> prof_recs;
   void* nccl_comm = nullptr;
+  void* peer = nullptr;  // PeerState* (comm.cu): IPC-mapped mailboxes of all ranks, or null
   int rank = 0, world = 1;
   long long shard_N = 0;  // global row count of the sharded problem in flight
   // optional per-phase timing of the row-sharded paths (bench.py "phases"): event pairs per phase id

@@ -146,9 +146,29 @@ int coldot(Ctx* ctx, const double* X, const double* Y, int n, int PS, int P, dou
 //   alpha_out / beta_out: [P][m] device.  T_p = tridiag(alpha_out[p], beta_out[p][0..m-2]).
 //   flag: device int set to 1 on breakdown (beta <= 1e-12).
 // apply(v, w): w = A v for this rank's rows; v, w are n_loc x PS blocks with P live columns.
+// A "rider" shares the Lanczos block mat-vecs: while it is active, its vector travels as column P of the block
+// (put), the operator is applied to P + 1 columns in the same pass over the recomputed kernel tiles, and the
+// rider's product is handed back (take).  Used to run the first m PCG iterations of the iterative LML inside the
+// SLQ mat-vecs (a 31st column costs nothing: the tensor-core tile is 32 columns wide).
+struct LanczosRider {
+  std::function<bool()> active;
+  std::function<int(double* block, int col, int PS)> put;
+  std::function<int(const double* W, int col, int PS)> take;
+};
+
+int lanczos_core_rider(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+                       const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
+                       LanczosRider* rider, cudaStream_t s);
+
 int lanczos_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
                  const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
                  cudaStream_t s) {
+  return lanczos_core_rider(ctx, n_loc, N, apply, U, P, PS, m, alpha_out, beta_out, flag, nullptr, s);
+}
+
+int lanczos_core_rider(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+                       const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
+                       LanczosRider* rider, cudaStream_t s) {
   GPXB_ARG_CHECK(P >= 1 && P <= MAXP && m >= 1, -30);
   ctx->shard_N = N;
   const size_t blk = (size_t)n_loc * PS;
@@ -165,7 +185,10 @@ int lanczos_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const
 
   for (int j = 0; j < m; ++j) {
     double* vj = vecs + blk * j;
+    const bool ride = rider && rider->active();
+    if (ride) GPXB_TRY(rider->put(vj, P, PS));
     GPXB_TRY(apply(vj, W));                                      // w = A v_j
+    if (ride) GPXB_TRY(rider->take(W, P, PS));
     GPXB_TRY(coldot(ctx, W, vj, n_loc, PS, P, part, alpha, s));  // alpha = w . v_j
     {
       PhaseScope ph(ctx, PH_VECOPS, s);
@@ -555,29 +578,27 @@ int precond_build(Ctx* ctx, const double* F, long long ldf, int k, int n_loc, do
   return 0;
 }
 
-// Solves (K + diag_add I) x = b (b: local rows, length n_loc).  F/Pkk: preconditioner (k may be 0:
-// identity).  Host-synchronous: one scalar read per iteration for the stopping test.
-// apply(p, Ap): Ap[n_loc] = A p for this rank's rows; p is the local search direction stored with stride 2.
-int pcg_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
-             const double* b, const double* F, long long ldf, int k, const double* Pkk, double sigma, double tol,
-             double atol, int maxiter, double* x, int* iters_out, cudaStream_t s) {
+// Preconditioned CG as a resumable object: init() -> while (active()) { Ap = A p(); step(Ap); }.
+// (K + diag_add I) x = b with b the local rows (length n_loc); F / Pkk: preconditioner (k may be 0: identity).
+// Host-synchronous: one scalar read per iteration for the stopping test.  p() is the local search direction
+// stored with stride 2 (the padded single-column layout of the mat-vec).
+struct PcgRun {
+  Ctx* ctx = nullptr;
+  cudaStream_t s = nullptr;
+  int n_loc = 0, k = 0, maxiter = 0, it = 0, nb = 0;
+  const double* F = nullptr;
+  long long ldf = 0;
+  const double* Pkk = nullptr;
+  double isig2 = 0.0, atol2 = 0.0, rs = 0.0;
+  double* x = nullptr;
   DevBuf bR, bZ, bP, bAp, bPart, bSc, bT;
-  ctx->shard_N = N;
-  GPXB_TRY(bR.alloc(sizeof(double) * n_loc, s));
-  GPXB_TRY(bZ.alloc(sizeof(double) * n_loc, s));
-  GPXB_TRY(bP.alloc(sizeof(double) * ((size_t)n_loc * 2 + 16), s));
-  GPXB_TRY(bAp.alloc(sizeof(double) * n_loc, s));
-  GPXB_TRY(bPart.alloc(sizeof(double) * (ceil_div(n_loc, 1024) + 1), s));
-  GPXB_TRY(bSc.alloc(sizeof(double) * 8, s));
-  GPXB_TRY(bT.alloc(sizeof(double) * (2 * (size_t)std::max(k, 1)), s));
-  double *r = bR.as<double>(), *z = bZ.as<double>(), *p = bP.as<double>(), *Ap = bAp.as<double>();
-  double* sc = bSc.as<double>();  // [0] bs, [1] gamma, [2] pAp, [3] gamma_new, [4] rs
-  double *t1 = bT.as<double>(), *t2 = t1 + std::max(k, 1);
-  VecOps vo{ctx, s, bPart.as<double>(), n_loc};
-  const int nb = ceil_div(n_loc, 256);
-  const double isig2 = 1.0 / (sigma * sigma);
+  double *r = nullptr, *z = nullptr, *pv = nullptr, *Ap = nullptr, *sc = nullptr, *t1 = nullptr, *t2 = nullptr;
 
-  auto precond = [&](const double* in, double* out) -> int {
+  int dot(const double* a, int sa, const double* b, int sb, double* out) {
+    VecOps vo{ctx, s, bPart.as<double>(), n_loc};
+    return vo.dot(a, sa, b, sb, out);
+  }
+  int precond(const double* in, double* out) {
     if (k <= 0) {
       GPXB_CUDA_CHECK(cudaMemcpyAsync(out, in, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, s));
       return 0;
@@ -592,42 +613,88 @@ int pcg_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const dou
     GPXB_LAUNCH_CHECK();
     ctx->launches += 3;
     return 0;
-  };
-
-  GPXB_CUDA_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * n_loc, s));
-  GPXB_CUDA_CHECK(cudaMemcpyAsync(r, b, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, s));
-  GPXB_TRY(vo.dot(b, 1, b, 1, sc + 0));
-  GPXB_TRY(precond(r, z));
-  pad_copy_kernel<<<nb, 256, 0, s>>>(z, n_loc, p);
-  GPXB_LAUNCH_CHECK();
-  ctx->launches++;
-  GPXB_TRY(vo.dot(r, 1, z, 1, sc + 1));
-  double h[2];
-  GPXB_CUDA_CHECK(cudaMemcpyAsync(h, sc, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
-  GPXB_CUDA_CHECK(cudaStreamSynchronize(s));
-  const double atol2 = std::max(tol * tol * h[0], atol * atol);
-  double rs = (k <= 0) ? h[1] : h[0];  // r0 = b
-  int it = 0;
-  while (rs > atol2 && it < maxiter) {
-    GPXB_TRY(apply(p, Ap));
-    GPXB_TRY(vo.dot(p, 2, Ap, 1, sc + 2));
-    vaxpby_kernel<<<nb, 256, 0, s>>>(x, 1, p, 2, n_loc, sc + 1, sc + 2, 1.0, 1.0);    // x += alpha p
-    vaxpby_kernel<<<nb, 256, 0, s>>>(r, 1, Ap, 1, n_loc, sc + 1, sc + 2, -1.0, 1.0);  // r -= alpha Ap
-    GPXB_LAUNCH_CHECK();
-    ctx->launches += 2;
+  }
+  int init(Ctx* ctx_, int n_loc_, long long N, const double* b, const double* F_, long long ldf_, int k_,
+           const double* Pkk_, double sigma, double tol, double atol, int maxiter_, double* x_, cudaStream_t s_) {
+    ctx = ctx_; s = s_; n_loc = n_loc_; k = k_; maxiter = maxiter_; F = F_; ldf = ldf_; Pkk = Pkk_; x = x_;
+    ctx->shard_N = N;
+    GPXB_TRY(bR.alloc(sizeof(double) * n_loc, s));
+    GPXB_TRY(bZ.alloc(sizeof(double) * n_loc, s));
+    GPXB_TRY(bP.alloc(sizeof(double) * ((size_t)n_loc * 2 + 16), s));
+    GPXB_TRY(bAp.alloc(sizeof(double) * n_loc, s));
+    GPXB_TRY(bPart.alloc(sizeof(double) * (ceil_div(n_loc, 1024) + 1), s));
+    GPXB_TRY(bSc.alloc(sizeof(double) * 8, s));
+    GPXB_TRY(bT.alloc(sizeof(double) * (2 * (size_t)std::max(k, 1)), s));
+    r = bR.as<double>(); z = bZ.as<double>(); pv = bP.as<double>(); Ap = bAp.as<double>();
+    sc = bSc.as<double>();  // [0] bs, [1] gamma, [2] pAp, [3] gamma_new, [4] rs
+    t1 = bT.as<double>(); t2 = t1 + std::max(k, 1);
+    nb = ceil_div(n_loc, 256);
+    isig2 = 1.0 / (sigma * sigma);
+    GPXB_CUDA_CHECK(cudaMemsetAsync(x, 0, sizeof(double) * n_loc, s));
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(r, b, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, s));
+    GPXB_TRY(dot(b, 1, b, 1, sc + 0));
     GPXB_TRY(precond(r, z));
-    GPXB_TRY(vo.dot(r, 1, z, 1, sc + 3));
-    vxpby_kernel<<<nb, 256, 0, s>>>(p, 2, z, n_loc, sc + 3, sc + 1);  // p = z + (gn/g) p
-    GPXB_LAUNCH_CHECK();
-    ctx->launches++;
-    GPXB_TRY(vo.dot(r, 1, r, 1, sc + 4));
+    {
+      PhaseScope ph(ctx, PH_VECOPS, s);
+      pad_copy_kernel<<<nb, 256, 0, s>>>(z, n_loc, pv);
+      GPXB_LAUNCH_CHECK();
+      ctx->launches++;
+    }
+    GPXB_TRY(dot(r, 1, z, 1, sc + 1));
+    double h[2];
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(h, sc, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+    GPXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    atol2 = std::max(tol * tol * h[0], atol * atol);
+    rs = (k <= 0) ? h[1] : h[0];  // r0 = b
+    it = 0;
+    return 0;
+  }
+  bool active() const { return rs > atol2 && it < maxiter; }
+  const double* p() const { return pv; }
+  double* p_mut() { return pv; }
+  double* ap() { return Ap; }
+  // the updates of one CG iteration once Ap = A p is in ap()
+  int step() {
+    GPXB_TRY(dot(pv, 2, Ap, 1, sc + 2));
+    {
+      PhaseScope ph(ctx, PH_VECOPS, s);
+      vaxpby_kernel<<<nb, 256, 0, s>>>(x, 1, pv, 2, n_loc, sc + 1, sc + 2, 1.0, 1.0);    // x += alpha p
+      vaxpby_kernel<<<nb, 256, 0, s>>>(r, 1, Ap, 1, n_loc, sc + 1, sc + 2, -1.0, 1.0);  // r -= alpha Ap
+      GPXB_LAUNCH_CHECK();
+      ctx->launches += 2;
+    }
+    GPXB_TRY(precond(r, z));
+    GPXB_TRY(dot(r, 1, z, 1, sc + 3));
+    {
+      PhaseScope ph(ctx, PH_VECOPS, s);
+      vxpby_kernel<<<nb, 256, 0, s>>>(pv, 2, z, n_loc, sc + 3, sc + 1);  // p = z + (gn/g) p
+      GPXB_LAUNCH_CHECK();
+      ctx->launches++;
+    }
+    GPXB_TRY(dot(r, 1, r, 1, sc + 4));
+    double h[2];
     GPXB_CUDA_CHECK(cudaMemcpyAsync(sc + 1, sc + 3, sizeof(double), cudaMemcpyDeviceToDevice, s));
     GPXB_CUDA_CHECK(cudaMemcpyAsync(h, sc + 3, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
     GPXB_CUDA_CHECK(cudaStreamSynchronize(s));
     rs = (k <= 0) ? h[0] : h[1];
     ++it;
+    return 0;
   }
-  if (iters_out) *iters_out = it;
+};
+
+// Solves (K + diag_add I) x = b (b: local rows, length n_loc).  F/Pkk: preconditioner (k may be 0:
+// identity).  Host-synchronous: one scalar read per iteration for the stopping test.
+// apply(p, Ap): Ap[n_loc] = A p for this rank's rows; p is the local search direction stored with stride 2.
+int pcg_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+             const double* b, const double* F, long long ldf, int k, const double* Pkk, double sigma, double tol,
+             double atol, int maxiter, double* x, int* iters_out, cudaStream_t s) {
+  PcgRun run;
+  GPXB_TRY(run.init(ctx, n_loc, N, b, F, ldf, k, Pkk, sigma, tol, atol, maxiter, x, s));
+  while (run.active()) {
+    GPXB_TRY(apply(run.p(), run.ap()));
+    GPXB_TRY(run.step());
+  }
+  if (iters_out) *iters_out = run.it;
   return 0;
 }
 
@@ -654,6 +721,88 @@ int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, c
     return kmatvec_launch(ctx, a, s);
   };
   return pcg_core(ctx, n_loc, N, apply, b, F, ldf, k, Pkk, sigma, tol, atol, maxiter, x, iters_out, s);
+}
+
+
+namespace {
+// block[i][col] = p[2 i]   /   out[i] = W[i][col]
+__global__ void put_col_kernel(double* __restrict__ block, int PS, int col, const double* __restrict__ p, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) block[i * PS + col] = p[2 * i];
+}
+__global__ void take_col_kernel(const double* __restrict__ W, int PS, int col, double* __restrict__ out, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = W[i * PS + col];
+}
+}  // namespace
+
+// The two device parts of the iterative LML (_lml_iter, gpx/models/_gpr.py:772-821) in one sweep: the PCG solve
+// c = (K + s2 I)^-1 b (RPCholesky preconditioner F / Pkk) and the m-step block Lanczos on the P start vectors U
+// (SLQ log-det).  While both run, the PCG search direction rides as column P of the Lanczos block, so the first m
+// CG iterations cost no extra pass over the recomputed kernel tiles; the remaining iterations use the
+// single-vector mat-vec.  The arithmetic of each part is the one of pcg_solve / lanczos_block.
+int lml_iter_fused(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N, ZLayout zl,
+                   double diag_add, const double* b, const double* F, long long ldf, int k, const double* Pkk,
+                   double sigma, double tol, double atol, int maxiter, double* x, int* iters_out, const double* U,
+                   int P, int PS, int m, double* alpha_out, double* beta_out, int* flag, cudaStream_t s) {
+  GPXB_ARG_CHECK(P >= 1 && P < 32 && PS >= P + 1, -31);
+  DevBuf bVall, bPall;
+  double *Vall = nullptr, *Pall = nullptr;
+  if (ctx->world > 1) {
+    GPXB_TRY(bVall.alloc(sizeof(double) * ((size_t)N * PS + 16), s));
+    GPXB_TRY(bPall.alloc(sizeof(double) * ((size_t)N * 2 + 16), s));
+    Vall = bVall.as<double>();
+    Pall = bPall.as<double>();
+  }
+  PcgRun run;
+  GPXB_TRY(run.init(ctx, n_loc, N, b, F, ldf, k, Pkk, sigma, tol, atol, maxiter, x, s));
+  int pcols = P;  // columns of the block the operator is applied to (P + 1 while the PCG vector rides)
+  auto apply_block = [&](const double* v, double* w) -> int {
+    const double* vfull = v;
+    if (ctx->world > 1) {
+      GPXB_TRY(comm_allgather_rows(ctx, v, Vall, n_loc, PS, s));
+      vfull = Vall;
+    }
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
+    a.V = vfull; a.PS = PS; a.P = pcols; a.W = w; a.ldw = PS; a.diag_add = diag_add;
+    return kmatvec_launch(ctx, a, s);
+  };
+  const int nb = ceil_div(n_loc, 256);
+  LanczosRider rider;
+  rider.active = [&]() {
+    pcols = run.active() ? P + 1 : P;
+    return run.active();
+  };
+  rider.put = [&](double* block, int col, int ps) -> int {
+    PhaseScope ph(ctx, PH_VECOPS, s);
+    put_col_kernel<<<nb, 256, 0, s>>>(block, ps, col, run.p(), n_loc);
+    GPXB_LAUNCHED(ctx);
+    return 0;
+  };
+  rider.take = [&](const double* W, int col, int ps) -> int {
+    {
+      PhaseScope ph(ctx, PH_VECOPS, s);
+      take_col_kernel<<<nb, 256, 0, s>>>(W, ps, col, run.ap(), n_loc);
+      GPXB_LAUNCHED(ctx);
+    }
+    return run.step();
+  };
+  GPXB_TRY(lanczos_core_rider(ctx, n_loc, N, apply_block, U, P, PS, m, alpha_out, beta_out, flag, &rider, s));
+  while (run.active()) {  // the rest of the CG iterations on the single-vector mat-vec
+    const double* pfull = run.p();
+    if (ctx->world > 1) {
+      GPXB_TRY(comm_allgather_rows(ctx, run.p(), Pall, n_loc, 2, s));
+      pfull = Pall;
+    }
+    KmvArgs a;
+    a.kind = kind; a.Zr = Zr; a.n_rows = n_loc; a.row_offset = row0; a.Za = Za; a.N = N; a.zl = zl;
+    a.V = pfull; a.PS = 2; a.P = 1; a.W = run.ap(); a.ldw = 1; a.diag_add = diag_add;
+    GPXB_TRY(kmatvec_launch(ctx, a, s));
+    GPXB_TRY(run.step());
+  }
+  if (iters_out) *iters_out = run.it;
+  return 0;
 }
 
 }  // namespace gpxb

@@ -125,11 +125,15 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
   };
   if (tid == 0 && ntiles > 0) issue(0);
 
-  double w[MF][NPF][2];
+  // NPF == 0: single-vector mode (PCG).  The 8-column DMMA GEMM 2 would spend 8 tensor instructions per 8 x 8 tile
+  // of K on one useful column; instead every lane multiplies its two kernel entries by the two vector entries with
+  // plain FMAs and the four lanes of a row are combined once, after the column loop.
+  constexpr int NPA = NPF > 0 ? NPF : 1;
+  double w[MF][NPA][2];
 #pragma unroll
   for (int i = 0; i < MF; ++i)
 #pragma unroll
-    for (int j = 0; j < NPF; ++j) w[i][j][0] = w[i][j][1] = 0.0;
+    for (int j = 0; j < NPA; ++j) w[i][j][0] = w[i][j][1] = 0.0;
 
   double a1[MF][KS > 0 ? KS : 1];
   double ni[MF];
@@ -228,14 +232,23 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
         c[mf][0] = (gj < jend) ? k0 : 0.0;
         c[mf][1] = (gj + 1 < jend) ? k1 : 0.0;
       }
-      const double* vb = sV + (jf * 8 + 2 * lq) * p.PS + lr;
+      if (NPF == 0) {
+        const double v0 = sV[(jf * 8 + 2 * lq) * p.PS], v1 = sV[(jf * 8 + 2 * lq + 1) * p.PS];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        for (int mf = 0; mf < MF; ++mf) {
+          w[mf][0][0] = fma(c[mf][0], v0, w[mf][0][0]);
+          w[mf][0][1] = fma(c[mf][1], v1, w[mf][0][1]);
+        }
+      } else {
+        const double* vb = sV + (jf * 8 + 2 * lq) * p.PS + lr;
 #pragma unroll
-        for (int pf = 0; pf < NPF; ++pf) {
-          const double v = vb[h * p.PS + pf * 8];
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int mf = 0; mf < MF; ++mf) dmma884(w[mf][pf][0], w[mf][pf][1], c[mf][h], v);
+          for (int pf = 0; pf < NPA; ++pf) {
+            const double v = vb[h * p.PS + pf * 8];
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf) dmma884(w[mf][pf][0], w[mf][pf][1], c[mf][h], v);
+          }
         }
       }
     }
@@ -243,7 +256,22 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
   }
 
   // ---- write the row block (+ diag_add * V[i] from the CTA whose column range holds the diagonal) ----
-  const int pw = 8 * NPF;
+  if (NPF == 0) {
+#pragma unroll
+    for (int mf = 0; mf < MF; ++mf) {
+      double t = w[mf][0][0] + w[mf][0][1];  // fixed order: lane pair sums, then the four lanes of the row
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      const int i = row0 + warp * 8 * MF + mf * 8 + lr;
+      if (lq != 0 || i >= p.n_rows) continue;
+      const long long gi = p.row_offset + i;
+      if ((p.row_offset >= 0) && (gi >= jbeg) && (gi < jend) && (p.diag_add != 0.0)) t += p.diag_add * p.V[gi * p.PS];
+      if (p.jsplit == 1) p.W[(long long)i * p.ldw] = t;
+      else p.W[(long long)blockIdx.y * p.n_rows + i] = t;
+    }
+    return;
+  }
+  const int pw = 8 * NPA;
 #pragma unroll
   for (int mf = 0; mf < MF; ++mf) {
     const int i = row0 + warp * 8 * MF + mf * 8 + lr;
@@ -251,7 +279,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) kmatvec_kernel(const KmvParams 
     const long long gi = p.row_offset + i;
     const bool own_diag = (p.row_offset >= 0) && (gi >= jbeg) && (gi < jend) && (p.diag_add != 0.0);
 #pragma unroll
-    for (int pf = 0; pf < NPF; ++pf) {
+    for (int pf = 0; pf < NPA; ++pf) {
       const int pc = pf * 8 + 2 * lq;
       double w0 = w[mf][pf][0], w1 = w[mf][pf][1];
       if (own_diag) {
@@ -357,7 +385,12 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   GPXB_ARG_CHECK(!a.wt || (a.wrow && a.wcol), -24);
   p.rl = a.dl_ell != 0.0 ? 1.0 / a.dl_ell : 0.0;
   GPXB_ARG_CHECK(!(a.wt && a.dl_ell != 0.0), -25);
-  const int NPF = a.P <= 8 ? 1 : 4;
+  static int gemv_pref = -1;
+  if (gemv_pref < 0) {
+    const char* e = getenv("GPXB_KMV_GEMV");  // "0": single vectors go through the 8-column DMMA path as before
+    gemv_pref = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int NPF = (a.P == 1 && gemv_pref) ? 0 : (a.P <= 8 ? 1 : 4);
   const int limit = 232448;
   // variants: (MF=4, 8 warps, 256 rows) default; (MF=2, 16 warps, 256 rows) via GPXB_KMV_WARPS=16;
   // (MF=2, 8 warps, 128 rows) when the 256-row tile does not fit in shared memory
@@ -389,7 +422,7 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   jsplit = ceil_div(a.N, jps);
   p.jsplit = jsplit; p.jps = jps;
   DevBuf part;
-  const int pw = 8 * NPF;
+  const int pw = NPF == 0 ? 1 : 8 * NPF;
   if (jsplit > 1) {
     GPXB_TRY(part.alloc(sizeof(double) * (size_t)jsplit * a.n_rows * pw, s));
     p.W = part.as<double>();
@@ -403,7 +436,8 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   const int KS = (BR == 256 && (p.Dp == 8 || p.Dp == 16 || p.Dp == 32)) ? p.Dp / 4 : 0;
   int rc;
 #define GO(mf, ks, npf, nw) rc = launch_t<mf, ks, npf, nw>(ctx, p, grid, smem, s)
-#define GO2(mf, ks, nw) do { if (NPF == 1) GO(mf, ks, 1, nw); else GO(mf, ks, 4, nw); } while (0)
+#define GO2(mf, ks, nw) \
+  do { if (NPF == 0) GO(mf, ks, 0, nw); else if (NPF == 1) GO(mf, ks, 1, nw); else GO(mf, ks, 4, nw); } while (0)
   if (BR == 128) GO2(2, 0, 8);
   else if (NW == 16) {
     if (KS == 2) GO2(2, 2, 16); else if (KS == 4) GO2(2, 4, 16); else if (KS == 8) GO2(2, 8, 16); else GO2(2, 0, 16);

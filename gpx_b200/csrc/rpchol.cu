@@ -17,6 +17,7 @@
 #include "mma.cuh"
 #include "rpchol.cuh"
 #include "comm.cuh"
+#include "peer.cuh"
 
 #include <algorithm>
 #include "threefry.cuh"
@@ -84,6 +85,8 @@ struct RpState {
   // from buffers instead of the stationary kernel of Z
   const double* ext_col;  // [n] column of the pivot, refreshed by the caller's generator each step
   const double* diag0;    // [n] initial diagonal
+  double* part;           // [ceil(M / CW)][nblk_loc * BLK] per-chunk partial dot products (rp_gemv_kernel)
+  int peer_mode;          // 1: the pivot buffer is the peer mailbox, filled by the owner (non-owners must not touch it)
 };
 
 __host__ __device__ __forceinline__ long long fb_index(long long r, int c, int M) {
@@ -104,7 +107,7 @@ __global__ void rp_init_kernel(RpState st, double d0) {
 
 // One CTA, identical on every rank: draw u, scan the block sums, locate the block b* that holds the
 // pivot.  Writes l1 = {b*, prefix, r, total}.
-__global__ void __launch_bounds__(BLK, 1) rp_pivot_l1_kernel(RpState st) {
+__device__ __forceinline__ void rp_pivot_l1(const RpState& st) {
   __shared__ double sh[32];
   __shared__ double s_total, s_r, s_prefix;
   __shared__ int s_cnt, s_bstar;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_l1_kernel(RpState st) {
 
   // total = sum(diag) from the block sums (fixed order)
   double t = 0.0;
-  for (int b = tid; b < st.nblk; b += BLK) t += st.blocksum[b];
+  for (int b = tid; b < st.nblk; b += BLK) t += __ldcg(st.blocksum + b);
   t = block_sum<BLK>(t, sh);
   if (tid == 0) {
     s_total = t;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_l1_kernel(RpState st) {
   double carry = 0.0;
   for (int base = 0; base < st.nblk; base += BLK) {
     const int b = base + tid;
-    double v = (b < st.nblk) ? st.blocksum[b] / total : 0.0;
+    double v = (b < st.nblk) ? __ldcg(st.blocksum + b) / total : 0.0;
     v = block_scan_1024(v, sh);
     __syncthreads();
     if (tid == BLK - 1) sh[0] = v;
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_l1_kernel(RpState st) {
   carry = 0.0;
   for (int base = 0; base < st.nblk; base += BLK) {
     const int b = base + tid;
-    double v = (b < st.nblk) ? st.blocksum[b] / total : 0.0;
+    double v = (b < st.nblk) ? __ldcg(st.blocksum + b) / total : 0.0;
     v = block_scan_1024(v, sh) + carry;
     const int below = (b < st.nblk && v < rr) ? 1 : 0;
     const int wcnt = __popc(__ballot_sync(0xffffffffu, below));
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_l1_kernel(RpState st) {
   carry = 0.0;
   for (int base = 0; base <= bstar; base += BLK) {
     const int b = base + tid;
-    double v = (b < st.nblk) ? st.blocksum[b] / total : 0.0;
+    double v = (b < st.nblk) ? __ldcg(st.blocksum + b) / total : 0.0;
     v = block_scan_1024(v, sh) + carry;
     if (b == bstar - 1) s_prefix = v;
     __syncthreads();
@@ -183,14 +186,15 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_l1_kernel(RpState st) {
 // One CTA: the rank that owns block b* finds the pivot row inside it and fills the pivot buffer
 // (s, g_s, z_s, F[s, :i]); every other rank zeroes its buffer so that a sum all-reduce
 // distributes the owner's values.
-__global__ void __launch_bounds__(BLK, 1) rp_pivot_l2_kernel(RpState st, int i) {
+__device__ __forceinline__ void rp_pivot_l2(const RpState& st, int i) {
   __shared__ double sh[32];
   __shared__ int s_cnt;
   const int tid = threadIdx.x;
   const int bstar = (int)st.l1[0];
   const int nbuf = 2 + st.S + i;
   if (bstar < st.blk0 || bstar >= st.blk0 + st.nblk_loc) {
-    for (int k = tid; k < nbuf; k += BLK) st.pbuf[k] = 0.0;
+    if (!st.peer_mode)
+      for (int k = tid; k < nbuf; k += BLK) st.pbuf[k] = 0.0;
     return;
   }
   const double prefix = st.l1[1], rr = st.l1[2], total = st.l1[3];
@@ -221,6 +225,62 @@ __global__ void __launch_bounds__(BLK, 1) rp_pivot_l2_kernel(RpState st, int i) 
   if (tid == 0) {
     st.pbuf[0] = (double)(st.row0 + sl);
     st.pbuf[1] = (st.diag0 ? st.diag0[sl] : kfun(st.kind, 1e-12)) - acc;
+  }
+}
+
+// One launch per pivot: level 1 (all ranks, identical), then level 2 (the owner of block b*; st.l1 was written by
+// this CTA's thread 0, made visible by the barrier).
+__global__ void __launch_bounds__(BLK, 1) rp_pivot_kernel(RpState st, int i) {
+  rp_pivot_l1(st);
+  __threadfence_block();
+  __syncthreads();
+  rp_pivot_l2(st, i);
+}
+
+// Multi-GPU pivot step in ONE launch over the peer mailboxes (comm.cuh), replacing
+// [NCCL all-reduce of the block sums] -> [pivot kernel] -> [NCCL all-reduce of the pivot buffer]:
+//   A. every rank stores its block sums into every rank's mailbox (its own range of the global array) and raises
+//      its flag there; everyone waits for all flags: the global block sums are now local;
+//   B. level 1 (identical on every rank) locates the pivot's block, the owner runs level 2 and fills the pivot
+//      buffer (s, g_s, z_s, F[s, :i]) in its own mailbox;
+//   C. the owner copies the pivot buffer into every peer's mailbox and raises the pivot flag; the others wait.
+// st.blocksum / st.pbuf point into this rank's mailbox at the parity of `seq`.
+__global__ void __launch_bounds__(BLK, 1) rp_pivot_exchange_kernel(RpState st, int i, PeerView pv, unsigned long long seq) {
+  const int par = (int)(seq & 1ULL), tid = threadIdx.x, W = pv.world, me = pv.me;
+  for (int r = 0; r < W; ++r) {
+    double* dst = pv.base[r] + peer_off_bs(par) + st.blk0;
+    for (int b = tid; b < st.nblk_loc; b += BLK) dst[b] = st.bs_local[st.blk0 + b];
+  }
+  __syncthreads();
+  if (tid < W) {
+    __threadfence_system();
+    peer_st_release(peer_flags(pv.base[tid]) + peer_flag_bs(par, me), seq);
+  }
+  if (tid < W) peer_wait(peer_flags(pv.base[me]) + peer_flag_bs(par, tid), seq);
+  __syncthreads();
+  rp_pivot_l1(st);
+  __threadfence_block();
+  __syncthreads();
+  const int bstar = (int)st.l1[0];
+  const bool owner = bstar >= st.blk0 && bstar < st.blk0 + st.nblk_loc;
+  if (owner) {
+    rp_pivot_l2(st, i);
+    __threadfence_block();
+    __syncthreads();
+    const int nbuf = 2 + st.S + i;
+    for (int r = 0; r < W; ++r) {
+      if (r == me) continue;
+      double* dst = pv.base[r] + peer_off_pb(par);
+      for (int k = tid; k < nbuf; k += BLK) dst[k] = st.pbuf[k];
+    }
+    __syncthreads();
+    if (tid < W && tid != me) {
+      __threadfence_system();
+      peer_st_release(peer_flags(pv.base[tid]) + peer_flag_pb(par), seq);
+    }
+  } else {
+    if (tid == 0) peer_wait(peer_flags(pv.base[me]) + peer_flag_pb(par), seq);
+    __syncthreads();
   }
 }
 
@@ -268,6 +328,88 @@ __global__ void __launch_bounds__(BLK, MINB) rp_column_kernel(RpState st, int i)
     }
     for (; c < i; ++c) a[0] += f[(long long)c * BLK] * sf[c];
     g -= ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    const double fnew = g / (sqrt(st.pbuf[1]) + 1e-6);
+    st.FB[fb_index(r, i, st.M)] = fnew;
+    dnew = st.diag[r] - fnew * fnew;
+    st.diag[r] = dnew;
+  }
+  dnew = block_sum<BLK>(dnew, sh);
+  if (threadIdx.x == 0) st.bs_local[st.blk0 + blockIdx.x] = dnew;
+}
+
+// ---- second generation of the column step (default) ---------------------------------------------------------
+// The GEMV  g_r -= sum_c F[r][c] F[s][c]  is split into units of (1024-row block) x (CW pivot columns), one CTA
+// each, so that the grid is thousands of equal units whatever the row count (the first generation ran one CTA per
+// row block over ALL columns: 977 CTAs on 296 slots = 3.3 waves, a quarter of the machine idle in the last one, and
+// on a row shard fewer CTAs than SMs).  512 threads, two adjacent rows per thread through 16-byte streaming loads,
+// eight loads in flight per thread, no spill at 64 registers.  Every unit leaves one partial sum per row; the
+// finishing kernel adds them in chunk order, so a row's arithmetic does not depend on the launch geometry or on
+// the number of GPUs.
+constexpr int CW = 128;  // pivot columns per unit (fixed: it defines the summation order)
+
+__global__ void __launch_bounds__(BLK / 2, 2) rp_gemv_kernel(RpState st, int i) {
+  __shared__ double sf[CW];
+  const int c0 = blockIdx.y * CW, cn = min(CW, i - c0);
+  if (threadIdx.x < cn) sf[threadIdx.x] = st.pbuf[2 + st.S + c0 + threadIdx.x];
+  __syncthreads();
+  const long long rb = (long long)blockIdx.x * BLK;  // first row of the block
+  const double2* f = reinterpret_cast<const double2*>(st.FB + (rb * st.M + (long long)c0 * BLK)) + threadIdx.x;
+  double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+  int c = 0;
+  for (; c + 8 <= cn; c += 8) {
+    double2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(f + (long long)(c + u) * (BLK / 2));  // streaming: read once
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0[u & 3] = fma(v[u].x, sf[c + u], a0[u & 3]);
+      a1[u & 3] = fma(v[u].y, sf[c + u], a1[u & 3]);
+    }
+  }
+  if (c < cn) {  // ragged tail, same accumulator assignment (c is a multiple of 8 here)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c + u < cn) {
+        const double2 v = __ldcs(f + (long long)(c + u) * (BLK / 2));
+        a0[u & 3] = fma(v.x, sf[c + u], a0[u & 3]);
+        a1[u & 3] = fma(v.y, sf[c + u], a1[u & 3]);
+      }
+    }
+  }
+  double2 o;
+  o.x = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+  o.y = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+  reinterpret_cast<double2*>(st.part + ((long long)blockIdx.y * st.nblk_loc * BLK + rb))[threadIdx.x] = o;
+}
+
+// One thread per data row: kernel column, minus the partial dot products in chunk order, scale, store the new
+// factor column, diagonal update, block sum of the new diagonal.
+__global__ void __launch_bounds__(BLK, 1) rp_finish_kernel(RpState st, int i) {
+  extern __shared__ double sz[];  // zs[S]
+  __shared__ double sh[32];
+  for (int d = threadIdx.x; d < st.S; d += BLK) sz[d] = st.pbuf[2 + d];
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * BLK + threadIdx.x;
+  const long long s = (long long)st.pbuf[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) st.pivots[i] = s;
+  double dnew = 0.0;
+  if (r < st.n) {
+    double g;
+    if (st.ext_col) {
+      g = st.ext_col[r];
+    } else {
+      const double* zr = st.Z + r * st.S;
+      double dot = 0.0;
+      for (int d = 0; d < st.Dp; ++d) dot += sz[d] * zr[d];
+      double d2 = ((sz[st.Dp] - 2.0 * dot) + zr[st.Dp]) + 1e-12;
+      if (r + st.row0 == s) d2 = 1e-12;
+      g = kfun(st.kind, d2);
+    }
+    const int nch = (i + CW - 1) / CW;
+    const long long stride = (long long)st.nblk_loc * BLK;
+    double acc = 0.0;
+    for (int k = 0; k < nch; ++k) acc += st.part[k * stride + r];
+    g -= acc;
     const double fnew = g / (sqrt(st.pbuf[1]) + 1e-6);
     st.FB[fb_index(r, i, st.M)] = fnew;
     dnew = st.diag[r] - fnew * fnew;
@@ -347,9 +489,13 @@ static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, l
   st.FB = FB; st.M = M; st.Z = Z; st.n = n; st.S = zl.S; st.Dp = zl.Dp; st.nblk = nblk; st.kind = kind;
   st.pivots = pivots; st.key = bKey.as<uint32_t>(); st.pbuf = bP.as<double>(); st.l1 = bL1.as<double>();
   st.row0 = row0; st.blk0 = (int)(row0 / BLK); st.nblk_loc = nblk_loc; st.partitionable = partitionable;
-  st.ext_col = ext_col; st.diag0 = diag0;
+  st.ext_col = ext_col; st.diag0 = diag0; st.part = nullptr;
   const bool multi = ctx->world > 1 && !gen;  // the external-column variant runs replicated
   if (!multi) st.blocksum = st.bs_local;  // one buffer, no reduction
+  st.peer_mode = 0;
+  PeerView pv;
+  const bool fused = multi && comm_peer_view(ctx, &pv) && nblk <= PEER_SLOT && 2 + zl.S + M <= PEER_SLOT;
+  double* pbuf_nccl = st.pbuf;
   GPXB_CUDA_CHECK(cudaMemcpyAsync(st.key, key, sizeof(uint32_t) * 2, cudaMemcpyHostToDevice, s));
   GPXB_CUDA_CHECK(cudaMemsetAsync(st.bs_local, 0, sizeof(double) * nblk, s));
   // diag_i = k(x_i, x_i) via the batched kernel: d2 = 1e-12 (approximations.py:88-93)
@@ -373,6 +519,16 @@ static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, l
     const char* e = getenv("GPXB_RP_MINBLOCKS");
     return e && atoi(e) == 1;
   }();
+  // GPXB_RP_COLUMN=v1: the first-generation single-kernel column step (kept for comparison)
+  static const bool gen1 = [] {
+    const char* e = getenv("GPXB_RP_COLUMN");
+    return e && e[0] == 'v' && e[1] == '1';
+  }();
+  DevBuf bPart;
+  if (!gen1) {
+    GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)ceil_div(M, CW) * std::max(nblk_loc, 1) * BLK, s));
+    st.part = bPart.as<double>();
+  }
   GPXB_CUDA_CHECK(cudaFuncSetAttribute(one_cta ? rp_column_kernel<1> : rp_column_kernel<2>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(double) * (M + zl.S)));
   // phase profiling brackets every 16th pivot only (weight 16): thousands of event pairs would perturb the loop
@@ -385,18 +541,39 @@ static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, l
   ctx->phase_weight = every;
   for (int i = 0; i < M; ++i) {
     ctx->phase_prof = sampling.on && (i % every == 0);
-    if (multi) GPXB_TRY(comm_allreduce_sum2(ctx, st.bs_local, bBs.as<double>(), nblk, s));
-    {
+    if (fused) {
+      // one launch: block sums and pivot buffer travel through the peer mailboxes (NVLink stores)
       PhaseScope ph(ctx, PH_RP_PIVOT, s);
-      rp_pivot_l1_kernel<<<1, BLK, 0, s>>>(st);
+      const unsigned long long seq = comm_peer_next_seq(ctx);
+      const int par = (int)(seq & 1ULL);
+      st.peer_mode = 1;
+      st.blocksum = pv.base[pv.me] + peer_off_bs(par);
+      st.pbuf = pv.base[pv.me] + peer_off_pb(par);
+      rp_pivot_exchange_kernel<<<1, BLK, 0, s>>>(st, i, pv, seq);
       GPXB_LAUNCH_CHECK();
-      rp_pivot_l2_kernel<<<1, BLK, 0, s>>>(st, i);
-      GPXB_LAUNCH_CHECK();
+    } else {
+      st.pbuf = pbuf_nccl;
+      if (multi) GPXB_TRY(comm_allreduce_sum2(ctx, st.bs_local, bBs.as<double>(), nblk, s));
+      {
+        PhaseScope ph(ctx, PH_RP_PIVOT, s);
+        rp_pivot_kernel<<<1, BLK, 0, s>>>(st, i);
+        GPXB_LAUNCH_CHECK();
+      }
+      if (multi) GPXB_TRY(comm_allreduce_sum(ctx, st.pbuf, 2 + zl.S + i, s));
     }
-    if (multi) GPXB_TRY(comm_allreduce_sum(ctx, st.pbuf, 2 + zl.S + i, s));
-    ctx->launches += 2;
+    ctx->launches += 1;
     if (gen) GPXB_TRY((*gen)(st.pbuf, s));
-    if (nblk_loc > 0) {
+    if (nblk_loc > 0 && !gen1) {
+      PhaseScope ph(ctx, PH_RP_COLUMN, s);
+      if (i > 0) {
+        rp_gemv_kernel<<<dim3(nblk_loc, ceil_div(i, CW)), BLK / 2, 0, s>>>(st, i);
+        GPXB_LAUNCH_CHECK();
+        ctx->launches++;
+      }
+      rp_finish_kernel<<<nblk_loc, BLK, sizeof(double) * zl.S, s>>>(st, i);
+      GPXB_LAUNCH_CHECK();
+      ctx->launches++;
+    } else if (nblk_loc > 0) {
       PhaseScope ph(ctx, PH_RP_COLUMN, s);
       if (one_cta) rp_column_kernel<1><<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);
       else rp_column_kernel<2><<<nblk_loc, BLK, sizeof(double) * (i + zl.S), s>>>(st, i);

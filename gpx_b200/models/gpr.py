@@ -30,6 +30,8 @@ def _xy(state, x, y):
     yd = _to_device(y)
     if yd.dim() == 1:
         yd = yd.reshape(-1, 1)
+    if xd.dim() != 2 or yd.shape[0] != xd.shape[0]:
+        raise ValueError(f"x {tuple(xd.shape)} and y {tuple(yd.shape)} must have the same number of rows")
     return xd, yd
 
 
@@ -177,6 +179,10 @@ def _xyj(state, x, y, jacobian):
     xd = _to_device(x)
     Jd = _to_device(jacobian)
     yd = None if y is None else _to_device(y)
+    if xd.dim() != 2 or Jd.dim() != 3 or Jd.shape[0] != xd.shape[0] or Jd.shape[1] != xd.shape[1]:
+        raise ValueError(f"jacobian {tuple(Jd.shape)} must be (n, nf, nv) for x {tuple(xd.shape)}")
+    if yd is not None and yd.numel() != Jd.shape[0] * Jd.shape[2]:
+        raise ValueError(f"y {tuple(yd.shape)} must hold n*nv = {Jd.shape[0] * Jd.shape[2]} derivative values")
     return xd, yd, Jd
 
 

@@ -24,6 +24,24 @@ def _require(cond, msg) -> None:
         raise ValueError(msg)
 
 
+def _rows(t: torch.Tensor) -> int:
+    return t.shape[0] if t.dim() > 0 else 1
+
+
+def _check_xy(x, y, what="x and y"):
+    """x (N, D) and y (N,) or (N, T): the C ABI sees only pointers, so a mismatch would read past a buffer."""
+    _require(x.dim() == 2, f"{what}: x must be (N, D), got {tuple(x.shape)}")
+    _require(y.dim() in (1, 2) and y.shape[0] == x.shape[0],
+             f"{what}: y has {tuple(y.shape)} but x has {x.shape[0]} rows")
+
+
+def _check_xJ(x, J, what="x and jacobian"):
+    """x (N, nf), J (N, nf, nv)."""
+    _require(x.dim() == 2 and J.dim() == 3, f"{what}: expected x (N, nf) and jacobian (N, nf, nv)")
+    _require(J.shape[0] == x.shape[0] and J.shape[1] == x.shape[1],
+             f"{what}: jacobian {tuple(J.shape)} does not match x {tuple(x.shape)}")
+
+
 def _f64(t: torch.Tensor) -> torch.Tensor:
     if not (t.is_cuda and t.dtype == torch.float64):
         raise _lib.GpxbError(f"expected a CUDA float64 tensor, got {t.device} {t.dtype} (there is no CPU path)")
@@ -56,6 +74,8 @@ def gram_dl_contract(kind, x1, x2, ell, Y, sym_lower=False):
     ctx = context()
     x1, x2, Y = _f64(x1), _f64(x2), _f64(Y)
     n1, D = x1.shape
+    _require(x2.dim() == 2 and x2.shape[1] == D, "shape mismatch between the operands")
+    _require(Y.dim() == 2 and Y.shape == (n1, x2.shape[0]), f"Y must be ({n1}, {x2.shape[0]}), got {tuple(Y.shape)}")
     out = torch.empty(1, dtype=torch.float64, device=x1.device)
     check(
         ctx.lib.gpxb_gram_dl_contract(ctx.handle, _kind(kind), ptr(x1), n1, ptr(x2), x2.shape[0], D, float(ell), ptr(Y),
@@ -111,6 +131,8 @@ def trsm(L, inv, B, trans=True):
     ctx = context()
     B = _f64(B)
     m, n = B.shape
+    _require(L.dim() == 2 and L.shape[0] >= n and L.shape[1] >= n, "trsm: B has more columns than L has rows")
+    _require(inv.numel() >= int(ctx.lib.gpxb_potrf_inv_size(n)), "trsm: the leaf-inverse buffer is too small")
     check(
         ctx.lib.gpxb_trsm(ctx.handle, ptr(L), L.stride(0), ptr(inv), n, ptr(B), B.stride(0), m, int(bool(trans)),
                           stream_ptr()),
@@ -142,6 +164,7 @@ def gpr_lml_grad(kind, x, y, ell, sigma, mean_mode=MEAN_DATA, want_grad=True):
     """Device tensor [lml/N, d/d ell, d/d sigma]."""
     ctx = context()
     x, y = _f64(x), _f64(y)
+    _check_xy(x, y, "gpr_lml_grad")
     N, D = x.shape
     T = y.shape[1] if y.dim() > 1 else 1
     out = torch.empty(3, dtype=torch.float64, device=x.device)
@@ -156,6 +179,7 @@ def gpr_lml_grad(kind, x, y, ell, sigma, mean_mode=MEAN_DATA, want_grad=True):
 def gpr_fit(kind, x, y, ell, sigma, mean_mode=MEAN_DATA):
     ctx = context()
     x, y = _f64(x), _f64(y)
+    _check_xy(x, y, "gpr_fit")
     N, D = x.shape
     T = y.shape[1] if y.dim() > 1 else 1
     c = torch.empty((N, T), dtype=torch.float64, device=x.device)
@@ -172,6 +196,9 @@ def gpr_predict(kind, x_train, x, c, mu, ell, sigma, full_covariance=False):
     ctx = context()
     x_train, x, c = _f64(x_train), _f64(x), _f64(c)
     N, D = x_train.shape
+    _require(x.dim() == 2 and x.shape[1] == D, f"gpr_predict: x has {tuple(x.shape)} but the model has {D} features")
+    _require(c.shape[0] == N, f"gpr_predict: c has {c.shape[0]} rows but x_train has {N}")
+    _require(mu.numel() >= 1, "gpr_predict: mu must hold the mean")
     ns = x.shape[0]
     T = c.shape[1] if c.dim() > 1 else 1
     mean = torch.empty((ns, T), dtype=torch.float64, device=x.device)
@@ -190,6 +217,9 @@ def hess_gram(kind, x1, J1, x2, J2, ell, diag_add=0.0, lower_only=False):
     x1, J1 = _f64(x1), _f64(J1)
     sym = (x2 is x1 or x2 is None) and (J2 is J1 or J2 is None)
     x2, J2 = (x1, J1) if sym else (_f64(x2), _f64(J2))
+    _check_xJ(x1, J1, "hess_gram (first operand)")
+    _check_xJ(x2, J2, "hess_gram (second operand)")
+    _require(x2.shape[1] == x1.shape[1], "hess_gram: the operands have different feature counts")
     n1, nf, nv1 = J1.shape
     n2, _, nv2 = J2.shape
     out = torch.empty((n1 * nv1, n2 * nv2), dtype=torch.float64, device=x1.device)
@@ -207,7 +237,9 @@ def hess_gram(kind, x1, J1, x2, J2, ell, diag_add=0.0, lower_only=False):
 def gpr_lml_derivs(kind, x, J, y, ell, sigma):
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)
+    _check_xJ(x, J, "gpr_lml_derivs")
     N, nf, nv = J.shape
+    _require(y.numel() == N * nv, f"gpr_lml_derivs: y has {y.numel()} values, expected N*nv = {N * nv}")
     out = torch.empty(1, dtype=torch.float64, device=x.device)
     check(
         ctx.lib.gpxb_gpr_lml_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), N, nf, nv, float(ell),
@@ -221,7 +253,9 @@ def gpr_lml_grad_derivs(kind, x, J, y, ell, sigma, want_grad=True):
     """-> device tensor [lml, d lml/d lengthscale, d lml/d sigma] of the derivative-trained GPR."""
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)
+    _check_xJ(x, J, "gpr_lml_grad_derivs")
     N, nf, nv = J.shape
+    _require(y.numel() == N * nv, f"gpr_lml_grad_derivs: y has {y.numel()} values, expected N*nv = {N * nv}")
     out = torch.empty(3, dtype=torch.float64, device=x.device)
     check(
         ctx.lib.gpxb_gpr_lml_grad_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), N, nf, nv, float(ell),
@@ -236,6 +270,8 @@ def gpr_predict_y_derivs(kind, x_train, jaccoef, x, ell, mu=0.0):
     ctx = context()
     x_train, jaccoef, x = _f64(x_train), _f64(jaccoef), _f64(x)
     N, nf = x_train.shape
+    _require(tuple(jaccoef.shape) == (N, nf), f"gpr_predict_y_derivs: jaccoef must be ({N}, {nf}), got {tuple(jaccoef.shape)}")
+    _require(x.dim() == 2 and x.shape[1] == nf, f"gpr_predict_y_derivs: x has {tuple(x.shape)}, expected {nf} features")
     ns = x.shape[0]
     out = torch.empty(ns, dtype=torch.float64, device=x.device)
     check(
@@ -250,7 +286,11 @@ def gpr_predict_derivs_full(kind, x_train, J_train, x, J, c, ell, sigma, mu=0.0,
     """Derivative values from the uncontracted coefficients: mean (ns*nvs,) [, covariance (ns*nvs, ns*nvs)]."""
     ctx = context()
     x_train, J_train, x, J, c = _f64(x_train), _f64(J_train), _f64(x), _f64(J), _f64(c)
+    _check_xJ(x_train, J_train, "gpr_predict_derivs_full (training set)")
+    _check_xJ(x, J, "gpr_predict_derivs_full (prediction set)")
     N, nf, nv = J_train.shape
+    _require(x.shape[1] == nf, "gpr_predict_derivs_full: feature counts differ")
+    _require(c.numel() == N * nv, f"gpr_predict_derivs_full: c has {c.numel()} values, expected N*nv = {N * nv}")
     ns, _, nvs = J.shape
     mean = torch.empty(ns * nvs, dtype=torch.float64, device=x.device)
     cov = torch.empty((ns * nvs, ns * nvs), dtype=torch.float64, device=x.device) if full_covariance else None
@@ -267,7 +307,10 @@ def gpr_predict_y_derivs_full(kind, x_train, J_train, x, c, ell, sigma, mu=0.0, 
     """Target values from the uncontracted coefficients: mean (ns,) [, covariance (ns, ns)]."""
     ctx = context()
     x_train, J_train, x, c = _f64(x_train), _f64(J_train), _f64(x), _f64(c)
+    _check_xJ(x_train, J_train, "gpr_predict_y_derivs_full")
     N, nf, nv = J_train.shape
+    _require(x.dim() == 2 and x.shape[1] == nf, "gpr_predict_y_derivs_full: feature counts differ")
+    _require(c.numel() == N * nv, f"gpr_predict_y_derivs_full: c has {c.numel()} values, expected N*nv = {N * nv}")
     ns = x.shape[0]
     mean = torch.empty(ns, dtype=torch.float64, device=x.device)
     cov = torch.empty((ns, ns), dtype=torch.float64, device=x.device) if full_covariance else None
@@ -288,7 +331,9 @@ def gpr_fit_derivs_iter(kind, x, J, y, ell, sigma, n_pivots, key, partitionable=
 
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)
+    _check_xJ(x, J, "gpr_fit_derivs_iter")
     N, nf, nv = J.shape
+    _require(y.numel() == N * nv, f"gpr_fit_derivs_iter: y has {y.numel()} values, expected N*nv = {N * nv}")
     c = torch.empty(N * nv, dtype=torch.float64, device=x.device)
     jc = torch.empty((N, nf), dtype=torch.float64, device=x.device)
     iters = ctypes.c_int(0)
@@ -309,7 +354,9 @@ def hess_matvec_dl(kind, x, J, V, ell):
     one_d = V.dim() == 1
     if one_d:
         V = V.reshape(-1, 1)
+    _check_xJ(x, J, "hess_matvec_dl")
     N, nf, nv = J.shape
+    _require(V.shape[0] == N * nv, f"hess_matvec_dl: V has {V.shape[0]} rows, expected N*nv = {N * nv}")
     P = V.shape[1]
     W = torch.empty((N * nv, P), dtype=torch.float64, device=V.device)
     check(
@@ -324,7 +371,9 @@ def lanczos_grad_derivs(kind, x, J, ell, sigma, U, m):
     """lanczos_derivs plus the tangents (2, P, m) of the tridiagonals w.r.t. (lengthscale, sigma)."""
     ctx = context()
     x, J, U = _f64(x), _f64(J), _f64(U)
+    _check_xJ(x, J, "lanczos_grad_derivs")
     N, nf, nv = J.shape
+    _require(U.dim() == 2 and U.shape[0] == N * nv, f"lanczos_grad_derivs: U has {tuple(U.shape)}, expected {N * nv} rows")
     P = U.shape[1]
     alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
@@ -344,6 +393,7 @@ def rpcholesky_derivs(kind, x, J, n_pivots, ell, key, partitionable=True, want_f
     """(F (N*nv, M) or None, pivots int64 (M,)) -- gpx/kernels/approximations.py:132-242."""
     ctx = context()
     x, J = _f64(x), _f64(J)
+    _check_xJ(x, J, "rpcholesky_derivs")
     N, nf, nv = J.shape
     piv = torch.empty(n_pivots, dtype=torch.int64, device=x.device)
     F = torch.empty((N * nv, n_pivots), dtype=torch.float64, device=x.device) if want_factor else None
@@ -360,7 +410,9 @@ def lanczos_derivs(kind, x, J, ell, sigma, U, m):
     """(alpha (P, m), beta (P, m), breakdown) of the block Lanczos on d01kj + (sigma^2+1e-10) I, matrix-free."""
     ctx = context()
     x, J, U = _f64(x), _f64(J), _f64(U)
+    _check_xJ(x, J, "lanczos_derivs")
     N, nf, nv = J.shape
+    _require(U.dim() == 2 and U.shape[0] == N * nv, f"lanczos_derivs: U has {tuple(U.shape)}, expected {N * nv} rows")
     P = U.shape[1]
     alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
@@ -380,8 +432,12 @@ def hess_matvec(kind, x1, J1, x2, J2, V, ell, diag_add=0.0):
     one_d = V.dim() == 1
     if one_d:
         V = V.reshape(-1, 1)
+    _check_xJ(x1, J1, "hess_matvec (rows)")
+    _check_xJ(x2, J2, "hess_matvec (columns)")
     n1, nf, nv1 = J1.shape
     n2, _, nv2 = J2.shape
+    _require(x2.shape[1] == nf, "hess_matvec: the operands have different feature counts")
+    _require(V.shape[0] == n2 * nv2, f"hess_matvec: V has {V.shape[0]} rows, expected n2*nv2 = {n2 * nv2}")
     P = V.shape[1]
     W = torch.empty((n1 * nv1, P), dtype=torch.float64, device=V.device)
     check(
@@ -396,6 +452,9 @@ def td_gram(kind, x1, J1, x2, J2, ell, add_targets=0.0, add_derivs=0.0, lower_on
     """Block kernel matrix of GPR_TD: [[k, d1kj], [d0kj, d01kj]] -> (n1 + n1*nv1, n2 + n2*nv2)."""
     ctx = context()
     x1, J1, x2, J2 = _f64(x1), _f64(J1), _f64(x2), _f64(J2)
+    _check_xJ(x1, J1, "td_gram (first operand)")
+    _check_xJ(x2, J2, "td_gram (second operand)")
+    _require(x2.shape[1] == x1.shape[1], "td_gram: the operands have different feature counts")
     n1, nf, nv1 = J1.shape
     n2, _, nv2 = J2.shape
     out = torch.zeros((n1 + n1 * nv1, n2 + n2 * nv2), dtype=torch.float64, device=x1.device)
@@ -412,6 +471,7 @@ def gpr_td_lml_grad(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, m
     """-> device tensor [lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs]."""
     ctx = context()
     x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    _check_xJ(x, J, "gpr_td")
     N, nf, nv = J.shape
     _require(y.numel() == N and yd.numel() == N * nv, "shape mismatch between the operands")
     out = torch.empty(4, dtype=torch.float64, device=x.device)
@@ -428,6 +488,7 @@ def gpr_td_fit(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_m
     """-> (c (N + N*nv, 1), mu (1,))."""
     ctx = context()
     x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    _check_xJ(x, J, "gpr_td")
     N, nf, nv = J.shape
     _require(y.numel() == N and yd.numel() == N * nv, "shape mismatch between the operands")
     c = torch.empty((N + N * nv, 1), dtype=torch.float64, device=x.device)
@@ -447,6 +508,7 @@ def gpr_td2_lml_grad(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigm
     -> device tensor [lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs, d/d sigma_derivs2]."""
     ctx = context()
     x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    _check_xJ(x, J, "gpr_td")
     N, nf, nv = J.shape
     _require(y.numel() == N and yd.numel() == N * nv and 0 < nv_first <= nv, "shape mismatch between the operands")
     out = torch.empty(5, dtype=torch.float64, device=x.device)
@@ -464,6 +526,7 @@ def gpr_td2_fit(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_der
     """-> (c (N + N*nv, 1) in the library's row order [targets; (sample, variable)], mu (1,))."""
     ctx = context()
     x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    _check_xJ(x, J, "gpr_td")
     N, nf, nv = J.shape
     _require(y.numel() == N and yd.numel() == N * nv and 0 < nv_first <= nv, "shape mismatch between the operands")
     c = torch.empty((N + N * nv, 1), dtype=torch.float64, device=x.device)
@@ -480,7 +543,9 @@ def gpr_td2_fit(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_der
 def gpr_fit_derivs(kind, x, J, y, ell, sigma):
     ctx = context()
     x, J, y = _f64(x), _f64(J), _f64(y)
+    _check_xJ(x, J, "gpr_fit_derivs")
     N, nf, nv = J.shape
+    _require(y.numel() == N * nv, f"gpr_fit_derivs: y has {y.numel()} values, expected N*nv = {N * nv}")
     c = torch.empty((N * nv, 1), dtype=torch.float64, device=x.device)
     jc = torch.empty((N, nf), dtype=torch.float64, device=x.device)
     check(
@@ -503,7 +568,7 @@ def kmatvec(kind, x_rows, x_all, V, ell, diag_add=0.0, row_offset=None):
         V = V.reshape(-1, 1)
     n_rows, D = x_rows.shape
     N, P = V.shape
-    _require(x_all.shape[0] == N, "shape mismatch between the operands")
+    _require(x_all.shape[0] == N and x_all.shape[1] == D, "shape mismatch between the operands")
     if row_offset is None:
         row_offset = 0 if same else -1
     W = torch.empty((n_rows, P), dtype=torch.float64, device=V.device)
@@ -546,6 +611,7 @@ def lanczos(kind, x, ell, diag_add, U, m):
     ctx = context()
     x, U = _f64(x), _f64(U)
     N, D = x.shape
+    _require(U.dim() == 2 and U.shape[0] == N, f"lanczos: U has {tuple(U.shape)} but x has {N} rows")
     P = U.shape[1]
     alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
@@ -564,6 +630,7 @@ def lanczos_grad(kind, x, ell, sigma, U, m):
     ctx = context()
     x, U = _f64(x), _f64(U)
     N, D = x.shape
+    _require(U.dim() == 2 and U.shape[0] == N, f"lanczos_grad: U has {tuple(U.shape)} but x has {N} rows")
     P = U.shape[1]
     alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
@@ -585,6 +652,7 @@ def kmatvec_dl(kind, x, V, ell):
     if V.dim() == 1:
         V = V.reshape(-1, 1)
     N, D = x.shape
+    _require(V.shape[0] == N, f"kmatvec_dl: V has {V.shape[0]} rows but x has {N}")
     P = V.shape[1]
     W = torch.empty((N, P), dtype=torch.float64, device=x.device)
     check(
@@ -602,6 +670,7 @@ def gpr_fit_iter(kind, x, y, ell, sigma, n_pivots, key, mean_mode=MEAN_DATA, par
 
     ctx = context()
     x, y = _f64(x), _f64(y)
+    _check_xy(x, y, "gpr_fit_iter")
     N, D = x.shape
     _require(y.numel() == N, "the iterative path supports a single output column")
     c = torch.empty((N, 1), dtype=torch.float64, device=x.device)
@@ -620,6 +689,9 @@ def gpr_fit_iter(kind, x, y, ell, sigma, n_pivots, key, mean_mode=MEAN_DATA, par
 def sgpr_lml(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    _check_xy(x, y, "sgpr")
+    _require(x_locs.dim() == 2 and x_locs.shape[1] == x.shape[1],
+             f"sgpr: x_locs has {tuple(x_locs.shape)} but x has {x.shape[1]} features")
     N, D = x.shape
     T = y.shape[1] if y.dim() > 1 else 1
     out = torch.empty(1, dtype=torch.float64, device=x.device)
@@ -635,6 +707,9 @@ def sgpr_lml_grad(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, want_grad
     """Device tensor [lml/N, d/d ell, d/d sigma] of the SGPR LML with fixed landmarks."""
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    _check_xy(x, y, "sgpr")
+    _require(x_locs.dim() == 2 and x_locs.shape[1] == x.shape[1],
+             f"sgpr: x_locs has {tuple(x_locs.shape)} but x has {x.shape[1]} features")
     N, D = x.shape
     _require(y.numel() == N, "the SGPR gradient supports a single output column")
     out = torch.empty(3, dtype=torch.float64, device=x.device)
@@ -653,6 +728,9 @@ def sgpr_fit_iter(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, tol=1e-5,
 
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    _check_xy(x, y, "sgpr")
+    _require(x_locs.dim() == 2 and x_locs.shape[1] == x.shape[1],
+             f"sgpr: x_locs has {tuple(x_locs.shape)} but x has {x.shape[1]} features")
     N, D = x.shape
     _require(y.numel() == N, "the iterative SGPR path supports a single output column")
     M = x_locs.shape[0]
@@ -674,6 +752,9 @@ def sgpr_lml_iter_parts(kind, x, y, x_locs, ell, sigma, U, m, mean_mode=MEAN_DAT
 
     ctx = context()
     x, y, x_locs, U = _f64(x), _f64(y), _f64(x_locs), _f64(U)
+    _check_xy(x, y, "sgpr_lml_iter_parts")
+    _require(x_locs.dim() == 2 and x_locs.shape[1] == x.shape[1], "sgpr_lml_iter_parts: x_locs feature count differs")
+    _require(U.dim() == 2 and U.shape[0] == x.shape[0], "sgpr_lml_iter_parts: U must have one row per data row")
     N, D = x.shape
     _require(y.numel() == N, "the iterative SGPR path supports a single output column")
     P = U.shape[1]
@@ -696,6 +777,9 @@ def sgpr_lml_grad_locs(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     """-> ([lml/N, d/d ell, d/d sigma], d(lml/N)/d x_locs (M, D)) for trainable landmark coordinates."""
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    _check_xy(x, y, "sgpr")
+    _require(x_locs.dim() == 2 and x_locs.shape[1] == x.shape[1],
+             f"sgpr: x_locs has {tuple(x_locs.shape)} but x has {x.shape[1]} features")
     N, D = x.shape
     _require(y.numel() == N, "the SGPR gradient supports a single output column")
     out = torch.empty(3, dtype=torch.float64, device=x.device)
@@ -711,6 +795,9 @@ def sgpr_lml_grad_locs(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
 def sgpr_fit(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)
+    _check_xy(x, y, "sgpr")
+    _require(x_locs.dim() == 2 and x_locs.shape[1] == x.shape[1],
+             f"sgpr: x_locs has {tuple(x_locs.shape)} but x has {x.shape[1]} features")
     N, D = x.shape
     T = y.shape[1] if y.dim() > 1 else 1
     M = x_locs.shape[0]
@@ -728,6 +815,8 @@ def sgpr_predict(kind, x_locs, x, c, mu, ell, sigma, full_covariance=False):
     ctx = context()
     x_locs, x, c = _f64(x_locs), _f64(x), _f64(c)
     M, D = x_locs.shape
+    _require(x.dim() == 2 and x.shape[1] == D, f"sgpr_predict: x has {tuple(x.shape)} but the landmarks have {D} features")
+    _require(c.shape[0] == M, f"sgpr_predict: c has {c.shape[0]} rows but there are {M} landmarks")
     ns = x.shape[0]
     T = c.shape[1] if c.dim() > 1 else 1
     mean = torch.empty((ns, T), dtype=torch.float64, device=x.device)
@@ -743,6 +832,7 @@ def sgpr_predict(kind, x_locs, x, c, mu, ell, sigma, full_covariance=False):
 def gather_rows(x, idx):
     ctx = context()
     x = _f64(x)
+    _require(idx.dtype == torch.int64 and idx.is_cuda, "gather_rows: idx must be a CUDA int64 tensor")
     M, D = idx.shape[0], x.shape[1]
     out = torch.empty((M, D), dtype=torch.float64, device=x.device)
     check(ctx.lib.gpxb_gather_rows(ctx.handle, ptr(x), D, ptr(idx), M, ptr(out), stream_ptr()), "gpxb_gather_rows")

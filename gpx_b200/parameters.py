@@ -135,6 +135,17 @@ class ModelState:
         z = np.load(state_file, allow_pickle=allow_pickle)
         st = self
         upd = {}
+        # the reference raises "Wrong number of parameters in dumped file" when the structures differ
+        # (model_state.py:321-327); here the keys are compared, so the message names what is wrong
+        have = {"params:" + ":".join(path): pp for path, pp in _flatten_params(self.params)}
+        in_file = {k for k in z.files if k.startswith("params:")}
+        if in_file != set(have):
+            raise ValueError("Wrong number of parameters in dumped file: missing "
+                             f"{sorted(set(have) - in_file)}, unknown {sorted(in_file - set(have))}")
+        for k in in_file:
+            if tuple(np.shape(z[k])) != tuple(have[k].value.shape):
+                raise ValueError(f"parameter {k}: the file holds shape {tuple(np.shape(z[k]))}, the model expects "
+                                 f"{tuple(have[k].value.shape)}")
         for k in z.files:
             try:
                 v = z[k]

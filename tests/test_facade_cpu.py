@@ -163,3 +163,102 @@ def test_array_valued_trainables_ravel_like_ravel_pytree():
     np.testing.assert_allclose(st.params["sigma"].value, Softplus().forward(xt[1]))
     assert [v.shape for _, v in _split(paths, xt)] == [(), (), (6, 2)]
     assert m.state.params["x_locs"].value[0, 0] == 0.0  # the original state is untouched
+
+
+def test_ops_wrappers_reject_mismatched_shapes_before_reaching_the_c_abi(monkeypatch):
+    """The C ABI sees only pointers: N, D, T are taken from one tensor, so every wrapper must check the OTHER
+    operands itself (a wrong feature count or a short y would make a kernel read outside its buffers).  The
+    reference raises a shape error from jnp; here it is a ValueError raised before any library call."""
+    import torch
+
+    from gpx_b200 import ops
+
+    class _Lib:
+        def __getattr__(self, name):
+            if name == "gpxb_potrf_inv_size":
+                return lambda n: 0
+            raise AssertionError(f"{name} reached with mismatched shapes")
+
+    class _Ctx:
+        lib, handle = _Lib(), None
+
+    monkeypatch.setattr(ops, "context", lambda: _Ctx())
+    monkeypatch.setattr(ops, "_f64", lambda t: t.contiguous())
+    z = lambda *s: torch.zeros(s, dtype=torch.float64)  # noqa: E731
+    N, D, nv, M = 6, 3, 2, 4
+    x, y, J = z(N, D), z(N, 1), z(N, D, nv)
+    bad = [
+        lambda: ops.gpr_lml_grad("se", x, z(N - 1, 1), 1.0, 0.1),
+        lambda: ops.gpr_fit("se", x, z(N + 2, 1), 1.0, 0.1),
+        lambda: ops.gpr_predict("se", x, z(5, D + 1), z(N, 1), z(1), 1.0, 0.1),
+        lambda: ops.gpr_predict("se", x, z(5, D), z(N - 1, 1), z(1), 1.0, 0.1),
+        lambda: ops.hess_gram("se", x, z(N, D + 1, nv), None, None, 1.0),
+        lambda: ops.hess_gram("se", x, J, z(4, D + 1), z(4, D + 1, nv), 1.0),
+        lambda: ops.gpr_lml_derivs("se", x, J, z(N, nv + 1), 1.0, 0.1),
+        lambda: ops.gpr_lml_grad_derivs("se", x, z(N - 1, D, nv), z(N, nv), 1.0, 0.1),
+        lambda: ops.gpr_fit_derivs("se", x, J, z(N - 1, nv), 1.0, 0.1),
+        lambda: ops.gpr_predict_y_derivs("se", x, z(N, D + 1), z(5, D), 1.0),
+        lambda: ops.gpr_predict_derivs_full("se", x, J, z(5, D), z(5, D, nv), z(N * nv + 1), 1.0, 0.1),
+        lambda: ops.gpr_predict_y_derivs_full("se", x, J, z(5, D + 1), z(N * nv), 1.0, 0.1),
+        lambda: ops.hess_matvec("se", x, J, x, J, z(N * nv + 1, 2), 1.0),
+        lambda: ops.td_gram("se", x, J, z(4, D), z(4, D + 1, nv), 1.0),
+        lambda: ops.gpr_td_lml_grad("se", x, J, z(N - 1), z(N, nv), 1.0, 0.1, 0.1),
+        lambda: ops.kmatvec("se", z(5, D + 1), x, z(N, 2), 1.0),
+        lambda: ops.lanczos("se", x, 1.0, 0.1, z(N + 1, 2), 3),
+        lambda: ops.kmatvec_dl("se", x, z(N - 1, 2), 1.0),
+        lambda: ops.gpr_fit_iter("se", x, z(N - 1, 1), 1.0, 0.1, 2, (0, 1)),
+        lambda: ops.sgpr_lml("se", x, z(N - 1, 1), z(M, D), 1.0, 0.1),
+        lambda: ops.sgpr_lml_grad("se", x, y, z(M, D + 1), 1.0, 0.1),
+        lambda: ops.sgpr_fit("se", x, z(N + 1, 1), z(M, D), 1.0, 0.1),
+        lambda: ops.sgpr_predict("se", z(M, D), z(5, D + 1), z(M, 1), z(1), 1.0, 0.1),
+        lambda: ops.sgpr_predict("se", z(M, D), z(5, D), z(M + 1, 1), z(1), 1.0, 0.1),
+        lambda: ops.gram_dl_contract("se", x, z(4, D), 1.0, z(N, 5)),
+    ]
+    for i, call in enumerate(bad):
+        with pytest.raises(ValueError):
+            call()
+            raise AssertionError(f"case {i} was accepted")
+
+
+def test_facade_rejects_x_y_row_mismatch_before_any_device_call():
+    from gpx_b200.models import gpr as gpr_mod
+
+    class _K:
+        active_dims = None
+
+        @staticmethod
+        def _slice(x):
+            return x
+
+    class _S:
+        kernel = _K()
+
+    import _fake_ops as F
+
+    saved = gpr_mod._to_device
+    gpr_mod._to_device = F.to_device
+    try:
+        with pytest.raises(ValueError):
+            gpr_mod._xy(_S(), np.zeros((5, 2)), np.zeros((4, 1)))
+        with pytest.raises(ValueError):
+            gpr_mod._xyj(_S(), np.zeros((5, 2)), np.zeros((5, 3)), np.zeros((5, 3, 3)))
+        with pytest.raises(ValueError):
+            gpr_mod._xyj(_S(), np.zeros((5, 2)), np.zeros((4, 3)), np.zeros((5, 2, 3)))
+    finally:
+        gpr_mod._to_device = saved
+
+
+def test_load_rejects_a_checkpoint_with_other_parameters(tmp_path):
+    """gpx/parameters/model_state.py:321-327: 'Wrong number of parameters in dumped file'."""
+    m = GPR(SquaredExponential())
+    f = str(tmp_path / "s.npz")
+    d = m.state.save(f)
+    np.savez(f, **{k: v for k, v in d.items() if k != "params:sigma"})
+    with pytest.raises(ValueError, match="Wrong number of parameters"):
+        m.state.load(f)
+    np.savez(f, **dict(d, **{"params:kernel_params:period": np.array(1.0)}))
+    with pytest.raises(ValueError, match="unknown"):
+        m.state.load(f)
+    np.savez(f, **dict(d, **{"params:sigma": np.ones(3)}))
+    with pytest.raises(ValueError, match="shape"):
+        m.state.load(f)
