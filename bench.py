@@ -375,28 +375,28 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
                     non_compute_s=non_compute(t, ph))
 
     def lml_iter_full():
-        Nf = max(4096, int(131072 * scale))
+        Nf = int(os.environ.get("GPXB_BENCH_ITER_N", "0")) or max(4096, int(262144 * scale))
+        npiv = int(os.environ.get("GPXB_BENCH_ITER_PIVOTS", "1024" if scale >= 1.0 else "64"))
         x16, y16 = data(Nf, D16, 4)
         ell, sigma, m = 4.0, 0.5, 50
 
-        def run():
-            c, mu, iters = ops.gpr_fit_iter("se", x16, y16, ell, sigma, 100, key)
-            U = ops.rademacher_probes(key, Nf, P, True)
-            al, be, flag = ops.lanczos("se", x16, ell, sigma**2 + 1e-10, U, m)
-            return c, mu, iters, al, be, flag
+        def run(xx, yy, mm):
+            U = ops.rademacher_probes(key, xx.shape[0], P, True)
+            return ops.gpr_lml_iter("se", xx, yy, ell, sigma, npiv, key, U, mm)
 
-        run()  # warm-up (allocator pools, NCCL channels)
-        t, (c, mu, iters, al, be, flag), ph = timed(run)
+        run(x16[:16384].contiguous(), y16[:16384].contiguous(), 4)  # warm-up at toy size (allocator pools, NCCL channels)
+        t, (c, mu, iters, al, be, flag), ph = timed(lambda: run(x16, y16, m))
         logdet = slq_logdet(al.cpu().numpy(), be.cpu().numpy(), Nf)
         quad = float(((y16 - mu) * c).sum().cpu())
         lml = (-0.5 * quad - 0.5 * logdet - 0.5 * Nf * np.log(2 * np.pi)) / Nf
         fl = float(Nf) ** 2 * ((2 * D16 + 4 + 2 * P) * m + (2 * D16 + 4 + 2) * iters)
-        return dict(id="lml_iter_full", what="COMPLETE iterative LML (_lml_iter: PCG fit to tol 1e-5 with the 100-pivot "
-                    "RPCholesky preconditioner + SLQ log-det, 30 probes x 50 Lanczos steps), rows sharded; host eigh of the "
-                    "30 tridiagonals excluded", N=Nf, D=D16, P=P, m=m, pcg_iters=int(iters), s=t, evals_per_s=1.0 / t,
-                    bound="tensor", alg_flops=fl, achieved_tflops_per_gpu=fl / t / 1e12 / world, peak_tflops=dgemm_tflops,
-                    frac=fl / t / 1e12 / world / dgemm_tflops, lml=lml, breakdown=int(flag.cpu()[0]), phases=ph,
-                    non_compute_s=non_compute(t, ph))
+        return dict(id="lml_iter_full", what=f"COMPLETE iterative LML (_lml_iter, ONE gpxb_gpr_lml_iter call: probes, "
+                    f"{npiv}-pivot RPCholesky preconditioner, PCG fit to tol 1e-5 whose first {m} iterations ride in the "
+                    f"SLQ block mat-vecs, SLQ log-det with 30 probes x {m} Lanczos steps), rows sharded; host eigh of the "
+                    "30 tridiagonals excluded", N=Nf, D=D16, P=P, m=m, n_pivots=npiv, pcg_iters=int(iters), s=t,
+                    evals_per_s=1.0 / t, bound="tensor", alg_flops=fl, achieved_tflops_per_gpu=fl / t / 1e12 / world,
+                    peak_tflops=dgemm_tflops, frac=fl / t / 1e12 / world / dgemm_tflops, lml=lml,
+                    breakdown=int(flag.cpu()[0]), phases=ph, non_compute_s=non_compute(t, ph))
 
     entry(f"configs[3] SGPR + RPCholesky, N={N} D=32 M={M}: landmark selection", rpchol)
     entry(f"configs[3] SGPR + RPCholesky, N={N} D=32 M={M}: LML", sgpr)
@@ -404,7 +404,7 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
     torch.cuda.empty_cache()
     entry(f"configs[4] Lanczos/SLQ, SE kernel, D=16, 30 probes, N={N2}: Lanczos steps", lanczos_steps)
     entry(f"configs[4] iterative LML, SE kernel, D=16, N={N2}: PCG iterations", pcg_iters)
-    entry("configs[4] iterative LML end to end at a size that converges in seconds", lml_iter_full)
+    entry("configs[4] iterative LML end to end (LML evals/s)", lml_iter_full)
     return out
 
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "gpxb_lanczos": (_int, [C.c_void_p, _int, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _ll, _int, _int, _c_dp, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_lanczos_grad": (_int, [C.c_void_p, _int, _c_dp, _int, _int, _dbl, _dbl, _c_dp, _ll, _int, _int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_kmatvec_dl": (_int, [C.c_void_p, _int, _c_dp, _int, _int, _dbl, _c_dp, _ll, _int, _c_dp, _ll, C.c_void_p]),
+    "gpxb_gpr_lml_iter": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _dbl, _dbl, _int, _int, C.c_uint32, C.c_uint32, _int, _dbl, _dbl, _int, _c_dp, _ll, _int, _int, _c_dp, _c_dp, C.POINTER(_int), _c_dp, _c_dp, C.c_void_p, C.c_void_p]),
     "gpxb_gpr_fit_iter": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _dbl, _dbl, _int, _int, C.c_uint32, C.c_uint32, _int, _dbl, _dbl, _int, _c_dp, _c_dp, C.POINTER(_int), C.c_void_p]),
     "gpxb_sgpr_lml": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _c_dp, _int, _dbl, _dbl, _int, _c_dp, C.c_void_p]),
     "gpxb_sgpr_fit_iter": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _c_dp, _int, _dbl, _dbl, _int, _dbl, _dbl, _int, _c_dp, _c_dp, C.POINTER(_int), C.c_void_p]),

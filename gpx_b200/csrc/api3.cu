@@ -22,6 +22,10 @@ int pcg_solve(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, c
               ZLayout zl, double diag_add, const double* b, const double* F, long long ldf, int k,
               const double* Pkk, double sigma, double tol, double atol, int maxiter, double* x, int* iters_out,
               cudaStream_t s);
+int lml_iter_fused(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N, ZLayout zl,
+                   double diag_add, const double* b, const double* F, long long ldf, int k, const double* Pkk,
+                   double sigma, double tol, double atol, int maxiter, double* x, int* iters_out, const double* U,
+                   int P, int PS, int m, double* alpha_out, double* beta_out, int* flag, cudaStream_t s);
 int lanczos_block_grad(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
                        ZLayout zl, double ell, double sigma, const double* U, int P, int PS, int m,
                        double* alpha_out, double* beta_out, double* dalpha_out, double* dbeta_out, int Ptot,
@@ -238,6 +242,64 @@ int gpxb_gpr_fit_iter(gpxb_ctx* ctx_, int kind, const double* x, const double* y
   GPXB_TRY(pcg_solve(ctx, kind, za.as<double>() + sh.b * zl.S, sh.n(), sh.b, za.as<double>(), N, zl, s2,
                      r.as<double>() + sh.b, n_pivots > 0 ? ft.as<double>() : nullptr, ldf, n_pivots,
                      pkk.as<double>(), sigma, tol, atol, maxiter, xl.as<double>(), iters_out, s));
+  if (ctx->world > 1) {
+    ctx->shard_N = N;
+    GPXB_TRY(comm_allgather_rows(ctx, xl.as<double>(), c_out, sh.n(), 1, s));
+  } else {
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(c_out, xl.as<double>(), sizeof(double) * N, cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+int gpxb_gpr_lml_iter(gpxb_ctx* ctx_, int kind, const double* x, const double* y, int N, int D, double ell,
+                      double sigma, int mean_mode, int n_pivots, uint32_t key0, uint32_t key1, int partitionable,
+                      double tol, double atol, int maxiter, const double* U, long long ldu, int P, int m,
+                      double* c_out, double* mu_out, int* iters_out, double* alpha_out, double* beta_out,
+                      int* breakdown_flag, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && x && y && c_out && mu_out && U && alpha_out && beta_out && breakdown_flag, -1);
+  GPXB_ARG_CHECK(kind >= 0 && kind <= 3 && N > 0 && D > 0 && n_pivots >= 0 && P > 0 && m > 0, -2);
+  if (P > 31) {  // the PCG vector rides as column P of ONE 32-column block: larger probe sets run the two parts in turn
+    GPXB_TRY(gpxb_gpr_fit_iter(ctx_, kind, x, y, N, D, ell, sigma, mean_mode, n_pivots, key0, key1, partitionable, tol,
+                               atol, maxiter, c_out, mu_out, iters_out, stream));
+    return gpxb_lanczos(ctx_, kind, x, N, D, ell, sigma * sigma + 1e-10, U, ldu, P, m, alpha_out, beta_out,
+                        breakdown_flag, stream);
+  }
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  cudaStream_t s = (cudaStream_t)stream;
+  const ZLayout zl = z_layout(D);
+  const Shard sh = shard_of(ctx, N);
+  const double s2 = sigma * sigma + 1e-10;
+  DevBuf za, r, ft, piv, pkk, xl, up;
+  GPXB_TRY(za.alloc(sizeof(double) * ((size_t)N * zl.S + 16), s));
+  GPXB_TRY(prep_z(ctx, x, D, N, zl, ell, za.as<double>(), s));
+  GPXB_TRY(r.alloc(sizeof(double) * N, s));
+  sk::mean_kernel<<<1, 1024, 0, s>>>(y, (long long)N, mean_mode == GPXB_MEAN_DATA, mu_out);
+  GPXB_LAUNCHED(ctx);
+  sk::center_kernel<<<ceil_div(N, 256), 256, 0, s>>>(y, N, mu_out, r.as<double>());
+  GPXB_LAUNCHED(ctx);
+  const long long ldf = round_up(N, 2);
+  if (n_pivots > 0) {
+    DevBuf fb;
+    GPXB_TRY(fb.alloc(sizeof(double) * std::max<size_t>(rp_factor_doubles(sh.n(), n_pivots), 8), s));
+    GPXB_TRY(ft.alloc(sizeof(double) * (size_t)n_pivots * ldf, s));
+    GPXB_TRY(piv.alloc(sizeof(long long) * n_pivots, s));
+    GPXB_TRY(pkk.alloc(sizeof(double) * (size_t)n_pivots * n_pivots, s));
+    const uint32_t key[2] = {key0, key1};
+    GPXB_TRY(rpcholesky_z(ctx, kind, za.as<double>() + sh.b * zl.S, sh.n(), sh.b, N, zl, key, n_pivots,
+                          partitionable, fb.as<double>(), piv.as<long long>(), s));
+    GPXB_TRY(rp_unblock_transposed(ctx, fb.as<double>(), sh.n(), n_pivots, ft.as<double>(), ldf, s));
+    GPXB_TRY(precond_build(ctx, ft.as<double>(), ldf, n_pivots, sh.n(), sigma, pkk.as<double>(), s));
+  }
+  GPXB_TRY(xl.alloc(sizeof(double) * std::max(sh.n(), 1), s));
+  if (maxiter <= 0) maxiter = 10 * N;
+  GPXB_CUDA_CHECK(cudaMemsetAsync(breakdown_flag, 0, sizeof(int), s));
+  const int PS = v_padded_stride(P + 1);
+  GPXB_TRY(up.alloc(sizeof(double) * ((size_t)std::max(sh.n(), 1) * PS + 16), s));
+  GPXB_TRY(pack_v(ctx, U + sh.b * ldu, ldu, sh.n(), 0, P, PS, up.as<double>(), s));
+  GPXB_TRY(lml_iter_fused(ctx, kind, za.as<double>() + sh.b * zl.S, sh.n(), sh.b, za.as<double>(), N, zl, s2,
+                          r.as<double>() + sh.b, n_pivots > 0 ? ft.as<double>() : nullptr, ldf, n_pivots,
+                          pkk.as<double>(), sigma, tol, atol, maxiter, xl.as<double>(), iters_out, up.as<double>(), P,
+                          PS, m, alpha_out, beta_out, breakdown_flag, s));
   if (ctx->world > 1) {
     ctx->shard_N = N;
     GPXB_TRY(comm_allgather_rows(ctx, xl.as<double>(), c_out, sh.n(), 1, s));

@@ -50,12 +50,24 @@ def lanczos_logdet(kind, xd, ell, diag_add, num_evals, num_lanczos, key):
 
 
 def lml_iter(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond):
+    """_lml_iter (gpx/models/_gpr.py:772-821).  One device sweep (gpxb_gpr_lml_iter): the PCG search direction rides as
+    an extra column of the SLQ block mat-vecs, so fit and log-det share the passes over the recomputed kernel tiles."""
+    if n_pivots is None:
+        raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
     m = yd.shape[0]
-    c, mu = fit_iter(state, xd, yd, ell, sigma, n_pivots, key_precond)
+    part = threefry_partitionable()
+    subkey, _ = split(as_key(key_lanczos), 2, part)
+    U = ops.rademacher_probes(subkey, m, int(num_evals), part)
+    kp = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
+    c, mu, _, alpha, beta, flag = ops.gpr_lml_iter(state.kernel.kind, xd, yd, ell, sigma, int(n_pivots), kp, U,
+                                                   int(num_lanczos), mean_mode(state.mean_function), part)
+    if int(flag.cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
+                           "use fewer Lanczos steps than data points")
+    c, mu = c.cpu().numpy(), np.float64(mu.cpu().numpy()[0])
     r = yd.cpu().numpy() - mu
     mll = -0.5 * float(np.sum(r.T @ c))
-    mll -= 0.5 * lanczos_logdet(state.kernel.kind, xd, ell, sigma**2 + 1e-10, num_evals, num_lanczos,
-                                as_key(key_lanczos))
+    mll -= 0.5 * slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), m)
     mll -= m * 0.5 * np.log(2.0 * np.pi)
     return mll / m
 

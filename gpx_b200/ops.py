@@ -686,6 +686,35 @@ def gpr_fit_iter(kind, x, y, ell, sigma, n_pivots, key, mean_mode=MEAN_DATA, par
     return c, mu, iters.value
 
 
+def gpr_lml_iter(kind, x, y, ell, sigma, n_pivots, key, U, m, mean_mode=MEAN_DATA, partitionable=True, tol=1e-5,
+                 atol=1e-7, maxiter=0):
+    """The device parts of the iterative LML in one sweep (gpx/models/_gpr.py:772-821): PCG fit + m-step Lanczos on the
+    probes U, the PCG vector riding in the Lanczos block mat-vecs.  -> (c, mu, iterations, alpha, beta, breakdown)."""
+    import ctypes
+
+    ctx = context()
+    x, y, U = _f64(x), _f64(y), _f64(U)
+    _check_xy(x, y, "gpr_lml_iter")
+    N, D = x.shape
+    _require(y.numel() == N, "the iterative path supports a single output column")
+    _require(U.dim() == 2 and U.shape[0] == N, f"gpr_lml_iter: U has {tuple(U.shape)} but x has {N} rows")
+    P = U.shape[1]
+    c = torch.empty((N, 1), dtype=torch.float64, device=x.device)
+    mu = torch.empty(1, dtype=torch.float64, device=x.device)
+    alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    iters = ctypes.c_int(0)
+    check(
+        ctx.lib.gpxb_gpr_lml_iter(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, float(ell), float(sigma),
+                                  int(mean_mode), int(n_pivots), int(key[0]), int(key[1]), int(bool(partitionable)),
+                                  float(tol), float(atol), int(maxiter), ptr(U), U.stride(0), P, int(m), ptr(c),
+                                  ptr(mu), ctypes.byref(iters), ptr(alpha), ptr(beta), ptr(flag), stream_ptr()),
+        "gpxb_gpr_lml_iter",
+    )
+    return c, mu, iters.value, alpha, beta, flag
+
+
 def sgpr_lml(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):
     ctx = context()
     x, y, x_locs = _f64(x), _f64(y), _f64(x_locs)

@@ -299,6 +299,17 @@ int gpxb_gpr_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* y,
                       int partitionable, double tol, double atol, int maxiter, double* c_out, double* mu_out,
                       int* iters_out, gpxb_stream stream);
 
+/* The two device parts of the iterative LML in ONE sweep (gpx/models/_gpr.py:772-821 _lml_iter): the PCG solve of
+ * gpxb_gpr_fit_iter and the m-step Lanczos of gpxb_lanczos on the P start vectors U with diag_add = sigma^2+1e-10.
+ * While both run, the PCG search direction travels as column P of the Lanczos block, so the first m CG iterations
+ * share the block mat-vec's pass over the recomputed kernel tiles (P <= 31; larger P runs the two parts in turn).
+ * Outputs as of the two separate calls.  Host-synchronous like gpxb_gpr_fit_iter; *iters_out is a HOST int. */
+int gpxb_gpr_lml_iter(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, double ell,
+                      double sigma, int mean_mode, int n_pivots, uint32_t key0, uint32_t key1, int partitionable,
+                      double tol, double atol, int maxiter, const double* U, long long ldu, int P, int m,
+                      double* c_out, double* mu_out, int* iters_out, double* alpha_out, double* beta_out,
+                      int* breakdown_flag, gpxb_stream stream);
+
 /* ---- SGPR, Projected Processes --------------------------------------------------------- */
 /* *out (device) = lml / N of gpx/models/_sgpr.py:659-697, evaluated in the Woodbury form. */
 int gpxb_sgpr_lml(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D, int T,

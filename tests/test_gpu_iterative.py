@@ -122,6 +122,31 @@ def test_pcg_fit_iter_matches_oracle_iteration_for_iteration():
     assert abs(q - q_ref) < 1e-8 * abs(q_ref)
 
 
+@pytest.mark.parametrize("P,m,npiv", [(8, 20, 40), (30, 4, 5), (31, 6, 0), (33, 5, 20)])
+def test_lml_iter_one_sweep_equals_the_two_separate_calls(P, m, npiv):
+    """gpxb_gpr_lml_iter (PCG vector riding in the Lanczos block mat-vecs) against gpxb_gpr_fit_iter + gpxb_lanczos:
+    the tridiagonals are the same arithmetic, the PCG iterates see a different summation order in the mat-vec."""
+    from gpx_b200 import ops
+
+    N, D = 3000, 16
+    x, y = _data(N, D, 4)
+    ell, sigma = 4.0, 0.5
+    key = R.PRNGKey(2023)
+    us, _ = R.rademacher_probes(R.PRNGKey(5), N, P)
+    kw = dict(tol=1e-13, atol=0.0)  # converged solves: the comparison is not limited by the stopping point
+    c0, mu0, it0 = ops.gpr_fit_iter("se", dev(x), dev(y), ell, sigma, npiv, key, **kw)
+    a0, b0, f0 = ops.lanczos("se", dev(x), ell, sigma**2 + 1e-10, dev(us), m)
+    c1, mu1, it1, a1, b1, f1 = ops.gpr_lml_iter("se", dev(x), dev(y), ell, sigma, npiv, key, dev(us), m, **kw)
+    assert int(host(f0)[0]) == 0 and int(host(f1)[0]) == 0
+    assert rel(host(a1), host(a0)) < 1e-12 and rel(host(b1)[:, : m - 1], host(b0)[:, : m - 1]) < 1e-12
+    assert abs(it1 - it0) <= 2 and float(host(mu1)[0]) == float(host(mu0)[0])
+    assert rel(host(c1), host(c0)) < 1e-8
+    # and against the exact solve of the oracle's matrix (both CG runs are converged)
+    K = R.kernel("se", x, x, ell) + (sigma**2 + 1e-10) * np.eye(N)
+    c_ref = np.linalg.solve(K, y - y.mean())
+    assert rel(host(c1), c_ref) < 1e-8
+
+
 def test_lml_iter_facade_matches_oracle():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import gpr
