@@ -176,6 +176,37 @@ bool comm_peer_view(const Ctx* ctx, PeerView* v) {
 }
 unsigned long long comm_peer_next_seq(Ctx* ctx) { return ++reinterpret_cast<PeerState*>(ctx->peer)->seq; }
 
+namespace {
+// NCCL sets up the channels of a communication pattern at its first use (hundreds of ms for the all-to-all send /
+// receive of the unequal-shard all-gather).  Run every pattern the library uses once, on a few bytes, at communicator
+// creation, so that the first sharded mat-vec does not pay for it.  Collective: every rank calls it from comm_init.
+int comm_warmup(Ctx* ctx) {
+  const int W = ctx->world, me = ctx->rank;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  double* buf = nullptr;
+  GPXB_CUDA_CHECK(cudaMalloc(&buf, sizeof(double) * 8 * (size_t)(W + 1)));
+  GPXB_CUDA_CHECK(cudaMemset(buf, 0, sizeof(double) * 8 * (size_t)(W + 1)));
+  cudaStream_t st = nullptr;  // the legacy default stream: ordered with the memset, synchronised below
+  ncclResult_t rc = g.AllReduce(buf, buf, 8, ncclFloat64, ncclSum, comm, st);
+  if (rc == 0) rc = g.AllGather(buf + 8 * (size_t)me, buf, 8, ncclFloat64, comm, st);
+  if (rc == 0) {
+    rc = g.GroupStart();
+    for (int k = 1; k < W && rc == 0; ++k) {
+      const int to = (me + k) % W, from = (me - k + W) % W;
+      rc = g.Send(buf + 8 * (size_t)W, 8, ncclFloat64, to, comm, st);
+      if (rc == 0) rc = g.Recv(buf + 8 * (size_t)from, 8, ncclFloat64, from, comm, st);
+    }
+    const ncclResult_t rc_end = g.GroupEnd();
+    if (rc == 0) rc = rc_end;
+  }
+  const cudaError_t ce = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  NCCL_CHECK(rc);
+  GPXB_CUDA_CHECK(ce);
+  return 0;
+}
+}  // namespace
+
 int comm_unique_id(void* out) {
   GPXB_TRY(load_nccl());
   ncclUniqueId id;
@@ -196,7 +227,8 @@ int comm_init(Ctx* ctx, const void* uid, int rank, int world) {
   GPXB_CUDA_CHECK(cudaSetDevice(ctx->device));
   NCCL_CHECK(g.CommInitRank(&c, world, id, rank));
   ctx->nccl_comm = c;
-  return peer_setup(ctx);
+  GPXB_TRY(peer_setup(ctx));
+  return comm_warmup(ctx);
 }
 
 int comm_destroy(Ctx* ctx) {

@@ -14,12 +14,12 @@ from ..mean_functions import mean_mode
 from ..random import as_key, split
 
 
-def fit_iter(state, xd, yd, ell, sigma, n_pivots, key_precond, return_iters=False):
+def fit_iter(state, xd, yd, ell, sigma, n_pivots, key_precond, return_iters=False, tol=1e-5, atol=1e-7):
     if n_pivots is None:
         raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
     key = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
     c, mu, iters = ops.gpr_fit_iter(state.kernel.kind, xd, yd, ell, sigma, int(n_pivots), key,
-                                    mean_mode(state.mean_function), threefry_partitionable())
+                                    mean_mode(state.mean_function), threefry_partitionable(), tol=tol, atol=atol)
     c, mu = c.cpu().numpy(), np.float64(mu.cpu().numpy()[0])
     return (c, mu, iters) if return_iters else (c, mu)
 
@@ -49,7 +49,8 @@ def lanczos_logdet(kind, xd, ell, diag_add, num_evals, num_lanczos, key):
     return slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), N)
 
 
-def lml_iter(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond):
+def lml_iter(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond, tol=1e-5,
+             atol=1e-7):
     """_lml_iter (gpx/models/_gpr.py:772-821).  One device sweep (gpxb_gpr_lml_iter): the PCG search direction rides as
     an extra column of the SLQ block mat-vecs, so fit and log-det share the passes over the recomputed kernel tiles."""
     if n_pivots is None:
@@ -60,7 +61,8 @@ def lml_iter(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_p
     U = ops.rademacher_probes(subkey, m, int(num_evals), part)
     kp = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
     c, mu, _, alpha, beta, flag = ops.gpr_lml_iter(state.kernel.kind, xd, yd, ell, sigma, int(n_pivots), kp, U,
-                                                   int(num_lanczos), mean_mode(state.mean_function), part)
+                                                   int(num_lanczos), mean_mode(state.mean_function), part, tol=tol,
+                                                   atol=atol)
     if int(flag.cpu().numpy()[0]) != 0:
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
                            "use fewer Lanczos steps than data points")
@@ -101,7 +103,8 @@ def slq_logdet_grad(alpha, beta, dalpha, dbeta, dim_mat):
     return (dim_mat / P) * acc, (dim_mat / P) * dacc
 
 
-def lml_iter_grad(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond):
+def lml_iter_grad(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond, tol=1e-5,
+                  atol=1e-7):
     """(lml, d lml/d lengthscale, d lml/d sigma) of _lml_iter as jit(value_and_grad) propagates it
     (gpx/models/_gpr.py:772-821 under gpx/optimizers/scipy_optimize.py:72-78): the CG solve is a
     lax.custom_linear_solve, so d(r.c) = -c^T dA c with c the computed PCG solution; the SLQ term is
@@ -110,7 +113,7 @@ def lml_iter_grad(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos
 
     kind = state.kernel.kind
     N = yd.shape[0]
-    c, mu = fit_iter(state, xd, yd, ell, sigma, n_pivots, key_precond)
+    c, mu = fit_iter(state, xd, yd, ell, sigma, n_pivots, key_precond, tol=tol, atol=atol)
     r = yd.cpu().numpy() - mu
     cd = torch.as_tensor(c, dtype=torch.float64, device=xd.device).reshape(-1, 1)
     c_dK_c = float((cd * ops.kmatvec_dl(kind, xd, cd, ell)).sum().cpu())

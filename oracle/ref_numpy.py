@@ -982,13 +982,13 @@ def lanczos_logdet_grad(kind, x, ell, sigma, num_evals, num_lanczos, key, partit
 
 
 def lml_iter_grad(kind, x, y, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
-                  mean_function=data_mean, partitionable=True):
+                  mean_function=data_mean, partitionable=True, cg_tol=1e-5, cg_atol=1e-7):
     """(lml, d/d ell, d/d sigma) of _lml_iter (_gpr.py:772-821) as jit(value_and_grad) propagates it:
     the CG solve is a lax.custom_linear_solve, so d(r.c) = -c^T dA c with c the computed PCG solution
     (nothing flows through the preconditioner or the iteration count); the SLQ term is differentiated
     through the Lanczos recursion and the eigendecomposition."""
     m = y.shape[0]
-    c, mu, _ = fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function, partitionable)
+    c, mu, _ = fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function, partitionable, cg_tol, cg_atol)
     r = y - mu
     ld, ld_l, ld_s = lanczos_logdet_grad(kind, x, ell, sigma, num_evals, num_lanczos, key_lanczos, partitionable)
     _, dK = kernel_dl(kind, x, x, ell)
@@ -1070,21 +1070,23 @@ def lml_derivs_iter_grad(kind, x, y, J, ell, sigma, num_evals, num_lanczos, key_
     return mll, g_l, g_s
 
 
-def fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function=data_mean, partitionable=True):
-    """_gpr.py:285-310."""
+def fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function=data_mean, partitionable=True,
+             cg_tol=1e-5, cg_atol=1e-7):
+    """_gpr.py:285-310.  cg_tol / cg_atol default to the reference's stopping rule (jax cg: tol=1e-5; atol=1e-7 at the
+    call site); the tests tighten them on BOTH sides to compare converged solves at 1e-8 (a test knob, not in GPX)."""
     mu = mean_function(y)
     r = y - mu
     mv = make_matvec(kind, x, ell, sigma)
     pre = precond_rpcholesky(kind, x, ell, sigma, n_pivots, key_precond, partitionable)
-    c, iters = cg(mv, r, M=pre, atol=1e-7)
+    c, iters = cg(mv, r, M=pre, tol=cg_tol, atol=cg_atol)
     return c, mu, iters
 
 
 def lml_iter(kind, x, y, ell, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
-             mean_function=data_mean, partitionable=True):
-    """_gpr.py:772-821."""
+             mean_function=data_mean, partitionable=True, cg_tol=1e-5, cg_atol=1e-7):
+    """_gpr.py:772-821 (cg_tol / cg_atol: see fit_iter)."""
     m = y.shape[0]
-    c, mu, _ = fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function, partitionable)
+    c, mu, _ = fit_iter(kind, x, y, ell, sigma, n_pivots, key_precond, mean_function, partitionable, cg_tol, cg_atol)
     r = y - mu
     mv = make_matvec(kind, x, ell, sigma)
     mll = -0.5 * np.sum(r.T @ c)

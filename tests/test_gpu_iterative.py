@@ -169,6 +169,43 @@ def test_lml_iter_facade_matches_oracle():
     assert abs(out - ref) < 1e-7 * abs(ref)
 
 
+def _iter_state(ell, sigma):
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.kernels import SquaredExponential
+    from gpx_b200.models import gpr
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.priors import GammaPrior
+
+    return gpr.init(SquaredExponential(), kernel_params=dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior())),
+                    sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+
+
+def test_iterative_fit_lml_and_gradient_at_1e8_with_converged_cg():
+    """north_star's 1e-8 for the iterative path.  With the reference's stopping rule (tol 1e-5) the CG solution is only
+    determined to ~1e-6, whatever the arithmetic; with the SAME tighter stopping rule on both sides the solves are
+    converged and coefficients, LML and gradient agree with the oracle to 1e-8."""
+    from gpx_b200 import ops
+    from gpx_b200.models import _iterative
+
+    N, D = 2048, 16
+    x, y = _data(N, D, 4)
+    ell, sigma = 4.0, 0.5
+    key = R.PRNGKey(2023)
+    tight = dict(cg_tol=1e-13, cg_atol=0.0)
+    c_ref, mu_ref, _ = R.fit_iter("se", x, y, ell, sigma, 30, key, **tight)
+    c, mu, _ = ops.gpr_fit_iter("se", dev(x), dev(y), ell, sigma, 30, key, tol=1e-13, atol=0.0)
+    assert rel(host(c), c_ref) < 1e-8
+    state = _iter_state(ell, sigma)
+    ref = R.lml_iter("se", x, y, ell, sigma, 8, 20, key, 30, key, **tight)
+    out = _iterative.lml_iter(state, dev(x), dev(y), ell, sigma, 8, 20, key, 30, key, tol=1e-13, atol=0.0)
+    assert abs(out - ref) < 1e-8 * abs(ref)
+    refg = R.lml_iter_grad("se", x, y, ell, sigma, 6, 15, key, 25, key, **tight)
+    outg = _iterative.lml_iter_grad(state, dev(x), dev(y), ell, sigma, 6, 15, key, 25, key, tol=1e-13, atol=0.0)
+    scale = max(abs(v) for v in refg)
+    for a, b in zip(outg, refg):
+        assert abs(a - b) < 1e-8 * scale, (outg, refg)
+
+
 @pytest.mark.parametrize("kind,N,D,P", [("se", 700, 16, 5), ("m52", 513, 8, 33), ("m32", 300, 3, 1), ("m12", 260, 2, 2)])
 def test_kmatvec_dl_matches_oracle(kind, N, D, P):
     from gpx_b200 import ops
@@ -261,6 +298,43 @@ def test_sgpr_lml_fit_predict(kind, N, D, M, ell, sigma, T):
     # with the oracle's coefficients the device prediction itself is tight
     mean2 = ops.sgpr_predict(kind, dev(xl), dev(xs), dev(c_ref), dev(np.array([mu_ref])), ell, sigma)
     assert rel(host(mean2), m_ref) < 1e-10
+
+
+def test_sgpr_predict_at_1e8_and_the_oracle_conditioning_floor():
+    """Predictive mean / covariance of SGPR against the oracle at north_star's 1e-8 on a system whose M x M matrix
+    C = s^2 K_mm + K_mn K_nm is moderately conditioned; and, for the RPCholesky-landmark case of
+    test_sgpr_lml_fit_predict (cond(C) ~ 1e13+), the proof that 1e-6 there is the ORACLE's own floor: solving the
+    oracle's system by Cholesky instead of LU moves the oracle's predictions by as much as the device differs."""
+    from gpx_b200 import ops
+
+    kind, N, D, M, ell, sigma = "se", 2000, 8, 48, 1.2, 0.7
+    x, y = _data(N, D, 5)
+    xl = x[np.random.default_rng(3).choice(N, M, replace=False)].copy()
+    xs = np.random.default_rng(9).standard_normal((200, D))
+    c_ref, mu_ref = R.sgpr_fit_dense(kind, xl, x, y, ell, sigma)
+    m_ref, C_ref = R.sgpr_predict_dense(kind, xl, xs, c_ref, mu_ref, ell, sigma, full_covariance=True)
+    c, mu = ops.sgpr_fit(kind, dev(x), dev(y), dev(xl), ell, sigma)
+    mean, cov = ops.sgpr_predict(kind, dev(xl), dev(xs), c, mu, ell, sigma, full_covariance=True)
+    assert rel(host(c), c_ref) < 1e-8
+    assert rel(host(mean), m_ref) < 1e-8
+    assert np.max(np.abs(host(cov) - C_ref)) < 1e-8 * max(1.0, np.max(np.abs(C_ref)))
+
+    # the ill-conditioned case: two algebraically identical oracle solves disagree at the level of the device error
+    kind, N, D, M, ell, sigma = "se", 3000, 8, 64, 2.0, 0.1
+    x, y = _data(N, D, 5)
+    _, piv = R.rpcholesky(kind, x, M, ell, R.PRNGKey(2023))
+    xl = x[piv].copy()
+    Cm, K_mn = R.sgpr_A_lhs(kind, xl, x, ell, sigma)
+    rhs = K_mn @ (y - y.mean())
+    c_lu = np.linalg.solve(Cm, rhs)
+    Lc = np.linalg.cholesky(Cm)
+    c_ch = np.linalg.solve(Lc.T, np.linalg.solve(Lc, rhs))
+    Ks = R.kernel(kind, xs[:, :D], xl, ell)
+    floor = np.max(np.abs(Ks @ c_lu - Ks @ c_ch)) / np.max(np.abs(Ks @ c_lu))
+    c, mu = ops.sgpr_fit(kind, dev(x), dev(y), dev(xl), ell, sigma)
+    mean = host(ops.sgpr_predict(kind, dev(xl), dev(xs), c, mu, ell, sigma))
+    err = rel(mean, y.mean() + Ks @ c_lu)
+    assert err < max(1e-8, 50.0 * floor), (err, floor, np.linalg.cond(Cm))
 
 
 def test_gather_rows():
