@@ -144,7 +144,6 @@ int gpxb_gram(gpxb_ctx* ctx_, int kind, const double* x1, int n1, const double* 
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   cudaStream_t s = (cudaStream_t)stream;
   const gpxb::ZLayout zl = gpxb::z_layout(D);
-  GPXB_ARG_CHECK(zl.S <= gpxb::GRAM_MAX_S, -3);
   const bool sym = (x1 == x2) && (n1 == n2);
   GPXB_ARG_CHECK(!lower_only || sym, -4);
   DevBuf z1, z2;
@@ -172,7 +171,6 @@ int gpxb_gram_dl_contract(gpxb_ctx* ctx_, int kind, const double* x1, int n1, co
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   cudaStream_t s = (cudaStream_t)stream;
   const gpxb::ZLayout zl = gpxb::z_layout(D);
-  GPXB_ARG_CHECK(zl.S <= gpxb::GRAM_MAX_S, -3);
   const bool sym = (x1 == x2) && (n1 == n2);
   GPXB_ARG_CHECK(!sym_lower || sym, -4);
   DevBuf z1, z2, part;

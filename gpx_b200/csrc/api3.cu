@@ -126,6 +126,16 @@ int gpxb_rademacher_probes(gpxb_ctx* ctx_, uint32_t key0, uint32_t key1, int N, 
                            (cudaStream_t)stream);
 }
 
+int gpxb_lanczos_set_restart(gpxb_ctx* ctx_, int enabled, uint32_t key0, uint32_t key1, int partitionable) {
+  GPXB_ARG_CHECK(ctx_, -1);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  ctx->restart_on = enabled != 0;
+  ctx->restart_key[0] = key0;
+  ctx->restart_key[1] = key1;
+  ctx->restart_partitionable = partitionable != 0;
+  return 0;
+}
+
 int gpxb_lanczos(gpxb_ctx* ctx_, int kind, const double* x, int N, int D, double ell, double diag_add,
                  const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out,
                  int* breakdown_flag, gpxb_stream stream) {

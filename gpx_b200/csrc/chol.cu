@@ -386,15 +386,13 @@ int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s)
     gen = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
   }
   if (gen == 2) {
-    GPXB_CUDA_CHECK(cudaFuncSetAttribute(potrf_leaf_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         LEAF2_SMEM));
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(potrf_leaf_dmma_kernel), LEAF2_SMEM));
     potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv);
     GPXB_LAUNCH_CHECK();
     ctx->launches++;
     return 0;
   }
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       LEAF_SMEM));
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(potrf_leaf_kernel), LEAF_SMEM));
   potrf_leaf_kernel<<<1, LEAF_NT, LEAF_SMEM, s>>>(A, lda, n, inv);
   GPXB_LAUNCH_CHECK();
   ctx->launches++;

@@ -1,5 +1,7 @@
 // Common device/host helpers for libgpxb200 (sm_100a only).
 #pragma once
+#include <unordered_map>
+#include <mutex>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -51,6 +53,19 @@ static inline long long round_up(long long a, long long b) { return (a + b - 1) 
 // All scratch memory is stream-ordered (cudaMallocAsync on the caller's stream),
 // so every entry point is enqueue-only and re-entrant per context.
 // ---------------------------------------------------------------------------
+// Raises a kernel's dynamic shared-memory limit the first time (or when a larger size is asked for): the driver call
+// costs microseconds and the launch paths run thousands of times per LML evaluation.
+inline cudaError_t ensure_dyn_smem(const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = seen.find(fn);
+  if (it != seen.end() && it->second >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) seen[fn] = bytes;
+  return e;
+}
+
 struct Ctx {
   int device = 0;
   int num_sms = 148;
@@ -79,6 +94,10 @@ struct Ctx {
   struct ProfRec { cudaEvent_t e0, e1; double flops; };
   std::vector<ProfRec> prof_recs;
   void* nccl_comm = nullptr;
+  // Lanczos breakdown branch (gpx/lanczos.py:92-108): key carried into lanczos_tridiagonal; off: breakdown only flags
+  bool restart_on = false;
+  uint32_t restart_key[2] = {0u, 0u};
+  int restart_partitionable = 1;
   void* peer = nullptr;  // PeerState* (comm.cu): IPC-mapped mailboxes of all ranks, or null
   int rank = 0, world = 1;
   long long shard_N = 0;  // global row count of the sharded problem in flight

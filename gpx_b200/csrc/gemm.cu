@@ -333,12 +333,10 @@ int launch(Ctx* ctx, const GemmParams& p, int grid1, int batch, cudaStream_t str
     GPXB_CUDA_CHECK(cudaEventRecord(rec.e0, stream));
   }
   if (gemm_variant() == 8) {
-    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<AK, BKM, 2, 4>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 2, 4>), SMEM_BYTES));
     gemm_f64_kernel<AK, BKM, 2, 4><<<grid, 256, SMEM_BYTES, stream>>>(p);
   } else {
-    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gemm_f64_kernel<AK, BKM, 4, 4>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 4, 4>), SMEM_BYTES));
     gemm_f64_kernel<AK, BKM, 4, 4><<<grid, 512, SMEM_BYTES, stream>>>(p);
   }
   GPXB_LAUNCH_CHECK();

@@ -31,6 +31,7 @@ struct GramParams {
   int S, Dp;
   double ell, diag_add;
   int sym, lower_only;
+  long long doff;
   double* out;
   long long ldo;
   int vec_out;
@@ -91,13 +92,22 @@ __global__ void prep_z_kernel(const double* __restrict__ x, long long ldx, int n
   zi[Dp] = nrm;
 }
 
-template <bool CONTRACT, int KIND>
+// KT = false: the whole feature range of both operand tiles fits in shared memory (S <= GRAM_MAX_S): one bulk copy
+// per operand.  KT = true (any feature count): the features stream through two stages of KTC-column slabs; a slab
+// of a row-major operand is one bulk copy per row (KTC * 8 bytes each), issued by warp 0 one slab ahead of the DMMA
+// loop; |z|^2 comes from two small shared arrays filled from column Dp of the operands.
+constexpr int KTC = 32;   // features per slab
+constexpr int KTS = 36;   // slab row stride in shared memory (== 4 mod 8: conflict-free fragment reads)
+constexpr int KT_STAGE_DBL = 2 * TB * KTS;
+
+template <bool CONTRACT, int KIND, bool KT>
 __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sZ1 = reinterpret_cast<double*>(smem_raw + 128);
-  double* sZ2 = sZ1 + TB * p.S;
+  double* sZ2 = sZ1 + (KT ? TB * KTS : TB * p.S);
   __shared__ double red[NT / 32];
+  __shared__ double sN[KT ? 2 * TB : 2];  // KT: |z_i|^2 of the row tile, then of the column tile
   __shared__ double etab[64];  // 2^(j/64) for exp_tab
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -121,17 +131,11 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
   const int rows1 = min(TB, p.n1 - row0), rows2 = min(TB, p.n2 - col0);
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    const uint32_t b1 = (uint32_t)rows1 * p.S * 8u, b2 = (uint32_t)rows2 * p.S * 8u;
-    mbar_arrive_expect_tx(bar, b1 + b2);
-    tma_bulk_g2s(sZ1, p.Z1 + (long long)row0 * p.S, b1, bar);
-    tma_bulk_g2s(sZ2, p.Z2 + (long long)col0 * p.S, b2, bar);
-  }
-  mbar_wait(bar, 0);
 
   double acc[8][4][2];
 #pragma unroll
@@ -139,35 +143,86 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const double* a_base = sZ1 + (wm * 64 + lr) * p.S + lq;
-  const double* b_base = sZ2 + (wn * 32 + lr) * p.S + lq;
-  const int S8 = 8 * p.S;
-  for (int k = 0; k < p.Dp; k += 4) {
-    double a[8], b[4];
+  if (!KT) {
+    if (tid == 0) {
+      const uint32_t b1 = (uint32_t)rows1 * p.S * 8u, b2 = (uint32_t)rows2 * p.S * 8u;
+      mbar_arrive_expect_tx(bar, b1 + b2);
+      tma_bulk_g2s(sZ1, p.Z1 + (long long)row0 * p.S, b1, bar);
+      tma_bulk_g2s(sZ2, p.Z2 + (long long)col0 * p.S, b2, bar);
+    }
+    mbar_wait(bar, 0);
+    const double* a_base = sZ1 + (wm * 64 + lr) * p.S + lq;
+    const double* b_base = sZ2 + (wn * 32 + lr) * p.S + lq;
+    const int S8 = 8 * p.S;
+    for (int k = 0; k < p.Dp; k += 4) {
+      double a[8], b[4];
 #pragma unroll
-    for (int mf = 0; mf < 8; ++mf) a[mf] = a_base[mf * S8 + k];
+      for (int mf = 0; mf < 8; ++mf) a[mf] = a_base[mf * S8 + k];
 #pragma unroll
-    for (int nf = 0; nf < 4; ++nf) b[nf] = b_base[nf * S8 + k];
+      for (int nf = 0; nf < 4; ++nf) b[nf] = b_base[nf * S8 + k];
 #pragma unroll
-    for (int mf = 0; mf < 8; ++mf)
+      for (int mf = 0; mf < 8; ++mf)
 #pragma unroll
-      for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
+        for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
+    }
+  } else {
+    // rows beyond the matrix edge are never copied: zero both stages once so that their (masked) products stay finite
+    for (int i = tid; i < 2 * KT_STAGE_DBL; i += NT) sZ1[i] = 0.0;
+    if (tid < TB) sN[tid] = (tid < rows1) ? p.Z1[(long long)(row0 + tid) * p.S + p.Dp] : 0.0;
+    else sN[tid] = (tid - TB < rows2) ? p.Z2[(long long)(col0 + tid - TB) * p.S + p.Dp] : 0.0;
+    fence_proxy_async();  // the generic-proxy zero fill is ordered before the async-proxy bulk copies
+    __syncthreads();
+    const int nslab = (p.Dp + KTC - 1) / KTC;
+    auto issue = [&](int sl) {  // warp 0: slab sl of both operands into stage sl & 1
+      const int k0 = sl * KTC, kc = min(KTC, p.Dp - k0);
+      double* d1 = sZ1 + (sl & 1) * KT_STAGE_DBL;
+      double* d2 = d1 + TB * KTS;
+      if (lane == 0) mbar_arrive_expect_tx(&bar[sl & 1], (uint32_t)(rows1 + rows2) * kc * 8u);
+      __syncwarp();
+      for (int r = lane; r < rows1; r += 32)
+        tma_bulk_g2s(d1 + r * KTS, p.Z1 + (long long)(row0 + r) * p.S + k0, (uint32_t)kc * 8u, &bar[sl & 1]);
+      for (int r = lane; r < rows2; r += 32)
+        tma_bulk_g2s(d2 + r * KTS, p.Z2 + (long long)(col0 + r) * p.S + k0, (uint32_t)kc * 8u, &bar[sl & 1]);
+    };
+    if (warp == 0) issue(0);
+    for (int sl = 0; sl < nslab; ++sl) {
+      if (warp == 0 && sl + 1 < nslab) issue(sl + 1);  // stage (sl + 1) & 1 was released by the barrier below
+      mbar_wait(&bar[sl & 1], (sl >> 1) & 1);
+      const int kc = min(KTC, p.Dp - sl * KTC);
+      const double* a_base = sZ1 + (sl & 1) * KT_STAGE_DBL + (wm * 64 + lr) * KTS + lq;
+      const double* b_base = sZ1 + (sl & 1) * KT_STAGE_DBL + TB * KTS + (wn * 32 + lr) * KTS + lq;
+      for (int k = 0; k < kc; k += 4) {
+        double a[8], b[4];
+#pragma unroll
+        for (int mf = 0; mf < 8; ++mf) a[mf] = a_base[mf * 8 * KTS + k];
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) b[nf] = b_base[nf * 8 * KTS + k];
+#pragma unroll
+        for (int mf = 0; mf < 8; ++mf)
+#pragma unroll
+          for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
+      }
+      __syncthreads();
+    }
   }
+  // |z|^2 of local row r / local column c
+  auto nrm1 = [&](int r) { return KT ? sN[r] : sZ1[r * p.S + p.Dp]; };
+  auto nrm2 = [&](int c) { return KT ? sN[TB + c] : sZ2[c * p.S + p.Dp]; };
 
   // ---- fused epilogue ----
   double nj[4][2];
 #pragma unroll
   for (int nf = 0; nf < 4; ++nf) {
     const int c = wn * 32 + nf * 8 + lq * 2;
-    nj[nf][0] = sZ2[c * p.S + p.Dp];
-    nj[nf][1] = sZ2[(c + 1) * p.S + p.Dp];
+    nj[nf][0] = nrm2(c);
+    nj[nf][1] = nrm2(c + 1);
   }
   if (!CONTRACT) {
 #pragma unroll
     for (int mf = 0; mf < 8; ++mf) {
       const int rloc = wm * 64 + mf * 8 + lr;
       const int gi = row0 + rloc;
-      const double ni = sZ1[rloc * p.S + p.Dp];
+      const double ni = nrm1(rloc);
 #pragma unroll
       for (int nf = 0; nf < 4; ++nf) {
         const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
@@ -178,8 +233,9 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
           const int j = gj + e;
           ok[e] = (gi < p.n1) && (j < p.n2) && (!p.lower_only || j <= gi);
           double d2 = ((ni - 2.0 * acc[mf][nf][e]) + nj[nf][e]) + 1e-12;
-          if (p.sym && (gi == j)) d2 = 1e-12;
-          v[e] = kfun_t<KIND>(d2, etab) + ((gi == j) ? p.diag_add : 0.0);
+          const bool on_diag = (gi + p.doff == j);
+          if (p.sym && on_diag) d2 = 1e-12;
+          v[e] = kfun_t<KIND>(d2, etab) + (on_diag ? p.diag_add : 0.0);
         }
         double* o = p.out + (long long)gi * p.ldo + gj;
         if (p.vec_out && ok[0] && ok[1]) {
@@ -212,7 +268,7 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
     for (int mf = 0; mf < 8; ++mf) {
       const int rloc = wm * 64 + mf * 8 + lr;
       const int gi = row0 + rloc;
-      const double ni = sZ1[rloc * p.S + p.Dp];
+      const double ni = nrm1(rloc);
       const double ai = p.t ? p.alpha[gi] : 0.0;
       double2 y[4];
 #pragma unroll
@@ -236,7 +292,7 @@ __global__ void __launch_bounds__(NT, 1) gram_kernel(const GramParams p) {
     for (int mf = 0; mf < 8; ++mf) {
       const int rloc = wm * 64 + mf * 8 + lr;
       const int gi = row0 + rloc;
-      const double ni = sZ1[rloc * p.S + p.Dp];
+      const double ni = nrm1(rloc);
 #pragma unroll
       for (int nf = 0; nf < 4; ++nf) {
         const int gj = col0 + wn * 32 + nf * 8 + lq * 2;
@@ -281,14 +337,15 @@ long long gram_num_ctas(const GramArgs& a) {
 
 int gram_launch(Ctx* ctx, const GramArgs& a, cudaStream_t s) {
   if (a.n1 <= 0 || a.n2 <= 0) return 0;
-  GPXB_ARG_CHECK(a.zl.S <= GRAM_MAX_S, -10);
   GPXB_ARG_CHECK(!a.lower_only || a.n1 == a.n2, -11);
+  const bool kt = a.zl.S > GRAM_MAX_S;  // more features than two whole operand tiles hold: stream them in slabs
   GramParams p;
   p.kind = a.kind;
   p.Z1 = a.Z1; p.n1 = a.n1; p.Z2 = a.Z2; p.n2 = a.n2;
   p.S = a.zl.S; p.Dp = a.zl.Dp;
   p.ell = a.ell; p.diag_add = a.diag_add;
-  p.sym = a.sym; p.lower_only = a.lower_only;
+  p.sym = a.sym; p.lower_only = a.lower_only; p.doff = a.diag_off;
+  GPXB_ARG_CHECK(a.diag_off == 0 || (a.out && !a.lower_only), -15);
   p.out = a.out; p.ldo = a.ldo;
   p.vec_out = a.out && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) && (a.ldo % 2 == 0);
   p.Ainv = a.Ainv; p.ldainv = a.ldainv; p.alpha = a.alpha; p.alpha2 = a.alpha2 ? a.alpha2 : a.alpha;
@@ -297,15 +354,20 @@ int gram_launch(Ctx* ctx, const GramArgs& a, cudaStream_t s) {
   p.tiles_n = ceil_div(a.n2, TB);
   const long long grid = gram_num_ctas(a);
   GPXB_ARG_CHECK(grid < (1LL << 31), -12);
-  const int smem = 128 + 2 * TB * p.S * (int)sizeof(double);
+  const int smem = 128 + (kt ? 2 * KT_STAGE_DBL : 2 * TB * p.S) * (int)sizeof(double);
   if (!a.out) {
     GPXB_ARG_CHECK(a.Ainv && a.partials && (a.alpha || a.t == 0), -13);
     GPXB_ARG_CHECK(a.t == 0 || a.alpha2 || (a.sym && a.n1 == a.n2), -14);
   }
-#define GPXB_GRAM_GO(C, K)                                                                                   \
-  do {                                                                                                       \
-    GPXB_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    gram_kernel<C, K><<<(int)grid, NT, smem, s>>>(p);                                                        \
+#define GPXB_GRAM_GO2(C, K, T)                                                                                    \
+  do {                                                                                                            \
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gram_kernel<C, K, T>), smem)); \
+    gram_kernel<C, K, T><<<(int)grid, NT, smem, s>>>(p);                                                          \
+  } while (0)
+#define GPXB_GRAM_GO(C, K)                 \
+  do {                                     \
+    if (kt) GPXB_GRAM_GO2(C, K, true);     \
+    else GPXB_GRAM_GO2(C, K, false);       \
   } while (0)
 #define GPXB_GRAM_KIND(C)                                  \
   do {                                                     \
@@ -320,6 +382,7 @@ int gram_launch(Ctx* ctx, const GramArgs& a, cudaStream_t s) {
   else GPXB_GRAM_KIND(true);
 #undef GPXB_GRAM_KIND
 #undef GPXB_GRAM_GO
+#undef GPXB_GRAM_GO2
   GPXB_LAUNCH_CHECK();
   ctx->launches++;
   return 0;

@@ -22,7 +22,7 @@ inline ZLayout z_layout(int D) {
   z.S = s;
   return z;
 }
-constexpr int GRAM_MAX_S = 108;  // 2 tiles * 128 rows * S * 8 B must fit in 227 KB of smem
+constexpr int GRAM_MAX_S = 108;  // 2 tiles * 128 rows * S * 8 B fit in 227 KB of smem; beyond: the K-tiled variant
 
 int prep_z(Ctx* ctx, const double* x, long long ldx, int n, ZLayout zl, double ell, double* Z,
            cudaStream_t s);
@@ -37,6 +37,7 @@ struct GramArgs {
   double ell = 1.0;
   double diag_add = 0.0;  // added where global row == col
   int sym = 0;            // Z1 and Z2 are the same points: exact d2 = 1e-12 on the diagonal
+  long long diag_off = 0;  // store mode: the diagonal is where row + diag_off == col (Z1 is a row range of Z2)
   int lower_only = 0;
   // store mode
   double* out = nullptr;

@@ -282,7 +282,7 @@ static int hess_run(Ctx* ctx, int kind, const double* x1, const double* J1, int 
   const int smem = 128 + 2 * TB * p.S * (int)sizeof(double);
   p.Ainv = Ainv; p.ldainv = ldainv; p.alpha = alpha; p.partials = nullptr;
   if (!contract) {
-    GPXB_CUDA_CHECK(cudaFuncSetAttribute(hess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(hess_kernel<false>), smem));
     hess_kernel<false><<<(int)grid, NT, smem, s>>>(p);
     GPXB_LAUNCHED(ctx);
     return 0;
@@ -290,7 +290,7 @@ static int hess_run(Ctx* ctx, int kind, const double* x1, const double* J1, int 
   DevBuf bPart;
   GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)grid, s));
   p.partials = bPart.as<double>();
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(hess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(hess_kernel<true>), smem));
   hess_kernel<true><<<(int)grid, NT, smem, s>>>(p);
   GPXB_LAUNCHED(ctx);
   sk::sum_kernel<<<1, 1024, 0, s>>>(p.partials, grid, contract_out);  // fixed order: deterministic
@@ -828,6 +828,295 @@ int gpr_derivs_iter(Ctx* ctx, int kind, const double* x, const double* J, const 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Iterative GPR on targets AND derivatives (gpx/models/gpr_td.py: _Ax_lhs_fun 162-310, rpcholesky_TD 313-460,
+// _precond_rpcholesky_TD 463-504, _fit_iter 685-747, _lml_iter 562-637; one derivative block).
+//         / K + s_t I      d1kj      \      rows / columns ordered [targets (N); derivatives (sample, variable)]
+//     A = |                           |
+//         \   d0kj     d01kj + s_d I /
+// With C1_st the gradient profile (d k/d x2 = C1 (x1 - x2), d k/d x1 = -C1 (x1 - x2); HessOp's C1) and m_t the
+// jacobian-contracted derivative part of the vector (HessOp's M), r_t = m_t . x_t:
+//   (d1kj z2)_s     =  x_s . (C1 M)_s - (C1 r)_s
+//   (d0kj z1)_(s,v) = -J_s[:, v] . (x_s (C1 z1)_s - (C1 (X o z1))_s)
+// so one extra N x N x (nf + 2) GEMM with C1 and one GEMV with K ride on the three GEMMs of the Hessian operator.
+// ------------------------------------------------------------------------------------------------
+namespace {
+// B[i] = (z1[i], x[i][:] * z1[i], r[i])      N x (nf + 2)
+__global__ void td_build_b_kernel(const double* __restrict__ z1, long long ldv, const double* __restrict__ x,
+                                  const double* __restrict__ r, int N, int nf, double* __restrict__ B) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = nf + 2;
+  if (idx >= (long long)N * w) return;
+  const int i = (int)(idx / w), c = (int)(idx % w);
+  const double z = z1[(long long)i * ldv];
+  B[idx] = c == 0 ? z : (c <= nf ? x[(long long)i * nf + c - 1] * z : r[i]);
+}
+// W1[i] = (K z1)[i] + s_t z1[i] + x_i . H1_i - T[i][nf + 1]
+__global__ void td_out1_kernel(const double* __restrict__ t0, const double* __restrict__ z1, long long ldv,
+                               const double* __restrict__ x, const double* __restrict__ H1,
+                               const double* __restrict__ T, int N, int nf, double s_t, double* __restrict__ W,
+                               long long ldw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double a = 0.0;
+  for (int f = 0; f < nf; ++f) a += x[(long long)i * nf + f] * H1[(long long)i * nf + f];
+  W[(long long)i * ldw] = t0[i] + s_t * z1[(long long)i * ldv] + a - T[(long long)i * (nf + 2) + nf + 1];
+}
+// W2[(i,u)] -= sum_f J[i][f][u] (x[i][f] T[i][0] - T[i][1 + f])
+__global__ void td_out2_kernel(const double* __restrict__ J, const double* __restrict__ x,
+                               const double* __restrict__ T, int N, int nf, int nv, double* __restrict__ W,
+                               long long ldw) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (long long)N * nv) return;
+  const int i = (int)(r / nv), u = (int)(r % nv);
+  const double* Ji = J + (long long)i * nf * nv + u;
+  const double* Ti = T + (long long)i * (nf + 2);
+  const double* xi = x + (long long)i * nf;
+  double a = 0.0;
+  for (int f = 0; f < nf; ++f) a += Ji[(long long)f * nv] * (xi[f] * Ti[0] - Ti[1 + f]);
+  W[r * ldw] -= a;
+}
+// rows of the pivot-buffer layout: zero for the targets, J_t[:, u] for the derivative rows
+__global__ void td_rows_kernel(const double* __restrict__ J, int N, int nf, int nv, int S, double* __restrict__ rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)N + (long long)N * nv;
+  if (idx >= n * S) return;
+  const long long r = idx / S;
+  const int f = (int)(idx % S);
+  double v = 0.0;
+  if (r >= N && f < nf) {
+    const long long q = r - N;
+    v = J[(q / nv) * nf * nv + (long long)f * nv + q % nv];
+  }
+  rows[idx] = v;
+}
+// diag0 = [k(x, x) (d2 = 1e-12); c1(1e-12) |J_t[:, u]|^2]
+__global__ void td_diag_kernel(const double* __restrict__ J, int N, int nf, int nv, double k0, double c1_0,
+                               double* __restrict__ diag0) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (long long)N + (long long)N * nv) return;
+  if (r < N) {
+    diag0[r] = k0;
+    return;
+  }
+  const long long q = r - N;
+  const double* Jt = J + (q / nv) * nf * nv + q % nv;
+  double a = 0.0;
+  for (int f = 0; f < nf; ++f) a += Jt[(long long)f * nv] * Jt[(long long)f * nv];
+  diag0[r] = c1_0 * a;
+}
+// column `piv` of the block matrix without the noise terms (rpcholesky_TD first_row / second_row, :389-420)
+__global__ void td_column_kernel(const double* __restrict__ x, const double* __restrict__ J, int N, int nf, int nv,
+                                 int kind, double ell, const double* __restrict__ pbuf, double* __restrict__ col) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (long long)N + (long long)N * nv) return;
+  const long long piv = (long long)pbuf[0];
+  const bool prow_t = piv < N;  // the pivot is a target row
+  const long long s1 = prow_t ? piv : (piv - N) / nv;
+  const int v1 = prow_t ? 0 : (int)((piv - N) % nv);
+  const bool rrow_t = r < N;
+  const long long t = rrow_t ? r : (r - N) / nv;
+  const int u = rrow_t ? 0 : (int)((r - N) % nv);
+  const double* xs = x + s1 * nf;
+  const double* xt = x + t * nf;
+  const double* a = J + s1 * nf * nv + v1;  // J_s1[:, v1] (stride nv), used when the pivot is a derivative row
+  const double* b = J + t * nf * nv + u;    // J_t[:, u]
+  double dd = 0.0, ab = 0.0, ad = 0.0, bd = 0.0;
+  for (int f = 0; f < nf; ++f) {
+    const double d = xs[f] - xt[f];  // x_pivot - x_row
+    dd += d * d;
+    const double af = prow_t ? 0.0 : a[(long long)f * nv], bf = rrow_t ? 0.0 : b[(long long)f * nv];
+    ab += af * bf;
+    ad += af * d;
+    bd += bf * d;
+  }
+  double d2 = dd / (ell * ell) + 1e-12;
+  if (t == s1) d2 = 1e-12;
+  double k, c1, c2, kappa;
+  if (kind == KIND_SE) {
+    k = exp(-d2);
+    kappa = 2.0 / (ell * ell);
+    c2 = k;
+    c1 = kappa * k;
+  } else {
+    const double d = 2.23606797749979 * sqrt(fmax(d2, 1e-36));
+    const double e = exp(-d);
+    k = (1.0 + d + d * d / 3.0) * e;
+    c2 = (5.0 / (3.0 * ell * ell)) * e;
+    c1 = c2 * (1.0 + d);
+    kappa = 2.23606797749979 / ell;
+  }
+  double out;
+  if (prow_t && rrow_t) out = k;                       // k(x_s, x_t)
+  else if (prow_t) out = c1 * bd;                      // d1kj: d k(x_s, x_t)/d x_t . J_t[:, u] = c1 (x_s - x_t) . b
+  else if (rrow_t) out = -c1 * ad;                     // d0kj: d k(x_s1, x_t)/d x_s1 . a = -c1 (x_s1 - x_t) . a
+  else out = c1 * ab - kappa * kappa * c2 * ad * bd;   // d01kj (hess_column_kernel)
+  col[r] = out;
+}
+}  // namespace
+
+struct TdOp {
+  HessOp h;
+  int N = 0, nf = 0, nv = 0;
+  const double *x = nullptr, *J = nullptr;
+  double s_t = 0.0;
+  DevBuf C0, B, T, t0;
+  long long rows() const { return (long long)N + (long long)N * nv; }
+};
+
+int td_op_prepare(Ctx* ctx, TdOp& op, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                  double s_t, double s_d, cudaStream_t s) {
+  op.N = N; op.nf = nf; op.nv = nv; op.x = x; op.J = J; op.s_t = s_t;
+  op.h.kind = kind; op.h.N1 = op.h.N2 = N; op.h.nv1 = op.h.nv2 = nv; op.h.nf = nf;
+  op.h.x1 = op.h.x2 = x; op.h.J1 = op.h.J2 = J; op.h.ell = ell; op.h.diag_add = s_d;
+  GPXB_TRY(hess_op_prepare(ctx, op.h, s));
+  const ZLayout zl = z_layout(nf);
+  DevBuf bZ;
+  GPXB_TRY(bZ.alloc(sizeof(double) * (size_t)N * zl.S, s));
+  GPXB_TRY(op.C0.alloc(sizeof(double) * (size_t)N * N, s));
+  GPXB_TRY(op.B.alloc(sizeof(double) * (size_t)N * (nf + 2), s));
+  GPXB_TRY(op.T.alloc(sizeof(double) * (size_t)N * (nf + 2), s));
+  GPXB_TRY(op.t0.alloc(sizeof(double) * (size_t)N, s));
+  GPXB_TRY(prep_z(ctx, x, nf, N, zl, ell, bZ.as<double>(), s));
+  GramArgs g;
+  g.kind = kind; g.Z1 = bZ.as<double>(); g.n1 = N; g.Z2 = bZ.as<double>(); g.n2 = N; g.zl = zl; g.ell = ell;
+  g.sym = 1; g.out = op.C0.as<double>(); g.ldo = N;
+  return gram_launch(ctx, g, s);
+}
+
+// one column: W = A V, V / W of length N + N nv with strides ldv / ldw
+int td_op_apply(Ctx* ctx, TdOp& op, const double* V, long long ldv, double* W, long long ldw, cudaStream_t s) {
+  const int N = op.N, nf = op.nf, nv = op.nv;
+  const double* z2 = V + (long long)N * ldv;
+  double* W2 = W + (long long)N * ldw;
+  GPXB_TRY(hess_op_apply(ctx, op.h, z2, ldv, W2, ldw, s));  // W2 = (d01kj + s_d) z2; leaves M, r, H1 = C1 M
+  double *B = op.B.as<double>(), *T = op.T.as<double>(), *t0 = op.t0.as<double>();
+  td_build_b_kernel<<<ceil_div((long long)N * (nf + 2), 256), 256, 0, s>>>(V, ldv, op.x, op.h.r.as<double>(), N, nf, B);
+  GPXB_LAUNCHED(ctx);
+  {
+    GemmArgs g;  // T = C1 [z1 | X o z1 | r]
+    g.M = N; g.N = nf + 2; g.K = N;
+    g.A = op.h.C1.as<double>(); g.lda = N; g.a_kmajor = true;
+    g.B = B; g.ldb = nf + 2; g.b_kmajor = false;
+    g.C = T; g.ldc = nf + 2;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  {
+    GemmArgs g;  // t0 = K z1
+    g.M = N; g.N = 1; g.K = N;
+    g.A = op.C0.as<double>(); g.lda = N; g.a_kmajor = true;
+    g.B = V; g.ldb = ldv; g.b_kmajor = false;
+    g.C = t0; g.ldc = 1;
+    GPXB_TRY(gemm_f64(ctx, g, s));
+  }
+  td_out1_kernel<<<ceil_div(N, 128), 128, 0, s>>>(t0, V, ldv, op.x, op.h.H1.as<double>(), T, N, nf, op.s_t, W, ldw);
+  GPXB_LAUNCHED(ctx);
+  td_out2_kernel<<<ceil_div((long long)N * nv, 128), 128, 0, s>>>(op.J, op.x, T, N, nf, nv, W2, ldw);
+  GPXB_LAUNCHED(ctx);
+  return 0;
+}
+
+// rpcholesky_TD (gpx/models/gpr_td.py:313-460): FB row-blocked factor over the N + N nv rows, pivots [M] int64
+int td_rpcholesky(Ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                  const uint32_t key[2], int M, int partitionable, double* FB, long long* pivots, cudaStream_t s) {
+  GPXB_ARG_CHECK(kind == KIND_SE || kind == KIND_M52, -50);
+  const long long n = (long long)N + (long long)N * nv;
+  GPXB_ARG_CHECK(n < (1LL << 31), -2);
+  const ZLayout zl = z_layout(nf);
+  DevBuf bRows, bD0, bCol;
+  GPXB_TRY(bRows.alloc(sizeof(double) * (size_t)n * zl.S, s));
+  GPXB_TRY(bD0.alloc(sizeof(double) * (size_t)n, s));
+  GPXB_TRY(bCol.alloc(sizeof(double) * (size_t)n, s));
+  double* col = bCol.as<double>();
+  td_rows_kernel<<<ceil_div(n * zl.S, 256), 256, 0, s>>>(J, N, nf, nv, zl.S, bRows.as<double>());
+  GPXB_LAUNCHED(ctx);
+  double k0, c1_0;
+  if (kind == KIND_SE) {
+    k0 = std::exp(-1e-12);
+    c1_0 = (2.0 / (ell * ell)) * k0;
+  } else {
+    const double d = 2.23606797749979 * 1e-6;
+    k0 = (1.0 + d + d * d / 3.0) * std::exp(-d);
+    c1_0 = (5.0 / (3.0 * ell * ell)) * std::exp(-d) * (1.0 + d);
+  }
+  td_diag_kernel<<<ceil_div(n, 256), 256, 0, s>>>(J, N, nf, nv, k0, c1_0, bD0.as<double>());
+  GPXB_LAUNCHED(ctx);
+  RpColumnGen gen = [&](const double* pbuf, cudaStream_t st) -> int {
+    td_column_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, J, N, nf, nv, kind, ell, pbuf, col);
+    GPXB_LAUNCHED(ctx);
+    return 0;
+  };
+  return rpcholesky_ext(ctx, bRows.as<double>(), (int)n, zl, bD0.as<double>(), col, gen, key, M, partitionable, FB,
+                        pivots, s);
+}
+
+namespace {
+// b = [y - mu; y_derivs]
+__global__ void td_rhs_kernel(const double* __restrict__ y, const double* __restrict__ yd, const double* __restrict__ mu,
+                              int N, long long n, double* __restrict__ b) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  b[r] = r < N ? y[r] - mu[0] : yd[r - N];
+}
+}  // namespace
+
+// c = A^-1 [y - mu; y_derivs] by PCG with the rpcholesky_TD preconditioner (which uses sigma_targets for every row,
+// gpr_td.py:478-503) and / or the m-step block Lanczos on A for the start vectors U (SLQ part of _lml_iter).
+int gpr_td_iter(Ctx* ctx, int kind, const double* x, const double* J, const double* y, const double* yd, int N, int nf,
+                int nv, double ell, double sigma_t, double sigma_d, int mean_mode, int n_pivots, const uint32_t key[2],
+                int partitionable, double tol, double atol, int maxiter, double* c_out, double* mu_out, int* iters_out,
+                const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out, int* flag,
+                cudaStream_t s) {
+  GPXB_ARG_CHECK(ctx->world == 1, -61);  // replicas only, like the derivative-only iterative path
+  const long long n = (long long)N + (long long)N * nv;
+  GPXB_ARG_CHECK(N > 0 && n < (1LL << 31) && n_pivots >= 0, -1);
+  TdOp op;
+  GPXB_TRY(td_op_prepare(ctx, op, kind, x, J, N, nf, nv, ell, sigma_t * sigma_t + 1e-10, sigma_d * sigma_d + 1e-10, s));
+  if (c_out) {
+    DevBuf bFB, bFT, bPiv, bPkk, bB;
+    const long long ldf = (n + 1) / 2 * 2;
+    const int k = n_pivots;
+    GPXB_TRY(bB.alloc(sizeof(double) * (size_t)n, s));
+    sk::mean_kernel<<<1, 1024, 0, s>>>(y, (long long)N, mean_mode == GPXB_MEAN_DATA, mu_out);
+    GPXB_LAUNCHED(ctx);
+    td_rhs_kernel<<<ceil_div(n, 256), 256, 0, s>>>(y, yd, mu_out, N, n, bB.as<double>());
+    GPXB_LAUNCHED(ctx);
+    if (k > 0) {
+      GPXB_TRY(bFB.alloc(sizeof(double) * std::max<size_t>(rp_factor_doubles((int)n, k), 8), s));
+      GPXB_TRY(bFT.alloc(sizeof(double) * (size_t)k * ldf, s));
+      GPXB_TRY(bPiv.alloc(sizeof(long long) * k, s));
+      GPXB_TRY(bPkk.alloc(sizeof(double) * (size_t)k * k, s));
+      GPXB_TRY(td_rpcholesky(ctx, kind, x, J, N, nf, nv, ell, key, k, partitionable, bFB.as<double>(),
+                             bPiv.as<long long>(), s));
+      GPXB_TRY(rp_unblock_transposed(ctx, bFB.as<double>(), (int)n, k, bFT.as<double>(), ldf, s));
+      bFB.release();
+      GPXB_TRY(precond_build(ctx, bFT.as<double>(), ldf, k, (int)n, sigma_t, bPkk.as<double>(), s));
+    }
+    auto apply = [&](const double* p, double* Ap) -> int { return td_op_apply(ctx, op, p, 2, Ap, 1, s); };
+    GPXB_TRY(pcg_core(ctx, (int)n, n, apply, bB.as<double>(), bFT.as<double>(), ldf, k, bPkk.as<double>(), sigma_t,
+                      tol, atol, maxiter > 0 ? maxiter : (int)std::min<long long>(10 * n, 2000000000LL), c_out,
+                      iters_out, s));
+  }
+  if (U && alpha_out) {
+    GPXB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    DevBuf up;
+    for (int c0 = 0; c0 < P; c0 += 32) {
+      const int pb = std::min(32, P - c0);
+      const int PS = v_padded_stride(pb);
+      GPXB_TRY(up.alloc(sizeof(double) * ((size_t)n * PS + 16), s));
+      GPXB_TRY(pack_v(ctx, U, ldu, (int)n, c0, pb, PS, up.as<double>(), s));
+      auto apply = [&](const double* v, double* w) -> int {
+        for (int p = 0; p < pb; ++p) GPXB_TRY(td_op_apply(ctx, op, v + p, PS, w + p, PS, s));
+        return 0;
+      };
+      GPXB_TRY(lanczos_core(ctx, (int)n, n, apply, up.as<double>(), pb, PS, m, alpha_out + (size_t)c0 * m,
+                            beta_out + (size_t)c0 * m, flag, s));
+      up.release();
+    }
+  }
+  return 0;
+}
+
 int lanczos_grad_core(Ctx* ctx, int n_loc, long long N,
                       const std::function<int(const double*, double*, bool)>& matvec, double sigma, const double* U,
                       int P, int PS, int m, double* alpha_out, double* beta_out, double* dalpha_out,
@@ -1142,6 +1431,44 @@ int gpxb_rpcholesky_derivs(gpxb_ctx* ctx_, int kind, const double* x, const doub
   const uint32_t key[2] = {key0, key1};
   GPXB_TRY(gpxb::hess_rpcholesky(ctx, kind, x, J, N, nf, nv, ell, key, M, partitionable, fb.as<double>(), pivots_out,
                                  s));
+  if (F_out) GPXB_TRY(gpxb::rp_unblock_rowmajor(ctx, fb.as<double>(), (int)n, M, F_out, s));
+  return 0;
+}
+
+int gpxb_gpr_td_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y,
+                         const double* y_derivs, int N, int nf, int nv, double ell, double sigma_targets,
+                         double sigma_derivs, int mean_mode, int n_pivots, uint32_t key0, uint32_t key1,
+                         int partitionable, double tol, double atol, int maxiter, double* c_out, double* mu_out,
+                         int* iters_out, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && y && y_derivs && c_out && mu_out && N > 0 && nf > 0 && nv > 0, -1);
+  const uint32_t key[2] = {key0, key1};
+  return gpxb::gpr_td_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, ell, sigma_targets,
+                           sigma_derivs, mean_mode, n_pivots, key, partitionable, tol, atol, maxiter, c_out, mu_out,
+                           iters_out, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int gpxb_lanczos_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                    double sigma_targets, double sigma_derivs, const double* U, long long ldu, int P, int m,
+                    double* alpha_out, double* beta_out, int* breakdown_flag, gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && U && alpha_out && beta_out && breakdown_flag && P > 0 && m > 0, -1);
+  const uint32_t key[2] = {0, 0};
+  return gpxb::gpr_td_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, nullptr, nullptr, N, nf, nv, ell, sigma_targets,
+                           sigma_derivs, 0, 0, key, 1, 0.0, 0.0, 0, nullptr, nullptr, nullptr, U, ldu, P, m, alpha_out,
+                           beta_out, breakdown_flag, (cudaStream_t)stream);
+}
+
+int gpxb_rpcholesky_td(gpxb_ctx* ctx_, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                       uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out, long long* pivots_out,
+                       gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx_ && x && J && pivots_out && N > 0 && nf > 0 && nv > 0 && M > 0, -1);
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = (long long)N + (long long)N * nv;
+  GPXB_ARG_CHECK(n < (1LL << 31), -2);
+  gpxb::DevBuf fb;
+  GPXB_TRY(fb.alloc(sizeof(double) * std::max<size_t>(gpxb::rp_factor_doubles((int)n, M), 8), s));
+  const uint32_t key[2] = {key0, key1};
+  GPXB_TRY(gpxb::td_rpcholesky(ctx, kind, x, J, N, nf, nv, ell, key, M, partitionable, fb.as<double>(), pivots_out, s));
   if (F_out) GPXB_TRY(gpxb::rp_unblock_rowmajor(ctx, fb.as<double>(), (int)n, M, F_out, s));
   return 0;
 }

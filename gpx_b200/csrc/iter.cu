@@ -17,6 +17,8 @@
 #include "matvec.cuh"
 #include "mma.cuh"
 #include "small_kernels.cuh"
+#include <vector>
+
 #include "threefry.cuh"
 
 namespace gpxb {
@@ -160,16 +162,45 @@ int lanczos_core_rider(Ctx* ctx, int n_loc, long long N, const std::function<int
                        const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
                        LanczosRider* rider, cudaStream_t s);
 
+// Breakdown branch of lanczos_tridiagonal (gpx/lanczos.py:92-108): column p of the next Lanczos block becomes
+// orthonormalize(random.normal(subkey, (N,)), vecs) for every probe p in `bad` (defined after the vector helpers).
+int lanczos_restart_columns(Ctx* ctx, cudaStream_t s, double* vecs, size_t blk, int n_loc, long long N, int PS, int j,
+                            const std::vector<int>& bad, uint32_t sk0, uint32_t sk1, int partitionable);
+
 int lanczos_core(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
                  const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
                  cudaStream_t s) {
   return lanczos_core_rider(ctx, n_loc, N, apply, U, P, PS, m, alpha_out, beta_out, flag, nullptr, s);
 }
 
+namespace {
+int lanczos_pass(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+                 const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
+                 LanczosRider* rider, bool restarts, cudaStream_t s);
+}  // namespace
+
+// Fast pass first: enqueue-only, a breakdown (beta <= 1e-12) only raises the device flag.  With the restart key set
+// on the context (gpxb_lanczos_set_restart) the flag is read back once at the end; in the rare case that it is set
+// the recursion is redone with the reference's breakdown branch, which needs one host read of beta per step.
 int lanczos_core_rider(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
                        const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
                        LanczosRider* rider, cudaStream_t s) {
+  GPXB_TRY(lanczos_pass(ctx, n_loc, N, apply, U, P, PS, m, alpha_out, beta_out, flag, rider, false, s));
+  if (!ctx->restart_on || m < 2) return 0;
+  int h = 0;
+  GPXB_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  GPXB_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (h == 0) return 0;
+  GPXB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  return lanczos_pass(ctx, n_loc, N, apply, U, P, PS, m, alpha_out, beta_out, flag, nullptr, true, s);
+}
+
+namespace {
+int lanczos_pass(Ctx* ctx, int n_loc, long long N, const std::function<int(const double*, double*)>& apply,
+                 const double* U, int P, int PS, int m, double* alpha_out, double* beta_out, int* flag,
+                 LanczosRider* rider, bool restarts, cudaStream_t s) {
   GPXB_ARG_CHECK(P >= 1 && P <= MAXP && m >= 1, -30);
+  uint32_t rk0 = ctx->restart_key[0], rk1 = ctx->restart_key[1];  // the key lanczos_tridiagonal carries
   ctx->shard_N = N;
   const size_t blk = (size_t)n_loc * PS;
   DevBuf bVecs, bW, bPart, bSc;
@@ -218,10 +249,28 @@ int lanczos_core_rider(Ctx* ctx, int n_loc, long long N, const std::function<int
       colnormalize_kernel<<<nblk_e, nthr, 0, s>>>(W, nrm2, vecs + blk * (j + 1), n_loc, PS, P, flag);
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
+      if (restarts) {
+        // subkey, key = random.split(key) at every step, used or not (lanczos.py:99)
+        uint32_t sk0, sk1, nk0, nk1;
+        jax_split2(rk0, rk1, 0, ctx->restart_partitionable, sk0, sk1);
+        jax_split2(rk0, rk1, 1, ctx->restart_partitionable, nk0, nk1);
+        rk0 = nk0; rk1 = nk1;
+        double hb[MAXP];
+        GPXB_CUDA_CHECK(cudaMemcpyAsync(hb, beta, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
+        GPXB_CUDA_CHECK(cudaStreamSynchronize(s));
+        std::vector<int> bad;
+        for (int p = 0; p < P; ++p)
+          if (!(hb[p] > 1e-12)) bad.push_back(p);
+        if (!bad.empty())
+          GPXB_TRY(lanczos_restart_columns(ctx, s, vecs, blk, n_loc, N, PS, j, bad, sk0, sk1,
+                                           ctx->restart_partitionable));
+      }
     }
   }
+  if (restarts) GPXB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));  // every breakdown was handled
   return 0;
 }
+}  // namespace
 
 int lanczos_block(Ctx* ctx, int kind, const double* Zr, int n_loc, long long row0, const double* Za, int N,
                   ZLayout zl, double diag_add, const double* U, int P, int PS, int m, double* alpha_out,
@@ -545,7 +594,61 @@ struct VecOps {
   }
 };
 
+// out[i] = element (row0 + i) of jax.random.normal(key, (N,), float64): sqrt(2) erfinv(u), u uniform on
+// [nextafter(-1, 0), 1) (jax._src.random._normal_real); erfinv is CUDA's (a few ulp from SciPy's / XLA's)
+__global__ void jax_normal_kernel(uint32_t k0, uint32_t k1, long long N, long long row0, int n, int partitionable,
+                                  double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double lo = -0.99999999999999989;  // nextafter(-1, 0)
+  double u = jax_uniform_f64(k0, k1, (unsigned long long)(row0 + i), (unsigned long long)N, partitionable);
+  u = fmax(lo, u * (1.0 - lo) + lo);
+  out[i] = 1.4142135623730951 * erfinv(u);
+}
+// t -= coef * v (v with stride sv)
+__global__ void restart_axpy_kernel(double* __restrict__ t, const double* __restrict__ v, int sv, int n,
+                                    const double* __restrict__ coef) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] -= coef[0] * v[i * sv];
+}
+// dst (stride sd) = t / sqrt(nrm2)
+__global__ void restart_store_kernel(const double* __restrict__ t, const double* __restrict__ nrm2,
+                                     double* __restrict__ dst, int sd, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i * sd] = t[i] / sqrt(nrm2[0]);
+}
+
 }  // namespace
+
+int lanczos_restart_columns(Ctx* ctx, cudaStream_t s, double* vecs, size_t blk, int n_loc, long long N, int PS, int j,
+                            const std::vector<int>& bad, uint32_t sk0, uint32_t sk1, int partitionable) {
+  DevBuf bR, bT, bPart, bSc;
+  GPXB_TRY(bR.alloc(sizeof(double) * std::max(n_loc, 1), s));
+  GPXB_TRY(bT.alloc(sizeof(double) * std::max(n_loc, 1), s));
+  GPXB_TRY(bPart.alloc(sizeof(double) * (ceil_div(n_loc, 1024) + 1), s));
+  GPXB_TRY(bSc.alloc(sizeof(double) * 2, s));
+  double *rv = bR.as<double>(), *t = bT.as<double>(), *sc = bSc.as<double>();
+  const long long row0 = (n_loc == N || ctx->world <= 1) ? 0 : shard_begin(N, ctx->world, ctx->rank);
+  const int nb = std::max(ceil_div(n_loc, 256), 1);
+  jax_normal_kernel<<<nb, 256, 0, s>>>(sk0, sk1, N, row0, n_loc, partitionable, rv);  // the same draw for every probe
+  GPXB_LAUNCHED(ctx);
+  VecOps vo{ctx, s, bPart.as<double>(), n_loc};
+  for (int p : bad) {
+    GPXB_CUDA_CHECK(cudaMemcpyAsync(t, rv, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, s));
+    // orthonormalize(randv, vecs): modified Gram-Schmidt over the columns of vecs in order; the columns beyond
+    // j are still zero in the reference (vecs.at[:, j + 1] is set after this call) and change nothing
+    for (int c = 0; c <= j; ++c) {
+      const double* vc = vecs + blk * c + p;
+      GPXB_TRY(vo.dot(t, 1, vc, PS, sc));
+      restart_axpy_kernel<<<nb, 256, 0, s>>>(t, vc, PS, n_loc, sc);
+      GPXB_LAUNCHED(ctx);
+    }
+    GPXB_TRY(vo.dot(t, 1, t, 1, sc + 1));
+    restart_store_kernel<<<nb, 256, 0, s>>>(t, sc + 1, vecs + blk * (j + 1) + p, PS, n_loc);
+    GPXB_LAUNCHED(ctx);
+  }
+  return 0;
+}
 
 // Builds the RPCholesky preconditioner pieces from F (stored [k][ldf], local rows):
 // Pkk = inv(sigma^2 I + F^T F) (full symmetric k x k, device).

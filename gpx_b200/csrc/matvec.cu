@@ -16,6 +16,8 @@
 // V is stored with a padded row stride PS (PS % 8 == 2) so that a tile is contiguous (one
 // bulk copy) and the GEMM-2 B-fragment reads are bank-conflict free.
 #include "kfun.cuh"
+#include "gemm.cuh"
+#include "gram.cuh"
 #include "matvec.cuh"
 #include "mma.cuh"
 
@@ -322,8 +324,7 @@ __global__ void pack_v_kernel(const double* __restrict__ V, long long ldv, int n
 
 template <int MF, int KS, int NPF, int NWARP, int KMODE>
 int launch_k(Ctx* ctx, const KmvParams& p, dim3 grid, int smem, cudaStream_t s) {
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(kmatvec_kernel<MF, KS, NPF, NWARP, KMODE>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(kmatvec_kernel<MF, KS, NPF, NWARP, KMODE>), smem));
   kmatvec_kernel<MF, KS, NPF, NWARP, KMODE><<<grid, NWARP * 32, smem, s>>>(p);
   GPXB_LAUNCH_CHECK();
   ctx->launches++;
@@ -369,6 +370,36 @@ int v_padded_stride(int P) {
   return ps;
 }
 
+namespace {
+// More features than the fused kernel's shared-memory tiles hold (D > 64): the pair distances are a real GEMM then
+// (2 D >= 130 flops per entry against 2 P for the product with V), so the operator is applied in row chunks --
+// K-tiled Gram kernel (gram.cu) into a chunk buffer of at most ~1 GB, then one DMMA GEMM with the block V.  K is
+// still never held as a whole.
+int kmatvec_chunked(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
+  const long long ldk = round_up((long long)a.N, 2);
+  long long rc_max = std::max<long long>(128, (1LL << 27) / std::max<long long>(ldk, 1) / 128 * 128);
+  rc_max = std::min<long long>(rc_max, round_up((long long)a.n_rows, 128));
+  DevBuf kc;
+  GPXB_TRY(kc.alloc(sizeof(double) * (size_t)rc_max * ldk, s));
+  for (long long r0 = 0; r0 < a.n_rows; r0 += rc_max) {
+    const int rc = (int)std::min<long long>(rc_max, a.n_rows - r0);
+    GramArgs g;
+    g.kind = a.kind;
+    g.Z1 = a.Zr + r0 * a.zl.S; g.n1 = rc; g.Z2 = a.Za; g.n2 = a.N; g.zl = a.zl;
+    g.out = kc.as<double>(); g.ldo = ldk;
+    if (a.row_offset >= 0) { g.sym = 1; g.diag_off = a.row_offset + r0; g.diag_add = a.diag_add; }
+    GPXB_TRY(gram_launch(ctx, g, s));
+    GemmArgs m;
+    m.M = rc; m.N = a.P; m.K = a.N;
+    m.A = kc.as<double>(); m.lda = ldk; m.a_kmajor = true;
+    m.B = a.V; m.ldb = a.PS; m.b_kmajor = false;
+    m.C = a.W + r0 * a.ldw; m.ldc = a.ldw;
+    GPXB_TRY(gemm_f64(ctx, m, s));
+  }
+  return 0;
+}
+}  // namespace
+
 int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   if (a.n_rows <= 0) return 0;
   PhaseScope ph(ctx, PH_MATVEC, s);
@@ -401,7 +432,10 @@ int kmatvec_launch(Ctx* ctx, const KmvArgs& a, cudaStream_t s) {
   }
   int BR = 256, MF = warps_pref == 16 ? 2 : 4, NW = warps_pref;
   if (smem_bytes(256, p.S, p.PS) > limit) { BR = 128; MF = 2; NW = 8; }
-  GPXB_ARG_CHECK(smem_bytes(BR, p.S, p.PS) <= limit, -23);
+  if (smem_bytes(BR, p.S, p.PS) > limit) {
+    GPXB_ARG_CHECK(!a.wt && a.dl_ell == 0.0, -23);  // the derivative profiles keep the shared-memory feature limit
+    return kmatvec_chunked(ctx, a, s);
+  }
   const int row_ctas = ceil_div(a.n_rows, BR);
   // column split so that small row counts still fill the GPU (deterministic two-pass reduce)
   int jsplit = 1;

@@ -529,8 +529,7 @@ static int rp_core(Ctx* ctx, int kind, const double* Z, int n, long long row0, l
     GPXB_TRY(bPart.alloc(sizeof(double) * (size_t)ceil_div(M, CW) * std::max(nblk_loc, 1) * BLK, s));
     st.part = bPart.as<double>();
   }
-  GPXB_CUDA_CHECK(cudaFuncSetAttribute(one_cta ? rp_column_kernel<1> : rp_column_kernel<2>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(double) * (M + zl.S)));
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(one_cta ? rp_column_kernel<1> : rp_column_kernel<2>), (int)sizeof(double) * (M + zl.S)));
   // phase profiling brackets every 16th pivot only (weight 16): thousands of event pairs would perturb the loop
   struct PhaseSampling {
     Ctx* c; bool on; double w;

@@ -44,7 +44,6 @@ int sgpr_lml(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, lo
              cudaStream_t s) {
   GPXB_ARG_CHECK(n_loc >= 0 && D > 0 && T > 0 && M > 0, -1);
   const ZLayout zl = z_layout(D);
-  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
   const double s2 = sigma * sigma + 1e-10;
   const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
   const int nchunks = ceil_div(std::max(n_loc, 1), CHUNK);
@@ -245,7 +244,6 @@ int sgpr_lml_grad(Ctx* ctx, int kind, const double* x, const double* y, int n_lo
   GPXB_ARG_CHECK(n_loc >= 0 && D > 0 && M > 0, -1);
   GPXB_ARG_CHECK(!grad_locs || (want_grad && kmatvec_supports(D)), -4);
   const ZLayout zl = z_layout(D);
-  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
   const double s2 = sigma * sigma + 1e-10;
   const size_t mm = (size_t)M * M;
   const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
@@ -506,7 +504,6 @@ int sgpr_fit(Ctx* ctx, int kind, const double* x, const double* y, int n_loc, in
              cudaStream_t s) {
   GPXB_ARG_CHECK(n_loc >= 0 && D > 0 && T > 0 && M > 0, -1);
   const ZLayout zl = z_layout(D);
-  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
   const int nc_max = std::min(CHUNK, std::max(n_loc, 1));
   DevBuf bZl, bC, bInv, bV, bZc, bKc, bRc, bVt;
   GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
@@ -583,7 +580,6 @@ int sgpr_predict(Ctx* ctx, int kind, const double* x_locs, int M, int D, const d
                  double* cov_out, cudaStream_t s) {
   GPXB_ARG_CHECK(ns > 0 && D > 0 && T > 0 && M > 0, -1);
   const ZLayout zl = z_layout(D);
-  GPXB_ARG_CHECK(zl.S <= GRAM_MAX_S, -3);
   DevBuf bZl, bZs, bKs;
   GPXB_TRY(bZl.alloc(sizeof(double) * (size_t)M * zl.S, s));
   GPXB_TRY(bZs.alloc(sizeof(double) * (size_t)ns * zl.S, s));

@@ -78,7 +78,7 @@ int sgpr_fit_iter(Ctx* ctx, int kind, const double* x, const double* y, int N, i
                   double ell, double sigma, const double* mu, double tol, double atol, int maxiter, double* c_out,
                   int* iters_out, cudaStream_t s) {
   GPXB_ARG_CHECK(ctx->world == 1, -61);
-  GPXB_ARG_CHECK(N > 0 && D > 0 && M > 0 && kmatvec_supports(D), -1);
+  GPXB_ARG_CHECK(N > 0 && D > 0 && M > 0, -1);
   const ZLayout zl = z_layout(D);
   DevBuf bZ, bZl, bR, bB, bT, bU, bW;
   GPXB_TRY(bZ.alloc(sizeof(double) * ((size_t)N * zl.S + 16), s));
@@ -117,7 +117,7 @@ int sgpr_hx_iter(Ctx* ctx, int kind, const double* x, const double* y, int N, in
                  int* iters_out, const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out,
                  int* flag, cudaStream_t s) {
   GPXB_ARG_CHECK(ctx->world == 1, -61);
-  GPXB_ARG_CHECK(N > 0 && D > 0 && M > 0 && kmatvec_supports(D), -1);
+  GPXB_ARG_CHECK(N > 0 && D > 0 && M > 0, -1);
   const ZLayout zl = z_layout(D);
   const double shift = sigma * sigma + 1e-10;
   const size_t mm = (size_t)M * M;

@@ -39,10 +39,11 @@ def slq_logdet(alpha: np.ndarray, beta: np.ndarray, dim_mat: int) -> float:
 
 
 def lanczos_logdet(kind, xd, ell, diag_add, num_evals, num_lanczos, key):
-    subkey, _ = split(key, 2, threefry_partitionable())
+    subkey, carried = split(key, 2, threefry_partitionable())
     N = xd.shape[0]
     U = ops.rademacher_probes(subkey, N, int(num_evals), threefry_partitionable())
-    alpha, beta, flag = ops.lanczos(kind, xd, ell, diag_add, U, int(num_lanczos))
+    alpha, beta, flag = ops.lanczos(kind, xd, ell, diag_add, U, int(num_lanczos), restart_key=carried,
+                                    partitionable=threefry_partitionable())
     if int(flag.cpu().numpy()[0]) != 0:
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
                            "use fewer Lanczos steps than data points")
@@ -57,12 +58,12 @@ def lml_iter(state, xd, yd, ell, sigma, num_evals, num_lanczos, key_lanczos, n_p
         raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
     m = yd.shape[0]
     part = threefry_partitionable()
-    subkey, _ = split(as_key(key_lanczos), 2, part)
+    subkey, carried = split(as_key(key_lanczos), 2, part)
     U = ops.rademacher_probes(subkey, m, int(num_evals), part)
     kp = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
     c, mu, _, alpha, beta, flag = ops.gpr_lml_iter(state.kernel.kind, xd, yd, ell, sigma, int(n_pivots), kp, U,
                                                    int(num_lanczos), mean_mode(state.mean_function), part, tol=tol,
-                                                   atol=atol)
+                                                   atol=atol, restart_key=carried)
     if int(flag.cpu().numpy()[0]) != 0:
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
                            "use fewer Lanczos steps than data points")

@@ -502,6 +502,67 @@ def gpr_td_fit(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_m
     return c, mu
 
 
+def gpr_td_fit_iter(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, n_pivots, key, mean_mode=MEAN_DATA,
+                    partitionable=True, tol=1e-5, atol=1e-7, maxiter=0):
+    """(c (N + N nv, 1) rows [targets; (sample, variable)], mu (1,), iterations): PCG on the matrix-free block
+    operator with the rpcholesky_TD preconditioner (gpx/models/gpr_td.py:685-747)."""
+    import ctypes
+
+    ctx = context()
+    x, J, y, yd = _f64(x), _f64(J), _f64(y), _f64(y_derivs)
+    _check_xJ(x, J, "gpr_td_fit_iter")
+    N, nf, nv = J.shape
+    _require(y.numel() == N and yd.numel() == N * nv, "shape mismatch between the operands")
+    c = torch.empty((N + N * nv, 1), dtype=torch.float64, device=x.device)
+    mu = torch.empty(1, dtype=torch.float64, device=x.device)
+    iters = ctypes.c_int(0)
+    check(
+        ctx.lib.gpxb_gpr_td_fit_iter(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv, float(ell),
+                                     float(sigma_targets), float(sigma_derivs), int(mean_mode), int(n_pivots),
+                                     int(key[0]), int(key[1]), int(bool(partitionable)), float(tol), float(atol),
+                                     int(maxiter), ptr(c), ptr(mu), ctypes.byref(iters), stream_ptr()),
+        "gpxb_gpr_td_fit_iter",
+    )
+    return c, mu, iters.value
+
+
+def lanczos_td(kind, x, J, ell, sigma_targets, sigma_derivs, U, m):
+    """(alpha (P, m), beta (P, m), breakdown) of the block Lanczos on the GPR_TD operator, matrix-free."""
+    ctx = context()
+    x, J, U = _f64(x), _f64(J), _f64(U)
+    _check_xJ(x, J, "lanczos_td")
+    N, nf, nv = J.shape
+    _require(U.dim() == 2 and U.shape[0] == N + N * nv, f"lanczos_td: U has {tuple(U.shape)}, expected {N + N * nv} rows")
+    P = U.shape[1]
+    alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    check(
+        ctx.lib.gpxb_lanczos_td(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), float(sigma_targets),
+                                float(sigma_derivs), ptr(U), U.stride(0), P, int(m), ptr(alpha), ptr(beta), ptr(flag),
+                                stream_ptr()),
+        "gpxb_lanczos_td",
+    )
+    return alpha, beta, flag
+
+
+def rpcholesky_td(kind, x, J, n_pivots, ell, key, partitionable=True, want_factor=True):
+    """(F (N + N nv, M) or None, pivots int64 (M,)) -- rpcholesky_TD, gpx/models/gpr_td.py:313-460."""
+    ctx = context()
+    x, J = _f64(x), _f64(J)
+    _check_xJ(x, J, "rpcholesky_td")
+    N, nf, nv = J.shape
+    piv = torch.empty(n_pivots, dtype=torch.int64, device=x.device)
+    F = torch.empty((N + N * nv, n_pivots), dtype=torch.float64, device=x.device) if want_factor else None
+    check(
+        ctx.lib.gpxb_rpcholesky_td(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), int(key[0]),
+                                   int(key[1]), int(n_pivots), int(bool(partitionable)), ptr(F) if want_factor else None,
+                                   ptr(piv), stream_ptr()),
+        "gpxb_rpcholesky_td",
+    )
+    return F, piv
+
+
 def gpr_td2_lml_grad(kind, x, J, y, y_derivs, nv_first, ell, sigma_targets, sigma_derivs, sigma_derivs2,
                      mean_mode=MEAN_DATA, want_grad=True):
     """GPR_TD with two derivative blocks concatenated along the variable axis (block 1 = the first nv_first variables)
@@ -606,8 +667,29 @@ def rademacher_probes(key, N, P, partitionable=True):
     return U
 
 
-def lanczos(kind, x, ell, diag_add, U, m):
-    """(alpha (P, m), beta (P, m), breakdown) for the unit start vectors in U's columns."""
+class _lanczos_restart:
+    """Scope in which the library follows the reference's breakdown branch (gpx/lanczos.py:92-108) with `key` the key
+    lanczos_tridiagonal carries; key None: breakdown only flags."""
+
+    def __init__(self, key, partitionable=True):
+        self.key, self.part = key, partitionable
+
+    def __enter__(self):
+        if self.key is not None:
+            ctx = context()
+            check(ctx.lib.gpxb_lanczos_set_restart(ctx.handle, 1, int(self.key[0]), int(self.key[1]),
+                                                   int(bool(self.part))), "gpxb_lanczos_set_restart")
+
+    def __exit__(self, *exc):
+        if self.key is not None:
+            ctx = context()
+            check(ctx.lib.gpxb_lanczos_set_restart(ctx.handle, 0, 0, 0, 1), "gpxb_lanczos_set_restart")
+        return False
+
+
+def lanczos(kind, x, ell, diag_add, U, m, restart_key=None, partitionable=True):
+    """(alpha (P, m), beta (P, m), breakdown) for the unit start vectors in U's columns.  restart_key: the key
+    lanczos_tridiagonal receives; given, a breakdown restarts with a random orthonormal vector as in the reference."""
     ctx = context()
     x, U = _f64(x), _f64(U)
     N, D = x.shape
@@ -616,11 +698,12 @@ def lanczos(kind, x, ell, diag_add, U, m):
     alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
     flag = torch.zeros(1, dtype=torch.int32, device=x.device)
-    check(
-        ctx.lib.gpxb_lanczos(ctx.handle, _kind(kind), ptr(x), N, D, float(ell), float(diag_add), ptr(U), U.stride(0),
-                             P, int(m), ptr(alpha), ptr(beta), ptr(flag), stream_ptr()),
-        "gpxb_lanczos",
-    )
+    with _lanczos_restart(restart_key, partitionable):
+        check(
+            ctx.lib.gpxb_lanczos(ctx.handle, _kind(kind), ptr(x), N, D, float(ell), float(diag_add), ptr(U),
+                                 U.stride(0), P, int(m), ptr(alpha), ptr(beta), ptr(flag), stream_ptr()),
+            "gpxb_lanczos",
+        )
     return alpha, beta, flag
 
 
@@ -687,7 +770,7 @@ def gpr_fit_iter(kind, x, y, ell, sigma, n_pivots, key, mean_mode=MEAN_DATA, par
 
 
 def gpr_lml_iter(kind, x, y, ell, sigma, n_pivots, key, U, m, mean_mode=MEAN_DATA, partitionable=True, tol=1e-5,
-                 atol=1e-7, maxiter=0):
+                 atol=1e-7, maxiter=0, restart_key=None):
     """The device parts of the iterative LML in one sweep (gpx/models/_gpr.py:772-821): PCG fit + m-step Lanczos on the
     probes U, the PCG vector riding in the Lanczos block mat-vecs.  -> (c, mu, iterations, alpha, beta, breakdown)."""
     import ctypes
@@ -705,13 +788,15 @@ def gpr_lml_iter(kind, x, y, ell, sigma, n_pivots, key, U, m, mean_mode=MEAN_DAT
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
     flag = torch.zeros(1, dtype=torch.int32, device=x.device)
     iters = ctypes.c_int(0)
-    check(
-        ctx.lib.gpxb_gpr_lml_iter(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, float(ell), float(sigma),
-                                  int(mean_mode), int(n_pivots), int(key[0]), int(key[1]), int(bool(partitionable)),
-                                  float(tol), float(atol), int(maxiter), ptr(U), U.stride(0), P, int(m), ptr(c),
-                                  ptr(mu), ctypes.byref(iters), ptr(alpha), ptr(beta), ptr(flag), stream_ptr()),
-        "gpxb_gpr_lml_iter",
-    )
+    with _lanczos_restart(restart_key, partitionable):
+        check(
+            ctx.lib.gpxb_gpr_lml_iter(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, float(ell), float(sigma),
+                                      int(mean_mode), int(n_pivots), int(key[0]), int(key[1]),
+                                      int(bool(partitionable)), float(tol), float(atol), int(maxiter), ptr(U),
+                                      U.stride(0), P, int(m), ptr(c), ptr(mu), ctypes.byref(iters), ptr(alpha),
+                                      ptr(beta), ptr(flag), stream_ptr()),
+            "gpxb_gpr_lml_iter",
+        )
     return c, mu, iters.value, alpha, beta, flag
 
 

@@ -154,6 +154,27 @@ int gpxb_lanczos_grad_derivs(gpxb_ctx* ctx, int kind, const double* x, const dou
 int gpxb_rpcholesky_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv,
                            double ell, uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out,
                            long long* pivots_out, gpxb_stream stream);
+/* ---- GPR on targets and derivatives, iterative (gpx/models/gpr_td.py, one derivative block) ------------------ */
+/* c[N + N nv] (rows [targets; derivatives (sample, variable)]) = PCG solve of
+ *   [[K + s_t I, d1kj], [d0kj, d01kj + s_d I]] c = [y - mu; y_derivs],  s_* = sigma_*^2 + 1e-10
+ * with the rpcholesky_TD preconditioner (_fit_iter gpr_td.py:685-747, _Ax_lhs_fun :162-310,
+ * _precond_rpcholesky_TD :463-504 -- the preconditioner uses sigma_targets for every row, as the reference does).
+ * Matrix-free on the configuration level: N x N pair-coefficient matrices, never the (N + N nv)^2 kernel.
+ * SquaredExponential and Matern-5/2.  Host-synchronous like gpxb_gpr_fit_iter; *iters_out is a HOST int. */
+int gpxb_gpr_td_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y,
+                         const double* y_derivs, int N, int nf, int nv, double ell, double sigma_targets,
+                         double sigma_derivs, int mean_mode, int n_pivots, uint32_t key0, uint32_t key1,
+                         int partitionable, double tol, double atol, int maxiter, double* c_out, double* mu_out,
+                         int* iters_out, gpxb_stream stream);
+/* gpxb_lanczos on the same block operator (the SLQ part of _lml_iter, gpr_td.py:562-637); U: (N + N nv) x ldu. */
+int gpxb_lanczos_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                    double sigma_targets, double sigma_derivs, const double* U, long long ldu, int P, int m,
+                    double* alpha_out, double* beta_out, int* breakdown_flag, gpxb_stream stream);
+/* rpcholesky_TD (gpr_td.py:313-460): randomly pivoted Cholesky of the noise-free block kernel over the
+ * N + N nv rows; F_out ((N + N nv) x M row-major, may be NULL), pivots_out [M] int64. */
+int gpxb_rpcholesky_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+                       uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out, long long* pivots_out,
+                       gpxb_stream stream);
 /* gpxb_lanczos on the matrix-free operator d01kj + (sigma^2+1e-10) I (the SLQ part of _lml_derivs_iter,
  * gpx/models/_gpr.py:873-935); U: (N nv) x P unit start vectors. */
 int gpxb_lanczos_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
@@ -271,6 +292,14 @@ int gpxb_rpcholesky(gpxb_ctx* ctx, int kind, const double* x, int N, int D, doub
 /* U_out[N x P] = jax.random.rademacher(key, (N, P)) / sqrt(N)   (gpx/lanczos.py:168-170) */
 int gpxb_rademacher_probes(gpxb_ctx* ctx, uint32_t key0, uint32_t key1, int N, int P, int partitionable,
                            double* U_out, gpxb_stream stream);
+/* Breakdown branch of lanczos_tridiagonal (gpx/lanczos.py:92-108: when beta <= 1e-12 the next Lanczos vector is
+ * orthonormalize(random.normal(subkey, (N,)), vecs), subkey drawn from the key carried through the loop).  While
+ * enabled, gpxb_lanczos and gpxb_gpr_lml_iter read the breakdown flag back once at the end of the (enqueue-only)
+ * recursion and, in the rare case that it is set, redo the recursion with that branch (one host read of beta per
+ * step) and clear the flag.  key = the key lanczos_tridiagonal receives (the second half of the split in
+ * lanczos_logdet, :166).  Disabled (default): a breakdown only sets the flag.  The tangent and derivative-kernel
+ * variants (gpxb_lanczos_grad, gpxb_lanczos_derivs, ...) always only flag. */
+int gpxb_lanczos_set_restart(gpxb_ctx* ctx, int enabled, uint32_t key0, uint32_t key1, int partitionable);
 /* m-step Lanczos with full MGS re-orthogonalisation on A = K(x,x) + diag_add I for the P unit
  * start vectors in the columns of U (gpx/lanczos.py:46-133, all probes advanced together).
  * alpha_out[P x m]: diagonals; beta_out[P x m]: beta_out[p][j] = T_p[j][j+1] for j < m-1.

@@ -420,6 +420,68 @@ def td_predict_dense(kind, x_train, J_train, x, J, c, mu, ell):
     return pred[:ns], pred[ns:ns + ns * nv].reshape(ns, -1)
 
 
+def rpcholesky_td(kind, x, J, n_pivots, ell, key, partitionable=True):
+    """gpx/models/gpr_td.py:313-460 (one derivative block): randomly pivoted Cholesky of the noise-free block kernel
+    [[k, d1kj], [d0kj, d01kj]] over the rows [targets; derivatives (sample, variable)]."""
+    n = x.shape[0]
+    nv = J.shape[2]
+    ntot = n + n * nv
+    F = np.zeros((ntot, n_pivots))
+    pivots = np.zeros(n_pivots, dtype=np.int64)
+    dk = np.array([kernel(kind, x[i:i + 1], x[i:i + 1], ell)[0, 0] for i in range(n)])
+    dh = np.concatenate([np.diagonal(d01kj(kind, x[i:i + 1], x[i:i + 1], ell, J[i:i + 1], J[i:i + 1]))
+                         for i in range(n)])
+    diag = np.concatenate([dk, dh])
+    key = np.asarray(key, dtype=np.uint32)
+    for i in range(n_pivots):
+        prob = diag / np.sum(diag)
+        key = split(key, 2, partitionable)[0]   # `key, subkey = split(key)`, then choice(key, ...)  (:387-388)
+        s = choice_p(key, prob, partitionable)
+        pivots[i] = s
+        if s < n:      # first_row (:397-407)
+            xs = x[s:s + 1]
+            row = np.concatenate([kernel(kind, xs, x, ell)[0], d0kj(kind, x, xs, ell, J).reshape(-1)])
+        else:          # second_row (:409-421)
+            i1, i2 = (int(s) - n) // nv, (int(s) - n) % nv
+            xs, js = x[i1:i1 + 1], J[i1:i1 + 1]
+            row = np.concatenate([d0kj(kind, xs, x, ell, js)[i2], d01kj(kind, xs, x, ell, js, J)[i2]])
+        g = row - F @ F[s]
+        F[:, i] = g / (g[s] ** 0.5 + 1e-6)
+        diag = diag - F[:, i] ** 2
+    return F, pivots
+
+
+def td_fit_iter(kind, x, y, J, y_derivs, ell, sigma_t, sigma_d, n_pivots, key_precond, mean_function=data_mean,
+                partitionable=True, cg_tol=1e-5, cg_atol=1e-7):
+    """gpr_td.py:685-747 with _precond_rpcholesky_TD :463-504 (sigma_targets in the preconditioner for every row)."""
+    mu = mean_function(y)
+    ym = np.concatenate([(y - mu).reshape(-1, 1), y_derivs.reshape(-1, 1)])
+    A = td_A_lhs(kind, x, J, x, J, ell, sigma_t, sigma_d)
+    F, _ = rpcholesky_td(kind, x, J, n_pivots, ell, key_precond, partitionable)
+    P = np.linalg.inv(sigma_t**2 * np.eye(n_pivots) + F.T @ F)
+
+    def precond(z):
+        res = P @ (F.T @ z)
+        return -(sigma_t ** (-2)) * (F @ res) + sigma_t ** (-2) * z
+
+    c, iters = cg(lambda v: A @ v, ym, M=precond, tol=cg_tol, atol=cg_atol)
+    return c, mu, iters
+
+
+def td_lml_iter(kind, x, y, J, y_derivs, ell, sigma_t, sigma_d, num_evals, num_lanczos, key_lanczos, n_pivots,
+                key_precond, mean_function=data_mean, partitionable=True, cg_tol=1e-5, cg_atol=1e-7):
+    """gpr_td.py:562-637."""
+    c, mu, _ = td_fit_iter(kind, x, y, J, y_derivs, ell, sigma_t, sigma_d, n_pivots, key_precond, mean_function,
+                           partitionable, cg_tol, cg_atol)
+    ym = np.concatenate([(y - mu).reshape(-1, 1), y_derivs.reshape(-1, 1)])
+    m = ym.shape[0]
+    A = td_A_lhs(kind, x, J, x, J, ell, sigma_t, sigma_d)
+    mll = -0.5 * np.sum(ym.T @ c)
+    mll -= 0.5 * lanczos_logdet(lambda v: A @ v, num_evals, m, num_lanczos, key_lanczos, partitionable)
+    mll -= m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
+
+
 def td2_A_lhs(kind, x1, J1a, J1b, x2, J2a, J2b, ell, sigma_t, sigma_d, sigma_d2, noise=True):
     """gpr_td.py:43-159 with the second derivative block, literal 3 x 3 assembly:
     [[K, d1kj_1, d1kj_2], [d0kj_1, d01kj_11, d01kj_12], [d0kj_2, d01kj_21, d01kj_22]]."""

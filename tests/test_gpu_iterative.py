@@ -102,6 +102,47 @@ def test_lanczos_tridiagonals_match_oracle():
         assert rel(beta[p, : m - 1], np.diag(T, 1)) < 1e-8
 
 
+def _block_diagonal_problem():
+    """Two far-apart groups of points: exp(-d2) underflows to exactly 0 between them, so K is block diagonal and a
+    start vector supported on the small group exhausts its Krylov space after 5 steps (beta <= 1e-12)."""
+    rng = np.random.default_rng(12)
+    D, n1, n2 = 3, 5, 35
+    x = np.vstack([rng.standard_normal((n1, D)), 100.0 + rng.standard_normal((n2, D))])
+    N = n1 + n2
+    U = np.zeros((N, 3))
+    U[:n1, 0] = rng.standard_normal(n1)          # breaks down at step 5
+    U[:, 1] = rng.choice([-1.0, 1.0], N)         # generic
+    U[n1:, 2] = rng.standard_normal(n2)          # supported on the large block: no breakdown within m steps
+    U /= np.linalg.norm(U, axis=0)
+    return x, U
+
+
+@pytest.mark.parametrize("partitionable", [True, False])
+def test_lanczos_breakdown_branch_matches_oracle(partitionable):
+    """gpx/lanczos.py:92-108: at beta <= 1e-12 the next vector is orthonormalize(random.normal(subkey), vecs)."""
+    from gpx_b200 import ops
+
+    x, U = _block_diagonal_problem()
+    m, ell, sigma = 20, 1.0, 0.3
+    key = R.PRNGKey(7)
+    mv = R.make_matvec("se", x, ell, sigma)
+    alpha, beta, flag = ops.lanczos("se", dev(x), ell, sigma**2 + 1e-10, dev(U), m)
+    assert int(host(flag)[0]) == 1  # without the key the breakdown is only flagged
+    alpha, beta, flag = ops.lanczos("se", dev(x), ell, sigma**2 + 1e-10, dev(U), m, restart_key=key,
+                                    partitionable=partitionable)
+    alpha, beta = host(alpha), host(beta)
+    assert int(host(flag)[0]) == 0
+    hit = False
+    for p in range(U.shape[1]):
+        T, _ = R.lanczos_tridiagonal(mv, m, U[:, p], key=key, partitionable=partitionable)
+        b_ref = np.diag(T, 1)
+        hit = hit or bool(np.any(b_ref <= 1e-12))
+        assert rel(alpha[p], np.diag(T)) < 1e-8, p
+        # the breakdown beta itself is rounding noise (~1e-16) on both sides: absolute comparison
+        assert np.max(np.abs(beta[p, : m - 1] - b_ref)) < 1e-8 * np.max(b_ref), p
+    assert hit  # the oracle did take the branch
+
+
 def test_pcg_fit_iter_matches_oracle_iteration_for_iteration():
     from gpx_b200 import ops
 
