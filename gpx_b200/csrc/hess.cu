@@ -1117,6 +1117,56 @@ int gpr_td_iter(Ctx* ctx, int kind, const double* x, const double* J, const doub
   return 0;
 }
 
+namespace {
+// out[i] = a * w[i] + u[i] + eps * p[2 i]
+__global__ void sgpr_derivs_lin_kernel(double* __restrict__ out, double a, const double* __restrict__ w,
+                                       const double* __restrict__ u, double eps, const double* __restrict__ p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a * w[i] + u[i] + eps * p[2 * i];
+}
+}  // namespace
+
+// SGPR trained on derivative values, CG fit (_fit_derivs_iter gpx/models/_sgpr.py:399-428, _Ax_derivs_lhs_fun
+// :145-201): c = cg(sigma^2 H_mm + H_mn H_nm + 1e-10 I, H_mn y), H = d01kj, zero mean, no preconditioner; every
+// product goes through the matrix-free Hessian operator (three operators: mm, mn, nm).
+int sgpr_fit_derivs_iter(Ctx* ctx, int kind, const double* x, const double* J, const double* y, int N, int nf, int nv,
+                         const double* x_locs, const double* J_locs, int M, int nvl, double ell, double sigma,
+                         double tol, double atol, int maxiter, double* c_out, int* iters_out, cudaStream_t s) {
+  GPXB_ARG_CHECK(ctx->world == 1, -61);
+  const long long nm = (long long)M * nvl, nn = (long long)N * nv;
+  GPXB_ARG_CHECK(nm > 0 && nn > 0 && nm < (1LL << 31) && nn < (1LL << 31), -1);
+  HessOp mm, mn, nmop;
+  auto setup = [&](HessOp& op, const double* x1, const double* J1, int N1, int nv1, const double* x2, const double* J2,
+                   int N2, int nv2) {
+    op.kind = kind; op.nf = nf; op.ell = ell; op.diag_add = 0.0;
+    op.x1 = x1; op.J1 = J1; op.N1 = N1; op.nv1 = nv1; op.x2 = x2; op.J2 = J2; op.N2 = N2; op.nv2 = nv2;
+  };
+  setup(mm, x_locs, J_locs, M, nvl, x_locs, J_locs, M, nvl);
+  setup(mn, x_locs, J_locs, M, nvl, x, J, N, nv);
+  setup(nmop, x, J, N, nv, x_locs, J_locs, M, nvl);
+  GPXB_TRY(hess_op_prepare(ctx, mm, s));
+  GPXB_TRY(hess_op_prepare(ctx, mn, s));
+  GPXB_TRY(hess_op_prepare(ctx, nmop, s));
+  DevBuf bB, bT, bU, bW;
+  GPXB_TRY(bB.alloc(sizeof(double) * (size_t)nm, s));
+  GPXB_TRY(bT.alloc(sizeof(double) * (size_t)nn, s));
+  GPXB_TRY(bU.alloc(sizeof(double) * (size_t)nm, s));
+  GPXB_TRY(bW.alloc(sizeof(double) * (size_t)nm, s));
+  double *b = bB.as<double>(), *t = bT.as<double>(), *u = bU.as<double>(), *w = bW.as<double>();
+  GPXB_TRY(hess_op_apply(ctx, mn, y, 1, b, 1, s));  // rhs = H_mn y
+  const double s2 = sigma * sigma;
+  auto apply = [&](const double* p, double* Ap) -> int {
+    GPXB_TRY(hess_op_apply(ctx, nmop, p, 2, t, 1, s));  // t = H_nm p
+    GPXB_TRY(hess_op_apply(ctx, mn, t, 1, u, 1, s));    // u = H_mn t
+    GPXB_TRY(hess_op_apply(ctx, mm, p, 2, w, 1, s));    // w = H_mm p
+    sgpr_derivs_lin_kernel<<<ceil_div(nm, 256), 256, 0, s>>>(Ap, s2, w, u, 1e-10, p, nm);
+    GPXB_LAUNCHED(ctx);
+    return 0;
+  };
+  return pcg_core(ctx, (int)nm, nm, apply, b, nullptr, 0, 0, nullptr, sigma, tol, atol,
+                  maxiter > 0 ? maxiter : (int)std::min<long long>(10 * nm, 2000000000LL), c_out, iters_out, s);
+}
+
 int lanczos_grad_core(Ctx* ctx, int n_loc, long long N,
                       const std::function<int(const double*, double*, bool)>& matvec, double sigma, const double* U,
                       int P, int PS, int m, double* alpha_out, double* beta_out, double* dalpha_out,
@@ -1433,6 +1483,15 @@ int gpxb_rpcholesky_derivs(gpxb_ctx* ctx_, int kind, const double* x, const doub
                                  s));
   if (F_out) GPXB_TRY(gpxb::rp_unblock_rowmajor(ctx, fb.as<double>(), (int)n, M, F_out, s));
   return 0;
+}
+
+int gpxb_sgpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N,
+                              int nf, int nv, const double* x_locs, const double* J_locs, int M, int nv_locs, double ell,
+                              double sigma, double tol, double atol, int maxiter, double* c_out, int* iters_out,
+                              gpxb_stream stream) {
+  GPXB_ARG_CHECK(ctx && x && J && y && x_locs && J_locs && c_out && N > 0 && M > 0 && nf > 0 && nv > 0 && nv_locs > 0, -1);
+  return gpxb::sgpr_fit_derivs_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, N, nf, nv, x_locs, J_locs, M, nv_locs,
+                                    ell, sigma, tol, atol, maxiter, c_out, iters_out, (cudaStream_t)stream);
 }
 
 int gpxb_gpr_td_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y,

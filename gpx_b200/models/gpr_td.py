@@ -20,6 +20,9 @@ from ..kernels import Kernel, _to_device
 from ..mean_functions import mean_mode, zero_mean
 from ..parameters import ModelState, Parameter
 from ..priors import GammaPrior
+from ..defaults import gpxargs, threefry_partitionable
+from ..random import as_key, split
+from ._iterative import slq_logdet
 from .utils import randomized_minimization
 
 
@@ -32,9 +35,50 @@ def _hyper(state):
             float(np.asarray(state.params["sigma_derivs"].value)))
 
 
-def _dense_only(iterative):
-    if iterative:
-        raise NotImplementedError("the iterative GPR_TD paths (gpr_td.py:162-505, 562-747) are not implemented")
+def _iter_single_block(jacobian_2):
+    if jacobian_2 is not None:
+        raise NotImplementedError("the iterative GPR_TD paths take one derivative block; the reference's row order "
+                                  "[targets; block 1; block 2] of rpcholesky_TD with a second block (gpr_td.py:422-436) "
+                                  "is not implemented on the device")
+
+
+def _fit_iter(state, x, y, jacobian, y_derivs, n_pivots, key_precond, tol=1e-5, atol=1e-7):
+    """_fit_iter (gpx/models/gpr_td.py:685-747): PCG on the matrix-free block operator with the rpcholesky_TD
+    preconditioner.  -> (c (N + N nv, 1) device, mu device (1,), iterations)."""
+    if n_pivots is None:
+        raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
+    kernel, ell, st, sd = _hyper(state)
+    J = np.asarray(jacobian, dtype=np.float64)
+    yd = np.asarray(y_derivs, dtype=np.float64).reshape(J.shape[0], J.shape[2])
+    key = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
+    return ops.gpr_td_fit_iter(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), ell, st, sd,
+                               int(n_pivots), key, mean_mode(state.mean_function), threefry_partitionable(), tol=tol,
+                               atol=atol)
+
+
+def _lml_iter(state, x, y, jacobian, y_derivs, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond, tol=1e-5,
+              atol=1e-7):
+    """_lml_iter (gpx/models/gpr_td.py:562-637): quadratic form from the PCG solution, log-determinant by stochastic
+    Lanczos quadrature on the same operator (host eigh of the P tridiagonals as in _iterative.slq_logdet)."""
+    kernel, ell, st, sd = _hyper(state)
+    J = np.asarray(jacobian, dtype=np.float64)
+    ns, _, nv = J.shape
+    m = ns + ns * nv
+    c, mu, _ = _fit_iter(state, x, y, jacobian, y_derivs, n_pivots, key_precond, tol, atol)
+    mu_h = float(mu.cpu().numpy()[0])
+    ym = np.concatenate([np.asarray(y, dtype=np.float64).reshape(-1, 1) - mu_h,
+                         np.asarray(y_derivs, dtype=np.float64).reshape(-1, 1)])
+    part = threefry_partitionable()
+    subkey, _ = split(as_key(key_lanczos), 2, part)
+    U = ops.rademacher_probes(subkey, m, int(num_evals), part)
+    alpha, beta, flag = ops.lanczos_td(kernel.kind, _to_device(x), _to_device(J), ell, st, sd, U, int(num_lanczos))
+    if int(flag.cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
+                           "use fewer Lanczos steps than rows")
+    mll = -0.5 * float(np.sum(ym.T @ c.cpu().numpy()))
+    mll -= 0.5 * slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), m)
+    mll -= m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
 
 
 def _cat_blocks(state, jacobian, y_derivs, jacobian_2, y_derivs_2):
@@ -88,9 +132,12 @@ def _lml_grad(state, x, y, jacobian, y_derivs, jacobian_2, y_derivs_2, want_grad
 
 
 def log_marginal_likelihood(state, x, y, jacobian, y_derivs, jacobian_2=None, y_derivs_2=None, iterative=False,
-                            **_ignored):
-    """gpx/models/gpr_td.py:848-911 -> _lml_dense (507-560)."""
-    _dense_only(iterative)
+                            num_evals=gpxargs.num_evals, num_lanczos=gpxargs.num_lanczos,
+                            key_lanczos=gpxargs.key_lanczos, n_pivots=None, key_precond=None, **_ignored):
+    """gpx/models/gpr_td.py:848-911 -> _lml_dense (507-560) / _lml_iter (562-637)."""
+    if iterative:
+        _iter_single_block(jacobian_2)
+        return _lml_iter(state, x, y, jacobian, y_derivs, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond)
     return _lml_grad(state, x, y, jacobian, y_derivs, jacobian_2, y_derivs_2, want_grad=False)[0]
 
 
@@ -102,7 +149,9 @@ def neg_log_marginal_likelihood(state, x, y, jacobian, y_derivs, **kwargs):
 def loss_and_grad(state, x, y, jacobian, y_derivs, jacobian_2=None, y_derivs_2=None, iterative=False, **_ignored):
     """Negative LML and its gradient w.r.t. the constrained (lengthscale, sigma_targets, sigma_derivs[, sigma_derivs2])
     from one fused device call: what jit(value_and_grad(loss)) returns inside scipy_minimize_ol."""
-    _dense_only(iterative)
+    if iterative:
+        raise NotImplementedError("the gradient of the iterative GPR_TD LML is not implemented: train with "
+                                  "iterative=False, or fit(..., iterative=True, minimize=False)")
     if state.loss_fn is not neg_log_marginal_likelihood:
         raise NotImplementedError("only neg_log_marginal_likelihood has a fused device gradient")
     lml, g_ell, g_st, g_sd, g_sd2 = _lml_grad(state, x, y, jacobian, y_derivs, jacobian_2, y_derivs_2, want_grad=True)
@@ -154,8 +203,13 @@ class GPR_TD:
     def fit(self, x, y, jacobian, y_derivs, jacobian_2=None, y_derivs_2=None, iterative=False, key=None, num_restarts=0,
             minimize=True, return_history=False, loss_kwargs=None, n_pivots=None, key_precond=None, c_guess=None,
             opt_kwargs=None):
-        """gpx/models/gpr_td.py:982-1108."""
-        _dense_only(iterative)
+        """gpx/models/gpr_td.py:982-1108.  iterative=True: the coefficients come from the PCG solve (_fit_iter); the
+        hyperparameters can only be trained on the dense LML (minimize=True needs iterative=False)."""
+        if iterative:
+            _iter_single_block(jacobian_2)
+            if minimize:
+                raise NotImplementedError("the gradient of the iterative GPR_TD LML is not implemented: pass "
+                                          "minimize=False (or train with iterative=False first)")
         if minimize:
             def loss_and_grad_fn(state, xx, yy):
                 return loss_and_grad(state, xx, yy, jacobian, y_derivs, jacobian_2=jacobian_2, y_derivs_2=y_derivs_2)
@@ -173,7 +227,9 @@ class GPR_TD:
         J, yd, nv1, sd2 = _cat_blocks(self.state, jacobian, y_derivs, jacobian_2, y_derivs_2)
         ns, _, nv = J.shape
         nv2 = nv - nv1
-        if nv2 == 0:
+        if iterative:
+            c, mu, self.cg_iterations_ = _fit_iter(self.state, x, y, jacobian, y_derivs, n_pivots, key_precond)
+        elif nv2 == 0:
             c, mu = ops.gpr_td_fit(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), ell, st, sd,
                                    mean_mode(self.state.mean_function))
         else:
@@ -197,7 +253,8 @@ class GPR_TD:
         [, derivatives of the second block (ns, nv_2)])."""
         if not self.state.is_fitted:
             raise RuntimeError("Model is not fitted. Run `fit` to fit the model before prediction.")
-        _dense_only(iterative)
+        # iterative=True (gpr_td.py:799-845) is ONE rectangular mat-vec K_nm c: the blocks below are that product,
+        # evaluated in chunks of test samples so that the (test rows) x (train rows) block never exceeds ~1 GB
         kernel, ell, _, _ = _hyper(self.state)
         Jt2 = getattr(self.state, "jacobian_train_2", None)
         if (jacobian_2 is None) != (Jt2 is None):
@@ -206,10 +263,18 @@ class GPR_TD:
         Jt, _, nt1, _ = _cat_blocks(self.state, self.state.jacobian_train, None, Jt2, None)
         nt = Jt.shape[0]
         c_lib = _to_lib_order(np.asarray(self.state.c, dtype=np.float64).reshape(-1, 1), nt, nt1, Jt.shape[2] - nt1)
-        K_nm = ops.td_gram(kernel.kind, _to_device(x), _to_device(Js), _to_device(self.state.x_train), _to_device(Jt),
-                           ell)                                            # (test rows) x (train rows) = K_mn^T
-        pred = ops.gemm(K_nm, _to_device(c_lib)).cpu().numpy()
         ns, _, nv = Js.shape
+        xs = np.asarray(x, dtype=np.float64)
+        cols = nt * (1 + Jt.shape[2])
+        step = max(1, min(ns, (1 << 27) // max(cols * (1 + nv), 1)))
+        xt_d, Jt_d, c_d = _to_device(self.state.x_train), _to_device(Jt), _to_device(c_lib)
+        pred = np.empty((ns + ns * nv, c_lib.shape[1]))
+        for a in range(0, ns, step):
+            b = min(ns, a + step)
+            K_nm = ops.td_gram(kernel.kind, _to_device(xs[a:b]), _to_device(Js[a:b]), xt_d, Jt_d, ell)  # K_mn^T rows
+            blk = ops.gemm(K_nm, c_d).cpu().numpy()
+            pred[a:b] = blk[:b - a]
+            pred[ns + a * nv:ns + b * nv] = blk[b - a:]
         pred[:ns] += float(self.state.mu)
         d = pred[ns:ns + ns * nv].reshape(ns, nv)
         if jacobian_2 is None:

@@ -87,12 +87,47 @@ def _loss_and_grad_with_locs(state, xd, yd, x_locs_dev, locs_trainable=False):
     return -lml, grads
 
 
+def _loss_and_grad_iter_with_locs(state, xd, yd, x_locs_dev, num_evals, num_lanczos, key_lanczos, tol=1e-5):
+    """value_and_grad of _sgpr._lml_iter (gpx/models/_sgpr.py:700-737) w.r.t. (lengthscale, sigma), landmarks fixed:
+    d(r.c) = -c^T dA c (the CG solve is a custom_linear_solve), SLQ differentiated through the Lanczos recursion
+    (gpxb_sgpr_lml_iter_grad_parts) and the host eigendecomposition (_iterative.slq_logdet_grad)."""
+    from ..defaults import threefry_partitionable
+    from ..random import as_key, split
+    from ._iterative import slq_logdet_grad
+
+    kernel, ell, sigma = _hyper(state)
+    N = yd.shape[0]
+    subkey, _ = split(as_key(key_lanczos), 2, threefry_partitionable())
+    U = ops.rademacher_probes(subkey, N, int(num_evals), threefry_partitionable())
+    quad, gq, _, alpha, beta, dalpha, dbeta, flag = ops.sgpr_lml_iter_grad_parts(
+        kernel.kind, xd, yd, x_locs_dev, ell, sigma, U, int(num_lanczos), mean_mode(state.mean_function), tol=tol)
+    if int(flag.cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps")
+    ld, dld = slq_logdet_grad(alpha.cpu().numpy(), beta.cpu().numpy(), dalpha.cpu().numpy(), dbeta.cpu().numpy(), N)
+    q = float(quad.cpu().numpy()[0])
+    g0, g1, cc = (float(v) for v in gq.cpu().numpy())
+    lml = (-0.5 * q - 0.5 * ld - N * 0.5 * np.log(2.0 * np.pi)) / N
+    g_ell = (0.5 * (2.0 * g0 - g1) - 0.5 * dld[0]) / N
+    g_sigma = (sigma * cc - 0.5 * dld[1]) / N
+    grads = {}
+    if state.params["kernel_params"]["lengthscale"].trainable:
+        grads[("kernel_params", "lengthscale")] = -g_ell
+    if state.params["sigma"].trainable:
+        grads[("sigma",)] = -g_sigma
+    return -lml, grads
+
+
 def loss_and_grad(state, x, y, iterative=False, **kwargs):
     """Negative SGPR LML and its gradient w.r.t. (lengthscale, sigma) and, when the `x_locs` Parameter is
     trainable, the landmark coordinates, from one fused device call (stands in for
     jit(value_and_grad(loss)))."""
     if iterative:
-        raise NotImplementedError("gradient of the iterative SGPR LML is not implemented")
+        if _composite_guard(state) or state.params["x_locs"].trainable:
+            raise NotImplementedError("the gradient of the iterative SGPR LML covers fixed landmarks and plain kernels")
+        xd, yd = _xy(state, x, y)
+        return _loss_and_grad_iter_with_locs(state, xd, yd, _locs(state), kwargs.get("num_evals", gpxargs.num_evals),
+                                             kwargs.get("num_lanczos", gpxargs.num_lanczos),
+                                             kwargs.get("key_lanczos", gpxargs.key_lanczos))
     if _composite_guard(state):
         if state.params["x_locs"].trainable:
             raise NotImplementedError("trainable x_locs with a composite kernel is not supported")
@@ -163,11 +198,16 @@ def fit_derivs(state, x, y, jacobian, iterative=False, **_ignored):
     Cholesky solve here)."""
     import torch
 
-    if iterative:
-        raise NotImplementedError("SGPR CG fit on derivatives (_sgpr.py:399-432) is not implemented")
     kernel, ell, sigma = _hyper(state)
     xl, Jl = _locs_jac(state)
     xd, Jd = _to_device(x), _to_device(jacobian)
+    if iterative:  # _fit_derivs_iter (gpx/models/_sgpr.py:399-428): CG on the matrix-free Hessian operators
+        c, _ = ops.sgpr_fit_derivs_iter(kernel.kind, xd, Jd, _to_device(y).reshape(-1), xl, Jl, ell, sigma)
+        ml, _, nvl = Jl.shape
+        jaccoef = torch.einsum("sv,sfv->sf", c.reshape(ml, nvl), Jl)
+        return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), jacobian_train=np.asarray(jacobian),
+                                 jaccoef=jaccoef.cpu().numpy(), c=c.cpu().numpy(), mu=np.float64(0.0), is_fitted=False,
+                                 is_fitted_derivs=True))
     yd = _to_device(y).reshape(1, -1)
     K_mn = ops.hess_gram(kernel.kind, xl, Jl, xd, Jd, ell)                      # (M nv_l, N nv)
     C = ops.hess_gram(kernel.kind, xl, Jl, xl, Jl, ell)                         # K_mm (full)

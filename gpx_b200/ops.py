@@ -502,6 +502,30 @@ def gpr_td_fit(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, mean_m
     return c, mu
 
 
+def sgpr_fit_derivs_iter(kind, x, J, y, x_locs, J_locs, ell, sigma, tol=1e-5, atol=0.0, maxiter=0):
+    """(c (M nv_locs, 1), iterations): CG solve of (sigma^2 H_mm + H_mn H_nm + 1e-10 I) c = H_mn y with the
+    matrix-free Hessian operators (gpx/models/_sgpr.py:399-428)."""
+    import ctypes
+
+    ctx = context()
+    x, J, y, x_locs, J_locs = _f64(x), _f64(J), _f64(y), _f64(x_locs), _f64(J_locs)
+    _check_xJ(x, J, "sgpr_fit_derivs_iter (data)")
+    _check_xJ(x_locs, J_locs, "sgpr_fit_derivs_iter (landmarks)")
+    N, nf, nv = J.shape
+    M, _, nvl = J_locs.shape
+    _require(x_locs.shape[1] == nf, "sgpr_fit_derivs_iter: feature counts differ")
+    _require(y.numel() == N * nv, f"sgpr_fit_derivs_iter: y has {y.numel()} values, expected N*nv = {N * nv}")
+    c = torch.empty((M * nvl, 1), dtype=torch.float64, device=x.device)
+    iters = ctypes.c_int(0)
+    check(
+        ctx.lib.gpxb_sgpr_fit_derivs_iter(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), N, nf, nv, ptr(x_locs),
+                                          ptr(J_locs), M, nvl, float(ell), float(sigma), float(tol), float(atol),
+                                          int(maxiter), ptr(c), ctypes.byref(iters), stream_ptr()),
+        "gpxb_sgpr_fit_derivs_iter",
+    )
+    return c, iters.value
+
+
 def gpr_td_fit_iter(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, n_pivots, key, mean_mode=MEAN_DATA,
                     partitionable=True, tol=1e-5, atol=1e-7, maxiter=0):
     """(c (N + N nv, 1) rows [targets; (sample, variable)], mu (1,), iterations): PCG on the matrix-free block
@@ -885,6 +909,40 @@ def sgpr_lml_iter_parts(kind, x, y, x_locs, ell, sigma, U, m, mean_mode=MEAN_DAT
         "gpxb_sgpr_lml_iter_parts",
     )
     return quad, iters.value, alpha, beta, flag
+
+
+def sgpr_lml_iter_grad_parts(kind, x, y, x_locs, ell, sigma, U, m, mean_mode=MEAN_DATA, tol=1e-5, atol=0.0, maxiter=0):
+    """sgpr_lml_iter_parts plus what value_and_grad needs: gquad (3,) = [(dK_mn c).g, g.(dK_mm g), c.c] and the
+    tangents (2, P, m) of the tridiagonals w.r.t. (lengthscale, sigma).
+    -> (quad, gquad, iterations, alpha, beta, dalpha, dbeta, breakdown)."""
+    import ctypes
+
+    ctx = context()
+    x, y, x_locs, U = _f64(x), _f64(y), _f64(x_locs), _f64(U)
+    _check_xy(x, y, "sgpr")
+    _require(x_locs.dim() == 2 and x_locs.shape[1] == x.shape[1],
+             f"sgpr: x_locs has {tuple(x_locs.shape)} but x has {x.shape[1]} features")
+    N, D = x.shape
+    _require(y.numel() == N, "the iterative SGPR path supports a single output column")
+    _require(U.dim() == 2 and U.shape[0] == N, f"sgpr: U has {tuple(U.shape)} but x has {N} rows")
+    P = U.shape[1]
+    quad = torch.empty(1, dtype=torch.float64, device=x.device)
+    gquad = torch.empty(3, dtype=torch.float64, device=x.device)
+    alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
+    dalpha = torch.empty((2, P, m), dtype=torch.float64, device=x.device)
+    dbeta = torch.empty((2, P, m), dtype=torch.float64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    iters = ctypes.c_int(0)
+    check(
+        ctx.lib.gpxb_sgpr_lml_iter_grad_parts(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, ptr(x_locs),
+                                              x_locs.shape[0], float(ell), float(sigma), int(mean_mode), float(tol),
+                                              float(atol), int(maxiter), ptr(quad), ptr(gquad), ctypes.byref(iters),
+                                              ptr(U), U.stride(0), P, int(m), ptr(alpha), ptr(beta), ptr(dalpha),
+                                              ptr(dbeta), ptr(flag), stream_ptr()),
+        "gpxb_sgpr_lml_iter_grad_parts",
+    )
+    return quad, gquad, iters.value, alpha, beta, dalpha, dbeta, flag
 
 
 def sgpr_lml_grad_locs(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA):

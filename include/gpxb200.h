@@ -154,6 +154,14 @@ int gpxb_lanczos_grad_derivs(gpxb_ctx* ctx, int kind, const double* x, const dou
 int gpxb_rpcholesky_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv,
                            double ell, uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out,
                            long long* pivots_out, gpxb_stream stream);
+/* SGPR trained on derivative values, CG fit (_fit_derivs_iter gpx/models/_sgpr.py:399-428 with _Ax_derivs_lhs_fun
+ * :145-201): c[M nv_locs] = cg(sigma^2 H_mm + H_mn H_nm + 1e-10 I, H_mn y), H = d01kj, zero mean, no preconditioner,
+ * jax cg stopping rule (tol, atol, maxiter <= 0: 10 M nv_locs).  All products are matrix-free Hessian operators.
+ * Host-synchronous like gpxb_gpr_fit_iter; *iters_out is a HOST int. */
+int gpxb_sgpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y, int N,
+                              int nf, int nv, const double* x_locs, const double* J_locs, int M, int nv_locs, double ell,
+                              double sigma, double tol, double atol, int maxiter, double* c_out, int* iters_out,
+                              gpxb_stream stream);
 /* ---- GPR on targets and derivatives, iterative (gpx/models/gpr_td.py, one derivative block) ------------------ */
 /* c[N + N nv] (rows [targets; derivatives (sample, variable)]) = PCG solve of
  *   [[K + s_t I, d1kj], [d0kj, d01kj + s_d I]] c = [y - mu; y_derivs],  s_* = sigma_*^2 + 1e-10
@@ -373,6 +381,16 @@ int gpxb_sgpr_lml_iter_parts(gpxb_ctx* ctx, int kind, const double* x, const dou
                              double atol, int maxiter, double* quad_out, int* iters_out, const double* U,
                              long long ldu, int P, int m, double* alpha_out, double* beta_out, int* breakdown_flag,
                              gpxb_stream stream);
+/* gpxb_sgpr_lml_iter_parts plus what jit(value_and_grad) of _lml_iter (gpx/models/_sgpr.py:700-737) needs for fixed
+ * landmarks: gquad_out[3] (device) = { (dK_mn c).g, g.(dK_mm g), c.c } with c the CG solution and g = K_mm^-1 K_mn c
+ * (c^T dA/d ell c = 2 gquad[0] - gquad[1]; c^T dA/d sigma c = 2 sigma gquad[2]; d(r.c) = -c^T dA c because the CG
+ * solve is a lax.custom_linear_solve), and dalpha_out / dbeta_out [2][P][m]: the tangents of the Lanczos
+ * tridiagonals w.r.t. (lengthscale, sigma) (forward mode through gpx/lanczos.py:46-133).  D <= 64. */
+int gpxb_sgpr_lml_iter_grad_parts(gpxb_ctx* ctx, int kind, const double* x, const double* y, int N, int D,
+                                  const double* x_locs, int M, double ell, double sigma, int mean_mode, double tol,
+                                  double atol, int maxiter, double* quad_out, double* gquad_out, int* iters_out,
+                                  const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out,
+                                  double* dalpha_out, double* dbeta_out, int* breakdown_flag, gpxb_stream stream);
 /* gpx/models/_sgpr.py:434-467 (covariance built from the test points, as the reference does) */
 int gpxb_sgpr_predict(gpxb_ctx* ctx, int kind, const double* x_locs, int M, int D, const double* x, int ns,
                       const double* c, int T, const double* mu, double ell, double sigma, double* mean_out,

@@ -1309,6 +1309,42 @@ def sgpr_lml_iter(kind, x_locs, x, y, ell, sigma, num_evals, num_lanczos, key_la
     return mll / n
 
 
+def sgpr_lml_iter_grad(kind, x_locs, x, y, ell, sigma, num_evals, num_lanczos, key_lanczos, mean_function=data_mean,
+                       partitionable=True, cg_tol=1e-5):
+    """(lml, d/d ell, d/d sigma) of sgpr_lml_iter as jit(value_and_grad) propagates it (_sgpr.py:700-737; landmarks
+    fixed): the CG solve is a custom_linear_solve, d(r.c) = -c^T dA c; the SLQ term is differentiated through the
+    Lanczos recursion.  A = K_nm (K_mm + 1e-10 I)^-1 K_mn + (sigma^2 + 1e-10) I,
+    dA/d ell = dK_nm W K_mn + K_nm W dK_mn - K_nm W dK_mm W K_mn (W the explicit inverse), dA/d sigma = 2 sigma I."""
+    mu = mean_function(y)
+    r = y - mu
+    n, m = y.shape[0], x_locs.shape[0]
+    K_mm, dK_mm = kernel_dl(kind, x_locs, x_locs, ell)
+    np.fill_diagonal(dK_mm, 0.0)  # the diagonal distance is the constant jitter
+    W = np.linalg.inv(K_mm + 1e-10 * np.eye(m))
+    K_nm, dK_nm = kernel_dl(kind, x, x_locs, ell)
+    shift = sigma**2 + 1e-10
+
+    def mv(v):
+        return K_nm @ (W @ (K_nm.T @ v)) + shift * v
+
+    def dmv(v):
+        g = W @ (K_nm.T @ v)
+        return dK_nm @ g + K_nm @ (W @ (dK_nm.T @ v - dK_mm @ g))
+
+    c, _ = cg(mv, r, tol=cg_tol)
+    us, _ = rademacher_probes(key_lanczos, n, num_evals, partitionable)
+    acc, dacc = 0.0, np.zeros(2)
+    for p in range(num_evals):
+        T, dT = lanczos_tridiagonal_jvp(mv, [dmv, lambda v: 2.0 * sigma * v], num_lanczos, us[:, p])
+        acc += slq_from_tridiag(T)
+        dacc += np.array([slq_from_tridiag_jvp(T, dT[0]), slq_from_tridiag_jvp(T, dT[1])])
+    ld, dld = (n / num_evals) * acc, (n / num_evals) * dacc
+    mll = (-0.5 * np.sum(r.T @ c) - 0.5 * ld - n * 0.5 * np.log(2.0 * np.pi)) / n
+    g_l = (0.5 * np.sum(c * dmv(c)) - 0.5 * dld[0]) / n
+    g_s = (sigma * np.sum(c * c) - 0.5 * dld[1]) / n
+    return mll, g_l, g_s
+
+
 def kernel_dx_profile(kind: str, x1, x2, ell: float):
     """h with d kernel(x1_i, x2_j)/d x1_if = -h_ij (x1_if - x2_jf): h = -(2/ell^2) dk/d(d2) of the matrix
     kernels above (d2 carries the 1e-12 jitter of squared_distances; the Matern clamp is inactive)."""

@@ -323,6 +323,48 @@ def test_sgpr_fit_and_predict_on_derivatives(kind):
     assert np.max(np.abs(yp - ref_y)) < 1e-7 * np.max(np.abs(ref_y))
 
 
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_sgpr_cg_fit_on_derivatives(kind):
+    """_fit_derivs_iter (gpx/models/_sgpr.py:399-428): CG on sigma^2 H_mm + H_mn H_nm + 1e-10 I through the
+    matrix-free Hessian operators, against the oracle's CG on the dense matrices (same iteration count with the
+    reference's stopping rule; 1e-8 on the coefficients' effect with both solves converged) and via the facade."""
+    from gpx_b200 import ops
+    from gpx_b200.kernels import Matern52, SquaredExponential
+    from gpx_b200.models import SGPR
+    from gpx_b200.models.sgpr import locs_parameter
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Identity, Softplus
+    from gpx_b200.priors import GammaPrior, NormalPrior
+
+    N, nf, nv, Ml = 60, 5, 4, 8
+    x, J, y = _xj(N, nf, nv, 51)
+    xl, Jl, _ = _xj(Ml, nf, nv, 52)
+    xs, Js, _ = _xj(9, nf, nv, 53)
+    ell, sigma = 2.0, 0.5
+    yf = y.reshape(-1, 1)
+    K_mn = R.d01kj(kind, xl, x, ell, Jl, J)
+    C = sigma**2 * R.d01kj(kind, xl, xl, ell, Jl, Jl) + K_mn @ K_mn.T + 1e-10 * np.eye(K_mn.shape[0])
+    c_cg, it_ref = R.cg(lambda v: C @ v, K_mn @ yf)
+    c, it = ops.sgpr_fit_derivs_iter(kind, dev(x), dev(J), dev(y.reshape(-1)), dev(xl), dev(Jl), ell, sigma)
+    assert abs(it - it_ref) <= 1
+    pred_ref = R.d01kj(kind, xs, xl, ell, Js, Jl) @ c_cg
+    pred = R.d01kj(kind, xs, xl, ell, Js, Jl) @ host(c)
+    assert np.max(np.abs(pred - pred_ref)) < 1e-4 * np.max(np.abs(pred_ref))  # both stopped at tol 1e-5
+    # converged on both sides: the solution itself
+    c_t, _ = ops.sgpr_fit_derivs_iter(kind, dev(x), dev(J), dev(y.reshape(-1)), dev(xl), dev(Jl), ell, sigma, tol=1e-14,
+                                      maxiter=20000)
+    c_d = np.linalg.solve(C, K_mn @ yf)
+    pred_d = R.d01kj(kind, xs, xl, ell, Js, Jl) @ c_d
+    pred_t = R.d01kj(kind, xs, xl, ell, Js, Jl) @ host(c_t)
+    assert np.max(np.abs(pred_t - pred_d)) < 1e-8 * np.max(np.abs(pred_d))
+    kern = SquaredExponential() if kind == "se" else Matern52()
+    m = SGPR(kern, x_locs=locs_parameter(xl), jacobian_locs=Parameter(Jl, False, Identity(), NormalPrior(shape=Jl.shape)),
+             kernel_params=dict(lengthscale=Parameter(ell, True, Softplus(), GammaPrior())),
+             sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+    m.fit_derivs(x, y, J, minimize=False, iterative=True)
+    assert np.max(np.abs(m.predict_derivs(xs, Js).reshape(-1, 1) - pred_ref)) < 1e-4 * np.max(np.abs(pred_ref))
+
+
 def test_facade_fit_and_predict_derivs():
     from gpx_b200.kernels import SquaredExponential
     from gpx_b200.models import GPR

@@ -378,6 +378,38 @@ def test_sgpr_predict_at_1e8_and_the_oracle_conditioning_floor():
     assert err < max(1e-8, 50.0 * floor), (err, floor, np.linalg.cond(Cm))
 
 
+@pytest.mark.parametrize("kind", ["se", "m52"])
+def test_sgpr_iterative_lml_gradient_matches_oracle(kind):
+    """value_and_grad of the iterative SGPR LML (_sgpr.py:700-737, fixed landmarks) through SGPR.loss_and_grad(
+    iterative=True) against the oracle's statement-by-statement tangent (itself checked against finite differences)."""
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.kernels import Matern52, SquaredExponential
+    from gpx_b200.models import SGPR
+    from gpx_b200.models import sgpr as S
+    from gpx_b200.models.sgpr import locs_parameter
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.priors import GammaPrior
+
+    N, D, M = 700, 4, 24
+    x, y = _data(N, D, 4)
+    xl = x[np.random.default_rng(2).choice(N, M, replace=False)].copy()
+    ell, sigma = 1.5, 0.4
+    key = R.PRNGKey(5)
+    P = lambda v: Parameter(v, True, Softplus(), GammaPrior())  # noqa: E731
+    m = SGPR(SquaredExponential() if kind == "se" else Matern52(), x_locs=locs_parameter(xl),
+             kernel_params=dict(lengthscale=P(ell)), sigma=P(sigma))
+    ref = R.sgpr_lml_iter_grad(kind, xl, x, y, ell, sigma, 5, 12, key, cg_tol=1e-13)
+    loss, grads = S._loss_and_grad_iter_with_locs(m.state, dev(x), dev(y), dev(xl), 5, 12, key, tol=1e-13)
+    scale = max(abs(v) for v in ref)
+    assert abs(-loss - ref[0]) < 1e-8 * abs(ref[0])
+    assert abs(-grads[("kernel_params", "lengthscale")] - ref[1]) < 1e-8 * scale
+    assert abs(-grads[("sigma",)] - ref[2]) < 1e-8 * scale
+    # the public entry with the reference's stopping rule (tol 1e-5)
+    loss2, grads2 = m.loss_and_grad(x, y, iterative=True, num_evals=5, num_lanczos=12, key_lanczos=key)
+    assert abs(loss2 - loss) < 1e-6 * abs(loss)
+    assert abs(grads2[("sigma",)] - grads[("sigma",)]) < 1e-4 * scale
+
+
 def test_gather_rows():
     from gpx_b200 import ops
 

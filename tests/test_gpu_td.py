@@ -203,3 +203,80 @@ def test_td_second_derivative_block(kind, N, nf, nv1, nv2, mean):
         l0, _ = m2.loss_and_grad(x, y, Ja, ya, jacobian_2=Jb, y_derivs_2=yb)
         m2.fit(x, y, Ja, ya, jacobian_2=Jb, y_derivs_2=yb, opt_kwargs=dict(options=dict(maxiter=15)))
         assert m2.optimize_results_.fun < l0
+
+
+# ---- iterative paths (gpx/models/gpr_td.py:162-505, 562-747) ---------------------------------------------------------
+@pytest.mark.parametrize("kind,N,nf,nv", [("se", 60, 6, 4), ("m52", 45, 9, 9), ("se", 24, 30, 30)])
+@pytest.mark.parametrize("partitionable", [True, False])
+def test_td_rpcholesky_pivots_bit_exact(kind, N, nf, nv, partitionable):
+    from gpx_b200 import ops
+
+    x, J, _, _ = _data(N, nf, nv, 3)
+    ell, M = 0.9 * np.sqrt(nf), 25
+    key = R.PRNGKey(2023)
+    Fref, pref = R.rpcholesky_td(kind, x, J, M, ell, key, partitionable)
+    F, piv = ops.rpcholesky_td(kind, dev(x), dev(J), M, ell, key, partitionable)
+    assert np.array_equal(host(piv), pref)
+    assert np.max(np.abs(host(F) - Fref)) < 1e-9 * max(1.0, np.max(np.abs(Fref)))
+
+
+@pytest.mark.parametrize("kind,N,nf,nv,mean", [("se", 60, 6, 4, "data"), ("m52", 45, 9, 9, "zero")])
+def test_td_iterative_operator_fit_and_lml(kind, N, nf, nv, mean):
+    """The matrix-free block operator against the dense block matrix (through a Lanczos step on unit vectors), the PCG
+    fit against the dense solve with both CG runs converged, and the iterative LML against the oracle's."""
+    from gpx_b200 import ops
+    from gpx_b200.kernels import Matern52, SquaredExponential
+    from gpx_b200.mean_functions import data_mean, zero_mean
+    from gpx_b200.models import GPR_TD
+    from gpx_b200.models import gpr_td as T
+
+    x, J, y, yd = _data(N, nf, nv, 4)
+    ell, st, sd = 0.9 * np.sqrt(nf), 0.3, 0.2
+    key = R.PRNGKey(2023)
+    mfun = R.data_mean if mean == "data" else R.zero_mean
+    n = N + N * nv
+    A = R.td_A_lhs(kind, x, J, x, J, ell, st, sd)
+    # operator: one Lanczos step gives alpha = v^T A v, beta = |A v - alpha v| for each start vector
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal((n, 7))
+    U /= np.linalg.norm(U, axis=0)
+    alpha, beta, flag = ops.lanczos_td(kind, dev(x), dev(J), ell, st, sd, dev(U), 3)
+    for p in range(U.shape[1]):
+        Tref, _ = R.lanczos_tridiagonal(lambda v: A @ v, 3, U[:, p])
+        assert np.max(np.abs(host(alpha)[p] - np.diag(Tref))) < 1e-9 * np.max(np.abs(np.diag(Tref)))
+        assert np.max(np.abs(host(beta)[p, :2] - np.diag(Tref, 1))) < 1e-9 * np.max(np.abs(np.diag(Tref)))
+    # fit
+    c_ref, mu_ref, _ = R.td_fit_iter(kind, x, y, J, yd, ell, st, sd, 20, key, mfun, cg_tol=1e-13, cg_atol=0.0)
+    c, mu, iters = ops.gpr_td_fit_iter(kind, dev(x), dev(J), dev(y), dev(yd), ell, st, sd, 20, key,
+                                       1 if mean == "data" else 0, tol=1e-13, atol=0.0)
+    assert abs(float(host(mu)[0]) - float(mu_ref)) < 1e-14
+    assert np.max(np.abs(host(c) - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
+    c_d, _ = R.td_fit_dense(kind, x, y, J, yd, ell, st, sd, mfun)
+    assert np.max(np.abs(host(c) - c_d)) < 1e-8 * np.max(np.abs(c_d))
+    # with the reference's stopping rule: same iteration count as the oracle's CG
+    _, _, it_ref = R.td_fit_iter(kind, x, y, J, yd, ell, st, sd, 20, key, mfun)
+    _, _, it_dev = ops.gpr_td_fit_iter(kind, dev(x), dev(J), dev(y), dev(yd), ell, st, sd, 20, key,
+                                       1 if mean == "data" else 0)
+    assert abs(it_dev - it_ref) <= 1
+    # iterative LML through the facade against the oracle (converged solves) and, loosely, the dense LML
+    K = SquaredExponential() if kind == "se" else Matern52()
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    P = lambda v: Parameter(v, True, Softplus(), GammaPrior())  # noqa: E731
+    model = GPR_TD(K, mean_function=data_mean if mean == "data" else zero_mean, kernel_params=dict(lengthscale=P(ell)),
+                   sigma_targets=P(st), sigma_derivs=P(sd))
+    ref = R.td_lml_iter(kind, x, y, J, yd, ell, st, sd, 6, 12, key, 20, key, mfun, cg_tol=1e-13, cg_atol=0.0)
+    out = T._lml_iter(model.state, x, y, J, yd, 6, 12, key, 20, key, tol=1e-13, atol=0.0)
+    assert abs(out - ref) < 1e-8 * abs(ref)
+    lml_facade = model.log_marginal_likelihood(x, y, J, yd, iterative=True, num_evals=6, num_lanczos=12, key_lanczos=key,
+                                               n_pivots=20, key_precond=key)
+    assert abs(lml_facade - ref) < 1e-6 * abs(ref)
+    # fit(iterative=True, minimize=False) + predict(iterative=True) reproduce the dense model's predictions
+    model.fit(x, y, J, yd, iterative=True, minimize=False, n_pivots=20, key_precond=key)
+    xs, Js, _, _ = _data(11, nf, nv, 9)
+    yp, dp = model.predict(xs, Js, iterative=True)
+    y_ref, d_ref = R.td_predict_dense(kind, x, J, xs, Js, c_d, mfun(y), ell)
+    assert np.max(np.abs(yp - y_ref)) < 1e-4 * max(1.0, np.max(np.abs(y_ref)))  # CG stopped at tol 1e-5
+    assert np.max(np.abs(dp - d_ref)) < 1e-4 * max(1.0, np.max(np.abs(d_ref)))
