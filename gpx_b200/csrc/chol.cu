@@ -242,7 +242,9 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lq = lane & 3;
 
-  // lower triangle in, identity padding beyond n (keeps every block operation well defined)
+  // lower triangle in, identity padding beyond n (keeps every block operation well defined); eight independent
+  // loads per thread in flight: the block comes from L2 / HBM and one CTA has no other latency hiding
+#pragma unroll 8
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
     const int i = idx >> 7, k = idx & (LB - 1);
     double v = 0.0;
@@ -341,9 +343,10 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
       __syncthreads();
     }
   }
-  for (int idx = tid; idx < n * n; idx += LEAF_NT) {
-    const int i = idx / n, k = idx - i * n;
-    if (k <= i) A[(long long)i * lda + k] = S[i * L2S + k];
+#pragma unroll 8
+  for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    if (i < n && k <= i) A[(long long)i * lda + k] = S[i * L2S + k];
   }
   if (inv == nullptr) return;
   __syncthreads();
@@ -364,6 +367,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   __syncthreads();
   cta_mm(S + 64 * L2S, L2S, S + 64 * L2S + 64, L2S, T, T2S, 64, 64, 64, -1.0, warp, lane);
   __syncthreads();
+#pragma unroll 8
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
     const int i = idx >> 7, k = idx & (LB - 1);
     inv[idx] = (i < n && k <= i) ? S[i * L2S + k] : 0.0;
@@ -551,9 +555,263 @@ __global__ void logdet_bcp_kernel(const double* __restrict__ Lp, BcpLayout lay, 
   if (threadIdx.x == 0) *out = scale * s;
 }
 
+// ---- few right-hand sides, second generation: ONE launch per 128-column step ---------------------------------
+// The first generation ran [diagonal solve, 1 CTA] -> [update of the remaining right-hand side, many CTAs] as two
+// dependent launches per step, and the diagonal kernel read its 128 x 128 inverse one row at a time (36 us per
+// step by ncu, barrier / long-scoreboard bound).  Here CTA 0 of the update launch first updates the NEXT block's
+// 128 entries, then applies that block's inverse to them, while the other CTAs update the rest: one launch per
+// step on the dependency chain, and every thread issues its loads before it consumes them.
+
+// so[r][t] = sum_{c <= t} inv[t][c] sb[r][c]: one warp per output row, four rows in flight (16 loads per lane)
+__device__ __forceinline__ void trsv_diag_fwd_apply(const double* __restrict__ inv, double (*sb)[LB], double (*so)[LB],
+                                                    int nb, int tid, int m) {
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int t0 = warp; t0 < nb; t0 += 32) {
+    double v[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int t = t0 + 8 * i, c = lane + 32 * q;
+        v[i][q] = (t < nb && c <= t) ? inv[t * LB + c] : 0.0;
+      }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + 8 * i;
+      double acc[TRSV_MAXM];
+#pragma unroll
+      for (int r = 0; r < TRSV_MAXM; ++r) {
+        acc[r] = 0.0;
+        if (r < m) {  // m is uniform: no reduction for absent right-hand sides
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[r] += v[i][q] * sb[r][lane + 32 * q];
+          acc[r] = warp_sum(acc[r]);
+        }
+      }
+      if (lane == 0 && t < nb) {
+#pragma unroll
+        for (int r = 0; r < TRSV_MAXM; ++r) so[r][t] = acc[r];
+      }
+    }
+  }
+}
+// so[r][t] = sum_{c >= t} inv[c][t] sb[r][c]: thread (t, half) sums half of the c range, halves combined through
+// shared memory in a fixed order
+__device__ __forceinline__ void trsv_diag_bwd_apply(const double* __restrict__ inv, double (*sb)[LB], double (*so)[LB],
+                                                    double (*tmp)[LB], int nb, int tid) {
+  const int t = tid & (LB - 1), half = tid >> 7;
+  double acc[TRSV_MAXM];
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
+  const int cb = half * (LB / 2), ce = min(nb, cb + LB / 2);
+  if (t < nb) {
+#pragma unroll 8
+    for (int c = cb; c < ce; ++c) {
+      const double v = (c >= t) ? inv[c * LB + t] : 0.0;
+#pragma unroll
+      for (int r = 0; r < TRSV_MAXM; ++r) acc[r] += v * sb[r][c];
+    }
+  }
+  if (half == 1) {
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) tmp[r][t] = acc[r];
+  }
+  __syncthreads();
+  if (half == 0 && t < nb) {
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) so[r][t] = acc[r] + tmp[r][t];
+  }
+}
+
+// forward step: x = X[:, 0:nb) solved.  CTA 0: next block (rows [0, nb_next) below) updated, then solved against
+// inv_next; CTAs >= 1: B[:, j] -= sum_c L[j][c] x[c] for the rows j >= nb_next below (one warp per row).
+__global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __restrict__ Lblk, long long ldl,
+                                                            const double* __restrict__ X, double* __restrict__ Bb,
+                                                            long long ldb, int m, int nb, int nrows,
+                                                            const double* __restrict__ inv_next, int nb_next) {
+  __shared__ double sx[TRSV_MAXM][LB];
+  __shared__ double sb[TRSV_MAXM][LB];
+  __shared__ double so[TRSV_MAXM][LB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
+    const int r = i / LB, c = i % LB;
+    sx[r][c] = (r < m && c < nb) ? X[(long long)r * ldb + c] : 0.0;
+  }
+  __syncthreads();
+  auto row_dot = [&](int j, double* acc) {  // acc[r] = sum_c L[j][c] x[r][c], reduced over the warp
+    const double* Lr = Lblk + (long long)j * ldl;
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = (lane + 32 * q < nb) ? Lr[lane + 32 * q] : 0.0;
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) {
+      acc[r] = 0.0;
+      if (r < m) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r] += v[q] * sx[r][lane + 32 * q];
+        acc[r] = warp_sum(acc[r]);
+      }
+    }
+  };
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
+      const int r = i / LB, c = i % LB;
+      sb[r][c] = (r < m && c < nb_next) ? Bb[(long long)r * ldb + c] : 0.0;
+    }
+    __syncthreads();
+    for (int j0 = warp; j0 < nb_next; j0 += 32) {  // four rows per pass: their loads are independent
+      double acc[4][TRSV_MAXM];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (j0 + 8 * i < nb_next) row_dot(j0 + 8 * i, acc[i]);
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (j0 + 8 * i < nb_next) {
+#pragma unroll
+            for (int r = 0; r < TRSV_MAXM; ++r) sb[r][j0 + 8 * i] -= acc[i][r];
+          }
+      }
+    }
+    __syncthreads();
+    trsv_diag_fwd_apply(inv_next, sb, so, nb_next, tid, m);
+    __syncthreads();
+    for (int i = tid; i < m * nb_next; i += 256) {
+      const int r = i / nb_next, c = i % nb_next;
+      Bb[(long long)r * ldb + c] = so[r][c];
+    }
+    return;
+  }
+  const int j = nb_next + (blockIdx.x - 1) * 8 + warp;
+  if (j >= nrows) return;
+  double acc[TRSV_MAXM];
+  row_dot(j, acc);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r)
+      if (r < m) Bb[(long long)r * ldb + j] -= acc[r];
+  }
+}
+
+// backward step: x = X[:, 0:nb) solved (block at column c0).  CTA 0: the previous block (columns [c0 - 128, c0))
+// updated, then solved against inv_prev^T; CTAs >= 1: B[:, j] -= sum_c L[c0 + c][j] x[c] for the columns j < c0 - 128.
+__global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __restrict__ Lrows, long long ldl,
+                                                            const double* __restrict__ X, double* __restrict__ B,
+                                                            long long ldb, int m, int nb, int c0,
+                                                            const double* __restrict__ inv_prev) {
+  __shared__ double sx[TRSV_MAXM][LB];
+  __shared__ double sb[TRSV_MAXM][LB];
+  __shared__ double so[TRSV_MAXM][LB];
+  __shared__ double tmp[TRSV_MAXM][LB];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
+    const int r = i / LB, c = i % LB;
+    sx[r][c] = (r < m && c < nb) ? X[(long long)r * ldb + c] : 0.0;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    const int t = tid & (LB - 1), half = tid >> 7, j = c0 - LB + t;
+    double acc[TRSV_MAXM];
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
+    const int cb = half * (LB / 2), ce = min(nb, cb + LB / 2);
+#pragma unroll 8
+    for (int c = cb; c < ce; ++c) {
+      const double v = Lrows[(long long)c * ldl + j];
+#pragma unroll
+      for (int r = 0; r < TRSV_MAXM; ++r) acc[r] += v * sx[r][c];
+    }
+    if (half == 1) {
+#pragma unroll
+      for (int r = 0; r < TRSV_MAXM; ++r) tmp[r][t] = acc[r];
+    }
+    __syncthreads();
+    if (half == 0) {
+#pragma unroll
+      for (int r = 0; r < TRSV_MAXM; ++r) sb[r][t] = (r < m) ? B[(long long)r * ldb + j] - (acc[r] + tmp[r][t]) : 0.0;
+    }
+    __syncthreads();
+    trsv_diag_bwd_apply(inv_prev, sb, so, tmp, LB, tid);
+    __syncthreads();
+    for (int i = tid; i < m * LB; i += 256) {
+      const int r = i / LB, c = i % LB;
+      B[(long long)r * ldb + c0 - LB + c] = so[r][c];
+    }
+    return;
+  }
+  const int j = (blockIdx.x - 1) * 256 + tid;
+  if (j >= c0 - LB) return;
+  double acc[TRSV_MAXM];
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r) acc[r] = 0.0;
+#pragma unroll 8
+  for (int c = 0; c < nb; ++c) {
+    const double v = Lrows[(long long)c * ldl + j];
+#pragma unroll
+    for (int r = 0; r < TRSV_MAXM; ++r) acc[r] += v * sx[r][c];
+  }
+#pragma unroll
+  for (int r = 0; r < TRSV_MAXM; ++r)
+    if (r < m) B[(long long)r * ldb + j] -= acc[r];
+}
+
+// the first block of a sweep (nothing to update yet)
+__global__ void __launch_bounds__(256) trsv_first_kernel(const double* __restrict__ inv, double* __restrict__ B,
+                                                         long long ldb, int m, int nb, int backward) {
+  __shared__ double sb[TRSV_MAXM][LB];
+  __shared__ double so[TRSV_MAXM][LB];
+  __shared__ double tmp[TRSV_MAXM][LB];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
+    const int r = i / LB, c = i % LB;
+    sb[r][c] = (r < m && c < nb) ? B[(long long)r * ldb + c] : 0.0;
+  }
+  __syncthreads();
+  if (backward) trsv_diag_bwd_apply(inv, sb, so, tmp, nb, tid);
+  else trsv_diag_fwd_apply(inv, sb, so, nb, tid, m);
+  __syncthreads();
+  for (int i = tid; i < m * nb; i += 256) {
+    const int r = i / nb, c = i % nb;
+    B[(long long)r * ldb + c] = so[r][c];
+  }
+}
+
+int trsv_few_v2(Ctx* ctx, const double* L, long long ldl, const double* inv, double* B, long long ldb, int m, int n,
+                bool transposed_solve, cudaStream_t s) {
+  const int nblk = (n + LB - 1) / LB;
+  if (transposed_solve) {  // L x = b: forward over blocks
+    trsv_first_kernel<<<1, 256, 0, s>>>(inv, B, ldb, m, min(LB, n), 0);
+    ctx->launches++;
+    for (int k = 0; k + 1 < nblk; ++k) {
+      const int c0 = k * LB, below = n - c0 - LB, nb_next = min(LB, below);
+      trsv_fwd_step_kernel<<<1 + (below - nb_next + 7) / 8, 256, 0, s>>>(L + (long long)(c0 + LB) * ldl + c0, ldl, B + c0,
+                                                                          B + c0 + LB, ldb, m, LB, below,
+                                                                          inv + (long long)(k + 1) * LB * LB, nb_next);
+      ctx->launches++;
+    }
+  } else {  // L^T x = b: backward over blocks
+    const int cl = (nblk - 1) * LB;
+    trsv_first_kernel<<<1, 256, 0, s>>>(inv + (long long)(nblk - 1) * LB * LB, B + cl, ldb, m, n - cl, 1);
+    ctx->launches++;
+    for (int k = nblk - 1; k >= 1; --k) {
+      const int c0 = k * LB, nb = min(LB, n - c0);
+      trsv_bwd_step_kernel<<<1 + (c0 - LB + 255) / 256, 256, 0, s>>>(L + (long long)c0 * ldl, ldl, B + c0, B, ldb, m, nb, c0,
+                                                                      inv + (long long)(k - 1) * LB * LB);
+      ctx->launches++;
+    }
+  }
+  GPXB_LAUNCH_CHECK();
+  return 0;
+}
+
 // few right-hand sides (m <= 4): blocked substitution with GEMV updates -- HBM bound (reads L once)
 int trsv_few(Ctx* ctx, const double* L, long long ldl, const double* inv, double* B, long long ldb, int m, int n,
              bool transposed_solve, cudaStream_t s) {
+  static const bool v1 = [] {
+    const char* e = getenv("GPXB_TRSV");  // "v1": two launches per step (kept for comparison)
+    return e && e[0] == 'v' && e[1] == '1';
+  }();
+  if (!v1) return trsv_few_v2(ctx, L, ldl, inv, B, ldb, m, n, transposed_solve, s);
   const int nblk = (n + LB - 1) / LB;
   if (transposed_solve) {
     // X L^T = B  <=>  L x = b: forward over blocks
