@@ -398,6 +398,49 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
                     peak_tflops=dgemm_tflops, frac=fl / t / 1e12 / world / dgemm_tflops, lml=lml,
                     breakdown=int(flag.cpu()[0]), phases=ph, non_compute_s=non_compute(t, ph))
 
+    def cfg0():
+        """configs[0]: exact GPR, SquaredExponential, N = 2000, D = 8: LML+grad and predict (every rank runs its own
+        replica: the dense path does not shard).  Latency bound: 16 sequential 128-column panel steps."""
+        n0, d0 = 2000, 8
+        xa, ya = data(n0, d0, 11)
+        xs, _ = data(512, d0, 12)
+        f = lambda: ops.gpr_lml_grad("se", xa, ya, 2.0, 0.1)  # noqa: E731
+        for _ in range(3):
+            f()
+        best = min(timed(f, phases=False)[0] for _ in range(5))
+        c, mu = ops.gpr_fit("se", xa, ya, 2.0, 0.1)
+        gp = lambda: ops.gpr_predict("se", xa, xs, c, mu, 2.0, 0.1)  # noqa: E731
+        gp()
+        tp = min(timed(gp, phases=False)[0] for _ in range(5))
+        fl = float(n0) ** 3 + 2.0 * n0 * n0 * d0
+        return dict(id="cfg0_lml_grad", what="exact GPR SE N=2000 D=8: LML+grad (one fused call) and predict mean of 512 "
+                    "points; replicas, best of 5", N=n0, D=d0, s=best, ms=best * 1e3, evals_per_s=1.0 / best,
+                    predict_ms=tp * 1e3, bound="tensor", alg_flops=fl, achieved_tflops_per_gpu=fl / best / 1e12,
+                    peak_tflops=dgemm_tflops, frac=fl / best / 1e12 / dgemm_tflops,
+                    note="latency bound: the chain leaf -> head solve -> head update of 16 panel steps, not flops")
+
+    def cfg2_iter():
+        """configs[2]: GPR on derivative values, 30 atoms (nf = nv = 90), N = 2000 configurations = a 180 000-row
+        Hessian system (259 GB as a dense square: over one GPU's HBM as such; the dense packed-lower path takes
+        63 s, profiles/r1_configs.jsonl).  Here: the matrix-free path (PCG fit with the rpcholesky_derivs
+        preconditioner + SLQ log-det on the Hessian operator), replicas."""
+        from gpx_b200.models import _iterative as it
+
+        nc, nf = max(16, int(2000 * min(scale, 1.0))), 90
+        g = torch.Generator(device="cuda").manual_seed(21)
+        xa = torch.randn((nc, nf), dtype=torch.float64, device="cuda", generator=g)
+        Ja = torch.eye(nf, dtype=torch.float64, device="cuda").repeat(nc, 1, 1).contiguous()
+        ya = torch.randn((nc * nf,), dtype=torch.float64, device="cuda", generator=g)
+        npv = 200 if scale >= 1.0 else 16
+        t, lml, _ = timed(lambda: it.lml_derivs_iter("se", xa, Ja, ya, 9.0, 0.3, 30, 50, key, npv, key), phases=False)
+        return dict(id="cfg2_lml_derivs_iter", what="derivative-trained GPR, Hessian kernel, matrix-free LML (PCG + SLQ "
+                    "30 probes x 50 steps on the Hessian operator; host eigh included); replicas", N=nc, nf=nf, nv=nf,
+                    rows=nc * nf, n_pivots=npv, s=t, evals_per_s=1.0 / t, lml=float(lml))
+
+    if world == 1:  # single-GPU configurations (nothing to shard): reported at --gpus 1 only
+        entry("configs[0] exact GPR SE N=2000 D=8: LML+grad, predict", cfg0)
+        entry("configs[2] GPR on derivatives, 30 atoms (D=90), N=2000 (180k-row Hessian system): iterative LML",
+              cfg2_iter)
     entry(f"configs[3] SGPR + RPCholesky, N={N} D=32 M={M}: landmark selection", rpchol)
     entry(f"configs[3] SGPR + RPCholesky, N={N} D=32 M={M}: LML", sgpr)
     del x32, y32

@@ -54,6 +54,7 @@ int gpxb_ctx_create(int device, gpxb_ctx** out) {
   int prio_lo = 0, prio_hi = 0;
   GPXB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   GPXB_CUDA_CHECK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
+  GPXB_CUDA_CHECK(cudaStreamCreateWithPriority(&c->crit, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 3; ++i) GPXB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
   GPXB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   GPXB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -70,6 +71,7 @@ int gpxb_ctx_destroy(gpxb_ctx* ctx) {
   if (!ctx) return 0;
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (c->side) cudaStreamDestroy(c->side);
+  if (c->crit) cudaStreamDestroy(c->crit);
   for (int i = 0; i < 3; ++i)
     if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);

@@ -272,6 +272,8 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
         } else if (lane > c) {
           a[c] *= rd;
         }
+        // multipliers by shuffle: a shared-memory broadcast (STS + __syncwarp + LDS) was measured 12 % SLOWER on the
+        // whole factorisation -- its round trip sits on the column-to-column dependency chain
 #pragma unroll
         for (int c2 = 0; c2 < 32; ++c2) {  // rectangular bounds: the triangular condition folds after unrolling
           if (c2 > c) {
@@ -905,9 +907,128 @@ int trsm_right_l(Ctx* ctx, const double* L, long long ldl, const double* inv, do
 // of the panel; then one rank-1024 SYRK on the trailing matrix.  Every GEMM is tall, so only
 // the leaves run on a single SM.
 namespace {
-// Factor the tall panel A[k0:n, k0:k0+w] (its w x w head is the diagonal block).
-int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, double* inv,
-                 cudaStream_t s) {
+// ---- small-tile kernels of the panel's dependency chain -----------------------------------------------------
+// Inside a panel the chain  leaf(j) -> rows of block j+1 solved -> diagonal block j+1 updated -> leaf(j+1)  is what
+// bounds a mid-size factorisation (n <= 8192): run through the 128 x 128-tile GEMM each link costs ~25 us whatever
+// its size (one tile = 4.2 MFLOP on ONE SM at 250 GFLOP/s).  These two kernels cut the links into 32-row pieces
+// spread over several SMs; the bulk of the solve / update runs beside them on the other stream.
+constexpr int PSL = LB + 4;  // shared-memory row stride (== 4 mod 8: conflict-free DMMA fragment reads)
+constexpr int TRSM32_SMEM = (32 + LB) * PSL * (int)sizeof(double);
+constexpr int SYRK32_SMEM = 2 * 32 * PSL * (int)sizeof(double);
+
+// B[r0 : r0 + 32, 0 : jb) <- B[same] inv^T in place (C[i][n] = sum_k B[i][k] inv[n][k]); inv: packed 128 x 128 leaf
+// inverse (zero above the diagonal and beyond jb).  One CTA per 32 rows, 8 warps x (32 rows x 16 columns).
+__global__ void __launch_bounds__(256) panel_trsm32_kernel(double* __restrict__ B, long long ldb, int rows, int jb,
+                                                           const double* __restrict__ inv) {
+  extern __shared__ __align__(16) double psm[];
+  double* sB = psm;               // [32][PSL]
+  double* sI = psm + 32 * PSL;    // [128][PSL]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lq = lane & 3;
+  const int r0 = blockIdx.x * 32;
+#pragma unroll 8
+  for (int idx = tid; idx < LB * LB / 2; idx += 256) {  // inv: 16-byte loads (the packed block is 16-byte aligned)
+    const int i = idx >> 6, k2 = (idx & 63) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(inv + i * LB + k2);
+    sI[i * PSL + k2] = v.x;
+    sI[i * PSL + k2 + 1] = v.y;
+  }
+#pragma unroll 4
+  for (int idx = tid; idx < 32 * LB; idx += 256) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    sB[i * PSL + k] = (r0 + i < rows && k < jb) ? B[(long long)(r0 + i) * ldb + k] : 0.0;
+  }
+  __syncthreads();
+  double c[4][2][2];
+#pragma unroll
+  for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) c[mf][nf][0] = c[mf][nf][1] = 0.0;
+  const double* ap = sB + lr * PSL + lq;
+  const double* bp = sI + (warp * 16 + lr) * PSL + lq;
+  const int kend = (jb + 3) & ~3;
+  for (int k = 0; k < kend; k += 4) {
+    double a[4], b[2];
+#pragma unroll
+    for (int mf = 0; mf < 4; ++mf) a[mf] = ap[mf * 8 * PSL + k];
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) b[nf] = bp[nf * 8 * PSL + k];
+#pragma unroll
+    for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+      for (int nf = 0; nf < 2; ++nf) dmma884(c[mf][nf][0], c[mf][nf][1], a[mf], b[nf]);
+  }
+#pragma unroll
+  for (int mf = 0; mf < 4; ++mf) {
+    const int row = r0 + mf * 8 + lr;
+    if (row >= rows) continue;
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) {
+      const int col = warp * 16 + nf * 8 + 2 * lq;
+      if (col < jb) B[(long long)row * ldb + col] = c[mf][nf][0];
+      if (col + 1 < jb) B[(long long)row * ldb + col + 1] = c[mf][nf][1];
+    }
+  }
+}
+
+// C[nbn x nbn] (lower) -= P P^T, P = [nbn x jb] row-major (ld ldp): one CTA per 32 x 32 tile of the lower
+// triangle, 4 warps x (16 x 16).
+__global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restrict__ P, long long ldp,
+                                                           double* __restrict__ C, long long ldc, int nbn, int jb) {
+  extern __shared__ __align__(16) double psm[];
+  double* sA = psm;              // rows of tile row ti   [32][PSL]
+  double* sT = psm + 32 * PSL;   // rows of tile column tj
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lq = lane & 3;
+  int ti = 0, t = blockIdx.x;
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  const int tj = t - ti * (ti + 1) / 2;
+  const int r0 = ti * 32, c0 = tj * 32;
+#pragma unroll 4
+  for (int idx = tid; idx < 32 * LB; idx += 128) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    sA[i * PSL + k] = (r0 + i < nbn && k < jb) ? P[(long long)(r0 + i) * ldp + k] : 0.0;
+    sT[i * PSL + k] = (c0 + i < nbn && k < jb) ? P[(long long)(c0 + i) * ldp + k] : 0.0;
+  }
+  __syncthreads();
+  const int wm = warp >> 1, wn = warp & 1;
+  double c[2][2][2];
+#pragma unroll
+  for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) c[mf][nf][0] = c[mf][nf][1] = 0.0;
+  const double* ap = sA + (wm * 16 + lr) * PSL + lq;
+  const double* bp = sT + (wn * 16 + lr) * PSL + lq;
+  const int kend = (jb + 3) & ~3;
+  for (int k = 0; k < kend; k += 4) {
+    double a[2], b[2];
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf) a[mf] = ap[mf * 8 * PSL + k];
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) b[nf] = bp[nf * 8 * PSL + k];
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+      for (int nf = 0; nf < 2; ++nf) dmma884(c[mf][nf][0], c[mf][nf][1], a[mf], b[nf]);
+  }
+#pragma unroll
+  for (int mf = 0; mf < 2; ++mf) {
+    const int row = r0 + wm * 16 + mf * 8 + lr;
+    if (row >= nbn) continue;
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) {
+      const int col = c0 + wn * 16 + nf * 8 + 2 * lq;
+      if (col <= row) C[(long long)row * ldc + col] -= c[mf][nf][0];
+      if (col + 1 <= row) C[(long long)row * ldc + col + 1] -= c[mf][nf][1];
+    }
+  }
+}
+
+// Factor the tall panel A[k0:n, k0:k0+w] (its w x w head is the diagonal block); everything this panel reads has been
+// written on stream s.  First generation (GPXB_PANEL=v1): leaf -> tall TRSM -> rank-128 update, three dependent
+// launches per 128 columns on one stream.
+int factor_panel_v1(Ctx* ctx, double* A, long long lda, int n, int k0, int w, double* inv,
+                    cudaStream_t s) {
   for (int j = 0; j < w; j += LB) {
     const int jb = min(LB, w - j);
     const int c0 = k0 + j;  // global first column of this step
@@ -937,6 +1058,85 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
       GPXB_TRY(gemm_f64(ctx, g, s));
     }
   }
+  return 0;
+}
+
+// Second generation (default): the chain  leaf(j) -> [rows of block j+1] inv^T -> diagonal block j+1 -= ...  runs on
+// the high-priority stream ctx->crit through the 32-row kernels above, while the tall part of the solve and the
+// rest of the rank-128 update (every 128-tile but the next diagonal block) run on s, one step behind:
+//   crit:  leaf j | trsm32 head j | syrk32 head j | leaf j+1 | ...
+//   s   :           TRSM rows below the head of j (after leaf j) | update j minus tile (0,0) (after head j) | ...
+// crit waits for the bulk update of step j-1 before it touches block j+1 (that update wrote the head rows' entries
+// in block column j+1 and the diagonal block itself).
+int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, double* inv,
+                 cudaStream_t s) {
+  static const bool v1 = [] {
+    const char* e = getenv("GPXB_PANEL");
+    return e && e[0] == 'v' && e[1] == '1';
+  }();
+  if (v1 || ctx->serialize || !ctx->crit || w <= LB) return factor_panel_v1(ctx, A, lda, n, k0, w, inv, s);
+  cudaStream_t cs = ctx->crit;
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_trsm32_kernel, TRSM32_SMEM));
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_syrk32_kernel, SYRK32_SMEM));
+  cudaEvent_t ev, ev_bulk_prev = nullptr;
+  GPXB_TRY(ctx->next_event(&ev));
+  GPXB_CUDA_CHECK(cudaEventRecord(ev, s));
+  GPXB_CUDA_CHECK(cudaStreamWaitEvent(cs, ev, 0));
+  for (int j = 0; j < w; j += LB) {
+    const int jb = min(LB, w - j);
+    const int c0 = k0 + j;
+    double* Ajj = A + (long long)c0 * lda + c0;
+    double* invj = inv + (long long)(c0 / LB) * LB * LB;
+    GPXB_TRY(leaf(ctx, Ajj, lda, jb, invj, cs));
+    const int below = n - c0 - jb;
+    if (below <= 0) continue;
+    cudaEvent_t ev_leaf, ev_head;
+    GPXB_TRY(ctx->next_event(&ev_leaf));
+    GPXB_CUDA_CHECK(cudaEventRecord(ev_leaf, cs));
+    double* B = A + (long long)(c0 + jb) * lda + c0;  // below x jb
+    const int wr = w - j - jb;                         // panel columns still to update
+    const int nbn = min(LB, below);                    // rows of the next block (the "head")
+    // ---- critical chain on cs ----
+    if (ev_bulk_prev) GPXB_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_bulk_prev, 0));
+    panel_trsm32_kernel<<<ceil_div(nbn, 32), 256, TRSM32_SMEM, cs>>>(B, lda, nbn, jb, invj);
+    GPXB_LAUNCH_CHECK();
+    ctx->launches++;
+    if (wr > 0) {
+      const int nt = ceil_div(min(nbn, wr), 32);
+      panel_syrk32_kernel<<<nt * (nt + 1) / 2, 128, SYRK32_SMEM, cs>>>(B, lda, B + jb, lda, min(nbn, wr), jb);
+      GPXB_LAUNCH_CHECK();
+      ctx->launches++;
+    }
+    GPXB_TRY(ctx->next_event(&ev_head));
+    GPXB_CUDA_CHECK(cudaEventRecord(ev_head, cs));
+    // ---- bulk on s ----
+    GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_leaf, 0));
+    if (below > nbn) {
+      GemmArgs g;  // rows below the head: B <- B inv^T (in place)
+      g.M = below - nbn; g.N = jb; g.K = jb;
+      g.A = B + (long long)nbn * lda; g.lda = lda; g.a_kmajor = true;
+      g.B = invj; g.ldb = LB; g.b_kmajor = true;
+      g.C = B + (long long)nbn * lda; g.ldc = lda;
+      GPXB_TRY(gemm_f64(ctx, g, s));
+    }
+    GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_head, 0));
+    if (wr > 0 && below > nbn) {
+      GemmArgs g;  // C -= B B[0:wr]^T on the lower trapezoid, except the diagonal block the head kernels own
+      g.M = below; g.N = wr; g.K = jb;
+      g.A = B; g.lda = lda; g.a_kmajor = true;
+      g.B = B; g.ldb = lda; g.b_kmajor = true;
+      g.C = B + jb; g.ldc = lda;
+      g.alpha = -1.0; g.beta = 1.0;
+      g.lower_only = 1;
+      g.skip_tile0 = 1;
+      GPXB_TRY(gemm_f64(ctx, g, s));
+    }
+    GPXB_TRY(ctx->next_event(&ev_bulk_prev));
+    GPXB_CUDA_CHECK(cudaEventRecord(ev_bulk_prev, s));
+  }
+  GPXB_TRY(ctx->next_event(&ev));
+  GPXB_CUDA_CHECK(cudaEventRecord(ev, cs));
+  GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
   return 0;
 }
 

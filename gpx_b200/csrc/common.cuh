@@ -70,6 +70,7 @@ struct Ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t side = nullptr;  // high-priority stream (panel factorisation look-ahead)
+  cudaStream_t crit = nullptr;  // high-priority stream of the leaf -> head-solve -> head-update chain inside a panel
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // concurrent branches of the triangular inverse
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_pool;  // reusable timing-free events, grown on demand

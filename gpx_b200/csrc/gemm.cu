@@ -38,7 +38,7 @@ struct GemmParams {
   double* C;
   long long ldc;
   double alpha, beta;
-  int lower_only, klo_mode, khi_mode;
+  int lower_only, klo_mode, khi_mode, skip_tile0;
   int tiles_m, tiles_n;
   int vecA, vecB, vecC;
   long long strideA, strideB, strideC;  // batched launch: blockIdx.y selects the product
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
   // ---- tile coordinates ----
   int ti, tj;
   if (p.lower_only) {
+    if (p.skip_tile0 && blockIdx.x == 0) return;  // tile (0, 0) belongs to another kernel
     // trapezoid (M >= N): tiles_n*(tiles_n+1)/2 triangular tiles, then full tile rows
     const long long t = blockIdx.x;
     const long long ntri = (long long)p.tiles_n * (p.tiles_n + 1) / 2;
@@ -361,6 +362,7 @@ int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream) {
   p.A = g.A; p.lda = g.lda; p.B = g.B; p.ldb = g.ldb; p.C = g.C; p.ldc = g.ldc;
   p.alpha = g.alpha; p.beta = g.beta;
   p.lower_only = g.lower_only; p.klo_mode = g.klo_mode; p.khi_mode = g.khi_mode;
+  p.skip_tile0 = g.lower_only ? g.skip_tile0 : 0;
   p.tiles_m = ceil_div(g.M, BM);
   p.tiles_n = ceil_div(g.N, BN);
   GPXB_ARG_CHECK(g.batch >= 1 && g.batch <= 65535, -4);

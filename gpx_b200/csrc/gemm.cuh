@@ -28,6 +28,7 @@ struct GemmArgs {
   int lower_only = 0;
   int klo_mode = 0;
   int khi_mode = 0;
+  int skip_tile0 = 0;  // lower_only: tile (0, 0) is left alone (another kernel owns the first diagonal block)
   // batch > 1: `batch` independent products of identical shape in one launch; operand z starts strideX * z
   // doubles after operand 0 (same leading dimensions)
   int batch = 1;
