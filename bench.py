@@ -284,10 +284,16 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
         y = torch.sin(x.sum(1, keepdim=True)) + 0.1 * torch.randn((n, 1), dtype=torch.float64, device="cuda", generator=g)
         return x, y
 
+    only = [v for v in os.environ.get("GPXB_BENCH_ONLY", "").split(",") if v]  # builder's aid: run these entries only
+
     def entry(name, fn):
+        if only and fn.__name__ not in only:
+            return
         try:
             d = dict(config=name, n_gpus=world, scaling="strong", **fn())
             ref = n1ref.get(d.get("id", ""))
+            if isinstance(ref, dict):  # {"s": seconds, "N": rows}: only the same problem size is comparable
+                ref = ref.get("s") if ref.get("N") == d.get("N") else None
             if ref and world > 1 and d.get("s"):
                 d["n1_reference_s"] = ref
                 d["speedup_vs_committed_n1"] = ref / d["s"]

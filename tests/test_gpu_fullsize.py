@@ -31,6 +31,29 @@ def test_config1_lml_gradient_vs_finite_differences_N32768():
     assert abs(out[2] - (sp - sm) / (2 * h)) < 1e-6 * max(1.0, abs(out[2]))
 
 
+def test_config1_matches_the_committed_oracle_result_N32768():
+    """Oracle parity AT the headline size: tests/golden/headline_N32768.json holds oracle/ref_numpy.py's LML and
+    gradient on bench.py's synthetic inputs (N = 32768, D = 16, Matern-5/2; one 164 s run on 8 host cores,
+    tools/make_golden_headline.py).  1e-8 relative, as north_star states."""
+    import json
+    import os
+    import sys
+
+    from gpx_b200 import ops
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
+    gold = json.load(open(os.path.join(root, "tests", "golden", "headline_N32768.json")))
+    cfg = gold["config"]
+    x, y = bench.synth(cfg["N"], cfg["D"], cfg["seed"])
+    out = ops.gpr_lml_grad(cfg["kind"], torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda(), cfg["ell"],
+                           cfg["sigma"]).cpu().numpy()
+    ref = np.array([gold["lml"]] + list(gold["grad"]))
+    assert np.max(np.abs(out - ref) / np.abs(ref)) < 1e-8, (out, ref)
+
+
 def test_cholesky_inverse_identity_on_probes_N16384():
     from gpx_b200 import ops
 
