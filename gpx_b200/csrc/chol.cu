@@ -1024,6 +1024,19 @@ __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restr
   }
 }
 
+// Joins a forked stream back into the caller's stream on EVERY exit path: if a launch fails mid-loop the callers'
+// stream-ordered frees (DevBuf destructors on s) must still come after the work already queued on the side stream.
+struct StreamJoin {
+  Ctx* ctx;
+  cudaStream_t from, into;
+  ~StreamJoin() {
+    if (!from || from == into) return;
+    cudaEvent_t e;
+    if (ctx->next_event(&e) != 0) return;
+    if (cudaEventRecord(e, from) == cudaSuccess) cudaStreamWaitEvent(into, e, 0);
+  }
+};
+
 // Factor the tall panel A[k0:n, k0:k0+w] (its w x w head is the diagonal block); everything this panel reads has been
 // written on stream s.  First generation (GPXB_PANEL=v1): leaf -> tall TRSM -> rank-128 update, three dependent
 // launches per 128 columns on one stream.
@@ -1076,6 +1089,7 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
   }();
   if (v1 || ctx->serialize || !ctx->crit || w <= LB) return factor_panel_v1(ctx, A, lda, n, k0, w, inv, s);
   cudaStream_t cs = ctx->crit;
+  StreamJoin join_crit{ctx, cs, s};
   GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_trsm32_kernel, TRSM32_SMEM));
   GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_syrk32_kernel, SYRK32_SMEM));
   cudaEvent_t ev, ev_bulk_prev = nullptr;
@@ -1164,6 +1178,7 @@ int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStre
   // Depth-1 look-ahead: panel p+1 is factorised on the high-priority stream hp while the
   // caller's stream s applies panel p's rank-NB update to the columns right of panel p+1.
   cudaStream_t hp = ctx->serialize ? s : ctx->side;
+  StreamJoin join_hp{ctx, hp, s};
   cudaEvent_t ev, ev_rest_prev = nullptr;
   GPXB_TRY(ctx->next_event(&ev));
   GPXB_CUDA_CHECK(cudaEventRecord(ev, s));
@@ -1218,6 +1233,7 @@ int potrf_lower_bcp(Ctx* ctx, double* Ap, int n, double* inv, cudaStream_t s) {
     return gemm_f64(ctx, g, st);
   };
   cudaStream_t hp = ctx->serialize ? s : ctx->side;
+  StreamJoin join_hp{ctx, hp, s};
   cudaEvent_t ev, ev_next_prev = nullptr;
   GPXB_TRY(ctx->next_event(&ev));
   GPXB_CUDA_CHECK(cudaEventRecord(ev, s));

@@ -227,10 +227,40 @@ class _Composite(Kernel):
                 out.append((prefix + (name,), k, params[name]))
         return out
 
-    def k_device(self, x1d, x2d, params):
-        """Device kernel matrix from (already sliced per leaf) raw device inputs."""
+    def program(self, params):
+        """The tree in postfix order for gpxb_gram_composite: ([(leaf kernel, leaf params)], [leaf index | OP_SUM | OP_PROD])."""
         from . import ops
 
+        leaves, prog = [], []
+
+        def walk(node, p):
+            if isinstance(node, _Composite):
+                walk(node.kernel1, p["kernel1"])
+                walk(node.kernel2, p["kernel2"])
+                prog.append(ops.OP_SUM if node.op == "sum" else ops.OP_PROD)
+            else:
+                prog.append(len(leaves))
+                leaves.append((node, p))
+
+        walk(self, params)
+        return leaves, prog
+
+    def k_device(self, x1d, x2d, params):
+        """Device kernel matrix from raw (unsliced) device inputs; `x2d is x1d` marks the symmetric case.  One fused
+        tile-level pass over all leaves (gpxb_gram_composite) when their operand tiles fit in shared memory and the
+        tree is at most 8 leaves / 4 stack levels; else component matrices combined by gpxb_elementwise."""
+        from . import ops
+
+        leaves, prog = self.program(params)
+        kinds = [k.kind for k, _ in leaves]
+        if all(kd in ("se", "m12", "m32", "m52", "linear") for kd in kinds) and len(leaves) <= 8 and _stack_depth(prog) <= 4:
+            sym = x2d is x1d
+            x1l = [x1d if k.active_dims is None else x1d[:, k.active_dims].contiguous() for k, _ in leaves]
+            if ops.gram_composite_fits([t.shape[1] for t in x1l]):
+                x2l = None if sym else [x2d if k.active_dims is None else x2d[:, k.active_dims].contiguous()
+                                        for k, _ in leaves]
+                ells = [1.0 if k.kind == "linear" else k.lengthscale(p) for k, p in leaves]
+                return ops.gram_composite(kinds, ells, x1l, x2l, prog)
         mats = [k.k_device(x1d, x2d, params[name])
                 for name, k in (("kernel1", self.kernel1), ("kernel2", self.kernel2))]
         return ops.elementwise("axpby" if self.op == "sum" else "mul", mats[0], mats[1], out=mats[0])
@@ -243,6 +273,14 @@ class _Composite(Kernel):
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.kernel1!r}, {self.kernel2!r})"
+
+
+def _stack_depth(prog) -> int:
+    sp = deep = 0
+    for t in prog:
+        sp += 1 if t >= 0 else -1
+        deep = max(deep, sp)
+    return deep
 
 
 class Sum(_Composite):

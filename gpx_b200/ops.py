@@ -69,6 +69,53 @@ def gram(kind, x1, x2, ell, diag_add=0.0, lower_only=False, out=None):
     return out
 
 
+KIND_LINEAR = 4
+OP_SUM, OP_PROD = -1, -2
+
+
+def gram_composite_fits(leaf_dims) -> bool:
+    """True when the fused composite Gram kernel can hold the operand tiles of all leaves in shared memory."""
+    import ctypes
+
+    ctx = context()
+    arr = (ctypes.c_int * len(leaf_dims))(*[int(d) for d in leaf_dims])
+    return bool(ctx.lib.gpxb_gram_composite_fits(len(leaf_dims), arr))
+
+
+def gram_composite(kinds, ells, x1_leaves, x2_leaves, prog, diag_add=0.0, lower_only=False, out=None):
+    """Gram matrix of a Sum / Prod tree in one tile-level pass.  kinds: per leaf "se" | "m12" | "m32" | "m52" |
+    "linear"; x1_leaves / x2_leaves: per leaf the (already sliced) device inputs (x2_leaves None: symmetric);
+    prog: postfix program (leaf indices, OP_SUM, OP_PROD)."""
+    import ctypes
+
+    ctx = context()
+    L = len(kinds)
+    sym = x2_leaves is None
+    x1_leaves = [_f64(t) for t in x1_leaves]
+    x2_leaves = x1_leaves if sym else [_f64(t) for t in x2_leaves]
+    n1, n2 = x1_leaves[0].shape[0], x2_leaves[0].shape[0]
+    for a, b in zip(x1_leaves, x2_leaves):
+        _require(a.dim() == 2 and b.dim() == 2 and a.shape[0] == n1 and b.shape[0] == n2 and a.shape[1] == b.shape[1],
+                 "gram_composite: leaf operands disagree in shape")
+    _require(len(ells) == L and len(x1_leaves) == L, "gram_composite: one lengthscale and one operand per leaf")
+    kid = (ctypes.c_int * L)(*[KIND_LINEAR if k == "linear" else _kind(k) for k in kinds])
+    el = (ctypes.c_double * L)(*[float(e) for e in ells])
+    dd = (ctypes.c_int * L)(*[int(t.shape[1]) for t in x1_leaves])
+    p1 = (ctypes.c_void_p * L)(*[t.data_ptr() for t in x1_leaves])
+    p2 = (ctypes.c_void_p * L)(*[t.data_ptr() for t in x2_leaves])
+    pr = (ctypes.c_int * len(prog))(*[int(v) for v in prog])
+    if out is None:
+        out = torch.empty((n1, n2), dtype=torch.float64, device=x1_leaves[0].device)
+        if lower_only:
+            out.zero_()
+    check(
+        ctx.lib.gpxb_gram_composite(ctx.handle, L, kid, el, dd, p1, p2, n1, n2, pr, len(prog), float(diag_add),
+                                    int(sym), int(bool(lower_only)), ptr(out), out.stride(0), stream_ptr()),
+        "gpxb_gram_composite",
+    )
+    return out
+
+
 def gram_dl_contract(kind, x1, x2, ell, Y, sym_lower=False):
     """sum_ij Y_ij d k(x1_i, x2_j)/d lengthscale (device scalar tensor), dK never formed."""
     ctx = context()

@@ -78,6 +78,19 @@ int gpxb_gram(gpxb_ctx* ctx, int kind, const double* x1, int n1, const double* x
               double ell, double diag_add, double* out, long long ldo, int lower_only,
               gpxb_stream stream);
 
+/* Gram matrix of a Sum / Prod tree of kernels in ONE tile-level pass (gpx/kernels/kernels.py:1794-1848 Sum, :1851-1942
+ * Prod; leaves: kinds 0..3 as in gpxb_gram, 4 = Linear, kernels.py:226-236).  Leaf l sees its own feature slice
+ * x1_leaf[l] (n1 x leaf_D[l]) / x2_leaf[l] (n2 x leaf_D[l]) and lengthscale ells[l] (ignored for Linear).  prog: the
+ * tree in postfix order, entries >= 0 are leaf indices, -1 = Sum, -2 = Prod (at most 8 leaves, stack depth <= 4).
+ * sym: x2_leaf == x1_leaf (exact d2 = 1e-12 on the diagonal of the stationary leaves); diag_add, lower_only as in
+ * gpxb_gram.  No component matrix is written.  gpxb_gram_composite_fits: 1 when the leaves' operand tiles fit in
+ * shared memory (sum over the leaves of 2 * 128 * S(leaf_D) * 8 bytes <= 227 KB), else the caller combines component
+ * matrices with gpxb_elementwise. */
+int gpxb_gram_composite_fits(int nleaf, const int* leaf_D);
+int gpxb_gram_composite(gpxb_ctx* ctx, int nleaf, const int* kinds, const double* ells, const int* leaf_D,
+                        const double* const* x1_leaf, const double* const* x2_leaf, int n1, int n2, const int* prog,
+                        int nprog, double diag_add, int sym, int lower_only, double* out, long long ldo,
+                        gpxb_stream stream);
 /* *out (device) = sum_ij Y_ij d k(x1_i, x2_j)/d lengthscale without forming dK (the contraction epilogue of
  * the Gram kernel): the building block of hyper-parameter gradients of composite kernels
  * (gpx/kernels/kernels.py:1794-1942 Sum / Prod under value_and_grad).  sym_lower (identical operands): Y is the

@@ -52,6 +52,38 @@ def gram(kind, x1, x2, ell, diag_add=0.0, lower_only=False, out=None):
     return out
 
 
+def gram_composite_fits(leaf_dims):
+    return True
+
+
+def gram_composite(kinds, ells, x1_leaves, x2_leaves, prog, diag_add=0.0, lower_only=False, out=None):
+    """NumPy stand-in of the fused composite Gram kernel: leaf matrices by the stand-in `gram` (Linear: a dot product),
+    combined by the postfix program."""
+    sym = x2_leaves is None
+    stack = []
+    for t in prog:
+        if t >= 0:
+            a = x1_leaves[t]
+            b = a if sym else x2_leaves[t]
+            if kinds[t] == "linear":
+                stack.append(_np(a) @ _np(b).T)
+            else:
+                stack.append(_np(gram(kinds[t], a, b, ells[t])))
+        else:
+            y, x = stack.pop(), stack.pop()
+            stack.append(x + y if t == -1 else x * y)
+    K = stack[0]
+    if diag_add:
+        K = K + diag_add * np.eye(K.shape[0], K.shape[1])
+    if lower_only:
+        K = np.tril(K)
+    res = _t(K)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
 def gram_dl_contract(kind, x1, x2, ell, Y, sym_lower=False):
     dK = R.kernel_dl(kind, _np(x1), _np(x2), float(ell))[1]
     Yn = _np(Y)
@@ -314,7 +346,8 @@ def hess_matvec(kind, x1, J1, x2, J2, V, ell, diag_add=0.0):
     return _t(K @ v)
 
 
-FAKES = dict(gram=gram, gram_dl_contract=gram_dl_contract, elementwise=elementwise, gemm=gemm, potrf=potrf, trsm=trsm,
+FAKES = dict(gram=gram, gram_composite=gram_composite, gram_composite_fits=gram_composite_fits,
+             gram_dl_contract=gram_dl_contract, elementwise=elementwise, gemm=gemm, potrf=potrf, trsm=trsm,
              logdet=logdet, potri=potri, gpr_lml_grad=gpr_lml_grad, gpr_fit=gpr_fit, gpr_predict=gpr_predict,
              kmatvec=kmatvec, rpcholesky=rpcholesky, gather_rows=gather_rows, sgpr_lml=sgpr_lml,
              sgpr_lml_grad=sgpr_lml_grad, sgpr_fit=sgpr_fit, sgpr_predict=sgpr_predict, td_gram=td_gram,

@@ -231,3 +231,73 @@ def test_composite_kernel_sgpr_fit_minimize_and_limits():
     mt = SGPR(K.SquaredExponential() + K.Matern32(), x_locs=locs_parameter(xl, trainable=True))
     with pytest.raises(NotImplementedError):
         mt.loss_and_grad(x, y)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fused_composite_gram_kernel_entries(name):
+    """gpxb_gram_composite (every leaf and operator of the tree in one tile-level pass) against the oracle's literal
+    composition: symmetric with the exact diagonal, rectangular with ragged tiles, lower-only with a diagonal shift;
+    and against the component-matrix path it replaces (same numbers to rounding)."""
+    import gpx_b200.kernels as K
+    from gpx_b200 import ops
+
+    mk, spec_of, ells = CASES[name]
+    kernel = mk(K)
+    m = _model(kernel, ells, 0.3)
+    kp = m.state.params["kernel_params"]
+    spec = spec_of(ells)
+    rng = np.random.default_rng(3)
+    x1, x2 = rng.standard_normal((333, 3)), rng.standard_normal((150, 3))
+    d1, d2 = torch.as_tensor(x1).cuda(), torch.as_tensor(x2).cuda()
+    Ks = kernel.k_device(d1, d1, kp).cpu().numpy()
+    assert np.max(np.abs(Ks - R.composite_kernel(spec, x1, x1))) < 1e-12 * max(1.0, np.max(np.abs(Ks)))
+    Kr = kernel.k_device(d1, d2, kp).cpu().numpy()
+    assert np.max(np.abs(Kr - R.composite_kernel(spec, x1, x2))) < 1e-12 * max(1.0, np.max(np.abs(Kr)))
+    # the fused kernel is what ran
+    leaves, prog = kernel.program(kp)
+    assert ops.gram_composite_fits([3 if k.active_dims is None else len(k.active_dims) for k, _ in leaves])
+    x1l = [d1 if k.active_dims is None else d1[:, k.active_dims].contiguous() for k, _ in leaves]
+    kinds = [k.kind for k, _ in leaves]
+    el = [1.0 if k.kind == "linear" else k.lengthscale(p) for k, p in leaves]
+    Kl = ops.gram_composite(kinds, el, x1l, None, prog, diag_add=0.5, lower_only=True).cpu().numpy()
+    ref = np.tril(R.composite_kernel(spec, x1, x1) + 0.5 * np.eye(333))
+    assert np.max(np.abs(Kl - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+    assert np.all(np.triu(Kl, 1) == 0.0)
+    # component-matrix path (what round 1 did) gives the same numbers
+    mats = [k.k_device(d1, d1, p).cpu().numpy() for k, p in leaves]
+    st = []
+    for t in prog:
+        if t >= 0:
+            st.append(mats[t])
+        else:
+            b, a = st.pop(), st.pop()
+            st.append(a + b if t == ops.OP_SUM else a * b)
+    assert np.max(np.abs(Ks - st[0])) < 1e-12 * max(1.0, np.max(np.abs(Ks)))
+
+
+def test_fused_composite_gram_eight_leaves_and_fallback():
+    import gpx_b200.kernels as K
+    from gpx_b200 import ops
+
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((200, 6))
+    d = torch.as_tensor(x).cuda()
+    # balanced tree of 8 leaves: stack depth 4
+    mk = lambda i: (K.SquaredExponential if i % 2 else K.Matern52)(active_dims=[i % 6, (i + 1) % 6])  # noqa: E731
+    kernel = ((mk(0) + mk(1)) * (mk(2) + mk(3))) + ((mk(4) * mk(5)) + (mk(6) * mk(7)))
+    kp = kernel.default_params()
+    leaves, prog = kernel.program(kp)
+    assert len(leaves) == 8
+    spec_leaf = lambda i: ("leaf", "se" if i % 2 else "m52", 1.0, [i % 6, (i + 1) % 6])  # noqa: E731
+    spec = ("sum", ("prod", ("sum", spec_leaf(0), spec_leaf(1)), ("sum", spec_leaf(2), spec_leaf(3))),
+            ("sum", ("prod", spec_leaf(4), spec_leaf(5)), ("prod", spec_leaf(6), spec_leaf(7))))
+    Kd = kernel.k_device(d, d, kp).cpu().numpy()
+    assert np.max(np.abs(Kd - R.composite_kernel(spec, x, x))) < 1e-12 * np.max(np.abs(Kd))
+    # leaves too wide for shared memory: the component-matrix path takes over, same numbers
+    xw = rng.standard_normal((150, 120))
+    dw = torch.as_tensor(xw).cuda()
+    kw = K.SquaredExponential() + K.Matern52()
+    assert not ops.gram_composite_fits([120, 120])
+    kpw = kw.default_params()
+    ref = R.composite_kernel(("sum", ("leaf", "se", 1.0, None), ("leaf", "m52", 1.0, None)), xw, xw)
+    assert np.max(np.abs(kw.k_device(dw, dw, kpw).cpu().numpy() - ref)) < 1e-12
