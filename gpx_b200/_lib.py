@@ -40,6 +40,8 @@ SIGNATURES = {
     "gpxb_gpr_predict": (_int, [C.c_void_p, _int, _c_dp, _int, _int, _c_dp, _int, _c_dp, _int, _c_dp, _dbl, _dbl, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_gram_composite_fits": (_int, [_int, C.c_void_p]),
     "gpxb_gram_composite": (_int, [C.c_void_p, _int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _int, _int, C.c_void_p, _int, _dbl, _int, _int, _c_dp, _ll, C.c_void_p]),
+    "gpxb_rpcholesky_composite": (_int, [C.c_void_p, _int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _int, C.c_void_p, _int, C.c_uint32, C.c_uint32, _int, _int, _c_dp, _c_dp, C.c_void_p]),
+    "gpxb_gpr_iter_composite": (_int, [C.c_void_p, _int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _int, C.c_void_p, _int, _c_dp, _dbl, _int, _int, C.c_uint32, C.c_uint32, _int, _dbl, _dbl, _int, _c_dp, _c_dp, C.POINTER(_int), _c_dp, _ll, _int, _int, _c_dp, _c_dp, C.c_void_p, C.c_void_p]),
     "gpxb_gram_dl_contract": (_int, [C.c_void_p, _int, _c_dp, _int, _c_dp, _int, _int, _dbl, _c_dp, _ll, _int, _c_dp, C.c_void_p]),
     "gpxb_elementwise": (_int, [C.c_void_p, _int, _ll, _dbl, _c_dp, _dbl, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_hess_gram": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _c_dp, _ll, _int, C.c_void_p]),

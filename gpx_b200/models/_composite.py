@@ -106,3 +106,82 @@ def predict(state, x, full_covariance=False):
     cov = state.kernel.k_device(xs, xs, kp)
     ops.gemm(G, G, transb=True, alpha=-1.0, beta=1.0, C=cov)
     return mean.cpu().numpy(), cov.cpu().numpy()
+
+
+# ---- composite kernels in the matrix-free paths (one GPU) ---------------------------------------------------------
+def _leaf_desc(state, xd):
+    """(kinds, lengthscales, per-leaf sliced inputs, postfix program) of the state's kernel for the device calls."""
+    kernel = state.kernel
+    kp = state.params["kernel_params"]
+    if isinstance(kernel, _Composite):
+        leaves, prog = kernel.program(kp)
+    else:  # a lone Linear kernel
+        leaves, prog = [(kernel, kp)], [0]
+    kinds = [k.kind for k, _ in leaves]
+    ells = [1.0 if k.kind == "linear" else k.lengthscale(p) for k, p in leaves]
+    xl = [_slice_leaf(k, xd) for k, _ in leaves]
+    if not ops.gram_composite_fits([t.shape[1] for t in xl]):
+        raise NotImplementedError("the iterative / RPCholesky paths of a composite kernel need the operand tiles of all "
+                                  "leaves in shared memory (sum over leaves of 2*128*(D+pad)*8 bytes <= 227 KB)")
+    return kinds, ells, xl, prog
+
+
+def fit_iter(state, x, y, n_pivots, key_precond, tol=1e-5, atol=1e-7, return_iters=False):
+    """_fit_iter (gpx/models/_gpr.py:285-310) with a Sum / Prod kernel: PCG on the row-chunked composite operator with
+    the composite RPCholesky preconditioner (gpxb_gpr_iter_composite)."""
+    from ..defaults import gpxargs, threefry_partitionable
+    from ..random import as_key
+
+    if n_pivots is None:
+        raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
+    xd, yd = _to_device(x), _to_device(y)
+    kinds, ells, xl, prog = _leaf_desc(state, xd)
+    sigma = float(np.asarray(state.params["sigma"].value))
+    key = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
+    r = ops.gpr_iter_composite(kinds, ells, xl, prog, sigma, y=yd.reshape(-1), n_pivots=int(n_pivots), key=key,
+                               mean_mode=mean_mode(state.mean_function), partitionable=threefry_partitionable(),
+                               tol=tol, atol=atol)
+    c, mu = r["c"].cpu().numpy(), np.float64(r["mu"].cpu().numpy()[0])
+    return (c, mu, r["iters"]) if return_iters else (c, mu)
+
+
+def lml_iter(state, x, y, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond, tol=1e-5, atol=1e-7):
+    """_lml_iter (gpx/models/_gpr.py:772-821) with a Sum / Prod kernel."""
+    from ..defaults import threefry_partitionable
+    from ..random import as_key, split
+    from ._iterative import slq_logdet
+
+    xd, yd = _to_device(x), _to_device(y)
+    N = xd.shape[0]
+    c, mu = fit_iter(state, x, y, n_pivots, key_precond, tol, atol)
+    kinds, ells, xl, prog = _leaf_desc(state, xd)
+    sigma = float(np.asarray(state.params["sigma"].value))
+    part = threefry_partitionable()
+    subkey, _ = split(as_key(key_lanczos), 2, part)
+    U = ops.rademacher_probes(subkey, N, int(num_evals), part)
+    r = ops.gpr_iter_composite(kinds, ells, xl, prog, sigma, U=U, m=int(num_lanczos))
+    if int(r["flag"].cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps than data points")
+    res = yd.cpu().numpy().reshape(-1, 1) - mu
+    mll = -0.5 * float(np.sum(res.T @ c))
+    mll -= 0.5 * slq_logdet(r["alpha"].cpu().numpy(), r["beta"].cpu().numpy(), N)
+    mll -= N * 0.5 * np.log(2.0 * np.pi)
+    return mll / N
+
+
+def fit_state_iter(state, x, y, n_pivots, key_precond):
+    c, mu = fit_iter(state, x, y, n_pivots, key_precond)
+    return state.update(dict(x_train=np.asarray(x), y_train=np.asarray(y), c=c, mu=mu, is_fitted=True,
+                             is_fitted_derivs=False))
+
+
+def select_locs(state, xd, n_locs, key):
+    """RPCholesky landmark selection with a Sum / Prod kernel (gpx/models/_sgpr_rpchol.py:36-67 with
+    gpx/kernels/approximations.py:30-129): -> (x_locs device (M, D) raw rows, pivots)."""
+    from ..defaults import threefry_partitionable
+    from ..random import as_key
+
+    kinds, ells, xl, prog = _leaf_desc(state, xd)
+    _, piv = ops.rpcholesky_composite(kinds, ells, xl, prog, int(n_locs), as_key(key), threefry_partitionable(),
+                                      want_factor=False)
+    return ops.gather_rows(xd, piv), piv

@@ -51,9 +51,9 @@ def _woodbury(state, xd, xl):
     return Lm, invm, GT, LB, invB, s2
 
 
-def lml_and_grad(state, x, y, want_grad):
+def lml_and_grad(state, x, y, want_grad, x_locs=None):
     """(lml, {param path: d lml / d value}) for fixed landmarks."""
-    xd, xl = _to_device(x), _locs_raw(state)
+    xd, xl = _to_device(x), (_locs_raw(state) if x_locs is None else x_locs)
     rT, _ = _center(state, y)                                                    # (T, N)
     N, M = xd.shape[0], xl.shape[0]
     Lm, invm, GT, LB, invB, s2 = _woodbury(state, xd, xl)
@@ -117,9 +117,9 @@ def _fit_matrix(state, xd, xl):
     return LC, invC, Knm
 
 
-def fit(state, x, y):
+def fit(state, x, y, x_locs=None):
     """_sgpr.py:319-339 (the reference's LU solve is a Cholesky solve here)."""
-    xd, xl = _to_device(x), _locs_raw(state)
+    xd, xl = _to_device(x), (_locs_raw(state) if x_locs is None else x_locs)
     rT, mu = _center(state, y)
     LC, invC, Knm = _fit_matrix(state, xd, xl)
     cT = ops.gemm(rT, Knm)                                                       # (K_mn r)^T, (T, M)
@@ -129,11 +129,11 @@ def fit(state, x, y):
                              mu=np.float64(mu), is_fitted=True, is_fitted_derivs=False))
 
 
-def predict(state, x, full_covariance=False):
+def predict(state, x, full_covariance=False, x_locs=None):
     """_sgpr.py:434-467: mu + K_*m c;  K_** - G*^T G* + sigma^2 H*^T H*, where -- as the reference writes it
     (:457, `_A_lhs(x1=x_locs, x2=x)`) -- H* = chol(sigma^2 K_mm + K_m* K_*m + 1e-10 I)^-1 K_m* is built from the
     PREDICTION inputs, not from the training set."""
-    xs, xl = _to_device(x), _locs_raw(state)
+    xs, xl = _to_device(x), (_locs_raw(state) if x_locs is None else x_locs)
     kp = state.params["kernel_params"]
     Ksm = state.kernel.k_device(xs, xl, kp)                                      # (ns, M)
     c = _to_device(state.c)

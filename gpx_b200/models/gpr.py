@@ -41,7 +41,7 @@ def log_marginal_likelihood(state, x, y, iterative=False, num_evals=gpxargs.num_
     """gpx/models/gpr.py:70-118 -> _lml_dense / _lml_iter (gpx/models/_gpr.py:737-821)."""
     if _composite.is_composite(state.kernel):
         if iterative:
-            raise NotImplementedError("composite kernels are supported by the dense paths only")
+            return _composite.lml_iter(state, x, y, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond)
         return _composite.lml_and_grad(state, x, y, want_grad=False)[0]
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
@@ -94,7 +94,8 @@ def loss_and_grad(state, x, y, iterative=False, **kwargs):
         raise NotImplementedError("only neg_log_marginal_likelihood and neg_log_posterior have a device gradient")
     if _composite.is_composite(state.kernel):
         if iterative:
-            raise NotImplementedError("composite kernels are supported by the dense paths only")
+            raise NotImplementedError("the gradient of the iterative LML with a composite kernel is not implemented "
+                                      "(train with iterative=False, or fit(..., iterative=True, minimize=False))")
         lml, g = _composite.lml_and_grad(state, x, y, want_grad=True)
         flat = dict(state.flat_params())
         return -lml, {path: -v for path, v in g.items() if flat[path].trainable}
@@ -126,7 +127,7 @@ def fit(state, x, y, iterative=False, n_pivots=None, key_precond=None):
     """gpx/models/gpr.py:397-434 -> _fit_dense / _fit_iter (gpx/models/_gpr.py:262-310)."""
     if _composite.is_composite(state.kernel):
         if iterative:
-            raise NotImplementedError("composite kernels are supported by the dense paths only")
+            return _composite.fit_state_iter(state, x, y, n_pivots, key_precond)
         return _composite.fit(state, x, y)
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
@@ -151,8 +152,7 @@ def predict(state, x, full_covariance=False, iterative=False):
     if full_covariance and iterative:
         raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
     if _composite.is_composite(state.kernel):
-        if iterative:
-            raise NotImplementedError("composite kernels are supported by the dense paths only")
+        # iterative=True (_predict_iter, _gpr.py:466-486) is one rectangular mat-vec K_nm c: the same product
         return _composite.predict(state, x, full_covariance)
     kernel, ell, sigma = _hyper(state)
     import torch

@@ -14,12 +14,19 @@ from ..defaults import gpxargs, threefry_partitionable
 from ..mean_functions import data_mean, mean_mode
 from ..parameters import ModelState
 from ..random import PRNGKey, as_key
+from . import _composite, _composite_sparse
 from . import sgpr as _sgpr
 from .base import BaseGP
 from .gpr import _hyper, _xy
 
 
+def _is_comp(state):
+    return _composite.is_composite(state.kernel)
+
+
 def _select_locs(state, xd):
+    if _is_comp(state):  # Sum / Prod kernel: the pivot column is evaluated pair by pair (gpxb_rpcholesky_composite)
+        return _composite.select_locs(state, xd, state.n_locs, state.key)
     kernel, ell, _ = _hyper(state)
     _, piv = ops.rpcholesky(kernel.kind, xd, int(state.n_locs), ell, as_key(state.key), threefry_partitionable(),
                             want_factor=False)
@@ -29,6 +36,13 @@ def _select_locs(state, xd):
 def log_marginal_likelihood(state, x, y, iterative=False, num_evals=gpxargs.num_evals,
                             num_lanczos=gpxargs.num_lanczos, key_lanczos=gpxargs.key_lanczos, **_ignored):
     """gpx/models/sgpr_rpchol.py:63-106 -> _sgpr_rpchol._lml_dense (178-208)."""
+    if _is_comp(state):
+        if iterative:
+            raise NotImplementedError("composite kernels in SGPR_RPChol: the dense paths only")
+        from ..kernels import _to_device
+
+        x_locs, _ = _select_locs(state, _to_device(x))
+        return _composite_sparse.lml_and_grad(state, x, y, want_grad=False, x_locs=x_locs)[0]
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     x_locs, _ = _select_locs(state, xd)
@@ -45,15 +59,34 @@ def neg_log_marginal_likelihood(state, x, y, **kwargs):
 def loss_and_grad(state, x, y, iterative=False, **kwargs):
     """Pivots are re-drawn with the current hyper-parameters and treated as constants (integer
     indices carry no gradient in the reference either), then the SGPR gradient applies."""
-    if iterative:
-        raise NotImplementedError("gradient of the iterative SGPR_RPChol LML is not implemented")
+    if _is_comp(state):
+        if iterative:
+            raise NotImplementedError("composite kernels in SGPR_RPChol: the dense paths only")
+        from ..kernels import _to_device
+
+        x_locs, _ = _select_locs(state, _to_device(x))
+        lml, g = _composite_sparse.lml_and_grad(state, x, y, want_grad=True, x_locs=x_locs)
+        flat = dict(state.flat_params())
+        return -lml, {path: -v for path, v in g.items() if flat[path].trainable}
     xd, yd = _xy(state, x, y)
     x_locs, _ = _select_locs(state, xd)
+    if iterative:  # the pivots are constants here too; _sgpr._lml_iter under value_and_grad
+        return _sgpr._loss_and_grad_iter_with_locs(state, xd, yd, x_locs, kwargs.get("num_evals", gpxargs.num_evals),
+                                                   kwargs.get("num_lanczos", gpxargs.num_lanczos),
+                                                   kwargs.get("key_lanczos", gpxargs.key_lanczos))
     return _sgpr._loss_and_grad_with_locs(state, xd, yd, x_locs)
 
 
 def fit(state, x, y, iterative=False, **_ignored):
     """gpx/models/sgpr_rpchol.py:309-348 -> _sgpr_rpchol._fit_dense (36-67)."""
+    if _is_comp(state):
+        if iterative:
+            raise NotImplementedError("composite kernels in SGPR_RPChol: the dense paths only")
+        from ..kernels import _to_device
+
+        x_locs, piv = _select_locs(state, _to_device(x))
+        st = _composite_sparse.fit(state, x, y, x_locs=x_locs)
+        return st.update(dict(x_locs=x_locs.cpu().numpy(), pivots=piv.cpu().numpy()))
     kernel, ell, sigma = _hyper(state)
     xd, yd = _xy(state, x, y)
     x_locs, piv = _select_locs(state, xd)
@@ -73,6 +106,8 @@ def predict(state, x, full_covariance=False, iterative=False):
         raise RuntimeError("'full_covariance=True' is not compatible with 'iterative=True'")
     from ..kernels import _to_device
 
+    if _is_comp(state):
+        return _composite_sparse.predict(state, x, full_covariance, x_locs=_to_device(state.x_locs))
     return _sgpr._predict_with_locs(state, _to_device(state.x_locs), x, full_covariance, iterative)
 
 

@@ -116,6 +116,84 @@ def gram_composite(kinds, ells, x1_leaves, x2_leaves, prog, diag_add=0.0, lower_
     return out
 
 
+def _comp_desc(kinds, ells, x_leaves, prog):
+    """ctypes arrays describing a composite kernel over per-leaf inputs (kept alive by the caller)."""
+    import ctypes
+
+    L = len(kinds)
+    _require(len(ells) == L and len(x_leaves) == L, "composite kernel: one lengthscale and one operand per leaf")
+    kid = (ctypes.c_int * L)(*[KIND_LINEAR if k == "linear" else _kind(k) for k in kinds])
+    el = (ctypes.c_double * L)(*[float(e) for e in ells])
+    dd = (ctypes.c_int * L)(*[int(t.shape[1]) for t in x_leaves])
+    px = (ctypes.c_void_p * L)(*[t.data_ptr() for t in x_leaves])
+    pr = (ctypes.c_int * len(prog))(*[int(v) for v in prog])
+    return L, kid, el, dd, px, pr
+
+
+def rpcholesky_composite(kinds, ells, x_leaves, prog, n_pivots, key, partitionable=True, want_factor=True):
+    """(F (N, M) or None, pivots int64 (M,)) -- RPCholesky (gpx/kernels/approximations.py:30-129) of a Sum / Prod kernel."""
+    ctx = context()
+    x_leaves = [_f64(t) for t in x_leaves]
+    N = x_leaves[0].shape[0]
+    L, kid, el, dd, px, pr = _comp_desc(kinds, ells, x_leaves, prog)
+    piv = torch.empty(n_pivots, dtype=torch.int64, device=x_leaves[0].device)
+    F = torch.empty((N, n_pivots), dtype=torch.float64, device=piv.device) if want_factor else None
+    check(
+        ctx.lib.gpxb_rpcholesky_composite(ctx.handle, L, kid, el, dd, px, N, pr, len(prog), int(key[0]), int(key[1]),
+                                          int(n_pivots), int(bool(partitionable)), ptr(F) if want_factor else None,
+                                          ptr(piv), stream_ptr()),
+        "gpxb_rpcholesky_composite",
+    )
+    return F, piv
+
+
+def gpr_iter_composite(kinds, ells, x_leaves, prog, sigma, y=None, n_pivots=0, key=(0, 0), mean_mode=MEAN_DATA,
+                       partitionable=True, tol=1e-5, atol=1e-7, maxiter=0, U=None, m=0):
+    """The iterative GPR paths with a Sum / Prod kernel.  y given: PCG fit -> c (N, 1), mu (1,), iterations;
+    U given: m-step block Lanczos on K + (sigma^2+1e-10) I -> alpha, beta (P, m), breakdown flag.
+    Returns a dict with the parts that were asked for."""
+    import ctypes
+
+    ctx = context()
+    x_leaves = [_f64(t) for t in x_leaves]
+    N = x_leaves[0].shape[0]
+    dev = x_leaves[0].device
+    L, kid, el, dd, px, pr = _comp_desc(kinds, ells, x_leaves, prog)
+    out = {}
+    c = mu = alpha = beta = flag = None
+    iters = ctypes.c_int(0)
+    if y is not None:
+        y = _f64(y)
+        _require(y.numel() == N, "the iterative path supports a single output column")
+        c = torch.empty((N, 1), dtype=torch.float64, device=dev)
+        mu = torch.empty(1, dtype=torch.float64, device=dev)
+    P = 0
+    if U is not None:
+        U = _f64(U)
+        _require(U.dim() == 2 and U.shape[0] == N, f"U has {tuple(U.shape)} but x has {N} rows")
+        P = U.shape[1]
+        alpha = torch.empty((P, m), dtype=torch.float64, device=dev)
+        beta = torch.empty((P, m), dtype=torch.float64, device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(
+        ctx.lib.gpxb_gpr_iter_composite(ctx.handle, L, kid, el, dd, px, N, pr, len(prog),
+                                        ptr(y) if y is not None else None, float(sigma), int(mean_mode), int(n_pivots),
+                                        int(key[0]), int(key[1]), int(bool(partitionable)), float(tol), float(atol),
+                                        int(maxiter), ptr(c) if c is not None else None,
+                                        ptr(mu) if mu is not None else None, ctypes.byref(iters),
+                                        ptr(U) if U is not None else None, U.stride(0) if U is not None else 0, P,
+                                        int(m), ptr(alpha) if alpha is not None else None,
+                                        ptr(beta) if beta is not None else None,
+                                        ptr(flag) if flag is not None else None, stream_ptr()),
+        "gpxb_gpr_iter_composite",
+    )
+    if y is not None:
+        out.update(c=c, mu=mu, iters=iters.value)
+    if U is not None:
+        out.update(alpha=alpha, beta=beta, flag=flag)
+    return out
+
+
 def gram_dl_contract(kind, x1, x2, ell, Y, sym_lower=False):
     """sum_ij Y_ij d k(x1_i, x2_j)/d lengthscale (device scalar tensor), dK never formed."""
     ctx = context()

@@ -91,6 +91,25 @@ int gpxb_gram_composite(gpxb_ctx* ctx, int nleaf, const int* kinds, const double
                         const double* const* x1_leaf, const double* const* x2_leaf, int n1, int n2, const int* prog,
                         int nprog, double diag_add, int sym, int lower_only, double* out, long long ldo,
                         gpxb_stream stream);
+/* Composite (Sum / Prod tree) kernels outside the dense paths; leaf / program description as in gpxb_gram_composite,
+ * x_leaf[l]: N x leaf_D[l].  Single GPU.
+ * gpxb_rpcholesky_composite: randomly pivoted Cholesky (gpx/kernels/approximations.py:30-129) with the composite kernel:
+ *   the pivot's column is evaluated pair by pair (external-column mode of the pivot loop); F_out may be NULL.
+ * gpxb_gpr_iter_composite: the iterative GPR paths (_fit_iter gpx/models/_gpr.py:285-310 with _precond_rpcholesky
+ *   :180-216; the SLQ part of _lml_iter :772-821) on the operator K + (sigma^2+1e-10) I applied in row chunks (fused
+ *   composite Gram of chunk x all rows, then one DMMA GEMM with the block).  c_out != NULL: PCG fit (y, mu_out,
+ *   iters_out as in gpxb_gpr_fit_iter); U != NULL: m-step block Lanczos as in gpxb_lanczos.  The leaves' operand
+ *   tiles must fit in shared memory (gpxb_gram_composite_fits). */
+int gpxb_rpcholesky_composite(gpxb_ctx* ctx, int nleaf, const int* kinds, const double* ells, const int* leaf_D,
+                              const double* const* x_leaf, int N, const int* prog, int nprog, uint32_t key0,
+                              uint32_t key1, int M, int partitionable, double* F_out, long long* pivots_out,
+                              gpxb_stream stream);
+int gpxb_gpr_iter_composite(gpxb_ctx* ctx, int nleaf, const int* kinds, const double* ells, const int* leaf_D,
+                            const double* const* x_leaf, int N, const int* prog, int nprog, const double* y,
+                            double sigma, int mean_mode, int n_pivots, uint32_t key0, uint32_t key1, int partitionable,
+                            double tol, double atol, int maxiter, double* c_out, double* mu_out, int* iters_out,
+                            const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out,
+                            int* breakdown_flag, gpxb_stream stream);
 /* *out (device) = sum_ij Y_ij d k(x1_i, x2_j)/d lengthscale without forming dK (the contraction epilogue of
  * the Gram kernel): the building block of hyper-parameter gradients of composite kernels
  * (gpx/kernels/kernels.py:1794-1942 Sum / Prod under value_and_grad).  sym_lower (identical operands): Y is the

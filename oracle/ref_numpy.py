@@ -900,6 +900,56 @@ def rpcholesky(kind, x, n_pivots, ell, key, partitionable=True):
     return F, pivots
 
 
+def rpcholesky_composite(spec, x, n_pivots, key, partitionable=True):
+    """gpx/kernels/approximations.py:30-129 with a Sum / Prod kernel (kernels.py:1794-1942): the reference calls the
+    kernel object, whatever its class -- the diagonal through single-point evaluations (:88-93), each pivot's row through
+    kernel(x[s], x)."""
+    n = x.shape[0]
+    F = np.zeros((n, n_pivots))
+    pivots = np.zeros(n_pivots, dtype=np.int64)
+    diag = np.array([composite_kernel(spec, x[i:i + 1], x[i:i + 1])[0, 0] for i in range(n)])
+    key = np.asarray(key, dtype=np.uint32)
+    for i in range(n_pivots):
+        prob = diag / np.sum(diag)
+        key = split(key, 2, partitionable)[0]
+        s = choice_p(key, prob, partitionable)
+        pivots[i] = s
+        g = composite_kernel(spec, x[s:s + 1], x)[0] - F @ F[s]
+        F[:, i] = g / (g[s] ** 0.5 + 1e-6)
+        diag = diag - F[:, i] ** 2
+    return F, pivots
+
+
+def composite_fit_iter(spec, x, y, sigma, n_pivots, key_precond, mean_function=data_mean, partitionable=True,
+                       cg_tol=1e-5, cg_atol=1e-7):
+    """_gpr.py:285-310 with a composite kernel (dense matrix as the operator: the row scan is the same product)."""
+    mu = mean_function(y)
+    r = y - mu
+    n = x.shape[0]
+    A = composite_kernel(spec, x, x) + (sigma**2 + 1e-10) * np.eye(n)
+    F, _ = rpcholesky_composite(spec, x, n_pivots, key_precond, partitionable)
+    P = np.linalg.inv(sigma**2 * np.eye(n_pivots) + F.T @ F)
+
+    def precond(z):
+        return -(sigma ** (-2)) * (F @ (P @ (F.T @ z))) + sigma ** (-2) * z
+
+    c, iters = cg(lambda v: A @ v, r, M=precond, tol=cg_tol, atol=cg_atol)
+    return c, mu, iters
+
+
+def composite_lml_iter(spec, x, y, sigma, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
+                       mean_function=data_mean, partitionable=True, cg_tol=1e-5, cg_atol=1e-7):
+    """_gpr.py:772-821 with a composite kernel."""
+    m = y.shape[0]
+    c, mu, _ = composite_fit_iter(spec, x, y, sigma, n_pivots, key_precond, mean_function, partitionable, cg_tol, cg_atol)
+    r = y - mu
+    A = composite_kernel(spec, x, x) + (sigma**2 + 1e-10) * np.eye(m)
+    mll = -0.5 * np.sum(r.T @ c)
+    mll -= 0.5 * lanczos_logdet(lambda v: A @ v, num_evals, m, num_lanczos, key_lanczos, partitionable)
+    mll -= m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
+
+
 def _phi(kind, d2):
     if kind == "se":
         return np.exp(-d2)

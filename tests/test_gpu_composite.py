@@ -104,8 +104,8 @@ def test_composite_kernel_fit_minimize():
     l0, _ = m.loss_and_grad(x, y)
     m.fit(x, y)
     assert m.optimize_results_.fun < l0 - 0.05
-    with pytest.raises(NotImplementedError):
-        m.log_marginal_likelihood(x, y, iterative=True)
+    with pytest.raises(NotImplementedError):  # the iterative LML of a composite kernel exists, its gradient does not
+        m.loss_and_grad(x, y, iterative=True)
 
 
 def test_reference_notebook_composite_kernel_matrices_on_the_device():
@@ -301,3 +301,93 @@ def test_fused_composite_gram_eight_leaves_and_fallback():
     kpw = kw.default_params()
     ref = R.composite_kernel(("sum", ("leaf", "se", 1.0, None), ("leaf", "m52", 1.0, None)), xw, xw)
     assert np.max(np.abs(kw.k_device(dw, dw, kpw).cpu().numpy() - ref)) < 1e-12
+
+
+# ---- composite kernels outside the dense paths (SURVEY 8f N3 remainder) -----------------------------------------------
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("partitionable", [True, False])
+def test_composite_rpcholesky_pivots_bit_exact(name, partitionable):
+    import gpx_b200.kernels as K
+    from gpx_b200 import ops
+    from gpx_b200.models import _composite
+
+    mk, spec_of, ells = CASES[name]
+    kernel = mk(K)
+    m = _model(kernel, ells, 0.3)
+    spec = spec_of(ells)
+    x, _ = _data(700, 3, 8)
+    key = R.PRNGKey(2023)
+    Fref, pref = R.rpcholesky_composite(spec, x, 40, key, partitionable)
+    d = torch.as_tensor(x).cuda()
+    kinds, el, xl, prog = _composite._leaf_desc(m.state, d)
+    F, piv = ops.rpcholesky_composite(kinds, el, xl, prog, 40, key, partitionable)
+    assert np.array_equal(piv.cpu().numpy(), pref)
+    assert np.max(np.abs(F.cpu().numpy() - Fref)) < 1e-9 * max(1.0, np.max(np.abs(Fref)))
+
+
+@pytest.mark.parametrize("name", ["sum", "nested", "linear"])
+def test_composite_iterative_fit_and_lml(name):
+    """GPR(Sum / Prod kernel).fit(iterative=True) and log_marginal_likelihood(iterative=True): PCG with the composite
+    RPCholesky preconditioner and SLQ on the row-chunked composite operator against the oracle (converged solves: 1e-8)."""
+    import gpx_b200.kernels as K
+    from gpx_b200.models import _composite
+
+    mk, spec_of, ells = CASES[name]
+    kernel = mk(K)
+    sigma = 0.4
+    m = _model(kernel, ells, sigma)
+    spec = spec_of(ells)
+    x, y = _data(600, 3, 9)
+    key = R.PRNGKey(2023)
+    c_ref, mu_ref, it_ref = R.composite_fit_iter(spec, x, y, sigma, 25, key, cg_tol=1e-13, cg_atol=0.0)
+    c, mu, it = _composite.fit_iter(m.state, x, y, 25, key, tol=1e-13, atol=0.0, return_iters=True)
+    assert abs(float(mu) - float(mu_ref)) < 1e-14
+    assert np.max(np.abs(c - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
+    ref = R.composite_lml_iter(spec, x, y, sigma, 6, 12, key, 25, key, cg_tol=1e-13, cg_atol=0.0)
+    out = _composite.lml_iter(m.state, x, y, 6, 12, key, 25, key, tol=1e-13, atol=0.0)
+    assert abs(out - ref) < 1e-8 * abs(ref)
+    # the public entries with the reference's stopping rule
+    _, _, it_ref5 = R.composite_fit_iter(spec, x, y, sigma, 25, key)
+    _, _, it5 = _composite.fit_iter(m.state, x, y, 25, key, return_iters=True)
+    assert abs(it5 - it_ref5) <= 1
+    lml = m.log_marginal_likelihood(x, y, iterative=True, num_evals=6, num_lanczos=12, key_lanczos=key, n_pivots=25,
+                                    key_precond=key)
+    assert abs(lml - ref) < 1e-6 * abs(ref)
+    m.fit(x, y, iterative=True, minimize=False, n_pivots=25)  # preconditioner key: gpxargs.key_precond, as in the reference
+    xs, _ = _data(40, 3, 10)
+    pred = m.predict(xs)
+    pref = float(mu_ref) + R.composite_kernel(spec, xs, x) @ c_ref
+    assert np.max(np.abs(pred - pref)) < 1e-4 * max(1.0, np.max(np.abs(pref)))
+
+
+def test_sgpr_rpchol_with_a_composite_kernel():
+    """SGPR_RPChol(Sum kernel): landmarks drawn by RPCholesky of the composite kernel, then the dense composite SGPR."""
+    import gpx_b200.kernels as K
+    from gpx_b200.models import SGPR_RPChol
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    mk, spec_of, ells = CASES["nested"]
+    kernel = mk(K)
+    spec = spec_of(ells)
+    x, y = _data(800, 3, 11)
+    key = R.PRNGKey(7)
+    M, sigma = 30, 0.3
+    model = SGPR_RPChol(kernel, n_locs=M, key=key, sigma=Parameter(sigma, True, Softplus(), GammaPrior()))
+    st = model.state
+    for (path, _, _), ell in zip(_ell_leaves(kernel, st.params["kernel_params"]), ells):
+        st = st.with_param_value(("kernel_params",) + path + ("lengthscale",), np.float64(ell))
+    model.state = st
+    _, piv = R.rpcholesky_composite(spec, x, M, key)
+    xl = x[piv]
+    ref = R.sgpr_composite_lml_dense_nxn(spec, xl, x, y, sigma)
+    out = model.log_marginal_likelihood(x, y)
+    assert abs(out - ref) < 1e-8 * abs(ref)
+    model.fit(x, y, minimize=False)
+    assert np.array_equal(np.asarray(model.state.pivots), piv)
+    c_ref, mu_ref = R.sgpr_composite_fit_dense(spec, xl, x, y, sigma)
+    xs, _ = _data(50, 3, 12)
+    pred = model.predict(xs)
+    pref, _ = R.sgpr_composite_predict_dense(spec, xl, xs, c_ref, mu_ref, sigma)
+    assert np.max(np.abs(pred - pref)) < 1e-6 * max(1.0, np.max(np.abs(pref)))
