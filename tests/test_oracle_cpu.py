@@ -640,3 +640,72 @@ def test_exact_diagonal_deviation_is_far_below_the_parity_tolerance(kind):
 
     a, b = lml(K), lml(Kx)
     assert abs(a - b) < (1e-9 if kind == "m12" else 1e-12) * abs(a), (noise, a, b)
+
+
+# ---- round-2 additions to the oracle: self-consistency anchors (no reference vectors exist for these paths) -----------
+def test_oracle_rpcholesky_td_and_iterative_td_fit():
+    """rpcholesky_TD restated (gpr_td.py:313-460): F F^T reproduces the pivot rows of the noise-free block kernel up to
+    the 1e-6 jitter in the denominators; the PCG fit with that preconditioner converges to the dense solve; the
+    iterative LML is a stochastic estimate of the dense one."""
+    rng = np.random.default_rng(0)
+    N, nf, nv = 30, 6, 4
+    x, J = rng.standard_normal((N, nf)), rng.standard_normal((N, nf, nv))
+    y, yd = rng.standard_normal((N, 1)), rng.standard_normal((N, nv))
+    for kind in ("se", "m52"):
+        F, p = R.rpcholesky_td(kind, x, J, 12, 1.5, R.PRNGKey(3))
+        A = R.td_A_lhs(kind, x, J, x, J, 1.5, 0.0, 0.0, noise=False)
+        assert np.max(np.abs((F @ F.T)[p] - A[p])) < 1e-4
+        assert len(set(p.tolist())) == 12
+        c, mu, _ = R.td_fit_iter(kind, x, y, J, yd, 1.5, 0.3, 0.2, 12, R.PRNGKey(3), cg_tol=1e-13, cg_atol=0.0)
+        c2, _ = R.td_fit_dense(kind, x, y, J, yd, 1.5, 0.3, 0.2)
+        assert np.max(np.abs(c - c2)) < 1e-10 * np.max(np.abs(c2))
+        li = R.td_lml_iter(kind, x, y, J, yd, 1.5, 0.3, 0.2, 8, 12, R.PRNGKey(1), 12, R.PRNGKey(3))
+        assert abs(li - R.td_lml_dense(kind, x, y, J, yd, 1.5, 0.3, 0.2)) < 0.1
+
+
+def test_oracle_iterative_sgpr_gradient_against_finite_differences():
+    rng = np.random.default_rng(1)
+    N, D, M = 300, 4, 20
+    x = rng.standard_normal((N, D))
+    y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((N, 1))
+    xl = x[rng.choice(N, M, replace=False)].copy()
+    key = R.PRNGKey(5)
+    f = lambda e, s: R.sgpr_lml_iter_grad("se", xl, x, y, e, s, 5, 12, key, cg_tol=1e-13)  # noqa: E731
+    v, gl, gs = f(1.5, 0.4)
+    assert abs(v - R.sgpr_lml_iter("se", xl, x, y, 1.5, 0.4, 5, 12, key)) < 1e-6 * abs(v)
+    h = 1e-5
+    assert abs(gl - (f(1.5 + h, 0.4)[0] - f(1.5 - h, 0.4)[0]) / (2 * h)) < 1e-7 * max(1.0, abs(gl))
+    assert abs(gs - (f(1.5, 0.4 + h)[0] - f(1.5, 0.4 - h)[0]) / (2 * h)) < 1e-7 * max(1.0, abs(gs))
+
+
+def test_oracle_composite_rpcholesky_and_iterative_fit():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((200, 3))
+    y = np.sin(x.sum(1, keepdims=True))
+    spec = ("sum", ("leaf", "se", 1.2, [0, 1]), ("prod", ("leaf", "m52", 2.5, None), ("leaf", "m12", 1.9, [2])))
+    F, p = R.rpcholesky_composite(spec, x, 20, R.PRNGKey(1))
+    K = R.composite_kernel(spec, x, x)
+    assert np.max(np.abs((F @ F.T)[p] - K[p])) < 1e-4
+    c, mu, _ = R.composite_fit_iter(spec, x, y, 0.4, 20, R.PRNGKey(1), cg_tol=1e-13, cg_atol=0.0)
+    assert np.max(np.abs(c - np.linalg.solve(K + (0.16 + 1e-10) * np.eye(200), y - mu))) < 1e-10
+    # a single stationary leaf: the composite loop is the plain one
+    Fk, pk = R.rpcholesky("m52", x, 15, 1.7, R.PRNGKey(4))
+    Fc, pc = R.rpcholesky_composite(("leaf", "m52", 1.7, None), x, 15, R.PRNGKey(4))
+    assert np.array_equal(pk, pc) and np.max(np.abs(Fk - Fc)) < 1e-12
+
+
+def test_oracle_lanczos_breakdown_branch_is_taken_and_continues():
+    """gpx/lanczos.py:92-108 on a block-diagonal kernel matrix (two far-apart groups of points): a start vector
+    supported on the 5-point group exhausts its Krylov space after 5 steps; the restarted recursion continues in the
+    other block with an orthonormal basis."""
+    rng = np.random.default_rng(12)
+    D, n1, n2 = 3, 5, 35
+    x = np.vstack([rng.standard_normal((n1, D)), 100.0 + rng.standard_normal((n2, D))])
+    v1 = np.zeros(n1 + n2)
+    v1[:n1] = rng.standard_normal(n1)
+    v1 /= np.linalg.norm(v1)
+    mv = R.make_matvec("se", x, 1.0, 0.3)
+    T, vecs = R.lanczos_tridiagonal(mv, 20, v1, key=R.PRNGKey(7))
+    b = np.diag(T, 1)
+    assert b[4] <= 1e-12 and np.all(b[:4] > 1e-6) and np.all(b[5:] > 1e-3)
+    assert np.max(np.abs(vecs.T @ vecs - np.eye(20))) < 1e-10
