@@ -55,9 +55,9 @@ SIGNATURES = {
     "gpxb_hess_matvec_dl": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, _c_dp, _ll, _int, _c_dp, _ll, C.c_void_p]),
     "gpxb_lanczos_grad_derivs": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _c_dp, _ll, _int, _int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_sgpr_fit_derivs_iter": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _c_dp, _int, _int, _int, _c_dp, _c_dp, _int, _int, _dbl, _dbl, _dbl, _dbl, _int, _c_dp, C.POINTER(_int), C.c_void_p]),
-    "gpxb_gpr_td_fit_iter": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _dbl, _int, _int, C.c_uint32, C.c_uint32, _int, _dbl, _dbl, _int, _c_dp, _c_dp, C.POINTER(_int), C.c_void_p]),
-    "gpxb_lanczos_td": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _dbl, _c_dp, _ll, _int, _int, _c_dp, _c_dp, _c_dp, C.c_void_p]),
-    "gpxb_rpcholesky_td": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, C.c_uint32, C.c_uint32, _int, _int, _c_dp, _c_dp, C.c_void_p]),
+    "gpxb_gpr_td_fit_iter": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _c_dp, _c_dp, _int, _int, _int, _int, _dbl, _dbl, _dbl, _dbl, _int, _int, C.c_uint32, C.c_uint32, _int, _dbl, _dbl, _int, _c_dp, _c_dp, C.POINTER(_int), C.c_void_p]),
+    "gpxb_lanczos_td": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _int, _dbl, _dbl, _dbl, _dbl, _c_dp, _ll, _int, _int, _c_dp, _c_dp, _c_dp, C.c_void_p]),
+    "gpxb_rpcholesky_td": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _int, _dbl, C.c_uint32, C.c_uint32, _int, _int, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_rpcholesky_derivs": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, C.c_uint32, C.c_uint32, _int, _int, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_lanczos_derivs": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _c_dp, _ll, _int, _int, _c_dp, _c_dp, _c_dp, C.c_void_p]),
     "gpxb_td_gram": (_int, [C.c_void_p, _int, _c_dp, _c_dp, _int, _int, _c_dp, _c_dp, _int, _int, _int, _dbl, _dbl, _dbl, _c_dp, _ll, _int, C.c_void_p]),

@@ -876,51 +876,68 @@ __global__ void td_out2_kernel(const double* __restrict__ J, const double* __res
   for (int f = 0; f < nf; ++f) a += Ji[(long long)f * nv] * (xi[f] * Ti[0] - Ti[1 + f]);
   W[r * ldw] -= a;
 }
+// Row r of the REFERENCE's ordering [targets (N); block 1 (sample, variable) (N nv1); block 2 (N nv2)] ->
+// (is_target, sample t, column u of the concatenated jacobian [J1 | J2], nv = nv1 + nv2).  nv2 = 0: one block.
+struct TdRow {
+  bool target;
+  long long t;
+  int u;
+};
+__device__ __forceinline__ TdRow td_row(long long r, int N, int nv1, int nv2) {
+  TdRow o;
+  o.target = r < N;
+  if (o.target) { o.t = r; o.u = 0; return o; }
+  long long q = r - N;
+  if (q < (long long)N * nv1) { o.t = q / nv1; o.u = (int)(q % nv1); return o; }
+  q -= (long long)N * nv1;
+  o.t = q / nv2; o.u = nv1 + (int)(q % nv2);
+  return o;
+}
 // rows of the pivot-buffer layout: zero for the targets, J_t[:, u] for the derivative rows
-__global__ void td_rows_kernel(const double* __restrict__ J, int N, int nf, int nv, int S, double* __restrict__ rows) {
+__global__ void td_rows_kernel(const double* __restrict__ J, int N, int nf, int nv1, int nv2, int S,
+                               double* __restrict__ rows) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = nv1 + nv2;
   const long long n = (long long)N + (long long)N * nv;
   if (idx >= n * S) return;
   const long long r = idx / S;
   const int f = (int)(idx % S);
   double v = 0.0;
-  if (r >= N && f < nf) {
-    const long long q = r - N;
-    v = J[(q / nv) * nf * nv + (long long)f * nv + q % nv];
-  }
+  const TdRow w = td_row(r, N, nv1, nv2);
+  if (!w.target && f < nf) v = J[w.t * nf * nv + (long long)f * nv + w.u];
   rows[idx] = v;
 }
 // diag0 = [k(x, x) (d2 = 1e-12); c1(1e-12) |J_t[:, u]|^2]
-__global__ void td_diag_kernel(const double* __restrict__ J, int N, int nf, int nv, double k0, double c1_0,
+__global__ void td_diag_kernel(const double* __restrict__ J, int N, int nf, int nv1, int nv2, double k0, double c1_0,
                                double* __restrict__ diag0) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = nv1 + nv2;
   if (r >= (long long)N + (long long)N * nv) return;
-  if (r < N) {
+  const TdRow w = td_row(r, N, nv1, nv2);
+  if (w.target) {
     diag0[r] = k0;
     return;
   }
-  const long long q = r - N;
-  const double* Jt = J + (q / nv) * nf * nv + q % nv;
+  const double* Jt = J + w.t * nf * nv + w.u;
   double a = 0.0;
   for (int f = 0; f < nf; ++f) a += Jt[(long long)f * nv] * Jt[(long long)f * nv];
   diag0[r] = c1_0 * a;
 }
-// column `piv` of the block matrix without the noise terms (rpcholesky_TD first_row / second_row, :389-420)
-__global__ void td_column_kernel(const double* __restrict__ x, const double* __restrict__ J, int N, int nf, int nv,
-                                 int kind, double ell, const double* __restrict__ pbuf, double* __restrict__ col) {
+// column `piv` of the block matrix without the noise terms (rpcholesky_TD first_row / second_row / third_row,
+// gpr_td.py:389-436), rows in the reference's order
+__global__ void td_column_kernel(const double* __restrict__ x, const double* __restrict__ J, int N, int nf, int nv1,
+                                 int nv2, int kind, double ell, const double* __restrict__ pbuf,
+                                 double* __restrict__ col) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = nv1 + nv2;
   if (r >= (long long)N + (long long)N * nv) return;
-  const long long piv = (long long)pbuf[0];
-  const bool prow_t = piv < N;  // the pivot is a target row
-  const long long s1 = prow_t ? piv : (piv - N) / nv;
-  const int v1 = prow_t ? 0 : (int)((piv - N) % nv);
-  const bool rrow_t = r < N;
-  const long long t = rrow_t ? r : (r - N) / nv;
-  const int u = rrow_t ? 0 : (int)((r - N) % nv);
+  const TdRow pw = td_row((long long)pbuf[0], N, nv1, nv2), rw = td_row(r, N, nv1, nv2);
+  const bool prow_t = pw.target, rrow_t = rw.target;
+  const long long s1 = pw.t, t = rw.t;
   const double* xs = x + s1 * nf;
   const double* xt = x + t * nf;
-  const double* a = J + s1 * nf * nv + v1;  // J_s1[:, v1] (stride nv), used when the pivot is a derivative row
-  const double* b = J + t * nf * nv + u;    // J_t[:, u]
+  const double* a = J + s1 * nf * nv + pw.u;  // J_s1[:, v1] (stride nv), used when the pivot is a derivative row
+  const double* b = J + t * nf * nv + rw.u;   // J_t[:, u]
   double dd = 0.0, ab = 0.0, ad = 0.0, bd = 0.0;
   for (int f = 0; f < nf; ++f) {
     const double d = xs[f] - xt[f];  // x_pivot - x_row
@@ -953,22 +970,47 @@ __global__ void td_column_kernel(const double* __restrict__ x, const double* __r
   else out = c1 * ab - kappa * kappa * c2 * ad * bd;   // d01kj (hess_column_kernel)
   col[r] = out;
 }
+// FT_lib[c][l] = FT_ref[c][r(l)]: the factor's rows from the reference's order to the library's
+// [targets; (sample, [block 1 | block 2])]
+__global__ void td_permute_ft_kernel(const double* __restrict__ src, double* __restrict__ dst, long long ldf, int k,
+                                     int N, int nv1, int nv2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = nv1 + nv2;
+  const long long n = (long long)N + (long long)N * nv;
+  if (idx >= n * k) return;
+  const long long l = idx % n;
+  const int c = (int)(idx / n);
+  long long r = l;
+  if (l >= N) {
+    const long long q = l - N, t = q / nv;
+    const int u = (int)(q % nv);
+    r = u < nv1 ? N + t * nv1 + u : N + (long long)N * nv1 + t * nv2 + (u - nv1);
+  }
+  dst[(long long)c * ldf + l] = src[(long long)c * ldf + r];
+}
+// W2[(i,u)] += shift(u) V2[(i,u)]: sigma_derivs for the first nv1 variables, sigma_derivs2 for the rest
+__global__ void td_shift2_kernel(double* __restrict__ W, long long ldw, const double* __restrict__ V, long long ldv,
+                                 long long n, int nv, int nv1, double s1, double s2) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  W[r * ldw] += ((int)(r % nv) < nv1 ? s1 : s2) * V[r * ldv];
+}
 }  // namespace
 
 struct TdOp {
   HessOp h;
-  int N = 0, nf = 0, nv = 0;
+  int N = 0, nf = 0, nv = 0, nv1 = 0;  // nv1 < nv: a second derivative block with its own noise
   const double *x = nullptr, *J = nullptr;
-  double s_t = 0.0;
+  double s_t = 0.0, s_d = 0.0, s_d2 = 0.0;
   DevBuf C0, B, T, t0;
   long long rows() const { return (long long)N + (long long)N * nv; }
 };
 
-int td_op_prepare(Ctx* ctx, TdOp& op, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
-                  double s_t, double s_d, cudaStream_t s) {
-  op.N = N; op.nf = nf; op.nv = nv; op.x = x; op.J = J; op.s_t = s_t;
+int td_op_prepare(Ctx* ctx, TdOp& op, int kind, const double* x, const double* J, int N, int nf, int nv, int nv1,
+                  double ell, double s_t, double s_d, double s_d2, cudaStream_t s) {
+  op.N = N; op.nf = nf; op.nv = nv; op.nv1 = nv1; op.x = x; op.J = J; op.s_t = s_t; op.s_d = s_d; op.s_d2 = s_d2;
   op.h.kind = kind; op.h.N1 = op.h.N2 = N; op.h.nv1 = op.h.nv2 = nv; op.h.nf = nf;
-  op.h.x1 = op.h.x2 = x; op.h.J1 = op.h.J2 = J; op.h.ell = ell; op.h.diag_add = s_d;
+  op.h.x1 = op.h.x2 = x; op.h.J1 = op.h.J2 = J; op.h.ell = ell; op.h.diag_add = nv1 < nv ? 0.0 : s_d;
   GPXB_TRY(hess_op_prepare(ctx, op.h, s));
   const ZLayout zl = z_layout(nf);
   DevBuf bZ;
@@ -990,6 +1032,11 @@ int td_op_apply(Ctx* ctx, TdOp& op, const double* V, long long ldv, double* W, l
   const double* z2 = V + (long long)N * ldv;
   double* W2 = W + (long long)N * ldw;
   GPXB_TRY(hess_op_apply(ctx, op.h, z2, ldv, W2, ldw, s));  // W2 = (d01kj + s_d) z2; leaves M, r, H1 = C1 M
+  if (op.nv1 < nv) {  // two derivative blocks: the noise depends on the variable
+    const long long n2 = (long long)N * nv;
+    td_shift2_kernel<<<ceil_div(n2, 256), 256, 0, s>>>(W2, ldw, z2, ldv, n2, nv, op.nv1, op.s_d, op.s_d2);
+    GPXB_LAUNCHED(ctx);
+  }
   double *B = op.B.as<double>(), *T = op.T.as<double>(), *t0 = op.t0.as<double>();
   td_build_b_kernel<<<ceil_div((long long)N * (nf + 2), 256), 256, 0, s>>>(V, ldv, op.x, op.h.r.as<double>(), N, nf, B);
   GPXB_LAUNCHED(ctx);
@@ -1017,9 +1064,11 @@ int td_op_apply(Ctx* ctx, TdOp& op, const double* V, long long ldv, double* W, l
 }
 
 // rpcholesky_TD (gpx/models/gpr_td.py:313-460): FB row-blocked factor over the N + N nv rows, pivots [M] int64
-int td_rpcholesky(Ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
+int td_rpcholesky(Ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, int nv1, double ell,
                   const uint32_t key[2], int M, int partitionable, double* FB, long long* pivots, cudaStream_t s) {
   GPXB_ARG_CHECK(kind == KIND_SE || kind == KIND_M52, -50);
+  GPXB_ARG_CHECK(nv1 >= 1 && nv1 <= nv, -51);
+  const int nv2 = nv - nv1;
   const long long n = (long long)N + (long long)N * nv;
   GPXB_ARG_CHECK(n < (1LL << 31), -2);
   const ZLayout zl = z_layout(nf);
@@ -1028,7 +1077,7 @@ int td_rpcholesky(Ctx* ctx, int kind, const double* x, const double* J, int N, i
   GPXB_TRY(bD0.alloc(sizeof(double) * (size_t)n, s));
   GPXB_TRY(bCol.alloc(sizeof(double) * (size_t)n, s));
   double* col = bCol.as<double>();
-  td_rows_kernel<<<ceil_div(n * zl.S, 256), 256, 0, s>>>(J, N, nf, nv, zl.S, bRows.as<double>());
+  td_rows_kernel<<<ceil_div(n * zl.S, 256), 256, 0, s>>>(J, N, nf, nv1, nv2, zl.S, bRows.as<double>());
   GPXB_LAUNCHED(ctx);
   double k0, c1_0;
   if (kind == KIND_SE) {
@@ -1039,10 +1088,10 @@ int td_rpcholesky(Ctx* ctx, int kind, const double* x, const double* J, int N, i
     k0 = (1.0 + d + d * d / 3.0) * std::exp(-d);
     c1_0 = (5.0 / (3.0 * ell * ell)) * std::exp(-d) * (1.0 + d);
   }
-  td_diag_kernel<<<ceil_div(n, 256), 256, 0, s>>>(J, N, nf, nv, k0, c1_0, bD0.as<double>());
+  td_diag_kernel<<<ceil_div(n, 256), 256, 0, s>>>(J, N, nf, nv1, nv2, k0, c1_0, bD0.as<double>());
   GPXB_LAUNCHED(ctx);
   RpColumnGen gen = [&](const double* pbuf, cudaStream_t st) -> int {
-    td_column_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, J, N, nf, nv, kind, ell, pbuf, col);
+    td_column_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, J, N, nf, nv1, nv2, kind, ell, pbuf, col);
     GPXB_LAUNCHED(ctx);
     return 0;
   };
@@ -1063,7 +1112,8 @@ __global__ void td_rhs_kernel(const double* __restrict__ y, const double* __rest
 // c = A^-1 [y - mu; y_derivs] by PCG with the rpcholesky_TD preconditioner (which uses sigma_targets for every row,
 // gpr_td.py:478-503) and / or the m-step block Lanczos on A for the start vectors U (SLQ part of _lml_iter).
 int gpr_td_iter(Ctx* ctx, int kind, const double* x, const double* J, const double* y, const double* yd, int N, int nf,
-                int nv, double ell, double sigma_t, double sigma_d, int mean_mode, int n_pivots, const uint32_t key[2],
+                int nv, int nv1, double ell, double sigma_t, double sigma_d, double sigma_d2, int mean_mode, int n_pivots,
+                const uint32_t key[2],
                 int partitionable, double tol, double atol, int maxiter, double* c_out, double* mu_out, int* iters_out,
                 const double* U, long long ldu, int P, int m, double* alpha_out, double* beta_out, int* flag,
                 cudaStream_t s) {
@@ -1071,7 +1121,9 @@ int gpr_td_iter(Ctx* ctx, int kind, const double* x, const double* J, const doub
   const long long n = (long long)N + (long long)N * nv;
   GPXB_ARG_CHECK(N > 0 && n < (1LL << 31) && n_pivots >= 0, -1);
   TdOp op;
-  GPXB_TRY(td_op_prepare(ctx, op, kind, x, J, N, nf, nv, ell, sigma_t * sigma_t + 1e-10, sigma_d * sigma_d + 1e-10, s));
+  GPXB_ARG_CHECK(nv1 >= 1 && nv1 <= nv, -51);
+  GPXB_TRY(td_op_prepare(ctx, op, kind, x, J, N, nf, nv, nv1, ell, sigma_t * sigma_t + 1e-10, sigma_d * sigma_d + 1e-10,
+                         sigma_d2 * sigma_d2 + 1e-10, s));
   if (c_out) {
     DevBuf bFB, bFT, bPiv, bPkk, bB;
     const long long ldf = (n + 1) / 2 * 2;
@@ -1086,10 +1138,19 @@ int gpr_td_iter(Ctx* ctx, int kind, const double* x, const double* J, const doub
       GPXB_TRY(bFT.alloc(sizeof(double) * (size_t)k * ldf, s));
       GPXB_TRY(bPiv.alloc(sizeof(long long) * k, s));
       GPXB_TRY(bPkk.alloc(sizeof(double) * (size_t)k * k, s));
-      GPXB_TRY(td_rpcholesky(ctx, kind, x, J, N, nf, nv, ell, key, k, partitionable, bFB.as<double>(),
+      GPXB_TRY(td_rpcholesky(ctx, kind, x, J, N, nf, nv, nv1, ell, key, k, partitionable, bFB.as<double>(),
                              bPiv.as<long long>(), s));
       GPXB_TRY(rp_unblock_transposed(ctx, bFB.as<double>(), (int)n, k, bFT.as<double>(), ldf, s));
       bFB.release();
+      if (nv1 < nv) {  // the factor's rows follow the reference's [targets; block 1; block 2]: bring them to the operator's order
+        DevBuf bTmp;
+        GPXB_TRY(bTmp.alloc(sizeof(double) * (size_t)k * ldf, s));
+        GPXB_CUDA_CHECK(cudaMemcpyAsync(bTmp.as<double>(), bFT.as<double>(), sizeof(double) * (size_t)k * ldf,
+                                        cudaMemcpyDeviceToDevice, s));
+        td_permute_ft_kernel<<<ceil_div(n * k, 256), 256, 0, s>>>(bTmp.as<double>(), bFT.as<double>(), ldf, k, N, nv1,
+                                                                  nv - nv1);
+        GPXB_LAUNCHED(ctx);
+      }
       GPXB_TRY(precond_build(ctx, bFT.as<double>(), ldf, k, (int)n, sigma_t, bPkk.as<double>(), s));
     }
     auto apply = [&](const double* p, double* Ap) -> int { return td_op_apply(ctx, op, p, 2, Ap, 1, s); };
@@ -1495,30 +1556,32 @@ int gpxb_sgpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const do
 }
 
 int gpxb_gpr_td_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y,
-                         const double* y_derivs, int N, int nf, int nv, double ell, double sigma_targets,
-                         double sigma_derivs, int mean_mode, int n_pivots, uint32_t key0, uint32_t key1,
-                         int partitionable, double tol, double atol, int maxiter, double* c_out, double* mu_out,
-                         int* iters_out, gpxb_stream stream) {
+                         const double* y_derivs, int N, int nf, int nv, int nv_first, double ell, double sigma_targets,
+                         double sigma_derivs, double sigma_derivs2, int mean_mode, int n_pivots, uint32_t key0,
+                         uint32_t key1, int partitionable, double tol, double atol, int maxiter, double* c_out,
+                         double* mu_out, int* iters_out, gpxb_stream stream) {
   GPXB_ARG_CHECK(ctx && x && J && y && y_derivs && c_out && mu_out && N > 0 && nf > 0 && nv > 0, -1);
   const uint32_t key[2] = {key0, key1};
-  return gpxb::gpr_td_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, ell, sigma_targets,
-                           sigma_derivs, mean_mode, n_pivots, key, partitionable, tol, atol, maxiter, c_out, mu_out,
-                           iters_out, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+  return gpxb::gpr_td_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, y, y_derivs, N, nf, nv, nv_first, ell,
+                           sigma_targets, sigma_derivs, sigma_derivs2, mean_mode, n_pivots, key, partitionable, tol, atol,
+                           maxiter, c_out, mu_out, iters_out, nullptr, 0, 0, 0, nullptr, nullptr, nullptr,
+                           (cudaStream_t)stream);
 }
 
-int gpxb_lanczos_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
-                    double sigma_targets, double sigma_derivs, const double* U, long long ldu, int P, int m,
-                    double* alpha_out, double* beta_out, int* breakdown_flag, gpxb_stream stream) {
+int gpxb_lanczos_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, int nv_first,
+                    double ell, double sigma_targets, double sigma_derivs, double sigma_derivs2, const double* U,
+                    long long ldu, int P, int m, double* alpha_out, double* beta_out, int* breakdown_flag,
+                    gpxb_stream stream) {
   GPXB_ARG_CHECK(ctx && x && J && U && alpha_out && beta_out && breakdown_flag && P > 0 && m > 0, -1);
   const uint32_t key[2] = {0, 0};
-  return gpxb::gpr_td_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, nullptr, nullptr, N, nf, nv, ell, sigma_targets,
-                           sigma_derivs, 0, 0, key, 1, 0.0, 0.0, 0, nullptr, nullptr, nullptr, U, ldu, P, m, alpha_out,
-                           beta_out, breakdown_flag, (cudaStream_t)stream);
+  return gpxb::gpr_td_iter(reinterpret_cast<Ctx*>(ctx), kind, x, J, nullptr, nullptr, N, nf, nv, nv_first, ell,
+                           sigma_targets, sigma_derivs, sigma_derivs2, 0, 0, key, 1, 0.0, 0.0, 0, nullptr, nullptr,
+                           nullptr, U, ldu, P, m, alpha_out, beta_out, breakdown_flag, (cudaStream_t)stream);
 }
 
-int gpxb_rpcholesky_td(gpxb_ctx* ctx_, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
-                       uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out, long long* pivots_out,
-                       gpxb_stream stream) {
+int gpxb_rpcholesky_td(gpxb_ctx* ctx_, int kind, const double* x, const double* J, int N, int nf, int nv, int nv_first,
+                       double ell, uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out,
+                       long long* pivots_out, gpxb_stream stream) {
   GPXB_ARG_CHECK(ctx_ && x && J && pivots_out && N > 0 && nf > 0 && nv > 0 && M > 0, -1);
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   cudaStream_t s = (cudaStream_t)stream;
@@ -1527,7 +1590,8 @@ int gpxb_rpcholesky_td(gpxb_ctx* ctx_, int kind, const double* x, const double* 
   gpxb::DevBuf fb;
   GPXB_TRY(fb.alloc(sizeof(double) * std::max<size_t>(gpxb::rp_factor_doubles((int)n, M), 8), s));
   const uint32_t key[2] = {key0, key1};
-  GPXB_TRY(gpxb::td_rpcholesky(ctx, kind, x, J, N, nf, nv, ell, key, M, partitionable, fb.as<double>(), pivots_out, s));
+  GPXB_TRY(gpxb::td_rpcholesky(ctx, kind, x, J, N, nf, nv, nv_first, ell, key, M, partitionable, fb.as<double>(),
+                               pivots_out, s));
   if (F_out) GPXB_TRY(gpxb::rp_unblock_rowmajor(ctx, fb.as<double>(), (int)n, M, F_out, s));
   return 0;
 }

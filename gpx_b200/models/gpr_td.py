@@ -35,52 +35,6 @@ def _hyper(state):
             float(np.asarray(state.params["sigma_derivs"].value)))
 
 
-def _iter_single_block(jacobian_2):
-    if jacobian_2 is not None:
-        raise NotImplementedError("the iterative GPR_TD paths take one derivative block; the reference's row order "
-                                  "[targets; block 1; block 2] of rpcholesky_TD with a second block (gpr_td.py:422-436) "
-                                  "is not implemented on the device")
-
-
-def _fit_iter(state, x, y, jacobian, y_derivs, n_pivots, key_precond, tol=1e-5, atol=1e-7):
-    """_fit_iter (gpx/models/gpr_td.py:685-747): PCG on the matrix-free block operator with the rpcholesky_TD
-    preconditioner.  -> (c (N + N nv, 1) device, mu device (1,), iterations)."""
-    if n_pivots is None:
-        raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
-    kernel, ell, st, sd = _hyper(state)
-    J = np.asarray(jacobian, dtype=np.float64)
-    yd = np.asarray(y_derivs, dtype=np.float64).reshape(J.shape[0], J.shape[2])
-    key = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
-    return ops.gpr_td_fit_iter(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), ell, st, sd,
-                               int(n_pivots), key, mean_mode(state.mean_function), threefry_partitionable(), tol=tol,
-                               atol=atol)
-
-
-def _lml_iter(state, x, y, jacobian, y_derivs, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond, tol=1e-5,
-              atol=1e-7):
-    """_lml_iter (gpx/models/gpr_td.py:562-637): quadratic form from the PCG solution, log-determinant by stochastic
-    Lanczos quadrature on the same operator (host eigh of the P tridiagonals as in _iterative.slq_logdet)."""
-    kernel, ell, st, sd = _hyper(state)
-    J = np.asarray(jacobian, dtype=np.float64)
-    ns, _, nv = J.shape
-    m = ns + ns * nv
-    c, mu, _ = _fit_iter(state, x, y, jacobian, y_derivs, n_pivots, key_precond, tol, atol)
-    mu_h = float(mu.cpu().numpy()[0])
-    ym = np.concatenate([np.asarray(y, dtype=np.float64).reshape(-1, 1) - mu_h,
-                         np.asarray(y_derivs, dtype=np.float64).reshape(-1, 1)])
-    part = threefry_partitionable()
-    subkey, _ = split(as_key(key_lanczos), 2, part)
-    U = ops.rademacher_probes(subkey, m, int(num_evals), part)
-    alpha, beta, flag = ops.lanczos_td(kernel.kind, _to_device(x), _to_device(J), ell, st, sd, U, int(num_lanczos))
-    if int(flag.cpu().numpy()[0]) != 0:
-        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
-                           "use fewer Lanczos steps than rows")
-    mll = -0.5 * float(np.sum(ym.T @ c.cpu().numpy()))
-    mll -= 0.5 * slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), m)
-    mll -= m * 0.5 * np.log(2.0 * np.pi)
-    return mll / m
-
-
 def _cat_blocks(state, jacobian, y_derivs, jacobian_2, y_derivs_2):
     """(J, y_derivs) of both derivative blocks concatenated along the variable axis, the number of variables of the
     first block and sigma_derivs2 (None / nv / 0.0 without a second block)."""
@@ -118,6 +72,60 @@ def _to_lib_order(c, ns, nv1, nv2):
     return np.concatenate([c[:ns], np.concatenate([a, b], axis=1).reshape(ns * (nv1 + nv2), -1)])
 
 
+def _ref_to_lib_perm(ns, nv1, nv2):
+    """perm with v_lib = v_ref[perm]: rows [targets; block 1; block 2] -> [targets; (sample, [block 1 | block 2])]."""
+    nv = nv1 + nv2
+    u = np.arange(nv)[None, :]
+    t = np.arange(ns)[:, None]
+    d = np.where(u < nv1, ns + t * nv1 + u, ns + ns * nv1 + t * nv2 + (u - nv1))
+    return np.concatenate([np.arange(ns), d.reshape(-1)])
+
+
+def _fit_iter(state, x, y, jacobian, y_derivs, n_pivots, key_precond, jacobian_2=None, y_derivs_2=None, tol=1e-5,
+              atol=1e-7):
+    """_fit_iter (gpx/models/gpr_td.py:685-747): PCG on the matrix-free block operator with the rpcholesky_TD
+    preconditioner.  -> (c (N + N nv, 1) device in the library's row order, mu device (1,), iterations)."""
+    if n_pivots is None:
+        raise ValueError("iterative fitting needs n_pivots (RPCholesky preconditioner size)")
+    kernel, ell, st, sd = _hyper(state)
+    J, yd, nv1, sd2 = _cat_blocks(state, jacobian, y_derivs, jacobian_2, y_derivs_2)
+    key = as_key(key_precond if key_precond is not None else gpxargs.key_precond)
+    return ops.gpr_td_fit_iter(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), ell, st, sd,
+                               int(n_pivots), key, mean_mode(state.mean_function), threefry_partitionable(), tol=tol,
+                               atol=atol, nv_first=nv1, sigma_derivs2=sd2)
+
+
+def _lml_iter(state, x, y, jacobian, y_derivs, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
+              jacobian_2=None, y_derivs_2=None, tol=1e-5, atol=1e-7):
+    """_lml_iter (gpx/models/gpr_td.py:562-637): quadratic form from the PCG solution, log-determinant by stochastic
+    Lanczos quadrature on the same operator (host eigh of the P tridiagonals as in _iterative.slq_logdet).  The
+    Rademacher probes are drawn in the reference's row order and permuted to the library's, so that the estimate is
+    the reference's number and not just an equally good one."""
+    kernel, ell, st, sd = _hyper(state)
+    J, yd, nv1, sd2 = _cat_blocks(state, jacobian, y_derivs, jacobian_2, y_derivs_2)
+    ns, _, nv = J.shape
+    m = ns + ns * nv
+    c, mu, _ = _fit_iter(state, x, y, jacobian, y_derivs, n_pivots, key_precond, jacobian_2, y_derivs_2, tol, atol)
+    mu_h = float(mu.cpu().numpy()[0])
+    ym = np.concatenate([np.asarray(y, dtype=np.float64).reshape(-1, 1) - mu_h, yd.reshape(-1, 1)])  # library order
+    part = threefry_partitionable()
+    subkey, _ = split(as_key(key_lanczos), 2, part)
+    U = ops.rademacher_probes(subkey, m, int(num_evals), part)
+    if nv1 < nv:
+        import torch
+
+        U = U[torch.as_tensor(_ref_to_lib_perm(ns, nv1, nv - nv1), device=U.device)].contiguous()
+    alpha, beta, flag = ops.lanczos_td(kernel.kind, _to_device(x), _to_device(J), ell, st, sd, U, int(num_lanczos),
+                                       nv_first=nv1, sigma_derivs2=sd2)
+    if int(flag.cpu().numpy()[0]) != 0:
+        raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
+                           "use fewer Lanczos steps than rows")
+    mll = -0.5 * float(np.sum(ym.T @ c.cpu().numpy()))
+    mll -= 0.5 * slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), m)
+    mll -= m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
+
+
 def _lml_grad(state, x, y, jacobian, y_derivs, jacobian_2, y_derivs_2, want_grad):
     """[lml, d/d lengthscale, d/d sigma_targets, d/d sigma_derivs, d/d sigma_derivs2] (host floats)."""
     kernel, ell, st, sd = _hyper(state)
@@ -136,8 +144,8 @@ def log_marginal_likelihood(state, x, y, jacobian, y_derivs, jacobian_2=None, y_
                             key_lanczos=gpxargs.key_lanczos, n_pivots=None, key_precond=None, **_ignored):
     """gpx/models/gpr_td.py:848-911 -> _lml_dense (507-560) / _lml_iter (562-637)."""
     if iterative:
-        _iter_single_block(jacobian_2)
-        return _lml_iter(state, x, y, jacobian, y_derivs, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond)
+        return _lml_iter(state, x, y, jacobian, y_derivs, num_evals, num_lanczos, key_lanczos, n_pivots, key_precond,
+                         jacobian_2, y_derivs_2)
     return _lml_grad(state, x, y, jacobian, y_derivs, jacobian_2, y_derivs_2, want_grad=False)[0]
 
 
@@ -206,7 +214,6 @@ class GPR_TD:
         """gpx/models/gpr_td.py:982-1108.  iterative=True: the coefficients come from the PCG solve (_fit_iter); the
         hyperparameters can only be trained on the dense LML (minimize=True needs iterative=False)."""
         if iterative:
-            _iter_single_block(jacobian_2)
             if minimize:
                 raise NotImplementedError("the gradient of the iterative GPR_TD LML is not implemented: pass "
                                           "minimize=False (or train with iterative=False first)")
@@ -228,7 +235,8 @@ class GPR_TD:
         ns, _, nv = J.shape
         nv2 = nv - nv1
         if iterative:
-            c, mu, self.cg_iterations_ = _fit_iter(self.state, x, y, jacobian, y_derivs, n_pivots, key_precond)
+            c, mu, self.cg_iterations_ = _fit_iter(self.state, x, y, jacobian, y_derivs, n_pivots, key_precond,
+                                                   jacobian_2, y_derivs_2)
         elif nv2 == 0:
             c, mu = ops.gpr_td_fit(kernel.kind, _to_device(x), _to_device(J), _to_device(y), _to_device(yd), ell, st, sd,
                                    mean_mode(self.state.mean_function))

@@ -652,9 +652,10 @@ def sgpr_fit_derivs_iter(kind, x, J, y, x_locs, J_locs, ell, sigma, tol=1e-5, at
 
 
 def gpr_td_fit_iter(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, n_pivots, key, mean_mode=MEAN_DATA,
-                    partitionable=True, tol=1e-5, atol=1e-7, maxiter=0):
+                    partitionable=True, tol=1e-5, atol=1e-7, maxiter=0, nv_first=None, sigma_derivs2=0.0):
     """(c (N + N nv, 1) rows [targets; (sample, variable)], mu (1,), iterations): PCG on the matrix-free block
-    operator with the rpcholesky_TD preconditioner (gpx/models/gpr_td.py:685-747)."""
+    operator with the rpcholesky_TD preconditioner (gpx/models/gpr_td.py:685-747).  nv_first < nv: J holds two
+    derivative blocks concatenated along the variable axis, the second with noise sigma_derivs2."""
     import ctypes
 
     ctx = context()
@@ -666,8 +667,10 @@ def gpr_td_fit_iter(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, n
     mu = torch.empty(1, dtype=torch.float64, device=x.device)
     iters = ctypes.c_int(0)
     check(
-        ctx.lib.gpxb_gpr_td_fit_iter(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv, float(ell),
-                                     float(sigma_targets), float(sigma_derivs), int(mean_mode), int(n_pivots),
+        ctx.lib.gpxb_gpr_td_fit_iter(ctx.handle, _kind(kind), ptr(x), ptr(J), ptr(y), ptr(yd), N, nf, nv,
+                                     int(nv if nv_first is None else nv_first), float(ell),
+                                     float(sigma_targets), float(sigma_derivs), float(sigma_derivs2), int(mean_mode),
+                                     int(n_pivots),
                                      int(key[0]), int(key[1]), int(bool(partitionable)), float(tol), float(atol),
                                      int(maxiter), ptr(c), ptr(mu), ctypes.byref(iters), stream_ptr()),
         "gpxb_gpr_td_fit_iter",
@@ -675,7 +678,7 @@ def gpr_td_fit_iter(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, n
     return c, mu, iters.value
 
 
-def lanczos_td(kind, x, J, ell, sigma_targets, sigma_derivs, U, m):
+def lanczos_td(kind, x, J, ell, sigma_targets, sigma_derivs, U, m, nv_first=None, sigma_derivs2=0.0):
     """(alpha (P, m), beta (P, m), breakdown) of the block Lanczos on the GPR_TD operator, matrix-free."""
     ctx = context()
     x, J, U = _f64(x), _f64(J), _f64(U)
@@ -687,16 +690,18 @@ def lanczos_td(kind, x, J, ell, sigma_targets, sigma_derivs, U, m):
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
     flag = torch.zeros(1, dtype=torch.int32, device=x.device)
     check(
-        ctx.lib.gpxb_lanczos_td(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), float(sigma_targets),
-                                float(sigma_derivs), ptr(U), U.stride(0), P, int(m), ptr(alpha), ptr(beta), ptr(flag),
-                                stream_ptr()),
+        ctx.lib.gpxb_lanczos_td(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv,
+                                int(nv if nv_first is None else nv_first), float(ell), float(sigma_targets),
+                                float(sigma_derivs), float(sigma_derivs2), ptr(U), U.stride(0), P, int(m), ptr(alpha),
+                                ptr(beta), ptr(flag), stream_ptr()),
         "gpxb_lanczos_td",
     )
     return alpha, beta, flag
 
 
-def rpcholesky_td(kind, x, J, n_pivots, ell, key, partitionable=True, want_factor=True):
-    """(F (N + N nv, M) or None, pivots int64 (M,)) -- rpcholesky_TD, gpx/models/gpr_td.py:313-460."""
+def rpcholesky_td(kind, x, J, n_pivots, ell, key, partitionable=True, want_factor=True, nv_first=None):
+    """(F (N + N nv, M) or None, pivots int64 (M,)) -- rpcholesky_TD, gpx/models/gpr_td.py:313-460; rows and pivot
+    indices in the reference's order [targets; block 1; block 2] (nv_first < nv: two blocks concatenated in J)."""
     ctx = context()
     x, J = _f64(x), _f64(J)
     _check_xJ(x, J, "rpcholesky_td")
@@ -704,7 +709,8 @@ def rpcholesky_td(kind, x, J, n_pivots, ell, key, partitionable=True, want_facto
     piv = torch.empty(n_pivots, dtype=torch.int64, device=x.device)
     F = torch.empty((N + N * nv, n_pivots), dtype=torch.float64, device=x.device) if want_factor else None
     check(
-        ctx.lib.gpxb_rpcholesky_td(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), int(key[0]),
+        ctx.lib.gpxb_rpcholesky_td(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv,
+                                   int(nv if nv_first is None else nv_first), float(ell), int(key[0]),
                                    int(key[1]), int(n_pivots), int(bool(partitionable)), ptr(F) if want_factor else None,
                                    ptr(piv), stream_ptr()),
         "gpxb_rpcholesky_td",

@@ -194,27 +194,33 @@ int gpxb_sgpr_fit_derivs_iter(gpxb_ctx* ctx, int kind, const double* x, const do
                               int nf, int nv, const double* x_locs, const double* J_locs, int M, int nv_locs, double ell,
                               double sigma, double tol, double atol, int maxiter, double* c_out, int* iters_out,
                               gpxb_stream stream);
-/* ---- GPR on targets and derivatives, iterative (gpx/models/gpr_td.py, one derivative block) ------------------ */
-/* c[N + N nv] (rows [targets; derivatives (sample, variable)]) = PCG solve of
- *   [[K + s_t I, d1kj], [d0kj, d01kj + s_d I]] c = [y - mu; y_derivs],  s_* = sigma_*^2 + 1e-10
+/* ---- GPR on targets and derivatives, iterative (gpx/models/gpr_td.py; one or two derivative blocks) ------------ */
+/* J: N x nf x nv with nv = nv_first + nv_second: the jacobians of both derivative blocks concatenated along the
+ * variable axis (nv_first == nv: one block; sigma_derivs2 is then ignored).  Vectors (c, y_derivs, U) are ordered
+ * [targets (N); derivatives (sample, variable of [block 1 | block 2])] -- a symmetric permutation of the reference's
+ * [targets; block 1; block 2] (the caller permutes, gpx_b200/models/gpr_td.py).
+ * gpxb_gpr_td_fit_iter: c = PCG solve of
+ *   [[K + s_t I, d1kj], [d0kj, d01kj + diag(s_d | s_d2)]] c = [y - mu; y_derivs],  s_* = sigma_*^2 + 1e-10
  * with the rpcholesky_TD preconditioner (_fit_iter gpr_td.py:685-747, _Ax_lhs_fun :162-310,
- * _precond_rpcholesky_TD :463-504 -- the preconditioner uses sigma_targets for every row, as the reference does).
+ * _precond_rpcholesky_TD :463-504 -- the preconditioner uses sigma_targets for every row, as the reference does; its
+ * pivots are drawn over the reference's row order and the factor's rows are then permuted to the order above).
  * Matrix-free on the configuration level: N x N pair-coefficient matrices, never the (N + N nv)^2 kernel.
  * SquaredExponential and Matern-5/2.  Host-synchronous like gpxb_gpr_fit_iter; *iters_out is a HOST int. */
 int gpxb_gpr_td_fit_iter(gpxb_ctx* ctx, int kind, const double* x, const double* J, const double* y,
-                         const double* y_derivs, int N, int nf, int nv, double ell, double sigma_targets,
-                         double sigma_derivs, int mean_mode, int n_pivots, uint32_t key0, uint32_t key1,
-                         int partitionable, double tol, double atol, int maxiter, double* c_out, double* mu_out,
-                         int* iters_out, gpxb_stream stream);
+                         const double* y_derivs, int N, int nf, int nv, int nv_first, double ell, double sigma_targets,
+                         double sigma_derivs, double sigma_derivs2, int mean_mode, int n_pivots, uint32_t key0,
+                         uint32_t key1, int partitionable, double tol, double atol, int maxiter, double* c_out,
+                         double* mu_out, int* iters_out, gpxb_stream stream);
 /* gpxb_lanczos on the same block operator (the SLQ part of _lml_iter, gpr_td.py:562-637); U: (N + N nv) x ldu. */
-int gpxb_lanczos_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
-                    double sigma_targets, double sigma_derivs, const double* U, long long ldu, int P, int m,
-                    double* alpha_out, double* beta_out, int* breakdown_flag, gpxb_stream stream);
-/* rpcholesky_TD (gpr_td.py:313-460): randomly pivoted Cholesky of the noise-free block kernel over the
- * N + N nv rows; F_out ((N + N nv) x M row-major, may be NULL), pivots_out [M] int64. */
-int gpxb_rpcholesky_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,
-                       uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out, long long* pivots_out,
-                       gpxb_stream stream);
+int gpxb_lanczos_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, int nv_first,
+                    double ell, double sigma_targets, double sigma_derivs, double sigma_derivs2, const double* U,
+                    long long ldu, int P, int m, double* alpha_out, double* beta_out, int* breakdown_flag,
+                    gpxb_stream stream);
+/* rpcholesky_TD (gpr_td.py:313-460): randomly pivoted Cholesky of the noise-free block kernel; rows of F_out
+ * ((N + N nv) x M row-major, may be NULL) and pivot indices in the REFERENCE's order [targets; block 1; block 2]. */
+int gpxb_rpcholesky_td(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, int nv_first,
+                       double ell, uint32_t key0, uint32_t key1, int M, int partitionable, double* F_out,
+                       long long* pivots_out, gpxb_stream stream);
 /* gpxb_lanczos on the matrix-free operator d01kj + (sigma^2+1e-10) I (the SLQ part of _lml_derivs_iter,
  * gpx/models/_gpr.py:873-935); U: (N nv) x P unit start vectors. */
 int gpxb_lanczos_derivs(gpxb_ctx* ctx, int kind, const double* x, const double* J, int N, int nf, int nv, double ell,

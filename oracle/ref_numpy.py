@@ -499,6 +499,71 @@ def td2_A_lhs(kind, x1, J1a, J1b, x2, J2a, J2b, ell, sigma_t, sigma_d, sigma_d2,
     return np.block([[K, D1a, D1b], [D0a, D11, D12], [D0b, D21, D22]])
 
 
+def rpcholesky_td2(kind, x, Ja, Jb, n_pivots, ell, key, partitionable=True):
+    """gpx/models/gpr_td.py:313-460 with jacobian_2: rows [targets; block 1 (sample, variable); block 2]."""
+    n = x.shape[0]
+    n1, n2 = Ja.shape[2], Jb.shape[2]
+    ntot = n + n * n1 + n * n2
+    F = np.zeros((ntot, n_pivots))
+    pivots = np.zeros(n_pivots, dtype=np.int64)
+    dk = np.array([kernel(kind, x[i:i + 1], x[i:i + 1], ell)[0, 0] for i in range(n)])
+    da = np.concatenate([np.diagonal(d01kj(kind, x[i:i + 1], x[i:i + 1], ell, Ja[i:i + 1], Ja[i:i + 1])) for i in range(n)])
+    db = np.concatenate([np.diagonal(d01kj(kind, x[i:i + 1], x[i:i + 1], ell, Jb[i:i + 1], Jb[i:i + 1])) for i in range(n)])
+    diag = np.concatenate([dk, da, db])
+    key = np.asarray(key, dtype=np.uint32)
+    for i in range(n_pivots):
+        prob = diag / np.sum(diag)
+        key = split(key, 2, partitionable)[0]
+        s = int(choice_p(key, prob, partitionable))
+        pivots[i] = s
+        if s < n:                       # first_row (:397-407)
+            xs = x[s:s + 1]
+            row = np.concatenate([kernel(kind, xs, x, ell)[0], d0kj(kind, x, xs, ell, Ja).reshape(-1),
+                                  d0kj(kind, x, xs, ell, Jb).reshape(-1)])
+        else:                           # second_row / third_row (:409-436)
+            first = s < n + n * n1
+            q = s - n if first else s - n - n * n1
+            nvq, Jq = (n1, Ja) if first else (n2, Jb)
+            i1, i2 = q // nvq, q % nvq
+            xs, js = x[i1:i1 + 1], Jq[i1:i1 + 1]
+            row = np.concatenate([d0kj(kind, xs, x, ell, js)[i2], d01kj(kind, xs, x, ell, js, Ja)[i2],
+                                  d01kj(kind, xs, x, ell, js, Jb)[i2]])
+        g = row - F @ F[s]
+        F[:, i] = g / (g[s] ** 0.5 + 1e-6)
+        diag = diag - F[:, i] ** 2
+    return F, pivots
+
+
+def td2_fit_iter(kind, x, y, Ja, Jb, yd_a, yd_b, ell, sigma_t, sigma_d, sigma_d2, n_pivots, key_precond,
+                 mean_function=data_mean, partitionable=True, cg_tol=1e-5, cg_atol=1e-7):
+    """gpr_td.py:685-747 with jacobian_2 / y_derivs_2 (c in the reference's order)."""
+    mu = mean_function(y)
+    ym = np.concatenate([(y - mu).reshape(-1, 1), yd_a.reshape(-1, 1), yd_b.reshape(-1, 1)])
+    A = td2_A_lhs(kind, x, Ja, Jb, x, Ja, Jb, ell, sigma_t, sigma_d, sigma_d2)
+    F, _ = rpcholesky_td2(kind, x, Ja, Jb, n_pivots, ell, key_precond, partitionable)
+    P = np.linalg.inv(sigma_t**2 * np.eye(n_pivots) + F.T @ F)
+
+    def precond(z):
+        return -(sigma_t ** (-2)) * (F @ (P @ (F.T @ z))) + sigma_t ** (-2) * z
+
+    c, iters = cg(lambda v: A @ v, ym, M=precond, tol=cg_tol, atol=cg_atol)
+    return c, mu, iters
+
+
+def td2_lml_iter(kind, x, y, Ja, Jb, yd_a, yd_b, ell, sigma_t, sigma_d, sigma_d2, num_evals, num_lanczos, key_lanczos,
+                 n_pivots, key_precond, mean_function=data_mean, partitionable=True, cg_tol=1e-5, cg_atol=1e-7):
+    """gpr_td.py:562-637 with jacobian_2 / y_derivs_2."""
+    c, mu, _ = td2_fit_iter(kind, x, y, Ja, Jb, yd_a, yd_b, ell, sigma_t, sigma_d, sigma_d2, n_pivots, key_precond,
+                            mean_function, partitionable, cg_tol, cg_atol)
+    ym = np.concatenate([(y - mu).reshape(-1, 1), yd_a.reshape(-1, 1), yd_b.reshape(-1, 1)])
+    m = ym.shape[0]
+    A = td2_A_lhs(kind, x, Ja, Jb, x, Ja, Jb, ell, sigma_t, sigma_d, sigma_d2)
+    mll = -0.5 * np.sum(ym.T @ c)
+    mll -= 0.5 * lanczos_logdet(lambda v: A @ v, num_evals, m, num_lanczos, key_lanczos, partitionable)
+    mll -= m * 0.5 * np.log(2.0 * np.pi)
+    return mll / m
+
+
 def td2_lml_dense(kind, x, y, Ja, Jb, yd_a, yd_b, ell, sigma_t, sigma_d, sigma_d2, mean_function=data_mean):
     """gpr_td.py:507-560 with jacobian_2 / y_derivs_2."""
     mu = mean_function(y)

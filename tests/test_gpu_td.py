@@ -280,3 +280,49 @@ def test_td_iterative_operator_fit_and_lml(kind, N, nf, nv, mean):
     y_ref, d_ref = R.td_predict_dense(kind, x, J, xs, Js, c_d, mfun(y), ell)
     assert np.max(np.abs(yp - y_ref)) < 1e-4 * max(1.0, np.max(np.abs(y_ref)))  # CG stopped at tol 1e-5
     assert np.max(np.abs(dp - d_ref)) < 1e-4 * max(1.0, np.max(np.abs(d_ref)))
+
+
+@pytest.mark.parametrize("kind,N,nf,nv1,nv2", [("se", 30, 6, 4, 3), ("m52", 24, 8, 2, 5)])
+def test_td_iterative_second_derivative_block(kind, N, nf, nv1, nv2):
+    """The iterative GPR_TD paths with jacobian_2 / y_derivs_2: rpcholesky_TD pivots drawn over the reference's row
+    order [targets; block 1; block 2] (bit-exact), PCG fit and iterative LML against the oracle with converged solves."""
+    from gpx_b200 import ops
+    from gpx_b200.kernels import Matern52, SquaredExponential
+    from gpx_b200.models import GPR_TD
+    from gpx_b200.models import gpr_td as T
+    from gpx_b200.parameters import Parameter
+    from gpx_b200.bijectors import Softplus
+    from gpx_b200.priors import GammaPrior
+
+    x, Ja, y, ya = _data(N, nf, nv1, 5)
+    _, Jb, _, yb = _data(N, nf, nv2, 6)
+    ell, st, sd, sd2 = 0.9 * np.sqrt(nf), 0.3, 0.2, 0.25
+    key = R.PRNGKey(2023)
+    Jc = np.concatenate([Ja, Jb], axis=2)
+    for part in (True, False):
+        Fref, pref = R.rpcholesky_td2(kind, x, Ja, Jb, 20, ell, key, part)
+        F, piv = ops.rpcholesky_td(kind, dev(x), dev(Jc), 20, ell, key, part, nv_first=nv1)
+        assert np.array_equal(host(piv), pref)
+        assert np.max(np.abs(host(F) - Fref)) < 1e-9 * max(1.0, np.max(np.abs(Fref)))
+    P = lambda v: Parameter(v, True, Softplus(), GammaPrior())  # noqa: E731
+    K = SquaredExponential() if kind == "se" else Matern52()
+    model = GPR_TD(K, kernel_params=dict(lengthscale=P(ell)), sigma_targets=P(st), sigma_derivs=P(sd), sigma_derivs2=P(sd2))
+    c_ref, mu_ref, _ = R.td2_fit_iter(kind, x, y, Ja, Jb, ya, yb, ell, st, sd, sd2, 20, key, R.zero_mean, cg_tol=1e-13,
+                                      cg_atol=0.0)
+    c, mu, _ = T._fit_iter(model.state, x, y, Ja, ya, 20, key, Jb, yb, tol=1e-13, atol=0.0)
+    c_np = T._to_ref_order(host(c), N, nv1, nv2)
+    assert np.max(np.abs(c_np - c_ref)) < 1e-8 * np.max(np.abs(c_ref))
+    ref = R.td2_lml_iter(kind, x, y, Ja, Jb, ya, yb, ell, st, sd, sd2, 6, 12, key, 20, key, R.zero_mean, cg_tol=1e-13,
+                         cg_atol=0.0)
+    out = T._lml_iter(model.state, x, y, Ja, ya, 6, 12, key, 20, key, Jb, yb, tol=1e-13, atol=0.0)
+    assert abs(out - ref) < 1e-8 * abs(ref)
+    # facade: fit(iterative=True, minimize=False) stores c in the reference's order; predictions match the dense model
+    model.fit(x, y, Ja, ya, jacobian_2=Jb, y_derivs_2=yb, iterative=True, minimize=False, n_pivots=20)
+    c_d, mu_d = R.td2_fit_dense(kind, x, y, Ja, Jb, ya, yb, ell, st, sd, sd2, R.zero_mean)
+    assert np.max(np.abs(np.asarray(model.state.c) - c_d)) < 1e-3 * np.max(np.abs(c_d))  # CG stopped at tol 1e-5
+    xs, Jsa, _, _ = _data(7, nf, nv1, 8)
+    _, Jsb, _, _ = _data(7, nf, nv2, 9)
+    yp, d1, d2 = model.predict(xs, Jsa, jacobian_2=Jsb, iterative=True)
+    y_ref, d1_ref, d2_ref = R.td2_predict_dense(kind, x, Ja, Jb, xs, Jsa, Jsb, c_d, mu_d, ell)
+    assert np.max(np.abs(yp - y_ref)) < 1e-3 * max(1.0, np.max(np.abs(y_ref)))
+    assert np.max(np.abs(d2 - d2_ref)) < 1e-3 * max(1.0, np.max(np.abs(d2_ref)))

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_td.py -m gpu -q -k "iterative or rpcholesky" > gpurun_out/r2f_pytest.log 2>&1; echo "pytest_rc=$?" >> gpurun_out/r2f_pytest.log
-grep -E "^E  |FAILED|passed|failed|pytest_rc" gpurun_out/r2f_pytest.log | head -40
+timeout 900 python -m pytest tests/test_gpu_td.py -m gpu -q > gpurun_out/r2o_pytest.log 2>&1; echo "pytest_rc=$?" >> gpurun_out/r2o_pytest.log
+grep -E "^E  |FAILED|passed|failed|pytest_rc" gpurun_out/r2o_pytest.log | head -40
