@@ -286,8 +286,12 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (c <= lane) rowo[c] = a[c];
-      __syncwarp();
-      // ---- its inverse: lane = column j of X, forward substitution; L[r][k] is a broadcast read of smem ----
+    }
+    __syncthreads();  // L11 and the pivot reciprocals are visible
+    const int r0 = jb + 32, R = LB - r0;  // rows below the block
+    if (warp == 0) {
+      // ---- inverse of the diagonal block, OFF the panel's path (the panel below is solved by substitution): lane =
+      // column j of X, forward substitution; L[r][k] is a broadcast read of smem ----
       double x[32];
       const double* Lb = S + jb * L2S + jb;
 #pragma unroll
@@ -300,35 +304,29 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
       }
 #pragma unroll
       for (int r = 0; r < 32; ++r) Dinv[r * DIS + lane] = x[r];
-    }
-    __syncthreads();
-    const int r0 = jb + 32, R = LB - r0;  // rows below the block
-    if (R > 0) {
-      // ---- panel: L21 = A21 Dinv^T, one warp per 8-row block (in place: fragments first, stores last) ----
-      for (int rb = warp; rb < (R >> 3); rb += 8) {
-        double* ab = S + (r0 + rb * 8 + lr) * L2S + jb;
-        double av[8];
+    } else if (R > 0) {
+      // ---- panel: L21 = A21 L11^-T by forward substitution, one thread per row (warps 1..3), L11[c][k] a broadcast
+      // read; the packed inverse is not needed here, so warp 0 computes it meanwhile ----
+      const int pr = tid - 32;
+      if (pr < R) {
+        double* arow = S + (r0 + pr) * L2S + jb;
+        const double* Lb = S + jb * L2S + jb;
+        double xr[32];
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) av[ks] = ab[ks * 4 + lq];
-        double c[4][2];
+        for (int c = 0; c < 32; ++c) {
+          double v[4] = {arow[c], 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int nf = 0; nf < 4; ++nf) {
-          c[nf][0] = c[nf][1] = 0.0;
-          const double* bp = Dinv + (nf * 8 + lr) * DIS + lq;  // B[k][n] = Dinv[n][k]
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) dmma884(c[nf][0], c[nf][1], av[ks], bp[ks * 4]);
+          for (int k = 0; k < 32; ++k)
+            if (k < c) v[k & 3] -= xr[k] * Lb[c * L2S + k];
+          xr[c] = ((v[0] + v[1]) + (v[2] + v[3])) * rds[c];
         }
-        __syncwarp();
 #pragma unroll
-        for (int nf = 0; nf < 4; ++nf) {
-          ab[nf * 8 + 2 * lq] = c[nf][0];
-          ab[nf * 8 + 2 * lq + 1] = c[nf][1];
-        }
+        for (int c = 0; c < 32; ++c) arow[c] = xr[c];
       }
-      __syncthreads();
-      // ---- trailing update: A22 -= L21 L21^T on the lower 8x8 tiles ----
+      asm volatile("bar.sync 1, 224;" ::: "memory");  // warps 1..7: the panel is complete
+      // ---- trailing update: A22 -= L21 L21^T on the lower 8x8 tiles (warps 1..7) ----
       const int nt = R >> 3, ntiles = nt * (nt + 1) / 2;
-      for (int t = warp; t < ntiles; t += 8) {
+      for (int t = warp - 1; t < ntiles; t += 7) {
         int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while (ti * (ti + 1) / 2 > t) --ti;
         while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
@@ -342,8 +340,8 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
         cp[0] -= c0;
         cp[1] -= c1;
       }
-      __syncthreads();
     }
+    __syncthreads();  // trailing matrix and Dinv complete
   }
 #pragma unroll 8
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
