@@ -213,7 +213,7 @@ potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restri
 constexpr int L2S = 132;   // row stride of the 128x128 matrix in smem (== 4 mod 16: conflict-free fragment reads)
 constexpr int DIS = 36;    // row stride of a 32x32 diagonal-block inverse
 constexpr int T2S = 68;    // row stride of the 64x64 scratch
-constexpr int LEAF2_SMEM = (LB * L2S + 4 * 32 * DIS + 64 * T2S + 32) * (int)sizeof(double);
+constexpr int LEAF2_SMEM = (LB * L2S + 4 * 32 * DIS + 64 * T2S + LB) * (int)sizeof(double);
 
 // C[M x N] (ldc) = alpha * A[M x K] (row-major, lda) * B[K x N] (row-major, ldb); 8x8 tiles over the CTA's 8 warps
 __device__ __forceinline__ void cta_mm(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
@@ -238,7 +238,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   double* S = sm;                       // [128][L2S]  A -> L -> inverse, in place
   double* DI = S + LB * L2S;            // [4][32][DIS] inverses of the diagonal blocks
   double* T = DI + 4 * 32 * DIS;        // [64][T2S]
-  double* rds = T + 64 * T2S;           // [32] reciprocals of the current diagonal block's pivots
+  double* rds = T + 64 * T2S;           // [128] reciprocals of the pivots, per diagonal block
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lq = lane & 3;
 
@@ -254,8 +254,20 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   }
   __syncthreads();
 
+  // Roles inside the CTA.  The column-by-column elimination of a 32 x 32 diagonal block is a latency chain that one
+  // warp must walk alone (warp 0, the eliminator); everything else is arranged so that the chain waits for as little
+  // as possible:
+  //   warp 7 (inverter): the inverse of the block just eliminated -- needed only for the packed inverse at the end;
+  //   warps 1..6 (workers): the panel below it (forward substitution, one thread per row), then the trailing update
+  //     on DMMA -- FIRST the ten 8 x 8 tiles of the NEXT diagonal block, after which the eliminator is released
+  //     (barrier 2) while the rest of the trailing update continues.
+  // Barrier 0 (__syncthreads): the eliminated block and its pivot reciprocals are visible, and all work of the
+  // previous block has ended.  Barrier 1 (workers, 192 threads): panel complete.  Barrier 2 (eliminator + workers,
+  // 224 threads): next diagonal block up to date.  The pivot reciprocals are kept per block: the inverter may still
+  // read block jb's while the eliminator writes block jb + 32's.
   for (int jb = 0; jb < LB; jb += 32) {
     double* Dinv = DI + (jb >> 5) * 32 * DIS;
+    double* rd_blk = rds + jb;
     if (warp == 0) {
       // ---- 32x32 diagonal block: lane = row; right-looking elimination through shuffles ----
       double a[32];
@@ -268,7 +280,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
         const double rd = rsqrt(piv);  // NaN for a non-PD pivot: propagates like JAX
         if (lane == c) {
           a[c] = piv * rd;
-          rds[c] = rd;
+          rd_blk[c] = rd;
         } else if (lane > c) {
           a[c] *= rd;
         }
@@ -287,11 +299,10 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
       for (int c = 0; c < 32; ++c)
         if (c <= lane) rowo[c] = a[c];
     }
-    __syncthreads();  // L11 and the pivot reciprocals are visible
+    __syncthreads();  // barrier 0
     const int r0 = jb + 32, R = LB - r0;  // rows below the block
-    if (warp == 0) {
-      // ---- inverse of the diagonal block, OFF the panel's path (the panel below is solved by substitution): lane =
-      // column j of X, forward substitution; L[r][k] is a broadcast read of smem ----
+    if (warp == 7) {
+      // ---- inverse of the diagonal block: lane = column j of X, forward substitution; L[r][k] is a broadcast read ----
       double x[32];
       const double* Lb = S + jb * L2S + jb;
 #pragma unroll
@@ -300,33 +311,34 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
 #pragma unroll
         for (int k = 0; k < 32; ++k)
           if (k < r) v[k & 3] -= Lb[r * L2S + k] * x[k];
-        x[r] = (r >= lane) ? ((v[0] + v[1]) + (v[2] + v[3])) * rds[r] : 0.0;
+        x[r] = (r >= lane) ? ((v[0] + v[1]) + (v[2] + v[3])) * rd_blk[r] : 0.0;
       }
 #pragma unroll
       for (int r = 0; r < 32; ++r) Dinv[r * DIS + lane] = x[r];
     } else if (R > 0) {
-      // ---- panel: L21 = A21 L11^-T by forward substitution, one thread per row (warps 1..3), L11[c][k] a broadcast
-      // read; the packed inverse is not needed here, so warp 0 computes it meanwhile ----
-      const int pr = tid - 32;
-      if (pr < R) {
-        double* arow = S + (r0 + pr) * L2S + jb;
-        const double* Lb = S + jb * L2S + jb;
-        double xr[32];
+      if (warp != 0) {
+        // ---- panel: L21 = A21 L11^-T by forward substitution, one thread per row (warps 1..3) ----
+        const int pr = tid - 32;
+        if (pr < R) {
+          double* arow = S + (r0 + pr) * L2S + jb;
+          const double* Lb = S + jb * L2S + jb;
+          double xr[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          double v[4] = {arow[c], 0.0, 0.0, 0.0};
+          for (int c = 0; c < 32; ++c) {
+            double v[4] = {arow[c], 0.0, 0.0, 0.0};
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (k < c) v[k & 3] -= xr[k] * Lb[c * L2S + k];
-          xr[c] = ((v[0] + v[1]) + (v[2] + v[3])) * rds[c];
+            for (int k = 0; k < 32; ++k)
+              if (k < c) v[k & 3] -= xr[k] * Lb[c * L2S + k];
+            xr[c] = ((v[0] + v[1]) + (v[2] + v[3])) * rd_blk[c];
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) arow[c] = xr[c];
         }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) arow[c] = xr[c];
+        asm volatile("bar.sync 1, 192;" ::: "memory");  // workers: the panel is complete
       }
-      asm volatile("bar.sync 1, 224;" ::: "memory");  // warps 1..7: the panel is complete
-      // ---- trailing update: A22 -= L21 L21^T on the lower 8x8 tiles (warps 1..7) ----
+      // ---- trailing update A22 -= L21 L21^T on the lower 8 x 8 tiles: tiles 0..9 are the next diagonal block ----
       const int nt = R >> 3, ntiles = nt * (nt + 1) / 2;
-      for (int t = warp - 1; t < ntiles; t += 7) {
+      auto tile = [&](int t) {
         int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while (ti * (ti + 1) / 2 > t) --ti;
         while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
@@ -339,10 +351,15 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
         double* cp = S + (r0 + ti * 8 + lr) * L2S + r0 + tj * 8 + 2 * lq;
         cp[0] -= c0;
         cp[1] -= c1;
-      }
+      };
+      if (warp != 0)
+        for (int t = warp - 1; t < 10; t += 6) tile(t);
+      asm volatile("bar.sync 2, 224;" ::: "memory");  // the next diagonal block is up to date: release the eliminator
+      if (warp != 0)
+        for (int t = 10 + warp - 1; t < ntiles; t += 6) tile(t);
     }
-    __syncthreads();  // trailing matrix and Dinv complete
   }
+  __syncthreads();  // the last inverse (warp 7) is complete
 #pragma unroll 8
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
     const int i = idx >> 7, k = idx & (LB - 1);
