@@ -72,6 +72,7 @@ int gpxb_ctx_destroy(gpxb_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->crit) cudaStreamDestroy(c->crit);
+  if (c->head_counter) cudaFree(c->head_counter);
   for (int i = 0; i < 3; ++i)
     if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);

@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(256) panel_trsm32_kernel(double* __restrict__ 
     for (int nf = 0; nf < 2; ++nf) c[mf][nf][0] = c[mf][nf][1] = 0.0;
   const double* ap = sB + lr * PSL + lq;
   const double* bp = sI + (warp * 16 + lr) * PSL + lq;
-  const int kend = (jb + 3) & ~3;
+  const int kend = min((jb + 3) & ~3, warp * 16 + 16);  // inv is lower triangular: inv[n][k] = 0 for k > n
   for (int k = 0; k < kend; k += 4) {
     double a[4], b[2];
 #pragma unroll
@@ -1039,6 +1039,125 @@ __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restr
   }
 }
 
+// Both links in ONE launch (the common case: the next block's columns are inside the panel): CTA (ti, tj), tj <= ti,
+// solves the two 32-row pieces ti and tj of the head rows against inv^T itself (a 32 x 128 x 128 triangular product
+// is 0.5 MFLOP: cheaper than a kernel boundary), keeps them in shared memory, subtracts their product from its
+// 32 x 32 tile of the next diagonal block, and -- diagonal CTAs only -- writes its solved rows back.  One dependent
+// launch less per 128 columns and no second trip of the head rows through L2.
+constexpr int HEAD_SMEM = (LB + 64) * PSL * (int)sizeof(double);
+
+// The head rows are solved IN PLACE while other CTAs of the same launch still have to read their unsolved values:
+// every CTA announces the end of its loads on a ticket counter, and a diagonal CTA writes back only when all CTAs of
+// the launch have announced (the launches are ordered on one stream, so `target` = CTAs of all launches so far; ten
+// CTAs are always co-resident or become so as independent kernels drain).
+__global__ void __launch_bounds__(256) panel_head_kernel(double* __restrict__ B, long long ldb, int nbn, int jb,
+                                                         const double* __restrict__ inv, double* __restrict__ C,
+                                                         long long ldc, unsigned long long* __restrict__ counter,
+                                                         unsigned long long target) {
+  extern __shared__ __align__(16) double psm[];
+  double* sI = psm;                   // [128][PSL]
+  double* sBi = psm + LB * PSL;       // [32][PSL] rows of piece ti, then their solved values
+  double* sBj = sBi + 32 * PSL;       // [32][PSL] rows of piece tj
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lq = lane & 3;
+  int ti = 0, t = blockIdx.x;
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  const int tj = t - ti * (ti + 1) / 2;
+  const bool diag = (ti == tj);
+  const int ri = ti * 32, rj = tj * 32;
+#pragma unroll 8
+  for (int idx = tid; idx < LB * LB / 2; idx += 256) {
+    const int i = idx >> 6, k2 = (idx & 63) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(inv + i * LB + k2);
+    sI[i * PSL + k2] = v.x;
+    sI[i * PSL + k2 + 1] = v.y;
+  }
+#pragma unroll 4
+  for (int idx = tid; idx < 32 * LB; idx += 256) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    sBi[i * PSL + k] = (ri + i < nbn && k < jb) ? B[(long long)(ri + i) * ldb + k] : 0.0;
+    if (!diag) sBj[i * PSL + k] = (rj + i < nbn && k < jb) ? B[(long long)(rj + i) * ldb + k] : 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) {  // this CTA holds its copies of the unsolved rows
+    __threadfence();
+    atomicAdd(counter, 1ULL);
+  }
+  // ---- the two solves: X = B inv^T, warp w owns columns 16 w .. 16 w + 15 ----
+  double ci[4][2][2], cj[4][2][2];
+#pragma unroll
+  for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) ci[mf][nf][0] = ci[mf][nf][1] = cj[mf][nf][0] = cj[mf][nf][1] = 0.0;
+  {
+    const double* bp = sI + (warp * 16 + lr) * PSL + lq;
+    const double* api = sBi + lr * PSL + lq;
+    const double* apj = sBj + lr * PSL + lq;
+    const int kend = min((jb + 3) & ~3, warp * 16 + 16);
+    for (int k = 0; k < kend; k += 4) {
+      double b[2];
+#pragma unroll
+      for (int nf = 0; nf < 2; ++nf) b[nf] = bp[nf * 8 * PSL + k];
+#pragma unroll
+      for (int mf = 0; mf < 4; ++mf) {
+        const double a = api[mf * 8 * PSL + k];
+#pragma unroll
+        for (int nf = 0; nf < 2; ++nf) dmma884(ci[mf][nf][0], ci[mf][nf][1], a, b[nf]);
+      }
+      if (!diag) {
+#pragma unroll
+        for (int mf = 0; mf < 4; ++mf) {
+          const double a = apj[mf * 8 * PSL + k];
+#pragma unroll
+          for (int nf = 0; nf < 2; ++nf) dmma884(cj[mf][nf][0], cj[mf][nf][1], a, b[nf]);
+        }
+      }
+    }
+  }
+  if (diag && tid == 0) {  // in-place write-back only after every CTA of this launch has read (bounded wait)
+    unsigned long long v;
+    long long spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+      if (++spins > (1LL << 31)) __trap();
+    } while (v < target);
+  }
+  __syncthreads();  // every warp has read the unsolved rows (and, diagonal CTAs: so has every other CTA)
+#pragma unroll
+  for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < 2; ++nf) {
+      const int col = warp * 16 + nf * 8 + 2 * lq, r = mf * 8 + lr;
+      sBi[r * PSL + col] = ci[mf][nf][0];
+      sBi[r * PSL + col + 1] = ci[mf][nf][1];
+      if (!diag) {
+        sBj[r * PSL + col] = cj[mf][nf][0];
+        sBj[r * PSL + col + 1] = cj[mf][nf][1];
+      } else if (ri + r < nbn) {  // the diagonal CTA of a piece owns its write-back
+        if (col < jb) B[(long long)(ri + r) * ldb + col] = ci[mf][nf][0];
+        if (col + 1 < jb) B[(long long)(ri + r) * ldb + col + 1] = ci[mf][nf][1];
+      }
+    }
+  __syncthreads();
+  // ---- C[ti][tj] -= X_i X_j^T: 16 fragments of 8 x 8 over 8 warps ----
+  const double* sXj = diag ? sBi : sBj;
+  const int mf = warp & 3;
+  const int kend = (jb + 3) & ~3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int nf = (warp >> 2) * 2 + h;
+    const double* ap = sBi + (mf * 8 + lr) * PSL + lq;
+    const double* bp = sXj + (nf * 8 + lr) * PSL + lq;
+    double c0 = 0.0, c1 = 0.0;
+    for (int k = 0; k < kend; k += 4) dmma884(c0, c1, ap[k], bp[k]);
+    const int row = ri + mf * 8 + lr, col = rj + nf * 8 + 2 * lq;
+    if (row < nbn) {
+      if (col <= row) C[(long long)row * ldc + col] -= c0;
+      if (col + 1 <= row) C[(long long)row * ldc + col + 1] -= c1;
+    }
+  }
+}
+
 // Joins a forked stream back into the caller's stream on EVERY exit path: if a launch fails mid-loop the callers'
 // stream-ordered frees (DevBuf destructors on s) must still come after the work already queued on the side stream.
 struct StreamJoin {
@@ -1107,6 +1226,15 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
   StreamJoin join_crit{ctx, cs, s};
   GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_trsm32_kernel, TRSM32_SMEM));
   GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_syrk32_kernel, SYRK32_SMEM));
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_head_kernel, HEAD_SMEM));
+  // Default: head solve and head update as two launches.  GPXB_PANEL_HEAD=fused selects panel_head_kernel (both in
+  // one launch, every CTA solving the pieces it multiplies): measured equal within noise on potrf 2000 / 4096 / 8192
+  // (1.55 / 3.43 / 10.24 ms fused vs 1.52-1.55 / 3.39-3.46 / 10.17-10.29 ms split over two boxes) -- each of its ten CTAs stages the whole 128 x 128
+  // inverse -- so the simpler pair stays the default.
+  static const bool split_head = [] {
+    const char* e = getenv("GPXB_PANEL_HEAD");
+    return !(e && e[0] == 'f');
+  }();
   cudaEvent_t ev, ev_bulk_prev = nullptr;
   GPXB_TRY(ctx->next_event(&ev));
   GPXB_CUDA_CHECK(cudaEventRecord(ev, s));
@@ -1127,14 +1255,29 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
     const int nbn = min(LB, below);                    // rows of the next block (the "head")
     // ---- critical chain on cs ----
     if (ev_bulk_prev) GPXB_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_bulk_prev, 0));
-    panel_trsm32_kernel<<<ceil_div(nbn, 32), 256, TRSM32_SMEM, cs>>>(B, lda, nbn, jb, invj);
-    GPXB_LAUNCH_CHECK();
-    ctx->launches++;
-    if (wr > 0) {
-      const int nt = ceil_div(min(nbn, wr), 32);
-      panel_syrk32_kernel<<<nt * (nt + 1) / 2, 128, SYRK32_SMEM, cs>>>(B, lda, B + jb, lda, min(nbn, wr), jb);
+    if (wr >= nbn && !split_head) {
+      // both links in one launch: every CTA solves the head pieces it multiplies
+      const int nt = ceil_div(nbn, 32), nctas = nt * (nt + 1) / 2;
+      if (!ctx->head_counter) {
+        GPXB_CUDA_CHECK(cudaMalloc(&ctx->head_counter, sizeof(unsigned long long)));
+        GPXB_CUDA_CHECK(cudaMemsetAsync(ctx->head_counter, 0, sizeof(unsigned long long), cs));
+        ctx->head_ticket = 0;
+      }
+      ctx->head_ticket += (unsigned long long)nctas;
+      panel_head_kernel<<<nctas, 256, HEAD_SMEM, cs>>>(B, lda, nbn, jb, invj, B + jb, lda, ctx->head_counter,
+                                                        ctx->head_ticket);
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
+    } else {
+      panel_trsm32_kernel<<<ceil_div(nbn, 32), 256, TRSM32_SMEM, cs>>>(B, lda, nbn, jb, invj);
+      GPXB_LAUNCH_CHECK();
+      ctx->launches++;
+      if (wr > 0) {
+        const int nt = ceil_div(min(nbn, wr), 32);
+        panel_syrk32_kernel<<<nt * (nt + 1) / 2, 128, SYRK32_SMEM, cs>>>(B, lda, B + jb, lda, min(nbn, wr), jb);
+        GPXB_LAUNCH_CHECK();
+        ctx->launches++;
+      }
     }
     GPXB_TRY(ctx->next_event(&ev_head));
     GPXB_CUDA_CHECK(cudaEventRecord(ev_head, cs));

@@ -71,6 +71,10 @@ struct Ctx {
   int num_sms = 148;
   cudaStream_t side = nullptr;  // high-priority stream (panel factorisation look-ahead)
   cudaStream_t crit = nullptr;  // high-priority stream of the leaf -> head-solve -> head-update chain inside a panel
+  // ticket counter of panel_head_kernel (chol.cu): CTAs of launch k have all read their inputs once the device
+  // counter reaches the sum of the CTA counts of launches 0..k (launches are ordered on `crit`)
+  unsigned long long* head_counter = nullptr;
+  unsigned long long head_ticket = 0;
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // concurrent branches of the triangular inverse
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_pool;  // reusable timing-free events, grown on demand
