@@ -38,7 +38,7 @@ struct GemmParams {
   double* C;
   long long ldc;
   double alpha, beta;
-  int lower_only, klo_mode, khi_mode, skip_tile0;
+  int lower_only, klo_mode, khi_mode, skip_tile0, tri_group;
   int tiles_m, tiles_n;
   int vecA, vecB, vecC;
   long long strideA, strideB, strideC;  // batched launch: blockIdx.y selects the product
@@ -152,7 +152,28 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
     // trapezoid (M >= N): tiles_n*(tiles_n+1)/2 triangular tiles, then full tile rows
     const long long t = blockIdx.x;
     const long long ntri = (long long)p.tiles_n * (p.tiles_n + 1) / 2;
-    if (t < ntri) {
+    if (t < ntri && p.tri_group > 1) {
+      // grouped raster on the triangle (as on the rectangle below): tile rows in groups of G, column-major inside a
+      // group, so that concurrently resident CTAs share B column panels as well as A row panels
+      const int G = p.tri_group;
+      long long g = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5) / G;  // first guess from the row index
+      auto before = [&](long long gg) { const long long r = gg * G; return r * (r + 1) / 2; };
+      while (before(g) > t) --g;
+      while (before(g + 1) <= t && (g + 1) * G < p.tiles_n) ++g;
+      const int row_lo = (int)(g * G), rows = min(G, p.tiles_n - row_lo);
+      long long u = t - before(g);
+      const long long full = (long long)rows * row_lo;  // columns left of the group's own diagonal block: all rows
+      if (u < full) {
+        tj = (int)(u / rows);
+        ti = row_lo + (int)(u % rows);
+      } else {
+        u -= full;  // the rows x rows lower triangle on the diagonal, column-major: column c holds rows c .. rows-1
+        int c = 0;
+        while (u >= rows - c) { u -= rows - c; ++c; }
+        tj = row_lo + c;
+        ti = row_lo + c + (int)u;
+      }
+    } else if (t < ntri) {
       long long i = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
       while (i * (i + 1) / 2 > t) --i;
       while ((i + 1) * (i + 2) / 2 <= t) ++i;
@@ -363,6 +384,16 @@ int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream) {
   p.alpha = g.alpha; p.beta = g.beta;
   p.lower_only = g.lower_only; p.klo_mode = g.klo_mode; p.khi_mode = g.khi_mode;
   p.skip_tile0 = g.lower_only ? g.skip_tile0 : 0;
+  static const int tri_group = [] {
+    // tile rows per raster group on the lower triangle; 1 (default): row-major.  Measured on the trailing-update
+    // shapes (tools/bench_syrk.py, profiles/r2_syrk_raster.jsonl): groups of 4 / 8 / 16 change nothing (31.7 vs
+    // 31.8 TFLOP/s at n = 16384, K = 1024) -- the 134 MB operand is L2-resident either way; the gap to the square
+    // GEMM is per-tile prologue / read-modify-write epilogue at K = 1024, not operand locality.
+    const char* e = getenv("GPXB_GEMM_TRI_GROUP");
+    const int v = e ? atoi(e) : 1;
+    return v >= 1 && v <= 64 ? v : 1;
+  }();
+  p.tri_group = (g.skip_tile0 || g.klo_mode || g.khi_mode) ? 1 : tri_group;  // tile 0 must stay block 0 when it is skipped
   p.tiles_m = ceil_div(g.M, BM);
   p.tiles_n = ceil_div(g.N, BN);
   GPXB_ARG_CHECK(g.batch >= 1 && g.batch <= 65535, -4);
