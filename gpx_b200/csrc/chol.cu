@@ -232,8 +232,35 @@ __device__ __forceinline__ void cta_mm(double* C, int ldc, const double* A, int 
   }
 }
 
+// The merge levels of the packed inverse: S holds L with its four 32 x 32 diagonal blocks already replaced by their
+// inverses; X21 = -X22 (L21 X11) for the 32 -> 64 and 64 -> 128 levels on DMMA, then the 128 x 128 block goes to inv.
+__device__ __forceinline__ void leaf_merge_and_store(double* S, double* T, int n, double* __restrict__ inv, int tid,
+                                                     int warp, int lane, bool skip_diag_blocks) {
+  for (int p = 0; p < LB; p += 64)  // T_p = L21 X11   (32 x 32 x 32)
+    cta_mm(T + (p >> 1) * T2S, T2S, S + (p + 32) * L2S + p, L2S, S + p * L2S + p, L2S, 32, 32, 32, 1.0, warp, lane);
+  __syncthreads();
+  for (int p = 0; p < LB; p += 64)  // X21 = -X22 T_p
+    cta_mm(S + (p + 32) * L2S + p, L2S, S + (p + 32) * L2S + p + 32, L2S, T + (p >> 1) * T2S, T2S, 32, 32, 32, -1.0,
+           warp, lane);
+  __syncthreads();
+  cta_mm(T, T2S, S + 64 * L2S, L2S, S, L2S, 64, 64, 64, 1.0, warp, lane);
+  __syncthreads();
+  cta_mm(S + 64 * L2S, L2S, S + 64 * L2S + 64, L2S, T, T2S, 64, 64, 64, -1.0, warp, lane);
+  __syncthreads();
+#pragma unroll 8
+  for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    if (skip_diag_blocks && (i >> 5) == (k >> 5)) continue;  // final already, and being read by the head solve
+    inv[idx] = (i < n && k <= i) ? S[i * L2S + k] : 0.0;
+  }
+}
+
+// merge == 0: the kernel stops after the factor and the four diagonal-block inverses (written into the diagonal
+// 32 x 32 blocks of inv): the merge levels and the 128 KB store of the packed inverse leave the panel's dependency
+// chain -- the head rows are solved by blocked substitution on L and those four blocks (panel_trsm32s_kernel), and
+// potrf_leaf_merge_kernel completes inv beside the chain, before the tall solve needs it.
 __global__ void __launch_bounds__(LEAF_NT, 1)
-potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv) {
+potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv, int merge) {
   extern __shared__ __align__(16) double sm[];
   double* S = sm;                       // [128][L2S]  A -> L -> inverse, in place
   double* DI = S + LB * L2S;            // [4][32][DIS] inverses of the diagonal blocks
@@ -366,29 +393,41 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
     if (i < n && k <= i) A[(long long)i * lda + k] = S[i * L2S + k];
   }
   if (inv == nullptr) return;
+  if (!merge) {  // the four diagonal-block inverses only (the rest of the block is written by potrf_leaf_merge_kernel)
+    for (int idx = tid; idx < 4 * 32 * 32; idx += LEAF_NT) {
+      const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
+      inv[(b * 32 + r) * LB + b * 32 + c] = DI[(b * 32 + r) * DIS + c];
+    }
+    return;
+  }
   __syncthreads();
-  // ---- inverse in place: diagonal blocks, then X21 = -X22 (L21 X11) for the 32 -> 64 and 64 -> 128 merges ----
+  // ---- inverse in place: diagonal blocks, then the merge levels ----
   for (int idx = tid; idx < 4 * 32 * 32; idx += LEAF_NT) {
     const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
     S[(b * 32 + r) * L2S + b * 32 + c] = DI[(b * 32 + r) * DIS + c];
   }
   __syncthreads();
-  for (int p = 0; p < LB; p += 64)  // T_p = L21 X11   (32 x 32 x 32)
-    cta_mm(T + (p >> 1) * T2S, T2S, S + (p + 32) * L2S + p, L2S, S + p * L2S + p, L2S, 32, 32, 32, 1.0, warp, lane);
-  __syncthreads();
-  for (int p = 0; p < LB; p += 64)  // X21 = -X22 T_p
-    cta_mm(S + (p + 32) * L2S + p, L2S, S + (p + 32) * L2S + p + 32, L2S, T + (p >> 1) * T2S, T2S, 32, 32, 32, -1.0,
-           warp, lane);
-  __syncthreads();
-  cta_mm(T, T2S, S + 64 * L2S, L2S, S, L2S, 64, 64, 64, 1.0, warp, lane);
-  __syncthreads();
-  cta_mm(S + 64 * L2S, L2S, S + 64 * L2S + 64, L2S, T, T2S, 64, 64, 64, -1.0, warp, lane);
-  __syncthreads();
+  leaf_merge_and_store(S, T, n, inv, tid, warp, lane, false);
+}
+
+// Completes the packed inverse of a leaf factorised with merge == 0: L from A (lower triangle, identity padding beyond
+// n), the diagonal-block inverses from inv, merge levels, store.  One CTA, beside the panel's dependency chain.
+__global__ void __launch_bounds__(LEAF_NT, 1)
+potrf_leaf_merge_kernel(const double* __restrict__ A, long long lda, int n, double* __restrict__ inv) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;
+  double* T = S + LB * L2S + 4 * 32 * DIS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll 8
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
     const int i = idx >> 7, k = idx & (LB - 1);
-    inv[idx] = (i < n && k <= i) ? S[i * L2S + k] : 0.0;
+    double v = 0.0;
+    if ((i >> 5) == (k >> 5)) v = inv[idx];                      // diagonal 32 x 32 blocks: their inverses
+    else if (i < n && k < i) v = A[(long long)i * lda + k];      // below them: L
+    S[i * L2S + k] = v;
   }
+  __syncthreads();
+  leaf_merge_and_store(S, T, n, inv, tid, warp, lane, true);
 }
 
 __global__ void logdet_kernel(const double* __restrict__ L, long long ld, int n,
@@ -400,21 +439,36 @@ __global__ void logdet_kernel(const double* __restrict__ L, long long ld, int n,
   if (threadIdx.x == 0) *out = scale * s;
 }
 
-int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s) {
+int leaf_generation() {
   static int gen = -1;
   if (gen < 0) {
     const char* e = getenv("GPXB_LEAF");  // "v1": the register-panel leaf kept for comparison
     gen = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
   }
+  return gen;
+}
+
+// merge == 0 (second-generation leaf only): inv receives the four 32 x 32 diagonal-block inverses; leaf_merge
+// completes it later
+int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s, int merge = 1) {
+  const int gen = leaf_generation();
   if (gen == 2) {
     GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(potrf_leaf_dmma_kernel), LEAF2_SMEM));
-    potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv);
+    potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv, merge);
     GPXB_LAUNCH_CHECK();
     ctx->launches++;
     return 0;
   }
   GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(potrf_leaf_kernel), LEAF_SMEM));
   potrf_leaf_kernel<<<1, LEAF_NT, LEAF_SMEM, s>>>(A, lda, n, inv);
+  GPXB_LAUNCH_CHECK();
+  ctx->launches++;
+  return 0;
+}
+
+int leaf_merge(Ctx* ctx, const double* A, long long lda, int n, double* inv, cudaStream_t s) {
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(potrf_leaf_merge_kernel), LEAF2_SMEM));
+  potrf_leaf_merge_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv);
   GPXB_LAUNCH_CHECK();
   ctx->launches++;
   return 0;
@@ -986,6 +1040,77 @@ __global__ void __launch_bounds__(256) panel_trsm32_kernel(double* __restrict__ 
   }
 }
 
+// The same solve from L itself and the four 32 x 32 diagonal-block inverses (the leaf's merge-less mode): blocked
+// forward substitution over the four column blocks,  X_q = (B_q - sum_{p<q} X_p L_qp^T) D_q^-T,  both products on
+// DMMA from shared memory.  Lj: the factorised diagonal block in A (ld ldl); dinv: inv with (at least) its diagonal
+// 32 x 32 blocks valid.  One CTA per 32 rows.
+constexpr int TRSM32S_SMEM = ((LB + 32) * PSL + 4 * 32 * 36 + 32 * 36) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256) panel_trsm32s_kernel(double* __restrict__ B, long long ldb, int rows, int jb,
+                                                            const double* __restrict__ Lj, long long ldl,
+                                                            const double* __restrict__ dinv) {
+  extern __shared__ __align__(16) double psm[];
+  double* sL = psm;                    // [128][PSL] lower triangle of L (identity beyond jb)
+  double* sX = sL + LB * PSL;          // [32][PSL]  B rows -> X in place
+  double* sD = sX + 32 * PSL;          // [4][32][36] diagonal-block inverses
+  double* sR = sD + 4 * 32 * 36;       // [32][36]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lq = lane & 3;
+  const int r0 = blockIdx.x * 32;
+#pragma unroll 8
+  for (int idx = tid; idx < LB * LB; idx += 256) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    double v = 0.0;
+    if (i < jb) { if (k < i) v = Lj[(long long)i * ldl + k]; }
+    else if (k == i) v = 1.0;
+    sL[i * PSL + k] = v;
+  }
+  for (int idx = tid; idx < 4 * 32 * 32; idx += 256) {
+    const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
+    sD[(b * 32 + r) * 36 + c] = dinv[(b * 32 + r) * LB + b * 32 + c];
+  }
+#pragma unroll 4
+  for (int idx = tid; idx < 32 * LB; idx += 256) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    sX[i * PSL + k] = (r0 + i < rows && k < jb) ? B[(long long)(r0 + i) * ldb + k] : 0.0;
+  }
+  __syncthreads();
+  const int mf = warp & 3, nf0 = (warp >> 2) * 2;  // this warp's two 8 x 8 fragments of a 32 x 32 block
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // R = B_q - X_{<q} L_{q,<q}^T
+      const int nf = nf0 + h;
+      const double* ap = sX + (mf * 8 + lr) * PSL + lq;
+      const double* bp = sL + (q * 32 + nf * 8 + lr) * PSL + lq;  // B[k][n] = L[n][k]
+      double c0 = 0.0, c1 = 0.0;
+      for (int k = 0; k < 32 * q; k += 4) dmma884(c0, c1, ap[k], bp[k]);
+      const double* xp = sX + (mf * 8 + lr) * PSL + q * 32 + nf * 8 + 2 * lq;
+      double* rp = sR + (mf * 8 + lr) * 36 + nf * 8 + 2 * lq;
+      rp[0] = xp[0] - c0;
+      rp[1] = xp[1] - c1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // X_q = R D_q^-T
+      const int nf = nf0 + h;
+      const double* ap = sR + (mf * 8 + lr) * 36 + lq;
+      const double* bp = sD + (q * 32 + nf * 8 + lr) * 36 + lq;   // B[k][n] = Dinv[n][k]
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) dmma884(c0, c1, ap[k], bp[k]);
+      double* xp = sX + (mf * 8 + lr) * PSL + q * 32 + nf * 8 + 2 * lq;
+      xp[0] = c0;
+      xp[1] = c1;
+    }
+    __syncthreads();
+  }
+#pragma unroll 4
+  for (int idx = tid; idx < 32 * LB; idx += 256) {
+    const int i = idx >> 7, k = idx & (LB - 1);
+    if (r0 + i < rows && k < jb) B[(long long)(r0 + i) * ldb + k] = sX[i * PSL + k];
+  }
+}
+
 // C[nbn x nbn] (lower) -= P P^T, P = [nbn x jb] row-major (ld ldp): one CTA per 32 x 32 tile of the lower
 // triangle, 4 warps x (16 x 16).
 __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restrict__ P, long long ldp,
@@ -1227,6 +1352,15 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
   GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_trsm32_kernel, TRSM32_SMEM));
   GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_syrk32_kernel, SYRK32_SMEM));
   GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_head_kernel, HEAD_SMEM));
+  GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)panel_trsm32s_kernel, TRSM32S_SMEM));
+  // GPXB_LEAF_SPLIT=1: merge-less leaf + substitution head solve + merge kernel beside the chain.  Measured SLOWER
+  // than the leaf that finishes its own packed inverse (potrf 2000 / 4096 / 8192: 1.69 / 3.76 / 11.0 ms against
+  // 1.52 / 3.39 / 10.2 ms): the substitution solve pays eight block barriers and a predicated load of L, and the
+  // merge launch delays the tall solve on the other stream.  Off by default, kept for the record.
+  static const bool no_split_leaf = [] {
+    const char* e = getenv("GPXB_LEAF_SPLIT");
+    return !(e && e[0] == '1');
+  }();
   // Default: head solve and head update as two launches.  GPXB_PANEL_HEAD=fused selects panel_head_kernel (both in
   // one launch, every CTA solving the pieces it multiplies): measured equal within noise on potrf 2000 / 4096 / 8192
   // (1.55 / 3.43 / 10.24 ms fused vs 1.52-1.55 / 3.39-3.46 / 10.17-10.29 ms split over two boxes) -- each of its ten CTAs stages the whole 128 x 128
@@ -1244,8 +1378,10 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
     const int c0 = k0 + j;
     double* Ajj = A + (long long)c0 * lda + c0;
     double* invj = inv + (long long)(c0 / LB) * LB * LB;
-    GPXB_TRY(leaf(ctx, Ajj, lda, jb, invj, cs));
     const int below = n - c0 - jb;
+    // merge-less leaf when a head solve follows: the merge levels of the packed inverse run on s, beside the chain
+    const bool split_leaf = below > 0 && jb == LB && leaf_generation() == 2 && !no_split_leaf;
+    GPXB_TRY(leaf(ctx, Ajj, lda, jb, invj, cs, split_leaf ? 0 : 1));
     if (below <= 0) continue;
     cudaEvent_t ev_leaf, ev_head;
     GPXB_TRY(ctx->next_event(&ev_leaf));
@@ -1255,7 +1391,7 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
     const int nbn = min(LB, below);                    // rows of the next block (the "head")
     // ---- critical chain on cs ----
     if (ev_bulk_prev) GPXB_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_bulk_prev, 0));
-    if (wr >= nbn && !split_head) {
+    if (wr >= nbn && !split_head && !split_leaf) {
       // both links in one launch: every CTA solves the head pieces it multiplies
       const int nt = ceil_div(nbn, 32), nctas = nt * (nt + 1) / 2;
       if (!ctx->head_counter) {
@@ -1269,7 +1405,8 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
     } else {
-      panel_trsm32_kernel<<<ceil_div(nbn, 32), 256, TRSM32_SMEM, cs>>>(B, lda, nbn, jb, invj);
+      if (split_leaf) panel_trsm32s_kernel<<<ceil_div(nbn, 32), 256, TRSM32S_SMEM, cs>>>(B, lda, nbn, jb, Ajj, lda, invj);
+      else panel_trsm32_kernel<<<ceil_div(nbn, 32), 256, TRSM32_SMEM, cs>>>(B, lda, nbn, jb, invj);
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
       if (wr > 0) {
@@ -1283,6 +1420,7 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
     GPXB_CUDA_CHECK(cudaEventRecord(ev_head, cs));
     // ---- bulk on s ----
     GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_leaf, 0));
+    if (split_leaf) GPXB_TRY(leaf_merge(ctx, Ajj, lda, jb, invj, s));  // the packed inverse, off the chain
     if (below > nbn) {
       GemmArgs g;  // rows below the head: B <- B inv^T (in place)
       g.M = below - nbn; g.N = jb; g.K = jb;
