@@ -157,9 +157,10 @@ def lml_iter(state, x, y, num_evals, num_lanczos, key_lanczos, n_pivots, key_pre
     kinds, ells, xl, prog = _leaf_desc(state, xd)
     sigma = float(np.asarray(state.params["sigma"].value))
     part = threefry_partitionable()
-    subkey, _ = split(as_key(key_lanczos), 2, part)
+    subkey, carried = split(as_key(key_lanczos), 2, part)
     U = ops.rademacher_probes(subkey, N, int(num_evals), part)
-    r = ops.gpr_iter_composite(kinds, ells, xl, prog, sigma, U=U, m=int(num_lanczos))
+    r = ops.gpr_iter_composite(kinds, ells, xl, prog, sigma, U=U, m=int(num_lanczos), restart_key=carried,
+                               restart_partitionable=part)
     if int(r["flag"].cpu().numpy()[0]) != 0:
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps than data points")
     res = yd.cpu().numpy().reshape(-1, 1) - mu

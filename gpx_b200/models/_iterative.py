@@ -146,9 +146,10 @@ def lml_derivs_iter(kind, xd, Jd, yd, ell, sigma, num_evals, num_lanczos, key_la
     n = yd.numel()
     c, _ = fit_derivs_iter(kind, xd, Jd, yd, ell, sigma, n_pivots, key_precond)
     quad = float((yd.reshape(-1) * c).sum().cpu())
-    subkey, _ = split(as_key(key_lanczos), 2, threefry_partitionable())
+    subkey, carried = split(as_key(key_lanczos), 2, threefry_partitionable())
     U = ops.rademacher_probes(subkey, n, int(num_evals), threefry_partitionable())
-    alpha, beta, flag = ops.lanczos_derivs(kind, xd, Jd, ell, sigma, U, int(num_lanczos))
+    alpha, beta, flag = ops.lanczos_derivs(kind, xd, Jd, ell, sigma, U, int(num_lanczos), restart_key=carried,
+                                           restart_partitionable=threefry_partitionable())
     if int(flag.cpu().numpy()[0]) != 0:
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps than rows")
     logdet = slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), n)

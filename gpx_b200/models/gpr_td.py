@@ -109,14 +109,17 @@ def _lml_iter(state, x, y, jacobian, y_derivs, num_evals, num_lanczos, key_lancz
     mu_h = float(mu.cpu().numpy()[0])
     ym = np.concatenate([np.asarray(y, dtype=np.float64).reshape(-1, 1) - mu_h, yd.reshape(-1, 1)])  # library order
     part = threefry_partitionable()
-    subkey, _ = split(as_key(key_lanczos), 2, part)
+    subkey, carried = split(as_key(key_lanczos), 2, part)
     U = ops.rademacher_probes(subkey, m, int(num_evals), part)
     if nv1 < nv:
         import torch
 
         U = U[torch.as_tensor(_ref_to_lib_perm(ns, nv1, nv - nv1), device=U.device)].contiguous()
+    # breakdown restart (lanczos.py:92-108) only with one block: with two, the reference's normal deviates follow its
+    # own row order
     alpha, beta, flag = ops.lanczos_td(kernel.kind, _to_device(x), _to_device(J), ell, st, sd, U, int(num_lanczos),
-                                       nv_first=nv1, sigma_derivs2=sd2)
+                                       nv_first=nv1, sigma_derivs2=sd2, restart_key=carried if nv1 == nv else None,
+                                       restart_partitionable=part)
     if int(flag.cpu().numpy()[0]) != 0:
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): the Krylov space is exhausted; "
                            "use fewer Lanczos steps than rows")

@@ -52,10 +52,12 @@ def _lml_iter_with_locs(state, xd, yd, x_locs_dev, num_evals, num_lanczos, key_l
 
     kernel, ell, sigma = _hyper(state)
     N = yd.shape[0]
-    subkey, _ = split(as_key(key_lanczos), 2, threefry_partitionable())
+    subkey, carried = split(as_key(key_lanczos), 2, threefry_partitionable())
     U = ops.rademacher_probes(subkey, N, int(num_evals), threefry_partitionable())
     quad, _, alpha, beta, flag = ops.sgpr_lml_iter_parts(kernel.kind, xd, yd, x_locs_dev, ell, sigma, U,
-                                                         int(num_lanczos), mean_mode(state.mean_function))
+                                                         int(num_lanczos), mean_mode(state.mean_function),
+                                                         restart_key=carried,
+                                                         restart_partitionable=threefry_partitionable())
     if int(flag.cpu().numpy()[0]) != 0:
         raise RuntimeError("Lanczos breakdown (beta <= 1e-12): use fewer Lanczos steps")
     logdet = slq_logdet(alpha.cpu().numpy(), beta.cpu().numpy(), N)

@@ -148,7 +148,8 @@ def rpcholesky_composite(kinds, ells, x_leaves, prog, n_pivots, key, partitionab
 
 
 def gpr_iter_composite(kinds, ells, x_leaves, prog, sigma, y=None, n_pivots=0, key=(0, 0), mean_mode=MEAN_DATA,
-                       partitionable=True, tol=1e-5, atol=1e-7, maxiter=0, U=None, m=0):
+                       partitionable=True, tol=1e-5, atol=1e-7, maxiter=0, U=None, m=0, restart_key=None,
+                       restart_partitionable=True):
     """The iterative GPR paths with a Sum / Prod kernel.  y given: PCG fit -> c (N, 1), mu (1,), iterations;
     U given: m-step block Lanczos on K + (sigma^2+1e-10) I -> alpha, beta (P, m), breakdown flag.
     Returns a dict with the parts that were asked for."""
@@ -175,18 +176,19 @@ def gpr_iter_composite(kinds, ells, x_leaves, prog, sigma, y=None, n_pivots=0, k
         alpha = torch.empty((P, m), dtype=torch.float64, device=dev)
         beta = torch.empty((P, m), dtype=torch.float64, device=dev)
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    check(
-        ctx.lib.gpxb_gpr_iter_composite(ctx.handle, L, kid, el, dd, px, N, pr, len(prog),
-                                        ptr(y) if y is not None else None, float(sigma), int(mean_mode), int(n_pivots),
-                                        int(key[0]), int(key[1]), int(bool(partitionable)), float(tol), float(atol),
-                                        int(maxiter), ptr(c) if c is not None else None,
-                                        ptr(mu) if mu is not None else None, ctypes.byref(iters),
-                                        ptr(U) if U is not None else None, U.stride(0) if U is not None else 0, P,
-                                        int(m), ptr(alpha) if alpha is not None else None,
-                                        ptr(beta) if beta is not None else None,
-                                        ptr(flag) if flag is not None else None, stream_ptr()),
-        "gpxb_gpr_iter_composite",
-    )
+    with _lanczos_restart(restart_key, restart_partitionable):
+        check(
+            ctx.lib.gpxb_gpr_iter_composite(ctx.handle, L, kid, el, dd, px, N, pr, len(prog),
+                                            ptr(y) if y is not None else None, float(sigma), int(mean_mode), int(n_pivots),
+                                            int(key[0]), int(key[1]), int(bool(partitionable)), float(tol), float(atol),
+                                            int(maxiter), ptr(c) if c is not None else None,
+                                            ptr(mu) if mu is not None else None, ctypes.byref(iters),
+                                            ptr(U) if U is not None else None, U.stride(0) if U is not None else 0, P,
+                                            int(m), ptr(alpha) if alpha is not None else None,
+                                            ptr(beta) if beta is not None else None,
+                                            ptr(flag) if flag is not None else None, stream_ptr()),
+            "gpxb_gpr_iter_composite",
+        )
     if y is not None:
         out.update(c=c, mu=mu, iters=iters.value)
     if U is not None:
@@ -531,7 +533,7 @@ def rpcholesky_derivs(kind, x, J, n_pivots, ell, key, partitionable=True, want_f
     return F, piv
 
 
-def lanczos_derivs(kind, x, J, ell, sigma, U, m):
+def lanczos_derivs(kind, x, J, ell, sigma, U, m, restart_key=None, restart_partitionable=True):
     """(alpha (P, m), beta (P, m), breakdown) of the block Lanczos on d01kj + (sigma^2+1e-10) I, matrix-free."""
     ctx = context()
     x, J, U = _f64(x), _f64(J), _f64(U)
@@ -542,11 +544,12 @@ def lanczos_derivs(kind, x, J, ell, sigma, U, m):
     alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
     flag = torch.zeros(1, dtype=torch.int32, device=x.device)
-    check(
-        ctx.lib.gpxb_lanczos_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), float(sigma), ptr(U),
-                                    U.stride(0), P, int(m), ptr(alpha), ptr(beta), ptr(flag), stream_ptr()),
-        "gpxb_lanczos_derivs",
-    )
+    with _lanczos_restart(restart_key, restart_partitionable):
+        check(
+            ctx.lib.gpxb_lanczos_derivs(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv, float(ell), float(sigma), ptr(U),
+                                        U.stride(0), P, int(m), ptr(alpha), ptr(beta), ptr(flag), stream_ptr()),
+            "gpxb_lanczos_derivs",
+        )
     return alpha, beta, flag
 
 
@@ -678,7 +681,8 @@ def gpr_td_fit_iter(kind, x, J, y, y_derivs, ell, sigma_targets, sigma_derivs, n
     return c, mu, iters.value
 
 
-def lanczos_td(kind, x, J, ell, sigma_targets, sigma_derivs, U, m, nv_first=None, sigma_derivs2=0.0):
+def lanczos_td(kind, x, J, ell, sigma_targets, sigma_derivs, U, m, nv_first=None, sigma_derivs2=0.0, restart_key=None,
+               restart_partitionable=True):
     """(alpha (P, m), beta (P, m), breakdown) of the block Lanczos on the GPR_TD operator, matrix-free."""
     ctx = context()
     x, J, U = _f64(x), _f64(J), _f64(U)
@@ -689,13 +693,14 @@ def lanczos_td(kind, x, J, ell, sigma_targets, sigma_derivs, U, m, nv_first=None
     alpha = torch.empty((P, m), dtype=torch.float64, device=x.device)
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
     flag = torch.zeros(1, dtype=torch.int32, device=x.device)
-    check(
-        ctx.lib.gpxb_lanczos_td(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv,
-                                int(nv if nv_first is None else nv_first), float(ell), float(sigma_targets),
-                                float(sigma_derivs), float(sigma_derivs2), ptr(U), U.stride(0), P, int(m), ptr(alpha),
-                                ptr(beta), ptr(flag), stream_ptr()),
-        "gpxb_lanczos_td",
-    )
+    with _lanczos_restart(restart_key, restart_partitionable):
+        check(
+            ctx.lib.gpxb_lanczos_td(ctx.handle, _kind(kind), ptr(x), ptr(J), N, nf, nv,
+                                    int(nv if nv_first is None else nv_first), float(ell), float(sigma_targets),
+                                    float(sigma_derivs), float(sigma_derivs2), ptr(U), U.stride(0), P, int(m), ptr(alpha),
+                                    ptr(beta), ptr(flag), stream_ptr()),
+            "gpxb_lanczos_td",
+        )
     return alpha, beta, flag
 
 
@@ -1015,7 +1020,8 @@ def sgpr_fit_iter(kind, x, y, x_locs, ell, sigma, mean_mode=MEAN_DATA, tol=1e-5,
     return c, mu, iters.value
 
 
-def sgpr_lml_iter_parts(kind, x, y, x_locs, ell, sigma, U, m, mean_mode=MEAN_DATA, tol=1e-5, atol=0.0, maxiter=0):
+def sgpr_lml_iter_parts(kind, x, y, x_locs, ell, sigma, U, m, mean_mode=MEAN_DATA, tol=1e-5, atol=0.0, maxiter=0,
+                        restart_key=None, restart_partitionable=True):
     """(quad (1,), iterations, alpha (P, m), beta (P, m), breakdown) on the Nystrom operator H + (sigma^2+1e-10) I."""
     import ctypes
 
@@ -1032,13 +1038,14 @@ def sgpr_lml_iter_parts(kind, x, y, x_locs, ell, sigma, U, m, mean_mode=MEAN_DAT
     beta = torch.empty((P, m), dtype=torch.float64, device=x.device)
     flag = torch.zeros(1, dtype=torch.int32, device=x.device)
     iters = ctypes.c_int(0)
-    check(
-        ctx.lib.gpxb_sgpr_lml_iter_parts(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, ptr(x_locs), x_locs.shape[0],
-                                         float(ell), float(sigma), int(mean_mode), float(tol), float(atol), int(maxiter),
-                                         ptr(quad), ctypes.byref(iters), ptr(U), U.stride(0), P, int(m), ptr(alpha),
-                                         ptr(beta), ptr(flag), stream_ptr()),
-        "gpxb_sgpr_lml_iter_parts",
-    )
+    with _lanczos_restart(restart_key, restart_partitionable):
+        check(
+            ctx.lib.gpxb_sgpr_lml_iter_parts(ctx.handle, _kind(kind), ptr(x), ptr(y), N, D, ptr(x_locs), x_locs.shape[0],
+                                             float(ell), float(sigma), int(mean_mode), float(tol), float(atol), int(maxiter),
+                                             ptr(quad), ctypes.byref(iters), ptr(U), U.stride(0), P, int(m), ptr(alpha),
+                                             ptr(beta), ptr(flag), stream_ptr()),
+            "gpxb_sgpr_lml_iter_parts",
+        )
     return quad, iters.value, alpha, beta, flag
 
 

@@ -391,3 +391,41 @@ def test_sgpr_rpchol_with_a_composite_kernel():
     pred = model.predict(xs)
     pref, _ = R.sgpr_composite_predict_dense(spec, xl, xs, c_ref, mu_ref, sigma)
     assert np.max(np.abs(pred - pref)) < 1e-6 * max(1.0, np.max(np.abs(pref)))
+
+
+def test_composite_lanczos_breakdown_branch():
+    """The breakdown restart (gpx/lanczos.py:92-108) lives in the shared Lanczos core: here through the composite
+    operator, on a kernel matrix that is exactly block diagonal (two far-apart groups of points)."""
+    import gpx_b200.kernels as K
+    from gpx_b200 import ops
+    from gpx_b200.models import _composite
+
+    rng = np.random.default_rng(12)
+    D, n1, n2 = 3, 5, 35
+    x = np.vstack([rng.standard_normal((n1, D)), 100.0 + rng.standard_normal((n2, D))])
+    N = n1 + n2
+    U = np.zeros((N, 2))
+    U[:n1, 0] = rng.standard_normal(n1)
+    U[:, 1] = rng.choice([-1.0, 1.0], N)
+    U /= np.linalg.norm(U, axis=0)
+    kernel = K.SquaredExponential() + K.Matern52()
+    ells, sigma, m = [1.0, 1.3], 0.3, 16
+    model = _model(kernel, ells, sigma)
+    spec = ("sum", ("leaf", "se", ells[0], None), ("leaf", "m52", ells[1], None))
+    A = R.composite_kernel(spec, x, x) + (sigma**2 + 1e-10) * np.eye(N)
+    d = torch.as_tensor(x).cuda()
+    kinds, el, xl, prog = _composite._leaf_desc(model.state, d)
+    key = R.PRNGKey(7)
+    r0 = ops.gpr_iter_composite(kinds, el, xl, prog, sigma, U=torch.as_tensor(U).cuda(), m=m)
+    assert int(r0["flag"].cpu()[0]) == 1
+    r = ops.gpr_iter_composite(kinds, el, xl, prog, sigma, U=torch.as_tensor(U).cuda(), m=m, restart_key=key)
+    assert int(r["flag"].cpu()[0]) == 0
+    alpha, beta = r["alpha"].cpu().numpy(), r["beta"].cpu().numpy()
+    hit = False
+    for p in range(2):
+        T, _ = R.lanczos_tridiagonal(lambda v: A @ v, m, U[:, p], key=key)
+        b_ref = np.diag(T, 1)
+        hit = hit or bool(np.any(b_ref <= 1e-12))
+        assert np.max(np.abs(alpha[p] - np.diag(T))) < 1e-8 * np.max(np.abs(np.diag(T)))
+        assert np.max(np.abs(beta[p, : m - 1] - b_ref)) < 1e-8 * np.max(b_ref)
+    assert hit
