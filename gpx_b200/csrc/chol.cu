@@ -210,6 +210,11 @@ potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restri
 // off-diagonal operation (panel solve against the inverted diagonal block, rank-32 trailing update, the two
 // merge levels of the inverse) runs on the FP64 tensor pipe from shared memory.  12 block barriers in the
 // factorisation instead of 256.
+#ifdef GPXB_LEAF_STAMPS  // developer build (tools/leaf_timing.cu): merge >> 8 names a phase after which the kernel returns
+#define LEAF_STAMP(k) do { if ((merge >> 8) == (k)) return; } while (0)
+#else
+#define LEAF_STAMP(k) do {} while (0)
+#endif
 constexpr int L2S = 132;   // row stride of the 128x128 matrix in smem (== 4 mod 16: conflict-free fragment reads)
 constexpr int DIS = 36;    // row stride of a 32x32 diagonal-block inverse
 constexpr int T2S = 68;    // row stride of the 64x64 scratch
@@ -232,20 +237,73 @@ __device__ __forceinline__ void cta_mm(double* C, int ldc, const double* A, int 
   }
 }
 
+// C = alpha * A B on (8 NT)^2 operands in shared memory with ONE lower-triangular factor.  A_LOWER: A is lower
+// triangular (k < 8 (w + 1)) and the warp owns tile row w; otherwise B is (k >= 8 w) and the warp owns tile column w.
+template <int NT, bool A_LOWER>
+__device__ __forceinline__ void tri_mm(double* C, int ldc, const double* A, int lda, const double* B, int ldb,
+                                       double alpha, int w, int lane) {
+  const int lr = lane >> 2, lq = lane & 3;
+#pragma unroll
+  for (int g = 0; g < NT; g += 4) {
+    double c0[4] = {0.0, 0.0, 0.0, 0.0}, c1[4] = {0.0, 0.0, 0.0, 0.0};
+    if (A_LOWER) {
+      const double* ap = A + (w * 8 + lr) * lda + lq;
+      const double* bp = B + lq * ldb + g * 8 + lr;
+      for (int k = 0; k < (w + 1) * 8; k += 4) {
+        const double a = ap[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dmma884(c0[q], c1[q], a, bp[k * ldb + q * 8]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double* cp = C + (w * 8 + lr) * ldc + (g + q) * 8 + 2 * lq;
+        cp[0] = alpha * c0[q];
+        cp[1] = alpha * c1[q];
+      }
+    } else {
+      const double* ap = A + (g * 8 + lr) * lda + lq;
+      const double* bp = B + lq * ldb + w * 8 + lr;
+      for (int k = w * 8; k < NT * 8; k += 4) {
+        const double b = bp[k * ldb];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dmma884(c0[q], c1[q], ap[q * 8 * lda + k], b);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double* cp = C + ((g + q) * 8 + lr) * ldc + w * 8 + 2 * lq;
+        cp[0] = alpha * c0[q];
+        cp[1] = alpha * c1[q];
+      }
+    }
+  }
+}
+
 // The merge levels of the packed inverse: S holds L with its four 32 x 32 diagonal blocks already replaced by their
 // inverses; X21 = -X22 (L21 X11) for the 32 -> 64 and 64 -> 128 levels on DMMA, then the 128 x 128 block goes to inv.
 __device__ __forceinline__ void leaf_merge_and_store(double* S, double* T, int n, double* __restrict__ inv, int tid,
-                                                     int warp, int lane, bool skip_diag_blocks) {
-  for (int p = 0; p < LB; p += 64)  // T_p = L21 X11   (32 x 32 x 32)
-    cta_mm(T + (p >> 1) * T2S, T2S, S + (p + 32) * L2S + p, L2S, S + p * L2S + p, L2S, 32, 32, 32, 1.0, warp, lane);
+                                                     int warp, int lane, bool skip_diag_blocks, bool bulk_out) {
+  // every product has one triangular factor: the k range is cut to its non-zero part (exact zeros skipped: the
+  // sums are unchanged) and each warp runs four independent accumulator chains that share one fragment load
+  {
+    const int p = (warp >> 2) * 64, q = warp & 3;
+    tri_mm<4, false>(T + (p >> 1) * T2S, T2S, S + (p + 32) * L2S + p, L2S, S + p * L2S + p, L2S, 1.0, q, lane);
+    __syncthreads();  // T_p = L21 X11   (32 x 32 x 32, X11 lower)
+    tri_mm<4, true>(S + (p + 32) * L2S + p, L2S, S + (p + 32) * L2S + p + 32, L2S, T + (p >> 1) * T2S, T2S, -1.0, q,
+                    lane);
+    __syncthreads();  // X21 = -X22 T_p  (X22 lower)
+  }
+  tri_mm<8, false>(T, T2S, S + 64 * L2S, L2S, S, L2S, 1.0, warp, lane);
   __syncthreads();
-  for (int p = 0; p < LB; p += 64)  // X21 = -X22 T_p
-    cta_mm(S + (p + 32) * L2S + p, L2S, S + (p + 32) * L2S + p + 32, L2S, T + (p >> 1) * T2S, T2S, 32, 32, 32, -1.0,
-           warp, lane);
-  __syncthreads();
-  cta_mm(T, T2S, S + 64 * L2S, L2S, S, L2S, 64, 64, 64, 1.0, warp, lane);
-  __syncthreads();
-  cta_mm(S + 64 * L2S, L2S, S + 64 * L2S + 64, L2S, T, T2S, 64, 64, 64, -1.0, warp, lane);
+  tri_mm<8, true>(S + 64 * L2S, L2S, S + 64 * L2S + 64, L2S, T, T2S, -1.0, warp, lane);
+  if (bulk_out) {  // S is the packed inverse exactly (zero upper triangle): one 1 KB bulk store per row
+    fence_proxy_async();
+    __syncthreads();
+    if (tid < LB) {
+      tma_bulk_s2g(inv + tid * LB, S + tid * L2S, LB * (int)sizeof(double));
+      tma_bulk_commit_wait_read();
+    }
+    return;
+  }
   __syncthreads();
 #pragma unroll 8
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
@@ -260,7 +318,8 @@ __device__ __forceinline__ void leaf_merge_and_store(double* S, double* T, int n
 // chain -- the head rows are solved by blocked substitution on L and those four blocks (panel_trsm32s_kernel), and
 // potrf_leaf_merge_kernel completes inv beside the chain, before the tall solve needs it.
 __global__ void __launch_bounds__(LEAF_NT, 1)
-potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv, int merge) {
+potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv, int merge,
+                       int leaf_bulk_io) {
   extern __shared__ __align__(16) double sm[];
   double* S = sm;                       // [128][L2S]  A -> L -> inverse, in place
   double* DI = S + LB * L2S;            // [4][32][DIS] inverses of the diagonal blocks
@@ -269,17 +328,40 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lq = lane & 3;
 
-  // lower triangle in, identity padding beyond n (keeps every block operation well defined); eight independent
-  // loads per thread in flight: the block comes from L2 / HBM and one CTA has no other latency hiding
+  LEAF_STAMP(0);
+  // A full, aligned leaf comes in by bulk TMA: row i up to the end of its diagonal 32 x 32 block (one 256..1024-byte
+  // copy per row, all 128 in flight at once; the element-wise loop below costs ~20 us of exposed L2 latency on the
+  // panel's critical chain), zeros to the right of it.  What lands above the diagonal inside the diagonal blocks is
+  // never read.
+  __shared__ __align__(8) uint64_t lbar;
+  const bool bulk = (n == LB) && ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && leaf_bulk_io;
+  if (bulk) {
+    if (tid == 0) {
+      mbar_init(&lbar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) mbar_arrive_expect_tx(&lbar, 32 * (256 + 512 + 768 + 1024));
+    if (tid < LB) tma_bulk_g2s(S + tid * L2S, A + (long long)tid * lda, ((tid >> 5) + 1) * 256, &lbar);
+    for (int idx = tid; idx < 96 * 96; idx += LEAF_NT) {  // rows 0..95, columns beyond the row's diagonal block
+      const int i = idx / 96, k = ((i >> 5) + 1) * 32 + (idx - i * 96);
+      if (k < LB) S[i * L2S + k] = 0.0;
+    }
+    mbar_wait(&lbar, 0);
+  } else {
+    // lower triangle in, identity padding beyond n (keeps every block operation well defined); eight independent
+    // loads per thread in flight
 #pragma unroll 8
-  for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
-    const int i = idx >> 7, k = idx & (LB - 1);
-    double v = 0.0;
-    if (i < n) { if (k <= i) v = A[(long long)i * lda + k]; }
-    else if (k == i) v = 1.0;
-    S[i * L2S + k] = v;
+    for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
+      const int i = idx >> 7, k = idx & (LB - 1);
+      double v = 0.0;
+      if (i < n) { if (k <= i) v = A[(long long)i * lda + k]; }
+      else if (k == i) v = 1.0;
+      S[i * L2S + k] = v;
+    }
   }
   __syncthreads();
+  LEAF_STAMP(1);
 
   // Roles inside the CTA.  The column-by-column elimination of a 32 x 32 diagonal block is a latency chain that one
   // warp must walk alone (warp 0, the eliminator); everything else is arranged so that the chain waits for as little
@@ -327,6 +409,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
         if (c <= lane) rowo[c] = a[c];
     }
     __syncthreads();  // barrier 0
+    LEAF_STAMP(4 + (jb >> 5) * 6);
     const int r0 = jb + 32, R = LB - r0;  // rows below the block
     if (warp == 7) {
       // ---- inverse of the diagonal block: lane = column j of X, forward substitution; L[r][k] is a broadcast read ----
@@ -385,15 +468,18 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
       if (warp != 0)
         for (int t = 10 + warp - 1; t < ntiles; t += 6) tile(t);
     }
+    LEAF_STAMP(7 + (jb >> 5) * 6);
   }
   __syncthreads();  // the last inverse (warp 7) is complete
+  LEAF_STAMP(27);
 #pragma unroll 8
   for (int idx = tid; idx < LB * LB; idx += LEAF_NT) {
     const int i = idx >> 7, k = idx & (LB - 1);
     if (i < n && k <= i) A[(long long)i * lda + k] = S[i * L2S + k];
   }
+  LEAF_STAMP(28);
   if (inv == nullptr) return;
-  if (!merge) {  // the four diagonal-block inverses only (the rest of the block is written by potrf_leaf_merge_kernel)
+  if (!(merge & 0xff)) {  // the four diagonal-block inverses only (the rest of the block is written by potrf_leaf_merge_kernel)
     for (int idx = tid; idx < 4 * 32 * 32; idx += LEAF_NT) {
       const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
       inv[(b * 32 + r) * LB + b * 32 + c] = DI[(b * 32 + r) * DIS + c];
@@ -407,7 +493,10 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
     S[(b * 32 + r) * L2S + b * 32 + c] = DI[(b * 32 + r) * DIS + c];
   }
   __syncthreads();
-  leaf_merge_and_store(S, T, n, inv, tid, warp, lane, false);
+  LEAF_STAMP(29);
+  leaf_merge_and_store(S, T, n, inv, tid, warp, lane, false,
+                       bulk && (reinterpret_cast<uintptr_t>(inv) & 15) == 0);
+  LEAF_STAMP(31);
 }
 
 // Completes the packed inverse of a leaf factorised with merge == 0: L from A (lower triangle, identity padding beyond
@@ -427,7 +516,7 @@ potrf_leaf_merge_kernel(const double* __restrict__ A, long long lda, int n, doub
     S[i * L2S + k] = v;
   }
   __syncthreads();
-  leaf_merge_and_store(S, T, n, inv, tid, warp, lane, true);
+  leaf_merge_and_store(S, T, n, inv, tid, warp, lane, true, false);
 }
 
 __global__ void logdet_kernel(const double* __restrict__ L, long long ld, int n,
@@ -437,6 +526,15 @@ __global__ void logdet_kernel(const double* __restrict__ L, long long ld, int n,
   for (int i = threadIdx.x; i < n; i += 1024) s += log(L[(long long)i * ld + i]);
   s = block_sum<1024>(s, sh);
   if (threadIdx.x == 0) *out = scale * s;
+}
+
+int leaf_bulk_io() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GPXB_LEAF_IO");  // "ldg": the element-wise load / store loops kept for comparison
+    on = (e && e[0] == 'l') ? 0 : 1;
+  }
+  return on;
 }
 
 int leaf_generation() {
@@ -454,7 +552,7 @@ int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s,
   const int gen = leaf_generation();
   if (gen == 2) {
     GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(potrf_leaf_dmma_kernel), LEAF2_SMEM));
-    potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv, merge);
+    potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv, merge, leaf_bulk_io());
     GPXB_LAUNCH_CHECK();
     ctx->launches++;
     return 0;
@@ -988,26 +1086,44 @@ constexpr int SYRK32_SMEM = 2 * 32 * PSL * (int)sizeof(double);
 // B[r0 : r0 + 32, 0 : jb) <- B[same] inv^T in place (C[i][n] = sum_k B[i][k] inv[n][k]); inv: packed 128 x 128 leaf
 // inverse (zero above the diagonal and beyond jb).  One CTA per 32 rows, 8 warps x (32 rows x 16 columns).
 __global__ void __launch_bounds__(256) panel_trsm32_kernel(double* __restrict__ B, long long ldb, int rows, int jb,
-                                                           const double* __restrict__ inv) {
+                                                           const double* __restrict__ inv, int bulk_io) {
   extern __shared__ __align__(16) double psm[];
   double* sB = psm;               // [32][PSL]
   double* sI = psm + 32 * PSL;    // [128][PSL]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lq = lane & 3;
   const int r0 = blockIdx.x * 32;
+  // Full, aligned pieces come in by bulk TMA -- 160 row copies in flight at once (inv: row i up to the end of its
+  // 16-column group, all the product reads); the element-wise loops cost several exposed L2 round trips on the
+  // panel's critical chain.
+  __shared__ __align__(8) uint64_t bar;
+  const bool bulk = bulk_io && jb == LB && r0 + 32 <= rows && (ldb & 1) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(inv)) & 15) == 0;
+  if (bulk) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) mbar_arrive_expect_tx(&bar, 32 * 1024 + 16 * 128 * 36);
+    if (tid < LB) tma_bulk_g2s(sI + tid * PSL, inv + tid * LB, ((tid >> 4) + 1) * 128, &bar);
+    else if (tid < LB + 32) tma_bulk_g2s(sB + (tid - LB) * PSL, B + (long long)(r0 + tid - LB) * ldb, 1024, &bar);
+    mbar_wait(&bar, 0);
+  } else {
 #pragma unroll 8
-  for (int idx = tid; idx < LB * LB / 2; idx += 256) {  // inv: 16-byte loads (the packed block is 16-byte aligned)
-    const int i = idx >> 6, k2 = (idx & 63) * 2;
-    const double2 v = *reinterpret_cast<const double2*>(inv + i * LB + k2);
-    sI[i * PSL + k2] = v.x;
-    sI[i * PSL + k2 + 1] = v.y;
-  }
+    for (int idx = tid; idx < LB * LB / 2; idx += 256) {  // inv: 16-byte loads (the packed block is 16-byte aligned)
+      const int i = idx >> 6, k2 = (idx & 63) * 2;
+      const double2 v = *reinterpret_cast<const double2*>(inv + i * LB + k2);
+      sI[i * PSL + k2] = v.x;
+      sI[i * PSL + k2 + 1] = v.y;
+    }
 #pragma unroll 4
-  for (int idx = tid; idx < 32 * LB; idx += 256) {
-    const int i = idx >> 7, k = idx & (LB - 1);
-    sB[i * PSL + k] = (r0 + i < rows && k < jb) ? B[(long long)(r0 + i) * ldb + k] : 0.0;
+    for (int idx = tid; idx < 32 * LB; idx += 256) {
+      const int i = idx >> 7, k = idx & (LB - 1);
+      sB[i * PSL + k] = (r0 + i < rows && k < jb) ? B[(long long)(r0 + i) * ldb + k] : 0.0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   double c[4][2][2];
 #pragma unroll
   for (int mf = 0; mf < 4; ++mf)
@@ -1114,7 +1230,8 @@ __global__ void __launch_bounds__(256) panel_trsm32s_kernel(double* __restrict__
 // C[nbn x nbn] (lower) -= P P^T, P = [nbn x jb] row-major (ld ldp): one CTA per 32 x 32 tile of the lower
 // triangle, 4 warps x (16 x 16).
 __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restrict__ P, long long ldp,
-                                                           double* __restrict__ C, long long ldc, int nbn, int jb) {
+                                                           double* __restrict__ C, long long ldc, int nbn, int jb,
+                                                           int bulk_io) {
   extern __shared__ __align__(16) double psm[];
   double* sA = psm;              // rows of tile row ti   [32][PSL]
   double* sT = psm + 32 * PSL;   // rows of tile column tj
@@ -1124,13 +1241,28 @@ __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restr
   while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
   const int tj = t - ti * (ti + 1) / 2;
   const int r0 = ti * 32, c0 = tj * 32;
+  __shared__ __align__(8) uint64_t bar;
+  const bool bulk = bulk_io && jb == LB && r0 + 32 <= nbn && c0 + 32 <= nbn && (ldp & 1) == 0 &&
+                    (reinterpret_cast<uintptr_t>(P) & 15) == 0;
+  if (bulk) {  // 64 row copies of 1 KB in flight at once instead of 16 exposed L2 round trips
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) mbar_arrive_expect_tx(&bar, 64 * 1024);
+    if (tid < 32) tma_bulk_g2s(sA + tid * PSL, P + (long long)(r0 + tid) * ldp, 1024, &bar);
+    else if (tid < 64) tma_bulk_g2s(sT + (tid - 32) * PSL, P + (long long)(c0 + tid - 32) * ldp, 1024, &bar);
+    mbar_wait(&bar, 0);
+  } else {
 #pragma unroll 4
-  for (int idx = tid; idx < 32 * LB; idx += 128) {
-    const int i = idx >> 7, k = idx & (LB - 1);
-    sA[i * PSL + k] = (r0 + i < nbn && k < jb) ? P[(long long)(r0 + i) * ldp + k] : 0.0;
-    sT[i * PSL + k] = (c0 + i < nbn && k < jb) ? P[(long long)(c0 + i) * ldp + k] : 0.0;
+    for (int idx = tid; idx < 32 * LB; idx += 128) {
+      const int i = idx >> 7, k = idx & (LB - 1);
+      sA[i * PSL + k] = (r0 + i < nbn && k < jb) ? P[(long long)(r0 + i) * ldp + k] : 0.0;
+      sT[i * PSL + k] = (c0 + i < nbn && k < jb) ? P[(long long)(c0 + i) * ldp + k] : 0.0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int wm = warp >> 1, wn = warp & 1;
   double c[2][2][2];
 #pragma unroll
@@ -1406,12 +1538,13 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
       ctx->launches++;
     } else {
       if (split_leaf) panel_trsm32s_kernel<<<ceil_div(nbn, 32), 256, TRSM32S_SMEM, cs>>>(B, lda, nbn, jb, Ajj, lda, invj);
-      else panel_trsm32_kernel<<<ceil_div(nbn, 32), 256, TRSM32_SMEM, cs>>>(B, lda, nbn, jb, invj);
+      else panel_trsm32_kernel<<<ceil_div(nbn, 32), 256, TRSM32_SMEM, cs>>>(B, lda, nbn, jb, invj, leaf_bulk_io());
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
       if (wr > 0) {
         const int nt = ceil_div(min(nbn, wr), 32);
-        panel_syrk32_kernel<<<nt * (nt + 1) / 2, 128, SYRK32_SMEM, cs>>>(B, lda, B + jb, lda, min(nbn, wr), jb);
+        panel_syrk32_kernel<<<nt * (nt + 1) / 2, 128, SYRK32_SMEM, cs>>>(B, lda, B + jb, lda, min(nbn, wr), jb,
+                                                                         leaf_bulk_io());
         GPXB_LAUNCH_CHECK();
         ctx->launches++;
       }
