@@ -211,9 +211,30 @@ potrf_leaf_kernel(double* __restrict__ A, long long lda, int n, double* __restri
 // merge levels of the inverse) runs on the FP64 tensor pipe from shared memory.  12 block barriers in the
 // factorisation instead of 256.
 #ifdef GPXB_LEAF_STAMPS  // developer build (tools/leaf_timing.cu): merge >> 8 names a phase after which the kernel returns
-#define LEAF_STAMP(k) do { if ((merge >> 8) == (k)) return; } while (0)
+#define LEAF_STAMP(k) do { if ((merge >> 8) == (k) + 1) return; } while (0)
+// timeline of the panel's chain kernels: (kernel id, begin, end) in ns of %globaltimer, block 0 / thread 0
+__device__ unsigned long long g_chain_log[3 * 4096];
+__device__ unsigned int g_chain_n;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CHAIN_BEGIN(id)                                                              \
+  unsigned int chain_slot = 0;                                                       \
+  if (threadIdx.x == 0 && blockIdx.x == 0) {                                         \
+    chain_slot = atomicAdd(&g_chain_n, 1u) & 4095u;                                  \
+    g_chain_log[3 * chain_slot] = (id);                                              \
+    g_chain_log[3 * chain_slot + 1] = gtimer();                                      \
+  }
+#define CHAIN_END()                                                                  \
+  do {                                                                               \
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_chain_log[3 * chain_slot + 2] = gtimer(); \
+  } while (0)
 #else
 #define LEAF_STAMP(k) do {} while (0)
+#define CHAIN_BEGIN(id)
+#define CHAIN_END() do {} while (0)
 #endif
 constexpr int L2S = 132;   // row stride of the 128x128 matrix in smem (== 4 mod 16: conflict-free fragment reads)
 constexpr int DIS = 36;    // row stride of a 32x32 diagonal-block inverse
@@ -329,6 +350,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   const int lr = lane >> 2, lq = lane & 3;
 
   LEAF_STAMP(0);
+  CHAIN_BEGIN(0)
   // A full, aligned leaf comes in by bulk TMA: row i up to the end of its diagonal 32 x 32 block (one 256..1024-byte
   // copy per row, all 128 in flight at once; the element-wise loop below costs ~20 us of exposed L2 latency on the
   // panel's critical chain), zeros to the right of it.  What lands above the diagonal inside the diagonal blocks is
@@ -496,6 +518,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   LEAF_STAMP(29);
   leaf_merge_and_store(S, T, n, inv, tid, warp, lane, false,
                        bulk && (reinterpret_cast<uintptr_t>(inv) & 15) == 0);
+  CHAIN_END();
   LEAF_STAMP(31);
 }
 
@@ -1093,6 +1116,7 @@ __global__ void __launch_bounds__(256) panel_trsm32_kernel(double* __restrict__ 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lq = lane & 3;
   const int r0 = blockIdx.x * 32;
+  CHAIN_BEGIN(1)
   // Full, aligned pieces come in by bulk TMA -- 160 row copies in flight at once (inv: row i up to the end of its
   // 16-column group, all the product reads); the element-wise loops cost several exposed L2 round trips on the
   // panel's critical chain.
@@ -1154,6 +1178,7 @@ __global__ void __launch_bounds__(256) panel_trsm32_kernel(double* __restrict__ 
       if (col + 1 < jb) B[(long long)row * ldb + col + 1] = c[mf][nf][1];
     }
   }
+  CHAIN_END();
 }
 
 // The same solve from L itself and the four 32 x 32 diagonal-block inverses (the leaf's merge-less mode): blocked
@@ -1241,6 +1266,7 @@ __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restr
   while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
   const int tj = t - ti * (ti + 1) / 2;
   const int r0 = ti * 32, c0 = tj * 32;
+  CHAIN_BEGIN(2)
   __shared__ __align__(8) uint64_t bar;
   const bool bulk = bulk_io && jb == LB && r0 + 32 <= nbn && c0 + 32 <= nbn && (ldp & 1) == 0 &&
                     (reinterpret_cast<uintptr_t>(P) & 15) == 0;
@@ -1294,6 +1320,7 @@ __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restr
       if (col + 1 <= row) C[(long long)row * ldc + col + 1] -= c[mf][nf][1];
     }
   }
+  CHAIN_END();
 }
 
 // Both links in ONE launch (the common case: the next block's columns are inside the panel): CTA (ti, tj), tj <= ti,
@@ -1555,12 +1582,27 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
     GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_leaf, 0));
     if (split_leaf) GPXB_TRY(leaf_merge(ctx, Ajj, lda, jb, invj, s));  // the packed inverse, off the chain
     if (below > nbn) {
-      GemmArgs g;  // rows below the head: B <- B inv^T (in place)
-      g.M = below - nbn; g.N = jb; g.K = jb;
-      g.A = B + (long long)nbn * lda; g.lda = lda; g.a_kmajor = true;
-      g.B = invj; g.ldb = LB; g.b_kmajor = true;
-      g.C = B + (long long)nbn * lda; g.ldc = lda;
-      GPXB_TRY(gemm_f64(ctx, g, s));
+      // rows below the head: B <- B inv^T (in place).  Full 128-column steps go through the 32-row solve kernel as
+      // well (one CTA per 32 rows at the DMMA rate of its SM, half the flops of a general product: 2.2 us per CTA
+      // against 17-27 us for the latency of one GEMM tile at K = 128); GPXB_PANEL_TRSM=gemm keeps the GEMM.
+      static const bool trsm_gemm = [] {
+        const char* e = getenv("GPXB_PANEL_TRSM");
+        return e && e[0] == 'g';
+      }();
+      if (jb == LB && !trsm_gemm && !split_leaf && below - nbn <= 4096) {  // beyond: equal (n = 8192: 9.45 vs 9.30 ms)
+        panel_trsm32_kernel<<<ceil_div(below - nbn, 32), 256, TRSM32_SMEM, s>>>(B + (long long)nbn * lda, lda,
+                                                                                  below - nbn, jb, invj, leaf_bulk_io());
+        GPXB_LAUNCH_CHECK();
+        ctx->launches++;
+      } else {
+        GemmArgs g;
+        g.M = below - nbn; g.N = jb; g.K = jb;
+        g.A = B + (long long)nbn * lda; g.lda = lda; g.a_kmajor = true;
+        g.B = invj; g.ldb = LB; g.b_kmajor = true;
+        g.C = B + (long long)nbn * lda; g.ldc = lda;
+        g.small_tile_max = 35;  // <= 140 CTAs of 64 x 64: SMs stay free for the chain kernels
+        GPXB_TRY(gemm_f64(ctx, g, s));
+      }
     }
     GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_head, 0));
     if (wr > 0 && below > nbn) {
@@ -1572,6 +1614,7 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
       g.alpha = -1.0; g.beta = 1.0;
       g.lower_only = 1;
       g.skip_tile0 = 1;
+      g.small_tile_max = 35;
       GPXB_TRY(gemm_f64(ctx, g, s));
     }
     GPXB_TRY(ctx->next_event(&ev_bulk_prev));
@@ -1602,7 +1645,13 @@ int panel_update(Ctx* ctx, double* A, long long lda, int n, int k0, int w, int c
 
 int potrf_lower(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s) {
   if (n <= 0) return 0;
-  constexpr int NB = 1024;
+  static const int nb_env = [] {
+    const char* e = getenv("GPXB_POTRF_NB");  // panel width (multiple of 128); default 1024
+    const int v = e ? atoi(e) : 0;
+    return (v >= LB && v % LB == 0) ? v : 0;
+  }();
+  // one panel up to n = 2048: the rank-1024 update between two panels stalls the leaf chain for ~180 us
+  const int NB = nb_env ? nb_env : (n <= 4096 ? 2048 : 1024);  // measured: 4096: 2.55 vs 2.70 ms; 8192: 9.7 vs 9.3 ms
   if (n <= NB) return factor_panel(ctx, A, lda, n, 0, n, inv, s);
   // Depth-1 look-ahead: panel p+1 is factorised on the high-priority stream hp while the
   // caller's stream s applies panel p's rank-NB update to the columns right of panel p+1.

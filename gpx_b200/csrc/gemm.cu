@@ -21,13 +21,20 @@ namespace {
 #endif
 // BK = 32 with 3 stages (216 KB of shared memory) halves the number of CTA-wide barriers per flop
 // relative to BK = 16 with 4 stages: measured 34.5 vs 33.4 TFLOP/s at 8192^3.
-constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GPXB_GEMM_BK, STAGES = (BK == 32 ? 3 : 4);
+constexpr int BK = GPXB_GEMM_BK, STAGES = (BK == 32 ? 3 : 4);
 constexpr int KCH = BK / 2;  // 16-byte chunks per K-major tile row
-constexpr int LDK = BK + 4;   // row stride of a K-major tile  [128][16]  (doubles)
-constexpr int LDM = BM + 4;   // row stride of an MN-major tile [16][128] (doubles)
-constexpr int TILE_DBL = BM * LDK;  // 2560 doubles >= BK*LDM = 2112
-constexpr int STAGE_DBL = 2 * TILE_DBL;
-constexpr int SMEM_BYTES = STAGES * STAGE_DBL * (int)sizeof(double);  // 163840
+constexpr int LDK = BK + 4;   // row stride of a K-major tile  [T][BK]  (doubles)
+// The CTA tile is T x T: 128 (16 warps, one CTA per SM) for anything that fills the machine, 64 (4 warps, two CTAs
+// per SM) for launches of a few hundred big tiles or less -- a 128 x 128 tile costs 17 us per 128 of K on ONE SM
+// whatever the size of the problem, which is what bounds the small GEMMs of a mid-size factorisation.
+template <int T> struct TileGeom {
+  static constexpr int LDM = T + 4;                 // row stride of an MN-major tile [BK][T] (doubles)
+  static constexpr int TILE_DBL = T * LDK;          // >= BK * LDM
+  static constexpr int STAGE_DBL = 2 * TILE_DBL;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_DBL * (int)sizeof(double);
+};
+static_assert(TileGeom<128>::TILE_DBL >= BK * TileGeom<128>::LDM && TileGeom<64>::TILE_DBL >= BK * TileGeom<64>::LDM,
+              "tile buffer too small for the MN-major layout");
 
 struct GemmParams {
   int M, N, K;
@@ -39,7 +46,7 @@ struct GemmParams {
   long long ldc;
   double alpha, beta;
   int lower_only, klo_mode, khi_mode, skip_tile0, tri_group;
-  int tiles_m, tiles_n;
+  int tiles_m, tiles_n, tile;
   int vecA, vecB, vecC;
   long long strideA, strideB, strideC;  // batched launch: blockIdx.y selects the product
 };
@@ -47,9 +54,10 @@ struct GemmParams {
 // Per-thread loader state for one operand: the thread's 16-byte chunks of a tile
 // (128 rows of the M/N index x 16 of K).  Row/column validity is fixed for the whole K
 // loop, so interior K tiles cost one LDGSTS per chunk and a pointer bump.
-template <bool KMAJ, int NTHR>
+template <bool KMAJ, int NTHR, int T>
 struct TileLoader {
-  static constexpr int CH = (BM * BK / 2) / NTHR;
+  static constexpr int CH = (T * BK / 2) / NTHR;
+  static constexpr int LDM = TileGeom<T>::LDM;
   const double* ptr[CH];  // global address of the chunk at k = k_lo (clamped when invalid)
   int soff[CH];           // smem offset in doubles
   int nb[CH];             // bytes valid along the fixed index (0, 8 or 16)
@@ -76,7 +84,7 @@ struct TileLoader {
         nb[i] = gr < rmax_ ? 16 : 0;
         ptr[i] = nb[i] ? g + (long long)gr * ld_ + k_lo + kc : g;
       } else {
-        const int k = c >> 6, mc = (c & 63) * 2;
+        const int k = c / (T / 2), mc = (c % (T / 2)) * 2;
         const int gm = r0_ + mc;
         soff[i] = k * LDM + mc;
         kk[i] = k;
@@ -125,7 +133,7 @@ struct TileLoader {
             const bool ok = (gr < rmax) && (gk < kmax);
             s[soff[i] + e] = ok ? base[(long long)gr * ld + gk] : 0.0;
           } else {
-            const int gk = k0 + (c >> 6), gm = r0 + (c & 63) * 2 + e;
+            const int gk = k0 + c / (T / 2), gm = r0 + (c % (T / 2)) * 2 + e;
             const bool ok = (gk < kmax) && (gm < rmax);
             s[soff[i] + e] = ok ? base[(long long)gk * ld + gm] : 0.0;
           }
@@ -135,10 +143,13 @@ struct TileLoader {
   }
 };
 
-// WM x WN warps, each a (8*MF) x (8*NF) tile:  2x4 warps of 64x32, or 4x4 warps of 32x32.
-template <bool AK, bool BKM, int WM, int WN>
-__global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmParams p) {
+// WM x WN warps, each a (8*MF) x (8*NF) tile:  2x4 warps of 64x32, or 4x4 warps of 32x32 (T = 128); 2x2 warps of
+// 32x32 (T = 64).
+template <bool AK, bool BKM, int WM, int WN, int T>
+__global__ void __launch_bounds__(WM * WN * 32, T == 64 ? 2 : 1) gemm_f64_kernel(const GemmParams p) {
   constexpr int NTHR = WM * WN * 32;
+  constexpr int BM = T, BN = T;
+  constexpr int LDM = TileGeom<T>::LDM, TILE_DBL = TileGeom<T>::TILE_DBL, STAGE_DBL = TileGeom<T>::STAGE_DBL;
   constexpr int MF = BM / (8 * WM), NF = BN / (8 * WN);
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -148,7 +159,6 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
   // ---- tile coordinates ----
   int ti, tj;
   if (p.lower_only) {
-    if (p.skip_tile0 && blockIdx.x == 0) return;  // tile (0, 0) belongs to another kernel
     // trapezoid (M >= N): tiles_n*(tiles_n+1)/2 triangular tiles, then full tile rows
     const long long t = blockIdx.x;
     const long long ntri = (long long)p.tiles_n * (p.tiles_n + 1) / 2;
@@ -196,6 +206,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
     tj = (t % per_group) / gsz;
   }
   const int row0 = ti * BM, col0 = tj * BN;
+  if (p.skip_tile0 && row0 < 128 && col0 < 128) return;  // the leading 128 x 128 block belongs to another kernel
 
   int k_lo = (p.klo_mode == 1) ? col0 : (p.klo_mode == 2 ? row0 : 0);
   if (k_lo > p.K) k_lo = p.K;
@@ -209,8 +220,8 @@ __global__ void __launch_bounds__(WM * WN * 32, 1) gemm_f64_kernel(const GemmPar
 #pragma unroll
     for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  TileLoader<AK, NTHR> la;
-  TileLoader<BKM, NTHR> lb;
+  TileLoader<AK, NTHR, T> la;
+  TileLoader<BKM, NTHR, T> lb;
   const double* Ab = p.A + (long long)blockIdx.y * p.strideA;
   const double* Bb = p.B + (long long)blockIdx.y * p.strideB;
   double* Cb = p.C + (long long)blockIdx.y * p.strideC;
@@ -326,6 +337,7 @@ double launch_flops(const GemmParams& p, long long grid) {
     return 2.0 * area * (double)p.K;
   }
   double fl = 0.0;
+  const int BM = p.tile, BN = p.tile;
   for (int ti = 0; ti < p.tiles_m; ++ti) {
     const int row0 = ti * BM, rows = std::min(BM, p.M - row0);
     const int tj_end = p.lower_only ? std::min(p.tiles_n, ti + 1) : p.tiles_n;
@@ -354,12 +366,18 @@ int launch(Ctx* ctx, const GemmParams& p, int grid1, int batch, cudaStream_t str
     rec.flops = launch_flops(p, grid1) * batch;
     GPXB_CUDA_CHECK(cudaEventRecord(rec.e0, stream));
   }
-  if (gemm_variant() == 8) {
-    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 2, 4>), SMEM_BYTES));
-    gemm_f64_kernel<AK, BKM, 2, 4><<<grid, 256, SMEM_BYTES, stream>>>(p);
+  if (p.tile == 64) {
+    constexpr int SM64 = TileGeom<64>::SMEM_BYTES;
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 2, 2, 64>), SM64));
+    gemm_f64_kernel<AK, BKM, 2, 2, 64><<<grid, 128, SM64, stream>>>(p);
+  } else if (gemm_variant() == 8) {
+    constexpr int SM128 = TileGeom<128>::SMEM_BYTES;
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 2, 4, 128>), SM128));
+    gemm_f64_kernel<AK, BKM, 2, 4, 128><<<grid, 256, SM128, stream>>>(p);
   } else {
-    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 4, 4>), SMEM_BYTES));
-    gemm_f64_kernel<AK, BKM, 4, 4><<<grid, 512, SMEM_BYTES, stream>>>(p);
+    constexpr int SM128 = TileGeom<128>::SMEM_BYTES;
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 4, 4, 128>), SM128));
+    gemm_f64_kernel<AK, BKM, 4, 4, 128><<<grid, 512, SM128, stream>>>(p);
   }
   GPXB_LAUNCH_CHECK();
   if (prof) {
@@ -394,8 +412,28 @@ int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream) {
     return v >= 1 && v <= 64 ? v : 1;
   }();
   p.tri_group = (g.skip_tile0 || g.klo_mode || g.khi_mode) ? 1 : tri_group;  // tile 0 must stay block 0 when it is skipped
-  p.tiles_m = ceil_div(g.M, BM);
-  p.tiles_n = ceil_div(g.N, BN);
+  // 64 x 64 tiles when 128 x 128 ones would not give every SM a few CTAs (GPXB_GEMM_SMALL_MAX: the largest count of
+  // big tiles still served by the small kernel; 0 turns it off)
+  static const long long small_max = [] {
+    const char* e = getenv("GPXB_GEMM_SMALL_MAX");
+    return e ? atoll(e) : -1;
+  }();
+  auto tiles_of = [&](int T, int& tm, int& tn) -> long long {
+    tm = ceil_div(g.M, T);
+    tn = ceil_div(g.N, T);
+    return g.lower_only ? (long long)tn * (tn + 1) / 2 + (long long)(tm - tn) * tn : (long long)tm * tn;
+  };
+  int tm128, tn128;
+  const long long grid128 = tiles_of(128, tm128, tn128) * g.batch;
+  // default: less than ~3/4 of a wave of big tiles (measured, tools/bench_gemm_small.py: 1024^3 85 vs 152 us, skinny
+  // K = 128 products 17 vs 27 us; from one full wave on the big tile wins: 2048^2 x 1024 lower 155 vs 169 us)
+  // triangular-operand products (per-tile k ranges of very different length) balance better on small tiles: up to
+  // four waves of big ones (LML + gradient at n = 2000: 2.06 vs 2.34 ms)
+  const long long lim = small_max >= 0 ? small_max
+                        : (g.small_tile_max > 0 ? g.small_tile_max : ((g.klo_mode || g.khi_mode) ? 592 : 110));
+  p.tile = (grid128 <= lim) ? 64 : 128;
+  p.tiles_m = ceil_div(g.M, p.tile);
+  p.tiles_n = ceil_div(g.N, p.tile);
   GPXB_ARG_CHECK(g.batch >= 1 && g.batch <= 65535, -4);
   p.strideA = g.strideA; p.strideB = g.strideB; p.strideC = g.strideC;
   const bool even_strides = g.batch == 1 || (g.strideA % 2 == 0 && g.strideB % 2 == 0 && g.strideC % 2 == 0);

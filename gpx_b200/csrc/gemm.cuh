@@ -28,7 +28,11 @@ struct GemmArgs {
   int lower_only = 0;
   int klo_mode = 0;
   int khi_mode = 0;
-  int skip_tile0 = 0;  // lower_only: tile (0, 0) is left alone (another kernel owns the first diagonal block)
+  int skip_tile0 = 0;  // lower_only: the leading 128 x 128 block is left alone (another kernel owns it)
+  // 64 x 64 tiles are used when the launch has at most this many 128 x 128 tiles (0: the library default).  The
+  // panel factorisation passes a small number: its GEMMs run beside the one-CTA leaf chain, which needs whole SMs
+  // to stay free, and 4x as many CTAs at two per SM would occupy every SM.
+  int small_tile_max = 0;
   // batch > 1: `batch` independent products of identical shape in one launch; operand z starts strideX * z
   // doubles after operand 0 (same leading dimensions)
   int batch = 1;
