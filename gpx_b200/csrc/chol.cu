@@ -1337,7 +1337,7 @@ constexpr int HEAD_SMEM = (LB + 64) * PSL * (int)sizeof(double);
 __global__ void __launch_bounds__(256) panel_head_kernel(double* __restrict__ B, long long ldb, int nbn, int jb,
                                                          const double* __restrict__ inv, double* __restrict__ C,
                                                          long long ldc, unsigned long long* __restrict__ counter,
-                                                         unsigned long long target) {
+                                                         unsigned long long target, int bulk_io) {
   extern __shared__ __align__(16) double psm[];
   double* sI = psm;                   // [128][PSL]
   double* sBi = psm + LB * PSL;       // [32][PSL] rows of piece ti, then their solved values
@@ -1349,20 +1349,38 @@ __global__ void __launch_bounds__(256) panel_head_kernel(double* __restrict__ B,
   const int tj = t - ti * (ti + 1) / 2;
   const bool diag = (ti == tj);
   const int ri = ti * 32, rj = tj * 32;
+  __shared__ __align__(8) uint64_t bar;
+  const bool bulk = bulk_io && jb == LB && ri + 32 <= nbn && rj + 32 <= nbn && (ldb & 1) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(inv)) & 15) == 0;
+  if (bulk) {  // as in panel_trsm32_kernel: every row copy in flight at once
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) mbar_arrive_expect_tx(&bar, (diag ? 32 : 64) * 1024 + 16 * 128 * 36);
+    if (tid < LB) tma_bulk_g2s(sI + tid * PSL, inv + tid * LB, ((tid >> 4) + 1) * 128, &bar);
+    else if (tid < LB + 32) tma_bulk_g2s(sBi + (tid - LB) * PSL, B + (long long)(ri + tid - LB) * ldb, 1024, &bar);
+    else if (tid < LB + 64 && !diag)
+      tma_bulk_g2s(sBj + (tid - LB - 32) * PSL, B + (long long)(rj + tid - LB - 32) * ldb, 1024, &bar);
+    mbar_wait(&bar, 0);
+    __syncthreads();  // every thread's wait is over before the ticket below announces the reads
+  } else {
 #pragma unroll 8
-  for (int idx = tid; idx < LB * LB / 2; idx += 256) {
-    const int i = idx >> 6, k2 = (idx & 63) * 2;
-    const double2 v = *reinterpret_cast<const double2*>(inv + i * LB + k2);
-    sI[i * PSL + k2] = v.x;
-    sI[i * PSL + k2 + 1] = v.y;
-  }
+    for (int idx = tid; idx < LB * LB / 2; idx += 256) {
+      const int i = idx >> 6, k2 = (idx & 63) * 2;
+      const double2 v = *reinterpret_cast<const double2*>(inv + i * LB + k2);
+      sI[i * PSL + k2] = v.x;
+      sI[i * PSL + k2 + 1] = v.y;
+    }
 #pragma unroll 4
-  for (int idx = tid; idx < 32 * LB; idx += 256) {
-    const int i = idx >> 7, k = idx & (LB - 1);
-    sBi[i * PSL + k] = (ri + i < nbn && k < jb) ? B[(long long)(ri + i) * ldb + k] : 0.0;
-    if (!diag) sBj[i * PSL + k] = (rj + i < nbn && k < jb) ? B[(long long)(rj + i) * ldb + k] : 0.0;
+    for (int idx = tid; idx < 32 * LB; idx += 256) {
+      const int i = idx >> 7, k = idx & (LB - 1);
+      sBi[i * PSL + k] = (ri + i < nbn && k < jb) ? B[(long long)(ri + i) * ldb + k] : 0.0;
+      if (!diag) sBj[i * PSL + k] = (rj + i < nbn && k < jb) ? B[(long long)(rj + i) * ldb + k] : 0.0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (tid == 0) {  // this CTA holds its copies of the unsolved rows
     __threadfence();
     atomicAdd(counter, 1ULL);
@@ -1560,7 +1578,7 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
       }
       ctx->head_ticket += (unsigned long long)nctas;
       panel_head_kernel<<<nctas, 256, HEAD_SMEM, cs>>>(B, lda, nbn, jb, invj, B + jb, lda, ctx->head_counter,
-                                                        ctx->head_ticket);
+                                                        ctx->head_ticket, leaf_bulk_io());
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
     } else {
