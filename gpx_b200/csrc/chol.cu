@@ -1117,6 +1117,9 @@ __global__ void __launch_bounds__(256) panel_trsm32_kernel(double* __restrict__ 
   const int lr = lane >> 2, lq = lane & 3;
   const int r0 = blockIdx.x * 32;
   CHAIN_BEGIN(1)
+  // programmatic dependent launch: the head update that follows on the chain stream may be scheduled now (it waits
+  // for this grid's completion itself, griddepcontrol.wait) -- hides its launch latency behind this kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // Full, aligned pieces come in by bulk TMA -- 160 row copies in flight at once (inv: row i up to the end of its
   // 16-column group, all the product reads); the element-wise loops cost several exposed L2 round trips on the
   // panel's critical chain.
@@ -1267,6 +1270,7 @@ __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restr
   const int tj = t - ti * (ti + 1) / 2;
   const int r0 = ti * 32, c0 = tj * 32;
   CHAIN_BEGIN(2)
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched as a programmatic dependent
   __shared__ __align__(8) uint64_t bar;
   const bool bulk = bulk_io && jb == LB && r0 + 32 <= nbn && c0 + 32 <= nbn && (ldp & 1) == 0 &&
                     (reinterpret_cast<uintptr_t>(P) & 15) == 0;
@@ -1588,8 +1592,27 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
       ctx->launches++;
       if (wr > 0) {
         const int nt = ceil_div(min(nbn, wr), 32);
-        panel_syrk32_kernel<<<nt * (nt + 1) / 2, 128, SYRK32_SMEM, cs>>>(B, lda, B + jb, lda, min(nbn, wr), jb,
-                                                                         leaf_bulk_io());
+        static const bool pdl = [] {
+          const char* e = getenv("GPXB_PANEL_PDL");  // "0": plain stream order
+          return !(e && e[0] == '0');
+        }();
+        if (pdl && !split_leaf) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(nt * (nt + 1) / 2);
+          cfg.blockDim = dim3(128);
+          cfg.dynamicSmemBytes = SYRK32_SMEM;
+          cfg.stream = cs;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          at[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = at;
+          cfg.numAttrs = 1;
+          GPXB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, panel_syrk32_kernel, (const double*)B, (long long)lda, B + jb,
+                                             (long long)lda, min(nbn, wr), jb, leaf_bulk_io()));
+        } else {
+          panel_syrk32_kernel<<<nt * (nt + 1) / 2, 128, SYRK32_SMEM, cs>>>(B, lda, B + jb, lda, min(nbn, wr), jb,
+                                                                           leaf_bulk_io());
+        }
         GPXB_LAUNCH_CHECK();
         ctx->launches++;
       }
