@@ -825,6 +825,7 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __rest
   __shared__ double sb[TRSV_MAXM][LB];
   __shared__ double so[TRSV_MAXM][LB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  GPXB_PDL_WAIT_THEN_RELEASE();  // the sweep is a chain of short dependent launches (trsv_few_v2)
   for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
     const int r = i / LB, c = i % LB;
     sx[r][c] = (r < m && c < nb) ? X[(long long)r * ldb + c] : 0.0;
@@ -896,6 +897,7 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __rest
   __shared__ double so[TRSV_MAXM][LB];
   __shared__ double tmp[TRSV_MAXM][LB];
   const int tid = threadIdx.x;
+  GPXB_PDL_WAIT_THEN_RELEASE();
   for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
     const int r = i / LB, c = i % LB;
     sx[r][c] = (r < m && c < nb) ? X[(long long)r * ldb + c] : 0.0;
@@ -954,6 +956,7 @@ __global__ void __launch_bounds__(256) trsv_first_kernel(const double* __restric
   __shared__ double so[TRSV_MAXM][LB];
   __shared__ double tmp[TRSV_MAXM][LB];
   const int tid = threadIdx.x;
+  GPXB_PDL_WAIT_THEN_RELEASE();
   for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
     const int r = i / LB, c = i % LB;
     sb[r][c] = (r < m && c < nb) ? B[(long long)r * ldb + c] : 0.0;
@@ -976,9 +979,9 @@ int trsv_few_v2(Ctx* ctx, const double* L, long long ldl, const double* inv, dou
     ctx->launches++;
     for (int k = 0; k + 1 < nblk; ++k) {
       const int c0 = k * LB, below = n - c0 - LB, nb_next = min(LB, below);
-      trsv_fwd_step_kernel<<<1 + (below - nb_next + 7) / 8, 256, 0, s>>>(L + (long long)(c0 + LB) * ldl + c0, ldl, B + c0,
-                                                                          B + c0 + LB, ldb, m, LB, below,
-                                                                          inv + (long long)(k + 1) * LB * LB, nb_next);
+      GPXB_CUDA_CHECK(launch_pdl(trsv_fwd_step_kernel, dim3(1 + (below - nb_next + 7) / 8), dim3(256), 0, s,
+                                 L + (long long)(c0 + LB) * ldl + c0, ldl, B + c0, B + c0 + LB, ldb, m, LB, below,
+                                 inv + (long long)(k + 1) * LB * LB, nb_next));
       ctx->launches++;
     }
   } else {  // L^T x = b: backward over blocks
@@ -987,8 +990,9 @@ int trsv_few_v2(Ctx* ctx, const double* L, long long ldl, const double* inv, dou
     ctx->launches++;
     for (int k = nblk - 1; k >= 1; --k) {
       const int c0 = k * LB, nb = min(LB, n - c0);
-      trsv_bwd_step_kernel<<<1 + (c0 - LB + 255) / 256, 256, 0, s>>>(L + (long long)c0 * ldl, ldl, B + c0, B, ldb, m, nb, c0,
-                                                                      inv + (long long)(k - 1) * LB * LB);
+      GPXB_CUDA_CHECK(launch_pdl(trsv_bwd_step_kernel, dim3(1 + (c0 - LB + 255) / 256), dim3(256), 0, s,
+                                 L + (long long)c0 * ldl, ldl, B + c0, B, ldb, m, nb, c0,
+                                 inv + (long long)(k - 1) * LB * LB));
       ctx->launches++;
     }
   }

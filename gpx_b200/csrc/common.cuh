@@ -66,6 +66,31 @@ inline cudaError_t ensure_dyn_smem(const void* fn, int bytes) {
   return e;
 }
 
+// Launch `kernel` as a programmatic dependent of the previous kernel on the stream (its CTAs may become resident
+// before that kernel has finished; it must execute griddepcontrol.wait before touching anything the predecessor
+// writes).  Hides the dependent-launch latency of chains of short kernels.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// inside such a kernel: wait for the predecessor grid (no-op for a plain launch), then let the successor in
+#define GPXB_PDL_WAIT_THEN_RELEASE()                              \
+  do {                                                            \
+    asm volatile("griddepcontrol.wait;" ::: "memory");            \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
 struct Ctx {
   int device = 0;
   int num_sms = 148;
