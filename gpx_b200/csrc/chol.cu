@@ -357,11 +357,14 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   // never read.
   __shared__ __align__(8) uint64_t lbar;
   const bool bulk = (n == LB) && ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && leaf_bulk_io;
+  if (bulk && tid == 0) {
+    mbar_init(&lbar, 1);
+    fence_mbar_init();
+  }
+  // no-ops unless launched as a programmatic dependent: wait for the head update, then let the head solve that
+  // follows become resident (its four CTAs wait for this grid themselves)
+  GPXB_PDL_WAIT_THEN_RELEASE();
   if (bulk) {
-    if (tid == 0) {
-      mbar_init(&lbar, 1);
-      fence_mbar_init();
-    }
     __syncthreads();
     if (tid == 0) mbar_arrive_expect_tx(&lbar, 32 * (256 + 512 + 768 + 1024));
     if (tid < LB) tma_bulk_g2s(S + tid * L2S, A + (long long)tid * lda, ((tid >> 5) + 1) * 256, &lbar);
@@ -571,11 +574,15 @@ int leaf_generation() {
 
 // merge == 0 (second-generation leaf only): inv receives the four 32 x 32 diagonal-block inverses; leaf_merge
 // completes it later
-int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s, int merge = 1) {
+int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s, int merge = 1, bool pdl = false) {
   const int gen = leaf_generation();
   if (gen == 2) {
     GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(potrf_leaf_dmma_kernel), LEAF2_SMEM));
-    potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv, merge, leaf_bulk_io());
+    if (pdl)
+      GPXB_CUDA_CHECK(launch_pdl(potrf_leaf_dmma_kernel, dim3(1), dim3(LEAF_NT), LEAF2_SMEM, s, A, lda, n, inv, merge,
+                                 leaf_bulk_io()));
+    else
+      potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv, merge, leaf_bulk_io());
     GPXB_LAUNCH_CHECK();
     ctx->launches++;
     return 0;
@@ -1124,6 +1131,7 @@ __global__ void __launch_bounds__(256) panel_trsm32_kernel(double* __restrict__ 
   // programmatic dependent launch: the head update that follows on the chain stream may be scheduled now (it waits
   // for this grid's completion itself, griddepcontrol.wait) -- hides its launch latency behind this kernel
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the leaf, when this grid is its programmatic dependent
   // Full, aligned pieces come in by bulk TMA -- 160 row copies in flight at once (inv: row i up to the end of its
   // 16-column group, all the product reads); the element-wise loops cost several exposed L2 round trips on the
   // panel's critical chain.
@@ -1274,7 +1282,9 @@ __global__ void __launch_bounds__(128) panel_syrk32_kernel(const double* __restr
   const int tj = t - ti * (ti + 1) / 2;
   const int r0 = ti * 32, c0 = tj * 32;
   CHAIN_BEGIN(2)
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched as a programmatic dependent
+  // no-ops unless launched as a programmatic dependent: wait for the head solve, then let the next leaf become
+  // resident (it claims its SM before the bulk update's CTAs arrive, and waits for this grid itself)
+  GPXB_PDL_WAIT_THEN_RELEASE();
   __shared__ __align__(8) uint64_t bar;
   const bool bulk = bulk_io && jb == LB && r0 + 32 <= nbn && c0 + 32 <= nbn && (ldp & 1) == 0 &&
                     (reinterpret_cast<uintptr_t>(P) & 15) == 0;
@@ -1554,6 +1564,14 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
     const char* e = getenv("GPXB_PANEL_HEAD");
     return !(e && e[0] == 'f');
   }();
+  // GPXB_PANEL_PDL: 0 plain stream order; 1 head update as a programmatic dependent of the head solve; 2 (default)
+  // also the next leaf as a dependent of the head update -- the event the bulk update waits for is then recorded
+  // right after the head solve (the update skips the diagonal block the head update writes).
+  static const int pdl_mode = [] {
+    const char* e = getenv("GPXB_PANEL_PDL");
+    return e ? atoi(e) : 2;
+  }();
+  bool leaf_follows_update = false;  // the previous operation on cs is a head update launched in this loop
   cudaEvent_t ev, ev_bulk_prev = nullptr;
   GPXB_TRY(ctx->next_event(&ev));
   GPXB_CUDA_CHECK(cudaEventRecord(ev, s));
@@ -1566,7 +1584,8 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
     const int below = n - c0 - jb;
     // merge-less leaf when a head solve follows: the merge levels of the packed inverse run on s, beside the chain
     const bool split_leaf = below > 0 && jb == LB && leaf_generation() == 2 && !no_split_leaf;
-    GPXB_TRY(leaf(ctx, Ajj, lda, jb, invj, cs, split_leaf ? 0 : 1));
+    GPXB_TRY(leaf(ctx, Ajj, lda, jb, invj, cs, split_leaf ? 0 : 1, pdl_mode >= 2 && leaf_follows_update));
+    leaf_follows_update = false;
     if (below <= 0) continue;
     cudaEvent_t ev_leaf, ev_head;
     GPXB_TRY(ctx->next_event(&ev_leaf));
@@ -1575,6 +1594,7 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
     const int wr = w - j - jb;                         // panel columns still to update
     const int nbn = min(LB, below);                    // rows of the next block (the "head")
     // ---- critical chain on cs ----
+    bool head_recorded = false;
     if (ev_bulk_prev) GPXB_CUDA_CHECK(cudaStreamWaitEvent(cs, ev_bulk_prev, 0));
     if (wr >= nbn && !split_head && !split_leaf) {
       // both links in one launch: every CTA solves the head pieces it multiplies
@@ -1591,15 +1611,20 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
       ctx->launches++;
     } else {
       if (split_leaf) panel_trsm32s_kernel<<<ceil_div(nbn, 32), 256, TRSM32S_SMEM, cs>>>(B, lda, nbn, jb, Ajj, lda, invj);
+      else if (pdl_mode >= 3)
+        GPXB_CUDA_CHECK(launch_pdl(panel_trsm32_kernel, dim3(ceil_div(nbn, 32)), dim3(256), TRSM32_SMEM, cs, B,
+                                   (long long)lda, nbn, jb, (const double*)invj, leaf_bulk_io()));
       else panel_trsm32_kernel<<<ceil_div(nbn, 32), 256, TRSM32_SMEM, cs>>>(B, lda, nbn, jb, invj, leaf_bulk_io());
       GPXB_LAUNCH_CHECK();
       ctx->launches++;
+      if (pdl_mode >= 2 && !split_leaf) {
+        GPXB_TRY(ctx->next_event(&ev_head));
+        GPXB_CUDA_CHECK(cudaEventRecord(ev_head, cs));
+        head_recorded = true;
+      }
       if (wr > 0) {
         const int nt = ceil_div(min(nbn, wr), 32);
-        static const bool pdl = [] {
-          const char* e = getenv("GPXB_PANEL_PDL");  // "0": plain stream order
-          return !(e && e[0] == '0');
-        }();
+        const bool pdl = pdl_mode >= 1;
         if (pdl && !split_leaf) {
           cudaLaunchConfig_t cfg = {};
           cfg.gridDim = dim3(nt * (nt + 1) / 2);
@@ -1619,10 +1644,13 @@ int factor_panel(Ctx* ctx, double* A, long long lda, int n, int k0, int w, doubl
         }
         GPXB_LAUNCH_CHECK();
         ctx->launches++;
+        leaf_follows_update = head_recorded;
       }
     }
-    GPXB_TRY(ctx->next_event(&ev_head));
-    GPXB_CUDA_CHECK(cudaEventRecord(ev_head, cs));
+    if (!head_recorded) {
+      GPXB_TRY(ctx->next_event(&ev_head));
+      GPXB_CUDA_CHECK(cudaEventRecord(ev_head, cs));
+    }
     // ---- bulk on s ----
     GPXB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_leaf, 0));
     if (split_leaf) GPXB_TRY(leaf_merge(ctx, Ajj, lda, jb, invj, s));  // the packed inverse, off the chain
