@@ -431,7 +431,12 @@ int gemm_f64(Ctx* ctx, const GemmArgs& g, cudaStream_t stream) {
   // four waves of big ones (LML + gradient at n = 2000: 2.06 vs 2.34 ms)
   const long long lim = small_max >= 0 ? small_max
                         : (g.small_tile_max > 0 ? g.small_tile_max : ((g.klo_mode || g.khi_mode) ? 592 : 110));
-  p.tile = (grid128 <= lim) ? 64 : 128;
+  // In-place products (C aliasing an operand: the callers' B <- B inv^T with N <= 128) rely on ONE column tile per
+  // tile row -- each CTA consumes its whole operand rows before its epilogue writes them -- so they keep the 128-wide
+  // tile: with 64-wide tiles the CTA of columns 0..63 may overwrite what the CTA of columns 64..127 still reads.
+  const bool in_place = (g.C == g.A) || (g.C == g.B);
+  GPXB_ARG_CHECK(!in_place || g.N <= 128, -5);
+  p.tile = (grid128 <= lim && !in_place) ? 64 : 128;
   p.tiles_m = ceil_div(g.M, p.tile);
   p.tiles_n = ceil_div(g.N, p.tile);
   GPXB_ARG_CHECK(g.batch >= 1 && g.batch <= 65535, -4);

@@ -80,6 +80,25 @@ def test_potrf_trsm_potri_logdet(n):
     assert rel(Ainv, np.tril(np.linalg.inv(A))) < 1e-8
 
 
+@pytest.mark.parametrize("n", [128, 300])
+def test_trsm_in_place_many_rows(n):
+    """The right solve multiplies B by the inverted diagonal blocks IN PLACE through the GEMM; with many rows and few
+    columns the launch is small enough for the 64 x 64 tile rule, which must not apply to in-place products (two
+    column tiles of one tile row would read and overwrite the same operand rows).  Repeated: the hazard is a race."""
+    from gpx_b200 import ops
+
+    A = _spd(n, 11 + n)
+    Lref = sla.cholesky(A, lower=True)
+    L, inv = ops.potrf(dev(A))
+    rng = np.random.default_rng(4)
+    B = rng.standard_normal((6000, n))
+    ref_t = sla.solve_triangular(Lref, B.T, lower=True).T
+    ref_n = sla.solve_triangular(Lref, B.T, lower=True, trans="T").T
+    for _ in range(8):
+        assert rel(host(ops.trsm(L, inv, dev(B), trans=True)), ref_t) < 1e-9
+        assert rel(host(ops.trsm(L, inv, dev(B), trans=False)), ref_n) < 1e-9
+
+
 @pytest.mark.parametrize("kind", R.KINDS)
 @pytest.mark.parametrize("n1,n2,D", [(200, 333, 8), (129, 1, 3), (64, 64, 16), (300, 257, 32), (50, 70, 90)])
 def test_gram_entries(kind, n1, n2, D):
