@@ -332,7 +332,9 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
                     peak_gbs=hbm, peak_source=hbm_src, frac=alg / t / 1e9 / world / hbm,
                     pivots_head=[int(v) for v in piv[:6].cpu().tolist()],
                     pivots_checksum=int(piv.sum().cpu()), phases=ph, non_compute_s=non_compute(t, ph),
-                    phases_note="phase events are sampled on every 16th pivot and scaled by 16")
+                    phases_note="phase events are sampled on every 16th pivot and scaled by 16",
+                    frac_note="denominator = measured COPY bandwidth (read + write streams); this pass is 99.9 % "
+                              "reads, and a read-only stream can exceed the copy rate, so frac may pass 1")
 
     def sgpr():
         piv = state.get("piv")
