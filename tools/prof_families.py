@@ -8,6 +8,7 @@
     python tools/prof_families.py rpchol    # rp_gemv_kernel / rp_finish_kernel (N = 262144, 600 pivots)
     python tools/prof_families.py matvec1   # single-vector mat-vec (P = 1 FMA path), N = 65536
     python tools/prof_families.py matvec    # block mat-vec (P = 30), N = 65536
+    python tools/prof_families.py gemm64    # gemm_f64_kernel with 64 x 64 tiles (1024^3 and the skinny K = 128 product)
 """
 import sys
 
@@ -53,6 +54,11 @@ elif what in ("matvec", "matvec1"):
     V = rn(N, 30 if what == "matvec" else 1)
     for _ in range(2):
         ops.kmatvec("se", x, x, V, 4.0, diag_add=0.25)
+elif what == "gemm64":
+    A, B = rn(1024, 1024), rn(1024, 1024)
+    C = torch.zeros((1024, 1024), dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        ops.gemm(A, B, transb=True, alpha=-1.0, beta=1.0, C=C)
 else:
     raise SystemExit(f"unknown case {what}")
 torch.cuda.synchronize()
