@@ -28,7 +28,7 @@ int main() {
   cudaMalloc(&A, n * n * 8);
   cudaMalloc(&inv, n * n * 8);
   cudaFuncSetAttribute((const void*)potrf_leaf_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF2_SMEM);
-  for (int io = 0; io < 2; ++io) {
+  for (int io : {0, 1, 3}) {  // bit 0: bulk-TMA I/O; bit 1: experimental eliminator (when compiled in)
   printf("bulk io = %d\n", io);
   const int stops[] = {0, 1, 4, 7, 10, 13, 16, 19, 22, 25, 27, 28, 29, 31};
   for (int stop : stops) {
