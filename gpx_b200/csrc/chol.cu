@@ -301,8 +301,9 @@ __device__ __forceinline__ void tri_mm(double* C, int ldc, const double* A, int 
 
 // The merge levels of the packed inverse: S holds L with its four 32 x 32 diagonal blocks already replaced by their
 // inverses; X21 = -X22 (L21 X11) for the 32 -> 64 and 64 -> 128 levels on DMMA, then the 128 x 128 block goes to inv.
+template <bool BULK_OUT>
 __device__ __forceinline__ void leaf_merge_and_store(double* S, double* T, int n, double* __restrict__ inv, int tid,
-                                                     int warp, int lane, bool skip_diag_blocks, bool bulk_out) {
+                                                     int warp, int lane, bool skip_diag_blocks) {
   // every product has one triangular factor: the k range is cut to its non-zero part (exact zeros skipped: the
   // sums are unchanged) and each warp runs four independent accumulator chains that share one fragment load
   {
@@ -316,7 +317,7 @@ __device__ __forceinline__ void leaf_merge_and_store(double* S, double* T, int n
   tri_mm<8, false>(T, T2S, S + 64 * L2S, L2S, S, L2S, 1.0, warp, lane);
   __syncthreads();
   tri_mm<8, true>(S + 64 * L2S, L2S, S + 64 * L2S + 64, L2S, T, T2S, -1.0, warp, lane);
-  if (bulk_out) {  // S is the packed inverse exactly (zero upper triangle): one 1 KB bulk store per row
+  if (BULK_OUT) {  // S is the packed inverse exactly (zero upper triangle): one 1 KB bulk store per row
     fence_proxy_async();
     __syncthreads();
     if (tid < LB) {
@@ -338,9 +339,13 @@ __device__ __forceinline__ void leaf_merge_and_store(double* S, double* T, int n
 // 32 x 32 blocks of inv): the merge levels and the 128 KB store of the packed inverse leave the panel's dependency
 // chain -- the head rows are solved by blocked substitution on L and those four blocks (panel_trsm32s_kernel), and
 // potrf_leaf_merge_kernel completes inv beside the chain, before the tall solve needs it.
+// FAST (chosen by the host: a full 128 x 128 leaf, 16-byte aligned rows, packed inverse wanted and merged here):
+// bulk-TMA load and store only -- the element-wise loops and the merge-less exit are not even compiled in; the leaf
+// is straight-line unrolled code executed once per 32-column block and its instruction footprint is part of its cost
+// (carrying a second eliminator in the kernel slowed the first one by 6 us).
+template <bool FAST>
 __global__ void __launch_bounds__(LEAF_NT, 1)
-potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv, int merge,
-                       int leaf_bulk_io) {
+potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __restrict__ inv, int merge) {
   extern __shared__ __align__(16) double sm[];
   double* S = sm;                       // [128][L2S]  A -> L -> inverse, in place
   double* DI = S + LB * L2S;            // [4][32][DIS] inverses of the diagonal blocks
@@ -356,7 +361,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   // panel's critical chain), zeros to the right of it.  What lands above the diagonal inside the diagonal blocks is
   // never read.
   __shared__ __align__(8) uint64_t lbar;
-  const bool bulk = (n == LB) && ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && leaf_bulk_io;
+  constexpr bool bulk = FAST;
   if (bulk && tid == 0) {
     mbar_init(&lbar, 1);
     fence_mbar_init();
@@ -503,8 +508,8 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
     if (i < n && k <= i) A[(long long)i * lda + k] = S[i * L2S + k];
   }
   LEAF_STAMP(28);
-  if (inv == nullptr) return;
-  if (!(merge & 0xff)) {  // the four diagonal-block inverses only (the rest of the block is written by potrf_leaf_merge_kernel)
+  if (!FAST && inv == nullptr) return;
+  if (!FAST && !(merge & 0xff)) {  // the four diagonal-block inverses only (the rest of the block is written by potrf_leaf_merge_kernel)
     for (int idx = tid; idx < 4 * 32 * 32; idx += LEAF_NT) {
       const int b = idx >> 10, r = (idx >> 5) & 31, c = idx & 31;
       inv[(b * 32 + r) * LB + b * 32 + c] = DI[(b * 32 + r) * DIS + c];
@@ -519,8 +524,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   }
   __syncthreads();
   LEAF_STAMP(29);
-  leaf_merge_and_store(S, T, n, inv, tid, warp, lane, false,
-                       bulk && (reinterpret_cast<uintptr_t>(inv) & 15) == 0);
+  leaf_merge_and_store<FAST>(S, T, n, inv, tid, warp, lane, false);
   CHAIN_END();
   LEAF_STAMP(31);
 }
@@ -542,7 +546,7 @@ potrf_leaf_merge_kernel(const double* __restrict__ A, long long lda, int n, doub
     S[i * L2S + k] = v;
   }
   __syncthreads();
-  leaf_merge_and_store(S, T, n, inv, tid, warp, lane, true, false);
+  leaf_merge_and_store<false>(S, T, n, inv, tid, warp, lane, true);
 }
 
 __global__ void logdet_kernel(const double* __restrict__ L, long long ld, int n,
@@ -577,12 +581,12 @@ int leaf_generation() {
 int leaf(Ctx* ctx, double* A, long long lda, int n, double* inv, cudaStream_t s, int merge = 1, bool pdl = false) {
   const int gen = leaf_generation();
   if (gen == 2) {
-    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(potrf_leaf_dmma_kernel), LEAF2_SMEM));
-    if (pdl)
-      GPXB_CUDA_CHECK(launch_pdl(potrf_leaf_dmma_kernel, dim3(1), dim3(LEAF_NT), LEAF2_SMEM, s, A, lda, n, inv, merge,
-                                 leaf_bulk_io()));
-    else
-      potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv, merge, leaf_bulk_io());
+    const bool fast = leaf_bulk_io() && n == LB && (lda & 1) == 0 && inv != nullptr && merge == 1 &&
+                      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(inv)) & 15) == 0;
+    auto kern = fast ? potrf_leaf_dmma_kernel<true> : potrf_leaf_dmma_kernel<false>;
+    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)kern, LEAF2_SMEM));
+    if (pdl) GPXB_CUDA_CHECK(launch_pdl(kern, dim3(1), dim3(LEAF_NT), LEAF2_SMEM, s, A, lda, n, inv, merge));
+    else kern<<<1, LEAF_NT, LEAF2_SMEM, s>>>(A, lda, n, inv, merge);
     GPXB_LAUNCH_CHECK();
     ctx->launches++;
     return 0;

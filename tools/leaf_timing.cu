@@ -27,8 +27,9 @@ int main() {
   double *A, *inv;
   cudaMalloc(&A, n * n * 8);
   cudaMalloc(&inv, n * n * 8);
-  cudaFuncSetAttribute((const void*)potrf_leaf_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF2_SMEM);
-  for (int io : {0, 1, 3}) {  // bit 0: bulk-TMA I/O; bit 1: experimental eliminator (when compiled in)
+  cudaFuncSetAttribute((const void*)potrf_leaf_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF2_SMEM);
+  cudaFuncSetAttribute((const void*)potrf_leaf_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF2_SMEM);
+  for (int io : {0, 1}) {  // 1: the FAST instantiation (bulk-TMA I/O only)
   printf("bulk io = %d\n", io);
   const int stops[] = {0, 1, 4, 7, 10, 13, 16, 19, 22, 25, 27, 28, 29, 31};
   for (int stop : stops) {
@@ -39,7 +40,8 @@ int main() {
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
       cudaEventRecord(e0);
-      potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM>>>(A, n, n, inv, 1 | ((stop + 1) << 8), io);
+      if (io) potrf_leaf_dmma_kernel<true><<<1, LEAF_NT, LEAF2_SMEM>>>(A, n, n, inv, 1 | ((stop + 1) << 8));
+      else potrf_leaf_dmma_kernel<false><<<1, LEAF_NT, LEAF2_SMEM>>>(A, n, n, inv, 1 | ((stop + 1) << 8));
       cudaEventRecord(e1);
       cudaDeviceSynchronize();
       float ms;
@@ -87,7 +89,7 @@ int main() {
           for (int r = 0; r < reps; ++r) {
             double* Ajj = M;                       // values drift; timing only
             double* B = M + (size_t)128 * lda2;
-            if (mode == 0 || mode == 3) potrf_leaf_dmma_kernel<<<1, LEAF_NT, LEAF2_SMEM>>>(Ajj, lda2, 128, invs, 1, io);
+            if (mode == 0 || mode == 3) { if (io) potrf_leaf_dmma_kernel<true><<<1, LEAF_NT, LEAF2_SMEM>>>(Ajj, lda2, 128, invs, 1); else potrf_leaf_dmma_kernel<false><<<1, LEAF_NT, LEAF2_SMEM>>>(Ajj, lda2, 128, invs, 1); }
             if (mode == 1 || mode == 3) panel_trsm32_kernel<<<4, 256, TRSM32_SMEM>>>(B, lda2, 128, 128, invs, io);
             if (mode == 2 || mode == 3) panel_syrk32_kernel<<<10, 128, SYRK32_SMEM>>>(B, lda2, B + 128, lda2, 128, 128, io);
           }
