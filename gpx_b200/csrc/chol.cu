@@ -351,7 +351,10 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   double* DI = S + LB * L2S;            // [4][32][DIS] inverses of the diagonal blocks
   double* T = DI + 4 * 32 * DIS;        // [64][T2S]
   double* rds = T + 64 * T2S;           // [128] reciprocals of the pivots, per diagonal block
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the warp index through a lane-0 shuffle: provably warp-uniform for the compiler, so the role branches below are
+  // uniform branches and the eliminator's shuffles compile to bare SHFL (with `tid >> 5` every __shfl_sync inside
+  // `if (warp == 0)` was wrapped in WARPSYNC.COLLECTIVE ... ENDCOLLECTIVE plus register moves: 14 400 instructions)
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lr = lane >> 2, lq = lane & 3;
 
   LEAF_STAMP(0);
