@@ -354,7 +354,7 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
   // the warp index through a lane-0 shuffle: provably warp-uniform for the compiler, so the role branches below are
   // uniform branches and the eliminator's shuffles compile to bare SHFL (with `tid >> 5` every __shfl_sync inside
   // `if (warp == 0)` was wrapped in WARPSYNC.COLLECTIVE ... ENDCOLLECTIVE plus register moves: 14 400 instructions)
-  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
   const int lr = lane >> 2, lq = lane & 3;
 
   LEAF_STAMP(0);
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(256) trsv_diag_kernel(const double* __restrict
   }
   __syncthreads();
   if (!backward) {
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = uniform_warp_id(), lane = tid & 31;
     for (int t = warp; t < nb; t += 8) {  // x[t] = sum_{c <= t} inv[t][c] b[c]
       double acc[TRSV_MAXM];
 #pragma unroll
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(256) trsv_fwd_update_kernel(const double* __re
     sx[r][c] = (r < m && c < nb) ? X[(long long)r * ldb + c] : 0.0;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + warp;
   if (j >= nrows) return;
   const double* lrow = Lblk + (long long)j * ldl;
@@ -771,7 +771,7 @@ __global__ void logdet_bcp_kernel(const double* __restrict__ Lp, BcpLayout lay, 
 // so[r][t] = sum_{c <= t} inv[t][c] sb[r][c]: one warp per output row, four rows in flight (16 loads per lane)
 __device__ __forceinline__ void trsv_diag_fwd_apply(const double* __restrict__ inv, double (*sb)[LB], double (*so)[LB],
                                                     int nb, int tid, int m) {
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = uniform_warp_id(), lane = tid & 31;
   for (int t0 = warp; t0 < nb; t0 += 32) {
     double v[4][4];
 #pragma unroll
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __rest
   __shared__ double sx[TRSV_MAXM][LB];
   __shared__ double sb[TRSV_MAXM][LB];
   __shared__ double so[TRSV_MAXM][LB];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   GPXB_PDL_WAIT_THEN_RELEASE();  // the sweep is a chain of short dependent launches (trsv_few_v2)
   for (int i = tid; i < TRSV_MAXM * LB; i += 256) {
     const int r = i / LB, c = i % LB;

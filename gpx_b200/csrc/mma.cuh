@@ -93,6 +93,12 @@ __device__ __forceinline__ void tma_bulk_commit_wait_read() {
   asm volatile("cp.async.bulk.commit_group;\ncp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
 
+// The warp index through a lane-0 shuffle: a value the compiler can prove warp-uniform.  Branching on it keeps the
+// warp converged in the compiler's eyes, so __shfl_sync / warp reductions below such a branch compile to bare SHFL;
+// with `threadIdx.x >> 5` each one is wrapped in WARPSYNC.COLLECTIVE ... ENDCOLLECTIVE and register moves (the
+// Cholesky leaf shrank from 14 440 to 6 448 instructions).  Must be called by all lanes of the warp.
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

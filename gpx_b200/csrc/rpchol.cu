@@ -42,7 +42,7 @@ __device__ __forceinline__ double kfun(int kind, double d2) {
 
 // inclusive scan of one value per thread across a 1024-thread CTA (fixed tree order)
 __device__ __forceinline__ double block_scan_1024(double v, double* sh /*32*/) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = uniform_warp_id();  // warp-uniform: the `w == 0` branch keeps bare shuffles
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const double t = __shfl_up_sync(0xffffffffu, v, o);
