@@ -1,6 +1,15 @@
-// Time to each phase boundary of the one-CTA Cholesky leaf (developer tool, not part of the library):
+// Developer tool (not part of the library): where the time of the panel factorisation's dependency chain goes.
+//   1. the one-CTA Cholesky leaf timed to each phase boundary (the same kernel returning after phase k: no clock
+//      reads inside the measured code), for the element-wise and the bulk-TMA instantiation;
+//   2. the three chain kernels back to back on one stream;
+//   3. the in-context timeline (%globaltimer stamps of block 0) of leaf / head solve / head update inside
+//      potrf_lower at n = 1024 and 2000.
+// chol.cu is compiled into this translation unit with -DGPXB_LEAF_STAMPS (which adds the phase exits and the stamps);
+// everything else comes from the built library:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -DGPXB_LEAF_STAMPS \
-//        -I gpx_b200/csrc -I include tools/leaf_timing.cu $(ls gpx_b200/build/*.o | grep -v chol.o) -o tools/_leaf_timing -ldl
+//        -I gpx_b200/csrc -I include tools/leaf_timing.cu -o tools/_leaf_timing \
+//        -L gpx_b200 -l:libgpxb200.so -Xlinker -rpath='$ORIGIN/../gpx_b200' -ldl
+// Output of the round-2 runs: profiles/r2_leaf_phase_timeline.txt.
 #include "../gpx_b200/csrc/chol.cu"
 
 #include <cstdio>
