@@ -145,7 +145,10 @@ struct TileLoader {
 
 // WM x WN warps, each a (8*MF) x (8*NF) tile:  2x4 warps of 64x32, or 4x4 warps of 32x32 (T = 128); 2x2 warps of
 // 32x32 (T = 64).
-template <bool AK, bool BKM, int WM, int WN, int T>
+// FAST (chosen by the host: both operands 16-byte aligned and K a multiple of BK, so every K tile is interior): the
+// main loop carries only the one-LDGSTS-per-chunk loader.  The general loader (K-edge clamping, element-wise path for
+// unaligned operands) inlined into the same loop made its body 1 845 instructions (30 KB) for 128 DMMAs.
+template <bool AK, bool BKM, int WM, int WN, int T, bool FAST>
 __global__ void __launch_bounds__(WM * WN * 32, T == 64 ? 2 : 1) gemm_f64_kernel(const GemmParams p) {
   constexpr int NTHR = WM * WN * 32;
   constexpr int BM = T, BN = T;
@@ -233,8 +236,13 @@ __global__ void __launch_bounds__(WM * WN * 32, T == 64 ? 2 : 1) gemm_f64_kernel
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
       double* sa = smem + s * STAGE_DBL;
-      la.load(sa, k_lo + s * BK, p.K, s);
-      lb.load(sa + TILE_DBL, k_lo + s * BK, p.K, s);
+      if (FAST) {
+        la.load_fast(sa, s);
+        lb.load_fast(sa + TILE_DBL, s);
+      } else {
+        la.load(sa, k_lo + s * BK, p.K, s);
+        lb.load(sa + TILE_DBL, k_lo + s * BK, p.K, s);
+      }
     }
     cp_async_commit();
   }
@@ -259,7 +267,7 @@ __global__ void __launch_bounds__(WM * WN * 32, T == 64 ? 2 : 1) gemm_f64_kernel
     for (int ks = 0; ks < BK / 4; ++ks) {
       if (ks == lpos) {
         if (do_load) {
-          if (interior) {
+          if (FAST || interior) {
             la.load_fast(sn, nxt);
             lb.load_fast(sn + TILE_DBL, nxt);
           } else {
@@ -366,18 +374,27 @@ int launch(Ctx* ctx, const GemmParams& p, int grid1, int batch, cudaStream_t str
     rec.flops = launch_flops(p, grid1) * batch;
     GPXB_CUDA_CHECK(cudaEventRecord(rec.e0, stream));
   }
+  // every K tile interior and both operands aligned: the instantiation whose main loop has only the fast loader
+  static const bool allow_fast = [] {
+    const char* e = getenv("GPXB_GEMM_FAST");  // "0": always the general loader (comparison)
+    return !(e && e[0] == '0');
+  }();
+  const bool fast = allow_fast && p.vecA && p.vecB && (p.K % BK == 0) && p.K > 0;
+  auto go = [&](void (*kern)(const GemmParams), int threads, int smem) -> cudaError_t {
+    const cudaError_t e = ensure_dyn_smem((const void*)kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, threads, smem, stream>>>(p);
+    return cudaSuccess;
+  };
+  constexpr int SM64 = TileGeom<64>::SMEM_BYTES, SM128 = TileGeom<128>::SMEM_BYTES;
   if (p.tile == 64) {
-    constexpr int SM64 = TileGeom<64>::SMEM_BYTES;
-    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 2, 2, 64>), SM64));
-    gemm_f64_kernel<AK, BKM, 2, 2, 64><<<grid, 128, SM64, stream>>>(p);
+    if (fast) GPXB_CUDA_CHECK(go(gemm_f64_kernel<AK, BKM, 2, 2, 64, true>, 128, SM64));
+    else GPXB_CUDA_CHECK(go(gemm_f64_kernel<AK, BKM, 2, 2, 64, false>, 128, SM64));
   } else if (gemm_variant() == 8) {
-    constexpr int SM128 = TileGeom<128>::SMEM_BYTES;
-    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 2, 4, 128>), SM128));
-    gemm_f64_kernel<AK, BKM, 2, 4, 128><<<grid, 256, SM128, stream>>>(p);
+    GPXB_CUDA_CHECK(go(gemm_f64_kernel<AK, BKM, 2, 4, 128, false>, 256, SM128));
   } else {
-    constexpr int SM128 = TileGeom<128>::SMEM_BYTES;
-    GPXB_CUDA_CHECK(ensure_dyn_smem((const void*)(gemm_f64_kernel<AK, BKM, 4, 4, 128>), SM128));
-    gemm_f64_kernel<AK, BKM, 4, 4, 128><<<grid, 512, SM128, stream>>>(p);
+    if (fast) GPXB_CUDA_CHECK(go(gemm_f64_kernel<AK, BKM, 4, 4, 128, true>, 512, SM128));
+    else GPXB_CUDA_CHECK(go(gemm_f64_kernel<AK, BKM, 4, 4, 128, false>, 512, SM128));
   }
   GPXB_LAUNCH_CHECK();
   if (prof) {
