@@ -339,6 +339,89 @@ __device__ __forceinline__ void leaf_merge_and_store(double* S, double* T, int n
 // 32 x 32 blocks of inv): the merge levels and the 128 KB store of the packed inverse leave the panel's dependency
 // chain -- the head rows are solved by blocked substitution on L and those four blocks (panel_trsm32s_kernel), and
 // potrf_leaf_merge_kernel completes inv beside the chain, before the tall solve needs it.
+// Inverse of the 32 x 32 lower-triangular block at Lb (row stride L2S; rd: reciprocals of its diagonal) into Dinv (row
+// stride DIS, zeros above the diagonal), by ONE warp: the four 8 x 8 diagonal blocks by forward substitution (lane =
+// block x column, 8 dependent steps), then the levels 8 -> 16 and 16 -> 32 as  X21 = -X22 (L21 X11)  on DMMA, the
+// intermediate T going through `sc` (>= 288 doubles of scratch) to change from the accumulator to the operand layout.
+// Replaces a 32-step substitution with lane = column (496 dependent FMA + broadcast LDS per lane, 4.2 us): the last
+// block's inverse has nothing to hide behind.
+__device__ __forceinline__ void inv32_warp(const double* __restrict__ Lb, const double* __restrict__ rd,
+                                           double* __restrict__ Dinv, double* __restrict__ sc, int lane) {
+  const int lr = lane >> 2, lq = lane & 3;
+  constexpr int TS = 10, TS2 = 18;
+#pragma unroll
+  for (int e = lane; e < 6 * 64; e += 32) {  // the six 8 x 8 blocks above the block diagonal
+    const int blk = e >> 6, r = (e >> 3) & 7, c = e & 7;
+    const int bi = blk < 3 ? 0 : (blk < 5 ? 1 : 2);
+    const int bj = blk < 3 ? blk + 1 : (blk < 5 ? blk - 1 : 3);
+    Dinv[(bi * 8 + r) * DIS + bj * 8 + c] = 0.0;
+  }
+  {
+    const int b = lane >> 3, j = lane & 7;
+    const double* Lbb = Lb + (b * 8) * L2S + b * 8;
+    double x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      double v = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < r) v -= Lbb[r * L2S + k] * x[k];
+      x[r] = (r >= j) ? v * rd[b * 8 + r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) Dinv[(b * 8 + r) * DIS + b * 8 + j] = x[r];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // 8 -> 16: T = L21 X11 for the pairs at p = 0 and p = 16
+    const int p = h * 16;
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+      dmma884(c0, c1, Lb[(p + 8 + lr) * L2S + p + lq + 4 * s2], Dinv[(p + lq + 4 * s2) * DIS + p + lr]);
+    sc[h * 8 * TS + lr * TS + 2 * lq] = c0;
+    sc[h * 8 * TS + lr * TS + 2 * lq + 1] = c1;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // X21 = -X22 T
+    const int p = h * 16;
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+      dmma884(c0, c1, Dinv[(p + 8 + lr) * DIS + p + 8 + lq + 4 * s2], sc[h * 8 * TS + (lq + 4 * s2) * TS + lr]);
+    Dinv[(p + 8 + lr) * DIS + p + 2 * lq] = -c0;
+    Dinv[(p + 8 + lr) * DIS + p + 2 * lq + 1] = -c1;
+  }
+  __syncwarp();
+  double t[2][2][2];
+#pragma unroll
+  for (int ti = 0; ti < 2; ++ti)  // 16 -> 32: T = L21 X11 (16 x 16 x 16)
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) {
+      t[ti][tj][0] = t[ti][tj][1] = 0.0;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4)
+        dmma884(t[ti][tj][0], t[ti][tj][1], Lb[(16 + ti * 8 + lr) * L2S + lq + 4 * s4],
+                Dinv[(lq + 4 * s4) * DIS + tj * 8 + lr]);
+      sc[(ti * 8 + lr) * TS2 + tj * 8 + 2 * lq] = t[ti][tj][0];
+      sc[(ti * 8 + lr) * TS2 + tj * 8 + 2 * lq + 1] = t[ti][tj][1];
+    }
+  __syncwarp();
+#pragma unroll
+  for (int ti = 0; ti < 2; ++ti)  // X21 = -X22 T
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) {
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4)
+        dmma884(c0, c1, Dinv[(16 + ti * 8 + lr) * DIS + 16 + lq + 4 * s4], sc[(lq + 4 * s4) * TS2 + tj * 8 + lr]);
+      Dinv[(16 + ti * 8 + lr) * DIS + tj * 8 + 2 * lq] = -c0;
+      Dinv[(16 + ti * 8 + lr) * DIS + tj * 8 + 2 * lq + 1] = -c1;
+    }
+  __syncwarp();
+}
+
 // FAST (chosen by the host: a full 128 x 128 leaf, 16-byte aligned rows, packed inverse wanted and merged here):
 // bulk-TMA load and store only -- the element-wise loops and the merge-less exit are not even compiled in; the leaf
 // is straight-line unrolled code executed once per 32-column block and its instruction footprint is part of its cost
@@ -445,19 +528,8 @@ potrf_leaf_dmma_kernel(double* __restrict__ A, long long lda, int n, double* __r
     LEAF_STAMP(4 + (jb >> 5) * 6);
     const int r0 = jb + 32, R = LB - r0;  // rows below the block
     if (warp == 7) {
-      // ---- inverse of the diagonal block: lane = column j of X, forward substitution; L[r][k] is a broadcast read ----
-      double x[32];
-      const double* Lb = S + jb * L2S + jb;
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        double v[4] = {(r == lane) ? 1.0 : 0.0, 0.0, 0.0, 0.0};  // four independent chains: FP64 FMA latency
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if (k < r) v[k & 3] -= Lb[r * L2S + k] * x[k];
-        x[r] = (r >= lane) ? ((v[0] + v[1]) + (v[2] + v[3])) * rd_blk[r] : 0.0;
-      }
-#pragma unroll
-      for (int r = 0; r < 32; ++r) Dinv[r * DIS + lane] = x[r];
+      // ---- inverse of the diagonal block (needed only for the packed inverse at the end) ----
+      inv32_warp(S + jb * L2S + jb, rd_blk, Dinv, T, lane);
     } else if (R > 0) {
       if (warp != 0) {
         // ---- panel: L21 = A21 L11^-T by forward substitution, one thread per row (warps 1..3) ----
