@@ -324,10 +324,24 @@ def other_configs(dgemm_tflops, world, rank, scale=1.0):
     state = {}
 
     def rpchol():
-        t, (_, piv), ph = timed(lambda: ops.rpcholesky("se", x32, M, ell32, key, True, want_factor=False))
+        call = lambda: ops.rpcholesky("se", x32, M, ell32, key, True, want_factor=False)  # noqa: E731
+        t, (_, piv), ph = timed(call)
+        extra = {}
+        if non_compute(t, ph) > 0.03 * t:
+            # The call's first act is a stream-ordered allocation of its 8 N M-byte factor workspace; on a box whose
+            # driver maps those 32 GB slowly that is up to seconds inside the first timed call (seen: 0.16, 0.6 and 2.8 s;
+            # the kernels' own 9.9 s unchanged).  The library's pool keeps the memory, so a second call measures the
+            # landmark loop itself; both times are reported.
+            t2, (_, piv2), ph2 = timed(call)
+            extra = dict(first_call_s=t, first_call_non_compute_s=non_compute(t, ph),
+                         retimed="the first call spent >3 % of its time outside the kernels (workspace allocation); "
+                                 "s is the second call")
+            if t2 < t:
+                t, piv, ph = t2, piv2, ph2
         state["piv"], state["t_rp"] = piv, t
         alg = 8.0 * N * M * (M - 1) / 2 + 5 * 8.0 * N * M
         return dict(id="rpcholesky", what="RPCholesky landmark loop (pivots only), rows sharded", N=N, D=32, M=M, s=t,
+                    **extra,
                     bound="hbm", alg_bytes=alg, achieved_gbs_total=alg / t / 1e9, achieved_gbs_per_gpu=alg / t / 1e9 / world,
                     peak_gbs=hbm, peak_source=hbm_src, frac=alg / t / 1e9 / world / hbm,
                     pivots_head=[int(v) for v in piv[:6].cpu().tolist()],
